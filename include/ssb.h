@@ -1,0 +1,210 @@
+/* ssb.h -- C ABI of the B200 Sugarscape timestep engine (libssb.so).
+ *
+ * The reference (nkremerh/sugarscape) is pure Python and has NO plugin / FFI interface
+ * (SURVEY.md section 8b), so this ABI is new.  The seam it replaces is
+ *
+ *     Sugarscape.doTimestep()                      reference sugarscape.py:389-421
+ *       environment.doTimestep(t)                  reference environment.py:105-109
+ *       random.shuffle(self.agents)                reference sugarscape.py:400
+ *       for agent in self.agents: agent.doTimestep reference sugarscape.py:404-407, agent.py:568-598
+ *       removeDeadAgents()                         reference sugarscape.py:843-853
+ *       updateRuntimeStats() (the reductions)      reference sugarscape.py:1005-1426
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch / C++ types.
+ *   - Every call returns 0 on success, <0 on error; ssb_last_error() gives the text.
+ *   - The library never allocates or frees SIMULATION buffers.  The host owns them (PyTorch
+ *     CUDA tensors in the shipped host code) and passes raw device pointers in ssb_grid_t /
+ *     ssb_agents_t.  The engine owns only scratch (RNG state, marks, work lists, partials).
+ *   - Grid arrays are x-major like the reference's grid[x][y] (environment.py:4,44):
+ *     idx = x * height + y.
+ *   - Agent arrays are slot-indexed struct-of-arrays with `capacity` slots.  `order[0..n_list)`
+ *     holds the reference's agent LIST (sugarscape.py:61) as slot numbers, in list order.
+ *   - All calls on one engine must come from one host thread; work is enqueued on the CUDA
+ *     stream passed in (`stream` is a cudaStream_t cast to void*); only ssb_stats,
+ *     ssb_get_* and ssb_sync block.
+ *
+ * The same structs (with HOST pointers) drive the CPU oracle in oracle/ (test infrastructure).
+ */
+#ifndef SSB_H
+#define SSB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSB_ABI_VERSION 1
+
+/* RNG modes */
+#define SSB_RNG_EXACT    0 /* mode E: CPython MT19937 word-for-word replay, ordered execution   */
+#define SSB_RNG_SCALABLE 1 /* mode S: counter-based per-agent substreams, parallel execution    */
+
+/* cause of death codes (agent.py:296-313 causeOfDeath strings) */
+#define SSB_ALIVE       0
+#define SSB_STARVATION  1
+#define SSB_AGING       2
+#define SSB_COMBAT      3
+#define SSB_OTHER       4
+
+/* sexes (agent.py:47) */
+#define SSB_SEX_NONE   0
+#define SSB_SEX_MALE   1
+#define SSB_SEX_FEMALE 2
+
+/* rule flags (params.flags): which optional rule families are live in this run */
+#define SSB_F_SPICE     (1 << 0) /* any spice capacity / metabolism / holdings               */
+#define SSB_F_POLLUTION (1 << 1) /* pollution timeframe configured                           */
+#define SSB_F_REPRO     (1 << 2) /* some agent has fertilityFactor > 0                       */
+#define SSB_F_TAGS      (1 << 3) /* tag strings present                                      */
+#define SSB_F_TAGGING   (1 << 4) /* agentTagging                                             */
+#define SSB_F_COMBAT    (1 << 5) /* some agent has aggression > 0                            */
+#define SSB_F_TRADE     (1 << 6) /* some agent has tradeFactor != 0                          */
+#define SSB_F_TAGPREF   (1 << 7) /* agentTagPreferences                                      */
+
+typedef struct ssb_params {
+    int32_t abi_version;
+    int32_t width, height;          /* environmentWidth / environmentHeight                    */
+    int32_t rng_mode;               /* SSB_RNG_*                                               */
+    uint64_t seed;                  /* configuration["seed"]                                   */
+    int32_t flags;                  /* SSB_F_*                                                 */
+    int32_t max_cell_distance;      /* environment.py:132-146                                  */
+    /* growback + seasons (environment.py:61-96,199-211) */
+    int32_t sugar_regrow, spice_regrow;
+    int32_t season_interval, seasonal_growback_delay, equator;
+    /* pollution (environment.py:97-103,192-197; cell.py:27-45) */
+    int32_t pollution_start, pollution_end;
+    int32_t diffusion_start, diffusion_end, diffusion_delay;
+    double sugar_prod_pollution, spice_prod_pollution;
+    double sugar_cons_pollution, spice_cons_pollution;
+    /* agents */
+    double max_combat_loot;         /* environmentMaxCombatLoot                                */
+    int32_t tag_len, max_tribes;    /* agentTagStringLength, environmentMaxTribes              */
+    int32_t max_timestep;           /* configuration["timesteps"]                              */
+    int32_t id_bits;                /* mode S: agent IDs must stay below 1 << id_bits (<= 26)   */
+} ssb_params_t;
+
+typedef struct ssb_grid {
+    int64_t n_cells;                /* width * height                                          */
+    int32_t *sugar, *sugar_cap;     /* cell.sugar / cell.maxSugar  (cell.py:8,19)              */
+    int32_t *spice, *spice_cap;     /* cell.spice / cell.maxSpice                              */
+    double  *pollution;             /* cell.pollution (cell.py:14)                             */
+    double  *pollution_flux;        /* scratch for the Jacobi pass (cell.py:104-109)           */
+    int32_t *occ;                   /* cell.agent as a slot number, -1 when empty              */
+} ssb_grid_t;
+
+/* counters[] layout (int64 each, device memory owned by the host) */
+#define SSB_C_N_LIST   0  /* len(sugarscape.agents)                                           */
+#define SSB_C_N_SLOTS  1  /* high-water mark of used slots                                    */
+#define SSB_C_NEXT_ID  2  /* sugarscape.nextAgentID                                           */
+#define SSB_C_N_FREE   3  /* entries in free_slots[]                                          */
+#define SSB_C_N_BORN   4  /* births during the current step                                   */
+#define SSB_C_N_DEAD   5  /* agents removed at the end of the current step                    */
+#define SSB_C_ROUNDS   6  /* mode S: commit rounds used by the last agent step                */
+#define SSB_C_OVERFLOW 7  /* != 0 if a capacity was exceeded (births dropped) -> host raises  */
+#define SSB_C_COUNT    16
+
+typedef struct ssb_agents {
+    int64_t capacity;               /* slots allocated in every array below                    */
+    int64_t *counters;              /* SSB_C_COUNT int64 values                                */
+    int32_t *order;                 /* agent list as slots, list order                         */
+    int32_t *free_slots;            /* recycled slots                                          */
+    int32_t *dead_list;             /* slots removed at the end of the current step            */
+    /* identity and position */
+    int32_t *id;                    /* agent.ID                                                */
+    int32_t *pos;                   /* cell index x*H+y, -1 once dead                          */
+    int32_t *born;                  /* agent.born                                              */
+    int32_t *cod;                   /* SSB_ALIVE or cause of death                             */
+    /* endowments (agent.py:14-62) */
+    double  *sugar, *spice;
+    int32_t *sugar_metab, *spice_metab;
+    int32_t *vision, *movement;
+    int32_t *age, *max_age;
+    int32_t *sex;
+    int32_t *fert_age, *infert_age;
+    double  *fert_factor;
+    double  *start_sugar, *start_spice;
+    double  *aggression;
+    double  *lookahead;
+    double  *trade_factor;
+    double  *mrs;                   /* marginalRateOfSubstitution (agent.py:102)               */
+    uint32_t *tags;                 /* bit i = tags[i]                                         */
+    int32_t *tribe;
+    /* per-transaction by-products that feed the log (agent.py:734-745,1555-1561) */
+    int32_t *last_moved;            /* lastMovedTimestep                                       */
+    double  *last_sugar, *last_spice;
+    int32_t *n_neighborhood;        /* len(movementNeighborhood)                               */
+    int32_t *n_valid_moves;         /* len(validMoves)                                         */
+    double  *happiness;             /* agent.happiness (sum of the five components)            */
+    double  *wealth_happiness;
+    double  *family_happiness;
+    int32_t *trade_volume;          /* agent.tradeVolume of its last transaction               */
+    double  *trade_price;           /* max(spicePrice, sugarPrice) of its last transaction     */
+    int32_t *last_repro;            /* lastReproducedTimestep                                  */
+    int32_t *n_children_alive, *n_children_dead; /* family happiness bookkeeping              */
+    int32_t *father, *mother;       /* parent IDs (-1 none)                                    */
+} ssb_agents_t;
+
+/* Raw reductions for the reference's runtimeStats (sugarscape.py:1005-1426).  The host turns
+ * them into the 59 log keys (means, Python round(), JSON). */
+typedef struct ssb_stats {
+    int64_t timestep;
+    int64_t population;
+    int64_t sum_sugar_metab, sum_spice_metab, sum_movement, sum_vision, sum_age;
+    double  sum_wealth, max_wealth, min_wealth;
+    double  sum_wealth_collected;       /* live agents: wealth - (lastSugar + lastSpice)        */
+    double  sum_burn_rate;              /* sum findTimeToLive()                                 */
+    double  sum_ttl_age_limited;        /* sum findTimeToLive(True)                             */
+    int64_t sum_neighbors, sum_valid_moves;
+    int64_t n_traders, trade_volume;
+    double  sum_trade_price;
+    double  sum_happiness, sum_wealth_happiness, sum_family_happiness;
+    int64_t tribe_count[32];            /* agents per tribe (tribes dict, 1171-1174)            */
+    int64_t tribe_first[32];            /* list index of the first agent of each tribe          */
+    /* dead agents removed this step (1213-1265) */
+    int64_t n_dead, n_dead_moved, dead_starvation, dead_aging, dead_combat, sum_age_at_death;
+    double  dead_wealth_collected;
+    int64_t n_born, n_replaced;
+    /* environment (1044-1051) */
+    int64_t env_wealth_total;           /* sum sugar + spice                                    */
+    int64_t env_wealth_created;         /* sum sugarLastProduced + spiceLastProduced            */
+    int64_t env_capacity_total;         /* sum maxSugar + maxSpice (added once at t == 1)       */
+    double  lorenz_weighted_sum;        /* sum_i (cumulative wealth after i sorted agents), trapezoid form */
+    int64_t rounds;                     /* mode S commit rounds of this step                    */
+} ssb_stats_t;
+
+typedef struct ssb_engine ssb_engine_t;
+
+/* lifecycle */
+int  ssb_create(const ssb_params_t *params, int device, ssb_engine_t **out);
+int  ssb_bind(ssb_engine_t *e, const ssb_grid_t *grid, const ssb_agents_t *agents);
+void ssb_destroy(ssb_engine_t *e);
+const char *ssb_last_error(const ssb_engine_t *e);
+int  ssb_abi_version(void);
+
+/* mode E: the CPython MT19937 main stream; maps 1:1 to random.getstate()[1] */
+int  ssb_set_mt_state(ssb_engine_t *e, const uint32_t state[624], int32_t index);
+int  ssb_get_mt_state(ssb_engine_t *e, uint32_t state[624], int32_t *index);
+
+/* one timestep, in the reference's phase order (sugarscape.py:395-410) */
+int  ssb_env_step(ssb_engine_t *e, int32_t t, void *stream);     /* environment.doTimestep     */
+int  ssb_agent_step(ssb_engine_t *e, int32_t t, double prev_mean_wealth, void *stream);
+                                                                  /* shuffle + agent loop       */
+int  ssb_compact(ssb_engine_t *e, int32_t t, void *stream);      /* removeDeadAgents + births  */
+int  ssb_reduce_stats(ssb_engine_t *e, int32_t t, void *stream); /* device reductions          */
+int  ssb_step(ssb_engine_t *e, int32_t t, double prev_mean_wealth, void *stream);
+                                                                  /* the four above, in order   */
+int  ssb_stats(ssb_engine_t *e, ssb_stats_t *host_out);          /* synchronises               */
+int  ssb_sync(ssb_engine_t *e, void *stream);
+
+/* instrumentation: number of kernels this engine has launched, device time of the last
+ * ssb_env_step / ssb_agent_step in ms (CUDA events on the caller's stream; ssb_timing syncs) */
+int64_t ssb_launch_count(const ssb_engine_t *e);
+int  ssb_timing(ssb_engine_t *e, float *env_ms, float *agent_ms, float *compact_ms, float *stats_ms);
+int  ssb_enable_timing(ssb_engine_t *e, int32_t on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSB_H */

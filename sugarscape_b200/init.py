@@ -1,0 +1,386 @@
+"""Initial state of a simulation, as struct-of-arrays (host side, cold path).
+
+Restates the reference's start-up sequence so that the main CPython ``random`` stream is at
+exactly the same position when the first timestep begins:
+
+  configureEnvironment / addResourcePeak   reference sugarscape.py:348-387,154-169
+  findActiveQuadrants                      reference sugarscape.py:475-497
+  randomizeAgentEndowments                 reference sugarscape.py:577-758
+  configureAgents (initial + replacement)  reference sugarscape.py:171-267
+  generateTribeTags                        reference sugarscape.py:548-559
+  configureDiseases (the unconditional list shuffle)  reference sugarscape.py:305
+
+Everything that draws random numbers uses the stdlib ``random`` module, i.e. the very generator
+the reference uses; the resulting MT19937 state is then handed to the device
+(``ssb_set_mt_state``).  The arrays built here become the device SoA of include/ssb.h.
+"""
+import hashlib
+import math
+import random
+
+import numpy as np
+
+from . import layout
+
+
+class UnsupportedConfiguration(NotImplementedError):
+    """Raised loudly for rule families this engine does not implement yet (no CPU fallback)."""
+
+
+# reference sugarscape.py:625-657 -- name of the endowment, option holding its [min, max]
+_RANGED_ENDOWMENTS = (
+    ("aggressionFactor", "agentAggressionFactor"),
+    ("baseInterestRate", "agentBaseInterestRate"),
+    ("decisionModelAgeismFactor", "agentDecisionModelAgeismFactor"),
+    ("decisionModelFactor", "agentDecisionModelFactor"),
+    ("decisionModelLookaheadDiscount", "agentDecisionModelLookaheadDiscount"),
+    ("decisionModelRacismFactor", "agentDecisionModelRacismFactor"),
+    ("decisionModelSexismFactor", "agentDecisionModelSexismFactor"),
+    ("decisionModelTribalFactor", "agentDecisionModelTribalFactor"),
+    ("diseaseProtectionChance", "agentDiseaseProtectionChance"),
+    ("dynamicDecisionModelFactor", "agentDynamicDecisionModelFactor"),
+    ("dynamicSelfishnessFactor", "agentDynamicSelfishnessFactor"),
+    ("dynamicSocialPressureFactor", "agentDynamicSocialPressureFactor"),
+    ("femaleFertilityAge", "agentFemaleFertilityAge"),
+    ("femaleInfertilityAge", "agentFemaleInfertilityAge"),
+    ("fertilityFactor", "agentFertilityFactor"),
+    ("lendingFactor", "agentLendingFactor"),
+    ("loanDuration", "agentLoanDuration"),
+    ("lookaheadFactor", "agentLookaheadFactor"),
+    ("maleFertilityAge", "agentMaleFertilityAge"),
+    ("maleInfertilityAge", "agentMaleInfertilityAge"),
+    ("maxAge", "agentMaxAge"),
+    ("maxFriends", "agentMaxFriends"),
+    ("movement", "agentMovement"),
+    ("selfishnessFactor", "agentSelfishnessFactor"),
+    ("spice", "agentStartingSpice"),
+    ("spiceMetabolism", "agentSpiceMetabolism"),
+    ("sugar", "agentStartingSugar"),
+    ("sugarMetabolism", "agentSugarMetabolism"),
+    ("tradeFactor", "agentTradeFactor"),
+    ("universalSpice", "agentUniversalSpice"),
+    ("universalSugar", "agentUniversalSugar"),
+    ("vision", "agentVision"),
+)
+
+
+def _md5_int(name):
+    return int(hashlib.md5(name.encode()).hexdigest(), 16)
+
+
+def _decimals(value):
+    parts = str(value).split(".")
+    return len(parts[1]) if len(parts) == 2 else None
+
+
+def check_supported(c):
+    """Fail loudly on rule families without a CUDA implementation yet (DESIGN.md 'scope')."""
+    problems = []
+    if c["agentVisionMode"] != "cardinal" or c["agentMovementMode"] != "cardinal":
+        problems.append("radial vision/movement")
+    if c["neighborhoodMode"] != "vonNeumann":
+        problems.append("moore neighbourhood")
+    if not c["environmentWraparound"]:
+        problems.append("environmentWraparound=false")
+    if c["environmentFile"] is not None:
+        problems.append("environmentFile")
+    if c["agentLeader"]:
+        problems.append("agentLeader")
+    if c["startingDiseases"] > 0 or c["diseaseList"]:
+        problems.append("diseases")
+    if c["agentDepressionPercentage"] > 0:
+        problems.append("depression")
+    if c["agentLendingFactor"][1] > 0:
+        problems.append("lending")
+    if c["agentRacialTagStringLength"] > 0 and c["environmentMaxRaces"] > 0:
+        problems.append("racial tags")
+    if c["agentInheritancePolicy"] != "none":
+        problems.append("inheritance")
+    if c["agentMaxFriends"][1] > 0:
+        problems.append("friends")
+    if c["agentUniversalSugar"][1] != 0 or c["agentUniversalSpice"][1] != 0:
+        problems.append("universal income")
+    if any(m not in ("none", "rawSugarscape") for m in c["agentDecisionModels"]):
+        problems.append("decision models other than rawSugarscape")
+    if c["agentDecisionModelFactor"][1] > 0:
+        problems.append("agentDecisionModelFactor")
+    for k in ("agentDecisionModelAgeismFactor", "agentDecisionModelRacismFactor",
+              "agentDecisionModelSexismFactor", "agentDecisionModelTribalFactor"):
+        if c[k][1] >= 0:
+            problems.append(k)
+    if c["experimentalGroup"] is not None:
+        problems.append("experimentalGroup")
+    if c["agentTagStringLength"] > 32:
+        problems.append("tag strings longer than 32")
+    for k in ("environmentSugarRegrowRate", "environmentSpiceRegrowRate"):
+        if c[k] != int(c[k]):
+            problems.append("fractional " + k)
+    for k in ("agentSugarMetabolism", "agentSpiceMetabolism", "agentVision", "agentMovement",
+              "agentMaxAge"):
+        if any(v != int(v) for v in c[k]):
+            problems.append("fractional " + k)
+    if c["environmentHeight"] != c["environmentWidth"] and c["environmentPollutionDiffusionDelay"] > 0:
+        # reference quirk: diffusion indexes grid[i][j] with i over height
+        problems.append("pollution diffusion on a non-square map")
+    if c["agentLogfile"] is not None:
+        problems.append("agentLogfile")
+    if problems:
+        raise UnsupportedConfiguration(
+            "this engine has no CUDA implementation yet for: " + ", ".join(problems))
+
+
+# ---------------------------------------------------------------------------------------------
+# environment
+# ---------------------------------------------------------------------------------------------
+
+def capacity_field(width, height, peaks):
+    """addResourcePeak (sugarscape.py:154-169) for all peaks; x-major int32 [W, H]."""
+    cap = np.zeros((width, height), dtype=np.int64)
+    radius = math.ceil(math.sqrt(2 * (height + width)))
+    xs = np.arange(width, dtype=np.float64)[:, None]
+    ys = np.arange(height, dtype=np.float64)[None, :]
+    for px, py, value in peaks:
+        dispersion = math.sqrt(max(px, width - px) ** 2 + max(py, height - py) ** 2) * (radius / width)
+        dist = np.sqrt((px - xs) ** 2 + (py - ys) ** 2)
+        level = np.ceil(np.minimum(1 + value * (1 - dist / dispersion), value)).astype(np.int64)
+        cap = np.maximum(cap, level)
+    return cap.astype(np.int32)
+
+
+def max_cell_distance(c):
+    """environment.py:132-146 (cardinal modes, wraparound)."""
+    max_vision = c["startingDiseases"] * max(c["diseaseVisionPenalty"][1], 0) + c["agentVision"][1]
+    max_movement = c["startingDiseases"] * max(c["diseaseMovementPenalty"][1], 0) + c["agentMovement"][1]
+    rng = max(max_vision, max_movement)
+    return int(max(min(rng, c["environmentWidth"] // 2), min(rng, c["environmentHeight"] // 2)))
+
+
+def active_quadrants(c):
+    """findActiveQuadrants (sugarscape.py:475-497): lists of cell indices (x*H + y), built
+    y-outer / x-inner like the reference's comprehensions."""
+    W, H = c["environmentWidth"], c["environmentHeight"]
+    qw = math.floor(W / 2 * c["environmentQuadrantSizeFactor"])
+    qh = math.floor(H / 2 * c["environmentQuadrantSizeFactor"])
+    spans = {1: (range(qh), range(qw)),
+             2: (range(qh), range(W - qw, W)),
+             3: (range(H - qh, H), range(W - qw, W)),
+             4: (range(H - qh, H), range(qw))}
+    quadrants = []
+    for q in (1, 2, 3, 4):
+        if q in c["environmentStartingQuadrants"]:
+            ys, xs = spans[q]
+            quadrants.append([x * H + y for y in ys for x in xs])
+    return quadrants
+
+
+# ---------------------------------------------------------------------------------------------
+# endowments
+# ---------------------------------------------------------------------------------------------
+
+def generate_tribe_tags(c, tribe):
+    """generateTribeTags (sugarscape.py:548-559): one randint + one shuffle."""
+    length = c["agentTagStringLength"]
+    tribe_size = (length + 1) / c["environmentMaxTribes"]
+    min_zeroes = math.floor(tribe * tribe_size)
+    max_zeroes = min(math.floor((tribe + 1) * tribe_size) - 1, length)
+    zeroes = random.randint(min_zeroes, max_zeroes)
+    tags = [0] * zeroes + [1] * (length - zeroes)
+    random.shuffle(tags)
+    return tags
+
+
+def randomize_endowments(c, n, timestep):
+    """randomizeAgentEndowments (sugarscape.py:577-758) -> list of endowment dicts."""
+    n_depressed = int(math.ceil(n * c["agentDepressionPercentage"]))
+    depression = [1] * n_depressed + [0] * (n - n_depressed)
+    random.shuffle(depression)  # always drawn, even when all zero (Appendix C.6)
+
+    ranged = {}
+    for name, option in _RANGED_ENDOWMENTS:
+        lo, hi = c[option][0], c[option][1]
+        if name == "universalSpice":
+            hi = c["agentUniversalSugar"][1]  # reference quirk (sugarscape.py:654)
+        decs = [d for d in (_decimals(lo), _decimals(hi)) if d is not None]
+        decimals = max(decs) if decs else 0
+        ranged[name] = {"values": [], "curr": lo, "min": lo, "max": hi,
+                        "inc": 10 ** (-1 * decimals), "decimals": decimals}
+
+    # racial tags (sugarscape.py:504-515) -- refused by check_supported when enabled
+    racial_tags = [None] * n
+    # tribe tags (sugarscape.py:517-528)
+    if c["agentTagStringLength"] == 0 or c["environmentMaxTribes"] == 0 or c["environmentTribePerQuadrant"]:
+        tags = [None] * n
+    else:
+        tags = [generate_tribe_tags(c, i % c["environmentMaxTribes"]) for i in range(n)]
+        random.shuffle(tags)
+
+    ratio = c["agentMaleToFemaleRatio"]
+    sexed = ratio is not None and ratio != 0
+    males_left = math.floor(n / (ratio + 1)) * ratio if sexed else n
+    sexes, models, immune = [], [], []
+    model_names = c["agentDecisionModels"]
+    for i in range(n):
+        for r in ranged.values():
+            r["values"].append(r["curr"])
+            r["curr"] = round(r["curr"] + r["inc"], r["decimals"])
+            if r["curr"] > r["max"]:
+                r["curr"] = r["min"]
+        if c["agentImmuneSystemLength"] > 0:
+            immune.append([random.randrange(2) for _ in range(c["agentImmuneSystemLength"])])
+        else:
+            immune.append(None)
+        if sexed:
+            if males_left == 0:
+                sexes.append("female")
+            else:
+                sexes.append("male")
+                males_left -= 1
+        else:
+            sexes.append(None)
+        model = model_names[i % len(model_names)]
+        models.append("none" if model == "rawSugarscape" else model)
+
+    # private hash-seeded shuffles: no main-stream consumption (sugarscape.py:725-729)
+    saved = random.getstate()
+    for name, r in ranged.items():
+        random.seed(_md5_int(name) + timestep)
+        random.shuffle(r["values"])
+    random.setstate(saved)
+    random.shuffle(sexes)
+    random.shuffle(models)
+
+    sex_specific = {"femaleFertilityAge": ("female", "fertilityAge"),
+                    "femaleInfertilityAge": ("female", "infertilityAge"),
+                    "maleFertilityAge": ("male", "fertilityAge"),
+                    "maleInfertilityAge": ("male", "infertilityAge")}
+    endowments = []
+    for i in range(n):
+        e = {"sex": sexes[i], "racialTags": racial_tags.pop(), "tags": tags.pop(),
+             "immuneSystem": immune.pop(), "decisionModel": models.pop(),
+             "depressionFactor": depression[i]}
+        for name, r in ranged.items():
+            if name in sex_specific:
+                sex, target = sex_specific[name]
+                if sexes[i] == sex:
+                    e[target] = r["values"].pop()
+                continue
+            e[name] = r["values"].pop()
+        if sexes[i] is None:
+            e["fertilityAge"] = 0
+            e["infertilityAge"] = 0
+        endowments.append(e)
+    return endowments
+
+
+def find_tribe(c, tags):
+    """agent.py:1142-1151."""
+    if tags is None:
+        return -1
+    zeroes = tags.count(0)
+    tribe_size = (c["agentTagStringLength"] + 1) / c["environmentMaxTribes"]
+    return min(math.ceil((zeroes + 1) / tribe_size) - 1, c["environmentMaxTribes"] - 1)
+
+
+def tags_mask(tags):
+    m = 0
+    for i, b in enumerate(tags or ()):
+        if b:
+            m |= 1 << i
+    return m
+
+
+# ---------------------------------------------------------------------------------------------
+# placement (initial population and replacements)
+# ---------------------------------------------------------------------------------------------
+
+class Population:
+    """Host-side bookkeeping that outlives init: the endowment list reused cyclically by
+    replacements (sugarscape.py:207-208) and the ID counter."""
+
+    def __init__(self, configuration):
+        self.c = configuration
+        self.endowments = []
+        self.endowment_index = 0
+        self.quadrants = active_quadrants(configuration)
+
+    def place(self, num_agents, occupied, timestep, next_id):
+        """configureAgents (sugarscape.py:171-267) without the object graph.
+
+        occupied: boolean array over cells (True = cell.agent is not None).
+        Returns a list of new-agent dicts (cell, id, endowment fields, tags, tribe) in list
+        order; consumes the main random stream exactly like the reference."""
+        c = self.c
+        empty = [[cell for cell in quadrant if not occupied[cell]] for quadrant in self.quadrants]
+        total = sum(len(q) for q in empty)
+        if total == 0:
+            return []
+        num_agents = int(min(num_agents, total))
+        if not self.endowments:
+            self.endowments = randomize_endowments(c, num_agents, timestep)
+        for quadrant in empty:
+            random.shuffle(quadrant)
+        indices = list(range(len(empty)))
+        random.shuffle(indices)
+        new_agents = []
+        for i in range(num_agents):
+            q = indices[i % len(empty)]
+            cell = empty[q].pop()
+            e = self.endowments[self.endowment_index % len(self.endowments)]
+            self.endowment_index += 1
+            tags = e["tags"]
+            if c["environmentTribePerQuadrant"]:
+                tags = generate_tribe_tags(c, q)
+            new_agents.append({"cell": cell, "id": next_id + i, "born": timestep,
+                               "endowment": e, "tags": tags, "tribe": find_tribe(c, tags)})
+        return new_agents
+
+
+def rule_flags(c):
+    f = 0
+    if (c["environmentMaxSpice"] > 0 and c["environmentSpicePeaks"]) or c["agentSpiceMetabolism"][1] > 0 \
+            or c["agentStartingSpice"][1] > 0 or c["environmentSpiceRegrowRate"] > 0:
+        f |= layout.F_SPICE
+    if c["environmentPollutionTimeframe"] != [0, 0] or c["environmentPollutionDiffusionDelay"] > 0:
+        f |= layout.F_POLLUTION
+    if c["agentFertilityFactor"][1] > 0:
+        f |= layout.F_REPRO
+    if c["agentTagStringLength"] > 0 and c["environmentMaxTribes"] > 0:
+        f |= layout.F_TAGS
+    if c["agentTagging"]:
+        f |= layout.F_TAGGING
+    if c["agentAggressionFactor"][1] > 0:
+        f |= layout.F_COMBAT
+    if c["agentTradeFactor"][1] != 0:
+        f |= layout.F_TRADE
+    if c["agentTagPreferences"]:
+        f |= layout.F_TAGPREF
+    return f
+
+
+def build_initial_state(c, capacity=None):
+    """Environment + initial population + the init-time list shuffle; returns (state, population).
+
+    Must be called right after verify_random_seed/verify_configuration so the main stream is
+    positioned as in the reference's Sugarscape.__init__ (sugarscape.py:19-75)."""
+    check_supported(c)
+    W, H = c["environmentWidth"], c["environmentHeight"]
+    sugar_cap = capacity_field(W, H, c["environmentSugarPeaks"])
+    spice_cap = capacity_field(W, H, c["environmentSpicePeaks"])
+    pop = Population(c)
+    n0 = int(c["startingAgents"])
+    if capacity is None:
+        capacity = layout.default_capacity(c, n0)
+    state = layout.HostState.empty(W, H, capacity)
+    state.sugar_cap[:] = sugar_cap.reshape(-1)
+    state.spice_cap[:] = spice_cap.reshape(-1)
+    state.sugar[:] = state.sugar_cap
+    state.spice[:] = state.spice_cap
+
+    occupied = np.zeros(W * H, dtype=bool)
+    new_agents = pop.place(n0, occupied, 0, 0) if n0 > 0 else []
+    # configureDiseases always shuffles the agent list once (sugarscape.py:305) when any agent exists
+    if new_agents:
+        random.shuffle(new_agents)
+    state.append_agents(new_agents)
+    state.counters[layout.C_NEXT_ID] = len(new_agents)
+    return state, pop

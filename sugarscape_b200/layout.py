@@ -1,0 +1,244 @@
+"""Struct-of-arrays layout shared by the host code and the C ABI (mirror of include/ssb.h).
+
+One table (``AGENT_FIELDS`` / ``GRID_FIELDS``) drives the numpy host arrays, the torch device
+tensors and the ctypes structs, so the three cannot drift apart.  tests/test_abi.py checks the
+ctypes struct sizes against ``sizeof`` values exported by the built library.
+"""
+import ctypes as C
+
+import numpy as np
+
+ABI_VERSION = 1
+RNG_EXACT, RNG_SCALABLE = 0, 1
+ALIVE, STARVATION, AGING, COMBAT, OTHER = 0, 1, 2, 3, 4
+SEX_NONE, SEX_MALE, SEX_FEMALE = 0, 1, 2
+SEX_CODE = {None: SEX_NONE, "male": SEX_MALE, "female": SEX_FEMALE}
+
+F_SPICE, F_POLLUTION, F_REPRO, F_TAGS, F_TAGGING, F_COMBAT, F_TRADE, F_TAGPREF = (
+    1 << 0, 1 << 1, 1 << 2, 1 << 3, 1 << 4, 1 << 5, 1 << 6, 1 << 7)
+
+(C_N_LIST, C_N_SLOTS, C_NEXT_ID, C_N_FREE, C_N_BORN, C_N_DEAD, C_ROUNDS, C_OVERFLOW) = range(8)
+C_COUNT = 16
+
+# (name, numpy dtype) in the order of ssb_grid_t
+GRID_FIELDS = (
+    ("sugar", np.int32), ("sugar_cap", np.int32), ("spice", np.int32), ("spice_cap", np.int32),
+    ("pollution", np.float64), ("pollution_flux", np.float64), ("occ", np.int32),
+)
+# (name, numpy dtype, fill) in the order of ssb_agents_t after `counters`
+AGENT_FIELDS = (
+    ("order", np.int32, -1), ("free_slots", np.int32, -1), ("dead_list", np.int32, -1),
+    ("id", np.int32, -1), ("pos", np.int32, -1), ("born", np.int32, 0), ("cod", np.int32, 0),
+    ("sugar", np.float64, 0), ("spice", np.float64, 0),
+    ("sugar_metab", np.int32, 0), ("spice_metab", np.int32, 0),
+    ("vision", np.int32, 0), ("movement", np.int32, 0),
+    ("age", np.int32, 0), ("max_age", np.int32, -1),
+    ("sex", np.int32, 0),
+    ("fert_age", np.int32, 0), ("infert_age", np.int32, 0),
+    ("fert_factor", np.float64, 0),
+    ("start_sugar", np.float64, 0), ("start_spice", np.float64, 0),
+    ("aggression", np.float64, 0), ("lookahead", np.float64, 0),
+    ("trade_factor", np.float64, 0), ("mrs", np.float64, 1),
+    ("tags", np.uint32, 0), ("tribe", np.int32, -1),
+    ("last_moved", np.int32, -1),
+    ("last_sugar", np.float64, 0), ("last_spice", np.float64, 0),
+    ("n_neighborhood", np.int32, 0), ("n_valid_moves", np.int32, 0),
+    ("happiness", np.float64, 0), ("wealth_happiness", np.float64, 0),
+    ("family_happiness", np.float64, 0),
+    ("trade_volume", np.int32, 0), ("trade_price", np.float64, 0),
+    ("last_repro", np.int32, -1),
+    ("n_children_alive", np.int32, 0), ("n_children_dead", np.int32, 0),
+    ("father", np.int32, -1), ("mother", np.int32, -1),
+)
+
+_CT = {np.int32: C.c_int32, np.uint32: C.c_uint32, np.float64: C.c_double, np.int64: C.c_int64}
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
+        ("rng_mode", C.c_int32), ("seed", C.c_uint64), ("flags", C.c_int32),
+        ("max_cell_distance", C.c_int32),
+        ("sugar_regrow", C.c_int32), ("spice_regrow", C.c_int32),
+        ("season_interval", C.c_int32), ("seasonal_growback_delay", C.c_int32),
+        ("equator", C.c_int32),
+        ("pollution_start", C.c_int32), ("pollution_end", C.c_int32),
+        ("diffusion_start", C.c_int32), ("diffusion_end", C.c_int32),
+        ("diffusion_delay", C.c_int32),
+        ("sugar_prod_pollution", C.c_double), ("spice_prod_pollution", C.c_double),
+        ("sugar_cons_pollution", C.c_double), ("spice_cons_pollution", C.c_double),
+        ("max_combat_loot", C.c_double),
+        ("tag_len", C.c_int32), ("max_tribes", C.c_int32),
+        ("max_timestep", C.c_int32), ("id_bits", C.c_int32),
+    ]
+
+
+class Grid(C.Structure):
+    _fields_ = [("n_cells", C.c_int64)] + [(n, C.c_void_p) for n, _ in GRID_FIELDS]
+
+
+class Agents(C.Structure):
+    _fields_ = ([("capacity", C.c_int64), ("counters", C.c_void_p)]
+                + [(n, C.c_void_p) for n, _, _ in AGENT_FIELDS])
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("timestep", C.c_int64), ("population", C.c_int64),
+        ("sum_sugar_metab", C.c_int64), ("sum_spice_metab", C.c_int64),
+        ("sum_movement", C.c_int64), ("sum_vision", C.c_int64), ("sum_age", C.c_int64),
+        ("sum_wealth", C.c_double), ("max_wealth", C.c_double), ("min_wealth", C.c_double),
+        ("sum_wealth_collected", C.c_double), ("sum_burn_rate", C.c_double),
+        ("sum_ttl_age_limited", C.c_double),
+        ("sum_neighbors", C.c_int64), ("sum_valid_moves", C.c_int64),
+        ("n_traders", C.c_int64), ("trade_volume", C.c_int64), ("sum_trade_price", C.c_double),
+        ("sum_happiness", C.c_double), ("sum_wealth_happiness", C.c_double),
+        ("sum_family_happiness", C.c_double),
+        ("tribe_count", C.c_int64 * 32), ("tribe_first", C.c_int64 * 32),
+        ("n_dead", C.c_int64), ("n_dead_moved", C.c_int64), ("dead_starvation", C.c_int64),
+        ("dead_aging", C.c_int64), ("dead_combat", C.c_int64), ("sum_age_at_death", C.c_int64),
+        ("dead_wealth_collected", C.c_double),
+        ("n_born", C.c_int64), ("n_replaced", C.c_int64),
+        ("env_wealth_total", C.c_int64), ("env_wealth_created", C.c_int64),
+        ("env_capacity_total", C.c_int64),
+        ("lorenz_weighted_sum", C.c_double), ("rounds", C.c_int64),
+    ]
+
+
+def default_capacity(c, n0):
+    """Slots to allocate: births and replacements append, dead slots are recycled."""
+    cells = c["environmentWidth"] * c["environmentHeight"]
+    want = max(n0, int(c["agentReplacements"]), 1)
+    if c["agentFertilityFactor"][1] > 0:
+        want = max(want * 4, cells // 2)
+    return int(min(max(2 * want, 1024), 2 * cells + 1024))
+
+
+def make_params(c, rng_mode, flags, max_cell_distance, equator):
+    p = Params()
+    p.abi_version = ABI_VERSION
+    p.width, p.height = c["environmentWidth"], c["environmentHeight"]
+    p.rng_mode = rng_mode
+    p.seed = c["seed"] & 0xFFFFFFFFFFFFFFFF
+    p.flags = flags
+    p.max_cell_distance = max_cell_distance
+    p.sugar_regrow = int(c["environmentSugarRegrowRate"])
+    p.spice_regrow = int(c["environmentSpiceRegrowRate"])
+    p.season_interval = int(c["environmentSeasonInterval"])
+    p.seasonal_growback_delay = int(c["environmentSeasonalGrowbackDelay"])
+    p.equator = equator
+    p.pollution_start, p.pollution_end = c["environmentPollutionTimeframe"]
+    p.diffusion_start, p.diffusion_end = c["environmentPollutionDiffusionTimeframe"]
+    p.diffusion_delay = int(c["environmentPollutionDiffusionDelay"])
+    p.sugar_prod_pollution = c["environmentSugarProductionPollutionFactor"]
+    p.spice_prod_pollution = c["environmentSpiceProductionPollutionFactor"]
+    p.sugar_cons_pollution = c["environmentSugarConsumptionPollutionFactor"]
+    p.spice_cons_pollution = c["environmentSpiceConsumptionPollutionFactor"]
+    p.max_combat_loot = c["environmentMaxCombatLoot"]
+    p.tag_len = c["agentTagStringLength"]
+    p.max_tribes = c["environmentMaxTribes"]
+    p.max_timestep = int(min(c["timesteps"], 2 ** 31 - 1))
+    p.id_bits = 26
+    return p
+
+
+class HostState:
+    """The whole simulation state as numpy arrays (host mirror of the device SoA)."""
+
+    def __init__(self, width, height, capacity):
+        self.width, self.height, self.capacity = width, height, capacity
+
+    @classmethod
+    def empty(cls, width, height, capacity):
+        s = cls(width, height, capacity)
+        n = width * height
+        for name, dt in GRID_FIELDS:
+            fill = -1 if name == "occ" else 0
+            setattr(s, name, np.full(n, fill, dtype=dt))
+        s.counters = np.zeros(C_COUNT, dtype=np.int64)
+        for name, dt, fill in AGENT_FIELDS:
+            setattr(s, "a_" + name, np.full(capacity, fill, dtype=dt))
+        return s
+
+    def copy(self):
+        s = HostState(self.width, self.height, self.capacity)
+        for name, _ in GRID_FIELDS:
+            setattr(s, name, getattr(self, name).copy())
+        s.counters = self.counters.copy()
+        for name, _, _ in AGENT_FIELDS:
+            setattr(s, "a_" + name, getattr(self, "a_" + name).copy())
+        return s
+
+    # -- agents -------------------------------------------------------------------------------
+    def append_agents(self, new_agents):
+        """Append freshly placed agents (init / replacement) at the end of the list."""
+        n_list = int(self.counters[C_N_LIST])
+        n_slots = int(self.counters[C_N_SLOTS])
+        n_free = int(self.counters[C_N_FREE])
+        for a in new_agents:
+            if n_free > 0:
+                n_free -= 1
+                slot = int(self.a_free_slots[n_free])
+            else:
+                slot = n_slots
+                n_slots += 1
+            if slot >= self.capacity or n_list >= self.capacity:
+                raise MemoryError("agent capacity exceeded")
+            e = a["endowment"]
+            for name, _, fill in AGENT_FIELDS[3:]:
+                getattr(self, "a_" + name)[slot] = fill
+            self.a_id[slot] = a["id"]
+            self.a_pos[slot] = a["cell"]
+            self.a_born[slot] = a["born"]
+            self.a_sugar[slot] = e["sugar"]
+            self.a_spice[slot] = e["spice"]
+            self.a_start_sugar[slot] = e["sugar"]
+            self.a_start_spice[slot] = e["spice"]
+            self.a_sugar_metab[slot] = e["sugarMetabolism"]
+            self.a_spice_metab[slot] = e["spiceMetabolism"]
+            self.a_vision[slot] = e["vision"]
+            self.a_movement[slot] = e["movement"]
+            self.a_max_age[slot] = e["maxAge"]
+            self.a_sex[slot] = SEX_CODE[e["sex"]]
+            self.a_fert_age[slot] = e["fertilityAge"]
+            self.a_infert_age[slot] = e["infertilityAge"]
+            self.a_fert_factor[slot] = e["fertilityFactor"]
+            self.a_aggression[slot] = e["aggressionFactor"]
+            self.a_lookahead[slot] = e["lookaheadFactor"]
+            self.a_trade_factor[slot] = e["tradeFactor"]
+            tags = a["tags"]
+            self.a_tags[slot] = sum((1 << i) for i, b in enumerate(tags or ()) if b)
+            self.a_tribe[slot] = a["tribe"]
+            self.a_order[n_list] = slot
+            self.occ[a["cell"]] = slot
+            n_list += 1
+        self.counters[C_N_LIST] = n_list
+        self.counters[C_N_SLOTS] = n_slots
+        self.counters[C_N_FREE] = n_free
+
+    def list_view(self):
+        """Arrays of the live agent list in list order (for parity checks and stats)."""
+        n = int(self.counters[C_N_LIST])
+        slots = self.a_order[:n]
+        H = self.height
+        pos = self.a_pos[slots]
+        return {
+            "a_id": self.a_id[slots].astype(np.int64), "a_x": (pos // H).astype(np.int64),
+            "a_y": (pos % H).astype(np.int64), "a_age": self.a_age[slots].astype(np.int64),
+            "a_sugar": self.a_sugar[slots].copy(), "a_spice": self.a_spice[slots].copy(),
+            "a_tags": np.where(self.a_tribe[slots] >= 0, self.a_tags[slots].astype(np.int64), -1),
+            "a_tribe": self.a_tribe[slots].astype(np.int64),
+        }
+
+    def canonical(self):
+        """Canonical snapshot in the format of tests/golden/ref_harness.snapshot."""
+        W, H = self.width, self.height
+        snap = self.list_view()
+        occ_id = np.where(self.occ >= 0, self.a_id[np.maximum(self.occ, 0)], -1).astype(np.int64)
+        snap.update({
+            "sugar": self.sugar.astype(np.float64).reshape(W, H),
+            "spice": self.spice.astype(np.float64).reshape(W, H),
+            "pollution": self.pollution.reshape(W, H).copy(),
+            "occ": occ_id.reshape(W, H),
+        })
+        return snap
