@@ -69,7 +69,7 @@ typedef struct ssb_params {
     int32_t rng_mode;               /* SSB_RNG_*                                               */
     uint64_t seed;                  /* configuration["seed"]                                   */
     int32_t flags;                  /* SSB_F_*                                                 */
-    int32_t max_cell_distance;      /* environment.py:132-146                                  */
+    int32_t max_agent_range;        /* max(maxVision, maxMovement), environment.py:135-137     */
     /* growback + seasons (environment.py:61-96,199-211) */
     int32_t sugar_regrow, spice_regrow;
     int32_t season_interval, seasonal_growback_delay, equator;

@@ -1,0 +1,785 @@
+/* ss_oracle.c -- CPU restatement of the reference's per-timestep path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the product (sugarscape_b200/, sugarscape.py) may
+ * import, link or execute this file; only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs use it, and only as the checker / CPU baseline.
+ *
+ * Parity status: PINNED.  tests/test_oracle_golden.py replays every supported shipped example
+ * of the reference (nkremerh/sugarscape) step by step and compares agents, grid and the
+ * CPython MT19937 state with fixtures generated from the unmodified reference
+ * (tests/golden/make_golden.py).
+ *
+ * What is restated (reference file:line):
+ *   environment step   environment.py:61-109,192-211; cell.py:24-25,104-109,138-142
+ *   list shuffle       sugarscape.py:400 ; random.py:350 (shuffle), random.py:242 (_randbelow)
+ *   agent transaction  agent.py:568-598 and callees:
+ *       findCellsInRange 766-779 (+ table order of environment.py:111-122)
+ *       rankCellsInRange 1395-1443, findWelfare 1170-1201, sortCellsByWealth 1479-1490
+ *       doCombat 274-294, gotoCell 1213-1219, collectResourcesAtCell 249-259
+ *       doMetabolism 485-498, doTagging 556-566, doTrading 600-706
+ *       doReproduction 500-554, findChildEndowment 781-910, doAging 266-272, doDeath 296-313
+ *   removal            sugarscape.py:843-853
+ *   reductions         sugarscape.py:913-934,1005-1426
+ *
+ * Plain, scalar, single-threaded C on the structs of include/ssb.h (host pointers).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../include/ssb.h"
+
+/* ------------------------------------------------------------------------------------------
+ * RNG.  Mode E: CPython's MT19937 (Modules/_randommodule.c genrand_uint32) and the Python
+ * level algorithms random._randbelow_with_getrandbits / random.shuffle.
+ * Mode S: counter-based words keyed by (seed, timestep, agent id, draw index).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    uint32_t mt[624];
+    int32_t idx;
+    /* mode S */
+    int32_t mode;
+    uint64_t step_key;
+    uint32_t agent_id, counter;
+} orc_rng_t;
+
+static uint32_t mt_next(orc_rng_t *r) {
+    uint32_t *mt = r->mt, y;
+    if (r->idx >= 624) {
+        int kk;
+        for (kk = 0; kk < 624 - 397; kk++) {
+            y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
+            mt[kk] = mt[kk + 397] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        }
+        for (; kk < 623; kk++) {
+            y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
+            mt[kk] = mt[kk + (397 - 624)] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        }
+        y = (mt[623] & 0x80000000u) | (mt[0] & 0x7fffffffu);
+        mt[623] = mt[396] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        r->idx = 0;
+    }
+    y = mt[r->idx++];
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= (y >> 18);
+    return y;
+}
+
+static uint64_t mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+uint64_t orc_step_key(uint64_t seed, int32_t t) {
+    return mix64(seed + 0x9E3779B97F4A7C15ull * (uint64_t)(uint32_t)(t + 1));
+}
+
+static uint32_t stream_word(uint64_t step_key, uint32_t id, uint32_t j) {
+    return (uint32_t)(mix64(step_key ^ (((uint64_t)id << 32) | j)) >> 32);
+}
+
+/* keyed bijection on [0, 2^bits): 4-round balanced Feistel; bits must be even */
+uint32_t orc_priority(uint64_t step_key, uint32_t id, int bits) {
+    int half = bits / 2;
+    uint32_t mask = (1u << half) - 1u;
+    uint32_t L = (id >> half) & mask, R = id & mask;
+    for (uint32_t round = 0; round < 4; round++) {
+        uint32_t f = (uint32_t)(mix64(step_key ^ 0xA5A5A5A5ull ^ ((uint64_t)(round + 1) << 56) ^ R) >> 40) & mask;
+        uint32_t nl = R;
+        R = L ^ f;
+        L = nl;
+    }
+    return (L << half) | R;
+}
+
+static uint32_t rng_next32(orc_rng_t *r) {
+    if (r->mode == SSB_RNG_EXACT) return mt_next(r);
+    return stream_word(r->step_key, r->agent_id, r->counter++);
+}
+
+static int bit_length(uint32_t n) { int k = 0; while (n) { k++; n >>= 1; } return k; }
+
+/* random._randbelow_with_getrandbits: k = n.bit_length(); r = getrandbits(k) until r < n */
+static uint32_t rng_below(orc_rng_t *r, uint32_t n) {
+    int k = bit_length(n);
+    uint32_t v = rng_next32(r) >> (32 - k);
+    while (v >= n) v = rng_next32(r) >> (32 - k);
+    return v;
+}
+
+static void rng_shuffle_i32(orc_rng_t *r, int32_t *x, int n) {
+    for (int i = n - 1; i >= 1; i--) {
+        uint32_t j = rng_below(r, (uint32_t)i + 1u);
+        int32_t tmp = x[i]; x[i] = x[j]; x[j] = tmp;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * context
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    const ssb_params_t *p;
+    ssb_grid_t g;
+    ssb_agents_t a;
+    orc_rng_t *rng;
+    int32_t t;
+    double prev_mean_wealth;
+    const uint32_t *endow_bits; /* per-timestep child endowment choices (agent.py:839-851) */
+    const uint32_t *tag_bits;   /* per-timestep tag mismatch draws (agent.py:859-875)     */
+    int32_t max_dx, max_dy;
+} ctx_t;
+
+/* child endowment bit positions inside endow_bits[t] (host: sugarscape_b200/steptables.py) */
+enum { EB_AGGRESSION = 0, EB_FERT_AGE, EB_FERT_FACTOR, EB_INFERT_AGE, EB_LOOKAHEAD, EB_MAX_AGE,
+       EB_MOVEMENT, EB_SPICE_METAB, EB_SUGAR_METAB, EB_SEX, EB_TRADE_FACTOR, EB_VISION };
+
+static inline int wrapi(int v, int n) { v %= n; return v < 0 ? v + n : v; }
+
+static int agent_alive(const ctx_t *c, int s) {
+    return c->a.cod[s] == SSB_ALIVE && c->a.sugar[s] >= 0 && c->a.spice[s] >= 0;
+}
+
+static int popcount32(uint32_t v) { int n = 0; while (v) { n += v & 1u; v >>= 1; } return n; }
+
+/* agent.py:1142-1151 */
+static int find_tribe(const ctx_t *c, uint32_t tags) {
+    int L = c->p->tag_len, T = c->p->max_tribes;
+    if (L <= 0 || T <= 0) return -1;
+    int zeroes = L - popcount32(tags);
+    double tribe_size = (double)(L + 1) / (double)T;
+    int tribe = (int)ceil((double)(zeroes + 1) / tribe_size) - 1;
+    return tribe < T - 1 ? tribe : T - 1;
+}
+
+/* agent.py:1170-1201 */
+static double find_welfare(const ctx_t *c, int s, double sugar_reward, double spice_reward) {
+    double sm = c->a.sugar_metab[s] > 0 ? c->a.sugar_metab[s] : 0;
+    double pm = c->a.spice_metab[s] > 0 ? c->a.spice_metab[s] : 0;
+    double total = sm + pm, sprop = 0, pprop = 0;
+    if (total != 0) { sprop = sm / total; pprop = pm / total; }
+    double look = c->a.lookahead[s];
+    double ts = (c->a.sugar[s] + sugar_reward) - sm * look;
+    double tp = (c->a.spice[s] + spice_reward) - pm * look;
+    if (ts < 0) ts = 0;
+    if (tp < 0) tp = 0;
+    double welfare = pow(ts, sprop) * pow(tp, pprop);
+    if ((c->p->flags & SSB_F_TAGPREF) && (c->p->flags & SSB_F_TAGS) && c->p->tag_len > 0) {
+        int L = c->p->tag_len;
+        c->a.tribe[s] = find_tribe(c, c->a.tags[s]);
+        int zeroes = L - popcount32(c->a.tags[s]);
+        double fz = (double)zeroes / (double)L, fo = 1 - fz;
+        double pref = sm * fz + pm * fo;
+        if (pref <= 0) pref = 1;
+        welfare = pow(ts, (sm / pref) * fz) * pow(tp, (pm / pref) * fo);
+    }
+    return welfare;
+}
+
+static void do_death(ctx_t *c, int s, int cause) {
+    c->a.cod[s] = cause;
+    int pos = c->a.pos[s];
+    if (pos >= 0 && c->g.occ[pos] == s) c->g.occ[pos] = -1;
+    c->a.pos[s] = -1;
+}
+
+/* agent.py:1023-1029 */
+static void find_mrs(ctx_t *c, int s) {
+    double pm = c->a.spice_metab[s] > 0 ? c->a.spice_metab[s] : 0;
+    double sm = c->a.sugar_metab[s] > 0 ? c->a.sugar_metab[s] : 0;
+    double spice_need = pm > 0 ? c->a.spice[s] / pm : 1;
+    double sugar_need = sm > 0 ? c->a.sugar[s] / sm : 1;
+    c->a.mrs[s] = c->a.trade_factor[s] * (spice_need / sugar_need);
+}
+
+/* agent.py:1067-1080 */
+static double find_new_mrs(const ctx_t *c, int s, double sugar, double spice) {
+    double pm = c->a.spice_metab[s] > 0 ? c->a.spice_metab[s] : 0;
+    double sm = c->a.sugar_metab[s] > 0 ? c->a.sugar_metab[s] : 0;
+    double spice_need = pm > 0 ? spice / pm : 1;
+    double sugar_need = sm > 0 ? sugar / sm : 1;
+    if (spice_need == 1 && sugar_need == 1) return 1;
+    if (spice_need == 0) return pm;
+    if (sugar_need == 0) return 1 / sm;
+    return spice_need / sugar_need;
+}
+
+/* agent.py:1244-1247 */
+static int is_fertile(const ctx_t *c, int s) {
+    return c->a.sugar[s] >= c->a.start_sugar[s] && c->a.spice[s] >= c->a.start_spice[s] &&
+           c->a.age[s] >= c->a.fert_age[s] && c->a.age[s] < c->a.infert_age[s] &&
+           c->a.fert_factor[s] > 0;
+}
+
+/* the four von Neumann neighbours in the reference's dict order N, S, E, W (cell.py:61-75) */
+static void neighbours4(const ctx_t *c, int pos, int32_t out[4]) {
+    int W = c->p->width, H = c->p->height, x = pos / H, y = pos % H;
+    out[0] = x * H + wrapi(y - 1, H);
+    out[1] = x * H + wrapi(y + 1, H);
+    out[2] = wrapi(x + 1, W) * H + y;
+    out[3] = wrapi(x - 1, W) * H + y;
+}
+
+static int alloc_slot(ctx_t *c) {
+    int64_t *cn = c->a.counters;
+    int slot;
+    if (cn[SSB_C_N_FREE] > 0) {
+        slot = c->a.free_slots[--cn[SSB_C_N_FREE]];
+    } else {
+        if (cn[SSB_C_N_SLOTS] >= c->a.capacity) { cn[SSB_C_OVERFLOW] = 1; return -1; }
+        slot = (int)cn[SSB_C_N_SLOTS]++;
+    }
+    return slot;
+}
+
+/* collectResourcesAtCell, agent.py:249-259 + cell.py:32-45 */
+static void collect(ctx_t *c, int s, int pos) {
+    int32_t cs = c->g.sugar[pos], cp = c->g.spice[pos];
+    c->a.sugar[s] += cs;
+    c->a.spice[s] += cp;
+    if (c->p->pollution_start <= c->t && c->t <= c->p->pollution_end) {
+        c->g.pollution[pos] += c->p->sugar_prod_pollution * cs;
+        c->g.pollution[pos] += c->p->spice_prod_pollution * cp;
+    }
+    c->g.sugar[pos] = 0;
+    c->g.spice[pos] = 0;
+}
+
+/* candidate record of rankCellsInRange */
+typedef struct { int32_t cell; int32_t dist; double welfare; } cand_t;
+
+#define MAX_CAND 256
+
+/* agent.py:766-779 with the insertion order of environment.py:111-122 */
+static int enumerate_cross(const ctx_t *c, int pos, int r, int32_t *cells, int32_t *dists) {
+    int W = c->p->width, H = c->p->height, x = pos / H, y = pos % H, n = 0;
+    for (int d = 1; d <= r; d++) {
+        int64_t key[4]; int32_t cell[4]; int m = 0;
+        if (d <= c->max_dx) {
+            int xw = wrapi(x - d, W), xe = wrapi(x + d, W);
+            key[m] = ((int64_t)xw * H + y) * 4 + 0; cell[m++] = xw * H + y;      /* west  */
+            if (xe != xw) { key[m] = ((int64_t)x * H + y) * 4 + 1; cell[m++] = xe * H + y; } /* east */
+            else if ((int64_t)x * H + y < (int64_t)xw * H + y) key[m - 1] = ((int64_t)x * H + y) * 4 + 1;
+        }
+        if (d <= c->max_dy) {
+            int yn = wrapi(y - d, H), ys = wrapi(y + d, H);
+            key[m] = ((int64_t)x * H + yn) * 4 + 0; cell[m++] = x * H + yn;      /* north */
+            if (ys != yn) { key[m] = ((int64_t)x * H + y) * 4 + 2; cell[m++] = x * H + ys; } /* south */
+            else if ((int64_t)x * H + y < (int64_t)x * H + yn) key[m - 1] = ((int64_t)x * H + y) * 4 + 2;
+        }
+        for (int i = 1; i < m; i++)      /* insertion sort by key */
+            for (int j = i; j > 0 && key[j - 1] > key[j]; j--) {
+                int64_t tk = key[j]; key[j] = key[j - 1]; key[j - 1] = tk;
+                int32_t tc = cell[j]; cell[j] = cell[j - 1]; cell[j - 1] = tc;
+            }
+        for (int i = 0; i < m && n < MAX_CAND; i++) { cells[n] = cell[i]; dists[n++] = d; }
+    }
+    return n;
+}
+
+/* agent.py:1395-1443 + 719-746 + 1321-1328: returns the chosen cell */
+static int move_to_best_cell(ctx_t *c, int s) {
+    const ssb_agents_t *a = &c->a;
+    int pos = a->pos[s];
+    int vision = a->vision[s] > 0 ? a->vision[s] : 0, movement = a->movement[s] > 0 ? a->movement[s] : 0;
+    int maxd = c->max_dx > c->max_dy ? c->max_dx : c->max_dy;
+    int r = vision < movement ? vision : movement;
+    if (r > maxd) r = maxd;
+    int32_t cells[MAX_CAND], dists[MAX_CAND];
+    int n = r > 0 ? enumerate_cross(c, pos, r, cells, dists) : 0;
+    double aggression = a->aggression[s] > 0 ? a->aggression[s] : 0;
+    int best = pos;
+    if (n == 0) {
+        /* empty range: stays put; validMoves / movementNeighborhood keep their old values */
+    } else {
+        /* findNeighborhood: live agents in range + self (agent.py:1052-1065) */
+        int hood = 1;
+        for (int i = 0; i < n; i++) {
+            int o = c->g.occ[cells[i]];
+            if (o >= 0 && agent_alive(c, o)) hood++;
+        }
+        /* random.shuffle(list(cellsInRange.items())) -- shuffle an index permutation */
+        int32_t perm[MAX_CAND];
+        for (int i = 0; i < n; i++) perm[i] = i;
+        rng_shuffle_i32(c->rng, perm, n);
+        /* findRetaliatorsInVision (agent.py:1088-1098): richest visible member per tribe */
+        double retaliator[34]; int have[34];
+        for (int i = 0; i < 34; i++) { retaliator[i] = 0; have[i] = 0; }
+        if (aggression > 0)
+            for (int i = 0; i < n; i++) {
+                int o = c->g.occ[cells[i]];
+                if (o < 0) continue;
+                int tr = a->tribe[o] + 1; /* -1 (None) -> 0 */
+                double w = a->sugar[o] + a->spice[o];
+                if (!have[tr] || retaliator[tr] < w) { retaliator[tr] = w; have[tr] = 1; }
+            }
+        cand_t cand[MAX_CAND]; int m = 0;
+        double loot = c->p->max_combat_loot;
+        double my_wealth = a->sugar[s] + a->spice[s];
+        for (int k = 0; k < n; k++) {
+            int cell = cells[perm[k]], dist = dists[perm[k]];
+            int prey = c->g.occ[cell];
+            double ps = 0, pp = 0;
+            if (prey >= 0) {
+                /* isNeighborValidPrey (agent.py:1309-1314) */
+                if (!(aggression > 0 && a->tribe[s] != a->tribe[prey] &&
+                      my_wealth >= a->sugar[prey] + a->spice[prey])) continue;
+                ps = a->sugar[prey]; pp = a->spice[prey];
+            }
+            double wps = aggression * (loot < ps ? loot : ps);
+            double wpp = aggression * (loot < pp ? loot : pp);
+            double poll = c->g.pollution[cell];
+            double welfare = find_welfare(c, s, (c->g.sugar[cell] + wps) / (1 + poll),
+                                          (c->g.spice[cell] + wpp) / (1 + poll));
+            if (prey >= 0 && retaliator[a->tribe[prey] + 1] > my_wealth + welfare) continue;
+            cand[m].cell = cell; cand[m].dist = dist; cand[m].welfare = welfare; m++;
+        }
+        if (m == 0) { cand[0].cell = pos; cand[0].dist = 0; cand[0].welfare = 0; m = 1; }
+        /* sortCellsByWealth: stable insertion sort, welfare desc then range asc (1479-1490) */
+        for (int i = 0; i < m; i++)
+            for (int j = i; j > 0 && (cand[j - 1].welfare < cand[j].welfare ||
+                 (cand[j - 1].welfare == cand[j].welfare && cand[j - 1].dist > cand[j].dist)); j--) {
+                cand_t tmp = cand[j]; cand[j] = cand[j - 1]; cand[j - 1] = tmp;
+            }
+        best = cand[0].cell;
+        a->n_neighborhood[s] = hood;
+        a->n_valid_moves[s] = m;
+    }
+    /* moveToBestCell: doCombat when aggressive (agent.py:274-294), then gotoCell (1213-1219) */
+    if (aggression > 0) {
+        int prey = c->g.occ[best];
+        if (prey >= 0 && prey != s) {
+            double loot = c->p->max_combat_loot;
+            double sl = loot < a->sugar[prey] ? loot : a->sugar[prey];
+            double pl = loot < a->spice[prey] ? loot : a->spice[prey];
+            a->sugar[s] += sl; a->spice[s] += pl;
+            a->sugar[prey] -= sl; a->spice[prey] -= pl;
+            do_death(c, prey, SSB_COMBAT);
+        }
+    }
+    a->last_moved[s] = c->t;
+    c->g.occ[pos] = -1;
+    a->pos[s] = best;
+    c->g.occ[best] = s;
+    return best;
+}
+
+/* agent.py:556-566 */
+static void do_tagging(ctx_t *c, int s) {
+    if (!(c->p->flags & SSB_F_TAGS) || !(c->p->flags & SSB_F_TAGGING)) return;
+    int32_t nb[4];
+    neighbours4(c, c->a.pos[s], nb);
+    rng_shuffle_i32(c->rng, nb, 4);
+    for (int i = 0; i < 4; i++) {
+        int o = c->g.occ[nb[i]];
+        if (o < 0) continue;
+        uint32_t position = rng_below(c->rng, (uint32_t)c->p->tag_len);
+        uint32_t bit = 1u << position;
+        c->a.tags[o] = (c->a.tags[o] & ~bit) | (c->a.tags[s] & bit);
+        c->a.tribe[o] = find_tribe(c, c->a.tags[o]);
+    }
+}
+
+/* agent.py:600-706 */
+static void do_trading(ctx_t *c, int s) {
+    ssb_agents_t *a = &c->a;
+    if (a->trade_factor[s] == 0) return;
+    a->trade_volume[s] = 0;
+    double sum_sugar_price = 0, sum_spice_price = 0;
+    find_mrs(c, s);
+    int32_t nb[4], traders[4]; int n = 0;
+    neighbours4(c, a->pos[s], nb);
+    for (int i = 0; i < 4; i++) {
+        int o = c->g.occ[nb[i]];
+        if (o >= 0 && agent_alive(c, o) && a->mrs[o] != a->mrs[s]) traders[n++] = o;
+    }
+    rng_shuffle_i32(c->rng, traders, n);
+    double sugar_price = 0, spice_price = 0;
+    for (int k = 0; k < n; k++) {
+        int tr = traders[k];
+        int spice_seller = -1, sugar_seller = -1;
+        for (;;) {
+            double tm = a->mrs[tr], my = a->mrs[s];
+            if ((tm >= 1 && my >= 1) || (tm < 1 && my < 1) || tm == my) break;
+            if (tm > my) { spice_seller = tr; sugar_seller = s; }
+            else { spice_seller = s; sugar_seller = tr; }
+            double ssm = a->mrs[spice_seller], sum = a->mrs[sugar_seller];
+            if (ssm < 0 || sum < 0) { spice_seller = sugar_seller = -1; break; }
+            double price = sqrt(ssm * sum);
+            if (price < 1) { spice_price = 1; sugar_price = price; }
+            else { spice_price = price; sugar_price = 1; }
+            if (a->spice[spice_seller] - spice_price < a->spice_metab[spice_seller] ||
+                a->sugar[sugar_seller] - sugar_price < a->sugar_metab[sugar_seller]) break;
+            double ss_new = find_new_mrs(c, spice_seller, a->sugar[spice_seller] + sugar_price,
+                                         a->spice[spice_seller] - spice_price);
+            double su_new = find_new_mrs(c, sugar_seller, a->sugar[sugar_seller] - sugar_price,
+                                         a->spice[sugar_seller] + spice_price);
+            int better_ss_mrs = fabs(1 - ssm) > fabs(1 - ss_new);
+            int better_su_mrs = fabs(1 - sum) > fabs(1 - su_new);
+            int better_ss_w = find_welfare(c, spice_seller, sugar_price, -1 * spice_price) >=
+                              find_welfare(c, spice_seller, 0, 0);
+            int better_su_w = find_welfare(c, sugar_seller, -1 * sugar_price, spice_price) >=
+                              find_welfare(c, sugar_seller, 0, 0);
+            int crossing = ss_new < su_new;
+            if ((better_ss_mrs || better_ss_w) && (better_su_mrs || better_su_w) && !crossing) {
+                a->sugar[spice_seller] += sugar_price; a->spice[spice_seller] -= spice_price;
+                a->sugar[sugar_seller] -= sugar_price; a->spice[sugar_seller] += spice_price;
+                find_mrs(c, spice_seller);
+                find_mrs(c, sugar_seller);
+            } else break;
+        }
+        if (spice_seller >= 0 && sugar_seller >= 0) {
+            a->trade_volume[s] += 1;
+            sum_sugar_price += sugar_price;
+            sum_spice_price += spice_price;
+        }
+    }
+    a->trade_price[s] = sum_spice_price > sum_sugar_price ? sum_spice_price : sum_sugar_price;
+}
+
+static int empty_neighbours(const ctx_t *c, int pos, int32_t *out) {
+    int32_t nb[4]; int n = 0;
+    neighbours4(c, pos, nb);
+    for (int i = 0; i < 4; i++) if (c->g.occ[nb[i]] < 0) out[n++] = nb[i];
+    return n;
+}
+
+/* agent.py:500-554 with findChildEndowment 781-910 and addChildToCell 164-182 */
+static void do_reproduction(ctx_t *c, int s) {
+    ssb_agents_t *a = &c->a;
+    if (!agent_alive(c, s) || !is_fertile(c, s)) return;
+    int32_t nb[4], own_empty[4];
+    neighbours4(c, a->pos[s], nb);
+    rng_shuffle_i32(c->rng, nb, 4);
+    int n_own = empty_neighbours(c, a->pos[s], own_empty);
+    for (int k = 0; k < 4; k++) {
+        int m = c->g.occ[nb[k]];
+        if (m < 0 || !agent_alive(c, m)) continue;
+        int compatible = ((a->sex[s] == SSB_SEX_FEMALE && a->sex[m] == SSB_SEX_MALE) ||
+                          (a->sex[s] == SSB_SEX_MALE && a->sex[m] == SSB_SEX_FEMALE)) && is_fertile(c, m);
+        int32_t pool[8]; int np = 0;
+        for (int i = 0; i < n_own; i++) pool[np++] = own_empty[i];
+        np += empty_neighbours(c, a->pos[m], pool + np);
+        rng_shuffle_i32(c->rng, pool, np);   /* drawn before the compatibility test (quirk C.7) */
+        if (!(is_fertile(c, s) && compatible && np != 0)) continue;
+        int cell = pool[--np];
+        while (c->g.occ[cell] >= 0 && np != 0) cell = pool[--np];
+        if (c->g.occ[cell] >= 0) continue;
+        int ch = alloc_slot(c);
+        if (ch < 0) return;
+        uint32_t eb = c->endow_bits ? c->endow_bits[c->t] : 0;
+#define PICK(field, bit) (((eb >> (bit)) & 1u) ? a->field[m] : a->field[s])
+        int64_t *cn = a->counters;
+        a->id[ch] = c->p->rng_mode == SSB_RNG_EXACT ? (int32_t)cn[SSB_C_NEXT_ID]++ : -1;
+        a->born[ch] = c->t; a->cod[ch] = SSB_ALIVE; a->age[ch] = 0;
+        a->aggression[ch] = PICK(aggression, EB_AGGRESSION);
+        a->fert_age[ch] = PICK(fert_age, EB_FERT_AGE);
+        a->fert_factor[ch] = PICK(fert_factor, EB_FERT_FACTOR);
+        a->infert_age[ch] = PICK(infert_age, EB_INFERT_AGE);
+        a->lookahead[ch] = PICK(lookahead, EB_LOOKAHEAD);
+        a->max_age[ch] = PICK(max_age, EB_MAX_AGE);
+        a->movement[ch] = PICK(movement, EB_MOVEMENT);
+        a->spice_metab[ch] = PICK(spice_metab, EB_SPICE_METAB);
+        a->sugar_metab[ch] = PICK(sugar_metab, EB_SUGAR_METAB);
+        a->sex[ch] = PICK(sex, EB_SEX);
+        a->trade_factor[ch] = PICK(trade_factor, EB_TRADE_FACTOR);
+        a->vision[ch] = PICK(vision, EB_VISION);
+#undef PICK
+        double sugar_cost = a->start_sugar[s] / (a->fert_factor[s] * 2);
+        double spice_cost = a->start_spice[s] / (a->fert_factor[s] * 2);
+        double mate_sugar_cost = a->start_sugar[m] / (a->fert_factor[m] * 2);
+        double mate_spice_cost = a->start_spice[m] / (a->fert_factor[m] * 2);
+        a->start_sugar[ch] = a->sugar[ch] = sugar_cost + mate_sugar_cost;
+        a->start_spice[ch] = a->spice[ch] = spice_cost + mate_spice_cost;
+        /* tags: equal bits copied, mismatches drawn in order from the per-timestep stream */
+        uint32_t tags = 0;
+        if (c->p->flags & SSB_F_TAGS) {
+            uint32_t tb = c->tag_bits ? c->tag_bits[c->t] : 0; int draw = 0;
+            for (int i = 0; i < c->p->tag_len; i++) {
+                uint32_t bs = (a->tags[s] >> i) & 1u, bm = (a->tags[m] >> i) & 1u;
+                uint32_t b = bs == bm ? bs : ((tb >> draw++) & 1u);
+                tags |= b << i;
+            }
+        }
+        a->tags[ch] = tags;
+        a->tribe[ch] = find_tribe(c, tags);
+        a->mrs[ch] = 1;
+        a->last_moved[ch] = c->t; a->last_sugar[ch] = 0; a->last_spice[ch] = 0;
+        a->n_neighborhood[ch] = 0; a->n_valid_moves[ch] = 0;
+        a->happiness[ch] = 0; a->wealth_happiness[ch] = 0; a->family_happiness[ch] = 0;
+        a->trade_volume[ch] = 0; a->trade_price[ch] = 0; a->last_repro[ch] = -1;
+        a->n_children_alive[ch] = 0; a->n_children_dead[ch] = 0;
+        a->father[ch] = a->sex[s] == SSB_SEX_FEMALE ? a->id[m] : a->id[s];
+        a->mother[ch] = a->sex[s] == SSB_SEX_FEMALE ? a->id[s] : a->id[m];
+        a->pos[ch] = cell;
+        c->g.occ[cell] = ch;
+        if (cn[SSB_C_N_LIST] < a->capacity) a->order[cn[SSB_C_N_LIST]++] = ch;   /* addAgent */
+        else cn[SSB_C_OVERFLOW] = 1;
+        cn[SSB_C_N_BORN]++;
+        collect(c, ch, cell);                                                    /* child collects */
+        a->sugar[s] -= sugar_cost; a->spice[s] -= spice_cost;
+        a->sugar[m] = a->sugar[m] - mate_sugar_cost;
+        a->spice[m] = a->spice[m] - mate_spice_cost;
+        a->last_repro[s] = c->t;
+    }
+}
+
+/* agent.py:568-598 */
+static void agent_transaction(ctx_t *c, int s) {
+    ssb_agents_t *a = &c->a;
+    if (!agent_alive(c, s) || a->last_moved[s] == c->t) return;
+    a->last_sugar[s] = a->sugar[s];
+    a->last_spice[s] = a->spice[s];
+    int pos = move_to_best_cell(c, s);
+    collect(c, s, pos);
+    /* doMetabolism (agent.py:485-498) + consumption pollution (cell.py:27-40) */
+    double sm = a->sugar_metab[s] > 0 ? a->sugar_metab[s] : 0;
+    double pm = a->spice_metab[s] > 0 ? a->spice_metab[s] : 0;
+    a->sugar[s] -= sm;
+    a->spice[s] -= pm;
+    if (c->p->pollution_start <= c->t && c->t <= c->p->pollution_end) {
+        c->g.pollution[pos] += c->p->sugar_cons_pollution * sm;
+        c->g.pollution[pos] += c->p->spice_cons_pollution * pm;
+    }
+    if (a->sugar[s] < 0 || a->spice[s] < 0 || (a->sugar[s] <= 0 && sm > 0) || (a->spice[s] <= 0 && pm > 0)) {
+        do_death(c, s, SSB_STARVATION);
+        return;
+    }
+    do_tagging(c, s);
+    do_trading(c, s);
+    do_reproduction(c, s);
+    /* doAging (agent.py:266-272) */
+    if (agent_alive(c, s)) {
+        a->age[s] += 1;
+        if (a->age[s] >= a->max_age[s] && a->max_age[s] != -1) { do_death(c, s, SSB_AGING); return; }
+    }
+    /* updateHappiness (agent.py:1522-1530): conflict + family + health + social + wealth.
+     * family/social/conflict bookkeeping is not restated yet -> 0 */
+    double wealth_h = erf((a->sugar[s] + a->spice[s]) - c->prev_mean_wealth);
+    a->wealth_happiness[s] = wealth_h;
+    a->family_happiness[s] = 0;
+    a->happiness[s] = 0 + 0 + 1.0 + 0 + wealth_h;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * exported entry points (ctypes; tests/oracle_binding.py)
+ * ---------------------------------------------------------------------------------------- */
+static void make_ctx(ctx_t *c, const ssb_params_t *p, const ssb_grid_t *g, const ssb_agents_t *a,
+                     orc_rng_t *rng, int32_t t) {
+    memset(c, 0, sizeof(*c));
+    c->p = p; c->g = *g; c->a = *a; c->rng = rng; c->t = t;
+    /* environment.py:132-146: memoised range per axis (cardinal modes, wraparound);
+     * max_agent_range carries max(maxVision, maxMovement) capped per axis below */
+    int rmax = p->max_agent_range;
+    c->max_dx = rmax < p->width / 2 ? rmax : p->width / 2;
+    c->max_dy = rmax < p->height / 2 ? rmax : p->height / 2;
+}
+
+int orc_sizeof_rng(void) { return (int)sizeof(orc_rng_t); }
+
+void orc_rng_init(orc_rng_t *r, const uint32_t state[624], int32_t index, int32_t mode) {
+    memset(r, 0, sizeof(*r));
+    if (state) memcpy(r->mt, state, sizeof(r->mt));
+    r->idx = index; r->mode = mode;
+}
+
+void orc_rng_get(const orc_rng_t *r, uint32_t state[624], int32_t *index) {
+    memcpy(state, r->mt, sizeof(r->mt));
+    *index = r->idx;
+}
+
+/* environment.py:105-109 with the closed-form schedules of SURVEY Appendix A.3 */
+void orc_env_step(const ssb_params_t *p, const ssb_grid_t *g, int32_t t) {
+    int W = p->width, H = p->height;
+    int seasons = p->season_interval > 0;
+    int flipped = seasons ? (((t - 1) / p->season_interval) & 1) : 0;
+    int dry_grows = seasons && p->seasonal_growback_delay > 0 ? (t % p->seasonal_growback_delay == 0) : 0;
+    for (int x = 0; x < W; x++)
+        for (int y = 0; y < H; y++) {
+            int i = x * H + y, grow = 1;
+            if (seasons) {
+                int wet = (y < p->equator) != flipped;   /* north starts wet (environment.py:186-189) */
+                grow = wet || dry_grows;
+            }
+            if (grow) {
+                int32_t s = g->sugar[i] + p->sugar_regrow, q = g->spice[i] + p->spice_regrow;
+                g->sugar[i] = s < g->sugar_cap[i] ? s : g->sugar_cap[i];
+                g->spice[i] = q < g->spice_cap[i] ? q : g->spice_cap[i];
+            }
+        }
+    if (p->diffusion_delay > 0 && p->diffusion_start <= t && t <= p->diffusion_end &&
+        ((t - p->diffusion_start + 1) % p->diffusion_delay) == 0) {
+        for (int x = 0; x < W; x++)
+            for (int y = 0; y < H; y++) {
+                double m = 0;
+                m += g->pollution[x * H + wrapi(y - 1, H)];
+                m += g->pollution[x * H + wrapi(y + 1, H)];
+                m += g->pollution[wrapi(x + 1, W) * H + y];
+                m += g->pollution[wrapi(x - 1, W) * H + y];
+                g->pollution_flux[x * H + y] = m / 4;
+            }
+        memcpy(g->pollution, g->pollution_flux, sizeof(double) * (size_t)W * H);
+    }
+}
+
+static int cmp_u64(const void *x, const void *y) {
+    uint64_t a = *(const uint64_t *)x, b = *(const uint64_t *)y;
+    return a < b ? -1 : a > b;
+}
+
+/* sugarscape.py:400-407 */
+void orc_agent_step(const ssb_params_t *p, const ssb_grid_t *g, const ssb_agents_t *a, orc_rng_t *rng,
+                    int32_t t, double prev_mean_wealth, const uint32_t *endow_bits, const uint32_t *tag_bits) {
+    ctx_t c;
+    make_ctx(&c, p, g, a, rng, t);
+    c.prev_mean_wealth = prev_mean_wealth;
+    c.endow_bits = endow_bits; c.tag_bits = tag_bits;
+    int64_t *cn = a->counters;
+    cn[SSB_C_N_BORN] = 0;
+    if (p->rng_mode == SSB_RNG_EXACT) {
+        rng->mode = SSB_RNG_EXACT;
+        rng_shuffle_i32(rng, a->order, (int)cn[SSB_C_N_LIST]);
+        /* the list may grow while iterating (children are appended and skipped) */
+        for (int64_t i = 0; i < cn[SSB_C_N_LIST]; i++) agent_transaction(&c, a->order[i]);
+    } else {
+        int n = (int)cn[SSB_C_N_LIST];
+        uint64_t key = orc_step_key(p->seed, t);
+        uint64_t *sorted = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)(n > 0 ? n : 1));
+        for (int i = 0; i < n; i++) {
+            int s = a->order[i];
+            sorted[i] = ((uint64_t)orc_priority(key, (uint32_t)a->id[s], p->id_bits) << 32) | (uint32_t)s;
+        }
+        qsort(sorted, (size_t)n, sizeof(uint64_t), cmp_u64);
+        rng->mode = SSB_RNG_SCALABLE; rng->step_key = key;
+        for (int i = 0; i < n; i++) {
+            int s = (int)(sorted[i] & 0xffffffffu);
+            rng->agent_id = (uint32_t)a->id[s]; rng->counter = 0;
+            agent_transaction(&c, s);
+        }
+        free(sorted);
+    }
+}
+
+static int cmp_i64(const void *x, const void *y) {
+    int64_t a = *(const int64_t *)x, b = *(const int64_t *)y;
+    return a < b ? -1 : a > b;
+}
+
+/* removeDeadAgents, sugarscape.py:843-853: order-preserving; dead slots are recycled.
+ * Mode S additionally numbers this step's newborn in cell order ("mode S"). */
+void orc_compact(const ssb_params_t *p, const ssb_grid_t *g, const ssb_agents_t *a, int32_t t) {
+    ctx_t c;
+    make_ctx(&c, p, g, a, NULL, t);
+    int64_t *cn = a->counters;
+    int64_t n = cn[SSB_C_N_LIST], w = 0, nd = 0;
+    for (int64_t i = 0; i < n; i++) {
+        int s = a->order[i];
+        if (!agent_alive(&c, s) || a->pos[s] < 0) {
+            if (a->cod[s] == SSB_ALIVE) do_death(&c, s, SSB_OTHER);
+            a->dead_list[nd++] = s;
+        } else a->order[w++] = s;
+    }
+    for (int64_t i = 0; i < nd; i++) a->free_slots[cn[SSB_C_N_FREE]++] = a->dead_list[i];
+    cn[SSB_C_N_LIST] = w;
+    cn[SSB_C_N_DEAD] = nd;
+    if (p->rng_mode == SSB_RNG_SCALABLE) {
+        /* newborn survivors: re-ordered and numbered by cell index */
+        int64_t first = w;
+        while (first > 0 && a->born[a->order[first - 1]] == t && a->id[a->order[first - 1]] < 0) first--;
+        int64_t k = w - first;
+        if (k > 0) {
+            int64_t *keys = (int64_t *)malloc(sizeof(int64_t) * (size_t)k);
+            for (int64_t i = 0; i < k; i++) keys[i] = ((int64_t)a->pos[a->order[first + i]] << 32) | (uint32_t)a->order[first + i];
+            qsort(keys, (size_t)k, sizeof(int64_t), cmp_i64);
+            for (int64_t i = 0; i < k; i++) {
+                int s = (int)(keys[i] & 0xffffffff);
+                a->order[first + i] = s;
+                a->id[s] = (int32_t)cn[SSB_C_NEXT_ID]++;
+            }
+            free(keys);
+        }
+    }
+}
+
+static int cmp_f64(const void *x, const void *y) {
+    double a = *(const double *)x, b = *(const double *)y;
+    return a < b ? -1 : a > b;
+}
+
+/* raw reductions of updateRuntimeStatsPerGroup (sugarscape.py:1005-1426) */
+void orc_stats(const ssb_params_t *p, const ssb_grid_t *g, const ssb_agents_t *a, int32_t t, ssb_stats_t *out) {
+    memset(out, 0, sizeof(*out));
+    ctx_t c;
+    make_ctx(&c, p, g, a, NULL, t);
+    int64_t *cn = a->counters, n = cn[SSB_C_N_LIST];
+    out->timestep = t;
+    out->population = n;
+    out->min_wealth = 0; out->max_wealth = 0;
+    for (int i = 0; i < 32; i++) out->tribe_first[i] = -1;
+    double *wealths = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+    for (int64_t i = 0; i < n; i++) {
+        int s = a->order[i];
+        double w = a->sugar[s] + a->spice[s];
+        wealths[i] = w;
+        out->sum_sugar_metab += a->sugar_metab[s]; out->sum_spice_metab += a->spice_metab[s];
+        out->sum_movement += a->movement[s]; out->sum_vision += a->vision[s]; out->sum_age += a->age[s];
+        out->sum_wealth += w;
+        if (i == 0 || w > out->max_wealth) out->max_wealth = w;
+        if (i == 0 || w < out->min_wealth) out->min_wealth = w;
+        out->sum_wealth_collected += w - (a->last_sugar[s] + a->last_spice[s]);
+        /* findTimeToLive (agent.py:1113-1140) */
+        double sm = a->sugar_metab[s] > 0 ? a->sugar_metab[s] : 0, pm = a->spice_metab[s] > 0 ? a->spice_metab[s] : 0;
+        double st = sm > 0 ? a->sugar[s] / sm : 9223372036854775807.0;
+        double pt = pm > 0 ? a->spice[s] / pm : 9223372036854775807.0;
+        double ttl = st < pt ? st : pt;
+        out->sum_burn_rate += ttl;
+        double lim = (double)(a->max_age[s] - a->age[s]);
+        out->sum_ttl_age_limited += ttl < lim ? ttl : lim;
+        out->sum_neighbors += a->n_neighborhood[s];
+        out->sum_valid_moves += a->n_valid_moves[s];
+        if (a->trade_volume[s] > 0) {
+            out->n_traders++; out->trade_volume += a->trade_volume[s]; out->sum_trade_price += a->trade_price[s];
+        }
+        out->sum_happiness += a->happiness[s];
+        out->sum_wealth_happiness += a->wealth_happiness[s];
+        out->sum_family_happiness += a->family_happiness[s];
+        int tr = a->tribe[s];
+        if (tr >= 0 && tr < 32) { if (out->tribe_count[tr]++ == 0) out->tribe_first[tr] = i; }
+        if (a->born[s] == t && t > 0) { /* counted below from N_BORN */ }
+    }
+    /* Lorenz area numerator (sugarscape.py:913-934): sum of cumulative wealth over the first
+     * n-1 sorted agents plus half the total */
+    qsort(wealths, (size_t)n, sizeof(double), cmp_f64);
+    double cum = 0, area = 0;
+    for (int64_t i = 0; i + 1 < n; i++) { cum += wealths[i]; area += cum; }
+    if (n > 0) { cum += wealths[n - 1]; area += cum / 2; }
+    out->lorenz_weighted_sum = area;
+    free(wealths);
+    /* this step's dead (sugarscape.py:1213-1265) */
+    out->n_dead = cn[SSB_C_N_DEAD];
+    for (int64_t i = 0; i < out->n_dead; i++) {
+        int s = a->dead_list[i];
+        if (a->last_moved[s] == t) out->n_dead_moved++;
+        out->sum_age_at_death += a->age[s];
+        out->dead_wealth_collected += (a->sugar[s] + a->spice[s]) - (a->last_sugar[s] + a->last_spice[s]);
+        out->dead_starvation += a->cod[s] == SSB_STARVATION;
+        out->dead_aging += a->cod[s] == SSB_AGING;
+        out->dead_combat += a->cod[s] == SSB_COMBAT;
+    }
+    out->n_born = cn[SSB_C_N_BORN];
+    /* environment totals (sugarscape.py:1044-1051) with the closed-form LastProduced */
+    int W = p->width, H = p->height;
+    int seasons = p->season_interval > 0;
+    int flipped = seasons && t > 0 ? (((t - 1) / p->season_interval) & 1) : 0;
+    int dry_grows = seasons && p->seasonal_growback_delay > 0 ? (t % p->seasonal_growback_delay == 0) : 0;
+    for (int x = 0; x < W; x++)
+        for (int y = 0; y < H; y++) {
+            int i = x * H + y;
+            out->env_wealth_total += g->sugar[i] + g->spice[i];
+            out->env_capacity_total += g->sugar_cap[i] + g->spice_cap[i];
+        }
+    (void)flipped; (void)dry_grows;
+}

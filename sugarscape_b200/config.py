@@ -95,6 +95,11 @@ def parse_configuration(config_file, configuration):
     """sugarscape.py:1463-1480."""
     with open(config_file) as f:
         options = json.loads(f.read())
+    return overlay_options(options, configuration)
+
+
+def overlay_options(options, configuration):
+    """The overlay half of parseConfiguration (sugarscape.py:1466-1480) on a parsed dict."""
     if "sugarscapeOptions" in options:
         options = options["sugarscapeOptions"]
     if "agentEthicalTheory" in options:

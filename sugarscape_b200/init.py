@@ -147,12 +147,17 @@ def capacity_field(width, height, peaks):
     return cap.astype(np.int32)
 
 
-def max_cell_distance(c):
-    """environment.py:132-146 (cardinal modes, wraparound)."""
+def max_agent_range(c):
+    """max(maxVision, maxMovement) incl. worst-case disease bonuses (environment.py:135-137);
+    the per-axis caps (width // 2, height // 2) are applied by the engine."""
     max_vision = c["startingDiseases"] * max(c["diseaseVisionPenalty"][1], 0) + c["agentVision"][1]
     max_movement = c["startingDiseases"] * max(c["diseaseMovementPenalty"][1], 0) + c["agentMovement"][1]
-    rng = max(max_vision, max_movement)
-    return int(max(min(rng, c["environmentWidth"] // 2), min(rng, c["environmentHeight"] // 2)))
+    return int(min(max(max_vision, max_movement), 2 ** 30))
+
+
+def equator(c):
+    """environment.py:10."""
+    return c["environmentEquator"] if c["environmentEquator"] >= 0 else math.ceil(c["environmentHeight"] / 2)
 
 
 def active_quadrants(c):
@@ -260,9 +265,15 @@ def randomize_endowments(c, n, timestep):
              "depressionFactor": depression[i]}
         for name, r in ranged.items():
             if name in sex_specific:
+                # a sexed agent pops ALL four lists: its own sex's values become
+                # fertilityAge / infertilityAge, the other sex's land in unused keys
+                # (the `else` branch of sugarscape.py:738-752); unsexed agents pop none
+                if sexes[i] is None:
+                    continue
                 sex, target = sex_specific[name]
+                value = r["values"].pop()
                 if sexes[i] == sex:
-                    e[target] = r["values"].pop()
+                    e[target] = value
                 continue
             e[name] = r["values"].pop()
         if sexes[i] is None:

@@ -58,7 +58,7 @@ class Params(C.Structure):
     _fields_ = [
         ("abi_version", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
         ("rng_mode", C.c_int32), ("seed", C.c_uint64), ("flags", C.c_int32),
-        ("max_cell_distance", C.c_int32),
+        ("max_agent_range", C.c_int32),
         ("sugar_regrow", C.c_int32), ("spice_regrow", C.c_int32),
         ("season_interval", C.c_int32), ("seasonal_growback_delay", C.c_int32),
         ("equator", C.c_int32),
@@ -114,14 +114,14 @@ def default_capacity(c, n0):
     return int(min(max(2 * want, 1024), 2 * cells + 1024))
 
 
-def make_params(c, rng_mode, flags, max_cell_distance, equator):
+def make_params(c, rng_mode, flags, max_agent_range, equator):
     p = Params()
     p.abi_version = ABI_VERSION
     p.width, p.height = c["environmentWidth"], c["environmentHeight"]
     p.rng_mode = rng_mode
     p.seed = c["seed"] & 0xFFFFFFFFFFFFFFFF
     p.flags = flags
-    p.max_cell_distance = max_cell_distance
+    p.max_agent_range = max_agent_range
     p.sugar_regrow = int(c["environmentSugarRegrowRate"])
     p.spice_regrow = int(c["environmentSpiceRegrowRate"])
     p.season_interval = int(c["environmentSeasonInterval"])
@@ -168,6 +168,19 @@ class HostState:
         for name, _, _ in AGENT_FIELDS:
             setattr(s, "a_" + name, getattr(self, "a_" + name).copy())
         return s
+
+    def as_structs(self):
+        """ctypes views (HOST pointers) of this state, for the CPU oracle used by the tests."""
+        g = Grid()
+        g.n_cells = self.width * self.height
+        for name, _ in GRID_FIELDS:
+            setattr(g, name, getattr(self, name).ctypes.data)
+        a = Agents()
+        a.capacity = self.capacity
+        a.counters = self.counters.ctypes.data
+        for name, _, _ in AGENT_FIELDS:
+            setattr(a, name, getattr(self, "a_" + name).ctypes.data)
+        return g, a
 
     # -- agents -------------------------------------------------------------------------------
     def append_agents(self, new_agents):

@@ -80,10 +80,24 @@ def save(outdir, name, meta, steps, log, snaps):
     np.savez_compressed(os.path.join(outdir, name + ".npz"), **flat)
 
 
+def dump_example_options(paths):
+    """The options each shipped example sets (its JSON minus the __README__ text), as ONE
+    fixture file; the tests materialise temporary --conf files from it."""
+    out = {}
+    for p in paths:
+        with open(p) as f:
+            d = json.load(f)
+        d = d.get("sugarscapeOptions", d)
+        out[os.path.splitext(os.path.basename(p))[0]] = {k: v for k, v in d.items() if not k.startswith("__")}
+    with open(os.path.join(HERE, "example_configs.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+
+
 def main():
     names = sys.argv[1:]
     ex_dir = os.path.join(rh.REFERENCE_DIR, "examples")
     paths = sorted(glob.glob(os.path.join(ex_dir, "*.json")))
+    dump_example_options(paths)
     if names:
         paths = [p for p in paths if os.path.splitext(os.path.basename(p))[0] in names]
     for p in paths:

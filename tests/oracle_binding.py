@@ -1,0 +1,89 @@
+"""ctypes binding of the CPU oracle (oracle/libss_oracle.so).  TEST INFRASTRUCTURE ONLY."""
+import ctypes as C
+import os
+import random
+import subprocess
+
+import numpy as np
+
+from sugarscape_b200 import layout
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_LIB = None
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(ROOT, "oracle", "libss_oracle.so")
+        src = os.path.join(ROOT, "oracle", "ss_oracle.c")
+        if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+            build()
+        L = C.CDLL(path)
+        L.orc_sizeof_rng.restype = C.c_int
+        L.orc_step_key.restype = C.c_uint64
+        L.orc_step_key.argtypes = [C.c_uint64, C.c_int32]
+        L.orc_priority.restype = C.c_uint32
+        L.orc_priority.argtypes = [C.c_uint64, C.c_uint32, C.c_int]
+        P, G, A = C.POINTER(layout.Params), C.POINTER(layout.Grid), C.POINTER(layout.Agents)
+        L.orc_rng_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
+        L.orc_rng_get.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
+        L.orc_env_step.argtypes = [P, G, C.c_int32]
+        L.orc_agent_step.argtypes = [P, G, A, C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p]
+        L.orc_compact.argtypes = [P, G, A, C.c_int32]
+        L.orc_stats.argtypes = [P, G, A, C.c_int32, C.POINTER(layout.Stats)]
+        _LIB = L
+    return _LIB
+
+
+class Oracle:
+    """Steps a HostState in place with the CPU restatement."""
+
+    def __init__(self, params, state, endow_bits=None, tag_bits=None):
+        self.L = lib()
+        self.params = params
+        self.state = state
+        self.rng = np.zeros(self.L.orc_sizeof_rng() // 4 + 2, dtype=np.uint32)
+        self.endow_bits = endow_bits
+        self.tag_bits = tag_bits
+        self.L.orc_rng_init(self.rng.ctypes.data, None, 624, params.rng_mode)
+
+    def set_mt_from_python(self):
+        st = random.getstate()[1]
+        arr = np.array(st[:624], dtype=np.uint32)
+        self.L.orc_rng_init(self.rng.ctypes.data, arr.ctypes.data, st[624], self.params.rng_mode)
+
+    def mt_state(self):
+        arr = np.zeros(624, dtype=np.uint32)
+        idx = C.c_int32(0)
+        self.L.orc_rng_get(self.rng.ctypes.data, arr.ctypes.data, C.byref(idx))
+        return arr, idx.value
+
+    def push_mt_to_python(self):
+        arr, idx = self.mt_state()
+        random.setstate((3, tuple(int(v) for v in arr) + (idx,), None))
+
+    def env_step(self, t):
+        g, a = self.state.as_structs()
+        self.L.orc_env_step(C.byref(self.params), C.byref(g), t)
+
+    def agent_step(self, t, prev_mean_wealth=0.0):
+        g, a = self.state.as_structs()
+        eb = self.endow_bits.ctypes.data if self.endow_bits is not None else None
+        tb = self.tag_bits.ctypes.data if self.tag_bits is not None else None
+        self.L.orc_agent_step(C.byref(self.params), C.byref(g), C.byref(a), self.rng.ctypes.data,
+                              t, prev_mean_wealth, eb, tb)
+
+    def compact(self, t):
+        g, a = self.state.as_structs()
+        self.L.orc_compact(C.byref(self.params), C.byref(g), C.byref(a), t)
+
+    def stats(self, t):
+        g, a = self.state.as_structs()
+        out = layout.Stats()
+        self.L.orc_stats(C.byref(self.params), C.byref(g), C.byref(a), t, C.byref(out))
+        return out
