@@ -166,6 +166,7 @@ typedef struct ssb_stats {
     int64_t n_dead, n_dead_moved, dead_starvation, dead_aging, dead_combat, sum_age_at_death;
     double  dead_wealth_collected;
     int64_t n_born, n_replaced;
+    int64_t n_acted;                    /* live agents with age > 0: healthHappiness == 1 (agent.py:1017-1021) */
     /* environment (1044-1051) */
     int64_t env_wealth_total;           /* sum sugar + spice                                    */
     int64_t env_wealth_created;         /* sum sugarLastProduced + spiceLastProduced            */
@@ -186,6 +187,21 @@ int  ssb_abi_version(void);
 /* mode E: the CPython MT19937 main stream; maps 1:1 to random.getstate()[1] */
 int  ssb_set_mt_state(ssb_engine_t *e, const uint32_t state[624], int32_t index);
 int  ssb_get_mt_state(ssb_engine_t *e, uint32_t state[624], int32_t *index);
+
+/* Per-timestep child-endowment tables (host-precomputed; reference agent.py:827-875 draws them
+ * from private streams that are a pure function of the timestep -- SURVEY.md Appendix A.9).
+ * endow_bits[t] bit k = inherit endowment k from the mate (1) or the acting parent (0);
+ * tag_bits[t] bit k = k-th draw for tag positions where the parents differ. */
+int  ssb_set_step_tables(ssb_engine_t *e, const uint32_t *endow_bits, const uint32_t *tag_bits, int32_t n);
+
+/* mode S tuning: reservation marks live on a grid coarsened by 2^shift cells per side */
+int  ssb_set_mark_shift(ssb_engine_t *e, int32_t shift);
+
+/* sizeof() of the ABI structs, for binding self-checks */
+int  ssb_sizeof_params(void);
+int  ssb_sizeof_grid(void);
+int  ssb_sizeof_agents(void);
+int  ssb_sizeof_stats(void);
 
 /* one timestep, in the reference's phase order (sugarscape.py:395-410) */
 int  ssb_env_step(ssb_engine_t *e, int32_t t, void *stream);     /* environment.doTimestep     */

@@ -726,6 +726,7 @@ void orc_stats(const ssb_params_t *p, const ssb_grid_t *g, const ssb_agents_t *a
         wealths[i] = w;
         out->sum_sugar_metab += a->sugar_metab[s]; out->sum_spice_metab += a->spice_metab[s];
         out->sum_movement += a->movement[s]; out->sum_vision += a->vision[s]; out->sum_age += a->age[s];
+        out->n_acted += a->age[s] > 0;
         out->sum_wealth += w;
         if (i == 0 || w > out->max_wealth) out->max_wealth = w;
         if (i == 0 || w < out->min_wealth) out->min_wealth = w;

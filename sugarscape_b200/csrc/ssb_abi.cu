@@ -1,0 +1,384 @@
+// ssb_abi.cu -- the C ABI of include/ssb.h: engine lifecycle, scratch memory and kernel launches.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false (see sugarscape_b200/build.py;
+// -fmad=false keeps a*b+c un-fused so fp64 results match the reference's CPython arithmetic).
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/ssb.h"
+#include "ssb_agent_step.cuh"
+#include "ssb_kernels.cuh"
+#include "ssb_sort.cuh"
+
+using namespace ssb;
+
+struct ssb_engine {
+    ssb_params_t p;
+    int device;
+    bool bound;
+    char err[512];
+    DevCtx ctx;
+    int num_sms;
+    int64_t launches;
+    // mode E
+    uint32_t *d_mt;
+    // step tables
+    uint32_t *d_endow, *d_tagbits;
+    int32_t n_tables;
+    // compaction scratch
+    int32_t *d_tile_counts;
+    int32_t n_tile_counts;
+    int32_t *d_new_order;
+    int64_t *d_scalars;      // [0]=n_alive after compaction, [1]=n_newborn, [2]=n_cells
+    int32_t *d_born_list;
+    // mode S rounds
+    RoundCtx rc;
+    int coop_blocks;
+    // stats
+    StatsPartial *d_partials;
+    int n_partials;
+    TribeCensus *d_tribes;
+    ssb_stats_t *d_stats;
+    uint64_t *d_keys_a, *d_keys_b;
+    uint32_t *d_radix_hist;
+    double *d_lorenz_blocks;
+    // timing
+    bool timing;
+    cudaEvent_t ev[5];
+    bool ev_recorded;
+};
+
+static int fail(ssb_engine *e, int code, const char *fmt, ...) {
+    if (e) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(e->err, sizeof(e->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t err__ = (call);                                                           \
+        if (err__ != cudaSuccess)                                                             \
+            return fail(e, -2, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), __FILE__, __LINE__); \
+    } while (0)
+
+#define LAUNCHED(e) do { (e)->launches++; CU(cudaGetLastError()); } while (0)
+
+static int grid_for(long long n, int threads, int cap) {
+    long long b = (n + threads - 1) / threads;
+    if (b < 1) b = 1;
+    if (b > cap) b = cap;
+    return (int)b;
+}
+
+extern "C" {
+
+int ssb_abi_version(void) { return SSB_ABI_VERSION; }
+
+// struct sizes, so that the host binding can verify its ctypes mirrors (tests/test_abi.py)
+int ssb_sizeof_params(void) { return (int)sizeof(ssb_params_t); }
+int ssb_sizeof_grid(void) { return (int)sizeof(ssb_grid_t); }
+int ssb_sizeof_agents(void) { return (int)sizeof(ssb_agents_t); }
+int ssb_sizeof_stats(void) { return (int)sizeof(ssb_stats_t); }
+
+const char *ssb_last_error(const ssb_engine_t *e) { return e ? e->err : "null engine"; }
+
+int ssb_create(const ssb_params_t *params, int device, ssb_engine_t **out) {
+    if (!params || !out) return -1;
+    ssb_engine *e = new ssb_engine();
+    memset(e, 0, sizeof(*e));
+    *out = e;
+    if (params->abi_version != SSB_ABI_VERSION) return fail(e, -1, "ABI version mismatch: host %d, library %d", params->abi_version, SSB_ABI_VERSION);
+    if (params->width <= 0 || params->height <= 0) return fail(e, -1, "bad map size %d x %d", params->width, params->height);
+    if (params->rng_mode != SSB_RNG_EXACT && params->rng_mode != SSB_RNG_SCALABLE) return fail(e, -1, "bad rng_mode %d", params->rng_mode);
+    if (params->id_bits < 2 || params->id_bits > 32 - TAG_BITS || (params->id_bits & 1)) return fail(e, -1, "id_bits must be even and <= %d", 32 - TAG_BITS);
+    if (params->tag_len > 32 || params->max_tribes > 26) return fail(e, -1, "tag_len <= 32 and max_tribes <= 26 required");
+    e->p = *params;
+    e->device = device;
+    int count = 0;
+    CU(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) return fail(e, -3, "CUDA device %d not available (%d visible)", device, count);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    e->num_sms = prop.multiProcessorCount;
+    if (params->rng_mode == SSB_RNG_SCALABLE && !prop.cooperativeLaunch) return fail(e, -3, "device lacks cooperative launch");
+    CU(cudaMalloc(&e->d_mt, 625 * sizeof(uint32_t)));
+    CU(cudaMemset(e->d_mt, 0, 625 * sizeof(uint32_t)));
+    CU(cudaMalloc(&e->d_scalars, 8 * sizeof(int64_t)));
+    CU(cudaMemset(e->d_scalars, 0, 8 * sizeof(int64_t)));
+    CU(cudaMalloc(&e->d_stats, sizeof(ssb_stats_t)));
+    CU(cudaMemset(e->d_stats, 0, sizeof(ssb_stats_t)));
+    CU(cudaMalloc(&e->d_tribes, sizeof(TribeCensus)));
+    for (int i = 0; i < 5; i++) CU(cudaEventCreate(&e->ev[i]));
+    return 0;
+}
+
+void ssb_destroy(ssb_engine_t *e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    void *ptrs[] = {e->d_mt, e->d_endow, e->d_tagbits, e->d_tile_counts, e->d_new_order, e->d_scalars,
+                    e->d_born_list, e->rc.mark, e->rc.prio, e->rc.list_a, e->rc.list_b, e->rc.ready, e->rc.cnt,
+                    e->d_partials, e->d_tribes, e->d_stats, e->d_keys_a, e->d_keys_b, e->d_radix_hist,
+                    e->d_lorenz_blocks};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    for (int i = 0; i < 5; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+    delete e;
+}
+
+int ssb_bind(ssb_engine_t *e, const ssb_grid_t *grid, const ssb_agents_t *agents) {
+    if (!e || !grid || !agents) return -1;
+    if (e->bound) return fail(e, -1, "engine already bound");
+    if (grid->n_cells != (int64_t)e->p.width * e->p.height) return fail(e, -1, "grid size mismatch");
+    if (agents->capacity <= 0 || agents->capacity > (1LL << 31) - 2) return fail(e, -1, "bad agent capacity");
+    CU(cudaSetDevice(e->device));
+    DevCtx &c = e->ctx;
+    memset(&c, 0, sizeof(c));
+    c.p = e->p; c.g = *grid; c.a = *agents;
+    const int rmax = e->p.max_agent_range;
+    c.max_dx = rmax < e->p.width / 2 ? rmax : e->p.width / 2;
+    c.max_dy = rmax < e->p.height / 2 ? rmax : e->p.height / 2;
+    const int maxd = c.max_dx > c.max_dy ? c.max_dx : c.max_dy;
+    if (e->p.rng_mode == SSB_RNG_EXACT && 4 * maxd > MAXC_EXACT) return fail(e, -1, "agent range %d exceeds the exact-mode limit %d", maxd, MAXC_EXACT / 4);
+    if (e->p.rng_mode == SSB_RNG_SCALABLE && 4 * maxd > MAXC_SCALABLE) return fail(e, -1, "agent range %d exceeds the scalable-mode limit %d", maxd, MAXC_SCALABLE / 4);
+    const int64_t cap = agents->capacity, cells = grid->n_cells;
+    const int64_t big = cap > cells ? cap : cells;
+    e->n_tile_counts = (int32_t)((big + COMPACT_TILE - 1) / COMPACT_TILE) + 1;
+    CU(cudaMalloc(&e->d_tile_counts, sizeof(int32_t) * e->n_tile_counts));
+    CU(cudaMalloc(&e->d_new_order, sizeof(int32_t) * cap));
+    CU(cudaMalloc(&e->d_born_list, sizeof(int32_t) * cap));
+    c.born_list = e->d_born_list;
+    const int64_t scal[3] = {0, 0, cells};
+    CU(cudaMemcpy(e->d_scalars, scal, sizeof(scal), cudaMemcpyHostToDevice));
+    // stats scratch
+    e->n_partials = e->num_sms * 4;
+    CU(cudaMalloc(&e->d_partials, sizeof(StatsPartial) * e->n_partials));
+    CU(cudaMalloc(&e->d_keys_a, sizeof(uint64_t) * cap));
+    CU(cudaMalloc(&e->d_keys_b, sizeof(uint64_t) * cap));
+    const int64_t radix_tiles = (cap + RADIX_TILE - 1) / RADIX_TILE;
+    CU(cudaMalloc(&e->d_radix_hist, sizeof(uint32_t) * 256 * radix_tiles));
+    CU(cudaMalloc(&e->d_lorenz_blocks, sizeof(double) * e->num_sms * 4));
+    if (e->p.rng_mode == SSB_RNG_SCALABLE) {
+        RoundCtx &rc = e->rc;
+        int sh = 0;
+        while (sh < 2 && (e->p.width % (2 << sh)) == 0 && (e->p.height % (2 << sh)) == 0) sh++;
+        rc.mark_shift = sh;
+        rc.wc = e->p.width >> sh; rc.hc = e->p.height >> sh;
+        CU(cudaMalloc(&rc.mark, sizeof(uint32_t) * (size_t)rc.wc * rc.hc));
+        CU(cudaMalloc(&rc.prio, sizeof(uint32_t) * cap));
+        CU(cudaMalloc(&rc.list_a, sizeof(int32_t) * cap));
+        CU(cudaMalloc(&rc.list_b, sizeof(int32_t) * cap));
+        CU(cudaMalloc(&rc.ready, sizeof(int32_t) * cap));
+        CU(cudaMalloc(&rc.cnt, sizeof(int32_t) * 8));
+        CU(cudaMemset(rc.cnt, 0, sizeof(int32_t) * 8));
+        int per_sm = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_agent_step_scalable, 256, 0));
+        if (per_sm < 1) return fail(e, -3, "cooperative kernel does not fit on an SM");
+        e->coop_blocks = per_sm * e->num_sms;
+    }
+    e->bound = true;
+    return 0;
+}
+
+int ssb_set_mark_shift(ssb_engine_t *e, int32_t shift) {
+    if (!e || !e->bound || e->p.rng_mode != SSB_RNG_SCALABLE) return fail(e, -1, "mark shift needs a bound scalable engine");
+    if (shift < 0 || shift > 6 || (e->p.width % (1 << shift)) || (e->p.height % (1 << shift))) return fail(e, -1, "mark shift %d does not divide the map", shift);
+    CU(cudaSetDevice(e->device));
+    RoundCtx &rc = e->rc;
+    if (shift < rc.mark_shift) {   // finer grid needs a larger buffer
+        CU(cudaFree(rc.mark));
+        CU(cudaMalloc(&rc.mark, sizeof(uint32_t) * (size_t)(e->p.width >> shift) * (e->p.height >> shift)));
+    }
+    rc.mark_shift = shift; rc.wc = e->p.width >> shift; rc.hc = e->p.height >> shift;
+    return 0;
+}
+
+int ssb_set_mt_state(ssb_engine_t *e, const uint32_t state[624], int32_t index) {
+    if (!e || !state) return -1;
+    CU(cudaSetDevice(e->device));
+    uint32_t tmp[625];
+    memcpy(tmp, state, 624 * sizeof(uint32_t));
+    tmp[624] = (uint32_t)index;
+    CU(cudaMemcpy(e->d_mt, tmp, sizeof(tmp), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int ssb_get_mt_state(ssb_engine_t *e, uint32_t state[624], int32_t *index) {
+    if (!e || !state || !index) return -1;
+    CU(cudaSetDevice(e->device));
+    uint32_t tmp[625];
+    CU(cudaMemcpy(tmp, e->d_mt, sizeof(tmp), cudaMemcpyDeviceToHost));
+    memcpy(state, tmp, 624 * sizeof(uint32_t));
+    *index = (int32_t)tmp[624];
+    return 0;
+}
+
+int ssb_set_step_tables(ssb_engine_t *e, const uint32_t *endow_bits, const uint32_t *tag_bits, int32_t n) {
+    if (!e || n < 0) return -1;
+    CU(cudaSetDevice(e->device));
+    if (e->d_endow) { cudaFree(e->d_endow); cudaFree(e->d_tagbits); e->d_endow = e->d_tagbits = nullptr; }
+    e->n_tables = n;
+    if (n > 0) {
+        CU(cudaMalloc(&e->d_endow, sizeof(uint32_t) * n));
+        CU(cudaMalloc(&e->d_tagbits, sizeof(uint32_t) * n));
+        CU(cudaMemcpy(e->d_endow, endow_bits, sizeof(uint32_t) * n, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(e->d_tagbits, tag_bits, sizeof(uint32_t) * n, cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+static DevCtx step_ctx(ssb_engine *e, int32_t t, double prev_mean_wealth) {
+    DevCtx c = e->ctx;
+    c.t = t;
+    c.prev_mean_wealth = prev_mean_wealth;
+    c.endow_bits = e->d_endow; c.tag_bits = e->d_tagbits; c.n_step_tables = e->n_tables;
+    return c;
+}
+
+#define CHECK_BOUND(e) do { if (!(e)) return -1; if (!(e)->bound) return fail(e, -1, "engine not bound"); CU(cudaSetDevice((e)->device)); } while (0)
+
+// environment.doTimestep(t): environment.py:105-109
+int ssb_env_step(ssb_engine_t *e, int32_t t, void *stream_) {
+    CHECK_BOUND(e);
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (e->timing) CU(cudaEventRecord(e->ev[0], st));
+    const ssb_params_t &p = e->p;
+    GrowArgs g;
+    g.height = p.height; g.equator = p.equator; g.n_cells = e->ctx.g.n_cells;
+    g.seasons = p.season_interval > 0;
+    g.flipped = g.seasons ? (((t - 1) / p.season_interval) & 1) : 0;
+    g.dry_grows = (g.seasons && p.seasonal_growback_delay > 0) ? (t % p.seasonal_growback_delay == 0) : 0;
+    const bool vec = (p.height % 4) == 0;
+    const int blocks = grid_for(vec ? g.n_cells / 4 : g.n_cells, 256, e->num_sms * 8);
+    for (int res = 0; res < 2; res++) {
+        g.level = res == 0 ? e->ctx.g.sugar : e->ctx.g.spice;
+        g.cap = res == 0 ? e->ctx.g.sugar_cap : e->ctx.g.spice_cap;
+        g.rate = res == 0 ? p.sugar_regrow : p.spice_regrow;
+        if (g.rate == 0 || (res == 1 && !(p.flags & SSB_F_SPICE))) continue;
+        if (vec) k_growback_v4<<<blocks, 256, 0, st>>>(g); else k_growback_scalar<<<blocks, 256, 0, st>>>(g);
+        LAUNCHED(e);
+    }
+    if (p.diffusion_delay > 0 && p.diffusion_start <= t && t <= p.diffusion_end &&
+        ((t - p.diffusion_start + 1) % p.diffusion_delay) == 0) {
+        k_diffuse<<<grid_for(g.n_cells, 256, e->num_sms * 8), 256, 0, st>>>(e->ctx.g.pollution, e->ctx.g.pollution_flux, p.width, p.height);
+        LAUNCHED(e);
+        CU(cudaMemcpyAsync(e->ctx.g.pollution, e->ctx.g.pollution_flux, sizeof(double) * g.n_cells, cudaMemcpyDeviceToDevice, st));
+    }
+    if (e->timing) CU(cudaEventRecord(e->ev[1], st));
+    return 0;
+}
+
+// random.shuffle(self.agents) + the agent loop: sugarscape.py:400-407
+int ssb_agent_step(ssb_engine_t *e, int32_t t, double prev_mean_wealth, void *stream_) {
+    CHECK_BOUND(e);
+    cudaStream_t st = (cudaStream_t)stream_;
+    DevCtx c = step_ctx(e, t, prev_mean_wealth);
+    if (e->p.rng_mode == SSB_RNG_EXACT) {
+        k_agent_step_exact<<<1, 32, 0, st>>>(c, e->d_mt);
+        LAUNCHED(e);
+    } else {
+        RoundCtx rc = e->rc;
+        rc.key = step_key(e->p.seed, t);
+        void *args[] = {&c, &rc};
+        CU(cudaLaunchCooperativeKernel((void *)k_agent_step_scalable, dim3(e->coop_blocks), dim3(256), args, 0, st));
+        LAUNCHED(e);
+    }
+    if (e->timing) CU(cudaEventRecord(e->ev[2], st));
+    return 0;
+}
+
+// removeDeadAgents: sugarscape.py:843-853 (+ mode S newborn numbering)
+int ssb_compact(ssb_engine_t *e, int32_t t, void *stream_) {
+    CHECK_BOUND(e);
+    cudaStream_t st = (cudaStream_t)stream_;
+    DevCtx c = step_ctx(e, t, 0.0);
+    const int64_t cap = c.a.capacity;
+    const int tiles = (int)((cap + COMPACT_TILE - 1) / COMPACT_TILE);
+    k_compact_count<<<tiles, COMPACT_THREADS, 0, st>>>(c, e->d_tile_counts); LAUNCHED(e);
+    k_scan_tiles<<<1, COMPACT_THREADS, 0, st>>>(e->d_tile_counts, c.a.counters + SSB_C_N_LIST, COMPACT_TILE, e->d_scalars + 0); LAUNCHED(e);
+    k_compact_scatter<<<tiles, COMPACT_THREADS, 0, st>>>(c, e->d_tile_counts, e->d_new_order); LAUNCHED(e);
+    k_compact_finish<<<grid_for(cap, 256, e->num_sms * 4), 256, 0, st>>>(c, e->d_new_order, e->d_scalars + 0); LAUNCHED(e);
+    k_compact_counters<<<1, 1, 0, st>>>(c, e->d_scalars + 0); LAUNCHED(e);
+    if (e->p.rng_mode == SSB_RNG_SCALABLE && (e->p.flags & SSB_F_REPRO)) {
+        const int ctiles = (int)((c.g.n_cells + COMPACT_TILE - 1) / COMPACT_TILE);
+        k_newborn_count<<<ctiles, COMPACT_THREADS, 0, st>>>(c, e->d_tile_counts); LAUNCHED(e);
+        k_scan_tiles<<<1, COMPACT_THREADS, 0, st>>>(e->d_tile_counts, e->d_scalars + 2, COMPACT_TILE, e->d_scalars + 1); LAUNCHED(e);
+        k_newborn_scatter<<<ctiles, COMPACT_THREADS, 0, st>>>(c, e->d_tile_counts); LAUNCHED(e);
+        k_newborn_counters<<<1, 1, 0, st>>>(c, e->d_scalars + 1); LAUNCHED(e);
+    }
+    if (e->timing) CU(cudaEventRecord(e->ev[3], st));
+    return 0;
+}
+
+// the reductions of updateRuntimeStats: sugarscape.py:1005-1426, 913-934
+int ssb_reduce_stats(ssb_engine_t *e, int32_t t, void *stream_) {
+    CHECK_BOUND(e);
+    cudaStream_t st = (cudaStream_t)stream_;
+    DevCtx c = step_ctx(e, t, 0.0);
+    k_stats_reset<<<1, 32, 0, st>>>(e->d_tribes); LAUNCHED(e);
+    k_stats_partials<<<e->n_partials, STATS_THREADS, 0, st>>>(c, e->d_partials, (double *)e->d_keys_a, e->d_tribes); LAUNCHED(e);
+    k_stats_final<<<1, STATS_THREADS, 0, st>>>(c, e->d_partials, e->n_partials, e->d_tribes, e->d_stats); LAUNCHED(e);
+    // Lorenz numerator: sort the wealths (non-negative doubles order like their bit patterns)
+    const int64_t cap = c.a.capacity;
+    const int tiles = (int)((cap + RADIX_TILE - 1) / RADIX_TILE);
+    const int64_t *n_ptr = c.a.counters + SSB_C_N_LIST;
+    uint64_t *src = e->d_keys_a, *dst = e->d_keys_b;
+    for (int shift = 0; shift < 64; shift += 8) {
+        k_radix_hist<<<tiles, RADIX_THREADS, 0, st>>>(src, n_ptr, shift, e->d_radix_hist, tiles); LAUNCHED(e);
+        k_radix_scan<<<1, RADIX_THREADS, 0, st>>>(e->d_radix_hist, n_ptr); LAUNCHED(e);
+        k_radix_scatter<<<tiles, RADIX_THREADS, 0, st>>>(src, dst, n_ptr, shift, e->d_radix_hist); LAUNCHED(e);
+        uint64_t *tmp = src; src = dst; dst = tmp;
+    }
+    const int lb = e->num_sms * 4;
+    k_lorenz<<<lb, 256, 0, st>>>((const double *)src, n_ptr, e->d_lorenz_blocks); LAUNCHED(e);
+    k_lorenz_final<<<1, 1, 0, st>>>(e->d_lorenz_blocks, lb, e->d_stats); LAUNCHED(e);
+    if (e->timing) { CU(cudaEventRecord(e->ev[4], st)); e->ev_recorded = true; }
+    return 0;
+}
+
+int ssb_step(ssb_engine_t *e, int32_t t, double prev_mean_wealth, void *stream) {
+    int rc;
+    if ((rc = ssb_env_step(e, t, stream))) return rc;
+    if ((rc = ssb_agent_step(e, t, prev_mean_wealth, stream))) return rc;
+    if ((rc = ssb_compact(e, t, stream))) return rc;
+    return ssb_reduce_stats(e, t, stream);
+}
+
+int ssb_stats(ssb_engine_t *e, ssb_stats_t *host_out) {
+    CHECK_BOUND(e);
+    if (!host_out) return -1;
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(host_out, e->d_stats, sizeof(ssb_stats_t), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int ssb_sync(ssb_engine_t *e, void *stream) {
+    CHECK_BOUND(e);
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+}
+
+int64_t ssb_launch_count(const ssb_engine_t *e) { return e ? e->launches : 0; }
+
+int ssb_enable_timing(ssb_engine_t *e, int32_t on) {
+    if (!e) return -1;
+    e->timing = on != 0;
+    e->ev_recorded = false;
+    return 0;
+}
+
+int ssb_timing(ssb_engine_t *e, float *env_ms, float *agent_ms, float *compact_ms, float *stats_ms) {
+    CHECK_BOUND(e);
+    if (!e->timing || !e->ev_recorded) return fail(e, -1, "timing not enabled or no full step recorded");
+    CU(cudaEventSynchronize(e->ev[4]));
+    float *out[4] = {env_ms, agent_ms, compact_ms, stats_ms};
+    for (int i = 0; i < 4; i++)
+        if (out[i]) CU(cudaEventElapsedTime(out[i], e->ev[i], e->ev[i + 1]));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,429 @@
+// ssb_kernels.cuh -- environment stencil, list compaction and the runtimeStats reductions.
+#pragma once
+#include "ssb_rules.cuh"
+
+namespace ssb {
+
+// ---------------------------------------------------------------------------------------------
+// K1 env_step: growback with season gating (environment.py:61-96, cell.py:138-142), closed-form
+// schedules of SURVEY.md Appendix A.3.  HBM-bound: 12 B per cell per resource (level read,
+// capacity read, level write); the write is skipped for vectors that did not change.
+// ---------------------------------------------------------------------------------------------
+struct GrowArgs {
+    int32_t *level;
+    const int32_t *cap;
+    int32_t rate;
+    int32_t height, equator;
+    int32_t seasons, flipped, dry_grows;
+    long long n_cells;
+};
+
+__device__ __forceinline__ int grow_one(int level, int cap, int rate, bool allowed) {
+    return allowed ? min(level + rate, cap) : level;
+}
+
+// 128-bit path: requires height % 4 == 0 so that a vector never straddles two x-lines
+__global__ void __launch_bounds__(256) k_growback_v4(GrowArgs g) {
+    const long long n4 = g.n_cells >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < n4; v += stride) {
+        int4 lv = reinterpret_cast<const int4 *>(g.level)[v];
+        const int4 cp = __ldg(reinterpret_cast<const int4 *>(g.cap) + v);
+        bool a0 = true, a1 = true, a2 = true, a3 = true;
+        if (g.seasons) {
+            const int y = (int)((v << 2) % g.height);
+            a0 = ((y + 0 < g.equator) != (bool)g.flipped) || g.dry_grows;
+            a1 = ((y + 1 < g.equator) != (bool)g.flipped) || g.dry_grows;
+            a2 = ((y + 2 < g.equator) != (bool)g.flipped) || g.dry_grows;
+            a3 = ((y + 3 < g.equator) != (bool)g.flipped) || g.dry_grows;
+        }
+        int4 nv;
+        nv.x = grow_one(lv.x, cp.x, g.rate, a0);
+        nv.y = grow_one(lv.y, cp.y, g.rate, a1);
+        nv.z = grow_one(lv.z, cp.z, g.rate, a2);
+        nv.w = grow_one(lv.w, cp.w, g.rate, a3);
+        if (nv.x != lv.x || nv.y != lv.y || nv.z != lv.z || nv.w != lv.w)
+            reinterpret_cast<int4 *>(g.level)[v] = nv;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_growback_scalar(GrowArgs g) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < g.n_cells; i += stride) {
+        bool allowed = true;
+        if (g.seasons) {
+            const int y = (int)(i % g.height);
+            allowed = ((y < g.equator) != (bool)g.flipped) || g.dry_grows;
+        }
+        const int lv = g.level[i], nv = grow_one(lv, g.cap[i], g.rate, allowed);
+        if (nv != lv) g.level[i] = nv;
+    }
+}
+
+// Pollution diffusion (cell.py:104-109,24-25): Jacobi mean of N, S, E, W from the OLD field, the
+// centre excluded, summed in that order starting from 0.  16 B per cell (read + write).
+__global__ void __launch_bounds__(256) k_diffuse(const double *__restrict__ p, double *__restrict__ flux,
+                                                 int W, int H) {
+    const long long n = (long long)W * H;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int x = (int)(i / H), y = (int)(i - (long long)x * H);
+        const long long row = (long long)x * H;
+        double m = 0.0;
+        m += p[row + (y == 0 ? H - 1 : y - 1)];
+        m += p[row + (y == H - 1 ? 0 : y + 1)];
+        m += p[(long long)(x == W - 1 ? 0 : x + 1) * H + y];
+        m += p[(long long)(x == 0 ? W - 1 : x - 1) * H + y];
+        flux[i] = m / 4;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5 death_compact: removeDeadAgents (sugarscape.py:843-853), order preserving.
+// count -> scan -> scatter over tiles of COMPACT_TILE list entries.
+// ---------------------------------------------------------------------------------------------
+constexpr int COMPACT_THREADS = 256;
+constexpr int COMPACT_ITEMS = 4;
+constexpr int COMPACT_TILE = COMPACT_THREADS * COMPACT_ITEMS;
+
+__device__ __forceinline__ bool list_entry_survives(const DevCtx &c, int s) {
+    return agent_alive(c, s) && c.a.pos[s] >= 0;
+}
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int *total) {
+    // 256-thread exclusive scan: warp shuffles + one shared level
+    __shared__ int warp_sums[COMPACT_THREADS / 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+    }
+    if (lane == 31) warp_sums[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        int ws = lane < COMPACT_THREADS / 32 ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < COMPACT_THREADS / 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, ws, o);
+            if (lane >= o) ws += u;
+        }
+        if (lane < COMPACT_THREADS / 32) warp_sums[lane] = ws;
+    }
+    __syncthreads();
+    const int base = w > 0 ? warp_sums[w - 1] : 0;
+    *total = warp_sums[COMPACT_THREADS / 32 - 1];
+    __syncthreads();
+    return base + inc - v;
+}
+
+__global__ void __launch_bounds__(COMPACT_THREADS) k_compact_count(DevCtx c, int32_t *tile_alive) {
+    const long long n = c.a.counters[SSB_C_N_LIST];
+    const long long tile0 = (long long)blockIdx.x * COMPACT_TILE;
+    if (tile0 >= n) { if (threadIdx.x == 0) tile_alive[blockIdx.x] = 0; return; }
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < COMPACT_ITEMS; k++) {
+        const long long i = tile0 + (long long)threadIdx.x * COMPACT_ITEMS + k;
+        if (i < n && list_entry_survives(c, c.a.order[i])) cnt++;
+    }
+    int total;
+    block_exclusive_scan(cnt, &total);
+    if (threadIdx.x == 0) tile_alive[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of per-tile counts (in place); writes the grand total to *total
+__global__ void __launch_bounds__(COMPACT_THREADS) k_scan_tiles(int32_t *tile_counts, const int64_t *n_items_ptr,
+                                                                int items_per_tile, int64_t *total_out) {
+    const long long n_items = *n_items_ptr;
+    const int n_tiles = (int)((n_items + items_per_tile - 1) / items_per_tile);
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n_tiles; base += COMPACT_THREADS) {
+        const int i = base + threadIdx.x;
+        const int v = i < n_tiles ? tile_counts[i] : 0;
+        int total;
+        const int ex = block_exclusive_scan(v, &total);
+        if (i < n_tiles) tile_counts[i] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total_out = carry;
+}
+
+__global__ void __launch_bounds__(COMPACT_THREADS) k_compact_scatter(DevCtx c, const int32_t *tile_offset,
+                                                                     int32_t *new_order) {
+    const long long n = c.a.counters[SSB_C_N_LIST];
+    const long long tile0 = (long long)blockIdx.x * COMPACT_TILE;
+    if (tile0 >= n) return;
+    int slots[COMPACT_ITEMS];
+    bool alive[COMPACT_ITEMS];
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < COMPACT_ITEMS; k++) {
+        const long long i = tile0 + (long long)threadIdx.x * COMPACT_ITEMS + k;
+        slots[k] = i < n ? c.a.order[i] : -1;
+        alive[k] = slots[k] >= 0 && list_entry_survives(c, slots[k]);
+        cnt += alive[k];
+    }
+    int total;
+    int at = block_exclusive_scan(cnt, &total);
+    // survivors keep list order; the dead of this tile go to dead_list[(tile0 - offset) ...]
+    const int alive_base = tile_offset[blockIdx.x];
+    int dead_at = (int)(tile0 - alive_base) + (threadIdx.x * COMPACT_ITEMS - at);
+    at += alive_base;
+#pragma unroll
+    for (int k = 0; k < COMPACT_ITEMS; k++) {
+        if (slots[k] < 0) continue;
+        if (alive[k]) new_order[at++] = slots[k];
+        else {
+            const int s = slots[k];
+            if (c.a.cod[s] == SSB_ALIVE) do_death(c, s, SSB_OTHER);   // removeDeadAgents -> doDeath()
+            else if (c.a.pos[s] >= 0) do_death(c, s, c.a.cod[s]);
+            c.a.dead_list[dead_at++] = s;
+        }
+    }
+}
+
+// finish: publish the new list, recycle dead slots
+__global__ void __launch_bounds__(256) k_compact_finish(DevCtx c, const int32_t *new_order, const int64_t *n_alive_ptr) {
+    const long long n_old = c.a.counters[SSB_C_N_LIST];
+    const long long n_alive = *n_alive_ptr, n_dead = n_old - n_alive;
+    const long long n_free = c.a.counters[SSB_C_N_FREE];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long i = tid; i < n_alive; i += stride) c.a.order[i] = new_order[i];
+    for (long long i = tid; i < n_dead; i += stride) c.a.free_slots[n_free + i] = c.a.dead_list[i];
+}
+
+__global__ void k_compact_counters(DevCtx c, const int64_t *n_alive_ptr) {
+    const long long n_old = c.a.counters[SSB_C_N_LIST];
+    const long long n_alive = *n_alive_ptr;
+    c.a.counters[SSB_C_N_DEAD] = n_old - n_alive;
+    c.a.counters[SSB_C_N_FREE] += n_old - n_alive;
+    c.a.counters[SSB_C_N_LIST] = n_alive;
+}
+
+// Mode S: this step's surviving newborn are numbered and appended in CELL order (the oracle does
+// the same; DESIGN.md "mode S").  Same count / scan / scatter pattern, over the cells.
+__device__ __forceinline__ bool cell_has_unnumbered_newborn(const DevCtx &c, long long cell) {
+    const int s = c.g.occ[cell];
+    return s >= 0 && c.a.id[s] < 0;
+}
+
+__global__ void __launch_bounds__(COMPACT_THREADS) k_newborn_count(DevCtx c, int32_t *tile_counts) {
+    const long long n = c.g.n_cells;
+    const long long tile0 = (long long)blockIdx.x * COMPACT_TILE;
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < COMPACT_ITEMS; k++) {
+        const long long i = tile0 + (long long)threadIdx.x * COMPACT_ITEMS + k;
+        if (i < n && cell_has_unnumbered_newborn(c, i)) cnt++;
+    }
+    int total;
+    block_exclusive_scan(cnt, &total);
+    if (threadIdx.x == 0) tile_counts[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(COMPACT_THREADS) k_newborn_scatter(DevCtx c, const int32_t *tile_offset) {
+    const long long n = c.g.n_cells;
+    const long long tile0 = (long long)blockIdx.x * COMPACT_TILE;
+    int slots[COMPACT_ITEMS];
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < COMPACT_ITEMS; k++) {
+        const long long i = tile0 + (long long)threadIdx.x * COMPACT_ITEMS + k;
+        slots[k] = (i < n && cell_has_unnumbered_newborn(c, i)) ? c.g.occ[i] : -1;
+        cnt += slots[k] >= 0;
+    }
+    int total;
+    int at = block_exclusive_scan(cnt, &total) + tile_offset[blockIdx.x];
+    const long long n_list = c.a.counters[SSB_C_N_LIST], next_id = c.a.counters[SSB_C_NEXT_ID];
+#pragma unroll
+    for (int k = 0; k < COMPACT_ITEMS; k++) {
+        if (slots[k] < 0) continue;
+        if (n_list + at < c.a.capacity) c.a.order[n_list + at] = slots[k];
+        else c.a.counters[SSB_C_OVERFLOW] = 1;
+        c.a.id[slots[k]] = (int32_t)(next_id + at);
+        at++;
+    }
+}
+
+__global__ void k_newborn_counters(DevCtx c, const int64_t *n_new_ptr) {
+    c.a.counters[SSB_C_N_LIST] += *n_new_ptr;
+    c.a.counters[SSB_C_NEXT_ID] += *n_new_ptr;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6 stats_reduce: raw sums of updateRuntimeStatsPerGroup (sugarscape.py:1005-1426).
+// Two deterministic stages: per-block partials in list order, then one block folds them.
+// ---------------------------------------------------------------------------------------------
+struct StatsPartial {
+    long long population, sum_sugar_metab, sum_spice_metab, sum_movement, sum_vision, sum_age;
+    long long sum_neighbors, sum_valid_moves, n_traders, trade_volume;
+    long long n_dead, n_dead_moved, dead_starvation, dead_aging, dead_combat, sum_age_at_death;
+    long long env_wealth_total, env_capacity_total, n_acted;
+    double sum_wealth, max_wealth, min_wealth, sum_wealth_collected, sum_burn_rate, sum_ttl_age_limited;
+    double sum_trade_price, sum_happiness, sum_wealth_happiness, sum_family_happiness;
+    double dead_wealth_collected;
+};
+
+__device__ __forceinline__ void partial_zero(StatsPartial &p) {
+    memset(&p, 0, sizeof(p));
+    p.max_wealth = -1.0e300; p.min_wealth = 1.0e300;
+}
+
+__device__ __forceinline__ void partial_merge(StatsPartial &a, const StatsPartial &b) {
+    long long *ai = &a.population; const long long *bi = &b.population;
+    for (int i = 0; i < 19; i++) ai[i] += bi[i];
+    a.sum_wealth += b.sum_wealth; a.max_wealth = fmax(a.max_wealth, b.max_wealth);
+    a.min_wealth = fmin(a.min_wealth, b.min_wealth);
+    a.sum_wealth_collected += b.sum_wealth_collected; a.sum_burn_rate += b.sum_burn_rate;
+    a.sum_ttl_age_limited += b.sum_ttl_age_limited; a.sum_trade_price += b.sum_trade_price;
+    a.sum_happiness += b.sum_happiness; a.sum_wealth_happiness += b.sum_wealth_happiness;
+    a.sum_family_happiness += b.sum_family_happiness; a.dead_wealth_collected += b.dead_wealth_collected;
+}
+
+constexpr int STATS_THREADS = 128;
+
+// block-level fold through shared memory, fixed tree order -> deterministic
+__device__ void block_fold(StatsPartial &mine, StatsPartial *smem) {
+    smem[threadIdx.x] = mine;
+    __syncthreads();
+    for (int o = STATS_THREADS / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) partial_merge(smem[threadIdx.x], smem[threadIdx.x + o]);
+        __syncthreads();
+    }
+}
+
+// tribe census (tribes dict, sugarscape.py:1171-1174; max(dict, key=get) needs first-seen order)
+struct TribeCensus { unsigned long long count[32]; unsigned long long first[32]; };
+
+__global__ void k_stats_reset(TribeCensus *tc) {
+    if (threadIdx.x < 32) { tc->count[threadIdx.x] = 0; tc->first[threadIdx.x] = ~0ull; }
+}
+
+__global__ void __launch_bounds__(STATS_THREADS) k_stats_partials(DevCtx c, StatsPartial *out, double *wealth_keys,
+                                                                  TribeCensus *tc) {
+    __shared__ StatsPartial smem[STATS_THREADS];
+    __shared__ unsigned long long tr_count[32], tr_first[32];
+    if (threadIdx.x < 32) { tr_count[threadIdx.x] = 0; tr_first[threadIdx.x] = ~0ull; }
+    __syncthreads();
+    StatsPartial p;
+    partial_zero(p);
+    const long long n = c.a.counters[SSB_C_N_LIST], n_dead = c.a.counters[SSB_C_N_DEAD];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long i = tid; i < n; i += stride) {
+        const int s = c.a.order[i];
+        const double w = c.a.sugar[s] + c.a.spice[s];
+        if (wealth_keys) wealth_keys[i] = w;
+        p.population++;
+        p.sum_sugar_metab += c.a.sugar_metab[s]; p.sum_spice_metab += c.a.spice_metab[s];
+        p.sum_movement += c.a.movement[s]; p.sum_vision += c.a.vision[s]; p.sum_age += c.a.age[s];
+        p.n_acted += c.a.age[s] > 0;
+        p.sum_wealth += w; p.max_wealth = fmax(p.max_wealth, w); p.min_wealth = fmin(p.min_wealth, w);
+        p.sum_wealth_collected += w - (c.a.last_sugar[s] + c.a.last_spice[s]);
+        // findTimeToLive (agent.py:1113-1140), sys.maxsize when a metabolism is zero
+        const double sm = (double)max(c.a.sugar_metab[s], 0), pm = (double)max(c.a.spice_metab[s], 0);
+        const double st = sm > 0 ? c.a.sugar[s] / sm : 9223372036854775807.0;
+        const double pt = pm > 0 ? c.a.spice[s] / pm : 9223372036854775807.0;
+        const double ttl = fmin(st, pt);
+        p.sum_burn_rate += ttl;
+        p.sum_ttl_age_limited += fmin(ttl, (double)(c.a.max_age[s] - c.a.age[s]));
+        p.sum_neighbors += c.a.n_neighborhood[s]; p.sum_valid_moves += c.a.n_valid_moves[s];
+        if (c.a.trade_volume[s] > 0) {
+            p.n_traders++; p.trade_volume += c.a.trade_volume[s]; p.sum_trade_price += c.a.trade_price[s];
+        }
+        p.sum_happiness += c.a.happiness[s]; p.sum_wealth_happiness += c.a.wealth_happiness[s];
+        p.sum_family_happiness += c.a.family_happiness[s];
+        const int tr = c.a.tribe[s];
+        if (tr >= 0 && tr < 32) { atomicAdd(&tr_count[tr], 1ull); atomicMin(&tr_first[tr], (unsigned long long)i); }
+    }
+    for (long long i = tid; i < n_dead; i += stride) {      // this step's dead (1213-1265)
+        const int s = c.a.dead_list[i];
+        p.n_dead++;
+        p.n_dead_moved += c.a.last_moved[s] == c.t;
+        p.sum_age_at_death += c.a.age[s];
+        p.dead_wealth_collected += (c.a.sugar[s] + c.a.spice[s]) - (c.a.last_sugar[s] + c.a.last_spice[s]);
+        p.dead_starvation += c.a.cod[s] == SSB_STARVATION;
+        p.dead_aging += c.a.cod[s] == SSB_AGING;
+        p.dead_combat += c.a.cod[s] == SSB_COMBAT;
+    }
+    for (long long i = tid; i < c.g.n_cells; i += stride) { // environment totals (1044-1051)
+        p.env_wealth_total += c.g.sugar[i] + c.g.spice[i];
+        p.env_capacity_total += c.g.sugar_cap[i] + c.g.spice_cap[i];
+    }
+    block_fold(p, smem);
+    if (threadIdx.x == 0) out[blockIdx.x] = smem[0];
+    if (threadIdx.x < 32 && tr_count[threadIdx.x]) {
+        atomicAdd(&tc->count[threadIdx.x], tr_count[threadIdx.x]);
+        atomicMin(&tc->first[threadIdx.x], tr_first[threadIdx.x]);
+    }
+}
+
+__global__ void __launch_bounds__(STATS_THREADS) k_stats_final(DevCtx c, const StatsPartial *partials, int n_partials,
+                                                               const TribeCensus *tc, ssb_stats_t *out) {
+    __shared__ StatsPartial smem[STATS_THREADS];
+    StatsPartial p;
+    partial_zero(p);
+    for (int i = threadIdx.x; i < n_partials; i += STATS_THREADS) partial_merge(p, partials[i]);
+    block_fold(p, smem);
+    if (threadIdx.x != 0) return;
+    const StatsPartial &r = smem[0];
+    out->timestep = c.t;
+    out->population = r.population;
+    out->sum_sugar_metab = r.sum_sugar_metab; out->sum_spice_metab = r.sum_spice_metab;
+    out->sum_movement = r.sum_movement; out->sum_vision = r.sum_vision; out->sum_age = r.sum_age;
+    out->sum_wealth = r.sum_wealth;
+    out->max_wealth = r.population ? r.max_wealth : 0; out->min_wealth = r.population ? r.min_wealth : 0;
+    out->sum_wealth_collected = r.sum_wealth_collected; out->sum_burn_rate = r.sum_burn_rate;
+    out->sum_ttl_age_limited = r.sum_ttl_age_limited;
+    out->sum_neighbors = r.sum_neighbors; out->sum_valid_moves = r.sum_valid_moves;
+    out->n_traders = r.n_traders; out->trade_volume = r.trade_volume; out->sum_trade_price = r.sum_trade_price;
+    out->sum_happiness = r.sum_happiness; out->sum_wealth_happiness = r.sum_wealth_happiness;
+    out->sum_family_happiness = r.sum_family_happiness;
+    for (int i = 0; i < 32; i++) {
+        out->tribe_count[i] = (int64_t)tc->count[i];
+        out->tribe_first[i] = tc->count[i] ? (int64_t)tc->first[i] : -1;
+    }
+    out->n_dead = r.n_dead; out->n_dead_moved = r.n_dead_moved; out->dead_starvation = r.dead_starvation;
+    out->dead_aging = r.dead_aging; out->dead_combat = r.dead_combat; out->sum_age_at_death = r.sum_age_at_death;
+    out->dead_wealth_collected = r.dead_wealth_collected;
+    out->n_born = c.a.counters[SSB_C_N_BORN];
+    out->n_replaced = 0;
+    out->n_acted = r.n_acted;
+    out->env_wealth_total = r.env_wealth_total;
+    out->env_capacity_total = r.env_capacity_total;
+    out->env_wealth_created = 0;   // closed form, filled in by the host
+    out->rounds = c.a.counters[SSB_C_ROUNDS];
+}
+
+// Lorenz numerator from the ascending wealth keys (updateGiniCoefficient, sugarscape.py:913-934):
+// sum_{i<n-1} cum_i + cum_{n-1}/2 = sum_j w_j * (n - 1 - j) + w_j / 2 ... folded per block.
+__global__ void __launch_bounds__(256) k_lorenz(const double *sorted, const int64_t *n_ptr, double *block_sums) {
+    const long long n = *n_ptr;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    double acc = 0;
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride)
+        acc += sorted[j] * ((double)(n - 1 - j) + 0.5);
+    __shared__ double sm[256];
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = sm[0];
+}
+
+__global__ void k_lorenz_final(const double *block_sums, int n_blocks, ssb_stats_t *out) {
+    double acc = 0;
+    for (int i = 0; i < n_blocks; i++) acc += block_sums[i];
+    out->lorenz_weighted_sum = acc;
+}
+
+}  // namespace ssb

@@ -1,0 +1,490 @@
+// ssb_rules.cuh -- one agent's timestep transaction on the device SoA.
+//
+// Restates reference agent.py:568-598 (Agent.doTimestep) and what it calls; each function cites
+// the lines it follows.  One thread runs one transaction.  In mode E the single ordered CTA calls
+// it for every agent in list order; in mode S every agent that won its reservation in the
+// current commit round runs it concurrently (footprints of concurrent agents are disjoint, see
+// ssb_agent_step.cuh), so no atomics are needed on cells or neighbours -- only on the shared
+// slot / birth counters.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/ssb.h"
+#include "ssb_rng.cuh"
+
+namespace ssb {
+
+// child endowment bit positions inside endow_bits[t] (sugarscape_b200/steptables.py)
+enum { EB_AGGRESSION = 0, EB_FERT_AGE, EB_FERT_FACTOR, EB_INFERT_AGE, EB_LOOKAHEAD, EB_MAX_AGE,
+       EB_MOVEMENT, EB_SPICE_METAB, EB_SUGAR_METAB, EB_SEX, EB_TRADE_FACTOR, EB_VISION };
+
+struct DevCtx {
+    ssb_params_t p;
+    ssb_grid_t g;
+    ssb_agents_t a;
+    int32_t max_dx, max_dy;          // per-axis memoised range (environment.py:138-139)
+    int32_t t;
+    double prev_mean_wealth;         // runtimeStats["meanWealth"] of the previous step (agent.py:1166)
+    const uint32_t *endow_bits;      // per-timestep child endowment choices (agent.py:839-851)
+    const uint32_t *tag_bits;        // per-timestep tag mismatch draws (agent.py:859-875)
+    int32_t n_step_tables;
+    // mode S
+    int32_t *born_list;              // slots of this step's newborn (unordered)
+};
+
+__device__ __forceinline__ int wrapi(int v, int n) { v %= n; return v < 0 ? v + n : v; }
+
+// Agent.isAlive (agent.py:1221-1224)
+__device__ __forceinline__ bool agent_alive(const DevCtx &c, int s) {
+    return c.a.cod[s] == SSB_ALIVE && c.a.sugar[s] >= 0 && c.a.spice[s] >= 0;
+}
+
+// Agent.findTribe (agent.py:1142-1151)
+__device__ __forceinline__ int find_tribe(const DevCtx &c, uint32_t tags) {
+    const int L = c.p.tag_len, T = c.p.max_tribes;
+    if (L <= 0 || T <= 0) return -1;
+    const int zeroes = L - __popc(tags);
+    const double tribe_size = (double)(L + 1) / (double)T;
+    const int tribe = (int)ceil((double)(zeroes + 1) / tribe_size) - 1;
+    return min(tribe, T - 1);
+}
+
+// Python float ** with the two exponents that must be exact special-cased; the general case is
+// CUDA's pow (see DESIGN.md "floating point").
+__device__ __forceinline__ double py_pow(double x, double y) {
+    if (y == 0.0) return 1.0;
+    if (y == 1.0) return x;
+    return pow(x, y);
+}
+
+// Agent.findWelfare (agent.py:1170-1201)
+__device__ double find_welfare(const DevCtx &c, int s, double sugar_reward, double spice_reward) {
+    const double sm = (double)max(c.a.sugar_metab[s], 0), pm = (double)max(c.a.spice_metab[s], 0);
+    const double total = sm + pm;
+    double sprop = 0, pprop = 0;
+    if (total != 0) { sprop = sm / total; pprop = pm / total; }
+    const double look = c.a.lookahead[s];
+    double ts = (c.a.sugar[s] + sugar_reward) - sm * look;
+    double tp = (c.a.spice[s] + spice_reward) - pm * look;
+    if (ts < 0) ts = 0;
+    if (tp < 0) tp = 0;
+    double welfare = py_pow(ts, sprop) * py_pow(tp, pprop);
+    if ((c.p.flags & SSB_F_TAGPREF) && (c.p.flags & SSB_F_TAGS) && c.p.tag_len > 0) {
+        const int L = c.p.tag_len;
+        c.a.tribe[s] = find_tribe(c, c.a.tags[s]);
+        const int zeroes = L - __popc(c.a.tags[s]);
+        const double fz = (double)zeroes / (double)L, fo = 1 - fz;
+        double pref = sm * fz + pm * fo;
+        if (pref <= 0) pref = 1;
+        welfare = py_pow(ts, (sm / pref) * fz) * py_pow(tp, (pm / pref) * fo);
+    }
+    return welfare;
+}
+
+// Agent.doDeath (agent.py:296-313) with inheritance policy "none"
+__device__ __forceinline__ void do_death(const DevCtx &c, int s, int cause) {
+    c.a.cod[s] = cause;
+    const int pos = c.a.pos[s];
+    if (pos >= 0 && c.g.occ[pos] == s) c.g.occ[pos] = -1;
+    c.a.pos[s] = -1;
+}
+
+// Agent.findMarginalRateOfSubstitution (agent.py:1023-1029)
+__device__ __forceinline__ void find_mrs(const DevCtx &c, int s) {
+    const double pm = (double)max(c.a.spice_metab[s], 0), sm = (double)max(c.a.sugar_metab[s], 0);
+    const double spice_need = pm > 0 ? c.a.spice[s] / pm : 1;
+    const double sugar_need = sm > 0 ? c.a.sugar[s] / sm : 1;
+    c.a.mrs[s] = c.a.trade_factor[s] * (spice_need / sugar_need);
+}
+
+// Agent.findNewMarginalRateOfSubstitution (agent.py:1067-1080)
+__device__ __forceinline__ double find_new_mrs(const DevCtx &c, int s, double sugar, double spice) {
+    const double pm = (double)max(c.a.spice_metab[s], 0), sm = (double)max(c.a.sugar_metab[s], 0);
+    const double spice_need = pm > 0 ? spice / pm : 1;
+    const double sugar_need = sm > 0 ? sugar / sm : 1;
+    if (spice_need == 1 && sugar_need == 1) return 1;
+    if (spice_need == 0) return pm;
+    if (sugar_need == 0) return 1 / sm;
+    return spice_need / sugar_need;
+}
+
+// Agent.isFertile (agent.py:1244-1247)
+__device__ __forceinline__ bool is_fertile(const DevCtx &c, int s) {
+    return c.a.sugar[s] >= c.a.start_sugar[s] && c.a.spice[s] >= c.a.start_spice[s] &&
+           c.a.age[s] >= c.a.fert_age[s] && c.a.age[s] < c.a.infert_age[s] && c.a.fert_factor[s] > 0;
+}
+
+// the four von Neumann neighbours in the reference's dict order N, S, E, W (cell.py:61-75)
+__device__ __forceinline__ void neighbours4(const DevCtx &c, int pos, int32_t out[4]) {
+    const int W = c.p.width, H = c.p.height, x = pos / H, y = pos - x * H;
+    out[0] = x * H + (y == 0 ? H - 1 : y - 1);
+    out[1] = x * H + (y == H - 1 ? 0 : y + 1);
+    out[2] = (x == W - 1 ? 0 : x + 1) * H + y;
+    out[3] = (x == 0 ? W - 1 : x - 1) * H + y;
+}
+
+// collectResourcesAtCell (agent.py:249-259) + production pollution (cell.py:32-45)
+__device__ __forceinline__ void collect(const DevCtx &c, int s, int pos) {
+    const int32_t cs = c.g.sugar[pos];
+    const int32_t cp = (c.p.flags & SSB_F_SPICE) ? c.g.spice[pos] : 0;
+    c.a.sugar[s] += cs;
+    c.a.spice[s] += cp;
+    if (c.p.pollution_start <= c.t && c.t <= c.p.pollution_end) {
+        double pl = c.g.pollution[pos];
+        pl += c.p.sugar_prod_pollution * cs;
+        pl += c.p.spice_prod_pollution * cp;
+        c.g.pollution[pos] = pl;
+    }
+    c.g.sugar[pos] = 0;
+    if (c.p.flags & SSB_F_SPICE) c.g.spice[pos] = 0;
+}
+
+// Candidate cells of Agent.findCellsInRange (agent.py:766-779) in the dictionary insertion
+// order produced by Environment.findCardinalCellRanges (environment.py:111-122): per distance d
+// the (up to) four cells sorted by the time they were inserted -- SURVEY.md Appendix A.5.
+template <int MAXC>
+__device__ int enumerate_cross(const DevCtx &c, int pos, int r, int32_t *cells, uint8_t *dists) {
+    const int W = c.p.width, H = c.p.height, x = pos / H, y = pos - x * H;
+    const long long self_key = (long long)x * H + y;
+    int n = 0;
+    for (int d = 1; d <= r; d++) {
+        long long key[4];
+        int32_t cell[4];
+        int m = 0;
+        if (d <= c.max_dx) {
+            const int xw = wrapi(x - d, W), xe = wrapi(x + d, W);
+            key[m] = ((long long)xw * H + y) * 4; cell[m++] = xw * H + y;                 // west
+            if (xe != xw) { key[m] = self_key * 4 + 1; cell[m++] = xe * H + y; }          // east
+            else if (self_key < (long long)xw * H + y) key[m - 1] = self_key * 4 + 1;
+        }
+        if (d <= c.max_dy) {
+            const int yn = wrapi(y - d, H), ys = wrapi(y + d, H);
+            key[m] = ((long long)x * H + yn) * 4; cell[m++] = x * H + yn;                 // north
+            if (ys != yn) { key[m] = self_key * 4 + 2; cell[m++] = x * H + ys; }          // south
+            else if (self_key < (long long)x * H + yn) key[m - 1] = self_key * 4 + 2;
+        }
+        for (int i = 1; i < m; i++)
+            for (int j = i; j > 0 && key[j - 1] > key[j]; j--) {
+                long long tk = key[j]; key[j] = key[j - 1]; key[j - 1] = tk;
+                int32_t tc = cell[j]; cell[j] = cell[j - 1]; cell[j - 1] = tc;
+            }
+        for (int i = 0; i < m && n < MAXC; i++) { cells[n] = cell[i]; dists[n++] = (uint8_t)d; }
+    }
+    return n;
+}
+
+__device__ __forceinline__ int agent_range(const DevCtx &c, int s) {
+    const int vision = max(c.a.vision[s], 0), movement = max(c.a.movement[s], 0);
+    return min(min(vision, movement), max(c.max_dx, c.max_dy));
+}
+
+// rankCellsInRange + findBestCell + moveToBestCell (agent.py:1395-1443, 719-746, 1321-1328).
+// Only the head of the stable sort (agent.py:1479-1490) is needed: the winner is the candidate
+// with the highest welfare, then the smallest distance, then the earliest shuffled position.
+template <class Rng, int MAXC>
+__device__ int move_to_best_cell(const DevCtx &c, int s, Rng &rng) {
+    const ssb_agents_t &a = c.a;
+    const int pos = a.pos[s];
+    const int r = agent_range(c, s);
+    int32_t cells[MAXC];
+    uint8_t dists[MAXC];
+    const int n = r > 0 ? enumerate_cross<MAXC>(c, pos, r, cells, dists) : 0;
+    const double aggression = fmax(a.aggression[s], 0.0);
+    int best = pos;
+    if (n > 0) {
+        int hood = 1;   // findNeighborhood (agent.py:1052-1065): live agents in range + self
+        for (int i = 0; i < n; i++) {
+            const int o = c.g.occ[cells[i]];
+            if (o >= 0 && agent_alive(c, o)) hood++;
+        }
+        uint8_t perm[MAXC];
+        for (int i = 0; i < n; i++) perm[i] = (uint8_t)i;
+        shuffle(rng, perm, n);      // random.shuffle(cellsInRange), agent.py:1400-1401
+        // findRetaliatorsInVision (agent.py:1088-1098), only consulted for prey cells
+        double retaliator[27];
+        if (aggression > 0) {
+            for (int i = 0; i < 27; i++) retaliator[i] = -1.0;
+            for (int i = 0; i < n; i++) {
+                const int o = c.g.occ[cells[i]];
+                if (o < 0) continue;
+                const int tr = min(a.tribe[o] + 1, 26);
+                const double w = a.sugar[o] + a.spice[o];
+                if (retaliator[tr] < w) retaliator[tr] = w;
+            }
+        }
+        const double loot = c.p.max_combat_loot;
+        const double my_wealth = a.sugar[s] + a.spice[s];
+        const bool polluted = (c.p.flags & SSB_F_POLLUTION) != 0;
+        const bool spicy = (c.p.flags & SSB_F_SPICE) != 0;
+        int m = 0, best_dist = 0;
+        double best_welfare = 0;
+        for (int k = 0; k < n; k++) {
+            const int cell = cells[perm[k]], dist = dists[perm[k]];
+            const int prey = c.g.occ[cell];
+            double ps = 0, pp = 0;
+            if (prey >= 0) {
+                // isNeighborValidPrey (agent.py:1309-1314)
+                if (!(aggression > 0 && a.tribe[s] != a.tribe[prey] &&
+                      my_wealth >= a.sugar[prey] + a.spice[prey])) continue;
+                ps = a.sugar[prey]; pp = a.spice[prey];
+            }
+            const double wps = aggression * fmin(loot, ps), wpp = aggression * fmin(loot, pp);
+            const double poll = polluted ? c.g.pollution[cell] : 0.0;
+            const double cell_spice = spicy ? (double)c.g.spice[cell] : 0.0;
+            const double welfare = find_welfare(c, s, ((double)c.g.sugar[cell] + wps) / (1 + poll),
+                                                (cell_spice + wpp) / (1 + poll));
+            if (prey >= 0 && retaliator[min(a.tribe[prey] + 1, 26)] > my_wealth + welfare) continue;
+            if (m == 0 || welfare > best_welfare || (welfare == best_welfare && dist < best_dist)) {
+                best = cell; best_welfare = welfare; best_dist = dist;
+            }
+            m++;
+        }
+        if (m == 0) { best = pos; m = 1; }
+        a.n_neighborhood[s] = hood;
+        a.n_valid_moves[s] = m;
+    }
+    // doCombat (agent.py:274-294) then gotoCell (agent.py:1213-1219)
+    if (aggression > 0) {
+        const int prey = c.g.occ[best];
+        if (prey >= 0 && prey != s) {
+            const double loot = c.p.max_combat_loot;
+            const double sl = fmin(loot, a.sugar[prey]), pl = fmin(loot, a.spice[prey]);
+            a.sugar[s] += sl; a.spice[s] += pl;
+            a.sugar[prey] -= sl; a.spice[prey] -= pl;
+            do_death(c, prey, SSB_COMBAT);
+        }
+    }
+    a.last_moved[s] = c.t;
+    c.g.occ[pos] = -1;
+    a.pos[s] = best;
+    c.g.occ[best] = s;
+    return best;
+}
+
+// Agent.doTagging (agent.py:556-566)
+template <class Rng>
+__device__ void do_tagging(const DevCtx &c, int s, Rng &rng) {
+    int32_t nb[4];
+    neighbours4(c, c.a.pos[s], nb);
+    shuffle(rng, nb, 4);
+    for (int i = 0; i < 4; i++) {
+        const int o = c.g.occ[nb[i]];
+        if (o < 0) continue;
+        const uint32_t bit = 1u << rand_below(rng, (uint32_t)c.p.tag_len);
+        c.a.tags[o] = (c.a.tags[o] & ~bit) | (c.a.tags[s] & bit);
+        c.a.tribe[o] = find_tribe(c, c.a.tags[o]);
+    }
+}
+
+// Agent.doTrading (agent.py:600-706)
+template <class Rng>
+__device__ void do_trading(const DevCtx &c, int s, Rng &rng) {
+    const ssb_agents_t &a = c.a;
+    if (a.trade_factor[s] == 0) return;
+    a.trade_volume[s] = 0;
+    double sum_sugar_price = 0, sum_spice_price = 0;
+    find_mrs(c, s);
+    int32_t nb[4], traders[4];
+    int n = 0;
+    neighbours4(c, a.pos[s], nb);
+    for (int i = 0; i < 4; i++) {
+        const int o = c.g.occ[nb[i]];
+        if (o >= 0 && agent_alive(c, o) && a.mrs[o] != a.mrs[s]) traders[n++] = o;
+    }
+    shuffle(rng, traders, n);
+    double sugar_price = 0, spice_price = 0;
+    for (int k = 0; k < n; k++) {
+        const int tr = traders[k];
+        int spice_seller = -1, sugar_seller = -1;
+        for (;;) {
+            const double tm = a.mrs[tr], my = a.mrs[s];
+            if ((tm >= 1 && my >= 1) || (tm < 1 && my < 1) || tm == my) break;   // canTradeWithNeighbor
+            if (tm > my) { spice_seller = tr; sugar_seller = s; }
+            else { spice_seller = s; sugar_seller = tr; }
+            const double ssm = a.mrs[spice_seller], sum = a.mrs[sugar_seller];
+            if (ssm < 0 || sum < 0) { spice_seller = sugar_seller = -1; break; }
+            const double price = sqrt(ssm * sum);
+            if (price < 1) { spice_price = 1; sugar_price = price; }
+            else { spice_price = price; sugar_price = 1; }
+            if (a.spice[spice_seller] - spice_price < (double)a.spice_metab[spice_seller] ||
+                a.sugar[sugar_seller] - sugar_price < (double)a.sugar_metab[sugar_seller]) break;
+            const double ss_new = find_new_mrs(c, spice_seller, a.sugar[spice_seller] + sugar_price,
+                                               a.spice[spice_seller] - spice_price);
+            const double su_new = find_new_mrs(c, sugar_seller, a.sugar[sugar_seller] - sugar_price,
+                                               a.spice[sugar_seller] + spice_price);
+            const bool better_ss_mrs = fabs(1 - ssm) > fabs(1 - ss_new);
+            const bool better_su_mrs = fabs(1 - sum) > fabs(1 - su_new);
+            const bool better_ss_w = find_welfare(c, spice_seller, sugar_price, -1 * spice_price) >=
+                                     find_welfare(c, spice_seller, 0, 0);
+            const bool better_su_w = find_welfare(c, sugar_seller, -1 * sugar_price, spice_price) >=
+                                     find_welfare(c, sugar_seller, 0, 0);
+            const bool crossing = ss_new < su_new;
+            if ((better_ss_mrs || better_ss_w) && (better_su_mrs || better_su_w) && !crossing) {
+                a.sugar[spice_seller] += sugar_price; a.spice[spice_seller] -= spice_price;
+                a.sugar[sugar_seller] -= sugar_price; a.spice[sugar_seller] += spice_price;
+                find_mrs(c, spice_seller);
+                find_mrs(c, sugar_seller);
+            } else break;
+        }
+        if (spice_seller >= 0 && sugar_seller >= 0) {   // "a trade occurred" as the reference logs it
+            a.trade_volume[s] += 1;
+            sum_sugar_price += sugar_price;
+            sum_spice_price += spice_price;
+        }
+    }
+    a.trade_price[s] = fmax(sum_spice_price, sum_sugar_price);
+}
+
+__device__ __forceinline__ int empty_neighbours(const DevCtx &c, int pos, int32_t *out) {
+    int32_t nb[4];
+    int n = 0;
+    neighbours4(c, pos, nb);
+    for (int i = 0; i < 4; i++) if (c.g.occ[nb[i]] < 0) out[n++] = nb[i];
+    return n;
+}
+
+// slot for a newborn: recycled slot if any, else bump the high-water mark
+__device__ __forceinline__ int alloc_slot(const DevCtx &c) {
+    unsigned long long *cn = (unsigned long long *)c.a.counters;
+    long long k = (long long)atomicAdd(&cn[SSB_C_N_FREE], (unsigned long long)-1LL) - 1;
+    if (k >= 0) return c.a.free_slots[k];
+    atomicAdd(&cn[SSB_C_N_FREE], 1ull);   // undo: the free list was empty
+    const long long slot = (long long)atomicAdd(&cn[SSB_C_N_SLOTS], 1ull);
+    if (slot >= c.a.capacity) {
+        atomicAdd(&cn[SSB_C_N_SLOTS], (unsigned long long)-1LL);
+        atomicExch(&cn[SSB_C_OVERFLOW], 1ull);
+        return -1;
+    }
+    return (int)slot;
+}
+
+// Agent.doReproduction (agent.py:500-554) with findChildEndowment (781-910) and addChildToCell
+// (164-182).  EXACT = mode E (children join the list immediately, IDs in birth order).
+template <class Rng, bool EXACT>
+__device__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
+    const ssb_agents_t &a = c.a;
+    if (!agent_alive(c, s) || !is_fertile(c, s)) return;
+    int32_t nb[4], own_empty[4];
+    neighbours4(c, a.pos[s], nb);
+    shuffle(rng, nb, 4);
+    const int n_own = empty_neighbours(c, a.pos[s], own_empty);
+    unsigned long long *cn = (unsigned long long *)a.counters;
+    for (int k = 0; k < 4; k++) {
+        const int m = c.g.occ[nb[k]];
+        if (m < 0 || !agent_alive(c, m)) continue;
+        const bool compatible = ((a.sex[s] == SSB_SEX_FEMALE && a.sex[m] == SSB_SEX_MALE) ||
+                                 (a.sex[s] == SSB_SEX_MALE && a.sex[m] == SSB_SEX_FEMALE)) && is_fertile(c, m);
+        int32_t pool[8];
+        int np = 0;
+        for (int i = 0; i < n_own; i++) pool[np++] = own_empty[i];
+        np += empty_neighbours(c, a.pos[m], pool + np);
+        shuffle(rng, pool, np);    // drawn before the compatibility test (reference quirk)
+        if (!(is_fertile(c, s) && compatible && np != 0)) continue;
+        int cell = pool[--np];
+        while (c.g.occ[cell] >= 0 && np != 0) cell = pool[--np];
+        if (c.g.occ[cell] >= 0) continue;
+        const int ch = alloc_slot(c);
+        if (ch < 0) return;
+        const uint32_t eb = (c.endow_bits && c.t < c.n_step_tables) ? c.endow_bits[c.t] : 0u;
+#define SSB_PICK(field, bit) (((eb >> (bit)) & 1u) ? a.field[m] : a.field[s])
+        a.id[ch] = EXACT ? (int32_t)atomicAdd(&cn[SSB_C_NEXT_ID], 1ull) : -1;
+        a.born[ch] = c.t; a.cod[ch] = SSB_ALIVE; a.age[ch] = 0;
+        a.aggression[ch] = SSB_PICK(aggression, EB_AGGRESSION);
+        a.fert_age[ch] = SSB_PICK(fert_age, EB_FERT_AGE);
+        a.fert_factor[ch] = SSB_PICK(fert_factor, EB_FERT_FACTOR);
+        a.infert_age[ch] = SSB_PICK(infert_age, EB_INFERT_AGE);
+        a.lookahead[ch] = SSB_PICK(lookahead, EB_LOOKAHEAD);
+        a.max_age[ch] = SSB_PICK(max_age, EB_MAX_AGE);
+        a.movement[ch] = SSB_PICK(movement, EB_MOVEMENT);
+        a.spice_metab[ch] = SSB_PICK(spice_metab, EB_SPICE_METAB);
+        a.sugar_metab[ch] = SSB_PICK(sugar_metab, EB_SUGAR_METAB);
+        a.sex[ch] = SSB_PICK(sex, EB_SEX);
+        a.trade_factor[ch] = SSB_PICK(trade_factor, EB_TRADE_FACTOR);
+        a.vision[ch] = SSB_PICK(vision, EB_VISION);
+#undef SSB_PICK
+        const double sugar_cost = a.start_sugar[s] / (a.fert_factor[s] * 2);
+        const double spice_cost = a.start_spice[s] / (a.fert_factor[s] * 2);
+        const double mate_sugar_cost = a.start_sugar[m] / (a.fert_factor[m] * 2);
+        const double mate_spice_cost = a.start_spice[m] / (a.fert_factor[m] * 2);
+        a.start_sugar[ch] = a.sugar[ch] = sugar_cost + mate_sugar_cost;
+        a.start_spice[ch] = a.spice[ch] = spice_cost + mate_spice_cost;
+        uint32_t tags = 0;
+        if (c.p.flags & SSB_F_TAGS) {
+            const uint32_t tb = (c.tag_bits && c.t < c.n_step_tables) ? c.tag_bits[c.t] : 0u;
+            int draw = 0;
+            for (int i = 0; i < c.p.tag_len; i++) {
+                const uint32_t bs = (a.tags[s] >> i) & 1u, bm = (a.tags[m] >> i) & 1u;
+                const uint32_t b = bs == bm ? bs : ((tb >> draw++) & 1u);
+                tags |= b << i;
+            }
+        }
+        a.tags[ch] = tags;
+        a.tribe[ch] = find_tribe(c, tags);
+        a.mrs[ch] = 1;
+        a.last_moved[ch] = c.t; a.last_sugar[ch] = 0; a.last_spice[ch] = 0;
+        a.n_neighborhood[ch] = 0; a.n_valid_moves[ch] = 0;
+        a.happiness[ch] = 0; a.wealth_happiness[ch] = 0; a.family_happiness[ch] = 0;
+        a.trade_volume[ch] = 0; a.trade_price[ch] = 0; a.last_repro[ch] = -1;
+        a.n_children_alive[ch] = 0; a.n_children_dead[ch] = 0;
+        a.father[ch] = a.sex[s] == SSB_SEX_FEMALE ? a.id[m] : a.id[s];
+        a.mother[ch] = a.sex[s] == SSB_SEX_FEMALE ? a.id[s] : a.id[m];
+        a.pos[ch] = cell;
+        c.g.occ[cell] = ch;
+        const long long nth = (long long)atomicAdd(&cn[SSB_C_N_BORN], 1ull);
+        if (EXACT) {   // sugarscape.addAgent: the list grows while it is being iterated
+            const long long at = (long long)atomicAdd(&cn[SSB_C_N_LIST], 1ull);
+            if (at < a.capacity) a.order[at] = ch; else atomicExch(&cn[SSB_C_OVERFLOW], 1ull);
+        } else {
+            if (nth < a.capacity) c.born_list[nth] = ch; else atomicExch(&cn[SSB_C_OVERFLOW], 1ull);
+        }
+        collect(c, ch, cell);      // the child collects at birth (agent.py:175)
+        a.sugar[s] -= sugar_cost; a.spice[s] -= spice_cost;
+        a.sugar[m] = a.sugar[m] - mate_sugar_cost;
+        a.spice[m] = a.spice[m] - mate_spice_cost;
+        a.last_repro[s] = c.t;
+    }
+}
+
+// Agent.doTimestep (agent.py:568-598)
+template <class Rng, bool EXACT, int MAXC>
+__device__ void agent_transaction(const DevCtx &c, int s, Rng &rng) {
+    const ssb_agents_t &a = c.a;
+    if (!agent_alive(c, s) || a.last_moved[s] == c.t) return;
+    a.last_sugar[s] = a.sugar[s];
+    a.last_spice[s] = a.spice[s];
+    const int pos = move_to_best_cell<Rng, MAXC>(c, s, rng);
+    collect(c, s, pos);
+    // doMetabolism (agent.py:485-498) + consumption pollution (cell.py:27-40)
+    const double sm = (double)max(a.sugar_metab[s], 0), pm = (double)max(a.spice_metab[s], 0);
+    const double sugar = a.sugar[s] - sm, spice = a.spice[s] - pm;
+    a.sugar[s] = sugar;
+    a.spice[s] = spice;
+    if (c.p.pollution_start <= c.t && c.t <= c.p.pollution_end) {
+        double pl = c.g.pollution[pos];
+        pl += c.p.sugar_cons_pollution * sm;
+        pl += c.p.spice_cons_pollution * pm;
+        c.g.pollution[pos] = pl;
+    }
+    if (sugar < 0 || spice < 0 || (sugar <= 0 && sm > 0) || (spice <= 0 && pm > 0)) {
+        do_death(c, s, SSB_STARVATION);
+        return;
+    }
+    if ((c.p.flags & SSB_F_TAGS) && (c.p.flags & SSB_F_TAGGING)) do_tagging(c, s, rng);
+    if (c.p.flags & SSB_F_TRADE) do_trading(c, s, rng);
+    if (c.p.flags & SSB_F_REPRO) do_reproduction<Rng, EXACT>(c, s, rng);
+    // doAging (agent.py:266-272)
+    if (agent_alive(c, s)) {
+        const int age = a.age[s] + 1;
+        a.age[s] = age;
+        if (age >= a.max_age[s] && a.max_age[s] != -1) { do_death(c, s, SSB_AGING); return; }
+    }
+    // updateHappiness (agent.py:1522-1530): conflict + family + health + social + wealth; the
+    // family / social / conflict bookkeeping is not implemented yet (DESIGN.md scope) -> 0
+    const double wealth_h = erf((a.sugar[s] + a.spice[s]) - c.prev_mean_wealth);
+    a.wealth_happiness[s] = wealth_h;
+    a.family_happiness[s] = 0;
+    a.happiness[s] = 1.0 + wealth_h;
+}
+
+}  // namespace ssb

@@ -1,0 +1,115 @@
+// ssb_sort.cuh -- keys-only LSD radix sort of 64-bit keys (8-bit digits), used to order agent
+// wealths for the Lorenz / Gini reduction (reference sugarscape.py:913-934 sorts the wealth list).
+// Non-negative doubles sort correctly as their raw bit patterns.
+//
+// Per pass: k_radix_hist (per-tile digit histograms, digit-major) -> k_radix_scan (exclusive scan
+// of the whole table, one block) -> k_radix_scatter (stable: warp match-any ranking in striped
+// order, warps of a tile combined by a per-digit prefix).  n lives in device memory so that no
+// host synchronisation is needed between the compaction and the sort.
+#pragma once
+#include <stdint.h>
+
+namespace ssb {
+
+constexpr int RADIX_THREADS = 256;
+constexpr int RADIX_ITEMS = 16;
+constexpr int RADIX_TILE = RADIX_THREADS * RADIX_ITEMS;   // 4096 keys per block
+constexpr int RADIX_WARPS = RADIX_THREADS / 32;
+
+__global__ void __launch_bounds__(RADIX_THREADS) k_radix_hist(const uint64_t *keys, const int64_t *n_ptr, int shift,
+                                                              uint32_t *hist, int n_tiles_max) {
+    const long long n = *n_ptr;
+    const int n_tiles = (int)((n + RADIX_TILE - 1) / RADIX_TILE);
+    if ((int)blockIdx.x >= n_tiles) return;
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const long long tile0 = (long long)blockIdx.x * RADIX_TILE;
+#pragma unroll
+    for (int k = 0; k < RADIX_ITEMS; k++) {
+        const long long i = tile0 + k * RADIX_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&h[(keys[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[(long long)threadIdx.x * n_tiles + blockIdx.x] = h[threadIdx.x];
+}
+
+// exclusive scan over hist[256 * n_tiles] (digit-major), single block
+__global__ void __launch_bounds__(RADIX_THREADS) k_radix_scan(uint32_t *hist, const int64_t *n_ptr) {
+    const long long n = *n_ptr;
+    const int n_tiles = (int)((n + RADIX_TILE - 1) / RADIX_TILE);
+    const long long total = 256LL * n_tiles;
+    __shared__ uint32_t warp_sums[RADIX_WARPS];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (long long base = 0; base < total; base += RADIX_THREADS) {
+        const long long i = base + threadIdx.x;
+        const uint32_t v = i < total ? hist[i] : 0u;
+        uint32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        if (lane == 31) warp_sums[w] = inc;
+        __syncthreads();
+        uint32_t wbase = 0;
+        for (int j = 0; j < w; j++) wbase += warp_sums[j];
+        if (i < total) hist[i] = carry + wbase + inc - v;
+        __syncthreads();
+        if (threadIdx.x == RADIX_THREADS - 1) carry += wbase + inc;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(RADIX_THREADS) k_radix_scatter(const uint64_t *keys, uint64_t *out, const int64_t *n_ptr,
+                                                                 int shift, const uint32_t *hist) {
+    const long long n = *n_ptr;
+    const int n_tiles = (int)((n + RADIX_TILE - 1) / RADIX_TILE);
+    if ((int)blockIdx.x >= n_tiles) return;
+    __shared__ uint32_t cnt[RADIX_WARPS][256];
+    for (int i = threadIdx.x; i < RADIX_WARPS * 256; i += RADIX_THREADS) (&cnt[0][0])[i] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long warp0 = (long long)blockIdx.x * RADIX_TILE + (long long)w * (32 * RADIX_ITEMS);
+    uint64_t key[RADIX_ITEMS];
+    uint16_t rank[RADIX_ITEMS];
+#pragma unroll
+    for (int r = 0; r < RADIX_ITEMS; r++) {
+        const long long i = warp0 + r * 32 + lane;
+        const bool valid = i < n;
+        key[r] = valid ? keys[i] : 0ull;
+        const uint32_t d = (uint32_t)(key[r] >> shift) & 255u;
+        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+        uint32_t pre = 0, peers = 0;
+        if (valid) {
+            peers = __match_any_sync(vmask, d);
+            pre = cnt[w][d];
+        }
+        __syncwarp();
+        if (valid && lane == __ffs(peers) - 1) cnt[w][d] = pre + __popc(peers);
+        __syncwarp();
+        rank[r] = (uint16_t)(pre + __popc(peers & ((1u << lane) - 1u)));
+    }
+    __syncthreads();
+    {   // per digit: exclusive prefix over the warps of this tile, on top of the global offset
+        const int d = threadIdx.x;
+        uint32_t running = hist[(long long)d * n_tiles + blockIdx.x];
+#pragma unroll
+        for (int j = 0; j < RADIX_WARPS; j++) {
+            const uint32_t t = cnt[j][d];
+            cnt[j][d] = running;
+            running += t;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RADIX_ITEMS; r++) {
+        const long long i = warp0 + r * 32 + lane;
+        if (i < n) out[cnt[w][(uint32_t)(key[r] >> shift) & 255u] + rank[r]] = key[r];
+    }
+}
+
+}  // namespace ssb

@@ -1,0 +1,225 @@
+"""ctypes binding of the CUDA engine (libssb.so, include/ssb.h).
+
+PyTorch owns every simulation buffer (device tensors); the library receives raw device pointers.
+There is NO CPU fallback: if the CUDA extension or a CUDA device is missing this module raises.
+"""
+import ctypes as C
+import os
+import random
+
+import numpy as np
+
+from . import build as _build
+from . import layout
+
+_LIB = None
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def load_library():
+    """Load libssb.so (built in-tree by sugarscape_b200/build.py); fail loudly if absent."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.OUT
+    if not os.path.exists(path):
+        raise EngineError(f"CUDA engine {path} is missing: run `python -m sugarscape_b200.build` "
+                          "(needs nvcc); this engine has no CPU fallback")
+    L = C.CDLL(path)
+    P, G, A, S = (C.POINTER(layout.Params), C.POINTER(layout.Grid), C.POINTER(layout.Agents),
+                  C.POINTER(layout.Stats))
+    E = C.c_void_p
+    L.ssb_abi_version.restype = C.c_int
+    for name in ("ssb_sizeof_params", "ssb_sizeof_grid", "ssb_sizeof_agents", "ssb_sizeof_stats"):
+        getattr(L, name).restype = C.c_int
+    L.ssb_create.argtypes = [P, C.c_int, C.POINTER(E)]
+    L.ssb_bind.argtypes = [E, G, A]
+    L.ssb_destroy.argtypes = [E]
+    L.ssb_destroy.restype = None
+    L.ssb_last_error.argtypes = [E]
+    L.ssb_last_error.restype = C.c_char_p
+    L.ssb_set_mt_state.argtypes = [E, C.c_void_p, C.c_int32]
+    L.ssb_get_mt_state.argtypes = [E, C.c_void_p, C.POINTER(C.c_int32)]
+    L.ssb_set_step_tables.argtypes = [E, C.c_void_p, C.c_void_p, C.c_int32]
+    L.ssb_set_mark_shift.argtypes = [E, C.c_int32]
+    L.ssb_env_step.argtypes = [E, C.c_int32, C.c_void_p]
+    L.ssb_agent_step.argtypes = [E, C.c_int32, C.c_double, C.c_void_p]
+    L.ssb_compact.argtypes = [E, C.c_int32, C.c_void_p]
+    L.ssb_reduce_stats.argtypes = [E, C.c_int32, C.c_void_p]
+    L.ssb_step.argtypes = [E, C.c_int32, C.c_double, C.c_void_p]
+    L.ssb_stats.argtypes = [E, S]
+    L.ssb_sync.argtypes = [E, C.c_void_p]
+    L.ssb_launch_count.argtypes = [E]
+    L.ssb_launch_count.restype = C.c_int64
+    L.ssb_enable_timing.argtypes = [E, C.c_int32]
+    L.ssb_timing.argtypes = [E] + [C.POINTER(C.c_float)] * 4
+    if L.ssb_abi_version() != layout.ABI_VERSION:
+        raise EngineError("libssb.so ABI version does not match sugarscape_b200.layout")
+    for name, struct in (("params", layout.Params), ("grid", layout.Grid), ("agents", layout.Agents),
+                         ("stats", layout.Stats)):
+        if getattr(L, "ssb_sizeof_" + name)() != C.sizeof(struct):
+            raise EngineError(f"struct ssb_{name}_t: library and ctypes mirror disagree on size")
+    _LIB = L
+    return L
+
+
+EXPORTED_SYMBOLS = (
+    "ssb_abi_version", "ssb_create", "ssb_bind", "ssb_destroy", "ssb_last_error",
+    "ssb_set_mt_state", "ssb_get_mt_state", "ssb_set_step_tables", "ssb_set_mark_shift",
+    "ssb_sizeof_params", "ssb_sizeof_grid", "ssb_sizeof_agents", "ssb_sizeof_stats",
+    "ssb_env_step", "ssb_agent_step", "ssb_compact", "ssb_reduce_stats", "ssb_step", "ssb_stats",
+    "ssb_sync", "ssb_launch_count", "ssb_timing", "ssb_enable_timing",
+)
+
+
+class Engine:
+    """One simulation resident on one GPU."""
+
+    def __init__(self, params, host_state, device=0, endow_bits=None, tag_bits=None):
+        import torch
+        if not torch.cuda.is_available():
+            raise EngineError("no CUDA device visible: the Sugarscape engine runs on the GPU only")
+        self.torch = torch
+        self.L = load_library()
+        self.params = params
+        self.device = torch.device("cuda", device)
+        self.width, self.height, self.capacity = host_state.width, host_state.height, host_state.capacity
+        self.tensors = {}
+        self._upload_all(host_state)
+        self.handle = C.c_void_p()
+        self._check(self.L.ssb_create(C.byref(params), device, C.byref(self.handle)))
+        g, a = self._structs()
+        self._check(self.L.ssb_bind(self.handle, C.byref(g), C.byref(a)))
+        if endow_bits is not None:
+            eb = np.ascontiguousarray(endow_bits, dtype=np.uint32)
+            tb = np.ascontiguousarray(tag_bits, dtype=np.uint32)
+            self._check(self.L.ssb_set_step_tables(self.handle, eb.ctypes.data, tb.ctypes.data, len(eb)))
+
+    # -- plumbing ------------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            msg = self.L.ssb_last_error(self.handle)
+            raise EngineError(f"libssb error {rc}: {msg.decode() if msg else '?'}")
+
+    def _to_device(self, arr):
+        t = self.torch
+        if arr.dtype == np.uint32:
+            return t.from_numpy(arr.view(np.int32).copy()).to(self.device)
+        return t.from_numpy(np.ascontiguousarray(arr)).to(self.device)
+
+    def _upload_all(self, hs):
+        for name, _ in layout.GRID_FIELDS:
+            self.tensors[name] = self._to_device(getattr(hs, name))
+        self.tensors["counters"] = self._to_device(hs.counters)
+        for name, _, _ in layout.AGENT_FIELDS:
+            self.tensors["a_" + name] = self._to_device(getattr(hs, "a_" + name))
+
+    def _structs(self):
+        g = layout.Grid()
+        g.n_cells = self.width * self.height
+        for name, _ in layout.GRID_FIELDS:
+            setattr(g, name, self.tensors[name].data_ptr())
+        a = layout.Agents()
+        a.capacity = self.capacity
+        a.counters = self.tensors["counters"].data_ptr()
+        for name, _, _ in layout.AGENT_FIELDS:
+            setattr(a, name, self.tensors["a_" + name].data_ptr())
+        return g, a
+
+    @property
+    def stream(self):
+        return self.torch.cuda.current_stream(self.device).cuda_stream
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.torch.cuda.synchronize(self.device)
+            self.L.ssb_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- state transfer ------------------------------------------------------------------------
+    def download(self, fields=None):
+        """Copy the device state back into a HostState (all fields, or the named subset)."""
+        hs = layout.HostState(self.width, self.height, self.capacity)
+        self.torch.cuda.synchronize(self.device)
+        for key, tensor in self.tensors.items():
+            if fields is not None and key not in fields:
+                continue
+            arr = tensor.cpu().numpy()
+            if key == "a_tags":
+                arr = arr.view(np.uint32)
+            setattr(hs, key, arr)
+        return hs
+
+    def upload(self, hs, fields):
+        for key in fields:
+            arr = getattr(hs, key)
+            if arr.dtype == np.uint32:
+                arr = arr.view(np.int32)
+            self.tensors[key].copy_(self.torch.from_numpy(np.ascontiguousarray(arr)))
+
+    def counters(self):
+        return self.tensors["counters"].cpu().numpy()
+
+    # -- RNG (mode E) --------------------------------------------------------------------------
+    def set_mt_from_python(self):
+        st = random.getstate()[1]
+        arr = np.array(st[:624], dtype=np.uint32)
+        self._check(self.L.ssb_set_mt_state(self.handle, arr.ctypes.data, st[624]))
+
+    def mt_state(self):
+        arr = np.zeros(624, dtype=np.uint32)
+        idx = C.c_int32(0)
+        self._check(self.L.ssb_get_mt_state(self.handle, arr.ctypes.data, C.byref(idx)))
+        return arr, idx.value
+
+    def push_mt_to_python(self):
+        arr, idx = self.mt_state()
+        random.setstate((3, tuple(int(v) for v in arr) + (idx,), None))
+
+    # -- stepping ------------------------------------------------------------------------------
+    def env_step(self, t):
+        self._check(self.L.ssb_env_step(self.handle, t, self.stream))
+
+    def agent_step(self, t, prev_mean_wealth=0.0):
+        self._check(self.L.ssb_agent_step(self.handle, t, float(prev_mean_wealth), self.stream))
+
+    def compact(self, t):
+        self._check(self.L.ssb_compact(self.handle, t, self.stream))
+
+    def reduce_stats(self, t):
+        self._check(self.L.ssb_reduce_stats(self.handle, t, self.stream))
+
+    def step(self, t, prev_mean_wealth=0.0):
+        self._check(self.L.ssb_step(self.handle, t, float(prev_mean_wealth), self.stream))
+
+    def stats(self):
+        out = layout.Stats()
+        self._check(self.L.ssb_stats(self.handle, C.byref(out)))
+        return out
+
+    def sync(self):
+        self._check(self.L.ssb_sync(self.handle, self.stream))
+
+    def set_mark_shift(self, shift):
+        self._check(self.L.ssb_set_mark_shift(self.handle, shift))
+
+    def launch_count(self):
+        return int(self.L.ssb_launch_count(self.handle))
+
+    def enable_timing(self, on=True):
+        self._check(self.L.ssb_enable_timing(self.handle, 1 if on else 0))
+
+    def timing(self):
+        vals = [C.c_float(0) for _ in range(4)]
+        self._check(self.L.ssb_timing(self.handle, *[C.byref(v) for v in vals]))
+        return {"env_ms": vals[0].value, "agent_ms": vals[1].value, "compact_ms": vals[2].value,
+                "stats_ms": vals[3].value}

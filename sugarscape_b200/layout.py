@@ -98,7 +98,7 @@ class Stats(C.Structure):
         ("n_dead", C.c_int64), ("n_dead_moved", C.c_int64), ("dead_starvation", C.c_int64),
         ("dead_aging", C.c_int64), ("dead_combat", C.c_int64), ("sum_age_at_death", C.c_int64),
         ("dead_wealth_collected", C.c_double),
-        ("n_born", C.c_int64), ("n_replaced", C.c_int64),
+        ("n_born", C.c_int64), ("n_replaced", C.c_int64), ("n_acted", C.c_int64),
         ("env_wealth_total", C.c_int64), ("env_wealth_created", C.c_int64),
         ("env_capacity_total", C.c_int64),
         ("lorenz_weighted_sum", C.c_double), ("rounds", C.c_int64),
@@ -183,11 +183,16 @@ class HostState:
         return g, a
 
     # -- agents -------------------------------------------------------------------------------
-    def append_agents(self, new_agents):
-        """Append freshly placed agents (init / replacement) at the end of the list."""
+    def append_agents(self, new_agents, protect_last=0):
+        """Append freshly placed agents (init / replacement) at the end of the list.
+
+        protect_last: number of entries on top of the free-slot stack that must not be reused
+        yet (the slots of this step's dead, which the stats reduction still has to read)."""
         n_list = int(self.counters[C_N_LIST])
         n_slots = int(self.counters[C_N_SLOTS])
         n_free = int(self.counters[C_N_FREE])
+        protected = self.a_free_slots[n_free - protect_last:n_free].copy() if protect_last else None
+        n_free -= protect_last
         for a in new_agents:
             if n_free > 0:
                 n_free -= 1
@@ -225,6 +230,9 @@ class HostState:
             self.a_order[n_list] = slot
             self.occ[a["cell"]] = slot
             n_list += 1
+        if protect_last:
+            self.a_free_slots[n_free:n_free + protect_last] = protected
+            n_free += protect_last
         self.counters[C_N_LIST] = n_list
         self.counters[C_N_SLOTS] = n_slots
         self.counters[C_N_FREE] = n_free

@@ -1,0 +1,202 @@
+"""Host half of updateRuntimeStats: raw device reductions -> the reference's 59 log keys.
+
+The device (K6, csrc/ssb_kernels.cuh) produces sums / extrema / counts; this module applies the
+reference's arithmetic on top (means, Python ``round()``, the carrying-capacity recurrence, the
+closed-form ``*LastProduced`` totals) so the resulting dict equals ``Sugarscape.runtimeStats``
+(reference sugarscape.py:81-92 key order, 1005-1426 semantics).
+"""
+import math
+
+# reference sugarscape.py:81-92
+LOG_KEYS = (
+    "timestep", "population", "meanMetabolism", "meanMovement", "meanVision", "meanWealth", "meanAge",
+    "giniCoefficient", "meanTradePrice", "tradeVolume", "maxWealth", "minWealth", "meanHappiness",
+    "meanWealthHappiness", "meanHealthHappiness", "meanSocialHappiness", "meanFamilyHappiness",
+    "meanConflictHappiness", "meanAgeAtDeath", "seed", "agentsReplaced", "agentsBorn",
+    "agentStarvationDeaths", "agentDiseaseDeaths", "environmentWealthCreated", "agentWealthTotal",
+    "environmentWealthTotal", "agentWealthCollected", "agentWealthBurnRate", "agentMeanTimeToLive",
+    "agentTotalMetabolism", "agentCombatDeaths", "agentAgingDeaths", "agentDeaths", "largestRace",
+    "largestTribe", "largestRaceSize", "largestTribeSize", "remainingRaces", "remainingTribes",
+    "sickAgents", "carryingCapacity", "meanDeathsPercentage", "sickAgentsPercentage", "meanSelfishness",
+    "diseaseEffectiveReproductionRate", "diseaseIncidence", "diseasePrevalence",
+    "agentLastMoveOptimalityPercentage", "meanNeighbors", "meanMoveRank", "meanMoveDifferenceFromOptimal",
+    "meanValidMoves", "totalHappiness", "loanVolume", "meanAgeismFactor", "meanRacismFactor",
+    "meanSexismFactor", "moveSpace",
+)
+
+# Keys whose device-side bookkeeping is not implemented yet (family / conflict happiness need the
+# children / mates / combat history); they are still written, from what is known.
+UNVERIFIED_KEYS = ("meanHappiness", "meanFamilyHappiness", "meanConflictHappiness", "totalHappiness")
+
+
+def initial_runtime_stats(c):
+    """The all-zero entry the reference logs at t = 0 (sugarscape.py:81-92, 887-905)."""
+    s = {k: 0 for k in LOG_KEYS}
+    s["seed"] = c["seed"]
+    s["remainingRaces"] = c["environmentMaxRaces"]
+    s["remainingTribes"] = c["environmentMaxTribes"]
+    return s
+
+
+def _as_number(x):
+    """Values that are integral by construction print as ints in the reference's JSON; the
+    device carries them in fp64."""
+    return int(x) if float(x).is_integer() and abs(x) < 2 ** 53 else x
+
+
+def environment_wealth_created(c, equator, t, n_cells_north, n_cells_south, capacity_total):
+    """sum(sugarLastProduced + spiceLastProduced) in closed form:
+    a cell's *LastProduced equals the regrow rate once the cell has been allowed to grow at
+    least once (it is never cleared afterwards), plus all capacities at t == 1
+    (sugarscape.py:1048-1051)."""
+    if t <= 0:
+        return 0
+    rate = 0
+    for key in ("environmentSugarRegrowRate", "environmentSpiceRegrowRate"):
+        rate += c[key] if c[key] != 0 else 0
+    interval, delay = c["environmentSeasonInterval"], c["environmentSeasonalGrowbackDelay"]
+    if interval <= 0:
+        created = (n_cells_north + n_cells_south) * rate
+    else:
+        # north starts wet (grows from t = 1); south starts dry: first growth at the first
+        # t with t % delay == 0, or when it turns wet (t = interval + 1)
+        south_first = interval + 1
+        if delay > 0:
+            south_first = min(south_first, delay)
+        created = n_cells_north * rate + (n_cells_south * rate if t >= south_first else 0)
+    if t == 1:
+        created += capacity_total
+    return created
+
+
+class StatsBuilder:
+    """Carries the cross-step state of the stats (carrying capacity, previous dict)."""
+
+    def __init__(self, c, equator):
+        self.c = c
+        self.equator = equator
+        self.runtime_stats = initial_runtime_stats(c)
+        W, H = c["environmentWidth"], c["environmentHeight"]
+        north_rows = min(max(equator, 0), H)
+        self.n_north = W * north_rows
+        self.n_south = W * (H - north_rows)
+        self.constant = {}
+        for key, option in (("meanSelfishness", "agentSelfishnessFactor"),
+                            ("meanAgeismFactor", "agentDecisionModelAgeismFactor"),
+                            ("meanRacismFactor", "agentDecisionModelRacismFactor"),
+                            ("meanSexismFactor", "agentDecisionModelSexismFactor")):
+            lo, hi = c[option]
+            self.constant[key] = lo if lo == hi else None
+
+    def update(self, st, t, n_replaced=0):
+        """st: layout.Stats filled by the device (or by the oracle in the tests)."""
+        c, rs = self.c, self.runtime_stats
+        n = int(st.population)
+        prev_cc = rs["carryingCapacity"]
+        carrying = math.ceil(0.05 * n + 0.95 * prev_cc)
+        if t == 0:
+            carrying = n
+        out = {}
+        out["agentAgingDeaths"] = int(st.dead_aging)
+        out["agentCombatDeaths"] = int(st.dead_combat)
+        out["agentDeaths"] = int(st.n_dead)
+        out["agentDiseaseDeaths"] = 0
+        out["agentsBorn"] = int(st.n_born) if t > 0 else 0
+        out["agentsReplaced"] = int(n_replaced)
+        out["agentStarvationDeaths"] = int(st.dead_starvation)
+        out["agentTotalMetabolism"] = int(st.sum_sugar_metab + st.sum_spice_metab)
+        out["agentWealthCollected"] = _as_number(st.sum_wealth_collected + st.dead_wealth_collected)
+        out["carryingCapacity"] = carrying
+        out["meanAgeAtDeath"] = round(st.sum_age_at_death / st.n_dead, 2) if st.n_dead > 0 else 0
+        out["sickAgents"] = 0
+        out["diseaseIncidence"] = 0
+        out["diseasePrevalence"] = 0
+        out["moveSpace"] = int(st.sum_valid_moves)
+        out["population"] = n
+        moves_optimal = n + int(st.n_dead)
+        if n > 0:
+            out["agentMeanTimeToLive"] = round(st.sum_ttl_age_limited / n, 2)
+            out["agentWealthBurnRate"] = round(st.sum_burn_rate / n, 2)
+            out["agentWealthTotal"] = _as_number(round(st.sum_wealth, 2))
+            out["loanVolume"] = 0
+            counts = [(int(st.tribe_first[i]), i, int(st.tribe_count[i])) for i in range(32) if st.tribe_count[i] > 0]
+            if counts:
+                # max(tribes, key=tribes.get): the first-inserted tribe among the largest
+                best = max(cnt for _, _, cnt in counts)
+                first, tribe, _ = min((f, i, cnt) for f, i, cnt in counts if cnt == best)
+                out["largestTribe"], out["largestTribeSize"], out["remainingTribes"] = tribe, best, len(counts)
+            else:
+                out["largestTribe"], out["largestTribeSize"], out["remainingTribes"] = None, n, 1
+            out["largestRace"], out["largestRaceSize"], out["remainingRaces"] = None, n, 1
+            out["maxWealth"] = _as_number(round(st.max_wealth, 2))
+            out["minWealth"] = _as_number(round(st.min_wealth, 2))
+            out["meanAge"] = round(st.sum_age / n, 2)
+            out["meanConflictHappiness"] = round(0 / n, 2)
+            out["meanFamilyHappiness"] = round(st.sum_family_happiness / n, 2)
+            out["meanHappiness"] = round(st.sum_happiness / n, 2)
+            out["meanHealthHappiness"] = round(st.n_acted / n, 2)
+            combined = st.sum_sugar_metab + st.sum_spice_metab
+            if st.sum_sugar_metab > 0 and st.sum_spice_metab > 0:
+                combined = round(combined / 2, 2)
+            out["meanMetabolism"] = round(combined / n, 2)
+            out["meanMovement"] = round(st.sum_movement / n, 2)
+            out["meanSocialHappiness"] = round(0 / n, 2)
+            out["meanTradePrice"] = round(st.sum_trade_price / st.n_traders, 2) if st.n_traders > 0 else 0
+            out["meanVision"] = round(st.sum_vision / n, 2)
+            out["meanWealth"] = round(st.sum_wealth / n, 2)
+            out["meanWealthHappiness"] = round(st.sum_wealth_happiness / n, 2)
+            out["tradeVolume"] = int(st.trade_volume)
+            out["meanDeathsPercentage"] = round((st.n_dead / n) * 100, 2)
+            out["sickAgentsPercentage"] = round((0 / n) * 100, 2)
+            out["diseaseEffectiveReproductionRate"] = 0
+            out["agentLastMoveOptimalityPercentage"] = round((moves_optimal / moves_optimal) * 100, 2)
+            out["meanNeighbors"] = round(st.sum_neighbors / n, 2)
+            out["meanValidMoves"] = round(st.sum_valid_moves / n, 2)
+            out["meanMoveRank"] = round(0 / n, 2)
+            out["meanMoveDifferenceFromOptimal"] = round(0 / out["meanNeighbors"], 2) if out["meanNeighbors"] > 0 else 0
+            out["totalHappiness"] = st.sum_happiness
+            for key, value in self.constant.items():
+                if value is None:
+                    raise NotImplementedError(key + " needs per-agent factors")
+                out[key] = round(value * n / n, 2)
+        else:
+            # zero population: the reference resets some keys and leaves others stale/raw
+            # (sugarscape.py:1325-1351)
+            for key in ("agentMeanTimeToLive", "agentWealthBurnRate", "largestRace", "largestTribe", "maxWealth",
+                        "meanAge", "meanAgeismFactor", "meanConflictHappiness", "meanFamilyHappiness",
+                        "meanHappiness", "meanHealthHappiness", "meanMetabolism", "meanMovement",
+                        "meanRacismFactor", "meanSelfishness", "meanSexismFactor", "meanSocialHappiness",
+                        "meanVision", "meanWealth", "meanWealthHappiness", "minWealth", "remainingRaces",
+                        "remainingTribes", "totalHappiness", "tradeVolume", "diseaseEffectiveReproductionRate"):
+                out[key] = 0
+            out["agentWealthTotal"] = 0
+            out["loanVolume"] = 0
+            out["largestRaceSize"] = 0
+            out["largestTribeSize"] = 0
+            out["meanTradePrice"] = 0
+            out["meanDeathsPercentage"] = 0
+            out["sickAgentsPercentage"] = 0
+            out["agentLastMoveOptimalityPercentage"] = int(st.n_dead)
+            out["meanNeighbors"] = 0
+            out["meanValidMoves"] = 0
+            out["meanMoveRank"] = 0
+            out["meanMoveDifferenceFromOptimal"] = 0
+        for key, value in out.items():
+            rs[key] = value
+        rs["environmentWealthCreated"] = environment_wealth_created(
+            c, self.equator, t, self.n_north, self.n_south, int(st.env_capacity_total))
+        rs["environmentWealthTotal"] = int(st.env_wealth_total)
+        rs["giniCoefficient"] = self.gini(st, n)
+        rs["timestep"] = t
+        return rs
+
+    @staticmethod
+    def gini(st, n):
+        """updateGiniCoefficient (sugarscape.py:913-934) from the sorted-wealth reduction."""
+        if n == 0:
+            return 0
+        total = st.sum_wealth
+        if total == 0:
+            return 1
+        area = (st.lorenz_weighted_sum / total) / n
+        return round((0.5 - area) / 0.5, 3)

@@ -64,6 +64,6 @@ def replace_dead_agents(c, state, pop, t):
     if n >= c["agentReplacements"]:
         return 0
     new_agents = pop.place(c["agentReplacements"] - n, state.occ >= 0, t, int(state.counters[layout.C_NEXT_ID]))
-    state.append_agents(new_agents)
+    state.append_agents(new_agents, protect_last=int(state.counters[layout.C_N_DEAD]))
     state.counters[layout.C_NEXT_ID] += len(new_agents)
     return len(new_agents)

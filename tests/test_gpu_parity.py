@@ -1,0 +1,199 @@
+"""Parity of the CUDA engine (through the C ABI) with the golden fixtures of the unmodified
+reference and with the CPU oracle.  Integer / index state must be bit-exact; fp64 holdings and
+pollution are compared bit-exact too when the arithmetic is exactly restated (sugar-only rules)
+and within 1e-9 relative otherwise (two-resource welfare uses pow)."""
+import json
+import math
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import parity_util as pu
+from sugarscape_b200 import init, layout, stats
+
+pytestmark = pytest.mark.gpu
+
+EXACT_EXAMPLES = [
+    "constant_growback", "immediate_growback", "blank", "diagonal_waves", "agent_replacement",
+    "seasonal_migration", "pollution_formation", "combat_limited", "combat_unlimited",
+    "cultural_combat_unlimited", "cultural_tagging", "reproduction_basic",
+    "reproduction_oscillation_small", "reproduction_oscillation_large", "reproduction_oscillation_severe",
+]
+POW_EXAMPLES = ["spice_growback", "foresight_basic", "trade_basic", "trade_replacement", "trade_tagging",
+                "trade_pollution", "trade_reproduction", "trade_tagging_reproduction"]
+
+
+def _engine(name, rng_mode=layout.RNG_EXACT, overrides=None):
+    from sugarscape_b200.engine import Engine
+    c, state, pop, params, endow, tags = pu.build(name, rng_mode, overrides)
+    eng = Engine(params, state, 0, endow, tags)
+    if rng_mode == layout.RNG_EXACT:
+        eng.set_mt_from_python()
+    return c, state, pop, params, endow, tags, eng
+
+
+def _replace(c, eng, pop, t):
+    n = int(eng.counters()[layout.C_N_LIST])
+    if n >= c["agentReplacements"]:
+        return 0
+    hs = eng.download()
+    eng.push_mt_to_python()
+    k = pu.replace_dead_agents(c, hs, pop, t)
+    eng.upload(hs, [key for key in eng.tensors if key != "pollution_flux"])
+    eng.set_mt_from_python()
+    return k
+
+
+def _close(a, b):
+    if a is None or b is None:
+        return a is b
+    if isinstance(a, float) or isinstance(b, float):
+        return math.isclose(a, b, rel_tol=1e-9, abs_tol=1e-9)
+    return a == b
+
+
+@pytest.mark.parametrize("name", EXACT_EXAMPLES)
+def test_exact_mode_trajectory_matches_reference_bit_for_bit(name):
+    """Every step of the reference's 200-step protocol: digests of (IDs, positions, ages),
+    fp64 holdings, tags/tribes, grid + occupancy, pollution and the MT19937 state."""
+    c, state, pop, params, endow, tags, eng = _engine(name)
+    meta, _ = pu.load_golden(name)
+    gold, log = meta["steps"], meta["log"]
+    sb = stats.StatsBuilder(c, init.equator(c))
+    eng.reduce_stats(0)
+    rs = sb.update(eng.stats(), 0)
+    skip = set(stats.UNVERIFIED_KEYS) if c["agentFertilityFactor"][1] > 0 else set()
+    for t in range(1, len(gold)):
+        eng.env_step(t)
+        eng.agent_step(t, rs["meanWealth"])
+        eng.compact(t)
+        replaced = _replace(c, eng, pop, t) if c["agentReplacements"] > 0 else 0
+        eng.reduce_stats(t)
+        rs = sb.update(eng.stats(), t, replaced)
+        d, snap = pu.state_digests(eng.download(), *eng.mt_state())
+        assert d == gold[t]["digests"], f"{name}: state differs from the reference at t={t}"
+        for k in stats.LOG_KEYS:
+            if k not in skip:
+                assert _close(rs[k], log[t][k]), f"{name}: log key {k} at t={t}: {rs[k]} vs {log[t][k]}"
+    eng.close()
+
+
+@pytest.mark.parametrize("name", POW_EXAMPLES)
+def test_two_resource_rules_match_reference(name):
+    """Spice / trade configs evaluate welfare with pow: integer state bit-exact, fp64 within
+    1e-9 relative, checked against the full golden snapshots."""
+    c, state, pop, params, endow, tags, eng = _engine(name)
+    meta, snaps = pu.load_golden(name)
+    gold = meta["steps"]
+    rs = {"meanWealth": meta["log"][0]["meanWealth"]}
+    sb = stats.StatsBuilder(c, init.equator(c))
+    eng.reduce_stats(0)
+    rs = sb.update(eng.stats(), 0)
+    for t in range(1, len(gold)):
+        eng.env_step(t)
+        eng.agent_step(t, rs["meanWealth"])
+        eng.compact(t)
+        replaced = _replace(c, eng, pop, t) if c["agentReplacements"] > 0 else 0
+        eng.reduce_stats(t)
+        rs = sb.update(eng.stats(), t, replaced)
+        d, snap = pu.state_digests(eng.download(), *eng.mt_state())
+        g = gold[t]["digests"]
+        for k in ("agents_int", "agents_tags", "grid_int", "mt"):
+            assert d[k] == g[k], f"{name}: {k} differs from the reference at t={t}"
+        if f"t{t}_a_sugar" in snaps:
+            np.testing.assert_allclose(snap["a_sugar"], snaps[f"t{t}_a_sugar"], rtol=1e-9, atol=0)
+            np.testing.assert_allclose(snap["a_spice"], snaps[f"t{t}_a_spice"], rtol=1e-9, atol=0)
+            np.testing.assert_allclose(snap["pollution"], snaps[f"t{t}_pollution"], rtol=1e-9, atol=0)
+    eng.close()
+
+
+SCALABLE_CASES = [("constant_growback", {}), ("pollution_formation", {}), ("reproduction_basic", {}),
+                  ("cultural_tagging", {}), ("trade_basic", {}), ("combat_unlimited", {"agentAggressionFactor": [1, 1]}),
+                  ("reproduction_basic", {"environmentWidth": 100, "environmentHeight": 100, "startingAgents": 1500,
+                                          "agentMovement": [6, 6],
+                                          "environmentSugarPeaks": [[70, 30, 4], [30, 70, 4], [20, 20, 4], [80, 80, 4]]})]
+
+
+@pytest.mark.parametrize("name,overrides", SCALABLE_CASES)
+def test_scalable_mode_parallel_rounds_equal_sequential_oracle(name, overrides):
+    """Mode S: the parallel reservation rounds must reproduce the sequential priority order
+    exactly -- compared step by step with the CPU oracle run in the same mode."""
+    from oracle_binding import Oracle
+    ov = dict(overrides)
+    ov.setdefault("agentMovement", [6, 6])
+    c, state, pop, params, endow, tags, eng = _engine(name, layout.RNG_SCALABLE, ov)
+    ostate = state.copy()
+    orc = Oracle(params, ostate, endow, tags)
+    steps = 60
+    for t in range(1, steps + 1):
+        eng.step(t, 0.0)
+        orc.env_step(t); orc.agent_step(t, 0.0); orc.compact(t)
+        d_gpu, s_gpu = pu.state_digests(eng.download())
+        d_cpu, s_cpu = pu.state_digests(ostate)
+        counters = eng.counters()
+        assert counters[layout.C_OVERFLOW] == 0
+        for k in ("agents_int", "agents_tags", "grid_int"):
+            assert d_gpu[k] == d_cpu[k], f"{name}: {k} differs from the oracle at t={t} (rounds={counters[layout.C_ROUNDS]})"
+        np.testing.assert_allclose(s_gpu["a_sugar"], s_cpu["a_sugar"], rtol=1e-9, atol=0)
+        np.testing.assert_allclose(s_gpu["a_spice"], s_cpu["a_spice"], rtol=1e-9, atol=0)
+        np.testing.assert_allclose(s_gpu["pollution"], s_cpu["pollution"], rtol=1e-9, atol=0)
+        st_gpu, st_cpu = eng.stats(), orc.stats(t)
+        for field, _ in layout.Stats._fields_:
+            a, b = getattr(st_gpu, field), getattr(st_cpu, field)
+            if field in ("rounds", "env_wealth_created", "n_replaced"):
+                continue
+            if hasattr(a, "__len__"):
+                assert list(a) == list(b), field
+            else:
+                assert _close(float(a), float(b)), f"stats.{field} at t={t}: {a} vs {b}"
+    eng.close()
+
+
+def test_env_step_properties_at_full_size():
+    """K1 at 4096 x 4096 (BASELINE S1 map): growback is monotone, bounded by capacity, idempotent at
+    capacity, and equals the closed form min(level + k, cap) after k steps."""
+    import torch
+    from sugarscape_b200.engine import Engine
+    c = pu.example_configuration("constant_growback", {"environmentWidth": 4096, "environmentHeight": 4096,
+                                                          "startingAgents": 0})
+    W = H = 4096
+    state = layout.HostState.empty(W, H, 1024)
+    rng = np.random.default_rng(1)
+    state.sugar_cap[:] = rng.integers(0, 5, W * H, dtype=np.int32)
+    state.sugar[:] = rng.integers(0, 5, W * H, dtype=np.int32)
+    state.sugar[:] = np.minimum(state.sugar, state.sugar_cap)
+    params = layout.make_params(c, layout.RNG_EXACT, 0, 6, init.equator(c))
+    eng = Engine(params, state, 0)
+    start = state.sugar.copy()
+    for t in range(1, 4):
+        eng.env_step(t)
+        got = eng.tensors["sugar"].cpu().numpy()
+        assert np.array_equal(got, np.minimum(start + t, state.sugar_cap))
+    for t in range(4, 7):
+        eng.env_step(t)
+    assert np.array_equal(eng.tensors["sugar"].cpu().numpy(), state.sugar_cap)
+    eng.close()
+
+
+def test_cli_writes_the_reference_log(tmp_path):
+    """python sugarscape.py --conf X -> log.json json-equal (1e-9) to the reference's log."""
+    name = "constant_growback"
+    conf = dict(pu.EXAMPLE_OPTIONS[name])
+    log_path = tmp_path / "log.json"
+    conf.update({"headlessMode": True, "debugMode": ["none"], "timesteps": 200, "logfile": str(log_path)})
+    conf_path = tmp_path / "conf.json"
+    conf_path.write_text(json.dumps(conf))
+    subprocess.check_call([sys.executable, os.path.join(pu.ROOT, "sugarscape.py"), "--conf", str(conf_path)])
+    mine = json.loads(log_path.read_text())
+    meta, _ = pu.load_golden(name)
+    ref = meta["log"]
+    # the reference's file = zero entry, then t = 1 .. last (the golden "log" list holds the
+    # post-update stats from t = 0 on; entry 0 of the file is the all-zero dict)
+    assert mine[0]["population"] == 0 and mine[0]["timestep"] == 0
+    assert len(mine) == len(ref)
+    for entry, gold in zip(mine[1:], ref[1:]):
+        for k in stats.LOG_KEYS:
+            assert _close(entry[k], gold[k]), (entry["timestep"], k, entry[k], gold[k])
