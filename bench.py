@@ -1,0 +1,312 @@
+#!/usr/bin/env python3
+"""Benchmark of the per-timestep simulation path (BASELINE.json metric: agent-steps/s and HBM GB/s).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA engine
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm (oracle port, see below)
+
+A "step" is one full Sugarscape timestep (environment stencil, agent loop, removal of the dead,
+stats reductions) of the synthetic S1 workload: 4096 x 4096 map, 1.6 M agents,
+reproduction_basic rules, scalable RNG mode.  With N > 1 every rank runs its
+own S1 replica (weak scaling, no data-path collective yet: the slab-sharded S2 path with halo
+exchange is not built -- DESIGN.md section "multi-GPU").
+
+Timed regions
+  value   K steps enqueued back to back, state resident in HBM, CUDA events on the launching
+          stream, barrier + synchronize on both sides, max over ranks.
+  e2e     the same K steps through the public host API (Sugarscape-style doTimestep: stats read
+          back to the host every step and turned into the log dict) INCLUDING the upload of the
+          whole initial state from host memory and the download of the final agent state.
+  roofline  average duration of the dominant kernel (the agent-step kernel) from CUDA events
+          recorded inside libssb around each phase, over separately run steps.
+  cpu_baseline  the CPU oracle (C port of the reference's algorithm, oracle/ss_oracle.c) on a
+          bounded sample of the same workload, one host core.  The reference itself is pure
+          Python (about 6-8 k agent-steps/s/core measured in the build container)
+          and is not present on the GPU box.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "agent_steps_per_second"
+UNIT = "agent-steps/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=4096, help="map side (S1 = 4096)")
+    ap.add_argument("--agents", type=int, default=0, help="agents (default: S1 density, 1.6 M at 4096)")
+    ap.add_argument("--mark-shift", type=int, default=-1)
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    return ap.parse_args()
+
+
+def workload(args, rank=0):
+    from sugarscape_b200 import synthetic
+    n_agents = args.agents or int(round(1600000 * (args.size / 4096.0) ** 2))
+    c = synthetic.configuration(synthetic.S1_OPTIONS, {
+        "environmentWidth": args.size, "environmentHeight": args.size, "startingAgents": n_agents,
+        "seed": 12345 + rank, "timesteps": 1 << 20})
+    return c, n_agents
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                parts = [p.strip() for p in out.stdout.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+# algorithmic bytes (canonical dtypes): growback 12 B per cell; agent step with
+# reproduction rules 232 B per acting agent
+BYTES_PER_CELL_GROWBACK = 12
+BYTES_PER_AGENT_STEP = 232
+
+
+def run_cpu_port(args, c, steps):
+    """The oracle port on one host core over `steps` timesteps of the same initial state."""
+    from oracle_binding import Oracle
+    from sugarscape_b200 import synthetic, steptables
+    state, params = synthetic.build_state(c)
+    endow, tags = steptables.step_tables(1, steps + 2, c["agentTagStringLength"])
+    orc = Oracle(params, state, endow, tags)
+    agent_steps = 0
+    t0 = time.perf_counter()
+    for t in range(1, steps + 1):
+        agent_steps += int(state.counters[0])
+        orc.env_step(t)
+        orc.agent_step(t, 0.0)
+        orc.compact(t)
+        orc.stats(t)
+    dt = time.perf_counter() - t0
+    return agent_steps / dt, dt, agent_steps
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        c, n_agents = workload(args)
+        steps = max(1, min(args.steps, args.cpu_steps))
+        value, dt, agent_steps = run_cpu_port(args, c, steps)
+        line = {
+            "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": 0, "ms_per_step": 1000.0 * dt / steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"S1 synthetic {args.size}x{args.size}, {n_agents} agents, reproduction_basic rules",
+                       "rng_mode": "scalable"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": f"{steps} timesteps of the S1 initial state, oracle/ss_oracle.c, 1 thread "
+                                       "(the reference is pure Python and absent from this box: 6-8 k agent-steps/s/core "
+                                       "measured in the build container, BASELINE.md)"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from sugarscape_b200 import layout, stats as stats_mod, steptables, synthetic, init
+    from sugarscape_b200.engine import Engine
+
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    c, n_agents = workload(args, rank)
+    horizon = args.warmup + 3 * args.steps + 64
+    endow, tags = steptables.step_tables(1, horizon, c["agentTagStringLength"])
+    state, params = synthetic.build_state(c)
+    eng = Engine(params, state, local_rank, endow, tags)
+    if args.mark_shift >= 0:
+        eng.set_mark_shift(args.mark_shift)
+    n_cells = args.size * args.size
+
+    # ---- device-resident throughput -------------------------------------------------------------
+    t = 0
+    for _ in range(args.warmup):
+        t += 1
+        eng.step(t, 0.0)
+    barrier()
+    launches0 = eng.launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    first = t + 1
+    for _ in range(args.steps):
+        t += 1
+        eng.step(t, 0.0)
+    ev1.record()
+    barrier()
+    sampler.stop_flag = True
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.launch_count() - launches0
+    # agents acting in step s = population after step s - 1
+    acting = [int(eng.stats_history(s - 1).population) if s > 1 else n_agents for s in range(first, t + 1)]
+    rounds = [int(eng.stats_history(s).rounds) for s in range(first, t + 1)]
+    agent_steps = sum(acting)
+    if int(eng.counters()[layout.C_OVERFLOW]) != 0:
+        raise RuntimeError("agent capacity overflow during the benchmark")
+    tm = torch.tensor([ms, float(agent_steps)], device=dev, dtype=torch.float64)
+    if world > 1:
+        mx = tm.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm_ = tm.clone()
+        dist.all_reduce(sm_, op=dist.ReduceOp.SUM)
+        ms, agent_steps = float(mx[0]), float(sm_[1])
+    value = agent_steps / (ms / 1000.0)
+
+    # ---- per-phase kernel times (separate steps, CUDA events inside libssb) ---------------------------
+    eng.enable_timing(True)
+    phase = {"env_ms": [], "agent_ms": [], "compact_ms": [], "stats_ms": []}
+    phase_acting = []
+    for _ in range(min(args.steps, 10)):
+        phase_acting.append(int(eng.stats_history(t).population))
+        t += 1
+        eng.step(t, 0.0)
+        tim = eng.timing()
+        for k in phase:
+            phase[k].append(tim[k])
+    eng.enable_timing(False)
+    avg = {k: float(np.mean(v)) for k, v in phase.items()}
+    peak, peak_kind = measured_peak_gbs()
+    agent_bytes = float(np.mean(phase_acting)) * BYTES_PER_AGENT_STEP
+    achieved = agent_bytes / (avg["agent_ms"] / 1000.0) / 1e9
+    env_bytes = n_cells * BYTES_PER_CELL_GROWBACK
+    roofline = {"bound": "hbm", "kernel": "k_agent_step_scalable", "achieved": achieved, "peak": peak,
+                "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback 6.65 TB/s",
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "algorithmic_bytes_per_launch": agent_bytes, "avg_launch_ms": avg["agent_ms"],
+                "env_step": {"kernel": "k_growback_v4", "achieved": env_bytes / (avg["env_ms"] / 1000.0) / 1e9,
+                             "frac": env_bytes / (avg["env_ms"] / 1000.0) / 1e9 / peak, "avg_launch_ms": avg["env_ms"]},
+                "phase_ms": avg}
+
+    # ---- end to end through the host API ------------------------------------------------------------
+    e2e = None
+    if not args.skip_e2e:
+        eng.close()
+        del eng
+        torch.cuda.empty_cache()
+        state2, params2 = synthetic.build_state(c)
+        barrier()
+        w0 = time.perf_counter()
+        eng = Engine(params2, state2, local_rank, endow, tags)      # H2D of the whole initial state
+        h2d = sum(v.numel() * v.element_size() for v in eng.tensors.values())
+        sb = stats_mod.StatsBuilder(c, init.equator(c))
+        eng.reduce_stats(0)
+        rs = sb.update(eng.stats(), 0)
+        e2e_agent_steps = 0
+        for s in range(1, args.steps + 1):
+            e2e_agent_steps += rs["population"]
+            eng.step(s, rs["meanWealth"])
+            rs = sb.update(eng.stats(), s)                          # D2H of the step's reductions
+            json.dumps(rs)                                          # the log line the CLI writes
+        final = eng.download(["a_order", "a_id", "a_pos", "a_sugar", "a_age", "counters"])   # D2H final agents
+        d2h = sum(getattr(final, k).nbytes for k in ("a_order", "a_id", "a_pos", "a_sugar", "a_age", "counters"))
+        d2h += args.steps * C.sizeof(layout.Stats)
+        barrier()
+        wall = time.perf_counter() - w0
+        tw = torch.tensor([wall, float(e2e_agent_steps)], device=dev, dtype=torch.float64)
+        if world > 1:
+            mx = tw.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sm_ = tw.clone(); dist.all_reduce(sm_, op=dist.ReduceOp.SUM)
+            wall, e2e_agent_steps = float(mx[0]), float(sm_[1])
+        e2e = {"value": e2e_agent_steps / wall, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps,
+               "d2h_bytes_per_step": d2h / args.steps, "wall_s": wall,
+               "includes": "upload of the initial state, per-step stats readback + log formatting, download of the final agents"}
+
+    # ---- CPU baseline (rank 0, N = 1 only) --------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        v, dt, n_as = run_cpu_port(args, c, args.cpu_steps)
+        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"{args.cpu_steps} timesteps of the same S1 initial state ({n_as} agent-steps, {dt:.1f} s), "
+                         "oracle/ss_oracle.c single thread; the Python reference itself runs 6-8 k agent-steps/s/core "
+                         "(build container, BASELINE.md) and cannot instantiate this map"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"S1 synthetic {args.size}x{args.size}, {n_agents} agents, reproduction_basic rules"
+                                   + (f", {world} independent replicas" if world > 1 else ""),
+                       "rng_mode": "scalable", "l2": "inputs larger than L2 (state > 500 MB per GPU)",
+                       "parallelism": "replicas" if world > 1 else "single GPU",
+                       "mean_commit_rounds": float(np.mean(rounds)), "mean_acting_agents": float(np.mean(acting))},
+            "clocks": sampler.summary(), "gpu_launches": launches, "roofline": roofline,
+        }
+        if e2e is not None:
+            line["e2e"] = e2e
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -212,6 +212,8 @@ int  ssb_reduce_stats(ssb_engine_t *e, int32_t t, void *stream); /* device reduc
 int  ssb_step(ssb_engine_t *e, int32_t t, double prev_mean_wealth, void *stream);
                                                                   /* the four above, in order   */
 int  ssb_stats(ssb_engine_t *e, ssb_stats_t *host_out);          /* synchronises               */
+#define SSB_STATS_RING 1024
+int  ssb_stats_history(ssb_engine_t *e, int32_t t, ssb_stats_t *host_out); /* stats of a recent step t (device ring of SSB_STATS_RING entries); synchronises */
 int  ssb_sync(ssb_engine_t *e, void *stream);
 
 /* instrumentation: number of kernels this engine has launched, device time of the last

@@ -40,6 +40,7 @@ struct ssb_engine {
     int n_partials;
     TribeCensus *d_tribes;
     ssb_stats_t *d_stats;
+    ssb_stats_t *d_ring;     // last SSB_STATS_RING steps, so that K steps can run without host syncs
     uint64_t *d_keys_a, *d_keys_b;
     uint32_t *d_radix_hist;
     double *d_lorenz_blocks;
@@ -114,6 +115,8 @@ int ssb_create(const ssb_params_t *params, int device, ssb_engine_t **out) {
     CU(cudaMalloc(&e->d_stats, sizeof(ssb_stats_t)));
     CU(cudaMemset(e->d_stats, 0, sizeof(ssb_stats_t)));
     CU(cudaMalloc(&e->d_tribes, sizeof(TribeCensus)));
+    CU(cudaMalloc(&e->d_ring, sizeof(ssb_stats_t) * SSB_STATS_RING));
+    CU(cudaMemset(e->d_ring, 0, sizeof(ssb_stats_t) * SSB_STATS_RING));
     for (int i = 0; i < 5; i++) CU(cudaEventCreate(&e->ev[i]));
     return 0;
 }
@@ -123,7 +126,7 @@ void ssb_destroy(ssb_engine_t *e) {
     cudaSetDevice(e->device);
     void *ptrs[] = {e->d_mt, e->d_endow, e->d_tagbits, e->d_tile_counts, e->d_new_order, e->d_scalars,
                     e->d_born_list, e->rc.mark, e->rc.prio, e->rc.list_a, e->rc.list_b, e->rc.ready, e->rc.cnt,
-                    e->d_partials, e->d_tribes, e->d_stats, e->d_keys_a, e->d_keys_b, e->d_radix_hist,
+                    e->d_partials, e->d_tribes, e->d_stats, e->d_ring, e->d_keys_a, e->d_keys_b, e->d_radix_hist,
                     e->d_lorenz_blocks};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < 5; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
@@ -322,6 +325,7 @@ int ssb_reduce_stats(ssb_engine_t *e, int32_t t, void *stream_) {
     k_stats_reset<<<1, 32, 0, st>>>(e->d_tribes); LAUNCHED(e);
     k_stats_partials<<<e->n_partials, STATS_THREADS, 0, st>>>(c, e->d_partials, (double *)e->d_keys_a, e->d_tribes); LAUNCHED(e);
     k_stats_final<<<1, STATS_THREADS, 0, st>>>(c, e->d_partials, e->n_partials, e->d_tribes, e->d_stats); LAUNCHED(e);
+    if (e->p.rng_mode == SSB_RNG_EXACT) { k_stats_ordered<<<1, 32, 0, st>>>(c, e->d_stats); LAUNCHED(e); }
     // Lorenz numerator: sort the wealths (non-negative doubles order like their bit patterns)
     const int64_t cap = c.a.capacity;
     const int tiles = (int)((cap + RADIX_TILE - 1) / RADIX_TILE);
@@ -335,7 +339,7 @@ int ssb_reduce_stats(ssb_engine_t *e, int32_t t, void *stream_) {
     }
     const int lb = e->num_sms * 4;
     k_lorenz<<<lb, 256, 0, st>>>((const double *)src, n_ptr, e->d_lorenz_blocks); LAUNCHED(e);
-    k_lorenz_final<<<1, 1, 0, st>>>(e->d_lorenz_blocks, lb, e->d_stats); LAUNCHED(e);
+    k_lorenz_final<<<1, 1, 0, st>>>(e->d_lorenz_blocks, lb, e->d_stats, e->d_ring + (((t % SSB_STATS_RING) + SSB_STATS_RING) % SSB_STATS_RING)); LAUNCHED(e);
     if (e->timing) { CU(cudaEventRecord(e->ev[4], st)); e->ev_recorded = true; }
     return 0;
 }
@@ -353,6 +357,15 @@ int ssb_stats(ssb_engine_t *e, ssb_stats_t *host_out) {
     if (!host_out) return -1;
     CU(cudaDeviceSynchronize());
     CU(cudaMemcpy(host_out, e->d_stats, sizeof(ssb_stats_t), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int ssb_stats_history(ssb_engine_t *e, int32_t t, ssb_stats_t *host_out) {
+    CHECK_BOUND(e);
+    if (!host_out) return -1;
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(host_out, e->d_ring + (((t % SSB_STATS_RING) + SSB_STATS_RING) % SSB_STATS_RING), sizeof(ssb_stats_t), cudaMemcpyDeviceToHost));
+    if (host_out->timestep != t) return fail(e, -1, "step %d is no longer (or not yet) in the stats ring", t);
     return 0;
 }
 

@@ -402,6 +402,38 @@ __global__ void __launch_bounds__(STATS_THREADS) k_stats_final(DevCtx c, const S
     out->rounds = c.a.counters[SSB_C_ROUNDS];
 }
 
+// Mode E: the reference accumulates its float sums agent by agent in list order and rounds the
+// means to 2 decimals, so a last-bit difference can flip a logged value.  One thread re-folds the
+// order-sensitive fp64 sums sequentially (example scale: <= a few thousand agents).
+__global__ void k_stats_ordered(DevCtx c, ssb_stats_t *out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const long long n = c.a.counters[SSB_C_N_LIST], n_dead = c.a.counters[SSB_C_N_DEAD];
+    double sum_wealth = 0, collected = 0, burn = 0, ttl_lim = 0, price = 0, hap = 0, whap = 0, fhap = 0;
+    for (long long i = 0; i < n; i++) {
+        const int s = c.a.order[i];
+        const double w = c.a.sugar[s] + c.a.spice[s];
+        sum_wealth += w;
+        collected += w - (c.a.last_sugar[s] + c.a.last_spice[s]);
+        const double sm = (double)max(c.a.sugar_metab[s], 0), pm = (double)max(c.a.spice_metab[s], 0);
+        const double st = sm > 0 ? c.a.sugar[s] / sm : 9223372036854775807.0;
+        const double pt = pm > 0 ? c.a.spice[s] / pm : 9223372036854775807.0;
+        const double ttl = fmin(st, pt);
+        burn += ttl;
+        ttl_lim += fmin(ttl, (double)(c.a.max_age[s] - c.a.age[s]));
+        if (c.a.trade_volume[s] > 0) price += c.a.trade_price[s];
+        hap += c.a.happiness[s]; whap += c.a.wealth_happiness[s]; fhap += c.a.family_happiness[s];
+    }
+    double dead_collected = 0;
+    for (long long i = 0; i < n_dead; i++) {
+        const int s = c.a.dead_list[i];
+        dead_collected += (c.a.sugar[s] + c.a.spice[s]) - (c.a.last_sugar[s] + c.a.last_spice[s]);
+    }
+    out->sum_wealth = sum_wealth; out->sum_wealth_collected = collected; out->sum_burn_rate = burn;
+    out->sum_ttl_age_limited = ttl_lim; out->sum_trade_price = price; out->sum_happiness = hap;
+    out->sum_wealth_happiness = whap; out->sum_family_happiness = fhap;
+    out->dead_wealth_collected = dead_collected;
+}
+
 // Lorenz numerator from the ascending wealth keys (updateGiniCoefficient, sugarscape.py:913-934):
 // sum_{i<n-1} cum_i + cum_{n-1}/2 = sum_j w_j * (n - 1 - j) + w_j / 2 ... folded per block.
 __global__ void __launch_bounds__(256) k_lorenz(const double *sorted, const int64_t *n_ptr, double *block_sums) {
@@ -420,10 +452,11 @@ __global__ void __launch_bounds__(256) k_lorenz(const double *sorted, const int6
     if (threadIdx.x == 0) block_sums[blockIdx.x] = sm[0];
 }
 
-__global__ void k_lorenz_final(const double *block_sums, int n_blocks, ssb_stats_t *out) {
+__global__ void k_lorenz_final(const double *block_sums, int n_blocks, ssb_stats_t *out, ssb_stats_t *ring_slot) {
     double acc = 0;
     for (int i = 0; i < n_blocks; i++) acc += block_sums[i];
     out->lorenz_weighted_sum = acc;
+    *ring_slot = *out;      // the step's stats are complete: publish them in the history ring
 }
 
 }  // namespace ssb

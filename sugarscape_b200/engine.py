@@ -51,6 +51,7 @@ def load_library():
     L.ssb_reduce_stats.argtypes = [E, C.c_int32, C.c_void_p]
     L.ssb_step.argtypes = [E, C.c_int32, C.c_double, C.c_void_p]
     L.ssb_stats.argtypes = [E, S]
+    L.ssb_stats_history.argtypes = [E, C.c_int32, S]
     L.ssb_sync.argtypes = [E, C.c_void_p]
     L.ssb_launch_count.argtypes = [E]
     L.ssb_launch_count.restype = C.c_int64
@@ -70,7 +71,7 @@ EXPORTED_SYMBOLS = (
     "ssb_abi_version", "ssb_create", "ssb_bind", "ssb_destroy", "ssb_last_error",
     "ssb_set_mt_state", "ssb_get_mt_state", "ssb_set_step_tables", "ssb_set_mark_shift",
     "ssb_sizeof_params", "ssb_sizeof_grid", "ssb_sizeof_agents", "ssb_sizeof_stats",
-    "ssb_env_step", "ssb_agent_step", "ssb_compact", "ssb_reduce_stats", "ssb_step", "ssb_stats",
+    "ssb_env_step", "ssb_agent_step", "ssb_compact", "ssb_reduce_stats", "ssb_step", "ssb_stats", "ssb_stats_history",
     "ssb_sync", "ssb_launch_count", "ssb_timing", "ssb_enable_timing",
 )
 
@@ -204,6 +205,11 @@ class Engine:
     def stats(self):
         out = layout.Stats()
         self._check(self.L.ssb_stats(self.handle, C.byref(out)))
+        return out
+
+    def stats_history(self, t):
+        out = layout.Stats()
+        self._check(self.L.ssb_stats_history(self.handle, t, C.byref(out)))
         return out
 
     def sync(self):
