@@ -197,6 +197,10 @@ int  ssb_set_step_tables(ssb_engine_t *e, const uint32_t *endow_bits, const uint
 /* mode S tuning: reservation marks live on a grid coarsened by 2^shift cells per side */
 int  ssb_set_mark_shift(ssb_engine_t *e, int32_t shift);
 
+/* test hook: out[i] = x[i] ** y[i] with the engine's bit-exact restatement of glibc's pow
+ * (device pointers; exact[i] = 0 where the argument fell outside the restated path) */
+int  ssb_test_pow(const double *x, const double *y, double *out, int32_t *exact, int32_t n);
+
 /* sizeof() of the ABI structs, for binding self-checks */
 int  ssb_sizeof_params(void);
 int  ssb_sizeof_grid(void);

@@ -76,7 +76,21 @@ static int grid_for(long long n, int threads, int cap) {
     return (int)b;
 }
 
+__global__ void k_test_pow(const double *x, const double *y, double *out, int32_t *exact, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int ex;
+    out[i] = ssb_py_pow(x[i], y[i], &ex);
+    exact[i] = ex;
+}
+
 extern "C" {
+
+// test hook: out[i] = x[i] ** y[i] with the engine's pow (device pointers, default stream)
+int ssb_test_pow(const double *x, const double *y, double *out, int32_t *exact, int32_t n) {
+    k_test_pow<<<(n + 255) / 256, 256>>>(x, y, out, exact, n);
+    return cudaDeviceSynchronize() == cudaSuccess ? 0 : -2;
+}
 
 int ssb_abi_version(void) { return SSB_ABI_VERSION; }
 

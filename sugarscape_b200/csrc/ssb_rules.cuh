@@ -11,6 +11,7 @@
 #include <stdint.h>
 
 #include "../../include/ssb.h"
+#include "ssb_pow.cuh"
 #include "ssb_rng.cuh"
 
 namespace ssb {
@@ -50,12 +51,11 @@ __device__ __forceinline__ int find_tribe(const DevCtx &c, uint32_t tags) {
     return min(tribe, T - 1);
 }
 
-// Python float ** with the two exponents that must be exact special-cased; the general case is
-// CUDA's pow (see DESIGN.md "floating point").
+// Python float ** : glibc's pow restated bit for bit (ssb_pow.cuh) -- candidate cells that are
+// mathematically tied are separated by pow's rounding alone, so "accurate" is not enough.
 __device__ __forceinline__ double py_pow(double x, double y) {
-    if (y == 0.0) return 1.0;
-    if (y == 1.0) return x;
-    return pow(x, y);
+    int exact;
+    return ssb_py_pow(x, y, &exact);
 }
 
 // Agent.findWelfare (agent.py:1170-1201)

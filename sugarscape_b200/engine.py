@@ -53,6 +53,7 @@ def load_library():
     L.ssb_stats.argtypes = [E, S]
     L.ssb_stats_history.argtypes = [E, C.c_int32, S]
     L.ssb_sync.argtypes = [E, C.c_void_p]
+    L.ssb_test_pow.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
     L.ssb_launch_count.argtypes = [E]
     L.ssb_launch_count.restype = C.c_int64
     L.ssb_enable_timing.argtypes = [E, C.c_int32]
@@ -72,7 +73,7 @@ EXPORTED_SYMBOLS = (
     "ssb_set_mt_state", "ssb_get_mt_state", "ssb_set_step_tables", "ssb_set_mark_shift",
     "ssb_sizeof_params", "ssb_sizeof_grid", "ssb_sizeof_agents", "ssb_sizeof_stats",
     "ssb_env_step", "ssb_agent_step", "ssb_compact", "ssb_reduce_stats", "ssb_step", "ssb_stats", "ssb_stats_history",
-    "ssb_sync", "ssb_launch_count", "ssb_timing", "ssb_enable_timing",
+    "ssb_sync", "ssb_test_pow", "ssb_launch_count", "ssb_timing", "ssb_enable_timing",
 )
 
 
