@@ -201,6 +201,11 @@ int  ssb_set_mark_shift(ssb_engine_t *e, int32_t shift);
  * (device pointers; exact[i] = 0 where the argument fell outside the restated path) */
 int  ssb_test_pow(const double *x, const double *y, double *out, int32_t *exact, int32_t n);
 
+/* debug: per-round trace of the last mode S agent step.  enable_rounds > 0 allocates the trace;
+ * out (host, may be NULL) receives per round {active, ready, ns at start, after mark, after
+ * select, after execute} */
+int  ssb_round_trace(ssb_engine_t *e, int32_t enable_rounds, uint64_t *out, int32_t out_rounds);
+
 /* sizeof() of the ABI structs, for binding self-checks */
 int  ssb_sizeof_params(void);
 int  ssb_sizeof_grid(void);

@@ -139,7 +139,7 @@ void ssb_destroy(ssb_engine_t *e) {
     if (!e) return;
     cudaSetDevice(e->device);
     void *ptrs[] = {e->d_mt, e->d_endow, e->d_tagbits, e->d_tile_counts, e->d_new_order, e->d_scalars,
-                    e->d_born_list, e->rc.mark, e->rc.prio, e->rc.list_a, e->rc.list_b, e->rc.ready, e->rc.cnt,
+                    e->d_born_list, e->rc.mark, e->rc.prio, e->rc.list_a, e->rc.list_b, e->rc.ready, e->rc.cnt, e->rc.trace,
                     e->d_partials, e->d_tribes, e->d_stats, e->d_ring, e->d_keys_a, e->d_keys_b, e->d_radix_hist,
                     e->d_lorenz_blocks};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -211,6 +211,24 @@ int ssb_set_mark_shift(ssb_engine_t *e, int32_t shift) {
         CU(cudaMalloc(&rc.mark, sizeof(uint32_t) * (size_t)(e->p.width >> shift) * (e->p.height >> shift)));
     }
     rc.mark_shift = shift; rc.wc = e->p.width >> shift; rc.hc = e->p.height >> shift;
+    return 0;
+}
+
+// debug: per-round trace of the last scalable agent step; out[round * 6 + {0: active, 1: ready,
+// 2..5: globaltimer ns at round start / after mark / after select / after execute}]
+int ssb_round_trace(ssb_engine_t *e, int32_t enable_rounds, uint64_t *out, int32_t out_rounds) {
+    if (!e || !e->bound || e->p.rng_mode != SSB_RNG_SCALABLE) return fail(e, -1, "round trace needs a bound scalable engine");
+    CU(cudaSetDevice(e->device));
+    if (enable_rounds > 0 && !e->rc.trace) {
+        CU(cudaMalloc(&e->rc.trace, sizeof(unsigned long long) * 6 * enable_rounds));
+        CU(cudaMemset(e->rc.trace, 0, sizeof(unsigned long long) * 6 * enable_rounds));
+        e->rc.trace_rounds = enable_rounds;
+    }
+    if (out && e->rc.trace) {
+        CU(cudaDeviceSynchronize());
+        const int n = out_rounds < e->rc.trace_rounds ? out_rounds : e->rc.trace_rounds;
+        CU(cudaMemcpy(out, e->rc.trace, sizeof(unsigned long long) * 6 * n, cudaMemcpyDeviceToHost));
+    }
     return 0;
 }
 

@@ -66,7 +66,15 @@ struct RoundCtx {
     int32_t *list_a, *list_b, *ready;
     int32_t *cnt;            // [0..1] list lengths (ping-pong), [2..3] ready counts (ping-pong)
     uint64_t key;
+    unsigned long long *trace;   // optional: per round {n_active, n_ready, ns after mark, select, execute}
+    int32_t trace_rounds;
 };
+
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
 // dilation of the footprint required by the rule set, for agent s (agent.py:585-588)
 __device__ __forceinline__ int footprint_dilation(const DevCtx &c, int s) {
@@ -202,12 +210,17 @@ __global__ void __launch_bounds__(256) k_agent_step_scalable(DevCtx c, RoundCtx 
         }
         int32_t *n_next = &rc.cnt[(round + 1) & 1], *n_ready = &rc.cnt[2 + (round & 1)];
         if (tid == 0) { *n_next = 0; *n_ready = 0; }
+        const bool tr = rc.trace && tid == 0 && round < rc.trace_rounds;
+        if (tr) { rc.trace[round * 6 + 0] = n; rc.trace[round * 6 + 2] = global_ns(); }
         phase_mark(c, rc, cur, n, round, tid, nthreads);
         grid.sync();
+        if (tr) rc.trace[round * 6 + 3] = global_ns();
         phase_select(c, rc, cur, n, nxt, n_next, n_ready, round, tid, nthreads);
         grid.sync();
+        if (tr) { rc.trace[round * 6 + 1] = *(volatile int32_t *)n_ready; rc.trace[round * 6 + 4] = global_ns(); }
         phase_execute(c, rc, *(volatile int32_t *)n_ready, tid, nthreads);
         grid.sync();
+        if (tr) rc.trace[round * 6 + 5] = global_ns();
         int32_t *tmp = cur; cur = nxt; nxt = tmp;
         round++;
     }

@@ -53,6 +53,7 @@ def load_library():
     L.ssb_stats.argtypes = [E, S]
     L.ssb_stats_history.argtypes = [E, C.c_int32, S]
     L.ssb_sync.argtypes = [E, C.c_void_p]
+    L.ssb_round_trace.argtypes = [E, C.c_int32, C.c_void_p, C.c_int32]
     L.ssb_test_pow.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
     L.ssb_launch_count.argtypes = [E]
     L.ssb_launch_count.restype = C.c_int64
@@ -73,7 +74,7 @@ EXPORTED_SYMBOLS = (
     "ssb_set_mt_state", "ssb_get_mt_state", "ssb_set_step_tables", "ssb_set_mark_shift",
     "ssb_sizeof_params", "ssb_sizeof_grid", "ssb_sizeof_agents", "ssb_sizeof_stats",
     "ssb_env_step", "ssb_agent_step", "ssb_compact", "ssb_reduce_stats", "ssb_step", "ssb_stats", "ssb_stats_history",
-    "ssb_sync", "ssb_test_pow", "ssb_launch_count", "ssb_timing", "ssb_enable_timing",
+    "ssb_sync", "ssb_test_pow", "ssb_round_trace", "ssb_launch_count", "ssb_timing", "ssb_enable_timing",
 )
 
 
@@ -215,6 +216,12 @@ class Engine:
 
     def sync(self):
         self._check(self.L.ssb_sync(self.handle, self.stream))
+
+    def round_trace(self, rounds=1024, fetch=True):
+        """Enable (first call) and fetch the per-round trace of the last scalable agent step."""
+        out = np.zeros((rounds, 6), dtype=np.uint64)
+        self._check(self.L.ssb_round_trace(self.handle, rounds, out.ctypes.data if fetch else None, rounds))
+        return out
 
     def set_mark_shift(self, shift):
         self._check(self.L.ssb_set_mark_shift(self.handle, shift))
