@@ -50,7 +50,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=4096, help="map side (S1 = 4096)")
     ap.add_argument("--agents", type=int, default=0, help="agents (default: S1 density, 1.6 M at 4096)")
-    ap.add_argument("--mark-shift", type=int, default=-1)
+    ap.add_argument("--epochs", type=int, default=0)
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=3)
@@ -178,8 +178,8 @@ def main():
     endow, tags = steptables.step_tables(1, horizon, c["agentTagStringLength"])
     state, params = synthetic.build_state(c)
     eng = Engine(params, state, local_rank, endow, tags)
-    if args.mark_shift >= 0:
-        eng.set_mark_shift(args.mark_shift)
+    if args.epochs > 0:
+        eng.set_epochs(args.epochs)
     n_cells = args.size * args.size
 
     # ---- device-resident throughput -------------------------------------------------------------

@@ -194,8 +194,8 @@ int  ssb_get_mt_state(ssb_engine_t *e, uint32_t state[624], int32_t *index);
  * tag_bits[t] bit k = k-th draw for tag positions where the parents differ. */
 int  ssb_set_step_tables(ssb_engine_t *e, const uint32_t *endow_bits, const uint32_t *tag_bits, int32_t n);
 
-/* mode S tuning: reservation marks live on a grid coarsened by 2^shift cells per side */
-int  ssb_set_mark_shift(ssb_engine_t *e, int32_t shift);
+/* mode S tuning: number of priority epochs of the sliding-prefix commit (power of two, default 64) */
+int  ssb_set_epochs(ssb_engine_t *e, int32_t epochs);
 
 /* test hook: out[i] = x[i] ** y[i] with the engine's bit-exact restatement of glibc's pow
  * (device pointers; exact[i] = 0 where the argument fell outside the restated path) */

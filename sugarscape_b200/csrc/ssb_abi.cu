@@ -139,7 +139,7 @@ void ssb_destroy(ssb_engine_t *e) {
     if (!e) return;
     cudaSetDevice(e->device);
     void *ptrs[] = {e->d_mt, e->d_endow, e->d_tagbits, e->d_tile_counts, e->d_new_order, e->d_scalars,
-                    e->d_born_list, e->rc.mark, e->rc.prio, e->rc.list_a, e->rc.list_b, e->rc.ready, e->rc.cnt, e->rc.trace,
+                    e->d_born_list, e->rc.mark, e->rc.prio, e->rc.list_a, e->rc.list_b, e->rc.ready, e->rc.cnt, e->rc.trace, e->rc.bucketed, e->rc.epoch_count, e->rc.epoch_start, e->rc.epoch_fill,
                     e->d_partials, e->d_tribes, e->d_stats, e->d_ring, e->d_keys_a, e->d_keys_b, e->d_radix_hist,
                     e->d_lorenz_blocks};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -181,11 +181,15 @@ int ssb_bind(ssb_engine_t *e, const ssb_grid_t *grid, const ssb_agents_t *agents
     CU(cudaMalloc(&e->d_lorenz_blocks, sizeof(double) * e->num_sms * 4));
     if (e->p.rng_mode == SSB_RNG_SCALABLE) {
         RoundCtx &rc = e->rc;
-        int sh = 0;
-        while (sh < 2 && (e->p.width % (2 << sh)) == 0 && (e->p.height % (2 << sh)) == 0) sh++;
-        rc.mark_shift = sh;
-        rc.wc = e->p.width >> sh; rc.hc = e->p.height >> sh;
-        CU(cudaMalloc(&rc.mark, sizeof(uint32_t) * (size_t)rc.wc * rc.hc));
+        CU(cudaMalloc(&rc.mark, sizeof(uint32_t) * (size_t)cells));
+        CU(cudaMalloc(&rc.bucketed, sizeof(int32_t) * cap));
+        CU(cudaMalloc(&rc.epoch_count, sizeof(int32_t) * MAX_EPOCHS));
+        CU(cudaMalloc(&rc.epoch_start, sizeof(int32_t) * (MAX_EPOCHS + 1)));
+        CU(cudaMalloc(&rc.epoch_fill, sizeof(int32_t) * MAX_EPOCHS));
+        rc.epochs = 64;
+        if (rc.epochs > (1 << e->p.id_bits)) rc.epochs = 1 << e->p.id_bits;
+        rc.epoch_shift = e->p.id_bits;
+        for (int v = rc.epochs; v > 1; v >>= 1) rc.epoch_shift--;
         CU(cudaMalloc(&rc.prio, sizeof(uint32_t) * cap));
         CU(cudaMalloc(&rc.list_a, sizeof(int32_t) * cap));
         CU(cudaMalloc(&rc.list_b, sizeof(int32_t) * cap));
@@ -193,7 +197,7 @@ int ssb_bind(ssb_engine_t *e, const ssb_grid_t *grid, const ssb_agents_t *agents
         CU(cudaMalloc(&rc.cnt, sizeof(int32_t) * 8));
         CU(cudaMemset(rc.cnt, 0, sizeof(int32_t) * 8));
         int per_sm = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_agent_step_scalable, 256, 0));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_agent_step_scalable, AGENT_THREADS, 0));
         if (per_sm < 1) return fail(e, -3, "cooperative kernel does not fit on an SM");
         e->coop_blocks = per_sm * e->num_sms;
     }
@@ -201,16 +205,12 @@ int ssb_bind(ssb_engine_t *e, const ssb_grid_t *grid, const ssb_agents_t *agents
     return 0;
 }
 
-int ssb_set_mark_shift(ssb_engine_t *e, int32_t shift) {
-    if (!e || !e->bound || e->p.rng_mode != SSB_RNG_SCALABLE) return fail(e, -1, "mark shift needs a bound scalable engine");
-    if (shift < 0 || shift > 6 || (e->p.width % (1 << shift)) || (e->p.height % (1 << shift))) return fail(e, -1, "mark shift %d does not divide the map", shift);
-    CU(cudaSetDevice(e->device));
-    RoundCtx &rc = e->rc;
-    if (shift < rc.mark_shift) {   // finer grid needs a larger buffer
-        CU(cudaFree(rc.mark));
-        CU(cudaMalloc(&rc.mark, sizeof(uint32_t) * (size_t)(e->p.width >> shift) * (e->p.height >> shift)));
-    }
-    rc.mark_shift = shift; rc.wc = e->p.width >> shift; rc.hc = e->p.height >> shift;
+int ssb_set_epochs(ssb_engine_t *e, int32_t epochs) {
+    if (!e || !e->bound || e->p.rng_mode != SSB_RNG_SCALABLE) return fail(e, -1, "epochs need a bound scalable engine");
+    if (epochs < 1 || epochs > MAX_EPOCHS || (epochs & (epochs - 1)) || epochs > (1 << e->p.id_bits)) return fail(e, -1, "epochs must be a power of two <= %d", MAX_EPOCHS);
+    e->rc.epochs = epochs;
+    e->rc.epoch_shift = e->p.id_bits;
+    for (int v = epochs; v > 1; v >>= 1) e->rc.epoch_shift--;
     return 0;
 }
 
@@ -319,7 +319,7 @@ int ssb_agent_step(ssb_engine_t *e, int32_t t, double prev_mean_wealth, void *st
         RoundCtx rc = e->rc;
         rc.key = step_key(e->p.seed, t);
         void *args[] = {&c, &rc};
-        CU(cudaLaunchCooperativeKernel((void *)k_agent_step_scalable, dim3(e->coop_blocks), dim3(256), args, 0, st));
+        CU(cudaLaunchCooperativeKernel((void *)k_agent_step_scalable, dim3(e->coop_blocks), dim3(AGENT_THREADS), args, 0, st));
         LAUNCHED(e);
     }
     if (e->timing) CU(cudaEventRecord(e->ev[2], st));

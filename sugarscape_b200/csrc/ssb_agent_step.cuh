@@ -7,20 +7,28 @@
 //
 // Mode S (scalable): the step is DEFINED as "agents act one at a time in ascending priority"
 //   (priority = keyed bijection of the agent id, ssb_rng.cuh).  The kernel below reproduces that
-//   sequential result in parallel with deterministic reservations:
-//     round k:  MARK    every uncommitted agent atomicMin's (tag_k | priority) onto every mark
-//                       cell of its footprint F (all cells its transaction may read or write),
-//               SELECT  an agent whose own value survived on ALL of F is first among every
-//                       uncommitted agent it could interact with -> ready,
-//               EXECUTE ready agents run their whole transaction concurrently (their footprints
-//                       are pairwise disjoint), everyone else retries next round.
+//   sequential result in parallel with deterministic reservations over a SLIDING PREFIX of the
+//   priority order (after Blelloch et al., "Internally deterministic parallel algorithms can be
+//   fast", PPoPP'12):
+//     prepare   agents are bucketed by the top bits of their priority into E epochs;
+//     round k   the active set is epoch k plus the agents of earlier epochs that have not
+//               committed yet;
+//       MARK    every active agent atomicMin's (tag_k | priority) onto every cell of its
+//               footprint F (all cells its transaction may read or write),
+//       SELECT  an agent whose own value survived on ALL of F is first among every uncommitted
+//               agent it could interact with -> ready (agents of later epochs have later
+//               priorities and are not acting yet, so they cannot matter),
+//       EXECUTE ready agents run their whole transaction concurrently (their footprints are
+//               pairwise disjoint); everyone else stays active.
 //   Two agents whose footprints intersect are therefore always committed in priority order, which
-//   is the sequential semantics.  Marks carry a descending round tag in their high bits, so stale
-//   marks of earlier rounds lose every atomicMin and never need clearing inside a step.
+//   is the sequential semantics; activating only a slice of the order per round keeps the
+//   conflict rate low, so an agent marks its footprint ~2 times per step instead of ~50.
+//   Marks carry a descending round tag in their high bits: stale marks lose every atomicMin and
+//   are cleared only when the 6-bit tag wraps.
 //   Footprint: the cross of radius r around the agent (cells it may inspect / move to) dilated by
-//   k = 0 (movement / combat only), 1 (tagging or trading touch the 4 neighbours of the new cell)
-//   or 2 (reproduction reads the mate's empty neighbours and places a child there); marks live on
-//   a grid coarsened by 2^mark_shift cells per side (a superset is always safe).
+//   a diamond of radius k = 0 (movement / combat only), 1 (tagging or trading touch the 4
+//   neighbours of the new cell) or 2 (reproduction reads the mate's empty neighbours and places
+//   a child there).  In the x-major grid it is one contiguous y-interval per x-column.
 //   All rounds of a step run inside ONE persistent cooperative kernel (grid.sync between phases).
 #pragma once
 #include <cooperative_groups.h>
@@ -58,15 +66,21 @@ __global__ void __launch_bounds__(32, 1) k_agent_step_exact(DevCtx c, uint32_t *
 // ---------------------------------------------------------------------------------------------
 constexpr int MAXC_SCALABLE = 32;     // 4 * 8 candidate cells; the host refuses larger ranges
 constexpr int TAG_BITS = 6;
+constexpr int MAX_EPOCHS = 1024;
+constexpr int AGENT_THREADS = 256;
 
 struct RoundCtx {
-    uint32_t *mark;          // coarse mark grid, wc * hc words
-    int32_t mark_shift, wc, hc;
+    uint32_t *mark;          // one word per cell
     uint32_t *prio;          // per slot, this step's priority
+    int32_t *bucketed;       // the agent list grouped by epoch
     int32_t *list_a, *list_b, *ready;
-    int32_t *cnt;            // [0..1] list lengths (ping-pong), [2..3] ready counts (ping-pong)
+    int32_t *cnt;            // [0..1] carry-list lengths (ping-pong), [2..3] ready counts (ping-pong)
+    int32_t *epoch_count;    // [MAX_EPOCHS]
+    int32_t *epoch_start;    // [MAX_EPOCHS + 1]
+    int32_t *epoch_fill;     // [MAX_EPOCHS]
+    int32_t epochs, epoch_shift;
     uint64_t key;
-    unsigned long long *trace;   // optional: per round {n_active, n_ready, ns after mark, select, execute}
+    unsigned long long *trace;   // optional: per round {n_active, n_ready, ns at start / after mark / select / execute}
     int32_t trace_rounds;
 };
 
@@ -85,64 +99,62 @@ __device__ __forceinline__ int footprint_dilation(const DevCtx &c, int s) {
     return k;
 }
 
-// Visit every coarse mark cell covering the two dilated arms of the cross, as rectangles:
-// horizontal band [x-rx-k, x+rx+k] x [y-k, y+k], vertical band [x-k, x+k] x [y-ry-k, y+ry+k]
-// (only its parts above and below the horizontal band).  A cell may be visited twice on tiny
-// maps (harmless: atomicMin / equality are idempotent).  f returns false to stop early.
-template <class F>
-__device__ __forceinline__ bool for_each_mark(const DevCtx &c, const RoundCtx &rc, int pos, int r, int k, F f) {
-    const int H = c.p.height, sh = rc.mark_shift;
-    const int x = pos / H, y = pos - x * H;
-    const int rx = min(r, c.max_dx), ry = min(r, c.max_dy);
-    const int ax0 = (x - rx - k) >> sh, ax1 = min((x + rx + k) >> sh, ax0 + rc.wc - 1);   // >> floors
-    const int ay0 = (y - k) >> sh, ay1 = min((y + k) >> sh, ay0 + rc.hc - 1);
-    for (int cx = ax0; cx <= ax1; cx++) {
-        const int base = wrapi(cx, rc.wc) * rc.hc;
-        for (int cy = ay0; cy <= ay1; cy++)
-            if (!f(base + wrapi(cy, rc.hc))) return false;
+// Footprint = union over the cells c of (cross of radius r) + {pos} of the diamond of radius k
+// around c.  Per x-column offset i it is the y-interval [-h(i), h(i)] with
+//   h(i) = max( |i| <= k ? ry + k - |i| : -1 ,                  (north-south arm, dilated)
+//               |i| <= rx ? k : k - (|i| - rx) )                (east-west arm, dilated)
+// f(base_index_of_column, y_lo, y_hi) is called once per column with the (unwrapped) interval.
+struct Footprint {
+    int x, y, rx, ry, k, W, H;
+    __device__ __forceinline__ void init(const DevCtx &c, int pos, int r, int k_) {
+        W = c.p.width; H = c.p.height;
+        x = pos / H; y = pos - x * H;
+        rx = min(r, c.max_dx); ry = min(r, c.max_dy); k = k_;
+        // on tiny maps the intervals may wrap onto themselves: cells are then visited twice,
+        // which is harmless (atomicMin and the ownership test are idempotent)
     }
-    const int bx0 = (x - k) >> sh, bx1 = min((x + k) >> sh, bx0 + rc.wc - 1);
-    const int by0 = max((y - ry - k) >> sh, ay0 - rc.hc), by1 = min((y + ry + k) >> sh, ay1 + rc.hc);
-    for (int cx = bx0; cx <= bx1; cx++) {
-        const int base = wrapi(cx, rc.wc) * rc.hc;
-        for (int cy = by0; cy < ay0; cy++)
-            if (!f(base + wrapi(cy, rc.hc))) return false;
-        for (int cy = ay1 + 1; cy <= by1; cy++)
-            if (!f(base + wrapi(cy, rc.hc))) return false;
+    __device__ __forceinline__ int half_height(int i) const {
+        const int ai = abs(i);
+        const int ns = ai <= k ? ry + k - ai : -1;
+        const int ew = ai <= rx ? k : k - (ai - rx);
+        return max(ns, ew);
     }
-    return true;
-}
-
-__device__ __forceinline__ void phase_prepare(const DevCtx &c, const RoundCtx &rc, int tid, int nthreads) {
-    const int n = (int)c.a.counters[SSB_C_N_LIST];
-    for (int i = tid; i < n; i += nthreads) {
-        const int s = c.a.order[i];
-        rc.prio[s] = priority_of(rc.key, (uint32_t)c.a.id[s], c.p.id_bits);
-        rc.list_a[i] = s;
-    }
-    if (tid == 0) {
-        rc.cnt[0] = n; rc.cnt[1] = 0; rc.cnt[2] = 0; rc.cnt[3] = 0;
-        c.a.counters[SSB_C_N_BORN] = 0;
-    }
-}
-
-constexpr int ROUNDS_PER_EPOCH = (1 << TAG_BITS) - 1;   // tag 63 is the cleared value
+};
 
 __device__ __forceinline__ uint32_t round_tag(const DevCtx &c, int round) {
-    return (uint32_t)(ROUNDS_PER_EPOCH - 1 - (round % ROUNDS_PER_EPOCH)) << c.p.id_bits;
+    constexpr int per_epoch = (1 << TAG_BITS) - 1;          // tag 63 is the cleared value
+    return (uint32_t)(per_epoch - 1 - (round % per_epoch)) << c.p.id_bits;
+}
+constexpr int ROUNDS_PER_TAG_EPOCH = (1 << TAG_BITS) - 1;
+
+__device__ __forceinline__ void mark_footprint(const DevCtx &c, const RoundCtx &rc, int s, uint32_t v) {
+    const int pos = c.a.pos[s];
+    if (pos < 0) return;                         // killed earlier this step: nothing to reserve
+    Footprint f;
+    f.init(c, pos, agent_range(c, s), footprint_dilation(c, s));
+    for (int i = -(f.rx + f.k); i <= f.rx + f.k; i++) {
+        const int h = f.half_height(i);
+        if (h < 0) continue;
+        uint32_t *col = rc.mark + (size_t)wrapi(f.x + i, f.W) * f.H;
+        for (int j = -h; j <= h; j++) atomicMin(col + wrapi(f.y + j, f.H), v);
+    }
 }
 
-__device__ __forceinline__ void phase_mark(const DevCtx &c, const RoundCtx &rc, const int32_t *list, int n,
-                                           int round, int tid, int nthreads) {
-    const uint32_t tag = round_tag(c, round);
-    for (int i = tid; i < n; i += nthreads) {
-        const int s = list[i];
-        const int pos = c.a.pos[s];
-        if (pos < 0) continue;                       // killed earlier this step: nothing to reserve
-        const uint32_t v = tag | rc.prio[s];
-        for_each_mark(c, rc, pos, agent_range(c, s), footprint_dilation(c, s),
-                      [&](int m) { atomicMin(&rc.mark[m], v); return true; });
+__device__ __forceinline__ bool owns_footprint(const DevCtx &c, const RoundCtx &rc, int s, uint32_t v) {
+    const int pos = c.a.pos[s];
+    if (pos < 0) return true;
+    Footprint f;
+    f.init(c, pos, agent_range(c, s), footprint_dilation(c, s));
+    unsigned bad = 0;
+    for (int i = -(f.rx + f.k); i <= f.rx + f.k; i++) {
+        const int h = f.half_height(i);
+        if (h < 0) continue;
+        const uint32_t *col = rc.mark + (size_t)wrapi(f.x + i, f.W) * f.H;
+        // independent loads, no early exit inside a column: keeps the requests in flight
+        for (int j = -h; j <= h; j++) bad |= __ldcg(col + wrapi(f.y + j, f.H)) ^ v;
+        if (bad) return false;
     }
+    return true;
 }
 
 // warp-aggregated append: every lane of the warp calls this (full mask)
@@ -156,69 +168,106 @@ __device__ __forceinline__ void warp_append(bool want, int32_t *list, int32_t *c
     if (want) list[base + __popc(mask & ((1u << lane) - 1u))] = value;
 }
 
-__device__ __forceinline__ void phase_select(const DevCtx &c, const RoundCtx &rc, const int32_t *list, int n,
-                                             int32_t *next, int32_t *n_next, int32_t *n_ready,
-                                             int round, int tid, int nthreads) {
-    const uint32_t tag = round_tag(c, round);
-    const int lane = threadIdx.x & 31;
-    for (int base = tid - lane; base < n; base += nthreads) {     // warp-uniform trip count
-        const int i = base + lane;
-        int s = -1;
-        bool ok = false;
-        if (i < n) {
-            s = list[i];
-            const int pos = c.a.pos[s];
-            ok = true;
-            if (pos >= 0) {
-                const uint32_t v = tag | rc.prio[s];
-                ok = for_each_mark(c, rc, pos, agent_range(c, s), footprint_dilation(c, s),
-                                   [&](int m) { return rc.mark[m] == v; });
-            }
-        }
-        __syncwarp();
-        warp_append(i < n && ok, rc.ready, n_ready, s);
-        warp_append(i < n && !ok, next, n_next, s);
-    }
-}
-
-__device__ __forceinline__ void phase_execute(const DevCtx &c, const RoundCtx &rc, int n_ready, int tid, int nthreads) {
-    for (int i = tid; i < n_ready; i += nthreads) {
-        const int s = rc.ready[i];
-        RngStream rng{rc.key, (uint32_t)c.a.id[s], 0u};
-        agent_transaction<RngStream, false, MAXC_SCALABLE>(c, s, rng);
-    }
-}
-
-// One persistent cooperative kernel per step: prepare, then commit rounds until every agent of
-// the list has acted.  Per round: MARK | sync | SELECT | sync | EXECUTE | sync.
-__global__ void __launch_bounds__(256) k_agent_step_scalable(DevCtx c, RoundCtx rc) {
+// One persistent cooperative kernel per step.
+__global__ void __launch_bounds__(AGENT_THREADS) k_agent_step_scalable(DevCtx c, RoundCtx rc) {
     cg::grid_group grid = cg::this_grid();
+    __shared__ int32_t sh_count[MAX_EPOCHS], sh_base[MAX_EPOCHS];
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nthreads = gridDim.x * blockDim.x;
-    const int n_marks = rc.wc * rc.hc;
-    phase_prepare(c, rc, tid, nthreads);
-    for (int i = tid; i < n_marks; i += nthreads) rc.mark[i] = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const long long n_cells = c.g.n_cells;
+    const int n_list = (int)c.a.counters[SSB_C_N_LIST];
+    const int E = rc.epochs;
+
+    // ---- prepare: priorities, epoch histogram ------------------------------------------------------
+    for (int i = tid; i < E; i += nthreads) { rc.epoch_count[i] = 0; rc.epoch_fill[i] = 0; }
+    for (long long i = tid; i < n_cells; i += nthreads) rc.mark[i] = 0xffffffffu;
+    if (tid == 0) { rc.cnt[0] = 0; rc.cnt[1] = 0; rc.cnt[2] = 0; rc.cnt[3] = 0; c.a.counters[SSB_C_N_BORN] = 0; }
     grid.sync();
+    for (int e = threadIdx.x; e < E; e += blockDim.x) sh_count[e] = 0;
+    __syncthreads();
+    for (int i = tid; i < n_list; i += nthreads) {
+        const int s = c.a.order[i];
+        const uint32_t pr = priority_of(rc.key, (uint32_t)c.a.id[s], c.p.id_bits);
+        rc.prio[s] = pr;
+        atomicAdd(&sh_count[pr >> rc.epoch_shift], 1);
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < E; e += blockDim.x) if (sh_count[e]) atomicAdd(&rc.epoch_count[e], sh_count[e]);
+    grid.sync();
+    if (blockIdx.x == 0) {   // exclusive scan of the epoch histogram (E <= 1024)
+        if (threadIdx.x == 0) {
+            int run = 0;
+            for (int e = 0; e < E; e++) { rc.epoch_start[e] = run; run += rc.epoch_count[e]; }
+            rc.epoch_start[E] = run;
+        }
+    }
+    grid.sync();
+    // scatter into epoch segments: one range reservation per block and epoch
+    for (int e = threadIdx.x; e < E; e += blockDim.x) sh_count[e] = 0;
+    __syncthreads();
+    for (int i = tid; i < n_list; i += nthreads) atomicAdd(&sh_count[rc.prio[c.a.order[i]] >> rc.epoch_shift], 1);
+    __syncthreads();
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+        sh_base[e] = sh_count[e] ? rc.epoch_start[e] + atomicAdd(&rc.epoch_fill[e], sh_count[e]) : 0;
+        sh_count[e] = 0;
+    }
+    __syncthreads();
+    for (int i = tid; i < n_list; i += nthreads) {
+        const int s = c.a.order[i];
+        const int e = rc.prio[s] >> rc.epoch_shift;
+        rc.bucketed[sh_base[e] + atomicAdd(&sh_count[e], 1)] = s;
+    }
+    grid.sync();
+
+    // ---- commit rounds -------------------------------------------------------------------------------
     int32_t *cur = rc.list_a, *nxt = rc.list_b;
     int round = 0;
     for (;;) {
-        const int n = ((volatile int32_t *)rc.cnt)[round & 1];
-        if (n == 0) break;
-        if (round > 0 && round % ROUNDS_PER_EPOCH == 0) {   // tags exhausted: clear and restart
-            for (int i = tid; i < n_marks; i += nthreads) rc.mark[i] = 0xffffffffu;
+        const int n_carry = ((volatile int32_t *)rc.cnt)[round & 1];
+        const int e0 = round < E ? rc.epoch_start[round] : 0;
+        const int n_new = round < E ? rc.epoch_start[round + 1] - e0 : 0;
+        const int n = n_carry + n_new;
+        if (round >= E && n == 0) break;
+        if (round > 0 && round % ROUNDS_PER_TAG_EPOCH == 0) {   // tags exhausted: clear and restart
+            for (long long i = tid; i < n_cells; i += nthreads) rc.mark[i] = 0xffffffffu;
             grid.sync();
         }
         int32_t *n_next = &rc.cnt[(round + 1) & 1], *n_ready = &rc.cnt[2 + (round & 1)];
-        if (tid == 0) { *n_next = 0; *n_ready = 0; }
         const bool tr = rc.trace && tid == 0 && round < rc.trace_rounds;
+        if (tid == 0) { *n_next = 0; *n_ready = 0; }
         if (tr) { rc.trace[round * 6 + 0] = n; rc.trace[round * 6 + 2] = global_ns(); }
-        phase_mark(c, rc, cur, n, round, tid, nthreads);
+        const uint32_t tag = round_tag(c, round);
+        const int32_t *fresh = rc.bucketed + e0;
+        // MARK
+        for (int i = tid; i < n; i += nthreads) {
+            const int s = i < n_carry ? cur[i] : fresh[i - n_carry];
+            mark_footprint(c, rc, s, tag | rc.prio[s]);
+        }
         grid.sync();
         if (tr) rc.trace[round * 6 + 3] = global_ns();
-        phase_select(c, rc, cur, n, nxt, n_next, n_ready, round, tid, nthreads);
+        // SELECT
+        for (int base = tid - lane; base < n; base += nthreads) {     // warp-uniform trip count
+            const int i = base + lane;
+            int s = -1;
+            bool ok = false;
+            if (i < n) {
+                s = i < n_carry ? cur[i] : fresh[i - n_carry];
+                ok = owns_footprint(c, rc, s, tag | rc.prio[s]);
+            }
+            __syncwarp();
+            warp_append(i < n && ok, rc.ready, n_ready, s);
+            warp_append(i < n && !ok, nxt, n_next, s);
+        }
         grid.sync();
-        if (tr) { rc.trace[round * 6 + 1] = *(volatile int32_t *)n_ready; rc.trace[round * 6 + 4] = global_ns(); }
-        phase_execute(c, rc, *(volatile int32_t *)n_ready, tid, nthreads);
+        const int nr = *(volatile int32_t *)n_ready;
+        if (tr) { rc.trace[round * 6 + 1] = nr; rc.trace[round * 6 + 4] = global_ns(); }
+        // EXECUTE
+        for (int i = tid; i < nr; i += nthreads) {
+            const int s = rc.ready[i];
+            RngStream rng{rc.key, (uint32_t)c.a.id[s], 0u};
+            agent_transaction<RngStream, false, MAXC_SCALABLE>(c, s, rng);
+        }
         grid.sync();
         if (tr) rc.trace[round * 6 + 5] = global_ns();
         int32_t *tmp = cur; cur = nxt; nxt = tmp;

@@ -58,28 +58,45 @@ __device__ __forceinline__ double py_pow(double x, double y) {
     return ssb_py_pow(x, y, &exact);
 }
 
-// Agent.findWelfare (agent.py:1170-1201)
-__device__ double find_welfare(const DevCtx &c, int s, double sugar_reward, double spice_reward) {
-    const double sm = (double)max(c.a.sugar_metab[s], 0), pm = (double)max(c.a.spice_metab[s], 0);
-    const double total = sm + pm;
-    double sprop = 0, pprop = 0;
-    if (total != 0) { sprop = sm / total; pprop = pm / total; }
-    const double look = c.a.lookahead[s];
-    double ts = (c.a.sugar[s] + sugar_reward) - sm * look;
-    double tp = (c.a.spice[s] + spice_reward) - pm * look;
-    if (ts < 0) ts = 0;
-    if (tp < 0) tp = 0;
-    double welfare = py_pow(ts, sprop) * py_pow(tp, pprop);
-    if ((c.p.flags & SSB_F_TAGPREF) && (c.p.flags & SSB_F_TAGS) && c.p.tag_len > 0) {
-        const int L = c.p.tag_len;
-        c.a.tribe[s] = find_tribe(c, c.a.tags[s]);
-        const int zeroes = L - __popc(c.a.tags[s]);
-        const double fz = (double)zeroes / (double)L, fo = 1 - fz;
-        double pref = sm * fz + pm * fo;
-        if (pref <= 0) pref = 1;
-        welfare = py_pow(ts, (sm / pref) * fz) * py_pow(tp, (pm / pref) * fo);
+// Agent.findWelfare (agent.py:1170-1201).  The per-agent part (holdings, lookahead, exponents)
+// is loaded once into registers; eval() is then pure arithmetic, so the candidate loop of the
+// move ranking issues no dependent loads.
+struct Welfare {
+    double sugar, spice, s_look, p_look, e_s, e_p;
+
+    __device__ __forceinline__ void load(const DevCtx &c, int s) {
+        const double sm = (double)max(c.a.sugar_metab[s], 0), pm = (double)max(c.a.spice_metab[s], 0);
+        const double look = c.a.lookahead[s];
+        sugar = c.a.sugar[s]; spice = c.a.spice[s];
+        s_look = sm * look; p_look = pm * look;
+        const double total = sm + pm;
+        e_s = 0; e_p = 0;
+        if (total != 0) { e_s = sm / total; e_p = pm / total; }
+        if ((c.p.flags & SSB_F_TAGPREF) && (c.p.flags & SSB_F_TAGS) && c.p.tag_len > 0) {
+            // tag preferences replace the exponents (agent.py:1190-1200); findWelfare also
+            // refreshes self.tribe as a side effect (1192)
+            const int L = c.p.tag_len;
+            c.a.tribe[s] = find_tribe(c, c.a.tags[s]);
+            const int zeroes = L - __popc(c.a.tags[s]);
+            const double fz = (double)zeroes / (double)L, fo = 1 - fz;
+            double pref = sm * fz + pm * fo;
+            if (pref <= 0) pref = 1;
+            e_s = (sm / pref) * fz; e_p = (pm / pref) * fo;
+        }
     }
-    return welfare;
+    __device__ __forceinline__ double eval(double sugar_reward, double spice_reward) const {
+        double ts = (sugar + sugar_reward) - s_look;
+        double tp = (spice + spice_reward) - p_look;
+        if (ts < 0) ts = 0;
+        if (tp < 0) tp = 0;
+        return py_pow(ts, e_s) * py_pow(tp, e_p);
+    }
+};
+
+__device__ __forceinline__ double find_welfare(const DevCtx &c, int s, double sugar_reward, double spice_reward) {
+    Welfare w;
+    w.load(c, s);
+    return w.eval(sugar_reward, spice_reward);
 }
 
 // Agent.doDeath (agent.py:296-313) with inheritance policy "none"
@@ -181,62 +198,100 @@ __device__ __forceinline__ int agent_range(const DevCtx &c, int s) {
 
 // rankCellsInRange + findBestCell + moveToBestCell (agent.py:1395-1443, 719-746, 1321-1328).
 // Only the head of the stable sort (agent.py:1479-1490) is needed: the winner is the candidate
-// with the highest welfare, then the smallest distance, then the earliest shuffled position.
+// with the highest welfare, then the smallest distance, then the earliest shuffled position --
+// a strict total order, so candidates can be evaluated in any order.  Loads are batched in
+// chunks of CH independent requests (cells first, then their occupants) to keep many memory
+// requests in flight per thread; the transaction is otherwise a chain of dependent DRAM reads.
 template <class Rng, int MAXC>
 __device__ int move_to_best_cell(const DevCtx &c, int s, Rng &rng) {
+    constexpr int CH = 8;
     const ssb_agents_t &a = c.a;
     const int pos = a.pos[s];
     const int r = agent_range(c, s);
+    const double aggression = fmax(a.aggression[s], 0.0);
+    Welfare w;
+    w.load(c, s);
+    const int my_tribe = a.tribe[s];
     int32_t cells[MAXC];
     uint8_t dists[MAXC];
     const int n = r > 0 ? enumerate_cross<MAXC>(c, pos, r, cells, dists) : 0;
-    const double aggression = fmax(a.aggression[s], 0.0);
     int best = pos;
     if (n > 0) {
-        int hood = 1;   // findNeighborhood (agent.py:1052-1065): live agents in range + self
-        for (int i = 0; i < n; i++) {
-            const int o = c.g.occ[cells[i]];
-            if (o >= 0 && agent_alive(c, o)) hood++;
-        }
-        uint8_t perm[MAXC];
-        for (int i = 0; i < n; i++) perm[i] = (uint8_t)i;
-        shuffle(rng, perm, n);      // random.shuffle(cellsInRange), agent.py:1400-1401
-        // findRetaliatorsInVision (agent.py:1088-1098), only consulted for prey cells
-        double retaliator[27];
-        if (aggression > 0) {
-            for (int i = 0; i < 27; i++) retaliator[i] = -1.0;
-            for (int i = 0; i < n; i++) {
-                const int o = c.g.occ[cells[i]];
-                if (o < 0) continue;
-                const int tr = min(a.tribe[o] + 1, 26);
-                const double w = a.sugar[o] + a.spice[o];
-                if (retaliator[tr] < w) retaliator[tr] = w;
-            }
-        }
-        const double loot = c.p.max_combat_loot;
-        const double my_wealth = a.sugar[s] + a.spice[s];
         const bool polluted = (c.p.flags & SSB_F_POLLUTION) != 0;
         const bool spicy = (c.p.flags & SSB_F_SPICE) != 0;
-        int m = 0, best_dist = 0;
-        double best_welfare = 0;
-        for (int k = 0; k < n; k++) {
-            const int cell = cells[perm[k]], dist = dists[perm[k]];
-            const int prey = c.g.occ[cell];
-            double ps = 0, pp = 0;
-            if (prey >= 0) {
-                // isNeighborValidPrey (agent.py:1309-1314)
-                if (!(aggression > 0 && a.tribe[s] != a.tribe[prey] &&
-                      my_wealth >= a.sugar[prey] + a.spice[prey])) continue;
-                ps = a.sugar[prey]; pp = a.spice[prey];
+        const bool fighter = aggression > 0;
+        // random.shuffle(cellsInRange), agent.py:1400-1401: rank[i] = shuffled position of cell i
+        uint8_t perm[MAXC], rank[MAXC];
+        for (int i = 0; i < n; i++) perm[i] = (uint8_t)i;
+        shuffle(rng, perm, n);
+        for (int k = 0; k < n; k++) rank[perm[k]] = (uint8_t)k;
+        // pass 1: cell contents and occupants
+        int32_t occ_v[MAXC];
+        double gain_s[MAXC], gain_p[MAXC], prey_w[MAXC];
+        int8_t prey_tribe[MAXC];
+        double retaliator[27];
+        if (fighter) for (int i = 0; i < 27; i++) retaliator[i] = -1.0;
+        int hood = 1;   // findNeighborhood (agent.py:1052-1065): live agents in range + self
+        for (int base = 0; base < n; base += CH) {
+            int o[CH], cs[CH], cp[CH];
+            double pl[CH];
+#pragma unroll
+            for (int j = 0; j < CH; j++) {
+                const int i = base + j;
+                const int cell = i < n ? cells[i] : pos;
+                o[j] = c.g.occ[cell];
+                cs[j] = c.g.sugar[cell];
+                cp[j] = spicy ? c.g.spice[cell] : 0;
+                pl[j] = polluted ? c.g.pollution[cell] : 0.0;
             }
-            const double wps = aggression * fmin(loot, ps), wpp = aggression * fmin(loot, pp);
-            const double poll = polluted ? c.g.pollution[cell] : 0.0;
-            const double cell_spice = spicy ? (double)c.g.spice[cell] : 0.0;
-            const double welfare = find_welfare(c, s, ((double)c.g.sugar[cell] + wps) / (1 + poll),
-                                                (cell_spice + wpp) / (1 + poll));
-            if (prey >= 0 && retaliator[min(a.tribe[prey] + 1, 26)] > my_wealth + welfare) continue;
-            if (m == 0 || welfare > best_welfare || (welfare == best_welfare && dist < best_dist)) {
-                best = cell; best_welfare = welfare; best_dist = dist;
+            int ocod[CH], otribe[CH];
+            double osug[CH], ospi[CH];
+#pragma unroll
+            for (int j = 0; j < CH; j++) {
+                const bool has = base + j < n && o[j] >= 0;
+                ocod[j] = has ? a.cod[o[j]] : SSB_ALIVE;
+                osug[j] = has ? a.sugar[o[j]] : 0.0;
+                ospi[j] = has ? a.spice[o[j]] : 0.0;
+                otribe[j] = (has && fighter) ? a.tribe[o[j]] : -1;
+            }
+#pragma unroll
+            for (int j = 0; j < CH; j++) {
+                const int i = base + j;
+                if (i >= n) break;
+                occ_v[i] = o[j];
+                double ps = 0, pp = 0;
+                if (o[j] >= 0) {
+                    if (ocod[j] == SSB_ALIVE && osug[j] >= 0 && ospi[j] >= 0) hood++;
+                    if (fighter) {   // findRetaliatorsInVision (agent.py:1088-1098)
+                        const int tr = min(otribe[j] + 1, 26);
+                        const double ow = osug[j] + ospi[j];
+                        if (retaliator[tr] < ow) retaliator[tr] = ow;
+                        ps = osug[j]; pp = ospi[j];
+                    }
+                }
+                const double loot = c.p.max_combat_loot;
+                const double wps = aggression * fmin(loot, ps), wpp = aggression * fmin(loot, pp);
+                gain_s[i] = ((double)cs[j] + wps) / (1 + pl[j]);
+                gain_p[i] = ((double)cp[j] + wpp) / (1 + pl[j]);
+                prey_w[i] = osug[j] + ospi[j];
+                prey_tribe[i] = (int8_t)otribe[j];
+            }
+        }
+        // pass 2: filters and welfare (agent.py:1412-1436), pure arithmetic
+        const double my_wealth = w.sugar + w.spice;
+        int m = 0, best_dist = 0, best_rank = 0;
+        double best_welfare = 0;
+        for (int i = 0; i < n; i++) {
+            const bool occupied = occ_v[i] >= 0;
+            if (occupied) {   // isNeighborValidPrey (agent.py:1309-1314)
+                if (!(fighter && my_tribe != (int)prey_tribe[i] && my_wealth >= prey_w[i])) continue;
+            }
+            const double welfare = w.eval(gain_s[i], gain_p[i]);
+            if (occupied && retaliator[min((int)prey_tribe[i] + 1, 26)] > my_wealth + welfare) continue;
+            const int dist = dists[i], rk = rank[i];
+            if (m == 0 || welfare > best_welfare ||
+                (welfare == best_welfare && (dist < best_dist || (dist == best_dist && rk < best_rank)))) {
+                best = cells[i]; best_welfare = welfare; best_dist = dist; best_rank = rk;
             }
             m++;
         }
