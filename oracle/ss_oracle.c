@@ -33,7 +33,7 @@
 /* ------------------------------------------------------------------------------------------
  * RNG.  Mode E: CPython's MT19937 (Modules/_randommodule.c genrand_uint32) and the Python
  * level algorithms random._randbelow_with_getrandbits / random.shuffle.
- * Mode S: counter-based words keyed by (seed, timestep, agent id, draw index).
+ * Mode S: counter-based words keyed by (seed, timestep, agent id, call site, draw index).
  * ---------------------------------------------------------------------------------------- */
 typedef struct {
     uint32_t mt[624];
@@ -41,8 +41,11 @@ typedef struct {
     /* mode S */
     int32_t mode;
     uint64_t step_key;
-    uint32_t agent_id, counter;
+    uint32_t agent_id, site, counter;
 } orc_rng_t;
+
+/* call sites of the transaction that draw (agent.py:1401, 560-564, 616, 505-513): one substream each */
+enum { SITE_MOVE = 0, SITE_TAGGING = 1, SITE_TRADING = 2, SITE_REPRODUCTION = 3 };
 
 static uint32_t mt_next(orc_rng_t *r) {
     uint32_t *mt = r->mt, y;
@@ -78,8 +81,8 @@ uint64_t orc_step_key(uint64_t seed, int32_t t) {
     return mix64(seed + 0x9E3779B97F4A7C15ull * (uint64_t)(uint32_t)(t + 1));
 }
 
-static uint32_t stream_word(uint64_t step_key, uint32_t id, uint32_t j) {
-    return (uint32_t)(mix64(step_key ^ (((uint64_t)id << 32) | j)) >> 32);
+static uint32_t stream_word(uint64_t step_key, uint32_t id, uint32_t site, uint32_t j) {
+    return (uint32_t)(mix64(step_key ^ (((uint64_t)id << 32) | ((uint64_t)site << 24) | j)) >> 32);
 }
 
 /* keyed bijection on [0, 2^bits): 4-round balanced Feistel; bits must be even */
@@ -98,8 +101,10 @@ uint32_t orc_priority(uint64_t step_key, uint32_t id, int bits) {
 
 static uint32_t rng_next32(orc_rng_t *r) {
     if (r->mode == SSB_RNG_EXACT) return mt_next(r);
-    return stream_word(r->step_key, r->agent_id, r->counter++);
+    return stream_word(r->step_key, r->agent_id, r->site, r->counter++);
 }
+
+static void rng_at(orc_rng_t *r, uint32_t site) { r->site = site; r->counter = 0; }
 
 static int bit_length(uint32_t n) { int k = 0; while (n) { k++; n >>= 1; } return k; }
 
@@ -304,6 +309,7 @@ static int move_to_best_cell(ctx_t *c, int s) {
         /* random.shuffle(list(cellsInRange.items())) -- shuffle an index permutation */
         int32_t perm[MAX_CAND];
         for (int i = 0; i < n; i++) perm[i] = i;
+        rng_at(c->rng, SITE_MOVE);
         rng_shuffle_i32(c->rng, perm, n);
         /* findRetaliatorsInVision (agent.py:1088-1098): richest visible member per tribe */
         double retaliator[34]; int have[34];
@@ -372,6 +378,7 @@ static void do_tagging(ctx_t *c, int s) {
     if (!(c->p->flags & SSB_F_TAGS) || !(c->p->flags & SSB_F_TAGGING)) return;
     int32_t nb[4];
     neighbours4(c, c->a.pos[s], nb);
+    rng_at(c->rng, SITE_TAGGING);
     rng_shuffle_i32(c->rng, nb, 4);
     for (int i = 0; i < 4; i++) {
         int o = c->g.occ[nb[i]];
@@ -396,6 +403,7 @@ static void do_trading(ctx_t *c, int s) {
         int o = c->g.occ[nb[i]];
         if (o >= 0 && agent_alive(c, o) && a->mrs[o] != a->mrs[s]) traders[n++] = o;
     }
+    rng_at(c->rng, SITE_TRADING);
     rng_shuffle_i32(c->rng, traders, n);
     double sugar_price = 0, spice_price = 0;
     for (int k = 0; k < n; k++) {
@@ -453,6 +461,7 @@ static void do_reproduction(ctx_t *c, int s) {
     if (!agent_alive(c, s) || !is_fertile(c, s)) return;
     int32_t nb[4], own_empty[4];
     neighbours4(c, a->pos[s], nb);
+    rng_at(c->rng, SITE_REPRODUCTION);
     rng_shuffle_i32(c->rng, nb, 4);
     int n_own = empty_neighbours(c, a->pos[s], own_empty);
     for (int k = 0; k < 4; k++) {

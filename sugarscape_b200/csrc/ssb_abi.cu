@@ -197,7 +197,8 @@ int ssb_bind(ssb_engine_t *e, const ssb_grid_t *grid, const ssb_agents_t *agents
         CU(cudaMalloc(&rc.cnt, sizeof(int32_t) * 8));
         CU(cudaMemset(rc.cnt, 0, sizeof(int32_t) * 8));
         int per_sm = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_agent_step_scalable, AGENT_THREADS, 0));
+        CU(cudaFuncSetAttribute(k_agent_step_scalable, cudaFuncAttributeMaxDynamicSharedMemorySize, AGENT_SMEM_BYTES));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_agent_step_scalable, AGENT_THREADS, AGENT_SMEM_BYTES));
         if (per_sm < 1) return fail(e, -3, "cooperative kernel does not fit on an SM");
         e->coop_blocks = per_sm * e->num_sms;
     }
@@ -319,7 +320,7 @@ int ssb_agent_step(ssb_engine_t *e, int32_t t, double prev_mean_wealth, void *st
         RoundCtx rc = e->rc;
         rc.key = step_key(e->p.seed, t);
         void *args[] = {&c, &rc};
-        CU(cudaLaunchCooperativeKernel((void *)k_agent_step_scalable, dim3(e->coop_blocks), dim3(AGENT_THREADS), args, 0, st));
+        CU(cudaLaunchCooperativeKernel((void *)k_agent_step_scalable, dim3(e->coop_blocks), dim3(AGENT_THREADS), args, AGENT_SMEM_BYTES, st));
         LAUNCHED(e);
     }
     if (e->timing) CU(cudaEventRecord(e->ev[2], st));

@@ -25,10 +25,20 @@
 //   conflict rate low, so an agent marks its footprint ~2 times per step instead of ~50.
 //   Marks carry a descending round tag in their high bits: stale marks lose every atomicMin and
 //   are cleared only when the 6-bit tag wraps.
-//   Footprint: the cross of radius r around the agent (cells it may inspect / move to) dilated by
-//   a diamond of radius k = 0 (movement / combat only), 1 (tagging or trading touch the 4
-//   neighbours of the new cell) or 2 (reproduction reads the mate's empty neighbours and places
-//   a child there).  In the x-major grid it is one contiguous y-interval per x-column.
+//   Footprints and the two commit phases.  A transaction has a MOVE part (inspect the cross of
+//   radius r, move, collect, metabolise: touches cross + own cell only) and an INTERACT part
+//   (tagging, trade, reproduction, aging around the NEW cell p': touches the diamond D_k(p'),
+//   k = 1 for tagging / trading, 2 for reproduction, 0 if none of them applies to the agent).
+//     phase 0 agent  marks  M0 = D_k(cross + own cell)   (everything it may ever touch)
+//                    needs  C0 = cross + own cell        -> commits its move part; if it also
+//                           owns D_k(p') (a subset of M0) it finishes in the same round,
+//     phase 1 agent  marks and needs D_k(p')             -> commits the interact part.
+//   An earlier agent that could still touch a cell of C0 (or of D_k(p')) would have its smaller
+//   value there, so owning the set means every earlier interferer has committed; later agents are
+//   kept out by the marks, which always cover whatever the agent may still touch.  Checking only
+//   the 4r + 1 cells of the cross instead of the dilated footprint cuts the conflict rate of
+//   reproduction rule sets by an order of magnitude.
+//   In the x-major grid a footprint is one contiguous y-interval per x-column.
 //   All rounds of a step run inside ONE persistent cooperative kernel (grid.sync between phases).
 #pragma once
 #include <cooperative_groups.h>
@@ -45,17 +55,22 @@ constexpr int MAXC_EXACT = 128;   // up to 4 * 32 candidate cells
 
 __global__ void __launch_bounds__(32, 1) k_agent_step_exact(DevCtx c, uint32_t *mt_global) {
     __shared__ uint32_t mt[625];
+    __shared__ __align__(8) unsigned char scratch_mem[scratch_bytes_per_thread(MAXC_EXACT)];
     for (int i = threadIdx.x; i < 625; i += 32) mt[i] = mt_global[i];
     __syncwarp();
     if (threadIdx.x == 0) {
         RngExact rng{mt};
+        const Scratch sc = make_scratch(scratch_mem, MAXC_EXACT, 1, 0);
         unsigned long long *cn = (unsigned long long *)c.a.counters;
         cn[SSB_C_N_BORN] = 0;
         // random.shuffle(self.agents), sugarscape.py:400
         shuffle(rng, c.a.order, (int)cn[SSB_C_N_LIST]);
         // the list grows while it is iterated: children are appended, visited and skipped
-        for (long long i = 0; i < (long long)((volatile unsigned long long *)cn)[SSB_C_N_LIST]; i++)
-            agent_transaction<RngExact, true, MAXC_EXACT>(c, c.a.order[i], rng);
+        for (long long i = 0; i < (long long)((volatile unsigned long long *)cn)[SSB_C_N_LIST]; i++) {
+            const int s = c.a.order[i];
+            if (transaction_move_phase(c, s, rng, sc, MAXC_EXACT))
+                transaction_interact_phase<RngExact, true>(c, s, rng);
+        }
     }
     __syncwarp();
     for (int i = threadIdx.x; i < 625; i += 32) mt_global[i] = mt[i];
@@ -68,6 +83,8 @@ constexpr int MAXC_SCALABLE = 32;     // 4 * 8 candidate cells; the host refuses
 constexpr int TAG_BITS = 6;
 constexpr int MAX_EPOCHS = 1024;
 constexpr int AGENT_THREADS = 256;
+constexpr int AGENT_SMEM_BYTES = scratch_bytes_per_thread(MAXC_SCALABLE) * AGENT_THREADS;
+constexpr int PHASE1_BIT = 0x40000000;   // list entries: slot | PHASE1_BIT once the move part has committed
 
 struct RoundCtx {
     uint32_t *mark;          // one word per cell
@@ -127,11 +144,11 @@ __device__ __forceinline__ uint32_t round_tag(const DevCtx &c, int round) {
 }
 constexpr int ROUNDS_PER_TAG_EPOCH = (1 << TAG_BITS) - 1;
 
-__device__ __forceinline__ void mark_footprint(const DevCtx &c, const RoundCtx &rc, int s, uint32_t v) {
-    const int pos = c.a.pos[s];
-    if (pos < 0) return;                         // killed earlier this step: nothing to reserve
+// visit the footprint D_k(cross of radius (rx, ry) + centre) column by column; f(column base
+// pointer offset, y) style callbacks are inlined below for the two users
+__device__ __forceinline__ void mark_region(const DevCtx &c, const RoundCtx &rc, int pos, int r, int k, uint32_t v) {
     Footprint f;
-    f.init(c, pos, agent_range(c, s), footprint_dilation(c, s));
+    f.init(c, pos, r, k);
     for (int i = -(f.rx + f.k); i <= f.rx + f.k; i++) {
         const int h = f.half_height(i);
         if (h < 0) continue;
@@ -140,11 +157,9 @@ __device__ __forceinline__ void mark_footprint(const DevCtx &c, const RoundCtx &
     }
 }
 
-__device__ __forceinline__ bool owns_footprint(const DevCtx &c, const RoundCtx &rc, int s, uint32_t v) {
-    const int pos = c.a.pos[s];
-    if (pos < 0) return true;
+__device__ __forceinline__ bool owns_region(const DevCtx &c, const RoundCtx &rc, int pos, int r, int k, uint32_t v) {
     Footprint f;
-    f.init(c, pos, agent_range(c, s), footprint_dilation(c, s));
+    f.init(c, pos, r, k);
     unsigned bad = 0;
     for (int i = -(f.rx + f.k); i <= f.rx + f.k; i++) {
         const int h = f.half_height(i);
@@ -169,9 +184,11 @@ __device__ __forceinline__ void warp_append(bool want, int32_t *list, int32_t *c
 }
 
 // One persistent cooperative kernel per step.
-__global__ void __launch_bounds__(AGENT_THREADS) k_agent_step_scalable(DevCtx c, RoundCtx rc) {
+__global__ void __launch_bounds__(AGENT_THREADS, 2) k_agent_step_scalable(DevCtx c, RoundCtx rc) {
     cg::grid_group grid = cg::this_grid();
     __shared__ int32_t sh_count[MAX_EPOCHS], sh_base[MAX_EPOCHS];
+    extern __shared__ __align__(8) unsigned char scratch_mem[];
+    const Scratch sc = make_scratch(scratch_mem, MAXC_SCALABLE, AGENT_THREADS, threadIdx.x);
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nthreads = gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
@@ -241,32 +258,60 @@ __global__ void __launch_bounds__(AGENT_THREADS) k_agent_step_scalable(DevCtx c,
         const int32_t *fresh = rc.bucketed + e0;
         // MARK
         for (int i = tid; i < n; i += nthreads) {
-            const int s = i < n_carry ? cur[i] : fresh[i - n_carry];
-            mark_footprint(c, rc, s, tag | rc.prio[s]);
+            const int entry = i < n_carry ? cur[i] : fresh[i - n_carry];
+            const int s = entry & ~PHASE1_BIT;
+            const int pos = c.a.pos[s];
+            if (pos < 0) continue;                   // killed earlier this step: nothing to reserve
+            const int k = footprint_dilation(c, s);
+            const int r = (entry & PHASE1_BIT) ? 0 : agent_range(c, s);
+            mark_region(c, rc, pos, r, k, tag | rc.prio[s]);
         }
         grid.sync();
         if (tr) rc.trace[round * 6 + 3] = global_ns();
         // SELECT
         for (int base = tid - lane; base < n; base += nthreads) {     // warp-uniform trip count
             const int i = base + lane;
-            int s = -1;
+            int entry = -1;
             bool ok = false;
             if (i < n) {
-                s = i < n_carry ? cur[i] : fresh[i - n_carry];
-                ok = owns_footprint(c, rc, s, tag | rc.prio[s]);
+                entry = i < n_carry ? cur[i] : fresh[i - n_carry];
+                const int s = entry & ~PHASE1_BIT;
+                const int pos = c.a.pos[s];
+                if (pos < 0) ok = true;
+                else if (entry & PHASE1_BIT) ok = owns_region(c, rc, pos, 0, footprint_dilation(c, s), tag | rc.prio[s]);
+                else ok = owns_region(c, rc, pos, agent_range(c, s), 0, tag | rc.prio[s]);
             }
             __syncwarp();
-            warp_append(i < n && ok, rc.ready, n_ready, s);
-            warp_append(i < n && !ok, nxt, n_next, s);
+            warp_append(i < n && ok, rc.ready, n_ready, entry);
+            warp_append(i < n && !ok, nxt, n_next, entry);
         }
         grid.sync();
         const int nr = *(volatile int32_t *)n_ready;
         if (tr) { rc.trace[round * 6 + 1] = nr; rc.trace[round * 6 + 4] = global_ns(); }
         // EXECUTE
-        for (int i = tid; i < nr; i += nthreads) {
-            const int s = rc.ready[i];
-            RngStream rng{rc.key, (uint32_t)c.a.id[s], 0u};
-            agent_transaction<RngStream, false, MAXC_SCALABLE>(c, s, rng);
+        for (int base = tid - lane; base < nr; base += nthreads) {    // warp-uniform trip count
+            const int i = base + lane;
+            int deferred = -1;
+            if (i < nr) {
+                const int entry = rc.ready[i];
+                const int s = entry & ~PHASE1_BIT;
+                RngStream rng{rc.key, (uint32_t)c.a.id[s], 0u, 0u};
+                if (entry & PHASE1_BIT) {
+                    transaction_interact_phase<RngStream, false>(c, s, rng);
+                } else {
+                    const int k = footprint_dilation(c, s);      // before the move part can age / kill the agent
+                    if (transaction_move_phase(c, s, rng, sc, MAXC_SCALABLE)) {
+                        // the interact part needs D_k(new cell); the marks of this round still
+                        // stand, so it can run right away if the agent owns that diamond too
+                        if (k == 0 || owns_region(c, rc, c.a.pos[s], 0, k, tag | rc.prio[s]))
+                            transaction_interact_phase<RngStream, false>(c, s, rng);
+                        else
+                            deferred = s | PHASE1_BIT;
+                    }
+                }
+            }
+            __syncwarp();
+            warp_append(deferred >= 0, nxt, n_next, deferred);
         }
         grid.sync();
         if (tr) rc.trace[round * 6 + 5] = global_ns();

@@ -5,7 +5,8 @@
 //   restated on top of genrand_uint32 (Modules/_randommodule.c).  State lives in shared memory
 //   of the single ordered CTA.
 // Mode S: counter-based substreams.  Word j of agent `id` in timestep t is
-//   mix64(step_key(seed, t) ^ (id << 32 | j)) >> 32 ; the processing order of a step is the
+//   mix64(step_key(seed, t) ^ (id << 32 | site << 24 | j)) >> 32 for the j-th word drawn at call
+//   site `site` of the transaction; the processing order of a step is the
 //   ascending order of a keyed 4-round Feistel bijection of the agent id.
 #pragma once
 #include <stdint.h>
@@ -58,6 +59,7 @@ struct RngExact {
         mt[623] = mt[396] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
         mt[624] = 0;
     }
+    __device__ __forceinline__ void at(uint32_t) {}      // one global stream: sites are not separated
     __device__ uint32_t next() {
         if (mt[624] >= 624u) twist();
         uint32_t y = mt[mt[624]++];
@@ -70,11 +72,17 @@ struct RngExact {
 };
 
 // ---- mode S -------------------------------------------------------------------------------
+// Call sites of the agent transaction that draw random numbers (reference agent.py:1401, 560-564,
+// 616, 505-513).  Each site of each agent has its own substream, so the two commit phases of the
+// scalable kernel need no RNG state between them.
+enum { SITE_MOVE = 0, SITE_TAGGING = 1, SITE_TRADING = 2, SITE_REPRODUCTION = 3 };
+
 struct RngStream {
     uint64_t key;
-    uint32_t id, ctr;
-    __device__ uint32_t next() {
-        return (uint32_t)(mix64(key ^ (((uint64_t)id << 32) | ctr++)) >> 32);
+    uint32_t id, site, ctr;
+    __device__ __forceinline__ void at(uint32_t site_) { site = site_; ctr = 0; }
+    __device__ __forceinline__ uint32_t next() {
+        return (uint32_t)(mix64(key ^ (((uint64_t)id << 32) | ((uint64_t)site << 24) | ctr++)) >> 32);
     }
 };
 

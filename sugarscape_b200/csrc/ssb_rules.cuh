@@ -35,6 +35,31 @@ struct DevCtx {
 };
 
 __device__ __forceinline__ int wrapi(int v, int n) { v %= n; return v < 0 ? v + n : v; }
+// wrap for |offset| < n (every neighbourhood access on maps at least as wide as the range)
+__device__ __forceinline__ int wrap1(int v, int n) { return v < 0 ? v + n : (v >= n ? v - n : v); }
+
+// Per-thread scratch of the move ranking.  It lives in SHARED memory, strided by the block size
+// (element i of thread t at [i * stride + t]): with hundreds of resident threads per SM, per-thread
+// local arrays of this size thrash L1 and turn every access into an L2 round trip.
+struct Scratch {
+    int32_t *cells;      // candidate cell index
+    uint8_t *perm, *rank, *dist;
+    int stride;
+    __device__ __forceinline__ int32_t &cell(int i) const { return cells[i * stride]; }
+    __device__ __forceinline__ uint8_t &pm(int i) const { return perm[i * stride]; }
+    __device__ __forceinline__ uint8_t &rk(int i) const { return rank[i * stride]; }
+    __device__ __forceinline__ uint8_t &ds(int i) const { return dist[i * stride]; }
+};
+__host__ __device__ constexpr int scratch_bytes_per_thread(int maxc) { return maxc * 7; }
+__device__ __forceinline__ Scratch make_scratch(unsigned char *smem, int maxc, int nthreads, int tid) {
+    Scratch sc;
+    sc.cells = reinterpret_cast<int32_t *>(smem) + tid;
+    sc.perm = smem + (size_t)maxc * nthreads * 4 + tid;
+    sc.rank = smem + (size_t)maxc * nthreads * 5 + tid;
+    sc.dist = smem + (size_t)maxc * nthreads * 6 + tid;
+    sc.stride = nthreads;
+    return sc;
+}
 
 // Agent.isAlive (agent.py:1221-1224)
 __device__ __forceinline__ bool agent_alive(const DevCtx &c, int s) {
@@ -158,35 +183,32 @@ __device__ __forceinline__ void collect(const DevCtx &c, int s, int pos) {
 }
 
 // Candidate cells of Agent.findCellsInRange (agent.py:766-779) in the dictionary insertion
-// order produced by Environment.findCardinalCellRanges (environment.py:111-122): per distance d
-// the (up to) four cells sorted by the time they were inserted -- SURVEY.md Appendix A.5.
-template <int MAXC>
-__device__ int enumerate_cross(const DevCtx &c, int pos, int r, int32_t *cells, uint8_t *dists) {
-    const int W = c.p.width, H = c.p.height, x = pos / H, y = pos - x * H;
-    const long long self_key = (long long)x * H + y;
+// order produced by Environment.findCardinalCellRanges (environment.py:111-122) -- SURVEY.md
+// Appendix A.5.  Per distance d the (up to) four cells appear in the order in which the table
+// builder inserted them: the west and north cells were inserted when THEY were the source cell
+// (time x'*H + y'), the east and south cells when this cell was the source.  That gives
+//   W, N, E, S in the interior;  N, E, S, W if x < d;  W, E, S, N if y < d;  E, S, N, W if both;
+// when 2d equals the width (height) the east and west (north and south) cells coincide and the
+// single entry sits at the earlier of the two positions.
+__device__ int enumerate_cross(const DevCtx &c, int x, int y, int r, const Scratch &sc, int maxc) {
+    const int W = c.p.width, H = c.p.height;
     int n = 0;
-    for (int d = 1; d <= r; d++) {
-        long long key[4];
-        int32_t cell[4];
-        int m = 0;
-        if (d <= c.max_dx) {
-            const int xw = wrapi(x - d, W), xe = wrapi(x + d, W);
-            key[m] = ((long long)xw * H + y) * 4; cell[m++] = xw * H + y;                 // west
-            if (xe != xw) { key[m] = self_key * 4 + 1; cell[m++] = xe * H + y; }          // east
-            else if (self_key < (long long)xw * H + y) key[m - 1] = self_key * 4 + 1;
-        }
-        if (d <= c.max_dy) {
-            const int yn = wrapi(y - d, H), ys = wrapi(y + d, H);
-            key[m] = ((long long)x * H + yn) * 4; cell[m++] = x * H + yn;                 // north
-            if (ys != yn) { key[m] = self_key * 4 + 2; cell[m++] = x * H + ys; }          // south
-            else if (self_key < (long long)x * H + yn) key[m - 1] = self_key * 4 + 2;
-        }
-        for (int i = 1; i < m; i++)
-            for (int j = i; j > 0 && key[j - 1] > key[j]; j--) {
-                long long tk = key[j]; key[j] = key[j - 1]; key[j - 1] = tk;
-                int32_t tc = cell[j]; cell[j] = cell[j - 1]; cell[j - 1] = tc;
-            }
-        for (int i = 0; i < m && n < MAXC; i++) { cells[n] = cell[i]; dists[n++] = (uint8_t)d; }
+    for (int d = 1; d <= r && n + 4 <= maxc; d++) {
+        const bool has_x = d <= c.max_dx, has_y = d <= c.max_dy;
+        const bool wx = x < d, wy = y < d;                  // west / north neighbour wraps around
+        const int xw = wx ? x - d + W : x - d, xe = x + d >= W ? x + d - W : x + d;
+        const int yn = wy ? y - d + H : y - d, ys = y + d >= H ? y + d - H : y + d;
+        const bool one_x = xw == xe, one_y = yn == ys;      // 2d == W / 2d == H
+        const int west = xw * H + y, east = xe * H + y, north = x * H + yn, south = x * H + ys;
+        // slot order: [W if !wx] [N if !wy] [E] [S] [N if wy] [W if wx]
+        const int n0 = n;
+        if (has_x && !wx) sc.cell(n++) = west;
+        if (has_y && !wy) sc.cell(n++) = north;
+        if (has_x && !(one_x && !wx)) sc.cell(n++) = east;   // a coinciding west already took the earlier slot
+        if (has_y && !(one_y && !wy)) sc.cell(n++) = south;
+        if (has_y && wy && !one_y) sc.cell(n++) = north;
+        if (has_x && wx && !one_x) sc.cell(n++) = west;
+        for (int i = n0; i < n; i++) sc.ds(i) = (uint8_t)d;
     }
     return n;
 }
@@ -201,48 +223,65 @@ __device__ __forceinline__ int agent_range(const DevCtx &c, int s) {
 // with the highest welfare, then the smallest distance, then the earliest shuffled position --
 // a strict total order, so candidates can be evaluated in any order.  Loads are batched in
 // chunks of CH independent requests (cells first, then their occupants) to keep many memory
-// requests in flight per thread; the transaction is otherwise a chain of dependent DRAM reads.
-template <class Rng, int MAXC>
-__device__ int move_to_best_cell(const DevCtx &c, int s, Rng &rng) {
+// requests in flight per thread.
+template <class Rng>
+__device__ int move_to_best_cell(const DevCtx &c, int s, Rng &rng, const Scratch &sc, int maxc) {
     constexpr int CH = 8;
     const ssb_agents_t &a = c.a;
     const int pos = a.pos[s];
+    const int H = c.p.height, x = pos / H, y = pos - x * H;
     const int r = agent_range(c, s);
     const double aggression = fmax(a.aggression[s], 0.0);
     Welfare w;
     w.load(c, s);
     const int my_tribe = a.tribe[s];
-    int32_t cells[MAXC];
-    uint8_t dists[MAXC];
-    const int n = r > 0 ? enumerate_cross<MAXC>(c, pos, r, cells, dists) : 0;
+    const int n = r > 0 ? enumerate_cross(c, x, y, r, sc, maxc) : 0;
     int best = pos;
     if (n > 0) {
         const bool polluted = (c.p.flags & SSB_F_POLLUTION) != 0;
         const bool spicy = (c.p.flags & SSB_F_SPICE) != 0;
         const bool fighter = aggression > 0;
         // random.shuffle(cellsInRange), agent.py:1400-1401: rank[i] = shuffled position of cell i
-        uint8_t perm[MAXC], rank[MAXC];
-        for (int i = 0; i < n; i++) perm[i] = (uint8_t)i;
-        shuffle(rng, perm, n);
-        for (int k = 0; k < n; k++) rank[perm[k]] = (uint8_t)k;
-        // pass 1: cell contents and occupants
-        int32_t occ_v[MAXC];
-        double gain_s[MAXC], gain_p[MAXC], prey_w[MAXC];
-        int8_t prey_tribe[MAXC];
+        rng.at(SITE_MOVE);
+        for (int i = 0; i < n; i++) sc.pm(i) = (uint8_t)i;
+        for (int i = n - 1; i >= 1; i--) {
+            const uint32_t j = rand_below(rng, (uint32_t)i + 1u);
+            const uint8_t t = sc.pm(i); sc.pm(i) = sc.pm(j); sc.pm(j) = t;
+        }
+        for (int k = 0; k < n; k++) sc.rk(sc.pm(k)) = (uint8_t)k;
+        const double loot = c.p.max_combat_loot;
+        const double my_wealth = w.sugar + w.spice;
+        // findRetaliatorsInVision (agent.py:1088-1098) needs every occupant before any prey cell
+        // can be judged: fighters take one extra pass over the occupants
         double retaliator[27];
-        if (fighter) for (int i = 0; i < 27; i++) retaliator[i] = -1.0;
+        if (fighter) {
+            for (int i = 0; i < 27; i++) retaliator[i] = -1.0;
+            for (int base = 0; base < n; base += CH) {
+                int o[CH];
+#pragma unroll
+                for (int j = 0; j < CH; j++) o[j] = base + j < n ? c.g.occ[sc.cell(base + j)] : -1;
+#pragma unroll
+                for (int j = 0; j < CH; j++) {
+                    if (o[j] < 0) continue;
+                    const int tr = min(a.tribe[o[j]] + 1, 26);
+                    const double ow = a.sugar[o[j]] + a.spice[o[j]];
+                    if (retaliator[tr] < ow) retaliator[tr] = ow;
+                }
+            }
+        }
         int hood = 1;   // findNeighborhood (agent.py:1052-1065): live agents in range + self
+        int m = 0, best_dist = 0, best_rank = 0;
+        double best_welfare = 0;
         for (int base = 0; base < n; base += CH) {
-            int o[CH], cs[CH], cp[CH];
+            int cell[CH], o[CH], cs[CH], cp[CH];
             double pl[CH];
 #pragma unroll
             for (int j = 0; j < CH; j++) {
-                const int i = base + j;
-                const int cell = i < n ? cells[i] : pos;
-                o[j] = c.g.occ[cell];
-                cs[j] = c.g.sugar[cell];
-                cp[j] = spicy ? c.g.spice[cell] : 0;
-                pl[j] = polluted ? c.g.pollution[cell] : 0.0;
+                cell[j] = base + j < n ? sc.cell(base + j) : pos;
+                o[j] = c.g.occ[cell[j]];
+                cs[j] = c.g.sugar[cell[j]];
+                cp[j] = spicy ? c.g.spice[cell[j]] : 0;
+                pl[j] = polluted ? c.g.pollution[cell[j]] : 0.0;
             }
             int ocod[CH], otribe[CH];
             double osug[CH], ospi[CH];
@@ -258,42 +297,24 @@ __device__ int move_to_best_cell(const DevCtx &c, int s, Rng &rng) {
             for (int j = 0; j < CH; j++) {
                 const int i = base + j;
                 if (i >= n) break;
-                occ_v[i] = o[j];
+                const bool occupied = o[j] >= 0;
                 double ps = 0, pp = 0;
-                if (o[j] >= 0) {
+                if (occupied) {
                     if (ocod[j] == SSB_ALIVE && osug[j] >= 0 && ospi[j] >= 0) hood++;
-                    if (fighter) {   // findRetaliatorsInVision (agent.py:1088-1098)
-                        const int tr = min(otribe[j] + 1, 26);
-                        const double ow = osug[j] + ospi[j];
-                        if (retaliator[tr] < ow) retaliator[tr] = ow;
-                        ps = osug[j]; pp = ospi[j];
-                    }
+                    // isNeighborValidPrey (agent.py:1309-1314)
+                    if (!(fighter && my_tribe != otribe[j] && my_wealth >= osug[j] + ospi[j])) continue;
+                    ps = osug[j]; pp = ospi[j];
                 }
-                const double loot = c.p.max_combat_loot;
                 const double wps = aggression * fmin(loot, ps), wpp = aggression * fmin(loot, pp);
-                gain_s[i] = ((double)cs[j] + wps) / (1 + pl[j]);
-                gain_p[i] = ((double)cp[j] + wpp) / (1 + pl[j]);
-                prey_w[i] = osug[j] + ospi[j];
-                prey_tribe[i] = (int8_t)otribe[j];
+                const double welfare = w.eval(((double)cs[j] + wps) / (1 + pl[j]), ((double)cp[j] + wpp) / (1 + pl[j]));
+                if (occupied && retaliator[min(otribe[j] + 1, 26)] > my_wealth + welfare) continue;
+                const int dist = sc.ds(i), rk = sc.rk(i);
+                if (m == 0 || welfare > best_welfare ||
+                    (welfare == best_welfare && (dist < best_dist || (dist == best_dist && rk < best_rank)))) {
+                    best = cell[j]; best_welfare = welfare; best_dist = dist; best_rank = rk;
+                }
+                m++;
             }
-        }
-        // pass 2: filters and welfare (agent.py:1412-1436), pure arithmetic
-        const double my_wealth = w.sugar + w.spice;
-        int m = 0, best_dist = 0, best_rank = 0;
-        double best_welfare = 0;
-        for (int i = 0; i < n; i++) {
-            const bool occupied = occ_v[i] >= 0;
-            if (occupied) {   // isNeighborValidPrey (agent.py:1309-1314)
-                if (!(fighter && my_tribe != (int)prey_tribe[i] && my_wealth >= prey_w[i])) continue;
-            }
-            const double welfare = w.eval(gain_s[i], gain_p[i]);
-            if (occupied && retaliator[min((int)prey_tribe[i] + 1, 26)] > my_wealth + welfare) continue;
-            const int dist = dists[i], rk = rank[i];
-            if (m == 0 || welfare > best_welfare ||
-                (welfare == best_welfare && (dist < best_dist || (dist == best_dist && rk < best_rank)))) {
-                best = cells[i]; best_welfare = welfare; best_dist = dist; best_rank = rk;
-            }
-            m++;
         }
         if (m == 0) { best = pos; m = 1; }
         a.n_neighborhood[s] = hood;
@@ -322,6 +343,7 @@ template <class Rng>
 __device__ void do_tagging(const DevCtx &c, int s, Rng &rng) {
     int32_t nb[4];
     neighbours4(c, c.a.pos[s], nb);
+    rng.at(SITE_TAGGING);
     shuffle(rng, nb, 4);
     for (int i = 0; i < 4; i++) {
         const int o = c.g.occ[nb[i]];
@@ -347,6 +369,7 @@ __device__ void do_trading(const DevCtx &c, int s, Rng &rng) {
         const int o = c.g.occ[nb[i]];
         if (o >= 0 && agent_alive(c, o) && a.mrs[o] != a.mrs[s]) traders[n++] = o;
     }
+    rng.at(SITE_TRADING);
     shuffle(rng, traders, n);
     double sugar_price = 0, spice_price = 0;
     for (int k = 0; k < n; k++) {
@@ -422,6 +445,7 @@ __device__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
     if (!agent_alive(c, s) || !is_fertile(c, s)) return;
     int32_t nb[4], own_empty[4];
     neighbours4(c, a.pos[s], nb);
+    rng.at(SITE_REPRODUCTION);
     shuffle(rng, nb, 4);
     const int n_own = empty_neighbours(c, a.pos[s], own_empty);
     unsigned long long *cn = (unsigned long long *)a.counters;
@@ -501,14 +525,18 @@ __device__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
     }
 }
 
-// Agent.doTimestep (agent.py:568-598)
-template <class Rng, bool EXACT, int MAXC>
-__device__ void agent_transaction(const DevCtx &c, int s, Rng &rng) {
+// Agent.doTimestep (agent.py:568-598), split where the scalable kernel may have to wait for a
+// second reservation (ssb_agent_step.cuh):
+//   move phase      lastSugar/lastSpice, moveToBestCell, collect, (universal income), metabolism
+//   interact phase  tagging, trading, reproduction, aging, happiness
+// Returns from the move phase: false if the agent is done for this step (it was skipped or died).
+template <class Rng>
+__device__ bool transaction_move_phase(const DevCtx &c, int s, Rng &rng, const Scratch &sc, int maxc) {
     const ssb_agents_t &a = c.a;
-    if (!agent_alive(c, s) || a.last_moved[s] == c.t) return;
+    if (!agent_alive(c, s) || a.last_moved[s] == c.t) return false;
     a.last_sugar[s] = a.sugar[s];
     a.last_spice[s] = a.spice[s];
-    const int pos = move_to_best_cell<Rng, MAXC>(c, s, rng);
+    const int pos = move_to_best_cell(c, s, rng, sc, maxc);
     collect(c, s, pos);
     // doMetabolism (agent.py:485-498) + consumption pollution (cell.py:27-40)
     const double sm = (double)max(a.sugar_metab[s], 0), pm = (double)max(a.spice_metab[s], 0);
@@ -523,8 +551,14 @@ __device__ void agent_transaction(const DevCtx &c, int s, Rng &rng) {
     }
     if (sugar < 0 || spice < 0 || (sugar <= 0 && sm > 0) || (spice <= 0 && pm > 0)) {
         do_death(c, s, SSB_STARVATION);
-        return;
+        return false;
     }
+    return true;
+}
+
+template <class Rng, bool EXACT>
+__device__ void transaction_interact_phase(const DevCtx &c, int s, Rng &rng) {
+    const ssb_agents_t &a = c.a;
     if ((c.p.flags & SSB_F_TAGS) && (c.p.flags & SSB_F_TAGGING)) do_tagging(c, s, rng);
     if (c.p.flags & SSB_F_TRADE) do_trading(c, s, rng);
     if (c.p.flags & SSB_F_REPRO) do_reproduction<Rng, EXACT>(c, s, rng);
