@@ -55,25 +55,29 @@ constexpr int MAXC_EXACT = 128;   // up to 4 * 32 candidate cells
 
 __global__ void __launch_bounds__(32, 1) k_agent_step_exact(DevCtx c, uint32_t *mt_global) {
     __shared__ uint32_t mt[625];
-    __shared__ __align__(8) unsigned char scratch_mem[scratch_bytes_per_thread(MAXC_EXACT)];
-    for (int i = threadIdx.x; i < 625; i += 32) mt[i] = mt_global[i];
+    __shared__ __align__(8) unsigned char scratch_mem[warp_scratch_bytes(MAXC_EXACT)];
+    const int lane = threadIdx.x;
+    for (int i = lane; i < 625; i += 32) mt[i] = mt_global[i];
     __syncwarp();
-    if (threadIdx.x == 0) {
-        RngExact rng{mt};
-        const Scratch sc = make_scratch(scratch_mem, MAXC_EXACT, 1, 0);
-        unsigned long long *cn = (unsigned long long *)c.a.counters;
+    RngExact rng{mt};
+    const WarpScratch ws = make_warp_scratch(scratch_mem, MAXC_EXACT);
+    volatile unsigned long long *cn = (volatile unsigned long long *)c.a.counters;
+    if (lane == 0) {
         cn[SSB_C_N_BORN] = 0;
-        // random.shuffle(self.agents), sugarscape.py:400
-        shuffle(rng, c.a.order, (int)cn[SSB_C_N_LIST]);
-        // the list grows while it is iterated: children are appended, visited and skipped
-        for (long long i = 0; i < (long long)((volatile unsigned long long *)cn)[SSB_C_N_LIST]; i++) {
-            const int s = c.a.order[i];
-            if (transaction_move_phase(c, s, rng, sc, MAXC_EXACT))
-                transaction_interact_phase<RngExact, true>(c, s, rng);
-        }
+        shuffle(rng, c.a.order, (int)cn[SSB_C_N_LIST]);        // random.shuffle(self.agents), sugarscape.py:400
     }
     __syncwarp();
-    for (int i = threadIdx.x; i < 625; i += 32) mt_global[i] = mt[i];
+    // the list grows while it is iterated: children are appended, visited and skipped
+    for (long long i = 0;; i++) {
+        const long long n_list = __shfl_sync(0xffffffffu, (long long)cn[SSB_C_N_LIST], 0);
+        if (i >= n_list) break;
+        const int s = c.a.order[i];
+        const bool go_on = transaction_move_phase(c, s, rng, ws, MAXC_EXACT);
+        if (go_on && lane == 0) transaction_interact_phase<RngExact, true>(c, s, rng);
+        __threadfence_block();
+        __syncwarp();
+    }
+    for (int i = lane; i < 625; i += 32) mt_global[i] = mt[i];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -83,7 +87,8 @@ constexpr int MAXC_SCALABLE = 32;     // 4 * 8 candidate cells; the host refuses
 constexpr int TAG_BITS = 6;
 constexpr int MAX_EPOCHS = 1024;
 constexpr int AGENT_THREADS = 256;
-constexpr int AGENT_SMEM_BYTES = scratch_bytes_per_thread(MAXC_SCALABLE) * AGENT_THREADS;
+constexpr int AGENT_WARPS = AGENT_THREADS / 32;
+constexpr int AGENT_SMEM_BYTES = warp_scratch_bytes(MAXC_SCALABLE) * AGENT_WARPS;
 constexpr int PHASE1_BIT = 0x40000000;   // list entries: slot | PHASE1_BIT once the move part has committed
 
 struct RoundCtx {
@@ -144,32 +149,31 @@ __device__ __forceinline__ uint32_t round_tag(const DevCtx &c, int round) {
 }
 constexpr int ROUNDS_PER_TAG_EPOCH = (1 << TAG_BITS) - 1;
 
-// visit the footprint D_k(cross of radius (rx, ry) + centre) column by column; f(column base
-// pointer offset, y) style callbacks are inlined below for the two users
-__device__ __forceinline__ void mark_region(const DevCtx &c, const RoundCtx &rc, int pos, int r, int k, uint32_t v) {
+// The footprint D_k(cross of radius (rx, ry) + centre), visited by a whole warp: one x-column per
+// iteration, the lanes cover its y-interval (at most 2 (ry + k) + 1 <= 21 cells).
+__device__ __forceinline__ void warp_mark_region(const DevCtx &c, const RoundCtx &rc, int pos, int r, int k, uint32_t v) {
+    const int lane = threadIdx.x & 31;
     Footprint f;
     f.init(c, pos, r, k);
     for (int i = -(f.rx + f.k); i <= f.rx + f.k; i++) {
         const int h = f.half_height(i);
-        if (h < 0) continue;
         uint32_t *col = rc.mark + (size_t)wrapi(f.x + i, f.W) * f.H;
-        for (int j = -h; j <= h; j++) atomicMin(col + wrapi(f.y + j, f.H), v);
+        for (int j = lane - h; j <= h; j += 32) atomicMin(col + wrapi(f.y + j, f.H), v);
     }
 }
 
-__device__ __forceinline__ bool owns_region(const DevCtx &c, const RoundCtx &rc, int pos, int r, int k, uint32_t v) {
+// true (on every lane) iff every cell of the region holds v
+__device__ __forceinline__ bool warp_owns_region(const DevCtx &c, const RoundCtx &rc, int pos, int r, int k, uint32_t v) {
+    const int lane = threadIdx.x & 31;
     Footprint f;
     f.init(c, pos, r, k);
     unsigned bad = 0;
     for (int i = -(f.rx + f.k); i <= f.rx + f.k; i++) {
         const int h = f.half_height(i);
-        if (h < 0) continue;
         const uint32_t *col = rc.mark + (size_t)wrapi(f.x + i, f.W) * f.H;
-        // independent loads, no early exit inside a column: keeps the requests in flight
-        for (int j = -h; j <= h; j++) bad |= __ldcg(col + wrapi(f.y + j, f.H)) ^ v;
-        if (bad) return false;
+        for (int j = lane - h; j <= h; j += 32) bad |= __ldcg(col + wrapi(f.y + j, f.H)) ^ v;
     }
-    return true;
+    return !__any_sync(0xffffffffu, bad != 0);
 }
 
 // warp-aggregated append: every lane of the warp calls this (full mask)
@@ -188,7 +192,9 @@ __global__ void __launch_bounds__(AGENT_THREADS, 2) k_agent_step_scalable(DevCtx
     cg::grid_group grid = cg::this_grid();
     __shared__ int32_t sh_count[MAX_EPOCHS], sh_base[MAX_EPOCHS];
     extern __shared__ __align__(8) unsigned char scratch_mem[];
-    const Scratch sc = make_scratch(scratch_mem, MAXC_SCALABLE, AGENT_THREADS, threadIdx.x);
+    const WarpScratch ws = make_warp_scratch(scratch_mem + (threadIdx.x >> 5) * warp_scratch_bytes(MAXC_SCALABLE), MAXC_SCALABLE);
+    const int warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nthreads = gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
@@ -256,62 +262,56 @@ __global__ void __launch_bounds__(AGENT_THREADS, 2) k_agent_step_scalable(DevCtx
         if (tr) { rc.trace[round * 6 + 0] = n; rc.trace[round * 6 + 2] = global_ns(); }
         const uint32_t tag = round_tag(c, round);
         const int32_t *fresh = rc.bucketed + e0;
-        // MARK
-        for (int i = tid; i < n; i += nthreads) {
+        // MARK: one agent per warp, lanes spread over the footprint cells
+        for (int i = warp_id; i < n; i += n_warps) {
             const int entry = i < n_carry ? cur[i] : fresh[i - n_carry];
             const int s = entry & ~PHASE1_BIT;
             const int pos = c.a.pos[s];
             if (pos < 0) continue;                   // killed earlier this step: nothing to reserve
             const int k = footprint_dilation(c, s);
             const int r = (entry & PHASE1_BIT) ? 0 : agent_range(c, s);
-            mark_region(c, rc, pos, r, k, tag | rc.prio[s]);
+            warp_mark_region(c, rc, pos, r, k, tag | rc.prio[s]);
         }
         grid.sync();
         if (tr) rc.trace[round * 6 + 3] = global_ns();
         // SELECT
-        for (int base = tid - lane; base < n; base += nthreads) {     // warp-uniform trip count
-            const int i = base + lane;
-            int entry = -1;
-            bool ok = false;
-            if (i < n) {
-                entry = i < n_carry ? cur[i] : fresh[i - n_carry];
-                const int s = entry & ~PHASE1_BIT;
-                const int pos = c.a.pos[s];
-                if (pos < 0) ok = true;
-                else if (entry & PHASE1_BIT) ok = owns_region(c, rc, pos, 0, footprint_dilation(c, s), tag | rc.prio[s]);
-                else ok = owns_region(c, rc, pos, agent_range(c, s), 0, tag | rc.prio[s]);
+        for (int i = warp_id; i < n; i += n_warps) {
+            const int entry = i < n_carry ? cur[i] : fresh[i - n_carry];
+            const int s = entry & ~PHASE1_BIT;
+            const int pos = c.a.pos[s];
+            bool ok = true;
+            if (pos >= 0) {
+                if (entry & PHASE1_BIT) ok = warp_owns_region(c, rc, pos, 0, footprint_dilation(c, s), tag | rc.prio[s]);
+                else ok = warp_owns_region(c, rc, pos, agent_range(c, s), 0, tag | rc.prio[s]);
             }
-            __syncwarp();
-            warp_append(i < n && ok, rc.ready, n_ready, entry);
-            warp_append(i < n && !ok, nxt, n_next, entry);
+            if (lane == 0) {
+                if (ok) rc.ready[atomicAdd(n_ready, 1)] = entry;
+                else nxt[atomicAdd(n_next, 1)] = entry;
+            }
         }
         grid.sync();
         const int nr = *(volatile int32_t *)n_ready;
         if (tr) { rc.trace[round * 6 + 1] = nr; rc.trace[round * 6 + 4] = global_ns(); }
-        // EXECUTE
-        for (int base = tid - lane; base < nr; base += nthreads) {    // warp-uniform trip count
-            const int i = base + lane;
-            int deferred = -1;
-            if (i < nr) {
-                const int entry = rc.ready[i];
-                const int s = entry & ~PHASE1_BIT;
-                RngStream rng{rc.key, (uint32_t)c.a.id[s], 0u, 0u};
-                if (entry & PHASE1_BIT) {
-                    transaction_interact_phase<RngStream, false>(c, s, rng);
-                } else {
-                    const int k = footprint_dilation(c, s);      // before the move part can age / kill the agent
-                    if (transaction_move_phase(c, s, rng, sc, MAXC_SCALABLE)) {
-                        // the interact part needs D_k(new cell); the marks of this round still
-                        // stand, so it can run right away if the agent owns that diamond too
-                        if (k == 0 || owns_region(c, rc, c.a.pos[s], 0, k, tag | rc.prio[s]))
-                            transaction_interact_phase<RngStream, false>(c, s, rng);
-                        else
-                            deferred = s | PHASE1_BIT;
+        // EXECUTE: one transaction per warp
+        for (int i = warp_id; i < nr; i += n_warps) {
+            const int entry = rc.ready[i];
+            const int s = entry & ~PHASE1_BIT;
+            RngStream rng{rc.key, (uint32_t)c.a.id[s], 0u, 0u, nullptr};
+            if (entry & PHASE1_BIT) {
+                if (lane == 0) transaction_interact_phase<RngStream, false>(c, s, rng);
+            } else {
+                const int k = footprint_dilation(c, s);      // before the transaction can age / kill the agent
+                if (transaction_move_phase(c, s, rng, ws, MAXC_SCALABLE)) {
+                    // the interact part needs D_k(new cell); the marks of this round still stand,
+                    // so it runs right away if the agent owns that diamond too
+                    const bool now = k == 0 || warp_owns_region(c, rc, c.a.pos[s], 0, k, tag | rc.prio[s]);
+                    if (lane == 0) {
+                        if (now) transaction_interact_phase<RngStream, false>(c, s, rng);
+                        else nxt[atomicAdd(n_next, 1)] = s | PHASE1_BIT;
                     }
                 }
             }
             __syncwarp();
-            warp_append(deferred >= 0, nxt, n_next, deferred);
         }
         grid.sync();
         if (tr) rc.trace[round * 6 + 5] = global_ns();

@@ -60,6 +60,8 @@ struct RngExact {
         mt[624] = 0;
     }
     __device__ __forceinline__ void at(uint32_t) {}      // one global stream: sites are not separated
+    __device__ __forceinline__ void prefetch(uint32_t *, int) {}
+    __device__ __forceinline__ void end_prefetch() {}
     __device__ uint32_t next() {
         if (mt[624] >= 624u) twist();
         uint32_t y = mt[mt[624]++];
@@ -80,9 +82,21 @@ enum { SITE_MOVE = 0, SITE_TAGGING = 1, SITE_TRADING = 2, SITE_REPRODUCTION = 3 
 struct RngStream {
     uint64_t key;
     uint32_t id, site, ctr;
-    __device__ __forceinline__ void at(uint32_t site_) { site = site_; ctr = 0; }
+    const uint32_t *pre;     // words 0..63 of the current site, computed by the whole warp
+    __device__ __forceinline__ uint32_t word(uint32_t j) const {
+        return (uint32_t)(mix64(key ^ (((uint64_t)id << 32) | ((uint64_t)site << 24) | j)) >> 32);
+    }
+    __device__ __forceinline__ void at(uint32_t site_) { site = site_; ctr = 0; pre = nullptr; }
+    // all 32 lanes: fill buf[0..63] with the first 64 words of the current site
+    __device__ __forceinline__ void prefetch(uint32_t *buf, int lane) {
+        buf[lane] = word((uint32_t)lane);
+        buf[lane + 32] = word((uint32_t)lane + 32u);
+        pre = buf;
+    }
+    __device__ __forceinline__ void end_prefetch() { pre = nullptr; }
     __device__ __forceinline__ uint32_t next() {
-        return (uint32_t)(mix64(key ^ (((uint64_t)id << 32) | ((uint64_t)site << 24) | ctr++)) >> 32);
+        const uint32_t j = ctr++;
+        return (pre && j < 64u) ? pre[j] : word(j);
     }
 };
 

@@ -1,11 +1,12 @@
 // ssb_rules.cuh -- one agent's timestep transaction on the device SoA.
 //
 // Restates reference agent.py:568-598 (Agent.doTimestep) and what it calls; each function cites
-// the lines it follows.  One thread runs one transaction.  In mode E the single ordered CTA calls
-// it for every agent in list order; in mode S every agent that won its reservation in the
-// current commit round runs it concurrently (footprints of concurrent agents are disjoint, see
-// ssb_agent_step.cuh), so no atomics are needed on cells or neighbours -- only on the shared
-// slot / birth counters.
+// the lines it follows.  One WARP runs one transaction: the move ranking (the reference's hot
+// spot, 54-58 % of its time) is lane-parallel over the candidate cells, the rest runs on lane 0.
+// In mode E the single ordered warp calls it for every agent in list order; in mode S every agent
+// that won its reservation in the current commit round runs it concurrently (footprints of
+// concurrent agents are disjoint, see ssb_agent_step.cuh), so no atomics are needed on cells or
+// neighbours -- only on the shared slot / birth counters.
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -38,27 +39,23 @@ __device__ __forceinline__ int wrapi(int v, int n) { v %= n; return v < 0 ? v + 
 // wrap for |offset| < n (every neighbourhood access on maps at least as wide as the range)
 __device__ __forceinline__ int wrap1(int v, int n) { return v < 0 ? v + n : (v >= n ? v - n : v); }
 
-// Per-thread scratch of the move ranking.  It lives in SHARED memory, strided by the block size
-// (element i of thread t at [i * stride + t]): with hundreds of resident threads per SM, per-thread
-// local arrays of this size thrash L1 and turn every access into an L2 round trip.
-struct Scratch {
-    int32_t *cells;      // candidate cell index
-    uint8_t *perm, *rank, *dist;
-    int stride;
-    __device__ __forceinline__ int32_t &cell(int i) const { return cells[i * stride]; }
-    __device__ __forceinline__ uint8_t &pm(int i) const { return perm[i * stride]; }
-    __device__ __forceinline__ uint8_t &rk(int i) const { return rank[i * stride]; }
-    __device__ __forceinline__ uint8_t &ds(int i) const { return dist[i * stride]; }
+// Per-warp scratch of the move ranking, in SHARED memory.
+struct WarpScratch {
+    int32_t *cells;          // [maxc] candidate cell index, reference enumeration order
+    uint8_t *perm, *rank, *dist;   // [maxc] shuffle permutation, its inverse, distance
+    uint32_t *words;         // [64] prefetched random words of the shuffle (mode S)
+    unsigned long long *retaliator;   // [27] richest visible agent per tribe, as ordered bits
 };
-__host__ __device__ constexpr int scratch_bytes_per_thread(int maxc) { return maxc * 7; }
-__device__ __forceinline__ Scratch make_scratch(unsigned char *smem, int maxc, int nthreads, int tid) {
-    Scratch sc;
-    sc.cells = reinterpret_cast<int32_t *>(smem) + tid;
-    sc.perm = smem + (size_t)maxc * nthreads * 4 + tid;
-    sc.rank = smem + (size_t)maxc * nthreads * 5 + tid;
-    sc.dist = smem + (size_t)maxc * nthreads * 6 + tid;
-    sc.stride = nthreads;
-    return sc;
+__host__ __device__ constexpr int warp_scratch_bytes(int maxc) { return maxc * 8 + 64 * 4 + 27 * 8; }
+__device__ __forceinline__ WarpScratch make_warp_scratch(unsigned char *base, int maxc) {
+    WarpScratch ws;   // base must be 8-byte aligned and maxc a multiple of 8
+    ws.retaliator = reinterpret_cast<unsigned long long *>(base);
+    ws.cells = reinterpret_cast<int32_t *>(base + 27 * 8);
+    ws.words = reinterpret_cast<uint32_t *>(base + 27 * 8 + maxc * 4);
+    ws.perm = base + 27 * 8 + maxc * 4 + 64 * 4;
+    ws.rank = ws.perm + maxc;
+    ws.dist = ws.rank + maxc;
+    return ws;
 }
 
 // Agent.isAlive (agent.py:1221-1224)
@@ -190,7 +187,7 @@ __device__ __forceinline__ void collect(const DevCtx &c, int s, int pos) {
 //   W, N, E, S in the interior;  N, E, S, W if x < d;  W, E, S, N if y < d;  E, S, N, W if both;
 // when 2d equals the width (height) the east and west (north and south) cells coincide and the
 // single entry sits at the earlier of the two positions.
-__device__ int enumerate_cross(const DevCtx &c, int x, int y, int r, const Scratch &sc, int maxc) {
+__device__ int enumerate_cross(const DevCtx &c, int x, int y, int r, const WarpScratch &ws, int maxc) {
     const int W = c.p.width, H = c.p.height;
     int n = 0;
     for (int d = 1; d <= r && n + 4 <= maxc; d++) {
@@ -202,13 +199,13 @@ __device__ int enumerate_cross(const DevCtx &c, int x, int y, int r, const Scrat
         const int west = xw * H + y, east = xe * H + y, north = x * H + yn, south = x * H + ys;
         // slot order: [W if !wx] [N if !wy] [E] [S] [N if wy] [W if wx]
         const int n0 = n;
-        if (has_x && !wx) sc.cell(n++) = west;
-        if (has_y && !wy) sc.cell(n++) = north;
-        if (has_x && !(one_x && !wx)) sc.cell(n++) = east;   // a coinciding west already took the earlier slot
-        if (has_y && !(one_y && !wy)) sc.cell(n++) = south;
-        if (has_y && wy && !one_y) sc.cell(n++) = north;
-        if (has_x && wx && !one_x) sc.cell(n++) = west;
-        for (int i = n0; i < n; i++) sc.ds(i) = (uint8_t)d;
+        if (has_x && !wx) ws.cells[n++] = west;
+        if (has_y && !wy) ws.cells[n++] = north;
+        if (has_x && !(one_x && !wx)) ws.cells[n++] = east;   // a coinciding west already took the earlier slot
+        if (has_y && !(one_y && !wy)) ws.cells[n++] = south;
+        if (has_y && wy && !one_y) ws.cells[n++] = north;
+        if (has_x && wx && !one_x) ws.cells[n++] = west;
+        for (int i = n0; i < n; i++) ws.dist[i] = (uint8_t)d;
     }
     return n;
 }
@@ -218,123 +215,138 @@ __device__ __forceinline__ int agent_range(const DevCtx &c, int s) {
     return min(min(vision, movement), max(c.max_dx, c.max_dy));
 }
 
-// rankCellsInRange + findBestCell + moveToBestCell (agent.py:1395-1443, 719-746, 1321-1328).
+// rankCellsInRange + findBestCell + moveToBestCell (agent.py:1395-1443, 719-746, 1321-1328),
+// executed by all 32 lanes of a warp for ONE agent.
 // Only the head of the stable sort (agent.py:1479-1490) is needed: the winner is the candidate
 // with the highest welfare, then the smallest distance, then the earliest shuffled position --
-// a strict total order, so candidates can be evaluated in any order.  Loads are batched in
-// chunks of CH independent requests (cells first, then their occupants) to keep many memory
-// requests in flight per thread.
+// a strict total order, so the lanes can evaluate candidates independently (lane l takes
+// candidates l, l + 32, ...) and a warp arg-best picks the move.  The dependent memory chain of
+// the whole ranking is two levels (cell, occupant) instead of two per candidate.
+// Returns the new cell (valid on every lane).
 template <class Rng>
-__device__ int move_to_best_cell(const DevCtx &c, int s, Rng &rng, const Scratch &sc, int maxc) {
-    constexpr int CH = 8;
+__device__ int move_to_best_cell(const DevCtx &c, int s, Rng &rng, const WarpScratch &ws, int maxc) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
     const ssb_agents_t &a = c.a;
-    const int pos = a.pos[s];
+    const int pos = a.pos[s];                                  // uniform loads: one transaction each
     const int H = c.p.height, x = pos / H, y = pos - x * H;
     const int r = agent_range(c, s);
     const double aggression = fmax(a.aggression[s], 0.0);
     Welfare w;
     w.load(c, s);
     const int my_tribe = a.tribe[s];
-    const int n = r > 0 ? enumerate_cross(c, x, y, r, sc, maxc) : 0;
+    int n = 0;
+    if (lane == 0 && r > 0) n = enumerate_cross(c, x, y, r, ws, maxc);
+    n = __shfl_sync(FULL, n, 0);
     int best = pos;
-    if (n > 0) {
+    if (n > 0) {                                               // warp-uniform branch
         const bool polluted = (c.p.flags & SSB_F_POLLUTION) != 0;
         const bool spicy = (c.p.flags & SSB_F_SPICE) != 0;
         const bool fighter = aggression > 0;
-        // random.shuffle(cellsInRange), agent.py:1400-1401: rank[i] = shuffled position of cell i
+        // random.shuffle(cellsInRange), agent.py:1400-1401: rank[i] = shuffled position of cell i.
+        // The draws are sequential (rejection sampling); mode S prefetches its counter-based
+        // words with all lanes first.
         rng.at(SITE_MOVE);
-        for (int i = 0; i < n; i++) sc.pm(i) = (uint8_t)i;
-        for (int i = n - 1; i >= 1; i--) {
-            const uint32_t j = rand_below(rng, (uint32_t)i + 1u);
-            const uint8_t t = sc.pm(i); sc.pm(i) = sc.pm(j); sc.pm(j) = t;
+        rng.prefetch(ws.words, lane);
+        for (int i = lane; i < n; i += 32) ws.perm[i] = (uint8_t)i;
+        __syncwarp();
+        if (lane == 0) {
+            for (int i = n - 1; i >= 1; i--) {
+                const uint32_t j = rand_below(rng, (uint32_t)i + 1u);
+                const uint8_t t = ws.perm[i]; ws.perm[i] = ws.perm[j]; ws.perm[j] = t;
+            }
+            rng.end_prefetch();
         }
-        for (int k = 0; k < n; k++) sc.rk(sc.pm(k)) = (uint8_t)k;
+        __syncwarp();
+        for (int k = lane; k < n; k += 32) ws.rank[ws.perm[k]] = (uint8_t)k;
         const double loot = c.p.max_combat_loot;
         const double my_wealth = w.sugar + w.spice;
-        // findRetaliatorsInVision (agent.py:1088-1098) needs every occupant before any prey cell
-        // can be judged: fighters take one extra pass over the occupants
-        double retaliator[27];
+        // findRetaliatorsInVision (agent.py:1088-1098): every occupant must be seen before any
+        // prey cell can be judged, so fighters take one extra pass
         if (fighter) {
-            for (int i = 0; i < 27; i++) retaliator[i] = -1.0;
-            for (int base = 0; base < n; base += CH) {
-                int o[CH];
-#pragma unroll
-                for (int j = 0; j < CH; j++) o[j] = base + j < n ? c.g.occ[sc.cell(base + j)] : -1;
-#pragma unroll
-                for (int j = 0; j < CH; j++) {
-                    if (o[j] < 0) continue;
-                    const int tr = min(a.tribe[o[j]] + 1, 26);
-                    const double ow = a.sugar[o[j]] + a.spice[o[j]];
-                    if (retaliator[tr] < ow) retaliator[tr] = ow;
-                }
+            if (lane < 27) ws.retaliator[lane] = 0ull;        // wealth >= 0: bit patterns order like values
+            __syncwarp();
+            for (int i = lane; i < n; i += 32) {
+                const int o = c.g.occ[ws.cells[i]];
+                if (o < 0) continue;
+                const double ow = a.sugar[o] + a.spice[o];
+                atomicMax(&ws.retaliator[min(a.tribe[o] + 1, 26)], (unsigned long long)__double_as_longlong(fmax(ow, 0.0)));
             }
         }
-        int hood = 1;   // findNeighborhood (agent.py:1052-1065): live agents in range + self
-        int m = 0, best_dist = 0, best_rank = 0;
-        double best_welfare = 0;
-        for (int base = 0; base < n; base += CH) {
-            int cell[CH], o[CH], cs[CH], cp[CH];
-            double pl[CH];
-#pragma unroll
-            for (int j = 0; j < CH; j++) {
-                cell[j] = base + j < n ? sc.cell(base + j) : pos;
-                o[j] = c.g.occ[cell[j]];
-                cs[j] = c.g.sugar[cell[j]];
-                cp[j] = spicy ? c.g.spice[cell[j]] : 0;
-                pl[j] = polluted ? c.g.pollution[cell[j]] : 0.0;
+        __syncwarp();
+        int hood = 0, m = 0;        // per-lane partial counts
+        int b_cell = pos, b_dist = 1 << 30, b_rank = 1 << 30;
+        double b_welfare = -1.0;
+        bool b_valid = false;
+        for (int i = lane; i < n; i += 32) {
+            const int cell = ws.cells[i];
+            const int o = c.g.occ[cell];
+            const int cs = c.g.sugar[cell];
+            const int cp = spicy ? c.g.spice[cell] : 0;
+            const double pl = polluted ? c.g.pollution[cell] : 0.0;
+            const bool occupied = o >= 0;
+            int ocod = SSB_ALIVE, otribe = -1;
+            double osug = 0, ospi = 0;
+            if (occupied) {
+                ocod = a.cod[o]; osug = a.sugar[o]; ospi = a.spice[o];
+                if (fighter) otribe = a.tribe[o];
             }
-            int ocod[CH], otribe[CH];
-            double osug[CH], ospi[CH];
-#pragma unroll
-            for (int j = 0; j < CH; j++) {
-                const bool has = base + j < n && o[j] >= 0;
-                ocod[j] = has ? a.cod[o[j]] : SSB_ALIVE;
-                osug[j] = has ? a.sugar[o[j]] : 0.0;
-                ospi[j] = has ? a.spice[o[j]] : 0.0;
-                otribe[j] = (has && fighter) ? a.tribe[o[j]] : -1;
+            double ps = 0, pp = 0;
+            if (occupied) {
+                // findNeighborhood (agent.py:1052-1065): live agents in range
+                if (ocod == SSB_ALIVE && osug >= 0 && ospi >= 0) hood++;
+                // isNeighborValidPrey (agent.py:1309-1314)
+                if (!(fighter && my_tribe != otribe && my_wealth >= osug + ospi)) continue;
+                ps = osug; pp = ospi;
             }
-#pragma unroll
-            for (int j = 0; j < CH; j++) {
-                const int i = base + j;
-                if (i >= n) break;
-                const bool occupied = o[j] >= 0;
-                double ps = 0, pp = 0;
-                if (occupied) {
-                    if (ocod[j] == SSB_ALIVE && osug[j] >= 0 && ospi[j] >= 0) hood++;
-                    // isNeighborValidPrey (agent.py:1309-1314)
-                    if (!(fighter && my_tribe != otribe[j] && my_wealth >= osug[j] + ospi[j])) continue;
-                    ps = osug[j]; pp = ospi[j];
-                }
-                const double wps = aggression * fmin(loot, ps), wpp = aggression * fmin(loot, pp);
-                const double welfare = w.eval(((double)cs[j] + wps) / (1 + pl[j]), ((double)cp[j] + wpp) / (1 + pl[j]));
-                if (occupied && retaliator[min(otribe[j] + 1, 26)] > my_wealth + welfare) continue;
-                const int dist = sc.ds(i), rk = sc.rk(i);
-                if (m == 0 || welfare > best_welfare ||
-                    (welfare == best_welfare && (dist < best_dist || (dist == best_dist && rk < best_rank)))) {
-                    best = cell[j]; best_welfare = welfare; best_dist = dist; best_rank = rk;
-                }
-                m++;
+            const double wps = aggression * fmin(loot, ps), wpp = aggression * fmin(loot, pp);
+            const double welfare = w.eval(((double)cs + wps) / (1 + pl), ((double)cp + wpp) / (1 + pl));
+            if (occupied && __longlong_as_double((long long)ws.retaliator[min(otribe + 1, 26)]) > my_wealth + welfare) continue;
+            const int dist = ws.dist[i], rk = ws.rank[i];
+            if (!b_valid || welfare > b_welfare ||
+                (welfare == b_welfare && (dist < b_dist || (dist == b_dist && rk < b_rank)))) {
+                b_cell = cell; b_welfare = welfare; b_dist = dist; b_rank = rk; b_valid = true;
             }
+            m++;
         }
-        if (m == 0) { best = pos; m = 1; }
-        a.n_neighborhood[s] = hood;
-        a.n_valid_moves[s] = m;
-    }
-    // doCombat (agent.py:274-294) then gotoCell (agent.py:1213-1219)
-    if (aggression > 0) {
-        const int prey = c.g.occ[best];
-        if (prey >= 0 && prey != s) {
-            const double loot = c.p.max_combat_loot;
-            const double sl = fmin(loot, a.sugar[prey]), pl = fmin(loot, a.spice[prey]);
-            a.sugar[s] += sl; a.spice[s] += pl;
-            a.sugar[prey] -= sl; a.spice[prey] -= pl;
-            do_death(c, prey, SSB_COMBAT);
+        // warp reductions: counts, then arg-best under the same strict order
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            hood += __shfl_xor_sync(FULL, hood, o);
+            m += __shfl_xor_sync(FULL, m, o);
+            const int o_cell = __shfl_xor_sync(FULL, b_cell, o), o_dist = __shfl_xor_sync(FULL, b_dist, o);
+            const int o_rank = __shfl_xor_sync(FULL, b_rank, o);
+            const double o_welfare = __shfl_xor_sync(FULL, b_welfare, o);
+            const bool o_valid = __shfl_xor_sync(FULL, (int)b_valid, o) != 0;
+            const bool take = o_valid && (!b_valid || o_welfare > b_welfare ||
+                (o_welfare == b_welfare && (o_dist < b_dist || (o_dist == b_dist && o_rank < b_rank))));
+            if (take) { b_cell = o_cell; b_welfare = o_welfare; b_dist = o_dist; b_rank = o_rank; b_valid = true; }
+        }
+        best = b_valid ? b_cell : pos;
+        if (m == 0) m = 1;
+        if (lane == 0) {
+            a.n_neighborhood[s] = hood + 1;      // + self
+            a.n_valid_moves[s] = m;
         }
     }
-    a.last_moved[s] = c.t;
-    c.g.occ[pos] = -1;
-    a.pos[s] = best;
-    c.g.occ[best] = s;
+    if (lane == 0) {
+        // doCombat (agent.py:274-294) then gotoCell (agent.py:1213-1219)
+        if (aggression > 0) {
+            const int prey = c.g.occ[best];
+            if (prey >= 0 && prey != s) {
+                const double loot = c.p.max_combat_loot;
+                const double sl = fmin(loot, a.sugar[prey]), pl = fmin(loot, a.spice[prey]);
+                a.sugar[s] += sl; a.spice[s] += pl;
+                a.sugar[prey] -= sl; a.spice[prey] -= pl;
+                do_death(c, prey, SSB_COMBAT);
+            }
+        }
+        a.last_moved[s] = c.t;
+        c.g.occ[pos] = -1;
+        a.pos[s] = best;
+        c.g.occ[best] = s;
+    }
+    __syncwarp();
     return best;
 }
 
@@ -531,31 +543,40 @@ __device__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
 //   interact phase  tagging, trading, reproduction, aging, happiness
 // Returns from the move phase: false if the agent is done for this step (it was skipped or died).
 template <class Rng>
-__device__ bool transaction_move_phase(const DevCtx &c, int s, Rng &rng, const Scratch &sc, int maxc) {
+__device__ bool transaction_move_phase(const DevCtx &c, int s, Rng &rng, const WarpScratch &ws, int maxc) {
+    // called by all 32 lanes; the ranking is lane-parallel, the bookkeeping runs on lane 0
     const ssb_agents_t &a = c.a;
-    if (!agent_alive(c, s) || a.last_moved[s] == c.t) return false;
-    a.last_sugar[s] = a.sugar[s];
-    a.last_spice[s] = a.spice[s];
-    const int pos = move_to_best_cell(c, s, rng, sc, maxc);
-    collect(c, s, pos);
-    // doMetabolism (agent.py:485-498) + consumption pollution (cell.py:27-40)
-    const double sm = (double)max(a.sugar_metab[s], 0), pm = (double)max(a.spice_metab[s], 0);
-    const double sugar = a.sugar[s] - sm, spice = a.spice[s] - pm;
-    a.sugar[s] = sugar;
-    a.spice[s] = spice;
-    if (c.p.pollution_start <= c.t && c.t <= c.p.pollution_end) {
-        double pl = c.g.pollution[pos];
-        pl += c.p.sugar_cons_pollution * sm;
-        pl += c.p.spice_cons_pollution * pm;
-        c.g.pollution[pos] = pl;
+    const int lane = threadIdx.x & 31;
+    if (!agent_alive(c, s) || a.last_moved[s] == c.t) return false;      // uniform
+    if (lane == 0) {
+        a.last_sugar[s] = a.sugar[s];
+        a.last_spice[s] = a.spice[s];
     }
-    if (sugar < 0 || spice < 0 || (sugar <= 0 && sm > 0) || (spice <= 0 && pm > 0)) {
-        do_death(c, s, SSB_STARVATION);
-        return false;
+    __syncwarp();
+    const int pos = move_to_best_cell(c, s, rng, ws, maxc);
+    int alive = 1;
+    if (lane == 0) {
+        collect(c, s, pos);
+        // doMetabolism (agent.py:485-498) + consumption pollution (cell.py:27-40)
+        const double sm = (double)max(a.sugar_metab[s], 0), pm = (double)max(a.spice_metab[s], 0);
+        const double sugar = a.sugar[s] - sm, spice = a.spice[s] - pm;
+        a.sugar[s] = sugar;
+        a.spice[s] = spice;
+        if (c.p.pollution_start <= c.t && c.t <= c.p.pollution_end) {
+            double pl = c.g.pollution[pos];
+            pl += c.p.sugar_cons_pollution * sm;
+            pl += c.p.spice_cons_pollution * pm;
+            c.g.pollution[pos] = pl;
+        }
+        if (sugar < 0 || spice < 0 || (sugar <= 0 && sm > 0) || (spice <= 0 && pm > 0)) {
+            do_death(c, s, SSB_STARVATION);
+            alive = 0;
+        }
     }
-    return true;
+    return __shfl_sync(0xffffffffu, alive, 0) != 0;
 }
 
+// lane 0 only
 template <class Rng, bool EXACT>
 __device__ void transaction_interact_phase(const DevCtx &c, int s, Rng &rng) {
     const ssb_agents_t &a = c.a;
