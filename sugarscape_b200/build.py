@@ -34,7 +34,10 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUT
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
+    extra = []
+    if os.environ.get("SSB_GROUP_LANES"):      # tuning builds: lanes cooperating on one agent (4, 8, 16, 32)
+        extra.append("-DSSB_GROUP_LANES=" + os.environ["SSB_GROUP_LANES"])
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

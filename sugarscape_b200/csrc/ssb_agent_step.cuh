@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(32, 1) k_agent_step_exact(DevCtx c, uint32_t *
         const long long n_list = __shfl_sync(0xffffffffu, (long long)cn[SSB_C_N_LIST], 0);
         if (i >= n_list) break;
         const int s = c.a.order[i];
-        const bool go_on = transaction_move_phase(c, s, rng, ws, MAXC_EXACT);
+        const bool go_on = transaction_move_phase<32>(c, s, rng, ws, MAXC_EXACT);
         if (go_on && lane == 0) transaction_interact_phase<RngExact, true>(c, s, rng);
         __threadfence_block();
         __syncwarp();
@@ -87,8 +87,12 @@ constexpr int MAXC_SCALABLE = 32;     // 4 * 8 candidate cells; the host refuses
 constexpr int TAG_BITS = 6;
 constexpr int MAX_EPOCHS = 1024;
 constexpr int AGENT_THREADS = 256;
-constexpr int AGENT_WARPS = AGENT_THREADS / 32;
-constexpr int AGENT_SMEM_BYTES = warp_scratch_bytes(MAXC_SCALABLE) * AGENT_WARPS;
+#ifndef SSB_GROUP_LANES
+#define SSB_GROUP_LANES 8
+#endif
+constexpr int GL = SSB_GROUP_LANES;          // lanes cooperating on one agent
+constexpr int AGENT_GROUPS = AGENT_THREADS / GL;
+constexpr int AGENT_SMEM_BYTES = warp_scratch_bytes(MAXC_SCALABLE) * AGENT_GROUPS;
 constexpr int PHASE1_BIT = 0x40000000;   // list entries: slot | PHASE1_BIT once the move part has committed
 
 struct RoundCtx {
@@ -149,31 +153,31 @@ __device__ __forceinline__ uint32_t round_tag(const DevCtx &c, int round) {
 }
 constexpr int ROUNDS_PER_TAG_EPOCH = (1 << TAG_BITS) - 1;
 
-// The footprint D_k(cross of radius (rx, ry) + centre), visited by a whole warp: one x-column per
+// The footprint D_k(cross of radius (rx, ry) + centre), visited by a lane group: one x-column per
 // iteration, the lanes cover its y-interval (at most 2 (ry + k) + 1 <= 21 cells).
-__device__ __forceinline__ void warp_mark_region(const DevCtx &c, const RoundCtx &rc, int pos, int r, int k, uint32_t v) {
-    const int lane = threadIdx.x & 31;
+__device__ __forceinline__ void group_mark_region(const DevCtx &c, const RoundCtx &rc, int pos, int r, int k, uint32_t v) {
+    const int lane = Group<GL>::lane();
     Footprint f;
     f.init(c, pos, r, k);
     for (int i = -(f.rx + f.k); i <= f.rx + f.k; i++) {
         const int h = f.half_height(i);
         uint32_t *col = rc.mark + (size_t)wrapi(f.x + i, f.W) * f.H;
-        for (int j = lane - h; j <= h; j += 32) atomicMin(col + wrapi(f.y + j, f.H), v);
+        for (int j = lane - h; j <= h; j += GL) atomicMin(col + wrapi(f.y + j, f.H), v);
     }
 }
 
-// true (on every lane) iff every cell of the region holds v
-__device__ __forceinline__ bool warp_owns_region(const DevCtx &c, const RoundCtx &rc, int pos, int r, int k, uint32_t v) {
-    const int lane = threadIdx.x & 31;
+// true (on every lane of the group) iff every cell of the region holds v
+__device__ __forceinline__ bool group_owns_region(const DevCtx &c, const RoundCtx &rc, int pos, int r, int k, uint32_t v) {
+    const int lane = Group<GL>::lane();
     Footprint f;
     f.init(c, pos, r, k);
     unsigned bad = 0;
     for (int i = -(f.rx + f.k); i <= f.rx + f.k; i++) {
         const int h = f.half_height(i);
         const uint32_t *col = rc.mark + (size_t)wrapi(f.x + i, f.W) * f.H;
-        for (int j = lane - h; j <= h; j += 32) bad |= __ldcg(col + wrapi(f.y + j, f.H)) ^ v;
+        for (int j = lane - h; j <= h; j += GL) bad |= __ldcg(col + wrapi(f.y + j, f.H)) ^ v;
     }
-    return !__any_sync(0xffffffffu, bad != 0);
+    return !Group<GL>::any(bad != 0);
 }
 
 // warp-aggregated append: every lane of the warp calls this (full mask)
@@ -192,9 +196,10 @@ __global__ void __launch_bounds__(AGENT_THREADS, 2) k_agent_step_scalable(DevCtx
     cg::grid_group grid = cg::this_grid();
     __shared__ int32_t sh_count[MAX_EPOCHS], sh_base[MAX_EPOCHS];
     extern __shared__ __align__(8) unsigned char scratch_mem[];
-    const WarpScratch ws = make_warp_scratch(scratch_mem + (threadIdx.x >> 5) * warp_scratch_bytes(MAXC_SCALABLE), MAXC_SCALABLE);
-    const int warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    const WarpScratch ws = make_warp_scratch(scratch_mem + (threadIdx.x / GL) * warp_scratch_bytes(MAXC_SCALABLE), MAXC_SCALABLE);
+    const int warp_id = (blockIdx.x * blockDim.x + threadIdx.x) / GL;      // lane-group index
+    const int n_warps = (gridDim.x * blockDim.x) / GL;
+    const int glane = Group<GL>::lane();
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nthreads = gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
@@ -262,7 +267,7 @@ __global__ void __launch_bounds__(AGENT_THREADS, 2) k_agent_step_scalable(DevCtx
         if (tr) { rc.trace[round * 6 + 0] = n; rc.trace[round * 6 + 2] = global_ns(); }
         const uint32_t tag = round_tag(c, round);
         const int32_t *fresh = rc.bucketed + e0;
-        // MARK: one agent per warp, lanes spread over the footprint cells
+        // MARK: one agent per lane group, lanes spread over the footprint cells
         for (int i = warp_id; i < n; i += n_warps) {
             const int entry = i < n_carry ? cur[i] : fresh[i - n_carry];
             const int s = entry & ~PHASE1_BIT;
@@ -270,7 +275,7 @@ __global__ void __launch_bounds__(AGENT_THREADS, 2) k_agent_step_scalable(DevCtx
             if (pos < 0) continue;                   // killed earlier this step: nothing to reserve
             const int k = footprint_dilation(c, s);
             const int r = (entry & PHASE1_BIT) ? 0 : agent_range(c, s);
-            warp_mark_region(c, rc, pos, r, k, tag | rc.prio[s]);
+            group_mark_region(c, rc, pos, r, k, tag | rc.prio[s]);
         }
         grid.sync();
         if (tr) rc.trace[round * 6 + 3] = global_ns();
@@ -281,10 +286,10 @@ __global__ void __launch_bounds__(AGENT_THREADS, 2) k_agent_step_scalable(DevCtx
             const int pos = c.a.pos[s];
             bool ok = true;
             if (pos >= 0) {
-                if (entry & PHASE1_BIT) ok = warp_owns_region(c, rc, pos, 0, footprint_dilation(c, s), tag | rc.prio[s]);
-                else ok = warp_owns_region(c, rc, pos, agent_range(c, s), 0, tag | rc.prio[s]);
+                if (entry & PHASE1_BIT) ok = group_owns_region(c, rc, pos, 0, footprint_dilation(c, s), tag | rc.prio[s]);
+                else ok = group_owns_region(c, rc, pos, agent_range(c, s), 0, tag | rc.prio[s]);
             }
-            if (lane == 0) {
+            if (glane == 0) {
                 if (ok) rc.ready[atomicAdd(n_ready, 1)] = entry;
                 else nxt[atomicAdd(n_next, 1)] = entry;
             }
@@ -292,26 +297,26 @@ __global__ void __launch_bounds__(AGENT_THREADS, 2) k_agent_step_scalable(DevCtx
         grid.sync();
         const int nr = *(volatile int32_t *)n_ready;
         if (tr) { rc.trace[round * 6 + 1] = nr; rc.trace[round * 6 + 4] = global_ns(); }
-        // EXECUTE: one transaction per warp
+        // EXECUTE: one transaction per lane group
         for (int i = warp_id; i < nr; i += n_warps) {
             const int entry = rc.ready[i];
             const int s = entry & ~PHASE1_BIT;
             RngStream rng{rc.key, (uint32_t)c.a.id[s], 0u, 0u, nullptr};
             if (entry & PHASE1_BIT) {
-                if (lane == 0) transaction_interact_phase<RngStream, false>(c, s, rng);
+                if (glane == 0) transaction_interact_phase<RngStream, false>(c, s, rng);
             } else {
                 const int k = footprint_dilation(c, s);      // before the transaction can age / kill the agent
-                if (transaction_move_phase(c, s, rng, ws, MAXC_SCALABLE)) {
+                if (transaction_move_phase<GL>(c, s, rng, ws, MAXC_SCALABLE)) {
                     // the interact part needs D_k(new cell); the marks of this round still stand,
                     // so it runs right away if the agent owns that diamond too
-                    const bool now = k == 0 || warp_owns_region(c, rc, c.a.pos[s], 0, k, tag | rc.prio[s]);
-                    if (lane == 0) {
+                    const bool now = k == 0 || group_owns_region(c, rc, c.a.pos[s], 0, k, tag | rc.prio[s]);
+                    if (glane == 0) {
                         if (now) transaction_interact_phase<RngStream, false>(c, s, rng);
                         else nxt[atomicAdd(n_next, 1)] = s | PHASE1_BIT;
                     }
                 }
             }
-            __syncwarp();
+            Group<GL>::sync();
         }
         grid.sync();
         if (tr) rc.trace[round * 6 + 5] = global_ns();

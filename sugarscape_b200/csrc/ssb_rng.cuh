@@ -60,7 +60,7 @@ struct RngExact {
         mt[624] = 0;
     }
     __device__ __forceinline__ void at(uint32_t) {}      // one global stream: sites are not separated
-    __device__ __forceinline__ void prefetch(uint32_t *, int) {}
+    template <int G> __device__ __forceinline__ void prefetch(uint32_t *, int) {}
     __device__ __forceinline__ void end_prefetch() {}
     __device__ uint32_t next() {
         if (mt[624] >= 624u) twist();
@@ -87,10 +87,10 @@ struct RngStream {
         return (uint32_t)(mix64(key ^ (((uint64_t)id << 32) | ((uint64_t)site << 24) | j)) >> 32);
     }
     __device__ __forceinline__ void at(uint32_t site_) { site = site_; ctr = 0; pre = nullptr; }
-    // all 32 lanes: fill buf[0..63] with the first 64 words of the current site
-    __device__ __forceinline__ void prefetch(uint32_t *buf, int lane) {
-        buf[lane] = word((uint32_t)lane);
-        buf[lane + 32] = word((uint32_t)lane + 32u);
+    // all G lanes of the group: fill buf[0..63] with the first 64 words of the current site
+    template <int G> __device__ __forceinline__ void prefetch(uint32_t *buf, int lane) {
+#pragma unroll
+        for (int j = lane; j < 64; j += G) buf[j] = word((uint32_t)j);
         pre = buf;
     }
     __device__ __forceinline__ void end_prefetch() { pre = nullptr; }

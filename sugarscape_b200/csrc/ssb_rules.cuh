@@ -39,7 +39,19 @@ __device__ __forceinline__ int wrapi(int v, int n) { v %= n; return v < 0 ? v + 
 // wrap for |offset| < n (every neighbourhood access on maps at least as wide as the range)
 __device__ __forceinline__ int wrap1(int v, int n) { return v < 0 ? v + n : (v >= n ? v - n : v); }
 
-// Per-warp scratch of the move ranking, in SHARED memory.
+// Lane groups: G consecutive lanes of a warp (G = 32, 16, 8, 4) cooperate on one agent.
+template <int G> struct Group {
+    static __device__ __forceinline__ int lane() { return threadIdx.x & (G - 1); }
+    static __device__ __forceinline__ unsigned mask() {
+        return G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (threadIdx.x & 31 & ~(G - 1)));
+    }
+    static __device__ __forceinline__ void sync() { __syncwarp(mask()); }
+    template <class T> static __device__ __forceinline__ T bcast(T v, int src) { return __shfl_sync(mask(), v, src, G); }
+    template <class T> static __device__ __forceinline__ T xor_(T v, int o) { return __shfl_xor_sync(mask(), v, o, G); }
+    static __device__ __forceinline__ bool any(bool p) { return __any_sync(mask(), p) != 0; }
+};
+
+// Per-group scratch of the move ranking, in SHARED memory.
 struct WarpScratch {
     int32_t *cells;          // [maxc] candidate cell index, reference enumeration order
     uint8_t *perm, *rank, *dist;   // [maxc] shuffle permutation, its inverse, distance
@@ -223,10 +235,10 @@ __device__ __forceinline__ int agent_range(const DevCtx &c, int s) {
 // candidates l, l + 32, ...) and a warp arg-best picks the move.  The dependent memory chain of
 // the whole ranking is two levels (cell, occupant) instead of two per candidate.
 // Returns the new cell (valid on every lane).
-template <class Rng>
+template <int G, class Rng>
 __device__ int move_to_best_cell(const DevCtx &c, int s, Rng &rng, const WarpScratch &ws, int maxc) {
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
+    typedef Group<G> Gr;
+    const int lane = Gr::lane();
     const ssb_agents_t &a = c.a;
     const int pos = a.pos[s];                                  // uniform loads: one transaction each
     const int H = c.p.height, x = pos / H, y = pos - x * H;
@@ -237,7 +249,7 @@ __device__ int move_to_best_cell(const DevCtx &c, int s, Rng &rng, const WarpScr
     const int my_tribe = a.tribe[s];
     int n = 0;
     if (lane == 0 && r > 0) n = enumerate_cross(c, x, y, r, ws, maxc);
-    n = __shfl_sync(FULL, n, 0);
+    n = Gr::bcast(n, 0);
     int best = pos;
     if (n > 0) {                                               // warp-uniform branch
         const bool polluted = (c.p.flags & SSB_F_POLLUTION) != 0;
@@ -247,9 +259,9 @@ __device__ int move_to_best_cell(const DevCtx &c, int s, Rng &rng, const WarpScr
         // The draws are sequential (rejection sampling); mode S prefetches its counter-based
         // words with all lanes first.
         rng.at(SITE_MOVE);
-        rng.prefetch(ws.words, lane);
-        for (int i = lane; i < n; i += 32) ws.perm[i] = (uint8_t)i;
-        __syncwarp();
+        rng.template prefetch<G>(ws.words, lane);
+        for (int i = lane; i < n; i += G) ws.perm[i] = (uint8_t)i;
+        Gr::sync();
         if (lane == 0) {
             for (int i = n - 1; i >= 1; i--) {
                 const uint32_t j = rand_below(rng, (uint32_t)i + 1u);
@@ -257,28 +269,28 @@ __device__ int move_to_best_cell(const DevCtx &c, int s, Rng &rng, const WarpScr
             }
             rng.end_prefetch();
         }
-        __syncwarp();
-        for (int k = lane; k < n; k += 32) ws.rank[ws.perm[k]] = (uint8_t)k;
+        Gr::sync();
+        for (int k = lane; k < n; k += G) ws.rank[ws.perm[k]] = (uint8_t)k;
         const double loot = c.p.max_combat_loot;
         const double my_wealth = w.sugar + w.spice;
         // findRetaliatorsInVision (agent.py:1088-1098): every occupant must be seen before any
         // prey cell can be judged, so fighters take one extra pass
         if (fighter) {
-            if (lane < 27) ws.retaliator[lane] = 0ull;        // wealth >= 0: bit patterns order like values
-            __syncwarp();
-            for (int i = lane; i < n; i += 32) {
+            for (int i = lane; i < 27; i += G) ws.retaliator[i] = 0ull;   // wealth >= 0: bit patterns order like values
+            Gr::sync();
+            for (int i = lane; i < n; i += G) {
                 const int o = c.g.occ[ws.cells[i]];
                 if (o < 0) continue;
                 const double ow = a.sugar[o] + a.spice[o];
                 atomicMax(&ws.retaliator[min(a.tribe[o] + 1, 26)], (unsigned long long)__double_as_longlong(fmax(ow, 0.0)));
             }
         }
-        __syncwarp();
+        Gr::sync();
         int hood = 0, m = 0;        // per-lane partial counts
         int b_cell = pos, b_dist = 1 << 30, b_rank = 1 << 30;
         double b_welfare = -1.0;
         bool b_valid = false;
-        for (int i = lane; i < n; i += 32) {
+        for (int i = lane; i < n; i += G) {
             const int cell = ws.cells[i];
             const int o = c.g.occ[cell];
             const int cs = c.g.sugar[cell];
@@ -311,13 +323,13 @@ __device__ int move_to_best_cell(const DevCtx &c, int s, Rng &rng, const WarpScr
         }
         // warp reductions: counts, then arg-best under the same strict order
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            hood += __shfl_xor_sync(FULL, hood, o);
-            m += __shfl_xor_sync(FULL, m, o);
-            const int o_cell = __shfl_xor_sync(FULL, b_cell, o), o_dist = __shfl_xor_sync(FULL, b_dist, o);
-            const int o_rank = __shfl_xor_sync(FULL, b_rank, o);
-            const double o_welfare = __shfl_xor_sync(FULL, b_welfare, o);
-            const bool o_valid = __shfl_xor_sync(FULL, (int)b_valid, o) != 0;
+        for (int o = G / 2; o > 0; o >>= 1) {
+            hood += Gr::xor_(hood, o);
+            m += Gr::xor_(m, o);
+            const int o_cell = Gr::xor_(b_cell, o), o_dist = Gr::xor_(b_dist, o);
+            const int o_rank = Gr::xor_(b_rank, o);
+            const double o_welfare = Gr::xor_(b_welfare, o);
+            const bool o_valid = Gr::xor_((int)b_valid, o) != 0;
             const bool take = o_valid && (!b_valid || o_welfare > b_welfare ||
                 (o_welfare == b_welfare && (o_dist < b_dist || (o_dist == b_dist && o_rank < b_rank))));
             if (take) { b_cell = o_cell; b_welfare = o_welfare; b_dist = o_dist; b_rank = o_rank; b_valid = true; }
@@ -346,7 +358,7 @@ __device__ int move_to_best_cell(const DevCtx &c, int s, Rng &rng, const WarpScr
         a.pos[s] = best;
         c.g.occ[best] = s;
     }
-    __syncwarp();
+    Gr::sync();
     return best;
 }
 
@@ -542,18 +554,19 @@ __device__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
 //   move phase      lastSugar/lastSpice, moveToBestCell, collect, (universal income), metabolism
 //   interact phase  tagging, trading, reproduction, aging, happiness
 // Returns from the move phase: false if the agent is done for this step (it was skipped or died).
-template <class Rng>
+template <int G, class Rng>
 __device__ bool transaction_move_phase(const DevCtx &c, int s, Rng &rng, const WarpScratch &ws, int maxc) {
-    // called by all 32 lanes; the ranking is lane-parallel, the bookkeeping runs on lane 0
+    // called by all G lanes of the group; the ranking is lane-parallel, the bookkeeping runs on lane 0
     const ssb_agents_t &a = c.a;
-    const int lane = threadIdx.x & 31;
+    typedef Group<G> Gr;
+    const int lane = Gr::lane();
     if (!agent_alive(c, s) || a.last_moved[s] == c.t) return false;      // uniform
     if (lane == 0) {
         a.last_sugar[s] = a.sugar[s];
         a.last_spice[s] = a.spice[s];
     }
-    __syncwarp();
-    const int pos = move_to_best_cell(c, s, rng, ws, maxc);
+    Gr::sync();
+    const int pos = move_to_best_cell<G>(c, s, rng, ws, maxc);
     int alive = 1;
     if (lane == 0) {
         collect(c, s, pos);
@@ -573,7 +586,7 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, Rng &rng, const W
             alive = 0;
         }
     }
-    return __shfl_sync(0xffffffffu, alive, 0) != 0;
+    return Gr::bcast(alive, 0) != 0;
 }
 
 // lane 0 only
