@@ -83,6 +83,7 @@ typedef struct ssb_params {
     int32_t tag_len, max_tribes;    /* agentTagStringLength, environmentMaxTribes              */
     int32_t max_timestep;           /* configuration["timesteps"]                              */
     int32_t id_bits;                /* mode S: agent IDs must stay below 1 << id_bits (<= 26)   */
+    int32_t max_sugar_capacity, max_spice_capacity; /* environmentMaxSugar / environmentMaxSpice: upper bound of any cell */
 } ssb_params_t;
 
 typedef struct ssb_grid {

@@ -162,6 +162,7 @@ int ssb_bind(ssb_engine_t *e, const ssb_grid_t *grid, const ssb_agents_t *agents
     const int maxd = c.max_dx > c.max_dy ? c.max_dx : c.max_dy;
     if (e->p.rng_mode == SSB_RNG_EXACT && 4 * maxd > MAXC_EXACT) return fail(e, -1, "agent range %d exceeds the exact-mode limit %d", maxd, MAXC_EXACT / 4);
     if (e->p.rng_mode == SSB_RNG_SCALABLE && 4 * maxd > MAXC_SCALABLE) return fail(e, -1, "agent range %d exceeds the scalable-mode limit %d", maxd, MAXC_SCALABLE / 4);
+    if (e->p.rng_mode == SSB_RNG_SCALABLE && (maxd + 2 >= e->p.width || maxd + 2 >= e->p.height)) return fail(e, -1, "map too small for the scalable mode footprints");
     const int64_t cap = agents->capacity, cells = grid->n_cells;
     const int64_t big = cap > cells ? cap : cells;
     e->n_tile_counts = (int32_t)((big + COMPACT_TILE - 1) / COMPACT_TILE) + 1;

@@ -116,12 +116,28 @@ __device__ __forceinline__ unsigned long long global_ns() {
     return t;
 }
 
-// dilation of the footprint required by the rule set, for agent s (agent.py:585-588)
-__device__ __forceinline__ int footprint_dilation(const DevCtx &c, int s) {
+// Dilation of the footprint required by the rule set, for agent s (agent.py:585-588).
+// Reproduction (k = 2) is only possible if the agent can be fertile when it gets there: fertile
+// age, and holdings that can still reach the starting endowment -- other agents can only LOWER
+// them (mate costs), the agent's own move adds at most one cell's capacity (plus combat loot)
+// and subtracts its metabolism.  `moved` = the move part has committed (holdings are final).
+__device__ __forceinline__ int footprint_dilation(const DevCtx &c, int s, bool moved) {
     int k = 0;
     if (c.p.flags & (SSB_F_TAGGING | SSB_F_TRADE)) k = 1;
     if ((c.p.flags & SSB_F_REPRO) && c.a.fert_factor[s] > 0 &&
-        c.a.age[s] >= c.a.fert_age[s] && c.a.age[s] < c.a.infert_age[s]) k = 2;
+        c.a.age[s] >= c.a.fert_age[s] && c.a.age[s] < c.a.infert_age[s]) {
+        bool can = true;
+        if (!(c.p.flags & SSB_F_TRADE)) {
+            double gain_s = 0, gain_p = 0;
+            if (!moved) {
+                const double loot = c.a.aggression[s] > 0 ? c.p.max_combat_loot : 0.0;
+                gain_s = (double)c.p.max_sugar_capacity + loot - (double)max(c.a.sugar_metab[s], 0);
+                gain_p = (double)c.p.max_spice_capacity + loot - (double)max(c.a.spice_metab[s], 0);
+            }
+            can = c.a.sugar[s] + gain_s >= c.a.start_sugar[s] && c.a.spice[s] + gain_p >= c.a.start_spice[s];
+        }
+        if (can) k = 2;
+    }
     return k;
 }
 
@@ -161,8 +177,8 @@ __device__ __forceinline__ void group_mark_region(const DevCtx &c, const RoundCt
     f.init(c, pos, r, k);
     for (int i = -(f.rx + f.k); i <= f.rx + f.k; i++) {
         const int h = f.half_height(i);
-        uint32_t *col = rc.mark + (size_t)wrapi(f.x + i, f.W) * f.H;
-        for (int j = lane - h; j <= h; j += GL) atomicMin(col + wrapi(f.y + j, f.H), v);
+        uint32_t *col = rc.mark + (size_t)wrap1(f.x + i, f.W) * f.H;
+        for (int j = lane - h; j <= h; j += GL) atomicMin(col + wrap1(f.y + j, f.H), v);
     }
 }
 
@@ -174,8 +190,8 @@ __device__ __forceinline__ bool group_owns_region(const DevCtx &c, const RoundCt
     unsigned bad = 0;
     for (int i = -(f.rx + f.k); i <= f.rx + f.k; i++) {
         const int h = f.half_height(i);
-        const uint32_t *col = rc.mark + (size_t)wrapi(f.x + i, f.W) * f.H;
-        for (int j = lane - h; j <= h; j += GL) bad |= __ldcg(col + wrapi(f.y + j, f.H)) ^ v;
+        const uint32_t *col = rc.mark + (size_t)wrap1(f.x + i, f.W) * f.H;
+        for (int j = lane - h; j <= h; j += GL) bad |= __ldcg(col + wrap1(f.y + j, f.H)) ^ v;
     }
     return !Group<GL>::any(bad != 0);
 }
@@ -273,8 +289,9 @@ __global__ void __launch_bounds__(AGENT_THREADS, 2) k_agent_step_scalable(DevCtx
             const int s = entry & ~PHASE1_BIT;
             const int pos = c.a.pos[s];
             if (pos < 0) continue;                   // killed earlier this step: nothing to reserve
-            const int k = footprint_dilation(c, s);
-            const int r = (entry & PHASE1_BIT) ? 0 : agent_range(c, s);
+            const bool moved = (entry & PHASE1_BIT) != 0;
+            const int k = footprint_dilation(c, s, moved);
+            const int r = moved ? 0 : agent_range(c, s);
             group_mark_region(c, rc, pos, r, k, tag | rc.prio[s]);
         }
         grid.sync();
@@ -286,7 +303,7 @@ __global__ void __launch_bounds__(AGENT_THREADS, 2) k_agent_step_scalable(DevCtx
             const int pos = c.a.pos[s];
             bool ok = true;
             if (pos >= 0) {
-                if (entry & PHASE1_BIT) ok = group_owns_region(c, rc, pos, 0, footprint_dilation(c, s), tag | rc.prio[s]);
+                if (entry & PHASE1_BIT) ok = group_owns_region(c, rc, pos, 0, footprint_dilation(c, s, true), tag | rc.prio[s]);
                 else ok = group_owns_region(c, rc, pos, agent_range(c, s), 0, tag | rc.prio[s]);
             }
             if (glane == 0) {
@@ -305,10 +322,11 @@ __global__ void __launch_bounds__(AGENT_THREADS, 2) k_agent_step_scalable(DevCtx
             if (entry & PHASE1_BIT) {
                 if (glane == 0) transaction_interact_phase<RngStream, false>(c, s, rng);
             } else {
-                const int k = footprint_dilation(c, s);      // before the transaction can age / kill the agent
                 if (transaction_move_phase<GL>(c, s, rng, ws, MAXC_SCALABLE)) {
-                    // the interact part needs D_k(new cell); the marks of this round still stand,
-                    // so it runs right away if the agent owns that diamond too
+                    // the interact part needs D_k(new cell), k from the now final holdings (never
+                    // larger than the k the marks were placed with); the marks of this round
+                    // still stand, so it runs right away if the agent owns that diamond too
+                    const int k = footprint_dilation(c, s, true);
                     const bool now = k == 0 || group_owns_region(c, rc, c.a.pos[s], 0, k, tag | rc.prio[s]);
                     if (glane == 0) {
                         if (now) transaction_interact_phase<RngStream, false>(c, s, rng);

@@ -18,9 +18,11 @@
 
 #if defined(__CUDACC__)
 #define SSB_POW_FN __device__ __forceinline__
+#define SSB_POW_CORE_FN __device__ __noinline__
 #define SSB_POW_TABLE static __device__ const
 #else
 #define SSB_POW_FN static inline
+#define SSB_POW_CORE_FN static inline
 #define SSB_POW_TABLE static const
 #endif
 #include "ssb_pow_tables.cuh"
@@ -41,7 +43,7 @@ SSB_POW_FN uint64_t ssb_as_u64_(double d) { uint64_t u; memcpy(&u, &d, 8); retur
 
 // Valid for finite x > 0 (normal), 2^-65 <= |y| < 2^63 and |y*log(x)| in [2^-54, 512): every
 // welfare evaluation of the simulation.  Returns 0 in *ok otherwise (callers fall back).
-SSB_POW_FN double ssb_glibc_pow_core(double x, double y, int *ok) {
+SSB_POW_CORE_FN double ssb_glibc_pow_core(double x, double y, int *ok) {
     const uint64_t ix = SSB_AS_U64(x);
     *ok = 1;
     // ---- log_inline: log(x) = k ln2 + log(c) + log1p(z/c - 1), as hi + lo ----

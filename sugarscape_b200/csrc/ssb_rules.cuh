@@ -364,7 +364,7 @@ __device__ int move_to_best_cell(const DevCtx &c, int s, Rng &rng, const WarpScr
 
 // Agent.doTagging (agent.py:556-566)
 template <class Rng>
-__device__ void do_tagging(const DevCtx &c, int s, Rng &rng) {
+__device__ __noinline__ void do_tagging(const DevCtx &c, int s, Rng &rng) {
     int32_t nb[4];
     neighbours4(c, c.a.pos[s], nb);
     rng.at(SITE_TAGGING);
@@ -380,7 +380,7 @@ __device__ void do_tagging(const DevCtx &c, int s, Rng &rng) {
 
 // Agent.doTrading (agent.py:600-706)
 template <class Rng>
-__device__ void do_trading(const DevCtx &c, int s, Rng &rng) {
+__device__ __noinline__ void do_trading(const DevCtx &c, int s, Rng &rng) {
     const ssb_agents_t &a = c.a;
     if (a.trade_factor[s] == 0) return;
     a.trade_volume[s] = 0;
@@ -464,7 +464,7 @@ __device__ __forceinline__ int alloc_slot(const DevCtx &c) {
 // Agent.doReproduction (agent.py:500-554) with findChildEndowment (781-910) and addChildToCell
 // (164-182).  EXACT = mode E (children join the list immediately, IDs in birth order).
 template <class Rng, bool EXACT>
-__device__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
+__device__ __noinline__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
     const ssb_agents_t &a = c.a;
     if (!agent_alive(c, s) || !is_fertile(c, s)) return;
     int32_t nb[4], own_empty[4];

@@ -70,6 +70,7 @@ class Params(C.Structure):
         ("max_combat_loot", C.c_double),
         ("tag_len", C.c_int32), ("max_tribes", C.c_int32),
         ("max_timestep", C.c_int32), ("id_bits", C.c_int32),
+        ("max_sugar_capacity", C.c_int32), ("max_spice_capacity", C.c_int32),
     ]
 
 
@@ -139,6 +140,8 @@ def make_params(c, rng_mode, flags, max_agent_range, equator):
     p.max_tribes = c["environmentMaxTribes"]
     p.max_timestep = int(min(c["timesteps"], 2 ** 31 - 1))
     p.id_bits = 26
+    p.max_sugar_capacity = int(max(c["environmentMaxSugar"], 0))
+    p.max_spice_capacity = int(max(c["environmentMaxSpice"], 0))
     return p
 
 
