@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(32, 1) k_agent_step_exact(DevCtx c, uint32_t *
 constexpr int MAXC_SCALABLE = 32;     // 4 * 8 candidate cells; the host refuses larger ranges
 constexpr int TAG_BITS = 6;
 constexpr int MAX_EPOCHS = 1024;
+constexpr int MAX_ROUNDS = 4096;
 constexpr int AGENT_THREADS = 256;
 #ifndef SSB_GROUP_LANES
 #define SSB_GROUP_LANES 8
@@ -273,6 +274,10 @@ __global__ void __launch_bounds__(AGENT_THREADS, 2) k_agent_step_scalable(DevCtx
         const int n_new = round < E ? rc.epoch_start[round + 1] - e0 : 0;
         const int n = n_carry + n_new;
         if (round >= E && n == 0) break;
+        if (round >= MAX_ROUNDS) {               // cannot happen (the earliest active agent always commits): fail loudly
+            if (tid == 0) c.a.counters[SSB_C_OVERFLOW] = 2;
+            break;
+        }
         if (round > 0 && round % ROUNDS_PER_TAG_EPOCH == 0) {   // tags exhausted: clear and restart
             for (long long i = tid; i < n_cells; i += nthreads) rc.mark[i] = 0xffffffffu;
             grid.sync();
