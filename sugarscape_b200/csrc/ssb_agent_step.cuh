@@ -331,8 +331,13 @@ __global__ void __launch_bounds__(AGENT_THREADS, 2) k_agent_step_scalable(DevCtx
                     // the interact part needs D_k(new cell), k from the now final holdings (never
                     // larger than the k the marks were placed with); the marks of this round
                     // still stand, so it runs right away if the agent owns that diamond too
-                    const int k = footprint_dilation(c, s, true);
-                    const bool now = k == 0 || group_owns_region(c, rc, c.a.pos[s], 0, k, tag | rc.prio[s]);
+                    // (lane 0 has just rewritten the agent's holdings and position: take both
+                    // from lane 0, the other lanes must not re-read them on their own)
+                    int k = 0, new_pos = 0;
+                    if (glane == 0) { k = footprint_dilation(c, s, true); new_pos = c.a.pos[s]; }
+                    k = Group<GL>::bcast(k, 0);
+                    new_pos = Group<GL>::bcast(new_pos, 0);
+                    const bool now = k == 0 || group_owns_region(c, rc, new_pos, 0, k, tag | rc.prio[s]);
                     if (glane == 0) {
                         if (now) transaction_interact_phase<RngStream, false>(c, s, rng);
                         else nxt[atomicAdd(n_next, 1)] = s | PHASE1_BIT;

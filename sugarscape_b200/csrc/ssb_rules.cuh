@@ -586,6 +586,7 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, Rng &rng, const W
             alive = 0;
         }
     }
+    Gr::sync();      // lane 0's writes to the agent record are ordered before anything the group reads next
     return Gr::bcast(alive, 0) != 0;
 }
 
