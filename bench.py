@@ -45,8 +45,8 @@ UNIT = "agent-steps/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=15)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=4096, help="map side (S1 = 4096)")
     ap.add_argument("--agents", type=int, default=0, help="agents (default: S1 density, 1.6 M at 4096)")

@@ -89,7 +89,7 @@ constexpr int MAX_EPOCHS = 1024;
 constexpr int MAX_ROUNDS = 4096;
 constexpr int AGENT_THREADS = 256;
 #ifndef SSB_GROUP_LANES
-#define SSB_GROUP_LANES 8
+#define SSB_GROUP_LANES 4
 #endif
 constexpr int GL = SSB_GROUP_LANES;          // lanes cooperating on one agent
 constexpr int AGENT_GROUPS = AGENT_THREADS / GL;
