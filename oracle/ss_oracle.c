@@ -789,7 +789,7 @@ void orc_stats(const ssb_params_t *p, const ssb_grid_t *g, const ssb_agents_t *a
         for (int y = 0; y < H; y++) {
             int i = x * H + y;
             out->env_wealth_total += g->sugar[i] + g->spice[i];
-            out->env_capacity_total += g->sugar_cap[i] + g->spice_cap[i];
+            if (t <= 1) out->env_capacity_total += g->sugar_cap[i] + g->spice_cap[i];   /* only logged at t == 1 */
         }
     (void)flipped; (void)dry_grows;
 }

@@ -366,9 +366,10 @@ int ssb_reduce_stats(ssb_engine_t *e, int32_t t, void *stream_) {
     const int64_t *n_ptr = c.a.counters + SSB_C_N_LIST;
     uint64_t *src = e->d_keys_a, *dst = e->d_keys_b;
     for (int shift = 0; shift < 64; shift += 8) {
-        k_radix_hist<<<tiles, RADIX_THREADS, 0, st>>>(src, n_ptr, shift, e->d_radix_hist, tiles); LAUNCHED(e);
-        k_radix_scan<<<1, RADIX_THREADS, 0, st>>>(e->d_radix_hist, n_ptr); LAUNCHED(e);
-        k_radix_scatter<<<tiles, RADIX_THREADS, 0, st>>>(src, dst, n_ptr, shift, e->d_radix_hist); LAUNCHED(e);
+        const unsigned long long *varying = &e->d_tribes->key_or;
+        k_radix_hist<<<tiles, RADIX_THREADS, 0, st>>>(src, n_ptr, shift, e->d_radix_hist, varying); LAUNCHED(e);
+        k_radix_scan<<<1, RADIX_THREADS, 0, st>>>(e->d_radix_hist, n_ptr, shift, varying); LAUNCHED(e);
+        k_radix_scatter<<<tiles, RADIX_THREADS, 0, st>>>(src, dst, n_ptr, shift, e->d_radix_hist, varying); LAUNCHED(e);
         uint64_t *tmp = src; src = dst; dst = tmp;
     }
     const int lb = e->num_sms * 4;

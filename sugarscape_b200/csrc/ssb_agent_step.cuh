@@ -91,7 +91,11 @@ constexpr int AGENT_THREADS = 256;
 #ifndef SSB_GROUP_LANES
 #define SSB_GROUP_LANES 4
 #endif
-constexpr int GL = SSB_GROUP_LANES;          // lanes cooperating on one agent
+#ifndef SSB_MARK_LANES
+#define SSB_MARK_LANES 8
+#endif
+constexpr int GL = SSB_GROUP_LANES;          // lanes cooperating on one transaction (EXECUTE)
+constexpr int GM = SSB_MARK_LANES;           // lanes cooperating on one footprint (MARK / SELECT)
 constexpr int AGENT_GROUPS = AGENT_THREADS / GL;
 constexpr int AGENT_SMEM_BYTES = warp_scratch_bytes(MAXC_SCALABLE) * AGENT_GROUPS;
 constexpr int PHASE1_BIT = 0x40000000;   // list entries: slot | PHASE1_BIT once the move part has committed
@@ -170,31 +174,33 @@ __device__ __forceinline__ uint32_t round_tag(const DevCtx &c, int round) {
 }
 constexpr int ROUNDS_PER_TAG_EPOCH = (1 << TAG_BITS) - 1;
 
-// The footprint D_k(cross of radius (rx, ry) + centre), visited by a lane group: one x-column per
-// iteration, the lanes cover its y-interval (at most 2 (ry + k) + 1 <= 21 cells).
+// The footprint D_k(cross of radius (rx, ry) + centre), visited by a lane group of G lanes: one
+// x-column per iteration, the lanes cover its y-interval (at most 2 (ry + k) + 1 <= 21 cells).
+template <int G>
 __device__ __forceinline__ void group_mark_region(const DevCtx &c, const RoundCtx &rc, int pos, int r, int k, uint32_t v) {
-    const int lane = Group<GL>::lane();
+    const int lane = Group<G>::lane();
     Footprint f;
     f.init(c, pos, r, k);
     for (int i = -(f.rx + f.k); i <= f.rx + f.k; i++) {
         const int h = f.half_height(i);
         uint32_t *col = rc.mark + (size_t)wrap1(f.x + i, f.W) * f.H;
-        for (int j = lane - h; j <= h; j += GL) atomicMin(col + wrap1(f.y + j, f.H), v);
+        for (int j = lane - h; j <= h; j += G) atomicMin(col + wrap1(f.y + j, f.H), v);
     }
 }
 
 // true (on every lane of the group) iff every cell of the region holds v
+template <int G>
 __device__ __forceinline__ bool group_owns_region(const DevCtx &c, const RoundCtx &rc, int pos, int r, int k, uint32_t v) {
-    const int lane = Group<GL>::lane();
+    const int lane = Group<G>::lane();
     Footprint f;
     f.init(c, pos, r, k);
     unsigned bad = 0;
     for (int i = -(f.rx + f.k); i <= f.rx + f.k; i++) {
         const int h = f.half_height(i);
         const uint32_t *col = rc.mark + (size_t)wrap1(f.x + i, f.W) * f.H;
-        for (int j = lane - h; j <= h; j += GL) bad |= __ldcg(col + wrap1(f.y + j, f.H)) ^ v;
+        for (int j = lane - h; j <= h; j += G) bad |= __ldcg(col + wrap1(f.y + j, f.H)) ^ v;
     }
-    return !Group<GL>::any(bad != 0);
+    return !Group<G>::any(bad != 0);
 }
 
 // warp-aggregated append: every lane of the warp calls this (full mask)
@@ -217,6 +223,8 @@ __global__ void __launch_bounds__(AGENT_THREADS, 2) k_agent_step_scalable(DevCtx
     const int warp_id = (blockIdx.x * blockDim.x + threadIdx.x) / GL;      // lane-group index
     const int n_warps = (gridDim.x * blockDim.x) / GL;
     const int glane = Group<GL>::lane();
+    const int mgroup_id = (blockIdx.x * blockDim.x + threadIdx.x) / GM, n_mgroups = (gridDim.x * blockDim.x) / GM;
+    const int mlane = Group<GM>::lane();
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nthreads = gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
@@ -289,7 +297,7 @@ __global__ void __launch_bounds__(AGENT_THREADS, 2) k_agent_step_scalable(DevCtx
         const uint32_t tag = round_tag(c, round);
         const int32_t *fresh = rc.bucketed + e0;
         // MARK: one agent per lane group, lanes spread over the footprint cells
-        for (int i = warp_id; i < n; i += n_warps) {
+        for (int i = mgroup_id; i < n; i += n_mgroups) {
             const int entry = i < n_carry ? cur[i] : fresh[i - n_carry];
             const int s = entry & ~PHASE1_BIT;
             const int pos = c.a.pos[s];
@@ -297,21 +305,21 @@ __global__ void __launch_bounds__(AGENT_THREADS, 2) k_agent_step_scalable(DevCtx
             const bool moved = (entry & PHASE1_BIT) != 0;
             const int k = footprint_dilation(c, s, moved);
             const int r = moved ? 0 : agent_range(c, s);
-            group_mark_region(c, rc, pos, r, k, tag | rc.prio[s]);
+            group_mark_region<GM>(c, rc, pos, r, k, tag | rc.prio[s]);
         }
         grid.sync();
         if (tr) rc.trace[round * 6 + 3] = global_ns();
         // SELECT
-        for (int i = warp_id; i < n; i += n_warps) {
+        for (int i = mgroup_id; i < n; i += n_mgroups) {
             const int entry = i < n_carry ? cur[i] : fresh[i - n_carry];
             const int s = entry & ~PHASE1_BIT;
             const int pos = c.a.pos[s];
             bool ok = true;
             if (pos >= 0) {
-                if (entry & PHASE1_BIT) ok = group_owns_region(c, rc, pos, 0, footprint_dilation(c, s, true), tag | rc.prio[s]);
-                else ok = group_owns_region(c, rc, pos, agent_range(c, s), 0, tag | rc.prio[s]);
+                if (entry & PHASE1_BIT) ok = group_owns_region<GM>(c, rc, pos, 0, footprint_dilation(c, s, true), tag | rc.prio[s]);
+                else ok = group_owns_region<GM>(c, rc, pos, agent_range(c, s), 0, tag | rc.prio[s]);
             }
-            if (glane == 0) {
+            if (mlane == 0) {
                 if (ok) rc.ready[atomicAdd(n_ready, 1)] = entry;
                 else nxt[atomicAdd(n_next, 1)] = entry;
             }
@@ -337,7 +345,7 @@ __global__ void __launch_bounds__(AGENT_THREADS, 2) k_agent_step_scalable(DevCtx
                     if (glane == 0) { k = footprint_dilation(c, s, true); new_pos = c.a.pos[s]; }
                     k = Group<GL>::bcast(k, 0);
                     new_pos = Group<GL>::bcast(new_pos, 0);
-                    const bool now = k == 0 || group_owns_region(c, rc, new_pos, 0, k, tag | rc.prio[s]);
+                    const bool now = k == 0 || group_owns_region<GL>(c, rc, new_pos, 0, k, tag | rc.prio[s]);
                     if (glane == 0) {
                         if (now) transaction_interact_phase<RngStream, false>(c, s, rng);
                         else nxt[atomicAdd(n_next, 1)] = s | PHASE1_BIT;

@@ -300,10 +300,11 @@ __device__ void block_fold(StatsPartial &mine, StatsPartial *smem) {
 }
 
 // tribe census (tribes dict, sugarscape.py:1171-1174; max(dict, key=get) needs first-seen order)
-struct TribeCensus { unsigned long long count[32]; unsigned long long first[32]; };
+struct TribeCensus { unsigned long long count[32]; unsigned long long first[32]; unsigned long long key_or, key_and; };
 
 __global__ void k_stats_reset(TribeCensus *tc) {
     if (threadIdx.x < 32) { tc->count[threadIdx.x] = 0; tc->first[threadIdx.x] = ~0ull; }
+    if (threadIdx.x == 0) { tc->key_or = 0ull; tc->key_and = ~0ull; }
 }
 
 __global__ void __launch_bounds__(STATS_THREADS) k_stats_partials(DevCtx c, StatsPartial *out, double *wealth_keys,
@@ -314,6 +315,7 @@ __global__ void __launch_bounds__(STATS_THREADS) k_stats_partials(DevCtx c, Stat
     __syncthreads();
     StatsPartial p;
     partial_zero(p);
+    unsigned long long key_or = 0ull, key_and = ~0ull;
     const long long n = c.a.counters[SSB_C_N_LIST], n_dead = c.a.counters[SSB_C_N_DEAD];
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -321,6 +323,7 @@ __global__ void __launch_bounds__(STATS_THREADS) k_stats_partials(DevCtx c, Stat
         const int s = c.a.order[i];
         const double w = c.a.sugar[s] + c.a.spice[s];
         if (wealth_keys) wealth_keys[i] = w;
+        key_or |= (unsigned long long)__double_as_longlong(w); key_and &= (unsigned long long)__double_as_longlong(w);
         p.population++;
         p.sum_sugar_metab += c.a.sugar_metab[s]; p.sum_spice_metab += c.a.spice_metab[s];
         p.sum_movement += c.a.movement[s]; p.sum_vision += c.a.vision[s]; p.sum_age += c.a.age[s];
@@ -353,16 +356,25 @@ __global__ void __launch_bounds__(STATS_THREADS) k_stats_partials(DevCtx c, Stat
         p.dead_aging += c.a.cod[s] == SSB_AGING;
         p.dead_combat += c.a.cod[s] == SSB_COMBAT;
     }
-    for (long long i = tid; i < c.g.n_cells; i += stride) { // environment totals (1044-1051)
-        p.env_wealth_total += c.g.sugar[i] + c.g.spice[i];
-        p.env_capacity_total += c.g.sugar_cap[i] + c.g.spice_cap[i];
-    }
+    const bool spicy = (c.p.flags & SSB_F_SPICE) != 0;      // spice arrays are all zero otherwise
+    for (long long i = tid; i < c.g.n_cells; i += stride)   // environment totals (1044-1051)
+        p.env_wealth_total += c.g.sugar[i] + (spicy ? c.g.spice[i] : 0);
+    if (c.t <= 1)                                           // capacities are constant: only t = 1 logs them
+        for (long long i = tid; i < c.g.n_cells; i += stride)
+            p.env_capacity_total += c.g.sugar_cap[i] + (spicy ? c.g.spice_cap[i] : 0);
     block_fold(p, smem);
     if (threadIdx.x == 0) out[blockIdx.x] = smem[0];
     if (threadIdx.x < 32 && tr_count[threadIdx.x]) {
         atomicAdd(&tc->count[threadIdx.x], tr_count[threadIdx.x]);
         atomicMin(&tc->first[threadIdx.x], tr_first[threadIdx.x]);
     }
+    // OR / AND of the wealth keys (which digits of the radix sort are constant)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        key_or |= __shfl_xor_sync(0xffffffffu, key_or, o);
+        key_and &= __shfl_xor_sync(0xffffffffu, key_and, o);
+    }
+    if ((threadIdx.x & 31) == 0 && n > 0) { atomicOr(&tc->key_or, key_or); atomicAnd(&tc->key_and, key_and); }
 }
 
 __global__ void __launch_bounds__(STATS_THREADS) k_stats_final(DevCtx c, const StatsPartial *partials, int n_partials,

@@ -463,30 +463,89 @@ __device__ __forceinline__ int alloc_slot(const DevCtx &c) {
 
 // Agent.doReproduction (agent.py:500-554) with findChildEndowment (781-910) and addChildToCell
 // (164-182).  EXACT = mode E (children join the list immediately, IDs in birth order).
+// The reference walks the four neighbours one after the other, each time re-reading the mate and
+// the mate's empty neighbours.  Here both rings (the 4 neighbours and their 16 neighbours) are
+// loaded up front in two batches of independent requests; nothing else can change those cells
+// while this agent holds its reservation, so the only updates are this call's own child
+// placements, which are tracked in the local copies.
 template <class Rng, bool EXACT>
 __device__ __noinline__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
     const ssb_agents_t &a = c.a;
     if (!agent_alive(c, s) || !is_fertile(c, s)) return;
-    int32_t nb[4], own_empty[4];
-    neighbours4(c, a.pos[s], nb);
+    const int pos = a.pos[s];
+    int32_t nb0[4], nb[4];
+    neighbours4(c, pos, nb0);
+    for (int i = 0; i < 4; i++) nb[i] = nb0[i];
     rng.at(SITE_REPRODUCTION);
     shuffle(rng, nb, 4);
-    const int n_own = empty_neighbours(c, a.pos[s], own_empty);
-    unsigned long long *cn = (unsigned long long *)a.counters;
+    // batch 1: occupancy of the neighbours (shuffled order) and of each neighbour's ring
+    int32_t o[4], ring[4][4], ring_occ[4][4];
+#pragma unroll
     for (int k = 0; k < 4; k++) {
-        const int m = c.g.occ[nb[k]];
-        if (m < 0 || !agent_alive(c, m)) continue;
-        const bool compatible = ((a.sex[s] == SSB_SEX_FEMALE && a.sex[m] == SSB_SEX_MALE) ||
-                                 (a.sex[s] == SSB_SEX_MALE && a.sex[m] == SSB_SEX_FEMALE)) && is_fertile(c, m);
+        o[k] = c.g.occ[nb[k]];
+        neighbours4(c, nb[k], ring[k]);
+#pragma unroll
+        for (int j = 0; j < 4; j++) ring_occ[k][j] = c.g.occ[ring[k][j]];
+    }
+    // batch 2: the mates' records
+    int m_cod[4], m_sex[4], m_age[4], m_fa[4], m_ia[4];
+    double m_sugar[4], m_spice[4], m_ss[4], m_sp[4], m_ff[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const bool has = o[k] >= 0;
+        const int m = has ? o[k] : s;
+        m_cod[k] = a.cod[m]; m_sex[k] = a.sex[m]; m_age[k] = a.age[m];
+        m_fa[k] = a.fert_age[m]; m_ia[k] = a.infert_age[m];
+        m_sugar[k] = a.sugar[m]; m_spice[k] = a.spice[m];
+        m_ss[k] = a.start_sugar[m]; m_sp[k] = a.start_spice[m]; m_ff[k] = a.fert_factor[m];
+    }
+    // own empty neighbours, N S E W order, computed ONCE (agent.py:506): stale by design
+    int32_t own_empty[4];
+    int n_own = 0;
+    for (int i = 0; i < 4; i++)
+        for (int k = 0; k < 4; k++)
+            if (nb[k] == nb0[i] && o[k] < 0) { own_empty[n_own++] = nb0[i]; break; }
+    // own record
+    const int my_sex = a.sex[s], my_age = a.age[s], my_fa = a.fert_age[s], my_ia = a.infert_age[s];
+    const double my_ss = a.start_sugar[s], my_sp = a.start_spice[s], my_ff = a.fert_factor[s];
+    double my_sugar = a.sugar[s], my_spice = a.spice[s];
+    const bool age_ok = my_age >= my_fa && my_age < my_ia && my_ff > 0;
+    unsigned long long *cn = (unsigned long long *)a.counters;
+    bool newborn_at[4] = {false, false, false, false};     // neighbour cell now holds a child of this call
+    for (int k = 0; k < 4; k++) {
+        if (o[k] < 0) continue;
+        const int m = o[k];
+        // neighbor.isAlive(): a newborn placed by this call is alive and never fertile at age 0
+        if (!newborn_at[k] && !(m_cod[k] == SSB_ALIVE && m_sugar[k] >= 0 && m_spice[k] >= 0)) continue;
+        bool mate_fertile = !newborn_at[k] && m_sugar[k] >= m_ss[k] && m_spice[k] >= m_sp[k] &&
+                            m_age[k] >= m_fa[k] && m_age[k] < m_ia[k] && m_ff[k] > 0;
+        int mate_sex = m_sex[k];
+        if (newborn_at[k]) {     // rare: evaluate the child exactly as the reference would
+            mate_sex = a.sex[m];
+            mate_fertile = is_fertile(c, m);
+            m_sugar[k] = a.sugar[m]; m_spice[k] = a.spice[m];
+            m_ss[k] = a.start_sugar[m]; m_sp[k] = a.start_spice[m]; m_ff[k] = a.fert_factor[m];
+        }
+        const bool compatible = ((my_sex == SSB_SEX_FEMALE && mate_sex == SSB_SEX_MALE) ||
+                                 (my_sex == SSB_SEX_MALE && mate_sex == SSB_SEX_FEMALE)) && mate_fertile;
         int32_t pool[8];
         int np = 0;
         for (int i = 0; i < n_own; i++) pool[np++] = own_empty[i];
-        np += empty_neighbours(c, a.pos[m], pool + np);
+        for (int j = 0; j < 4; j++) if (ring_occ[k][j] < 0) pool[np++] = ring[k][j];
         shuffle(rng, pool, np);    // drawn before the compatibility test (reference quirk)
-        if (!(is_fertile(c, s) && compatible && np != 0)) continue;
+        const bool fertile_now = age_ok && my_sugar >= my_ss && my_spice >= my_sp;
+        if (!(fertile_now && compatible && np != 0)) continue;
+        // current occupancy of a pool cell: neighbour cells and ring cells are all tracked locally
+        auto occupied_now = [&](int cell) {
+            for (int q = 0; q < 4; q++) {
+                if (nb[q] == cell) return o[q] >= 0;
+                for (int j = 0; j < 4; j++) if (ring[q][j] == cell) return ring_occ[q][j] >= 0;
+            }
+            return c.g.occ[cell] >= 0;
+        };
         int cell = pool[--np];
-        while (c.g.occ[cell] >= 0 && np != 0) cell = pool[--np];
-        if (c.g.occ[cell] >= 0) continue;
+        while (occupied_now(cell) && np != 0) cell = pool[--np];
+        if (occupied_now(cell)) continue;
         const int ch = alloc_slot(c);
         if (ch < 0) return;
         const uint32_t eb = (c.endow_bits && c.t < c.n_step_tables) ? c.endow_bits[c.t] : 0u;
@@ -506,18 +565,17 @@ __device__ __noinline__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
         a.trade_factor[ch] = SSB_PICK(trade_factor, EB_TRADE_FACTOR);
         a.vision[ch] = SSB_PICK(vision, EB_VISION);
 #undef SSB_PICK
-        const double sugar_cost = a.start_sugar[s] / (a.fert_factor[s] * 2);
-        const double spice_cost = a.start_spice[s] / (a.fert_factor[s] * 2);
-        const double mate_sugar_cost = a.start_sugar[m] / (a.fert_factor[m] * 2);
-        const double mate_spice_cost = a.start_spice[m] / (a.fert_factor[m] * 2);
+        const double sugar_cost = my_ss / (my_ff * 2), spice_cost = my_sp / (my_ff * 2);
+        const double mate_sugar_cost = m_ss[k] / (m_ff[k] * 2), mate_spice_cost = m_sp[k] / (m_ff[k] * 2);
         a.start_sugar[ch] = a.sugar[ch] = sugar_cost + mate_sugar_cost;
         a.start_spice[ch] = a.spice[ch] = spice_cost + mate_spice_cost;
         uint32_t tags = 0;
         if (c.p.flags & SSB_F_TAGS) {
             const uint32_t tb = (c.tag_bits && c.t < c.n_step_tables) ? c.tag_bits[c.t] : 0u;
+            const uint32_t ts = a.tags[s], tm = a.tags[m];
             int draw = 0;
             for (int i = 0; i < c.p.tag_len; i++) {
-                const uint32_t bs = (a.tags[s] >> i) & 1u, bm = (a.tags[m] >> i) & 1u;
+                const uint32_t bs = (ts >> i) & 1u, bm = (tm >> i) & 1u;
                 const uint32_t b = bs == bm ? bs : ((tb >> draw++) & 1u);
                 tags |= b << i;
             }
@@ -530,10 +588,15 @@ __device__ __noinline__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
         a.happiness[ch] = 0; a.wealth_happiness[ch] = 0; a.family_happiness[ch] = 0;
         a.trade_volume[ch] = 0; a.trade_price[ch] = 0; a.last_repro[ch] = -1;
         a.n_children_alive[ch] = 0; a.n_children_dead[ch] = 0;
-        a.father[ch] = a.sex[s] == SSB_SEX_FEMALE ? a.id[m] : a.id[s];
-        a.mother[ch] = a.sex[s] == SSB_SEX_FEMALE ? a.id[s] : a.id[m];
+        const int my_id = a.id[s], mate_id = a.id[m];
+        a.father[ch] = my_sex == SSB_SEX_FEMALE ? mate_id : my_id;
+        a.mother[ch] = my_sex == SSB_SEX_FEMALE ? my_id : mate_id;
         a.pos[ch] = cell;
         c.g.occ[cell] = ch;
+        for (int q = 0; q < 4; q++) {       // keep the local copies current
+            if (nb[q] == cell) { o[q] = ch; newborn_at[q] = true; }
+            for (int j = 0; j < 4; j++) if (ring[q][j] == cell) ring_occ[q][j] = ch;
+        }
         const long long nth = (long long)atomicAdd(&cn[SSB_C_N_BORN], 1ull);
         if (EXACT) {   // sugarscape.addAgent: the list grows while it is being iterated
             const long long at = (long long)atomicAdd(&cn[SSB_C_N_LIST], 1ull);
@@ -542,9 +605,11 @@ __device__ __noinline__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
             if (nth < a.capacity) c.born_list[nth] = ch; else atomicExch(&cn[SSB_C_OVERFLOW], 1ull);
         }
         collect(c, ch, cell);      // the child collects at birth (agent.py:175)
-        a.sugar[s] -= sugar_cost; a.spice[s] -= spice_cost;
-        a.sugar[m] = a.sugar[m] - mate_sugar_cost;
-        a.spice[m] = a.spice[m] - mate_spice_cost;
+        my_sugar -= sugar_cost; my_spice -= spice_cost;
+        a.sugar[s] = my_sugar; a.spice[s] = my_spice;
+        m_sugar[k] -= mate_sugar_cost; m_spice[k] -= mate_spice_cost;
+        a.sugar[m] = m_sugar[k];
+        a.spice[m] = m_spice[k];
         a.last_repro[s] = c.t;
     }
 }

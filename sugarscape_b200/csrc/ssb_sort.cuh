@@ -16,8 +16,15 @@ constexpr int RADIX_ITEMS = 16;
 constexpr int RADIX_TILE = RADIX_THREADS * RADIX_ITEMS;   // 4096 keys per block
 constexpr int RADIX_WARPS = RADIX_THREADS / 32;
 
+// varying[0] = OR of all keys, varying[1] = AND of all keys: a digit whose bits are all equal in
+// OR and AND is the same in every key, so its pass degenerates to a copy.
+__device__ __forceinline__ bool digit_is_constant(const unsigned long long *varying, int shift) {
+    return (((varying[0] ^ varying[1]) >> shift) & 255ull) == 0ull;
+}
+
 __global__ void __launch_bounds__(RADIX_THREADS) k_radix_hist(const uint64_t *keys, const int64_t *n_ptr, int shift,
-                                                              uint32_t *hist, int n_tiles_max) {
+                                                              uint32_t *hist, const unsigned long long *varying) {
+    if (digit_is_constant(varying, shift)) return;
     const long long n = *n_ptr;
     const int n_tiles = (int)((n + RADIX_TILE - 1) / RADIX_TILE);
     if ((int)blockIdx.x >= n_tiles) return;
@@ -34,41 +41,48 @@ __global__ void __launch_bounds__(RADIX_THREADS) k_radix_hist(const uint64_t *ke
     hist[(long long)threadIdx.x * n_tiles + blockIdx.x] = h[threadIdx.x];
 }
 
-// exclusive scan over hist[256 * n_tiles] (digit-major), single block
-__global__ void __launch_bounds__(RADIX_THREADS) k_radix_scan(uint32_t *hist, const int64_t *n_ptr) {
+// exclusive scan over hist[256 * n_tiles] (digit-major), single block: every thread owns a
+// contiguous chunk (serial), the chunk totals are scanned across the block
+__global__ void __launch_bounds__(RADIX_THREADS) k_radix_scan(uint32_t *hist, const int64_t *n_ptr, int shift,
+                                                              const unsigned long long *varying) {
+    if (digit_is_constant(varying, shift)) return;
     const long long n = *n_ptr;
     const int n_tiles = (int)((n + RADIX_TILE - 1) / RADIX_TILE);
     const long long total = 256LL * n_tiles;
+    const long long chunk = (total + RADIX_THREADS - 1) / RADIX_THREADS;
+    const long long lo = (long long)threadIdx.x * chunk, hi = lo + chunk < total ? lo + chunk : total;
+    uint32_t sum = 0;
+    for (long long i = lo; i < hi; i++) sum += hist[i];
     __shared__ uint32_t warp_sums[RADIX_WARPS];
-    __shared__ uint32_t carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (long long base = 0; base < total; base += RADIX_THREADS) {
-        const long long i = base + threadIdx.x;
-        const uint32_t v = i < total ? hist[i] : 0u;
-        uint32_t inc = v;
+    uint32_t inc = sum;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += u;
-        }
-        if (lane == 31) warp_sums[w] = inc;
-        __syncthreads();
-        uint32_t wbase = 0;
-        for (int j = 0; j < w; j++) wbase += warp_sums[j];
-        if (i < total) hist[i] = carry + wbase + inc - v;
-        __syncthreads();
-        if (threadIdx.x == RADIX_THREADS - 1) carry += wbase + inc;
-        __syncthreads();
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
     }
+    if (lane == 31) warp_sums[w] = inc;
+    __syncthreads();
+    uint32_t base = 0;
+    for (int j = 0; j < w; j++) base += warp_sums[j];
+    uint32_t run = base + inc - sum;
+    for (long long i = lo; i < hi; i++) { const uint32_t v = hist[i]; hist[i] = run; run += v; }
 }
 
 __global__ void __launch_bounds__(RADIX_THREADS) k_radix_scatter(const uint64_t *keys, uint64_t *out, const int64_t *n_ptr,
-                                                                 int shift, const uint32_t *hist) {
+                                                                 int shift, const uint32_t *hist,
+                                                                 const unsigned long long *varying) {
     const long long n = *n_ptr;
     const int n_tiles = (int)((n + RADIX_TILE - 1) / RADIX_TILE);
     if ((int)blockIdx.x >= n_tiles) return;
+    if (digit_is_constant(varying, shift)) {       // nothing to reorder: keep the ping-pong going
+        const long long tile0 = (long long)blockIdx.x * RADIX_TILE;
+        for (int k = 0; k < RADIX_ITEMS; k++) {
+            const long long i = tile0 + k * RADIX_THREADS + threadIdx.x;
+            if (i < n) out[i] = keys[i];
+        }
+        return;
+    }
     __shared__ uint32_t cnt[RADIX_WARPS][256];
     for (int i = threadIdx.x; i < RADIX_WARPS * 256; i += RADIX_THREADS) (&cnt[0][0])[i] = 0;
     __syncthreads();
