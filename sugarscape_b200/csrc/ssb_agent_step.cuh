@@ -72,8 +72,10 @@ __global__ void __launch_bounds__(32, 1) k_agent_step_exact(DevCtx c, uint32_t *
         const long long n_list = __shfl_sync(0xffffffffu, (long long)cn[SSB_C_N_LIST], 0);
         if (i >= n_list) break;
         const int s = c.a.order[i];
-        const bool go_on = transaction_move_phase<32>(c, s, rng, ws, MAXC_EXACT);
-        if (go_on && lane == 0) transaction_interact_phase<RngExact, true>(c, s, rng);
+        AgentRec rec;
+        rec.load(c, s);
+        const bool go_on = transaction_move_phase<32, 4>(c, s, rec, rng, ws, MAXC_EXACT);
+        if (go_on && lane == 0) transaction_interact_phase<RngExact, true>(c, s, rec, rng);
         __threadfence_block();
         __syncwarp();
     }
@@ -143,6 +145,15 @@ __device__ __forceinline__ int footprint_dilation(const DevCtx &c, int s, bool m
         }
         if (can) k = 2;
     }
+    return k;
+}
+
+// the same from the register copy of the record, after the move part (holdings are final)
+__device__ __forceinline__ int footprint_dilation_moved(const DevCtx &c, const AgentRec &rec) {
+    int k = 0;
+    if (c.p.flags & (SSB_F_TAGGING | SSB_F_TRADE)) k = 1;
+    if ((c.p.flags & SSB_F_REPRO) && rec.fert_factor > 0 && rec.age >= rec.fert_age && rec.age < rec.infert_age &&
+        ((c.p.flags & SSB_F_TRADE) || (rec.sugar >= rec.start_sugar && rec.spice >= rec.start_spice))) k = 2;
     return k;
 }
 
@@ -331,25 +342,21 @@ __global__ void __launch_bounds__(AGENT_THREADS, 2) k_agent_step_scalable(DevCtx
         for (int i = warp_id; i < nr; i += n_warps) {
             const int entry = rc.ready[i];
             const int s = entry & ~PHASE1_BIT;
-            RngStream rng{rc.key, (uint32_t)c.a.id[s], 0u, 0u, nullptr};
+            AgentRec rec;
+            rec.load(c, s);                                  // one latency level for the whole record
+            RngStream rng{rc.key, (uint32_t)rec.id, 0u, 0u, nullptr};
             if (entry & PHASE1_BIT) {
-                if (glane == 0) transaction_interact_phase<RngStream, false>(c, s, rng);
-            } else {
-                if (transaction_move_phase<GL>(c, s, rng, ws, MAXC_SCALABLE)) {
-                    // the interact part needs D_k(new cell), k from the now final holdings (never
-                    // larger than the k the marks were placed with); the marks of this round
-                    // still stand, so it runs right away if the agent owns that diamond too
-                    // (lane 0 has just rewritten the agent's holdings and position: take both
-                    // from lane 0, the other lanes must not re-read them on their own)
-                    int k = 0, new_pos = 0;
-                    if (glane == 0) { k = footprint_dilation(c, s, true); new_pos = c.a.pos[s]; }
-                    k = Group<GL>::bcast(k, 0);
-                    new_pos = Group<GL>::bcast(new_pos, 0);
-                    const bool now = k == 0 || group_owns_region<GL>(c, rc, new_pos, 0, k, tag | rc.prio[s]);
-                    if (glane == 0) {
-                        if (now) transaction_interact_phase<RngStream, false>(c, s, rng);
-                        else nxt[atomicAdd(n_next, 1)] = s | PHASE1_BIT;
-                    }
+                if (glane == 0) transaction_interact_phase<RngStream, false>(c, s, rec, rng);
+            } else if (transaction_move_phase<GL, 4>(c, s, rec, rng, ws, MAXC_SCALABLE)) {
+                // the interact part needs D_k(new cell), k from the now final holdings (never
+                // larger than the k the marks were placed with); the marks of this round still
+                // stand, so it runs right away if the agent owns that diamond too.  rec is the
+                // same on every lane (broadcast from lane 0), so the branch is group-uniform.
+                const int k = footprint_dilation_moved(c, rec);
+                const bool now = k == 0 || group_owns_region<GL>(c, rc, rec.pos, 0, k, tag | rc.prio[s]);
+                if (glane == 0) {
+                    if (now) transaction_interact_phase<RngStream, false>(c, s, rec, rng);
+                    else nxt[atomicAdd(n_next, 1)] = s | PHASE1_BIT;
                 }
             }
             Group<GL>::sync();

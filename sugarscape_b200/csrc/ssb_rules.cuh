@@ -118,6 +118,25 @@ struct Welfare {
             e_s = (sm / pref) * fz; e_p = (pm / pref) * fo;
         }
     }
+    // same, from values already in registers (tags / tribe refresh included)
+    __device__ __forceinline__ void set(const DevCtx &c, int s, double sugar_, double spice_, int sugar_metab,
+                                        int spice_metab, double look, uint32_t tags) {
+        const double sm = (double)max(sugar_metab, 0), pm = (double)max(spice_metab, 0);
+        sugar = sugar_; spice = spice_;
+        s_look = sm * look; p_look = pm * look;
+        const double total = sm + pm;
+        e_s = 0; e_p = 0;
+        if (total != 0) { e_s = sm / total; e_p = pm / total; }
+        if ((c.p.flags & SSB_F_TAGPREF) && (c.p.flags & SSB_F_TAGS) && c.p.tag_len > 0) {
+            const int L = c.p.tag_len;
+            c.a.tribe[s] = find_tribe(c, tags);
+            const int zeroes = L - __popc(tags);
+            const double fz = (double)zeroes / (double)L, fo = 1 - fz;
+            double pref = sm * fz + pm * fo;
+            if (pref <= 0) pref = 1;
+            e_s = (sm / pref) * fz; e_p = (pm / pref) * fo;
+        }
+    }
     __device__ __forceinline__ double eval(double sugar_reward, double spice_reward) const {
         double ts = (sugar + sugar_reward) - s_look;
         double tp = (spice + spice_reward) - p_look;
@@ -227,34 +246,69 @@ __device__ __forceinline__ int agent_range(const DevCtx &c, int s) {
     return min(min(vision, movement), max(c.max_dx, c.max_dy));
 }
 
-// rankCellsInRange + findBestCell + moveToBestCell (agent.py:1395-1443, 719-746, 1321-1328),
-// executed by all 32 lanes of a warp for ONE agent.
+// The agent's own record, loaded ONCE per transaction by every lane of the group (uniform
+// addresses: one memory transaction each, all independent -> a single latency level).
+struct AgentRec {
+    int id, pos, cod, last_moved, vision, movement, sugar_metab, spice_metab, tribe, age, max_age, fert_age, infert_age;
+    uint32_t tags;
+    double sugar, spice, aggression, lookahead, fert_factor, start_sugar, start_spice;
+    __device__ __forceinline__ void load(const DevCtx &c, int s) {
+        const ssb_agents_t &a = c.a;
+        id = a.id[s]; pos = a.pos[s]; cod = a.cod[s]; last_moved = a.last_moved[s];
+        vision = a.vision[s]; movement = a.movement[s];
+        sugar_metab = a.sugar_metab[s]; spice_metab = a.spice_metab[s];
+        tribe = a.tribe[s]; age = a.age[s]; max_age = a.max_age[s];
+        sugar = a.sugar[s]; spice = a.spice[s];
+        aggression = a.aggression[s]; lookahead = a.lookahead[s];
+        const bool repro = (c.p.flags & SSB_F_REPRO) != 0;
+        fert_age = repro ? a.fert_age[s] : 0; infert_age = repro ? a.infert_age[s] : 0;
+        fert_factor = repro ? a.fert_factor[s] : 0.0;
+        start_sugar = repro ? a.start_sugar[s] : 0.0; start_spice = repro ? a.start_spice[s] : 0.0;
+        tags = (c.p.flags & SSB_F_TAGS) ? a.tags[s] : 0u;
+    }
+    __device__ __forceinline__ bool alive() const { return cod == SSB_ALIVE && sugar >= 0 && spice >= 0; }
+    __device__ __forceinline__ bool fertile() const {       // Agent.isFertile (agent.py:1244-1247)
+        return sugar >= start_sugar && spice >= start_spice && age >= fert_age && age < infert_age && fert_factor > 0;
+    }
+};
+
+// MOVE part of Agent.doTimestep (agent.py:568-584), executed by the G lanes of a group for ONE
+// agent: lastSugar/lastSpice, rankCellsInRange + findBestCell + moveToBestCell (1395-1443,
+// 719-746, 1321-1328), collectResourcesAtCell (249-259), doMetabolism (485-498).
+//
 // Only the head of the stable sort (agent.py:1479-1490) is needed: the winner is the candidate
 // with the highest welfare, then the smallest distance, then the earliest shuffled position --
-// a strict total order, so the lanes can evaluate candidates independently (lane l takes
-// candidates l, l + 32, ...) and a warp arg-best picks the move.  The dependent memory chain of
-// the whole ranking is two levels (cell, occupant) instead of two per candidate.
-// Returns the new cell (valid on every lane).
-template <int G, class Rng>
-__device__ int move_to_best_cell(const DevCtx &c, int s, Rng &rng, const WarpScratch &ws, int maxc) {
+// a strict total order, so the lanes evaluate candidates independently (lane l takes candidates
+// l, l + G, ...) in chunks of CH: all cell loads of a chunk are issued together, then all occupant
+// loads, then the arithmetic.  The contents of the winning cell stay in registers for the collect
+// step.  Dependent memory levels of the whole move part: own record, cells, occupants.
+// Returns true (on every lane) if the agent is still alive and has to run the interact part;
+// rec is updated (lane 0's copy is authoritative and written back to memory).
+template <int G, int CH, class Rng>
+__device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rng &rng, const WarpScratch &ws, int maxc) {
     typedef Group<G> Gr;
     const int lane = Gr::lane();
     const ssb_agents_t &a = c.a;
-    const int pos = a.pos[s];                                  // uniform loads: one transaction each
+    if (!rec.alive() || rec.last_moved == c.t) return false;                 // uniform
+    const double last_sugar = rec.sugar, last_spice = rec.spice;
+    const int pos = rec.pos;
     const int H = c.p.height, x = pos / H, y = pos - x * H;
-    const int r = agent_range(c, s);
-    const double aggression = fmax(a.aggression[s], 0.0);
+    const int r = min(min(max(rec.vision, 0), max(rec.movement, 0)), max(c.max_dx, c.max_dy));
+    const double aggression = fmax(rec.aggression, 0.0);
     Welfare w;
-    w.load(c, s);
-    const int my_tribe = a.tribe[s];
+    w.set(c, s, rec.sugar, rec.spice, rec.sugar_metab, rec.spice_metab, rec.lookahead, rec.tags);
+    const int my_tribe = (c.p.flags & SSB_F_TAGPREF) ? find_tribe(c, rec.tags) : rec.tribe;
+    const bool polluted = (c.p.flags & SSB_F_POLLUTION) != 0;
+    const bool spicy = (c.p.flags & SSB_F_SPICE) != 0;
+    const bool fighter = aggression > 0;
     int n = 0;
     if (lane == 0 && r > 0) n = enumerate_cross(c, x, y, r, ws, maxc);
     n = Gr::bcast(n, 0);
-    int best = pos;
-    if (n > 0) {                                               // warp-uniform branch
-        const bool polluted = (c.p.flags & SSB_F_POLLUTION) != 0;
-        const bool spicy = (c.p.flags & SSB_F_SPICE) != 0;
-        const bool fighter = aggression > 0;
+    int b_cell = pos, b_dist = 1 << 30, b_rank = 1 << 30, b_cs = 0, b_cp = 0;
+    double b_welfare = -1.0, b_pl = 0.0;
+    bool b_valid = false;
+    int hood = 0, m = 0;
+    if (n > 0) {                                               // group-uniform branch
         // random.shuffle(cellsInRange), agent.py:1400-1401: rank[i] = shuffled position of cell i.
         // The draws are sequential (rejection sampling); mode S prefetches its counter-based
         // words with all lanes first.
@@ -286,80 +340,136 @@ __device__ int move_to_best_cell(const DevCtx &c, int s, Rng &rng, const WarpScr
             }
         }
         Gr::sync();
-        int hood = 0, m = 0;        // per-lane partial counts
-        int b_cell = pos, b_dist = 1 << 30, b_rank = 1 << 30;
-        double b_welfare = -1.0;
-        bool b_valid = false;
-        for (int i = lane; i < n; i += G) {
-            const int cell = ws.cells[i];
-            const int o = c.g.occ[cell];
-            const int cs = c.g.sugar[cell];
-            const int cp = spicy ? c.g.spice[cell] : 0;
-            const double pl = polluted ? c.g.pollution[cell] : 0.0;
-            const bool occupied = o >= 0;
-            int ocod = SSB_ALIVE, otribe = -1;
-            double osug = 0, ospi = 0;
-            if (occupied) {
-                ocod = a.cod[o]; osug = a.sugar[o]; ospi = a.spice[o];
-                if (fighter) otribe = a.tribe[o];
+        for (int base = 0; base < n; base += G * CH) {         // group-uniform trip count
+            int cell[CH], o[CH], cs[CH], cp[CH];
+            double pl[CH];
+            bool valid[CH];
+#pragma unroll
+            for (int q = 0; q < CH; q++) {                     // level 1: the cells
+                const int i = base + q * G + lane;
+                valid[q] = i < n;
+                cell[q] = valid[q] ? ws.cells[i] : pos;
+                o[q] = c.g.occ[cell[q]];
+                cs[q] = c.g.sugar[cell[q]];
+                cp[q] = spicy ? c.g.spice[cell[q]] : 0;
+                pl[q] = polluted ? c.g.pollution[cell[q]] : 0.0;
             }
-            double ps = 0, pp = 0;
-            if (occupied) {
-                // findNeighborhood (agent.py:1052-1065): live agents in range
-                if (ocod == SSB_ALIVE && osug >= 0 && ospi >= 0) hood++;
-                // isNeighborValidPrey (agent.py:1309-1314)
-                if (!(fighter && my_tribe != otribe && my_wealth >= osug + ospi)) continue;
-                ps = osug; pp = ospi;
+            int ocod[CH], otribe[CH];
+            double osug[CH], ospi[CH];
+#pragma unroll
+            for (int q = 0; q < CH; q++) {                     // level 2: their occupants
+                const bool has = valid[q] && o[q] >= 0;
+                const int oo = has ? o[q] : s;
+                ocod[q] = a.cod[oo]; osug[q] = a.sugar[oo]; ospi[q] = a.spice[oo];
+                otribe[q] = (has && fighter) ? a.tribe[oo] : -1;
             }
-            const double wps = aggression * fmin(loot, ps), wpp = aggression * fmin(loot, pp);
-            const double welfare = w.eval(((double)cs + wps) / (1 + pl), ((double)cp + wpp) / (1 + pl));
-            if (occupied && __longlong_as_double((long long)ws.retaliator[min(otribe + 1, 26)]) > my_wealth + welfare) continue;
-            const int dist = ws.dist[i], rk = ws.rank[i];
-            if (!b_valid || welfare > b_welfare ||
-                (welfare == b_welfare && (dist < b_dist || (dist == b_dist && rk < b_rank)))) {
-                b_cell = cell; b_welfare = welfare; b_dist = dist; b_rank = rk; b_valid = true;
+#pragma unroll
+            for (int q = 0; q < CH; q++) {                     // arithmetic
+                if (!valid[q]) continue;
+                const int i = base + q * G + lane;
+                const bool occupied = o[q] >= 0;
+                double ps = 0, pp = 0;
+                if (occupied) {
+                    // findNeighborhood (agent.py:1052-1065): live agents in range
+                    if (ocod[q] == SSB_ALIVE && osug[q] >= 0 && ospi[q] >= 0) hood++;
+                    // isNeighborValidPrey (agent.py:1309-1314)
+                    if (!(fighter && my_tribe != otribe[q] && my_wealth >= osug[q] + ospi[q])) continue;
+                    ps = osug[q]; pp = ospi[q];
+                }
+                const double wps = aggression * fmin(loot, ps), wpp = aggression * fmin(loot, pp);
+                const double welfare = w.eval(((double)cs[q] + wps) / (1 + pl[q]), ((double)cp[q] + wpp) / (1 + pl[q]));
+                if (occupied && __longlong_as_double((long long)ws.retaliator[min(otribe[q] + 1, 26)]) > my_wealth + welfare) continue;
+                const int dist = ws.dist[i], rk = ws.rank[i];
+                if (!b_valid || welfare > b_welfare ||
+                    (welfare == b_welfare && (dist < b_dist || (dist == b_dist && rk < b_rank)))) {
+                    b_cell = cell[q]; b_welfare = welfare; b_dist = dist; b_rank = rk; b_valid = true;
+                    b_cs = cs[q]; b_cp = cp[q]; b_pl = pl[q];
+                }
+                m++;
             }
-            m++;
         }
-        // warp reductions: counts, then arg-best under the same strict order
+        // group reductions: counts, then arg-best under the same strict order
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) {
             hood += Gr::xor_(hood, o);
             m += Gr::xor_(m, o);
-            const int o_cell = Gr::xor_(b_cell, o), o_dist = Gr::xor_(b_dist, o);
-            const int o_rank = Gr::xor_(b_rank, o);
-            const double o_welfare = Gr::xor_(b_welfare, o);
+            const int o_cell = Gr::xor_(b_cell, o), o_dist = Gr::xor_(b_dist, o), o_rank = Gr::xor_(b_rank, o);
+            const int o_cs = Gr::xor_(b_cs, o), o_cp = Gr::xor_(b_cp, o);
+            const double o_welfare = Gr::xor_(b_welfare, o), o_pl = Gr::xor_(b_pl, o);
             const bool o_valid = Gr::xor_((int)b_valid, o) != 0;
             const bool take = o_valid && (!b_valid || o_welfare > b_welfare ||
                 (o_welfare == b_welfare && (o_dist < b_dist || (o_dist == b_dist && o_rank < b_rank))));
-            if (take) { b_cell = o_cell; b_welfare = o_welfare; b_dist = o_dist; b_rank = o_rank; b_valid = true; }
+            if (take) {
+                b_cell = o_cell; b_welfare = o_welfare; b_dist = o_dist; b_rank = o_rank; b_valid = true;
+                b_cs = o_cs; b_cp = o_cp; b_pl = o_pl;
+            }
         }
-        best = b_valid ? b_cell : pos;
         if (m == 0) m = 1;
-        if (lane == 0) {
-            a.n_neighborhood[s] = hood + 1;      // + self
-            a.n_valid_moves[s] = m;
-        }
     }
+    int alive = 1;
+    double sugar = rec.sugar, spice = rec.spice;
+    const int best = b_valid ? b_cell : pos;
     if (lane == 0) {
+        if (n > 0) { a.n_neighborhood[s] = hood + 1; a.n_valid_moves[s] = m; }   // + self
+        if (!b_valid) {     // stays on its own cell: its contents were not among the candidates
+            b_cs = c.g.sugar[pos];
+            b_cp = spicy ? c.g.spice[pos] : 0;
+            b_pl = polluted ? c.g.pollution[pos] : 0.0;
+        }
         // doCombat (agent.py:274-294) then gotoCell (agent.py:1213-1219)
-        if (aggression > 0) {
+        if (fighter) {
             const int prey = c.g.occ[best];
             if (prey >= 0 && prey != s) {
                 const double loot = c.p.max_combat_loot;
                 const double sl = fmin(loot, a.sugar[prey]), pl = fmin(loot, a.spice[prey]);
-                a.sugar[s] += sl; a.spice[s] += pl;
+                sugar += sl; spice += pl;
                 a.sugar[prey] -= sl; a.spice[prey] -= pl;
                 do_death(c, prey, SSB_COMBAT);
             }
         }
-        a.last_moved[s] = c.t;
         c.g.occ[pos] = -1;
-        a.pos[s] = best;
         c.g.occ[best] = s;
+        // collectResourcesAtCell (agent.py:249-259) + production pollution (cell.py:32-45)
+        sugar += b_cs;
+        spice += b_cp;
+        const bool polluting = c.p.pollution_start <= c.t && c.t <= c.p.pollution_end;
+        double cell_poll = b_pl;
+        if (polluting) {
+            cell_poll += c.p.sugar_prod_pollution * b_cs;
+            cell_poll += c.p.spice_prod_pollution * b_cp;
+        }
+        c.g.sugar[best] = 0;
+        if (spicy) c.g.spice[best] = 0;
+        // doMetabolism (agent.py:485-498) + consumption pollution (cell.py:27-40)
+        const double sm = (double)max(rec.sugar_metab, 0), pm = (double)max(rec.spice_metab, 0);
+        sugar -= sm;
+        spice -= pm;
+        if (polluting) {
+            cell_poll += c.p.sugar_cons_pollution * sm;
+            cell_poll += c.p.spice_cons_pollution * pm;
+            c.g.pollution[best] = cell_poll;
+        }
+        a.last_sugar[s] = last_sugar;
+        a.last_spice[s] = last_spice;
+        a.last_moved[s] = c.t;
+        a.sugar[s] = sugar;
+        a.spice[s] = spice;
+        a.pos[s] = best;
+        if (sugar < 0 || spice < 0 || (sugar <= 0 && sm > 0) || (spice <= 0 && pm > 0)) {
+            // doDeath("starvation") (agent.py:296-313)
+            a.cod[s] = SSB_STARVATION;
+            c.g.occ[best] = -1;
+            a.pos[s] = -1;
+            alive = 0;
+        }
     }
-    Gr::sync();
-    return best;
+    Gr::sync();      // lane 0's writes are ordered before anything the group reads next
+    alive = Gr::bcast(alive, 0);
+    rec.sugar = Gr::bcast(sugar, 0);
+    rec.spice = Gr::bcast(spice, 0);
+    rec.pos = alive ? best : -1;
+    rec.last_moved = c.t;
+    return alive != 0;
 }
 
 // Agent.doTagging (agent.py:556-566)
@@ -614,63 +724,27 @@ __device__ __noinline__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
     }
 }
 
-// Agent.doTimestep (agent.py:568-598), split where the scalable kernel may have to wait for a
-// second reservation (ssb_agent_step.cuh):
-//   move phase      lastSugar/lastSpice, moveToBestCell, collect, (universal income), metabolism
-//   interact phase  tagging, trading, reproduction, aging, happiness
-// Returns from the move phase: false if the agent is done for this step (it was skipped or died).
-template <int G, class Rng>
-__device__ bool transaction_move_phase(const DevCtx &c, int s, Rng &rng, const WarpScratch &ws, int maxc) {
-    // called by all G lanes of the group; the ranking is lane-parallel, the bookkeeping runs on lane 0
-    const ssb_agents_t &a = c.a;
-    typedef Group<G> Gr;
-    const int lane = Gr::lane();
-    if (!agent_alive(c, s) || a.last_moved[s] == c.t) return false;      // uniform
-    if (lane == 0) {
-        a.last_sugar[s] = a.sugar[s];
-        a.last_spice[s] = a.spice[s];
-    }
-    Gr::sync();
-    const int pos = move_to_best_cell<G>(c, s, rng, ws, maxc);
-    int alive = 1;
-    if (lane == 0) {
-        collect(c, s, pos);
-        // doMetabolism (agent.py:485-498) + consumption pollution (cell.py:27-40)
-        const double sm = (double)max(a.sugar_metab[s], 0), pm = (double)max(a.spice_metab[s], 0);
-        const double sugar = a.sugar[s] - sm, spice = a.spice[s] - pm;
-        a.sugar[s] = sugar;
-        a.spice[s] = spice;
-        if (c.p.pollution_start <= c.t && c.t <= c.p.pollution_end) {
-            double pl = c.g.pollution[pos];
-            pl += c.p.sugar_cons_pollution * sm;
-            pl += c.p.spice_cons_pollution * pm;
-            c.g.pollution[pos] = pl;
-        }
-        if (sugar < 0 || spice < 0 || (sugar <= 0 && sm > 0) || (spice <= 0 && pm > 0)) {
-            do_death(c, s, SSB_STARVATION);
-            alive = 0;
-        }
-    }
-    Gr::sync();      // lane 0's writes to the agent record are ordered before anything the group reads next
-    return Gr::bcast(alive, 0) != 0;
-}
-
-// lane 0 only
+// INTERACT part of Agent.doTimestep (agent.py:585-598): tagging, trading, reproduction, aging,
+// happiness.  Lane 0 only.  `rec` holds the agent's record after the move part.
 template <class Rng, bool EXACT>
-__device__ void transaction_interact_phase(const DevCtx &c, int s, Rng &rng) {
+__device__ void transaction_interact_phase(const DevCtx &c, int s, const AgentRec &rec, Rng &rng) {
     const ssb_agents_t &a = c.a;
     if ((c.p.flags & SSB_F_TAGS) && (c.p.flags & SSB_F_TAGGING)) do_tagging(c, s, rng);
     if (c.p.flags & SSB_F_TRADE) do_trading(c, s, rng);
-    if (c.p.flags & SSB_F_REPRO) do_reproduction<Rng, EXACT>(c, s, rng);
-    // doAging (agent.py:266-272)
-    if (agent_alive(c, s)) {
-        const int age = a.age[s] + 1;
-        a.age[s] = age;
-        if (age >= a.max_age[s] && a.max_age[s] != -1) { do_death(c, s, SSB_AGING); return; }
-    }
+    // doReproduction starts with isFertile(): only trading can have raised the holdings since the
+    // move part, so without trade the record decides and most agents skip the call
+    if ((c.p.flags & SSB_F_REPRO) && ((c.p.flags & SSB_F_TRADE) || rec.fertile())) do_reproduction<Rng, EXACT>(c, s, rng);
+    // doAging (agent.py:266-272); reproduction and trading leave the agent alive (isAlive looks at
+    // the holdings, which they may have changed)
+    double sugar = rec.sugar, spice = rec.spice;
+    if (c.p.flags & (SSB_F_TRADE | SSB_F_REPRO)) { sugar = a.sugar[s]; spice = a.spice[s]; }
+    if (!(sugar >= 0 && spice >= 0)) return;     // isAlive() false: no aging, no happiness update
+    const int age = rec.age + 1;
+    a.age[s] = age;
+    if (age >= rec.max_age && rec.max_age != -1) { do_death(c, s, SSB_AGING); return; }
     // updateHappiness (agent.py:1522-1530): conflict + family + health + social + wealth; the
     // family / social / conflict bookkeeping is not implemented yet (DESIGN.md scope) -> 0
-    const double wealth_h = erf((a.sugar[s] + a.spice[s]) - c.prev_mean_wealth);
+    const double wealth_h = erf((sugar + spice) - c.prev_mean_wealth);
     a.wealth_happiness[s] = wealth_h;
     a.family_happiness[s] = 0;
     a.happiness[s] = 1.0 + wealth_h;
