@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--size", type=int, default=4096, help="map side (S1 = 4096)")
     ap.add_argument("--agents", type=int, default=0, help="agents (default: S1 density, 1.6 M at 4096)")
     ap.add_argument("--epochs", type=int, default=0)
+    ap.add_argument("--mark-shift", type=int, default=-1)
+    ap.add_argument("--l2-persist", type=int, default=-1)
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=3)
@@ -180,6 +182,10 @@ def main():
     eng = Engine(params, state, local_rank, endow, tags)
     if args.epochs > 0:
         eng.set_epochs(args.epochs)
+    if args.mark_shift >= 0:
+        eng.set_mark_shift(args.mark_shift)
+    if args.l2_persist >= 0:
+        eng.set_l2_persist(bool(args.l2_persist))
     n_cells = args.size * args.size
 
     # ---- device-resident throughput -------------------------------------------------------------

@@ -197,6 +197,10 @@ int  ssb_set_step_tables(ssb_engine_t *e, const uint32_t *endow_bits, const uint
 
 /* mode S tuning: number of priority epochs of the sliding-prefix commit (power of two, default 64) */
 int  ssb_set_epochs(ssb_engine_t *e, int32_t epochs);
+/* mode S tuning: reservation marks on a grid coarsened by 2^shift cells per side (default 0) */
+int  ssb_set_mark_shift(ssb_engine_t *e, int32_t shift);
+/* mode S tuning: keep the mark array resident in L2 (persisting access window on `stream`) */
+int  ssb_set_l2_persist(ssb_engine_t *e, void *stream, int32_t on);
 
 /* test hook: out[i] = x[i] ** y[i] with the engine's bit-exact restatement of glibc's pow
  * (device pointers; exact[i] = 0 where the argument fell outside the restated path) */

@@ -139,7 +139,7 @@ void ssb_destroy(ssb_engine_t *e) {
     if (!e) return;
     cudaSetDevice(e->device);
     void *ptrs[] = {e->d_mt, e->d_endow, e->d_tagbits, e->d_tile_counts, e->d_new_order, e->d_scalars,
-                    e->d_born_list, e->rc.mark, e->rc.prio, e->rc.list_a, e->rc.list_b, e->rc.ready, e->rc.cnt, e->rc.trace, e->rc.bucketed, e->rc.epoch_count, e->rc.epoch_start, e->rc.epoch_fill,
+                    e->d_born_list, e->rc.mark, e->rc.list_a, e->rc.list_b, e->rc.ready, e->rc.cnt, e->rc.trace, e->rc.bucketed, e->rc.epoch_count, e->rc.epoch_start, e->rc.epoch_fill,
                     e->d_partials, e->d_tribes, e->d_stats, e->d_ring, e->d_keys_a, e->d_keys_b, e->d_radix_hist,
                     e->d_lorenz_blocks};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -182,8 +182,9 @@ int ssb_bind(ssb_engine_t *e, const ssb_grid_t *grid, const ssb_agents_t *agents
     CU(cudaMalloc(&e->d_lorenz_blocks, sizeof(double) * e->num_sms * 4));
     if (e->p.rng_mode == SSB_RNG_SCALABLE) {
         RoundCtx &rc = e->rc;
+        rc.mark_shift = 0; rc.wc = e->p.width; rc.hc = e->p.height;
         CU(cudaMalloc(&rc.mark, sizeof(uint32_t) * (size_t)cells));
-        CU(cudaMalloc(&rc.bucketed, sizeof(int32_t) * cap));
+        CU(cudaMalloc(&rc.bucketed, sizeof(int4) * cap));
         CU(cudaMalloc(&rc.epoch_count, sizeof(int32_t) * MAX_EPOCHS));
         CU(cudaMalloc(&rc.epoch_start, sizeof(int32_t) * (MAX_EPOCHS + 1)));
         CU(cudaMalloc(&rc.epoch_fill, sizeof(int32_t) * MAX_EPOCHS));
@@ -191,10 +192,9 @@ int ssb_bind(ssb_engine_t *e, const ssb_grid_t *grid, const ssb_agents_t *agents
         if (rc.epochs > (1 << e->p.id_bits)) rc.epochs = 1 << e->p.id_bits;
         rc.epoch_shift = e->p.id_bits;
         for (int v = rc.epochs; v > 1; v >>= 1) rc.epoch_shift--;
-        CU(cudaMalloc(&rc.prio, sizeof(uint32_t) * cap));
-        CU(cudaMalloc(&rc.list_a, sizeof(int32_t) * cap));
-        CU(cudaMalloc(&rc.list_b, sizeof(int32_t) * cap));
-        CU(cudaMalloc(&rc.ready, sizeof(int32_t) * cap));
+        CU(cudaMalloc(&rc.list_a, sizeof(int4) * cap));
+        CU(cudaMalloc(&rc.list_b, sizeof(int4) * cap));
+        CU(cudaMalloc(&rc.ready, sizeof(int4) * cap));
         CU(cudaMalloc(&rc.cnt, sizeof(int32_t) * 8));
         CU(cudaMemset(rc.cnt, 0, sizeof(int32_t) * 8));
         int per_sm = 0;
@@ -204,6 +204,36 @@ int ssb_bind(ssb_engine_t *e, const ssb_grid_t *grid, const ssb_agents_t *agents
         e->coop_blocks = per_sm * e->num_sms;
     }
     e->bound = true;
+    return 0;
+}
+
+int ssb_set_mark_shift(ssb_engine_t *e, int32_t shift) {
+    if (!e || !e->bound || e->p.rng_mode != SSB_RNG_SCALABLE) return fail(e, -1, "mark shift needs a bound scalable engine");
+    if (shift < 0 || shift > 4 || (e->p.width % (1 << shift)) || (e->p.height % (1 << shift))) return fail(e, -1, "mark shift %d does not divide the map", shift);
+    const int maxd = e->ctx.max_dx > e->ctx.max_dy ? e->ctx.max_dx : e->ctx.max_dy;
+    if (((maxd + 2) >> shift) + 2 >= (e->p.width >> shift) || ((maxd + 2) >> shift) + 2 >= (e->p.height >> shift)) return fail(e, -1, "map too small for mark shift %d", shift);
+    e->rc.mark_shift = shift; e->rc.wc = e->p.width >> shift; e->rc.hc = e->p.height >> shift;
+    return 0;
+}
+
+// pin the mark array in L2 (persisting access window on the given stream)
+int ssb_set_l2_persist(ssb_engine_t *e, void *stream_, int32_t on) {
+    if (!e || !e->bound || e->p.rng_mode != SSB_RNG_SCALABLE) return fail(e, -1, "L2 persistence needs a bound scalable engine");
+    CU(cudaSetDevice(e->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, e->device));
+    size_t bytes = sizeof(uint32_t) * (size_t)e->rc.wc * e->rc.hc;
+    if (bytes > (size_t)prop.accessPolicyMaxWindowSize) bytes = (size_t)prop.accessPolicyMaxWindowSize;
+    size_t carve = bytes < (size_t)prop.persistingL2CacheMaxSize ? bytes : (size_t)prop.persistingL2CacheMaxSize;
+    CU(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, on ? carve : 0));
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof(attr));
+    attr.accessPolicyWindow.base_ptr = e->rc.mark;
+    attr.accessPolicyWindow.num_bytes = on ? bytes : 0;
+    attr.accessPolicyWindow.hitRatio = on ? (float)((double)carve / (double)bytes) : 0.f;
+    attr.accessPolicyWindow.hitProp = on ? cudaAccessPropertyPersisting : cudaAccessPropertyNormal;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    CU(cudaStreamSetAttribute((cudaStream_t)stream_, cudaStreamAttributeAccessPolicyWindow, &attr));
     return 0;
 }
 

@@ -102,11 +102,14 @@ constexpr int AGENT_GROUPS = AGENT_THREADS / GL;
 constexpr int AGENT_SMEM_BYTES = warp_scratch_bytes(MAXC_SCALABLE) * AGENT_GROUPS;
 constexpr int PHASE1_BIT = 0x40000000;   // list entries: slot | PHASE1_BIT once the move part has committed
 
+// One entry of the active lists: everything MARK and SELECT need, so that those phases read only
+// the (coalesced) list and the marks -- no per-agent gathers.
+//   x = slot | PHASE1_BIT, y = cell the footprint is centred on, z = priority, w = r | k << 8
 struct RoundCtx {
-    uint32_t *mark;          // one word per cell
-    uint32_t *prio;          // per slot, this step's priority
-    int32_t *bucketed;       // the agent list grouped by epoch
-    int32_t *list_a, *list_b, *ready;
+    uint32_t *mark;          // one word per mark cell (cells coarsened by 2^mark_shift per side)
+    int32_t mark_shift, wc, hc;
+    int4 *bucketed;          // the agent list grouped by epoch
+    int4 *list_a, *list_b, *ready;
     int32_t *cnt;            // [0..1] carry-list lengths (ping-pong), [2..3] ready counts (ping-pong)
     int32_t *epoch_count;    // [MAX_EPOCHS]
     int32_t *epoch_start;    // [MAX_EPOCHS + 1]
@@ -123,24 +126,22 @@ __device__ __forceinline__ unsigned long long global_ns() {
     return t;
 }
 
-// Dilation of the footprint required by the rule set, for agent s (agent.py:585-588).
-// Reproduction (k = 2) is only possible if the agent can be fertile when it gets there: fertile
-// age, and holdings that can still reach the starting endowment -- other agents can only LOWER
-// them (mate costs), the agent's own move adds at most one cell's capacity (plus combat loot)
-// and subtracts its metabolism.  `moved` = the move part has committed (holdings are final).
-__device__ __forceinline__ int footprint_dilation(const DevCtx &c, int s, bool moved) {
+// Dilation of the footprint required by the rule set, for agent s (agent.py:585-588), evaluated
+// BEFORE the agent moves.  Reproduction (k = 2) is only possible if the agent can be fertile when
+// it gets there: fertile age, and holdings that can still reach the starting endowment -- other
+// agents can only LOWER them (mate costs), the agent's own move adds at most one cell's capacity
+// (plus combat loot) and subtracts its metabolism.  Computed once per step: a value that was
+// valid at the start of the step stays a superset later.
+__device__ __forceinline__ int footprint_dilation(const DevCtx &c, int s) {
     int k = 0;
     if (c.p.flags & (SSB_F_TAGGING | SSB_F_TRADE)) k = 1;
     if ((c.p.flags & SSB_F_REPRO) && c.a.fert_factor[s] > 0 &&
         c.a.age[s] >= c.a.fert_age[s] && c.a.age[s] < c.a.infert_age[s]) {
         bool can = true;
         if (!(c.p.flags & SSB_F_TRADE)) {
-            double gain_s = 0, gain_p = 0;
-            if (!moved) {
-                const double loot = c.a.aggression[s] > 0 ? c.p.max_combat_loot : 0.0;
-                gain_s = (double)c.p.max_sugar_capacity + loot - (double)max(c.a.sugar_metab[s], 0);
-                gain_p = (double)c.p.max_spice_capacity + loot - (double)max(c.a.spice_metab[s], 0);
-            }
+            const double loot = c.a.aggression[s] > 0 ? c.p.max_combat_loot : 0.0;
+            const double gain_s = (double)c.p.max_sugar_capacity + loot - (double)max(c.a.sugar_metab[s], 0);
+            const double gain_p = (double)c.p.max_spice_capacity + loot - (double)max(c.a.spice_metab[s], 0);
             can = c.a.sugar[s] + gain_s >= c.a.start_sugar[s] && c.a.spice[s] + gain_p >= c.a.start_spice[s];
         }
         if (can) k = 2;
@@ -161,21 +162,28 @@ __device__ __forceinline__ int footprint_dilation_moved(const DevCtx &c, const A
 // around c.  Per x-column offset i it is the y-interval [-h(i), h(i)] with
 //   h(i) = max( |i| <= k ? ry + k - |i| : -1 ,                  (north-south arm, dilated)
 //               |i| <= rx ? k : k - (|i| - rx) )                (east-west arm, dilated)
-// f(base_index_of_column, y_lo, y_hi) is called once per column with the (unwrapped) interval.
+// Marks live on a grid coarsened by 2^sh cells per side (sh = 0: one mark per cell); a coarse
+// column takes the largest interval of the fine columns it contains -- a superset is always safe.
 struct Footprint {
-    int x, y, rx, ry, k, W, H;
+    int x, y, rx, ry, k;
     __device__ __forceinline__ void init(const DevCtx &c, int pos, int r, int k_) {
-        W = c.p.width; H = c.p.height;
+        const int H = c.p.height;
         x = pos / H; y = pos - x * H;
         rx = min(r, c.max_dx); ry = min(r, c.max_dy); k = k_;
-        // on tiny maps the intervals may wrap onto themselves: cells are then visited twice,
-        // which is harmless (atomicMin and the ownership test are idempotent)
     }
     __device__ __forceinline__ int half_height(int i) const {
         const int ai = abs(i);
         const int ns = ai <= k ? ry + k - ai : -1;
         const int ew = ai <= rx ? k : k - (ai - rx);
         return max(ns, ew);
+    }
+    // largest half height among the fine columns x + i that fall into coarse column cx
+    __device__ __forceinline__ int coarse_half_height(int cx, int sh) const {
+        const int c0 = cx * (1 << sh);
+        const int lo = max(c0 - x, -(rx + k)), hi = min(c0 + (1 << sh) - 1 - x, rx + k);
+        // h(i) is non-increasing in |i|: the maximum sits at the offset closest to 0
+        const int i = lo > 0 ? lo : (hi < 0 ? hi : 0);
+        return half_height(i);
     }
 };
 
@@ -185,44 +193,33 @@ __device__ __forceinline__ uint32_t round_tag(const DevCtx &c, int round) {
 }
 constexpr int ROUNDS_PER_TAG_EPOCH = (1 << TAG_BITS) - 1;
 
-// The footprint D_k(cross of radius (rx, ry) + centre), visited by a lane group of G lanes: one
-// x-column per iteration, the lanes cover its y-interval (at most 2 (ry + k) + 1 <= 21 cells).
+// Visit the mark cells of a footprint with a lane group of G lanes: one (coarse) x-column per
+// iteration, the lanes cover its rows.  f(mark index) is called once per lane and cell.
+template <int G, class F>
+__device__ __forceinline__ void for_each_mark_cell(const DevCtx &c, const RoundCtx &rc, int pos, int r, int k, F f) {
+    const int lane = Group<G>::lane(), sh = rc.mark_shift;
+    Footprint fp;
+    fp.init(c, pos, r, k);
+    const int cx0 = (fp.x - fp.rx - fp.k) >> sh, cx1 = (fp.x + fp.rx + fp.k) >> sh;     // >> floors
+    for (int cx = cx0; cx <= cx1; cx++) {
+        const int h = fp.coarse_half_height(cx, sh);
+        const int cy0 = (fp.y - h) >> sh, cy1 = (fp.y + h) >> sh;
+        const size_t col = (size_t)wrap1(cx, rc.wc) * rc.hc;
+        for (int cy = cy0 + lane; cy <= cy1; cy += G) f(col + wrap1(cy, rc.hc));
+    }
+}
+
 template <int G>
 __device__ __forceinline__ void group_mark_region(const DevCtx &c, const RoundCtx &rc, int pos, int r, int k, uint32_t v) {
-    const int lane = Group<G>::lane();
-    Footprint f;
-    f.init(c, pos, r, k);
-    for (int i = -(f.rx + f.k); i <= f.rx + f.k; i++) {
-        const int h = f.half_height(i);
-        uint32_t *col = rc.mark + (size_t)wrap1(f.x + i, f.W) * f.H;
-        for (int j = lane - h; j <= h; j += G) atomicMin(col + wrap1(f.y + j, f.H), v);
-    }
+    for_each_mark_cell<G>(c, rc, pos, r, k, [&](size_t m) { atomicMin(rc.mark + m, v); });
 }
 
-// true (on every lane of the group) iff every cell of the region holds v
+// true (on every lane of the group) iff every mark cell of the region holds v
 template <int G>
 __device__ __forceinline__ bool group_owns_region(const DevCtx &c, const RoundCtx &rc, int pos, int r, int k, uint32_t v) {
-    const int lane = Group<G>::lane();
-    Footprint f;
-    f.init(c, pos, r, k);
     unsigned bad = 0;
-    for (int i = -(f.rx + f.k); i <= f.rx + f.k; i++) {
-        const int h = f.half_height(i);
-        const uint32_t *col = rc.mark + (size_t)wrap1(f.x + i, f.W) * f.H;
-        for (int j = lane - h; j <= h; j += G) bad |= __ldcg(col + wrap1(f.y + j, f.H)) ^ v;
-    }
+    for_each_mark_cell<G>(c, rc, pos, r, k, [&](size_t m) { bad |= __ldcg(rc.mark + m) ^ v; });
     return !Group<G>::any(bad != 0);
-}
-
-// warp-aggregated append: every lane of the warp calls this (full mask)
-__device__ __forceinline__ void warp_append(bool want, int32_t *list, int32_t *counter, int value) {
-    const unsigned mask = __ballot_sync(0xffffffffu, want);
-    if (mask == 0) return;
-    const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
-    int base = 0;
-    if (lane == leader) base = atomicAdd(counter, __popc(mask));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (want) list[base + __popc(mask & ((1u << lane) - 1u))] = value;
 }
 
 // One persistent cooperative kernel per step.
@@ -231,47 +228,35 @@ __global__ void __launch_bounds__(AGENT_THREADS, 2) k_agent_step_scalable(DevCtx
     __shared__ int32_t sh_count[MAX_EPOCHS], sh_base[MAX_EPOCHS];
     extern __shared__ __align__(8) unsigned char scratch_mem[];
     const WarpScratch ws = make_warp_scratch(scratch_mem + (threadIdx.x / GL) * warp_scratch_bytes(MAXC_SCALABLE), MAXC_SCALABLE);
-    const int warp_id = (blockIdx.x * blockDim.x + threadIdx.x) / GL;      // lane-group index
-    const int n_warps = (gridDim.x * blockDim.x) / GL;
-    const int glane = Group<GL>::lane();
-    const int mgroup_id = (blockIdx.x * blockDim.x + threadIdx.x) / GM, n_mgroups = (gridDim.x * blockDim.x) / GM;
-    const int mlane = Group<GM>::lane();
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nthreads = gridDim.x * blockDim.x;
-    const int lane = threadIdx.x & 31;
-    const long long n_cells = c.g.n_cells;
+    const int xgroup_id = tid / GL, n_xgroups = nthreads / GL, xlane = Group<GL>::lane();   // EXECUTE groups
+    const int mgroup_id = tid / GM, n_mgroups = nthreads / GM, mlane = Group<GM>::lane();   // MARK / SELECT groups
+    const long long n_marks = (long long)rc.wc * rc.hc;
     const int n_list = (int)c.a.counters[SSB_C_N_LIST];
     const int E = rc.epochs;
 
-    // ---- prepare: priorities, epoch histogram ------------------------------------------------------
+    // ---- prepare: priorities, footprint parameters, epoch buckets ---------------------------------
     for (int i = tid; i < E; i += nthreads) { rc.epoch_count[i] = 0; rc.epoch_fill[i] = 0; }
-    for (long long i = tid; i < n_cells; i += nthreads) rc.mark[i] = 0xffffffffu;
+    for (long long i = tid; i < n_marks; i += nthreads) rc.mark[i] = 0xffffffffu;
     if (tid == 0) { rc.cnt[0] = 0; rc.cnt[1] = 0; rc.cnt[2] = 0; rc.cnt[3] = 0; c.a.counters[SSB_C_N_BORN] = 0; }
-    grid.sync();
     for (int e = threadIdx.x; e < E; e += blockDim.x) sh_count[e] = 0;
-    __syncthreads();
+    grid.sync();
+    // pass A: histogram of epochs (the per-block work assignment is repeated exactly in pass B)
     for (int i = tid; i < n_list; i += nthreads) {
-        const int s = c.a.order[i];
-        const uint32_t pr = priority_of(rc.key, (uint32_t)c.a.id[s], c.p.id_bits);
-        rc.prio[s] = pr;
+        const uint32_t pr = priority_of(rc.key, (uint32_t)c.a.id[c.a.order[i]], c.p.id_bits);
         atomicAdd(&sh_count[pr >> rc.epoch_shift], 1);
     }
     __syncthreads();
     for (int e = threadIdx.x; e < E; e += blockDim.x) if (sh_count[e]) atomicAdd(&rc.epoch_count[e], sh_count[e]);
     grid.sync();
-    if (blockIdx.x == 0) {   // exclusive scan of the epoch histogram (E <= 1024)
-        if (threadIdx.x == 0) {
-            int run = 0;
-            for (int e = 0; e < E; e++) { rc.epoch_start[e] = run; run += rc.epoch_count[e]; }
-            rc.epoch_start[E] = run;
-        }
+    if (tid == 0) {   // exclusive scan of the epoch histogram (E <= 1024)
+        int run = 0;
+        for (int e = 0; e < E; e++) { rc.epoch_start[e] = run; run += rc.epoch_count[e]; }
+        rc.epoch_start[E] = run;
     }
     grid.sync();
-    // scatter into epoch segments: one range reservation per block and epoch
-    for (int e = threadIdx.x; e < E; e += blockDim.x) sh_count[e] = 0;
-    __syncthreads();
-    for (int i = tid; i < n_list; i += nthreads) atomicAdd(&sh_count[rc.prio[c.a.order[i]] >> rc.epoch_shift], 1);
-    __syncthreads();
+    // pass B: one range reservation per block and epoch, then scatter the entries
     for (int e = threadIdx.x; e < E; e += blockDim.x) {
         sh_base[e] = sh_count[e] ? rc.epoch_start[e] + atomicAdd(&rc.epoch_fill[e], sh_count[e]) : 0;
         sh_count[e] = 0;
@@ -279,13 +264,16 @@ __global__ void __launch_bounds__(AGENT_THREADS, 2) k_agent_step_scalable(DevCtx
     __syncthreads();
     for (int i = tid; i < n_list; i += nthreads) {
         const int s = c.a.order[i];
-        const int e = rc.prio[s] >> rc.epoch_shift;
-        rc.bucketed[sh_base[e] + atomicAdd(&sh_count[e], 1)] = s;
+        const uint32_t pr = priority_of(rc.key, (uint32_t)c.a.id[s], c.p.id_bits);
+        const int e = pr >> rc.epoch_shift;
+        const int r = min(min(max(c.a.vision[s], 0), max(c.a.movement[s], 0)), max(c.max_dx, c.max_dy));
+        rc.bucketed[sh_base[e] + atomicAdd(&sh_count[e], 1)] =
+            make_int4(s, c.a.pos[s], (int)pr, r | (footprint_dilation(c, s) << 8));
     }
     grid.sync();
 
     // ---- commit rounds -------------------------------------------------------------------------------
-    int32_t *cur = rc.list_a, *nxt = rc.list_b;
+    int4 *cur = rc.list_a, *nxt = rc.list_b;
     int round = 0;
     for (;;) {
         const int n_carry = ((volatile int32_t *)rc.cnt)[round & 1];
@@ -298,7 +286,7 @@ __global__ void __launch_bounds__(AGENT_THREADS, 2) k_agent_step_scalable(DevCtx
             break;
         }
         if (round > 0 && round % ROUNDS_PER_TAG_EPOCH == 0) {   // tags exhausted: clear and restart
-            for (long long i = tid; i < n_cells; i += nthreads) rc.mark[i] = 0xffffffffu;
+            for (long long i = tid; i < n_marks; i += nthreads) rc.mark[i] = 0xffffffffu;
             grid.sync();
         }
         int32_t *n_next = &rc.cnt[(round + 1) & 1], *n_ready = &rc.cnt[2 + (round & 1)];
@@ -306,64 +294,55 @@ __global__ void __launch_bounds__(AGENT_THREADS, 2) k_agent_step_scalable(DevCtx
         if (tid == 0) { *n_next = 0; *n_ready = 0; }
         if (tr) { rc.trace[round * 6 + 0] = n; rc.trace[round * 6 + 2] = global_ns(); }
         const uint32_t tag = round_tag(c, round);
-        const int32_t *fresh = rc.bucketed + e0;
+        const int4 *fresh = rc.bucketed + e0;
         // MARK: one agent per lane group, lanes spread over the footprint cells
         for (int i = mgroup_id; i < n; i += n_mgroups) {
-            const int entry = i < n_carry ? cur[i] : fresh[i - n_carry];
-            const int s = entry & ~PHASE1_BIT;
-            const int pos = c.a.pos[s];
-            if (pos < 0) continue;                   // killed earlier this step: nothing to reserve
-            const bool moved = (entry & PHASE1_BIT) != 0;
-            const int k = footprint_dilation(c, s, moved);
-            const int r = moved ? 0 : agent_range(c, s);
-            group_mark_region<GM>(c, rc, pos, r, k, tag | rc.prio[s]);
+            const int4 en = i < n_carry ? cur[i] : fresh[i - n_carry];
+            const bool moved = (en.x & PHASE1_BIT) != 0;
+            group_mark_region<GM>(c, rc, en.y, moved ? 0 : (en.w & 255), en.w >> 8, tag | (uint32_t)en.z);
         }
         grid.sync();
         if (tr) rc.trace[round * 6 + 3] = global_ns();
-        // SELECT
+        // SELECT: phase 0 needs the cross + own cell (k = 0), phase 1 the diamond D_k(new cell)
         for (int i = mgroup_id; i < n; i += n_mgroups) {
-            const int entry = i < n_carry ? cur[i] : fresh[i - n_carry];
-            const int s = entry & ~PHASE1_BIT;
-            const int pos = c.a.pos[s];
-            bool ok = true;
-            if (pos >= 0) {
-                if (entry & PHASE1_BIT) ok = group_owns_region<GM>(c, rc, pos, 0, footprint_dilation(c, s, true), tag | rc.prio[s]);
-                else ok = group_owns_region<GM>(c, rc, pos, agent_range(c, s), 0, tag | rc.prio[s]);
-            }
+            const int4 en = i < n_carry ? cur[i] : fresh[i - n_carry];
+            const bool moved = (en.x & PHASE1_BIT) != 0;
+            const bool ok = group_owns_region<GM>(c, rc, en.y, moved ? 0 : (en.w & 255), moved ? (en.w >> 8) : 0,
+                                                  tag | (uint32_t)en.z);
             if (mlane == 0) {
-                if (ok) rc.ready[atomicAdd(n_ready, 1)] = entry;
-                else nxt[atomicAdd(n_next, 1)] = entry;
+                if (ok) rc.ready[atomicAdd(n_ready, 1)] = en;
+                else nxt[atomicAdd(n_next, 1)] = en;
             }
         }
         grid.sync();
         const int nr = *(volatile int32_t *)n_ready;
         if (tr) { rc.trace[round * 6 + 1] = nr; rc.trace[round * 6 + 4] = global_ns(); }
         // EXECUTE: one transaction per lane group
-        for (int i = warp_id; i < nr; i += n_warps) {
-            const int entry = rc.ready[i];
-            const int s = entry & ~PHASE1_BIT;
+        for (int i = xgroup_id; i < nr; i += n_xgroups) {
+            const int4 en = rc.ready[i];
+            const int s = en.x & ~PHASE1_BIT;
             AgentRec rec;
             rec.load(c, s);                                  // one latency level for the whole record
             RngStream rng{rc.key, (uint32_t)rec.id, 0u, 0u, nullptr};
-            if (entry & PHASE1_BIT) {
-                if (glane == 0) transaction_interact_phase<RngStream, false>(c, s, rec, rng);
+            if (en.x & PHASE1_BIT) {
+                if (xlane == 0) transaction_interact_phase<RngStream, false>(c, s, rec, rng);
             } else if (transaction_move_phase<GL, 4>(c, s, rec, rng, ws, MAXC_SCALABLE)) {
                 // the interact part needs D_k(new cell), k from the now final holdings (never
                 // larger than the k the marks were placed with); the marks of this round still
                 // stand, so it runs right away if the agent owns that diamond too.  rec is the
                 // same on every lane (broadcast from lane 0), so the branch is group-uniform.
-                const int k = footprint_dilation_moved(c, rec);
-                const bool now = k == 0 || group_owns_region<GL>(c, rc, rec.pos, 0, k, tag | rc.prio[s]);
-                if (glane == 0) {
+                const int k = min(footprint_dilation_moved(c, rec), en.w >> 8);
+                const bool now = k == 0 || group_owns_region<GL>(c, rc, rec.pos, 0, k, tag | (uint32_t)en.z);
+                if (xlane == 0) {
                     if (now) transaction_interact_phase<RngStream, false>(c, s, rec, rng);
-                    else nxt[atomicAdd(n_next, 1)] = s | PHASE1_BIT;
+                    else nxt[atomicAdd(n_next, 1)] = make_int4(s | PHASE1_BIT, rec.pos, en.z, k << 8);
                 }
             }
             Group<GL>::sync();
         }
         grid.sync();
         if (tr) rc.trace[round * 6 + 5] = global_ns();
-        int32_t *tmp = cur; cur = nxt; nxt = tmp;
+        int4 *tmp = cur; cur = nxt; nxt = tmp;
         round++;
     }
     if (tid == 0) c.a.counters[SSB_C_ROUNDS] = round;

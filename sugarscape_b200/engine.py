@@ -45,6 +45,8 @@ def load_library():
     L.ssb_get_mt_state.argtypes = [E, C.c_void_p, C.POINTER(C.c_int32)]
     L.ssb_set_step_tables.argtypes = [E, C.c_void_p, C.c_void_p, C.c_int32]
     L.ssb_set_epochs.argtypes = [E, C.c_int32]
+    L.ssb_set_mark_shift.argtypes = [E, C.c_int32]
+    L.ssb_set_l2_persist.argtypes = [E, C.c_void_p, C.c_int32]
     L.ssb_env_step.argtypes = [E, C.c_int32, C.c_void_p]
     L.ssb_agent_step.argtypes = [E, C.c_int32, C.c_double, C.c_void_p]
     L.ssb_compact.argtypes = [E, C.c_int32, C.c_void_p]
@@ -71,7 +73,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = (
     "ssb_abi_version", "ssb_create", "ssb_bind", "ssb_destroy", "ssb_last_error",
-    "ssb_set_mt_state", "ssb_get_mt_state", "ssb_set_step_tables", "ssb_set_epochs",
+    "ssb_set_mt_state", "ssb_get_mt_state", "ssb_set_step_tables", "ssb_set_epochs", "ssb_set_mark_shift", "ssb_set_l2_persist",
     "ssb_sizeof_params", "ssb_sizeof_grid", "ssb_sizeof_agents", "ssb_sizeof_stats",
     "ssb_env_step", "ssb_agent_step", "ssb_compact", "ssb_reduce_stats", "ssb_step", "ssb_stats", "ssb_stats_history",
     "ssb_sync", "ssb_test_pow", "ssb_round_trace", "ssb_launch_count", "ssb_timing", "ssb_enable_timing",
@@ -222,6 +224,12 @@ class Engine:
         out = np.zeros((rounds, 6), dtype=np.uint64)
         self._check(self.L.ssb_round_trace(self.handle, rounds, out.ctypes.data if fetch else None, rounds))
         return out
+
+    def set_mark_shift(self, shift):
+        self._check(self.L.ssb_set_mark_shift(self.handle, shift))
+
+    def set_l2_persist(self, on=True):
+        self._check(self.L.ssb_set_l2_persist(self.handle, self.stream, 1 if on else 0))
 
     def set_epochs(self, epochs):
         self._check(self.L.ssb_set_epochs(self.handle, epochs))

@@ -11,6 +11,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--size", type=int, default=4096)
 ap.add_argument("--steps", type=int, default=25)
 ap.add_argument("--epochs", type=int, default=0)
+ap.add_argument("--mark-shift", type=int, default=-1)
+ap.add_argument("--l2-persist", type=int, default=-1)
 args = ap.parse_args()
 n_agents = int(round(1600000 * (args.size / 4096.0) ** 2))
 c = synthetic.configuration(synthetic.S1_OPTIONS, {"environmentWidth": args.size, "environmentHeight": args.size,
@@ -20,6 +22,10 @@ endow, tags = steptables.step_tables(1, args.steps + 4, 0)
 eng = Engine(params, state, 0, endow, tags)
 if args.epochs > 0:
     eng.set_epochs(args.epochs)
+if args.mark_shift >= 0:
+    eng.set_mark_shift(args.mark_shift)
+if args.l2_persist >= 0:
+    eng.set_l2_persist(bool(args.l2_persist))
 eng.round_trace(1024, fetch=False)
 for t in range(1, args.steps + 1):
     eng.step(t, 0.0)
