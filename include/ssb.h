@@ -195,9 +195,9 @@ int  ssb_get_mt_state(ssb_engine_t *e, uint32_t state[624], int32_t *index);
  * tag_bits[t] bit k = k-th draw for tag positions where the parents differ. */
 int  ssb_set_step_tables(ssb_engine_t *e, const uint32_t *endow_bits, const uint32_t *tag_bits, int32_t n);
 
-/* mode S tuning: number of priority epochs of the sliding-prefix commit (power of two, default 64) */
+/* mode S tuning: number of priority epochs of the sliding-prefix commit (power of two, default 128) */
 int  ssb_set_epochs(ssb_engine_t *e, int32_t epochs);
-/* mode S tuning: reservation marks on a grid coarsened by 2^shift cells per side (default 0) */
+/* mode S tuning: reservation marks on a grid coarsened by 2^shift cells per side (default 1 when the map allows it) */
 int  ssb_set_mark_shift(ssb_engine_t *e, int32_t shift);
 /* mode S tuning: keep the mark array resident in L2 (persisting access window on `stream`) */
 int  ssb_set_l2_persist(ssb_engine_t *e, void *stream, int32_t on);

@@ -182,13 +182,18 @@ int ssb_bind(ssb_engine_t *e, const ssb_grid_t *grid, const ssb_agents_t *agents
     CU(cudaMalloc(&e->d_lorenz_blocks, sizeof(double) * e->num_sms * 4));
     if (e->p.rng_mode == SSB_RNG_SCALABLE) {
         RoundCtx &rc = e->rc;
-        rc.mark_shift = 0; rc.wc = e->p.width; rc.hc = e->p.height;
+        // marks on 2 x 2 cell blocks when the map allows it: a quarter of the mark array and about
+        // a third of the atomics, for ~1 % more commit rounds (profiles/README.md)
+        rc.mark_shift = 0;
+        if ((e->p.width % 2) == 0 && (e->p.height % 2) == 0 && ((maxd + 2) >> 1) + 2 < (e->p.width >> 1) &&
+            ((maxd + 2) >> 1) + 2 < (e->p.height >> 1)) rc.mark_shift = 1;
+        rc.wc = e->p.width >> rc.mark_shift; rc.hc = e->p.height >> rc.mark_shift;
         CU(cudaMalloc(&rc.mark, sizeof(uint32_t) * (size_t)cells));
         CU(cudaMalloc(&rc.bucketed, sizeof(int4) * cap));
         CU(cudaMalloc(&rc.epoch_count, sizeof(int32_t) * MAX_EPOCHS));
         CU(cudaMalloc(&rc.epoch_start, sizeof(int32_t) * (MAX_EPOCHS + 1)));
         CU(cudaMalloc(&rc.epoch_fill, sizeof(int32_t) * MAX_EPOCHS));
-        rc.epochs = 64;
+        rc.epochs = 128;
         if (rc.epochs > (1 << e->p.id_bits)) rc.epochs = 1 << e->p.id_bits;
         rc.epoch_shift = e->p.id_bits;
         for (int v = rc.epochs; v > 1; v >>= 1) rc.epoch_shift--;
