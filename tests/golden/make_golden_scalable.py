@@ -1,0 +1,174 @@
+#!/usr/bin/env python3
+"""Golden fixtures for the SCALABLE RNG mode, produced by the reference's own code.
+
+Mode S keeps every rule of the reference and only replaces its source of
+randomness: (1) the per-step agent order is the ascending order of a keyed bijection of the agent
+id instead of `random.shuffle(self.agents)` (reference sugarscape.py:400), (2) every draw inside
+an agent's transaction comes from that agent's counter-based substream of the current call site
+(agent.py:1401 move ranking, 560-564 tagging, 616 trading, 505-513 reproduction) instead of the
+global MT19937 stream, (3) a step's newborn are numbered in cell order at the end of the step.
+
+This script runs the UNMODIFIED reference classes with exactly those three substitutions applied
+from the outside (monkeypatching `random.shuffle` / `random.randrange` as seen by agent.py and
+sugarscape.py, plus a renumbering pass) and records per-step digests of the ID-sorted state.
+tests/test_oracle_golden.py requires the C oracle in mode S to reproduce them, which pins the
+mode S semantics to the reference's rule code (the GPU engine is then compared with the oracle).
+
+Run in the build container only:  python tests/golden/make_golden_scalable.py
+"""
+import gzip
+import json
+import os
+import random
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_harness as rh  # noqa: E402
+
+M64 = (1 << 64) - 1
+SITES = {"rankCellsInRange": 0, "doTagging": 1, "doTrading": 2, "doReproduction": 3}
+ID_BITS = 26
+
+
+def mix64(z):
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M64
+    return z ^ (z >> 31)
+
+
+def step_key(seed, t):
+    return mix64((seed + 0x9E3779B97F4A7C15 * ((t + 1) & 0xFFFFFFFF)) & M64)
+
+
+def priority_of(key, agent_id, bits=ID_BITS):
+    half = bits // 2
+    mask = (1 << half) - 1
+    L, R = (agent_id >> half) & mask, agent_id & mask
+    for rnd in range(4):
+        f = (mix64(key ^ 0xA5A5A5A5 ^ ((rnd + 1) << 56) ^ R) >> 40) & mask
+        L, R = R, L ^ f
+    return (L << half) | R
+
+
+class Substreams:
+    """random.shuffle / random.randrange as mode S defines them, for the agent whose transaction
+    is running (set by the doTimestep wrapper)."""
+
+    def __init__(self, seed):
+        self.seed = seed & M64
+        self.key = 0
+        self.agent_id = None
+        self.counters = {}
+        self.real_shuffle = random.shuffle
+        self.real_randrange = random.randrange
+
+    def word(self, site):
+        j = self.counters.get(site, 0)
+        self.counters[site] = j + 1
+        return mix64(self.key ^ ((self.agent_id << 32) | (site << 24) | j)) >> 32
+
+    def below(self, site, n):
+        k = n.bit_length()
+        r = self.word(site) >> (32 - k)
+        while r >= n:
+            r = self.word(site) >> (32 - k)
+        return r
+
+    def site_of_caller(self, depth):
+        return SITES.get(sys._getframe(depth).f_code.co_name)
+
+    def shuffle(self, x):
+        site = self.site_of_caller(3)      # reference function -> order_shuffle -> shuffle -> here
+        if site is None or self.agent_id is None:
+            if len(x) > 1:
+                raise RuntimeError("unexpected main-stream shuffle in " + sys._getframe(2).f_code.co_name)
+            return
+        for i in reversed(range(1, len(x))):
+            j = self.below(site, i + 1)
+            x[i], x[j] = x[j], x[i]
+
+    def randrange(self, n):
+        site = self.site_of_caller(2)      # reference function -> randrange -> here
+        if site is None:
+            return self.real_randrange(n)     # findChildEndowment's private hash-seeded streams
+        return self.below(site, n)
+
+
+def run(example, steps, overrides):
+    ref = rh.import_reference()
+    import agent as ref_agent
+    S = rh.build_reference(os.path.join(rh.REFERENCE_DIR, "examples", example + ".json"),
+                           dict({"timesteps": 1000}, **overrides))
+    S.updateRuntimeStats()
+    sub = Substreams(S.seed)
+    H = S.environment.height
+
+    def order_shuffle(x):
+        if x is S.agents:
+            key = step_key(sub.seed, S.timestep)
+            x.sort(key=lambda a: priority_of(key, a.ID))
+        else:
+            sub.shuffle(x)
+
+    orig_do_timestep = ref_agent.Agent.doTimestep
+
+    def do_timestep(self, timestep, predeterminedMove=None):
+        sub.agent_id, sub.counters, sub.key = self.ID, {}, step_key(sub.seed, timestep)
+        try:
+            return orig_do_timestep(self, timestep, predeterminedMove)
+        finally:
+            sub.agent_id = None
+
+    ref_agent.Agent.doTimestep = do_timestep
+    # agent.py and sugarscape.py both call random.shuffle / random.randrange through the module
+    ref.random.shuffle = order_shuffle
+    ref_agent.random.randrange = sub.randrange
+    records = []
+    try:
+        for t in range(1, steps + 1):
+            base = S.nextAgentID
+            existing = {a.ID for a in S.agents}
+            S.doTimestep()
+            newborn = [a for a in S.agents if a.ID not in existing]
+            newborn.sort(key=lambda a: a.cell.x * H + a.cell.y)
+            for k, a in enumerate(newborn):
+                a.ID = base + k
+            S.nextAgentID = base + len(newborn)
+            snap = rh.snapshot(S)
+            order = np.argsort(snap["a_id"], kind="stable")
+            for k in [k for k in snap if k.startswith("a_")]:
+                snap[k] = snap[k][order]
+            snap["mt"] = np.zeros(625, np.uint32)
+            records.append({"t": t, "population": len(S.agents), "digests": rh.digests(snap)})
+    finally:
+        ref_agent.Agent.doTimestep = orig_do_timestep
+        ref.random.shuffle = sub.real_shuffle
+        ref_agent.random.randrange = sub.real_randrange
+    return records
+
+
+CASES = [
+    ("constant_growback", 60, {"agentMovement": [6, 6]}),
+    ("pollution_formation", 120, {"agentMovement": [6, 6]}),
+    ("reproduction_basic", 80, {"agentMovement": [6, 6]}),
+    ("cultural_tagging", 60, {"agentMovement": [6, 6]}),
+    ("trade_basic", 60, {"agentMovement": [6, 6]}),
+    ("combat_unlimited", 60, {"agentMovement": [6, 6], "agentAggressionFactor": [1, 1]}),
+]
+
+
+def main():
+    out = {}
+    for example, steps, overrides in CASES:
+        recs = run(example, steps, overrides)
+        out[example] = {"overrides": overrides, "steps": recs}
+        print(example, "steps", len(recs), "final population", recs[-1]["population"], flush=True)
+    with gzip.open(os.path.join(HERE, "scalable_mode.json.gz"), "wt") as f:
+        json.dump(out, f)
+
+
+if __name__ == "__main__":
+    main()

@@ -67,3 +67,20 @@ def replace_dead_agents(c, state, pop, t):
     state.append_agents(new_agents, protect_last=int(state.counters[layout.C_N_DEAD]))
     state.counters[layout.C_NEXT_ID] += len(new_agents)
     return len(new_agents)
+
+
+def state_digests_by_id(state):
+    """Digests of the state with the agents sorted by ID (list order is not part of the
+    scalable-mode semantics)."""
+    snap = state.canonical()
+    order = np.argsort(snap["a_id"], kind="stable")
+    for k in [k for k in snap if k.startswith("a_")]:
+        snap[k] = snap[k][order]
+    snap["a_alive"] = np.ones_like(snap["a_id"])
+    snap["mt"] = np.zeros(625, np.uint32)
+    return ref_harness.digests(snap), snap
+
+
+def load_scalable_golden():
+    with gzip.open(os.path.join(GOLDEN, "scalable_mode.json.gz"), "rt") as f:
+        return json.load(f)

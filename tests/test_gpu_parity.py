@@ -152,6 +152,25 @@ def test_scalable_mode_parallel_rounds_equal_sequential_oracle(name, overrides):
     eng.close()
 
 
+SCALABLE_GOLDEN = pu.load_scalable_golden()
+
+
+@pytest.mark.parametrize("name", sorted(SCALABLE_GOLDEN))
+def test_scalable_mode_matches_patched_reference(name):
+    """The CUDA engine in mode S against the UNMODIFIED reference run with its randomness
+    redirected to the mode S definitions (tests/golden/make_golden_scalable.py)."""
+    case = SCALABLE_GOLDEN[name]
+    c, state, pop, params, endow, tags, eng = _engine(name, layout.RNG_SCALABLE, case["overrides"])
+    for rec in case["steps"]:
+        eng.step(rec["t"], 0.0)
+        d, snap = pu.state_digests_by_id(eng.download())
+        assert len(snap["a_id"]) == rec["population"]
+        for k in ("agents_int", "agents_f64", "agents_tags", "grid_int", "pollution"):
+            assert d[k] == rec["digests"][k], f"{name}: {k} differs from the patched reference at t={rec['t']}"
+    assert int(eng.counters()[layout.C_OVERFLOW]) == 0
+    eng.close()
+
+
 def test_env_step_properties_at_full_size():
     """K1 at 4096 x 4096 (BASELINE S1 map): growback is monotone, bounded by capacity, idempotent at
     capacity, and equals the closed form min(level + k, cap) after k steps."""
