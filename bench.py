@@ -114,6 +114,20 @@ BYTES_PER_CELL_GROWBACK = 12
 BYTES_PER_AGENT_STEP = 232
 
 
+def aggregate_over_ranks(elapsed, units, device=None):
+    """Whole-job numbers from per-rank ones: time = MAX over ranks (the slowest rank defines the
+    step), work = SUM over ranks.  Works with any initialised torch.distributed backend."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return float(elapsed), float(units)
+    t = torch.tensor([float(elapsed)], dtype=torch.float64, device=device)
+    u = torch.tensor([float(units)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(u, op=dist.ReduceOp.SUM)
+    return float(t[0]), float(u[0])
+
+
 def run_cpu_port(args, c, steps):
     """The oracle port on one host core over `steps` timesteps of the same initial state."""
     from oracle_binding import Oracle
@@ -215,13 +229,7 @@ def main():
     agent_steps = sum(acting)
     if int(eng.counters()[layout.C_OVERFLOW]) != 0:
         raise RuntimeError("agent capacity overflow during the benchmark")
-    tm = torch.tensor([ms, float(agent_steps)], device=dev, dtype=torch.float64)
-    if world > 1:
-        mx = tm.clone()
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm_ = tm.clone()
-        dist.all_reduce(sm_, op=dist.ReduceOp.SUM)
-        ms, agent_steps = float(mx[0]), float(sm_[1])
+    ms, agent_steps = aggregate_over_ranks(ms, agent_steps, dev)
     value = agent_steps / (ms / 1000.0)
 
     # ---- per-phase kernel times (separate steps, CUDA events inside libssb) ---------------------------
@@ -274,11 +282,7 @@ def main():
         d2h += args.steps * C.sizeof(layout.Stats)
         barrier()
         wall = time.perf_counter() - w0
-        tw = torch.tensor([wall, float(e2e_agent_steps)], device=dev, dtype=torch.float64)
-        if world > 1:
-            mx = tw.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-            sm_ = tw.clone(); dist.all_reduce(sm_, op=dist.ReduceOp.SUM)
-            wall, e2e_agent_steps = float(mx[0]), float(sm_[1])
+        wall, e2e_agent_steps = aggregate_over_ranks(wall, e2e_agent_steps, dev)
         e2e = {"value": e2e_agent_steps / wall, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps,
                "d2h_bytes_per_step": d2h / args.steps, "wall_s": wall,
                "includes": "upload of the initial state, per-step stats readback + log formatting, download of the final agents"}
