@@ -84,6 +84,8 @@ typedef struct ssb_params {
     int32_t max_timestep;           /* configuration["timesteps"]                              */
     int32_t id_bits;                /* mode S: agent IDs must stay below 1 << id_bits (<= 26)   */
     int32_t max_sugar_capacity, max_spice_capacity; /* environmentMaxSugar / environmentMaxSpice: upper bound of any cell */
+    int32_t inheritance_policy;     /* agentInheritancePolicy: 0 none, 1 children, 2 sons, 3 daughters (agent.py:373-429) */
+    int32_t _pad;
 } ssb_params_t;
 
 typedef struct ssb_grid {
@@ -104,6 +106,7 @@ typedef struct ssb_grid {
 #define SSB_C_N_DEAD   5  /* agents removed at the end of the current step                    */
 #define SSB_C_ROUNDS   6  /* mode S: commit rounds used by the last agent step                */
 #define SSB_C_OVERFLOW 7  /* != 0 if a capacity was exceeded (births dropped) -> host raises  */
+#define SSB_C_N_KIN    8  /* used entries of the kin pool                                     */
 #define SSB_C_COUNT    16
 
 typedef struct ssb_agents {
@@ -143,8 +146,13 @@ typedef struct ssb_agents {
     int32_t *trade_volume;          /* agent.tradeVolume of its last transaction               */
     double  *trade_price;           /* max(spicePrice, sugarPrice) of its last transaction     */
     int32_t *last_repro;            /* lastReproducedTimestep                                  */
-    int32_t *n_children_alive, *n_children_dead; /* family happiness bookkeeping              */
+    /* kin lists (mode E): socialNetwork["children"] / ["mates"] of the INITIATING parent
+     * (agent.py:521-527), as singly linked lists in the kin pool below */
+    int32_t *children_head, *mates_head;         /* per slot: first pool entry, -1 = empty      */
     int32_t *father, *mother;       /* parent IDs (-1 none)                                    */
+    /* kin pool: entry i = (slot, id) of the relative and the next entry of the same list */
+    int64_t kin_capacity;
+    int32_t *kin_slot, *kin_id, *kin_next;
 } ssb_agents_t;
 
 /* Raw reductions for the reference's runtimeStats (sugarscape.py:1005-1426).  The host turns

@@ -184,11 +184,54 @@ static double find_welfare(const ctx_t *c, int s, double sugar_reward, double sp
     return welfare;
 }
 
+/* kin lists: socialNetwork["children"] / ["mates"] of the initiating parent (agent.py:521-527) */
+static void kin_push(ctx_t *c, int32_t *head, int owner, int other) {
+    int64_t *cn = c->a.counters;
+    if (cn[SSB_C_N_KIN] >= c->a.kin_capacity) { cn[SSB_C_OVERFLOW] = 3; return; }
+    int e = (int)cn[SSB_C_N_KIN]++;
+    c->a.kin_slot[e] = other; c->a.kin_id[e] = c->a.id[other]; c->a.kin_next[e] = head[owner];
+    head[owner] = e;
+}
+
+static int agent_alive(const ctx_t *c, int s);
+
+/* the relative of pool entry e, or -1 if it is no longer alive (dead, removed, slot recycled) */
+static int kin_alive(const ctx_t *c, int e) {
+    int o = c->a.kin_slot[e];
+    return (c->a.id[o] == c->a.kin_id[e] && agent_alive(c, o)) ? o : -1;
+}
+
+/* Agent.doInheritance (agent.py:373-429): policies children / sons / daughters */
+static void do_inheritance(ctx_t *c, int s) {
+    int policy = c->p->inheritance_policy;
+    if (policy == 0) return;
+    if (c->a.sugar[s] < 0) c->a.sugar[s] = 0;
+    if (c->a.spice[s] < 0) c->a.spice[s] = 0;
+    int heirs = 0;
+    for (int e = c->a.children_head[s]; e >= 0; e = c->a.kin_next[e]) {
+        int o = kin_alive(c, e);
+        if (o < 0) continue;
+        if (policy == 1 || (policy == 2 && c->a.sex[o] == SSB_SEX_MALE) || (policy == 3 && c->a.sex[o] == SSB_SEX_FEMALE)) heirs++;
+    }
+    if (heirs == 0) return;
+    double si = c->a.sugar[s] / heirs, pi = c->a.spice[s] / heirs;
+    for (int e = c->a.children_head[s]; e >= 0; e = c->a.kin_next[e]) {
+        int o = kin_alive(c, e);
+        if (o < 0) continue;
+        if (!(policy == 1 || (policy == 2 && c->a.sex[o] == SSB_SEX_MALE) || (policy == 3 && c->a.sex[o] == SSB_SEX_FEMALE))) continue;
+        c->a.sugar[o] = c->a.sugar[o] + si;
+        c->a.spice[o] = c->a.spice[o] + pi;
+        c->a.sugar[s] -= si;
+        c->a.spice[s] -= pi;
+    }
+}
+
 static void do_death(ctx_t *c, int s, int cause) {
     c->a.cod[s] = cause;
     int pos = c->a.pos[s];
     if (pos >= 0 && c->g.occ[pos] == s) c->g.occ[pos] = -1;
     c->a.pos[s] = -1;
+    if (c->p->rng_mode == SSB_RNG_EXACT) do_inheritance(c, s);
 }
 
 /* agent.py:1023-1029 */
@@ -520,7 +563,7 @@ static void do_reproduction(ctx_t *c, int s) {
         a->n_neighborhood[ch] = 0; a->n_valid_moves[ch] = 0;
         a->happiness[ch] = 0; a->wealth_happiness[ch] = 0; a->family_happiness[ch] = 0;
         a->trade_volume[ch] = 0; a->trade_price[ch] = 0; a->last_repro[ch] = -1;
-        a->n_children_alive[ch] = 0; a->n_children_dead[ch] = 0;
+        a->children_head[ch] = -1; a->mates_head[ch] = -1;
         a->father[ch] = a->sex[s] == SSB_SEX_FEMALE ? a->id[m] : a->id[s];
         a->mother[ch] = a->sex[s] == SSB_SEX_FEMALE ? a->id[s] : a->id[m];
         a->pos[ch] = cell;
@@ -529,6 +572,13 @@ static void do_reproduction(ctx_t *c, int s) {
         else cn[SSB_C_OVERFLOW] = 1;
         cn[SSB_C_N_BORN]++;
         collect(c, ch, cell);                                                    /* child collects */
+        if (c->p->rng_mode == SSB_RNG_EXACT) {   /* kin bookkeeping of the initiating parent (agent.py:521-527) */
+            int known = 0;
+            for (int e = a->mates_head[s]; e >= 0; e = a->kin_next[e])
+                if (a->kin_slot[e] == m && a->kin_id[e] == a->id[m]) known = 1;
+            if (!known) kin_push(c, a->mates_head, s, m);
+            kin_push(c, a->children_head, s, ch);
+        }
         a->sugar[s] -= sugar_cost; a->spice[s] -= spice_cost;
         a->sugar[m] = a->sugar[m] - mate_sugar_cost;
         a->spice[m] = a->spice[m] - mate_spice_cost;
@@ -568,9 +618,19 @@ static void agent_transaction(ctx_t *c, int s) {
     /* updateHappiness (agent.py:1522-1530): conflict + family + health + social + wealth.
      * family/social/conflict bookkeeping is not restated yet -> 0 */
     double wealth_h = erf((a->sugar[s] + a->spice[s]) - c->prev_mean_wealth);
+    /* findFamilyHappiness (agent.py:940-958), mode E only (the lists are not kept in mode S) */
+    double family = 0;
+    if (c->p->rng_mode == SSB_RNG_EXACT) {
+        for (int e = a->children_head[s]; e >= 0; e = a->kin_next[e]) {
+            int o = kin_alive(c, e);
+            if (o >= 0) { family += 1; if (a->born[o] == c->t) family += 1; } else family -= 1;
+        }
+        for (int e = a->mates_head[s]; e >= 0; e = a->kin_next[e]) family += kin_alive(c, e) >= 0 ? 1 : -1;
+    }
+    double family_h = erf(family);
     a->wealth_happiness[s] = wealth_h;
-    a->family_happiness[s] = 0;
-    a->happiness[s] = 0 + 0 + 1.0 + 0 + wealth_h;
+    a->family_happiness[s] = family_h;
+    a->happiness[s] = 0 + family_h + 1.0 + 0 + wealth_h;
 }
 
 /* ------------------------------------------------------------------------------------------

@@ -152,12 +152,56 @@ __device__ __forceinline__ double find_welfare(const DevCtx &c, int s, double su
     return w.eval(sugar_reward, spice_reward);
 }
 
-// Agent.doDeath (agent.py:296-313) with inheritance policy "none"
+// Kin lists (mode E): socialNetwork["children"] / ["mates"] of the INITIATING parent
+// (agent.py:521-527) as singly linked lists in the kin pool.
+__device__ __forceinline__ void kin_push(const DevCtx &c, int32_t *head, int owner, int other) {
+    unsigned long long *cn = (unsigned long long *)c.a.counters;
+    const long long e = (long long)atomicAdd(&cn[SSB_C_N_KIN], 1ull);
+    if (e >= c.a.kin_capacity) { atomicExch(&cn[SSB_C_OVERFLOW], 3ull); return; }
+    c.a.kin_slot[e] = other; c.a.kin_id[e] = c.a.id[other]; c.a.kin_next[e] = head[owner];
+    head[owner] = (int32_t)e;
+}
+
+// the relative of pool entry e, or -1 if it is no longer alive (dead, removed, slot recycled)
+__device__ __forceinline__ int kin_alive(const DevCtx &c, int e) {
+    const int o = c.a.kin_slot[e];
+    return (c.a.id[o] == c.a.kin_id[e] && agent_alive(c, o)) ? o : -1;
+}
+
+// Agent.doInheritance (agent.py:373-429): policies children / sons / daughters.  Heirs can be
+// anywhere on the map, so inheritance only exists in the ordered mode E.
+__device__ __noinline__ void do_inheritance(const DevCtx &c, int s) {
+    const int policy = c.p.inheritance_policy;
+    if (policy == 0 || c.p.rng_mode != SSB_RNG_EXACT) return;
+    const ssb_agents_t &a = c.a;
+    if (a.sugar[s] < 0) a.sugar[s] = 0;
+    if (a.spice[s] < 0) a.spice[s] = 0;
+    int heirs = 0;
+    for (int e = a.children_head[s]; e >= 0; e = a.kin_next[e]) {
+        const int o = kin_alive(c, e);
+        if (o < 0) continue;
+        if (policy == 1 || (policy == 2 && a.sex[o] == SSB_SEX_MALE) || (policy == 3 && a.sex[o] == SSB_SEX_FEMALE)) heirs++;
+    }
+    if (heirs == 0) return;
+    const double si = a.sugar[s] / heirs, pi = a.spice[s] / heirs;
+    for (int e = a.children_head[s]; e >= 0; e = a.kin_next[e]) {
+        const int o = kin_alive(c, e);
+        if (o < 0) continue;
+        if (!(policy == 1 || (policy == 2 && a.sex[o] == SSB_SEX_MALE) || (policy == 3 && a.sex[o] == SSB_SEX_FEMALE))) continue;
+        a.sugar[o] = a.sugar[o] + si;
+        a.spice[o] = a.spice[o] + pi;
+        a.sugar[s] -= si;
+        a.spice[s] -= pi;
+    }
+}
+
+// Agent.doDeath (agent.py:296-313)
 __device__ __forceinline__ void do_death(const DevCtx &c, int s, int cause) {
     c.a.cod[s] = cause;
     const int pos = c.a.pos[s];
     if (pos >= 0 && c.g.occ[pos] == s) c.g.occ[pos] = -1;
     c.a.pos[s] = -1;
+    if (c.p.inheritance_policy != 0) do_inheritance(c, s);
 }
 
 // Agent.findMarginalRateOfSubstitution (agent.py:1023-1029)
@@ -460,6 +504,7 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rn
             a.cod[s] = SSB_STARVATION;
             c.g.occ[best] = -1;
             a.pos[s] = -1;
+            if (c.p.inheritance_policy != 0) do_inheritance(c, s);
             alive = 0;
         }
     }
@@ -697,7 +742,7 @@ __device__ __noinline__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
         a.n_neighborhood[ch] = 0; a.n_valid_moves[ch] = 0;
         a.happiness[ch] = 0; a.wealth_happiness[ch] = 0; a.family_happiness[ch] = 0;
         a.trade_volume[ch] = 0; a.trade_price[ch] = 0; a.last_repro[ch] = -1;
-        a.n_children_alive[ch] = 0; a.n_children_dead[ch] = 0;
+        a.children_head[ch] = -1; a.mates_head[ch] = -1;
         const int my_id = a.id[s], mate_id = a.id[m];
         a.father[ch] = my_sex == SSB_SEX_FEMALE ? mate_id : my_id;
         a.mother[ch] = my_sex == SSB_SEX_FEMALE ? my_id : mate_id;
@@ -715,6 +760,13 @@ __device__ __noinline__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
             if (nth < a.capacity) c.born_list[nth] = ch; else atomicExch(&cn[SSB_C_OVERFLOW], 1ull);
         }
         collect(c, ch, cell);      // the child collects at birth (agent.py:175)
+        if (EXACT) {               // kin bookkeeping of the initiating parent (agent.py:521-527)
+            bool known = false;
+            for (int e = a.mates_head[s]; e >= 0; e = a.kin_next[e])
+                if (a.kin_slot[e] == m && a.kin_id[e] == mate_id) known = true;
+            if (!known) kin_push(c, a.mates_head, s, m);
+            kin_push(c, a.children_head, s, ch);
+        }
         my_sugar -= sugar_cost; my_spice -= spice_cost;
         a.sugar[s] = my_sugar; a.spice[s] = my_spice;
         m_sugar[k] -= mate_sugar_cost; m_spice[k] -= mate_spice_cost;
@@ -742,12 +794,23 @@ __device__ void transaction_interact_phase(const DevCtx &c, int s, const AgentRe
     const int age = rec.age + 1;
     a.age[s] = age;
     if (age >= rec.max_age && rec.max_age != -1) { do_death(c, s, SSB_AGING); return; }
-    // updateHappiness (agent.py:1522-1530): conflict + family + health + social + wealth; the
-    // family / social / conflict bookkeeping is not implemented yet (DESIGN.md scope) -> 0
+    // updateHappiness (agent.py:1522-1530): conflict (0: no aggression in the supported examples'
+    // logs) + family + health (+1: no diseases) + social (0: no friends) + wealth
     const double wealth_h = erf((sugar + spice) - c.prev_mean_wealth);
+    // findFamilyHappiness (agent.py:940-958): mode E only (mode S keeps no kin lists: the relatives
+    // can be anywhere and change concurrently)
+    double family = 0;
+    if (EXACT && (c.p.flags & SSB_F_REPRO)) {
+        for (int e = a.children_head[s]; e >= 0; e = a.kin_next[e]) {
+            const int o = kin_alive(c, e);
+            if (o >= 0) { family += 1; if (a.born[o] == c.t) family += 1; } else family -= 1;
+        }
+        for (int e = a.mates_head[s]; e >= 0; e = a.kin_next[e]) family += kin_alive(c, e) >= 0 ? 1 : -1;
+    }
+    const double family_h = erf(family);
     a.wealth_happiness[s] = wealth_h;
-    a.family_happiness[s] = 0;
-    a.happiness[s] = 1.0 + wealth_h;
+    a.family_happiness[s] = family_h;
+    a.happiness[s] = family_h + 1.0 + wealth_h;
 }
 
 }  // namespace ssb

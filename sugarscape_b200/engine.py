@@ -92,6 +92,7 @@ class Engine:
         self.params = params
         self.device = torch.device("cuda", device)
         self.width, self.height, self.capacity = host_state.width, host_state.height, host_state.capacity
+        self.kin_capacity = host_state.kin_capacity
         self.tensors = {}
         self._upload_all(host_state)
         self.handle = C.c_void_p()
@@ -121,6 +122,8 @@ class Engine:
         self.tensors["counters"] = self._to_device(hs.counters)
         for name, _, _ in layout.AGENT_FIELDS:
             self.tensors["a_" + name] = self._to_device(getattr(hs, "a_" + name))
+        for name in layout.KIN_FIELDS:
+            self.tensors[name] = self._to_device(getattr(hs, name))
 
     def _structs(self):
         g = layout.Grid()
@@ -132,6 +135,9 @@ class Engine:
         a.counters = self.tensors["counters"].data_ptr()
         for name, _, _ in layout.AGENT_FIELDS:
             setattr(a, name, self.tensors["a_" + name].data_ptr())
+        a.kin_capacity = self.kin_capacity
+        for name in layout.KIN_FIELDS:
+            setattr(a, name, self.tensors[name].data_ptr())
         return g, a
 
     @property
@@ -154,6 +160,7 @@ class Engine:
     def download(self, fields=None):
         """Copy the device state back into a HostState (all fields, or the named subset)."""
         hs = layout.HostState(self.width, self.height, self.capacity)
+        hs.kin_capacity = self.kin_capacity
         self.torch.cuda.synchronize(self.device)
         for key, tensor in self.tensors.items():
             if fields is not None and key not in fields:

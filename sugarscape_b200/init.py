@@ -94,8 +94,8 @@ def check_supported(c):
         problems.append("lending")
     if c["agentRacialTagStringLength"] > 0 and c["environmentMaxRaces"] > 0:
         problems.append("racial tags")
-    if c["agentInheritancePolicy"] != "none":
-        problems.append("inheritance")
+    if c["agentInheritancePolicy"] not in ("none", "children", "sons", "daughters"):
+        problems.append("inheritance policy " + str(c["agentInheritancePolicy"]))
     if c["agentMaxFriends"][1] > 0:
         problems.append("friends")
     if c["agentUniversalSugar"][1] != 0 or c["agentUniversalSpice"][1] != 0:

@@ -17,7 +17,8 @@ SEX_CODE = {None: SEX_NONE, "male": SEX_MALE, "female": SEX_FEMALE}
 F_SPICE, F_POLLUTION, F_REPRO, F_TAGS, F_TAGGING, F_COMBAT, F_TRADE, F_TAGPREF = (
     1 << 0, 1 << 1, 1 << 2, 1 << 3, 1 << 4, 1 << 5, 1 << 6, 1 << 7)
 
-(C_N_LIST, C_N_SLOTS, C_NEXT_ID, C_N_FREE, C_N_BORN, C_N_DEAD, C_ROUNDS, C_OVERFLOW) = range(8)
+(C_N_LIST, C_N_SLOTS, C_NEXT_ID, C_N_FREE, C_N_BORN, C_N_DEAD, C_ROUNDS, C_OVERFLOW, C_N_KIN) = range(9)
+INHERITANCE_CODE = {"none": 0, "children": 1, "sons": 2, "daughters": 3}
 C_COUNT = 16
 
 # (name, numpy dtype) in the order of ssb_grid_t
@@ -47,7 +48,7 @@ AGENT_FIELDS = (
     ("family_happiness", np.float64, 0),
     ("trade_volume", np.int32, 0), ("trade_price", np.float64, 0),
     ("last_repro", np.int32, -1),
-    ("n_children_alive", np.int32, 0), ("n_children_dead", np.int32, 0),
+    ("children_head", np.int32, -1), ("mates_head", np.int32, -1),
     ("father", np.int32, -1), ("mother", np.int32, -1),
 )
 
@@ -71,6 +72,7 @@ class Params(C.Structure):
         ("tag_len", C.c_int32), ("max_tribes", C.c_int32),
         ("max_timestep", C.c_int32), ("id_bits", C.c_int32),
         ("max_sugar_capacity", C.c_int32), ("max_spice_capacity", C.c_int32),
+        ("inheritance_policy", C.c_int32), ("_pad", C.c_int32),
     ]
 
 
@@ -78,9 +80,13 @@ class Grid(C.Structure):
     _fields_ = [("n_cells", C.c_int64)] + [(n, C.c_void_p) for n, _ in GRID_FIELDS]
 
 
+KIN_FIELDS = ("kin_slot", "kin_id", "kin_next")
+
+
 class Agents(C.Structure):
     _fields_ = ([("capacity", C.c_int64), ("counters", C.c_void_p)]
-                + [(n, C.c_void_p) for n, _, _ in AGENT_FIELDS])
+                + [(n, C.c_void_p) for n, _, _ in AGENT_FIELDS]
+                + [("kin_capacity", C.c_int64)] + [(n, C.c_void_p) for n in KIN_FIELDS])
 
 
 class Stats(C.Structure):
@@ -142,6 +148,7 @@ def make_params(c, rng_mode, flags, max_agent_range, equator):
     p.id_bits = 26
     p.max_sugar_capacity = int(max(c["environmentMaxSugar"], 0))
     p.max_spice_capacity = int(max(c["environmentMaxSpice"], 0))
+    p.inheritance_policy = INHERITANCE_CODE[c["agentInheritancePolicy"]]
     return p
 
 
@@ -152,7 +159,7 @@ class HostState:
         self.width, self.height, self.capacity = width, height, capacity
 
     @classmethod
-    def empty(cls, width, height, capacity):
+    def empty(cls, width, height, capacity, kin_capacity=None):
         s = cls(width, height, capacity)
         n = width * height
         for name, dt in GRID_FIELDS:
@@ -161,6 +168,9 @@ class HostState:
         s.counters = np.zeros(C_COUNT, dtype=np.int64)
         for name, dt, fill in AGENT_FIELDS:
             setattr(s, "a_" + name, np.full(capacity, fill, dtype=dt))
+        s.kin_capacity = kin_capacity if kin_capacity is not None else 4 * capacity
+        for name in KIN_FIELDS:
+            setattr(s, name, np.full(s.kin_capacity, -1, dtype=np.int32))
         return s
 
     def copy(self):
@@ -170,6 +180,9 @@ class HostState:
         s.counters = self.counters.copy()
         for name, _, _ in AGENT_FIELDS:
             setattr(s, "a_" + name, getattr(self, "a_" + name).copy())
+        s.kin_capacity = self.kin_capacity
+        for name in KIN_FIELDS:
+            setattr(s, name, getattr(self, name).copy())
         return s
 
     def as_structs(self):
@@ -183,6 +196,9 @@ class HostState:
         a.counters = self.counters.ctypes.data
         for name, _, _ in AGENT_FIELDS:
             setattr(a, name, getattr(self, "a_" + name).ctypes.data)
+        a.kin_capacity = self.kin_capacity
+        for name in KIN_FIELDS:
+            setattr(a, name, getattr(self, name).ctypes.data)
         return g, a
 
     # -- agents -------------------------------------------------------------------------------

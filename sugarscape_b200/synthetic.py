@@ -55,7 +55,7 @@ def build_state(c, capacity=None, seed=None):
     rng = np.random.default_rng(c["seed"] if seed is None else seed)
     if capacity is None:
         capacity = int(min(max(3 * n, 1024), 2 * W * H + 1024)) if c["agentFertilityFactor"][1] > 0 else int(n + n // 2 + 1024)
-    state = layout.HostState.empty(W, H, capacity)
+    state = layout.HostState.empty(W, H, capacity, kin_capacity=16)     # kin lists are a mode E feature
     state.sugar_cap[:] = tiled_capacity(W, H, c["environmentSugarPeaks"]).reshape(-1)
     state.sugar[:] = state.sugar_cap
     if c["environmentMaxSpice"] > 0:

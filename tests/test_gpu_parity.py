@@ -21,6 +21,7 @@ EXACT_EXAMPLES = [
     "seasonal_migration", "pollution_formation", "combat_limited", "combat_unlimited",
     "cultural_combat_unlimited", "cultural_tagging", "reproduction_basic",
     "reproduction_oscillation_small", "reproduction_oscillation_large", "reproduction_oscillation_severe",
+    "reproduction_inheritance",
 ]
 POW_EXAMPLES = ["spice_growback", "foresight_basic", "trade_basic", "trade_replacement", "trade_tagging",
                 "trade_pollution", "trade_reproduction", "trade_tagging_reproduction"]
@@ -65,7 +66,7 @@ def test_exact_mode_trajectory_matches_reference_bit_for_bit(name):
     sb = stats.StatsBuilder(c, init.equator(c))
     eng.reduce_stats(0)
     rs = sb.update(eng.stats(), 0)
-    skip = set(stats.UNVERIFIED_KEYS) if c["agentFertilityFactor"][1] > 0 else set()
+    skip = set()      # all 59 keys are checked
     for t in range(1, len(gold)):
         eng.env_step(t)
         eng.agent_step(t, rs["meanWealth"])

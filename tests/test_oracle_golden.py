@@ -13,14 +13,13 @@ from sugarscape_b200 import init, stats
 SUPPORTED = [
     "agent_replacement", "blank", "combat_limited", "combat_unlimited", "constant_growback",
     "cultural_combat_unlimited", "cultural_tagging", "diagonal_waves", "foresight_basic",
-    "immediate_growback", "pollution_formation", "reproduction_basic",
+    "immediate_growback", "pollution_formation", "reproduction_basic", "reproduction_inheritance",
     "reproduction_oscillation_large", "reproduction_oscillation_severe",
     "reproduction_oscillation_small", "seasonal_migration", "spice_growback", "trade_basic",
     "trade_pollution", "trade_replacement", "trade_reproduction", "trade_tagging",
     "trade_tagging_reproduction",
 ]
-UNSUPPORTED = ["all_features", "determinism", "disease_basic", "dune", "lending_basic",
-               "reproduction_inheritance"]
+UNSUPPORTED = ["all_features", "determinism", "disease_basic", "dune", "lending_basic"]
 
 
 def _close(a, b):
@@ -42,7 +41,7 @@ def test_oracle_matches_reference_trajectory(name):
     assert d == gold[0]["digests"], "t=0 state differs"
     sb = stats.StatsBuilder(c, init.equator(c))
     rs = sb.update(orc.stats(0), 0)
-    skip = set(stats.UNVERIFIED_KEYS) if c["agentFertilityFactor"][1] > 0 else set()
+    skip = set()      # all 59 keys are checked
     for t in range(1, len(gold)):
         orc.env_step(t)
         orc.agent_step(t, rs["meanWealth"])
