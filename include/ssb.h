@@ -237,6 +237,9 @@ int  ssb_stats(ssb_engine_t *e, ssb_stats_t *host_out);          /* synchronises
 #define SSB_STATS_RING 1024
 int  ssb_stats_history(ssb_engine_t *e, int32_t t, ssb_stats_t *host_out); /* stats of a recent step t (device ring of SSB_STATS_RING entries); synchronises */
 int  ssb_sync(ssb_engine_t *e, void *stream);
+/* Diffusion steps write the new field into the other pollution buffer and swap roles: returns 1
+ * if the field currently lives in the buffer bound as grid->pollution_flux, else 0. */
+int  ssb_pollution_buffer(const ssb_engine_t *e);
 
 /* instrumentation: number of kernels this engine has launched, device time of the last
  * ssb_env_step / ssb_agent_step in ms (CUDA events on the caller's stream; ssb_timing syncs) */

@@ -48,6 +48,7 @@ struct ssb_engine {
     bool timing;
     cudaEvent_t ev[5];
     bool ev_recorded;
+    bool pollution_swapped;  // the pollution field currently lives in the buffer bound as pollution_flux
 };
 
 static int fail(ssb_engine *e, int code, const char *fmt, ...) {
@@ -336,9 +337,14 @@ int ssb_env_step(ssb_engine_t *e, int32_t t, void *stream_) {
     }
     if (p.diffusion_delay > 0 && p.diffusion_start <= t && t <= p.diffusion_end &&
         ((t - p.diffusion_start + 1) % p.diffusion_delay) == 0) {
-        k_diffuse<<<grid_for(g.n_cells, 256, e->num_sms * 8), 256, 0, st>>>(e->ctx.g.pollution, e->ctx.g.pollution_flux, p.width, p.height);
+        if ((p.height % 2) == 0)
+            k_diffuse_v2<<<grid_for(g.n_cells / 2, 256, e->num_sms * 8), 256, 0, st>>>(e->ctx.g.pollution, e->ctx.g.pollution_flux, p.width, p.height);
+        else
+            k_diffuse<<<grid_for(g.n_cells, 256, e->num_sms * 8), 256, 0, st>>>(e->ctx.g.pollution, e->ctx.g.pollution_flux, p.width, p.height);
         LAUNCHED(e);
-        CU(cudaMemcpyAsync(e->ctx.g.pollution, e->ctx.g.pollution_flux, sizeof(double) * g.n_cells, cudaMemcpyDeviceToDevice, st));
+        // the flux buffer now holds the field: swap the roles of the two host-owned buffers
+        double *tmp = e->ctx.g.pollution; e->ctx.g.pollution = e->ctx.g.pollution_flux; e->ctx.g.pollution_flux = tmp;
+        e->pollution_swapped = !e->pollution_swapped;
     }
     if (e->timing) CU(cudaEventRecord(e->ev[1], st));
     return 0;
@@ -438,6 +444,10 @@ int ssb_stats_history(ssb_engine_t *e, int32_t t, ssb_stats_t *host_out) {
     if (host_out->timestep != t) return fail(e, -1, "step %d is no longer (or not yet) in the stats ring", t);
     return 0;
 }
+
+// 1 if the pollution field currently lives in the buffer that was bound as grid->pollution_flux
+// (every diffusion step swaps the two buffers instead of copying), else 0
+int ssb_pollution_buffer(const ssb_engine_t *e) { return e && e->pollution_swapped ? 1 : 0; }
 
 int ssb_sync(ssb_engine_t *e, void *stream) {
     CHECK_BOUND(e);

@@ -61,7 +61,31 @@ __global__ void __launch_bounds__(256) k_growback_scalar(GrowArgs g) {
 }
 
 // Pollution diffusion (cell.py:104-109,24-25): Jacobi mean of N, S, E, W from the OLD field, the
-// centre excluded, summed in that order starting from 0.  16 B per cell (read + write).
+// centre excluded, summed in that order starting from 0.  16 B per cell (one read, one write):
+// the result goes to the second buffer and the two buffers swap roles (no copy back).
+// x-major layout: N / S are the neighbours in memory, E / W sit one x-line (H cells) away, so the
+// three x-lines a thread block touches are re-read from L1 / L2, not from HBM.
+__global__ void __launch_bounds__(256) k_diffuse_v2(const double *__restrict__ p, double *__restrict__ out,
+                                                    int W, int H) {
+    // two cells (one 128-bit vector) per thread along y; requires H % 2 == 0
+    const long long n2 = ((long long)W * H) >> 1;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const int H2 = H >> 1;
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < n2; v += stride) {
+        const int x = (int)(v / H2), y = (int)(v - (long long)x * H2) << 1;
+        const long long row = (long long)x * H;
+        const double2 e = *reinterpret_cast<const double2 *>(p + (long long)(x == W - 1 ? 0 : x + 1) * H + y);
+        const double2 w = *reinterpret_cast<const double2 *>(p + (long long)(x == 0 ? W - 1 : x - 1) * H + y);
+        const double2 c = *reinterpret_cast<const double2 *>(p + row + y);
+        const double n0 = p[row + (y == 0 ? H - 1 : y - 1)];
+        const double s1 = p[row + (y + 2 == H ? 0 : y + 2)];
+        double m0 = 0.0, m1 = 0.0;
+        m0 += n0;  m0 += c.y; m0 += e.x; m0 += w.x;      // cell y:     N = y-1, S = y+1
+        m1 += c.x; m1 += s1;  m1 += e.y; m1 += w.y;      // cell y + 1: N = y,   S = y+2
+        *reinterpret_cast<double2 *>(out + row + y) = make_double2(m0 / 4, m1 / 4);
+    }
+}
+
 __global__ void __launch_bounds__(256) k_diffuse(const double *__restrict__ p, double *__restrict__ flux,
                                                  int W, int H) {
     const long long n = (long long)W * H;

@@ -55,6 +55,8 @@ def load_library():
     L.ssb_stats.argtypes = [E, S]
     L.ssb_stats_history.argtypes = [E, C.c_int32, S]
     L.ssb_sync.argtypes = [E, C.c_void_p]
+    L.ssb_pollution_buffer.argtypes = [E]
+    L.ssb_pollution_buffer.restype = C.c_int
     L.ssb_round_trace.argtypes = [E, C.c_int32, C.c_void_p, C.c_int32]
     L.ssb_test_pow.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
     L.ssb_launch_count.argtypes = [E]
@@ -76,7 +78,7 @@ EXPORTED_SYMBOLS = (
     "ssb_set_mt_state", "ssb_get_mt_state", "ssb_set_step_tables", "ssb_set_epochs", "ssb_set_mark_shift", "ssb_set_l2_persist",
     "ssb_sizeof_params", "ssb_sizeof_grid", "ssb_sizeof_agents", "ssb_sizeof_stats",
     "ssb_env_step", "ssb_agent_step", "ssb_compact", "ssb_reduce_stats", "ssb_step", "ssb_stats", "ssb_stats_history",
-    "ssb_sync", "ssb_test_pow", "ssb_round_trace", "ssb_launch_count", "ssb_timing", "ssb_enable_timing",
+    "ssb_sync", "ssb_pollution_buffer", "ssb_test_pow", "ssb_round_trace", "ssb_launch_count", "ssb_timing", "ssb_enable_timing",
 )
 
 
@@ -162,9 +164,12 @@ class Engine:
         hs = layout.HostState(self.width, self.height, self.capacity)
         hs.kin_capacity = self.kin_capacity
         self.torch.cuda.synchronize(self.device)
+        swapped = bool(self.L.ssb_pollution_buffer(self.handle))
         for key, tensor in self.tensors.items():
             if fields is not None and key not in fields:
                 continue
+            if swapped and key in ("pollution", "pollution_flux"):      # the buffers swap roles at diffusion steps
+                tensor = self.tensors["pollution_flux" if key == "pollution" else "pollution"]
             arr = tensor.cpu().numpy()
             if key == "a_tags":
                 arr = arr.view(np.uint32)
@@ -172,8 +177,11 @@ class Engine:
         return hs
 
     def upload(self, hs, fields):
+        swapped = bool(self.L.ssb_pollution_buffer(self.handle))
         for key in fields:
             arr = getattr(hs, key)
+            if swapped and key in ("pollution", "pollution_flux"):
+                key = "pollution_flux" if key == "pollution" else "pollution"
             if arr.dtype == np.uint32:
                 arr = arr.view(np.int32)
             self.tensors[key].copy_(self.torch.from_numpy(np.ascontiguousarray(arr)))
