@@ -85,6 +85,11 @@ typedef struct ssb_params {
     int32_t id_bits;                /* mode S: agent IDs must stay below 1 << id_bits (<= 26)   */
     int32_t max_sugar_capacity, max_spice_capacity; /* environmentMaxSugar / environmentMaxSpice: upper bound of any cell */
     int32_t inheritance_policy;     /* agentInheritancePolicy: 0 none, 1 children, 2 sons, 3 daughters (agent.py:373-429) */
+    /* replacement in mode S (sugarscape.py:171-267,475-497,855-859) */
+    int32_t agent_replacements;     /* agentReplacements: population is topped up to this value  */
+    int32_t quad_w, quad_h;         /* quadrant size: floor(W/2 * factor), floor(H/2 * factor)    */
+    int32_t quad_mask;              /* bit q-1 set if quadrant q (1..4) is a starting quadrant    */
+    int32_t tribe_per_quadrant;     /* environmentTribePerQuadrant                                */
     int32_t _pad;
 } ssb_params_t;
 
@@ -107,6 +112,8 @@ typedef struct ssb_grid {
 #define SSB_C_ROUNDS   6  /* mode S: commit rounds used by the last agent step                */
 #define SSB_C_OVERFLOW 7  /* != 0 if a capacity was exceeded (births dropped) -> host raises  */
 #define SSB_C_N_KIN    8  /* used entries of the kin pool                                     */
+#define SSB_C_ENDOW_INDEX 9 /* sugarscape.agentEndowmentIndex                                  */
+#define SSB_C_N_REPLACED 10 /* agents created by the last replacement                           */
 #define SSB_C_COUNT    16
 
 typedef struct ssb_agents {
@@ -154,6 +161,17 @@ typedef struct ssb_agents {
     int64_t kin_capacity;
     int32_t *kin_slot, *kin_id, *kin_next;
 } ssb_agents_t;
+
+/* The endowment list that replacements reuse cyclically (sugarscape.agentEndowments,
+ * sugarscape.py:192-194,207-208), struct-of-arrays in creation order.  Mode S only: in mode E the
+ * host keeps the list and places replacements itself. */
+typedef struct ssb_endowments {
+    int64_t count;
+    double  *sugar, *spice;
+    int32_t *sugar_metab, *spice_metab, *vision, *movement, *max_age, *sex, *fert_age, *infert_age;
+    double  *fert_factor, *aggression, *lookahead, *trade_factor;
+    uint32_t *tags;                 /* endowment tags (used unless tribes are per quadrant)     */
+} ssb_endowments_t;
 
 /* Raw reductions for the reference's runtimeStats (sugarscape.py:1005-1426).  The host turns
  * them into the 59 log keys (means, Python round(), JSON). */
@@ -230,6 +248,8 @@ int  ssb_env_step(ssb_engine_t *e, int32_t t, void *stream);     /* environment.
 int  ssb_agent_step(ssb_engine_t *e, int32_t t, double prev_mean_wealth, void *stream);
                                                                   /* shuffle + agent loop       */
 int  ssb_compact(ssb_engine_t *e, int32_t t, void *stream);      /* removeDeadAgents + births  */
+int  ssb_bind_endowments(ssb_engine_t *e, const ssb_endowments_t *endowments);
+int  ssb_replace(ssb_engine_t *e, int32_t t, void *stream);      /* replaceDeadAgents, mode S  */
 int  ssb_reduce_stats(ssb_engine_t *e, int32_t t, void *stream); /* device reductions          */
 int  ssb_step(ssb_engine_t *e, int32_t t, double prev_mean_wealth, void *stream);
                                                                   /* the four above, in order   */

@@ -773,6 +773,116 @@ void orc_compact(const ssb_params_t *p, const ssb_grid_t *g, const ssb_agents_t 
     }
 }
 
+/* replaceDeadAgents -> configureAgents (sugarscape.py:855-859,171-267) with the mode S sources of
+ * randomness: the empty cells of a quadrant are ordered by a hash of the cell, the quadrants by a
+ * hash of their position, a new agent's tribe tags come from the substream of its own id
+ * (tests/golden/make_golden_scalable.py applies the same substitutions to the reference). */
+#define SALT_CELL 0x52455043454C4Cull
+#define SALT_QUAD 0x5245505155414Dull
+enum { SITE_NEWTAGS = 4 };
+
+static int quadrant_of_cell(const ssb_params_t *p, int x, int y) {
+    /* position (0-based) of the cell's quadrant among the ACTIVE quadrants, or -1 */
+    int W = p->width, H = p->height, qw = p->quad_w, qh = p->quad_h, q = 0;
+    if (x < qw && y < qh) q = 1;
+    else if (x >= W - qw && y < qh) q = 2;
+    else if (x >= W - qw && y >= H - qh) q = 3;
+    else if (x < qw && y >= H - qh) q = 4;
+    if (q == 0 || !((p->quad_mask >> (q - 1)) & 1)) return -1;
+    int pos = 0;
+    for (int k = 1; k < q; k++) pos += (p->quad_mask >> (k - 1)) & 1;
+    return pos;
+}
+
+void orc_replace(const ssb_params_t *p, const ssb_grid_t *g, const ssb_agents_t *a, const ssb_endowments_t *en, int32_t t) {
+    ctx_t c;
+    orc_rng_t rng;
+    memset(&rng, 0, sizeof(rng));
+    make_ctx(&c, p, g, a, &rng, t);
+    int64_t *cn = a->counters;
+    cn[SSB_C_N_REPLACED] = 0;
+    int64_t need = (int64_t)p->agent_replacements - cn[SSB_C_N_LIST];
+    if (need <= 0 || en->count <= 0) return;
+    int W = p->width, H = p->height, Q = 0;
+    for (int k = 0; k < 4; k++) Q += (p->quad_mask >> k) & 1;
+    if (Q == 0) return;
+    uint64_t key = orc_step_key(p->seed, t);
+    uint64_t *cells[4]; int64_t n_empty[4] = {0, 0, 0, 0}, total = 0;
+    for (int q = 0; q < Q; q++) cells[q] = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)(p->quad_w > 0 && p->quad_h > 0 ? (int64_t)p->quad_w * p->quad_h : 1));
+    for (int x = 0; x < W; x++)
+        for (int y = 0; y < H; y++) {
+            int q = quadrant_of_cell(p, x, y), cell = x * H + y;
+            if (q < 0 || g->occ[cell] >= 0) continue;
+            cells[q][n_empty[q]++] = ((mix64(key ^ SALT_CELL ^ (uint64_t)cell) >> 32) << 32) | (uint32_t)cell;
+            total++;
+        }
+    if (total > 0) {
+        if (need > total) need = total;
+        for (int q = 0; q < Q; q++) qsort(cells[q], (size_t)n_empty[q], sizeof(uint64_t), cmp_u64);
+        /* quadrant order: ascending (hash, position) */
+        int qorder[4]; uint64_t qk[4];
+        for (int q = 0; q < Q; q++) { qorder[q] = q; qk[q] = mix64(key ^ SALT_QUAD ^ (uint64_t)q); }
+        for (int i = 1; i < Q; i++)
+            for (int j = i; j > 0 && (qk[qorder[j - 1]] > qk[qorder[j]] || (qk[qorder[j - 1]] == qk[qorder[j]] && qorder[j - 1] > qorder[j])); j--) {
+                int tq = qorder[j]; qorder[j] = qorder[j - 1]; qorder[j - 1] = tq;
+            }
+        /* slots: recycled ones first, but not those of this step's dead (the stats still read them) */
+        int64_t n_dead = cn[SSB_C_N_DEAD], older = cn[SSB_C_N_FREE] - n_dead, n_free0 = cn[SSB_C_N_FREE];
+        rng.mode = SSB_RNG_SCALABLE; rng.step_key = key;
+        int64_t made = 0;
+        for (int64_t i = 0; i < need; i++) {
+            int q = qorder[i % Q];
+            if (n_empty[q] == 0) { cn[SSB_C_OVERFLOW] = 4; break; }   /* the reference would raise IndexError here */
+            int cell = (int)(cells[q][--n_empty[q]] & 0xffffffffu);
+            int slot;
+            if (older > 0) slot = a->free_slots[--older];
+            else { if (cn[SSB_C_N_SLOTS] >= a->capacity) { cn[SSB_C_OVERFLOW] = 1; break; } slot = (int)cn[SSB_C_N_SLOTS]++; }
+            int64_t ei = (cn[SSB_C_ENDOW_INDEX] + i) % en->count;
+            int id = (int)(cn[SSB_C_NEXT_ID] + i);
+            a->id[slot] = id; a->pos[slot] = cell; a->born[slot] = t; a->cod[slot] = SSB_ALIVE;
+            a->sugar[slot] = a->start_sugar[slot] = en->sugar[ei];
+            a->spice[slot] = a->start_spice[slot] = en->spice[ei];
+            a->sugar_metab[slot] = en->sugar_metab[ei]; a->spice_metab[slot] = en->spice_metab[ei];
+            a->vision[slot] = en->vision[ei]; a->movement[slot] = en->movement[ei];
+            a->age[slot] = 0; a->max_age[slot] = en->max_age[ei]; a->sex[slot] = en->sex[ei];
+            a->fert_age[slot] = en->fert_age[ei]; a->infert_age[slot] = en->infert_age[ei];
+            a->fert_factor[slot] = en->fert_factor[ei]; a->aggression[slot] = en->aggression[ei];
+            a->lookahead[slot] = en->lookahead[ei]; a->trade_factor[slot] = en->trade_factor[ei];
+            a->mrs[slot] = 1;
+            uint32_t tags = en->tags[ei];
+            if (p->tribe_per_quadrant && p->tag_len > 0 && p->max_tribes > 0) {
+                /* generateTribeTags(tribe = quadrant position), sugarscape.py:548-559 */
+                int L = p->tag_len;
+                double tribe_size = (double)(L + 1) / (double)p->max_tribes;
+                int min_z = (int)floor(q * tribe_size), max_z = (int)floor((q + 1) * tribe_size) - 1;
+                if (max_z > L) max_z = L;
+                rng.agent_id = (uint32_t)id; rng_at(&rng, SITE_NEWTAGS);
+                int zeroes = min_z + (int)rng_below(&rng, (uint32_t)(max_z - min_z + 1));
+                int32_t bits[32];
+                for (int k = 0; k < L; k++) bits[k] = k < zeroes ? 0 : 1;
+                rng_shuffle_i32(&rng, bits, L);
+                tags = 0;
+                for (int k = 0; k < L; k++) tags |= (uint32_t)bits[k] << k;
+            }
+            a->tags[slot] = tags;
+            a->tribe[slot] = find_tribe(&c, tags);
+            a->last_moved[slot] = -1; a->last_sugar[slot] = 0; a->last_spice[slot] = 0;
+            a->n_neighborhood[slot] = 0; a->n_valid_moves[slot] = 0;
+            a->happiness[slot] = 0; a->wealth_happiness[slot] = 0; a->family_happiness[slot] = 0;
+            a->trade_volume[slot] = 0; a->trade_price[slot] = 0; a->last_repro[slot] = -1;
+            a->children_head[slot] = -1; a->mates_head[slot] = -1; a->father[slot] = -1; a->mother[slot] = -1;
+            g->occ[cell] = slot;
+            a->order[cn[SSB_C_N_LIST] + i] = slot;
+            made++;
+        }
+        /* close the gap in the free stack left by the recycled slots */
+        memmove(a->free_slots + older, a->free_slots + (n_free0 - n_dead), sizeof(int32_t) * (size_t)n_dead);
+        cn[SSB_C_N_FREE] = older + n_dead;
+        cn[SSB_C_N_LIST] += made; cn[SSB_C_NEXT_ID] += made; cn[SSB_C_ENDOW_INDEX] += made; cn[SSB_C_N_REPLACED] = made;
+    }
+    for (int q = 0; q < Q; q++) free(cells[q]);
+}
+
 static int cmp_f64(const void *x, const void *y) {
     double a = *(const double *)x, b = *(const double *)y;
     return a < b ? -1 : a > b;
@@ -840,6 +950,7 @@ void orc_stats(const ssb_params_t *p, const ssb_grid_t *g, const ssb_agents_t *a
         out->dead_combat += a->cod[s] == SSB_COMBAT;
     }
     out->n_born = cn[SSB_C_N_BORN];
+    out->n_replaced = cn[SSB_C_N_REPLACED];
     /* environment totals (sugarscape.py:1044-1051) with the closed-form LastProduced */
     int W = p->width, H = p->height;
     int seasons = p->season_interval > 0;

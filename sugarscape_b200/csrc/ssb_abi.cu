@@ -10,6 +10,7 @@
 #include "ssb_agent_step.cuh"
 #include "ssb_kernels.cuh"
 #include "ssb_sort.cuh"
+#include "ssb_replace.cuh"
 
 using namespace ssb;
 
@@ -49,6 +50,12 @@ struct ssb_engine {
     cudaEvent_t ev[5];
     bool ev_recorded;
     bool pollution_swapped;  // the pollution field currently lives in the buffer bound as pollution_flux
+    // replacement (mode S)
+    ssb_endowments_t endow;
+    bool endow_bound;
+    ReplacePlan *d_plan;
+    uint64_t *d_cand;        // 4 quadrant regions of cand_capacity keys
+    int64_t cand_capacity;
 };
 
 static int fail(ssb_engine *e, int code, const char *fmt, ...) {
@@ -142,7 +149,7 @@ void ssb_destroy(ssb_engine_t *e) {
     void *ptrs[] = {e->d_mt, e->d_endow, e->d_tagbits, e->d_tile_counts, e->d_new_order, e->d_scalars,
                     e->d_born_list, e->rc.mark, e->rc.list_a, e->rc.list_b, e->rc.ready, e->rc.cnt, e->rc.trace, e->rc.bucketed, e->rc.epoch_count, e->rc.epoch_start, e->rc.epoch_fill,
                     e->d_partials, e->d_tribes, e->d_stats, e->d_ring, e->d_keys_a, e->d_keys_b, e->d_radix_hist,
-                    e->d_lorenz_blocks};
+                    e->d_lorenz_blocks, e->d_plan, e->d_cand};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < 5; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
     delete e;
@@ -392,6 +399,53 @@ int ssb_compact(ssb_engine_t *e, int32_t t, void *stream_) {
     return 0;
 }
 
+int ssb_bind_endowments(ssb_engine_t *e, const ssb_endowments_t *endowments) {
+    CHECK_BOUND(e);
+    if (!endowments || endowments->count <= 0) return fail(e, -1, "empty endowment table");
+    if (e->p.rng_mode != SSB_RNG_SCALABLE) return fail(e, -1, "device-side replacement exists in scalable mode only");
+    e->endow = *endowments;
+    if (!e->d_plan) {
+        CU(cudaMalloc(&e->d_plan, sizeof(ReplacePlan)));
+        e->cand_capacity = e->ctx.a.capacity;
+        CU(cudaMalloc(&e->d_cand, sizeof(uint64_t) * 4 * (size_t)e->cand_capacity));
+    }
+    e->endow_bound = true;
+    return 0;
+}
+
+// replaceDeadAgents: sugarscape.py:855-859 (scalable mode; exact mode replaces on the host)
+int ssb_replace(ssb_engine_t *e, int32_t t, void *stream_) {
+    CHECK_BOUND(e);
+    if (e->p.agent_replacements <= 0) return 0;
+    if (e->p.rng_mode != SSB_RNG_SCALABLE) return fail(e, -1, "ssb_replace: scalable mode only");
+    if (!e->endow_bound) return fail(e, -1, "ssb_replace: no endowment table bound");
+    cudaStream_t st = (cudaStream_t)stream_;
+    DevCtx c = step_ctx(e, t, 0.0);
+    const int cell_blocks = grid_for(c.g.n_cells, 256, e->num_sms * 8);
+    k_repl_reset<<<1, 32, 0, st>>>(e->d_plan); LAUNCHED(e);
+    k_repl_count<<<cell_blocks, 256, 0, st>>>(c, e->d_plan); LAUNCHED(e);
+    k_repl_plan<<<1, 1, 0, st>>>(c, e->d_plan, e->endow.count, e->cand_capacity); LAUNCHED(e);
+    k_repl_collect<<<cell_blocks, 256, 0, st>>>(c, e->d_plan, e->d_cand, e->cand_capacity); LAUNCHED(e);
+    k_repl_clamp<<<1, 32, 0, st>>>(e->d_plan, e->cand_capacity); LAUNCHED(e);
+    const int tiles = (int)((e->cand_capacity + RADIX_TILE - 1) / RADIX_TILE);
+    const int Q = __builtin_popcount(e->p.quad_mask & 15);
+    for (int q = 0; q < Q; q++) {
+        uint64_t *src = e->d_cand + (size_t)q * e->cand_capacity, *dst = e->d_keys_b;
+        const int64_t *n_ptr = (const int64_t *)&e->d_plan->cand_count[q];
+        const unsigned long long *varying = e->d_plan->varying;
+        for (int shift = 0; shift < 64; shift += 8) {      // 8 passes: the result lands back in `src`
+            k_radix_hist<<<tiles, RADIX_THREADS, 0, st>>>(src, n_ptr, shift, e->d_radix_hist, varying); LAUNCHED(e);
+            k_radix_scan<<<1, RADIX_THREADS, 0, st>>>(e->d_radix_hist, n_ptr, shift, varying); LAUNCHED(e);
+            k_radix_scatter<<<tiles, RADIX_THREADS, 0, st>>>(src, dst, n_ptr, shift, e->d_radix_hist, varying); LAUNCHED(e);
+            uint64_t *tmp = src; src = dst; dst = tmp;
+        }
+    }
+    k_repl_create<<<e->num_sms * 4, 256, 0, st>>>(c, e->d_plan, e->d_cand, e->cand_capacity, e->endow); LAUNCHED(e);
+    k_repl_free_stack<<<e->num_sms, 256, 0, st>>>(c, e->d_plan); LAUNCHED(e);
+    k_repl_finish<<<1, 1, 0, st>>>(c, e->d_plan); LAUNCHED(e);
+    return 0;
+}
+
 // the reductions of updateRuntimeStats: sugarscape.py:1005-1426, 913-934
 int ssb_reduce_stats(ssb_engine_t *e, int32_t t, void *stream_) {
     CHECK_BOUND(e);
@@ -425,6 +479,7 @@ int ssb_step(ssb_engine_t *e, int32_t t, double prev_mean_wealth, void *stream) 
     if ((rc = ssb_env_step(e, t, stream))) return rc;
     if ((rc = ssb_agent_step(e, t, prev_mean_wealth, stream))) return rc;
     if ((rc = ssb_compact(e, t, stream))) return rc;
+    if (e->p.rng_mode == SSB_RNG_SCALABLE && e->p.agent_replacements > 0 && (rc = ssb_replace(e, t, stream))) return rc;
     return ssb_reduce_stats(e, t, stream);
 }
 

@@ -430,7 +430,7 @@ __global__ void __launch_bounds__(STATS_THREADS) k_stats_final(DevCtx c, const S
     out->dead_aging = r.dead_aging; out->dead_combat = r.dead_combat; out->sum_age_at_death = r.sum_age_at_death;
     out->dead_wealth_collected = r.dead_wealth_collected;
     out->n_born = c.a.counters[SSB_C_N_BORN];
-    out->n_replaced = 0;
+    out->n_replaced = c.a.counters[SSB_C_N_REPLACED];
     out->n_acted = r.n_acted;
     out->env_wealth_total = r.env_wealth_total;
     out->env_capacity_total = r.env_capacity_total;

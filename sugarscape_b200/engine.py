@@ -51,6 +51,8 @@ def load_library():
     L.ssb_agent_step.argtypes = [E, C.c_int32, C.c_double, C.c_void_p]
     L.ssb_compact.argtypes = [E, C.c_int32, C.c_void_p]
     L.ssb_reduce_stats.argtypes = [E, C.c_int32, C.c_void_p]
+    L.ssb_bind_endowments.argtypes = [E, C.POINTER(layout.Endowments)]
+    L.ssb_replace.argtypes = [E, C.c_int32, C.c_void_p]
     L.ssb_step.argtypes = [E, C.c_int32, C.c_double, C.c_void_p]
     L.ssb_stats.argtypes = [E, S]
     L.ssb_stats_history.argtypes = [E, C.c_int32, S]
@@ -77,7 +79,7 @@ EXPORTED_SYMBOLS = (
     "ssb_abi_version", "ssb_create", "ssb_bind", "ssb_destroy", "ssb_last_error",
     "ssb_set_mt_state", "ssb_get_mt_state", "ssb_set_step_tables", "ssb_set_epochs", "ssb_set_mark_shift", "ssb_set_l2_persist",
     "ssb_sizeof_params", "ssb_sizeof_grid", "ssb_sizeof_agents", "ssb_sizeof_stats",
-    "ssb_env_step", "ssb_agent_step", "ssb_compact", "ssb_reduce_stats", "ssb_step", "ssb_stats", "ssb_stats_history",
+    "ssb_env_step", "ssb_agent_step", "ssb_compact", "ssb_bind_endowments", "ssb_replace", "ssb_reduce_stats", "ssb_step", "ssb_stats", "ssb_stats_history",
     "ssb_sync", "ssb_pollution_buffer", "ssb_test_pow", "ssb_round_trace", "ssb_launch_count", "ssb_timing", "ssb_enable_timing",
 )
 
@@ -214,6 +216,19 @@ class Engine:
 
     def compact(self, t):
         self._check(self.L.ssb_compact(self.handle, t, self.stream))
+
+    def bind_endowments(self, endowments):
+        """Upload the endowment table replacements draw from (list of dicts from
+        init.randomize_endowments, or the struct-of-arrays of layout.endowment_arrays)."""
+        arrays = endowments if isinstance(endowments, dict) else layout.endowment_arrays(endowments)
+        self.endowment_tensors = {k: self._to_device(v) for k, v in arrays.items()}
+        es = layout.endowments_struct(arrays, lambda a: None)
+        for name, _ in layout.ENDOWMENT_FIELDS:
+            setattr(es, name, self.endowment_tensors[name].data_ptr())
+        self._check(self.L.ssb_bind_endowments(self.handle, C.byref(es)))
+
+    def replace(self, t):
+        self._check(self.L.ssb_replace(self.handle, t, self.stream))
 
     def reduce_stats(self, t):
         self._check(self.L.ssb_reduce_stats(self.handle, t, self.stream))

@@ -394,4 +394,5 @@ def build_initial_state(c, capacity=None):
         random.shuffle(new_agents)
     state.append_agents(new_agents)
     state.counters[layout.C_NEXT_ID] = len(new_agents)
+    state.counters[layout.C_ENDOW_INDEX] = pop.endowment_index
     return state, pop

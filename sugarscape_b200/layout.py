@@ -17,7 +17,8 @@ SEX_CODE = {None: SEX_NONE, "male": SEX_MALE, "female": SEX_FEMALE}
 F_SPICE, F_POLLUTION, F_REPRO, F_TAGS, F_TAGGING, F_COMBAT, F_TRADE, F_TAGPREF = (
     1 << 0, 1 << 1, 1 << 2, 1 << 3, 1 << 4, 1 << 5, 1 << 6, 1 << 7)
 
-(C_N_LIST, C_N_SLOTS, C_NEXT_ID, C_N_FREE, C_N_BORN, C_N_DEAD, C_ROUNDS, C_OVERFLOW, C_N_KIN) = range(9)
+(C_N_LIST, C_N_SLOTS, C_NEXT_ID, C_N_FREE, C_N_BORN, C_N_DEAD, C_ROUNDS, C_OVERFLOW, C_N_KIN,
+ C_ENDOW_INDEX, C_N_REPLACED) = range(11)
 INHERITANCE_CODE = {"none": 0, "children": 1, "sons": 2, "daughters": 3}
 C_COUNT = 16
 
@@ -72,7 +73,9 @@ class Params(C.Structure):
         ("tag_len", C.c_int32), ("max_tribes", C.c_int32),
         ("max_timestep", C.c_int32), ("id_bits", C.c_int32),
         ("max_sugar_capacity", C.c_int32), ("max_spice_capacity", C.c_int32),
-        ("inheritance_policy", C.c_int32), ("_pad", C.c_int32),
+        ("inheritance_policy", C.c_int32), ("agent_replacements", C.c_int32),
+        ("quad_w", C.c_int32), ("quad_h", C.c_int32), ("quad_mask", C.c_int32),
+        ("tribe_per_quadrant", C.c_int32), ("_pad", C.c_int32),
     ]
 
 
@@ -81,6 +84,43 @@ class Grid(C.Structure):
 
 
 KIN_FIELDS = ("kin_slot", "kin_id", "kin_next")
+
+# (name, numpy dtype) in the order of ssb_endowments_t after `count`
+ENDOWMENT_FIELDS = (
+    ("sugar", np.float64), ("spice", np.float64),
+    ("sugar_metab", np.int32), ("spice_metab", np.int32), ("vision", np.int32), ("movement", np.int32),
+    ("max_age", np.int32), ("sex", np.int32), ("fert_age", np.int32), ("infert_age", np.int32),
+    ("fert_factor", np.float64), ("aggression", np.float64), ("lookahead", np.float64),
+    ("trade_factor", np.float64), ("tags", np.uint32),
+)
+
+
+class Endowments(C.Structure):
+    _fields_ = [("count", C.c_int64)] + [(n, C.c_void_p) for n, _ in ENDOWMENT_FIELDS]
+
+
+def endowment_arrays(endowments):
+    """The endowment dicts of init.randomize_endowments as struct-of-arrays (creation order)."""
+    n = len(endowments)
+    out = {name: np.zeros(n, dtype=dt) for name, dt in ENDOWMENT_FIELDS}
+    keys = {"sugar": "sugar", "spice": "spice", "sugar_metab": "sugarMetabolism", "spice_metab": "spiceMetabolism",
+            "vision": "vision", "movement": "movement", "max_age": "maxAge", "fert_age": "fertilityAge",
+            "infert_age": "infertilityAge", "fert_factor": "fertilityFactor", "aggression": "aggressionFactor",
+            "lookahead": "lookaheadFactor", "trade_factor": "tradeFactor"}
+    for i, e in enumerate(endowments):
+        for name, key in keys.items():
+            out[name][i] = e[key]
+        out["sex"][i] = SEX_CODE[e["sex"]]
+        out["tags"][i] = sum((1 << k) for k, b in enumerate(e["tags"] or ()) if b)
+    return out
+
+
+def endowments_struct(arrays, pointer_of):
+    e = Endowments()
+    e.count = len(arrays["sugar"])
+    for name, _ in ENDOWMENT_FIELDS:
+        setattr(e, name, pointer_of(arrays[name]))
+    return e
 
 
 class Agents(C.Structure):
@@ -149,6 +189,12 @@ def make_params(c, rng_mode, flags, max_agent_range, equator):
     p.max_sugar_capacity = int(max(c["environmentMaxSugar"], 0))
     p.max_spice_capacity = int(max(c["environmentMaxSpice"], 0))
     p.inheritance_policy = INHERITANCE_CODE[c["agentInheritancePolicy"]]
+    import math
+    p.agent_replacements = int(c["agentReplacements"])
+    p.quad_w = math.floor(c["environmentWidth"] / 2 * c["environmentQuadrantSizeFactor"])
+    p.quad_h = math.floor(c["environmentHeight"] / 2 * c["environmentQuadrantSizeFactor"])
+    p.quad_mask = sum(1 << (q - 1) for q in c["environmentStartingQuadrants"] if 1 <= q <= 4)
+    p.tribe_per_quadrant = 1 if c["environmentTribePerQuadrant"] else 0
     return p
 
 

@@ -32,8 +32,6 @@ class Sugarscape:
         if not c["headlessMode"]:
             raise init.UnsupportedConfiguration("the GUI is out of scope: set headlessMode to true")
         state, self.population = init.build_initial_state(c)
-        if self.rng_mode == layout.RNG_SCALABLE and c["agentReplacements"] > 0:
-            raise init.UnsupportedConfiguration("agentReplacements in scalable RNG mode")
         self.params = layout.make_params(c, self.rng_mode, init.rule_flags(c), init.max_agent_range(c),
                                          init.equator(c))
         horizon = int(min(c["timesteps"], 1 << 20))
@@ -42,6 +40,8 @@ class Sugarscape:
                              endow, tags)
         if self.rng_mode == layout.RNG_EXACT:
             self.engine.set_mt_from_python()
+        elif c["agentReplacements"] > 0:
+            self.engine.bind_endowments(self.population.endowments)
         self.stats_builder = stats.StatsBuilder(c, init.equator(c))
         self.runtimeStats = self.stats_builder.runtime_stats
         self.n_agents = int(state.counters[layout.C_N_LIST])
@@ -71,12 +71,16 @@ class Sugarscape:
             self.writeToLog()
 
     def replaceDeadAgents(self):
-        """sugarscape.py:855-859.  Placement of new agents is the init path (host, stdlib random
-        on the main stream); the device hands over occupancy + MT state and receives the agents."""
+        """sugarscape.py:855-859.  Exact mode: placement of new agents is the init path (host,
+        stdlib random on the main stream); the device hands over occupancy + MT state and receives
+        the agents.  Scalable mode: on the device (ssb_replace), counted in the step's stats."""
         c = self.configuration
         if c["agentReplacements"] <= 0:
             return 0
         eng = self.engine
+        if self.rng_mode == layout.RNG_SCALABLE:
+            eng.replace(self.timestep)
+            return None
         counters = eng.counters()
         n = int(counters[layout.C_N_LIST])
         if n >= c["agentReplacements"]:
@@ -95,7 +99,7 @@ class Sugarscape:
         if st is None:
             self.engine.reduce_stats(self.timestep)
             st = self.engine.stats()
-        self.stats_builder.update(st, self.timestep, replaced)
+        self.stats_builder.update(st, self.timestep, int(st.n_replaced) if replaced is None else replaced)
         self.n_agents = int(st.population)
 
     # -- the run loop and the log (format: SURVEY.md Appendix F) -----------------------------------

@@ -6,7 +6,10 @@ randomness: (1) the per-step agent order is the ascending order of a keyed bijec
 id instead of `random.shuffle(self.agents)` (reference sugarscape.py:400), (2) every draw inside
 an agent's transaction comes from that agent's counter-based substream of the current call site
 (agent.py:1401 move ranking, 560-564 tagging, 616 trading, 505-513 reproduction) instead of the
-global MT19937 stream, (3) a step's newborn are numbered in cell order at the end of the step.
+global MT19937 stream, (3) a step's newborn are numbered in cell order at the end of the step, (4) replacement
+(sugarscape.py:171-267,855-859): the empty cells of a quadrant are ordered by a hash of the cell,
+the quadrants by a hash of their index, and a new agent's tribe tags come from the substream of
+its own id.
 
 This script runs the UNMODIFIED reference classes with exactly those three substitutions applied
 from the outside (monkeypatching `random.shuffle` / `random.randrange` as seen by agent.py and
@@ -29,8 +32,18 @@ sys.path.insert(0, HERE)
 import ref_harness as rh  # noqa: E402
 
 M64 = (1 << 64) - 1
-SITES = {"rankCellsInRange": 0, "doTagging": 1, "doTrading": 2, "doReproduction": 3}
+SITES = {"rankCellsInRange": 0, "doTagging": 1, "doTrading": 2, "doReproduction": 3, "generateTribeTags": 4}
 ID_BITS = 26
+SALT_CELL = 0x52455043454C4C     # replacement: order of the empty cells of a quadrant
+SALT_QUAD = 0x5245505155414D     # replacement: order of the quadrants
+
+
+def cell_sort_key(key, cell):
+    return ((mix64(key ^ SALT_CELL ^ cell) >> 32) << 32) | cell
+
+
+def quadrant_sort_key(key, q):
+    return (mix64(key ^ SALT_QUAD ^ q), q)
 
 
 def mix64(z):
@@ -68,7 +81,8 @@ class Substreams:
     def word(self, site):
         j = self.counters.get(site, 0)
         self.counters[site] = j + 1
-        return mix64(self.key ^ ((self.agent_id << 32) | (site << 24) | j)) >> 32
+        agent_id = self.agent_id[1] if isinstance(self.agent_id, tuple) else self.agent_id
+        return mix64(self.key ^ ((agent_id << 32) | (site << 24) | j)) >> 32
 
     def below(self, site, n):
         k = n.bit_length()
@@ -107,11 +121,36 @@ def run(example, steps, overrides):
     H = S.environment.height
 
     def order_shuffle(x):
+        caller = sys._getframe(1).f_code.co_name
+        key = step_key(sub.seed, S.timestep)
         if x is S.agents:
-            key = step_key(sub.seed, S.timestep)
             x.sort(key=lambda a: priority_of(key, a.ID))
+        elif caller == "configureAgents":
+            if x and isinstance(x[0], int):
+                x.sort(key=lambda q: quadrant_sort_key(key, q))
+            else:
+                x.sort(key=lambda cell: cell_sort_key(key, cell.x * H + cell.y))
+        elif caller == "generateTribeTags":
+            begin_new_agent()
+            for i in reversed(range(1, len(x))):
+                j = sub.below(SITES["generateTribeTags"], i + 1)
+                x[i], x[j] = x[j], x[i]
         else:
             sub.shuffle(x)
+
+    def begin_new_agent():
+        # generateTribeTags runs right after generateAgentID (sugarscape.py:209,255-257)
+        new_id = S.nextAgentID - 1
+        if sub.agent_id != ("new", new_id):
+            sub.agent_id, sub.counters, sub.key = ("new", new_id), {}, step_key(sub.seed, S.timestep)
+
+    real_randint = random.randint
+
+    def randint(a, b):
+        if sys._getframe(1).f_code.co_name != "generateTribeTags":
+            return real_randint(a, b)
+        begin_new_agent()
+        return a + sub.below(SITES["generateTribeTags"], b - a + 1)
 
     orig_do_timestep = ref_agent.Agent.doTimestep
 
@@ -126,17 +165,24 @@ def run(example, steps, overrides):
     # agent.py and sugarscape.py both call random.shuffle / random.randrange through the module
     ref.random.shuffle = order_shuffle
     ref_agent.random.randrange = sub.randrange
+    ref.random.randint = randint
     records = []
     try:
         for t in range(1, steps + 1):
             base = S.nextAgentID
             existing = {a.ID for a in S.agents}
             S.doTimestep()
-            newborn = [a for a in S.agents if a.ID not in existing]
+            fresh = [a for a in S.agents if a.ID not in existing]
+            newborn = [a for a in fresh if a.socialNetwork["mother"] is not None]
+            replaced = sorted((a for a in fresh if a.socialNetwork["mother"] is None), key=lambda a: a.ID)
+            if replaced:      # their tags were drawn with the ids they got at creation
+                assert S.nextAgentID - base == len(fresh), "a newborn died in a step with replacements"
             newborn.sort(key=lambda a: a.cell.x * H + a.cell.y)
             for k, a in enumerate(newborn):
                 a.ID = base + k
-            S.nextAgentID = base + len(newborn)
+            for k, a in enumerate(replaced):
+                assert a.ID == base + len(newborn) + k
+            S.nextAgentID = base + len(fresh)
             snap = rh.snapshot(S)
             order = np.argsort(snap["a_id"], kind="stable")
             for k in [k for k in snap if k.startswith("a_")]:
@@ -147,6 +193,7 @@ def run(example, steps, overrides):
         ref_agent.Agent.doTimestep = orig_do_timestep
         ref.random.shuffle = sub.real_shuffle
         ref_agent.random.randrange = sub.real_randrange
+        ref.random.randint = real_randint
     return records
 
 
@@ -157,6 +204,9 @@ CASES = [
     ("cultural_tagging", 60, {"agentMovement": [6, 6]}),
     ("trade_basic", 60, {"agentMovement": [6, 6]}),
     ("combat_unlimited", 60, {"agentMovement": [6, 6], "agentAggressionFactor": [1, 1]}),
+    ("agent_replacement", 120, {"agentMovement": [6, 6]}),
+    ("combat_limited", 120, {"agentMovement": [6, 6]}),
+    ("trade_replacement", 80, {"agentMovement": [6, 6]}),
 ]
 
 

@@ -35,6 +35,7 @@ def lib():
         L.orc_env_step.argtypes = [P, G, C.c_int32]
         L.orc_agent_step.argtypes = [P, G, A, C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p]
         L.orc_compact.argtypes = [P, G, A, C.c_int32]
+        L.orc_replace.argtypes = [P, G, A, C.POINTER(layout.Endowments), C.c_int32]
         L.orc_stats.argtypes = [P, G, A, C.c_int32, C.POINTER(layout.Stats)]
         _LIB = L
     return _LIB
@@ -81,6 +82,15 @@ class Oracle:
     def compact(self, t):
         g, a = self.state.as_structs()
         self.L.orc_compact(C.byref(self.params), C.byref(g), C.byref(a), t)
+
+    def bind_endowments(self, endowments):
+        """endowments: list of endowment dicts (init.Population.endowments)."""
+        self.endow_arrays = layout.endowment_arrays(endowments)
+        self.endow = layout.endowments_struct(self.endow_arrays, lambda arr: arr.ctypes.data)
+
+    def replace(self, t):
+        g, a = self.state.as_structs()
+        self.L.orc_replace(C.byref(self.params), C.byref(g), C.byref(a), C.byref(self.endow), t)
 
     def stats(self, t):
         g, a = self.state.as_structs()

@@ -88,11 +88,13 @@ def test_scalable_mode_oracle_matches_patched_reference(name):
     case = SCALABLE_GOLDEN[name]
     c, state, pop, params, endow, tags = pu.build(name, layout.RNG_SCALABLE, case["overrides"])
     orc = Oracle(params, state, endow, tags)
+    orc.bind_endowments(pop.endowments)
     for rec in case["steps"]:
         t = rec["t"]
         orc.env_step(t)
         orc.agent_step(t, 0.0)
         orc.compact(t)
+        orc.replace(t)
         d, snap = pu.state_digests_by_id(state)
         assert len(snap["a_id"]) == rec["population"], f"population differs at t={t}"
         for k in ("agents_int", "agents_f64", "agents_tags", "grid_int", "pollution"):
