@@ -48,8 +48,10 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=15)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--size", type=int, default=4096, help="map side (S1 = 4096)")
-    ap.add_argument("--agents", type=int, default=0, help="agents (default: S1 density, 1.6 M at 4096)")
+    ap.add_argument("--workload", default="S1", choices=["S1", "S2"],
+                    help="S1 = reproduction_basic rules (BASELINE configs[3]); S2 = combat_limited rules with replacement (configs[4])")
+    ap.add_argument("--size", type=int, default=0, help="map side (S1 = 4096, S2 = 16384)")
+    ap.add_argument("--agents", type=int, default=0, help="agents (default: the workload's density: 1.6 M at 4096 / 25 M at 16384)")
     ap.add_argument("--epochs", type=int, default=0)
     ap.add_argument("--mark-shift", type=int, default=-1)
     ap.add_argument("--l2-persist", type=int, default=-1)
@@ -61,11 +63,24 @@ def parse_args():
 
 def workload(args, rank=0):
     from sugarscape_b200 import synthetic
+    if args.workload == "S2":
+        args.size = args.size or 16384
+        n_agents = args.agents or int(round(25000000 * (args.size / 16384.0) ** 2))
+        c = synthetic.configuration(synthetic.S2_OPTIONS, {
+            "environmentWidth": args.size, "environmentHeight": args.size, "startingAgents": n_agents,
+            "agentReplacements": n_agents, "seed": 12345 + rank, "timesteps": 1 << 20})
+        return c, n_agents
+    args.size = args.size or 4096
     n_agents = args.agents or int(round(1600000 * (args.size / 4096.0) ** 2))
     c = synthetic.configuration(synthetic.S1_OPTIONS, {
         "environmentWidth": args.size, "environmentHeight": args.size, "startingAgents": n_agents,
         "seed": 12345 + rank, "timesteps": 1 << 20})
     return c, n_agents
+
+
+def describe(args, n_agents):
+    rules = "reproduction_basic rules" if args.workload == "S1" else "combat_limited rules (tags, tribes per quadrant, replacement)"
+    return f"{args.workload} synthetic {args.size}x{args.size}, {n_agents} agents, {rules}"
 
 
 class ClockSampler(threading.Thread):
@@ -111,7 +126,7 @@ def measured_peak_gbs():
 # algorithmic bytes (canonical dtypes): growback 12 B per cell; agent step with
 # reproduction rules 232 B per acting agent
 BYTES_PER_CELL_GROWBACK = 12
-BYTES_PER_AGENT_STEP = 232
+BYTES_PER_AGENT_STEP = {"S1": 232, "S2": 196}
 
 
 def aggregate_over_ranks(elapsed, units, device=None):
@@ -135,6 +150,9 @@ def run_cpu_port(args, c, steps):
     state, params = synthetic.build_state(c)
     endow, tags = steptables.step_tables(1, steps + 2, c["agentTagStringLength"])
     orc = Oracle(params, state, endow, tags)
+    replacing = c["agentReplacements"] > 0
+    if replacing:
+        orc.bind_endowments(synthetic.endowment_table(state, int(c["startingAgents"])))
     agent_steps = 0
     t0 = time.perf_counter()
     for t in range(1, steps + 1):
@@ -142,6 +160,8 @@ def run_cpu_port(args, c, steps):
         orc.env_step(t)
         orc.agent_step(t, 0.0)
         orc.compact(t)
+        if replacing:
+            orc.replace(t)
         orc.stats(t)
     dt = time.perf_counter() - t0
     return agent_steps / dt, dt, agent_steps
@@ -163,10 +183,9 @@ def main():
             "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": 0, "ms_per_step": 1000.0 * dt / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"S1 synthetic {args.size}x{args.size}, {n_agents} agents, reproduction_basic rules",
-                       "rng_mode": "scalable"},
+            "config": {"workload": describe(args, n_agents), "rng_mode": "scalable"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
-                             "sample": f"{steps} timesteps of the S1 initial state, oracle/ss_oracle.c, 1 thread "
+                             "sample": f"{steps} timesteps of the {args.workload} initial state, oracle/ss_oracle.c, 1 thread "
                                        "(the reference is pure Python and absent from this box: 6-8 k agent-steps/s/core "
                                        "measured in the build container, BASELINE.md)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -194,6 +213,8 @@ def main():
     endow, tags = steptables.step_tables(1, horizon, c["agentTagStringLength"])
     state, params = synthetic.build_state(c)
     eng = Engine(params, state, local_rank, endow, tags)
+    if c["agentReplacements"] > 0:
+        eng.bind_endowments(synthetic.endowment_table(state, n_agents))
     if args.epochs > 0:
         eng.set_epochs(args.epochs)
     if args.mark_shift >= 0:
@@ -246,7 +267,7 @@ def main():
     eng.enable_timing(False)
     avg = {k: float(np.mean(v)) for k, v in phase.items()}
     peak, peak_kind = measured_peak_gbs()
-    agent_bytes = float(np.mean(phase_acting)) * BYTES_PER_AGENT_STEP
+    agent_bytes = float(np.mean(phase_acting)) * BYTES_PER_AGENT_STEP[args.workload]
     achieved = agent_bytes / (avg["agent_ms"] / 1000.0) / 1e9
     env_bytes = n_cells * BYTES_PER_CELL_GROWBACK
     roofline = {"bound": "hbm", "kernel": "k_agent_step_scalable", "achieved": achieved, "peak": peak,
@@ -268,6 +289,9 @@ def main():
         w0 = time.perf_counter()
         eng = Engine(params2, state2, local_rank, endow, tags)      # H2D of the whole initial state
         h2d = sum(v.numel() * v.element_size() for v in eng.tensors.values())
+        if c["agentReplacements"] > 0:
+            eng.bind_endowments(synthetic.endowment_table(state2, n_agents))
+            h2d += sum(v.numel() * v.element_size() for v in eng.endowment_tensors.values())
         sb = stats_mod.StatsBuilder(c, init.equator(c))
         eng.reduce_stats(0)
         rs = sb.update(eng.stats(), 0)
@@ -292,7 +316,7 @@ def main():
     if rank == 0 and world == 1 and not args.skip_cpu:
         v, dt, n_as = run_cpu_port(args, c, args.cpu_steps)
         cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": f"{args.cpu_steps} timesteps of the same S1 initial state ({n_as} agent-steps, {dt:.1f} s), "
+               "sample": f"{args.cpu_steps} timesteps of the same {args.workload} initial state ({n_as} agent-steps, {dt:.1f} s), "
                          "oracle/ss_oracle.c single thread; the Python reference itself runs 6-8 k agent-steps/s/core "
                          "(build container, BASELINE.md) and cannot instantiate this map"}
 
@@ -301,8 +325,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"S1 synthetic {args.size}x{args.size}, {n_agents} agents, reproduction_basic rules"
-                                   + (f", {world} independent replicas" if world > 1 else ""),
+            "config": {"workload": describe(args, n_agents) + (f", {world} independent replicas" if world > 1 else ""),
                        "rng_mode": "scalable", "l2": "inputs larger than L2 (state > 500 MB per GPU)",
                        "parallelism": "replicas" if world > 1 else "single GPU",
                        "mean_commit_rounds": float(np.mean(rounds)), "mean_acting_agents": float(np.mean(acting))},

@@ -24,7 +24,8 @@ S2_OPTIONS = {   # examples/combat_limited.json rules on a 16384^2 map with 25 M
     "agentTagStringLength": 11, "environmentMaxCombatLoot": 2, "environmentMaxTribes": 2,
     "environmentQuadrantSizeFactor": 0.8, "environmentStartingQuadrants": [2, 4],
     "environmentTribePerQuadrant": True, "seed": 12345,
-    "environmentWidth": 16384, "environmentHeight": 16384, "startingAgents": 25000000, "timesteps": 100,
+    "environmentWidth": 16384, "environmentHeight": 16384, "startingAgents": 25000000,
+    "agentReplacements": 25000000, "timesteps": 100,
 }
 
 
@@ -114,14 +115,26 @@ def build_state(c, capacity=None, seed=None):
         lo = np.floor(tribe * size).astype(np.int64)
         hi = np.minimum(np.floor((tribe + 1) * size).astype(np.int64) - 1, L)
         zeroes = lo + (rng.integers(0, 1 << 30, n) % (hi - lo + 1))
-        keys = rng.random((n, L))
-        ranks = keys.argsort(axis=1).argsort(axis=1)
-        bits = (ranks >= zeroes[:, None]).astype(np.uint32)     # `zeroes` zero bits at random positions
-        state.a_tags[sl] = (bits << np.arange(L, dtype=np.uint32)[None, :]).sum(axis=1).astype(np.uint32)
-        z = L - bits.sum(axis=1)
-        state.a_tribe[sl] = np.minimum(np.ceil((z + 1) / size).astype(np.int64) - 1, T - 1)
+        shifts = np.arange(L, dtype=np.uint32)[None, :]
+        for b0 in range(0, n, 1 << 21):                      # chunked: n x L temporaries are large at S2
+            b1 = min(n, b0 + (1 << 21))
+            ranks = rng.random((b1 - b0, L)).argsort(axis=1).argsort(axis=1)
+            bits = (ranks >= zeroes[b0:b1, None]).astype(np.uint32)     # `zeroes` zero bits at random positions
+            state.a_tags[b0:b1] = (bits << shifts).sum(axis=1).astype(np.uint32)
+            z = L - bits.sum(axis=1)
+            state.a_tribe[b0:b1] = np.minimum(np.ceil((z + 1) / size).astype(np.int64) - 1, T - 1)
     state.counters[layout.C_N_LIST] = n
     state.counters[layout.C_N_SLOTS] = n
     state.counters[layout.C_NEXT_ID] = n
     params = layout.make_params(c, layout.RNG_SCALABLE, init.rule_flags(c), init.max_agent_range(c), init.equator(c))
     return state, params
+
+
+def endowment_table(state, n):
+    """The endowment list replacements cycle through (reference sugarscape.py:171-267 pops the
+    configured endowments in creation order): here the starting agents' own endowments."""
+    src = {"sugar": "a_start_sugar", "spice": "a_start_spice", "sugar_metab": "a_sugar_metab",
+           "spice_metab": "a_spice_metab", "vision": "a_vision", "movement": "a_movement", "max_age": "a_max_age",
+           "sex": "a_sex", "fert_age": "a_fert_age", "infert_age": "a_infert_age", "fert_factor": "a_fert_factor",
+           "aggression": "a_aggression", "lookahead": "a_lookahead", "trade_factor": "a_trade_factor", "tags": "a_tags"}
+    return {name: np.ascontiguousarray(getattr(state, src[name])[:n]).astype(dt) for name, dt in layout.ENDOWMENT_FIELDS}

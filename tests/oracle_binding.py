@@ -84,8 +84,8 @@ class Oracle:
         self.L.orc_compact(C.byref(self.params), C.byref(g), C.byref(a), t)
 
     def bind_endowments(self, endowments):
-        """endowments: list of endowment dicts (init.Population.endowments)."""
-        self.endow_arrays = layout.endowment_arrays(endowments)
+        """endowments: list of endowment dicts (init.Population.endowments) or struct-of-arrays."""
+        self.endow_arrays = endowments if isinstance(endowments, dict) else layout.endowment_arrays(endowments)
         self.endow = layout.endowments_struct(self.endow_arrays, lambda arr: arr.ctypes.data)
 
     def replace(self, t):
