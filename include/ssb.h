@@ -204,6 +204,47 @@ typedef struct ssb_stats {
 
 typedef struct ssb_engine ssb_engine_t;
 
+/* ---- sharding one simulation over the GPUs of a box (x-slabs) -------------
+ * A fabric is one arena of device memory per rank (one process per GPU), exported as a POSIX file
+ * descriptor.  After every rank has imported every peer's descriptor, ssb_fabric_map() returns
+ * "stitched" arrays: world chunks of equal size, chunk p backed by rank p's HBM, at the same
+ * offsets on every rank.  The host binds stitched arrays as ssb_grid_t / ssb_agents_t, so a kernel
+ * reaches the neighbouring slab's cells and agents over NVLink with ordinary loads, stores and
+ * atomics.  All ranks must issue the same sequence of ssb_fabric_map calls. */
+#define SSB_MAX_RANKS 8
+typedef struct ssb_fabric ssb_fabric_t;
+int  ssb_fabric_create(int32_t rank, int32_t world, int32_t device, uint64_t arena_bytes,
+                       ssb_fabric_t **out, int32_t *fd_out);
+int  ssb_fabric_import(ssb_fabric_t *f, int32_t peer_rank, int32_t fd);   /* closes fd */
+int  ssb_fabric_map(ssb_fabric_t *f, uint64_t chunk_bytes, void **base_out);
+/* synchronous copies to / from stitched memory: kind 0 = host -> device, 1 = device -> host,
+ * 2 = zero `bytes` at dst (src ignored).  Callers split ranges at chunk boundaries. */
+int  ssb_fabric_copy(ssb_fabric_t *f, void *dst, const void *src, uint64_t bytes, int32_t kind);
+uint64_t ssb_fabric_granularity(ssb_fabric_t *f);
+uint64_t ssb_fabric_arena_bytes(ssb_fabric_t *f);
+int  ssb_fabric_destroy(ssb_fabric_t *f);
+const char *ssb_fabric_last_error(ssb_fabric_t *f);
+
+typedef struct ssb_shard_t {
+    int32_t rank, world;
+    int64_t cell_lo, cell_hi;       /* the cells of this rank's slab: [x_lo * H, x_hi * H)            */
+    int64_t slot_lo, slot_hi;       /* the agent slots this rank allocates from                      */
+    void   *ctrl;                   /* stitched control pages, zeroed: chunk p = rank p's page        */
+    uint64_t ctrl_stride;           /* bytes between pages (>= 4096)                                  */
+    void   *marks;                  /* stitched reservation marks (u32 per cell of the whole map)     */
+    uint64_t marks_stride;          /* bytes per rank chunk                                           */
+    void   *gather;                 /* stitched scratch for candidate / wealth-key all-gathers        */
+    uint64_t gather_stride;         /* bytes per rank chunk: >= 8 * (4 + 1) * slots per rank          */
+} ssb_shard_t;
+/* Scalable mode, rule sets without births (reproduction) only.  Call after ssb_bind, before the
+ * first step; grid and agent arrays bound must be stitched.  Per-rank state: order[], free_slots[],
+ * dead_list[], counters[] (N_LIST / N_SLOTS / N_FREE are per rank; NEXT_ID / ENDOW_INDEX global). */
+int  ssb_set_shard(ssb_engine_t *e, const ssb_shard_t *shard);
+/* box-wide barrier on `stream` (orders the peers' later kernels after this rank's earlier ones) */
+int  ssb_shard_barrier(ssb_engine_t *e, void *stream);
+/* 1 if a box-wide barrier timed out (a peer is gone); the engine is unusable afterwards */
+int  ssb_shard_broken(ssb_engine_t *e);
+
 /* lifecycle */
 int  ssb_create(const ssb_params_t *params, int device, ssb_engine_t **out);
 int  ssb_bind(ssb_engine_t *e, const ssb_grid_t *grid, const ssb_agents_t *agents);

@@ -11,6 +11,7 @@
 #include "ssb_kernels.cuh"
 #include "ssb_sort.cuh"
 #include "ssb_replace.cuh"
+#include "ssb_fabric.cuh"
 
 using namespace ssb;
 
@@ -56,6 +57,12 @@ struct ssb_engine {
     ReplacePlan *d_plan;
     uint64_t *d_cand;        // 4 quadrant regions of cand_capacity keys
     int64_t cand_capacity;
+    // x-slab sharding (ssb_shard.cuh)
+    bool sharded;
+    ShardCtx sh;
+    uint32_t *local_marks;   // the engine's own mark array (replaced by the stitched one when sharded)
+    int64_t local_slots;     // slots per rank = capacity of the per-rank parts of the gather scratch
+    unsigned long long *d_shard_vals;   // [0] = box population, [1..2] = OR / AND of all wealth keys, [8..] msg
 };
 
 static int fail(ssb_engine *e, int code, const char *fmt, ...) {
@@ -146,10 +153,11 @@ int ssb_create(const ssb_params_t *params, int device, ssb_engine_t **out) {
 void ssb_destroy(ssb_engine_t *e) {
     if (!e) return;
     cudaSetDevice(e->device);
+    if (e->sharded) e->rc.mark = e->local_marks;       // the stitched marks belong to the fabric
     void *ptrs[] = {e->d_mt, e->d_endow, e->d_tagbits, e->d_tile_counts, e->d_new_order, e->d_scalars,
                     e->d_born_list, e->rc.mark, e->rc.list_a, e->rc.list_b, e->rc.ready, e->rc.cnt, e->rc.trace, e->rc.bucketed, e->rc.epoch_count, e->rc.epoch_start, e->rc.epoch_fill,
                     e->d_partials, e->d_tribes, e->d_stats, e->d_ring, e->d_keys_a, e->d_keys_b, e->d_radix_hist,
-                    e->d_lorenz_blocks, e->d_plan, e->d_cand};
+                    e->d_lorenz_blocks, e->d_plan, e->d_cand, e->sh.peer_vals, e->sh.flags, e->d_shard_vals};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < 5; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
     delete e;
@@ -222,6 +230,7 @@ int ssb_bind(ssb_engine_t *e, const ssb_grid_t *grid, const ssb_agents_t *agents
 
 int ssb_set_mark_shift(ssb_engine_t *e, int32_t shift) {
     if (!e || !e->bound || e->p.rng_mode != SSB_RNG_SCALABLE) return fail(e, -1, "mark shift needs a bound scalable engine");
+    if (e->sharded) return fail(e, -1, "set the mark shift before ssb_set_shard");
     if (shift < 0 || shift > 4 || (e->p.width % (1 << shift)) || (e->p.height % (1 << shift))) return fail(e, -1, "mark shift %d does not divide the map", shift);
     const int maxd = e->ctx.max_dx > e->ctx.max_dy ? e->ctx.max_dx : e->ctx.max_dy;
     if (((maxd + 2) >> shift) + 2 >= (e->p.width >> shift) || ((maxd + 2) >> shift) + 2 >= (e->p.height >> shift)) return fail(e, -1, "map too small for mark shift %d", shift);
@@ -316,6 +325,7 @@ static DevCtx step_ctx(ssb_engine *e, int32_t t, double prev_mean_wealth) {
     c.t = t;
     c.prev_mean_wealth = prev_mean_wealth;
     c.endow_bits = e->d_endow; c.tag_bits = e->d_tagbits; c.n_step_tables = e->n_tables;
+    c.sh = e->sh;
     return c;
 }
 
@@ -329,11 +339,13 @@ int ssb_env_step(ssb_engine_t *e, int32_t t, void *stream_) {
     const ssb_params_t &p = e->p;
     GrowArgs g;
     g.height = p.height; g.equator = p.equator; g.n_cells = e->ctx.g.n_cells;
+    g.cell_lo = e->sharded ? e->sh.cell_lo : 0; g.cell_hi = e->sharded ? e->sh.cell_hi : g.n_cells;
+    const long long my_cells = g.cell_hi - g.cell_lo;
     g.seasons = p.season_interval > 0;
     g.flipped = g.seasons ? (((t - 1) / p.season_interval) & 1) : 0;
     g.dry_grows = (g.seasons && p.seasonal_growback_delay > 0) ? (t % p.seasonal_growback_delay == 0) : 0;
     const bool vec = (p.height % 4) == 0;
-    const int blocks = grid_for(vec ? g.n_cells / 4 : g.n_cells, 256, e->num_sms * 8);
+    const int blocks = grid_for(vec ? my_cells / 4 : my_cells, 256, e->num_sms * 8);
     for (int res = 0; res < 2; res++) {
         g.level = res == 0 ? e->ctx.g.sugar : e->ctx.g.spice;
         g.cap = res == 0 ? e->ctx.g.sugar_cap : e->ctx.g.spice_cap;
@@ -345,14 +357,16 @@ int ssb_env_step(ssb_engine_t *e, int32_t t, void *stream_) {
     if (p.diffusion_delay > 0 && p.diffusion_start <= t && t <= p.diffusion_end &&
         ((t - p.diffusion_start + 1) % p.diffusion_delay) == 0) {
         if ((p.height % 2) == 0)
-            k_diffuse_v2<<<grid_for(g.n_cells / 2, 256, e->num_sms * 8), 256, 0, st>>>(e->ctx.g.pollution, e->ctx.g.pollution_flux, p.width, p.height);
+            k_diffuse_v2<<<grid_for(my_cells / 2, 256, e->num_sms * 8), 256, 0, st>>>(e->ctx.g.pollution, e->ctx.g.pollution_flux, p.width, p.height, g.cell_lo, g.cell_hi);
         else
-            k_diffuse<<<grid_for(g.n_cells, 256, e->num_sms * 8), 256, 0, st>>>(e->ctx.g.pollution, e->ctx.g.pollution_flux, p.width, p.height);
+            k_diffuse<<<grid_for(my_cells, 256, e->num_sms * 8), 256, 0, st>>>(e->ctx.g.pollution, e->ctx.g.pollution_flux, p.width, p.height, g.cell_lo, g.cell_hi);
         LAUNCHED(e);
         // the flux buffer now holds the field: swap the roles of the two host-owned buffers
         double *tmp = e->ctx.g.pollution; e->ctx.g.pollution = e->ctx.g.pollution_flux; e->ctx.g.pollution_flux = tmp;
         e->pollution_swapped = !e->pollution_swapped;
     }
+    // the agent step reads the neighbouring slabs: every rank's environment must be done
+    if (e->sharded) { k_shard_barrier<<<1, 32, 0, st>>>(e->sh, nullptr, (long long *)e->ctx.a.counters + SSB_C_OVERFLOW); LAUNCHED(e); }
     if (e->timing) CU(cudaEventRecord(e->ev[1], st));
     return 0;
 }
@@ -421,12 +435,27 @@ int ssb_replace(ssb_engine_t *e, int32_t t, void *stream_) {
     if (!e->endow_bound) return fail(e, -1, "ssb_replace: no endowment table bound");
     cudaStream_t st = (cudaStream_t)stream_;
     DevCtx c = step_ctx(e, t, 0.0);
-    const int cell_blocks = grid_for(c.g.n_cells, 256, e->num_sms * 8);
+    const long long my_cells = e->sharded ? e->sh.cell_hi - e->sh.cell_lo : c.g.n_cells;
+    const int cell_blocks = grid_for(my_cells, 256, e->num_sms * 8);
+    long long *overflow = (long long *)c.a.counters + SSB_C_OVERFLOW;
     k_repl_reset<<<1, 32, 0, st>>>(e->d_plan); LAUNCHED(e);
     k_repl_count<<<cell_blocks, 256, 0, st>>>(c, e->d_plan); LAUNCHED(e);
-    k_repl_plan<<<1, 1, 0, st>>>(c, e->d_plan, e->endow.count, e->cand_capacity); LAUNCHED(e);
-    k_repl_collect<<<cell_blocks, 256, 0, st>>>(c, e->d_plan, e->d_cand, e->cand_capacity); LAUNCHED(e);
-    k_repl_clamp<<<1, 32, 0, st>>>(e->d_plan, e->cand_capacity); LAUNCHED(e);
+    if (e->sharded) {        // all-gather {population, empty cells per quadrant}
+        k_repl_pack_counts<<<1, 1, 0, st>>>(c, e->d_plan); LAUNCHED(e);
+        k_shard_barrier<<<1, 32, 0, st>>>(e->sh, e->d_plan->msg, overflow); LAUNCHED(e);
+    }
+    k_repl_plan<<<1, 1, 0, st>>>(c, e->d_plan, e->endow.count, e->sharded ? e->local_slots : e->cand_capacity); LAUNCHED(e);
+    if (!e->sharded) {
+        k_repl_collect<<<cell_blocks, 256, 0, st>>>(c, e->d_plan, e->d_cand, e->cand_capacity); LAUNCHED(e);
+        k_repl_clamp<<<1, 32, 0, st>>>(e->d_plan, e->cand_capacity); LAUNCHED(e);
+    } else {                 // candidates of this slab into this rank's part of the stitched scratch, then gather all
+        uint64_t *mine = (uint64_t *)(e->sh.gather + (long long)e->sh.rank * e->sh.gather_stride);
+        k_repl_collect<<<cell_blocks, 256, 0, st>>>(c, e->d_plan, mine, e->local_slots); LAUNCHED(e);
+        k_repl_clamp<<<1, 32, 0, st>>>(e->d_plan, e->local_slots); LAUNCHED(e);
+        k_shard_barrier<<<1, 32, 0, st>>>(e->sh, e->d_plan->msg, overflow); LAUNCHED(e);
+        k_repl_gather<<<e->num_sms * 4, 256, 0, st>>>(c, e->d_plan, e->d_cand, e->cand_capacity, e->local_slots); LAUNCHED(e);
+        k_repl_gather_counts<<<1, 32, 0, st>>>(c, e->d_plan, e->cand_capacity); LAUNCHED(e);
+    }
     const int tiles = (int)((e->cand_capacity + RADIX_TILE - 1) / RADIX_TILE);
     const int Q = __builtin_popcount(e->p.quad_mask & 15);
     for (int q = 0; q < Q; q++) {
@@ -452,16 +481,26 @@ int ssb_reduce_stats(ssb_engine_t *e, int32_t t, void *stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     DevCtx c = step_ctx(e, t, 0.0);
     k_stats_reset<<<1, 32, 0, st>>>(e->d_tribes); LAUNCHED(e);
-    k_stats_partials<<<e->n_partials, STATS_THREADS, 0, st>>>(c, e->d_partials, (double *)e->d_keys_a, e->d_tribes); LAUNCHED(e);
+    // sharded: the wealth keys go to this rank's part of the stitched scratch (behind the candidate lists)
+    double *keys_out = e->sharded ? (double *)(e->sh.gather + (long long)e->sh.rank * e->sh.gather_stride + 4 * e->local_slots)
+                                  : (double *)e->d_keys_a;
+    k_stats_partials<<<e->n_partials, STATS_THREADS, 0, st>>>(c, e->d_partials, keys_out, e->d_tribes); LAUNCHED(e);
     k_stats_final<<<1, STATS_THREADS, 0, st>>>(c, e->d_partials, e->n_partials, e->d_tribes, e->d_stats); LAUNCHED(e);
     if (e->p.rng_mode == SSB_RNG_EXACT) { k_stats_ordered<<<1, 32, 0, st>>>(c, e->d_stats); LAUNCHED(e); }
     // Lorenz numerator: sort the wealths (non-negative doubles order like their bit patterns)
     const int64_t cap = c.a.capacity;
     const int tiles = (int)((cap + RADIX_TILE - 1) / RADIX_TILE);
     const int64_t *n_ptr = c.a.counters + SSB_C_N_LIST;
+    const unsigned long long *varying = &e->d_tribes->key_or;
+    if (e->sharded) {        // the Gini coefficient is box-wide: every rank gathers all keys and sorts them
+        k_stats_pack<<<1, 1, 0, st>>>(c, e->d_tribes, e->d_shard_vals + 8); LAUNCHED(e);
+        k_shard_barrier<<<1, 32, 0, st>>>(e->sh, e->d_shard_vals + 8, (long long *)c.a.counters + SSB_C_OVERFLOW); LAUNCHED(e);
+        k_keys_gather<<<e->num_sms * 4, 256, 0, st>>>(c, e->d_keys_a, cap, e->local_slots, e->d_shard_vals); LAUNCHED(e);
+        n_ptr = (const int64_t *)e->d_shard_vals;
+        varying = e->d_shard_vals + 1;
+    }
     uint64_t *src = e->d_keys_a, *dst = e->d_keys_b;
     for (int shift = 0; shift < 64; shift += 8) {
-        const unsigned long long *varying = &e->d_tribes->key_or;
         k_radix_hist<<<tiles, RADIX_THREADS, 0, st>>>(src, n_ptr, shift, e->d_radix_hist, varying); LAUNCHED(e);
         k_radix_scan<<<1, RADIX_THREADS, 0, st>>>(e->d_radix_hist, n_ptr, shift, varying); LAUNCHED(e);
         k_radix_scatter<<<tiles, RADIX_THREADS, 0, st>>>(src, dst, n_ptr, shift, e->d_radix_hist, varying); LAUNCHED(e);
@@ -472,6 +511,60 @@ int ssb_reduce_stats(ssb_engine_t *e, int32_t t, void *stream_) {
     k_lorenz_final<<<1, 1, 0, st>>>(e->d_lorenz_blocks, lb, e->d_stats, e->d_ring + (((t % SSB_STATS_RING) + SSB_STATS_RING) % SSB_STATS_RING)); LAUNCHED(e);
     if (e->timing) { CU(cudaEventRecord(e->ev[4], st)); e->ev_recorded = true; }
     return 0;
+}
+
+int ssb_set_shard(ssb_engine_t *e, const ssb_shard_t *sd) {
+    CHECK_BOUND(e);
+    if (!sd || sd->world < 1 || sd->world > SSB_MAX_RANKS || sd->rank < 0 || sd->rank >= sd->world) return fail(e, -1, "bad shard description");
+    if (e->p.rng_mode != SSB_RNG_SCALABLE) return fail(e, -1, "sharding needs the scalable RNG mode (the exact mode is one global stream)");
+    if (e->p.flags & SSB_F_REPRO) return fail(e, -1, "sharded mode does not support births (reproduction) yet");
+    if (e->sharded) return fail(e, -1, "shard already set");
+    if (sd->world == 1) return 0;
+    const int64_t cells = e->ctx.g.n_cells, cap = e->ctx.a.capacity;
+    if (sd->cell_lo < 0 || sd->cell_hi > cells || sd->cell_lo >= sd->cell_hi || (sd->cell_lo % e->p.height) || (sd->cell_hi % e->p.height))
+        return fail(e, -1, "a slab must be a range of whole x-lines");
+    if (sd->slot_lo < 0 || sd->slot_hi > cap || sd->slot_lo >= sd->slot_hi) return fail(e, -1, "bad slot range");
+    if (!sd->ctrl || !sd->marks || !sd->gather || sd->ctrl_stride < 4096) return fail(e, -1, "stitched control / mark / gather arrays required");
+    // per-rank part of the scratch: 4 candidate lists + the wealth keys, each of local_slots words
+    // (derived from the stride so that every rank uses the same layout)
+    e->local_slots = (int64_t)(sd->gather_stride / 8 / 5);
+    if (e->local_slots < sd->slot_hi - sd->slot_lo) return fail(e, -1, "gather scratch too small: %lld bytes per rank needed", (long long)(8 * 5 * (sd->slot_hi - sd->slot_lo)));
+    if (sd->marks_stride * (uint64_t)sd->world < sizeof(uint32_t) * (uint64_t)cells) return fail(e, -1, "stitched mark array too small");
+    ShardCtx &sh = e->sh;
+    sh.rank = sd->rank; sh.world = sd->world;
+    sh.cell_lo = sd->cell_lo; sh.cell_hi = sd->cell_hi; sh.slot_lo = sd->slot_lo; sh.slot_hi = sd->slot_hi;
+    sh.ctrl = (unsigned long long *)sd->ctrl; sh.ctrl_stride = (long long)(sd->ctrl_stride / 8);
+    sh.gather = (unsigned long long *)sd->gather; sh.gather_stride = (long long)(sd->gather_stride / 8);
+    CU(cudaMalloc(&sh.peer_vals, sizeof(unsigned long long) * SSB_MAX_RANKS * SHARD_PAYLOAD));
+    CU(cudaMemset(sh.peer_vals, 0, sizeof(unsigned long long) * SSB_MAX_RANKS * SHARD_PAYLOAD));
+    CU(cudaMalloc(&sh.flags, sizeof(unsigned long long) * 8));
+    CU(cudaMemset(sh.flags, 0, sizeof(unsigned long long) * 8));
+    CU(cudaMalloc(&e->d_shard_vals, sizeof(unsigned long long) * 16));
+    CU(cudaMemset(e->d_shard_vals, 0, sizeof(unsigned long long) * 16));
+    e->local_marks = e->rc.mark;
+    e->rc.mark = (uint32_t *)sd->marks;
+    e->sharded = true;
+    // the part of the marks this rank clears: what its own HBM backs (chunk p of the stitched array)
+    const long long n_marks = (long long)e->rc.wc * e->rc.hc, per = (long long)(sd->marks_stride / sizeof(uint32_t));
+    sh.mark_lo = per * sd->rank < n_marks ? per * sd->rank : n_marks;
+    sh.mark_hi = per * (sd->rank + 1) < n_marks ? per * (sd->rank + 1) : n_marks;
+    return 0;
+}
+
+int ssb_shard_barrier(ssb_engine_t *e, void *stream) {
+    CHECK_BOUND(e);
+    if (!e->sharded) return 0;
+    k_shard_barrier<<<1, 32, 0, (cudaStream_t)stream>>>(e->sh, nullptr, (long long *)e->ctx.a.counters + SSB_C_OVERFLOW); LAUNCHED(e);
+    return 0;
+}
+
+int ssb_shard_broken(ssb_engine_t *e) {
+    if (!e || !e->sharded) return 0;
+    unsigned long long flag = 0;
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    cudaMemcpy(&flag, e->sh.ctrl + (long long)e->sh.rank * e->sh.ctrl_stride + SHARD_CTRL_ABORT, sizeof flag, cudaMemcpyDeviceToHost);
+    return flag != 0;
 }
 
 int ssb_step(ssb_engine_t *e, int32_t t, double prev_mean_wealth, void *stream) {

@@ -238,7 +238,9 @@ __global__ void __launch_bounds__(AGENT_THREADS, 2) k_agent_step_scalable(DevCtx
 
     // ---- prepare: priorities, footprint parameters, epoch buckets ---------------------------------
     for (int i = tid; i < E; i += nthreads) { rc.epoch_count[i] = 0; rc.epoch_fill[i] = 0; }
-    for (long long i = tid; i < n_marks; i += nthreads) rc.mark[i] = 0xffffffffu;
+    const bool sharded = c.sh.world > 1;       // x-slab sharding: this rank clears its part of the marks
+    const long long mark_lo = sharded ? c.sh.mark_lo : 0, mark_hi = sharded ? c.sh.mark_hi : n_marks;
+    for (long long i = mark_lo + tid; i < mark_hi; i += nthreads) rc.mark[i] = 0xffffffffu;
     if (tid == 0) { rc.cnt[0] = 0; rc.cnt[1] = 0; rc.cnt[2] = 0; rc.cnt[3] = 0; c.a.counters[SSB_C_N_BORN] = 0; }
     for (int e = threadIdx.x; e < E; e += blockDim.x) sh_count[e] = 0;
     grid.sync();
@@ -270,24 +272,26 @@ __global__ void __launch_bounds__(AGENT_THREADS, 2) k_agent_step_scalable(DevCtx
         rc.bucketed[sh_base[e] + atomicAdd(&sh_count[e], 1)] =
             make_int4(s, c.a.pos[s], (int)pr, r | (footprint_dilation(c, s) << 8));
     }
-    grid.sync();
+    // every rank has cleared its marks before any rank places one
+    bool box_ok = shard_grid_sync(grid, c.sh, nullptr, nullptr);
 
     // ---- commit rounds -------------------------------------------------------------------------------
     int4 *cur = rc.list_a, *nxt = rc.list_b;
     int round = 0;
+    unsigned long long box_carry = 0;            // uncommitted agents carried over, summed over the ranks
     for (;;) {
         const int n_carry = ((volatile int32_t *)rc.cnt)[round & 1];
         const int e0 = round < E ? rc.epoch_start[round] : 0;
         const int n_new = round < E ? rc.epoch_start[round + 1] - e0 : 0;
         const int n = n_carry + n_new;
-        if (round >= E && n == 0) break;
-        if (round >= MAX_ROUNDS) {               // cannot happen (the earliest active agent always commits): fail loudly
-            if (tid == 0) c.a.counters[SSB_C_OVERFLOW] = 2;
+        if (round >= E && box_carry == 0) break;
+        if (round >= MAX_ROUNDS || !box_ok) {    // cannot happen (the earliest active agent always commits) / lost peer: fail loudly
+            if (tid == 0) c.a.counters[SSB_C_OVERFLOW] = box_ok ? 2 : 7;
             break;
         }
         if (round > 0 && round % ROUNDS_PER_TAG_EPOCH == 0) {   // tags exhausted: clear and restart
-            for (long long i = tid; i < n_marks; i += nthreads) rc.mark[i] = 0xffffffffu;
-            grid.sync();
+            for (long long i = mark_lo + tid; i < mark_hi; i += nthreads) rc.mark[i] = 0xffffffffu;
+            box_ok = shard_grid_sync(grid, c.sh, nullptr, nullptr);
         }
         int32_t *n_next = &rc.cnt[(round + 1) & 1], *n_ready = &rc.cnt[2 + (round & 1)];
         const bool tr = rc.trace && tid == 0 && round < rc.trace_rounds;
@@ -301,7 +305,7 @@ __global__ void __launch_bounds__(AGENT_THREADS, 2) k_agent_step_scalable(DevCtx
             const bool moved = (en.x & PHASE1_BIT) != 0;
             group_mark_region<GM>(c, rc, en.y, moved ? 0 : (en.w & 255), en.w >> 8, tag | (uint32_t)en.z);
         }
-        grid.sync();
+        box_ok = shard_grid_sync(grid, c.sh, nullptr, nullptr) && box_ok;     // all marks of the box are placed
         if (tr) rc.trace[round * 6 + 3] = global_ns();
         // SELECT: phase 0 needs the cross + own cell (k = 0), phase 1 the diamond D_k(new cell)
         for (int i = mgroup_id; i < n; i += n_mgroups) {
@@ -340,7 +344,8 @@ __global__ void __launch_bounds__(AGENT_THREADS, 2) k_agent_step_scalable(DevCtx
             }
             Group<GL>::sync();
         }
-        grid.sync();
+        // all transactions of the box are done (their marks may be overwritten now); the carry-over counts add up
+        box_ok = shard_grid_sync(grid, c.sh, n_next, &box_carry) && box_ok;
         if (tr) rc.trace[round * 6 + 5] = global_ns();
         int4 *tmp = cur; cur = nxt; nxt = tmp;
         round++;

@@ -1,0 +1,168 @@
+// ssb_fabric.cuh -- one address space over the GPUs of a box (x-slab sharding).
+//
+// Every rank (one process per GPU) owns one physical arena (cuMemCreate, exported as a POSIX file
+// descriptor; the host side passes the descriptors between the ranks over a unix socket).  A
+// "stitched" array is a virtual range of world * chunk bytes whose p-th chunk is backed by rank p's
+// arena, mapped identically on every rank.  Kernels index it like an ordinary array: the part of
+// the map / the agent slots a rank owns is local HBM, the rest is reached over NVLink (loads,
+// stores and atomics), so the halo of the slab decomposition needs no packing or exchange step.
+// The driver entry points are resolved at run time (no link-time dependency on libcuda).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <unistd.h>
+#include <vector>
+#include "../../include/ssb.h"
+
+struct ssb_fabric {
+    int rank, world, device;
+    size_t granularity, arena_bytes, cursor;
+    CUmemGenericAllocationHandle arena[SSB_MAX_RANKS];
+    bool have[SSB_MAX_RANKS];
+    struct Mapping { CUdeviceptr base; size_t chunk; };
+    std::vector<Mapping> maps;
+    char err[256];
+    // driver entry points
+    CUresult (*memCreate)(CUmemGenericAllocationHandle *, size_t, const CUmemAllocationProp *, unsigned long long);
+    CUresult (*memRelease)(CUmemGenericAllocationHandle);
+    CUresult (*memGetGranularity)(size_t *, const CUmemAllocationProp *, CUmemAllocationGranularity_flags);
+    CUresult (*memExport)(void *, CUmemGenericAllocationHandle, CUmemAllocationHandleType, unsigned long long);
+    CUresult (*memImport)(CUmemGenericAllocationHandle *, void *, CUmemAllocationHandleType);
+    CUresult (*memAddressReserve)(CUdeviceptr *, size_t, size_t, CUdeviceptr, unsigned long long);
+    CUresult (*memAddressFree)(CUdeviceptr, size_t);
+    CUresult (*memMap)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long);
+    CUresult (*memUnmap)(CUdeviceptr, size_t);
+    CUresult (*memSetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc *, size_t);
+};
+
+namespace ssb {
+
+template <class F>
+static bool fabric_entry(const char *name, F *out) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) return false;
+    *out = (F)fn;
+    return true;
+}
+
+static int fabric_fail(ssb_fabric *f, const char *what, CUresult rc) {
+    snprintf(f->err, sizeof f->err, "%s failed (CUresult %d)", what, (int)rc);
+    return -1;
+}
+
+static CUmemAllocationProp fabric_prop(int device) {
+    CUmemAllocationProp prop;
+    memset(&prop, 0, sizeof prop);
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = device;
+    prop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+    return prop;
+}
+
+}  // namespace ssb
+
+extern "C" {
+
+const char *ssb_fabric_last_error(ssb_fabric_t *f) { return f ? f->err : "null fabric"; }
+
+int ssb_fabric_create(int32_t rank, int32_t world, int32_t device, uint64_t arena_bytes, ssb_fabric_t **out, int32_t *fd_out) {
+    using namespace ssb;
+    if (!out || !fd_out || world < 1 || world > SSB_MAX_RANKS || rank < 0 || rank >= world) return -1;
+    ssb_fabric *f = new ssb_fabric();
+    memset(f->have, 0, sizeof f->have);
+    f->err[0] = 0;
+    f->rank = rank; f->world = world; f->device = device; f->cursor = 0;
+    *out = f;
+    if (cudaSetDevice(device) != cudaSuccess || cudaFree(0) != cudaSuccess) { snprintf(f->err, sizeof f->err, "cudaSetDevice(%d) failed", device); return -1; }
+    const bool ok = fabric_entry("cuMemCreate", &f->memCreate) && fabric_entry("cuMemRelease", &f->memRelease) &&
+                    fabric_entry("cuMemGetAllocationGranularity", &f->memGetGranularity) &&
+                    fabric_entry("cuMemExportToShareableHandle", &f->memExport) &&
+                    fabric_entry("cuMemImportFromShareableHandle", &f->memImport) &&
+                    fabric_entry("cuMemAddressReserve", &f->memAddressReserve) && fabric_entry("cuMemAddressFree", &f->memAddressFree) &&
+                    fabric_entry("cuMemMap", &f->memMap) && fabric_entry("cuMemUnmap", &f->memUnmap) &&
+                    fabric_entry("cuMemSetAccess", &f->memSetAccess);
+    if (!ok) { snprintf(f->err, sizeof f->err, "CUDA virtual memory management entry points not available"); return -1; }
+    CUmemAllocationProp prop = fabric_prop(device);
+    CUresult rc = f->memGetGranularity(&f->granularity, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED);
+    if (rc != CUDA_SUCCESS) return fabric_fail(f, "cuMemGetAllocationGranularity", rc);
+    f->arena_bytes = (arena_bytes + f->granularity - 1) / f->granularity * f->granularity;
+    rc = f->memCreate(&f->arena[rank], f->arena_bytes, &prop, 0);
+    if (rc != CUDA_SUCCESS) return fabric_fail(f, "cuMemCreate", rc);
+    f->have[rank] = true;
+    int fd = -1;
+    rc = f->memExport(&fd, f->arena[rank], CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0);
+    if (rc != CUDA_SUCCESS) return fabric_fail(f, "cuMemExportToShareableHandle", rc);
+    *fd_out = fd;
+    return 0;
+}
+
+uint64_t ssb_fabric_granularity(ssb_fabric_t *f) { return f ? f->granularity : 0; }
+uint64_t ssb_fabric_arena_bytes(ssb_fabric_t *f) { return f ? f->arena_bytes : 0; }
+
+int ssb_fabric_import(ssb_fabric_t *f, int32_t peer, int32_t fd) {
+    if (!f || peer < 0 || peer >= f->world || peer == f->rank) return -1;
+    CUresult rc = f->memImport(&f->arena[peer], (void *)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR);
+    if (rc != CUDA_SUCCESS) return ssb::fabric_fail(f, "cuMemImportFromShareableHandle", rc);
+    f->have[peer] = true;
+    close(fd);
+    return 0;
+}
+
+// All ranks call this in the same order with the same chunk size.  base[p * chunk ..] lives on rank p.
+int ssb_fabric_map(ssb_fabric_t *f, uint64_t chunk_bytes, void **base_out) {
+    if (!f || !base_out) return -1;
+    for (int p = 0; p < f->world; p++) if (!f->have[p]) { snprintf(f->err, sizeof f->err, "arena of rank %d not imported", p); return -1; }
+    const size_t chunk = (chunk_bytes + f->granularity - 1) / f->granularity * f->granularity;
+    if (f->cursor + chunk > f->arena_bytes) { snprintf(f->err, sizeof f->err, "arena exhausted (%zu + %zu > %zu)", f->cursor, chunk, f->arena_bytes); return -1; }
+    CUdeviceptr base = 0;
+    CUresult rc = f->memAddressReserve(&base, chunk * f->world, f->granularity, 0, 0);
+    if (rc != CUDA_SUCCESS) return ssb::fabric_fail(f, "cuMemAddressReserve", rc);
+    for (int p = 0; p < f->world; p++) {
+        rc = f->memMap(base + (size_t)p * chunk, chunk, f->cursor, f->arena[p], 0);
+        if (rc != CUDA_SUCCESS) return ssb::fabric_fail(f, "cuMemMap", rc);
+    }
+    CUmemAccessDesc acc;
+    memset(&acc, 0, sizeof acc);
+    acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    acc.location.id = f->device;
+    acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    rc = f->memSetAccess(base, chunk * f->world, &acc, 1);
+    if (rc != CUDA_SUCCESS) return ssb::fabric_fail(f, "cuMemSetAccess", rc);
+    f->maps.push_back({base, chunk});
+    f->cursor += chunk;
+    *base_out = (void *)base;
+    return 0;
+}
+
+int ssb_fabric_copy(ssb_fabric_t *f, void *dst, const void *src, uint64_t bytes, int32_t kind) {
+    if (!f || !dst || (kind != 2 && !src)) return -1;
+    cudaError_t rc = cudaSetDevice(f->device);
+    if (rc == cudaSuccess) {
+        if (kind == 0) rc = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+        else if (kind == 1) rc = cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost);
+        else rc = cudaMemset(dst, 0, bytes);
+    }
+    if (rc == cudaSuccess) rc = cudaDeviceSynchronize();
+    if (rc != cudaSuccess) { snprintf(f->err, sizeof f->err, "fabric copy (kind %d, %llu bytes) failed: %s", kind, (unsigned long long)bytes, cudaGetErrorString(rc)); return -2; }
+    return 0;
+}
+
+int ssb_fabric_destroy(ssb_fabric_t *f) {
+    if (!f) return 0;
+    cudaSetDevice(f->device);
+    cudaDeviceSynchronize();
+    for (auto &m : f->maps) {
+        f->memUnmap(m.base, m.chunk * f->world);
+        f->memAddressFree(m.base, m.chunk * f->world);
+    }
+    for (int p = 0; p < f->world; p++) if (f->have[p]) f->memRelease(f->arena[p]);
+    delete f;
+    return 0;
+}
+
+}  // extern "C"

@@ -16,6 +16,7 @@ struct GrowArgs {
     int32_t height, equator;
     int32_t seasons, flipped, dry_grows;
     long long n_cells;
+    long long cell_lo, cell_hi;     // the cells this rank grows (the whole map unless sharded)
 };
 
 __device__ __forceinline__ int grow_one(int level, int cap, int rate, bool allowed) {
@@ -24,9 +25,9 @@ __device__ __forceinline__ int grow_one(int level, int cap, int rate, bool allow
 
 // 128-bit path: requires height % 4 == 0 so that a vector never straddles two x-lines
 __global__ void __launch_bounds__(256) k_growback_v4(GrowArgs g) {
-    const long long n4 = g.n_cells >> 2;
+    const long long n4 = g.cell_hi >> 2;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < n4; v += stride) {
+    for (long long v = (g.cell_lo >> 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; v < n4; v += stride) {
         int4 lv = reinterpret_cast<const int4 *>(g.level)[v];
         const int4 cp = __ldg(reinterpret_cast<const int4 *>(g.cap) + v);
         bool a0 = true, a1 = true, a2 = true, a3 = true;
@@ -49,7 +50,7 @@ __global__ void __launch_bounds__(256) k_growback_v4(GrowArgs g) {
 
 __global__ void __launch_bounds__(256) k_growback_scalar(GrowArgs g) {
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < g.n_cells; i += stride) {
+    for (long long i = g.cell_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < g.cell_hi; i += stride) {
         bool allowed = true;
         if (g.seasons) {
             const int y = (int)(i % g.height);
@@ -66,12 +67,12 @@ __global__ void __launch_bounds__(256) k_growback_scalar(GrowArgs g) {
 // x-major layout: N / S are the neighbours in memory, E / W sit one x-line (H cells) away, so the
 // three x-lines a thread block touches are re-read from L1 / L2, not from HBM.
 __global__ void __launch_bounds__(256) k_diffuse_v2(const double *__restrict__ p, double *__restrict__ out,
-                                                    int W, int H) {
+                                                    int W, int H, long long cell_lo, long long cell_hi) {
     // two cells (one 128-bit vector) per thread along y; requires H % 2 == 0
-    const long long n2 = ((long long)W * H) >> 1;
+    const long long n2 = cell_hi >> 1;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const int H2 = H >> 1;
-    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < n2; v += stride) {
+    for (long long v = (cell_lo >> 1) + (long long)blockIdx.x * blockDim.x + threadIdx.x; v < n2; v += stride) {
         const int x = (int)(v / H2), y = (int)(v - (long long)x * H2) << 1;
         const long long row = (long long)x * H;
         const double2 e = *reinterpret_cast<const double2 *>(p + (long long)(x == W - 1 ? 0 : x + 1) * H + y);
@@ -87,10 +88,9 @@ __global__ void __launch_bounds__(256) k_diffuse_v2(const double *__restrict__ p
 }
 
 __global__ void __launch_bounds__(256) k_diffuse(const double *__restrict__ p, double *__restrict__ flux,
-                                                 int W, int H) {
-    const long long n = (long long)W * H;
+                                                 int W, int H, long long cell_lo, long long cell_hi) {
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    for (long long i = cell_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cell_hi; i += stride) {
         const int x = (int)(i / H), y = (int)(i - (long long)x * H);
         const long long row = (long long)x * H;
         double m = 0.0;
@@ -381,10 +381,11 @@ __global__ void __launch_bounds__(STATS_THREADS) k_stats_partials(DevCtx c, Stat
         p.dead_combat += c.a.cod[s] == SSB_COMBAT;
     }
     const bool spicy = (c.p.flags & SSB_F_SPICE) != 0;      // spice arrays are all zero otherwise
-    for (long long i = tid; i < c.g.n_cells; i += stride)   // environment totals (1044-1051)
+    const long long cell_lo = c.sh.world > 1 ? c.sh.cell_lo : 0, cell_hi = c.sh.world > 1 ? c.sh.cell_hi : c.g.n_cells;
+    for (long long i = cell_lo + tid; i < cell_hi; i += stride)   // environment totals (1044-1051)
         p.env_wealth_total += c.g.sugar[i] + (spicy ? c.g.spice[i] : 0);
     if (c.t <= 1)                                           // capacities are constant: only t = 1 logs them
-        for (long long i = tid; i < c.g.n_cells; i += stride)
+        for (long long i = cell_lo + tid; i < cell_hi; i += stride)
             p.env_capacity_total += c.g.sugar_cap[i] + (spicy ? c.g.spice_cap[i] : 0);
     block_fold(p, smem);
     if (threadIdx.x == 0) out[blockIdx.x] = smem[0];
@@ -436,6 +437,31 @@ __global__ void __launch_bounds__(STATS_THREADS) k_stats_final(DevCtx c, const S
     out->env_capacity_total = r.env_capacity_total;
     out->env_wealth_created = 0;   // closed form, filled in by the host
     out->rounds = c.a.counters[SSB_C_ROUNDS];
+}
+
+// sharded: {population, OR, AND of the wealth keys} of this rank for the all-gather
+__global__ void k_stats_pack(DevCtx c, const TribeCensus *tc, unsigned long long *msg) {
+    msg[0] = (unsigned long long)c.a.counters[SSB_C_N_LIST];
+    msg[1] = tc->key_or; msg[2] = tc->key_and;
+    msg[3] = msg[4] = msg[5] = msg[6] = 0;
+}
+
+// sharded: all ranks' wealth keys (rank r's start at word r * gather_stride + 4 * local_slots of the
+// stitched scratch) into one local array; vals[0] = box population, vals[1..2] = OR / AND of all keys
+__global__ void __launch_bounds__(256) k_keys_gather(DevCtx c, uint64_t *keys, long long capacity, long long local_slots,
+                                                     unsigned long long *vals) {
+    const long long stride = (long long)gridDim.x * blockDim.x, tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long base = 0;
+    unsigned long long k_or = 0ull, k_and = ~0ull;
+    for (int r = 0; r < c.sh.world; r++) {
+        const long long n = (long long)c.sh.peer_vals[r * SHARD_PAYLOAD];
+        k_or |= c.sh.peer_vals[r * SHARD_PAYLOAD + 1]; k_and &= c.sh.peer_vals[r * SHARD_PAYLOAD + 2];
+        const unsigned long long *src = c.sh.gather + (long long)r * c.sh.gather_stride + 4 * local_slots;
+        for (long long i = tid; i < n; i += stride)
+            if (base + i < capacity) keys[base + i] = src[i];
+        base += n;
+    }
+    if (tid == 0) { vals[0] = (unsigned long long)(base < capacity ? base : capacity); vals[1] = k_or; vals[2] = k_and; }
 }
 
 // Mode E: the reference accumulates its float sums agent by agent in list order and rounds the

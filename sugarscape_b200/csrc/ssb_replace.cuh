@@ -15,6 +15,10 @@
 //            of the new id (generateTribeTags, sugarscape.py:548-559)
 //   finish   counters, free-slot stack (the slots of this step's dead stay untouched until the
 //            stats reduction has read them)
+// Sharded over x-slabs (ssb_shard.cuh): every rank counts and collects on its own slab; populations,
+// empty-cell counts and candidate counts are all-gathered with the box-wide barrier, every rank
+// gathers all candidates over NVLink, sorts them redundantly (they are few) and creates exactly the
+// replacements whose cell lies on its slab -- ids and endowments depend only on the global index i.
 #pragma once
 #include "ssb_rules.cuh"
 
@@ -33,6 +37,8 @@ struct ReplacePlan {
     int qorder[4];
     int Q;
     long long need, older;
+    unsigned long long created;        // replacements created by this rank
+    unsigned long long msg[SHARD_PAYLOAD];   // payload of the next box-wide exchange
 };
 
 // position (0-based) of the cell's quadrant among the ACTIVE quadrants (sugarscape.py:475-497), or -1
@@ -49,17 +55,19 @@ __device__ __forceinline__ int quadrant_of_cell(const ssb_params_t &p, int x, in
 
 __global__ void k_repl_reset(ReplacePlan *rp) {
     if (threadIdx.x < 4) { rp->empty[threadIdx.x] = 0; rp->cand_count[threadIdx.x] = 0; rp->quota[threadIdx.x] = 0; }
-    if (threadIdx.x == 0) { rp->varying[0] = ~0ull; rp->varying[1] = 0ull; rp->need = 0; rp->older = 0; rp->Q = 0; }
+    if (threadIdx.x == 0) { rp->varying[0] = ~0ull; rp->varying[1] = 0ull; rp->need = 0; rp->older = 0; rp->Q = 0; rp->created = 0; }
 }
 
 __global__ void __launch_bounds__(256) k_repl_count(DevCtx c, ReplacePlan *rp) {
-    if (c.a.counters[SSB_C_N_LIST] >= c.p.agent_replacements) return;
+    const bool sharded = c.sh.world > 1;
+    if (!sharded && c.a.counters[SSB_C_N_LIST] >= c.p.agent_replacements) return;
     __shared__ unsigned int cnt[4];
     if (threadIdx.x < 4) cnt[threadIdx.x] = 0;
     __syncthreads();
     const int H = c.p.height;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < c.g.n_cells; i += stride) {
+    const long long cell_lo = sharded ? c.sh.cell_lo : 0, cell_hi = sharded ? c.sh.cell_hi : c.g.n_cells;
+    for (long long i = cell_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cell_hi; i += stride) {
         if (c.g.occ[i] >= 0) continue;
         const int x = (int)(i / H), y = (int)(i - (long long)x * H);
         const int q = quadrant_of_cell(c.p, x, y);
@@ -69,10 +77,27 @@ __global__ void __launch_bounds__(256) k_repl_count(DevCtx c, ReplacePlan *rp) {
     if (threadIdx.x < 4 && cnt[threadIdx.x]) atomicAdd(&rp->empty[threadIdx.x], (unsigned long long)cnt[threadIdx.x]);
 }
 
+// sharded: {population, empty cells per quadrant} of this rank, for the all-gather before the plan
+__global__ void k_repl_pack_counts(DevCtx c, ReplacePlan *rp) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    rp->msg[0] = (unsigned long long)c.a.counters[SSB_C_N_LIST];
+    for (int q = 0; q < 4; q++) rp->msg[1 + q] = rp->empty[q];
+    rp->msg[5] = rp->msg[6] = 0;
+}
+
 __global__ void k_repl_plan(DevCtx c, ReplacePlan *rp, long long endow_count, long long cand_capacity) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     c.a.counters[SSB_C_N_REPLACED] = 0;
-    long long need = (long long)c.p.agent_replacements - c.a.counters[SSB_C_N_LIST];
+    long long population = c.a.counters[SSB_C_N_LIST];
+    if (c.sh.world > 1) {            // box-wide totals; rp->empty becomes the global count on every rank
+        population = 0;
+        for (int q = 0; q < 4; q++) rp->empty[q] = 0;
+        for (int r = 0; r < c.sh.world; r++) {
+            population += (long long)c.sh.peer_vals[r * SHARD_PAYLOAD];
+            for (int q = 0; q < 4; q++) rp->empty[q] += c.sh.peer_vals[r * SHARD_PAYLOAD + 1 + q];
+        }
+    }
+    long long need = (long long)c.p.agent_replacements - population;
     const int Q = __popc(c.p.quad_mask & 15);
     long long total = 0;
     for (int q = 0; q < Q; q++) total += (long long)rp->empty[q];
@@ -108,7 +133,9 @@ __global__ void __launch_bounds__(256) k_repl_collect(DevCtx c, ReplacePlan *rp,
     const int H = c.p.height;
     const uint64_t key = step_key(c.p.seed, c.t);
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < c.g.n_cells; i += stride) {
+    const bool sharded = c.sh.world > 1;
+    const long long cell_lo = sharded ? c.sh.cell_lo : 0, cell_hi = sharded ? c.sh.cell_hi : c.g.n_cells;
+    for (long long i = cell_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cell_hi; i += stride) {
         if (c.g.occ[i] >= 0) continue;
         const int x = (int)(i / H), y = (int)(i - (long long)x * H);
         const int q = quadrant_of_cell(c.p, x, y);
@@ -123,6 +150,38 @@ __global__ void __launch_bounds__(256) k_repl_collect(DevCtx c, ReplacePlan *rp,
 
 __global__ void k_repl_clamp(ReplacePlan *rp, long long cand_capacity) {
     if (threadIdx.x < 4 && rp->cand_count[threadIdx.x] > cand_capacity) rp->cand_count[threadIdx.x] = cand_capacity;
+    __syncwarp();
+    if (threadIdx.x == 0) {          // sharded: candidate counts of this rank for the all-gather
+        for (int q = 0; q < 4; q++) rp->msg[q] = (unsigned long long)rp->cand_count[q];
+        rp->msg[4] = rp->msg[5] = rp->msg[6] = 0;
+    }
+}
+
+// sharded: copy every rank's candidates (rank r's list of quadrant q starts at word
+// r * gather_stride + q * local_capacity of the stitched scratch) into the local buffer, rank
+// after rank; the sort that follows makes the order of arrival irrelevant
+__global__ void __launch_bounds__(256) k_repl_gather(DevCtx c, ReplacePlan *rp, uint64_t *cand, long long cand_capacity,
+                                                     long long local_capacity) {
+    if (rp->need <= 0) return;
+    const long long stride = (long long)gridDim.x * blockDim.x, tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int q = 0; q < 4; q++) {
+        long long base = 0;
+        for (int r = 0; r < c.sh.world; r++) {
+            const long long n = (long long)c.sh.peer_vals[r * SHARD_PAYLOAD + q];
+            const unsigned long long *src = c.sh.gather + (long long)r * c.sh.gather_stride + (long long)q * local_capacity;
+            for (long long i = tid; i < n; i += stride)
+                if (base + i < cand_capacity) cand[(long long)q * cand_capacity + base + i] = src[i];
+            base += n;
+        }
+    }
+}
+
+__global__ void k_repl_gather_counts(DevCtx c, ReplacePlan *rp, long long cand_capacity) {
+    if (threadIdx.x >= 4) return;
+    long long n = 0;
+    for (int r = 0; r < c.sh.world; r++) n += (long long)c.sh.peer_vals[r * SHARD_PAYLOAD + threadIdx.x];
+    if (n > cand_capacity) { n = cand_capacity; c.a.counters[SSB_C_OVERFLOW] = 5; }
+    rp->cand_count[threadIdx.x] = n;
 }
 
 __global__ void __launch_bounds__(256) k_repl_create(DevCtx c, ReplacePlan *rp, const uint64_t *cand, long long cand_capacity,
@@ -140,8 +199,14 @@ __global__ void __launch_bounds__(256) k_repl_create(DevCtx c, ReplacePlan *rp, 
         const long long rank = i / Q, have = rp->cand_count[q];
         if (rank >= have) { a.counters[SSB_C_OVERFLOW] = 6; continue; }      // threshold too tight (not expected)
         const int cell = (int)(cand[(long long)q * cand_capacity + (have - 1 - rank)] & 0xffffffffull);
-        long long slot = i < older ? (long long)a.free_slots[older - 1 - i] : n_slots + (i - older);
-        if (slot >= a.capacity || n_list + i >= a.capacity) { a.counters[SSB_C_OVERFLOW] = 1; continue; }
+        long long j = i;                   // index among the replacements THIS rank creates
+        if (c.sh.world > 1) {
+            if (cell < c.sh.cell_lo || cell >= c.sh.cell_hi) continue;       // another rank's slab
+            j = (long long)atomicAdd(&rp->created, 1ull);
+        }
+        long long slot = j < older ? (long long)a.free_slots[older - 1 - j] : n_slots + (j - older);
+        const long long slot_hi = c.sh.world > 1 ? c.sh.slot_hi : a.capacity;
+        if (slot >= slot_hi || n_list + j >= a.capacity) { a.counters[SSB_C_OVERFLOW] = 1; continue; }
         const int s = (int)slot;
         const long long ei = (cursor + i) % en.count;
         const int id = (int)(next_id + i);
@@ -179,15 +244,15 @@ __global__ void __launch_bounds__(256) k_repl_create(DevCtx c, ReplacePlan *rp, 
         a.trade_volume[s] = 0; a.trade_price[s] = 0; a.last_repro[s] = -1;
         a.children_head[s] = -1; a.mates_head[s] = -1; a.father[s] = -1; a.mother[s] = -1;
         c.g.occ[cell] = s;
-        a.order[n_list + i] = s;
+        a.order[n_list + j] = s;
     }
 }
 
 // the free stack keeps [older slots not consumed][this step's dead]; the dead block is rebuilt from
 // dead_list (same order as compaction pushed it)
 __global__ void __launch_bounds__(256) k_repl_free_stack(DevCtx c, const ReplacePlan *rp) {
-    const long long need = rp->need;
-    if (need <= 0) return;
+    if (rp->need <= 0) return;
+    const long long need = c.sh.world > 1 ? (long long)rp->created : rp->need;     // created by this rank
     const long long n_dead = c.a.counters[SSB_C_N_DEAD];
     const long long older_left = rp->older > need ? rp->older - need : 0;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -199,14 +264,15 @@ __global__ void k_repl_finish(DevCtx c, const ReplacePlan *rp) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const long long need = rp->need;
     if (need <= 0) return;
+    const long long mine = c.sh.world > 1 ? (long long)rp->created : need;         // created by this rank
     const long long older = rp->older;
-    const long long bumped = need > older ? need - older : 0;
+    const long long bumped = mine > older ? mine - older : 0;
     c.a.counters[SSB_C_N_SLOTS] += bumped;
-    c.a.counters[SSB_C_N_FREE] = (older > need ? older - need : 0) + c.a.counters[SSB_C_N_DEAD];
-    c.a.counters[SSB_C_N_LIST] += need;
-    c.a.counters[SSB_C_NEXT_ID] += need;
+    c.a.counters[SSB_C_N_FREE] = (older > mine ? older - mine : 0) + c.a.counters[SSB_C_N_DEAD];
+    c.a.counters[SSB_C_N_LIST] += mine;
+    c.a.counters[SSB_C_NEXT_ID] += need;          // ids and the endowment cursor are box-wide
     c.a.counters[SSB_C_ENDOW_INDEX] += need;
-    c.a.counters[SSB_C_N_REPLACED] = need;
+    c.a.counters[SSB_C_N_REPLACED] = mine;
 }
 
 }  // namespace ssb

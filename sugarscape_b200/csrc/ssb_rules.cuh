@@ -14,6 +14,7 @@
 #include "../../include/ssb.h"
 #include "ssb_pow.cuh"
 #include "ssb_rng.cuh"
+#include "ssb_shard.cuh"
 
 namespace ssb {
 
@@ -33,6 +34,7 @@ struct DevCtx {
     int32_t n_step_tables;
     // mode S
     int32_t *born_list;              // slots of this step's newborn (unordered)
+    ShardCtx sh;                     // world <= 1: the whole simulation lives on this GPU
 };
 
 __device__ __forceinline__ int wrapi(int v, int n) { v %= n; return v < 0 ? v + n : v; }

@@ -51,6 +51,21 @@ def load_library():
     L.ssb_agent_step.argtypes = [E, C.c_int32, C.c_double, C.c_void_p]
     L.ssb_compact.argtypes = [E, C.c_int32, C.c_void_p]
     L.ssb_reduce_stats.argtypes = [E, C.c_int32, C.c_void_p]
+    F = C.c_void_p
+    L.ssb_fabric_create.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.POINTER(F), C.POINTER(C.c_int32)]
+    L.ssb_fabric_import.argtypes = [F, C.c_int32, C.c_int32]
+    L.ssb_fabric_map.argtypes = [F, C.c_uint64, C.POINTER(C.c_void_p)]
+    L.ssb_fabric_copy.argtypes = [F, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32]
+    L.ssb_fabric_granularity.argtypes = [F]
+    L.ssb_fabric_granularity.restype = C.c_uint64
+    L.ssb_fabric_arena_bytes.argtypes = [F]
+    L.ssb_fabric_arena_bytes.restype = C.c_uint64
+    L.ssb_fabric_destroy.argtypes = [F]
+    L.ssb_fabric_last_error.argtypes = [F]
+    L.ssb_fabric_last_error.restype = C.c_char_p
+    L.ssb_set_shard.argtypes = [E, C.POINTER(layout.Shard)]
+    L.ssb_shard_barrier.argtypes = [E, C.c_void_p]
+    L.ssb_shard_broken.argtypes = [E]
     L.ssb_bind_endowments.argtypes = [E, C.POINTER(layout.Endowments)]
     L.ssb_replace.argtypes = [E, C.c_int32, C.c_void_p]
     L.ssb_step.argtypes = [E, C.c_int32, C.c_double, C.c_void_p]
@@ -80,6 +95,8 @@ EXPORTED_SYMBOLS = (
     "ssb_set_mt_state", "ssb_get_mt_state", "ssb_set_step_tables", "ssb_set_epochs", "ssb_set_mark_shift", "ssb_set_l2_persist",
     "ssb_sizeof_params", "ssb_sizeof_grid", "ssb_sizeof_agents", "ssb_sizeof_stats",
     "ssb_env_step", "ssb_agent_step", "ssb_compact", "ssb_bind_endowments", "ssb_replace", "ssb_reduce_stats", "ssb_step", "ssb_stats", "ssb_stats_history",
+    "ssb_fabric_create", "ssb_fabric_import", "ssb_fabric_map", "ssb_fabric_copy", "ssb_fabric_granularity", "ssb_fabric_arena_bytes",
+    "ssb_fabric_destroy", "ssb_fabric_last_error", "ssb_set_shard", "ssb_shard_barrier", "ssb_shard_broken",
     "ssb_sync", "ssb_pollution_buffer", "ssb_test_pow", "ssb_round_trace", "ssb_launch_count", "ssb_timing", "ssb_enable_timing",
 )
 
@@ -103,12 +120,16 @@ class Engine:
         self._check(self.L.ssb_create(C.byref(params), device, C.byref(self.handle)))
         g, a = self._structs()
         self._check(self.L.ssb_bind(self.handle, C.byref(g), C.byref(a)))
+        self._after_bind()
         if endow_bits is not None:
             eb = np.ascontiguousarray(endow_bits, dtype=np.uint32)
             tb = np.ascontiguousarray(tag_bits, dtype=np.uint32)
             self._check(self.L.ssb_set_step_tables(self.handle, eb.ctypes.data, tb.ctypes.data, len(eb)))
 
     # -- plumbing ------------------------------------------------------------------------------
+    def _after_bind(self):
+        pass
+
     def _check(self, rc):
         if rc != 0:
             msg = self.L.ssb_last_error(self.handle)

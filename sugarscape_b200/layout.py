@@ -123,6 +123,14 @@ def endowments_struct(arrays, pointer_of):
     return e
 
 
+class Shard(C.Structure):       # ssb_shard_t
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32),
+                ("cell_lo", C.c_int64), ("cell_hi", C.c_int64), ("slot_lo", C.c_int64), ("slot_hi", C.c_int64),
+                ("ctrl", C.c_void_p), ("ctrl_stride", C.c_uint64),
+                ("marks", C.c_void_p), ("marks_stride", C.c_uint64),
+                ("gather", C.c_void_p), ("gather_stride", C.c_uint64)]
+
+
 class Agents(C.Structure):
     _fields_ = ([("capacity", C.c_int64), ("counters", C.c_void_p)]
                 + [(n, C.c_void_p) for n, _, _ in AGENT_FIELDS]

@@ -1,0 +1,321 @@
+"""One simulation sharded over the GPUs of a box by x-slabs (BASELINE S2).
+
+One process per GPU (torchrun).  Grid and agent arrays are "stitched" (include/ssb.h, ssb_fabric_*):
+rank r's slab of the map and rank r's range of agent slots live in rank r's HBM, every rank maps the
+whole arrays, and kernels reach across the slab boundary over NVLink.  This module is the host
+plumbing: passing the arena file descriptors between the ranks (unix sockets, SCM_RIGHTS), laying
+the stitched arrays out, re-slotting a host state so that every agent's record sits on the rank that
+owns its cell, and combining the per-rank stats reductions.  Scalable RNG mode only.
+"""
+import ctypes as C
+import os
+import socket
+import struct
+
+import numpy as np
+
+from . import layout
+from .engine import Engine, EngineError, load_library
+
+LOCAL_AGENT_FIELDS = ("order", "free_slots", "dead_list")      # per rank; everything else is indexed by global slot
+
+
+def slab_bounds(width, world):
+    """x-lines [b[r], b[r+1]) belong to rank r."""
+    return [width * r // world for r in range(world + 1)]
+
+
+def slot_bounds(capacity, world):
+    return [capacity * r // world for r in range(world + 1)]
+
+
+def shard_host_state(state, world):
+    """Re-slot a freshly built single-GPU HostState for `world` ranks: an agent's record moves to the
+    slot range of the rank that owns its cell (list order is kept inside a rank).  Returns the new
+    global state and, per rank, its list of slots."""
+    n_list, n_slots = int(state.counters[layout.C_N_LIST]), int(state.counters[layout.C_N_SLOTS])
+    if int(state.counters[layout.C_N_FREE]) != 0 or n_list != n_slots:
+        raise ValueError("shard_host_state expects a freshly built state (no free slots)")
+    xb, sb = slab_bounds(state.width, world), slot_bounds(state.capacity, world)
+    old = state.a_order[:n_list].astype(np.int64)
+    x = state.a_pos[old] // state.height
+    owner = np.searchsorted(np.asarray(xb[1:]), x, side="right")
+    new = layout.HostState.empty(state.width, state.height, state.capacity, state.kin_capacity)
+    for name, _ in layout.GRID_FIELDS:
+        setattr(new, name, getattr(state, name).copy())
+    new.counters[:] = state.counters
+    lists = []
+    new_slot = np.empty(n_list, dtype=np.int64)
+    for r in range(world):
+        idx = np.flatnonzero(owner == r)
+        if len(idx) > sb[r + 1] - sb[r]:
+            raise MemoryError(f"rank {r}: {len(idx)} agents exceed its {sb[r + 1] - sb[r]} slots")
+        new_slot[idx] = sb[r] + np.arange(len(idx))
+        lists.append((sb[r] + np.arange(len(idx))).astype(np.int32))
+    for name, _, _ in layout.AGENT_FIELDS:
+        if name in LOCAL_AGENT_FIELDS:
+            continue
+        getattr(new, "a_" + name)[new_slot] = getattr(state, "a_" + name)[old]
+    new.occ[state.a_pos[old]] = new_slot.astype(np.int32)
+    return new, lists
+
+
+def exchange_fds(rank, world, fd, tag, barrier):
+    """All-to-all of one file descriptor per rank over unix sockets (SCM_RIGHTS)."""
+    if world == 1:
+        return {rank: fd}
+    path = lambda r: f"/tmp/ssb_fabric_{tag}_{r}.sock"
+    if os.path.exists(path(rank)):
+        os.unlink(path(rank))
+    server = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+    server.bind(path(rank))
+    server.listen(world)
+    try:
+        barrier()                                  # every rank is listening
+        for r in range(world):
+            if r == rank:
+                continue
+            with socket.socket(socket.AF_UNIX, socket.SOCK_STREAM) as c:
+                c.connect(path(r))
+                socket.send_fds(c, [struct.pack("i", rank)], [fd])
+        fds = {rank: fd}
+        for _ in range(world - 1):
+            conn, _ = server.accept()
+            with conn:
+                msg, got, _, _ = socket.recv_fds(conn, 16, 1)
+            fds[struct.unpack("i", msg[:4])[0]] = got[0]
+        barrier()
+    finally:
+        server.close()
+        os.unlink(path(rank))
+    return fds
+
+
+def combine_stats(parts):
+    """Per-rank ssb_stats_t -> the box-wide one (sums; extrema; the Lorenz sum is already global)."""
+    out = layout.Stats()
+    live = [p for p in parts if p.population > 0]
+    for field, _ in layout.Stats._fields_:
+        vals = [getattr(p, field) for p in parts]
+        if field == "timestep":
+            v = vals[0]
+        elif field in ("rounds",):
+            v = max(vals)
+        elif field == "lorenz_weighted_sum":
+            v = vals[0]
+        elif field == "max_wealth":
+            v = max((p.max_wealth for p in live), default=0.0)
+        elif field == "min_wealth":
+            v = min((p.min_wealth for p in live), default=0.0)
+        elif field == "tribe_first":
+            v = type(vals[0])(*[min((x[i] for x in vals if x[i] >= 0), default=-1) for i in range(len(vals[0]))])
+        elif hasattr(vals[0], "__len__"):
+            v = type(vals[0])(*[sum(x[i] for x in vals) for i in range(len(vals[0]))])
+        else:
+            v = sum(vals)
+        setattr(out, field, v)
+    return out
+
+
+class StitchedArray:
+    """A 1-D array in stitched device memory (chunk p backed by rank p's HBM), with the few tensor
+    methods the Engine uses.  Copies are synchronous and split at chunk boundaries."""
+
+    def __init__(self, owner, ptr, n, dtype, chunk_bytes, base=None, offset=0):
+        self.owner, self.ptr, self.n, self.dtype, self.chunk_bytes = owner, int(ptr), int(n), np.dtype(dtype), int(chunk_bytes)
+        self.base, self.offset = (self.ptr if base is None else base), offset          # byte offset of [0] in the mapping
+
+    def data_ptr(self):
+        return self.ptr
+
+    def numel(self):
+        return self.n
+
+    def element_size(self):
+        return self.dtype.itemsize
+
+    def __getitem__(self, sl):
+        lo, hi, step = sl.indices(self.n)
+        assert step == 1
+        return StitchedArray(self.owner, self.ptr + lo * self.dtype.itemsize, max(hi - lo, 0), self.dtype, self.chunk_bytes,
+                             self.base, self.offset + lo * self.dtype.itemsize)
+
+    def _pieces(self):
+        """(byte offset inside this view, bytes) pieces that do not straddle a chunk boundary."""
+        done, total = 0, self.n * self.dtype.itemsize
+        while done < total:
+            room = self.chunk_bytes - (self.offset + done) % self.chunk_bytes
+            step = min(room, total - done)
+            yield done, step
+            done += step
+
+    def _copy(self, host_ptr, kind):
+        for off, nbytes in self._pieces():
+            dev = self.ptr + off
+            args = (dev, host_ptr + off) if kind == 0 else ((host_ptr + off, dev) if kind == 1 else (dev, None))
+            self.owner._fcheck(self.owner.L.ssb_fabric_copy(self.owner.fabric, args[0], args[1], nbytes, kind))
+
+    def copy_(self, src):
+        arr = np.ascontiguousarray(src.numpy() if hasattr(src, "numpy") else src)
+        assert arr.nbytes == self.n * self.dtype.itemsize
+        self._copy(arr.ctypes.data, 0)
+        return self
+
+    def zero_(self):
+        self._copy(0, 2)
+        return self
+
+    def cpu(self):
+        return self
+
+    def numpy(self):
+        out = np.empty(self.n, dtype=self.dtype)
+        if self.n:
+            self._copy(out.ctypes.data, 1)
+        return out
+
+
+class ShardedEngine(Engine):
+    """Rank `rank` of `world` of one simulation.  `host_state` is the GLOBAL state as returned by
+    shard_host_state() (identical on every rank), `my_list` this rank's list of slots.  Needs an
+    initialised torch.distributed process group (any backend) for the set-up handshakes."""
+
+    def __init__(self, params, host_state, my_list, rank, world, device=0, endow_bits=None, tag_bits=None,
+                 mark_shift=None, tag="0"):
+        import torch.distributed as dist
+        self.rank, self.world, self.my_list, self.dist = rank, world, np.asarray(my_list, dtype=np.int32), dist
+        self.fabric = C.c_void_p()
+        self.mark_shift = mark_shift
+        self.tag = f"{os.environ.get('MASTER_PORT', '0')}_{tag}"
+        super().__init__(params, host_state, device, endow_bits, tag_bits)
+
+    # -- set-up --------------------------------------------------------------------------------------
+    def _barrier(self):
+        self.torch.cuda.synchronize(self.device)
+        self.dist.barrier()
+
+    def _fcheck(self, rc):
+        if rc != 0:
+            raise EngineError("fabric: " + (self.L.ssb_fabric_last_error(self.fabric) or b"?").decode())
+
+    def _upload_all(self, hs):
+        t, L, world, rank = self.torch, self.L, self.world, self.rank
+        t.cuda.set_device(self.device)
+        n_cells, cap = self.width * self.height, self.capacity
+        xb, sb = slab_bounds(self.width, world), slot_bounds(cap, world)
+        self.cell_lo, self.cell_hi = xb[rank] * self.height, xb[rank + 1] * self.height
+        self.slot_lo, self.slot_hi = sb[rank], sb[rank + 1]
+        local_slots = max(sb[r + 1] - sb[r] for r in range(world))
+        # (key, elements, dtype) of every stitched array, in mapping order (identical on all ranks)
+        plan = [(name, n_cells, dt) for name, dt in layout.GRID_FIELDS]
+        plan += [("a_" + name, cap, dt) for name, dt, _ in layout.AGENT_FIELDS if name not in LOCAL_AGENT_FIELDS]
+        plan += [("_ctrl", 512 * world, np.uint64), ("_marks", n_cells, np.uint32),
+                 ("_gather", 5 * local_slots * world, np.uint64)]
+        gran = 2 << 20
+        roundup = lambda b: (b + gran - 1) // gran * gran
+        chunk = {key: roundup(-(-n // world) * np.dtype(dt).itemsize) for key, n, dt in plan}
+        fd = C.c_int32(-1)
+        self._fcheck(L.ssb_fabric_create(rank, world, self.device.index, sum(chunk.values()), C.byref(self.fabric), C.byref(fd)))
+        if int(L.ssb_fabric_granularity(self.fabric)) > gran or gran % int(L.ssb_fabric_granularity(self.fabric)):
+            raise EngineError("unexpected allocation granularity %d" % L.ssb_fabric_granularity(self.fabric))
+        fds = exchange_fds(rank, world, fd.value, self.tag, self.dist.barrier)
+        for r, peer_fd in fds.items():
+            if r != rank:
+                self._fcheck(L.ssb_fabric_import(self.fabric, r, peer_fd))
+        os.close(fd.value)
+        self.stitched, self.chunk = {}, chunk
+        for key, n, dt in plan:
+            base = C.c_void_p()
+            self._fcheck(L.ssb_fabric_map(self.fabric, chunk[key], C.byref(base)))
+            view_dt = np.int32 if np.dtype(dt) == np.uint32 else dt       # like Engine._to_device
+            self.stitched[key] = StitchedArray(self, base.value, world * chunk[key] // np.dtype(dt).itemsize, view_dt, chunk[key])
+        # this rank zeroes / fills the memory it backs, then uploads its slab and its slots
+        for key, n, dt in plan:
+            per = chunk[key] // np.dtype(dt).itemsize
+            self.stitched[key][rank * per:(rank + 1) * per].zero_()
+        self._barrier()
+        for name, _ in layout.GRID_FIELDS:
+            self.tensors[name] = self.stitched[name][:n_cells]
+            self._put(self.tensors[name], getattr(hs, name), self.cell_lo, self.cell_hi)
+        counters = hs.counters.copy()
+        counters[layout.C_N_LIST] = len(self.my_list)
+        counters[layout.C_N_SLOTS] = self.slot_lo + len(self.my_list)
+        counters[layout.C_N_FREE] = 0
+        self.tensors["counters"] = self._to_device(counters)
+        for name, dt, fill in layout.AGENT_FIELDS:
+            if name in LOCAL_AGENT_FIELDS:
+                arr = np.full(cap, fill, dtype=dt)
+                if name == "order":
+                    arr[:len(self.my_list)] = self.my_list
+                self.tensors["a_" + name] = self._to_device(arr)
+            else:
+                self.tensors["a_" + name] = self.stitched["a_" + name][:cap]
+                self._put(self.tensors["a_" + name], getattr(hs, "a_" + name), self.slot_lo, self.slot_hi)
+        for name in layout.KIN_FIELDS:
+            self.tensors[name] = self._to_device(getattr(hs, name))
+        self._barrier()
+
+    def _put(self, tensor, host, lo, hi):
+        arr = host[lo:hi]
+        if arr.dtype == np.uint32:
+            arr = arr.view(np.int32)
+        tensor[lo:hi].copy_(self.torch.from_numpy(np.ascontiguousarray(arr)))
+
+    def _after_bind(self):
+        if self.mark_shift is not None:
+            self.set_mark_shift(self.mark_shift)
+        sd = layout.Shard()
+        sd.rank, sd.world = self.rank, self.world
+        sd.cell_lo, sd.cell_hi, sd.slot_lo, sd.slot_hi = self.cell_lo, self.cell_hi, self.slot_lo, self.slot_hi
+        sd.ctrl, sd.ctrl_stride = self.stitched["_ctrl"].data_ptr(), self.chunk["_ctrl"]
+        sd.marks, sd.marks_stride = self.stitched["_marks"].data_ptr(), self.chunk["_marks"]
+        sd.gather, sd.gather_stride = self.stitched["_gather"].data_ptr(), self.chunk["_gather"]
+        self._check(self.L.ssb_set_shard(self.handle, C.byref(sd)))
+        self._barrier()
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.torch.cuda.synchronize(self.device)
+            try:
+                self.dist.barrier()                # nobody unmaps memory a peer's kernel may still touch
+            except Exception:
+                pass
+            self.L.ssb_destroy(self.handle)
+            self.handle = None
+            self.tensors.clear()
+            self.stitched.clear()
+            if self.fabric:
+                self.L.ssb_fabric_destroy(self.fabric)
+                self.fabric = None
+
+    # -- box-wide views ----------------------------------------------------------------------------
+    def broken(self):
+        return bool(self.L.ssb_shard_broken(self.handle))
+
+    def gather_lists(self):
+        """Every rank's list of slots, concatenated in rank order (same result on every rank)."""
+        n = int(self.counters()[layout.C_N_LIST])
+        mine = self.tensors["a_order"][:n].cpu().numpy()
+        parts = [None] * self.world
+        self.dist.all_gather_object(parts, mine)
+        return np.concatenate(parts)
+
+    def download_global(self, fields=None):
+        """The box-wide state as one HostState (the stitched arrays are visible from every rank);
+        a_order / N_LIST describe the union of the ranks' lists."""
+        self._barrier()
+        hs = self.download(fields)
+        order = self.gather_lists()
+        hs.a_order = np.full(self.capacity, -1, dtype=np.int32)
+        hs.a_order[:len(order)] = order
+        counters = self.counters().copy()
+        counters[layout.C_N_LIST] = len(order)
+        hs.counters = counters
+        self._barrier()
+        return hs
+
+    def global_stats(self, t=None):
+        mine = self.stats() if t is None else self.stats_history(t)
+        parts = [None] * self.world
+        self.dist.all_gather_object(parts, bytes(mine))
+        return combine_stats([layout.Stats.from_buffer_copy(b) for b in parts])

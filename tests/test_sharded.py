@@ -1,0 +1,116 @@
+"""x-slab sharding (sugarscape_b200/sharded.py): host logic on CPU, box-wide parity on >= 2 GPUs."""
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+import parity_util as pu
+from sugarscape_b200 import layout, sharded
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_slab_and_slot_bounds_partition_everything():
+    for width, world in ((50, 2), (51, 4), (16384, 8), (7, 8)):
+        b = sharded.slab_bounds(width, world)
+        assert b[0] == 0 and b[-1] == width and all(b[i] <= b[i + 1] for i in range(world))
+    assert sharded.slot_bounds(1000, 3) == [0, 333, 666, 1000]
+
+
+def test_shard_host_state_moves_every_record_to_the_rank_that_owns_its_cell():
+    c, state, pop, params, endow, tags = pu.build("combat_limited", layout.RNG_SCALABLE, {"agentMovement": [6, 6]})
+    world = 4
+    new, lists = sharded.shard_host_state(state, world)
+    xb, sb = sharded.slab_bounds(state.width, world), sharded.slot_bounds(state.capacity, world)
+    assert sum(len(x) for x in lists) == int(state.counters[layout.C_N_LIST])
+    for r, slots in enumerate(lists):
+        assert np.all((slots >= sb[r]) & (slots < sb[r + 1]))
+        x = new.a_pos[slots] // state.height
+        assert np.all((x >= xb[r]) & (x < xb[r + 1]))
+        assert np.array_equal(new.occ[new.a_pos[slots]], slots)
+    # the same simulation: identical ID-sorted snapshot
+    new.a_order[:] = -1
+    order = np.concatenate(lists)
+    new.a_order[:len(order)] = order
+    d_old, _ = pu.state_digests_by_id(state)
+    d_new, _ = pu.state_digests_by_id(new)
+    assert d_old == d_new
+
+
+def test_combine_stats_sums_counts_and_keeps_extrema():
+    a, b = layout.Stats(), layout.Stats()
+    a.timestep = b.timestep = 7
+    a.population, b.population = 10, 0
+    a.sum_wealth, b.sum_wealth = 55.5, 0.0
+    a.max_wealth, a.min_wealth = 9.0, 1.0
+    b.max_wealth, b.min_wealth = -1e300, 1e300        # an empty rank must not leak its sentinels
+    a.tribe_count[1], b.tribe_count[1] = 4, 6
+    a.tribe_first[1], b.tribe_first[1] = 3, -1
+    a.lorenz_weighted_sum = b.lorenz_weighted_sum = 123.0
+    a.rounds, b.rounds = 140, 140
+    out = sharded.combine_stats([a, b])
+    assert (out.timestep, out.population, out.sum_wealth, out.max_wealth, out.min_wealth) == (7, 10, 55.5, 9.0, 1.0)
+    assert out.tribe_count[1] == 10 and out.tribe_first[1] == 3 and out.lorenz_weighted_sum == 123.0 and out.rounds == 140
+
+
+_FD_WORKER = r"""
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import torch.distributed as dist
+from sugarscape_b200 import sharded
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+r, w = os.pipe()
+os.write(w, b"hello from %d" % rank)
+fds = sharded.exchange_fds(rank, world, r, "t" + os.environ["MASTER_PORT"], dist.barrier)
+for src, fd in sorted(fds.items()):
+    if src != rank:          # (the peer drains this rank's pipe)
+        assert os.read(fd, 64) == b"hello from %d" % src, (rank, src)
+print("FD_EXCHANGE_OK", rank, flush=True)
+dist.destroy_process_group()
+"""
+
+
+def test_fd_exchange_between_two_gloo_ranks():
+    """The arena descriptors travel between the ranks over unix sockets: checked with pipes."""
+    with tempfile.NamedTemporaryFile("w", suffix=".py", delete=False) as f:
+        f.write(_FD_WORKER)
+    try:
+        res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                              "--master-addr", "127.0.0.1", "--master-port", str(29600 + os.getpid() % 300), f.name, ROOT],
+                             capture_output=True, text=True, timeout=120)
+    finally:
+        os.unlink(f.name)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert res.stdout.count("FD_EXCHANGE_OK") == 2
+
+
+SHARDED_CASES = [
+    ("constant_growback", {}, 40),
+    ("combat_unlimited", {"agentAggressionFactor": [1, 1]}, 40),
+    ("cultural_tagging", {}, 40),
+    ("pollution_formation", {}, 60),
+    ("combat_limited", {}, 60),
+    ("combat_limited", {"environmentWidth": 300, "environmentHeight": 300, "startingAgents": 4000, "agentReplacements": 4000,
+                        "agentMaxAge": [5, 30], "agentAggressionFactor": [0, 1]}, 40),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,overrides,steps", SHARDED_CASES)
+def test_two_gpu_slabs_equal_the_single_gpu_run(name, overrides, steps):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    world = 2
+    res = subprocess.run(["timeout", "240", sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                          "--master-addr", "127.0.0.1", "--master-port", str(29900 + os.getpid() % 90),
+                          os.path.join(ROOT, "tests", "sharded_worker.py"), "--case", name, "--overrides", json.dumps(overrides),
+                          "--steps", str(steps)], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, (res.stdout + res.stderr)[-4000:]
+    assert res.stdout.count("SHARDED_PARITY_OK") == world, res.stdout[-2000:]
