@@ -27,7 +27,7 @@ def test_aggregate_over_two_gloo_ranks(tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(WORKER.format(root=ROOT))
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                          "--master-addr", "127.0.0.1", "--master-port", "29541", str(script)],
+                          "--master-addr", "127.0.0.1", "--master-port", str(29400 + os.getpid() % 150), str(script)],
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "ok 0" in out.stdout and "ok 1" in out.stdout
