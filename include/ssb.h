@@ -205,23 +205,21 @@ typedef struct ssb_stats {
 typedef struct ssb_engine ssb_engine_t;
 
 /* ---- sharding one simulation over the GPUs of a box (x-slabs) -------------
- * A fabric is one arena of device memory per rank (one process per GPU), exported as a POSIX file
- * descriptor.  After every rank has imported every peer's descriptor, ssb_fabric_map() returns
- * "stitched" arrays: world chunks of equal size, chunk p backed by rank p's HBM, at the same
- * offsets on every rank.  The host binds stitched arrays as ssb_grid_t / ssb_agents_t, so a kernel
- * reaches the neighbouring slab's cells and agents over NVLink with ordinary loads, stores and
- * atomics.  All ranks must issue the same sequence of ssb_fabric_map calls. */
+ * A "stitched" array is world chunks of equal size, chunk p backed by rank p's HBM (one process per
+ * GPU), mapped at consecutive addresses on every rank.  ssb_fabric_alloc() creates this rank's chunk
+ * and exports it as a POSIX file descriptor; the host passes the descriptors between the ranks and
+ * ssb_fabric_map() imports the peers' chunks and maps the array.  The host binds stitched arrays as
+ * ssb_grid_t / ssb_agents_t, so a kernel reaches the neighbouring slab's cells and agents over NVLink
+ * with ordinary loads, stores and atomics.  All ranks issue the same sequence of alloc calls. */
 #define SSB_MAX_RANKS 8
 typedef struct ssb_fabric ssb_fabric_t;
-int  ssb_fabric_create(int32_t rank, int32_t world, int32_t device, uint64_t arena_bytes,
-                       ssb_fabric_t **out, int32_t *fd_out);
-int  ssb_fabric_import(ssb_fabric_t *f, int32_t peer_rank, int32_t fd);   /* closes fd */
-int  ssb_fabric_map(ssb_fabric_t *f, uint64_t chunk_bytes, void **base_out);
+int  ssb_fabric_create(int32_t rank, int32_t world, int32_t device, ssb_fabric_t **out);
+int  ssb_fabric_alloc(ssb_fabric_t *f, uint64_t chunk_bytes, int32_t *fd_out);    /* returns the array index (>= 0) */
+int  ssb_fabric_map(ssb_fabric_t *f, int32_t index, const int32_t *fds, void **base_out);  /* fds[world]; closes the peers' */
 /* synchronous copies to / from stitched memory: kind 0 = host -> device, 1 = device -> host,
  * 2 = zero `bytes` at dst (src ignored).  Callers split ranges at chunk boundaries. */
 int  ssb_fabric_copy(ssb_fabric_t *f, void *dst, const void *src, uint64_t bytes, int32_t kind);
 uint64_t ssb_fabric_granularity(ssb_fabric_t *f);
-uint64_t ssb_fabric_arena_bytes(ssb_fabric_t *f);
 int  ssb_fabric_destroy(ssb_fabric_t *f);
 const char *ssb_fabric_last_error(ssb_fabric_t *f);
 

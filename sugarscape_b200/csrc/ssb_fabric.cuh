@@ -1,9 +1,8 @@
 // ssb_fabric.cuh -- one address space over the GPUs of a box (x-slab sharding).
 //
-// Every rank (one process per GPU) owns one physical arena (cuMemCreate, exported as a POSIX file
-// descriptor; the host side passes the descriptors between the ranks over a unix socket).  A
-// "stitched" array is a virtual range of world * chunk bytes whose p-th chunk is backed by rank p's
-// arena, mapped identically on every rank.  Kernels index it like an ordinary array: the part of
+// A "stitched" array is a virtual range of world * chunk bytes whose p-th chunk is physical memory
+// of rank p's GPU (cuMemCreate, exported as a POSIX file descriptor; the host side passes the
+// descriptors between the ranks -- one process per GPU -- over unix sockets), mapped on every rank.  Kernels index it like an ordinary array: the part of
 // the map / the agent slots a rank owns is local HBM, the rest is reached over NVLink (loads,
 // stores and atomics), so the halo of the slab decomposition needs no packing or exchange step.
 // The driver entry points are resolved at run time (no link-time dependency on libcuda).
@@ -19,11 +18,15 @@
 
 struct ssb_fabric {
     int rank, world, device;
-    size_t granularity, arena_bytes, cursor;
-    CUmemGenericAllocationHandle arena[SSB_MAX_RANKS];
-    bool have[SSB_MAX_RANKS];
-    struct Mapping { CUdeviceptr base; size_t chunk; };
-    std::vector<Mapping> maps;
+    size_t granularity;
+    struct Array {
+        size_t chunk;
+        CUmemGenericAllocationHandle part[SSB_MAX_RANKS];
+        bool have[SSB_MAX_RANKS];
+        CUdeviceptr base;
+        bool mapped;
+    };
+    std::vector<Array> arrays;
     char err[256];
     // driver entry points
     CUresult (*memCreate)(CUmemGenericAllocationHandle *, size_t, const CUmemAllocationProp *, unsigned long long);
@@ -70,13 +73,12 @@ extern "C" {
 
 const char *ssb_fabric_last_error(ssb_fabric_t *f) { return f ? f->err : "null fabric"; }
 
-int ssb_fabric_create(int32_t rank, int32_t world, int32_t device, uint64_t arena_bytes, ssb_fabric_t **out, int32_t *fd_out) {
+int ssb_fabric_create(int32_t rank, int32_t world, int32_t device, ssb_fabric_t **out) {
     using namespace ssb;
-    if (!out || !fd_out || world < 1 || world > SSB_MAX_RANKS || rank < 0 || rank >= world) return -1;
+    if (!out || world < 1 || world > SSB_MAX_RANKS || rank < 0 || rank >= world) return -1;
     ssb_fabric *f = new ssb_fabric();
-    memset(f->have, 0, sizeof f->have);
     f->err[0] = 0;
-    f->rank = rank; f->world = world; f->device = device; f->cursor = 0;
+    f->rank = rank; f->world = world; f->device = device;
     *out = f;
     if (cudaSetDevice(device) != cudaSuccess || cudaFree(0) != cudaSuccess) { snprintf(f->err, sizeof f->err, "cudaSetDevice(%d) failed", device); return -1; }
     const bool ok = fabric_entry("cuMemCreate", &f->memCreate) && fabric_entry("cuMemRelease", &f->memRelease) &&
@@ -90,52 +92,62 @@ int ssb_fabric_create(int32_t rank, int32_t world, int32_t device, uint64_t aren
     CUmemAllocationProp prop = fabric_prop(device);
     CUresult rc = f->memGetGranularity(&f->granularity, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED);
     if (rc != CUDA_SUCCESS) return fabric_fail(f, "cuMemGetAllocationGranularity", rc);
-    f->arena_bytes = (arena_bytes + f->granularity - 1) / f->granularity * f->granularity;
-    rc = f->memCreate(&f->arena[rank], f->arena_bytes, &prop, 0);
-    if (rc != CUDA_SUCCESS) return fabric_fail(f, "cuMemCreate", rc);
-    f->have[rank] = true;
-    int fd = -1;
-    rc = f->memExport(&fd, f->arena[rank], CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0);
-    if (rc != CUDA_SUCCESS) return fabric_fail(f, "cuMemExportToShareableHandle", rc);
-    *fd_out = fd;
     return 0;
 }
 
 uint64_t ssb_fabric_granularity(ssb_fabric_t *f) { return f ? f->granularity : 0; }
-uint64_t ssb_fabric_arena_bytes(ssb_fabric_t *f) { return f ? f->arena_bytes : 0; }
 
-int ssb_fabric_import(ssb_fabric_t *f, int32_t peer, int32_t fd) {
-    if (!f || peer < 0 || peer >= f->world || peer == f->rank) return -1;
-    CUresult rc = f->memImport(&f->arena[peer], (void *)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR);
-    if (rc != CUDA_SUCCESS) return ssb::fabric_fail(f, "cuMemImportFromShareableHandle", rc);
-    f->have[peer] = true;
-    close(fd);
-    return 0;
+// This rank's chunk of the next stitched array: physical memory on this GPU, exported as a file
+// descriptor for the peers.  Returns the array's index.  (cuMemMap cannot map a sub-range of an
+// allocation, so every array has its own allocation per rank.)
+int ssb_fabric_alloc(ssb_fabric_t *f, uint64_t chunk_bytes, int32_t *fd_out) {
+    using namespace ssb;
+    if (!f || !fd_out || chunk_bytes == 0) return -1;
+    ssb_fabric::Array a;
+    memset(&a, 0, sizeof a);
+    a.chunk = (chunk_bytes + f->granularity - 1) / f->granularity * f->granularity;
+    CUmemAllocationProp prop = fabric_prop(f->device);
+    CUresult rc = f->memCreate(&a.part[f->rank], a.chunk, &prop, 0);
+    if (rc != CUDA_SUCCESS) return fabric_fail(f, "cuMemCreate", rc);
+    a.have[f->rank] = true;
+    int fd = -1;
+    rc = f->memExport(&fd, a.part[f->rank], CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0);
+    if (rc != CUDA_SUCCESS) return fabric_fail(f, "cuMemExportToShareableHandle", rc);
+    *fd_out = fd;
+    f->arrays.push_back(a);
+    return (int)f->arrays.size() - 1;
 }
 
-// All ranks call this in the same order with the same chunk size.  base[p * chunk ..] lives on rank p.
-int ssb_fabric_map(ssb_fabric_t *f, uint64_t chunk_bytes, void **base_out) {
-    if (!f || !base_out) return -1;
-    for (int p = 0; p < f->world; p++) if (!f->have[p]) { snprintf(f->err, sizeof f->err, "arena of rank %d not imported", p); return -1; }
-    const size_t chunk = (chunk_bytes + f->granularity - 1) / f->granularity * f->granularity;
-    if (f->cursor + chunk > f->arena_bytes) { snprintf(f->err, sizeof f->err, "arena exhausted (%zu + %zu > %zu)", f->cursor, chunk, f->arena_bytes); return -1; }
-    CUdeviceptr base = 0;
-    CUresult rc = f->memAddressReserve(&base, chunk * f->world, f->granularity, 0, 0);
-    if (rc != CUDA_SUCCESS) return ssb::fabric_fail(f, "cuMemAddressReserve", rc);
+// Import the peers' chunks of array `index` (fds[p] for every p != rank; closed here) and map the
+// stitched array: base[p * chunk ..] lives on rank p.
+int ssb_fabric_map(ssb_fabric_t *f, int32_t index, const int32_t *fds, void **base_out) {
+    using namespace ssb;
+    if (!f || !base_out || index < 0 || index >= (int)f->arrays.size() || (f->world > 1 && !fds)) return -1;
+    ssb_fabric::Array &a = f->arrays[index];
+    if (a.mapped) { snprintf(f->err, sizeof f->err, "array %d already mapped", index); return -1; }
+    CUresult rc;
     for (int p = 0; p < f->world; p++) {
-        rc = f->memMap(base + (size_t)p * chunk, chunk, f->cursor, f->arena[p], 0);
-        if (rc != CUDA_SUCCESS) return ssb::fabric_fail(f, "cuMemMap", rc);
+        if (p == f->rank) continue;
+        rc = f->memImport(&a.part[p], (void *)(uintptr_t)fds[p], CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR);
+        if (rc != CUDA_SUCCESS) return fabric_fail(f, "cuMemImportFromShareableHandle", rc);
+        a.have[p] = true;
+        close(fds[p]);
+    }
+    rc = f->memAddressReserve(&a.base, a.chunk * f->world, f->granularity, 0, 0);
+    if (rc != CUDA_SUCCESS) return fabric_fail(f, "cuMemAddressReserve", rc);
+    for (int p = 0; p < f->world; p++) {
+        rc = f->memMap(a.base + (size_t)p * a.chunk, a.chunk, 0, a.part[p], 0);
+        if (rc != CUDA_SUCCESS) return fabric_fail(f, "cuMemMap", rc);
     }
     CUmemAccessDesc acc;
     memset(&acc, 0, sizeof acc);
     acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
     acc.location.id = f->device;
     acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
-    rc = f->memSetAccess(base, chunk * f->world, &acc, 1);
-    if (rc != CUDA_SUCCESS) return ssb::fabric_fail(f, "cuMemSetAccess", rc);
-    f->maps.push_back({base, chunk});
-    f->cursor += chunk;
-    *base_out = (void *)base;
+    rc = f->memSetAccess(a.base, a.chunk * f->world, &acc, 1);
+    if (rc != CUDA_SUCCESS) return fabric_fail(f, "cuMemSetAccess", rc);
+    a.mapped = true;
+    *base_out = (void *)a.base;
     return 0;
 }
 
@@ -156,11 +168,13 @@ int ssb_fabric_destroy(ssb_fabric_t *f) {
     if (!f) return 0;
     cudaSetDevice(f->device);
     cudaDeviceSynchronize();
-    for (auto &m : f->maps) {
-        f->memUnmap(m.base, m.chunk * f->world);
-        f->memAddressFree(m.base, m.chunk * f->world);
+    for (auto &a : f->arrays) {
+        if (a.mapped) {
+            f->memUnmap(a.base, a.chunk * f->world);
+            f->memAddressFree(a.base, a.chunk * f->world);
+        }
+        for (int p = 0; p < f->world; p++) if (a.have[p]) f->memRelease(a.part[p]);
     }
-    for (int p = 0; p < f->world; p++) if (f->have[p]) f->memRelease(f->arena[p]);
     delete f;
     return 0;
 }

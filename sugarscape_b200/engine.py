@@ -52,14 +52,12 @@ def load_library():
     L.ssb_compact.argtypes = [E, C.c_int32, C.c_void_p]
     L.ssb_reduce_stats.argtypes = [E, C.c_int32, C.c_void_p]
     F = C.c_void_p
-    L.ssb_fabric_create.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.POINTER(F), C.POINTER(C.c_int32)]
-    L.ssb_fabric_import.argtypes = [F, C.c_int32, C.c_int32]
-    L.ssb_fabric_map.argtypes = [F, C.c_uint64, C.POINTER(C.c_void_p)]
+    L.ssb_fabric_create.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(F)]
+    L.ssb_fabric_alloc.argtypes = [F, C.c_uint64, C.POINTER(C.c_int32)]
+    L.ssb_fabric_map.argtypes = [F, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_void_p)]
     L.ssb_fabric_copy.argtypes = [F, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32]
     L.ssb_fabric_granularity.argtypes = [F]
     L.ssb_fabric_granularity.restype = C.c_uint64
-    L.ssb_fabric_arena_bytes.argtypes = [F]
-    L.ssb_fabric_arena_bytes.restype = C.c_uint64
     L.ssb_fabric_destroy.argtypes = [F]
     L.ssb_fabric_last_error.argtypes = [F]
     L.ssb_fabric_last_error.restype = C.c_char_p
@@ -95,7 +93,7 @@ EXPORTED_SYMBOLS = (
     "ssb_set_mt_state", "ssb_get_mt_state", "ssb_set_step_tables", "ssb_set_epochs", "ssb_set_mark_shift", "ssb_set_l2_persist",
     "ssb_sizeof_params", "ssb_sizeof_grid", "ssb_sizeof_agents", "ssb_sizeof_stats",
     "ssb_env_step", "ssb_agent_step", "ssb_compact", "ssb_bind_endowments", "ssb_replace", "ssb_reduce_stats", "ssb_step", "ssb_stats", "ssb_stats_history",
-    "ssb_fabric_create", "ssb_fabric_import", "ssb_fabric_map", "ssb_fabric_copy", "ssb_fabric_granularity", "ssb_fabric_arena_bytes",
+    "ssb_fabric_create", "ssb_fabric_alloc", "ssb_fabric_map", "ssb_fabric_copy", "ssb_fabric_granularity",
     "ssb_fabric_destroy", "ssb_fabric_last_error", "ssb_set_shard", "ssb_shard_barrier", "ssb_shard_broken",
     "ssb_sync", "ssb_pollution_buffer", "ssb_test_pow", "ssb_round_trace", "ssb_launch_count", "ssb_timing", "ssb_enable_timing",
 )

@@ -17,6 +17,7 @@ import numpy as np
 from . import layout
 from .engine import Engine, EngineError, load_library
 
+FDS_PER_MESSAGE = 64
 LOCAL_AGENT_FIELDS = ("order", "free_slots", "dead_list")      # per rank; everything else is indexed by global slot
 
 
@@ -60,10 +61,12 @@ def shard_host_state(state, world):
     return new, lists
 
 
-def exchange_fds(rank, world, fd, tag, barrier):
-    """All-to-all of one file descriptor per rank over unix sockets (SCM_RIGHTS)."""
+def exchange_fds(rank, world, fds, tag, barrier):
+    """All-to-all of a list of file descriptors per rank over unix sockets (SCM_RIGHTS).
+    Returns {rank: [fds]} (this rank's own list included as given)."""
+    fds = list(fds)
     if world == 1:
-        return {rank: fd}
+        return {rank: fds}
     path = lambda r: f"/tmp/ssb_fabric_{tag}_{r}.sock"
     if os.path.exists(path(rank)):
         os.unlink(path(rank))
@@ -77,13 +80,21 @@ def exchange_fds(rank, world, fd, tag, barrier):
                 continue
             with socket.socket(socket.AF_UNIX, socket.SOCK_STREAM) as c:
                 c.connect(path(r))
-                socket.send_fds(c, [struct.pack("i", rank)], [fd])
-        fds = {rank: fd}
+                for i in range(0, len(fds), FDS_PER_MESSAGE):
+                    # (a message's ancillary data is a barrier for recvmsg: descriptors of two messages never merge)
+                    socket.send_fds(c, [struct.pack("ii", rank, i)], fds[i:i + FDS_PER_MESSAGE])
+        out = {rank: fds}
         for _ in range(world - 1):
             conn, _ = server.accept()
             with conn:
-                msg, got, _, _ = socket.recv_fds(conn, 16, 1)
-            fds[struct.unpack("i", msg[:4])[0]] = got[0]
+                got = []
+                while len(got) < len(fds):
+                    msg, part, _, _ = socket.recv_fds(conn, 8, FDS_PER_MESSAGE)
+                    src, at = struct.unpack("ii", msg)
+                    assert at == len(got) and part
+                    got += part
+            out[src] = got
+        fds = out
         barrier()
     finally:
         server.close()
@@ -214,21 +225,25 @@ class ShardedEngine(Engine):
         gran = 2 << 20
         roundup = lambda b: (b + gran - 1) // gran * gran
         chunk = {key: roundup(-(-n // world) * np.dtype(dt).itemsize) for key, n, dt in plan}
-        fd = C.c_int32(-1)
-        self._fcheck(L.ssb_fabric_create(rank, world, self.device.index, sum(chunk.values()), C.byref(self.fabric), C.byref(fd)))
+        self._fcheck(L.ssb_fabric_create(rank, world, self.device.index, C.byref(self.fabric)))
         if int(L.ssb_fabric_granularity(self.fabric)) > gran or gran % int(L.ssb_fabric_granularity(self.fabric)):
             raise EngineError("unexpected allocation granularity %d" % L.ssb_fabric_granularity(self.fabric))
-        fds = exchange_fds(rank, world, fd.value, self.tag, self.dist.barrier)
-        for r, peer_fd in fds.items():
-            if r != rank:
-                self._fcheck(L.ssb_fabric_import(self.fabric, r, peer_fd))
-        os.close(fd.value)
+        mine = []
+        for i, (key, n, dt) in enumerate(plan):          # this rank's chunk of every array
+            fd = C.c_int32(-1)
+            if L.ssb_fabric_alloc(self.fabric, chunk[key], C.byref(fd)) != i:
+                self._fcheck(-1)
+            mine.append(fd.value)
+        fds = exchange_fds(rank, world, mine, self.tag, self.dist.barrier)
         self.stitched, self.chunk = {}, chunk
-        for key, n, dt in plan:
+        for i, (key, n, dt) in enumerate(plan):
             base = C.c_void_p()
-            self._fcheck(L.ssb_fabric_map(self.fabric, chunk[key], C.byref(base)))
+            per_rank = (C.c_int32 * world)(*[fds[r][i] for r in range(world)])
+            self._fcheck(L.ssb_fabric_map(self.fabric, i, per_rank, C.byref(base)))
             view_dt = np.int32 if np.dtype(dt) == np.uint32 else dt       # like Engine._to_device
             self.stitched[key] = StitchedArray(self, base.value, world * chunk[key] // np.dtype(dt).itemsize, view_dt, chunk[key])
+        for fd in mine:
+            os.close(fd)
         # this rank zeroes / fills the memory it backs, then uploads its slab and its slots
         for key, n, dt in plan:
             per = chunk[key] // np.dtype(dt).itemsize

@@ -65,12 +65,17 @@ import torch.distributed as dist
 from sugarscape_b200 import sharded
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
-r, w = os.pipe()
-os.write(w, b"hello from %d" % rank)
-fds = sharded.exchange_fds(rank, world, r, "t" + os.environ["MASTER_PORT"], dist.barrier)
-for src, fd in sorted(fds.items()):
-    if src != rank:          # (the peer drains this rank's pipe)
-        assert os.read(fd, 64) == b"hello from %d" % src, (rank, src)
+mine = []
+for i in range(150):         # more than one SCM_RIGHTS message
+    r, w = os.pipe()
+    os.write(w, b"hello %d from %d" % (i, rank))
+    mine.append(r)
+fds = sharded.exchange_fds(rank, world, mine, "t" + os.environ["MASTER_PORT"], dist.barrier)
+for src, got in sorted(fds.items()):
+    assert len(got) == 150
+    if src != rank:          # (the peer drains this rank's pipes)
+        for i, fd in enumerate(got):
+            assert os.read(fd, 64) == b"hello %d from %d" % (i, src), (rank, src, i)
 print("FD_EXCHANGE_OK", rank, flush=True)
 dist.destroy_process_group()
 """
