@@ -229,7 +229,7 @@ typedef struct ssb_shard_t {
     int64_t slot_lo, slot_hi;       /* the agent slots this rank allocates from                      */
     void   *ctrl;                   /* stitched control pages, zeroed: chunk p = rank p's page        */
     uint64_t ctrl_stride;           /* bytes between pages (>= 4096)                                  */
-    void   *marks;                  /* stitched reservation marks (u32 per cell of the whole map)     */
+    void   *marks;                  /* stitched reservation marks: u32 per (coarsened) cell, see ssb_set_mark_shift */
     uint64_t marks_stride;          /* bytes per rank chunk                                           */
     void   *gather;                 /* stitched scratch for candidate / wealth-key all-gathers        */
     uint64_t gather_stride;         /* bytes per rank chunk: >= 8 * (4 + 1) * slots per rank          */

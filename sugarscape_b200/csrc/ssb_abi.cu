@@ -529,7 +529,7 @@ int ssb_set_shard(ssb_engine_t *e, const ssb_shard_t *sd) {
     // (derived from the stride so that every rank uses the same layout)
     e->local_slots = (int64_t)(sd->gather_stride / 8 / 5);
     if (e->local_slots < sd->slot_hi - sd->slot_lo) return fail(e, -1, "gather scratch too small: %lld bytes per rank needed", (long long)(8 * 5 * (sd->slot_hi - sd->slot_lo)));
-    if (sd->marks_stride * (uint64_t)sd->world < sizeof(uint32_t) * (uint64_t)cells) return fail(e, -1, "stitched mark array too small");
+    if (sd->marks_stride * (uint64_t)sd->world < sizeof(uint32_t) * (uint64_t)e->rc.wc * (uint64_t)e->rc.hc) return fail(e, -1, "stitched mark array too small");
     ShardCtx &sh = e->sh;
     sh.rank = sd->rank; sh.world = sd->world;
     sh.cell_lo = sd->cell_lo; sh.cell_hi = sd->cell_hi; sh.slot_lo = sd->slot_lo; sh.slot_hi = sd->slot_hi;

@@ -111,7 +111,12 @@ __device__ __forceinline__ bool shard_grid_sync(cg::grid_group &grid, const Shar
         if (sum_out) *sum_out = payload ? (unsigned long long)*(const volatile int32_t *)payload : 0ull;
         return true;
     }
-    __threadfence_system();                       // this thread's remote writes are performed
+    // Everything this block wrote (also into the peers' HBM) is performed system-wide before the
+    // block arrives at the grid barrier: block barrier, then ONE system-scope fence, which is
+    // cumulative over the writes it observed through the barrier (the pattern of NCCL's
+    // primitives: workers -> bar.sync -> the posting thread fences and stores the flag).
+    __syncthreads();
+    if (threadIdx.x == 0) __threadfence_system();
     grid.sync();
     if (blockIdx.x == 0 && threadIdx.x < 32) {
         unsigned long long out[SHARD_PAYLOAD] = {payload ? (unsigned long long)*(const volatile int32_t *)payload : 0ull, 0, 0, 0, 0, 0, 0};

@@ -196,6 +196,10 @@ class ShardedEngine(Engine):
         import torch.distributed as dist
         self.rank, self.world, self.my_list, self.dist = rank, world, np.asarray(my_list, dtype=np.int32), dist
         self.fabric = C.c_void_p()
+        if mark_shift is None:         # the engine's own default (ssb_bind): 2 x 2 blocks when the map allows it
+            W, H = host_state.width, host_state.height
+            maxd = max(min(params.max_agent_range, W // 2), min(params.max_agent_range, H // 2))
+            mark_shift = 1 if (W % 2 == 0 and H % 2 == 0 and ((maxd + 2) >> 1) + 2 < (W >> 1) and ((maxd + 2) >> 1) + 2 < (H >> 1)) else 0
         self.mark_shift = mark_shift
         self.tag = f"{os.environ.get('MASTER_PORT', '0')}_{tag}"
         super().__init__(params, host_state, device, endow_bits, tag_bits)
@@ -220,7 +224,8 @@ class ShardedEngine(Engine):
         # (key, elements, dtype) of every stitched array, in mapping order (identical on all ranks)
         plan = [(name, n_cells, dt) for name, dt in layout.GRID_FIELDS]
         plan += [("a_" + name, cap, dt) for name, dt, _ in layout.AGENT_FIELDS if name not in LOCAL_AGENT_FIELDS]
-        plan += [("_ctrl", 512 * world, np.uint64), ("_marks", n_cells, np.uint32),
+        n_marks = (self.width >> self.mark_shift) * (self.height >> self.mark_shift)      # split like the slabs
+        plan += [("_ctrl", 512 * world, np.uint64), ("_marks", n_marks, np.uint32),
                  ("_gather", 5 * local_slots * world, np.uint64)]
         gran = 2 << 20
         roundup = lambda b: (b + gran - 1) // gran * gran
@@ -277,8 +282,7 @@ class ShardedEngine(Engine):
         tensor[lo:hi].copy_(self.torch.from_numpy(np.ascontiguousarray(arr)))
 
     def _after_bind(self):
-        if self.mark_shift is not None:
-            self.set_mark_shift(self.mark_shift)
+        self.set_mark_shift(self.mark_shift)
         sd = layout.Shard()
         sd.rank, sd.world = self.rank, self.world
         sd.cell_lo, sd.cell_hi, sd.slot_lo, sd.slot_hi = self.cell_lo, self.cell_hi, self.slot_lo, self.slot_hi
