@@ -114,6 +114,7 @@ typedef struct ssb_grid {
 #define SSB_C_N_KIN    8  /* used entries of the kin pool                                     */
 #define SSB_C_ENDOW_INDEX 9 /* sugarscape.agentEndowmentIndex                                  */
 #define SSB_C_N_REPLACED 10 /* agents created by the last replacement                           */
+#define SSB_C_N_MIGRATED 11 /* sharded: agents this rank handed to other ranks in the last step */
 #define SSB_C_COUNT    16
 
 typedef struct ssb_agents {
@@ -238,6 +239,9 @@ typedef struct ssb_shard_t {
  * first step; grid and agent arrays bound must be stitched.  Per-rank state: order[], free_slots[],
  * dead_list[], counters[] (N_LIST / N_SLOTS / N_FREE are per rank; NEXT_ID / ENDOW_INDEX global). */
 int  ssb_set_shard(ssb_engine_t *e, const ssb_shard_t *shard);
+/* last phase of a sharded step (ssb_step calls it): records of agents that walked onto another
+ * rank's slab move to that rank (slot of its range, its list); collective, no-op unless sharded */
+int  ssb_migrate(ssb_engine_t *e, int32_t t, void *stream);
 /* box-wide barrier on `stream` (orders the peers' later kernels after this rank's earlier ones) */
 int  ssb_shard_barrier(ssb_engine_t *e, void *stream);
 /* 1 if a box-wide barrier timed out (a peer is gone); the engine is unusable afterwards */

@@ -11,6 +11,7 @@
 #include "ssb_kernels.cuh"
 #include "ssb_sort.cuh"
 #include "ssb_replace.cuh"
+#include "ssb_migrate.cuh"
 #include "ssb_fabric.cuh"
 
 using namespace ssb;
@@ -44,7 +45,7 @@ struct ssb_engine {
     ssb_stats_t *d_stats;
     ssb_stats_t *d_ring;     // last SSB_STATS_RING steps, so that K steps can run without host syncs
     uint64_t *d_keys_a, *d_keys_b;
-    uint32_t *d_radix_hist;
+    uint32_t *d_radix_hist, *d_radix_rows;
     double *d_lorenz_blocks;
     // timing
     bool timing;
@@ -62,6 +63,7 @@ struct ssb_engine {
     ShardCtx sh;
     uint32_t *local_marks;   // the engine's own mark array (replaced by the stitched one when sharded)
     int64_t local_slots;     // slots per rank = capacity of the per-rank parts of the gather scratch
+    MigratePlan *d_migrate;
     unsigned long long *d_shard_vals;   // [0] = box population, [1..2] = OR / AND of all wealth keys, [8..] msg
 };
 
@@ -157,7 +159,7 @@ void ssb_destroy(ssb_engine_t *e) {
     void *ptrs[] = {e->d_mt, e->d_endow, e->d_tagbits, e->d_tile_counts, e->d_new_order, e->d_scalars,
                     e->d_born_list, e->rc.mark, e->rc.list_a, e->rc.list_b, e->rc.ready, e->rc.cnt, e->rc.trace, e->rc.bucketed, e->rc.epoch_count, e->rc.epoch_start, e->rc.epoch_fill,
                     e->d_partials, e->d_tribes, e->d_stats, e->d_ring, e->d_keys_a, e->d_keys_b, e->d_radix_hist,
-                    e->d_lorenz_blocks, e->d_plan, e->d_cand, e->sh.peer_vals, e->sh.flags, e->d_shard_vals};
+                    e->d_lorenz_blocks, e->d_plan, e->d_cand, e->sh.peer_vals, e->sh.flags, e->d_shard_vals, e->d_migrate};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < 5; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
     delete e;
@@ -194,7 +196,8 @@ int ssb_bind(ssb_engine_t *e, const ssb_grid_t *grid, const ssb_agents_t *agents
     CU(cudaMalloc(&e->d_keys_a, sizeof(uint64_t) * cap));
     CU(cudaMalloc(&e->d_keys_b, sizeof(uint64_t) * cap));
     const int64_t radix_tiles = (cap + RADIX_TILE - 1) / RADIX_TILE;
-    CU(cudaMalloc(&e->d_radix_hist, sizeof(uint32_t) * 256 * radix_tiles));
+    CU(cudaMalloc(&e->d_radix_hist, sizeof(uint32_t) * (256 * radix_tiles + 256)));      // + the 256 row totals
+    e->d_radix_rows = e->d_radix_hist + 256 * radix_tiles;
     CU(cudaMalloc(&e->d_lorenz_blocks, sizeof(double) * e->num_sms * 4));
     if (e->p.rng_mode == SSB_RNG_SCALABLE) {
         RoundCtx &rc = e->rc;
@@ -464,8 +467,8 @@ int ssb_replace(ssb_engine_t *e, int32_t t, void *stream_) {
         const unsigned long long *varying = e->d_plan->varying;
         for (int shift = 0; shift < 64; shift += 8) {      // 8 passes: the result lands back in `src`
             k_radix_hist<<<tiles, RADIX_THREADS, 0, st>>>(src, n_ptr, shift, e->d_radix_hist, varying); LAUNCHED(e);
-            k_radix_scan<<<1, RADIX_THREADS, 0, st>>>(e->d_radix_hist, n_ptr, shift, varying); LAUNCHED(e);
-            k_radix_scatter<<<tiles, RADIX_THREADS, 0, st>>>(src, dst, n_ptr, shift, e->d_radix_hist, varying); LAUNCHED(e);
+            k_radix_scan<<<256, RADIX_THREADS, 0, st>>>(e->d_radix_hist, n_ptr, shift, varying, e->d_radix_rows); LAUNCHED(e);
+            k_radix_scatter<<<tiles, RADIX_THREADS, 0, st>>>(src, dst, n_ptr, shift, e->d_radix_hist, varying, e->d_radix_rows); LAUNCHED(e);
             uint64_t *tmp = src; src = dst; dst = tmp;
         }
     }
@@ -502,14 +505,24 @@ int ssb_reduce_stats(ssb_engine_t *e, int32_t t, void *stream_) {
     uint64_t *src = e->d_keys_a, *dst = e->d_keys_b;
     for (int shift = 0; shift < 64; shift += 8) {
         k_radix_hist<<<tiles, RADIX_THREADS, 0, st>>>(src, n_ptr, shift, e->d_radix_hist, varying); LAUNCHED(e);
-        k_radix_scan<<<1, RADIX_THREADS, 0, st>>>(e->d_radix_hist, n_ptr, shift, varying); LAUNCHED(e);
-        k_radix_scatter<<<tiles, RADIX_THREADS, 0, st>>>(src, dst, n_ptr, shift, e->d_radix_hist, varying); LAUNCHED(e);
+        k_radix_scan<<<256, RADIX_THREADS, 0, st>>>(e->d_radix_hist, n_ptr, shift, varying, e->d_radix_rows); LAUNCHED(e);
+        k_radix_scatter<<<tiles, RADIX_THREADS, 0, st>>>(src, dst, n_ptr, shift, e->d_radix_hist, varying, e->d_radix_rows); LAUNCHED(e);
         uint64_t *tmp = src; src = dst; dst = tmp;
     }
     const int lb = e->num_sms * 4;
     k_lorenz<<<lb, 256, 0, st>>>((const double *)src, n_ptr, e->d_lorenz_blocks); LAUNCHED(e);
     k_lorenz_final<<<1, 1, 0, st>>>(e->d_lorenz_blocks, lb, e->d_stats, e->d_ring + (((t % SSB_STATS_RING) + SSB_STATS_RING) % SSB_STATS_RING)); LAUNCHED(e);
     if (e->timing) { CU(cudaEventRecord(e->ev[4], st)); e->ev_recorded = true; }
+    return 0;
+}
+
+// placeholder to keep the phase events of a sharded step meaningful: ssb_step runs the migration
+// after the stats and re-records the last event
+static int step_tail(ssb_engine *e, int32_t t, void *stream) {
+    if (!e->sharded) return 0;
+    int rc = ssb_migrate(e, t, stream);
+    if (rc) return rc;
+    if (e->timing) CU(cudaEventRecord(e->ev[4], (cudaStream_t)stream));
     return 0;
 }
 
@@ -539,6 +552,14 @@ int ssb_set_shard(ssb_engine_t *e, const ssb_shard_t *sd) {
     CU(cudaMemset(sh.peer_vals, 0, sizeof(unsigned long long) * SSB_MAX_RANKS * SHARD_PAYLOAD));
     CU(cudaMalloc(&sh.flags, sizeof(unsigned long long) * 8));
     CU(cudaMemset(sh.flags, 0, sizeof(unsigned long long) * 8));
+    for (int r = 0; r < SSB_MAX_RANKS; r++) {
+        const int64_t x_end = r < sd->world ? (int64_t)e->p.width * (r + 1) / sd->world : e->p.width;
+        sh.cell_end[r] = x_end * e->p.height;
+    }
+    if (sh.cell_end[sd->rank] != sd->cell_hi || (sd->rank > 0 ? sh.cell_end[sd->rank - 1] : 0) != sd->cell_lo)
+        return fail(e, -1, "slab of rank %d must be x-lines [width * r / world, width * (r + 1) / world)", sd->rank);
+    CU(cudaMalloc(&e->d_migrate, sizeof(MigratePlan)));
+    CU(cudaMemset(e->d_migrate, 0, sizeof(MigratePlan)));
     CU(cudaMalloc(&e->d_shard_vals, sizeof(unsigned long long) * 16));
     CU(cudaMemset(e->d_shard_vals, 0, sizeof(unsigned long long) * 16));
     e->local_marks = e->rc.mark;
@@ -548,6 +569,30 @@ int ssb_set_shard(ssb_engine_t *e, const ssb_shard_t *sd) {
     const long long n_marks = (long long)e->rc.wc * e->rc.hc, per = (long long)(sd->marks_stride / sizeof(uint32_t));
     sh.mark_lo = per * sd->rank < n_marks ? per * sd->rank : n_marks;
     sh.mark_hi = per * (sd->rank + 1) < n_marks ? per * (sd->rank + 1) : n_marks;
+    return 0;
+}
+
+int ssb_migrate(ssb_engine_t *e, int32_t t, void *stream_) {
+    CHECK_BOUND(e);
+    if (!e->sharded) return 0;
+    cudaStream_t st = (cudaStream_t)stream_;
+    DevCtx c = step_ctx(e, t, 0.0);
+    MigratePlan *mp = e->d_migrate;
+    long long *overflow = (long long *)c.a.counters + SSB_C_OVERFLOW;
+    const long long box_cap = 4 * e->local_slots / SSB_MAX_RANKS;      // outboxes share the candidate part of the scratch
+    const int blocks = e->num_sms * 4;
+    k_migrate_reset<<<1, 32, 0, st>>>(mp); LAUNCHED(e);
+    k_migrate_out<<<blocks, 256, 0, st>>>(c, mp, box_cap); LAUNCHED(e);
+    k_migrate_pack<<<1, 32, 0, st>>>(c, mp, box_cap); LAUNCHED(e);
+    k_migrate_holes<<<blocks, 256, 0, st>>>(c, mp, e->d_new_order, e->d_born_list); LAUNCHED(e);
+    k_migrate_fill<<<blocks, 256, 0, st>>>(c, mp, e->d_new_order, e->d_born_list); LAUNCHED(e);
+    k_migrate_out_finish<<<1, 1, 0, st>>>(c, mp); LAUNCHED(e);
+    k_shard_barrier<<<1, 32, 0, st>>>(e->sh, mp->msg, overflow); LAUNCHED(e);
+    k_migrate_in<<<blocks, 256, 0, st>>>(c, box_cap); LAUNCHED(e);
+    k_migrate_in_finish<<<1, 1, 0, st>>>(c); LAUNCHED(e);
+    k_shard_barrier<<<1, 32, 0, st>>>(e->sh, nullptr, overflow); LAUNCHED(e);
+    k_migrate_recycle<<<blocks, 256, 0, st>>>(c, mp, box_cap); LAUNCHED(e);
+    k_migrate_recycle_finish<<<1, 1, 0, st>>>(c, mp); LAUNCHED(e);
     return 0;
 }
 
@@ -573,7 +618,8 @@ int ssb_step(ssb_engine_t *e, int32_t t, double prev_mean_wealth, void *stream) 
     if ((rc = ssb_agent_step(e, t, prev_mean_wealth, stream))) return rc;
     if ((rc = ssb_compact(e, t, stream))) return rc;
     if (e->p.rng_mode == SSB_RNG_SCALABLE && e->p.agent_replacements > 0 && (rc = ssb_replace(e, t, stream))) return rc;
-    return ssb_reduce_stats(e, t, stream);
+    if ((rc = ssb_reduce_stats(e, t, stream))) return rc;
+    return step_tail(e, t, stream);
 }
 
 int ssb_stats(ssb_engine_t *e, ssb_stats_t *host_out) {

@@ -33,6 +33,7 @@ struct ShardCtx {
     long long cell_lo, cell_hi;                    // cells of this rank's slab
     long long slot_lo, slot_hi;                    // slots this rank allocates from
     long long mark_lo, mark_hi;                    // mark words this rank clears
+    long long cell_end[SSB_MAX_RANKS];             // rank r owns the cells below cell_end[r] (and not below cell_end[r - 1])
     unsigned long long *ctrl;                      // stitched: rank p's page at ctrl + p * ctrl_stride
     long long ctrl_stride;                         // in 64-bit words
     unsigned long long *gather;                    // stitched scratch, rank p's part at gather + p * gather_stride

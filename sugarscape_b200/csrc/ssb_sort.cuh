@@ -2,8 +2,8 @@
 // wealths for the Lorenz / Gini reduction (reference sugarscape.py:913-934 sorts the wealth list).
 // Non-negative doubles sort correctly as their raw bit patterns.
 //
-// Per pass: k_radix_hist (per-tile digit histograms, digit-major) -> k_radix_scan (exclusive scan
-// of the whole table, one block) -> k_radix_scatter (stable: warp match-any ranking in striped
+// Per pass: k_radix_hist (per-tile digit histograms, digit-major) -> k_radix_scan (one block per
+// digit row: exclusive scan of the row + row total) -> k_radix_scatter (stable: warp match-any ranking in striped
 // order, warps of a tile combined by a per-digit prefix).  n lives in device memory so that no
 // host synchronisation is needed between the compaction and the sort.
 #pragma once
@@ -41,18 +41,19 @@ __global__ void __launch_bounds__(RADIX_THREADS) k_radix_hist(const uint64_t *ke
     hist[(long long)threadIdx.x * n_tiles + blockIdx.x] = h[threadIdx.x];
 }
 
-// exclusive scan over hist[256 * n_tiles] (digit-major), single block: every thread owns a
-// contiguous chunk (serial), the chunk totals are scanned across the block
+// Scan of the digit-major histogram table hist[256][n_tiles], one block per digit row: the row is
+// scanned in place (exclusive) and its total goes to row_total[digit]; the scatter kernel adds the
+// exclusive prefix of the row totals.  Launch with 256 blocks.
 __global__ void __launch_bounds__(RADIX_THREADS) k_radix_scan(uint32_t *hist, const int64_t *n_ptr, int shift,
-                                                              const unsigned long long *varying) {
+                                                              const unsigned long long *varying, uint32_t *row_total) {
     if (digit_is_constant(varying, shift)) return;
     const long long n = *n_ptr;
     const int n_tiles = (int)((n + RADIX_TILE - 1) / RADIX_TILE);
-    const long long total = 256LL * n_tiles;
-    const long long chunk = (total + RADIX_THREADS - 1) / RADIX_THREADS;
-    const long long lo = (long long)threadIdx.x * chunk, hi = lo + chunk < total ? lo + chunk : total;
+    uint32_t *row = hist + (long long)blockIdx.x * n_tiles;
+    const int chunk = (n_tiles + RADIX_THREADS - 1) / RADIX_THREADS;
+    const int lo = min((int)threadIdx.x * chunk, n_tiles), hi = min(lo + chunk, n_tiles);
     uint32_t sum = 0;
-    for (long long i = lo; i < hi; i++) sum += hist[i];
+    for (int i = lo; i < hi; i++) sum += row[i];
     __shared__ uint32_t warp_sums[RADIX_WARPS];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     uint32_t inc = sum;
@@ -66,12 +67,13 @@ __global__ void __launch_bounds__(RADIX_THREADS) k_radix_scan(uint32_t *hist, co
     uint32_t base = 0;
     for (int j = 0; j < w; j++) base += warp_sums[j];
     uint32_t run = base + inc - sum;
-    for (long long i = lo; i < hi; i++) { const uint32_t v = hist[i]; hist[i] = run; run += v; }
+    for (int i = lo; i < hi; i++) { const uint32_t v = row[i]; row[i] = run; run += v; }
+    if (threadIdx.x == RADIX_THREADS - 1) row_total[blockIdx.x] = run;
 }
 
 __global__ void __launch_bounds__(RADIX_THREADS) k_radix_scatter(const uint64_t *keys, uint64_t *out, const int64_t *n_ptr,
                                                                  int shift, const uint32_t *hist,
-                                                                 const unsigned long long *varying) {
+                                                                 const unsigned long long *varying, const uint32_t *row_total) {
     const long long n = *n_ptr;
     const int n_tiles = (int)((n + RADIX_TILE - 1) / RADIX_TILE);
     if ((int)blockIdx.x >= n_tiles) return;
@@ -84,7 +86,24 @@ __global__ void __launch_bounds__(RADIX_THREADS) k_radix_scatter(const uint64_t 
         return;
     }
     __shared__ uint32_t cnt[RADIX_WARPS][256];
+    __shared__ uint32_t digit_base[256];
     for (int i = threadIdx.x; i < RADIX_WARPS * 256; i += RADIX_THREADS) (&cnt[0][0])[i] = 0;
+    {   // exclusive prefix of the row totals: where the keys of each digit start
+        const uint32_t mine = row_total[threadIdx.x];
+        uint32_t inc = mine;
+        const int ln = threadIdx.x & 31, wp = threadIdx.x >> 5;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (ln >= o) inc += u;
+        }
+        __shared__ uint32_t wsum[RADIX_WARPS];
+        if (ln == 31) wsum[wp] = inc;
+        __syncthreads();
+        uint32_t b = 0;
+        for (int j = 0; j < wp; j++) b += wsum[j];
+        digit_base[threadIdx.x] = b + inc - mine;
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const long long warp0 = (long long)blockIdx.x * RADIX_TILE + (long long)w * (32 * RADIX_ITEMS);
@@ -110,7 +129,7 @@ __global__ void __launch_bounds__(RADIX_THREADS) k_radix_scatter(const uint64_t 
     __syncthreads();
     {   // per digit: exclusive prefix over the warps of this tile, on top of the global offset
         const int d = threadIdx.x;
-        uint32_t running = hist[(long long)d * n_tiles + blockIdx.x];
+        uint32_t running = digit_base[d] + hist[(long long)d * n_tiles + blockIdx.x];
 #pragma unroll
         for (int j = 0; j < RADIX_WARPS; j++) {
             const uint32_t t = cnt[j][d];

@@ -63,6 +63,7 @@ def load_library():
     L.ssb_fabric_last_error.restype = C.c_char_p
     L.ssb_set_shard.argtypes = [E, C.POINTER(layout.Shard)]
     L.ssb_shard_barrier.argtypes = [E, C.c_void_p]
+    L.ssb_migrate.argtypes = [E, C.c_int32, C.c_void_p]
     L.ssb_shard_broken.argtypes = [E]
     L.ssb_bind_endowments.argtypes = [E, C.POINTER(layout.Endowments)]
     L.ssb_replace.argtypes = [E, C.c_int32, C.c_void_p]
@@ -94,7 +95,7 @@ EXPORTED_SYMBOLS = (
     "ssb_sizeof_params", "ssb_sizeof_grid", "ssb_sizeof_agents", "ssb_sizeof_stats",
     "ssb_env_step", "ssb_agent_step", "ssb_compact", "ssb_bind_endowments", "ssb_replace", "ssb_reduce_stats", "ssb_step", "ssb_stats", "ssb_stats_history",
     "ssb_fabric_create", "ssb_fabric_alloc", "ssb_fabric_map", "ssb_fabric_copy", "ssb_fabric_granularity",
-    "ssb_fabric_destroy", "ssb_fabric_last_error", "ssb_set_shard", "ssb_shard_barrier", "ssb_shard_broken",
+    "ssb_fabric_destroy", "ssb_fabric_last_error", "ssb_set_shard", "ssb_migrate", "ssb_shard_barrier", "ssb_shard_broken",
     "ssb_sync", "ssb_pollution_buffer", "ssb_test_pow", "ssb_round_trace", "ssb_launch_count", "ssb_timing", "ssb_enable_timing",
 )
 

@@ -54,7 +54,7 @@ def main():
     eng = sharded.ShardedEngine(params, global_state, lists[rank], rank, world, local, endow, tags)
     if replacing:
         eng.bind_endowments(pop.endowments)
-    remote = 0
+    remote, migrated = 0, 0
     for t in range(1, args.steps + 1):
         eng.step(t, 0.0)
         if eng.broken():
@@ -76,8 +76,12 @@ def main():
         n = int(eng.counters()[layout.C_N_LIST])
         pos = hs.a_pos[eng.tensors["a_order"][:n].cpu().numpy()]
         remote = int(np.sum((pos < eng.cell_lo) | (pos >= eng.cell_hi)))
+        assert remote == 0, f"rank {rank}: {remote} agents of its list stand on another rank's slab after the migration at t={t}"
+        slots = eng.tensors["a_order"][:n].cpu().numpy()
+        assert np.all((slots >= eng.slot_lo) & (slots < eng.slot_hi)), "a record outside this rank's slot range"
+        migrated += int(eng.counters()[layout.C_N_MIGRATED])
     print(f"SHARDED_PARITY_OK rank {rank}/{world} case {args.case} steps {args.steps} "
-          f"population {want_pop} own-list agents off-slab {remote}", flush=True)
+          f"population {want_pop} migrated away {migrated}", flush=True)
     eng.close()
     dist.destroy_process_group()
 
