@@ -19,7 +19,7 @@ assert units == 3000.0, units
 # the reference arm: only rank 0 works, the others exit 0 without output
 dist.barrier()
 dist.destroy_process_group()
-print("ok", rank)
+sys.stdout.write("rank%d-ok\n" % rank)
 """
 
 
@@ -30,7 +30,7 @@ def test_aggregate_over_two_gloo_ranks(tmp_path):
                           "--master-addr", "127.0.0.1", "--master-port", str(29400 + os.getpid() % 150), str(script)],
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
-    assert "ok 0" in out.stdout and "ok 1" in out.stdout
+    assert "rank0-ok" in out.stdout and "rank1-ok" in out.stdout
 
 
 def test_reference_arm_only_rank0_prints(tmp_path):
