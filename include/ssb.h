@@ -206,7 +206,7 @@ typedef struct ssb_stats {
 typedef struct ssb_engine ssb_engine_t;
 
 /* ---- sharding one simulation over the GPUs of a box (x-slabs) -------------
- * A "stitched" array is world chunks of equal size, chunk p backed by rank p's HBM (one process per
+ * A "stitched" array is world consecutive chunks, chunk p backed by rank p's HBM (one process per
  * GPU), mapped at consecutive addresses on every rank.  ssb_fabric_alloc() creates this rank's chunk
  * and exports it as a POSIX file descriptor; the host passes the descriptors between the ranks and
  * ssb_fabric_map() imports the peers' chunks and maps the array.  The host binds stitched arrays as
@@ -216,7 +216,8 @@ typedef struct ssb_engine ssb_engine_t;
 typedef struct ssb_fabric ssb_fabric_t;
 int  ssb_fabric_create(int32_t rank, int32_t world, int32_t device, ssb_fabric_t **out);
 int  ssb_fabric_alloc(ssb_fabric_t *f, uint64_t chunk_bytes, int32_t *fd_out);    /* returns the array index (>= 0) */
-int  ssb_fabric_map(ssb_fabric_t *f, int32_t index, const int32_t *fds, void **base_out);  /* fds[world]; closes the peers' */
+/* fds[world], chunk_bytes[world] (multiples of the granularity; chunk p follows chunk p - 1); closes the peers' fds */
+int  ssb_fabric_map(ssb_fabric_t *f, int32_t index, const int32_t *fds, const uint64_t *chunk_bytes, void **base_out);
 /* synchronous copies to / from stitched memory: kind 0 = host -> device, 1 = device -> host,
  * 2 = zero `bytes` at dst (src ignored).  Callers split ranges at chunk boundaries. */
 int  ssb_fabric_copy(ssb_fabric_t *f, void *dst, const void *src, uint64_t bytes, int32_t kind);
@@ -226,12 +227,13 @@ const char *ssb_fabric_last_error(ssb_fabric_t *f);
 
 typedef struct ssb_shard_t {
     int32_t rank, world;
-    int64_t cell_lo, cell_hi;       /* the cells of this rank's slab: [x_lo * H, x_hi * H)            */
+    int64_t cell_end[SSB_MAX_RANKS];/* rank r owns the cells [cell_end[r-1], cell_end[r]) -- whole x-lines; the host
+                                       balances the slabs by population                                   */
     int64_t slot_lo, slot_hi;       /* the agent slots this rank allocates from                      */
+    int64_t mark_lo, mark_hi;       /* the mark words this rank clears (the ranks' ranges partition the array) */
     void   *ctrl;                   /* stitched control pages, zeroed: chunk p = rank p's page        */
     uint64_t ctrl_stride;           /* bytes between pages (>= 4096)                                  */
     void   *marks;                  /* stitched reservation marks: u32 per (coarsened) cell, see ssb_set_mark_shift */
-    uint64_t marks_stride;          /* bytes per rank chunk                                           */
     void   *gather;                 /* stitched scratch for candidate / wealth-key all-gathers        */
     uint64_t gather_stride;         /* bytes per rank chunk: >= 8 * (4 + 1) * slots per rank          */
 } ssb_shard_t;

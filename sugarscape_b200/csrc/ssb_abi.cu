@@ -59,7 +59,7 @@ struct ssb_engine {
     uint64_t *d_cand;        // 4 quadrant regions of cand_capacity keys
     int64_t cand_capacity;
     // x-slab sharding (ssb_shard.cuh)
-    bool sharded;
+    bool sharded, epochs_set;
     ShardCtx sh;
     uint32_t *local_marks;   // the engine's own mark array (replaced by the stitched one when sharded)
     int64_t local_slots;     // slots per rank = capacity of the per-rank parts of the gather scratch
@@ -203,16 +203,23 @@ int ssb_bind(ssb_engine_t *e, const ssb_grid_t *grid, const ssb_agents_t *agents
         RoundCtx &rc = e->rc;
         // marks on 2 x 2 cell blocks when the map allows it: a quarter of the mark array and about
         // a third of the atomics, for ~1 % more commit rounds (profiles/README.md)
+        // (4 x 4 blocks for rule sets whose footprint is the bare cross -- no tagging / trade / births --
+        // on large maps: S2 measures 12 % faster agent steps, profiles/README.md)
         rc.mark_shift = 0;
         if ((e->p.width % 2) == 0 && (e->p.height % 2) == 0 && ((maxd + 2) >> 1) + 2 < (e->p.width >> 1) &&
             ((maxd + 2) >> 1) + 2 < (e->p.height >> 1)) rc.mark_shift = 1;
+        if (rc.mark_shift == 1 && !(e->p.flags & (SSB_F_TAGGING | SSB_F_TRADE | SSB_F_REPRO)) && cells >= (1LL << 24) &&
+            (e->p.width % 4) == 0 && (e->p.height % 4) == 0) rc.mark_shift = 2;
         rc.wc = e->p.width >> rc.mark_shift; rc.hc = e->p.height >> rc.mark_shift;
         CU(cudaMalloc(&rc.mark, sizeof(uint32_t) * (size_t)cells));
         CU(cudaMalloc(&rc.bucketed, sizeof(int4) * cap));
         CU(cudaMalloc(&rc.epoch_count, sizeof(int32_t) * MAX_EPOCHS));
         CU(cudaMalloc(&rc.epoch_start, sizeof(int32_t) * (MAX_EPOCHS + 1)));
         CU(cudaMalloc(&rc.epoch_fill, sizeof(int32_t) * MAX_EPOCHS));
-        rc.epochs = 128;
+        // priority epochs: 128, 256 from 8 M agents on (measured optimum 12 k .. 100 k agents per epoch)
+        int64_t n_list = 0;
+        CU(cudaMemcpy(&n_list, agents->counters + SSB_C_N_LIST, sizeof(n_list), cudaMemcpyDeviceToHost));
+        rc.epochs = n_list >= (8LL << 20) ? 256 : 128;
         if (rc.epochs > (1 << e->p.id_bits)) rc.epochs = 1 << e->p.id_bits;
         rc.epoch_shift = e->p.id_bits;
         for (int v = rc.epochs; v > 1; v >>= 1) rc.epoch_shift--;
@@ -266,6 +273,7 @@ int ssb_set_epochs(ssb_engine_t *e, int32_t epochs) {
     if (!e || !e->bound || e->p.rng_mode != SSB_RNG_SCALABLE) return fail(e, -1, "epochs need a bound scalable engine");
     if (epochs < 1 || epochs > MAX_EPOCHS || (epochs & (epochs - 1)) || epochs > (1 << e->p.id_bits)) return fail(e, -1, "epochs must be a power of two <= %d", MAX_EPOCHS);
     e->rc.epochs = epochs;
+    e->epochs_set = true;
     e->rc.epoch_shift = e->p.id_bits;
     for (int v = epochs; v > 1; v >>= 1) e->rc.epoch_shift--;
     return 0;
@@ -459,7 +467,7 @@ int ssb_replace(ssb_engine_t *e, int32_t t, void *stream_) {
         k_repl_gather<<<e->num_sms * 4, 256, 0, st>>>(c, e->d_plan, e->d_cand, e->cand_capacity, e->local_slots); LAUNCHED(e);
         k_repl_gather_counts<<<1, 32, 0, st>>>(c, e->d_plan, e->cand_capacity); LAUNCHED(e);
     }
-    const int tiles = (int)((e->cand_capacity + RADIX_TILE - 1) / RADIX_TILE);
+    const int tiles = grid_for(e->cand_capacity, RADIX_TILE, e->num_sms * 8);
     const int Q = __builtin_popcount(e->p.quad_mask & 15);
     for (int q = 0; q < Q; q++) {
         uint64_t *src = e->d_cand + (size_t)q * e->cand_capacity, *dst = e->d_keys_b;
@@ -492,7 +500,7 @@ int ssb_reduce_stats(ssb_engine_t *e, int32_t t, void *stream_) {
     if (e->p.rng_mode == SSB_RNG_EXACT) { k_stats_ordered<<<1, 32, 0, st>>>(c, e->d_stats); LAUNCHED(e); }
     // Lorenz numerator: sort the wealths (non-negative doubles order like their bit patterns)
     const int64_t cap = c.a.capacity;
-    const int tiles = (int)((cap + RADIX_TILE - 1) / RADIX_TILE);
+    const int tiles = grid_for(cap, RADIX_TILE, e->num_sms * 8);
     const int64_t *n_ptr = c.a.counters + SSB_C_N_LIST;
     const unsigned long long *varying = &e->d_tribes->key_or;
     if (e->sharded) {        // the Gini coefficient is box-wide: every rank gathers all keys and sorts them
@@ -534,41 +542,46 @@ int ssb_set_shard(ssb_engine_t *e, const ssb_shard_t *sd) {
     if (e->sharded) return fail(e, -1, "shard already set");
     if (sd->world == 1) return 0;
     const int64_t cells = e->ctx.g.n_cells, cap = e->ctx.a.capacity;
-    if (sd->cell_lo < 0 || sd->cell_hi > cells || sd->cell_lo >= sd->cell_hi || (sd->cell_lo % e->p.height) || (sd->cell_hi % e->p.height))
-        return fail(e, -1, "a slab must be a range of whole x-lines");
+    int64_t prev = 0;
+    for (int r = 0; r < sd->world; r++) {
+        if (sd->cell_end[r] < prev || (sd->cell_end[r] % e->p.height)) return fail(e, -1, "slabs must be consecutive ranges of whole x-lines");
+        prev = sd->cell_end[r];
+    }
+    if (prev != cells) return fail(e, -1, "the slabs must cover the map");
+    const int64_t cell_lo = sd->rank > 0 ? sd->cell_end[sd->rank - 1] : 0, cell_hi = sd->cell_end[sd->rank];
     if (sd->slot_lo < 0 || sd->slot_hi > cap || sd->slot_lo >= sd->slot_hi) return fail(e, -1, "bad slot range");
     if (!sd->ctrl || !sd->marks || !sd->gather || sd->ctrl_stride < 4096) return fail(e, -1, "stitched control / mark / gather arrays required");
     // per-rank part of the scratch: 4 candidate lists + the wealth keys, each of local_slots words
     // (derived from the stride so that every rank uses the same layout)
     e->local_slots = (int64_t)(sd->gather_stride / 8 / 5);
     if (e->local_slots < sd->slot_hi - sd->slot_lo) return fail(e, -1, "gather scratch too small: %lld bytes per rank needed", (long long)(8 * 5 * (sd->slot_hi - sd->slot_lo)));
-    if (sd->marks_stride * (uint64_t)sd->world < sizeof(uint32_t) * (uint64_t)e->rc.wc * (uint64_t)e->rc.hc) return fail(e, -1, "stitched mark array too small");
+    if (sd->mark_lo < 0 || sd->mark_hi < sd->mark_lo || sd->mark_hi > (int64_t)e->rc.wc * e->rc.hc) return fail(e, -1, "bad mark range");
     ShardCtx &sh = e->sh;
     sh.rank = sd->rank; sh.world = sd->world;
-    sh.cell_lo = sd->cell_lo; sh.cell_hi = sd->cell_hi; sh.slot_lo = sd->slot_lo; sh.slot_hi = sd->slot_hi;
+    sh.cell_lo = cell_lo; sh.cell_hi = cell_hi; sh.slot_lo = sd->slot_lo; sh.slot_hi = sd->slot_hi;
+    sh.mark_lo = sd->mark_lo; sh.mark_hi = sd->mark_hi;
+    for (int r = 0; r < SSB_MAX_RANKS; r++) sh.cell_end[r] = r < sd->world ? sd->cell_end[r] : cells;
     sh.ctrl = (unsigned long long *)sd->ctrl; sh.ctrl_stride = (long long)(sd->ctrl_stride / 8);
     sh.gather = (unsigned long long *)sd->gather; sh.gather_stride = (long long)(sd->gather_stride / 8);
     CU(cudaMalloc(&sh.peer_vals, sizeof(unsigned long long) * SSB_MAX_RANKS * SHARD_PAYLOAD));
     CU(cudaMemset(sh.peer_vals, 0, sizeof(unsigned long long) * SSB_MAX_RANKS * SHARD_PAYLOAD));
     CU(cudaMalloc(&sh.flags, sizeof(unsigned long long) * 8));
     CU(cudaMemset(sh.flags, 0, sizeof(unsigned long long) * 8));
-    for (int r = 0; r < SSB_MAX_RANKS; r++) {
-        const int64_t x_end = r < sd->world ? (int64_t)e->p.width * (r + 1) / sd->world : e->p.width;
-        sh.cell_end[r] = x_end * e->p.height;
-    }
-    if (sh.cell_end[sd->rank] != sd->cell_hi || (sd->rank > 0 ? sh.cell_end[sd->rank - 1] : 0) != sd->cell_lo)
-        return fail(e, -1, "slab of rank %d must be x-lines [width * r / world, width * (r + 1) / world)", sd->rank);
     CU(cudaMalloc(&e->d_migrate, sizeof(MigratePlan)));
     CU(cudaMemset(e->d_migrate, 0, sizeof(MigratePlan)));
     CU(cudaMalloc(&e->d_shard_vals, sizeof(unsigned long long) * 16));
     CU(cudaMemset(e->d_shard_vals, 0, sizeof(unsigned long long) * 16));
+    {   // the epoch default follows the box-wide population
+        int64_t n_list = 0;
+        CU(cudaMemcpy(&n_list, e->ctx.a.counters + SSB_C_N_LIST, sizeof(n_list), cudaMemcpyDeviceToHost));
+        if (!e->epochs_set && n_list * sd->world >= (8LL << 20) && (1 << e->p.id_bits) >= 256) {
+            e->rc.epochs = 256;
+            e->rc.epoch_shift = e->p.id_bits - 8;
+        }
+    }
     e->local_marks = e->rc.mark;
     e->rc.mark = (uint32_t *)sd->marks;
     e->sharded = true;
-    // the part of the marks this rank clears: what its own HBM backs (chunk p of the stitched array)
-    const long long n_marks = (long long)e->rc.wc * e->rc.hc, per = (long long)(sd->marks_stride / sizeof(uint32_t));
-    sh.mark_lo = per * sd->rank < n_marks ? per * sd->rank : n_marks;
-    sh.mark_hi = per * (sd->rank + 1) < n_marks ? per * (sd->rank + 1) : n_marks;
     return 0;
 }
 

@@ -20,7 +20,8 @@ struct ssb_fabric {
     int rank, world, device;
     size_t granularity;
     struct Array {
-        size_t chunk;
+        size_t chunk;                              // this rank's chunk
+        size_t size[SSB_MAX_RANKS], total;         // all chunks, once mapped
         CUmemGenericAllocationHandle part[SSB_MAX_RANKS];
         bool have[SSB_MAX_RANKS];
         CUdeviceptr base;
@@ -120,11 +121,18 @@ int ssb_fabric_alloc(ssb_fabric_t *f, uint64_t chunk_bytes, int32_t *fd_out) {
 
 // Import the peers' chunks of array `index` (fds[p] for every p != rank; closed here) and map the
 // stitched array: base[p * chunk ..] lives on rank p.
-int ssb_fabric_map(ssb_fabric_t *f, int32_t index, const int32_t *fds, void **base_out) {
+int ssb_fabric_map(ssb_fabric_t *f, int32_t index, const int32_t *fds, const uint64_t *chunk_bytes, void **base_out) {
     using namespace ssb;
-    if (!f || !base_out || index < 0 || index >= (int)f->arrays.size() || (f->world > 1 && !fds)) return -1;
+    if (!f || !base_out || !chunk_bytes || index < 0 || index >= (int)f->arrays.size() || (f->world > 1 && !fds)) return -1;
     ssb_fabric::Array &a = f->arrays[index];
     if (a.mapped) { snprintf(f->err, sizeof f->err, "array %d already mapped", index); return -1; }
+    a.total = 0;
+    for (int p = 0; p < f->world; p++) {
+        if (chunk_bytes[p] == 0 || chunk_bytes[p] % f->granularity) { snprintf(f->err, sizeof f->err, "chunk %d of array %d: %llu bytes is not a multiple of the granularity", p, index, (unsigned long long)chunk_bytes[p]); return -1; }
+        a.size[p] = chunk_bytes[p];
+        a.total += chunk_bytes[p];
+    }
+    if (a.size[f->rank] != a.chunk) { snprintf(f->err, sizeof f->err, "array %d: own chunk size mismatch", index); return -1; }
     CUresult rc;
     for (int p = 0; p < f->world; p++) {
         if (p == f->rank) continue;
@@ -133,18 +141,20 @@ int ssb_fabric_map(ssb_fabric_t *f, int32_t index, const int32_t *fds, void **ba
         a.have[p] = true;
         close(fds[p]);
     }
-    rc = f->memAddressReserve(&a.base, a.chunk * f->world, f->granularity, 0, 0);
+    rc = f->memAddressReserve(&a.base, a.total, f->granularity, 0, 0);
     if (rc != CUDA_SUCCESS) return fabric_fail(f, "cuMemAddressReserve", rc);
+    size_t at = 0;
     for (int p = 0; p < f->world; p++) {
-        rc = f->memMap(a.base + (size_t)p * a.chunk, a.chunk, 0, a.part[p], 0);
+        rc = f->memMap(a.base + at, a.size[p], 0, a.part[p], 0);
         if (rc != CUDA_SUCCESS) return fabric_fail(f, "cuMemMap", rc);
+        at += a.size[p];
     }
     CUmemAccessDesc acc;
     memset(&acc, 0, sizeof acc);
     acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
     acc.location.id = f->device;
     acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
-    rc = f->memSetAccess(a.base, a.chunk * f->world, &acc, 1);
+    rc = f->memSetAccess(a.base, a.total, &acc, 1);
     if (rc != CUDA_SUCCESS) return fabric_fail(f, "cuMemSetAccess", rc);
     a.mapped = true;
     *base_out = (void *)a.base;
@@ -170,8 +180,8 @@ int ssb_fabric_destroy(ssb_fabric_t *f) {
     cudaDeviceSynchronize();
     for (auto &a : f->arrays) {
         if (a.mapped) {
-            f->memUnmap(a.base, a.chunk * f->world);
-            f->memAddressFree(a.base, a.chunk * f->world);
+            f->memUnmap(a.base, a.total);
+            f->memAddressFree(a.base, a.total);
         }
         for (int p = 0; p < f->world; p++) if (a.have[p]) f->memRelease(a.part[p]);
     }

@@ -27,18 +27,19 @@ __global__ void __launch_bounds__(RADIX_THREADS) k_radix_hist(const uint64_t *ke
     if (digit_is_constant(varying, shift)) return;
     const long long n = *n_ptr;
     const int n_tiles = (int)((n + RADIX_TILE - 1) / RADIX_TILE);
-    if ((int)blockIdx.x >= n_tiles) return;
     __shared__ uint32_t h[256];
-    h[threadIdx.x] = 0;
-    __syncthreads();
-    const long long tile0 = (long long)blockIdx.x * RADIX_TILE;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {      // the grid is sized for the SMs, not for n
+        h[threadIdx.x] = 0;
+        __syncthreads();
+        const long long tile0 = (long long)tile * RADIX_TILE;
 #pragma unroll
-    for (int k = 0; k < RADIX_ITEMS; k++) {
-        const long long i = tile0 + k * RADIX_THREADS + threadIdx.x;
-        if (i < n) atomicAdd(&h[(keys[i] >> shift) & 255u], 1u);
+        for (int k = 0; k < RADIX_ITEMS; k++) {
+            const long long i = tile0 + k * RADIX_THREADS + threadIdx.x;
+            if (i < n) atomicAdd(&h[(keys[i] >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        hist[(long long)threadIdx.x * n_tiles + tile] = h[threadIdx.x];
     }
-    __syncthreads();
-    hist[(long long)threadIdx.x * n_tiles + blockIdx.x] = h[threadIdx.x];
 }
 
 // Scan of the digit-major histogram table hist[256][n_tiles], one block per digit row: the row is
@@ -76,72 +77,75 @@ __global__ void __launch_bounds__(RADIX_THREADS) k_radix_scatter(const uint64_t 
                                                                  const unsigned long long *varying, const uint32_t *row_total) {
     const long long n = *n_ptr;
     const int n_tiles = (int)((n + RADIX_TILE - 1) / RADIX_TILE);
-    if ((int)blockIdx.x >= n_tiles) return;
     if (digit_is_constant(varying, shift)) {       // nothing to reorder: keep the ping-pong going
-        const long long tile0 = (long long)blockIdx.x * RADIX_TILE;
-        for (int k = 0; k < RADIX_ITEMS; k++) {
-            const long long i = tile0 + k * RADIX_THREADS + threadIdx.x;
-            if (i < n) out[i] = keys[i];
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const long long tile0 = (long long)tile * RADIX_TILE;
+            for (int k = 0; k < RADIX_ITEMS; k++) {
+                const long long i = tile0 + k * RADIX_THREADS + threadIdx.x;
+                if (i < n) out[i] = keys[i];
+            }
         }
         return;
     }
     __shared__ uint32_t cnt[RADIX_WARPS][256];
     __shared__ uint32_t digit_base[256];
-    for (int i = threadIdx.x; i < RADIX_WARPS * 256; i += RADIX_THREADS) (&cnt[0][0])[i] = 0;
+    __shared__ uint32_t wsum[RADIX_WARPS];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     {   // exclusive prefix of the row totals: where the keys of each digit start
         const uint32_t mine = row_total[threadIdx.x];
         uint32_t inc = mine;
-        const int ln = threadIdx.x & 31, wp = threadIdx.x >> 5;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
-            if (ln >= o) inc += u;
+            if (lane >= o) inc += u;
         }
-        __shared__ uint32_t wsum[RADIX_WARPS];
-        if (ln == 31) wsum[wp] = inc;
+        if (lane == 31) wsum[w] = inc;
         __syncthreads();
         uint32_t b = 0;
-        for (int j = 0; j < wp; j++) b += wsum[j];
+        for (int j = 0; j < w; j++) b += wsum[j];
         digit_base[threadIdx.x] = b + inc - mine;
     }
-    __syncthreads();
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const long long warp0 = (long long)blockIdx.x * RADIX_TILE + (long long)w * (32 * RADIX_ITEMS);
-    uint64_t key[RADIX_ITEMS];
-    uint16_t rank[RADIX_ITEMS];
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < RADIX_WARPS * 256; i += RADIX_THREADS) (&cnt[0][0])[i] = 0;
+        __syncthreads();
+        const long long warp0 = (long long)tile * RADIX_TILE + (long long)w * (32 * RADIX_ITEMS);
+        uint64_t key[RADIX_ITEMS];
+        uint16_t rank[RADIX_ITEMS];
 #pragma unroll
-    for (int r = 0; r < RADIX_ITEMS; r++) {
-        const long long i = warp0 + r * 32 + lane;
-        const bool valid = i < n;
-        key[r] = valid ? keys[i] : 0ull;
-        const uint32_t d = (uint32_t)(key[r] >> shift) & 255u;
-        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-        uint32_t pre = 0, peers = 0;
-        if (valid) {
-            peers = __match_any_sync(vmask, d);
-            pre = cnt[w][d];
+        for (int r = 0; r < RADIX_ITEMS; r++) {
+            const long long i = warp0 + r * 32 + lane;
+            const bool valid = i < n;
+            key[r] = valid ? keys[i] : 0ull;
+            const uint32_t d = (uint32_t)(key[r] >> shift) & 255u;
+            const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+            uint32_t pre = 0, peers = 0;
+            if (valid) {
+                peers = __match_any_sync(vmask, d);
+                pre = cnt[w][d];
+            }
+            __syncwarp();
+            if (valid && lane == __ffs(peers) - 1) cnt[w][d] = pre + __popc(peers);
+            __syncwarp();
+            rank[r] = (uint16_t)(pre + __popc(peers & ((1u << lane) - 1u)));
         }
-        __syncwarp();
-        if (valid && lane == __ffs(peers) - 1) cnt[w][d] = pre + __popc(peers);
-        __syncwarp();
-        rank[r] = (uint16_t)(pre + __popc(peers & ((1u << lane) - 1u)));
-    }
-    __syncthreads();
-    {   // per digit: exclusive prefix over the warps of this tile, on top of the global offset
-        const int d = threadIdx.x;
-        uint32_t running = digit_base[d] + hist[(long long)d * n_tiles + blockIdx.x];
+        __syncthreads();
+        {   // per digit: exclusive prefix over the warps of this tile, on top of the global offset
+            const int d = threadIdx.x;
+            uint32_t running = digit_base[d] + hist[(long long)d * n_tiles + tile];
 #pragma unroll
-        for (int j = 0; j < RADIX_WARPS; j++) {
-            const uint32_t t = cnt[j][d];
-            cnt[j][d] = running;
-            running += t;
+            for (int j = 0; j < RADIX_WARPS; j++) {
+                const uint32_t t = cnt[j][d];
+                cnt[j][d] = running;
+                running += t;
+            }
         }
-    }
-    __syncthreads();
+        __syncthreads();
 #pragma unroll
-    for (int r = 0; r < RADIX_ITEMS; r++) {
-        const long long i = warp0 + r * 32 + lane;
-        if (i < n) out[cnt[w][(uint32_t)(key[r] >> shift) & 255u] + rank[r]] = key[r];
+        for (int r = 0; r < RADIX_ITEMS; r++) {
+            const long long i = warp0 + r * 32 + lane;
+            if (i < n) out[cnt[w][(uint32_t)(key[r] >> shift) & 255u] + rank[r]] = key[r];
+        }
     }
 }
 

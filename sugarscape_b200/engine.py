@@ -54,7 +54,7 @@ def load_library():
     F = C.c_void_p
     L.ssb_fabric_create.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(F)]
     L.ssb_fabric_alloc.argtypes = [F, C.c_uint64, C.POINTER(C.c_int32)]
-    L.ssb_fabric_map.argtypes = [F, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_void_p)]
+    L.ssb_fabric_map.argtypes = [F, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_uint64), C.POINTER(C.c_void_p)]
     L.ssb_fabric_copy.argtypes = [F, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32]
     L.ssb_fabric_granularity.argtypes = [F]
     L.ssb_fabric_granularity.restype = C.c_uint64

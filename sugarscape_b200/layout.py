@@ -123,11 +123,28 @@ def endowments_struct(arrays, pointer_of):
     return e
 
 
+def default_mark_shift(params):
+    """The reservation-mark coarsening ssb_bind picks (csrc/ssb_abi.cu): 2 x 2 cell blocks when the
+    map allows it, 4 x 4 on large maps for rule sets whose footprint is the bare cross."""
+    W, H = params.width, params.height
+    maxd = max(min(params.max_agent_range, W // 2), min(params.max_agent_range, H // 2))
+    shift = 0
+    if W % 2 == 0 and H % 2 == 0 and ((maxd + 2) >> 1) + 2 < (W >> 1) and ((maxd + 2) >> 1) + 2 < (H >> 1):
+        shift = 1
+    if shift == 1 and not (params.flags & (F_TAGGING | F_TRADE | F_REPRO)) and W * H >= (1 << 24) and W % 4 == 0 and H % 4 == 0:
+        shift = 2
+    return shift
+
+
+MAX_RANKS = 8
+
+
 class Shard(C.Structure):       # ssb_shard_t
     _fields_ = [("rank", C.c_int32), ("world", C.c_int32),
-                ("cell_lo", C.c_int64), ("cell_hi", C.c_int64), ("slot_lo", C.c_int64), ("slot_hi", C.c_int64),
+                ("cell_end", C.c_int64 * MAX_RANKS),
+                ("slot_lo", C.c_int64), ("slot_hi", C.c_int64), ("mark_lo", C.c_int64), ("mark_hi", C.c_int64),
                 ("ctrl", C.c_void_p), ("ctrl_stride", C.c_uint64),
-                ("marks", C.c_void_p), ("marks_stride", C.c_uint64),
+                ("marks", C.c_void_p),
                 ("gather", C.c_void_p), ("gather_stride", C.c_uint64)]
 
 

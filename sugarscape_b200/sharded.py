@@ -21,23 +21,49 @@ FDS_PER_MESSAGE = 64
 LOCAL_AGENT_FIELDS = ("order", "free_slots", "dead_list")      # per rank; everything else is indexed by global slot
 
 
+GRANULE = 2 << 20           # allocation granularity of the stitched arrays (checked against the driver's)
+
+
 def slab_bounds(width, world):
-    """x-lines [b[r], b[r+1]) belong to rank r."""
+    """Equal-width slabs: x-lines [b[r], b[r+1]) belong to rank r."""
     return [width * r // world for r in range(world + 1)]
+
+
+def balanced_slab_bounds(state, world):
+    """Slabs with equal POPULATION (agents act, cells only regrow): boundaries at the x-lines where
+    the cumulative agent count crosses r / world of the total, rounded to a multiple of `align`
+    x-lines so that a slab boundary is also a boundary of 2 MiB pages of the i32 grid arrays
+    (then a rank's slab lies in its own HBM to the last line).  Falls back to equal widths for
+    empty maps; every slab keeps at least one x-line."""
+    W, H = state.width, state.height
+    n = int(state.counters[layout.C_N_LIST])
+    if n == 0 or world == 1:
+        return slab_bounds(W, world)
+    align = GRANULE // (H * 4) if GRANULE % (H * 4) == 0 and GRANULE // (H * 4) * 4 * world <= W else 1
+    x = state.a_pos[state.a_order[:n]] // H
+    cum = np.cumsum(np.bincount(x, minlength=W))
+    bounds = [0]
+    for r in range(1, world):
+        b = int(np.searchsorted(cum, n * r / world, side="left")) + 1
+        b = int(round(b / align)) * align
+        bounds.append(min(max(b, bounds[-1] + align), W - (world - r) * align))
+    return bounds + [W]
 
 
 def slot_bounds(capacity, world):
     return [capacity * r // world for r in range(world + 1)]
 
 
-def shard_host_state(state, world):
+def shard_host_state(state, world, xb=None):
     """Re-slot a freshly built single-GPU HostState for `world` ranks: an agent's record moves to the
-    slot range of the rank that owns its cell (list order is kept inside a rank).  Returns the new
-    global state and, per rank, its list of slots."""
+    slot range of the rank that owns its cell (list order is kept inside a rank).  xb: slab
+    boundaries in x-lines (default: balanced_slab_bounds).  Returns the new global state and, per
+    rank, its list of slots; the boundaries are kept as new.slab_bounds."""
     n_list, n_slots = int(state.counters[layout.C_N_LIST]), int(state.counters[layout.C_N_SLOTS])
     if int(state.counters[layout.C_N_FREE]) != 0 or n_list != n_slots:
         raise ValueError("shard_host_state expects a freshly built state (no free slots)")
-    xb, sb = slab_bounds(state.width, world), slot_bounds(state.capacity, world)
+    xb = balanced_slab_bounds(state, world) if xb is None else list(xb)
+    sb = slot_bounds(state.capacity, world)
     old = state.a_order[:n_list].astype(np.int64)
     x = state.a_pos[old] // state.height
     owner = np.searchsorted(np.asarray(xb[1:]), x, side="right")
@@ -58,7 +84,21 @@ def shard_host_state(state, world):
             continue
         getattr(new, "a_" + name)[new_slot] = getattr(state, "a_" + name)[old]
     new.occ[state.a_pos[old]] = new_slot.astype(np.int32)
+    new.slab_bounds = xb
     return new, lists
+
+
+def chunk_boundaries(ends, itemsize, world):
+    """Byte boundaries b[0..world] of the chunks of a stitched array whose rank r should hold the
+    elements [ends[r-1], ends[r]): multiples of GRANULE, strictly increasing (a rank whose share
+    is smaller than a page still backs one page; small arrays simply live on the first ranks)."""
+    b = [0]
+    for r in range(world):
+        want = int(round(ends[r] * itemsize / GRANULE)) * GRANULE
+        if r == world - 1:
+            want = -(-ends[r] * itemsize // GRANULE) * GRANULE
+        b.append(max(want, b[-1] + GRANULE))
+    return b
 
 
 def exchange_fds(rank, world, fds, tag, barrier):
@@ -132,9 +172,9 @@ class StitchedArray:
     """A 1-D array in stitched device memory (chunk p backed by rank p's HBM), with the few tensor
     methods the Engine uses.  Copies are synchronous and split at chunk boundaries."""
 
-    def __init__(self, owner, ptr, n, dtype, chunk_bytes, base=None, offset=0):
-        self.owner, self.ptr, self.n, self.dtype, self.chunk_bytes = owner, int(ptr), int(n), np.dtype(dtype), int(chunk_bytes)
-        self.base, self.offset = (self.ptr if base is None else base), offset          # byte offset of [0] in the mapping
+    def __init__(self, owner, ptr, n, dtype, bounds, offset=0):
+        self.owner, self.ptr, self.n, self.dtype, self.bounds = owner, int(ptr), int(n), np.dtype(dtype), bounds
+        self.offset = offset          # byte offset of [0] in the mapping (bounds are offsets in the mapping too)
 
     def data_ptr(self):
         return self.ptr
@@ -148,15 +188,16 @@ class StitchedArray:
     def __getitem__(self, sl):
         lo, hi, step = sl.indices(self.n)
         assert step == 1
-        return StitchedArray(self.owner, self.ptr + lo * self.dtype.itemsize, max(hi - lo, 0), self.dtype, self.chunk_bytes,
-                             self.base, self.offset + lo * self.dtype.itemsize)
+        return StitchedArray(self.owner, self.ptr + lo * self.dtype.itemsize, max(hi - lo, 0), self.dtype, self.bounds,
+                             self.offset + lo * self.dtype.itemsize)
 
     def _pieces(self):
         """(byte offset inside this view, bytes) pieces that do not straddle a chunk boundary."""
         done, total = 0, self.n * self.dtype.itemsize
         while done < total:
-            room = self.chunk_bytes - (self.offset + done) % self.chunk_bytes
-            step = min(room, total - done)
+            at = self.offset + done
+            nxt = next(b for b in self.bounds if b > at)
+            step = min(nxt - at, total - done)
             yield done, step
             done += step
 
@@ -196,10 +237,8 @@ class ShardedEngine(Engine):
         import torch.distributed as dist
         self.rank, self.world, self.my_list, self.dist = rank, world, np.asarray(my_list, dtype=np.int32), dist
         self.fabric = C.c_void_p()
-        if mark_shift is None:         # the engine's own default (ssb_bind): 2 x 2 blocks when the map allows it
-            W, H = host_state.width, host_state.height
-            maxd = max(min(params.max_agent_range, W // 2), min(params.max_agent_range, H // 2))
-            mark_shift = 1 if (W % 2 == 0 and H % 2 == 0 and ((maxd + 2) >> 1) + 2 < (W >> 1) and ((maxd + 2) >> 1) + 2 < (H >> 1)) else 0
+        if mark_shift is None:
+            mark_shift = layout.default_mark_shift(params)
         self.mark_shift = mark_shift
         self.tag = f"{os.environ.get('MASTER_PORT', '0')}_{tag}"
         super().__init__(params, host_state, device, endow_bits, tag_bits)
@@ -217,42 +256,50 @@ class ShardedEngine(Engine):
         t, L, world, rank = self.torch, self.L, self.world, self.rank
         t.cuda.set_device(self.device)
         n_cells, cap = self.width * self.height, self.capacity
-        xb, sb = slab_bounds(self.width, world), slot_bounds(cap, world)
+        xb = list(getattr(hs, "slab_bounds", None) or slab_bounds(self.width, world))
+        sb = slot_bounds(cap, world)
+        self.slab_bounds = xb
         self.cell_lo, self.cell_hi = xb[rank] * self.height, xb[rank + 1] * self.height
         self.slot_lo, self.slot_hi = sb[rank], sb[rank + 1]
         local_slots = max(sb[r + 1] - sb[r] for r in range(world))
-        # (key, elements, dtype) of every stitched array, in mapping order (identical on all ranks)
-        plan = [(name, n_cells, dt) for name, dt in layout.GRID_FIELDS]
-        plan += [("a_" + name, cap, dt) for name, dt, _ in layout.AGENT_FIELDS if name not in LOCAL_AGENT_FIELDS]
-        n_marks = (self.width >> self.mark_shift) * (self.height >> self.mark_shift)      # split like the slabs
-        plan += [("_ctrl", 512 * world, np.uint64), ("_marks", n_marks, np.uint32),
-                 ("_gather", 5 * local_slots * world, np.uint64)]
-        gran = 2 << 20
-        roundup = lambda b: (b + gran - 1) // gran * gran
-        chunk = {key: roundup(-(-n // world) * np.dtype(dt).itemsize) for key, n, dt in plan}
+        sh = self.mark_shift
+        wc, hc = self.width >> sh, self.height >> sh
+        mark_end = [min(-(-xb[r + 1] // (1 << sh)), wc) * hc for r in range(world)]      # coarse columns, split like the slabs
+        mark_end[-1] = wc * hc
+        self.mark_lo, self.mark_hi = (mark_end[rank - 1] if rank else 0), mark_end[rank]
+        uniform = lambda n: [-(-n // world) * (r + 1) for r in range(world)]
+        # (key, elements, dtype, elements each rank should hold) of every stitched array, in mapping order
+        plan = [(name, n_cells, dt, [xb[r + 1] * self.height for r in range(world)]) for name, dt in layout.GRID_FIELDS]
+        plan += [("a_" + name, cap, dt, sb[1:]) for name, dt, _ in layout.AGENT_FIELDS if name not in LOCAL_AGENT_FIELDS]
+        plan += [("_ctrl", (GRANULE // 8) * world, np.uint64, uniform((GRANULE // 8) * world)), ("_marks", wc * hc, np.uint32, mark_end)]
+        gather_words = -(-5 * local_slots * 8 // GRANULE) * GRANULE // 8
+        plan += [("_gather", gather_words * world, np.uint64, uniform(gather_words * world))]
+        bounds = {key: chunk_boundaries(ends, np.dtype(dt).itemsize, world) for key, n, dt, ends in plan}
         self._fcheck(L.ssb_fabric_create(rank, world, self.device.index, C.byref(self.fabric)))
-        if int(L.ssb_fabric_granularity(self.fabric)) > gran or gran % int(L.ssb_fabric_granularity(self.fabric)):
+        if GRANULE % int(L.ssb_fabric_granularity(self.fabric)):
             raise EngineError("unexpected allocation granularity %d" % L.ssb_fabric_granularity(self.fabric))
         mine = []
-        for i, (key, n, dt) in enumerate(plan):          # this rank's chunk of every array
+        for i, (key, n, dt, ends) in enumerate(plan):          # this rank's chunk of every array
             fd = C.c_int32(-1)
-            if L.ssb_fabric_alloc(self.fabric, chunk[key], C.byref(fd)) != i:
+            if L.ssb_fabric_alloc(self.fabric, bounds[key][rank + 1] - bounds[key][rank], C.byref(fd)) != i:
                 self._fcheck(-1)
             mine.append(fd.value)
         fds = exchange_fds(rank, world, mine, self.tag, self.dist.barrier)
-        self.stitched, self.chunk = {}, chunk
-        for i, (key, n, dt) in enumerate(plan):
+        self.stitched, self.bounds = {}, bounds
+        for i, (key, n, dt, ends) in enumerate(plan):
             base = C.c_void_p()
+            b = bounds[key]
             per_rank = (C.c_int32 * world)(*[fds[r][i] for r in range(world)])
-            self._fcheck(L.ssb_fabric_map(self.fabric, i, per_rank, C.byref(base)))
+            sizes = (C.c_uint64 * world)(*[b[r + 1] - b[r] for r in range(world)])
+            self._fcheck(L.ssb_fabric_map(self.fabric, i, per_rank, sizes, C.byref(base)))
             view_dt = np.int32 if np.dtype(dt) == np.uint32 else dt       # like Engine._to_device
-            self.stitched[key] = StitchedArray(self, base.value, world * chunk[key] // np.dtype(dt).itemsize, view_dt, chunk[key])
+            self.stitched[key] = StitchedArray(self, base.value, b[-1] // np.dtype(dt).itemsize, view_dt, b)
         for fd in mine:
             os.close(fd)
         # this rank zeroes / fills the memory it backs, then uploads its slab and its slots
-        for key, n, dt in plan:
-            per = chunk[key] // np.dtype(dt).itemsize
-            self.stitched[key][rank * per:(rank + 1) * per].zero_()
+        for key, n, dt, ends in plan:
+            item, b = np.dtype(dt).itemsize, bounds[key]
+            self.stitched[key][b[rank] // item:b[rank + 1] // item].zero_()
         self._barrier()
         for name, _ in layout.GRID_FIELDS:
             self.tensors[name] = self.stitched[name][:n_cells]
@@ -285,10 +332,12 @@ class ShardedEngine(Engine):
         self.set_mark_shift(self.mark_shift)
         sd = layout.Shard()
         sd.rank, sd.world = self.rank, self.world
-        sd.cell_lo, sd.cell_hi, sd.slot_lo, sd.slot_hi = self.cell_lo, self.cell_hi, self.slot_lo, self.slot_hi
-        sd.ctrl, sd.ctrl_stride = self.stitched["_ctrl"].data_ptr(), self.chunk["_ctrl"]
-        sd.marks, sd.marks_stride = self.stitched["_marks"].data_ptr(), self.chunk["_marks"]
-        sd.gather, sd.gather_stride = self.stitched["_gather"].data_ptr(), self.chunk["_gather"]
+        for r in range(layout.MAX_RANKS):
+            sd.cell_end[r] = self.slab_bounds[min(r + 1, self.world)] * self.height
+        sd.slot_lo, sd.slot_hi, sd.mark_lo, sd.mark_hi = self.slot_lo, self.slot_hi, self.mark_lo, self.mark_hi
+        sd.ctrl, sd.ctrl_stride = self.stitched["_ctrl"].data_ptr(), self.bounds["_ctrl"][1]
+        sd.marks = self.stitched["_marks"].data_ptr()
+        sd.gather, sd.gather_stride = self.stitched["_gather"].data_ptr(), self.bounds["_gather"][1]
         self._check(self.L.ssb_set_shard(self.handle, C.byref(sd)))
         self._barrier()
 

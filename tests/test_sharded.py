@@ -26,7 +26,10 @@ def test_shard_host_state_moves_every_record_to_the_rank_that_owns_its_cell():
     c, state, pop, params, endow, tags = pu.build("combat_limited", layout.RNG_SCALABLE, {"agentMovement": [6, 6]})
     world = 4
     new, lists = sharded.shard_host_state(state, world)
-    xb, sb = sharded.slab_bounds(state.width, world), sharded.slot_bounds(state.capacity, world)
+    xb, sb = new.slab_bounds, sharded.slot_bounds(state.capacity, world)
+    assert xb[0] == 0 and xb[-1] == state.width and all(xb[i] < xb[i + 1] for i in range(world))
+    sizes = [len(x) for x in lists]
+    assert max(sizes) - min(sizes) <= 0.1 * sum(sizes) / world + state.height, sizes      # balanced by population
     assert sum(len(x) for x in lists) == int(state.counters[layout.C_N_LIST])
     for r, slots in enumerate(lists):
         assert np.all((slots >= sb[r]) & (slots < sb[r + 1]))
@@ -40,6 +43,16 @@ def test_shard_host_state_moves_every_record_to_the_rank_that_owns_its_cell():
     d_old, _ = pu.state_digests_by_id(state)
     d_new, _ = pu.state_digests_by_id(new)
     assert d_old == d_new
+
+
+def test_chunk_boundaries_are_page_multiples_and_follow_the_shares():
+    g = sharded.GRANULE
+    b = sharded.chunk_boundaries([100, 200, 300, 400], 4, 4)            # tiny array: one page per rank
+    assert b == [0, g, 2 * g, 3 * g, 4 * g]
+    ends = [3 * 1024 * 1024, 4 * 1024 * 1024, 9 * 1024 * 1024, 16 * 1024 * 1024]      # elements; 4-byte items
+    b = sharded.chunk_boundaries(ends, 4, 4)
+    assert b[0] == 0 and b[-1] >= ends[-1] * 4 and all(x % g == 0 for x in b) and all(b[i] < b[i + 1] for i in range(4))
+    assert [x // 4 for x in b[1:]] == ends
 
 
 def test_combine_stats_sums_counts_and_keeps_extrema():
