@@ -571,13 +571,10 @@ int ssb_set_shard(ssb_engine_t *e, const ssb_shard_t *sd) {
     CU(cudaMemset(e->d_migrate, 0, sizeof(MigratePlan)));
     CU(cudaMalloc(&e->d_shard_vals, sizeof(unsigned long long) * 16));
     CU(cudaMemset(e->d_shard_vals, 0, sizeof(unsigned long long) * 16));
-    {   // the epoch default follows the box-wide population
-        int64_t n_list = 0;
-        CU(cudaMemcpy(&n_list, e->ctx.a.counters + SSB_C_N_LIST, sizeof(n_list), cudaMemcpyDeviceToHost));
-        if (!e->epochs_set && n_list * sd->world >= (8LL << 20) && (1 << e->p.id_bits) >= 256) {
-            e->rc.epochs = 256;
-            e->rc.epoch_shift = e->p.id_bits - 8;
-        }
+    if (!e->epochs_set) {       // every round costs two box-wide barriers: fewer, larger rounds than on one GPU
+        e->rc.epochs = 128 < (1 << e->p.id_bits) ? 128 : (1 << e->p.id_bits);
+        e->rc.epoch_shift = e->p.id_bits;
+        for (int v = e->rc.epochs; v > 1; v >>= 1) e->rc.epoch_shift--;
     }
     e->local_marks = e->rc.mark;
     e->rc.mark = (uint32_t *)sd->marks;
