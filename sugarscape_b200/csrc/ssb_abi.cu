@@ -414,9 +414,14 @@ int ssb_compact(ssb_engine_t *e, int32_t t, void *stream_) {
     k_compact_finish<<<grid_for(cap, 256, e->num_sms * 4), 256, 0, st>>>(c, e->d_new_order, e->d_scalars + 0); LAUNCHED(e);
     k_compact_counters<<<1, 1, 0, st>>>(c, e->d_scalars + 0); LAUNCHED(e);
     if (e->p.rng_mode == SSB_RNG_SCALABLE && (e->p.flags & SSB_F_REPRO)) {
-        const int ctiles = (int)((c.g.n_cells + COMPACT_TILE - 1) / COMPACT_TILE);
+        const long long my_cells = e->sharded ? e->sh.cell_hi - e->sh.cell_lo : c.g.n_cells;     // d_scalars[2]
+        const int ctiles = (int)((my_cells + COMPACT_TILE - 1) / COMPACT_TILE);
         k_newborn_count<<<ctiles, COMPACT_THREADS, 0, st>>>(c, e->d_tile_counts); LAUNCHED(e);
         k_scan_tiles<<<1, COMPACT_THREADS, 0, st>>>(e->d_tile_counts, e->d_scalars + 2, COMPACT_TILE, e->d_scalars + 1); LAUNCHED(e);
+        if (e->sharded) {      // all-gather the slabs' newborn counts: ids follow the cell order of the whole map
+            k_newborn_pack<<<1, 1, 0, st>>>(e->d_scalars + 1, e->d_shard_vals + 8); LAUNCHED(e);
+            k_shard_barrier<<<1, 32, 0, st>>>(e->sh, e->d_shard_vals + 8, (long long *)c.a.counters + SSB_C_OVERFLOW); LAUNCHED(e);
+        }
         k_newborn_scatter<<<ctiles, COMPACT_THREADS, 0, st>>>(c, e->d_tile_counts); LAUNCHED(e);
         k_newborn_counters<<<1, 1, 0, st>>>(c, e->d_scalars + 1); LAUNCHED(e);
     }
@@ -538,7 +543,6 @@ int ssb_set_shard(ssb_engine_t *e, const ssb_shard_t *sd) {
     CHECK_BOUND(e);
     if (!sd || sd->world < 1 || sd->world > SSB_MAX_RANKS || sd->rank < 0 || sd->rank >= sd->world) return fail(e, -1, "bad shard description");
     if (e->p.rng_mode != SSB_RNG_SCALABLE) return fail(e, -1, "sharding needs the scalable RNG mode (the exact mode is one global stream)");
-    if (e->p.flags & SSB_F_REPRO) return fail(e, -1, "sharded mode does not support births (reproduction) yet");
     if (e->sharded) return fail(e, -1, "shard already set");
     if (sd->world == 1) return 0;
     const int64_t cells = e->ctx.g.n_cells, cap = e->ctx.a.capacity;
@@ -575,6 +579,10 @@ int ssb_set_shard(ssb_engine_t *e, const ssb_shard_t *sd) {
         e->rc.epochs = 128 < (1 << e->p.id_bits) ? 128 : (1 << e->p.id_bits);
         e->rc.epoch_shift = e->p.id_bits;
         for (int v = e->rc.epochs; v > 1; v >>= 1) e->rc.epoch_shift--;
+    }
+    {   // the newborn scan covers this rank's slab only
+        const int64_t my_cells = cell_hi - cell_lo;
+        CU(cudaMemcpy(e->d_scalars + 2, &my_cells, sizeof(my_cells), cudaMemcpyHostToDevice));
     }
     e->local_marks = e->rc.mark;
     e->rc.mark = (uint32_t *)sd->marks;

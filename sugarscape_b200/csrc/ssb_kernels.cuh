@@ -238,9 +238,14 @@ __device__ __forceinline__ bool cell_has_unnumbered_newborn(const DevCtx &c, lon
     return s >= 0 && c.a.id[s] < 0;
 }
 
+// Sharded: a rank numbers the newborn standing on ITS slab (cell order = rank order, so the ranks'
+// counts, all-gathered with the box-wide barrier, give every rank its first id); they join its list.
+__device__ __forceinline__ long long newborn_cell_lo(const DevCtx &c) { return c.sh.world > 1 ? c.sh.cell_lo : 0; }
+__device__ __forceinline__ long long newborn_cell_hi(const DevCtx &c) { return c.sh.world > 1 ? c.sh.cell_hi : c.g.n_cells; }
+
 __global__ void __launch_bounds__(COMPACT_THREADS) k_newborn_count(DevCtx c, int32_t *tile_counts) {
-    const long long n = c.g.n_cells;
-    const long long tile0 = (long long)blockIdx.x * COMPACT_TILE;
+    const long long n = newborn_cell_hi(c);
+    const long long tile0 = newborn_cell_lo(c) + (long long)blockIdx.x * COMPACT_TILE;
     int cnt = 0;
 #pragma unroll
     for (int k = 0; k < COMPACT_ITEMS; k++) {
@@ -252,9 +257,14 @@ __global__ void __launch_bounds__(COMPACT_THREADS) k_newborn_count(DevCtx c, int
     if (threadIdx.x == 0) tile_counts[blockIdx.x] = total;
 }
 
+__global__ void k_newborn_pack(const int64_t *n_new_ptr, unsigned long long *msg) {
+    msg[0] = (unsigned long long)*n_new_ptr;
+    for (int w = 1; w < SHARD_PAYLOAD; w++) msg[w] = 0;
+}
+
 __global__ void __launch_bounds__(COMPACT_THREADS) k_newborn_scatter(DevCtx c, const int32_t *tile_offset) {
-    const long long n = c.g.n_cells;
-    const long long tile0 = (long long)blockIdx.x * COMPACT_TILE;
+    const long long n = newborn_cell_hi(c);
+    const long long tile0 = newborn_cell_lo(c) + (long long)blockIdx.x * COMPACT_TILE;
     int slots[COMPACT_ITEMS];
     int cnt = 0;
 #pragma unroll
@@ -265,7 +275,9 @@ __global__ void __launch_bounds__(COMPACT_THREADS) k_newborn_scatter(DevCtx c, c
     }
     int total;
     int at = block_exclusive_scan(cnt, &total) + tile_offset[blockIdx.x];
-    const long long n_list = c.a.counters[SSB_C_N_LIST], next_id = c.a.counters[SSB_C_NEXT_ID];
+    const long long n_list = c.a.counters[SSB_C_N_LIST];
+    long long next_id = c.a.counters[SSB_C_NEXT_ID];
+    for (int r = 0; r < c.sh.rank && c.sh.world > 1; r++) next_id += (long long)c.sh.peer_vals[r * SHARD_PAYLOAD];   // lower slabs first
 #pragma unroll
     for (int k = 0; k < COMPACT_ITEMS; k++) {
         if (slots[k] < 0) continue;
@@ -277,8 +289,13 @@ __global__ void __launch_bounds__(COMPACT_THREADS) k_newborn_scatter(DevCtx c, c
 }
 
 __global__ void k_newborn_counters(DevCtx c, const int64_t *n_new_ptr) {
+    long long box = *n_new_ptr;
+    if (c.sh.world > 1) {
+        box = 0;
+        for (int r = 0; r < c.sh.world; r++) box += (long long)c.sh.peer_vals[r * SHARD_PAYLOAD];
+    }
     c.a.counters[SSB_C_N_LIST] += *n_new_ptr;
-    c.a.counters[SSB_C_NEXT_ID] += *n_new_ptr;
+    c.a.counters[SSB_C_NEXT_ID] += box;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -610,7 +610,7 @@ __device__ __forceinline__ int alloc_slot(const DevCtx &c) {
     if (k >= 0) return c.a.free_slots[k];
     atomicAdd(&cn[SSB_C_N_FREE], 1ull);   // undo: the free list was empty
     const long long slot = (long long)atomicAdd(&cn[SSB_C_N_SLOTS], 1ull);
-    if (slot >= c.a.capacity) {
+    if (slot >= (c.sh.world > 1 ? c.sh.slot_hi : c.a.capacity)) {
         atomicAdd(&cn[SSB_C_N_SLOTS], (unsigned long long)-1LL);
         atomicExch(&cn[SSB_C_OVERFLOW], 1ull);
         return -1;

@@ -111,7 +111,9 @@ def test_fd_exchange_between_two_gloo_ranks():
 SHARDED_CASES = [
     ("constant_growback", {}, 40),
     ("combat_unlimited", {"agentAggressionFactor": [1, 1]}, 40),
-    ("cultural_tagging", {"agentFertilityFactor": [0, 0]}, 40),      # tagging across the slab boundary (births are not sharded yet)
+    ("cultural_tagging", {}, 40),                                      # tagging + births across the slab boundary
+    ("reproduction_basic", {"environmentWidth": 100, "environmentHeight": 100, "startingAgents": 1500,
+                            "environmentSugarPeaks": [[70, 30, 4], [30, 70, 4], [20, 20, 4], [80, 80, 4]]}, 50),
     ("trade_basic", {}, 40),
     ("pollution_formation", {}, 60),
     ("combat_limited", {}, 60),
