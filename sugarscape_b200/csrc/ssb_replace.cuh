@@ -67,11 +67,20 @@ __global__ void __launch_bounds__(256) k_repl_count(DevCtx c, ReplacePlan *rp) {
     const int H = c.p.height;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long cell_lo = sharded ? c.sh.cell_lo : 0, cell_hi = sharded ? c.sh.cell_hi : c.g.n_cells;
+    unsigned int m0 = 0, m1 = 0, m2 = 0, m3 = 0;   // per thread, folded per warp: no same-address contention
     for (long long i = cell_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cell_hi; i += stride) {
         if (c.g.occ[i] >= 0) continue;
-        const int x = (int)(i / H), y = (int)(i - (long long)x * H);
+        const int x = (int)((unsigned int)i / (unsigned int)H), y = (int)i - x * H;      // n_cells < 2^31
         const int q = quadrant_of_cell(c.p, x, y);
-        if (q >= 0) atomicAdd(&cnt[q], 1u);
+        m0 += q == 0; m1 += q == 1; m2 += q == 2; m3 += q == 3;
+    }
+    const unsigned int mine[4] = {m0, m1, m2, m3};
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        unsigned int v = mine[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&cnt[q], v);
     }
     __syncthreads();
     if (threadIdx.x < 4 && cnt[threadIdx.x]) atomicAdd(&rp->empty[threadIdx.x], (unsigned long long)cnt[threadIdx.x]);
