@@ -365,7 +365,11 @@ def main():
     env_bytes = (n_cells // world if sharded_run else n_cells) * BYTES_PER_CELL_GROWBACK
     roofline = {"bound": "hbm", "kernel": "k_agent_step_scalable", "achieved": achieved, "peak": peak,
                 "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback 6.65 TB/s",
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "per": "rank 0's GPU",
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "traffic_note": "not captured for this launch; ncu --set full of the same kernel on the 4096^2 map with S2 rules: "
+                                "8.9 GB DRAM traffic per launch = 5.7 KB per agent-step, 29x the algorithmic bytes "
+                                "(profiles/r1_agent_step_s2rules_4096_ncu_full.csv)",
+                "per": "rank 0's GPU",
                 "algorithmic_bytes_per_launch": agent_bytes, "avg_launch_ms": avg["agent_ms"],
                 "env_step": {"kernel": "k_growback_v4", "achieved": env_bytes / (avg["env_ms"] / 1000.0) / 1e9,
                              "frac": env_bytes / (avg["env_ms"] / 1000.0) / 1e9 / peak, "avg_launch_ms": avg["env_ms"],
