@@ -23,6 +23,9 @@ Timed regions
           bounded sample of the same workload, one host core.  The reference itself is pure
           Python (about 6-8 k agent-steps/s/core measured in the build container)
           and is not present on the GPU box.
+  --impl reference  the same port on ALL host cores: one simulation is strictly serial in the
+          reference, its only parallelism is one process per seed (data/run.py:155-180), so the arm
+          runs os.cpu_count() independent replicas of a bounded sample (same rules and density).
 """
 import argparse
 import ctypes as C
@@ -176,6 +179,39 @@ def run_cpu_port(args, c, steps, state=None, table=None):
     return agent_steps / dt, dt, agent_steps
 
 
+def _cpu_replica(job):
+    """One worker of the all-core CPU arm: an independent replica (own seed) of a bounded sample."""
+    options, overrides, steps = job
+    from sugarscape_b200 import synthetic
+    c = synthetic.configuration(options, overrides)
+    value, dt, agent_steps = run_cpu_port(None, c, steps)
+    return agent_steps, dt
+
+
+def run_cpu_port_all_cores(args, c, steps):
+    """The reference's own parallelism is one process per seed (reference data/run.py:155-180): one
+    simulation cannot use a second core.  All-core CPU figure = os.cpu_count() independent replicas
+    of a bounded sample of the workload (same rules and density on a map of 1/64 the area; the cost
+    per agent-step is flat in the map size), each timed around its own step loop."""
+    import multiprocessing as mp
+    from sugarscape_b200 import synthetic
+    cores = os.cpu_count() or 1
+    side = max(256, args.size // 8)
+    n = max(1, int(round(c["startingAgents"] * (side / args.size) ** 2)))
+    options = synthetic.S2_OPTIONS if args.workload == "S2" else synthetic.S1_OPTIONS
+    jobs = []
+    for k in range(cores):
+        ov = {"environmentWidth": side, "environmentHeight": side, "startingAgents": n, "seed": 12345 + k, "timesteps": 1 << 20}
+        if c["agentReplacements"] > 0:
+            ov["agentReplacements"] = n
+        jobs.append((options, ov, steps))
+    with mp.get_context("fork").Pool(cores) as pool:
+        res = pool.map(_cpu_replica, jobs)
+    total = sum(r[0] for r in res)
+    slowest = max(r[1] for r in res)
+    return total / slowest, slowest, total, cores, f"{cores} replicas of {side}x{side} / {n} agents, {steps} timesteps each"
+
+
 class Job:
     """Host state of the workload (built once per process) and engines over it."""
 
@@ -315,16 +351,17 @@ def main():
         if rank != 0:
             return 0
         c, n_agents = workload(args)
-        steps = max(1, min(args.steps, args.cpu_steps))
-        value, dt, agent_steps = run_cpu_port(args, c, steps)
+        steps = max(3, min(args.steps, 8))
+        value, dt, agent_steps, cores, sample = run_cpu_port_all_cores(args, c, steps)
         line = {
             "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": 0, "ms_per_step": 1000.0 * dt / steps, "higher_is_better": True,
             "scaling": "strong" if args.workload == "S2" else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": describe(args, n_agents), "rng_mode": "scalable"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
-                             "sample": f"{steps} timesteps of the {args.workload} initial state, oracle/ss_oracle.c, 1 thread "
-                                       "(the reference is pure Python and absent from this box: 6-8 k agent-steps/s/core "
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": sample + "; oracle/ss_oracle.c (C port of the reference's algorithm), one process per "
+                                       "core like the reference's own data/run.py pool -- one simulation is strictly serial "
+                                       "(the reference itself is pure Python and absent from this box: 6-8 k agent-steps/s/core "
                                        "measured in the build container, BASELINE.md)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
