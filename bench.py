@@ -9,7 +9,8 @@ replacement, stats reductions) in scalable RNG mode.  Def
 16384 x 16384 map, 25 M agents, combat_limited rules -- the same simulation at every N (strong
 scaling): one GPU holds it whole, N > 1 shards it by x-slabs over NVLink-stitched memory
 (sugarscape_b200/sharded.py), results bit-identical to the single-GPU run.  --workload S1 is the
-4096 x 4096 / 1.6 M agents / reproduction_basic shape (sharded the same way; --replicas for N copies).
+4096 x 4096 / 1.6 M agents / reproduction_basic shape (one GPU, or N replicas: sharded births are
+experimental).
 
 Timed regions
   value   K steps enqueued back to back, state resident in HBM, CUDA events on the launching
@@ -345,6 +346,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload == "S1" and not os.environ.get("SSB_EXPERIMENTAL_SHARDED_BIRTHS"):
+        args.replicas = True            # births are not sharded yet (experimental): S1 runs on one GPU or as replicas
     sharded_run = world > 1 and not args.replicas
 
     if args.impl == "reference":

@@ -237,7 +237,8 @@ typedef struct ssb_shard_t {
     void   *gather;                 /* stitched scratch for candidate / wealth-key all-gathers        */
     uint64_t gather_stride;         /* bytes per rank chunk: >= 8 * (4 + 1) * slots per rank          */
 } ssb_shard_t;
-/* Scalable mode only.  Call after ssb_bind, before the
+/* Scalable mode, rule sets without births only (sharded births are experimental and refused
+ * unless SSB_EXPERIMENTAL_SHARDED_BIRTHS is set).  Call after ssb_bind, before the
  * first step; grid and agent arrays bound must be stitched.  Per-rank state: order[], free_slots[],
  * dead_list[], counters[] (N_LIST / N_SLOTS / N_FREE are per rank; NEXT_ID / ENDOW_INDEX global). */
 int  ssb_set_shard(ssb_engine_t *e, const ssb_shard_t *shard);
