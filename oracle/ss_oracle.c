@@ -283,11 +283,212 @@ static int alloc_slot(ctx_t *c) {
     return slot;
 }
 
+
+/* ------------------------------------------------------------------------------------------
+ * lending (agent.py:431-483 doLending, 190-212 addLoan*, 920-930 current debt, 1226-1245,
+ * 1285-1296, 1330-1360 payDebt, 1445-1449 removeDebt, 1532-1541 updateLoans, 1549-1553 mean income).
+ * ORACLE-PRIVATE state: the CUDA engine has no lending yet and refuses such
+ * configurations; this restatement is the checker its port will be held against.  Exact RNG mode.
+ * A loan is a record in two Python lists: the debtor's "creditors" and the creditor's "debtors";
+ * both lists are kept per slot with Python's list semantics (remove = first equal element,
+ * iteration by index over a list that changes underneath).  An agent is named by (slot, id):
+ * a slot that was reused by a newborn no longer is the agent the loan refers to (= dead).
+ * Not restated: payDebtToCreditorChildren (inheritance policy "children" together with lending).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct { int32_t other_slot, other_id; double sugar, spice; int32_t duration, origin; } orc_loan_t;
+typedef struct { orc_loan_t *v; int n, cap; } loan_list_t;
+typedef struct {
+    int64_t capacity;
+    double *lending_factor, *base_interest_rate;      /* per slot, host arrays */
+    int32_t *loan_duration;
+    double *sugar_mean_income, *spice_mean_income;
+    int32_t *last_lended, *last_loans;
+    loan_list_t *creditors, *debtors;                 /* per slot, owned here */
+} orc_lending_t;
+static orc_lending_t g_lend_store, *g_lend = NULL;
+enum { EB_BASE_INTEREST = 12, EB_LENDING_FACTOR = 13, EB_LOAN_DURATION = 14 };   /* steptables.ENDOWMENT_BITS */
+
+void orc_bind_lending(double *lending_factor, double *base_interest_rate, int32_t *loan_duration,
+                      double *sugar_mean_income, double *spice_mean_income, int32_t *last_lended,
+                      int32_t *last_loans, int64_t capacity) {
+    if (g_lend) {
+        for (int64_t i = 0; i < g_lend->capacity; i++) { free(g_lend->creditors[i].v); free(g_lend->debtors[i].v); }
+        free(g_lend->creditors); free(g_lend->debtors);
+        g_lend = NULL;
+    }
+    if (!lending_factor) return;                      /* unbind */
+    g_lend = &g_lend_store;
+    g_lend->capacity = capacity;
+    g_lend->lending_factor = lending_factor; g_lend->base_interest_rate = base_interest_rate;
+    g_lend->loan_duration = loan_duration;
+    g_lend->sugar_mean_income = sugar_mean_income; g_lend->spice_mean_income = spice_mean_income;
+    g_lend->last_lended = last_lended; g_lend->last_loans = last_loans;
+    g_lend->creditors = (loan_list_t *)calloc((size_t)capacity, sizeof(loan_list_t));
+    g_lend->debtors = (loan_list_t *)calloc((size_t)capacity, sizeof(loan_list_t));
+}
+
+/* loanVolume of the log (sugarscape.py:1130-1131): sum of lastLoans over the agents that lent in step t */
+int64_t orc_loan_volume(const ssb_agents_t *a, int32_t t) {
+    int64_t v = 0;
+    if (!g_lend) return 0;
+    for (int64_t i = 0; i < a->counters[SSB_C_N_LIST]; i++) {
+        int s = a->order[i];
+        if (g_lend->last_lended[s] == t) v += g_lend->last_loans[s];
+    }
+    return v;
+}
+
+static void loan_append(loan_list_t *L, orc_loan_t x) {
+    if (L->n == L->cap) { L->cap = L->cap ? 2 * L->cap : 4; L->v = (orc_loan_t *)realloc(L->v, sizeof(orc_loan_t) * (size_t)L->cap); }
+    L->v[L->n++] = x;
+}
+static int loan_equal(const orc_loan_t *x, const orc_loan_t *y) {
+    return x->other_slot == y->other_slot && x->other_id == y->other_id && x->sugar == y->sugar && x->spice == y->spice &&
+           x->duration == y->duration && x->origin == y->origin;
+}
+static void loan_remove_first(loan_list_t *L, const orc_loan_t *x) {      /* list.remove(x) */
+    for (int q = 0; q < L->n; q++)
+        if (loan_equal(&L->v[q], x)) { memmove(&L->v[q], &L->v[q + 1], sizeof(orc_loan_t) * (size_t)(L->n - q - 1)); L->n--; return; }
+}
+static void lending_reset_slot(int s) {               /* a new agent object starts with empty lists */
+    g_lend->creditors[s].n = 0; g_lend->debtors[s].n = 0;
+    g_lend->sugar_mean_income[s] = 1; g_lend->spice_mean_income[s] = 1;
+    g_lend->last_lended[s] = -1; g_lend->last_loans[s] = 0;
+}
+static int loan_other_alive(const ctx_t *c, const orc_loan_t *l) {
+    return c->a.id[l->other_slot] == l->other_id && agent_alive(c, l->other_slot);
+}
+static int is_fertile(const ctx_t *c, int s);
+
+/* addLoanToAgent (agent.py:199-211) incl. addLoanFromAgent (190-197) */
+static void add_loan(ctx_t *c, int creditor, int debtor, int origin, double sugar_principal, double sugar_loan,
+                     double spice_principal, double spice_loan, int duration) {
+    ssb_agents_t *a = &c->a;
+    orc_loan_t owed = {creditor, a->id[creditor], sugar_loan, spice_loan, duration, origin};
+    orc_loan_t due = {debtor, a->id[debtor], sugar_loan, spice_loan, duration, origin};
+    loan_append(&g_lend->creditors[debtor], owed);
+    loan_append(&g_lend->debtors[creditor], due);
+    a->sugar[creditor] -= sugar_principal;
+    a->spice[creditor] -= spice_principal;
+    a->sugar[debtor] = a->sugar[debtor] + sugar_principal;
+    a->spice[debtor] = a->spice[debtor] + spice_principal;
+}
+
+/* payDebt (agent.py:1330-1360); `loan` is an element of the creditors list of s */
+static void pay_debt(ctx_t *c, int s, orc_loan_t loan) {
+    ssb_agents_t *a = &c->a;
+    const int cr = loan.other_slot;
+    const orc_loan_t mirror = {s, a->id[s], loan.sugar, loan.spice, loan.duration, loan.origin};
+    const int same_object = a->id[cr] == loan.other_id;       /* the creditor's record still exists */
+    if (!loan_other_alive(c, &loan)) {
+        if (c->p->inheritance_policy == 1) { a->counters[SSB_C_OVERFLOW] = 9; return; }   /* payDebtToCreditorChildren: not restated */
+        loan_remove_first(&g_lend->creditors[s], &loan);
+        if (same_object) loan_remove_first(&g_lend->debtors[cr], &mirror);
+    } else if (a->sugar[s] - loan.sugar > 0 && a->spice[s] - loan.spice > 0) {
+        a->sugar[s] -= loan.sugar;
+        a->spice[s] -= loan.spice;
+        a->sugar[cr] = a->sugar[cr] + loan.sugar;
+        a->spice[cr] = a->spice[cr] + loan.spice;
+        loan_remove_first(&g_lend->creditors[s], &loan);
+        loan_remove_first(&g_lend->debtors[cr], &mirror);
+    } else {
+        const double sugar_payout = a->sugar[s] / 2, spice_payout = a->spice[s] / 2;
+        const double sugar_left = loan.sugar - sugar_payout, spice_left = loan.spice - spice_payout;
+        a->sugar[s] -= sugar_payout;
+        a->spice[s] -= spice_payout;
+        a->sugar[cr] = a->sugar[cr] + sugar_payout;
+        a->spice[cr] = a->spice[cr] + spice_payout;
+        const double rate = g_lend->lending_factor[cr] * g_lend->base_interest_rate[cr];
+        const double new_sugar = sugar_left + (rate * sugar_left), new_spice = spice_left + (rate * spice_left);
+        loan_remove_first(&g_lend->creditors[s], &loan);
+        loan_remove_first(&g_lend->debtors[cr], &mirror);
+        /* compounded on the previous loan, no new principal */
+        add_loan(c, cr, s, a->last_moved[s], 0, new_sugar, 0, new_spice, g_lend->loan_duration[cr]);
+    }
+}
+
+/* updateLoans (agent.py:1532-1541): Python for-loops over lists that shrink / grow underneath */
+static void update_loans(ctx_t *c, int s) {
+    loan_list_t *D = &g_lend->debtors[s], *C = &g_lend->creditors[s];
+    for (int p = 0; p < D->n; p++) {
+        orc_loan_t l = D->v[p];
+        if (!loan_other_alive(c, &l)) loan_remove_first(D, &l);
+    }
+    for (int p = 0; p < C->n; p++) {
+        orc_loan_t l = C->v[p];
+        const int remaining = (c->a.last_moved[s] - l.origin) - l.duration;
+        if (remaining == 0) pay_debt(c, s, l);
+    }
+}
+
+static double current_debt(const loan_list_t *C, int spice) {       /* agent.py:920-930 */
+    double d = 0;
+    for (int i = 0; i < C->n; i++) d += (spice ? C->v[i].spice : C->v[i].sugar) / C->v[i].duration;
+    return d;
+}
+
+/* doLending (agent.py:431-483) */
+static void do_lending(ctx_t *c, int s) {
+    ssb_agents_t *a = &c->a;
+    update_loans(c, s);
+    /* isLender (1285-1296) */
+    if (g_lend->lending_factor[s] == 0) return;
+    if (is_fertile(c, s) && (a->sugar[s] <= a->start_sugar[s] || a->spice[s] <= a->start_spice[s])) return;
+    if (a->age[s] < a->fert_age[s]) return;
+    double rate = g_lend->lending_factor[s] * g_lend->base_interest_rate[s];
+    if (rate > 1) rate = 1;
+    int32_t nb[4], borrowers[4];
+    int nbw = 0;
+    neighbours4(c, a->pos[s], nb);
+    for (int i = 0; i < 4; i++) {
+        int o = c->g.occ[nb[i]];
+        if (o < 0 || !agent_alive(c, o)) continue;
+        /* isBorrower (1226-1229) */
+        if (a->age[o] >= a->fert_age[o] && a->age[o] < a->infert_age[o] && !is_fertile(c, o)) borrowers[nbw++] = o;
+    }
+    rng_shuffle_i32(c->rng, borrowers, nbw);
+    const double pm = a->spice_metab[s] > 0 ? a->spice_metab[s] : 0, sm = a->sugar_metab[s] > 0 ? a->sugar_metab[s] : 0;
+    int loans = 0;
+    for (int k = 0; k < nbw; k++) {
+        const int b = borrowers[k];
+        double max_sugar = a->sugar[s] / 2, max_spice = a->spice[s] / 2;
+        if (is_fertile(c, s)) {
+            max_sugar = a->sugar[s] - a->start_sugar[s] > 0 ? a->sugar[s] - a->start_sugar[s] : 0;
+            max_spice = a->spice[s] - a->start_spice[s] > 0 ? a->spice[s] - a->start_spice[s] : 0;
+        }
+        if (max_sugar == 0 && max_spice == 0) return;           /* (skips the lastLoans bookkeeping, like the reference) */
+        const double sugar_need = a->start_sugar[b] - a->sugar[b] > 0 ? a->start_sugar[b] - a->sugar[b] : 0;
+        const double spice_need = a->start_spice[b] - a->spice[b] > 0 ? a->start_spice[b] - a->spice[b] : 0;
+        const double sugar_principal = max_sugar < sugar_need ? max_sugar : sugar_need;
+        const double spice_principal = max_spice < spice_need ? max_spice : spice_need;
+        const double sugar_amount = sugar_principal + (sugar_principal * rate);
+        const double spice_amount = spice_principal + (spice_principal * rate);
+        if ((sugar_need == 0 && spice_need == 0) || (sugar_amount == 0 && spice_amount == 0)) continue;
+        if (a->sugar[s] - sugar_principal <= sm || a->spice[s] - spice_principal <= pm) continue;
+        /* isCreditWorthy (1231-1242) */
+        const int duration = g_lend->loan_duration[s];
+        if (duration == 0) continue;
+        const double bpm = a->spice_metab[b] > 0 ? a->spice_metab[b] : 0, bsm = a->sugar_metab[b] > 0 ? a->sugar_metab[b] : 0;
+        const double sugar_cost = sugar_amount / duration, spice_cost = spice_amount / duration;
+        const double sugar_income = ((g_lend->sugar_mean_income[b] - bsm) - current_debt(&g_lend->creditors[b], 0)) - sugar_cost;
+        const double spice_income = ((g_lend->spice_mean_income[b] - bpm) - current_debt(&g_lend->creditors[b], 1)) - spice_cost;
+        if (!(sugar_income >= 0 && spice_income >= 0)) continue;
+        add_loan(c, s, b, a->last_moved[s], sugar_principal, sugar_amount, spice_principal, spice_amount, duration);
+        loans++;
+    }
+    if (loans > 0) { g_lend->last_lended[s] = c->t; g_lend->last_loans[s] = loans; }
+}
+
 /* collectResourcesAtCell, agent.py:249-259 + cell.py:32-45 */
 static void collect(ctx_t *c, int s, int pos) {
     int32_t cs = c->g.sugar[pos], cp = c->g.spice[pos];
     c->a.sugar[s] += cs;
     c->a.spice[s] += cp;
+    if (g_lend) {      /* updateMeanIncome (agent.py:1549-1553) */
+        const double alpha = 0.05;
+        g_lend->sugar_mean_income[s] = (alpha * cs) + ((1 - alpha) * g_lend->sugar_mean_income[s]);
+        g_lend->spice_mean_income[s] = (alpha * cp) + ((1 - alpha) * g_lend->spice_mean_income[s]);
+    }
     if (c->p->pollution_start <= c->t && c->t <= c->p->pollution_end) {
         c->g.pollution[pos] += c->p->sugar_prod_pollution * cs;
         c->g.pollution[pos] += c->p->spice_prod_pollution * cp;
@@ -539,6 +740,12 @@ static void do_reproduction(ctx_t *c, int s) {
         a->sex[ch] = PICK(sex, EB_SEX);
         a->trade_factor[ch] = PICK(trade_factor, EB_TRADE_FACTOR);
         a->vision[ch] = PICK(vision, EB_VISION);
+        if (g_lend) {
+            lending_reset_slot(ch);
+            g_lend->base_interest_rate[ch] = ((eb >> EB_BASE_INTEREST) & 1u) ? g_lend->base_interest_rate[m] : g_lend->base_interest_rate[s];
+            g_lend->lending_factor[ch] = ((eb >> EB_LENDING_FACTOR) & 1u) ? g_lend->lending_factor[m] : g_lend->lending_factor[s];
+            g_lend->loan_duration[ch] = ((eb >> EB_LOAN_DURATION) & 1u) ? g_lend->loan_duration[m] : g_lend->loan_duration[s];
+        }
 #undef PICK
         double sugar_cost = a->start_sugar[s] / (a->fert_factor[s] * 2);
         double spice_cost = a->start_spice[s] / (a->fert_factor[s] * 2);
@@ -610,6 +817,7 @@ static void agent_transaction(ctx_t *c, int s) {
     do_tagging(c, s);
     do_trading(c, s);
     do_reproduction(c, s);
+    if (g_lend) do_lending(c, s);
     /* doAging (agent.py:266-272) */
     if (agent_alive(c, s)) {
         a->age[s] += 1;

@@ -368,12 +368,14 @@ def rule_flags(c):
     return f
 
 
-def build_initial_state(c, capacity=None):
+def build_initial_state(c, capacity=None, check=True):
     """Environment + initial population + the init-time list shuffle; returns (state, population).
 
     Must be called right after verify_random_seed/verify_configuration so the main stream is
-    positioned as in the reference's Sugarscape.__init__ (sugarscape.py:19-75)."""
-    check_supported(c)
+    positioned as in the reference's Sugarscape.__init__ (sugarscape.py:19-75).
+    check=False skips the support check (oracle-only tests of rule families the engine refuses)."""
+    if check:
+        check_supported(c)
     W, H = c["environmentWidth"], c["environmentHeight"]
     sugar_cap = capacity_field(W, H, c["environmentSugarPeaks"])
     spice_cap = capacity_field(W, H, c["environmentSpicePeaks"])

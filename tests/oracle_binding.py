@@ -88,6 +88,36 @@ class Oracle:
         self.endow_arrays = endowments if isinstance(endowments, dict) else layout.endowment_arrays(endowments)
         self.endow = layout.endowments_struct(self.endow_arrays, lambda arr: arr.ctypes.data)
 
+    def bind_lending(self, endowments):
+        """Oracle-private lending state (the engine refuses lending configurations): per-slot
+        endowments of the initial agents from init.Population.endowments (agent id = index)."""
+        cap = self.state.capacity
+        f64 = lambda v: np.full(cap, v, dtype=np.float64)
+        self.lend = {"lending_factor": f64(0), "base_interest_rate": f64(0), "loan_duration": np.zeros(cap, np.int32),
+                     "sugar_mean_income": f64(1), "spice_mean_income": f64(1),
+                     "last_lended": np.full(cap, -1, np.int32), "last_loans": np.zeros(cap, np.int32)}
+        n = int(self.state.counters[layout.C_N_LIST])
+        for s in self.state.a_order[:n]:
+            e = endowments[int(self.state.a_id[s])]
+            self.lend["lending_factor"][s] = e["lendingFactor"]
+            self.lend["base_interest_rate"][s] = e["baseInterestRate"]
+            self.lend["loan_duration"][s] = e["loanDuration"]
+        L = self.L
+        L.orc_bind_lending.argtypes = [C.c_void_p] * 7 + [C.c_int64]
+        L.orc_bind_lending.restype = None
+        L.orc_loan_volume.argtypes = [C.c_void_p, C.c_int32]
+        L.orc_loan_volume.restype = C.c_int64
+        L.orc_bind_lending(*[self.lend[k].ctypes.data for k in ("lending_factor", "base_interest_rate", "loan_duration",
+                                                                "sugar_mean_income", "spice_mean_income", "last_lended",
+                                                                "last_loans")], cap)
+
+    def unbind_lending(self):
+        self.L.orc_bind_lending(*([None] * 7), 0)
+
+    def loan_volume(self, t):
+        g, a = self.state.as_structs()
+        return int(self.L.orc_loan_volume(C.byref(a), t))
+
     def replace(self, t):
         g, a = self.state.as_structs()
         self.L.orc_replace(C.byref(self.params), C.byref(g), C.byref(a), C.byref(self.endow), t)

@@ -39,9 +39,9 @@ def example_configuration(name, overrides=None):
     return config.verify_configuration(c)
 
 
-def build(name, rng_mode=layout.RNG_EXACT, overrides=None):
+def build(name, rng_mode=layout.RNG_EXACT, overrides=None, check=True):
     c = example_configuration(name, overrides)
-    state, pop = init.build_initial_state(c)
+    state, pop = init.build_initial_state(c, check=check)
     flags = init.rule_flags(c)
     params = layout.make_params(c, rng_mode, flags, init.max_agent_range(c), init.equator(c))
     endow, tags = steptables.step_tables(1, min(c["timesteps"], 100000), c["agentTagStringLength"])

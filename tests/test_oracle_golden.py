@@ -60,6 +60,41 @@ def test_oracle_matches_reference_trajectory(name):
                 assert _close(rs[k], log[t][k]), f"log key {k} differs at t={t}: {rs[k]} vs {log[t][k]}"
 
 
+def test_oracle_lending_matches_reference_trajectory():
+    """Lending (reference agent.py:431-483 and helpers) exists in the ORACLE only so far -- the engine
+    refuses lending configurations.  The restatement is pinned here against the unmodified
+    reference on examples/lending_basic.json: every digest of every step, the loanVolume log key
+    and the other 58 keys."""
+    name = "lending_basic"
+    c, state, pop, params, endow, tags = pu.build(name, check=False)
+    meta, _ = pu.load_golden(name)
+    gold, log = meta["steps"], meta["log"]
+    orc = Oracle(params, state, endow, tags)
+    orc.set_mt_from_python()
+    orc.bind_lending(pop.endowments)
+    try:
+        d, _ = pu.state_digests(state, *orc.mt_state())
+        assert d == gold[0]["digests"], "t=0 state differs"
+        sb = stats.StatsBuilder(c, init.equator(c))
+        rs = sb.update(orc.stats(0), 0)
+        volume = 0
+        for t in range(1, len(gold)):
+            orc.env_step(t)
+            orc.agent_step(t, rs["meanWealth"])
+            orc.compact(t)
+            d, snap = pu.state_digests(state, *orc.mt_state())
+            assert d == gold[t]["digests"], f"state differs at t={t}"
+            rs = sb.update(orc.stats(t), t, 0)
+            assert orc.loan_volume(t) == log[t]["loanVolume"], f"loanVolume differs at t={t}"
+            volume += orc.loan_volume(t)
+            for k in stats.LOG_KEYS:
+                if k != "loanVolume":
+                    assert _close(rs[k], log[t][k]), f"log key {k} differs at t={t}: {rs[k]} vs {log[t][k]}"
+        assert volume > 1000          # the rule was exercised (about 2.5 k loans in 200 steps)
+    finally:
+        orc.unbind_lending()
+
+
 @pytest.mark.parametrize("name", UNSUPPORTED)
 def test_unsupported_rule_families_fail_loudly(name):
     with pytest.raises(init.UnsupportedConfiguration):
