@@ -226,7 +226,9 @@ static void do_inheritance(ctx_t *c, int s) {
     }
 }
 
+static void lending_note_death(const ctx_t *c, int s);
 static void do_death(ctx_t *c, int s, int cause) {
+    lending_note_death(c, s);
     c->a.cod[s] = cause;
     int pos = c->a.pos[s];
     if (pos >= 0 && c->g.occ[pos] == s) c->g.occ[pos] = -1;
@@ -285,6 +287,80 @@ static int alloc_slot(ctx_t *c) {
 
 
 /* ------------------------------------------------------------------------------------------
+ * friends + conflict happiness (agent.py:1499-1520 updateFriends, 1563-1565 / 1622-1632
+ * updateNeighbors -> updateSocialNetwork, 1099-1105 findSocialHappiness, 912-918
+ * findConflictHappiness).  ORACLE-PRIVATE like lending below: they only move the happiness keys of
+ * the log; the engine reports social / conflict happiness as 0 and refuses "friends" configurations.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct { int32_t slot, id, hd; } orc_friend_t;
+typedef struct { orc_friend_t *v; int n, cap; } friend_list_t;
+typedef struct {
+    int64_t capacity;
+    int32_t *max_friends, *last_combat;               /* per slot, host arrays */
+    double *social_happiness, *conflict_happiness;
+    friend_list_t *friends;                           /* owned here */
+} orc_social_t;
+static orc_social_t g_social_store, *g_social = NULL;
+enum { EB_MAX_FRIENDS = 15 };                         /* steptables.ENDOWMENT_BITS */
+
+void orc_bind_social(int32_t *max_friends, int32_t *last_combat, double *social_happiness, double *conflict_happiness,
+                     int64_t capacity) {
+    if (g_social) {
+        for (int64_t i = 0; i < g_social->capacity; i++) free(g_social->friends[i].v);
+        free(g_social->friends);
+        g_social = NULL;
+    }
+    if (!max_friends) return;
+    g_social = &g_social_store;
+    g_social->capacity = capacity;
+    g_social->max_friends = max_friends; g_social->last_combat = last_combat;
+    g_social->social_happiness = social_happiness; g_social->conflict_happiness = conflict_happiness;
+    g_social->friends = (friend_list_t *)calloc((size_t)capacity, sizeof(friend_list_t));
+}
+
+/* sums over the agent list for meanSocialHappiness / meanConflictHappiness (sugarscape.py:1147-1160) */
+void orc_social_sums(const ssb_agents_t *a, double out[2]) {
+    out[0] = out[1] = 0;
+    if (!g_social) return;
+    for (int64_t i = 0; i < a->counters[SSB_C_N_LIST]; i++) {
+        int s = a->order[i];
+        out[0] += g_social->social_happiness[s];
+        out[1] += g_social->conflict_happiness[s];
+    }
+}
+
+static void social_reset_slot(int s) {
+    g_social->friends[s].n = 0;
+    g_social->last_combat[s] = -1;
+    g_social->social_happiness[s] = 0; g_social->conflict_happiness[s] = 0;
+}
+static void friend_append(friend_list_t *L, orc_friend_t x) {
+    if (L->n == L->cap) { L->cap = L->cap ? 2 * L->cap : 8; L->v = (orc_friend_t *)realloc(L->v, sizeof(orc_friend_t) * (size_t)L->cap); }
+    L->v[L->n++] = x;
+}
+static void friend_remove_first(friend_list_t *L, orc_friend_t x) {     /* list.remove: first entry with the same agent and distance */
+    for (int q = 0; q < L->n; q++)
+        if (L->v[q].slot == x.slot && L->v[q].id == x.id && L->v[q].hd == x.hd) {
+            memmove(&L->v[q], &L->v[q + 1], sizeof(orc_friend_t) * (size_t)(L->n - q - 1)); L->n--; return;
+        }
+}
+/* updateFriends (agent.py:1499-1520) */
+static void update_friends(ctx_t *c, int s, int nb) {
+    friend_list_t *L = &g_social->friends[s];
+    const int hd = (c->p->flags & SSB_F_TAGS) ? popcount32(c->a.tags[s] ^ c->a.tags[nb]) : 0;
+    const orc_friend_t entry = {nb, c->a.id[nb], hd};
+    if (L->n < g_social->max_friends[s]) { friend_append(L, entry); return; }
+    int max_hd = 0, have_max = 0;
+    orc_friend_t worst = {0, 0, 0};
+    for (int p = 0; p < L->n; p++) {
+        const orc_friend_t f = L->v[p];
+        if (f.id == entry.id) { friend_remove_first(L, f); friend_append(L, entry); return; }
+        if (f.hd > max_hd) { worst = f; max_hd = f.hd; have_max = 1; }
+    }
+    if (max_hd > hd && have_max) { friend_remove_first(L, worst); friend_append(L, entry); }
+}
+
+/* ------------------------------------------------------------------------------------------
  * lending (agent.py:431-483 doLending, 190-212 addLoan*, 920-930 current debt, 1226-1245,
  * 1285-1296, 1330-1360 payDebt, 1445-1449 removeDebt, 1532-1541 updateLoans, 1549-1553 mean income).
  * ORACLE-PRIVATE state: the CUDA engine has no lending yet and refuses such
@@ -293,7 +369,6 @@ static int alloc_slot(ctx_t *c) {
  * both lists are kept per slot with Python's list semantics (remove = first equal element,
  * iteration by index over a list that changes underneath).  An agent is named by (slot, id):
  * a slot that was reused by a newborn no longer is the agent the loan refers to (= dead).
- * Not restated: payDebtToCreditorChildren (inheritance policy "children" together with lending).
  * ---------------------------------------------------------------------------------------- */
 typedef struct { int32_t other_slot, other_id; double sugar, spice; int32_t duration, origin; } orc_loan_t;
 typedef struct { orc_loan_t *v; int n, cap; } loan_list_t;
@@ -306,6 +381,11 @@ typedef struct {
     loan_list_t *creditors, *debtors;                 /* per slot, owned here */
 } orc_lending_t;
 static orc_lending_t g_lend_store, *g_lend = NULL;
+/* a creditor that died keeps its children list in Python (the loan holds the object): remember the
+ * head of its kin list, which lives on in the pool after the slot was reused */
+typedef struct { int32_t slot, id, children_head; } dead_creditor_t;
+static dead_creditor_t *g_dead_creditors = NULL;
+static int g_n_dead_creditors = 0, g_cap_dead_creditors = 0;
 enum { EB_BASE_INTEREST = 12, EB_LENDING_FACTOR = 13, EB_LOAN_DURATION = 14 };   /* steptables.ENDOWMENT_BITS */
 
 void orc_bind_lending(double *lending_factor, double *base_interest_rate, int32_t *loan_duration,
@@ -316,6 +396,7 @@ void orc_bind_lending(double *lending_factor, double *base_interest_rate, int32_
         free(g_lend->creditors); free(g_lend->debtors);
         g_lend = NULL;
     }
+    free(g_dead_creditors); g_dead_creditors = NULL; g_n_dead_creditors = g_cap_dead_creditors = 0;
     if (!lending_factor) return;                      /* unbind */
     g_lend = &g_lend_store;
     g_lend->capacity = capacity;
@@ -374,6 +455,43 @@ static void add_loan(ctx_t *c, int creditor, int debtor, int origin, double suga
     a->spice[debtor] = a->spice[debtor] + spice_principal;
 }
 
+static void lending_note_death(const ctx_t *c, int s) {     /* called by do_death */
+    if (!g_lend || g_lend->debtors[s].n == 0) return;
+    if (g_n_dead_creditors == g_cap_dead_creditors) {
+        g_cap_dead_creditors = g_cap_dead_creditors ? 2 * g_cap_dead_creditors : 64;
+        g_dead_creditors = (dead_creditor_t *)realloc(g_dead_creditors, sizeof(dead_creditor_t) * (size_t)g_cap_dead_creditors);
+    }
+    const dead_creditor_t d = {s, c->a.id[s], c->a.children_head[s]};
+    g_dead_creditors[g_n_dead_creditors++] = d;
+}
+
+static void add_loan(ctx_t *c, int creditor, int debtor, int origin, double sugar_principal, double sugar_loan,
+                     double spice_principal, double spice_loan, int duration);
+
+/* payDebtToCreditorChildren (agent.py:1362-1377): the loan is split among the dead creditor's living
+ * children (the debtor itself excluded), each as a new one-step loan, in the children list's order */
+static void pay_debt_to_creditor_children(ctx_t *c, int s, orc_loan_t loan) {
+    ssb_agents_t *a = &c->a;
+    int head = -1;
+    if (a->id[loan.other_slot] == loan.other_id) head = a->children_head[loan.other_slot];
+    else for (int i = g_n_dead_creditors - 1; i >= 0; i--)
+        if (g_dead_creditors[i].slot == loan.other_slot && g_dead_creditors[i].id == loan.other_id) { head = g_dead_creditors[i].children_head; break; }
+    int32_t kids[256]; int n = 0;
+    for (int e = head; e >= 0 && n < 256; e = a->kin_next[e]) {          /* newest first (kin_push prepends) */
+        const int o = a->kin_slot[e];
+        if (a->id[o] == a->kin_id[e] && agent_alive(c, o) && o != s) kids[n++] = o;
+    }
+    if (n > 0) {
+        const double sugar_rep = loan.sugar / n, spice_rep = loan.spice / n;
+        for (int i = n - 1; i >= 0; i--) add_loan(c, kids[i], s, a->last_moved[s], 0, sugar_rep, 0, spice_rep, 1);   /* append order */
+    }
+    loan_remove_first(&g_lend->creditors[s], &loan);
+    if (a->id[loan.other_slot] == loan.other_id) {
+        const orc_loan_t mirror = {s, a->id[s], loan.sugar, loan.spice, loan.duration, loan.origin};
+        loan_remove_first(&g_lend->debtors[loan.other_slot], &mirror);
+    }
+}
+
 /* payDebt (agent.py:1330-1360); `loan` is an element of the creditors list of s */
 static void pay_debt(ctx_t *c, int s, orc_loan_t loan) {
     ssb_agents_t *a = &c->a;
@@ -381,7 +499,7 @@ static void pay_debt(ctx_t *c, int s, orc_loan_t loan) {
     const orc_loan_t mirror = {s, a->id[s], loan.sugar, loan.spice, loan.duration, loan.origin};
     const int same_object = a->id[cr] == loan.other_id;       /* the creditor's record still exists */
     if (!loan_other_alive(c, &loan)) {
-        if (c->p->inheritance_policy == 1) { a->counters[SSB_C_OVERFLOW] = 9; return; }   /* payDebtToCreditorChildren: not restated */
+        if (c->p->inheritance_policy == 1) { pay_debt_to_creditor_children(c, s, loan); return; }
         loan_remove_first(&g_lend->creditors[s], &loan);
         if (same_object) loan_remove_first(&g_lend->debtors[cr], &mirror);
     } else if (a->sugar[s] - loan.sugar > 0 && a->spice[s] - loan.spice > 0) {
@@ -607,6 +725,7 @@ static int move_to_best_cell(ctx_t *c, int s) {
             double pl = loot < a->spice[prey] ? loot : a->spice[prey];
             a->sugar[s] += sl; a->spice[s] += pl;
             a->sugar[prey] -= sl; a->spice[prey] -= pl;
+            if (g_social) g_social->last_combat[s] = c->t;
             do_death(c, prey, SSB_COMBAT);
         }
     }
@@ -740,6 +859,10 @@ static void do_reproduction(ctx_t *c, int s) {
         a->sex[ch] = PICK(sex, EB_SEX);
         a->trade_factor[ch] = PICK(trade_factor, EB_TRADE_FACTOR);
         a->vision[ch] = PICK(vision, EB_VISION);
+        if (g_social) {
+            social_reset_slot(ch);
+            g_social->max_friends[ch] = ((eb >> EB_MAX_FRIENDS) & 1u) ? g_social->max_friends[m] : g_social->max_friends[s];
+        }
         if (g_lend) {
             lending_reset_slot(ch);
             g_lend->base_interest_rate[ch] = ((eb >> EB_BASE_INTEREST) & 1u) ? g_lend->base_interest_rate[m] : g_lend->base_interest_rate[s];
@@ -800,6 +923,11 @@ static void agent_transaction(ctx_t *c, int s) {
     a->last_sugar[s] = a->sugar[s];
     a->last_spice[s] = a->spice[s];
     int pos = move_to_best_cell(c, s);
+    if (g_social) {      /* updateNeighbors -> updateSocialNetwork -> updateFriends, neighbours in N, S, E, W order */
+        int32_t nb4[4];
+        neighbours4(c, pos, nb4);
+        for (int i = 0; i < 4; i++) { int o = c->g.occ[nb4[i]]; if (o >= 0) update_friends(c, s, o); }
+    }
     collect(c, s, pos);
     /* doMetabolism (agent.py:485-498) + consumption pollution (cell.py:27-40) */
     double sm = a->sugar_metab[s] > 0 ? a->sugar_metab[s] : 0;
@@ -836,9 +964,15 @@ static void agent_transaction(ctx_t *c, int s) {
         for (int e = a->mates_head[s]; e >= 0; e = a->kin_next[e]) family += kin_alive(c, e) >= 0 ? 1 : -1;
     }
     double family_h = erf(family);
+    double conflict_h = 0, social_h = 0;
+    if (g_social) {
+        if (g_social->last_combat[s] == c->t) conflict_h = a->aggression[s] > 1 ? 1.0 : -1.0;
+        if (g_social->max_friends[s] != 0) social_h = (g_social->friends[s].n * (2.0 / g_social->max_friends[s])) - 1;
+        g_social->conflict_happiness[s] = conflict_h; g_social->social_happiness[s] = social_h;
+    }
     a->wealth_happiness[s] = wealth_h;
     a->family_happiness[s] = family_h;
-    a->happiness[s] = 0 + family_h + 1.0 + 0 + wealth_h;
+    a->happiness[s] = conflict_h + family_h + 1.0 + social_h + wealth_h;
 }
 
 /* ------------------------------------------------------------------------------------------

@@ -14,10 +14,10 @@ import random
 import numpy as np
 
 # bit positions inside endow_bits[t]; must match enum EB_* in csrc/ssb_rules.cuh and the oracle
-# (bits 12-14 are read by the oracle's lending restatement only; the engine has no lending yet)
+# (bits 12-15 are read by the oracle's lending / friends restatements only; the engine has neither yet)
 ENDOWMENT_BITS = ("aggressionFactor", "fertilityAge", "fertilityFactor", "infertilityAge",
                   "lookaheadFactor", "maxAge", "movement", "spiceMetabolism", "sugarMetabolism",
-                  "sex", "tradeFactor", "vision", "baseInterestRate", "lendingFactor", "loanDuration")
+                  "sex", "tradeFactor", "vision", "baseInterestRate", "lendingFactor", "loanDuration", "maxFriends")
 
 
 def _md5_int(name):

@@ -114,6 +114,32 @@ class Oracle:
     def unbind_lending(self):
         self.L.orc_bind_lending(*([None] * 7), 0)
 
+    def bind_social(self, endowments):
+        """Oracle-private friends lists + conflict happiness (log keys only)."""
+        cap = self.state.capacity
+        self.social = {"max_friends": np.zeros(cap, np.int32), "last_combat": np.full(cap, -1, np.int32),
+                       "social_happiness": np.zeros(cap, np.float64), "conflict_happiness": np.zeros(cap, np.float64)}
+        n = int(self.state.counters[layout.C_N_LIST])
+        for s in self.state.a_order[:n]:
+            self.social["max_friends"][s] = endowments[int(self.state.a_id[s])]["maxFriends"]
+        L = self.L
+        L.orc_bind_social.argtypes = [C.c_void_p] * 4 + [C.c_int64]
+        L.orc_bind_social.restype = None
+        L.orc_social_sums.argtypes = [C.c_void_p, C.POINTER(C.c_double * 2)]
+        L.orc_social_sums.restype = None
+        L.orc_bind_social(*[self.social[k].ctypes.data for k in ("max_friends", "last_combat", "social_happiness",
+                                                                 "conflict_happiness")], cap)
+
+    def unbind_social(self):
+        self.L.orc_bind_social(*([None] * 4), 0)
+
+    def social_sums(self):
+        """(sum of socialHappiness, sum of conflictHappiness) over the agent list."""
+        g, a = self.state.as_structs()
+        out = (C.c_double * 2)()
+        self.L.orc_social_sums(C.byref(a), C.byref(out))
+        return out[0], out[1]
+
     def loan_volume(self, t):
         g, a = self.state.as_structs()
         return int(self.L.orc_loan_volume(C.byref(a), t))

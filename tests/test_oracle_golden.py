@@ -95,6 +95,46 @@ def test_oracle_lending_matches_reference_trajectory():
         orc.unbind_lending()
 
 
+def test_oracle_dune_lending_friends_combat_matches_reference_trajectory():
+    """examples/dune.json = trade + tags + live combat + reproduction + inheritance to children on top
+    of lending (payDebtToCreditorChildren included) and friends.  Oracle-only restatements (the
+    engine refuses the configuration): every digest of every step and all 59 log keys, with the
+    social / conflict happiness means and loanVolume taken from the oracle-private state."""
+    name = "dune"
+    c, state, pop, params, endow, tags = pu.build(name, check=False)
+    meta, _ = pu.load_golden(name)
+    gold, log = meta["steps"], meta["log"]
+    orc = Oracle(params, state, endow, tags)
+    orc.set_mt_from_python()
+    orc.bind_lending(pop.endowments)
+    orc.bind_social(pop.endowments)
+    try:
+        d, _ = pu.state_digests(state, *orc.mt_state())
+        assert d == gold[0]["digests"], "t=0 state differs"
+        sb = stats.StatsBuilder(c, init.equator(c))
+        rs = sb.update(orc.stats(0), 0)
+        fights = 0
+        for t in range(1, len(gold)):
+            orc.env_step(t)
+            orc.agent_step(t, rs["meanWealth"])
+            orc.compact(t)
+            d, snap = pu.state_digests(state, *orc.mt_state())
+            assert d == gold[t]["digests"], f"state differs at t={t}"
+            rs = sb.update(orc.stats(t), t, 0)
+            n = rs["population"]
+            social, conflict = orc.social_sums()
+            rs["meanSocialHappiness"] = round(social / n, 2) if n else 0
+            rs["meanConflictHappiness"] = round(conflict / n, 2) if n else 0
+            rs["loanVolume"] = orc.loan_volume(t)
+            fights += conflict != 0
+            for k in stats.LOG_KEYS:
+                assert _close(rs[k], log[t][k]), f"log key {k} differs at t={t}: {rs[k]} vs {log[t][k]}"
+        assert fights > 50      # live combat moved the conflict happiness in most early steps
+    finally:
+        orc.unbind_lending()
+        orc.unbind_social()
+
+
 @pytest.mark.parametrize("name", UNSUPPORTED)
 def test_unsupported_rule_families_fail_loudly(name):
     with pytest.raises(init.UnsupportedConfiguration):
