@@ -116,6 +116,12 @@ static uint32_t rng_below(orc_rng_t *r, uint32_t n) {
     return v;
 }
 
+/* random.random(): (a >> 5, b >> 6) -> 53 bits (Modules/_randommodule.c) */
+static double rng_random(orc_rng_t *r) {
+    uint32_t a = rng_next32(r) >> 5, b = rng_next32(r) >> 6;
+    return (a * 67108864.0 + b) * (1.0 / 9007199254740992.0);
+}
+
 static void rng_shuffle_i32(orc_rng_t *r, int32_t *x, int n) {
     for (int i = n - 1; i >= 1; i--) {
         uint32_t j = rng_below(r, (uint32_t)i + 1u);
@@ -142,6 +148,51 @@ typedef struct {
 enum { EB_AGGRESSION = 0, EB_FERT_AGE, EB_FERT_FACTOR, EB_INFERT_AGE, EB_LOOKAHEAD, EB_MAX_AGE,
        EB_MOVEMENT, EB_SPICE_METAB, EB_SUGAR_METAB, EB_SEX, EB_TRADE_FACTOR, EB_VISION };
 
+
+/* ------------------------------------------------------------------------------------------
+ * diseases (condition.py:36-86; agent.py:184-188 addDisease, 227-247 catchDisease, 315-371 doDisease /
+ * doInfectionAttempt, 1034-1050 nearest Hamming distance, 716-717 / 1031-1032 / 1107-1111 / 1161-1162
+ * the "find" accessors with their modifiers).  ORACLE-PRIVATE state like lending and friends: the
+ * engine refuses disease configurations; exact RNG mode only.
+ * ---------------------------------------------------------------------------------------- */
+enum { DM_AGGRESSION = 0, DM_FERTILITY, DM_FRIENDLINESS, DM_HAPPINESS, DM_MOVEMENT, DM_SPICE_METAB, DM_SUGAR_METAB,
+       DM_VISION, DM_COUNT };
+typedef struct {
+    int32_t id, incubation, start_timestep, tag_len;
+    uint32_t tags, pad;                       /* bit j = diseaseTags[j] */
+    double transmission;
+    double penalty[DM_COUNT];
+    int64_t infected;                         /* len(disease.infected) */
+    int64_t listed;                           /* how often sugarscape.diseases holds it (appended once per initial infection) */
+} orc_disease_t;
+typedef struct { int32_t disease, start, end, caught, incubation, infector_slot, infector_id; } orc_sick_t;
+typedef struct { orc_sick_t *v; int n, cap; } sick_list_t;
+typedef struct {
+    int64_t capacity;
+    int32_t immune_len, n_diseases;
+    orc_disease_t *diseases;                  /* host array */
+    uint64_t *immune, *start_immune;          /* per slot, bit i = immuneSystem[i] */
+    double *protection;                       /* diseaseProtectionChance */
+    double *modifier;                         /* [slot][DM_COUNT] */
+    int32_t *disease_death, *last_spread, *n_spread;
+    double *health_happiness;                 /* healthHappiness as of the agent's last updateHappiness */
+    int32_t *last_valid_moves;                /* lastValidMoves: 1 when the range is empty (vision / movement pushed to 0) */
+    const uint64_t *immune_bits;              /* per timestep: draws for the child's mismatching immune positions */
+    sick_list_t *sick;                        /* owned here */
+} orc_dis_t;
+static orc_dis_t g_dis_store, *g_dis = NULL;
+enum { EB_PROTECTION = 16 };                  /* steptables.ENDOWMENT_BITS */
+
+static inline double dis_mod(int s, int which) { return g_dis ? g_dis->modifier[(size_t)s * DM_COUNT + which] : 0.0; }
+static inline double pos_part(double v) { return v > 0 ? v : 0; }
+/* findSugarMetabolism / findSpiceMetabolism / findVision / findMovement / findAggression */
+#define EFF_SUGAR_METAB(c, s) pos_part((c)->a.sugar_metab[s] + dis_mod(s, DM_SUGAR_METAB))
+#define EFF_SPICE_METAB(c, s) pos_part((c)->a.spice_metab[s] + dis_mod(s, DM_SPICE_METAB))
+#define EFF_VISION(c, s)      pos_part((c)->a.vision[s] + dis_mod(s, DM_VISION))
+#define EFF_MOVEMENT(c, s)    pos_part((c)->a.movement[s] + dis_mod(s, DM_MOVEMENT))
+#define EFF_AGGRESSION(c, s)  pos_part((c)->a.aggression[s] + dis_mod(s, DM_AGGRESSION))
+static inline int is_sick(int s) { return g_dis && g_dis->sick[s].n > 0; }
+
 static inline int wrapi(int v, int n) { v %= n; return v < 0 ? v + n : v; }
 
 static int agent_alive(const ctx_t *c, int s) {
@@ -162,8 +213,8 @@ static int find_tribe(const ctx_t *c, uint32_t tags) {
 
 /* agent.py:1170-1201 */
 static double find_welfare(const ctx_t *c, int s, double sugar_reward, double spice_reward) {
-    double sm = c->a.sugar_metab[s] > 0 ? c->a.sugar_metab[s] : 0;
-    double pm = c->a.spice_metab[s] > 0 ? c->a.spice_metab[s] : 0;
+    double sm = EFF_SUGAR_METAB(c, s);
+    double pm = EFF_SPICE_METAB(c, s);
     double total = sm + pm, sprop = 0, pprop = 0;
     if (total != 0) { sprop = sm / total; pprop = pm / total; }
     double look = c->a.lookahead[s];
@@ -227,8 +278,10 @@ static void do_inheritance(ctx_t *c, int s) {
 }
 
 static void lending_note_death(const ctx_t *c, int s);
+static void disease_note_death(int s);
 static void do_death(ctx_t *c, int s, int cause) {
     lending_note_death(c, s);
+    disease_note_death(s);
     c->a.cod[s] = cause;
     int pos = c->a.pos[s];
     if (pos >= 0 && c->g.occ[pos] == s) c->g.occ[pos] = -1;
@@ -238,8 +291,8 @@ static void do_death(ctx_t *c, int s, int cause) {
 
 /* agent.py:1023-1029 */
 static void find_mrs(ctx_t *c, int s) {
-    double pm = c->a.spice_metab[s] > 0 ? c->a.spice_metab[s] : 0;
-    double sm = c->a.sugar_metab[s] > 0 ? c->a.sugar_metab[s] : 0;
+    double pm = EFF_SPICE_METAB(c, s);
+    double sm = EFF_SUGAR_METAB(c, s);
     double spice_need = pm > 0 ? c->a.spice[s] / pm : 1;
     double sugar_need = sm > 0 ? c->a.sugar[s] / sm : 1;
     c->a.mrs[s] = c->a.trade_factor[s] * (spice_need / sugar_need);
@@ -247,8 +300,8 @@ static void find_mrs(ctx_t *c, int s) {
 
 /* agent.py:1067-1080 */
 static double find_new_mrs(const ctx_t *c, int s, double sugar, double spice) {
-    double pm = c->a.spice_metab[s] > 0 ? c->a.spice_metab[s] : 0;
-    double sm = c->a.sugar_metab[s] > 0 ? c->a.sugar_metab[s] : 0;
+    double pm = EFF_SPICE_METAB(c, s);
+    double sm = EFF_SUGAR_METAB(c, s);
     double spice_need = pm > 0 ? spice / pm : 1;
     double sugar_need = sm > 0 ? sugar / sm : 1;
     if (spice_need == 1 && sugar_need == 1) return 1;
@@ -261,7 +314,7 @@ static double find_new_mrs(const ctx_t *c, int s, double sugar, double spice) {
 static int is_fertile(const ctx_t *c, int s) {
     return c->a.sugar[s] >= c->a.start_sugar[s] && c->a.spice[s] >= c->a.start_spice[s] &&
            c->a.age[s] >= c->a.fert_age[s] && c->a.age[s] < c->a.infert_age[s] &&
-           c->a.fert_factor[s] > 0;
+           (c->a.fert_factor[s] + dis_mod(s, DM_FERTILITY)) > 0;
 }
 
 /* the four von Neumann neighbours in the reference's dict order N, S, E, W (cell.py:61-75) */
@@ -565,7 +618,7 @@ static void do_lending(ctx_t *c, int s) {
         if (a->age[o] >= a->fert_age[o] && a->age[o] < a->infert_age[o] && !is_fertile(c, o)) borrowers[nbw++] = o;
     }
     rng_shuffle_i32(c->rng, borrowers, nbw);
-    const double pm = a->spice_metab[s] > 0 ? a->spice_metab[s] : 0, sm = a->sugar_metab[s] > 0 ? a->sugar_metab[s] : 0;
+    const double pm = EFF_SPICE_METAB(c, s), sm = EFF_SUGAR_METAB(c, s);
     int loans = 0;
     for (int k = 0; k < nbw; k++) {
         const int b = borrowers[k];
@@ -586,7 +639,7 @@ static void do_lending(ctx_t *c, int s) {
         /* isCreditWorthy (1231-1242) */
         const int duration = g_lend->loan_duration[s];
         if (duration == 0) continue;
-        const double bpm = a->spice_metab[b] > 0 ? a->spice_metab[b] : 0, bsm = a->sugar_metab[b] > 0 ? a->sugar_metab[b] : 0;
+        const double bpm = EFF_SPICE_METAB(c, b), bsm = EFF_SUGAR_METAB(c, b);
         const double sugar_cost = sugar_amount / duration, spice_cost = spice_amount / duration;
         const double sugar_income = ((g_lend->sugar_mean_income[b] - bsm) - current_debt(&g_lend->creditors[b], 0)) - sugar_cost;
         const double spice_income = ((g_lend->spice_mean_income[b] - bpm) - current_debt(&g_lend->creditors[b], 1)) - spice_cost;
@@ -595,6 +648,189 @@ static void do_lending(ctx_t *c, int s) {
         loans++;
     }
     if (loans > 0) { g_lend->last_lended[s] = c->t; g_lend->last_loans[s] = loans; }
+}
+
+
+/* ---- disease runtime ------------------------------------------------------------------------ */
+void orc_bind_disease(orc_disease_t *diseases, int32_t n_diseases, int32_t immune_len, uint64_t *immune,
+                      uint64_t *start_immune, double *protection, double *modifier, int32_t *disease_death,
+                      int32_t *last_spread, int32_t *n_spread, double *health_happiness, int32_t *last_valid_moves,
+                      const uint64_t *immune_bits, int64_t capacity) {
+    if (g_dis) {
+        for (int64_t i = 0; i < g_dis->capacity; i++) free(g_dis->sick[i].v);
+        free(g_dis->sick);
+        g_dis = NULL;
+    }
+    if (!immune) return;
+    g_dis = &g_dis_store;
+    g_dis->capacity = capacity; g_dis->immune_len = immune_len; g_dis->n_diseases = n_diseases;
+    g_dis->diseases = diseases; g_dis->immune = immune; g_dis->start_immune = start_immune;
+    g_dis->protection = protection; g_dis->modifier = modifier; g_dis->disease_death = disease_death;
+    g_dis->last_spread = last_spread; g_dis->n_spread = n_spread; g_dis->immune_bits = immune_bits;
+    g_dis->health_happiness = health_happiness; g_dis->last_valid_moves = last_valid_moves;
+    g_dis->sick = (sick_list_t *)calloc((size_t)capacity, sizeof(sick_list_t));
+}
+int orc_sizeof_disease(void) { return (int)sizeof(orc_disease_t); }
+int32_t orc_disease_count(int32_t slot) { return g_dis ? g_dis->sick[slot].n : 0; }
+
+static void sick_append(sick_list_t *L, orc_sick_t x) {
+    if (L->n == L->cap) { L->cap = L->cap ? 2 * L->cap : 8; L->v = (orc_sick_t *)realloc(L->v, sizeof(orc_sick_t) * (size_t)L->cap); }
+    L->v[L->n++] = x;
+}
+static void disease_reset_slot(int s) {
+    g_dis->sick[s].n = 0;
+    for (int k = 0; k < DM_COUNT; k++) g_dis->modifier[(size_t)s * DM_COUNT + k] = 0;
+    g_dis->disease_death[s] = 0; g_dis->last_spread[s] = -1; g_dis->n_spread[s] = 0;
+    g_dis->health_happiness[s] = 0; g_dis->last_valid_moves[s] = 0;
+}
+static void disease_trigger(int s, const orc_disease_t *d) {      /* condition.py:57-65 */
+    for (int k = 0; k < DM_COUNT; k++) g_dis->modifier[(size_t)s * DM_COUNT + k] += d->penalty[k];
+}
+static void disease_recover(int s, orc_disease_t *d) {            /* condition.py:67-76 */
+    for (int k = 0; k < DM_COUNT; k++) g_dis->modifier[(size_t)s * DM_COUNT + k] -= d->penalty[k];
+    d->infected--;
+}
+static int infected_with(int s, int disease_id) {                 /* agent.py:1249-1254 */
+    const sick_list_t *L = &g_dis->sick[s];
+    for (int i = 0; i < L->n; i++) if (g_dis->diseases[L->v[i].disease].id == disease_id) return 1;
+    return 0;
+}
+/* findNearestHammingDistanceInDisease (agent.py:1034-1050) */
+int32_t orc_disease_nearest(int32_t s, int32_t di, int32_t *start, int32_t *end) {
+    const orc_disease_t *d = &g_dis->diseases[di];
+    const int len = d->tag_len;
+    int best = len, b0 = 0, b1 = len - 1;
+    for (int i = 0; i < g_dis->immune_len - len; i++) {
+        const uint32_t window = (uint32_t)((g_dis->immune[s] >> i) & ((len >= 32 ? 0xffffffffull : ((1ull << len) - 1ull))));
+        const int hd = popcount32(window ^ d->tags);
+        if (hd < best) { best = hd; b0 = i; b1 = i + (len - 1); }
+    }
+    if (start) *start = b0;
+    if (end) *end = b1;
+    return best;
+}
+/* catchDisease (agent.py:227-247); infector slot -1 = none (initial infections, timestep given) */
+void orc_disease_catch(int32_t s, int32_t di, int32_t infector, int32_t infector_id, int32_t timestep, int32_t initial,
+                       orc_rng_t *rng) {
+    orc_disease_t *d = &g_dis->diseases[di];
+    if (infected_with(s, d->id)) return;
+    orc_sick_t rec = {di, -1, -1, timestep, d->incubation, infector, infector_id};
+    {   /* generated diseases always carry a tag list (possibly empty: distance 0 = immune); tags None is the premade zombie virus only */
+        int32_t st, en;
+        if (orc_disease_nearest(s, di, &st, &en) == 0) return;        /* immune */
+        rec.start = st; rec.end = en;
+    }
+    int caught = initial;
+    if (!initial) {                            /* doInfectionAttempt (agent.py:363-371): two random.uniform(0, 1) */
+        const double attack = 0.0 + (1.0 - 0.0) * rng_random(rng), defense = 0.0 + (1.0 - 0.0) * rng_random(rng);
+        const int attack_ok = attack <= d->transmission && d->transmission != 0.0;
+        const int defense_ok = defense <= g_dis->protection[s] && g_dis->protection[s] != 0.0;
+        caught = attack_ok && !defense_ok;
+    }
+    if (caught) {                              /* addDisease (agent.py:184-188) */
+        sick_append(&g_dis->sick[s], rec);
+        d->infected++;
+        if (rec.incubation == 0) disease_trigger(s, d);
+    }
+}
+void orc_disease_listed(int32_t di) { g_dis->diseases[di].listed++; }
+
+/* doDisease (agent.py:315-361) */
+static void do_disease(ctx_t *c, int s) {
+    sick_list_t *L = &g_dis->sick[s];
+    /* random.shuffle(self.diseases) */
+    for (int i = L->n - 1; i >= 1; i--) {
+        uint32_t j = rng_below(c->rng, (uint32_t)i + 1u);
+        orc_sick_t tmp = L->v[i]; L->v[i] = L->v[j]; L->v[j] = tmp;
+    }
+    for (int p = 0; p < L->n; p++) {           /* Python for-loop over a list that may lose the current element */
+        orc_sick_t *rec = &L->v[p];
+        orc_disease_t *d = &g_dis->diseases[rec->disease];
+        if (rec->caught != c->t && rec->incubation > 0) rec->incubation -= 1;
+        if (rec->incubation == 0) disease_trigger(s, d);           /* (every step: the penalties pile up) */
+        if (d->tag_len > 0) {
+            const int st = rec->start;
+            int en = rec->end + 1;
+            if (en > g_dis->immune_len) en = g_dis->immune_len;
+            const int len = en - st;
+            const uint64_t mask = len >= 64 ? ~0ull : ((1ull << len) - 1ull);
+            const uint64_t response = (g_dis->immune[s] >> st) & mask;     /* the slice, taken before the flip */
+            for (int i = 0; i < len; i++)
+                if (((response >> i) & 1ull) != ((d->tags >> i) & 1u)) {
+                    g_dis->immune[s] = (g_dis->immune[s] & ~(1ull << (st + i))) | ((uint64_t)((d->tags >> i) & 1u) << (st + i));
+                    break;
+                }
+            if (len == d->tag_len && response == (uint64_t)d->tags) {      /* diseaseTags == immuneResponse */
+                const orc_sick_t gone = *rec;
+                /* list.remove(record): first equal record -- records are unique per disease */
+                memmove(&L->v[p], &L->v[p + 1], sizeof(orc_sick_t) * (size_t)(L->n - p - 1));
+                L->n--;
+                disease_recover(s, &g_dis->diseases[gone.disease]);
+            }
+        }
+    }
+    const int count = L->n;
+    if (count == 0) return;
+    int32_t nb4[4], neighbors[4];
+    int nn = 0;
+    neighbours4(c, c->a.pos[s], nb4);
+    for (int i = 0; i < 4; i++) { int o = c->g.occ[nb4[i]]; if (o >= 0 && agent_alive(c, o)) neighbors[nn++] = o; }
+    int spread = 0;
+    rng_shuffle_i32(c->rng, neighbors, nn);
+    for (int k = 0; k < nn; k++) {
+        const int di = L->v[rng_below(c->rng, (uint32_t)count)].disease;
+        orc_disease_catch(neighbors[k], di, s, c->a.id[s], c->t, 0, c->rng);
+        if (infected_with(neighbors[k], g_dis->diseases[di].id)) spread++;
+    }
+    if (spread > 0) { g_dis->last_spread[s] = c->t; g_dis->n_spread[s] = spread; }
+}
+
+static void disease_note_death(int s) {        /* doDeath (agent.py:302-313) */
+    if (!g_dis) return;
+    if (g_dis->sick[s].n > 0) g_dis->disease_death[s] = 1;
+    for (int i = 0; i < g_dis->sick[s].n; i++) disease_recover(s, &g_dis->diseases[g_dis->sick[s].v[i].disease]);
+    g_dis->sick[s].n = 0;
+}
+
+int64_t orc_move_space(const ssb_agents_t *a) {      /* moveSpace (sugarscape.py:1152) */
+    int64_t v = 0;
+    if (g_dis) for (int64_t i = 0; i < a->counters[SSB_C_N_LIST]; i++) v += g_dis->last_valid_moves[a->order[i]];
+    return v;
+}
+
+double orc_health_happiness_sum(const ssb_agents_t *a) {
+    double v = 0;
+    if (g_dis) for (int64_t i = 0; i < a->counters[SSB_C_N_LIST]; i++) v += g_dis->health_happiness[a->order[i]];
+    return v;
+}
+
+/* log keys (sugarscape.py:1162, 1200-1211, 1228, 1254-1277, 1316-1317): out = {sickAgents, diseaseIncidence,
+ * distinct infectors, diseasePrevalence, agentDiseaseDeaths} */
+void orc_disease_stats(const ssb_agents_t *a, int32_t t, int64_t out[5]) {
+    for (int k = 0; k < 5; k++) out[k] = 0;
+    if (!g_dis) return;
+    const int64_t n = a->counters[SSB_C_N_LIST], n_dead = a->counters[SSB_C_N_DEAD];
+    int64_t *infectors = (int64_t *)malloc(sizeof(int64_t) * (size_t)(4 * (n + n_dead) + 16));
+    int64_t ni = 0;
+    for (int64_t i = 0; i < n; i++) {
+        const int s = a->order[i];
+        const sick_list_t *L = &g_dis->sick[s];
+        if (L->n > 0) out[0]++;
+        for (int k = 0; k < L->n; k++)
+            if (L->v[k].caught == t) {
+                out[1]++;
+                if (t != 0) infectors[ni++] = ((int64_t)L->v[k].infector_slot << 32) | (uint32_t)L->v[k].infector_id;
+            }
+    }
+    for (int64_t i = 0; i < n_dead; i++) out[4] += g_dis->disease_death[a->dead_list[i]];    /* (their disease lists are empty) */
+    /* distinct infectors */
+    for (int64_t i = 0; i < ni; i++) {
+        int seen = 0;
+        for (int64_t j = 0; j < i && !seen; j++) seen = infectors[j] == infectors[i];
+        out[2] += !seen;
+    }
+    free(infectors);
+    for (int d = 0; d < g_dis->n_diseases; d++) out[3] += g_dis->diseases[d].listed * g_dis->diseases[d].infected;
 }
 
 /* collectResourcesAtCell, agent.py:249-259 + cell.py:32-45 */
@@ -651,16 +887,18 @@ static int enumerate_cross(const ctx_t *c, int pos, int r, int32_t *cells, int32
 static int move_to_best_cell(ctx_t *c, int s) {
     const ssb_agents_t *a = &c->a;
     int pos = a->pos[s];
-    int vision = a->vision[s] > 0 ? a->vision[s] : 0, movement = a->movement[s] > 0 ? a->movement[s] : 0;
+    int vision = (int)EFF_VISION(c, s), movement = (int)EFF_MOVEMENT(c, s);
     int maxd = c->max_dx > c->max_dy ? c->max_dx : c->max_dy;
     int r = vision < movement ? vision : movement;
     if (r > maxd) r = maxd;
     int32_t cells[MAX_CAND], dists[MAX_CAND];
     int n = r > 0 ? enumerate_cross(c, pos, r, cells, dists) : 0;
-    double aggression = a->aggression[s] > 0 ? a->aggression[s] : 0;
+    double aggression = EFF_AGGRESSION(c, s);
     int best = pos;
     if (n == 0) {
-        /* empty range: stays put; validMoves / movementNeighborhood keep their old values */
+        /* empty range: stays put; validMoves / movementNeighborhood keep their old values, but
+         * findBestCell still records lastValidMoves = len([own cell]) (agent.py:1398-1399, 745) */
+        if (g_dis) g_dis->last_valid_moves[s] = 1;
     } else {
         /* findNeighborhood: live agents in range + self (agent.py:1052-1065) */
         int hood = 1;
@@ -715,6 +953,7 @@ static int move_to_best_cell(ctx_t *c, int s) {
         best = cand[0].cell;
         a->n_neighborhood[s] = hood;
         a->n_valid_moves[s] = m;
+        if (g_dis) g_dis->last_valid_moves[s] = m;
     }
     /* moveToBestCell: doCombat when aggressive (agent.py:274-294), then gotoCell (1213-1219) */
     if (aggression > 0) {
@@ -859,6 +1098,20 @@ static void do_reproduction(ctx_t *c, int s) {
         a->sex[ch] = PICK(sex, EB_SEX);
         a->trade_factor[ch] = PICK(trade_factor, EB_TRADE_FACTOR);
         a->vision[ch] = PICK(vision, EB_VISION);
+        if (g_dis) {     /* immune system: equal bits copied, mismatches drawn from the per-timestep stream (agent.py:897-908) */
+            disease_reset_slot(ch);
+            /* startingImmuneSystem IS immuneSystem in the reference (agent.py:33,50 bind the same list), so the
+             * parents pass on what their immune responses have learnt */
+            const uint64_t mine = g_dis->immune[s], other = g_dis->immune[m], draws = g_dis->immune_bits ? g_dis->immune_bits[c->t] : 0;
+            uint64_t child = 0; int draw = 0;
+            for (int i = 0; i < g_dis->immune_len; i++) {
+                const uint64_t bs = (mine >> i) & 1ull, bm = (other >> i) & 1ull;
+                const uint64_t b = bs == bm ? bs : ((draws >> draw++) & 1ull);
+                child |= b << i;
+            }
+            g_dis->immune[ch] = g_dis->start_immune[ch] = child;
+            g_dis->protection[ch] = ((eb >> EB_PROTECTION) & 1u) ? g_dis->protection[m] : g_dis->protection[s];
+        }
         if (g_social) {
             social_reset_slot(ch);
             g_social->max_friends[ch] = ((eb >> EB_MAX_FRIENDS) & 1u) ? g_social->max_friends[m] : g_social->max_friends[s];
@@ -930,8 +1183,8 @@ static void agent_transaction(ctx_t *c, int s) {
     }
     collect(c, s, pos);
     /* doMetabolism (agent.py:485-498) + consumption pollution (cell.py:27-40) */
-    double sm = a->sugar_metab[s] > 0 ? a->sugar_metab[s] : 0;
-    double pm = a->spice_metab[s] > 0 ? a->spice_metab[s] : 0;
+    double sm = EFF_SUGAR_METAB(c, s);
+    double pm = EFF_SPICE_METAB(c, s);
     a->sugar[s] -= sm;
     a->spice[s] -= pm;
     if (c->p->pollution_start <= c->t && c->t <= c->p->pollution_end) {
@@ -946,6 +1199,7 @@ static void agent_transaction(ctx_t *c, int s) {
     do_trading(c, s);
     do_reproduction(c, s);
     if (g_lend) do_lending(c, s);
+    if (g_dis) do_disease(c, s);
     /* doAging (agent.py:266-272) */
     if (agent_alive(c, s)) {
         a->age[s] += 1;
@@ -959,20 +1213,25 @@ static void agent_transaction(ctx_t *c, int s) {
     if (c->p->rng_mode == SSB_RNG_EXACT) {
         for (int e = a->children_head[s]; e >= 0; e = a->kin_next[e]) {
             int o = kin_alive(c, e);
-            if (o >= 0) { family += 1; if (a->born[o] == c->t) family += 1; } else family -= 1;
+            if (o >= 0) { family += 1; if (is_sick(o)) family -= 1 * 0.5; if (a->born[o] == c->t) family += 1; } else family -= 1;
         }
-        for (int e = a->mates_head[s]; e >= 0; e = a->kin_next[e]) family += kin_alive(c, e) >= 0 ? 1 : -1;
+        for (int e = a->mates_head[s]; e >= 0; e = a->kin_next[e]) {
+            int o = kin_alive(c, e);
+            if (o >= 0) { family += 1; if (is_sick(o)) family -= 1 * 0.5; } else family -= 1;
+        }
     }
     double family_h = erf(family);
     double conflict_h = 0, social_h = 0;
     if (g_social) {
-        if (g_social->last_combat[s] == c->t) conflict_h = a->aggression[s] > 1 ? 1.0 : -1.0;
+        if (g_social->last_combat[s] == c->t) conflict_h = EFF_AGGRESSION(c, s) > 1 ? 1.0 : -1.0;
         if (g_social->max_friends[s] != 0) social_h = (g_social->friends[s].n * (2.0 / g_social->max_friends[s])) - 1;
         g_social->conflict_happiness[s] = conflict_h; g_social->social_happiness[s] = social_h;
     }
     a->wealth_happiness[s] = wealth_h;
     a->family_happiness[s] = family_h;
-    a->happiness[s] = conflict_h + family_h + 1.0 + social_h + wealth_h;
+    const double health_h = is_sick(s) ? -1.0 : 1.0;       /* findHealthHappiness (agent.py:1017-1021) */
+    if (g_dis) g_dis->health_happiness[s] = health_h;
+    a->happiness[s] = conflict_h + family_h + health_h + social_h + wealth_h;
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -1253,7 +1512,7 @@ void orc_stats(const ssb_params_t *p, const ssb_grid_t *g, const ssb_agents_t *a
         if (i == 0 || w < out->min_wealth) out->min_wealth = w;
         out->sum_wealth_collected += w - (a->last_sugar[s] + a->last_spice[s]);
         /* findTimeToLive (agent.py:1113-1140) */
-        double sm = a->sugar_metab[s] > 0 ? a->sugar_metab[s] : 0, pm = a->spice_metab[s] > 0 ? a->spice_metab[s] : 0;
+        double sm = pos_part(a->sugar_metab[s] + dis_mod(s, DM_SUGAR_METAB)), pm = pos_part(a->spice_metab[s] + dis_mod(s, DM_SPICE_METAB));
         double st = sm > 0 ? a->sugar[s] / sm : 9223372036854775807.0;
         double pt = pm > 0 ? a->spice[s] / pm : 9223372036854775807.0;
         double ttl = st < pt ? st : pt;

@@ -368,6 +368,50 @@ def rule_flags(c):
     return f
 
 
+_DISEASE_ENDOWMENTS = (          # key order of the reference's dict (sugarscape.py:775-787)
+    ("aggressionPenalty", "diseaseAggressionPenalty"), ("fertilityPenalty", "diseaseFertilityPenalty"),
+    ("friendlinessPenalty", "diseaseFriendlinessPenalty"), ("happinessPenalty", "diseaseHappinessPenalty"),
+    ("incubationPeriod", "diseaseIncubationPeriod"), ("movementPenalty", "diseaseMovementPenalty"),
+    ("spiceMetabolismPenalty", "diseaseSpiceMetabolismPenalty"), ("startTimestep", "diseaseTimeframe"),
+    ("sugarMetabolismPenalty", "diseaseSugarMetabolismPenalty"), ("tagLength", "diseaseTagStringLength"),
+    ("transmissionChance", "diseaseTransmissionChance"), ("visionPenalty", "diseaseVisionPenalty"),
+)
+
+
+def randomize_disease_endowments(c, n, timestep):
+    """randomizeDiseaseEndowments (sugarscape.py:760-840): list of disease configurations.  The tag
+    strings consume the main stream, the shuffles of the endowment lists private hash-seeded ones."""
+    ranged = {}
+    for name, option in _DISEASE_ENDOWMENTS:
+        lo, hi = c[option][0], c[option][1]
+        decs = [d for d in (_decimals(lo), _decimals(hi)) if d is not None]
+        decimals = max(decs) if decs else 0
+        ranged[name] = {"values": [], "curr": lo, "min": lo, "max": hi, "inc": 10 ** (-1 * decimals), "decimals": decimals}
+    tags = []
+    for _ in range(n):
+        for name, r in ranged.items():
+            if name == "tagLength":
+                tags.append([random.randrange(2) for _ in range(r["curr"])])
+            r["values"].append(r["curr"])
+            r["curr"] += r["inc"]
+            r["curr"] = round(r["curr"], r["decimals"])
+            if r["curr"] > r["max"]:
+                r["curr"] = r["min"]
+    saved = random.getstate()
+    for name, r in ranged.items():
+        random.seed(_md5_int(name) + timestep)
+        random.shuffle(r["values"])
+    random.setstate(saved)
+    random.shuffle(tags)
+    endowments = []
+    for _ in range(n):
+        e = {"tags": tags.pop()}
+        for name, r in ranged.items():
+            e[name] = r["values"].pop()
+        endowments.append(e)
+    return endowments
+
+
 def build_initial_state(c, capacity=None, check=True):
     """Environment + initial population + the init-time list shuffle; returns (state, population).
 
@@ -391,8 +435,11 @@ def build_initial_state(c, capacity=None, check=True):
 
     occupied = np.zeros(W * H, dtype=bool)
     new_agents = pop.place(n0, occupied, 0, 0) if n0 > 0 else []
-    # configureDiseases always shuffles the agent list once (sugarscape.py:305) when any agent exists
+    # configureDiseases (sugarscape.py:286-305): the disease endowments are drawn first, then the agent
+    # list is shuffled once -- always, when any agent exists
+    pop.disease_endowments = []
     if new_agents:
+        pop.disease_endowments = randomize_disease_endowments(c, min(len(new_agents), int(c["startingDiseases"])), 0)
         random.shuffle(new_agents)
     state.append_agents(new_agents)
     state.counters[layout.C_NEXT_ID] = len(new_agents)

@@ -14,17 +14,33 @@ import random
 import numpy as np
 
 # bit positions inside endow_bits[t]; must match enum EB_* in csrc/ssb_rules.cuh and the oracle
-# (bits 12-15 are read by the oracle's lending / friends restatements only; the engine has neither yet)
+# (bits 12-16 are read by the oracle's lending / friends / disease restatements only; the engine has none of them yet)
 ENDOWMENT_BITS = ("aggressionFactor", "fertilityAge", "fertilityFactor", "infertilityAge",
                   "lookaheadFactor", "maxAge", "movement", "spiceMetabolism", "sugarMetabolism",
-                  "sex", "tradeFactor", "vision", "baseInterestRate", "lendingFactor", "loanDuration", "maxFriends")
+                  "sex", "tradeFactor", "vision", "baseInterestRate", "lendingFactor", "loanDuration", "maxFriends",
+                  "diseaseProtectionChance")
 
 
 def _md5_int(name):
     return int(hashlib.md5(name.encode()).hexdigest(), 16)
 
 
-_HASH = {name: _md5_int(name) for name in ENDOWMENT_BITS + ("tags",)}
+_HASH = {name: _md5_int(name) for name in ENDOWMENT_BITS + ("tags", "immuneSystem")}
+
+
+def immune_tables(t_first, t_last, immune_len):
+    """immune_bits[t]: the randrange(2) draws for the positions where the parents' immune systems
+    differ (reference agent.py:897-907, private stream md5("immuneSystem") + timestep)."""
+    n = t_last + 1
+    out = np.zeros(n, dtype=np.uint64)
+    rng = random.Random()
+    for t in range(max(t_first, 0), n):
+        rng.seed(_HASH["immuneSystem"] + t)
+        bits = 0
+        for i in range(min(immune_len, 64)):
+            bits |= rng.randrange(2) << i
+        out[t] = bits
+    return out
 
 
 def step_tables(t_first, t_last, tag_len):

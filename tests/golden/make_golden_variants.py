@@ -1,0 +1,49 @@
+#!/usr/bin/env python3
+"""Extra fixtures from the UNMODIFIED reference: shipped examples with option overrides, for rule
+families whose shipped example exercises them too briefly (disease_basic is extinct after 5 steps).
+
+    python tests/golden/make_golden_variants.py [variant ...]        (build container only)
+
+Writes <variant>.json.gz = {"meta", "base", "overrides", "steps" (per-step digests), "log"}.
+"""
+import gzip
+import json
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import make_golden as mg  # noqa: E402
+import ref_harness as rh  # noqa: E402
+
+VARIANTS = {
+    # diseases that incubate, spread with a chance, can be resisted and are recovered from
+    "disease_mild": ("disease_basic", 150, {
+        "diseaseSugarMetabolismPenalty": [0, 1], "diseaseSpiceMetabolismPenalty": [0, 0],
+        "diseaseVisionPenalty": [-1, 1], "diseaseFertilityPenalty": [-1, 0], "diseaseIncubationPeriod": [0, 3],
+        "diseaseTransmissionChance": [0.3, 1.0], "agentDiseaseProtectionChance": [0.0, 0.5],
+        "startingDiseases": 12, "startingDiseasesPerAgent": [0, 2], "diseaseTagStringLength": [3, 8],
+        "agentImmuneSystemLength": 20}),
+    # long tag strings against a short immune system: slow recovery, the diseases stay around
+    "disease_endemic": ("disease_basic", 120, {
+        "diseaseSugarMetabolismPenalty": [0, 1], "diseaseSpiceMetabolismPenalty": [0, 0], "diseaseVisionPenalty": [-1, 0],
+        "diseaseIncubationPeriod": [0, 2], "diseaseTransmissionChance": [0.6, 1.0], "agentDiseaseProtectionChance": [0.0, 0.3],
+        "startingDiseases": 20, "startingDiseasesPerAgent": [1, 4], "diseaseTagStringLength": [10, 16],
+        "agentImmuneSystemLength": 24}),
+}
+
+
+def main():
+    names = sys.argv[1:] or sorted(VARIANTS)
+    for name in names:
+        base, timesteps, overrides = VARIANTS[name]
+        path = os.path.join(rh.REFERENCE_DIR, "examples", base + ".json")
+        _, meta, steps, log, _ = mg.run_example(path, timesteps, overrides)
+        with gzip.open(os.path.join(HERE, name + ".json.gz"), "wt") as f:
+            json.dump({"meta": meta, "base": base, "overrides": overrides, "steps": steps, "log": log}, f)
+        sick = [e["sickAgents"] for e in log]
+        print(f"{name}: {len(steps) - 1} steps, final pop {steps[-1]['population']}, sick agents min/max {min(sick)}/{max(sick)}", flush=True)
+
+
+if __name__ == "__main__":
+    main()

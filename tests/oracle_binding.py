@@ -114,6 +114,109 @@ class Oracle:
     def unbind_lending(self):
         self.L.orc_bind_lending(*([None] * 7), 0)
 
+    def bind_disease(self, c, endowments, disease_endowments, horizon):
+        """Oracle-private disease state + configureDiseases' initial infections (reference
+        sugarscape.py:306-337), driven from here with the stdlib main stream like the rest of the
+        init path.  Call before set_mt_from_python()."""
+        from sugarscape_b200 import steptables
+        cap, n_d = self.state.capacity, len(disease_endowments)
+        length = int(c["agentImmuneSystemLength"])
+        assert 0 < length <= 64
+
+        class Disease(C.Structure):
+            _fields_ = [("id", C.c_int32), ("incubation", C.c_int32), ("start_timestep", C.c_int32), ("tag_len", C.c_int32),
+                        ("tags", C.c_uint32), ("pad", C.c_uint32), ("transmission", C.c_double), ("penalty", C.c_double * 8),
+                        ("infected", C.c_int64), ("listed", C.c_int64)]
+        L = self.L
+        L.orc_sizeof_disease.restype = C.c_int
+        assert L.orc_sizeof_disease() == C.sizeof(Disease)
+        self.disease_table = (Disease * max(n_d, 1))()
+        order = ("aggressionPenalty", "fertilityPenalty", "friendlinessPenalty", "happinessPenalty", "movementPenalty",
+                 "spiceMetabolismPenalty", "sugarMetabolismPenalty", "visionPenalty")
+        for i, e in enumerate(disease_endowments):
+            d = self.disease_table[i]
+            assert e["startTimestep"] == 0 and len(e["tags"]) <= 32, "later-starting diseases are not restated"
+            d.id, d.incubation, d.start_timestep, d.tag_len = i, int(e["incubationPeriod"]), 0, len(e["tags"])
+            d.tags = sum(b << k for k, b in enumerate(e["tags"]))
+            d.transmission = float(e["transmissionChance"])
+            for k, name in enumerate(order):
+                d.penalty[k] = float(e[name])
+        self.dis = {"immune": np.zeros(cap, np.uint64), "start_immune": np.zeros(cap, np.uint64),
+                    "protection": np.zeros(cap, np.float64), "modifier": np.zeros(cap * 8, np.float64),
+                    "disease_death": np.zeros(cap, np.int32), "last_spread": np.full(cap, -1, np.int32),
+                    "n_spread": np.zeros(cap, np.int32), "health_happiness": np.zeros(cap, np.float64),
+                    "last_valid_moves": np.zeros(cap, np.int32),
+                    "immune_bits": steptables.immune_tables(1, horizon, length)}
+        n = int(self.state.counters[layout.C_N_LIST])
+        agents = [int(s) for s in self.state.a_order[:n]]
+        for s in agents:
+            e = endowments[int(self.state.a_id[s])]
+            bits = sum(b << k for k, b in enumerate(e["immuneSystem"]))
+            self.dis["immune"][s] = self.dis["start_immune"][s] = bits
+            self.dis["protection"][s] = e["diseaseProtectionChance"]
+        L.orc_bind_disease.argtypes = [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 10 + [C.c_int64]
+        L.orc_move_space.argtypes = [C.c_void_p]
+        L.orc_move_space.restype = C.c_int64
+        L.orc_health_happiness_sum.argtypes = [C.c_void_p]
+        L.orc_health_happiness_sum.restype = C.c_double
+        L.orc_bind_disease.restype = None
+        L.orc_disease_count.argtypes = [C.c_int32]
+        L.orc_disease_count.restype = C.c_int32
+        L.orc_disease_nearest.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+        L.orc_disease_nearest.restype = C.c_int32
+        L.orc_disease_catch.argtypes = [C.c_int32] * 6 + [C.c_void_p]
+        L.orc_disease_catch.restype = None
+        L.orc_disease_listed.argtypes = [C.c_int32]
+        L.orc_disease_listed.restype = None
+        L.orc_disease_stats.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int64 * 5)]
+        L.orc_disease_stats.restype = None
+        L.orc_bind_disease(C.cast(self.disease_table, C.c_void_p), n_d, length,
+                           *[self.dis[k].ctypes.data for k in ("immune", "start_immune", "protection", "modifier",
+                                                               "disease_death", "last_spread", "n_spread", "health_happiness",
+                                                               "last_valid_moves", "immune_bits")], cap)
+        # configureDiseases, after the agent shuffle (sugarscape.py:317-337)
+        initial = list(range(n_d))
+        lo, hi = c["startingDiseasesPerAgent"]
+        unlimited = [lo, hi] == [0, 0]
+        curr = lo
+        for s in agents:
+            random.shuffle(initial)
+            for d in initial:
+                if L.orc_disease_count(s) >= curr and not unlimited:
+                    curr += 1
+                    break
+                if L.orc_disease_nearest(s, d, None, None) == 0:
+                    continue
+                L.orc_disease_catch(s, d, -1, -1, 0, 1, None)
+                L.orc_disease_listed(d)
+                if unlimited:
+                    initial.remove(d)
+                    break
+            if curr > hi:
+                curr = lo
+
+    def unbind_disease(self):
+        self.L.orc_bind_disease(None, 0, 0, *([None] * 10), 0)
+
+    def disease_stats(self, t):
+        """sickAgents, diseaseIncidence, distinct infectors, diseasePrevalence, agentDiseaseDeaths."""
+        g, a = self.state.as_structs()
+        out = (C.c_int64 * 5)()
+        self.L.orc_disease_stats(C.byref(a), t, C.byref(out))
+        return list(out)
+
+    def disease_log_keys(self, t, population):
+        """The six disease keys of the log + meanHealthHappiness (sugarscape.py:1316-1317, 1147-1160)."""
+        sick, incidence, infectors, prevalence, deaths = self.disease_stats(t)
+        g, a = self.state.as_structs()
+        health = self.L.orc_health_happiness_sum(C.byref(a))
+        n = population
+        return {"sickAgents": sick, "sickAgentsPercentage": round((sick / n) * 100, 2) if n else 0,
+                "diseaseEffectiveReproductionRate": (round(incidence / infectors, 2) if infectors else 0) if n else 0,
+                "diseaseIncidence": incidence, "diseasePrevalence": prevalence, "agentDiseaseDeaths": deaths,
+                "meanHealthHappiness": round(health / n, 2) if n else 0,
+                "moveSpace": int(self.L.orc_move_space(C.byref(a)))}
+
     def bind_social(self, endowments):
         """Oracle-private friends lists + conflict happiness (log keys only)."""
         cap = self.state.capacity

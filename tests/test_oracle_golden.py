@@ -135,6 +135,57 @@ def test_oracle_dune_lending_friends_combat_matches_reference_trajectory():
         orc.unbind_social()
 
 
+def _disease_case(base, overrides, gold, log):
+    c, state, pop, params, endow, tags = pu.build(base, overrides=overrides, check=False)
+    orc = Oracle(params, state, endow, tags)
+    orc.bind_disease(c, pop.endowments, pop.disease_endowments, len(gold) + 8)     # initial infections use the main stream
+    orc.set_mt_from_python()
+    try:
+        d, _ = pu.state_digests(state, *orc.mt_state())
+        assert d == gold[0]["digests"], "t=0 state differs"
+        sb = stats.StatsBuilder(c, init.equator(c))
+        rs = sb.update(orc.stats(0), 0)
+        rs.update(orc.disease_log_keys(0, rs["population"]))
+        for k in ("sickAgents", "diseaseIncidence", "diseasePrevalence"):
+            assert rs[k] == log[0][k], f"{k} differs after init"
+        sick_steps = 0
+        for t in range(1, len(gold)):
+            orc.env_step(t)
+            orc.agent_step(t, rs["meanWealth"])
+            orc.compact(t)
+            d, snap = pu.state_digests(state, *orc.mt_state())
+            assert d == gold[t]["digests"], f"state differs at t={t}"
+            rs = sb.update(orc.stats(t), t, 0)
+            rs.update(orc.disease_log_keys(t, rs["population"]))
+            sick_steps += rs["sickAgents"] > 0
+            for k in stats.LOG_KEYS:
+                assert _close(rs[k], log[t][k]), f"log key {k} differs at t={t}: {rs[k]} vs {log[t][k]}"
+        return sick_steps
+    finally:
+        orc.unbind_disease()
+
+
+def test_oracle_disease_basic_matches_reference_trajectory():
+    """examples/disease_basic.json (oracle-only restatement of diseases; the engine refuses them):
+    the population is extinct after five steps, every digest and all 59 log keys on the way."""
+    meta, _ = pu.load_golden("disease_basic")
+    assert _disease_case("disease_basic", None, meta["steps"], meta["log"]) >= 4
+
+
+@pytest.mark.parametrize("variant,min_sick_steps", [("disease_mild", 15), ("disease_endemic", 80)])
+def test_oracle_disease_variants_match_reference_trajectory(variant, min_sick_steps):
+    """disease_basic with milder diseases (tests/golden/make_golden_variants.py, run on the unmodified
+    reference): incubation, transmission / protection draws, recovery through the immune response,
+    births with inherited immune systems, vision pushed to 0 -- digests + 59 log keys on every step."""
+    import gzip
+    import json
+    import os
+    with gzip.open(os.path.join(pu.GOLDEN, variant + ".json.gz"), "rt") as f:
+        meta = json.load(f)
+    overrides = dict(meta["overrides"], timesteps=meta["meta"]["timesteps"])
+    assert _disease_case(meta["base"], overrides, meta["steps"], meta["log"]) >= min_sick_steps
+
+
 @pytest.mark.parametrize("name", UNSUPPORTED)
 def test_unsupported_rule_families_fail_loudly(name):
     with pytest.raises(init.UnsupportedConfiguration):
