@@ -193,6 +193,36 @@ static inline double pos_part(double v) { return v > 0 ? v : 0; }
 #define EFF_AGGRESSION(c, s)  pos_part((c)->a.aggression[s] + dis_mod(s, DM_AGGRESSION))
 static inline int is_sick(int s) { return g_dis && g_dis->sick[s].n > 0; }
 
+
+/* ------------------------------------------------------------------------------------------
+ * universal income (agent.py:708-714, 1127-1134), racial tags (1082-1086; inheritance 879-887) and
+ * depression (condition.py:13-34; agent.py:137-141, 889-895).  ORACLE-PRIVATE, exact RNG mode.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int64_t capacity;
+    double *universal_sugar, *universal_spice;
+    int32_t *last_income_sugar, *last_income_spice;
+    int32_t income_interval_sugar, income_interval_spice;
+    uint32_t *racial_tags;                    /* 2 bits per position */
+    int32_t *race;                            /* -1 = None */
+    int32_t racial_len, n_races;
+    int32_t *depressed;
+    double *happiness_unit;
+    double depression_percentage;
+    const uint32_t *racial_picks;             /* per timestep */
+    const double *depression_draw;            /* per timestep */
+} orc_misc_t;
+static orc_misc_t g_misc_store, *g_misc = NULL;
+enum { EB_UNIVERSAL_SPICE = 17, EB_UNIVERSAL_SUGAR = 18 };
+
+void orc_bind_misc(const orc_misc_t *m) {
+    if (!m) { g_misc = NULL; return; }
+    g_misc_store = *m;
+    g_misc = &g_misc_store;
+}
+int orc_sizeof_misc(void) { return (int)sizeof(orc_misc_t); }
+static inline double happiness_unit(int s) { return g_misc ? g_misc->happiness_unit[s] : 1.0; }
+
 static inline int wrapi(int v, int n) { v %= n; return v < 0 ? v + n : v; }
 
 static int agent_alive(const ctx_t *c, int s) {
@@ -339,6 +369,53 @@ static int alloc_slot(ctx_t *c) {
 }
 
 
+/* findTimeToLive (agent.py:1113-1140) with the disease modifiers and the universal income term */
+static double time_to_live(const ssb_agents_t *a, int s, int age_limited) {
+    const double sm = pos_part(a->sugar_metab[s] + dis_mod(s, DM_SUGAR_METAB)), pm = pos_part(a->spice_metab[s] + dis_mod(s, DM_SPICE_METAB));
+    const double big = 9223372036854775807.0;            /* sys.maxsize */
+    double st = sm > 0 ? a->sugar[s] / sm : big;
+    double pt = pm > 0 ? a->spice[s] / pm : big;
+    if (g_misc) {
+        if (g_misc->universal_sugar[s] != 0) {
+            const double income = (st * g_misc->universal_sugar[s]) / g_misc->income_interval_sugar;
+            st = sm > 0 ? (a->sugar[s] + income) / sm : big;
+        }
+        if (g_misc->universal_spice[s] != 0) {
+            const double income = (pt * g_misc->universal_spice[s]) / g_misc->income_interval_spice;
+            pt = pm > 0 ? (a->spice[s] + income) / pm : big;
+        }
+    }
+    double ttl = st < pt ? st : pt;
+    if (age_limited) { const double lim = (double)(a->max_age[s] - a->age[s]); if (lim < ttl) ttl = lim; }
+    return ttl;
+}
+
+static int32_t race_of(uint32_t tags, int len) {          /* findRace: most common tag, the smallest among ties */
+    int cnt[4] = {0, 0, 0, 0};
+    for (int i = 0; i < len; i++) cnt[(tags >> (2 * i)) & 3u]++;
+    int best = 0;
+    for (int r = 1; r < 4; r++) if (cnt[r] > cnt[best]) best = r;
+    return best;
+}
+
+/* races census of the log (sugarscape.py:1167-1170, 1287-1288, 1312): out = {largestRace, size, remaining} */
+void orc_race_census(const ssb_agents_t *a, int64_t out[3]) {
+    out[0] = -1; out[1] = 0; out[2] = 0;
+    if (!g_misc || g_misc->racial_len == 0) return;
+    int64_t cnt[4] = {0, 0, 0, 0}, first[4] = {-1, -1, -1, -1};
+    for (int64_t i = 0; i < a->counters[SSB_C_N_LIST]; i++) {
+        const int r = g_misc->race[a->order[i]];
+        if (r < 0) continue;
+        if (cnt[r]++ == 0) first[r] = i;
+    }
+    for (int r = 0; r < 4; r++) {
+        if (!cnt[r]) continue;
+        out[2]++;
+        /* max(races, key=races.get): the first key, in insertion order, with the largest count */
+        if (cnt[r] > out[1] || (cnt[r] == out[1] && first[r] < first[out[0]])) { out[0] = r; out[1] = cnt[r]; }
+    }
+}
+
 /* ------------------------------------------------------------------------------------------
  * friends + conflict happiness (agent.py:1499-1520 updateFriends, 1563-1565 / 1622-1632
  * updateNeighbors -> updateSocialNetwork, 1099-1105 findSocialHappiness, 912-918
@@ -412,6 +489,18 @@ static void update_friends(ctx_t *c, int s, int nb) {
     }
     if (max_hd > hd && have_max) { friend_remove_first(L, worst); friend_append(L, entry); }
 }
+
+/* Depression.trigger (condition.py:27-33), at the creation of a depressed agent (agent.py:137-141) */
+void orc_depress(const ssb_agents_t *a, int32_t s) {
+    g_misc->depressed[s] = 1;
+    a->aggression[s] *= 1.145;
+    if (g_social) g_social->max_friends[s] = (int32_t)ceil(g_social->max_friends[s] * 0.6333);
+    g_misc->happiness_unit[s] *= 0.5763;
+    a->movement[s] *= (int32_t)ceil(a->movement[s] * 0.429);
+    a->spice_metab[s] *= (int32_t)ceil(a->spice_metab[s] * 1.544);
+    a->sugar_metab[s] *= (int32_t)ceil(a->sugar_metab[s] * 1.544);
+}
+
 
 /* ------------------------------------------------------------------------------------------
  * lending (agent.py:431-483 doLending, 190-212 addLoan*, 920-930 current debt, 1226-1245,
@@ -1112,6 +1201,23 @@ static void do_reproduction(ctx_t *c, int s) {
             g_dis->immune[ch] = g_dis->start_immune[ch] = child;
             g_dis->protection[ch] = ((eb >> EB_PROTECTION) & 1u) ? g_dis->protection[m] : g_dis->protection[s];
         }
+        if (g_misc) {
+            g_misc->universal_spice[ch] = ((eb >> EB_UNIVERSAL_SPICE) & 1u) ? g_misc->universal_spice[m] : g_misc->universal_spice[s];
+            g_misc->universal_sugar[ch] = ((eb >> EB_UNIVERSAL_SUGAR) & 1u) ? g_misc->universal_sugar[m] : g_misc->universal_sugar[s];
+            g_misc->last_income_sugar[ch] = 0; g_misc->last_income_spice[ch] = 0;
+            g_misc->depressed[ch] = 0; g_misc->happiness_unit[ch] = 1;
+            g_misc->race[ch] = -1; g_misc->racial_tags[ch] = 0;
+            if (g_misc->racial_len > 0) {      /* random.choice([mine, mate's]) per position (agent.py:885-886) */
+                const uint32_t picks = g_misc->racial_picks[c->t];
+                uint32_t rt = 0;
+                for (int i = 0; i < g_misc->racial_len; i++) {
+                    const uint32_t src = ((picks >> i) & 1u) ? g_misc->racial_tags[m] : g_misc->racial_tags[s];
+                    rt |= ((src >> (2 * i)) & 3u) << (2 * i);
+                }
+                g_misc->racial_tags[ch] = rt;
+                g_misc->race[ch] = race_of(rt, g_misc->racial_len);
+            }
+        }
         if (g_social) {
             social_reset_slot(ch);
             g_social->max_friends[ch] = ((eb >> EB_MAX_FRIENDS) & 1u) ? g_social->max_friends[m] : g_social->max_friends[s];
@@ -1149,6 +1255,8 @@ static void do_reproduction(ctx_t *c, int s) {
         a->children_head[ch] = -1; a->mates_head[ch] = -1;
         a->father[ch] = a->sex[s] == SSB_SEX_FEMALE ? a->id[m] : a->id[s];
         a->mother[ch] = a->sex[s] == SSB_SEX_FEMALE ? a->id[s] : a->id[m];
+        /* the child is depressed with the configured chance, decided by the private stream (agent.py:889-895) */
+        if (g_misc && g_misc->depression_draw[c->t] <= g_misc->depression_percentage) orc_depress(a, ch);
         a->pos[ch] = cell;
         c->g.occ[cell] = ch;
         if (cn[SSB_C_N_LIST] < a->capacity) a->order[cn[SSB_C_N_LIST]++] = ch;   /* addAgent */
@@ -1182,6 +1290,14 @@ static void agent_transaction(ctx_t *c, int s) {
         for (int i = 0; i < 4; i++) { int o = c->g.occ[nb4[i]]; if (o >= 0) update_friends(c, s, o); }
     }
     collect(c, s, pos);
+    if (g_misc) {        /* doUniversalIncome (agent.py:708-714): spice first */
+        if ((c->t - g_misc->last_income_spice[s]) >= g_misc->income_interval_spice) {
+            a->spice[s] += g_misc->universal_spice[s]; g_misc->last_income_spice[s] = c->t;
+        }
+        if ((c->t - g_misc->last_income_sugar[s]) >= g_misc->income_interval_sugar) {
+            a->sugar[s] += g_misc->universal_sugar[s]; g_misc->last_income_sugar[s] = c->t;
+        }
+    }
     /* doMetabolism (agent.py:485-498) + consumption pollution (cell.py:27-40) */
     double sm = EFF_SUGAR_METAB(c, s);
     double pm = EFF_SPICE_METAB(c, s);
@@ -1207,29 +1323,33 @@ static void agent_transaction(ctx_t *c, int s) {
     }
     /* updateHappiness (agent.py:1522-1530): conflict + family + health + social + wealth.
      * family/social/conflict bookkeeping is not restated yet -> 0 */
-    double wealth_h = erf((a->sugar[s] + a->spice[s]) - c->prev_mean_wealth);
+    const double unit = happiness_unit(s);                /* happinessUnit: 1, 0.5763 when depressed */
+    /* findWealthHappiness (agent.py:1164-1168) */
+    double diff_wealth = (a->sugar[s] + a->spice[s]) - c->prev_mean_wealth;
+    if (g_misc) diff_wealth *= unit;
+    double wealth_h = erf(diff_wealth);
     /* findFamilyHappiness (agent.py:940-958), mode E only (the lists are not kept in mode S) */
     double family = 0;
     if (c->p->rng_mode == SSB_RNG_EXACT) {
         for (int e = a->children_head[s]; e >= 0; e = a->kin_next[e]) {
             int o = kin_alive(c, e);
-            if (o >= 0) { family += 1; if (is_sick(o)) family -= 1 * 0.5; if (a->born[o] == c->t) family += 1; } else family -= 1;
+            if (o >= 0) { family += unit; if (is_sick(o)) family -= unit * 0.5; if (a->born[o] == c->t) family += unit; } else family -= unit;
         }
         for (int e = a->mates_head[s]; e >= 0; e = a->kin_next[e]) {
             int o = kin_alive(c, e);
-            if (o >= 0) { family += 1; if (is_sick(o)) family -= 1 * 0.5; } else family -= 1;
+            if (o >= 0) { family += unit; if (is_sick(o)) family -= unit * 0.5; } else family -= unit;
         }
     }
     double family_h = erf(family);
     double conflict_h = 0, social_h = 0;
     if (g_social) {
-        if (g_social->last_combat[s] == c->t) conflict_h = EFF_AGGRESSION(c, s) > 1 ? 1.0 : -1.0;
-        if (g_social->max_friends[s] != 0) social_h = (g_social->friends[s].n * (2.0 / g_social->max_friends[s])) - 1;
+        if (g_social->last_combat[s] == c->t) conflict_h = EFF_AGGRESSION(c, s) > 1 ? unit : unit * -1;
+        if (g_social->max_friends[s] != 0) social_h = ((g_social->friends[s].n * (2.0 / g_social->max_friends[s])) - 1) * unit;
         g_social->conflict_happiness[s] = conflict_h; g_social->social_happiness[s] = social_h;
     }
     a->wealth_happiness[s] = wealth_h;
     a->family_happiness[s] = family_h;
-    const double health_h = is_sick(s) ? -1.0 : 1.0;       /* findHealthHappiness (agent.py:1017-1021) */
+    const double health_h = is_sick(s) ? unit * -1 : unit;       /* findHealthHappiness (agent.py:1017-1021) */
     if (g_dis) g_dis->health_happiness[s] = health_h;
     a->happiness[s] = conflict_h + family_h + health_h + social_h + wealth_h;
 }
@@ -1512,13 +1632,8 @@ void orc_stats(const ssb_params_t *p, const ssb_grid_t *g, const ssb_agents_t *a
         if (i == 0 || w < out->min_wealth) out->min_wealth = w;
         out->sum_wealth_collected += w - (a->last_sugar[s] + a->last_spice[s]);
         /* findTimeToLive (agent.py:1113-1140) */
-        double sm = pos_part(a->sugar_metab[s] + dis_mod(s, DM_SUGAR_METAB)), pm = pos_part(a->spice_metab[s] + dis_mod(s, DM_SPICE_METAB));
-        double st = sm > 0 ? a->sugar[s] / sm : 9223372036854775807.0;
-        double pt = pm > 0 ? a->spice[s] / pm : 9223372036854775807.0;
-        double ttl = st < pt ? st : pt;
-        out->sum_burn_rate += ttl;
-        double lim = (double)(a->max_age[s] - a->age[s]);
-        out->sum_ttl_age_limited += ttl < lim ? ttl : lim;
+        out->sum_burn_rate += time_to_live(a, s, 0);
+        out->sum_ttl_age_limited += time_to_live(a, s, 1);
         out->sum_neighbors += a->n_neighborhood[s];
         out->sum_valid_moves += a->n_valid_moves[s];
         if (a->trade_volume[s] > 0) {

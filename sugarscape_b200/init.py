@@ -210,8 +210,24 @@ def randomize_endowments(c, n, timestep):
         ranged[name] = {"values": [], "curr": lo, "min": lo, "max": hi,
                         "inc": 10 ** (-1 * decimals), "decimals": decimals}
 
-    # racial tags (sugarscape.py:504-515) -- refused by check_supported when enabled
-    racial_tags = [None] * n
+    # racial tags (generateAgentRacialTags / generateRacialTags, sugarscape.py:504-515, 535-546); the engine
+    # refuses configurations with racial tags, the oracle-only tests use them
+    n_races, racial_len = c["environmentMaxRaces"], c["agentRacialTagStringLength"]
+    if racial_len == 0 or n_races == 0:
+        racial_tags = [None] * n
+    else:
+        racial_tags = []
+        for i in range(n):
+            race = i % n_races
+            if n_races == 1:
+                racial_tags.append([race] * racial_len)
+                continue
+            assigned = random.randint(math.floor(racial_len / 2) + 1, racial_len)
+            others = [r for r in range(n_races) if r != race]
+            rt = [race] * assigned + [random.choice(others) for _ in range(racial_len - assigned)]
+            random.shuffle(rt)
+            racial_tags.append(rt)
+        random.shuffle(racial_tags)
     # tribe tags (sugarscape.py:517-528)
     if c["agentTagStringLength"] == 0 or c["environmentMaxTribes"] == 0 or c["environmentTribePerQuadrant"]:
         tags = [None] * n

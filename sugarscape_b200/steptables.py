@@ -18,14 +18,33 @@ import numpy as np
 ENDOWMENT_BITS = ("aggressionFactor", "fertilityAge", "fertilityFactor", "infertilityAge",
                   "lookaheadFactor", "maxAge", "movement", "spiceMetabolism", "sugarMetabolism",
                   "sex", "tradeFactor", "vision", "baseInterestRate", "lendingFactor", "loanDuration", "maxFriends",
-                  "diseaseProtectionChance")
+                  "diseaseProtectionChance", "universalSpice", "universalSugar")
 
 
 def _md5_int(name):
     return int(hashlib.md5(name.encode()).hexdigest(), 16)
 
 
-_HASH = {name: _md5_int(name) for name in ENDOWMENT_BITS + ("tags", "immuneSystem")}
+_HASH = {name: _md5_int(name) for name in ENDOWMENT_BITS + ("tags", "immuneSystem", "racialTags")}
+
+
+def racial_tables(t_first, t_last, racial_len):
+    """(picks[t], depression[t]): the private stream md5("racialTags") + timestep first picks, per
+    racial tag position, the parent the child's tag comes from (random.choice of two, reference
+    agent.py:879-887; bit i of picks = index picked), then yields the random.random() the child's
+    depression is decided with (889-895).  Without racial tags only the depression draw is taken."""
+    n = t_last + 1
+    picks = np.zeros(n, dtype=np.uint32)
+    depression = np.ones(n, dtype=np.float64)
+    rng = random.Random()
+    for t in range(max(t_first, 0), n):
+        rng.seed(_HASH["racialTags"] + t)
+        bits = 0
+        for i in range(racial_len):
+            bits |= rng.choice([0, 1]) << i
+        picks[t] = bits
+        depression[t] = rng.random()
+    return picks, depression
 
 
 def immune_tables(t_first, t_last, immune_len):

@@ -30,6 +30,11 @@ VARIANTS = {
         "diseaseIncubationPeriod": [0, 2], "diseaseTransmissionChance": [0.6, 1.0], "agentDiseaseProtectionChance": [0.0, 0.3],
         "startingDiseases": 20, "startingDiseasesPerAgent": [1, 4], "diseaseTagStringLength": [10, 16],
         "agentImmuneSystemLength": 24}),
+    # determinism.json without the ethics decision models and the experimental-group log: diseases,
+    # depression, lending, friends, racial tags, universal income, combat, trade, tags, inheritance,
+    # pollution and seasons all at once
+    "determinism_plain": ("determinism", 200, {"agentDecisionModels": ["none"], "agentDecisionModelFactor": [0, 0],
+                                               "experimentalGroup": None}),
 }
 
 

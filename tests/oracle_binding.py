@@ -217,6 +217,70 @@ class Oracle:
                 "meanHealthHappiness": round(health / n, 2) if n else 0,
                 "moveSpace": int(self.L.orc_move_space(C.byref(a)))}
 
+    def bind_misc(self, c, endowments, horizon):
+        """Oracle-private universal income, racial tags and depression.  Call after bind_social (a
+        depressed agent's maxFriends shrinks) and before stepping."""
+        from sugarscape_b200 import steptables
+        cap = self.state.capacity
+        rl = int(c["agentRacialTagStringLength"]) if c["environmentMaxRaces"] > 0 else 0
+        assert rl <= 16 and c["environmentMaxRaces"] <= 4
+        picks, draw = steptables.racial_tables(1, horizon, rl)
+        self.misc = {"universal_sugar": np.zeros(cap), "universal_spice": np.zeros(cap),
+                     "last_income_sugar": np.zeros(cap, np.int32), "last_income_spice": np.zeros(cap, np.int32),
+                     "racial_tags": np.zeros(cap, np.uint32), "race": np.full(cap, -1, np.int32),
+                     "depressed": np.zeros(cap, np.int32), "happiness_unit": np.ones(cap), "picks": picks, "draw": draw}
+
+        class Misc(C.Structure):
+            _fields_ = [("capacity", C.c_int64), ("universal_sugar", C.c_void_p), ("universal_spice", C.c_void_p),
+                        ("last_income_sugar", C.c_void_p), ("last_income_spice", C.c_void_p),
+                        ("income_interval_sugar", C.c_int32), ("income_interval_spice", C.c_int32),
+                        ("racial_tags", C.c_void_p), ("race", C.c_void_p), ("racial_len", C.c_int32), ("n_races", C.c_int32),
+                        ("depressed", C.c_void_p), ("happiness_unit", C.c_void_p), ("depression_percentage", C.c_double),
+                        ("racial_picks", C.c_void_p), ("depression_draw", C.c_void_p)]
+        L = self.L
+        L.orc_sizeof_misc.restype = C.c_int
+        assert L.orc_sizeof_misc() == C.sizeof(Misc)
+        m = Misc()
+        m.capacity = cap
+        for k in ("universal_sugar", "universal_spice", "last_income_sugar", "last_income_spice", "racial_tags", "race",
+                  "depressed", "happiness_unit"):
+            setattr(m, k, self.misc[k].ctypes.data)
+        m.income_interval_sugar = int(c["environmentUniversalSugarIncomeInterval"])
+        m.income_interval_spice = int(c["environmentUniversalSpiceIncomeInterval"])
+        m.racial_len, m.n_races = rl, int(c["environmentMaxRaces"])
+        m.depression_percentage = float(c["agentDepressionPercentage"])
+        m.racial_picks, m.depression_draw = picks.ctypes.data, draw.ctypes.data
+        L.orc_bind_misc.argtypes = [C.c_void_p]
+        L.orc_bind_misc.restype = None
+        L.orc_depress.argtypes = [C.c_void_p, C.c_int32]
+        L.orc_depress.restype = None
+        L.orc_race_census.argtypes = [C.c_void_p, C.POINTER(C.c_int64 * 3)]
+        L.orc_race_census.restype = None
+        L.orc_bind_misc(C.byref(m))
+        g, a = self.state.as_structs()
+        n = int(self.state.counters[layout.C_N_LIST])
+        for s in self.state.a_order[:n]:
+            s = int(s)
+            e = endowments[int(self.state.a_id[s])]
+            self.misc["universal_sugar"][s] = e["universalSugar"]
+            self.misc["universal_spice"][s] = e["universalSpice"]
+            if e["racialTags"] is not None:
+                rt = e["racialTags"]
+                self.misc["racial_tags"][s] = sum(v << (2 * k) for k, v in enumerate(rt))
+                self.misc["race"][s] = max(set(rt), key=rt.count)
+            if e["depressionFactor"] == 1:
+                L.orc_depress(C.byref(a), s)
+
+    def unbind_misc(self):
+        self.L.orc_bind_misc(None)
+
+    def race_census(self):
+        """(largestRace or None, largestRaceSize, remainingRaces)."""
+        g, a = self.state.as_structs()
+        out = (C.c_int64 * 3)()
+        self.L.orc_race_census(C.byref(a), C.byref(out))
+        return (None if out[0] < 0 else int(out[0])), int(out[1]), int(out[2])
+
     def bind_social(self, endowments):
         """Oracle-private friends lists + conflict happiness (log keys only)."""
         cap = self.state.capacity

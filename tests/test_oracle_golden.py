@@ -186,6 +186,55 @@ def test_oracle_disease_variants_match_reference_trajectory(variant, min_sick_st
     assert _disease_case(meta["base"], overrides, meta["steps"], meta["log"]) >= min_sick_steps
 
 
+def test_oracle_determinism_without_ethics_matches_reference_trajectory():
+    """examples/determinism.json minus the ethics decision models and the experimental-group log
+    (variant fixture from the unmodified reference): diseases, depression, lending, friends, racial
+    tags, universal income, live combat, trade, tags, inheritance, pollution and seasons at once --
+    every digest and all 59 log keys for 200 steps.  Oracle-only: the engine refuses most of these."""
+    import gzip
+    import json
+    import os
+    with gzip.open(os.path.join(pu.GOLDEN, "determinism_plain.json.gz"), "rt") as f:
+        meta = json.load(f)
+    gold, log = meta["steps"], meta["log"]
+    overrides = dict(meta["overrides"], timesteps=meta["meta"]["timesteps"])
+    c, state, pop, params, endow, tags = pu.build(meta["base"], overrides=overrides, check=False)
+    orc = Oracle(params, state, endow, tags)
+    horizon = len(gold) + 8
+    orc.bind_lending(pop.endowments)
+    orc.bind_social(pop.endowments)
+    orc.bind_misc(c, pop.endowments, horizon)
+    orc.bind_disease(c, pop.endowments, pop.disease_endowments, horizon)
+    orc.set_mt_from_python()
+    try:
+        d, _ = pu.state_digests(state, *orc.mt_state())
+        assert d == gold[0]["digests"], "t=0 state differs"
+        sb = stats.StatsBuilder(c, init.equator(c))
+        rs = sb.update(orc.stats(0), 0)
+        for t in range(1, len(gold)):
+            orc.env_step(t)
+            orc.agent_step(t, rs["meanWealth"])
+            orc.compact(t)
+            d, snap = pu.state_digests(state, *orc.mt_state())
+            assert d == gold[t]["digests"], f"state differs at t={t}"
+            rs = sb.update(orc.stats(t), t, 0)
+            n = rs["population"]
+            rs.update(orc.disease_log_keys(t, n))
+            social, conflict = orc.social_sums()
+            rs["meanSocialHappiness"] = round(social / n, 2) if n else 0
+            rs["meanConflictHappiness"] = round(conflict / n, 2) if n else 0
+            rs["loanVolume"] = orc.loan_volume(t)
+            if n:
+                rs["largestRace"], rs["largestRaceSize"], rs["remainingRaces"] = orc.race_census()
+            for k in stats.LOG_KEYS:
+                assert _close(rs[k], log[t][k]), f"log key {k} differs at t={t}: {rs[k]} vs {log[t][k]}"
+    finally:
+        orc.unbind_lending()
+        orc.unbind_social()
+        orc.unbind_misc()
+        orc.unbind_disease()
+
+
 @pytest.mark.parametrize("name", UNSUPPORTED)
 def test_unsupported_rule_families_fail_loudly(name):
     with pytest.raises(init.UnsupportedConfiguration):
