@@ -223,6 +223,30 @@ void orc_bind_misc(const orc_misc_t *m) {
 int orc_sizeof_misc(void) { return (int)sizeof(orc_misc_t); }
 static inline double happiness_unit(int s) { return g_misc ? g_misc->happiness_unit[s] : 1.0; }
 
+
+/* ------------------------------------------------------------------------------------------
+ * ethics.Bentham decision models (ethics.py:105-244; spawn rules sugarscape.py:219-233).
+ * ORACLE-PRIVATE, exact RNG mode; the in-group factors (ageism / racism / sexism / tribal) and the
+ * dynamic selfishness are not restated (disabled, -1 / 0, in every shipped example).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int64_t capacity;
+    int32_t *model;                           /* 0 = plain Agent, 1 = Bentham class (altruist / bentham / egoist / negativeBentham) */
+    double *selfishness, *decision_factor, *lookahead_factor, *lookahead_discount;
+    int32_t *last_move_optimal, *move_rank;
+    double *move_diff;                        /* welfare of the top cell minus welfare of the chosen one */
+    double global_max_wealth;                 /* environment.globalMaxSugar + globalMaxSpice */
+} orc_eth_t;
+static orc_eth_t g_eth_store, *g_eth = NULL;
+enum { EB_DECISION_MODEL = 19 };
+
+void orc_bind_ethics(const orc_eth_t *e) {
+    if (!e) { g_eth = NULL; return; }
+    g_eth_store = *e;
+    g_eth = &g_eth_store;
+}
+int orc_sizeof_ethics(void) { return (int)sizeof(orc_eth_t); }
+
 static inline int wrapi(int v, int n) { v %= n; return v < 0 ? v + n : v; }
 
 static int agent_alive(const ctx_t *c, int s) {
@@ -887,6 +911,22 @@ int64_t orc_move_space(const ssb_agents_t *a) {      /* moveSpace (sugarscape.py
     return v;
 }
 
+/* out = {sum selfishness, optimal moves, moves, sum move rank, sum move difference} (sugarscape.py:1141-1160, 1218-1222) */
+void orc_ethics_stats(const ssb_agents_t *a, int32_t t, double out[5]) {
+    for (int k = 0; k < 5; k++) out[k] = 0;
+    if (!g_eth) return;
+    for (int64_t i = 0; i < a->counters[SSB_C_N_LIST]; i++) {
+        const int s = a->order[i];
+        out[0] += g_eth->selfishness[s];
+        out[1] += g_eth->last_move_optimal[s]; out[2] += 1;
+        out[3] += g_eth->move_rank[s]; out[4] += g_eth->move_diff[s];
+    }
+    /* this step's dead: doTimestep(t) was called on every one of them (it sets agent.timestep even when the
+     * agent is already dead), so the reference's `agent.timestep == self.timestep` holds for all */
+    (void)t;
+    for (int64_t i = 0; i < a->counters[SSB_C_N_DEAD]; i++) { out[1] += g_eth->last_move_optimal[a->dead_list[i]]; out[2] += 1; }
+}
+
 double orc_health_happiness_sum(const ssb_agents_t *a) {
     double v = 0;
     if (g_dis) for (int64_t i = 0; i < a->counters[SSB_C_N_LIST]; i++) v += g_dis->health_happiness[a->order[i]];
@@ -972,6 +1012,83 @@ static int enumerate_cross(const ctx_t *c, int pos, int r, int32_t *cells, int32
     return n;
 }
 
+
+/* ---- Bentham: findBestEthicalCell / findEthicalValueOfCell ------------------------------------ */
+static int agent_range(const ctx_t *c, int s) {           /* findCellsInRange (agent.py:766-779) */
+    int vision = (int)EFF_VISION(c, s), movement = (int)EFF_MOVEMENT(c, s);
+    int maxd = c->max_dx > c->max_dy ? c->max_dx : c->max_dy;
+    int r = vision < movement ? vision : movement;
+    return r > maxd ? maxd : r;
+}
+static int cell_in_cross(const ctx_t *c, int centre, int r, int cell) {
+    const int W = c->p->width, H = c->p->height;
+    const int x = centre / H, y = centre % H, cx = cell / H, cy = cell % H;
+    if (cell == centre || r <= 0) return 0;
+    if (cx == x) { int d = abs(cy - y); if (H - d < d) d = H - d; return d <= (r < c->max_dy ? r : c->max_dy); }
+    if (cy == y) { int d = abs(cx - x); if (W - d < d) d = W - d; return d <= (r < c->max_dx ? r : c->max_dx); }
+    return 0;
+}
+/* value of `cell` for the agents in view (ethics.py:141-244); selfishness < 0: happiness / unhappiness split */
+static double ethical_value(ctx_t *c, int s, int my_r, const int32_t *hood, int n_hood, int cell, double *happy, double *unhappy) {
+    const ssb_agents_t *a = &c->a;
+    double site = (double)(c->g.sugar[cell] + c->g.spice[cell]);
+    const double max_loot = c->p->max_combat_loot * 2;
+    double max_site = (double)(c->g.sugar_cap[cell] + c->g.spice_cap[cell]);
+    const int occupant = c->g.occ[cell];
+    if (occupant >= 0) {
+        const double w = a->sugar[occupant] + a->spice[occupant];
+        site += w < max_loot ? w : max_loot;
+        max_site += w < max_loot ? w : max_loot;
+    }
+    int32_t nb4[4];
+    neighbours4(c, cell, nb4);
+    double neighbor_wealth = 0;
+    for (int i = 0; i < 4; i++) neighbor_wealth += c->g.sugar[nb4[i]] + c->g.spice[nb4[i]];
+    const double lookahead = g_eth->lookahead_factor[s];
+    /* len(self.findNeighborhood(cell)): live agents in MY cross moved to `cell`, plus myself */
+    double future_hood = 1;
+    if (lookahead != 0) {
+        int32_t fc[MAX_CAND], fd[MAX_CAND];
+        const int fn = my_r > 0 ? enumerate_cross(c, cell, my_r, fc, fd) : 0;
+        int cnt = 1;
+        for (int i = 0; i < fn; i++) { int o = c->g.occ[fc[i]]; if (o >= 0 && agent_alive(c, o)) cnt++; }
+        future_hood = cnt;
+    }
+    const double selfish = g_eth->selfishness[s];
+    double value = 0, h = 0, u = 0;
+    for (int k = 0; k < n_hood; k++) {
+        const int nb = hood[k];
+        if (!agent_alive(c, nb)) continue;
+        const int rn = agent_range(c, nb);
+        if (!(cell == a->pos[nb] || cell_in_cross(c, a->pos[nb], rn, cell))) continue;      /* canReachCell */
+        const double metab = (double)(a->sugar_metab[nb] + a->spice_metab[nb]);            /* raw, not the find* accessors */
+        const double cell_duration = metab > 0 ? site / metab : 0;
+        const double proximity = 1.0 / 1;
+        const double intensity = (1 / (1 + time_to_live(a, nb, 0)) / (1 + c->g.pollution[cell]));
+        const double duration = max_site > 0 ? cell_duration / max_site : 0;
+        const double discount = g_eth->lookahead_factor[nb] != 0 ? g_eth->lookahead_discount[nb] : 0;
+        double future_duration = metab > 0 ? (site - metab) / metab : site;
+        future_duration = max_site > 0 ? future_duration / max_site : 0;
+        const double future_intensity = neighbor_wealth / (g_eth->global_max_wealth * 4);
+        int32_t tc[MAX_CAND], td[MAX_CAND];
+        const int in_range = rn > 0 ? enumerate_cross(c, a->pos[nb], rn, tc, td) : 0;          /* len(neighbor.cellsInRange) */
+        const double extent = in_range > 0 ? (double)n_hood / in_range : 1;
+        const double future_extent = (in_range > 0 && lookahead != 0) ? future_hood / in_range : 1;
+        const double current_reward = extent * (intensity + duration);
+        const double future_reward = future_extent * (future_intensity + future_duration);
+        double v = (1 * proximity) * (current_reward + (discount * future_reward));
+        if (nb != s && selfish < 1) {
+            v = -1 * v;
+            if (cell == a->pos[nb] && v > -1) v = -1;
+        }
+        if (selfish >= 0) v *= nb == s ? selfish : 1 - selfish;
+        else { if (v > 0) h += v; else u += v; }
+        value += v;
+    }
+    *happy = h; *unhappy = u;
+    return value;
+}
+
 /* agent.py:1395-1443 + 719-746 + 1321-1328: returns the chosen cell */
 static int move_to_best_cell(ctx_t *c, int s) {
     const ssb_agents_t *a = &c->a;
@@ -988,6 +1105,7 @@ static int move_to_best_cell(ctx_t *c, int s) {
         /* empty range: stays put; validMoves / movementNeighborhood keep their old values, but
          * findBestCell still records lastValidMoves = len([own cell]) (agent.py:1398-1399, 745) */
         if (g_dis) g_dis->last_valid_moves[s] = 1;
+        if (g_eth) g_eth->last_move_optimal[s] = 1;      /* [own cell] is its own best; validMoves (rank, difference) keep their values */
     } else {
         /* findNeighborhood: live agents in range + self (agent.py:1052-1065) */
         int hood = 1;
@@ -1039,7 +1157,27 @@ static int move_to_best_cell(ctx_t *c, int s) {
                  (cand[j - 1].welfare == cand[j].welfare && cand[j - 1].dist > cand[j].dist)); j--) {
                 cand_t tmp = cand[j]; cand[j] = cand[j - 1]; cand[j - 1] = tmp;
             }
-        best = cand[0].cell;
+        int rank = 0;
+        if (g_eth && g_eth->model[s] == 1 && g_eth->decision_factor[s] > 0) {
+            /* findBestEthicalCell (ethics.py:105-139): re-score the welfare-sorted cells */
+            int32_t hoodv[MAX_CAND + 1]; int nh = 0;
+            for (int i = 0; i < n; i++) { int o = c->g.occ[cells[i]]; if (o >= 0 && agent_alive(c, o)) hoodv[nh++] = o; }
+            hoodv[nh++] = s;
+            int chosen = -1;
+            double best_u = 0, best_h = 0;
+            for (int i = 0; i < m; i++) {
+                double h, u;
+                const double v = ethical_value(c, s, r, hoodv, nh, cand[i].cell, &h, &u);
+                if (g_eth->selfishness[s] >= 0) { if (v > 0) { chosen = i; break; } }
+                else if (chosen < 0 || u > best_u || (u == best_u && h > best_h)) { chosen = i; best_u = u; best_h = h; }   /* stable sort, reverse */
+            }
+            if (chosen >= 0) rank = chosen;
+        }
+        best = cand[rank].cell;
+        if (g_eth) {
+            g_eth->last_move_optimal[s] = rank == 0; g_eth->move_rank[s] = rank;
+            g_eth->move_diff[s] = cand[0].welfare - cand[rank].welfare;
+        }
         a->n_neighborhood[s] = hood;
         a->n_valid_moves[s] = m;
         if (g_dis) g_dis->last_valid_moves[s] = m;
@@ -1200,6 +1338,14 @@ static void do_reproduction(ctx_t *c, int s) {
             }
             g_dis->immune[ch] = g_dis->start_immune[ch] = child;
             g_dis->protection[ch] = ((eb >> EB_PROTECTION) & 1u) ? g_dis->protection[m] : g_dis->protection[s];
+        }
+        if (g_eth) {     /* the paired endowments follow ONE draw (agent.py:845-851); the child's class is that parent's */
+            const int from = ((eb >> EB_DECISION_MODEL) & 1u) ? m : s;
+            g_eth->model[ch] = g_eth->model[from]; g_eth->selfishness[ch] = g_eth->selfishness[from];
+            g_eth->decision_factor[ch] = g_eth->decision_factor[from];
+            g_eth->lookahead_factor[ch] = g_eth->lookahead_factor[from];
+            g_eth->lookahead_discount[ch] = g_eth->lookahead_discount[from];
+            g_eth->last_move_optimal[ch] = 1; g_eth->move_rank[ch] = 0; g_eth->move_diff[ch] = 0;      /* lastMoveOptimal starts True */
         }
         if (g_misc) {
             g_misc->universal_spice[ch] = ((eb >> EB_UNIVERSAL_SPICE) & 1u) ? g_misc->universal_spice[m] : g_misc->universal_spice[s];

@@ -14,11 +14,12 @@ import random
 import numpy as np
 
 # bit positions inside endow_bits[t]; must match enum EB_* in csrc/ssb_rules.cuh and the oracle
-# (bits 12-16 are read by the oracle's lending / friends / disease restatements only; the engine has none of them yet)
+# (bits 12-19 are read by the oracle-only restatements -- lending, friends, diseases, universal income, ethics -- the
+# engine has none of them yet)
 ENDOWMENT_BITS = ("aggressionFactor", "fertilityAge", "fertilityFactor", "infertilityAge",
                   "lookaheadFactor", "maxAge", "movement", "spiceMetabolism", "sugarMetabolism",
                   "sex", "tradeFactor", "vision", "baseInterestRate", "lendingFactor", "loanDuration", "maxFriends",
-                  "diseaseProtectionChance", "universalSpice", "universalSugar")
+                  "diseaseProtectionChance", "universalSpice", "universalSugar", "decisionModel")
 
 
 def _md5_int(name):

@@ -35,6 +35,9 @@ VARIANTS = {
     # pollution and seasons all at once
     "determinism_plain": ("determinism", 200, {"agentDecisionModels": ["none"], "agentDecisionModelFactor": [0, 0],
                                                "experimentalGroup": None}),
+    # determinism.json with the ethics decision models (bentham, altruist, egoist, negativeBentham), only the
+    # experimental-group split of the log switched off
+    "determinism_ethics": ("determinism", 200, {"experimentalGroup": None}),
 }
 
 

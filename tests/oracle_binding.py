@@ -281,6 +281,82 @@ class Oracle:
         self.L.orc_race_census(C.byref(a), C.byref(out))
         return (None if out[0] < 0 else int(out[0])), int(out[1]), int(out[2])
 
+    def bind_ethics(self, c, endowments):
+        """Oracle-private ethics.Bentham decision models (spawn rules: reference sugarscape.py:219-233)."""
+        cap = self.state.capacity
+        for k in ("agentDecisionModelAgeismFactor", "agentDecisionModelRacismFactor", "agentDecisionModelSexismFactor",
+                  "agentDecisionModelTribalFactor"):
+            assert c[k][1] < 0, "in-group factors are not restated"
+        assert c["agentDynamicSelfishnessFactor"][1] == 0
+        self.eth = {"model": np.zeros(cap, np.int32), "selfishness": np.zeros(cap), "decision_factor": np.zeros(cap),
+                    "lookahead_factor": np.zeros(cap), "lookahead_discount": np.zeros(cap),
+                    "last_move_optimal": np.ones(cap, np.int32), "move_rank": np.zeros(cap, np.int32), "move_diff": np.zeros(cap)}
+        n = int(self.state.counters[layout.C_N_LIST])
+        for s in self.state.a_order[:n]:
+            s = int(s)
+            e = endowments[int(self.state.a_id[s])]
+            name = e["decisionModel"]
+            selfish = e["selfishnessFactor"]
+            bentham = True
+            if "altruist" in name:
+                selfish = 0
+            elif "bentham" in name:
+                selfish = 0.5 if selfish < 0 else selfish
+            elif "egoist" in name:
+                selfish = 1
+            elif "negativeBentham" in name:
+                selfish = -1
+            else:
+                assert name == "none", name
+                bentham = False
+            look = c["agentDecisionModelLookaheadFactor"]
+            if "NoLookahead" in name:
+                look = 0
+            elif "HalfLookahead" in name:
+                look = 0.5
+            self.eth["model"][s] = int(bentham)
+            self.eth["selfishness"][s] = selfish
+            self.eth["decision_factor"][s] = e["decisionModelFactor"]
+            self.eth["lookahead_factor"][s] = look
+            self.eth["lookahead_discount"][s] = e["decisionModelLookaheadDiscount"]
+
+        class Ethics(C.Structure):
+            _fields_ = [("capacity", C.c_int64), ("model", C.c_void_p), ("selfishness", C.c_void_p), ("decision_factor", C.c_void_p),
+                        ("lookahead_factor", C.c_void_p), ("lookahead_discount", C.c_void_p), ("last_move_optimal", C.c_void_p),
+                        ("move_rank", C.c_void_p), ("move_diff", C.c_void_p), ("global_max_wealth", C.c_double)]
+        L = self.L
+        L.orc_sizeof_ethics.restype = C.c_int
+        assert L.orc_sizeof_ethics() == C.sizeof(Ethics)
+        e = Ethics()
+        e.capacity = cap
+        for k in ("model", "selfishness", "decision_factor", "lookahead_factor", "lookahead_discount", "last_move_optimal",
+                  "move_rank", "move_diff"):
+            setattr(e, k, self.eth[k].ctypes.data)
+        e.global_max_wealth = float(c["environmentMaxSugar"] + c["environmentMaxSpice"])
+        L.orc_bind_ethics.argtypes = [C.c_void_p]
+        L.orc_bind_ethics.restype = None
+        L.orc_ethics_stats.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_double * 5)]
+        L.orc_ethics_stats.restype = None
+        L.orc_bind_ethics(C.byref(e))
+
+    def unbind_ethics(self):
+        self.L.orc_bind_ethics(None)
+
+    def ethics_log_keys(self, t, population, mean_neighbors):
+        """meanSelfishness, agentLastMoveOptimalityPercentage, meanMoveRank, meanMoveDifferenceFromOptimal
+        (reference sugarscape.py:1304, 1318, 1323-1324)."""
+        g, a = self.state.as_structs()
+        out = (C.c_double * 5)()
+        self.L.orc_ethics_stats(C.byref(a), t, C.byref(out))
+        n = population
+        if n == 0:
+            return {"meanSelfishness": 0, "agentLastMoveOptimalityPercentage": 0, "meanMoveRank": 0,
+                    "meanMoveDifferenceFromOptimal": 0}
+        return {"meanSelfishness": round(out[0] / n, 2),
+                "agentLastMoveOptimalityPercentage": round((out[1] / out[2]) * 100, 2),
+                "meanMoveRank": round(out[3] / n, 2),
+                "meanMoveDifferenceFromOptimal": round(out[4] / mean_neighbors, 2) if mean_neighbors > 0 else 0}
+
     def bind_social(self, endowments):
         """Oracle-private friends lists + conflict happiness (log keys only)."""
         cap = self.state.capacity

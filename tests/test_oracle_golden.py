@@ -186,31 +186,63 @@ def test_oracle_disease_variants_match_reference_trajectory(variant, min_sick_st
     assert _disease_case(meta["base"], overrides, meta["steps"], meta["log"]) >= min_sick_steps
 
 
-def test_oracle_determinism_without_ethics_matches_reference_trajectory():
-    """examples/determinism.json minus the ethics decision models and the experimental-group log
-    (variant fixture from the unmodified reference): diseases, depression, lending, friends, racial
-    tags, universal income, live combat, trade, tags, inheritance, pollution and seasons at once --
-    every digest and all 59 log keys for 200 steps.  Oracle-only: the engine refuses most of these."""
+def _bind_everything(orc, c, pop, horizon, ethics):
+    orc.bind_lending(pop.endowments)
+    orc.bind_social(pop.endowments)
+    orc.bind_misc(c, pop.endowments, horizon)
+    if ethics:
+        orc.bind_ethics(c, pop.endowments)
+    orc.bind_disease(c, pop.endowments, pop.disease_endowments, horizon)      # (initial infections draw from the main stream)
+    orc.set_mt_from_python()
+
+
+def _unbind_everything(orc):
+    orc.unbind_lending()
+    orc.unbind_social()
+    orc.unbind_misc()
+    orc.unbind_ethics()
+    orc.unbind_disease()
+
+
+def _private_log_keys(orc, rs, t, ethics):
+    """The log keys that come from the oracle-private rule state."""
+    n = rs["population"]
+    rs.update(orc.disease_log_keys(t, n))
+    social, conflict = orc.social_sums()
+    rs["meanSocialHappiness"] = round(social / n, 2) if n else 0
+    rs["meanConflictHappiness"] = round(conflict / n, 2) if n else 0
+    rs["loanVolume"] = orc.loan_volume(t)
+    if n:
+        rs["largestRace"], rs["largestRaceSize"], rs["remainingRaces"] = orc.race_census()
+    if ethics:
+        rs.update(orc.ethics_log_keys(t, n, rs["meanNeighbors"]))
+
+
+@pytest.mark.parametrize("variant,ethics", [("determinism_plain", False), ("determinism_ethics", True)])
+def test_oracle_determinism_variants_match_reference_trajectory(variant, ethics):
+    """examples/determinism.json (variant fixtures from the unmodified reference,
+    tests/golden/make_golden_variants.py): diseases, depression, lending, friends, racial tags,
+    universal income, live combat, trade, tags, inheritance, pollution and seasons at once --
+    `_plain` without, `_ethics` with the ethics.Bentham decision models (bentham, altruist, egoist,
+    negativeBentham: SURVEY row a21; about a quarter of the moves are not the greedy one).  Only the
+    experimental-group split of the log is switched off.  Every digest and all 59 log keys for 200
+    steps.  Oracle-only: the engine refuses these rule families."""
     import gzip
     import json
     import os
-    with gzip.open(os.path.join(pu.GOLDEN, "determinism_plain.json.gz"), "rt") as f:
+    with gzip.open(os.path.join(pu.GOLDEN, variant + ".json.gz"), "rt") as f:
         meta = json.load(f)
     gold, log = meta["steps"], meta["log"]
     overrides = dict(meta["overrides"], timesteps=meta["meta"]["timesteps"])
     c, state, pop, params, endow, tags = pu.build(meta["base"], overrides=overrides, check=False)
     orc = Oracle(params, state, endow, tags)
-    horizon = len(gold) + 8
-    orc.bind_lending(pop.endowments)
-    orc.bind_social(pop.endowments)
-    orc.bind_misc(c, pop.endowments, horizon)
-    orc.bind_disease(c, pop.endowments, pop.disease_endowments, horizon)
-    orc.set_mt_from_python()
+    _bind_everything(orc, c, pop, len(gold) + 8, ethics)
     try:
         d, _ = pu.state_digests(state, *orc.mt_state())
         assert d == gold[0]["digests"], "t=0 state differs"
         sb = stats.StatsBuilder(c, init.equator(c))
         rs = sb.update(orc.stats(0), 0)
+        non_greedy = 0
         for t in range(1, len(gold)):
             orc.env_step(t)
             orc.agent_step(t, rs["meanWealth"])
@@ -218,21 +250,13 @@ def test_oracle_determinism_without_ethics_matches_reference_trajectory():
             d, snap = pu.state_digests(state, *orc.mt_state())
             assert d == gold[t]["digests"], f"state differs at t={t}"
             rs = sb.update(orc.stats(t), t, 0)
-            n = rs["population"]
-            rs.update(orc.disease_log_keys(t, n))
-            social, conflict = orc.social_sums()
-            rs["meanSocialHappiness"] = round(social / n, 2) if n else 0
-            rs["meanConflictHappiness"] = round(conflict / n, 2) if n else 0
-            rs["loanVolume"] = orc.loan_volume(t)
-            if n:
-                rs["largestRace"], rs["largestRaceSize"], rs["remainingRaces"] = orc.race_census()
+            _private_log_keys(orc, rs, t, ethics)
+            non_greedy += rs["agentLastMoveOptimalityPercentage"] < 100
             for k in stats.LOG_KEYS:
                 assert _close(rs[k], log[t][k]), f"log key {k} differs at t={t}: {rs[k]} vs {log[t][k]}"
+        assert (non_greedy > 150) == ethics
     finally:
-        orc.unbind_lending()
-        orc.unbind_social()
-        orc.unbind_misc()
-        orc.unbind_disease()
+        _unbind_everything(orc)
 
 
 @pytest.mark.parametrize("name", UNSUPPORTED)
