@@ -223,6 +223,28 @@ void orc_bind_misc(const orc_misc_t *m) {
 int orc_sizeof_misc(void) { return (int)sizeof(orc_misc_t); }
 static inline double happiness_unit(int s) { return g_misc ? g_misc->happiness_unit[s] : 1.0; }
 
+/* experimental group = "depressed" (agent.py:1256-1284 isInGroup; sugarscape.py:998-1003): the log repeats
+ * every statistic for the group and for its complement ("control").  g_pass selects which agents the
+ * statistics functions below see: 0 = everybody, 1 = the group, 2 = the control group. */
+enum { GI_COMBAT = 0, GI_DISEASE, GI_LENDING, GI_REPRODUCTION, GI_TRADE, GI_KINDS };
+typedef struct {
+    int64_t capacity;
+    int32_t *with_control, *with_experimental;    /* [slot][GI_KINDS]: interactions since the last statistics pass */
+    int32_t *control_neighbors, *experimental_neighbors;   /* movementNeighborhood split, as of the agent's last ranking */
+} orc_group_t;
+static orc_group_t g_group_store, *g_group = NULL;
+static int g_pass = 0;
+void orc_bind_group(const orc_group_t *g) { if (!g) { g_group = NULL; g_pass = 0; return; } g_group_store = *g; g_group = &g_group_store; }
+int orc_sizeof_group(void) { return (int)sizeof(orc_group_t); }
+void orc_set_pass(int32_t pass) { g_pass = pass; }
+static inline int is_member(int s) { return g_misc && g_misc->depressed[s]; }
+static inline int in_pass(int s) { return g_pass == 0 || (g_pass == 1) == is_member(s); }
+static inline void group_note(int s, int kind, int partner) {      /* <kind>With{Experimental,Control}Group += 1 */
+    if (!g_group) return;
+    if (is_member(partner)) g_group->with_experimental[(size_t)s * GI_KINDS + kind]++;
+    else g_group->with_control[(size_t)s * GI_KINDS + kind]++;
+}
+
 
 /* ------------------------------------------------------------------------------------------
  * ethics.Bentham decision models (ethics.py:105-244; spawn rules sugarscape.py:219-233).
@@ -429,7 +451,7 @@ void orc_race_census(const ssb_agents_t *a, int64_t out[3]) {
     int64_t cnt[4] = {0, 0, 0, 0}, first[4] = {-1, -1, -1, -1};
     for (int64_t i = 0; i < a->counters[SSB_C_N_LIST]; i++) {
         const int r = g_misc->race[a->order[i]];
-        if (r < 0) continue;
+        if (r < 0 || !in_pass(a->order[i])) continue;
         if (cnt[r]++ == 0) first[r] = i;
     }
     for (int r = 0; r < 4; r++) {
@@ -478,6 +500,7 @@ void orc_social_sums(const ssb_agents_t *a, double out[2]) {
     if (!g_social) return;
     for (int64_t i = 0; i < a->counters[SSB_C_N_LIST]; i++) {
         int s = a->order[i];
+        if (!in_pass(s)) continue;
         out[0] += g_social->social_happiness[s];
         out[1] += g_social->conflict_happiness[s];
     }
@@ -580,7 +603,7 @@ int64_t orc_loan_volume(const ssb_agents_t *a, int32_t t) {
     if (!g_lend) return 0;
     for (int64_t i = 0; i < a->counters[SSB_C_N_LIST]; i++) {
         int s = a->order[i];
-        if (g_lend->last_lended[s] == t) v += g_lend->last_loans[s];
+        if (in_pass(s) && g_lend->last_lended[s] == t) v += g_lend->last_loans[s];
     }
     return v;
 }
@@ -759,6 +782,7 @@ static void do_lending(ctx_t *c, int s) {
         if (!(sugar_income >= 0 && spice_income >= 0)) continue;
         add_loan(c, s, b, a->last_moved[s], sugar_principal, sugar_amount, spice_principal, spice_amount, duration);
         loans++;
+        group_note(s, GI_LENDING, b);
     }
     if (loans > 0) { g_lend->last_lended[s] = c->t; g_lend->last_loans[s] = loans; }
 }
@@ -894,6 +918,7 @@ static void do_disease(ctx_t *c, int s) {
         const int di = L->v[rng_below(c->rng, (uint32_t)count)].disease;
         orc_disease_catch(neighbors[k], di, s, c->a.id[s], c->t, 0, c->rng);
         if (infected_with(neighbors[k], g_dis->diseases[di].id)) spread++;
+        group_note(s, GI_DISEASE, neighbors[k]);
     }
     if (spread > 0) { g_dis->last_spread[s] = c->t; g_dis->n_spread[s] = spread; }
 }
@@ -907,7 +932,7 @@ static void disease_note_death(int s) {        /* doDeath (agent.py:302-313) */
 
 int64_t orc_move_space(const ssb_agents_t *a) {      /* moveSpace (sugarscape.py:1152) */
     int64_t v = 0;
-    if (g_dis) for (int64_t i = 0; i < a->counters[SSB_C_N_LIST]; i++) v += g_dis->last_valid_moves[a->order[i]];
+    if (g_dis) for (int64_t i = 0; i < a->counters[SSB_C_N_LIST]; i++) if (in_pass(a->order[i])) v += g_dis->last_valid_moves[a->order[i]];
     return v;
 }
 
@@ -917,6 +942,7 @@ void orc_ethics_stats(const ssb_agents_t *a, int32_t t, double out[5]) {
     if (!g_eth) return;
     for (int64_t i = 0; i < a->counters[SSB_C_N_LIST]; i++) {
         const int s = a->order[i];
+        if (!in_pass(s)) continue;
         out[0] += g_eth->selfishness[s];
         out[1] += g_eth->last_move_optimal[s]; out[2] += 1;
         out[3] += g_eth->move_rank[s]; out[4] += g_eth->move_diff[s];
@@ -924,12 +950,39 @@ void orc_ethics_stats(const ssb_agents_t *a, int32_t t, double out[5]) {
     /* this step's dead: doTimestep(t) was called on every one of them (it sets agent.timestep even when the
      * agent is already dead), so the reference's `agent.timestep == self.timestep` holds for all */
     (void)t;
-    for (int64_t i = 0; i < a->counters[SSB_C_N_DEAD]; i++) { out[1] += g_eth->last_move_optimal[a->dead_list[i]]; out[2] += 1; }
+    for (int64_t i = 0; i < a->counters[SSB_C_N_DEAD]; i++)
+        if (in_pass(a->dead_list[i])) { out[1] += g_eth->last_move_optimal[a->dead_list[i]]; out[2] += 1; }
+}
+
+/* Interaction counters of the current pass (sugarscape.py:1175-1198, 1230-1250): out[k] = to control,
+ * out[GI_KINDS + k] = to experimental, summed over the pass's live agents (then reset) and this
+ * step's dead; out[10], out[11] = control / experimental members of the movement neighbourhoods. */
+void orc_group_counters(const ssb_agents_t *a, int64_t out[12]) {
+    for (int k = 0; k < 12; k++) out[k] = 0;
+    if (!g_group) return;
+    for (int64_t i = 0; i < a->counters[SSB_C_N_LIST]; i++) {
+        const int s = a->order[i];
+        if (!in_pass(s)) continue;
+        for (int k = 0; k < GI_KINDS; k++) {
+            out[k] += g_group->with_control[(size_t)s * GI_KINDS + k];
+            out[GI_KINDS + k] += g_group->with_experimental[(size_t)s * GI_KINDS + k];
+            if (g_pass != 0) { g_group->with_control[(size_t)s * GI_KINDS + k] = 0; g_group->with_experimental[(size_t)s * GI_KINDS + k] = 0; }
+        }
+        out[10] += g_group->control_neighbors[s]; out[11] += g_group->experimental_neighbors[s];
+    }
+    for (int64_t i = 0; i < a->counters[SSB_C_N_DEAD]; i++) {
+        const int s = a->dead_list[i];
+        if (!in_pass(s)) continue;
+        for (int k = 0; k < GI_KINDS; k++) {
+            out[k] += g_group->with_control[(size_t)s * GI_KINDS + k];
+            out[GI_KINDS + k] += g_group->with_experimental[(size_t)s * GI_KINDS + k];
+        }
+    }
 }
 
 double orc_health_happiness_sum(const ssb_agents_t *a) {
     double v = 0;
-    if (g_dis) for (int64_t i = 0; i < a->counters[SSB_C_N_LIST]; i++) v += g_dis->health_happiness[a->order[i]];
+    if (g_dis) for (int64_t i = 0; i < a->counters[SSB_C_N_LIST]; i++) if (in_pass(a->order[i])) v += g_dis->health_happiness[a->order[i]];
     return v;
 }
 
@@ -941,17 +994,21 @@ void orc_disease_stats(const ssb_agents_t *a, int32_t t, int64_t out[5]) {
     const int64_t n = a->counters[SSB_C_N_LIST], n_dead = a->counters[SSB_C_N_DEAD];
     int64_t *infectors = (int64_t *)malloc(sizeof(int64_t) * (size_t)(4 * (n + n_dead) + 16));
     int64_t ni = 0;
+    /* isDiseaseExperimentalGroup() is false for every disease unless the group names one, so the pass over the
+     * experimental group skips all incidence / prevalence bookkeeping (sugarscape.py:1200-1211, 1266-1277) */
+    const int skip_diseases = g_pass == 1;
     for (int64_t i = 0; i < n; i++) {
         const int s = a->order[i];
+        if (!in_pass(s)) continue;
         const sick_list_t *L = &g_dis->sick[s];
         if (L->n > 0) out[0]++;
-        for (int k = 0; k < L->n; k++)
+        for (int k = 0; k < L->n && !skip_diseases; k++)
             if (L->v[k].caught == t) {
                 out[1]++;
                 if (t != 0) infectors[ni++] = ((int64_t)L->v[k].infector_slot << 32) | (uint32_t)L->v[k].infector_id;
             }
     }
-    for (int64_t i = 0; i < n_dead; i++) out[4] += g_dis->disease_death[a->dead_list[i]];    /* (their disease lists are empty) */
+    for (int64_t i = 0; i < n_dead; i++) if (in_pass(a->dead_list[i])) out[4] += g_dis->disease_death[a->dead_list[i]];    /* (their disease lists are empty) */
     /* distinct infectors */
     for (int64_t i = 0; i < ni; i++) {
         int seen = 0;
@@ -959,7 +1016,7 @@ void orc_disease_stats(const ssb_agents_t *a, int32_t t, int64_t out[5]) {
         out[2] += !seen;
     }
     free(infectors);
-    for (int d = 0; d < g_dis->n_diseases; d++) out[3] += g_dis->diseases[d].listed * g_dis->diseases[d].infected;
+    for (int d = 0; d < g_dis->n_diseases && !skip_diseases; d++) out[3] += g_dis->diseases[d].listed * g_dis->diseases[d].infected;
 }
 
 /* collectResourcesAtCell, agent.py:249-259 + cell.py:32-45 */
@@ -1109,10 +1166,12 @@ static int move_to_best_cell(ctx_t *c, int s) {
     } else {
         /* findNeighborhood: live agents in range + self (agent.py:1052-1065) */
         int hood = 1;
+        int hood_exp = is_member(s), hood_ctrl = !is_member(s);      /* self is part of the neighbourhood */
         for (int i = 0; i < n; i++) {
             int o = c->g.occ[cells[i]];
-            if (o >= 0 && agent_alive(c, o)) hood++;
+            if (o >= 0 && agent_alive(c, o)) { hood++; if (is_member(o)) hood_exp++; else hood_ctrl++; }
         }
+        if (g_group) { g_group->control_neighbors[s] = hood_ctrl; g_group->experimental_neighbors[s] = hood_exp; }
         /* random.shuffle(list(cellsInRange.items())) -- shuffle an index permutation */
         int32_t perm[MAX_CAND];
         for (int i = 0; i < n; i++) perm[i] = i;
@@ -1193,6 +1252,7 @@ static int move_to_best_cell(ctx_t *c, int s) {
             a->sugar[prey] -= sl; a->spice[prey] -= pl;
             if (g_social) g_social->last_combat[s] = c->t;
             do_death(c, prey, SSB_COMBAT);
+            group_note(s, GI_COMBAT, prey);
         }
     }
     a->last_moved[s] = c->t;
@@ -1272,6 +1332,7 @@ static void do_trading(ctx_t *c, int s) {
             a->trade_volume[s] += 1;
             sum_sugar_price += sugar_price;
             sum_spice_price += spice_price;
+            group_note(s, GI_TRADE, traders[k]);
         }
     }
     a->trade_price[s] = sum_spice_price > sum_sugar_price ? sum_spice_price : sum_sugar_price;
@@ -1338,6 +1399,10 @@ static void do_reproduction(ctx_t *c, int s) {
             }
             g_dis->immune[ch] = g_dis->start_immune[ch] = child;
             g_dis->protection[ch] = ((eb >> EB_PROTECTION) & 1u) ? g_dis->protection[m] : g_dis->protection[s];
+        }
+        if (g_group) {
+            for (int k = 0; k < GI_KINDS; k++) { g_group->with_control[(size_t)ch * GI_KINDS + k] = 0; g_group->with_experimental[(size_t)ch * GI_KINDS + k] = 0; }
+            g_group->control_neighbors[ch] = 0; g_group->experimental_neighbors[ch] = 0;
         }
         if (g_eth) {     /* the paired endowments follow ONE draw (agent.py:845-851); the child's class is that parent's */
             const int from = ((eb >> EB_DECISION_MODEL) & 1u) ? m : s;
@@ -1420,6 +1485,7 @@ static void do_reproduction(ctx_t *c, int s) {
         a->sugar[m] = a->sugar[m] - mate_sugar_cost;
         a->spice[m] = a->spice[m] - mate_spice_cost;
         a->last_repro[s] = c->t;
+        group_note(s, GI_REPRODUCTION, m);
     }
 }
 
@@ -1766,16 +1832,19 @@ void orc_stats(const ssb_params_t *p, const ssb_grid_t *g, const ssb_agents_t *a
     out->min_wealth = 0; out->max_wealth = 0;
     for (int i = 0; i < 32; i++) out->tribe_first[i] = -1;
     double *wealths = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+    int64_t seen = 0;                 /* agents of the current statistics pass (g_pass: all / group / control) */
     for (int64_t i = 0; i < n; i++) {
         int s = a->order[i];
+        if (!in_pass(s)) continue;
         double w = a->sugar[s] + a->spice[s];
-        wealths[i] = w;
+        wealths[seen] = w;
         out->sum_sugar_metab += a->sugar_metab[s]; out->sum_spice_metab += a->spice_metab[s];
         out->sum_movement += a->movement[s]; out->sum_vision += a->vision[s]; out->sum_age += a->age[s];
         out->n_acted += a->age[s] > 0;
         out->sum_wealth += w;
-        if (i == 0 || w > out->max_wealth) out->max_wealth = w;
-        if (i == 0 || w < out->min_wealth) out->min_wealth = w;
+        if (seen == 0 || w > out->max_wealth) out->max_wealth = w;
+        if (seen == 0 || w < out->min_wealth) out->min_wealth = w;
+        seen++;
         out->sum_wealth_collected += w - (a->last_sugar[s] + a->last_spice[s]);
         /* findTimeToLive (agent.py:1113-1140) */
         out->sum_burn_rate += time_to_live(a, s, 0);
@@ -1792,6 +1861,8 @@ void orc_stats(const ssb_params_t *p, const ssb_grid_t *g, const ssb_agents_t *a
         if (tr >= 0 && tr < 32) { if (out->tribe_count[tr]++ == 0) out->tribe_first[tr] = i; }
         if (a->born[s] == t && t > 0) { /* counted below from N_BORN */ }
     }
+    n = seen;
+    out->population = n;
     /* Lorenz area numerator (sugarscape.py:913-934): sum of cumulative wealth over the first
      * n-1 sorted agents plus half the total */
     qsort(wealths, (size_t)n, sizeof(double), cmp_f64);
@@ -1801,9 +1872,11 @@ void orc_stats(const ssb_params_t *p, const ssb_grid_t *g, const ssb_agents_t *a
     out->lorenz_weighted_sum = area;
     free(wealths);
     /* this step's dead (sugarscape.py:1213-1265) */
-    out->n_dead = cn[SSB_C_N_DEAD];
-    for (int64_t i = 0; i < out->n_dead; i++) {
+    out->n_dead = 0;
+    for (int64_t i = 0; i < cn[SSB_C_N_DEAD]; i++) {
         int s = a->dead_list[i];
+        if (!in_pass(s)) continue;
+        out->n_dead++;
         if (a->last_moved[s] == t) out->n_dead_moved++;
         out->sum_age_at_death += a->age[s];
         out->dead_wealth_collected += (a->sugar[s] + a->spice[s]) - (a->last_sugar[s] + a->last_spice[s]);
@@ -1813,6 +1886,11 @@ void orc_stats(const ssb_params_t *p, const ssb_grid_t *g, const ssb_agents_t *a
     }
     out->n_born = cn[SSB_C_N_BORN];
     out->n_replaced = cn[SSB_C_N_REPLACED];
+    if (g_pass != 0) {                /* bornAgents of the pass (sugarscape.py:1359-1362): this step's newborn, alive or not */
+        out->n_born = 0;
+        for (int64_t i = 0; i < cn[SSB_C_N_LIST]; i++) { int s = a->order[i]; if (a->born[s] == t && t > 0 && in_pass(s)) out->n_born++; }
+        for (int64_t i = 0; i < cn[SSB_C_N_DEAD]; i++) { int s = a->dead_list[i]; if (a->born[s] == t && t > 0 && in_pass(s)) out->n_born++; }
+    }
     /* environment totals (sugarscape.py:1044-1051) with the closed-form LastProduced */
     int W = p->width, H = p->height;
     int seasons = p->season_interval > 0;

@@ -349,13 +349,50 @@ class Oracle:
         out = (C.c_double * 5)()
         self.L.orc_ethics_stats(C.byref(a), t, C.byref(out))
         n = population
-        if n == 0:
-            return {"meanSelfishness": 0, "agentLastMoveOptimalityPercentage": 0, "meanMoveRank": 0,
+        if n == 0:      # the reference leaves the raw count of optimal moves (of the dead) in place (sugarscape.py:1325-1351)
+            return {"meanSelfishness": 0, "agentLastMoveOptimalityPercentage": int(out[1]), "meanMoveRank": 0,
                     "meanMoveDifferenceFromOptimal": 0}
         return {"meanSelfishness": round(out[0] / n, 2),
                 "agentLastMoveOptimalityPercentage": round((out[1] / out[2]) * 100, 2),
                 "meanMoveRank": round(out[3] / n, 2),
                 "meanMoveDifferenceFromOptimal": round(out[4] / mean_neighbors, 2) if mean_neighbors > 0 else 0}
+
+    def bind_group(self):
+        """Oracle-private bookkeeping of the experimental-group split of the log (group "depressed")."""
+        cap = self.state.capacity
+        self.grp = {"with_control": np.zeros(cap * 5, np.int32), "with_experimental": np.zeros(cap * 5, np.int32),
+                    "control_neighbors": np.zeros(cap, np.int32), "experimental_neighbors": np.zeros(cap, np.int32)}
+
+        class Group(C.Structure):
+            _fields_ = [("capacity", C.c_int64), ("with_control", C.c_void_p), ("with_experimental", C.c_void_p),
+                        ("control_neighbors", C.c_void_p), ("experimental_neighbors", C.c_void_p)]
+        L = self.L
+        L.orc_sizeof_group.restype = C.c_int
+        assert L.orc_sizeof_group() == C.sizeof(Group)
+        g = Group()
+        g.capacity = cap
+        for k in ("with_control", "with_experimental", "control_neighbors", "experimental_neighbors"):
+            setattr(g, k, self.grp[k].ctypes.data)
+        L.orc_bind_group.argtypes = [C.c_void_p]
+        L.orc_bind_group.restype = None
+        L.orc_set_pass.argtypes = [C.c_int32]
+        L.orc_set_pass.restype = None
+        L.orc_group_counters.argtypes = [C.c_void_p, C.POINTER(C.c_int64 * 12)]
+        L.orc_group_counters.restype = None
+        L.orc_bind_group(C.byref(g))
+
+    def unbind_group(self):
+        self.L.orc_bind_group(None)
+
+    def set_pass(self, which):
+        """0 = statistics over everybody, 1 = the experimental group, 2 = the control group."""
+        self.L.orc_set_pass(which)
+
+    def group_counters(self):
+        g, a = self.state.as_structs()
+        out = (C.c_int64 * 12)()
+        self.L.orc_group_counters(C.byref(a), C.byref(out))
+        return list(out)
 
     def bind_social(self, endowments):
         """Oracle-private friends lists + conflict happiness (log keys only)."""

@@ -262,32 +262,71 @@ def test_oracle_determinism_variants_match_reference_trajectory(variant, ethics)
         _unbind_everything(orc)
 
 
+_INTERACTIONS = ("combat", "disease", "lending", "reproduction", "trade")
+# keys a group pass does not compute: the log keeps their initial 0 (sugarscape.py:1403-1417)
+_GROUP_TEMPLATE_ZERO = ("timestep", "giniCoefficient", "seed", "environmentWealthCreated", "environmentWealthTotal")
+
+
+def _full_log_entry(orc, sb, group, t):
+    """The reference's runtimeStats with an experimental group (sugarscape.py:998-1003): the statistics of
+    the group, of its complement ("control") and of everybody -- 59 + 2 + 2 x (61 + 10) = 203 keys."""
+    import copy
+
+    def one_pass(which, builder):
+        orc.set_pass(which)
+        rs = builder.update(orc.stats(t), t, 0)
+        _private_log_keys(orc, rs, t, True)
+        counters = orc.group_counters()
+        n = rs["population"]
+        rs["meanControlNeighbors"] = round(counters[10] / n, 2) if n else 0
+        rs["meanExperimentalNeighbors"] = round(counters[11] / n, 2) if n else 0
+        return rs, counters
+
+    keys = tuple(stats.LOG_KEYS) + ("meanControlNeighbors", "meanExperimentalNeighbors")
+    passes = {group: one_pass(1, copy.deepcopy(sb)), "control": one_pass(2, copy.deepcopy(sb))}
+    everybody, _ = one_pass(0, sb)
+    entry = {k: everybody[k] for k in keys}
+    for prefix, (rs, counters) in passes.items():
+        rs["carryingCapacity"] = entry["carryingCapacity"]          # from len(self.agents), whatever the pass
+        for k in keys:
+            entry[prefix + k[0].upper() + k[1:]] = 0 if k in _GROUP_TEMPLATE_ZERO else rs[k]
+        side = "Control" if prefix == "control" else "Experimental"
+        for i, kind in enumerate(_INTERACTIONS):
+            entry[f"{kind}{side}GroupToControlGroup"] = counters[i]
+            entry[f"{kind}{side}GroupToExperimentalGroup"] = counters[5 + i]
+    return entry
+
+
 @pytest.mark.parametrize("name", ["determinism", "all_features"])
 def test_oracle_all_features_examples_match_reference_trajectory(name):
     """examples/determinism.json (the example BASELINE.json's north star names) and all_features.json as
-    shipped, oracle only: every digest of every step and the 59 base log keys.  Not produced: the 144
-    extra keys of the experimental-group split ("depressed" vs control) of the log."""
+    shipped, oracle only: every digest of every step and ALL 203 log keys -- the 59 base keys, the
+    movement-neighbourhood split and the complete experimental-group ("depressed") / control copies
+    with their interaction counters."""
     c, state, pop, params, endow, tags = pu.build(name, check=False)
     meta, _ = pu.load_golden(name)
     gold, log = meta["steps"], meta["log"]
     orc = Oracle(params, state, endow, tags)
+    orc.bind_group()
     _bind_everything(orc, c, pop, len(gold) + 8, True)
     try:
         d, _ = pu.state_digests(state, *orc.mt_state())
         assert d == gold[0]["digests"], "t=0 state differs"
         sb = stats.StatsBuilder(c, init.equator(c))
-        rs = sb.update(orc.stats(0), 0)
-        for t in range(1, len(gold)):
-            orc.env_step(t)
-            orc.agent_step(t, rs["meanWealth"])
-            orc.compact(t)
-            d, snap = pu.state_digests(state, *orc.mt_state())
-            assert d == gold[t]["digests"], f"state differs at t={t}"
-            rs = sb.update(orc.stats(t), t, 0)
-            _private_log_keys(orc, rs, t, True)
-            for k in stats.LOG_KEYS:
-                assert _close(rs[k], log[t][k]), f"log key {k} differs at t={t}: {rs[k]} vs {log[t][k]}"
+        rs = _full_log_entry(orc, sb, c["experimentalGroup"], 0)
+        assert len(log[1]) == 203
+        for t in range(0, len(gold)):
+            if t > 0:
+                orc.env_step(t)
+                orc.agent_step(t, rs["meanWealth"])
+                orc.compact(t)
+                d, snap = pu.state_digests(state, *orc.mt_state())
+                assert d == gold[t]["digests"], f"state differs at t={t}"
+                rs = _full_log_entry(orc, sb, c["experimentalGroup"], t)
+            for k in log[t]:
+                assert k in rs and _close(rs[k], log[t][k]), f"log key {k} differs at t={t}: {rs.get(k)} vs {log[t][k]}"
     finally:
+        orc.unbind_group()
         _unbind_everything(orc)
 
 
