@@ -310,6 +310,8 @@ class Oracle:
                 assert name == "none", name
                 bentham = False
             look = c["agentDecisionModelLookaheadFactor"]
+            if isinstance(look, list):      # the default is the list [0]: handed to the agents as is, and `[0] != 0` holds
+                look = 1.0
             if "NoLookahead" in name:
                 look = 0
             elif "HalfLookahead" in name:

@@ -1,5 +1,6 @@
 """Shared helpers of the parity tests: build a simulation from a shipped example config, step it
 with the CPU oracle (or the CUDA engine) and compare with the golden fixtures."""
+import copy
 import gzip
 import json
 import os
@@ -28,13 +29,14 @@ def load_golden(name):
 
 def example_configuration(name, overrides=None):
     """tests/test.py protocol of the reference (headless, no debug, 200 steps)."""
-    c = config.overlay_options(dict(EXAMPLE_OPTIONS[name]), config.default_configuration())
+    # deep copies: verify_configuration rewrites nested lists in place (out-of-range peaks, sorted ranges)
+    c = config.overlay_options(copy.deepcopy(EXAMPLE_OPTIONS[name]), config.default_configuration())
     c["headlessMode"] = True
     c["debugMode"] = ["none"]
     c["logfile"] = None
     c["timesteps"] = 200
     for k, v in (overrides or {}).items():
-        c[k] = v
+        c[k] = copy.deepcopy(v)
     config.verify_random_seed(c)
     return config.verify_configuration(c)
 
