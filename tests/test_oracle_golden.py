@@ -336,6 +336,38 @@ def test_unsupported_rule_families_fail_loudly(name):
         pu.build(name)
 
 
+@pytest.mark.parametrize("name,mode", [("reproduction_basic", "exact"), ("trade_tagging_reproduction", "exact"),
+                                       ("combat_limited", "scalable"), ("agent_replacement", "scalable"),
+                                       ("reproduction_basic", "scalable"), ("trade_replacement", "scalable")])
+def test_state_invariants_hold_on_the_oracle(name, mode):
+    """tests/invariants.py (the checks the GPU tests apply at BASELINE's full sizes) on oracle states."""
+    import invariants
+    from sugarscape_b200 import layout
+    rng_mode = layout.RNG_EXACT if mode == "exact" else layout.RNG_SCALABLE
+    c, state, pop, params, endow, tags = pu.build(name, rng_mode, {"agentMovement": [6, 6]})
+    orc = Oracle(params, state, endow, tags)
+    if rng_mode == layout.RNG_EXACT:
+        orc.set_mt_from_python()
+    elif c["agentReplacements"] > 0:
+        orc.bind_endowments(pop.endowments)
+    population = invariants.check_state(state)
+    for t in range(1, 41):
+        orc.env_step(t)
+        orc.agent_step(t, 0.0)
+        orc.compact(t)
+        if c["agentReplacements"] > 0:
+            if rng_mode == layout.RNG_EXACT:
+                orc.push_mt_to_python()
+                pu.replace_dead_agents(c, state, pop, t)
+                orc.set_mt_from_python()
+            else:
+                orc.replace(t)
+        st = orc.stats(t)
+        if rng_mode == layout.RNG_SCALABLE:
+            invariants.check_step_accounting(population, st)
+        population = invariants.check_state(state, st)
+
+
 def test_scalable_mode_priority_is_a_bijection():
     from oracle_binding import lib
     L = lib()
