@@ -1,0 +1,90 @@
+#!/usr/bin/env python3
+"""Fuzz the oracle's SCALABLE RNG mode against the unmodified reference run with its randomness
+redirected to the mode S definitions (make_golden_scalable.run) -- build container only.
+
+    python tests/golden/fuzz_scalable.py [cases] [seed]
+"""
+import os
+import random
+import sys
+import traceback
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+import make_golden_scalable as mgs  # noqa: E402
+import parity_util as pu  # noqa: E402
+from oracle_binding import Oracle  # noqa: E402
+from sugarscape_b200 import layout  # noqa: E402
+
+BASES = ["constant_growback", "pollution_formation", "reproduction_basic", "cultural_tagging", "trade_basic",
+         "combat_unlimited", "agent_replacement", "combat_limited", "trade_replacement", "trade_tagging_reproduction",
+         "seasonal_migration", "cultural_combat_unlimited", "reproduction_oscillation_small", "trade_pollution"]
+
+
+def draw(rng):
+    side = rng.choice([20, 30, 40, 50])
+    r = rng.randrange(1, 7)
+    n = rng.randrange(40, max(41, side * side // 5))
+    ov = {"seed": rng.randrange(1, 10 ** 6), "environmentWidth": side, "environmentHeight": side, "startingAgents": n,
+          "agentMovement": [r, r]}
+    if rng.random() < 0.5:
+        ov["agentVision"] = sorted([rng.randrange(1, 7), rng.randrange(1, 7)])
+    if rng.random() < 0.4:
+        ov["agentAggressionFactor"] = rng.choice([[0, 0], [1, 1], [0, 1]])
+    if rng.random() < 0.4:
+        ov["agentReplacements"] = rng.choice([0, n // 2, n])
+    if rng.random() < 0.3:
+        ov["environmentStartingQuadrants"] = rng.choice([[1, 2, 3, 4], [2, 4], [1], [1, 3]])
+        ov["environmentQuadrantSizeFactor"] = rng.choice([1, 0.8, 0.5])
+    if rng.random() < 0.3:
+        ov["agentMaxAge"] = rng.choice([[5, 30], [60, 100], [-1, -1]])
+    return ov
+
+
+def run_case(base, ov, steps):
+    try:
+        recs = mgs.run(base, steps, ov)
+    except Exception as e:
+        return "skipped (the patched reference raised %r)" % (e,)
+    c, state, pop, params, endow, tags = pu.build(base, layout.RNG_SCALABLE, ov)
+    orc = Oracle(params, state, endow, tags)
+    orc.bind_endowments(pop.endowments)
+    for rec in recs:
+        t = rec["t"]
+        orc.env_step(t)
+        orc.agent_step(t, 0.0)
+        orc.compact(t)
+        orc.replace(t)
+        d, snap = pu.state_digests_by_id(state)
+        if len(snap["a_id"]) != rec["population"]:
+            return f"t={t}: population {len(snap['a_id'])} != {rec['population']}"
+        bad = [k for k in ("agents_int", "agents_f64", "agents_tags", "grid_int", "pollution") if d[k] != rec["digests"][k]]
+        if bad:
+            return f"t={t} differs: {bad}"
+    return "ok %d steps, final population %d" % (len(recs), recs[-1]["population"] if recs else -1)
+
+
+def main():
+    cases = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+    rng = random.Random(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+    bad = 0
+    for i in range(cases):
+        base, ov = rng.choice(BASES), draw(rng)
+        try:
+            res = run_case(base, ov, 40)
+        except pu.init.UnsupportedConfiguration as e:
+            res = "skipped (engine scope: %s)" % e
+        except Exception as e:
+            res = "EXCEPTION " + repr(e) + "\n" + traceback.format_exc(limit=4)
+        flag = "" if res.startswith("ok") or res.startswith("skipped") else "   <<<<<<"
+        print(f"case {i} {base}: {res}{flag}", flush=True)
+        if flag:
+            bad += 1
+            print("   overrides:", ov, flush=True)
+    print("mismatching cases:", bad)
+
+
+if __name__ == "__main__":
+    main()
