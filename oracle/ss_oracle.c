@@ -980,6 +980,22 @@ void orc_group_counters(const ssb_agents_t *a, int64_t out[12]) {
     }
 }
 
+/* a slot handed to a brand-new agent by the HOST (exact-mode replacement): empty lists, default fields */
+void orc_private_reset(int32_t s) {
+    if (g_lend) lending_reset_slot(s);
+    if (g_social) social_reset_slot(s);
+    if (g_dis) disease_reset_slot(s);
+    if (g_group) {
+        for (int k = 0; k < GI_KINDS; k++) { g_group->with_control[(size_t)s * GI_KINDS + k] = 0; g_group->with_experimental[(size_t)s * GI_KINDS + k] = 0; }
+        g_group->control_neighbors[s] = 0; g_group->experimental_neighbors[s] = 0;
+    }
+    if (g_eth) { g_eth->last_move_optimal[s] = 1; g_eth->move_rank[s] = 0; g_eth->move_diff[s] = 0; }
+    if (g_misc) {
+        g_misc->last_income_sugar[s] = 0; g_misc->last_income_spice[s] = 0;
+        g_misc->depressed[s] = 0; g_misc->happiness_unit[s] = 1; g_misc->race[s] = -1; g_misc->racial_tags[s] = 0;
+    }
+}
+
 double orc_health_happiness_sum(const ssb_agents_t *a) {
     double v = 0;
     if (g_dis) for (int64_t i = 0; i < a->counters[SSB_C_N_LIST]; i++) if (in_pass(a->order[i])) v += g_dis->health_happiness[a->order[i]];

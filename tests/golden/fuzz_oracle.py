@@ -21,7 +21,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 import ref_harness as rh  # noqa: E402
 import parity_util as pu  # noqa: E402
 from oracle_binding import Oracle  # noqa: E402
-from sugarscape_b200 import init, stats  # noqa: E402
+from sugarscape_b200 import init, layout, stats  # noqa: E402
 
 BASES = ["determinism", "dune", "trade_tagging_reproduction", "combat_unlimited", "lending_basic", "disease_basic",
          "pollution_formation", "reproduction_inheritance", "seasonal_migration", "cultural_combat_unlimited"]
@@ -97,6 +97,11 @@ def run_case(base, ov, steps):
     c, state, pop, params, endow, tags = pu.build(base, overrides=ov, check=False)
     if c["experimentalGroup"] is not None or c["agentLeader"]:
         return "skipped"
+    if c["agentReplacements"] > 0 and ((c["agentTagging"] and c["agentTagStringLength"] > 0 and not c["environmentTribePerQuadrant"])
+                                       or (c["agentImmuneSystemLength"] > 0 and c["startingDiseases"] > 0)):
+        # Known deviation: the reference shares the tag / immune-system LIST objects between the
+        # agents created from one endowment entry
+        return "skipped (reference aliases list-valued endowments between replacement twins)"
     orc = Oracle(params, state, endow, tags)
     horizon = steps + 8
     orc.bind_lending(pop.endowments)
@@ -116,8 +121,15 @@ def run_case(base, ov, steps):
             orc.env_step(t)
             orc.agent_step(t, rs["meanWealth"])
             orc.compact(t)
-            if c["agentReplacements"] > 0:
-                return "skipped (host replacement does not know the oracle-private state)"
+            if c["agentReplacements"] > 0:          # replaceDeadAgents on the host, with the main stream (exact mode)
+                n = int(state.counters[layout.C_N_LIST])
+                if n < c["agentReplacements"]:
+                    orc.push_mt_to_python()
+                    new_agents = pop.place(c["agentReplacements"] - n, state.occ >= 0, t, int(state.counters[layout.C_NEXT_ID]))
+                    state.append_agents(new_agents, protect_last=int(state.counters[layout.C_N_DEAD]))
+                    state.counters[layout.C_NEXT_ID] += len(new_agents)
+                    orc.adopt_new_agents(new_agents, c)
+                    orc.set_mt_from_python()
             d, _ = pu.state_digests(state, *orc.mt_state())
             if d != ref_digests[t]:
                 return f"t={t} differs: " + str({k: d[k] == ref_digests[t][k] for k in d})

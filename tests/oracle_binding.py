@@ -98,10 +98,7 @@ class Oracle:
                      "last_lended": np.full(cap, -1, np.int32), "last_loans": np.zeros(cap, np.int32)}
         n = int(self.state.counters[layout.C_N_LIST])
         for s in self.state.a_order[:n]:
-            e = endowments[int(self.state.a_id[s])]
-            self.lend["lending_factor"][s] = e["lendingFactor"]
-            self.lend["base_interest_rate"][s] = e["baseInterestRate"]
-            self.lend["loan_duration"][s] = e["loanDuration"]
+            self._set_lending(int(s), endowments[int(self.state.a_id[s])])
         L = self.L
         L.orc_bind_lending.argtypes = [C.c_void_p] * 7 + [C.c_int64]
         L.orc_bind_lending.restype = None
@@ -110,6 +107,31 @@ class Oracle:
         L.orc_bind_lending(*[self.lend[k].ctypes.data for k in ("lending_factor", "base_interest_rate", "loan_duration",
                                                                 "sugar_mean_income", "spice_mean_income", "last_lended",
                                                                 "last_loans")], cap)
+
+    def _set_lending(self, s, e):
+        self.lend["lending_factor"][s] = e["lendingFactor"]
+        self.lend["base_interest_rate"][s] = e["baseInterestRate"]
+        self.lend["loan_duration"][s] = e["loanDuration"]
+
+    def adopt_new_agents(self, new_agents, c):
+        """Agents the HOST just placed (exact-mode replacement, init.Population.place + HostState.append_agents):
+        give them fresh oracle-private state from their endowments, like the reference's configureAgents."""
+        self.L.orc_private_reset.argtypes = [C.c_int32]
+        self.L.orc_private_reset.restype = None
+        g, a = self.state.as_structs()
+        for agent in new_agents:
+            s, e = int(self.state.occ[agent["cell"]]), agent["endowment"]
+            self.L.orc_private_reset(s)
+            if getattr(self, "lend", None) is not None:
+                self._set_lending(s, e)
+            if getattr(self, "social", None) is not None:
+                self.social["max_friends"][s] = e["maxFriends"]
+            if getattr(self, "eth", None) is not None:
+                self._set_ethics(s, e, c)
+            if getattr(self, "dis", None) is not None:
+                self._set_disease(s, e)
+            if getattr(self, "misc", None) is not None:
+                self._set_misc(s, e, a)
 
     def unbind_lending(self):
         self.L.orc_bind_lending(*([None] * 7), 0)
@@ -150,10 +172,7 @@ class Oracle:
         n = int(self.state.counters[layout.C_N_LIST])
         agents = [int(s) for s in self.state.a_order[:n]]
         for s in agents:
-            e = endowments[int(self.state.a_id[s])]
-            bits = sum(b << k for k, b in enumerate(e["immuneSystem"]))
-            self.dis["immune"][s] = self.dis["start_immune"][s] = bits
-            self.dis["protection"][s] = e["diseaseProtectionChance"]
+            self._set_disease(s, endowments[int(self.state.a_id[s])])
         L.orc_bind_disease.argtypes = [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 10 + [C.c_int64]
         L.orc_move_space.argtypes = [C.c_void_p]
         L.orc_move_space.restype = C.c_int64
@@ -194,6 +213,11 @@ class Oracle:
                     break
             if curr > hi:
                 curr = lo
+
+    def _set_disease(self, s, e):
+        bits = sum(b << k for k, b in enumerate(e["immuneSystem"]))
+        self.dis["immune"][s] = self.dis["start_immune"][s] = bits
+        self.dis["protection"][s] = e["diseaseProtectionChance"]
 
     def unbind_disease(self):
         self.L.orc_bind_disease(None, 0, 0, *([None] * 10), 0)
@@ -260,16 +284,17 @@ class Oracle:
         g, a = self.state.as_structs()
         n = int(self.state.counters[layout.C_N_LIST])
         for s in self.state.a_order[:n]:
-            s = int(s)
-            e = endowments[int(self.state.a_id[s])]
-            self.misc["universal_sugar"][s] = e["universalSugar"]
-            self.misc["universal_spice"][s] = e["universalSpice"]
-            if e["racialTags"] is not None:
-                rt = e["racialTags"]
-                self.misc["racial_tags"][s] = sum(v << (2 * k) for k, v in enumerate(rt))
-                self.misc["race"][s] = max(set(rt), key=rt.count)
-            if e["depressionFactor"] == 1:
-                L.orc_depress(C.byref(a), s)
+            self._set_misc(int(s), endowments[int(self.state.a_id[s])], a)
+
+    def _set_misc(self, s, e, a):
+        self.misc["universal_sugar"][s] = e["universalSugar"]
+        self.misc["universal_spice"][s] = e["universalSpice"]
+        if e["racialTags"] is not None:
+            rt = e["racialTags"]
+            self.misc["racial_tags"][s] = sum(v << (2 * k) for k, v in enumerate(rt))
+            self.misc["race"][s] = max(set(rt), key=rt.count)
+        if e["depressionFactor"] == 1:
+            self.L.orc_depress(C.byref(a), s)
 
     def unbind_misc(self):
         self.L.orc_bind_misc(None)
@@ -293,34 +318,7 @@ class Oracle:
                     "last_move_optimal": np.ones(cap, np.int32), "move_rank": np.zeros(cap, np.int32), "move_diff": np.zeros(cap)}
         n = int(self.state.counters[layout.C_N_LIST])
         for s in self.state.a_order[:n]:
-            s = int(s)
-            e = endowments[int(self.state.a_id[s])]
-            name = e["decisionModel"]
-            selfish = e["selfishnessFactor"]
-            bentham = True
-            if "altruist" in name:
-                selfish = 0
-            elif "bentham" in name:
-                selfish = 0.5 if selfish < 0 else selfish
-            elif "egoist" in name:
-                selfish = 1
-            elif "negativeBentham" in name:
-                selfish = -1
-            else:
-                assert name == "none", name
-                bentham = False
-            look = c["agentDecisionModelLookaheadFactor"]
-            if isinstance(look, list):      # the default is the list [0]: handed to the agents as is, and `[0] != 0` holds
-                look = 1.0
-            if "NoLookahead" in name:
-                look = 0
-            elif "HalfLookahead" in name:
-                look = 0.5
-            self.eth["model"][s] = int(bentham)
-            self.eth["selfishness"][s] = selfish
-            self.eth["decision_factor"][s] = e["decisionModelFactor"]
-            self.eth["lookahead_factor"][s] = look
-            self.eth["lookahead_discount"][s] = e["decisionModelLookaheadDiscount"]
+            self._set_ethics(int(s), endowments[int(self.state.a_id[s])], c)
 
         class Ethics(C.Structure):
             _fields_ = [("capacity", C.c_int64), ("model", C.c_void_p), ("selfishness", C.c_void_p), ("decision_factor", C.c_void_p),
@@ -340,6 +338,34 @@ class Oracle:
         L.orc_ethics_stats.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_double * 5)]
         L.orc_ethics_stats.restype = None
         L.orc_bind_ethics(C.byref(e))
+
+    def _set_ethics(self, s, e, c):
+        name = e["decisionModel"]
+        selfish = e["selfishnessFactor"]
+        bentham = True
+        if "altruist" in name:
+            selfish = 0
+        elif "bentham" in name:
+            selfish = 0.5 if selfish < 0 else selfish
+        elif "egoist" in name:
+            selfish = 1
+        elif "negativeBentham" in name:
+            selfish = -1
+        else:
+            assert name == "none", name
+            bentham = False
+        look = c["agentDecisionModelLookaheadFactor"]
+        if isinstance(look, list):      # the default is the list [0]: handed to the agents as is, and `[0] != 0` holds
+            look = 1.0
+        if "NoLookahead" in name:
+            look = 0
+        elif "HalfLookahead" in name:
+            look = 0.5
+        self.eth["model"][s] = int(bentham)
+        self.eth["selfishness"][s] = selfish
+        self.eth["decision_factor"][s] = e["decisionModelFactor"]
+        self.eth["lookahead_factor"][s] = look
+        self.eth["lookahead_discount"][s] = e["decisionModelLookaheadDiscount"]
 
     def unbind_ethics(self):
         self.L.orc_bind_ethics(None)
