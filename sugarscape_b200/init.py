@@ -82,8 +82,6 @@ def check_supported(c):
         problems.append("moore neighbourhood")
     if not c["environmentWraparound"]:
         problems.append("environmentWraparound=false")
-    if c["environmentFile"] is not None:
-        problems.append("environmentFile")
     if c["agentLeader"]:
         problems.append("agentLeader")
     if c["startingDiseases"] > 0 or c["diseaseList"]:
@@ -364,7 +362,8 @@ class Population:
 
 def rule_flags(c):
     f = 0
-    if (c["environmentMaxSpice"] > 0 and c["environmentSpicePeaks"]) or c["agentSpiceMetabolism"][1] > 0 \
+    if (c["environmentMaxSpice"] > 0 and c["environmentSpicePeaks"]) or c["environmentFile"] is not None \
+            or c["agentSpiceMetabolism"][1] > 0 \
             or c["agentStartingSpice"][1] > 0 or c["environmentSpiceRegrowRate"] > 0:
         f |= layout.F_SPICE
     if c["environmentPollutionTimeframe"] != [0, 0] or c["environmentPollutionDiffusionDelay"] > 0:
@@ -428,6 +427,30 @@ def randomize_disease_endowments(c, n, timestep):
     return endowments
 
 
+def load_environment_file(c):
+    """configureEnvironment with an environmentFile (sugarscape.py:370-384): a JSON list of lists of
+    {"sugar", "spice"}.  The reference passes (spice, sugar) into Cell(x, y, env, maxSugar, maxSpice), so the
+    file's "spice" becomes the SUGAR capacity and vice versa -- restated literally.  Cells start full."""
+    import json
+    with open(c["environmentFile"]) as f:
+        data = json.load(f)
+    W, H = c["environmentWidth"], c["environmentHeight"]
+    if len(data) != H or len(data[0]) != W or W != H:
+        # the reference sizes the grid from the options but indexes the file [x][y] with height = len(file)
+        raise UnsupportedConfiguration("environmentFile must be square and match environmentWidth / environmentHeight")
+    sugar_cap = np.zeros((W, H), dtype=np.int64)
+    spice_cap = np.zeros((W, H), dtype=np.int64)
+    for x in range(W):
+        for y in range(H):
+            sugar_cap[x, y] = data[x][y]["spice"]
+            spice_cap[x, y] = data[x][y]["sugar"]
+    if sugar_cap.max(initial=0) > max(c["environmentMaxSugar"], 0) or spice_cap.max(initial=0) > max(c["environmentMaxSpice"], 0) \
+            or sugar_cap.min(initial=0) < 0 or spice_cap.min(initial=0) < 0:
+        raise UnsupportedConfiguration("environmentFile capacities must lie within [0, environmentMaxSugar / environmentMaxSpice] "
+                                       "(note the reference swaps the file's sugar and spice)")
+    return sugar_cap, spice_cap
+
+
 def build_initial_state(c, capacity=None, check=True):
     """Environment + initial population + the init-time list shuffle; returns (state, population).
 
@@ -437,8 +460,11 @@ def build_initial_state(c, capacity=None, check=True):
     if check:
         check_supported(c)
     W, H = c["environmentWidth"], c["environmentHeight"]
-    sugar_cap = capacity_field(W, H, c["environmentSugarPeaks"])
-    spice_cap = capacity_field(W, H, c["environmentSpicePeaks"])
+    if c["environmentFile"] is None:
+        sugar_cap = capacity_field(W, H, c["environmentSugarPeaks"])
+        spice_cap = capacity_field(W, H, c["environmentSpicePeaks"])
+    else:
+        sugar_cap, spice_cap = load_environment_file(c)
     pop = Population(c)
     n0 = int(c["startingAgents"])
     if capacity is None:

@@ -38,6 +38,11 @@ VARIANTS = {
     # determinism.json with the ethics decision models (bentham, altruist, egoist, negativeBentham), only the
     # experimental-group split of the log switched off
     "determinism_ethics": ("determinism", 200, {"experimentalGroup": None}),
+    # the map comes from a file (tests/golden/environment_30.json) instead of the peak formula; note that the
+    # reference swaps the file's sugar and spice
+    "environment_file": ("trade_tagging_reproduction", 120, {"environmentFile": os.path.join(HERE, "environment_30.json"),
+                                                             "environmentWidth": 30, "environmentHeight": 30,
+                                                             "startingAgents": 150, "environmentMaxSugar": 4, "environmentMaxSpice": 4}),
 }
 
 
@@ -48,7 +53,8 @@ def main():
         path = os.path.join(rh.REFERENCE_DIR, "examples", base + ".json")
         _, meta, steps, log, _ = mg.run_example(path, timesteps, overrides)
         with gzip.open(os.path.join(HERE, name + ".json.gz"), "wt") as f:
-            json.dump({"meta": meta, "base": base, "overrides": overrides, "steps": steps, "log": log}, f)
+            stored = {k: (os.path.basename(v) if k == "environmentFile" else v) for k, v in overrides.items()}   # (relative to this directory)
+            json.dump({"meta": meta, "base": base, "overrides": stored, "steps": steps, "log": log}, f)
         sick = [e["sickAgents"] for e in log]
         print(f"{name}: {len(steps) - 1} steps, final pop {steps[-1]['population']}, sick agents min/max {min(sick)}/{max(sick)}", flush=True)
 

@@ -27,6 +27,16 @@ def load_golden(name):
     return meta, snaps
 
 
+def load_variant(name):
+    """A fixture of tests/golden/make_golden_variants.py: (base example, overrides, steps, log)."""
+    with gzip.open(os.path.join(GOLDEN, name + ".json.gz"), "rt") as f:
+        meta = json.load(f)
+    overrides = dict(meta["overrides"], timesteps=meta["meta"]["timesteps"])
+    if overrides.get("environmentFile"):
+        overrides["environmentFile"] = os.path.join(GOLDEN, overrides["environmentFile"])
+    return meta["base"], overrides, meta["steps"], meta["log"]
+
+
 def example_configuration(name, overrides=None):
     """tests/test.py protocol of the reference (headless, no debug, 200 steps)."""
     # deep copies: verify_configuration rewrites nested lists in place (out-of-range peaks, sorted ranges)

@@ -84,6 +84,29 @@ def test_exact_mode_trajectory_matches_reference_bit_for_bit(name):
     eng.close()
 
 
+def test_environment_file_matches_reference():
+    """`environmentFile`: the map of tests/golden/environment_30.json under trade + tagging + reproduction rules,
+    against the variant fixture generated from the unmodified reference (integer state and MT bit-exact, fp64
+    holdings through the digests of the oracle-pinned test; here within the digests' exact match where pow is not
+    involved in ties)."""
+    base, overrides, gold, log = pu.load_variant("environment_file")
+    c, state, pop, params, endow, tags, eng = _engine(base, layout.RNG_EXACT, overrides)
+    sb = stats.StatsBuilder(c, init.equator(c))
+    eng.reduce_stats(0)
+    rs = sb.update(eng.stats(), 0)
+    for t in range(1, len(gold)):
+        eng.env_step(t)
+        eng.agent_step(t, rs["meanWealth"])
+        eng.compact(t)
+        eng.reduce_stats(t)
+        rs = sb.update(eng.stats(), t, 0)
+        d, snap = pu.state_digests(eng.download(), *eng.mt_state())
+        for k in ("agents_int", "agents_tags", "grid_int", "mt"):
+            assert d[k] == gold[t]["digests"][k], f"{k} differs from the reference at t={t}"
+        assert _close(rs["meanWealth"], log[t]["meanWealth"]) and rs["population"] == log[t]["population"]
+    eng.close()
+
+
 @pytest.mark.parametrize("name", POW_EXAMPLES)
 def test_two_resource_rules_match_reference(name):
     """Spice / trade configs evaluate welfare with pow: integer state bit-exact, fp64 within

@@ -330,6 +330,29 @@ def test_oracle_all_features_examples_match_reference_trajectory(name):
         _unbind_everything(orc)
 
 
+def test_oracle_environment_file_matches_reference_trajectory():
+    """`environmentFile` (reference sugarscape.py:370-384, incl. its sugar / spice swap): trade + tagging +
+    reproduction rules on the 30 x 30 map of tests/golden/environment_30.json, variant fixture from the
+    unmodified reference.  The engine supports this option (it only changes the initial arrays)."""
+    base, overrides, gold, log = pu.load_variant("environment_file")
+    c, state, pop, params, endow, tags = pu.build(base, overrides=overrides)
+    orc = Oracle(params, state, endow, tags)
+    orc.set_mt_from_python()
+    d, _ = pu.state_digests(state, *orc.mt_state())
+    assert d == gold[0]["digests"], "t=0 state differs"
+    sb = stats.StatsBuilder(c, init.equator(c))
+    rs = sb.update(orc.stats(0), 0)
+    for t in range(1, len(gold)):
+        orc.env_step(t)
+        orc.agent_step(t, rs["meanWealth"])
+        orc.compact(t)
+        d, snap = pu.state_digests(state, *orc.mt_state())
+        assert d == gold[t]["digests"], f"state differs at t={t}"
+        rs = sb.update(orc.stats(t), t, 0)
+        for k in stats.LOG_KEYS:
+            assert _close(rs[k], log[t][k]), f"log key {k} differs at t={t}: {rs[k]} vs {log[t][k]}"
+
+
 @pytest.mark.parametrize("name", UNSUPPORTED)
 def test_unsupported_rule_families_fail_loudly(name):
     with pytest.raises(init.UnsupportedConfiguration):
