@@ -252,18 +252,24 @@ def test_state_invariants_at_full_size(workload):
                                                            "startingAgents": n_agents, "agentReplacements": n_agents,
                                                            "agentMaxAge": [5, 40], "timesteps": 1 << 20})
     state, params = synthetic.build_state(c)
-    endow, tags = steptables.step_tables(1, 16, c["agentTagStringLength"])
+    endow, tags = steptables.step_tables(1, 32, c["agentTagStringLength"])
     eng = Engine(params, state, 0, endow, tags)
     if c["agentReplacements"] > 0:
         eng.bind_endowments(synthetic.endowment_table(state, n_agents))
     population = invariants.check_state(eng.download())
     assert population == n_agents
     changed = 0
-    for t in range(1, 7):
+    # S1: the synthetic agents start at age 0 and become fertile at 12-15, so births begin around t = 13;
+    # S2 (maxAge 5-40 here): deaths and replacements from t = 5 on.  The full state is downloaded and
+    # checked at a few steps, the population accounting at every step.
+    last, downloads = (17, (1, 13, 15, 17)) if workload == "S1" else (8, (1, 5, 6, 8))
+    for t in range(1, last + 1):
         eng.step(t, 0.0)
         st = eng.stats()
         invariants.check_step_accounting(population, st)
-        population = invariants.check_state(eng.download(), st)
+        population = int(st.population)
+        if t in downloads:
+            assert invariants.check_state(eng.download(), st) == population
         changed += int(st.n_dead) + int(st.n_born) + int(st.n_replaced)
     assert changed > 0          # the rules were exercised (deaths, births or replacements happened)
     eng.close()
