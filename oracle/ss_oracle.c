@@ -45,7 +45,8 @@ typedef struct {
 } orc_rng_t;
 
 /* call sites of the transaction that draw (agent.py:1401, 560-564, 616, 505-513): one substream each */
-enum { SITE_MOVE = 0, SITE_TAGGING = 1, SITE_TRADING = 2, SITE_REPRODUCTION = 3 };
+enum { SITE_MOVE = 0, SITE_TAGGING = 1, SITE_TRADING = 2, SITE_REPRODUCTION = 3, /* 4 = new tribe tags */
+       SITE_LENDING = 5, SITE_DISEASE = 6 };
 
 static uint32_t mt_next(orc_rng_t *r) {
     uint32_t *mt = r->mt, y;
@@ -753,6 +754,7 @@ static void do_lending(ctx_t *c, int s) {
         /* isBorrower (1226-1229) */
         if (a->age[o] >= a->fert_age[o] && a->age[o] < a->infert_age[o] && !is_fertile(c, o)) borrowers[nbw++] = o;
     }
+    rng_at(c->rng, SITE_LENDING);
     rng_shuffle_i32(c->rng, borrowers, nbw);
     const double pm = EFF_SPICE_METAB(c, s), sm = EFF_SUGAR_METAB(c, s);
     int loans = 0;
@@ -875,6 +877,7 @@ void orc_disease_listed(int32_t di) { g_dis->diseases[di].listed++; }
 /* doDisease (agent.py:315-361) */
 static void do_disease(ctx_t *c, int s) {
     sick_list_t *L = &g_dis->sick[s];
+    rng_at(c->rng, SITE_DISEASE);          /* scalable mode: every draw of doDisease, infection attempts included */
     /* random.shuffle(self.diseases) */
     for (int i = L->n - 1; i >= 1; i--) {
         uint32_t j = rng_below(c->rng, (uint32_t)i + 1u);

@@ -391,6 +391,46 @@ def test_state_invariants_hold_on_the_oracle(name, mode):
         population = invariants.check_state(state, st)
 
 
+def _load_private_scalable():
+    import gzip
+    import json
+    import os
+    with gzip.open(os.path.join(pu.GOLDEN, "scalable_mode_private.json.gz"), "rt") as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("name", ["determinism", "disease_basic", "dune", "lending_basic"])
+def test_scalable_mode_private_families_match_patched_reference(name):
+    """The scalable-mode definitions extended to the oracle-only rule families: lending draws from site 5,
+    everything a disease step draws (shuffles, picks, infection attempts) from site 6 of the acting agent.
+    Fixtures: the unmodified reference with its randomness redirected (make_golden_scalable.py --private);
+    inheritance is off in these cases because the scalable mode keeps no kin lists."""
+    from sugarscape_b200 import layout
+    case = _load_private_scalable()[name]
+    c, state, pop, params, endow, tags = pu.build(name, layout.RNG_SCALABLE, case["overrides"], check=False)
+    orc = Oracle(params, state, endow, tags)
+    horizon = len(case["steps"]) + 8
+    orc.bind_lending(pop.endowments)
+    orc.bind_social(pop.endowments)
+    orc.bind_misc(c, pop.endowments, horizon)
+    orc.bind_ethics(c, pop.endowments)
+    diseases = c["agentImmuneSystemLength"] > 0
+    if diseases:
+        orc.bind_disease(c, pop.endowments, pop.disease_endowments, horizon)
+    try:
+        for rec in case["steps"]:
+            t = rec["t"]
+            orc.env_step(t)
+            orc.agent_step(t, 0.0)
+            orc.compact(t)
+            d, snap = pu.state_digests_by_id(state)
+            assert len(snap["a_id"]) == rec["population"], f"population differs at t={t}"
+            for k in ("agents_int", "agents_f64", "agents_tags", "grid_int", "pollution"):
+                assert d[k] == rec["digests"][k], f"{k} differs from the patched reference at t={t}"
+    finally:
+        _unbind_everything(orc)
+
+
 def test_scalable_mode_priority_is_a_bijection():
     from oracle_binding import lib
     L = lib()
