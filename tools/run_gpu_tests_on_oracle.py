@@ -27,6 +27,7 @@ class OracleEngine:
         self.orc = Oracle(params, host_state, endow_bits, tag_bits)
         self.t_stats = 0
         self.replacing = False
+        self.tensors = {}
 
     def set_mt_from_python(self):
         self.orc.set_mt_from_python()
