@@ -545,8 +545,9 @@ int ssb_set_shard(ssb_engine_t *e, const ssb_shard_t *sd) {
     if (!sd || sd->world < 1 || sd->world > SSB_MAX_RANKS || sd->rank < 0 || sd->rank >= sd->world) return fail(e, -1, "bad shard description");
     if (e->p.rng_mode != SSB_RNG_SCALABLE) return fail(e, -1, "sharding needs the scalable RNG mode (the exact mode is one global stream)");
     if (e->sharded) return fail(e, -1, "shard already set");
-    // Births across slabs (slab-wise newborn numbering, ssb_kernels.cuh) reproduced the single-GPU run
-    // in one 2-GPU environment and diverged at t = 25 of cultural_tagging in another: not trusted yet.
+    // Births across slabs (slab-wise newborn numbering, ssb_kernels.cuh) reproduced the single-GPU run in one
+    // 2-GPU environment and diverged in two others; the cause (range check applied to recycled slots in
+    // k_migrate_in) is fixed but not re-verified on two GPUs yet: opt-in until then.
     if ((e->p.flags & SSB_F_REPRO) && !getenv("SSB_EXPERIMENTAL_SHARDED_BIRTHS"))
         return fail(e, -1, "sharded mode does not support births (reproduction) yet");
     if (sd->world == 1) return 0;

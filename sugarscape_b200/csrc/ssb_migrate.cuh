@@ -102,8 +102,11 @@ __global__ void __launch_bounds__(256) k_migrate_in(DevCtx c, long long box_cap)
         const unsigned long long *box = c.sh.gather + (long long)r * c.sh.gather_stride + (long long)me * box_cap;
         for (long long k = tid; k < n; k += stride) {
             const long long j = base + k;
-            const long long slot = j < n_free ? (long long)a.free_slots[n_free - 1 - j] : n_slots + (j - n_free);
-            if (slot >= c.sh.slot_hi || n_list + j >= a.capacity) { a.counters[SSB_C_OVERFLOW] = 1; continue; }
+            // a recycled slot may lie in ANY rank's range (a child's record is allocated by the acting parent's
+            // rank); only the bump allocation is bounded by this rank's range
+            const bool bump = j >= n_free;
+            const long long slot = bump ? n_slots + (j - n_free) : (long long)a.free_slots[n_free - 1 - j];
+            if ((bump && slot >= c.sh.slot_hi) || n_list + j >= a.capacity) { a.counters[SSB_C_OVERFLOW] = 1; continue; }
             const int os = (int)box[k], ns = (int)slot;
             SSB_COPY_FIELD(id); SSB_COPY_FIELD(pos); SSB_COPY_FIELD(born); SSB_COPY_FIELD(cod);
             SSB_COPY_FIELD(sugar); SSB_COPY_FIELD(spice); SSB_COPY_FIELD(sugar_metab); SSB_COPY_FIELD(spice_metab);

@@ -213,9 +213,10 @@ __global__ void __launch_bounds__(256) k_repl_create(DevCtx c, ReplacePlan *rp, 
             if (cell < c.sh.cell_lo || cell >= c.sh.cell_hi) continue;       // another rank's slab
             j = (long long)atomicAdd(&rp->created, 1ull);
         }
-        long long slot = j < older ? (long long)a.free_slots[older - 1 - j] : n_slots + (j - older);
+        const bool bump = j >= older;          // (a recycled slot may lie in any rank's range; the bump allocation may not)
+        long long slot = bump ? n_slots + (j - older) : (long long)a.free_slots[older - 1 - j];
         const long long slot_hi = c.sh.world > 1 ? c.sh.slot_hi : a.capacity;
-        if (slot >= slot_hi || n_list + j >= a.capacity) { a.counters[SSB_C_OVERFLOW] = 1; continue; }
+        if ((bump && slot >= slot_hi) || n_list + j >= a.capacity) { a.counters[SSB_C_OVERFLOW] = 1; continue; }
         const int s = (int)slot;
         const long long ei = (cursor + i) % en.count;
         const int id = (int)(next_id + i);

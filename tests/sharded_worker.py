@@ -59,6 +59,7 @@ def main():
         eng.step(t, 0.0)
         if eng.broken():
             raise SystemExit(f"rank {rank}: box-wide barrier broke at t={t}")
+        assert int(eng.counters()[layout.C_OVERFLOW]) == 0, f"rank {rank}: engine failure flag {int(eng.counters()[layout.C_OVERFLOW])} at t={t}"
         hs = eng.download_global()
         d, snap = pu.state_digests_by_id(hs)
         want, want_pop, want_stats = expected[t - 1]
