@@ -43,7 +43,7 @@
 #pragma once
 #include <cooperative_groups.h>
 
-#include "ssb_rules.cuh"
+#include "ssb_exact.cuh"
 
 namespace ssb {
 namespace cg = cooperative_groups;
@@ -51,34 +51,14 @@ namespace cg = cooperative_groups;
 // ---------------------------------------------------------------------------------------------
 // mode E
 // ---------------------------------------------------------------------------------------------
-constexpr int MAXC_EXACT = 128;   // up to 4 * 32 candidate cells
-
 __global__ void __launch_bounds__(32, 1) k_agent_step_exact(DevCtx c, uint32_t *mt_global) {
     __shared__ uint32_t mt[625];
     __shared__ __align__(8) unsigned char scratch_mem[warp_scratch_bytes(MAXC_EXACT)];
     const int lane = threadIdx.x;
     for (int i = lane; i < 625; i += 32) mt[i] = mt_global[i];
     __syncwarp();
-    RngExact rng{mt};
-    const WarpScratch ws = make_warp_scratch(scratch_mem, MAXC_EXACT);
-    volatile unsigned long long *cn = (volatile unsigned long long *)c.a.counters;
-    if (lane == 0) {
-        cn[SSB_C_N_BORN] = 0;
-        shuffle(rng, c.a.order, (int)cn[SSB_C_N_LIST]);        // random.shuffle(self.agents), sugarscape.py:400
-    }
+    agent_step_exact_body<32>(c, mt, make_warp_scratch(scratch_mem, MAXC_EXACT));
     __syncwarp();
-    // the list grows while it is iterated: children are appended, visited and skipped
-    for (long long i = 0;; i++) {
-        const long long n_list = __shfl_sync(0xffffffffu, (long long)cn[SSB_C_N_LIST], 0);
-        if (i >= n_list) break;
-        const int s = c.a.order[i];
-        AgentRec rec;
-        rec.load(c, s);
-        const bool go_on = transaction_move_phase<32, 4>(c, s, rec, rng, ws, MAXC_EXACT);
-        if (go_on && lane == 0) transaction_interact_phase<RngExact, true>(c, s, rec, rng);
-        __threadfence_block();
-        __syncwarp();
-    }
     for (int i = lane; i < 625; i += 32) mt_global[i] = mt[i];
 }
 

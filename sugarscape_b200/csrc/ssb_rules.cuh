@@ -14,7 +14,9 @@
 #include "../../include/ssb.h"
 #include "ssb_pow.cuh"
 #include "ssb_rng.cuh"
+#ifndef SSB_HOSTEMU
 #include "ssb_shard.cuh"
+#endif                 // (tests/hostemu/cuda_shim.h supplies a plain ShardCtx for the host-compiled rule code)
 
 namespace ssb {
 

@@ -1,0 +1,53 @@
+"""ctypes binding of tests/hostemu/libssb_hostemu.so: the engine's mode E device rule source compiled
+for the host as one lane (tests/hostemu/cuda_shim.h).  TEST INFRASTRUCTURE ONLY -- the product has no CPU
+path.  `HostEmu` steps a HostState like `oracle_binding.Oracle`, but its agent step is the DEVICE source;
+environment step, compaction and reductions stay the oracle's."""
+import ctypes as C
+import os
+import random
+import subprocess
+
+import numpy as np
+
+from oracle_binding import Oracle
+from sugarscape_b200 import layout
+
+HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostemu")
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        subprocess.check_call(["make", "-s", "-C", HERE])
+        L = C.CDLL(os.path.join(HERE, "libssb_hostemu.so"))
+        P, G, A = C.POINTER(layout.Params), C.POINTER(layout.Grid), C.POINTER(layout.Agents)
+        L.emu_agent_step_exact.argtypes = [P, G, A, C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_int32]
+        assert L.emu_abi_version() == layout.ABI_VERSION
+        _LIB = L
+    return _LIB
+
+
+class HostEmu(Oracle):
+    def __init__(self, params, state, endow_bits=None, tag_bits=None):
+        super().__init__(params, state, endow_bits, tag_bits)
+        assert params.rng_mode == layout.RNG_EXACT, "the emulation covers the ordered mode E loop"
+        self.E = lib()
+        self.mt = np.zeros(625, dtype=np.uint32)
+        self.mt[624] = 624
+
+    # the MT19937 stream lives in the engine's layout: 624 words + index
+    def set_mt_from_python(self):
+        self.mt[:] = np.array(random.getstate()[1], dtype=np.uint32)
+
+    def mt_state(self):
+        return self.mt[:624].copy(), int(self.mt[624])
+
+    def agent_step(self, t, prev_mean_wealth=0.0):
+        g, a = self.state.as_structs()
+        eb = self.endow_bits.ctypes.data if self.endow_bits is not None else None
+        tb = self.tag_bits.ctypes.data if self.tag_bits is not None else None
+        n = len(self.endow_bits) if self.endow_bits is not None else 0
+        rc = self.E.emu_agent_step_exact(C.byref(self.params), C.byref(g), C.byref(a), self.mt.ctypes.data, t,
+                                         prev_mean_wealth, eb, tb, n)
+        assert rc == 0, f"emu_agent_step_exact failed: {rc}"
