@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define SSB_ABI_VERSION 1
+#define SSB_ABI_VERSION 2
 
 /* RNG modes */
 #define SSB_RNG_EXACT    0 /* mode E: CPython MT19937 word-for-word replay, ordered execution   */
@@ -204,6 +204,36 @@ typedef struct ssb_stats {
 } ssb_stats_t;
 
 typedef struct ssb_engine ssb_engine_t;
+
+/* ---- ABI 2: decision models (reference ethics.py:105-244, the Bentham family: bentham / altruist /
+ * egoist / negativeBentham and their lookahead variants; spawn rules sugarscape.py:219-233; SURVEY.md
+ * section 8 row a21).  Optional per-slot state, exact RNG mode; without it every agent is the plain
+ * rawSugarscape Agent.  The host owns the arrays (capacity = ssb_agents_t.capacity slots). */
+typedef struct ssb_ethics {
+    int64_t capacity;
+    int32_t *model;                 /* 0 = Agent (greedy findBestCell), 1 = ethics.Bentham             */
+    double  *selfishness;           /* selfishnessFactor after the spawn rules (-1 .. 1)              */
+    double  *decision_factor;       /* decisionModelFactor: the ethical ranking runs when > 0         */
+    double  *lookahead_factor;      /* decisionModelLookaheadFactor                                   */
+    double  *lookahead_discount;    /* decisionModelLookaheadDiscount                                 */
+    /* by-products of the agent's last ranking that feed the log (agent.py:734-745) */
+    int32_t *last_move_optimal;     /* lastMoveOptimal                                                */
+    int32_t *move_rank;             /* index of the chosen cell in the welfare-sorted list            */
+    double  *move_diff;             /* welfare of the top cell minus welfare of the chosen one        */
+    double  global_max_wealth;      /* environment.globalMaxSugar + globalMaxSpice                    */
+} ssb_ethics_t;
+/* raw sums of sugarscape.py:1141-1160, 1218-1222 over the agent list (+ this step's dead for the moves) */
+typedef struct ssb_ethics_stats {
+    double  sum_selfishness;
+    int64_t optimal_moves, moves;   /* agentLastMoveOptimalityPercentage = optimal / moves            */
+    int64_t sum_move_rank;
+    double  sum_move_diff;
+} ssb_ethics_stats_t;
+/* call after ssb_bind, before the first step (mode E only; mode S and sharded engines refuse) */
+int  ssb_bind_ethics(ssb_engine_t *e, const ssb_ethics_t *ethics);
+/* reductions of the last ssb_reduce_stats; synchronises */
+int  ssb_ethics_stats(ssb_engine_t *e, ssb_ethics_stats_t *host_out);
+int  ssb_sizeof_ethics(void);
 
 /* ---- sharding one simulation over the GPUs of a box (x-slabs) -------------
  * A "stitched" array is world consecutive chunks, chunk p backed by rank p's HBM (one process per

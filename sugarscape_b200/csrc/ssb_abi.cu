@@ -66,6 +66,9 @@ struct ssb_engine {
     int64_t local_slots;     // slots per rank = capacity of the per-rank parts of the gather scratch
     MigratePlan *d_migrate;
     unsigned long long *d_shard_vals;   // [0] = box population, [1..2] = OR / AND of all wealth keys, [8..] msg
+    // ABI 2: decision models (mode E)
+    bool ethics_bound;
+    ssb_ethics_stats_t *d_eth_stats;
 };
 
 static int fail(ssb_engine *e, int code, const char *fmt, ...) {
@@ -160,7 +163,7 @@ void ssb_destroy(ssb_engine_t *e) {
     void *ptrs[] = {e->d_mt, e->d_endow, e->d_tagbits, e->d_tile_counts, e->d_new_order, e->d_scalars,
                     e->d_born_list, e->rc.mark, e->rc.list_a, e->rc.list_b, e->rc.ready, e->rc.cnt, e->rc.trace, e->rc.bucketed, e->rc.epoch_count, e->rc.epoch_start, e->rc.epoch_fill,
                     e->d_partials, e->d_tribes, e->d_stats, e->d_ring, e->d_keys_a, e->d_keys_b, e->d_radix_hist,
-                    e->d_lorenz_blocks, e->d_plan, e->d_cand, e->sh.peer_vals, e->sh.flags, e->d_shard_vals, e->d_migrate};
+                    e->d_lorenz_blocks, e->d_plan, e->d_cand, e->sh.peer_vals, e->sh.flags, e->d_shard_vals, e->d_migrate, e->d_eth_stats};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < 5; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
     delete e;
@@ -332,6 +335,36 @@ int ssb_set_step_tables(ssb_engine_t *e, const uint32_t *endow_bits, const uint3
     return 0;
 }
 
+// ABI 2: decision models (ethics.py Bentham family).  The arrays stay host-owned device memory.
+int ssb_sizeof_ethics(void) { return (int)sizeof(ssb_ethics_t); }
+
+int ssb_bind_ethics(ssb_engine_t *e, const ssb_ethics_t *eth) {
+    if (!e || !eth) return -1;
+    if (!e->bound) return fail(e, -1, "engine not bound");
+    if (e->p.rng_mode != SSB_RNG_EXACT) return fail(e, -1, "decision models need the exact RNG mode (the ethical ranking reads agents anywhere in view)");
+    if (e->sharded) return fail(e, -1, "decision models are not available on a sharded engine");
+    if (eth->capacity != e->ctx.a.capacity) return fail(e, -1, "ethics capacity differs from the agent capacity");
+    if (!eth->model || !eth->selfishness || !eth->decision_factor || !eth->lookahead_factor || !eth->lookahead_discount ||
+        !eth->last_move_optimal || !eth->move_rank || !eth->move_diff) return fail(e, -1, "ethics: null array");
+    CU(cudaSetDevice(e->device));
+    if (!e->d_eth_stats) {
+        CU(cudaMalloc(&e->d_eth_stats, sizeof(ssb_ethics_stats_t)));
+        CU(cudaMemset(e->d_eth_stats, 0, sizeof(ssb_ethics_stats_t)));
+    }
+    e->ctx.eth = *eth;
+    e->ethics_bound = true;
+    return 0;
+}
+
+int ssb_ethics_stats(ssb_engine_t *e, ssb_ethics_stats_t *host_out) {
+    if (!e || !host_out) return -1;
+    if (!e->ethics_bound) return fail(e, -1, "no decision-model state bound");
+    CU(cudaSetDevice(e->device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(host_out, e->d_eth_stats, sizeof(ssb_ethics_stats_t), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 static DevCtx step_ctx(ssb_engine *e, int32_t t, double prev_mean_wealth) {
     DevCtx c = e->ctx;
     c.t = t;
@@ -389,7 +422,8 @@ int ssb_agent_step(ssb_engine_t *e, int32_t t, double prev_mean_wealth, void *st
     cudaStream_t st = (cudaStream_t)stream_;
     DevCtx c = step_ctx(e, t, prev_mean_wealth);
     if (e->p.rng_mode == SSB_RNG_EXACT) {
-        k_agent_step_exact<<<1, 32, 0, st>>>(c, e->d_mt);
+        if (e->ethics_bound) k_agent_step_exact<true><<<1, 32, 0, st>>>(c, e->d_mt);
+        else k_agent_step_exact<false><<<1, 32, 0, st>>>(c, e->d_mt);
         LAUNCHED(e);
     } else {
         RoundCtx rc = e->rc;
@@ -504,6 +538,7 @@ int ssb_reduce_stats(ssb_engine_t *e, int32_t t, void *stream_) {
     k_stats_partials<<<e->n_partials, STATS_THREADS, 0, st>>>(c, e->d_partials, keys_out, e->d_tribes); LAUNCHED(e);
     k_stats_final<<<1, STATS_THREADS, 0, st>>>(c, e->d_partials, e->n_partials, e->d_tribes, e->d_stats); LAUNCHED(e);
     if (e->p.rng_mode == SSB_RNG_EXACT) { k_stats_ordered<<<1, 32, 0, st>>>(c, e->d_stats); LAUNCHED(e); }
+    if (e->ethics_bound) { k_ethics_stats<<<1, 32, 0, st>>>(c, e->d_eth_stats); LAUNCHED(e); }
     // Lorenz numerator: sort the wealths (non-negative doubles order like their bit patterns)
     const int64_t cap = c.a.capacity;
     const int tiles = grid_for(cap, RADIX_TILE, e->num_sms * 8);

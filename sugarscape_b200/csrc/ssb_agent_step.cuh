@@ -51,15 +51,23 @@ namespace cg = cooperative_groups;
 // ---------------------------------------------------------------------------------------------
 // mode E
 // ---------------------------------------------------------------------------------------------
+// EXT = false: the plain Agent of the shipped book examples; EXT = true: an ABI 2 extension is bound
+// (decision models) -- a separate instantiation, so the plain kernel's code does not change.
+template <bool EXT>
 __global__ void __launch_bounds__(32, 1) k_agent_step_exact(DevCtx c, uint32_t *mt_global) {
     __shared__ uint32_t mt[625];
     __shared__ __align__(8) unsigned char scratch_mem[warp_scratch_bytes(MAXC_EXACT)];
     const int lane = threadIdx.x;
     for (int i = lane; i < 625; i += 32) mt[i] = mt_global[i];
     __syncwarp();
-    agent_step_exact_body<32>(c, mt, make_warp_scratch(scratch_mem, MAXC_EXACT));
+    agent_step_exact_body<32, EXT>(c, mt, make_warp_scratch(scratch_mem, MAXC_EXACT));
     __syncwarp();
     for (int i = lane; i < 625; i += 32) mt_global[i] = mt[i];
+}
+
+// decision-model reductions of the log, list order (mode E)
+__global__ void k_ethics_stats(DevCtx c, ssb_ethics_stats_t *out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) ethics_stats_body(c, out);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -7,11 +7,12 @@
 namespace ssb {
 
 constexpr int MAXC_EXACT = 128;   // up to 4 * 32 candidate cells
+static_assert(MAXC_EXACT == MAXC_EXACT_RULES, "ssb_rules.cuh sizes its ranking arrays for MAXC_EXACT candidates");
 
 // random.shuffle(self.agents), then every agent of the list in order; the list grows while it is
 // iterated: children are appended, visited and skipped (their lastMovedTimestep is this step).
 // All G lanes of the (single) group call this; `mt` is the 625-word MT19937 state (index last).
-template <int G>
+template <int G, bool EXT = false>
 __device__ void agent_step_exact_body(const DevCtx &c, uint32_t *mt, const WarpScratch &ws) {
     typedef Group<G> Gr;
     const int lane = Gr::lane();
@@ -28,11 +29,28 @@ __device__ void agent_step_exact_body(const DevCtx &c, uint32_t *mt, const WarpS
         const int s = c.a.order[i];
         AgentRec rec;
         rec.load(c, s);
-        const bool go_on = transaction_move_phase<G, 4>(c, s, rec, rng, ws, MAXC_EXACT);
-        if (go_on && lane == 0) transaction_interact_phase<RngExact, true>(c, s, rec, rng);
+        const bool go_on = transaction_move_phase<G, 4, RngExact, EXT>(c, s, rec, rng, ws, MAXC_EXACT);
+        if (go_on && lane == 0) transaction_interact_phase<RngExact, true, EXT>(c, s, rec, rng);
         __threadfence_block();
         Gr::sync();
     }
+}
+
+// Decision-model reductions of the log (sugarscape.py:1141-1160, 1218-1222): one lane, list order (the
+// difference sum is order-sensitive fp64); the dead of this step count towards the move optimality --
+// doTimestep(t) ran for every one of them.
+__device__ inline void ethics_stats_body(const DevCtx &c, ssb_ethics_stats_t *out) {
+    ssb_ethics_stats_t r;
+    r.sum_selfishness = 0; r.optimal_moves = 0; r.moves = 0; r.sum_move_rank = 0; r.sum_move_diff = 0;
+    const long long n = c.a.counters[SSB_C_N_LIST], n_dead = c.a.counters[SSB_C_N_DEAD];
+    for (long long i = 0; i < n; i++) {
+        const int s = c.a.order[i];
+        r.sum_selfishness += c.eth.selfishness[s];
+        r.optimal_moves += c.eth.last_move_optimal[s]; r.moves += 1;
+        r.sum_move_rank += c.eth.move_rank[s]; r.sum_move_diff += c.eth.move_diff[s];
+    }
+    for (long long i = 0; i < n_dead; i++) { r.optimal_moves += c.eth.last_move_optimal[c.a.dead_list[i]]; r.moves += 1; }
+    *out = r;
 }
 
 }  // namespace ssb

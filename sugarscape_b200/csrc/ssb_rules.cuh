@@ -22,7 +22,8 @@ namespace ssb {
 
 // child endowment bit positions inside endow_bits[t] (sugarscape_b200/steptables.py)
 enum { EB_AGGRESSION = 0, EB_FERT_AGE, EB_FERT_FACTOR, EB_INFERT_AGE, EB_LOOKAHEAD, EB_MAX_AGE,
-       EB_MOVEMENT, EB_SPICE_METAB, EB_SUGAR_METAB, EB_SEX, EB_TRADE_FACTOR, EB_VISION };
+       EB_MOVEMENT, EB_SPICE_METAB, EB_SUGAR_METAB, EB_SEX, EB_TRADE_FACTOR, EB_VISION,
+       EB_DECISION_MODEL = 19 };
 
 struct DevCtx {
     ssb_params_t p;
@@ -37,6 +38,7 @@ struct DevCtx {
     // mode S
     int32_t *born_list;              // slots of this step's newborn (unordered)
     ShardCtx sh;                     // world <= 1: the whole simulation lives on this GPU
+    ssb_ethics_t eth;                // ABI 2, mode E: decision models (eth.model == nullptr: every agent is a plain Agent)
 };
 
 __device__ __forceinline__ int wrapi(int v, int n) { v %= n; return v < 0 ? v + n : v; }
@@ -44,6 +46,8 @@ __device__ __forceinline__ int wrapi(int v, int n) { v %= n; return v < 0 ? v + 
 __device__ __forceinline__ int wrap1(int v, int n) { return v < 0 ? v + n : (v >= n ? v - n : v); }
 
 // Lane groups: G consecutive lanes of a warp (G = 32, 16, 8, 4) cooperate on one agent.
+constexpr int MAXC_EXACT_RULES = 128;   // = MAXC_EXACT (ssb_exact.cuh): candidate cells of one ranking in mode E
+
 template <int G> struct Group {
     static __device__ __forceinline__ int lane() { return threadIdx.x & (G - 1); }
     static __device__ __forceinline__ unsigned mask() {
@@ -294,6 +298,119 @@ __device__ __forceinline__ int agent_range(const DevCtx &c, int s) {
     return min(min(vision, movement), max(c.max_dx, c.max_dy));
 }
 
+// ---------------------------------------------------------------------------------------------
+// ethics.Bentham (reference ethics.py:105-244).  Mode E, lane 0: the
+// ethical ranking walks the WHOLE welfare-sorted candidate list and, per candidate, every agent in
+// view -- sequential like the rest of the ordered mode.
+// ---------------------------------------------------------------------------------------------
+// Agent.findTimeToLive (agent.py:1113-1140)
+__device__ __forceinline__ double time_to_live(const DevCtx &c, int s, bool age_limited) {
+    const double sm = (double)max(c.a.sugar_metab[s], 0), pm = (double)max(c.a.spice_metab[s], 0);
+    const double big = 9223372036854775807.0;            // sys.maxsize
+    const double st = sm > 0 ? c.a.sugar[s] / sm : big;
+    const double pt = pm > 0 ? c.a.spice[s] / pm : big;
+    double ttl = st < pt ? st : pt;
+    if (age_limited) { const double lim = (double)(c.a.max_age[s] - c.a.age[s]); if (lim < ttl) ttl = lim; }
+    return ttl;
+}
+
+// len(cellsInRange) of an agent with range r: the cross does not depend on where it stands
+__device__ __forceinline__ int cross_size(const DevCtx &c, int r) {
+    int n = 0;
+    for (int d = 1; d <= r; d++) {
+        if (d <= c.max_dx) n += (2 * d == c.p.width) ? 1 : 2;
+        if (d <= c.max_dy) n += (2 * d == c.p.height) ? 1 : 2;
+    }
+    return n;
+}
+
+// live agents standing on the cross of radius r around `centre` (findNeighborhood, agent.py:1052-1065)
+__device__ int cross_live_count(const DevCtx &c, int centre, int r) {
+    const int W = c.p.width, H = c.p.height, x = centre / H, y = centre - x * H;
+    int n = 0;
+    for (int d = 1; d <= r; d++) {
+        if (d <= c.max_dx) {
+            const int xw = wrapi(x - d, W), xe = wrapi(x + d, W);
+            int o = c.g.occ[xw * H + y];
+            if (o >= 0 && agent_alive(c, o)) n++;
+            if (xe != xw) { o = c.g.occ[xe * H + y]; if (o >= 0 && agent_alive(c, o)) n++; }
+        }
+        if (d <= c.max_dy) {
+            const int yn = wrapi(y - d, H), ys = wrapi(y + d, H);
+            int o = c.g.occ[x * H + yn];
+            if (o >= 0 && agent_alive(c, o)) n++;
+            if (ys != yn) { o = c.g.occ[x * H + ys]; if (o >= 0 && agent_alive(c, o)) n++; }
+        }
+    }
+    return n;
+}
+
+// is `cell` one of the cells in range of an agent standing on `centre` with range r
+__device__ __forceinline__ bool cell_in_cross(const DevCtx &c, int centre, int r, int cell) {
+    const int W = c.p.width, H = c.p.height;
+    const int x = centre / H, y = centre - x * H, cx = cell / H, cy = cell - cx * H;
+    if (cell == centre || r <= 0) return false;
+    if (cx == x) { int d = abs(cy - y); if (H - d < d) d = H - d; return d <= min(r, c.max_dy); }
+    if (cy == y) { int d = abs(cx - x); if (W - d < d) d = W - d; return d <= min(r, c.max_dx); }
+    return false;
+}
+
+// Bentham.findEthicalValueOfCell (ethics.py:141-244) for the agents in view; selfishness < 0 splits the
+// value into happiness and unhappiness (negativeBentham).  hood[] = live agents in range + the agent.
+__device__ __noinline__ double ethical_value(const DevCtx &c, int s, int my_r, const int32_t *hood, int n_hood, int cell,
+                                             double *happy, double *unhappy) {
+    const ssb_agents_t &a = c.a;
+    const bool spicy = (c.p.flags & SSB_F_SPICE) != 0;
+    double site = (double)(c.g.sugar[cell] + (spicy ? c.g.spice[cell] : 0));
+    const double max_loot = c.p.max_combat_loot * 2;
+    double max_site = (double)(c.g.sugar_cap[cell] + (spicy ? c.g.spice_cap[cell] : 0));
+    const int occupant = c.g.occ[cell];
+    if (occupant >= 0) {
+        const double w = a.sugar[occupant] + a.spice[occupant];
+        site += w < max_loot ? w : max_loot;
+        max_site += w < max_loot ? w : max_loot;
+    }
+    int32_t nb4[4];
+    neighbours4(c, cell, nb4);
+    double neighbor_wealth = 0;
+    for (int i = 0; i < 4; i++) neighbor_wealth += c.g.sugar[nb4[i]] + (spicy ? c.g.spice[nb4[i]] : 0);
+    const double lookahead = c.eth.lookahead_factor[s];
+    // len(self.findNeighborhood(cell)): live agents on MY cross moved to `cell`, plus myself
+    const double future_hood = lookahead != 0 ? (double)(1 + (my_r > 0 ? cross_live_count(c, cell, my_r) : 0)) : 1.0;
+    const double selfish = c.eth.selfishness[s];
+    double value = 0, h = 0, u = 0;
+    for (int k = 0; k < n_hood; k++) {
+        const int nb = hood[k];
+        if (!agent_alive(c, nb)) continue;
+        const int rn = agent_range(c, nb);
+        if (!(cell == a.pos[nb] || cell_in_cross(c, a.pos[nb], rn, cell))) continue;      // canReachCell
+        const double metab = (double)(a.sugar_metab[nb] + a.spice_metab[nb]);               // raw, not the find* accessors
+        const double cell_duration = metab > 0 ? site / metab : 0;
+        const double proximity = 1.0 / 1;
+        const double intensity = (1 / (1 + time_to_live(c, nb, false)) / (1 + c.g.pollution[cell]));
+        const double duration = max_site > 0 ? cell_duration / max_site : 0;
+        const double discount = c.eth.lookahead_factor[nb] != 0 ? c.eth.lookahead_discount[nb] : 0;
+        double future_duration = metab > 0 ? (site - metab) / metab : site;
+        future_duration = max_site > 0 ? future_duration / max_site : 0;
+        const double future_intensity = neighbor_wealth / (c.eth.global_max_wealth * 4);
+        const int in_range = rn > 0 ? cross_size(c, rn) : 0;                                // len(neighbor.cellsInRange)
+        const double extent = in_range > 0 ? (double)n_hood / in_range : 1;
+        const double future_extent = (in_range > 0 && lookahead != 0) ? future_hood / in_range : 1;
+        const double current_reward = extent * (intensity + duration);
+        const double future_reward = future_extent * (future_intensity + future_duration);
+        double v = (1 * proximity) * (current_reward + (discount * future_reward));
+        if (nb != s && selfish < 1) {
+            v = -1 * v;
+            if (cell == a.pos[nb] && v > -1) v = -1;
+        }
+        if (selfish >= 0) v *= nb == s ? selfish : 1 - selfish;
+        else { if (v > 0) h += v; else u += v; }
+        value += v;
+    }
+    *happy = h; *unhappy = u;
+    return value;
+}
+
 // The agent's own record, loaded ONCE per transaction by every lane of the group (uniform
 // addresses: one memory transaction each, all independent -> a single latency level).
 struct AgentRec {
@@ -320,6 +437,65 @@ struct AgentRec {
     }
 };
 
+// rankCellsInRange (agent.py:1395-1443) in full -- the whole welfare-sorted list, not only its head --
+// followed by Bentham.findBestEthicalCell (ethics.py:105-139).  Lane 0, after the group's ranking pass:
+// ws holds the candidate cells, their distances, the shuffle permutation and (fighters) the retaliator
+// table.  Returns false when no candidate is valid (the agent stays put; rank 0 by definition).
+__device__ __noinline__ bool ethical_pick(const DevCtx &c, int s, int r, int n, const Welfare &w, int my_tribe,
+                                          double aggression, const WarpScratch &ws, int *out_cell, int *out_rank,
+                                          double *out_diff) {
+    const ssb_agents_t &a = c.a;
+    const bool polluted = (c.p.flags & SSB_F_POLLUTION) != 0, spicy = (c.p.flags & SSB_F_SPICE) != 0;
+    const bool fighter = aggression > 0;
+    const double loot = c.p.max_combat_loot, my_wealth = w.sugar + w.spice;
+    int32_t cand_cell[MAXC_EXACT_RULES];
+    uint8_t cand_dist[MAXC_EXACT_RULES];
+    double cand_w[MAXC_EXACT_RULES];
+    int m = 0;
+    for (int k = 0; k < n && k < MAXC_EXACT_RULES; k++) {            // shuffled order
+        const int i = ws.perm[k], cell = ws.cells[i];
+        const int prey = c.g.occ[cell];
+        double ps = 0, pp = 0;
+        if (prey >= 0) {                                           // isNeighborValidPrey (agent.py:1309-1314)
+            if (!(fighter && my_tribe != a.tribe[prey] && my_wealth >= a.sugar[prey] + a.spice[prey])) continue;
+            ps = a.sugar[prey]; pp = a.spice[prey];
+        }
+        const double wps = aggression * fmin(loot, ps), wpp = aggression * fmin(loot, pp);
+        const double pl = polluted ? c.g.pollution[cell] : 0.0;
+        const double welfare = w.eval(((double)c.g.sugar[cell] + wps) / (1 + pl),
+                                      ((double)(spicy ? c.g.spice[cell] : 0) + wpp) / (1 + pl));
+        if (prey >= 0 && __longlong_as_double((long long)ws.retaliator[min(a.tribe[prey] + 1, 26)]) > my_wealth + welfare) continue;
+        // sortCellsByWealth (agent.py:1479-1490): stable, welfare descending then range ascending
+        int j = m++;
+        const uint8_t dist = ws.dist[i];
+        while (j > 0 && (cand_w[j - 1] < welfare || (cand_w[j - 1] == welfare && cand_dist[j - 1] > dist))) {
+            cand_cell[j] = cand_cell[j - 1]; cand_dist[j] = cand_dist[j - 1]; cand_w[j] = cand_w[j - 1];
+            j--;
+        }
+        cand_cell[j] = cell; cand_dist[j] = dist; cand_w[j] = welfare;
+    }
+    if (m == 0) return false;
+    int32_t hood[MAXC_EXACT_RULES + 1];
+    int nh = 0;
+    for (int i = 0; i < n && i < MAXC_EXACT_RULES; i++) {
+        const int o = c.g.occ[ws.cells[i]];
+        if (o >= 0 && agent_alive(c, o)) hood[nh++] = o;
+    }
+    hood[nh++] = s;
+    const bool positive = c.eth.selfishness[s] >= 0;
+    int chosen = -1;
+    double best_u = 0, best_h = 0;
+    for (int i = 0; i < m; i++) {
+        double h, u;
+        const double v = ethical_value(c, s, r, hood, nh, cand_cell[i], &h, &u);
+        if (positive) { if (v > 0) { chosen = i; break; } }
+        else if (chosen < 0 || u > best_u || (u == best_u && h > best_h)) { chosen = i; best_u = u; best_h = h; }   // stable sort, reverse
+    }
+    const int rank = chosen >= 0 ? chosen : 0;
+    *out_cell = cand_cell[rank]; *out_rank = rank; *out_diff = cand_w[0] - cand_w[rank];
+    return true;
+}
+
 // MOVE part of Agent.doTimestep (agent.py:568-584), executed by the G lanes of a group for ONE
 // agent: lastSugar/lastSpice, rankCellsInRange + findBestCell + moveToBestCell (1395-1443,
 // 719-746, 1321-1328), collectResourcesAtCell (249-259), doMetabolism (485-498).
@@ -332,7 +508,7 @@ struct AgentRec {
 // step.  Dependent memory levels of the whole move part: own record, cells, occupants.
 // Returns true (on every lane) if the agent is still alive and has to run the interact part;
 // rec is updated (lane 0's copy is authoritative and written back to memory).
-template <int G, int CH, class Rng>
+template <int G, int CH, class Rng, bool EXT = false>
 __device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rng &rng, const WarpScratch &ws, int maxc) {
     typedef Group<G> Gr;
     const int lane = Gr::lane();
@@ -453,6 +629,27 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rn
             }
         }
         if (m == 0) m = 1;
+    }
+    if (EXT && c.eth.model != nullptr) {                               // uniform
+        // decision models: the ethical ranking may override the greedy choice (ethics.py:105-139); the
+        // optimality of the move is logged for every agent (agent.py:734-745)
+        if (lane == 0) {
+            if (n > 0) {
+                int rank = 0, cell = b_cell;
+                double diff = 0;
+                if (b_valid && c.eth.model[s] == 1 && c.eth.decision_factor[s] > 0 &&
+                    ethical_pick(c, s, r, n, w, my_tribe, aggression, ws, &cell, &rank, &diff) && cell != b_cell) {
+                    b_cell = cell;
+                    b_cs = c.g.sugar[cell];
+                    b_cp = spicy ? c.g.spice[cell] : 0;
+                    b_pl = polluted ? c.g.pollution[cell] : 0.0;
+                }
+                c.eth.last_move_optimal[s] = rank == 0; c.eth.move_rank[s] = rank; c.eth.move_diff[s] = diff;
+            } else {
+                c.eth.last_move_optimal[s] = 1;      // [own cell] is its own best; rank and difference keep their values
+            }
+        }
+        b_cell = Gr::bcast(b_cell, 0);
     }
     int alive = 1;
     double sugar = rec.sugar, spice = rec.spice;
@@ -627,7 +824,7 @@ __device__ __forceinline__ int alloc_slot(const DevCtx &c) {
 // loaded up front in two batches of independent requests; nothing else can change those cells
 // while this agent holds its reservation, so the only updates are this call's own child
 // placements, which are tracked in the local copies.
-template <class Rng, bool EXACT>
+template <class Rng, bool EXACT, bool EXT = false>
 __device__ __noinline__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
     const ssb_agents_t &a = c.a;
     if (!agent_alive(c, s) || !is_fertile(c, s)) return;
@@ -750,6 +947,15 @@ __device__ __noinline__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
         const int my_id = a.id[s], mate_id = a.id[m];
         a.father[ch] = my_sex == SSB_SEX_FEMALE ? mate_id : my_id;
         a.mother[ch] = my_sex == SSB_SEX_FEMALE ? my_id : mate_id;
+        if (EXT && c.eth.model != nullptr) {
+            // the paired endowments follow ONE draw (agent.py:845-851); the child's class is that parent's
+            const int from = ((eb >> EB_DECISION_MODEL) & 1u) ? m : s;
+            c.eth.model[ch] = c.eth.model[from]; c.eth.selfishness[ch] = c.eth.selfishness[from];
+            c.eth.decision_factor[ch] = c.eth.decision_factor[from];
+            c.eth.lookahead_factor[ch] = c.eth.lookahead_factor[from];
+            c.eth.lookahead_discount[ch] = c.eth.lookahead_discount[from];
+            c.eth.last_move_optimal[ch] = 1; c.eth.move_rank[ch] = 0; c.eth.move_diff[ch] = 0;      // lastMoveOptimal starts True
+        }
         a.pos[ch] = cell;
         c.g.occ[cell] = ch;
         for (int q = 0; q < 4; q++) {       // keep the local copies current
@@ -782,14 +988,14 @@ __device__ __noinline__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
 
 // INTERACT part of Agent.doTimestep (agent.py:585-598): tagging, trading, reproduction, aging,
 // happiness.  Lane 0 only.  `rec` holds the agent's record after the move part.
-template <class Rng, bool EXACT>
+template <class Rng, bool EXACT, bool EXT = false>
 __device__ void transaction_interact_phase(const DevCtx &c, int s, const AgentRec &rec, Rng &rng) {
     const ssb_agents_t &a = c.a;
     if ((c.p.flags & SSB_F_TAGS) && (c.p.flags & SSB_F_TAGGING)) do_tagging(c, s, rng);
     if (c.p.flags & SSB_F_TRADE) do_trading(c, s, rng);
     // doReproduction starts with isFertile(): only trading can have raised the holdings since the
     // move part, so without trade the record decides and most agents skip the call
-    if ((c.p.flags & SSB_F_REPRO) && ((c.p.flags & SSB_F_TRADE) || rec.fertile())) do_reproduction<Rng, EXACT>(c, s, rng);
+    if ((c.p.flags & SSB_F_REPRO) && ((c.p.flags & SSB_F_TRADE) || rec.fertile())) do_reproduction<Rng, EXACT, EXT>(c, s, rng);
     // doAging (agent.py:266-272); reproduction and trading leave the agent alive (isAlive looks at
     // the holdings, which they may have changed)
     double sugar = rec.sugar, spice = rec.spice;

@@ -71,6 +71,9 @@ def load_library():
     L.ssb_stats.argtypes = [E, S]
     L.ssb_stats_history.argtypes = [E, C.c_int32, S]
     L.ssb_sync.argtypes = [E, C.c_void_p]
+    L.ssb_bind_ethics.argtypes = [E, C.POINTER(layout.Ethics)]
+    L.ssb_ethics_stats.argtypes = [E, C.POINTER(layout.EthicsStats)]
+    L.ssb_sizeof_ethics.restype = C.c_int
     L.ssb_pollution_buffer.argtypes = [E]
     L.ssb_pollution_buffer.restype = C.c_int
     L.ssb_round_trace.argtypes = [E, C.c_int32, C.c_void_p, C.c_int32]
@@ -82,7 +85,7 @@ def load_library():
     if L.ssb_abi_version() != layout.ABI_VERSION:
         raise EngineError("libssb.so ABI version does not match sugarscape_b200.layout")
     for name, struct in (("params", layout.Params), ("grid", layout.Grid), ("agents", layout.Agents),
-                         ("stats", layout.Stats)):
+                         ("stats", layout.Stats), ("ethics", layout.Ethics)):
         if getattr(L, "ssb_sizeof_" + name)() != C.sizeof(struct):
             raise EngineError(f"struct ssb_{name}_t: library and ctypes mirror disagree on size")
     _LIB = L
@@ -97,6 +100,7 @@ EXPORTED_SYMBOLS = (
     "ssb_fabric_create", "ssb_fabric_alloc", "ssb_fabric_map", "ssb_fabric_copy", "ssb_fabric_granularity",
     "ssb_fabric_destroy", "ssb_fabric_last_error", "ssb_set_shard", "ssb_migrate", "ssb_shard_barrier", "ssb_shard_broken",
     "ssb_sync", "ssb_pollution_buffer", "ssb_test_pow", "ssb_round_trace", "ssb_launch_count", "ssb_timing", "ssb_enable_timing",
+    "ssb_bind_ethics", "ssb_ethics_stats", "ssb_sizeof_ethics",
 )
 
 
@@ -120,6 +124,12 @@ class Engine:
         g, a = self._structs()
         self._check(self.L.ssb_bind(self.handle, C.byref(g), C.byref(a)))
         self._after_bind()
+        self.ethics = host_state.ethics          # HostEthics (its arrays live in self.tensors as eth_*) or None
+        if self.ethics is not None:
+            es = self.ethics.as_struct(lambda arr: None)
+            for name, _, _ in layout.ETHICS_FIELDS:
+                setattr(es, name, self.tensors["eth_" + name].data_ptr())
+            self._check(self.L.ssb_bind_ethics(self.handle, C.byref(es)))
         if endow_bits is not None:
             eb = np.ascontiguousarray(endow_bits, dtype=np.uint32)
             tb = np.ascontiguousarray(tag_bits, dtype=np.uint32)
@@ -148,6 +158,9 @@ class Engine:
             self.tensors["a_" + name] = self._to_device(getattr(hs, "a_" + name))
         for name in layout.KIN_FIELDS:
             self.tensors[name] = self._to_device(getattr(hs, name))
+        if hs.ethics is not None:
+            for name, _, _ in layout.ETHICS_FIELDS:
+                self.tensors["eth_" + name] = self._to_device(hs.ethics.arrays[name])
 
     def _structs(self):
         g = layout.Grid()
@@ -185,6 +198,8 @@ class Engine:
         """Copy the device state back into a HostState (all fields, or the named subset)."""
         hs = layout.HostState(self.width, self.height, self.capacity)
         hs.kin_capacity = self.kin_capacity
+        if self.ethics is not None:
+            hs.ethics = self.ethics.copy()
         self.torch.cuda.synchronize(self.device)
         swapped = bool(self.L.ssb_pollution_buffer(self.handle))
         for key, tensor in self.tensors.items():
@@ -195,13 +210,16 @@ class Engine:
             arr = tensor.cpu().numpy()
             if key == "a_tags":
                 arr = arr.view(np.uint32)
-            setattr(hs, key, arr)
+            if key.startswith("eth_"):
+                hs.ethics.arrays[key[4:]] = arr
+            else:
+                setattr(hs, key, arr)
         return hs
 
     def upload(self, hs, fields):
         swapped = bool(self.L.ssb_pollution_buffer(self.handle))
         for key in fields:
-            arr = getattr(hs, key)
+            arr = hs.ethics.arrays[key[4:]] if key.startswith("eth_") else getattr(hs, key)
             if swapped and key in ("pollution", "pollution_flux"):
                 key = "pollution_flux" if key == "pollution" else "pollution"
             if arr.dtype == np.uint32:
@@ -259,6 +277,14 @@ class Engine:
     def stats(self):
         out = layout.Stats()
         self._check(self.L.ssb_stats(self.handle, C.byref(out)))
+        return out
+
+    def ethics_stats(self):
+        """Decision-model reductions of the last reduce_stats (None without decision models)."""
+        if self.ethics is None:
+            return None
+        out = layout.EthicsStats()
+        self._check(self.L.ssb_ethics_stats(self.handle, C.byref(out)))
         return out
 
     def stats_history(self, t):

@@ -73,6 +73,17 @@ def _decimals(value):
     return len(parts[1]) if len(parts) == 2 else None
 
 
+# decisionModel strings with a CUDA implementation: the plain Agent and ethics.Bentham with its spawn
+# variants (sugarscape.py:219-233); "Dynamic" variants, Temperance, Asimov and the Leader are refused
+SUPPORTED_DECISION_MODELS = frozenset(("none", "rawSugarscape")) | frozenset(
+    base + suffix for base in layout.BENTHAM_MODELS for suffix in ("", "NoLookahead", "HalfLookahead"))
+
+
+def uses_decision_models(c):
+    """True if some agent may be an ethics.Bentham instance (needs the ssb_ethics_t extension, mode E)."""
+    return any(layout.decision_model_base(m) is not None for m in c["agentDecisionModels"])
+
+
 def check_supported(c):
     """Fail loudly on rule families without a CUDA implementation yet (DESIGN.md 'scope')."""
     problems = []
@@ -98,10 +109,13 @@ def check_supported(c):
         problems.append("friends")
     if c["agentUniversalSugar"][1] != 0 or c["agentUniversalSpice"][1] != 0:
         problems.append("universal income")
-    if any(m not in ("none", "rawSugarscape") for m in c["agentDecisionModels"]):
-        problems.append("decision models other than rawSugarscape")
-    if c["agentDecisionModelFactor"][1] > 0:
+    bad_models = [m for m in c["agentDecisionModels"] if m not in SUPPORTED_DECISION_MODELS]
+    if bad_models:
+        problems.append("decision models other than rawSugarscape and the Bentham family: " + ", ".join(bad_models))
+    if c["agentDecisionModelFactor"][1] > 0 and not uses_decision_models(c):
         problems.append("agentDecisionModelFactor")
+    if uses_decision_models(c) and c["agentDynamicSelfishnessFactor"][1] != 0:
+        problems.append("agentDynamicSelfishnessFactor")
     for k in ("agentDecisionModelAgeismFactor", "agentDecisionModelRacismFactor",
               "agentDecisionModelSexismFactor", "agentDecisionModelTribalFactor"):
         if c[k][1] >= 0:
@@ -474,6 +488,9 @@ def build_initial_state(c, capacity=None, check=True):
     state.spice_cap[:] = spice_cap.reshape(-1)
     state.sugar[:] = state.sugar_cap
     state.spice[:] = state.spice_cap
+
+    if uses_decision_models(c):
+        state.ethics = layout.HostEthics(capacity, c)
 
     occupied = np.zeros(W * H, dtype=bool)
     new_agents = pop.place(n0, occupied, 0, 0) if n0 > 0 else []

@@ -8,7 +8,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 RNG_EXACT, RNG_SCALABLE = 0, 1
 ALIVE, STARVATION, AGING, COMBAT, OTHER = 0, 1, 2, 3, 4
 SEX_NONE, SEX_MALE, SEX_FEMALE = 0, 1, 2
@@ -177,6 +177,90 @@ class Stats(C.Structure):
     ]
 
 
+# ---- ABI 2: decision models (ssb_ethics_t; reference ethics.py, spawn rules sugarscape.py:219-233) ----
+# (name, numpy dtype, fill) in the order of ssb_ethics_t after `capacity`
+ETHICS_FIELDS = (
+    ("model", np.int32, 0), ("selfishness", np.float64, 0), ("decision_factor", np.float64, 0),
+    ("lookahead_factor", np.float64, 0), ("lookahead_discount", np.float64, 0),
+    ("last_move_optimal", np.int32, 1), ("move_rank", np.int32, 0), ("move_diff", np.float64, 0),
+)
+BENTHAM_MODELS = ("altruist", "bentham", "egoist", "negativeBentham")
+
+
+class Ethics(C.Structure):
+    _fields_ = ([("capacity", C.c_int64)] + [(n, C.c_void_p) for n, _, _ in ETHICS_FIELDS]
+                + [("global_max_wealth", C.c_double)])
+
+
+class EthicsStats(C.Structure):
+    _fields_ = [("sum_selfishness", C.c_double), ("optimal_moves", C.c_int64), ("moves", C.c_int64),
+                ("sum_move_rank", C.c_int64), ("sum_move_diff", C.c_double)]
+
+
+def decision_model_base(name):
+    """The Bentham-family member a decisionModel string selects, in the reference's matching order
+    (sugarscape.py:219-233: substring tests, "altruist" first), or None for a plain Agent."""
+    for base in BENTHAM_MODELS:
+        if base in name:
+            return base
+    return None
+
+
+class HostEthics:
+    """Per-slot decision-model state (host mirror of ssb_ethics_t)."""
+
+    def __init__(self, capacity, c):
+        self.capacity = capacity
+        self.global_max_wealth = float(c["environmentMaxSugar"] + c["environmentMaxSpice"])
+        look = c["agentDecisionModelLookaheadFactor"]
+        # the reference's default is the LIST [0], handed to the agents as is; only `!= 0` is ever asked of
+        # it (ethics.py:160-190) and `[0] != 0` holds
+        self.lookahead_factor = 1.0 if isinstance(look, list) else float(look)
+        self.arrays = {n: np.full(capacity, fill, dtype=dt) for n, dt, fill in ETHICS_FIELDS}
+
+    def set_slot(self, slot, endowment):
+        """A freshly configured agent (sugarscape.py:219-233)."""
+        name = endowment["decisionModel"]
+        base = decision_model_base(name)
+        selfish = endowment["selfishnessFactor"]
+        if base == "altruist":
+            selfish = 0
+        elif base == "bentham":
+            selfish = 0.5 if selfish < 0 else selfish
+        elif base == "egoist":
+            selfish = 1
+        elif base == "negativeBentham":
+            selfish = -1
+        look = self.lookahead_factor
+        if "NoLookahead" in name:
+            look = 0
+        elif "HalfLookahead" in name:
+            look = 0.5
+        A = self.arrays
+        A["model"][slot] = int(base is not None)
+        A["selfishness"][slot] = selfish
+        A["decision_factor"][slot] = endowment["decisionModelFactor"]
+        A["lookahead_factor"][slot] = look
+        A["lookahead_discount"][slot] = endowment["decisionModelLookaheadDiscount"]
+        A["last_move_optimal"][slot] = 1
+        A["move_rank"][slot] = 0
+        A["move_diff"][slot] = 0
+
+    def as_struct(self, pointer_of=lambda arr: arr.ctypes.data):
+        e = Ethics()
+        e.capacity = self.capacity
+        for n, _, _ in ETHICS_FIELDS:
+            setattr(e, n, pointer_of(self.arrays[n]))
+        e.global_max_wealth = self.global_max_wealth
+        return e
+
+    def copy(self):
+        h = HostEthics.__new__(HostEthics)
+        h.capacity, h.global_max_wealth, h.lookahead_factor = self.capacity, self.global_max_wealth, self.lookahead_factor
+        h.arrays = {k: v.copy() for k, v in self.arrays.items()}
+        return h
+
+
 def default_capacity(c, n0):
     """Slots to allocate: births and replacements append, dead slots are recycled."""
     cells = c["environmentWidth"] * c["environmentHeight"]
@@ -228,6 +312,7 @@ class HostState:
 
     def __init__(self, width, height, capacity):
         self.width, self.height, self.capacity = width, height, capacity
+        self.ethics = None          # HostEthics when the configuration uses decision models (ABI 2)
 
     @classmethod
     def empty(cls, width, height, capacity, kin_capacity=None):
@@ -254,6 +339,7 @@ class HostState:
         s.kin_capacity = self.kin_capacity
         for name in KIN_FIELDS:
             setattr(s, name, getattr(self, name).copy())
+        s.ethics = self.ethics.copy() if self.ethics is not None else None
         return s
 
     def as_structs(self):
@@ -317,6 +403,8 @@ class HostState:
             tags = a["tags"]
             self.a_tags[slot] = sum((1 << i) for i, b in enumerate(tags or ()) if b)
             self.a_tribe[slot] = a["tribe"]
+            if self.ethics is not None:
+                self.ethics.set_slot(slot, e)
             self.a_order[n_list] = slot
             self.occ[a["cell"]] = slot
             n_list += 1

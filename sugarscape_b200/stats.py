@@ -88,8 +88,9 @@ class StatsBuilder:
             lo, hi = c[option]
             self.constant[key] = lo if lo == hi else None
 
-    def update(self, st, t, n_replaced=0):
-        """st: layout.Stats filled by the device (or by the oracle in the tests)."""
+    def update(self, st, t, n_replaced=0, ethics=None):
+        """st: layout.Stats filled by the device (or by the oracle in the tests); ethics: layout.EthicsStats
+        when the run uses decision models (sugarscape.py:1141-1160, 1218-1222, 1304, 1318, 1323-1324)."""
         c, rs = self.c, self.runtime_stats
         n = int(st.population)
         prev_cc = rs["carryingCapacity"]
@@ -156,9 +157,17 @@ class StatsBuilder:
             out["meanMoveDifferenceFromOptimal"] = round(0 / out["meanNeighbors"], 2) if out["meanNeighbors"] > 0 else 0
             out["totalHappiness"] = st.sum_happiness
             for key, value in self.constant.items():
+                if key == "meanSelfishness" and ethics is not None:
+                    continue
                 if value is None:
                     raise NotImplementedError(key + " needs per-agent factors")
                 out[key] = round(value * n / n, 2)
+            if ethics is not None:
+                out["meanSelfishness"] = round(ethics.sum_selfishness / n, 2)
+                out["agentLastMoveOptimalityPercentage"] = round((ethics.optimal_moves / ethics.moves) * 100, 2)
+                out["meanMoveRank"] = round(ethics.sum_move_rank / n, 2)
+                out["meanMoveDifferenceFromOptimal"] = (round(ethics.sum_move_diff / out["meanNeighbors"], 2)
+                                                        if out["meanNeighbors"] > 0 else 0)
         else:
             # zero population: the reference resets some keys and leaves others stale/raw
             # (sugarscape.py:1325-1351)
@@ -176,7 +185,8 @@ class StatsBuilder:
             out["meanTradePrice"] = 0
             out["meanDeathsPercentage"] = 0
             out["sickAgentsPercentage"] = 0
-            out["agentLastMoveOptimalityPercentage"] = int(st.n_dead)
+            # the raw count of optimal moves (of the dead) stays in place (sugarscape.py:1325-1351)
+            out["agentLastMoveOptimalityPercentage"] = int(ethics.optimal_moves) if ethics is not None else int(st.n_dead)
             out["meanNeighbors"] = 0
             out["meanValidMoves"] = 0
             out["meanMoveRank"] = 0

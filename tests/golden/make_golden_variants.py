@@ -16,6 +16,10 @@ sys.path.insert(0, HERE)
 import make_golden as mg  # noqa: E402
 import ref_harness as rh  # noqa: E402
 
+_ETHICS = {"agentDecisionModels": ["none", "bentham", "altruist", "egoist", "negativeBentham"],
+           "agentDecisionModelFactor": [1, 1], "agentDecisionModelLookaheadDiscount": [0.5, 0.5],
+           "agentDecisionModelLookaheadFactor": 0.5, "agentSelfishnessFactor": [-1, -1]}
+
 VARIANTS = {
     # diseases that incubate, spread with a chance, can be resisted and are recovered from
     "disease_mild": ("disease_basic", 150, {
@@ -43,6 +47,17 @@ VARIANTS = {
     "environment_file": ("trade_tagging_reproduction", 120, {"environmentFile": os.path.join(HERE, "environment_30.json"),
                                                              "environmentWidth": 30, "environmentHeight": 30,
                                                              "startingAgents": 150, "environmentMaxSugar": 4, "environmentMaxSpice": 4}),
+    # ---- ethics.Bentham decision models on top of rule families the ENGINE supports ----
+    # trade + tagging + reproduction: children inherit the decision model of one parent
+    "ethics_trade": ("trade_tagging_reproduction", 150, dict(_ETHICS)),
+    # live combat (prey, retaliators and loot enter the welfare the ethical ranking re-scores)
+    "ethics_combat": ("combat_limited", 150, dict(_ETHICS)),
+    # host-side replacement of the dead + the lookahead spawn variants + a selfishness range for bentham
+    "ethics_replacement": ("agent_replacement", 120, dict(_ETHICS, agentDecisionModels=[
+        "none", "benthamHalfLookahead", "altruistNoLookahead", "egoist", "negativeBenthamNoLookahead", "bentham"],
+        agentSelfishnessFactor=[0.2, 0.8])),
+    # pollution enters the intensity term of the ethical value
+    "ethics_pollution": ("trade_pollution", 120, dict(_ETHICS)),
 }
 
 
@@ -56,7 +71,9 @@ def main():
             stored = {k: (os.path.basename(v) if k == "environmentFile" else v) for k, v in overrides.items()}   # (relative to this directory)
             json.dump({"meta": meta, "base": base, "overrides": stored, "steps": steps, "log": log}, f)
         sick = [e["sickAgents"] for e in log]
-        print(f"{name}: {len(steps) - 1} steps, final pop {steps[-1]['population']}, sick agents min/max {min(sick)}/{max(sick)}", flush=True)
+        optimal = [e["agentLastMoveOptimalityPercentage"] for e in log[1:]]
+        print(f"{name}: {len(steps) - 1} steps, final pop {steps[-1]['population']}, sick agents min/max {min(sick)}/{max(sick)}, "
+              f"move optimality min/max {min(optimal)}/{max(optimal)}", flush=True)
 
 
 if __name__ == "__main__":

@@ -11,6 +11,7 @@
 #define SSB_HOSTEMU 1
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #define __device__

@@ -22,7 +22,9 @@ def lib():
         subprocess.check_call(["make", "-s", "-C", HERE])
         L = C.CDLL(os.path.join(HERE, "libssb_hostemu.so"))
         P, G, A = C.POINTER(layout.Params), C.POINTER(layout.Grid), C.POINTER(layout.Agents)
-        L.emu_agent_step_exact.argtypes = [P, G, A, C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_int32]
+        L.emu_agent_step_exact.argtypes = [P, G, A, C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_int32,
+                                           C.POINTER(layout.Ethics)]
+        L.emu_ethics_stats.argtypes = [A, C.POINTER(layout.Ethics), C.POINTER(layout.EthicsStats)]
         assert L.emu_abi_version() == layout.ABI_VERSION
         _LIB = L
     return _LIB
@@ -48,6 +50,14 @@ class HostEmu(Oracle):
         eb = self.endow_bits.ctypes.data if self.endow_bits is not None else None
         tb = self.tag_bits.ctypes.data if self.tag_bits is not None else None
         n = len(self.endow_bits) if self.endow_bits is not None else 0
+        eth = C.byref(self.state.ethics.as_struct()) if self.state.ethics is not None else None
         rc = self.E.emu_agent_step_exact(C.byref(self.params), C.byref(g), C.byref(a), self.mt.ctypes.data, t,
-                                         prev_mean_wealth, eb, tb, n)
+                                         prev_mean_wealth, eb, tb, n, eth)
         assert rc == 0, f"emu_agent_step_exact failed: {rc}"
+
+    def ethics_stats(self):
+        g, a = self.state.as_structs()
+        out = layout.EthicsStats()
+        rc = self.E.emu_ethics_stats(C.byref(a), C.byref(self.state.ethics.as_struct()), C.byref(out))
+        assert rc == 0
+        return out

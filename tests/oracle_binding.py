@@ -385,6 +385,16 @@ class Oracle:
                 "meanMoveRank": round(out[3] / n, 2),
                 "meanMoveDifferenceFromOptimal": round(out[4] / mean_neighbors, 2) if mean_neighbors > 0 else 0}
 
+    def ethics_stats(self, t):
+        """The oracle's decision-model reductions as a layout.EthicsStats (what StatsBuilder.update takes)."""
+        g, a = self.state.as_structs()
+        out = (C.c_double * 5)()
+        self.L.orc_ethics_stats(C.byref(a), t, C.byref(out))
+        es = layout.EthicsStats()
+        es.sum_selfishness, es.optimal_moves, es.moves, es.sum_move_rank, es.sum_move_diff = (
+            out[0], int(out[1]), int(out[2]), int(out[3]), out[4])
+        return es
+
     def bind_group(self):
         """Oracle-private bookkeeping of the experimental-group split of the log (group "depressed")."""
         cap = self.state.capacity

@@ -262,6 +262,46 @@ def test_oracle_determinism_variants_match_reference_trajectory(variant, ethics)
         _unbind_everything(orc)
 
 
+@pytest.mark.parametrize("variant", ["ethics_trade", "ethics_combat", "ethics_replacement", "ethics_pollution"])
+def test_oracle_ethics_variants_match_reference_trajectory(variant):
+    """The ethics.Bentham restatement alone (no lending / diseases / friends around it), on rule families the
+    engine supports: fixtures from the unmodified reference (make_golden_variants.py) with bentham, altruist,
+    egoist, negativeBentham and the NoLookahead / HalfLookahead spawn variants over trade + tagging +
+    reproduction, live combat, host-side replacement and pollution.  Digests and all 59 log keys."""
+    from sugarscape_b200 import layout
+    base, overrides, gold, log = pu.load_variant(variant)
+    c, state, pop, params, endow, tags = pu.build(base, overrides=overrides)
+    orc = Oracle(params, state, endow, tags)
+    orc.bind_ethics(c, pop.endowments)
+    orc.set_mt_from_python()
+    try:
+        d, _ = pu.state_digests(state, *orc.mt_state())
+        assert d == gold[0]["digests"], "t=0 state differs"
+        sb = stats.StatsBuilder(c, init.equator(c))
+        rs = sb.update(orc.stats(0), 0, 0, orc.ethics_stats(0))
+        for t in range(1, len(gold)):
+            orc.env_step(t)
+            orc.agent_step(t, rs["meanWealth"])
+            orc.compact(t)
+            replaced = 0
+            n = int(state.counters[layout.C_N_LIST])
+            if 0 < c["agentReplacements"] and n < c["agentReplacements"]:
+                orc.push_mt_to_python()
+                new_agents = pop.place(c["agentReplacements"] - n, state.occ >= 0, t, int(state.counters[layout.C_NEXT_ID]))
+                state.append_agents(new_agents, protect_last=int(state.counters[layout.C_N_DEAD]))
+                state.counters[layout.C_NEXT_ID] += len(new_agents)
+                orc.adopt_new_agents(new_agents, c)
+                orc.set_mt_from_python()
+                replaced = len(new_agents)
+            d, snap = pu.state_digests(state, *orc.mt_state())
+            assert d == gold[t]["digests"], f"state differs at t={t}"
+            rs = sb.update(orc.stats(t), t, replaced, orc.ethics_stats(t))
+            for k in stats.LOG_KEYS:
+                assert _close(rs[k], log[t][k]), f"log key {k} differs at t={t}: {rs[k]} vs {log[t][k]}"
+    finally:
+        orc.unbind_ethics()
+
+
 _INTERACTIONS = ("combat", "disease", "lending", "reproduction", "trade")
 # keys a group pass does not compute: the log keeps their initial 0 (sugarscape.py:1403-1417)
 _GROUP_TEMPLATE_ZERO = ("timestep", "giniCoefficient", "seed", "environmentWealthCreated", "environmentWealthTotal")

@@ -1,0 +1,67 @@
+"""SURVEY row a21 on the GPU: the ethics.Bentham decision models through the C ABI (ssb_bind_ethics, the
+extended instantiation of the mode E kernel) against fixtures generated from the unmodified reference
+(tests/golden/make_golden_variants.py: ethics on top of trade + tagging + reproduction, live combat, host-side
+replacement, pollution).  Integer state, tags, grid and the MT19937 stream bit-exact on every step, fp64 holdings
+through their digest, all 59 log keys.
+
+Status of this file: the same device source passes these fixtures compiled for the host
+(tests/test_hostemu.py); round 1 ran out of GPU minutes before the first run on a B200, so the cases are
+marked xfail(strict=False) -- XPASS in the GPU log is the confirmation, and the marker goes away with it.
+The file sorts last so that nothing runs after it in the same process."""
+import pytest
+
+import parity_util as pu
+from sugarscape_b200 import init, layout, stats
+from test_gpu_parity import _close, _engine, _replace
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="first GPU run of the decision-model kernels (validated on the "
+                                                     "host-compiled device source only, tests/test_hostemu.py)")]
+
+ETHICS_VARIANTS = ["ethics_trade", "ethics_combat", "ethics_replacement", "ethics_pollution"]
+
+
+@pytest.mark.parametrize("variant", ETHICS_VARIANTS)
+def test_decision_models_match_reference_trajectory(variant):
+    base, overrides, gold, log = pu.load_variant(variant)
+    c, state, pop, params, endow, tags, eng = _engine(base, layout.RNG_EXACT, overrides)
+    assert state.ethics is not None
+    sb = stats.StatsBuilder(c, init.equator(c))
+    eng.reduce_stats(0)
+    rs = sb.update(eng.stats(), 0, 0, eng.ethics_stats())
+    non_greedy = 0
+    for t in range(1, len(gold)):
+        eng.env_step(t)
+        eng.agent_step(t, rs["meanWealth"])
+        eng.compact(t)
+        replaced = _replace(c, eng, pop, t) if c["agentReplacements"] > 0 else 0
+        eng.reduce_stats(t)
+        rs = sb.update(eng.stats(), t, replaced, eng.ethics_stats())
+        d, snap = pu.state_digests(eng.download(), *eng.mt_state())
+        assert d == gold[t]["digests"], f"{variant}: state differs from the reference at t={t}"
+        non_greedy += rs["agentLastMoveOptimalityPercentage"] < 100
+        for k in stats.LOG_KEYS:
+            assert _close(rs[k], log[t][k]), f"{variant}: log key {k} at t={t}: {rs[k]} vs {log[t][k]}"
+    assert non_greedy > 0.9 * len(gold)
+    eng.close()
+
+
+def test_drop_in_driver_writes_the_reference_log_with_decision_models(tmp_path):
+    """The reference-facing entry point (sugarscape_b200.simulation.Sugarscape, what `sugarscape.py --conf` runs)
+    on the ethics_trade configuration: the log.json it writes equals the reference's log entry by entry."""
+    import json
+    from sugarscape_b200.simulation import Sugarscape
+    base, overrides, gold, log = pu.load_variant("ethics_trade")
+    c = pu.example_configuration(base, overrides)
+    c["logfile"] = str(tmp_path / "log.json")
+    S = Sugarscape(c)
+    S.runSimulation(c["timesteps"])
+    mine = json.load(open(c["logfile"]))
+    # the file = the all-zero entry, then t = 1 .. last (the fixture's "log" holds the post-update stats from t = 0 on)
+    assert mine[0]["population"] == 0 and mine[0]["timestep"] == 0
+    assert len(mine) == len(log)
+    for entry, ref in zip(mine[1:], log[1:]):
+        for k in stats.LOG_KEYS:
+            if entry is mine[-1] and k == "environmentWealthCreated":
+                continue          # endLog recomputes it (covered by the shipped-example log tests)
+            assert _close(entry[k], ref[k]), f"log key {k} at t={entry['timestep']}: {entry[k]} vs {ref[k]}"
