@@ -229,6 +229,59 @@ typedef struct ssb_ethics_stats {
     int64_t sum_move_rank;
     double  sum_move_diff;
 } ssb_ethics_stats_t;
+/* ---- ABI 2: the optional rule families of the reference beyond the book examples, exact RNG mode.  Every
+ * family is a set of per-slot arrays (capacity = ssb_agents_t.capacity) owned by the host; a family is off
+ * when its first array pointer is NULL.  Python lists of the reference (loans, friends) keep their list
+ * semantics: order of insertion, remove = first equal element. ---- */
+
+/* lending: agent.py:431-483 doLending, 190-212 addLoan*, 920-930, 1226-1245, 1285-1296, 1330-1377 payDebt*,
+ * 1532-1541 updateLoans, 1549-1553 mean income.  A loan is one record in the debtor's "creditors" list and
+ * one in the creditor's "debtors" list; lists are chains through the loan pool in list order. */
+#define SSB_LC_POOL_USED   0  /* high-water mark of the loan pool                                         */
+#define SSB_LC_FREE_HEAD   1  /* recycled pool entries: index of the first one + 1 (0 = none)             */
+#define SSB_LC_N_DEAD      2  /* entries of the dead-creditor table                                       */
+#define SSB_LC_OVERFLOW    3  /* != 0: a pool was exhausted -> host raises                                 */
+#define SSB_LC_COUNT       8
+typedef struct ssb_lending {
+    double  *lending_factor, *base_interest_rate;
+    int32_t *loan_duration;
+    double  *sugar_mean_income, *spice_mean_income;   /* updateMeanIncome, start at 1                      */
+    int32_t *last_lended, *last_loans;                /* timestep of the last lending / loans made then    */
+    int32_t *creditors_head, *debtors_head;           /* per slot: first pool entry of the list, -1 empty  */
+    int64_t pool_capacity;
+    int32_t *loan_other_slot, *loan_other_id;         /* the other party, named by (slot, id)              */
+    double  *loan_sugar, *loan_spice;
+    int32_t *loan_duration_v, *loan_origin, *loan_next;
+    /* a dead creditor's children list outlives its slot (payDebtToCreditorChildren, agent.py:1362-1377) */
+    int64_t dead_capacity;
+    int32_t *dead_slot, *dead_id, *dead_children_head;
+    int64_t *counters;                                /* SSB_LC_COUNT values                               */
+} ssb_lending_t;
+
+/* friends + conflict happiness: agent.py:1499-1520 updateFriends, 1099-1105, 912-918 */
+#define SSB_MAX_FRIENDS 16
+typedef struct ssb_social {
+    int32_t *max_friends, *last_combat;
+    double  *social_happiness, *conflict_happiness;   /* as of the agent's last updateHappiness            */
+    int32_t *n_friends;
+    int32_t *friend_slot, *friend_id, *friend_hd;     /* [slot][SSB_MAX_FRIENDS], list order               */
+} ssb_social_t;
+
+typedef struct ssb_ext {
+    int64_t capacity;
+    ssb_lending_t lending;
+    ssb_social_t social;
+} ssb_ext_t;
+/* raw sums for the log keys of the families (sugarscape.py:1130-1160) */
+typedef struct ssb_ext_stats {
+    int64_t loan_volume;                              /* sum of lastLoans over the agents that lent this step */
+    double  sum_social_happiness, sum_conflict_happiness;
+} ssb_ext_stats_t;
+/* call after ssb_bind, before the first step (mode E only) */
+int  ssb_bind_ext(ssb_engine_t *e, const ssb_ext_t *ext);
+int  ssb_ext_stats(ssb_engine_t *e, ssb_ext_stats_t *host_out);   /* of the last ssb_reduce_stats; synchronises */
+int  ssb_sizeof_ext(void);
+
 /* call after ssb_bind, before the first step (mode E only; mode S and sharded engines refuse) */
 int  ssb_bind_ethics(ssb_engine_t *e, const ssb_ethics_t *ethics);
 /* reductions of the last ssb_reduce_stats; synchronises */

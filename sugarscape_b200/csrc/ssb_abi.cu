@@ -69,6 +69,8 @@ struct ssb_engine {
     // ABI 2: decision models (mode E)
     bool ethics_bound;
     ssb_ethics_stats_t *d_eth_stats;
+    bool ext_bound;
+    ssb_ext_stats_t *d_ext_stats;
 };
 
 static int fail(ssb_engine *e, int code, const char *fmt, ...) {
@@ -163,7 +165,7 @@ void ssb_destroy(ssb_engine_t *e) {
     void *ptrs[] = {e->d_mt, e->d_endow, e->d_tagbits, e->d_tile_counts, e->d_new_order, e->d_scalars,
                     e->d_born_list, e->rc.mark, e->rc.list_a, e->rc.list_b, e->rc.ready, e->rc.cnt, e->rc.trace, e->rc.bucketed, e->rc.epoch_count, e->rc.epoch_start, e->rc.epoch_fill,
                     e->d_partials, e->d_tribes, e->d_stats, e->d_ring, e->d_keys_a, e->d_keys_b, e->d_radix_hist,
-                    e->d_lorenz_blocks, e->d_plan, e->d_cand, e->sh.peer_vals, e->sh.flags, e->d_shard_vals, e->d_migrate, e->d_eth_stats};
+                    e->d_lorenz_blocks, e->d_plan, e->d_cand, e->sh.peer_vals, e->sh.flags, e->d_shard_vals, e->d_migrate, e->d_eth_stats, e->d_ext_stats};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < 5; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
     delete e;
@@ -356,6 +358,47 @@ int ssb_bind_ethics(ssb_engine_t *e, const ssb_ethics_t *eth) {
     return 0;
 }
 
+// ABI 2: lending, friends (ssb_ext_t).  A family is off when its first array pointer is null.
+int ssb_sizeof_ext(void) { return (int)sizeof(ssb_ext_t); }
+
+int ssb_bind_ext(ssb_engine_t *e, const ssb_ext_t *ext) {
+    if (!e || !ext) return -1;
+    if (!e->bound) return fail(e, -1, "engine not bound");
+    if (e->p.rng_mode != SSB_RNG_EXACT) return fail(e, -1, "lending / friends need the exact RNG mode (their lists reach agents anywhere on the map)");
+    if (e->sharded) return fail(e, -1, "lending / friends are not available on a sharded engine");
+    if (ext->capacity != e->ctx.a.capacity) return fail(e, -1, "ext capacity differs from the agent capacity");
+    const ssb_lending_t &L = ext->lending;
+    if (L.lending_factor) {
+        const void *need[] = {L.base_interest_rate, L.loan_duration, L.sugar_mean_income, L.spice_mean_income, L.last_lended, L.last_loans,
+                              L.creditors_head, L.debtors_head, L.loan_other_slot, L.loan_other_id, L.loan_sugar, L.loan_spice,
+                              L.loan_duration_v, L.loan_origin, L.loan_next, L.dead_slot, L.dead_id, L.dead_children_head, L.counters};
+        for (const void *p : need) if (!p) return fail(e, -1, "lending: null array");
+        if (L.pool_capacity <= 0 || L.dead_capacity <= 0) return fail(e, -1, "lending: empty pools");
+    }
+    const ssb_social_t &S = ext->social;
+    if (S.max_friends) {
+        const void *need[] = {S.last_combat, S.social_happiness, S.conflict_happiness, S.n_friends, S.friend_slot, S.friend_id, S.friend_hd};
+        for (const void *p : need) if (!p) return fail(e, -1, "social: null array");
+    }
+    CU(cudaSetDevice(e->device));
+    if (!e->d_ext_stats) {
+        CU(cudaMalloc(&e->d_ext_stats, sizeof(ssb_ext_stats_t)));
+        CU(cudaMemset(e->d_ext_stats, 0, sizeof(ssb_ext_stats_t)));
+    }
+    e->ctx.x = *ext;
+    e->ext_bound = true;
+    return 0;
+}
+
+int ssb_ext_stats(ssb_engine_t *e, ssb_ext_stats_t *host_out) {
+    if (!e || !host_out) return -1;
+    if (!e->ext_bound) return fail(e, -1, "no lending / friends state bound");
+    CU(cudaSetDevice(e->device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(host_out, e->d_ext_stats, sizeof(ssb_ext_stats_t), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 int ssb_ethics_stats(ssb_engine_t *e, ssb_ethics_stats_t *host_out) {
     if (!e || !host_out) return -1;
     if (!e->ethics_bound) return fail(e, -1, "no decision-model state bound");
@@ -422,7 +465,7 @@ int ssb_agent_step(ssb_engine_t *e, int32_t t, double prev_mean_wealth, void *st
     cudaStream_t st = (cudaStream_t)stream_;
     DevCtx c = step_ctx(e, t, prev_mean_wealth);
     if (e->p.rng_mode == SSB_RNG_EXACT) {
-        if (e->ethics_bound) k_agent_step_exact<true><<<1, 32, 0, st>>>(c, e->d_mt);
+        if (e->ethics_bound || e->ext_bound) k_agent_step_exact<true><<<1, 32, 0, st>>>(c, e->d_mt);
         else k_agent_step_exact<false><<<1, 32, 0, st>>>(c, e->d_mt);
         LAUNCHED(e);
     } else {
@@ -539,6 +582,7 @@ int ssb_reduce_stats(ssb_engine_t *e, int32_t t, void *stream_) {
     k_stats_final<<<1, STATS_THREADS, 0, st>>>(c, e->d_partials, e->n_partials, e->d_tribes, e->d_stats); LAUNCHED(e);
     if (e->p.rng_mode == SSB_RNG_EXACT) { k_stats_ordered<<<1, 32, 0, st>>>(c, e->d_stats); LAUNCHED(e); }
     if (e->ethics_bound) { k_ethics_stats<<<1, 32, 0, st>>>(c, e->d_eth_stats); LAUNCHED(e); }
+    if (e->ext_bound) { k_ext_stats<<<1, 32, 0, st>>>(c, e->d_ext_stats); LAUNCHED(e); }
     // Lorenz numerator: sort the wealths (non-negative doubles order like their bit patterns)
     const int64_t cap = c.a.capacity;
     const int tiles = grid_for(cap, RADIX_TILE, e->num_sms * 8);

@@ -1,0 +1,311 @@
+// ssb_ext.cuh -- the reference's rule families beyond the book examples (ABI 2, include/ssb.h: ssb_ext_t),
+// mode E.  Included by ssb_rules.cuh after DevCtx and the basic predicates.  Everything here runs on lane 0
+// of the single ordered warp: the families walk Python lists (loans, friends) whose semantics are
+// sequential -- order of insertion, remove = first equal element, index loops over lists that change
+// underneath -- and they only exist at example scale.
+#pragma once
+
+namespace ssb {
+
+// child endowment bits of the families (sugarscape_b200/steptables.py ENDOWMENT_BITS)
+enum { EB_BASE_INTEREST = 12, EB_LENDING_FACTOR = 13, EB_LOAN_DURATION = 14, EB_MAX_FRIENDS = 15 };
+
+__device__ __forceinline__ bool has_lending(const DevCtx &c) { return c.x.lending.lending_factor != nullptr; }
+__device__ __forceinline__ bool has_social(const DevCtx &c) { return c.x.social.max_friends != nullptr; }
+
+// ---------------------------------------------------------------------------------------------
+// friends + conflict happiness (agent.py:1499-1520 updateFriends; 1099-1105, 912-918)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void social_reset_slot(const DevCtx &c, int s) {
+    const ssb_social_t &S = c.x.social;
+    S.n_friends[s] = 0; S.last_combat[s] = -1; S.social_happiness[s] = 0; S.conflict_happiness[s] = 0;
+}
+
+__device__ inline void friend_remove_at(const ssb_social_t &S, int s, int q) {
+    const long long b = (long long)s * SSB_MAX_FRIENDS;
+    const int n = S.n_friends[s];
+    for (int i = q; i + 1 < n; i++) {
+        S.friend_slot[b + i] = S.friend_slot[b + i + 1]; S.friend_id[b + i] = S.friend_id[b + i + 1];
+        S.friend_hd[b + i] = S.friend_hd[b + i + 1];
+    }
+    S.n_friends[s] = n - 1;
+}
+__device__ inline void friend_append(const ssb_social_t &S, int s, int slot, int id, int hd) {
+    const long long b = (long long)s * SSB_MAX_FRIENDS;
+    const int n = S.n_friends[s];
+    if (n >= SSB_MAX_FRIENDS) return;        // the host refuses agentMaxFriends > SSB_MAX_FRIENDS
+    S.friend_slot[b + n] = slot; S.friend_id[b + n] = id; S.friend_hd[b + n] = hd;
+    S.n_friends[s] = n + 1;
+}
+// list.remove: the first entry with the same agent and distance
+__device__ inline void friend_remove_first(const ssb_social_t &S, int s, int slot, int id, int hd) {
+    const long long b = (long long)s * SSB_MAX_FRIENDS;
+    for (int q = 0; q < S.n_friends[s]; q++)
+        if (S.friend_slot[b + q] == slot && S.friend_id[b + q] == id && S.friend_hd[b + q] == hd) { friend_remove_at(S, s, q); return; }
+}
+// updateFriends (agent.py:1499-1520)
+__device__ __noinline__ void update_friends(const DevCtx &c, int s, int nb) {
+    const ssb_social_t &S = c.x.social;
+    const long long b = (long long)s * SSB_MAX_FRIENDS;
+    const int hd = (c.p.flags & SSB_F_TAGS) ? __popc(c.a.tags[s] ^ c.a.tags[nb]) : 0;
+    const int id = c.a.id[nb];
+    if (S.n_friends[s] < S.max_friends[s]) { friend_append(S, s, nb, id, hd); return; }
+    int max_hd = 0, w_slot = 0, w_id = 0, w_hd = 0;
+    bool have_max = false;
+    for (int p = 0; p < S.n_friends[s]; p++) {
+        const int f_slot = S.friend_slot[b + p], f_id = S.friend_id[b + p], f_hd = S.friend_hd[b + p];
+        if (f_id == id) { friend_remove_first(S, s, f_slot, f_id, f_hd); friend_append(S, s, nb, id, hd); return; }
+        if (f_hd > max_hd) { w_slot = f_slot; w_id = f_id; w_hd = f_hd; max_hd = f_hd; have_max = true; }
+    }
+    if (max_hd > hd && have_max) { friend_remove_first(S, s, w_slot, w_id, w_hd); friend_append(S, s, nb, id, hd); }
+}
+// updateNeighbors -> updateSocialNetwork -> updateFriends, neighbours in N, S, E, W order (agent.py:1563-1565, 1622-1632)
+__device__ inline void update_neighbors(const DevCtx &c, int s, int pos) {
+    int32_t nb4[4];
+    neighbours4(c, pos, nb4);
+    for (int i = 0; i < 4; i++) { const int o = c.g.occ[nb4[i]]; if (o >= 0) update_friends(c, s, o); }
+}
+
+// ---------------------------------------------------------------------------------------------
+// lending
+// ---------------------------------------------------------------------------------------------
+struct Loan { int other_slot, other_id; double sugar, spice; int duration, origin; };
+
+__device__ __forceinline__ Loan loan_load(const ssb_lending_t &L, int e) {
+    Loan l;
+    l.other_slot = L.loan_other_slot[e]; l.other_id = L.loan_other_id[e]; l.sugar = L.loan_sugar[e]; l.spice = L.loan_spice[e];
+    l.duration = L.loan_duration_v[e]; l.origin = L.loan_origin[e];
+    return l;
+}
+__device__ __forceinline__ bool loan_equal(const Loan &x, const Loan &y) {
+    return x.other_slot == y.other_slot && x.other_id == y.other_id && x.sugar == y.sugar && x.spice == y.spice &&
+           x.duration == y.duration && x.origin == y.origin;
+}
+// pool entry p-th of a list, -1 past the end (Python's index loop over a list that changes underneath)
+__device__ inline int loan_at(const ssb_lending_t &L, int head, int p) {
+    int e = head;
+    for (int i = 0; i < p && e >= 0; i++) e = L.loan_next[e];
+    return e;
+}
+__device__ inline void loan_append(const ssb_lending_t &L, int32_t *head, int owner, const Loan &x) {
+    int e;
+    if (L.counters[SSB_LC_FREE_HEAD] > 0) { e = (int)L.counters[SSB_LC_FREE_HEAD] - 1; L.counters[SSB_LC_FREE_HEAD] = L.loan_next[e] + 1; }
+    else {
+        if (L.counters[SSB_LC_POOL_USED] >= L.pool_capacity) { L.counters[SSB_LC_OVERFLOW] = 1; return; }
+        e = (int)L.counters[SSB_LC_POOL_USED]++;
+    }
+    L.loan_other_slot[e] = x.other_slot; L.loan_other_id[e] = x.other_id; L.loan_sugar[e] = x.sugar; L.loan_spice[e] = x.spice;
+    L.loan_duration_v[e] = x.duration; L.loan_origin[e] = x.origin; L.loan_next[e] = -1;
+    if (head[owner] < 0) { head[owner] = e; return; }
+    int t = head[owner];
+    while (L.loan_next[t] >= 0) t = L.loan_next[t];
+    L.loan_next[t] = e;
+}
+__device__ __forceinline__ void loan_free(const ssb_lending_t &L, int e) {
+    L.loan_next[e] = (int)L.counters[SSB_LC_FREE_HEAD] - 1;
+    L.counters[SSB_LC_FREE_HEAD] = e + 1;
+}
+// list.remove(x): the first equal element
+__device__ inline void loan_remove_first(const ssb_lending_t &L, int32_t *head, int owner, const Loan &x) {
+    int prev = -1;
+    for (int e = head[owner]; e >= 0; prev = e, e = L.loan_next[e]) {
+        if (!loan_equal(loan_load(L, e), x)) continue;
+        if (prev < 0) head[owner] = L.loan_next[e]; else L.loan_next[prev] = L.loan_next[e];
+        loan_free(L, e);
+        return;
+    }
+}
+__device__ inline void loan_clear(const ssb_lending_t &L, int32_t *head, int owner) {
+    for (int e = head[owner]; e >= 0;) { const int nx = L.loan_next[e]; loan_free(L, e); e = nx; }
+    head[owner] = -1;
+}
+// a new agent object starts with empty lists
+__device__ inline void lending_reset_slot(const DevCtx &c, int s) {
+    const ssb_lending_t &L = c.x.lending;
+    loan_clear(L, L.creditors_head, s); loan_clear(L, L.debtors_head, s);
+    L.sugar_mean_income[s] = 1; L.spice_mean_income[s] = 1;
+    L.last_lended[s] = -1; L.last_loans[s] = 0;
+}
+__device__ __forceinline__ bool loan_other_alive(const DevCtx &c, const Loan &l) {
+    return c.a.id[l.other_slot] == l.other_id && agent_alive(c, l.other_slot);
+}
+// updateMeanIncome (agent.py:1549-1553), called by collectResourcesAtCell
+__device__ __forceinline__ void lending_note_income(const DevCtx &c, int s, int cs, int cp) {
+    const ssb_lending_t &L = c.x.lending;
+    const double alpha = 0.05;
+    L.sugar_mean_income[s] = (alpha * cs) + ((1 - alpha) * L.sugar_mean_income[s]);
+    L.spice_mean_income[s] = (alpha * cp) + ((1 - alpha) * L.spice_mean_income[s]);
+}
+// doDeath: a creditor that dies keeps its children list in Python (the loan holds the object); remember the
+// head of its kin list, which lives on in the pool after the slot was reused
+__device__ inline void lending_note_death(const DevCtx &c, int s) {
+    const ssb_lending_t &L = c.x.lending;
+    if (L.debtors_head[s] < 0) return;
+    // (atomic: removeDeadAgents' doDeath runs in the parallel compaction kernel)
+    const long long n = (long long)atomicAdd((unsigned long long *)&L.counters[SSB_LC_N_DEAD], 1ull);
+    if (n >= L.dead_capacity) { L.counters[SSB_LC_OVERFLOW] = 2; return; }
+    L.dead_slot[n] = s; L.dead_id[n] = c.a.id[s]; L.dead_children_head[n] = c.a.children_head[s];
+}
+// addLoanToAgent (agent.py:199-211) incl. addLoanFromAgent (190-197)
+__device__ inline void add_loan(const DevCtx &c, int creditor, int debtor, int origin, double sugar_principal, double sugar_loan,
+                                double spice_principal, double spice_loan, int duration) {
+    const ssb_lending_t &L = c.x.lending;
+    const ssb_agents_t &a = c.a;
+    const Loan owed = {creditor, a.id[creditor], sugar_loan, spice_loan, duration, origin};
+    const Loan due = {debtor, a.id[debtor], sugar_loan, spice_loan, duration, origin};
+    loan_append(L, L.creditors_head, debtor, owed);
+    loan_append(L, L.debtors_head, creditor, due);
+    a.sugar[creditor] -= sugar_principal;
+    a.spice[creditor] -= spice_principal;
+    a.sugar[debtor] = a.sugar[debtor] + sugar_principal;
+    a.spice[debtor] = a.spice[debtor] + spice_principal;
+}
+// payDebtToCreditorChildren (agent.py:1362-1377): the loan is split among the dead creditor's living children
+// (the debtor itself excluded), each as a new one-step loan, in the children list's order
+__device__ __noinline__ void pay_debt_to_creditor_children(const DevCtx &c, int s, const Loan &loan) {
+    const ssb_lending_t &L = c.x.lending;
+    const ssb_agents_t &a = c.a;
+    int head = -1;
+    if (a.id[loan.other_slot] == loan.other_id) head = a.children_head[loan.other_slot];
+    else for (long long i = min((long long)L.counters[SSB_LC_N_DEAD], (long long)L.dead_capacity) - 1; i >= 0; i--)
+        if (L.dead_slot[i] == loan.other_slot && L.dead_id[i] == loan.other_id) { head = L.dead_children_head[i]; break; }
+    int32_t kids[256];
+    int n = 0;
+    for (int e = head; e >= 0 && n < 256; e = a.kin_next[e]) {          // newest first (kin_push prepends)
+        const int o = a.kin_slot[e];
+        if (a.id[o] == a.kin_id[e] && agent_alive(c, o) && o != s) kids[n++] = o;
+    }
+    if (n > 0) {
+        const double sugar_rep = loan.sugar / n, spice_rep = loan.spice / n;
+        for (int i = n - 1; i >= 0; i--) add_loan(c, kids[i], s, a.last_moved[s], 0, sugar_rep, 0, spice_rep, 1);   // append order
+    }
+    loan_remove_first(L, L.creditors_head, s, loan);
+    if (a.id[loan.other_slot] == loan.other_id) {
+        const Loan mirror = {s, a.id[s], loan.sugar, loan.spice, loan.duration, loan.origin};
+        loan_remove_first(L, L.debtors_head, loan.other_slot, mirror);
+    }
+}
+// payDebt (agent.py:1330-1360); `loan` is an element of the creditors list of s
+__device__ __noinline__ void pay_debt(const DevCtx &c, int s, const Loan &loan) {
+    const ssb_lending_t &L = c.x.lending;
+    const ssb_agents_t &a = c.a;
+    const int cr = loan.other_slot;
+    const Loan mirror = {s, a.id[s], loan.sugar, loan.spice, loan.duration, loan.origin};
+    const bool same_object = a.id[cr] == loan.other_id;       // the creditor's record still exists
+    if (!loan_other_alive(c, loan)) {
+        if (c.p.inheritance_policy == 1) { pay_debt_to_creditor_children(c, s, loan); return; }
+        loan_remove_first(L, L.creditors_head, s, loan);
+        if (same_object) loan_remove_first(L, L.debtors_head, cr, mirror);
+    } else if (a.sugar[s] - loan.sugar > 0 && a.spice[s] - loan.spice > 0) {
+        a.sugar[s] -= loan.sugar;
+        a.spice[s] -= loan.spice;
+        a.sugar[cr] = a.sugar[cr] + loan.sugar;
+        a.spice[cr] = a.spice[cr] + loan.spice;
+        loan_remove_first(L, L.creditors_head, s, loan);
+        loan_remove_first(L, L.debtors_head, cr, mirror);
+    } else {
+        const double sugar_payout = a.sugar[s] / 2, spice_payout = a.spice[s] / 2;
+        const double sugar_left = loan.sugar - sugar_payout, spice_left = loan.spice - spice_payout;
+        a.sugar[s] -= sugar_payout;
+        a.spice[s] -= spice_payout;
+        a.sugar[cr] = a.sugar[cr] + sugar_payout;
+        a.spice[cr] = a.spice[cr] + spice_payout;
+        const double rate = L.lending_factor[cr] * L.base_interest_rate[cr];
+        const double new_sugar = sugar_left + (rate * sugar_left), new_spice = spice_left + (rate * spice_left);
+        loan_remove_first(L, L.creditors_head, s, loan);
+        loan_remove_first(L, L.debtors_head, cr, mirror);
+        // compounded on the previous loan, no new principal
+        add_loan(c, cr, s, a.last_moved[s], 0, new_sugar, 0, new_spice, L.loan_duration[cr]);
+    }
+}
+// updateLoans (agent.py:1532-1541): Python for-loops over lists that shrink / grow underneath
+__device__ inline void update_loans(const DevCtx &c, int s) {
+    const ssb_lending_t &L = c.x.lending;
+    for (int p = 0;; p++) {
+        const int e = loan_at(L, L.debtors_head[s], p);
+        if (e < 0) break;
+        const Loan l = loan_load(L, e);
+        if (!loan_other_alive(c, l)) loan_remove_first(L, L.debtors_head, s, l);
+    }
+    for (int p = 0;; p++) {
+        const int e = loan_at(L, L.creditors_head[s], p);
+        if (e < 0) break;
+        const Loan l = loan_load(L, e);
+        const int remaining = (c.a.last_moved[s] - l.origin) - l.duration;
+        if (remaining == 0) pay_debt(c, s, l);
+    }
+}
+__device__ inline double current_debt(const ssb_lending_t &L, int head, bool spice) {       // agent.py:920-930
+    double d = 0;
+    for (int e = head; e >= 0; e = L.loan_next[e]) d += (spice ? L.loan_spice[e] : L.loan_sugar[e]) / L.loan_duration_v[e];
+    return d;
+}
+// doLending (agent.py:431-483)
+template <class Rng>
+__device__ __noinline__ void do_lending(const DevCtx &c, int s, Rng &rng) {
+    const ssb_lending_t &L = c.x.lending;
+    const ssb_agents_t &a = c.a;
+    update_loans(c, s);
+    // isLender (agent.py:1285-1296)
+    if (L.lending_factor[s] == 0) return;
+    if (is_fertile(c, s) && (a.sugar[s] <= a.start_sugar[s] || a.spice[s] <= a.start_spice[s])) return;
+    if (a.age[s] < a.fert_age[s]) return;
+    double rate = L.lending_factor[s] * L.base_interest_rate[s];
+    if (rate > 1) rate = 1;
+    int32_t nb[4], borrowers[4];
+    int nbw = 0;
+    neighbours4(c, a.pos[s], nb);
+    for (int i = 0; i < 4; i++) {
+        const int o = c.g.occ[nb[i]];
+        if (o < 0 || !agent_alive(c, o)) continue;
+        // isBorrower (agent.py:1226-1229)
+        if (a.age[o] >= a.fert_age[o] && a.age[o] < a.infert_age[o] && !is_fertile(c, o)) borrowers[nbw++] = o;
+    }
+    rng.at(SITE_LENDING);
+    shuffle(rng, borrowers, nbw);
+    const double pm = eff_spice_metab(c, s), sm = eff_sugar_metab(c, s);
+    int loans = 0;
+    for (int k = 0; k < nbw; k++) {
+        const int b = borrowers[k];
+        double max_sugar = a.sugar[s] / 2, max_spice = a.spice[s] / 2;
+        if (is_fertile(c, s)) {
+            max_sugar = a.sugar[s] - a.start_sugar[s] > 0 ? a.sugar[s] - a.start_sugar[s] : 0;
+            max_spice = a.spice[s] - a.start_spice[s] > 0 ? a.spice[s] - a.start_spice[s] : 0;
+        }
+        if (max_sugar == 0 && max_spice == 0) return;           // (skips the lastLoans bookkeeping, like the reference)
+        const double sugar_need = a.start_sugar[b] - a.sugar[b] > 0 ? a.start_sugar[b] - a.sugar[b] : 0;
+        const double spice_need = a.start_spice[b] - a.spice[b] > 0 ? a.start_spice[b] - a.spice[b] : 0;
+        const double sugar_principal = max_sugar < sugar_need ? max_sugar : sugar_need;
+        const double spice_principal = max_spice < spice_need ? max_spice : spice_need;
+        const double sugar_amount = sugar_principal + (sugar_principal * rate);
+        const double spice_amount = spice_principal + (spice_principal * rate);
+        if ((sugar_need == 0 && spice_need == 0) || (sugar_amount == 0 && spice_amount == 0)) continue;
+        if (a.sugar[s] - sugar_principal <= sm || a.spice[s] - spice_principal <= pm) continue;
+        // isCreditWorthy (agent.py:1231-1242)
+        const int duration = L.loan_duration[s];
+        if (duration == 0) continue;
+        const double bpm = eff_spice_metab(c, b), bsm = eff_sugar_metab(c, b);
+        const double sugar_cost = sugar_amount / duration, spice_cost = spice_amount / duration;
+        const double sugar_income = ((L.sugar_mean_income[b] - bsm) - current_debt(L, L.creditors_head[b], false)) - sugar_cost;
+        const double spice_income = ((L.spice_mean_income[b] - bpm) - current_debt(L, L.creditors_head[b], true)) - spice_cost;
+        if (!(sugar_income >= 0 && spice_income >= 0)) continue;
+        add_loan(c, s, b, a.last_moved[s], sugar_principal, sugar_amount, spice_principal, spice_amount, duration);
+        loans++;
+    }
+    if (loans > 0) { L.last_lended[s] = c.t; L.last_loans[s] = loans; }
+}
+
+// reductions of the families' log keys, list order (sugarscape.py:1130-1160)
+__device__ inline void ext_stats_body(const DevCtx &c, ssb_ext_stats_t *out) {
+    ssb_ext_stats_t r;
+    r.loan_volume = 0; r.sum_social_happiness = 0; r.sum_conflict_happiness = 0;
+    const long long n = c.a.counters[SSB_C_N_LIST];
+    for (long long i = 0; i < n; i++) {
+        const int s = c.a.order[i];
+        if (has_lending(c) && c.x.lending.last_lended[s] == c.t) r.loan_volume += c.x.lending.last_loans[s];
+        if (has_social(c)) { r.sum_social_happiness += c.x.social.social_happiness[s]; r.sum_conflict_happiness += c.x.social.conflict_happiness[s]; }
+    }
+    *out = r;
+}
+
+}  // namespace ssb

@@ -205,8 +205,9 @@ __global__ void __launch_bounds__(COMPACT_THREADS) k_compact_scatter(DevCtx c, c
         if (alive[k]) new_order[at++] = slots[k];
         else {
             const int s = slots[k];
-            if (c.a.cod[s] == SSB_ALIVE) do_death(c, s, SSB_OTHER);   // removeDeadAgents -> doDeath()
-            else if (c.a.pos[s] >= 0) do_death(c, s, c.a.cod[s]);
+            // (the <true> instantiation only adds null checks of the optional families' arrays)
+            if (c.a.cod[s] == SSB_ALIVE) do_death<true>(c, s, SSB_OTHER);   // removeDeadAgents -> doDeath()
+            else if (c.a.pos[s] >= 0) do_death<true>(c, s, c.a.cod[s]);
             c.a.dead_list[dead_at++] = s;
         }
     }

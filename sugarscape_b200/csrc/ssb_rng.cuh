@@ -77,7 +77,8 @@ struct RngExact {
 // Call sites of the agent transaction that draw random numbers (reference agent.py:1401, 560-564,
 // 616, 505-513).  Each site of each agent has its own substream, so the two commit phases of the
 // scalable kernel need no RNG state between them.
-enum { SITE_MOVE = 0, SITE_TAGGING = 1, SITE_TRADING = 2, SITE_REPRODUCTION = 3 };
+enum { SITE_MOVE = 0, SITE_TAGGING = 1, SITE_TRADING = 2, SITE_REPRODUCTION = 3, /* 4 = new tribe tags */
+       SITE_LENDING = 5, SITE_DISEASE = 6 };
 
 struct RngStream {
     uint64_t key;

@@ -39,6 +39,7 @@ struct DevCtx {
     int32_t *born_list;              // slots of this step's newborn (unordered)
     ShardCtx sh;                     // world <= 1: the whole simulation lives on this GPU
     ssb_ethics_t eth;                // ABI 2, mode E: decision models (eth.model == nullptr: every agent is a plain Agent)
+    ssb_ext_t x;                     // ABI 2, mode E: lending, friends ... (a family is off when its first array is null)
 };
 
 __device__ __forceinline__ int wrapi(int v, int n) { v %= n; return v < 0 ? v + n : v; }
@@ -204,7 +205,12 @@ __device__ __noinline__ void do_inheritance(const DevCtx &c, int s) {
 }
 
 // Agent.doDeath (agent.py:296-313)
+__device__ __forceinline__ bool has_lending(const DevCtx &c);          // ssb_ext.cuh
+__device__ inline void lending_note_death(const DevCtx &c, int s);
+
+template <bool EXT = false>
 __device__ __forceinline__ void do_death(const DevCtx &c, int s, int cause) {
+    if (EXT && has_lending(c)) lending_note_death(c, s);
     c.a.cod[s] = cause;
     const int pos = c.a.pos[s];
     if (pos >= 0 && c.g.occ[pos] == s) c.g.occ[pos] = -1;
@@ -246,12 +252,23 @@ __device__ __forceinline__ void neighbours4(const DevCtx &c, int pos, int32_t ou
     out[3] = (x == 0 ? W - 1 : x - 1) * H + y;
 }
 
+// findSugarMetabolism / findSpiceMetabolism / findAggression (agent.py:716-717, 1031-1032, 1107-1111, 1161-1162)
+__device__ __forceinline__ double eff_sugar_metab(const DevCtx &c, int s) { return (double)max(c.a.sugar_metab[s], 0); }
+__device__ __forceinline__ double eff_spice_metab(const DevCtx &c, int s) { return (double)max(c.a.spice_metab[s], 0); }
+__device__ __forceinline__ double eff_aggression(const DevCtx &c, int s) { return fmax(c.a.aggression[s], 0.0); }
+
+}  // namespace ssb
+#include "ssb_ext.cuh"
+namespace ssb {
+
 // collectResourcesAtCell (agent.py:249-259) + production pollution (cell.py:32-45)
+template <bool EXT = false>
 __device__ __forceinline__ void collect(const DevCtx &c, int s, int pos) {
     const int32_t cs = c.g.sugar[pos];
     const int32_t cp = (c.p.flags & SSB_F_SPICE) ? c.g.spice[pos] : 0;
     c.a.sugar[s] += cs;
     c.a.spice[s] += cp;
+    if (EXT && has_lending(c)) lending_note_income(c, s, cs, cp);
     if (c.p.pollution_start <= c.t && c.t <= c.p.pollution_end) {
         double pl = c.g.pollution[pos];
         pl += c.p.sugar_prod_pollution * cs;
@@ -669,14 +686,22 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rn
                 const double sl = fmin(loot, a.sugar[prey]), pl = fmin(loot, a.spice[prey]);
                 sugar += sl; spice += pl;
                 a.sugar[prey] -= sl; a.spice[prey] -= pl;
-                do_death(c, prey, SSB_COMBAT);
+                if (EXT && has_social(c)) c.x.social.last_combat[s] = c.t;
+                // the prey's heirs may include the killer itself (its own parent fell): keep memory current
+                // around the inheritance (agent.py:274-294 updates self.sugar before prey.doDeath)
+                const bool heirs = c.p.inheritance_policy != 0;
+                if (heirs) { a.sugar[s] = sugar; a.spice[s] = spice; }
+                do_death<EXT>(c, prey, SSB_COMBAT);
+                if (heirs) { sugar = a.sugar[s]; spice = a.spice[s]; }
             }
         }
         c.g.occ[pos] = -1;
         c.g.occ[best] = s;
+        if (EXT && has_social(c)) update_neighbors(c, s, best);   // (updateFriends reads tags and ids only: the holdings are still in registers)
         // collectResourcesAtCell (agent.py:249-259) + production pollution (cell.py:32-45)
         sugar += b_cs;
         spice += b_cp;
+        if (EXT && has_lending(c)) lending_note_income(c, s, b_cs, b_cp);
         const bool polluting = c.p.pollution_start <= c.t && c.t <= c.p.pollution_end;
         double cell_poll = b_pl;
         if (polluting) {
@@ -702,6 +727,7 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rn
         a.pos[s] = best;
         if (sugar < 0 || spice < 0 || (sugar <= 0 && sm > 0) || (spice <= 0 && pm > 0)) {
             // doDeath("starvation") (agent.py:296-313)
+            if (EXT && has_lending(c)) lending_note_death(c, s);
             a.cod[s] = SSB_STARVATION;
             c.g.occ[best] = -1;
             a.pos[s] = -1;
@@ -956,6 +982,17 @@ __device__ __noinline__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
             c.eth.lookahead_discount[ch] = c.eth.lookahead_discount[from];
             c.eth.last_move_optimal[ch] = 1; c.eth.move_rank[ch] = 0; c.eth.move_diff[ch] = 0;      // lastMoveOptimal starts True
         }
+        if (EXT && has_social(c)) {
+            social_reset_slot(c, ch);
+            c.x.social.max_friends[ch] = ((eb >> EB_MAX_FRIENDS) & 1u) ? c.x.social.max_friends[m] : c.x.social.max_friends[s];
+        }
+        if (EXT && has_lending(c)) {
+            const ssb_lending_t &L = c.x.lending;
+            lending_reset_slot(c, ch);
+            L.base_interest_rate[ch] = ((eb >> EB_BASE_INTEREST) & 1u) ? L.base_interest_rate[m] : L.base_interest_rate[s];
+            L.lending_factor[ch] = ((eb >> EB_LENDING_FACTOR) & 1u) ? L.lending_factor[m] : L.lending_factor[s];
+            L.loan_duration[ch] = ((eb >> EB_LOAN_DURATION) & 1u) ? L.loan_duration[m] : L.loan_duration[s];
+        }
         a.pos[ch] = cell;
         c.g.occ[cell] = ch;
         for (int q = 0; q < 4; q++) {       // keep the local copies current
@@ -969,7 +1006,7 @@ __device__ __noinline__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
         } else {
             if (nth < a.capacity) c.born_list[nth] = ch; else atomicExch(&cn[SSB_C_OVERFLOW], 1ull);
         }
-        collect(c, ch, cell);      // the child collects at birth (agent.py:175)
+        collect<EXT>(c, ch, cell);      // the child collects at birth (agent.py:175)
         if (EXACT) {               // kin bookkeeping of the initiating parent (agent.py:521-527)
             bool known = false;
             for (int e = a.mates_head[s]; e >= 0; e = a.kin_next[e])
@@ -996,14 +1033,16 @@ __device__ void transaction_interact_phase(const DevCtx &c, int s, const AgentRe
     // doReproduction starts with isFertile(): only trading can have raised the holdings since the
     // move part, so without trade the record decides and most agents skip the call
     if ((c.p.flags & SSB_F_REPRO) && ((c.p.flags & SSB_F_TRADE) || rec.fertile())) do_reproduction<Rng, EXACT, EXT>(c, s, rng);
+    const bool lending = EXT && has_lending(c);
+    if (lending) do_lending(c, s, rng);
     // doAging (agent.py:266-272); reproduction and trading leave the agent alive (isAlive looks at
     // the holdings, which they may have changed)
     double sugar = rec.sugar, spice = rec.spice;
-    if (c.p.flags & (SSB_F_TRADE | SSB_F_REPRO)) { sugar = a.sugar[s]; spice = a.spice[s]; }
+    if ((c.p.flags & (SSB_F_TRADE | SSB_F_REPRO)) || lending) { sugar = a.sugar[s]; spice = a.spice[s]; }
     if (!(sugar >= 0 && spice >= 0)) return;     // isAlive() false: no aging, no happiness update
     const int age = rec.age + 1;
     a.age[s] = age;
-    if (age >= rec.max_age && rec.max_age != -1) { do_death(c, s, SSB_AGING); return; }
+    if (age >= rec.max_age && rec.max_age != -1) { do_death<EXT>(c, s, SSB_AGING); return; }
     // updateHappiness (agent.py:1522-1530): conflict (0: no aggression in the supported examples'
     // logs) + family + health (+1: no diseases) + social (0: no friends) + wealth
     const double wealth_h = erf((sugar + spice) - c.prev_mean_wealth);
@@ -1020,7 +1059,17 @@ __device__ void transaction_interact_phase(const DevCtx &c, int s, const AgentRe
     const double family_h = erf(family);
     a.wealth_happiness[s] = wealth_h;
     a.family_happiness[s] = family_h;
-    a.happiness[s] = family_h + 1.0 + wealth_h;
+    if (EXT && has_social(c)) {
+        // findConflictHappiness (agent.py:912-918), findSocialHappiness (1099-1105)
+        const ssb_social_t &S = c.x.social;
+        double conflict_h = 0, social_h = 0;
+        if (S.last_combat[s] == c.t) conflict_h = eff_aggression(c, s) > 1 ? 1.0 : 1.0 * -1;
+        if (S.max_friends[s] != 0) social_h = ((S.n_friends[s] * (2.0 / S.max_friends[s])) - 1) * 1.0;
+        S.conflict_happiness[s] = conflict_h; S.social_happiness[s] = social_h;
+        a.happiness[s] = conflict_h + family_h + 1.0 + social_h + wealth_h;
+    } else {
+        a.happiness[s] = family_h + 1.0 + wealth_h;
+    }
 }
 
 }  // namespace ssb

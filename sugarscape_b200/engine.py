@@ -74,6 +74,9 @@ def load_library():
     L.ssb_bind_ethics.argtypes = [E, C.POINTER(layout.Ethics)]
     L.ssb_ethics_stats.argtypes = [E, C.POINTER(layout.EthicsStats)]
     L.ssb_sizeof_ethics.restype = C.c_int
+    L.ssb_bind_ext.argtypes = [E, C.POINTER(layout.Ext)]
+    L.ssb_ext_stats.argtypes = [E, C.POINTER(layout.ExtStats)]
+    L.ssb_sizeof_ext.restype = C.c_int
     L.ssb_pollution_buffer.argtypes = [E]
     L.ssb_pollution_buffer.restype = C.c_int
     L.ssb_round_trace.argtypes = [E, C.c_int32, C.c_void_p, C.c_int32]
@@ -85,7 +88,7 @@ def load_library():
     if L.ssb_abi_version() != layout.ABI_VERSION:
         raise EngineError("libssb.so ABI version does not match sugarscape_b200.layout")
     for name, struct in (("params", layout.Params), ("grid", layout.Grid), ("agents", layout.Agents),
-                         ("stats", layout.Stats), ("ethics", layout.Ethics)):
+                         ("stats", layout.Stats), ("ethics", layout.Ethics), ("ext", layout.Ext)):
         if getattr(L, "ssb_sizeof_" + name)() != C.sizeof(struct):
             raise EngineError(f"struct ssb_{name}_t: library and ctypes mirror disagree on size")
     _LIB = L
@@ -100,7 +103,7 @@ EXPORTED_SYMBOLS = (
     "ssb_fabric_create", "ssb_fabric_alloc", "ssb_fabric_map", "ssb_fabric_copy", "ssb_fabric_granularity",
     "ssb_fabric_destroy", "ssb_fabric_last_error", "ssb_set_shard", "ssb_migrate", "ssb_shard_barrier", "ssb_shard_broken",
     "ssb_sync", "ssb_pollution_buffer", "ssb_test_pow", "ssb_round_trace", "ssb_launch_count", "ssb_timing", "ssb_enable_timing",
-    "ssb_bind_ethics", "ssb_ethics_stats", "ssb_sizeof_ethics",
+    "ssb_bind_ethics", "ssb_ethics_stats", "ssb_sizeof_ethics", "ssb_bind_ext", "ssb_ext_stats", "ssb_sizeof_ext",
 )
 
 
@@ -118,6 +121,8 @@ class Engine:
         self.width, self.height, self.capacity = host_state.width, host_state.height, host_state.capacity
         self.kin_capacity = host_state.kin_capacity
         self.tensors = {}
+        if (host_state.ethics is not None or host_state.ext is not None) and params.rng_mode != layout.RNG_EXACT:
+            raise EngineError("decision models, lending and friends exist in the exact RNG mode only")
         self._upload_all(host_state)
         self.handle = C.c_void_p()
         self._check(self.L.ssb_create(C.byref(params), device, C.byref(self.handle)))
@@ -130,6 +135,13 @@ class Engine:
             for name, _, _ in layout.ETHICS_FIELDS:
                 setattr(es, name, self.tensors["eth_" + name].data_ptr())
             self._check(self.L.ssb_bind_ethics(self.handle, C.byref(es)))
+        self.ext = host_state.ext                # HostExt (arrays in self.tensors as "ext:<family>.<member>") or None
+        if self.ext is not None:
+            xs = self.ext.as_struct(lambda arr: None)
+            for key in self.ext.arrays:
+                fam, member = key.split(".")
+                setattr(getattr(xs, fam), member, self.tensors["ext:" + key].data_ptr())
+            self._check(self.L.ssb_bind_ext(self.handle, C.byref(xs)))
         if endow_bits is not None:
             eb = np.ascontiguousarray(endow_bits, dtype=np.uint32)
             tb = np.ascontiguousarray(tag_bits, dtype=np.uint32)
@@ -161,6 +173,9 @@ class Engine:
         if hs.ethics is not None:
             for name, _, _ in layout.ETHICS_FIELDS:
                 self.tensors["eth_" + name] = self._to_device(hs.ethics.arrays[name])
+        if hs.ext is not None:
+            for key, arr in hs.ext.arrays.items():
+                self.tensors["ext:" + key] = self._to_device(arr)
 
     def _structs(self):
         g = layout.Grid()
@@ -200,6 +215,8 @@ class Engine:
         hs.kin_capacity = self.kin_capacity
         if self.ethics is not None:
             hs.ethics = self.ethics.copy()
+        if self.ext is not None:
+            hs.ext = self.ext.copy()
         self.torch.cuda.synchronize(self.device)
         swapped = bool(self.L.ssb_pollution_buffer(self.handle))
         for key, tensor in self.tensors.items():
@@ -212,6 +229,8 @@ class Engine:
                 arr = arr.view(np.uint32)
             if key.startswith("eth_"):
                 hs.ethics.arrays[key[4:]] = arr
+            elif key.startswith("ext:"):
+                hs.ext.arrays[key[4:]] = arr
             else:
                 setattr(hs, key, arr)
         return hs
@@ -219,7 +238,8 @@ class Engine:
     def upload(self, hs, fields):
         swapped = bool(self.L.ssb_pollution_buffer(self.handle))
         for key in fields:
-            arr = hs.ethics.arrays[key[4:]] if key.startswith("eth_") else getattr(hs, key)
+            arr = (hs.ethics.arrays[key[4:]] if key.startswith("eth_") else
+                   hs.ext.arrays[key[4:]] if key.startswith("ext:") else getattr(hs, key))
             if swapped and key in ("pollution", "pollution_flux"):
                 key = "pollution_flux" if key == "pollution" else "pollution"
             if arr.dtype == np.uint32:
@@ -285,6 +305,18 @@ class Engine:
             return None
         out = layout.EthicsStats()
         self._check(self.L.ssb_ethics_stats(self.handle, C.byref(out)))
+        return out
+
+    def ext_stats(self):
+        """Lending / friends reductions of the last reduce_stats (None without those families); raises when a
+        loan pool overflowed."""
+        if self.ext is None:
+            return None
+        if "lending" in self.ext.families:
+            if int(self.tensors["ext:lending.counters"][layout.LC_OVERFLOW].item()) != 0:
+                raise EngineError("loan pool exhausted")
+        out = layout.ExtStats()
+        self._check(self.L.ssb_ext_stats(self.handle, C.byref(out)))
         return out
 
     def stats_history(self, t):

@@ -99,14 +99,12 @@ def check_supported(c):
         problems.append("diseases")
     if c["agentDepressionPercentage"] > 0:
         problems.append("depression")
-    if c["agentLendingFactor"][1] > 0:
-        problems.append("lending")
     if c["agentRacialTagStringLength"] > 0 and c["environmentMaxRaces"] > 0:
         problems.append("racial tags")
     if c["agentInheritancePolicy"] not in ("none", "children", "sons", "daughters"):
         problems.append("inheritance policy " + str(c["agentInheritancePolicy"]))
-    if c["agentMaxFriends"][1] > 0:
-        problems.append("friends")
+    if c["agentMaxFriends"][1] > layout.MAX_FRIENDS:
+        problems.append("more than %d friends" % layout.MAX_FRIENDS)
     if c["agentUniversalSugar"][1] != 0 or c["agentUniversalSpice"][1] != 0:
         problems.append("universal income")
     bad_models = [m for m in c["agentDecisionModels"] if m not in SUPPORTED_DECISION_MODELS]
@@ -491,6 +489,8 @@ def build_initial_state(c, capacity=None, check=True):
 
     if uses_decision_models(c):
         state.ethics = layout.HostEthics(capacity, c)
+    if layout.HostExt.needed(c):
+        state.ext = layout.HostExt(capacity, c)
 
     occupied = np.zeros(W * H, dtype=bool)
     new_agents = pop.place(n0, occupied, 0, 0) if n0 > 0 else []

@@ -261,6 +261,128 @@ class HostEthics:
         return h
 
 
+# ---- ABI 2: optional rule families (ssb_ext_t): lending, friends ----
+_I32, _F64, _I64 = np.int32, np.float64, np.int64
+LC_POOL_USED, LC_FREE_HEAD, LC_N_DEAD, LC_OVERFLOW, LC_COUNT = 0, 1, 2, 3, 8
+MAX_FRIENDS = 16
+# (struct member, dtype, fill, length in units of: "cap" slots / "pool" loans / "dead" creditors / "friends" = cap * 16 / int)
+LENDING_LAYOUT = (
+    ("lending_factor", _F64, 0, "cap"), ("base_interest_rate", _F64, 0, "cap"), ("loan_duration", _I32, 0, "cap"),
+    ("sugar_mean_income", _F64, 1, "cap"), ("spice_mean_income", _F64, 1, "cap"),
+    ("last_lended", _I32, -1, "cap"), ("last_loans", _I32, 0, "cap"),
+    ("creditors_head", _I32, -1, "cap"), ("debtors_head", _I32, -1, "cap"),
+    ("pool_capacity", None, None, None),
+    ("loan_other_slot", _I32, -1, "pool"), ("loan_other_id", _I32, -1, "pool"),
+    ("loan_sugar", _F64, 0, "pool"), ("loan_spice", _F64, 0, "pool"),
+    ("loan_duration_v", _I32, 0, "pool"), ("loan_origin", _I32, 0, "pool"), ("loan_next", _I32, -1, "pool"),
+    ("dead_capacity", None, None, None),
+    ("dead_slot", _I32, -1, "dead"), ("dead_id", _I32, -1, "dead"), ("dead_children_head", _I32, -1, "dead"),
+    ("counters", _I64, 0, LC_COUNT),
+)
+SOCIAL_LAYOUT = (
+    ("max_friends", _I32, 0, "cap"), ("last_combat", _I32, -1, "cap"),
+    ("social_happiness", _F64, 0, "cap"), ("conflict_happiness", _F64, 0, "cap"), ("n_friends", _I32, 0, "cap"),
+    ("friend_slot", _I32, -1, "friends"), ("friend_id", _I32, -1, "friends"), ("friend_hd", _I32, 0, "friends"),
+)
+EXT_FAMILIES = (("lending", LENDING_LAYOUT), ("social", SOCIAL_LAYOUT))
+
+
+def _family_struct(name, table):
+    return type(name, (C.Structure,), {"_fields_": [(n, C.c_int64 if dt is None else C.c_void_p) for n, dt, _, _ in table]})
+
+
+Lending = _family_struct("Lending", LENDING_LAYOUT)
+Social = _family_struct("Social", SOCIAL_LAYOUT)
+
+
+class Ext(C.Structure):
+    _fields_ = [("capacity", C.c_int64), ("lending", Lending), ("social", Social)]
+
+
+class ExtStats(C.Structure):
+    _fields_ = [("loan_volume", C.c_int64), ("sum_social_happiness", C.c_double), ("sum_conflict_happiness", C.c_double)]
+
+
+class HostExt:
+    """Host mirror of ssb_ext_t: the per-slot state of the optional rule families that are live in this
+    configuration.  `arrays["<family>.<member>"]` are numpy arrays; a family that is off has none."""
+
+    def __init__(self, capacity, c):
+        self.capacity = capacity
+        self.families = set()
+        if c["agentLendingFactor"][1] > 0:
+            self.families.add("lending")
+        if c["agentMaxFriends"][1] > 0:
+            self.families.add("social")
+        self.sizes = {"cap": capacity, "pool": 8 * capacity, "dead": 4 * capacity, "friends": capacity * MAX_FRIENDS}
+        self.arrays = {}
+        for fam, table in EXT_FAMILIES:
+            if fam not in self.families:
+                continue
+            for n, dt, fill, length in table:
+                if dt is not None:
+                    self.arrays[fam + "." + n] = np.full(self.sizes.get(length, length), fill, dtype=dt)
+
+    @staticmethod
+    def needed(c):
+        return c["agentLendingFactor"][1] > 0 or c["agentMaxFriends"][1] > 0
+
+    def _free_chain(self, head):
+        """Give the loan records of a list back to the pool (a new agent object starts with empty lists)."""
+        A = self.arrays
+        nxt, cnt = A["lending.loan_next"], A["lending.counters"]
+        while head >= 0:
+            following = int(nxt[head])
+            nxt[head] = int(cnt[LC_FREE_HEAD]) - 1
+            cnt[LC_FREE_HEAD] = head + 1
+            head = following
+
+    def set_slot(self, slot, endowment):
+        """A freshly configured agent (initial population or replacement) takes `slot`."""
+        A = self.arrays
+        if "lending" in self.families:
+            for name in ("creditors_head", "debtors_head"):
+                self._free_chain(int(A["lending." + name][slot]))
+                A["lending." + name][slot] = -1
+            A["lending.lending_factor"][slot] = endowment["lendingFactor"]
+            A["lending.base_interest_rate"][slot] = endowment["baseInterestRate"]
+            A["lending.loan_duration"][slot] = endowment["loanDuration"]
+            A["lending.sugar_mean_income"][slot] = 1
+            A["lending.spice_mean_income"][slot] = 1
+            A["lending.last_lended"][slot] = -1
+            A["lending.last_loans"][slot] = 0
+        if "social" in self.families:
+            A["social.max_friends"][slot] = endowment["maxFriends"]
+            A["social.last_combat"][slot] = -1
+            A["social.social_happiness"][slot] = 0
+            A["social.conflict_happiness"][slot] = 0
+            A["social.n_friends"][slot] = 0
+
+    def as_struct(self, pointer_of=lambda arr: arr.ctypes.data):
+        x = Ext()
+        x.capacity = self.capacity
+        for fam, table in EXT_FAMILIES:
+            if fam not in self.families:
+                continue
+            sub = getattr(x, fam)
+            for n, dt, _, _ in table:
+                if dt is None:
+                    setattr(sub, n, self.sizes[n.split("_")[0]])      # pool_capacity / dead_capacity
+                else:
+                    setattr(sub, n, pointer_of(self.arrays[fam + "." + n]))
+        return x
+
+    def check_overflow(self):
+        if "lending" in self.families and self.arrays["lending.counters"][LC_OVERFLOW] != 0:
+            raise MemoryError("loan pool exhausted")
+
+    def copy(self):
+        h = HostExt.__new__(HostExt)
+        h.capacity, h.families, h.sizes = self.capacity, set(self.families), dict(self.sizes)
+        h.arrays = {k: v.copy() for k, v in self.arrays.items()}
+        return h
+
+
 def default_capacity(c, n0):
     """Slots to allocate: births and replacements append, dead slots are recycled."""
     cells = c["environmentWidth"] * c["environmentHeight"]
@@ -313,6 +435,7 @@ class HostState:
     def __init__(self, width, height, capacity):
         self.width, self.height, self.capacity = width, height, capacity
         self.ethics = None          # HostEthics when the configuration uses decision models (ABI 2)
+        self.ext = None             # HostExt when lending / friends ... are live (ABI 2)
 
     @classmethod
     def empty(cls, width, height, capacity, kin_capacity=None):
@@ -340,6 +463,7 @@ class HostState:
         for name in KIN_FIELDS:
             setattr(s, name, getattr(self, name).copy())
         s.ethics = self.ethics.copy() if self.ethics is not None else None
+        s.ext = self.ext.copy() if self.ext is not None else None
         return s
 
     def as_structs(self):
@@ -405,6 +529,8 @@ class HostState:
             self.a_tribe[slot] = a["tribe"]
             if self.ethics is not None:
                 self.ethics.set_slot(slot, e)
+            if self.ext is not None:
+                self.ext.set_slot(slot, e)
             self.a_order[n_list] = slot
             self.occ[a["cell"]] = slot
             n_list += 1

@@ -31,8 +31,8 @@ class Sugarscape:
         self.end = False
         if not c["headlessMode"]:
             raise init.UnsupportedConfiguration("the GUI is out of scope: set headlessMode to true")
-        if self.rng_mode != layout.RNG_EXACT and init.uses_decision_models(c):
-            raise init.UnsupportedConfiguration("the ethics decision models need b200RngMode 'exact'")
+        if self.rng_mode != layout.RNG_EXACT and (init.uses_decision_models(c) or layout.HostExt.needed(c)):
+            raise init.UnsupportedConfiguration("decision models, lending and friends need b200RngMode 'exact'")
         state, self.population = init.build_initial_state(c)
         self.params = layout.make_params(c, self.rng_mode, init.rule_flags(c), init.max_agent_range(c),
                                          init.equator(c))
@@ -102,7 +102,7 @@ class Sugarscape:
             self.engine.reduce_stats(self.timestep)
             st = self.engine.stats()
         self.stats_builder.update(st, self.timestep, int(st.n_replaced) if replaced is None else replaced,
-                                  self.engine.ethics_stats())
+                                  self.engine.ethics_stats(), self.engine.ext_stats())
         self.n_agents = int(st.population)
 
     # -- the run loop and the log (format: SURVEY.md Appendix F) -----------------------------------

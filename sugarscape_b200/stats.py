@@ -88,9 +88,10 @@ class StatsBuilder:
             lo, hi = c[option]
             self.constant[key] = lo if lo == hi else None
 
-    def update(self, st, t, n_replaced=0, ethics=None):
+    def update(self, st, t, n_replaced=0, ethics=None, ext=None):
         """st: layout.Stats filled by the device (or by the oracle in the tests); ethics: layout.EthicsStats
-        when the run uses decision models (sugarscape.py:1141-1160, 1218-1222, 1304, 1318, 1323-1324)."""
+        when the run uses decision models (sugarscape.py:1141-1160, 1218-1222, 1304, 1318, 1323-1324); ext:
+        layout.ExtStats when lending / friends are live (loanVolume, social and conflict happiness)."""
         c, rs = self.c, self.runtime_stats
         n = int(st.population)
         prev_cc = rs["carryingCapacity"]
@@ -162,6 +163,10 @@ class StatsBuilder:
                 if value is None:
                     raise NotImplementedError(key + " needs per-agent factors")
                 out[key] = round(value * n / n, 2)
+            if ext is not None:
+                out["loanVolume"] = int(ext.loan_volume)
+                out["meanSocialHappiness"] = round(ext.sum_social_happiness / n, 2)
+                out["meanConflictHappiness"] = round(ext.sum_conflict_happiness / n, 2)
             if ethics is not None:
                 out["meanSelfishness"] = round(ethics.sum_selfishness / n, 2)
                 out["agentLastMoveOptimalityPercentage"] = round((ethics.optimal_moves / ethics.moves) * 100, 2)

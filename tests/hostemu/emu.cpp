@@ -15,7 +15,7 @@ int emu_abi_version(void) { return SSB_ABI_VERSION; }
 /* mt: 624 state words + the index (the engine's d_mt layout) */
 int emu_agent_step_exact(const ssb_params_t *p, const ssb_grid_t *g, const ssb_agents_t *a, uint32_t *mt, int32_t t,
                          double prev_mean_wealth, const uint32_t *endow_bits, const uint32_t *tag_bits, int32_t n_tables,
-                         const ssb_ethics_t *ethics) {
+                         const ssb_ethics_t *ethics, const ssb_ext_t *ext) {
     if (!p || !g || !a || !mt || p->rng_mode != SSB_RNG_EXACT) return -1;
     DevCtx c;
     memset(&c, 0, sizeof(c));
@@ -28,12 +28,22 @@ int emu_agent_step_exact(const ssb_params_t *p, const ssb_grid_t *g, const ssb_a
     c.prev_mean_wealth = prev_mean_wealth;
     c.endow_bits = endow_bits; c.tag_bits = tag_bits; c.n_step_tables = n_tables;
     alignas(8) unsigned char scratch[warp_scratch_bytes(MAXC_EXACT)];
-    if (ethics) {          /* as ssb_agent_step: the extended instantiation only when an extension is bound */
-        c.eth = *ethics;
+    if (ethics || ext) {   /* as ssb_agent_step: the extended instantiation only when an extension is bound */
+        if (ethics) c.eth = *ethics;
+        if (ext) c.x = *ext;
         agent_step_exact_body<1, true>(c, mt, make_warp_scratch(scratch, MAXC_EXACT));
     } else {
         agent_step_exact_body<1, false>(c, mt, make_warp_scratch(scratch, MAXC_EXACT));
     }
+    return 0;
+}
+
+int emu_ext_stats(const ssb_agents_t *a, const ssb_ext_t *ext, int32_t t, ssb_ext_stats_t *out) {
+    if (!a || !ext || !out) return -1;
+    DevCtx c;
+    memset(&c, 0, sizeof(c));
+    c.a = *a; c.x = *ext; c.t = t;
+    ext_stats_body(c, out);
     return 0;
 }
 

@@ -23,7 +23,8 @@ def lib():
         L = C.CDLL(os.path.join(HERE, "libssb_hostemu.so"))
         P, G, A = C.POINTER(layout.Params), C.POINTER(layout.Grid), C.POINTER(layout.Agents)
         L.emu_agent_step_exact.argtypes = [P, G, A, C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_int32,
-                                           C.POINTER(layout.Ethics)]
+                                           C.POINTER(layout.Ethics), C.POINTER(layout.Ext)]
+        L.emu_ext_stats.argtypes = [A, C.POINTER(layout.Ext), C.c_int32, C.POINTER(layout.ExtStats)]
         L.emu_ethics_stats.argtypes = [A, C.POINTER(layout.Ethics), C.POINTER(layout.EthicsStats)]
         assert L.emu_abi_version() == layout.ABI_VERSION
         _LIB = L
@@ -51,11 +52,25 @@ class HostEmu(Oracle):
         tb = self.tag_bits.ctypes.data if self.tag_bits is not None else None
         n = len(self.endow_bits) if self.endow_bits is not None else 0
         eth = C.byref(self.state.ethics.as_struct()) if self.state.ethics is not None else None
+        ext = C.byref(self.state.ext.as_struct()) if self.state.ext is not None else None
         rc = self.E.emu_agent_step_exact(C.byref(self.params), C.byref(g), C.byref(a), self.mt.ctypes.data, t,
-                                         prev_mean_wealth, eb, tb, n, eth)
+                                         prev_mean_wealth, eb, tb, n, eth, ext)
         assert rc == 0, f"emu_agent_step_exact failed: {rc}"
+        if self.state.ext is not None:
+            self.state.ext.check_overflow()
+
+    def ext_stats(self, t):
+        if self.state.ext is None:
+            return None
+        g, a = self.state.as_structs()
+        out = layout.ExtStats()
+        rc = self.E.emu_ext_stats(C.byref(a), C.byref(self.state.ext.as_struct()), t, C.byref(out))
+        assert rc == 0
+        return out
 
     def ethics_stats(self):
+        if self.state.ethics is None:
+            return None
         g, a = self.state.as_structs()
         out = layout.EthicsStats()
         rc = self.E.emu_ethics_stats(C.byref(a), C.byref(self.state.ethics.as_struct()), C.byref(out))

@@ -87,3 +87,51 @@ def test_device_ethics_source_matches_reference_trajectory(variant):
         for k in stats.LOG_KEYS:
             assert _close(rs[k], log[t][k]), f"log key {k} differs at t={t}: {rs[k]} vs {log[t][k]}"
     assert seen["non_greedy"] > len(gold) * 0.9      # the ethical ranking overrode the greedy choice in (almost) every step
+
+
+def _run_with_extensions(c, state, pop, params, endow, tags, gold, log):
+    """The stepping loop with every ABI 2 extension the configuration needs (decision models, lending, friends)."""
+    emu = HostEmu(params, state, endow, tags)
+    emu.set_mt_from_python()
+    d, _ = pu.state_digests(state, *emu.mt_state())
+    assert d == gold[0]["digests"], "t=0 state differs"
+    sb = stats.StatsBuilder(c, init.equator(c))
+    rs = sb.update(emu.stats(0), 0, 0, emu.ethics_stats(), emu.ext_stats(0))
+    history = [dict(rs)]
+    for t in range(1, len(gold)):
+        emu.env_step(t)
+        emu.agent_step(t, rs["meanWealth"])
+        emu.compact(t)
+        replaced = 0
+        if c["agentReplacements"] > 0:
+            emu.push_mt_to_python()
+            replaced = pu.replace_dead_agents(c, state, pop, t)
+            emu.set_mt_from_python()
+        d, snap = pu.state_digests(state, *emu.mt_state())
+        assert d == gold[t]["digests"], f"state differs at t={t}"
+        rs = sb.update(emu.stats(t), t, replaced, emu.ethics_stats(), emu.ext_stats(t))
+        for k in stats.LOG_KEYS:
+            assert _close(rs[k], log[t][k]), f"log key {k} differs at t={t}: {rs[k]} vs {log[t][k]}"
+        history.append(dict(rs))
+    return history
+
+
+def test_device_lending_source_matches_reference_on_lending_basic():
+    """examples/lending_basic.json through the device source of doLending / payDebt / updateLoans (csrc/ssb_ext.cuh:
+    loan lists as chains through a pool with Python's list semantics): digests and all 59 log keys, loanVolume
+    included; about 2.5 k loans in 200 steps."""
+    c, state, pop, params, endow, tags = pu.build("lending_basic")
+    assert state.ext is not None and "lending" in state.ext.families
+    meta, _ = pu.load_golden("lending_basic")
+    history = _run_with_extensions(c, state, pop, params, endow, tags, meta["steps"], meta["log"])
+    assert sum(h["loanVolume"] for h in history) > 1000
+
+
+def test_device_lending_friends_combat_source_matches_reference_on_dune():
+    """examples/dune.json: lending with inheritance to children (payDebtToCreditorChildren), friends, live combat
+    (conflict happiness), trade, tags, reproduction -- digests and all 59 log keys."""
+    c, state, pop, params, endow, tags = pu.build("dune")
+    assert state.ext is not None and state.ext.families == {"lending", "social"}
+    meta, _ = pu.load_golden("dune")
+    history = _run_with_extensions(c, state, pop, params, endow, tags, meta["steps"], meta["log"])
+    assert sum(h["meanConflictHappiness"] != 0 for h in history) > 50

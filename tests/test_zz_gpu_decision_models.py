@@ -1,5 +1,5 @@
-"""SURVEY row a21 on the GPU: the ethics.Bentham decision models through the C ABI (ssb_bind_ethics, the
-extended instantiation of the mode E kernel) against fixtures generated from the unmodified reference
+"""SURVEY row a21 and the first (f)2 families on the GPU: the ethics.Bentham decision models, lending and
+friends through the C ABI (ssb_bind_ethics / ssb_bind_ext, the extended instantiation of the mode E kernel) against fixtures generated from the unmodified reference
 (tests/golden/make_golden_variants.py: ethics on top of trade + tagging + reproduction, live combat, host-side
 replacement, pollution).  Integer state, tags, grid and the MT19937 stream bit-exact on every step, fp64 holdings
 through their digest, all 59 log keys.
@@ -43,6 +43,34 @@ def test_decision_models_match_reference_trajectory(variant):
         for k in stats.LOG_KEYS:
             assert _close(rs[k], log[t][k]), f"{variant}: log key {k} at t={t}: {rs[k]} vs {log[t][k]}"
     assert non_greedy > 0.9 * len(gold)
+    eng.close()
+
+
+@pytest.mark.parametrize("name", ["lending_basic", "dune"])
+def test_lending_and_friends_examples_match_reference_trajectory(name):
+    """examples/lending_basic.json and examples/dune.json (lending incl. payDebtToCreditorChildren, friends, conflict
+    happiness on top of trade, tags, live combat, reproduction and inheritance) through ssb_bind_ext: every digest
+    of the 200-step protocol and all 59 log keys against the fixtures of the unmodified reference."""
+    c, state, pop, params, endow, tags, eng = _engine(name)
+    assert state.ext is not None
+    meta, _ = pu.load_golden(name)
+    gold, log = meta["steps"], meta["log"]
+    sb = stats.StatsBuilder(c, init.equator(c))
+    eng.reduce_stats(0)
+    rs = sb.update(eng.stats(), 0, 0, eng.ethics_stats(), eng.ext_stats())
+    volume = 0
+    for t in range(1, len(gold)):
+        eng.env_step(t)
+        eng.agent_step(t, rs["meanWealth"])
+        eng.compact(t)
+        eng.reduce_stats(t)
+        rs = sb.update(eng.stats(), t, 0, eng.ethics_stats(), eng.ext_stats())
+        d, snap = pu.state_digests(eng.download(), *eng.mt_state())
+        assert d == gold[t]["digests"], f"{name}: state differs from the reference at t={t}"
+        volume += rs["loanVolume"]
+        for k in stats.LOG_KEYS:
+            assert _close(rs[k], log[t][k]), f"{name}: log key {k} at t={t}: {rs[k]} vs {log[t][k]}"
+    assert volume > 100
     eng.close()
 
 

@@ -25,9 +25,13 @@ class HostEmuEngine(OracleEngine):
         super().__init__(params, host_state, device, endow_bits, tag_bits)
         self.orc = HostEmu(params, host_state, endow_bits, tag_bits)
         self.ethics = host_state.ethics
+        self.ext = host_state.ext
 
     def ethics_stats(self):
         return self.orc.ethics_stats() if self.ethics is not None else None
+
+    def ext_stats(self):
+        return self.orc.ext_stats(self.t_stats)
 
     def sync(self):
         pass
