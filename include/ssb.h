@@ -267,15 +267,57 @@ typedef struct ssb_social {
     int32_t *friend_slot, *friend_id, *friend_hd;     /* [slot][SSB_MAX_FRIENDS], list order               */
 } ssb_social_t;
 
+/* diseases: condition.py:36-86; agent.py:184-188 addDisease, 227-247 catchDisease, 315-371 doDisease /
+ * doInfectionAttempt, 1034-1050 nearest Hamming distance, and the find* accessors with their modifiers
+ * (716-717, 1031-1032, 1107-1111, 1161-1162).  An agent carries a disease at most once: its list of
+ * infections is a [slot][max_sick] table of records in list order. */
+#define SSB_DM_AGGRESSION   0
+#define SSB_DM_FERTILITY    1
+#define SSB_DM_FRIENDLINESS 2
+#define SSB_DM_HAPPINESS    3
+#define SSB_DM_MOVEMENT     4
+#define SSB_DM_SPICE_METAB  5
+#define SSB_DM_SUGAR_METAB  6
+#define SSB_DM_VISION       7
+#define SSB_DM_COUNT        8
+typedef struct ssb_disease_def {
+    int32_t id, incubation, start_timestep, tag_len;
+    uint32_t tags, _pad;                              /* bit j = diseaseTags[j]                             */
+    double  transmission;
+    double  penalty[SSB_DM_COUNT];
+    int64_t infected;                                 /* len(disease.infected)                              */
+    int64_t listed;                                   /* how often sugarscape.diseases holds it             */
+} ssb_disease_def_t;
+typedef struct ssb_diseases {
+    uint64_t *immune, *start_immune;                  /* bit i = immuneSystem[i]                            */
+    double  *protection;                              /* diseaseProtectionChance                            */
+    double  *modifier;                                /* [slot][SSB_DM_COUNT]: sum of the triggered penalties */
+    int32_t *disease_death, *last_spread, *n_spread;
+    double  *health_happiness;                        /* as of the agent's last updateHappiness             */
+    int32_t *last_valid_moves;                        /* lastValidMoves (1 when the range is empty)         */
+    int32_t *stat_mark;                               /* scratch of the reductions (distinct infectors)     */
+    int32_t *n_sick;
+    int32_t *sick_disease, *sick_start, *sick_end, *sick_caught, *sick_incubation, *sick_infector_slot, *sick_infector_id;
+    ssb_disease_def_t *defs;                          /* [n_diseases]                                       */
+    const uint64_t *immune_bits;                      /* per timestep: draws for a child's mismatching immune positions */
+    int32_t max_sick, immune_len, n_diseases, n_immune_bits;
+} ssb_diseases_t;
+
 typedef struct ssb_ext {
     int64_t capacity;
     ssb_lending_t lending;
     ssb_social_t social;
+    ssb_diseases_t diseases;
 } ssb_ext_t;
 /* raw sums for the log keys of the families (sugarscape.py:1130-1160) */
 typedef struct ssb_ext_stats {
     int64_t loan_volume;                              /* sum of lastLoans over the agents that lent this step */
     double  sum_social_happiness, sum_conflict_happiness;
+    /* diseases (sugarscape.py:1162, 1200-1211, 1228, 1254-1277, 1316-1317) */
+    int64_t sick_agents, disease_incidence, distinct_infectors, disease_prevalence, disease_deaths;
+    double  sum_health_happiness;
+    int64_t move_space;                               /* sum of lastValidMoves                              */
+    double  sum_burn_rate, sum_ttl_age_limited;       /* findTimeToLive with the disease modifiers, list order */
 } ssb_ext_stats_t;
 /* call after ssb_bind, before the first step (mode E only) */
 int  ssb_bind_ext(ssb_engine_t *e, const ssb_ext_t *ext);

@@ -364,7 +364,7 @@ int ssb_sizeof_ext(void) { return (int)sizeof(ssb_ext_t); }
 int ssb_bind_ext(ssb_engine_t *e, const ssb_ext_t *ext) {
     if (!e || !ext) return -1;
     if (!e->bound) return fail(e, -1, "engine not bound");
-    if (e->p.rng_mode != SSB_RNG_EXACT) return fail(e, -1, "lending / friends need the exact RNG mode (their lists reach agents anywhere on the map)");
+    if (e->p.rng_mode != SSB_RNG_EXACT) return fail(e, -1, "lending / friends / diseases need the exact RNG mode");
     if (e->sharded) return fail(e, -1, "lending / friends are not available on a sharded engine");
     if (ext->capacity != e->ctx.a.capacity) return fail(e, -1, "ext capacity differs from the agent capacity");
     const ssb_lending_t &L = ext->lending;
@@ -379,6 +379,14 @@ int ssb_bind_ext(ssb_engine_t *e, const ssb_ext_t *ext) {
     if (S.max_friends) {
         const void *need[] = {S.last_combat, S.social_happiness, S.conflict_happiness, S.n_friends, S.friend_slot, S.friend_id, S.friend_hd};
         for (const void *p : need) if (!p) return fail(e, -1, "social: null array");
+    }
+    const ssb_diseases_t &D = ext->diseases;
+    if (D.immune) {
+        const void *need[] = {D.start_immune, D.protection, D.modifier, D.disease_death, D.last_spread, D.n_spread, D.health_happiness,
+                              D.last_valid_moves, D.stat_mark, D.n_sick, D.sick_disease, D.sick_start, D.sick_end, D.sick_caught,
+                              D.sick_incubation, D.sick_infector_slot, D.sick_infector_id, D.defs, D.immune_bits};
+        for (const void *p : need) if (!p) return fail(e, -1, "diseases: null array");
+        if (D.max_sick < 1 || D.max_sick < D.n_diseases || D.immune_len < 1 || D.immune_len > 64) return fail(e, -1, "diseases: bad sizes");
     }
     CU(cudaSetDevice(e->device));
     if (!e->d_ext_stats) {

@@ -10,8 +10,180 @@ namespace ssb {
 // child endowment bits of the families (sugarscape_b200/steptables.py ENDOWMENT_BITS)
 enum { EB_BASE_INTEREST = 12, EB_LENDING_FACTOR = 13, EB_LOAN_DURATION = 14, EB_MAX_FRIENDS = 15 };
 
+enum { EB_PROTECTION = 16 };
+
 __device__ __forceinline__ bool has_lending(const DevCtx &c) { return c.x.lending.lending_factor != nullptr; }
 __device__ __forceinline__ bool has_social(const DevCtx &c) { return c.x.social.max_friends != nullptr; }
+__device__ __forceinline__ bool has_disease(const DevCtx &c) { return c.x.diseases.immune != nullptr; }
+
+// the find* accessors (agent.py:716-717, 1031-1032, 1107-1111, 1161-1162): endowment + disease modifier, floored at 0
+__device__ __forceinline__ double dis_mod(const DevCtx &c, int s, int which) {
+    return has_disease(c) ? c.x.diseases.modifier[(long long)s * SSB_DM_COUNT + which] : 0.0;
+}
+__device__ __forceinline__ double pos_part(double v) { return v > 0 ? v : 0; }
+__device__ __forceinline__ double eff_sugar_metab(const DevCtx &c, int s) { return pos_part(c.a.sugar_metab[s] + dis_mod(c, s, SSB_DM_SUGAR_METAB)); }
+__device__ __forceinline__ double eff_spice_metab(const DevCtx &c, int s) { return pos_part(c.a.spice_metab[s] + dis_mod(c, s, SSB_DM_SPICE_METAB)); }
+__device__ __forceinline__ double eff_vision(const DevCtx &c, int s) { return pos_part(c.a.vision[s] + dis_mod(c, s, SSB_DM_VISION)); }
+__device__ __forceinline__ double eff_movement(const DevCtx &c, int s) { return pos_part(c.a.movement[s] + dis_mod(c, s, SSB_DM_MOVEMENT)); }
+__device__ __forceinline__ double eff_aggression(const DevCtx &c, int s) { return pos_part(c.a.aggression[s] + dis_mod(c, s, SSB_DM_AGGRESSION)); }
+__device__ __forceinline__ bool is_sick(const DevCtx &c, int s) { return has_disease(c) && c.x.diseases.n_sick[s] > 0; }
+// Agent.isFertile with the fertility modifier (agent.py:1244-1247, 1007-1008)
+__device__ __forceinline__ bool is_fertile_x(const DevCtx &c, int s) {
+    return c.a.sugar[s] >= c.a.start_sugar[s] && c.a.spice[s] >= c.a.start_spice[s] &&
+           c.a.age[s] >= c.a.fert_age[s] && c.a.age[s] < c.a.infert_age[s] && (c.a.fert_factor[s] + dis_mod(c, s, SSB_DM_FERTILITY)) > 0;
+}
+// Agent.findTimeToLive (agent.py:1113-1140) with the modifiers
+__device__ __forceinline__ double time_to_live_x(const DevCtx &c, int s, bool age_limited) {
+    const double sm = eff_sugar_metab(c, s), pm = eff_spice_metab(c, s);
+    const double big = 9223372036854775807.0;            // sys.maxsize
+    const double st = sm > 0 ? c.a.sugar[s] / sm : big;
+    const double pt = pm > 0 ? c.a.spice[s] / pm : big;
+    double ttl = st < pt ? st : pt;
+    if (age_limited) { const double lim = (double)(c.a.max_age[s] - c.a.age[s]); if (lim < ttl) ttl = lim; }
+    return ttl;
+}
+
+// ---------------------------------------------------------------------------------------------
+// diseases
+// ---------------------------------------------------------------------------------------------
+struct SickRec { int disease, start, end, caught, incubation, infector_slot, infector_id; };
+__device__ __forceinline__ SickRec sick_load(const ssb_diseases_t &D, long long at) {
+    SickRec r;
+    r.disease = D.sick_disease[at]; r.start = D.sick_start[at]; r.end = D.sick_end[at]; r.caught = D.sick_caught[at];
+    r.incubation = D.sick_incubation[at]; r.infector_slot = D.sick_infector_slot[at]; r.infector_id = D.sick_infector_id[at];
+    return r;
+}
+__device__ __forceinline__ void sick_store(const ssb_diseases_t &D, long long at, const SickRec &r) {
+    D.sick_disease[at] = r.disease; D.sick_start[at] = r.start; D.sick_end[at] = r.end; D.sick_caught[at] = r.caught;
+    D.sick_incubation[at] = r.incubation; D.sick_infector_slot[at] = r.infector_slot; D.sick_infector_id[at] = r.infector_id;
+}
+__device__ inline void disease_reset_slot(const DevCtx &c, int s) {
+    const ssb_diseases_t &D = c.x.diseases;
+    D.n_sick[s] = 0;
+    for (int k = 0; k < SSB_DM_COUNT; k++) D.modifier[(long long)s * SSB_DM_COUNT + k] = 0;
+    D.disease_death[s] = 0; D.last_spread[s] = -1; D.n_spread[s] = 0; D.health_happiness[s] = 0; D.last_valid_moves[s] = 0;
+}
+__device__ inline void disease_trigger(const ssb_diseases_t &D, int s, int di) {      // condition.py:57-65
+    for (int k = 0; k < SSB_DM_COUNT; k++) D.modifier[(long long)s * SSB_DM_COUNT + k] += D.defs[di].penalty[k];
+}
+__device__ inline void disease_recover(const ssb_diseases_t &D, int s, int di) {      // condition.py:67-76
+    for (int k = 0; k < SSB_DM_COUNT; k++) D.modifier[(long long)s * SSB_DM_COUNT + k] -= D.defs[di].penalty[k];
+    D.defs[di].infected--;
+}
+__device__ inline bool infected_with(const ssb_diseases_t &D, int s, int disease_id) {   // agent.py:1249-1254
+    const long long b = (long long)s * D.max_sick;
+    for (int i = 0; i < D.n_sick[s]; i++) if (D.defs[D.sick_disease[b + i]].id == disease_id) return true;
+    return false;
+}
+// findNearestHammingDistanceInDisease (agent.py:1034-1050)
+__device__ inline int disease_nearest(const ssb_diseases_t &D, int s, int di, int *start, int *end) {
+    const int len = D.defs[di].tag_len;
+    int best = len, b0 = 0, b1 = len - 1;
+    for (int i = 0; i < D.immune_len - len; i++) {
+        const uint32_t window = (uint32_t)((D.immune[s] >> i) & (len >= 32 ? 0xffffffffull : ((1ull << len) - 1ull)));
+        const int hd = __popc(window ^ D.defs[di].tags);
+        if (hd < best) { best = hd; b0 = i; b1 = i + (len - 1); }
+    }
+    *start = b0; *end = b1;
+    return best;
+}
+// catchDisease (agent.py:227-247) through doInfectionAttempt (363-371): two random.uniform(0, 1)
+template <class Rng>
+__device__ __noinline__ void disease_catch(const DevCtx &c, int s, int di, int infector, Rng &rng) {
+    const ssb_diseases_t &D = c.x.diseases;
+    if (infected_with(D, s, D.defs[di].id)) return;
+    SickRec rec = {di, -1, -1, c.t, D.defs[di].incubation, infector, c.a.id[infector]};
+    if (disease_nearest(D, s, di, &rec.start, &rec.end) == 0) return;        // immune
+    const double attack = 0.0 + (1.0 - 0.0) * rand_double(rng), defense = 0.0 + (1.0 - 0.0) * rand_double(rng);
+    const bool attack_ok = attack <= D.defs[di].transmission && D.defs[di].transmission != 0.0;
+    const bool defense_ok = defense <= D.protection[s] && D.protection[s] != 0.0;
+    if (attack_ok && !defense_ok) {                       // addDisease (agent.py:184-188)
+        if (D.n_sick[s] >= D.max_sick) return;            // cannot happen: one record per disease
+        sick_store(D, (long long)s * D.max_sick + D.n_sick[s], rec);
+        D.n_sick[s] += 1;
+        D.defs[di].infected++;
+        if (rec.incubation == 0) disease_trigger(D, s, di);
+    }
+}
+// doDisease (agent.py:315-361)
+template <class Rng>
+__device__ __noinline__ void do_disease(const DevCtx &c, int s, Rng &rng) {
+    const ssb_diseases_t &D = c.x.diseases;
+    const long long b = (long long)s * D.max_sick;
+    rng.at(SITE_DISEASE);
+    for (int i = D.n_sick[s] - 1; i >= 1; i--) {          // random.shuffle(self.diseases)
+        const uint32_t j = rand_below(rng, (uint32_t)i + 1u);
+        const SickRec x = sick_load(D, b + i), y = sick_load(D, b + j);
+        sick_store(D, b + i, y); sick_store(D, b + j, x);
+    }
+    for (int p = 0; p < D.n_sick[s]; p++) {               // Python for-loop over a list that may lose the current element
+        SickRec rec = sick_load(D, b + p);
+        const int di = rec.disease;
+        if (rec.caught != c.t && rec.incubation > 0) { rec.incubation -= 1; D.sick_incubation[b + p] = rec.incubation; }
+        if (rec.incubation == 0) disease_trigger(D, s, di);           // (every step: the penalties pile up)
+        const int tag_len = D.defs[di].tag_len;
+        if (tag_len > 0) {
+            const uint32_t dtags = D.defs[di].tags;
+            const int st = rec.start;
+            int en = rec.end + 1;
+            if (en > D.immune_len) en = D.immune_len;
+            const int len = en - st;
+            const uint64_t mask = len >= 64 ? ~0ull : ((1ull << len) - 1ull);
+            const uint64_t response = (D.immune[s] >> st) & mask;     // the slice, taken before the flip
+            for (int i = 0; i < len; i++)
+                if (((response >> i) & 1ull) != ((dtags >> i) & 1u)) {
+                    D.immune[s] = (D.immune[s] & ~(1ull << (st + i))) | ((uint64_t)((dtags >> i) & 1u) << (st + i));
+                    break;
+                }
+            if (len == tag_len && response == (uint64_t)dtags) {      // diseaseTags == immuneResponse
+                // list.remove(record): records are unique per disease
+                const int n = D.n_sick[s];
+                for (int q = p; q + 1 < n; q++) sick_store(D, b + q, sick_load(D, b + q + 1));
+                D.n_sick[s] = n - 1;
+                disease_recover(D, s, di);
+            }
+        }
+    }
+    const int count = D.n_sick[s];
+    if (count == 0) return;
+    int32_t nb4[4], neighbors[4];
+    int nn = 0;
+    neighbours4(c, c.a.pos[s], nb4);
+    for (int i = 0; i < 4; i++) { const int o = c.g.occ[nb4[i]]; if (o >= 0 && agent_alive(c, o)) neighbors[nn++] = o; }
+    int spread = 0;
+    shuffle(rng, neighbors, nn);
+    for (int k = 0; k < nn; k++) {
+        const int di = D.sick_disease[b + rand_below(rng, (uint32_t)count)];
+        disease_catch(c, neighbors[k], di, s, rng);
+        if (infected_with(D, neighbors[k], D.defs[di].id)) spread++;
+    }
+    if (spread > 0) { D.last_spread[s] = c.t; D.n_spread[s] = spread; }
+}
+__device__ inline void disease_note_death(const DevCtx &c, int s) {        // doDeath (agent.py:302-313)
+    const ssb_diseases_t &D = c.x.diseases;
+    const long long b = (long long)s * D.max_sick;
+    if (D.n_sick[s] > 0) D.disease_death[s] = 1;
+    for (int i = 0; i < D.n_sick[s]; i++) disease_recover(D, s, D.sick_disease[b + i]);
+    D.n_sick[s] = 0;
+}
+// a child's immune system: equal bits copied, mismatches drawn from the per-timestep stream (agent.py:897-908).
+// startingImmuneSystem IS immuneSystem in the reference (agent.py:33,50 bind the same list): the parents pass on
+// what their immune responses have learnt.
+__device__ inline void disease_child(const DevCtx &c, int ch, int s, int m, uint32_t eb) {
+    const ssb_diseases_t &D = c.x.diseases;
+    disease_reset_slot(c, ch);
+    const uint64_t mine = D.immune[s], other = D.immune[m];
+    const uint64_t draws = (D.immune_bits && c.t < D.n_immune_bits) ? D.immune_bits[c.t] : 0;
+    uint64_t child = 0;
+    int draw = 0;
+    for (int i = 0; i < D.immune_len; i++) {
+        const uint64_t bs = (mine >> i) & 1ull, bm = (other >> i) & 1ull;
+        const uint64_t bit = bs == bm ? bs : ((draws >> draw++) & 1ull);
+        child |= bit << i;
+    }
+    D.immune[ch] = D.start_immune[ch] = child;
+    D.protection[ch] = ((eb >> EB_PROTECTION) & 1u) ? D.protection[m] : D.protection[s];
+}
 
 // ---------------------------------------------------------------------------------------------
 // friends + conflict happiness (agent.py:1499-1520 updateFriends; 1099-1105, 912-918)
@@ -248,7 +420,7 @@ __device__ __noinline__ void do_lending(const DevCtx &c, int s, Rng &rng) {
     update_loans(c, s);
     // isLender (agent.py:1285-1296)
     if (L.lending_factor[s] == 0) return;
-    if (is_fertile(c, s) && (a.sugar[s] <= a.start_sugar[s] || a.spice[s] <= a.start_spice[s])) return;
+    if (is_fertile_x(c, s) && (a.sugar[s] <= a.start_sugar[s] || a.spice[s] <= a.start_spice[s])) return;
     if (a.age[s] < a.fert_age[s]) return;
     double rate = L.lending_factor[s] * L.base_interest_rate[s];
     if (rate > 1) rate = 1;
@@ -259,7 +431,7 @@ __device__ __noinline__ void do_lending(const DevCtx &c, int s, Rng &rng) {
         const int o = c.g.occ[nb[i]];
         if (o < 0 || !agent_alive(c, o)) continue;
         // isBorrower (agent.py:1226-1229)
-        if (a.age[o] >= a.fert_age[o] && a.age[o] < a.infert_age[o] && !is_fertile(c, o)) borrowers[nbw++] = o;
+        if (a.age[o] >= a.fert_age[o] && a.age[o] < a.infert_age[o] && !is_fertile_x(c, o)) borrowers[nbw++] = o;
     }
     rng.at(SITE_LENDING);
     shuffle(rng, borrowers, nbw);
@@ -268,7 +440,7 @@ __device__ __noinline__ void do_lending(const DevCtx &c, int s, Rng &rng) {
     for (int k = 0; k < nbw; k++) {
         const int b = borrowers[k];
         double max_sugar = a.sugar[s] / 2, max_spice = a.spice[s] / 2;
-        if (is_fertile(c, s)) {
+        if (is_fertile_x(c, s)) {
             max_sugar = a.sugar[s] - a.start_sugar[s] > 0 ? a.sugar[s] - a.start_sugar[s] : 0;
             max_spice = a.spice[s] - a.start_spice[s] > 0 ? a.spice[s] - a.start_spice[s] : 0;
         }
@@ -295,15 +467,38 @@ __device__ __noinline__ void do_lending(const DevCtx &c, int s, Rng &rng) {
     if (loans > 0) { L.last_lended[s] = c.t; L.last_loans[s] = loans; }
 }
 
-// reductions of the families' log keys, list order (sugarscape.py:1130-1160)
+// reductions of the families' log keys, list order (sugarscape.py:1130-1160, 1162, 1200-1211, 1228, 1254-1277)
 __device__ inline void ext_stats_body(const DevCtx &c, ssb_ext_stats_t *out) {
     ssb_ext_stats_t r;
     r.loan_volume = 0; r.sum_social_happiness = 0; r.sum_conflict_happiness = 0;
-    const long long n = c.a.counters[SSB_C_N_LIST];
+    r.sick_agents = 0; r.disease_incidence = 0; r.distinct_infectors = 0; r.disease_prevalence = 0; r.disease_deaths = 0;
+    r.sum_health_happiness = 0; r.move_space = 0; r.sum_burn_rate = 0; r.sum_ttl_age_limited = 0;
+    const long long n = c.a.counters[SSB_C_N_LIST], n_dead = c.a.counters[SSB_C_N_DEAD];
+    const ssb_diseases_t &D = c.x.diseases;
     for (long long i = 0; i < n; i++) {
         const int s = c.a.order[i];
         if (has_lending(c) && c.x.lending.last_lended[s] == c.t) r.loan_volume += c.x.lending.last_loans[s];
         if (has_social(c)) { r.sum_social_happiness += c.x.social.social_happiness[s]; r.sum_conflict_happiness += c.x.social.conflict_happiness[s]; }
+        if (has_disease(c)) {
+            const long long b = (long long)s * D.max_sick;
+            if (D.n_sick[s] > 0) r.sick_agents++;
+            for (int k = 0; k < D.n_sick[s]; k++)
+                if (D.sick_caught[b + k] == c.t) {
+                    r.disease_incidence++;
+                    const int inf = D.sick_infector_slot[b + k];
+                    // distinct infectors: within one step a slot names one acting agent
+                    if (c.t != 0 && inf >= 0 && D.stat_mark[inf] != c.t) { D.stat_mark[inf] = c.t; r.distinct_infectors++; }
+                }
+            r.sum_health_happiness += D.health_happiness[s];
+            r.move_space += D.last_valid_moves[s];
+            const double ttl = time_to_live_x(c, s, false);
+            r.sum_burn_rate += ttl;
+            r.sum_ttl_age_limited += fmin(ttl, (double)(c.a.max_age[s] - c.a.age[s]));
+        }
+    }
+    if (has_disease(c)) {
+        for (long long i = 0; i < n_dead; i++) r.disease_deaths += D.disease_death[c.a.dead_list[i]];    // (their disease lists are empty)
+        for (int d = 0; d < D.n_diseases; d++) r.disease_prevalence += D.defs[d].listed * D.defs[d].infected;
     }
     *out = r;
 }

@@ -110,6 +110,13 @@ __device__ __forceinline__ uint32_t rand_below(Rng &rng, uint32_t n) {
     return v;
 }
 
+// random.random(): (a >> 5, b >> 6) -> 53 bits (Modules/_randommodule.c)
+template <class Rng>
+__device__ __forceinline__ double rand_double(Rng &rng) {
+    const uint32_t a = rng.next() >> 5, b = rng.next() >> 6;
+    return (a * 67108864.0 + b) * (1.0 / 9007199254740992.0);
+}
+
 // random.shuffle: for i = n-1 .. 1: j = _randbelow(i + 1); swap(x[i], x[j])
 template <class Rng, class T>
 __device__ __forceinline__ void shuffle(Rng &rng, T *x, int n) {

@@ -42,6 +42,14 @@ struct DevCtx {
     ssb_ext_t x;                     // ABI 2, mode E: lending, friends ... (a family is off when its first array is null)
 };
 
+// ssb_ext.cuh (included below, once the basic predicates exist)
+__device__ __forceinline__ bool has_lending(const DevCtx &c);
+__device__ __forceinline__ bool has_disease(const DevCtx &c);
+__device__ __forceinline__ double dis_mod(const DevCtx &c, int s, int which);
+__device__ __forceinline__ double pos_part(double v);
+__device__ inline void lending_note_death(const DevCtx &c, int s);
+__device__ inline void disease_note_death(const DevCtx &c, int s);
+
 __device__ __forceinline__ int wrapi(int v, int n) { v %= n; return v < 0 ? v + n : v; }
 // wrap for |offset| < n (every neighbourhood access on maps at least as wide as the range)
 __device__ __forceinline__ int wrap1(int v, int n) { return v < 0 ? v + n : (v >= n ? v - n : v); }
@@ -107,8 +115,13 @@ __device__ __forceinline__ double py_pow(double x, double y) {
 struct Welfare {
     double sugar, spice, s_look, p_look, e_s, e_p;
 
+    template <bool EXT = false>
     __device__ __forceinline__ void load(const DevCtx &c, int s) {
-        const double sm = (double)max(c.a.sugar_metab[s], 0), pm = (double)max(c.a.spice_metab[s], 0);
+        double sm = (double)max(c.a.sugar_metab[s], 0), pm = (double)max(c.a.spice_metab[s], 0);
+        if (EXT && has_disease(c)) {     // findSugarMetabolism / findSpiceMetabolism with the disease modifiers
+            sm = pos_part(c.a.sugar_metab[s] + dis_mod(c, s, SSB_DM_SUGAR_METAB));
+            pm = pos_part(c.a.spice_metab[s] + dis_mod(c, s, SSB_DM_SPICE_METAB));
+        }
         const double look = c.a.lookahead[s];
         sugar = c.a.sugar[s]; spice = c.a.spice[s];
         s_look = sm * look; p_look = pm * look;
@@ -128,9 +141,14 @@ struct Welfare {
         }
     }
     // same, from values already in registers (tags / tribe refresh included)
+    template <bool EXT = false>
     __device__ __forceinline__ void set(const DevCtx &c, int s, double sugar_, double spice_, int sugar_metab,
                                         int spice_metab, double look, uint32_t tags) {
-        const double sm = (double)max(sugar_metab, 0), pm = (double)max(spice_metab, 0);
+        double sm = (double)max(sugar_metab, 0), pm = (double)max(spice_metab, 0);
+        if (EXT && has_disease(c)) {
+            sm = pos_part(sugar_metab + dis_mod(c, s, SSB_DM_SUGAR_METAB));
+            pm = pos_part(spice_metab + dis_mod(c, s, SSB_DM_SPICE_METAB));
+        }
         sugar = sugar_; spice = spice_;
         s_look = sm * look; p_look = pm * look;
         const double total = sm + pm;
@@ -155,9 +173,10 @@ struct Welfare {
     }
 };
 
+template <bool EXT = false>
 __device__ __forceinline__ double find_welfare(const DevCtx &c, int s, double sugar_reward, double spice_reward) {
     Welfare w;
-    w.load(c, s);
+    w.template load<EXT>(c, s);
     return w.eval(sugar_reward, spice_reward);
 }
 
@@ -205,12 +224,10 @@ __device__ __noinline__ void do_inheritance(const DevCtx &c, int s) {
 }
 
 // Agent.doDeath (agent.py:296-313)
-__device__ __forceinline__ bool has_lending(const DevCtx &c);          // ssb_ext.cuh
-__device__ inline void lending_note_death(const DevCtx &c, int s);
-
 template <bool EXT = false>
 __device__ __forceinline__ void do_death(const DevCtx &c, int s, int cause) {
     if (EXT && has_lending(c)) lending_note_death(c, s);
+    if (EXT && has_disease(c)) disease_note_death(c, s);
     c.a.cod[s] = cause;
     const int pos = c.a.pos[s];
     if (pos >= 0 && c.g.occ[pos] == s) c.g.occ[pos] = -1;
@@ -219,16 +236,26 @@ __device__ __forceinline__ void do_death(const DevCtx &c, int s, int cause) {
 }
 
 // Agent.findMarginalRateOfSubstitution (agent.py:1023-1029)
+template <bool EXT = false>
 __device__ __forceinline__ void find_mrs(const DevCtx &c, int s) {
-    const double pm = (double)max(c.a.spice_metab[s], 0), sm = (double)max(c.a.sugar_metab[s], 0);
+    double pm = (double)max(c.a.spice_metab[s], 0), sm = (double)max(c.a.sugar_metab[s], 0);
+    if (EXT && has_disease(c)) {
+        pm = pos_part(c.a.spice_metab[s] + dis_mod(c, s, SSB_DM_SPICE_METAB));
+        sm = pos_part(c.a.sugar_metab[s] + dis_mod(c, s, SSB_DM_SUGAR_METAB));
+    }
     const double spice_need = pm > 0 ? c.a.spice[s] / pm : 1;
     const double sugar_need = sm > 0 ? c.a.sugar[s] / sm : 1;
     c.a.mrs[s] = c.a.trade_factor[s] * (spice_need / sugar_need);
 }
 
 // Agent.findNewMarginalRateOfSubstitution (agent.py:1067-1080)
+template <bool EXT = false>
 __device__ __forceinline__ double find_new_mrs(const DevCtx &c, int s, double sugar, double spice) {
-    const double pm = (double)max(c.a.spice_metab[s], 0), sm = (double)max(c.a.sugar_metab[s], 0);
+    double pm = (double)max(c.a.spice_metab[s], 0), sm = (double)max(c.a.sugar_metab[s], 0);
+    if (EXT && has_disease(c)) {
+        pm = pos_part(c.a.spice_metab[s] + dis_mod(c, s, SSB_DM_SPICE_METAB));
+        sm = pos_part(c.a.sugar_metab[s] + dis_mod(c, s, SSB_DM_SUGAR_METAB));
+    }
     const double spice_need = pm > 0 ? spice / pm : 1;
     const double sugar_need = sm > 0 ? sugar / sm : 1;
     if (spice_need == 1 && sugar_need == 1) return 1;
@@ -251,11 +278,6 @@ __device__ __forceinline__ void neighbours4(const DevCtx &c, int pos, int32_t ou
     out[2] = (x == W - 1 ? 0 : x + 1) * H + y;
     out[3] = (x == 0 ? W - 1 : x - 1) * H + y;
 }
-
-// findSugarMetabolism / findSpiceMetabolism / findAggression (agent.py:716-717, 1031-1032, 1107-1111, 1161-1162)
-__device__ __forceinline__ double eff_sugar_metab(const DevCtx &c, int s) { return (double)max(c.a.sugar_metab[s], 0); }
-__device__ __forceinline__ double eff_spice_metab(const DevCtx &c, int s) { return (double)max(c.a.spice_metab[s], 0); }
-__device__ __forceinline__ double eff_aggression(const DevCtx &c, int s) { return fmax(c.a.aggression[s], 0.0); }
 
 }  // namespace ssb
 #include "ssb_ext.cuh"
@@ -399,12 +421,12 @@ __device__ __noinline__ double ethical_value(const DevCtx &c, int s, int my_r, c
     for (int k = 0; k < n_hood; k++) {
         const int nb = hood[k];
         if (!agent_alive(c, nb)) continue;
-        const int rn = agent_range(c, nb);
+        const int rn = min(min((int)eff_vision(c, nb), (int)eff_movement(c, nb)), max(c.max_dx, c.max_dy));   // findCellsInRange with the modifiers
         if (!(cell == a.pos[nb] || cell_in_cross(c, a.pos[nb], rn, cell))) continue;      // canReachCell
         const double metab = (double)(a.sugar_metab[nb] + a.spice_metab[nb]);               // raw, not the find* accessors
         const double cell_duration = metab > 0 ? site / metab : 0;
         const double proximity = 1.0 / 1;
-        const double intensity = (1 / (1 + time_to_live(c, nb, false)) / (1 + c.g.pollution[cell]));
+        const double intensity = (1 / (1 + time_to_live_x(c, nb, false)) / (1 + c.g.pollution[cell]));
         const double duration = max_site > 0 ? cell_duration / max_site : 0;
         const double discount = c.eth.lookahead_factor[nb] != 0 ? c.eth.lookahead_discount[nb] : 0;
         double future_duration = metab > 0 ? (site - metab) / metab : site;
@@ -534,10 +556,12 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rn
     const double last_sugar = rec.sugar, last_spice = rec.spice;
     const int pos = rec.pos;
     const int H = c.p.height, x = pos / H, y = pos - x * H;
-    const int r = min(min(max(rec.vision, 0), max(rec.movement, 0)), max(c.max_dx, c.max_dy));
-    const double aggression = fmax(rec.aggression, 0.0);
+    const bool diseased = EXT && has_disease(c);             // uniform: the find* accessors carry disease modifiers
+    const int r = diseased ? min(min((int)eff_vision(c, s), (int)eff_movement(c, s)), max(c.max_dx, c.max_dy))
+                           : min(min(max(rec.vision, 0), max(rec.movement, 0)), max(c.max_dx, c.max_dy));
+    const double aggression = diseased ? eff_aggression(c, s) : fmax(rec.aggression, 0.0);
     Welfare w;
-    w.set(c, s, rec.sugar, rec.spice, rec.sugar_metab, rec.spice_metab, rec.lookahead, rec.tags);
+    w.template set<EXT>(c, s, rec.sugar, rec.spice, rec.sugar_metab, rec.spice_metab, rec.lookahead, rec.tags);
     const int my_tribe = (c.p.flags & SSB_F_TAGPREF) ? find_tribe(c, rec.tags) : rec.tribe;
     const bool polluted = (c.p.flags & SSB_F_POLLUTION) != 0;
     const bool spicy = (c.p.flags & SSB_F_SPICE) != 0;
@@ -673,6 +697,8 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rn
     const int best = b_valid ? b_cell : pos;
     if (lane == 0) {
         if (n > 0) { a.n_neighborhood[s] = hood + 1; a.n_valid_moves[s] = m; }   // + self
+        // lastValidMoves: findBestCell records len([own cell]) when the range is empty (agent.py:1398-1399, 745)
+        if (diseased) c.x.diseases.last_valid_moves[s] = n > 0 ? m : 1;
         if (!b_valid) {     // stays on its own cell: its contents were not among the candidates
             b_cs = c.g.sugar[pos];
             b_cp = spicy ? c.g.spice[pos] : 0;
@@ -711,7 +737,8 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rn
         c.g.sugar[best] = 0;
         if (spicy) c.g.spice[best] = 0;
         // doMetabolism (agent.py:485-498) + consumption pollution (cell.py:27-40)
-        const double sm = (double)max(rec.sugar_metab, 0), pm = (double)max(rec.spice_metab, 0);
+        const double sm = diseased ? eff_sugar_metab(c, s) : (double)max(rec.sugar_metab, 0);
+        const double pm = diseased ? eff_spice_metab(c, s) : (double)max(rec.spice_metab, 0);
         sugar -= sm;
         spice -= pm;
         if (polluting) {
@@ -728,6 +755,7 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rn
         if (sugar < 0 || spice < 0 || (sugar <= 0 && sm > 0) || (spice <= 0 && pm > 0)) {
             // doDeath("starvation") (agent.py:296-313)
             if (EXT && has_lending(c)) lending_note_death(c, s);
+            if (EXT && has_disease(c)) disease_note_death(c, s);
             a.cod[s] = SSB_STARVATION;
             c.g.occ[best] = -1;
             a.pos[s] = -1;
@@ -761,13 +789,13 @@ __device__ __noinline__ void do_tagging(const DevCtx &c, int s, Rng &rng) {
 }
 
 // Agent.doTrading (agent.py:600-706)
-template <class Rng>
+template <class Rng, bool EXT = false>
 __device__ __noinline__ void do_trading(const DevCtx &c, int s, Rng &rng) {
     const ssb_agents_t &a = c.a;
     if (a.trade_factor[s] == 0) return;
     a.trade_volume[s] = 0;
     double sum_sugar_price = 0, sum_spice_price = 0;
-    find_mrs(c, s);
+    find_mrs<EXT>(c, s);
     int32_t nb[4], traders[4];
     int n = 0;
     neighbours4(c, a.pos[s], nb);
@@ -793,22 +821,22 @@ __device__ __noinline__ void do_trading(const DevCtx &c, int s, Rng &rng) {
             else { spice_price = price; sugar_price = 1; }
             if (a.spice[spice_seller] - spice_price < (double)a.spice_metab[spice_seller] ||
                 a.sugar[sugar_seller] - sugar_price < (double)a.sugar_metab[sugar_seller]) break;
-            const double ss_new = find_new_mrs(c, spice_seller, a.sugar[spice_seller] + sugar_price,
+            const double ss_new = find_new_mrs<EXT>(c, spice_seller, a.sugar[spice_seller] + sugar_price,
                                                a.spice[spice_seller] - spice_price);
-            const double su_new = find_new_mrs(c, sugar_seller, a.sugar[sugar_seller] - sugar_price,
+            const double su_new = find_new_mrs<EXT>(c, sugar_seller, a.sugar[sugar_seller] - sugar_price,
                                                a.spice[sugar_seller] + spice_price);
             const bool better_ss_mrs = fabs(1 - ssm) > fabs(1 - ss_new);
             const bool better_su_mrs = fabs(1 - sum) > fabs(1 - su_new);
-            const bool better_ss_w = find_welfare(c, spice_seller, sugar_price, -1 * spice_price) >=
-                                     find_welfare(c, spice_seller, 0, 0);
-            const bool better_su_w = find_welfare(c, sugar_seller, -1 * sugar_price, spice_price) >=
-                                     find_welfare(c, sugar_seller, 0, 0);
+            const bool better_ss_w = find_welfare<EXT>(c, spice_seller, sugar_price, -1 * spice_price) >=
+                                     find_welfare<EXT>(c, spice_seller, 0, 0);
+            const bool better_su_w = find_welfare<EXT>(c, sugar_seller, -1 * sugar_price, spice_price) >=
+                                     find_welfare<EXT>(c, sugar_seller, 0, 0);
             const bool crossing = ss_new < su_new;
             if ((better_ss_mrs || better_ss_w) && (better_su_mrs || better_su_w) && !crossing) {
                 a.sugar[spice_seller] += sugar_price; a.spice[spice_seller] -= spice_price;
                 a.sugar[sugar_seller] -= sugar_price; a.spice[sugar_seller] += spice_price;
-                find_mrs(c, spice_seller);
-                find_mrs(c, sugar_seller);
+                find_mrs<EXT>(c, spice_seller);
+                find_mrs<EXT>(c, sugar_seller);
             } else break;
         }
         if (spice_seller >= 0 && sugar_seller >= 0) {   // "a trade occurred" as the reference logs it
@@ -853,7 +881,8 @@ __device__ __forceinline__ int alloc_slot(const DevCtx &c) {
 template <class Rng, bool EXACT, bool EXT = false>
 __device__ __noinline__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
     const ssb_agents_t &a = c.a;
-    if (!agent_alive(c, s) || !is_fertile(c, s)) return;
+    const bool diseased = EXT && has_disease(c);
+    if (!agent_alive(c, s) || !(diseased ? is_fertile_x(c, s) : is_fertile(c, s))) return;
     const int pos = a.pos[s];
     int32_t nb0[4], nb[4];
     neighbours4(c, pos, nb0);
@@ -871,7 +900,7 @@ __device__ __noinline__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
     }
     // batch 2: the mates' records
     int m_cod[4], m_sex[4], m_age[4], m_fa[4], m_ia[4];
-    double m_sugar[4], m_spice[4], m_ss[4], m_sp[4], m_ff[4];
+    double m_sugar[4], m_spice[4], m_ss[4], m_sp[4], m_ff[4], m_fmod[4];      // m_fmod: the mate's fertility modifier (diseases)
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const bool has = o[k] >= 0;
@@ -880,6 +909,7 @@ __device__ __noinline__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
         m_fa[k] = a.fert_age[m]; m_ia[k] = a.infert_age[m];
         m_sugar[k] = a.sugar[m]; m_spice[k] = a.spice[m];
         m_ss[k] = a.start_sugar[m]; m_sp[k] = a.start_spice[m]; m_ff[k] = a.fert_factor[m];
+        m_fmod[k] = diseased ? dis_mod(c, m, SSB_DM_FERTILITY) : 0.0;
     }
     // own empty neighbours, N S E W order, computed ONCE (agent.py:506): stale by design
     int32_t own_empty[4];
@@ -891,7 +921,8 @@ __device__ __noinline__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
     const int my_sex = a.sex[s], my_age = a.age[s], my_fa = a.fert_age[s], my_ia = a.infert_age[s];
     const double my_ss = a.start_sugar[s], my_sp = a.start_spice[s], my_ff = a.fert_factor[s];
     double my_sugar = a.sugar[s], my_spice = a.spice[s];
-    const bool age_ok = my_age >= my_fa && my_age < my_ia && my_ff > 0;
+    const double my_fmod = diseased ? dis_mod(c, s, SSB_DM_FERTILITY) : 0.0;
+    const bool age_ok = my_age >= my_fa && my_age < my_ia && (diseased ? (my_ff + my_fmod) > 0 : my_ff > 0);
     unsigned long long *cn = (unsigned long long *)a.counters;
     bool newborn_at[4] = {false, false, false, false};     // neighbour cell now holds a child of this call
     for (int k = 0; k < 4; k++) {
@@ -900,11 +931,11 @@ __device__ __noinline__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
         // neighbor.isAlive(): a newborn placed by this call is alive and never fertile at age 0
         if (!newborn_at[k] && !(m_cod[k] == SSB_ALIVE && m_sugar[k] >= 0 && m_spice[k] >= 0)) continue;
         bool mate_fertile = !newborn_at[k] && m_sugar[k] >= m_ss[k] && m_spice[k] >= m_sp[k] &&
-                            m_age[k] >= m_fa[k] && m_age[k] < m_ia[k] && m_ff[k] > 0;
+                            m_age[k] >= m_fa[k] && m_age[k] < m_ia[k] && (diseased ? (m_ff[k] + m_fmod[k]) > 0 : m_ff[k] > 0);
         int mate_sex = m_sex[k];
         if (newborn_at[k]) {     // rare: evaluate the child exactly as the reference would
             mate_sex = a.sex[m];
-            mate_fertile = is_fertile(c, m);
+            mate_fertile = diseased ? is_fertile_x(c, m) : is_fertile(c, m);
             m_sugar[k] = a.sugar[m]; m_spice[k] = a.spice[m];
             m_ss[k] = a.start_sugar[m]; m_sp[k] = a.start_spice[m]; m_ff[k] = a.fert_factor[m];
         }
@@ -982,6 +1013,7 @@ __device__ __noinline__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
             c.eth.lookahead_discount[ch] = c.eth.lookahead_discount[from];
             c.eth.last_move_optimal[ch] = 1; c.eth.move_rank[ch] = 0; c.eth.move_diff[ch] = 0;      // lastMoveOptimal starts True
         }
+        if (diseased) disease_child(c, ch, s, m, eb);
         if (EXT && has_social(c)) {
             social_reset_slot(c, ch);
             c.x.social.max_friends[ch] = ((eb >> EB_MAX_FRIENDS) & 1u) ? c.x.social.max_friends[m] : c.x.social.max_friends[s];
@@ -1029,12 +1061,14 @@ template <class Rng, bool EXACT, bool EXT = false>
 __device__ void transaction_interact_phase(const DevCtx &c, int s, const AgentRec &rec, Rng &rng) {
     const ssb_agents_t &a = c.a;
     if ((c.p.flags & SSB_F_TAGS) && (c.p.flags & SSB_F_TAGGING)) do_tagging(c, s, rng);
-    if (c.p.flags & SSB_F_TRADE) do_trading(c, s, rng);
+    if (c.p.flags & SSB_F_TRADE) do_trading<Rng, EXT>(c, s, rng);
     // doReproduction starts with isFertile(): only trading can have raised the holdings since the
     // move part, so without trade the record decides and most agents skip the call
-    if ((c.p.flags & SSB_F_REPRO) && ((c.p.flags & SSB_F_TRADE) || rec.fertile())) do_reproduction<Rng, EXACT, EXT>(c, s, rng);
+    const bool diseased = EXT && has_disease(c);
+    if ((c.p.flags & SSB_F_REPRO) && ((c.p.flags & SSB_F_TRADE) || diseased || rec.fertile())) do_reproduction<Rng, EXACT, EXT>(c, s, rng);
     const bool lending = EXT && has_lending(c);
     if (lending) do_lending(c, s, rng);
+    if (diseased) do_disease(c, s, rng);
     // doAging (agent.py:266-272); reproduction and trading leave the agent alive (isAlive looks at
     // the holdings, which they may have changed)
     double sugar = rec.sugar, spice = rec.spice;
@@ -1052,21 +1086,28 @@ __device__ void transaction_interact_phase(const DevCtx &c, int s, const AgentRe
     if (EXACT && (c.p.flags & SSB_F_REPRO)) {
         for (int e = a.children_head[s]; e >= 0; e = a.kin_next[e]) {
             const int o = kin_alive(c, e);
-            if (o >= 0) { family += 1; if (a.born[o] == c.t) family += 1; } else family -= 1;
+            if (o >= 0) { family += 1; if (diseased && is_sick(c, o)) family -= 1.0 * 0.5; if (a.born[o] == c.t) family += 1; } else family -= 1;
         }
-        for (int e = a.mates_head[s]; e >= 0; e = a.kin_next[e]) family += kin_alive(c, e) >= 0 ? 1 : -1;
+        for (int e = a.mates_head[s]; e >= 0; e = a.kin_next[e]) {
+            const int o = kin_alive(c, e);
+            if (o >= 0) { family += 1; if (diseased && is_sick(c, o)) family -= 1.0 * 0.5; } else family -= 1;
+        }
     }
     const double family_h = erf(family);
     a.wealth_happiness[s] = wealth_h;
     a.family_happiness[s] = family_h;
-    if (EXT && has_social(c)) {
-        // findConflictHappiness (agent.py:912-918), findSocialHappiness (1099-1105)
-        const ssb_social_t &S = c.x.social;
+    if (EXT && (has_social(c) || diseased)) {
+        // findConflictHappiness (agent.py:912-918), findSocialHappiness (1099-1105), findHealthHappiness (1017-1021)
         double conflict_h = 0, social_h = 0;
-        if (S.last_combat[s] == c.t) conflict_h = eff_aggression(c, s) > 1 ? 1.0 : 1.0 * -1;
-        if (S.max_friends[s] != 0) social_h = ((S.n_friends[s] * (2.0 / S.max_friends[s])) - 1) * 1.0;
-        S.conflict_happiness[s] = conflict_h; S.social_happiness[s] = social_h;
-        a.happiness[s] = conflict_h + family_h + 1.0 + social_h + wealth_h;
+        if (has_social(c)) {
+            const ssb_social_t &S = c.x.social;
+            if (S.last_combat[s] == c.t) conflict_h = eff_aggression(c, s) > 1 ? 1.0 : 1.0 * -1;
+            if (S.max_friends[s] != 0) social_h = ((S.n_friends[s] * (2.0 / S.max_friends[s])) - 1) * 1.0;
+            S.conflict_happiness[s] = conflict_h; S.social_happiness[s] = social_h;
+        }
+        const double health_h = is_sick(c, s) ? 1.0 * -1 : 1.0;
+        if (diseased) c.x.diseases.health_happiness[s] = health_h;
+        a.happiness[s] = conflict_h + family_h + health_h + social_h + wealth_h;
     } else {
         a.happiness[s] = family_h + 1.0 + wealth_h;
     }

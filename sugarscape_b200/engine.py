@@ -173,9 +173,10 @@ class Engine:
         if hs.ethics is not None:
             for name, _, _ in layout.ETHICS_FIELDS:
                 self.tensors["eth_" + name] = self._to_device(hs.ethics.arrays[name])
-        if hs.ext is not None:
+        if hs.ext is not None:      # as raw bytes: the families hold uint64 and struct arrays torch has no dtype for
+            self._ext_dtype = {key: arr.dtype for key, arr in hs.ext.arrays.items()}
             for key, arr in hs.ext.arrays.items():
-                self.tensors["ext:" + key] = self._to_device(arr)
+                self.tensors["ext:" + key] = self._to_device(np.ascontiguousarray(arr).view(np.uint8))
 
     def _structs(self):
         g = layout.Grid()
@@ -230,7 +231,7 @@ class Engine:
             if key.startswith("eth_"):
                 hs.ethics.arrays[key[4:]] = arr
             elif key.startswith("ext:"):
-                hs.ext.arrays[key[4:]] = arr
+                hs.ext.arrays[key[4:]] = arr.view(self._ext_dtype[key[4:]])
             else:
                 setattr(hs, key, arr)
         return hs
@@ -239,7 +240,7 @@ class Engine:
         swapped = bool(self.L.ssb_pollution_buffer(self.handle))
         for key in fields:
             arr = (hs.ethics.arrays[key[4:]] if key.startswith("eth_") else
-                   hs.ext.arrays[key[4:]] if key.startswith("ext:") else getattr(hs, key))
+                   np.ascontiguousarray(hs.ext.arrays[key[4:]]).view(np.uint8) if key.startswith("ext:") else getattr(hs, key))
             if swapped and key in ("pollution", "pollution_flux"):
                 key = "pollution_flux" if key == "pollution" else "pollution"
             if arr.dtype == np.uint32:
@@ -313,7 +314,7 @@ class Engine:
         if self.ext is None:
             return None
         if "lending" in self.ext.families:
-            if int(self.tensors["ext:lending.counters"][layout.LC_OVERFLOW].item()) != 0:
+            if int(self.tensors["ext:lending.counters"].cpu().numpy().view(np.int64)[layout.LC_OVERFLOW]) != 0:
                 raise EngineError("loan pool exhausted")
         out = layout.ExtStats()
         self._check(self.L.ssb_ext_stats(self.handle, C.byref(out)))

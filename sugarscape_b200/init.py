@@ -20,7 +20,7 @@ import random
 
 import numpy as np
 
-from . import layout
+from . import layout, steptables
 
 
 class UnsupportedConfiguration(NotImplementedError):
@@ -95,8 +95,11 @@ def check_supported(c):
         problems.append("environmentWraparound=false")
     if c["agentLeader"]:
         problems.append("agentLeader")
-    if c["startingDiseases"] > 0 or c["diseaseList"]:
-        problems.append("diseases")
+    if c["diseaseList"]:
+        problems.append("diseaseList")
+    if c["startingDiseases"] > 0 and (c["agentImmuneSystemLength"] > 64 or c["diseaseTagStringLength"][1] > 32 or
+                                      c["diseaseTimeframe"] != [0, 0] or c["startingDiseases"] > 64):
+        problems.append("immune systems longer than 64 / disease tags longer than 32 / later-starting diseases / more than 64 diseases")
     if c["agentDepressionPercentage"] > 0:
         problems.append("depression")
     if c["agentRacialTagStringLength"] > 0 and c["environmentMaxRaces"] > 0:
@@ -463,7 +466,36 @@ def load_environment_file(c):
     return sugar_cap, spice_cap
 
 
-def build_initial_state(c, capacity=None, check=True):
+def configure_diseases(c, state, disease_endowments):
+    """configureDiseases after the agent shuffle (sugarscape.py:317-337): the initial infections, drawn from
+    the main stream like the rest of the init path."""
+    ext = state.ext
+    ext.define_diseases(disease_endowments)
+    n = int(state.counters[layout.C_N_LIST])
+    agents = [int(s) for s in state.a_order[:n]]
+    initial = list(range(len(disease_endowments)))
+    lo, hi = c["startingDiseasesPerAgent"]
+    unlimited = [lo, hi] == [0, 0]
+    curr = lo
+    listed = ext.arrays["diseases.defs"]["listed"]
+    for s in agents:
+        random.shuffle(initial)
+        for d in initial:
+            if ext.disease_count(s) >= curr and not unlimited:
+                curr += 1
+                break
+            if ext.nearest_hamming(s, d)[0] == 0:
+                continue
+            ext.catch_initial(s, d)
+            listed[d] += 1          # sugarscape.diseases gains one entry per initial infection
+            if unlimited:
+                initial.remove(d)
+                break
+        if curr > hi:
+            curr = lo
+
+
+def build_initial_state(c, capacity=None, check=True, diseases=None):
     """Environment + initial population + the init-time list shuffle; returns (state, population).
 
     Must be called right after verify_random_seed/verify_configuration so the main stream is
@@ -489,8 +521,8 @@ def build_initial_state(c, capacity=None, check=True):
 
     if uses_decision_models(c):
         state.ethics = layout.HostEthics(capacity, c)
-    if layout.HostExt.needed(c):
-        state.ext = layout.HostExt(capacity, c)
+    diseased = layout.HostExt.uses_diseases(c)
+    horizon = int(min(c["timesteps"], 1 << 20)) + 8
 
     occupied = np.zeros(W * H, dtype=bool)
     new_agents = pop.place(n0, occupied, 0, 0) if n0 > 0 else []
@@ -500,7 +532,14 @@ def build_initial_state(c, capacity=None, check=True):
     if new_agents:
         pop.disease_endowments = randomize_disease_endowments(c, min(len(new_agents), int(c["startingDiseases"])), 0)
         random.shuffle(new_agents)
+    if layout.HostExt.needed(c):
+        state.ext = layout.HostExt(capacity, c, len(pop.disease_endowments) if diseased else 0, horizon)
+        if diseased:
+            state.ext.arrays["diseases.immune_bits"][:] = steptables.immune_tables(1, horizon, int(c["agentImmuneSystemLength"]))
     state.append_agents(new_agents)
+    # (oracle-only tests pass check=False and run configureDiseases through the oracle binding instead)
+    if diseased and (check if diseases is None else diseases) and new_agents:
+        configure_diseases(c, state, pop.disease_endowments)
     state.counters[layout.C_NEXT_ID] = len(new_agents)
     state.counters[layout.C_ENDOW_INDEX] = pop.endowment_index
     return state, pop

@@ -284,7 +284,25 @@ SOCIAL_LAYOUT = (
     ("social_happiness", _F64, 0, "cap"), ("conflict_happiness", _F64, 0, "cap"), ("n_friends", _I32, 0, "cap"),
     ("friend_slot", _I32, -1, "friends"), ("friend_id", _I32, -1, "friends"), ("friend_hd", _I32, 0, "friends"),
 )
-EXT_FAMILIES = (("lending", LENDING_LAYOUT), ("social", SOCIAL_LAYOUT))
+DM_AGGRESSION, DM_FERTILITY, DM_FRIENDLINESS, DM_HAPPINESS, DM_MOVEMENT, DM_SPICE_METAB, DM_SUGAR_METAB, DM_VISION, DM_COUNT = range(9)
+DISEASE_PENALTIES = ("aggressionPenalty", "fertilityPenalty", "friendlinessPenalty", "happinessPenalty", "movementPenalty",
+                     "spiceMetabolismPenalty", "sugarMetabolismPenalty", "visionPenalty")      # SSB_DM_* order
+DISEASE_DEF = np.dtype([("id", "<i4"), ("incubation", "<i4"), ("start_timestep", "<i4"), ("tag_len", "<i4"), ("tags", "<u4"),
+                        ("pad", "<u4"), ("transmission", "<f8"), ("penalty", "<f8", (DM_COUNT,)), ("infected", "<i8"),
+                        ("listed", "<i8")])      # ssb_disease_def_t
+_U64 = np.uint64
+DISEASE_LAYOUT = (
+    ("immune", _U64, 0, "cap"), ("start_immune", _U64, 0, "cap"), ("protection", _F64, 0, "cap"),
+    ("modifier", _F64, 0, "mods"),
+    ("disease_death", _I32, 0, "cap"), ("last_spread", _I32, -1, "cap"), ("n_spread", _I32, 0, "cap"),
+    ("health_happiness", _F64, 0, "cap"), ("last_valid_moves", _I32, 0, "cap"), ("stat_mark", _I32, -1, "cap"),
+    ("n_sick", _I32, 0, "cap"),
+    ("sick_disease", _I32, -1, "sick"), ("sick_start", _I32, 0, "sick"), ("sick_end", _I32, 0, "sick"),
+    ("sick_caught", _I32, 0, "sick"), ("sick_incubation", _I32, 0, "sick"), ("sick_infector_slot", _I32, -1, "sick"),
+    ("sick_infector_id", _I32, -1, "sick"),
+    ("defs", DISEASE_DEF, 0, "defs"), ("immune_bits", _U64, 0, "bits"),
+)
+EXT_FAMILIES = (("lending", LENDING_LAYOUT), ("social", SOCIAL_LAYOUT), ("diseases", DISEASE_LAYOUT))
 
 
 def _family_struct(name, table):
@@ -295,37 +313,55 @@ Lending = _family_struct("Lending", LENDING_LAYOUT)
 Social = _family_struct("Social", SOCIAL_LAYOUT)
 
 
+class Diseases(C.Structure):
+    _fields_ = ([(n, C.c_void_p) for n, _, _, _ in DISEASE_LAYOUT]
+                + [("max_sick", C.c_int32), ("immune_len", C.c_int32), ("n_diseases", C.c_int32), ("n_immune_bits", C.c_int32)])
+
+
 class Ext(C.Structure):
-    _fields_ = [("capacity", C.c_int64), ("lending", Lending), ("social", Social)]
+    _fields_ = [("capacity", C.c_int64), ("lending", Lending), ("social", Social), ("diseases", Diseases)]
 
 
 class ExtStats(C.Structure):
-    _fields_ = [("loan_volume", C.c_int64), ("sum_social_happiness", C.c_double), ("sum_conflict_happiness", C.c_double)]
+    _fields_ = [("loan_volume", C.c_int64), ("sum_social_happiness", C.c_double), ("sum_conflict_happiness", C.c_double),
+                ("sick_agents", C.c_int64), ("disease_incidence", C.c_int64), ("distinct_infectors", C.c_int64),
+                ("disease_prevalence", C.c_int64), ("disease_deaths", C.c_int64), ("sum_health_happiness", C.c_double),
+                ("move_space", C.c_int64), ("sum_burn_rate", C.c_double), ("sum_ttl_age_limited", C.c_double)]
 
 
 class HostExt:
     """Host mirror of ssb_ext_t: the per-slot state of the optional rule families that are live in this
     configuration.  `arrays["<family>.<member>"]` are numpy arrays; a family that is off has none."""
 
-    def __init__(self, capacity, c):
+    def __init__(self, capacity, c, n_diseases=0, horizon=0):
         self.capacity = capacity
         self.families = set()
         if c["agentLendingFactor"][1] > 0:
             self.families.add("lending")
         if c["agentMaxFriends"][1] > 0:
             self.families.add("social")
-        self.sizes = {"cap": capacity, "pool": 8 * capacity, "dead": 4 * capacity, "friends": capacity * MAX_FRIENDS}
+        if self.uses_diseases(c):
+            self.families.add("diseases")
+        self.n_diseases, self.max_sick = n_diseases, max(n_diseases, 1)
+        self.immune_len = int(c["agentImmuneSystemLength"])
+        self.sizes = {"cap": capacity, "pool": 8 * capacity, "dead": 4 * capacity, "friends": capacity * MAX_FRIENDS,
+                      "mods": capacity * DM_COUNT, "sick": capacity * self.max_sick, "defs": self.max_sick, "bits": horizon + 1}
         self.arrays = {}
         for fam, table in EXT_FAMILIES:
             if fam not in self.families:
                 continue
             for n, dt, fill, length in table:
                 if dt is not None:
-                    self.arrays[fam + "." + n] = np.full(self.sizes.get(length, length), fill, dtype=dt)
+                    count = self.sizes.get(length, length)
+                    self.arrays[fam + "." + n] = np.zeros(count, dtype=dt) if fill == 0 else np.full(count, fill, dtype=dt)
+
+    @staticmethod
+    def uses_diseases(c):
+        return c["startingDiseases"] > 0 and c["agentImmuneSystemLength"] > 0
 
     @staticmethod
     def needed(c):
-        return c["agentLendingFactor"][1] > 0 or c["agentMaxFriends"][1] > 0
+        return c["agentLendingFactor"][1] > 0 or c["agentMaxFriends"][1] > 0 or HostExt.uses_diseases(c)
 
     def _free_chain(self, head):
         """Give the loan records of a list back to the pool (a new agent object starts with empty lists)."""
@@ -357,6 +393,60 @@ class HostExt:
             A["social.social_happiness"][slot] = 0
             A["social.conflict_happiness"][slot] = 0
             A["social.n_friends"][slot] = 0
+        if "diseases" in self.families:
+            A["diseases.n_sick"][slot] = 0
+            A["diseases.modifier"][slot * DM_COUNT:(slot + 1) * DM_COUNT] = 0
+            for name, fill in (("disease_death", 0), ("last_spread", -1), ("n_spread", 0), ("health_happiness", 0),
+                               ("last_valid_moves", 0)):
+                A["diseases." + name][slot] = fill
+            bits = sum(b << k for k, b in enumerate(endowment["immuneSystem"]))
+            A["diseases.immune"][slot] = A["diseases.start_immune"][slot] = bits
+            A["diseases.protection"][slot] = endowment["diseaseProtectionChance"]
+
+    # -- diseases: the init-time part of the rule (configureDiseases, sugarscape.py:286-337) ----------------
+    def define_diseases(self, disease_endowments):
+        defs = self.arrays["diseases.defs"]
+        for i, e in enumerate(disease_endowments):
+            if e["startTimestep"] != 0 or len(e["tags"]) > 32:
+                raise NotImplementedError("later-starting diseases / disease tags longer than 32")
+            d = defs[i]
+            d["id"], d["incubation"], d["start_timestep"], d["tag_len"] = i, int(e["incubationPeriod"]), 0, len(e["tags"])
+            d["tags"] = sum(b << k for k, b in enumerate(e["tags"]))
+            d["transmission"] = float(e["transmissionChance"])
+            d["penalty"] = [float(e[name]) for name in DISEASE_PENALTIES]
+
+    def disease_count(self, slot):
+        return int(self.arrays["diseases.n_sick"][slot])
+
+    def nearest_hamming(self, slot, di):
+        """findNearestHammingDistanceInDisease (agent.py:1034-1050): (distance, start, end)."""
+        d = self.arrays["diseases.defs"][di]
+        length, tags, immune = int(d["tag_len"]), int(d["tags"]), int(self.arrays["diseases.immune"][slot])
+        best, b0, b1 = length, 0, length - 1
+        mask = (1 << length) - 1
+        for i in range(self.immune_len - length):
+            hd = bin(((immune >> i) & mask) ^ tags).count("1")
+            if hd < best:
+                best, b0, b1 = hd, i, i + (length - 1)
+        return best, b0, b1
+
+    def catch_initial(self, slot, di):
+        """catchDisease(disease, initial=True) (agent.py:227-247, 184-188): no infection attempt, no infector."""
+        A = self.arrays
+        base, n = slot * self.max_sick, int(A["diseases.n_sick"][slot])
+        if any(int(A["diseases.sick_disease"][base + k]) == di for k in range(n)):
+            return
+        hd, start, end = self.nearest_hamming(slot, di)
+        if hd == 0:
+            return
+        d = A["diseases.defs"][di]
+        for name, v in (("disease", di), ("start", start), ("end", end), ("caught", 0), ("incubation", int(d["incubation"])),
+                        ("infector_slot", -1), ("infector_id", -1)):
+            A["diseases.sick_" + name][base + n] = v
+        A["diseases.n_sick"][slot] = n + 1
+        d["infected"] += 1
+        if int(d["incubation"]) == 0:
+            A["diseases.modifier"][slot * DM_COUNT:(slot + 1) * DM_COUNT] += d["penalty"]
 
     def as_struct(self, pointer_of=lambda arr: arr.ctypes.data):
         x = Ext()
@@ -365,6 +455,9 @@ class HostExt:
             if fam not in self.families:
                 continue
             sub = getattr(x, fam)
+            if fam == "diseases":
+                sub.max_sick, sub.immune_len, sub.n_diseases = self.max_sick, self.immune_len, self.n_diseases
+                sub.n_immune_bits = len(self.arrays["diseases.immune_bits"])
             for n, dt, _, _ in table:
                 if dt is None:
                     setattr(sub, n, self.sizes[n.split("_")[0]])      # pool_capacity / dead_capacity
@@ -379,6 +472,7 @@ class HostExt:
     def copy(self):
         h = HostExt.__new__(HostExt)
         h.capacity, h.families, h.sizes = self.capacity, set(self.families), dict(self.sizes)
+        h.n_diseases, h.max_sick, h.immune_len = self.n_diseases, self.max_sick, self.immune_len
         h.arrays = {k: v.copy() for k, v in self.arrays.items()}
         return h
 

@@ -80,6 +80,7 @@ class StatsBuilder:
         north_rows = min(max(equator, 0), H)
         self.n_north = W * north_rows
         self.n_south = W * (H - north_rows)
+        self.diseased = c["startingDiseases"] > 0 and c["agentImmuneSystemLength"] > 0
         self.constant = {}
         for key, option in (("meanSelfishness", "agentSelfishnessFactor"),
                             ("meanAgeismFactor", "agentDecisionModelAgeismFactor"),
@@ -167,6 +168,14 @@ class StatsBuilder:
                 out["loanVolume"] = int(ext.loan_volume)
                 out["meanSocialHappiness"] = round(ext.sum_social_happiness / n, 2)
                 out["meanConflictHappiness"] = round(ext.sum_conflict_happiness / n, 2)
+            if ext is not None and self.diseased:
+                # sugarscape.py:1162, 1200-1211, 1228, 1254-1277, 1316-1317; time to live with the disease modifiers
+                out["sickAgentsPercentage"] = round((ext.sick_agents / n) * 100, 2)
+                out["diseaseEffectiveReproductionRate"] = (round(ext.disease_incidence / ext.distinct_infectors, 2)
+                                                           if ext.distinct_infectors else 0)
+                out["meanHealthHappiness"] = round(ext.sum_health_happiness / n, 2)
+                out["agentMeanTimeToLive"] = round(ext.sum_ttl_age_limited / n, 2)
+                out["agentWealthBurnRate"] = round(ext.sum_burn_rate / n, 2)
             if ethics is not None:
                 out["meanSelfishness"] = round(ethics.sum_selfishness / n, 2)
                 out["agentLastMoveOptimalityPercentage"] = round((ethics.optimal_moves / ethics.moves) * 100, 2)
@@ -196,6 +205,12 @@ class StatsBuilder:
             out["meanValidMoves"] = 0
             out["meanMoveRank"] = 0
             out["meanMoveDifferenceFromOptimal"] = 0
+        if ext is not None and self.diseased:
+            out["sickAgents"] = int(ext.sick_agents)
+            out["diseaseIncidence"] = int(ext.disease_incidence)
+            out["diseasePrevalence"] = int(ext.disease_prevalence)
+            out["agentDiseaseDeaths"] = int(ext.disease_deaths)
+            out["moveSpace"] = int(ext.move_space)
         for key, value in out.items():
             rs[key] = value
         rs["environmentWealthCreated"] = environment_wealth_created(

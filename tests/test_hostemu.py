@@ -135,3 +135,23 @@ def test_device_lending_friends_combat_source_matches_reference_on_dune():
     meta, _ = pu.load_golden("dune")
     history = _run_with_extensions(c, state, pop, params, endow, tags, meta["steps"], meta["log"])
     assert sum(h["meanConflictHappiness"] != 0 for h in history) > 50
+
+
+def test_device_disease_source_matches_reference_on_disease_basic():
+    """examples/disease_basic.json through the device source of doDisease / catchDisease (csrc/ssb_ext.cuh) and the
+    host's configureDiseases (init.configure_diseases): extinct after five steps, every digest and log key on the way."""
+    c, state, pop, params, endow, tags = pu.build("disease_basic")
+    assert state.ext is not None and "diseases" in state.ext.families
+    meta, _ = pu.load_golden("disease_basic")
+    history = _run_with_extensions(c, state, pop, params, endow, tags, meta["steps"], meta["log"])
+    assert sum(h["sickAgents"] > 0 for h in history) >= 4
+
+
+@pytest.mark.parametrize("variant,min_sick_steps", [("disease_mild", 15), ("disease_endemic", 80)])
+def test_device_disease_source_matches_reference_on_variants(variant, min_sick_steps):
+    """Milder diseases (variant fixtures from the unmodified reference): incubation, transmission / protection draws,
+    recovery through the immune response, births with inherited immune systems, vision pushed to 0."""
+    base, overrides, gold, log = pu.load_variant(variant)
+    c, state, pop, params, endow, tags = pu.build(base, overrides=overrides)
+    history = _run_with_extensions(c, state, pop, params, endow, tags, gold, log)
+    assert sum(h["sickAgents"] > 0 for h in history) >= min_sick_steps

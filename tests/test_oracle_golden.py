@@ -22,7 +22,7 @@ SUPPORTED = [
     "trade_pollution", "trade_replacement", "trade_reproduction", "trade_tagging",
     "trade_tagging_reproduction",
 ]
-UNSUPPORTED = ["all_features", "determinism", "disease_basic"]
+UNSUPPORTED = ["all_features", "determinism"]
 
 
 def _close(a, b):

@@ -74,6 +74,38 @@ def test_lending_and_friends_examples_match_reference_trajectory(name):
     eng.close()
 
 
+@pytest.mark.parametrize("case", ["disease_basic", "disease_mild", "disease_endemic"])
+def test_disease_cases_match_reference_trajectory(case):
+    """examples/disease_basic.json and two milder variants (fixtures of the unmodified reference): configureDiseases
+    on the host, doDisease / catchDisease, the find* modifiers, inherited immune systems on the device."""
+    if case == "disease_basic":
+        meta, _ = pu.load_golden(case)
+        base, overrides, gold, log = case, None, meta["steps"], meta["log"]
+    else:
+        base, overrides, gold, log = pu.load_variant(case)
+    c, state, pop, params, endow, tags, eng = _engine(base, layout.RNG_EXACT, overrides)
+    assert state.ext is not None and "diseases" in state.ext.families
+    sb = stats.StatsBuilder(c, init.equator(c))
+    eng.reduce_stats(0)
+    rs = sb.update(eng.stats(), 0, 0, eng.ethics_stats(), eng.ext_stats())
+    for k in ("sickAgents", "diseaseIncidence", "diseasePrevalence"):
+        assert rs[k] == log[0][k], f"{k} differs after init"
+    sick_steps = 0
+    for t in range(1, len(gold)):
+        eng.env_step(t)
+        eng.agent_step(t, rs["meanWealth"])
+        eng.compact(t)
+        eng.reduce_stats(t)
+        rs = sb.update(eng.stats(), t, 0, eng.ethics_stats(), eng.ext_stats())
+        d, snap = pu.state_digests(eng.download(), *eng.mt_state())
+        assert d == gold[t]["digests"], f"{case}: state differs from the reference at t={t}"
+        sick_steps += rs["sickAgents"] > 0
+        for k in stats.LOG_KEYS:
+            assert _close(rs[k], log[t][k]), f"{case}: log key {k} at t={t}: {rs[k]} vs {log[t][k]}"
+    assert sick_steps >= 4
+    eng.close()
+
+
 def test_drop_in_driver_writes_the_reference_log_with_decision_models(tmp_path):
     """The reference-facing entry point (sugarscape_b200.simulation.Sugarscape, what `sugarscape.py --conf` runs)
     on the ethics_trade configuration: the log.json it writes equals the reference's log entry by entry."""
