@@ -303,11 +303,28 @@ typedef struct ssb_diseases {
     int32_t max_sick, immune_len, n_diseases, n_immune_bits;
 } ssb_diseases_t;
 
+/* universal income (agent.py:708-714, 1127-1134), racial tags (1082-1086; inheritance 879-887) and depression
+ * (condition.py:13-34; agent.py:137-141, 889-895) */
+typedef struct ssb_misc {
+    double  *universal_sugar, *universal_spice;
+    int32_t *last_income_sugar, *last_income_spice;
+    uint32_t *racial_tags;                            /* 2 bits per position                                */
+    int32_t *race;                                    /* -1 = None                                          */
+    int32_t *depressed;
+    double  *happiness_unit;                          /* 1, 0.5763 when depressed                           */
+    double  *health_happiness;                        /* as of the agent's last updateHappiness (used when diseases are off) */
+    const uint32_t *racial_picks;                     /* per timestep: the parent each racial tag comes from */
+    const double *depression_draw;                    /* per timestep: the draw a child's depression is decided with */
+    double  depression_percentage;
+    int32_t income_interval_sugar, income_interval_spice, racial_len, n_races, n_tables, _pad;
+} ssb_misc_t;
+
 typedef struct ssb_ext {
     int64_t capacity;
     ssb_lending_t lending;
     ssb_social_t social;
     ssb_diseases_t diseases;
+    ssb_misc_t misc;
 } ssb_ext_t;
 /* raw sums for the log keys of the families (sugarscape.py:1130-1160) */
 typedef struct ssb_ext_stats {
@@ -318,6 +335,7 @@ typedef struct ssb_ext_stats {
     double  sum_health_happiness;
     int64_t move_space;                               /* sum of lastValidMoves                              */
     double  sum_burn_rate, sum_ttl_age_limited;       /* findTimeToLive with the disease modifiers, list order */
+    int64_t race_count[4], race_first[4];             /* agents per race, list index of the first one (-1 none) */
 } ssb_ext_stats_t;
 /* call after ssb_bind, before the first step (mode E only) */
 int  ssb_bind_ext(ssb_engine_t *e, const ssb_ext_t *ext);

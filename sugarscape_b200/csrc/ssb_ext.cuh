@@ -10,11 +10,14 @@ namespace ssb {
 // child endowment bits of the families (sugarscape_b200/steptables.py ENDOWMENT_BITS)
 enum { EB_BASE_INTEREST = 12, EB_LENDING_FACTOR = 13, EB_LOAN_DURATION = 14, EB_MAX_FRIENDS = 15 };
 
-enum { EB_PROTECTION = 16 };
+enum { EB_PROTECTION = 16, EB_UNIVERSAL_SPICE = 17, EB_UNIVERSAL_SUGAR = 18 };
 
 __device__ __forceinline__ bool has_lending(const DevCtx &c) { return c.x.lending.lending_factor != nullptr; }
 __device__ __forceinline__ bool has_social(const DevCtx &c) { return c.x.social.max_friends != nullptr; }
 __device__ __forceinline__ bool has_disease(const DevCtx &c) { return c.x.diseases.immune != nullptr; }
+__device__ __forceinline__ bool has_misc(const DevCtx &c) { return c.x.misc.universal_sugar != nullptr; }
+// happinessUnit: 1, 0.5763 when depressed
+__device__ __forceinline__ double happiness_unit(const DevCtx &c, int s) { return has_misc(c) ? c.x.misc.happiness_unit[s] : 1.0; }
 
 // the find* accessors (agent.py:716-717, 1031-1032, 1107-1111, 1161-1162): endowment + disease modifier, floored at 0
 __device__ __forceinline__ double dis_mod(const DevCtx &c, int s, int which) {
@@ -36,11 +39,63 @@ __device__ __forceinline__ bool is_fertile_x(const DevCtx &c, int s) {
 __device__ __forceinline__ double time_to_live_x(const DevCtx &c, int s, bool age_limited) {
     const double sm = eff_sugar_metab(c, s), pm = eff_spice_metab(c, s);
     const double big = 9223372036854775807.0;            // sys.maxsize
-    const double st = sm > 0 ? c.a.sugar[s] / sm : big;
-    const double pt = pm > 0 ? c.a.spice[s] / pm : big;
+    double st = sm > 0 ? c.a.sugar[s] / sm : big;
+    double pt = pm > 0 ? c.a.spice[s] / pm : big;
+    if (has_misc(c)) {                                   // the universal income term (agent.py:1127-1134)
+        const ssb_misc_t &M = c.x.misc;
+        if (M.universal_sugar[s] != 0) {
+            const double income = (st * M.universal_sugar[s]) / M.income_interval_sugar;
+            st = sm > 0 ? (c.a.sugar[s] + income) / sm : big;
+        }
+        if (M.universal_spice[s] != 0) {
+            const double income = (pt * M.universal_spice[s]) / M.income_interval_spice;
+            pt = pm > 0 ? (c.a.spice[s] + income) / pm : big;
+        }
+    }
     double ttl = st < pt ? st : pt;
     if (age_limited) { const double lim = (double)(c.a.max_age[s] - c.a.age[s]); if (lim < ttl) ttl = lim; }
     return ttl;
+}
+
+// ---------------------------------------------------------------------------------------------
+// universal income, racial tags, depression
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int race_of(uint32_t tags, int len) {          // findRace: most common tag, the smallest among ties
+    int cnt[4] = {0, 0, 0, 0};
+    for (int i = 0; i < len; i++) cnt[(tags >> (2 * i)) & 3u]++;
+    int best = 0;
+    for (int r = 1; r < 4; r++) if (cnt[r] > cnt[best]) best = r;
+    return best;
+}
+// Depression.trigger (condition.py:27-33), at the creation of a depressed agent (agent.py:137-141)
+__device__ inline void depress(const DevCtx &c, int s) {
+    const ssb_agents_t &a = c.a;
+    c.x.misc.depressed[s] = 1;
+    a.aggression[s] *= 1.145;
+    if (c.x.social.max_friends != nullptr) c.x.social.max_friends[s] = (int32_t)ceil(c.x.social.max_friends[s] * 0.6333);
+    c.x.misc.happiness_unit[s] *= 0.5763;
+    a.movement[s] *= (int32_t)ceil(a.movement[s] * 0.429);
+    a.spice_metab[s] *= (int32_t)ceil(a.spice_metab[s] * 1.544);
+    a.sugar_metab[s] *= (int32_t)ceil(a.sugar_metab[s] * 1.544);
+}
+// the child's share of the family (agent.py:845-851, 879-895); called once its endowments are in place
+__device__ inline void misc_child(const DevCtx &c, int ch, int s, int m, uint32_t eb) {
+    const ssb_misc_t &M = c.x.misc;
+    M.universal_spice[ch] = ((eb >> EB_UNIVERSAL_SPICE) & 1u) ? M.universal_spice[m] : M.universal_spice[s];
+    M.universal_sugar[ch] = ((eb >> EB_UNIVERSAL_SUGAR) & 1u) ? M.universal_sugar[m] : M.universal_sugar[s];
+    M.last_income_sugar[ch] = 0; M.last_income_spice[ch] = 0;
+    M.depressed[ch] = 0; M.happiness_unit[ch] = 1; M.health_happiness[ch] = 0;
+    M.race[ch] = -1; M.racial_tags[ch] = 0;
+    if (M.racial_len > 0) {      // random.choice([mine, mate's]) per position (agent.py:885-886)
+        const uint32_t picks = c.t < M.n_tables ? M.racial_picks[c.t] : 0u;
+        uint32_t rt = 0;
+        for (int i = 0; i < M.racial_len; i++) {
+            const uint32_t src = ((picks >> i) & 1u) ? M.racial_tags[m] : M.racial_tags[s];
+            rt |= ((src >> (2 * i)) & 3u) << (2 * i);
+        }
+        M.racial_tags[ch] = rt;
+        M.race[ch] = race_of(rt, M.racial_len);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -473,12 +528,23 @@ __device__ inline void ext_stats_body(const DevCtx &c, ssb_ext_stats_t *out) {
     r.loan_volume = 0; r.sum_social_happiness = 0; r.sum_conflict_happiness = 0;
     r.sick_agents = 0; r.disease_incidence = 0; r.distinct_infectors = 0; r.disease_prevalence = 0; r.disease_deaths = 0;
     r.sum_health_happiness = 0; r.move_space = 0; r.sum_burn_rate = 0; r.sum_ttl_age_limited = 0;
+    for (int k = 0; k < 4; k++) { r.race_count[k] = 0; r.race_first[k] = -1; }
     const long long n = c.a.counters[SSB_C_N_LIST], n_dead = c.a.counters[SSB_C_N_DEAD];
     const ssb_diseases_t &D = c.x.diseases;
     for (long long i = 0; i < n; i++) {
         const int s = c.a.order[i];
         if (has_lending(c) && c.x.lending.last_lended[s] == c.t) r.loan_volume += c.x.lending.last_loans[s];
         if (has_social(c)) { r.sum_social_happiness += c.x.social.social_happiness[s]; r.sum_conflict_happiness += c.x.social.conflict_happiness[s]; }
+        if (has_misc(c) && c.x.misc.racial_len > 0) {
+            const int race = c.x.misc.race[s];
+            if (race >= 0 && race < 4 && r.race_count[race]++ == 0) r.race_first[race] = i;
+        }
+        if (!has_disease(c) && has_misc(c)) r.sum_health_happiness += c.x.misc.health_happiness[s];
+        if (has_disease(c) || has_misc(c)) {      // findTimeToLive with the modifiers / the universal income term
+            const double ttl = time_to_live_x(c, s, false);
+            r.sum_burn_rate += ttl;
+            r.sum_ttl_age_limited += fmin(ttl, (double)(c.a.max_age[s] - c.a.age[s]));
+        }
         if (has_disease(c)) {
             const long long b = (long long)s * D.max_sick;
             if (D.n_sick[s] > 0) r.sick_agents++;
@@ -491,9 +557,6 @@ __device__ inline void ext_stats_body(const DevCtx &c, ssb_ext_stats_t *out) {
                 }
             r.sum_health_happiness += D.health_happiness[s];
             r.move_space += D.last_valid_moves[s];
-            const double ttl = time_to_live_x(c, s, false);
-            r.sum_burn_rate += ttl;
-            r.sum_ttl_age_limited += fmin(ttl, (double)(c.a.max_age[s] - c.a.age[s]));
         }
     }
     if (has_disease(c)) {

@@ -728,6 +728,11 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rn
         sugar += b_cs;
         spice += b_cp;
         if (EXT && has_lending(c)) lending_note_income(c, s, b_cs, b_cp);
+        if (EXT && has_misc(c)) {        // doUniversalIncome (agent.py:708-714): spice first
+            const ssb_misc_t &M = c.x.misc;
+            if ((c.t - M.last_income_spice[s]) >= M.income_interval_spice) { spice += M.universal_spice[s]; M.last_income_spice[s] = c.t; }
+            if ((c.t - M.last_income_sugar[s]) >= M.income_interval_sugar) { sugar += M.universal_sugar[s]; M.last_income_sugar[s] = c.t; }
+        }
         const bool polluting = c.p.pollution_start <= c.t && c.t <= c.p.pollution_end;
         double cell_poll = b_pl;
         if (polluting) {
@@ -1014,6 +1019,7 @@ __device__ __noinline__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
             c.eth.last_move_optimal[ch] = 1; c.eth.move_rank[ch] = 0; c.eth.move_diff[ch] = 0;      // lastMoveOptimal starts True
         }
         if (diseased) disease_child(c, ch, s, m, eb);
+        if (EXT && has_misc(c)) misc_child(c, ch, s, m, eb);
         if (EXT && has_social(c)) {
             social_reset_slot(c, ch);
             c.x.social.max_friends[ch] = ((eb >> EB_MAX_FRIENDS) & 1u) ? c.x.social.max_friends[m] : c.x.social.max_friends[s];
@@ -1024,6 +1030,11 @@ __device__ __noinline__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
             L.base_interest_rate[ch] = ((eb >> EB_BASE_INTEREST) & 1u) ? L.base_interest_rate[m] : L.base_interest_rate[s];
             L.lending_factor[ch] = ((eb >> EB_LENDING_FACTOR) & 1u) ? L.lending_factor[m] : L.lending_factor[s];
             L.loan_duration[ch] = ((eb >> EB_LOAN_DURATION) & 1u) ? L.loan_duration[m] : L.loan_duration[s];
+        }
+        if (EXT && has_misc(c)) {
+            // the child is depressed with the configured chance, decided by the private stream (agent.py:889-895)
+            const double draw = c.t < c.x.misc.n_tables ? c.x.misc.depression_draw[c.t] : 1.0;
+            if (draw <= c.x.misc.depression_percentage) depress(c, ch);
         }
         a.pos[ch] = cell;
         c.g.occ[cell] = ch;
@@ -1079,34 +1090,38 @@ __device__ void transaction_interact_phase(const DevCtx &c, int s, const AgentRe
     if (age >= rec.max_age && rec.max_age != -1) { do_death<EXT>(c, s, SSB_AGING); return; }
     // updateHappiness (agent.py:1522-1530): conflict (0: no aggression in the supported examples'
     // logs) + family + health (+1: no diseases) + social (0: no friends) + wealth
-    const double wealth_h = erf((sugar + spice) - c.prev_mean_wealth);
+    const double unit = EXT ? happiness_unit(c, s) : 1.0;       // happinessUnit: 0.5763 when depressed
+    double diff_wealth = (sugar + spice) - c.prev_mean_wealth;  // findWealthHappiness (agent.py:1164-1168)
+    if (EXT && has_misc(c)) diff_wealth *= unit;
+    const double wealth_h = erf(diff_wealth);
     // findFamilyHappiness (agent.py:940-958): mode E only (mode S keeps no kin lists: the relatives
     // can be anywhere and change concurrently)
     double family = 0;
     if (EXACT && (c.p.flags & SSB_F_REPRO)) {
         for (int e = a.children_head[s]; e >= 0; e = a.kin_next[e]) {
             const int o = kin_alive(c, e);
-            if (o >= 0) { family += 1; if (diseased && is_sick(c, o)) family -= 1.0 * 0.5; if (a.born[o] == c.t) family += 1; } else family -= 1;
+            if (o >= 0) { family += unit; if (diseased && is_sick(c, o)) family -= unit * 0.5; if (a.born[o] == c.t) family += unit; } else family -= unit;
         }
         for (int e = a.mates_head[s]; e >= 0; e = a.kin_next[e]) {
             const int o = kin_alive(c, e);
-            if (o >= 0) { family += 1; if (diseased && is_sick(c, o)) family -= 1.0 * 0.5; } else family -= 1;
+            if (o >= 0) { family += unit; if (diseased && is_sick(c, o)) family -= unit * 0.5; } else family -= unit;
         }
     }
     const double family_h = erf(family);
     a.wealth_happiness[s] = wealth_h;
     a.family_happiness[s] = family_h;
-    if (EXT && (has_social(c) || diseased)) {
+    if (EXT && (has_social(c) || diseased || has_misc(c))) {
         // findConflictHappiness (agent.py:912-918), findSocialHappiness (1099-1105), findHealthHappiness (1017-1021)
         double conflict_h = 0, social_h = 0;
         if (has_social(c)) {
             const ssb_social_t &S = c.x.social;
-            if (S.last_combat[s] == c.t) conflict_h = eff_aggression(c, s) > 1 ? 1.0 : 1.0 * -1;
-            if (S.max_friends[s] != 0) social_h = ((S.n_friends[s] * (2.0 / S.max_friends[s])) - 1) * 1.0;
+            if (S.last_combat[s] == c.t) conflict_h = eff_aggression(c, s) > 1 ? unit : unit * -1;
+            if (S.max_friends[s] != 0) social_h = ((S.n_friends[s] * (2.0 / S.max_friends[s])) - 1) * unit;
             S.conflict_happiness[s] = conflict_h; S.social_happiness[s] = social_h;
         }
-        const double health_h = is_sick(c, s) ? 1.0 * -1 : 1.0;
+        const double health_h = is_sick(c, s) ? unit * -1 : unit;
         if (diseased) c.x.diseases.health_happiness[s] = health_h;
+        else if (has_misc(c)) c.x.misc.health_happiness[s] = health_h;
         a.happiness[s] = conflict_h + family_h + health_h + social_h + wealth_h;
     } else {
         a.happiness[s] = family_h + 1.0 + wealth_h;

@@ -100,16 +100,12 @@ def check_supported(c):
     if c["startingDiseases"] > 0 and (c["agentImmuneSystemLength"] > 64 or c["diseaseTagStringLength"][1] > 32 or
                                       c["diseaseTimeframe"] != [0, 0] or c["startingDiseases"] > 64):
         problems.append("immune systems longer than 64 / disease tags longer than 32 / later-starting diseases / more than 64 diseases")
-    if c["agentDepressionPercentage"] > 0:
-        problems.append("depression")
-    if c["agentRacialTagStringLength"] > 0 and c["environmentMaxRaces"] > 0:
-        problems.append("racial tags")
+    if c["environmentMaxRaces"] > 0 and (c["agentRacialTagStringLength"] > 16 or c["environmentMaxRaces"] > 4):
+        problems.append("racial tag strings longer than 16 / more than 4 races")
     if c["agentInheritancePolicy"] not in ("none", "children", "sons", "daughters"):
         problems.append("inheritance policy " + str(c["agentInheritancePolicy"]))
     if c["agentMaxFriends"][1] > layout.MAX_FRIENDS:
         problems.append("more than %d friends" % layout.MAX_FRIENDS)
-    if c["agentUniversalSugar"][1] != 0 or c["agentUniversalSpice"][1] != 0:
-        problems.append("universal income")
     bad_models = [m for m in c["agentDecisionModels"] if m not in SUPPORTED_DECISION_MODELS]
     if bad_models:
         problems.append("decision models other than rawSugarscape and the Bentham family: " + ", ".join(bad_models))
@@ -536,6 +532,10 @@ def build_initial_state(c, capacity=None, check=True, diseases=None):
         state.ext = layout.HostExt(capacity, c, len(pop.disease_endowments) if diseased else 0, horizon)
         if diseased:
             state.ext.arrays["diseases.immune_bits"][:] = steptables.immune_tables(1, horizon, int(c["agentImmuneSystemLength"]))
+        if "misc" in state.ext.families:
+            picks, draw = steptables.racial_tables(1, horizon, state.ext.racial_len)
+            state.ext.arrays["misc.racial_picks"][:] = picks
+            state.ext.arrays["misc.depression_draw"][:] = draw
     state.append_agents(new_agents)
     # (oracle-only tests pass check=False and run configureDiseases through the oracle binding instead)
     if diseased and (check if diseases is None else diseases) and new_agents:

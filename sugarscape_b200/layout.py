@@ -302,7 +302,14 @@ DISEASE_LAYOUT = (
     ("sick_infector_id", _I32, -1, "sick"),
     ("defs", DISEASE_DEF, 0, "defs"), ("immune_bits", _U64, 0, "bits"),
 )
-EXT_FAMILIES = (("lending", LENDING_LAYOUT), ("social", SOCIAL_LAYOUT), ("diseases", DISEASE_LAYOUT))
+MISC_LAYOUT = (
+    ("universal_sugar", _F64, 0, "cap"), ("universal_spice", _F64, 0, "cap"),
+    ("last_income_sugar", _I32, 0, "cap"), ("last_income_spice", _I32, 0, "cap"),
+    ("racial_tags", np.uint32, 0, "cap"), ("race", _I32, -1, "cap"), ("depressed", _I32, 0, "cap"),
+    ("happiness_unit", _F64, 1, "cap"), ("health_happiness", _F64, 0, "cap"),
+    ("racial_picks", np.uint32, 0, "bits"), ("depression_draw", _F64, 1, "bits"),
+)
+EXT_FAMILIES = (("lending", LENDING_LAYOUT), ("social", SOCIAL_LAYOUT), ("diseases", DISEASE_LAYOUT), ("misc", MISC_LAYOUT))
 
 
 def _family_struct(name, table):
@@ -318,15 +325,22 @@ class Diseases(C.Structure):
                 + [("max_sick", C.c_int32), ("immune_len", C.c_int32), ("n_diseases", C.c_int32), ("n_immune_bits", C.c_int32)])
 
 
+class Misc(C.Structure):
+    _fields_ = ([(n, C.c_void_p) for n, _, _, _ in MISC_LAYOUT]
+                + [("depression_percentage", C.c_double), ("income_interval_sugar", C.c_int32), ("income_interval_spice", C.c_int32),
+                   ("racial_len", C.c_int32), ("n_races", C.c_int32), ("n_tables", C.c_int32), ("_pad", C.c_int32)])
+
+
 class Ext(C.Structure):
-    _fields_ = [("capacity", C.c_int64), ("lending", Lending), ("social", Social), ("diseases", Diseases)]
+    _fields_ = [("capacity", C.c_int64), ("lending", Lending), ("social", Social), ("diseases", Diseases), ("misc", Misc)]
 
 
 class ExtStats(C.Structure):
     _fields_ = [("loan_volume", C.c_int64), ("sum_social_happiness", C.c_double), ("sum_conflict_happiness", C.c_double),
                 ("sick_agents", C.c_int64), ("disease_incidence", C.c_int64), ("distinct_infectors", C.c_int64),
                 ("disease_prevalence", C.c_int64), ("disease_deaths", C.c_int64), ("sum_health_happiness", C.c_double),
-                ("move_space", C.c_int64), ("sum_burn_rate", C.c_double), ("sum_ttl_age_limited", C.c_double)]
+                ("move_space", C.c_int64), ("sum_burn_rate", C.c_double), ("sum_ttl_age_limited", C.c_double),
+                ("race_count", C.c_int64 * 4), ("race_first", C.c_int64 * 4)]
 
 
 class HostExt:
@@ -342,6 +356,11 @@ class HostExt:
             self.families.add("social")
         if self.uses_diseases(c):
             self.families.add("diseases")
+        if self.uses_misc(c):
+            self.families.add("misc")
+        self.racial_len = int(c["agentRacialTagStringLength"]) if c["environmentMaxRaces"] > 0 else 0
+        self.misc_scalars = (float(c["agentDepressionPercentage"]), int(c["environmentUniversalSugarIncomeInterval"]),
+                             int(c["environmentUniversalSpiceIncomeInterval"]), self.racial_len, int(c["environmentMaxRaces"]))
         self.n_diseases, self.max_sick = n_diseases, max(n_diseases, 1)
         self.immune_len = int(c["agentImmuneSystemLength"])
         self.sizes = {"cap": capacity, "pool": 8 * capacity, "dead": 4 * capacity, "friends": capacity * MAX_FRIENDS,
@@ -360,8 +379,14 @@ class HostExt:
         return c["startingDiseases"] > 0 and c["agentImmuneSystemLength"] > 0
 
     @staticmethod
+    def uses_misc(c):
+        return (c["agentUniversalSugar"][1] != 0 or c["agentUniversalSpice"][1] != 0 or c["agentDepressionPercentage"] > 0 or
+                (c["agentRacialTagStringLength"] > 0 and c["environmentMaxRaces"] > 0))
+
+    @staticmethod
     def needed(c):
-        return c["agentLendingFactor"][1] > 0 or c["agentMaxFriends"][1] > 0 or HostExt.uses_diseases(c)
+        return (c["agentLendingFactor"][1] > 0 or c["agentMaxFriends"][1] > 0 or HostExt.uses_diseases(c) or
+                HostExt.uses_misc(c))
 
     def _free_chain(self, head):
         """Give the loan records of a list back to the pool (a new agent object starts with empty lists)."""
@@ -402,6 +427,17 @@ class HostExt:
             bits = sum(b << k for k, b in enumerate(endowment["immuneSystem"]))
             A["diseases.immune"][slot] = A["diseases.start_immune"][slot] = bits
             A["diseases.protection"][slot] = endowment["diseaseProtectionChance"]
+
+        if "misc" in self.families:
+            A["misc.universal_sugar"][slot] = endowment["universalSugar"]
+            A["misc.universal_spice"][slot] = endowment["universalSpice"]
+            for name, fill in (("last_income_sugar", 0), ("last_income_spice", 0), ("depressed", 0), ("happiness_unit", 1),
+                               ("health_happiness", 0), ("race", -1), ("racial_tags", 0)):
+                A["misc." + name][slot] = fill
+            rt = endowment["racialTags"]
+            if rt is not None:
+                A["misc.racial_tags"][slot] = sum(v << (2 * k) for k, v in enumerate(rt))
+                A["misc.race"][slot] = max(set(rt), key=rt.count)
 
     # -- diseases: the init-time part of the rule (configureDiseases, sugarscape.py:286-337) ----------------
     def define_diseases(self, disease_endowments):
@@ -455,6 +491,10 @@ class HostExt:
             if fam not in self.families:
                 continue
             sub = getattr(x, fam)
+            if fam == "misc":
+                (sub.depression_percentage, sub.income_interval_sugar, sub.income_interval_spice, sub.racial_len,
+                 sub.n_races) = self.misc_scalars
+                sub.n_tables = len(self.arrays["misc.racial_picks"])
             if fam == "diseases":
                 sub.max_sick, sub.immune_len, sub.n_diseases = self.max_sick, self.immune_len, self.n_diseases
                 sub.n_immune_bits = len(self.arrays["diseases.immune_bits"])
@@ -473,6 +513,7 @@ class HostExt:
         h = HostExt.__new__(HostExt)
         h.capacity, h.families, h.sizes = self.capacity, set(self.families), dict(self.sizes)
         h.n_diseases, h.max_sick, h.immune_len = self.n_diseases, self.max_sick, self.immune_len
+        h.racial_len, h.misc_scalars = self.racial_len, self.misc_scalars
         h.arrays = {k: v.copy() for k, v in self.arrays.items()}
         return h
 
@@ -625,6 +666,8 @@ class HostState:
                 self.ethics.set_slot(slot, e)
             if self.ext is not None:
                 self.ext.set_slot(slot, e)
+                if "misc" in self.ext.families and e["depressionFactor"] == 1:
+                    self.depress(slot)
             self.a_order[n_list] = slot
             self.occ[a["cell"]] = slot
             n_list += 1
@@ -634,6 +677,19 @@ class HostState:
         self.counters[C_N_LIST] = n_list
         self.counters[C_N_SLOTS] = n_slots
         self.counters[C_N_FREE] = n_free
+
+    def depress(self, slot):
+        """Depression.trigger (condition.py:27-33) at the creation of a depressed agent (agent.py:137-141)."""
+        import math
+        A = self.ext.arrays
+        A["misc.depressed"][slot] = 1
+        self.a_aggression[slot] *= 1.145
+        if "social" in self.ext.families:
+            A["social.max_friends"][slot] = math.ceil(A["social.max_friends"][slot] * 0.6333)
+        A["misc.happiness_unit"][slot] *= 0.5763
+        self.a_movement[slot] *= math.ceil(self.a_movement[slot] * 0.429)
+        self.a_spice_metab[slot] *= math.ceil(self.a_spice_metab[slot] * 1.544)
+        self.a_sugar_metab[slot] *= math.ceil(self.a_sugar_metab[slot] * 1.544)
 
     def list_view(self):
         """Arrays of the live agent list in list order (for parity checks and stats)."""

@@ -81,6 +81,9 @@ class StatsBuilder:
         self.n_north = W * north_rows
         self.n_south = W * (H - north_rows)
         self.diseased = c["startingDiseases"] > 0 and c["agentImmuneSystemLength"] > 0
+        self.racial = c["agentRacialTagStringLength"] > 0 and c["environmentMaxRaces"] > 0
+        self.misc = (self.racial or c["agentUniversalSugar"][1] != 0 or c["agentUniversalSpice"][1] != 0 or
+                     c["agentDepressionPercentage"] > 0)
         self.constant = {}
         for key, option in (("meanSelfishness", "agentSelfishnessFactor"),
                             ("meanAgeismFactor", "agentDecisionModelAgeismFactor"),
@@ -168,6 +171,17 @@ class StatsBuilder:
                 out["loanVolume"] = int(ext.loan_volume)
                 out["meanSocialHappiness"] = round(ext.sum_social_happiness / n, 2)
                 out["meanConflictHappiness"] = round(ext.sum_conflict_happiness / n, 2)
+            if ext is not None and self.racial:
+                # max(races, key=races.get): the first race, in list order, among the largest (sugarscape.py:1167-1170, 1287-1288)
+                races = [(int(ext.race_first[r]), r, int(ext.race_count[r])) for r in range(4) if ext.race_count[r] > 0]
+                if races:
+                    best = max(cnt for _, _, cnt in races)
+                    _, race, _ = min((f, r, cnt) for f, r, cnt in races if cnt == best)
+                    out["largestRace"], out["largestRaceSize"], out["remainingRaces"] = race, best, len(races)
+            if ext is not None and self.misc and not self.diseased:
+                out["meanHealthHappiness"] = round(ext.sum_health_happiness / n, 2)
+                out["agentMeanTimeToLive"] = round(ext.sum_ttl_age_limited / n, 2)
+                out["agentWealthBurnRate"] = round(ext.sum_burn_rate / n, 2)
             if ext is not None and self.diseased:
                 # sugarscape.py:1162, 1200-1211, 1228, 1254-1277, 1316-1317; time to live with the disease modifiers
                 out["sickAgentsPercentage"] = round((ext.sick_agents / n) * 100, 2)

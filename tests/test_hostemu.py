@@ -155,3 +155,17 @@ def test_device_disease_source_matches_reference_on_variants(variant, min_sick_s
     c, state, pop, params, endow, tags = pu.build(base, overrides=overrides)
     history = _run_with_extensions(c, state, pop, params, endow, tags, gold, log)
     assert sum(h["sickAgents"] > 0 for h in history) >= min_sick_steps
+
+
+@pytest.mark.parametrize("variant,ethics", [("determinism_plain", False), ("determinism_ethics", True)])
+def test_device_source_matches_reference_on_determinism_variants(variant, ethics):
+    """examples/determinism.json (variant fixtures from the unmodified reference): diseases, depression, lending,
+    friends, racial tags, universal income, live combat, trade, tags, inheritance, pollution and seasons at once --
+    `_plain` without, `_ethics` with the ethics.Bentham decision models.  Only the experimental-group split of the
+    log is switched off.  Every digest and all 59 log keys for 200 steps, on the device source."""
+    base, overrides, gold, log = pu.load_variant(variant)
+    c, state, pop, params, endow, tags = pu.build(base, overrides=overrides)
+    assert state.ext.families == {"lending", "social", "diseases", "misc"} and (state.ethics is not None) == ethics
+    history = _run_with_extensions(c, state, pop, params, endow, tags, gold, log)
+    non_greedy = sum(h["agentLastMoveOptimalityPercentage"] < 100 for h in history)
+    assert (non_greedy > 150) == ethics
