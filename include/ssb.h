@@ -319,12 +319,27 @@ typedef struct ssb_misc {
     int32_t income_interval_sugar, income_interval_spice, racial_len, n_races, n_tables, _pad;
 } ssb_misc_t;
 
+/* experimental group (agent.py:1256-1284 isInGroup; sugarscape.py:998-1003, 1175-1198, 1230-1250): the log repeats
+ * every statistic for the group and for its complement ("control") and counts the interactions between them.
+ * Supported group: "depressed" (membership = ssb_misc_t.depressed). */
+#define SSB_GI_COMBAT 0
+#define SSB_GI_DISEASE 1
+#define SSB_GI_LENDING 2
+#define SSB_GI_REPRODUCTION 3
+#define SSB_GI_TRADE 4
+#define SSB_GI_KINDS 5
+typedef struct ssb_group {
+    int32_t *with_control, *with_experimental;        /* [slot][SSB_GI_KINDS]: interactions since the last statistics pass */
+    int32_t *control_neighbors, *experimental_neighbors;   /* movementNeighborhood split, as of the agent's last ranking */
+} ssb_group_t;
+
 typedef struct ssb_ext {
     int64_t capacity;
     ssb_lending_t lending;
     ssb_social_t social;
     ssb_diseases_t diseases;
     ssb_misc_t misc;
+    ssb_group_t group;
 } ssb_ext_t;
 /* raw sums for the log keys of the families (sugarscape.py:1130-1160) */
 typedef struct ssb_ext_stats {
@@ -337,6 +352,18 @@ typedef struct ssb_ext_stats {
     double  sum_burn_rate, sum_ttl_age_limited;       /* findTimeToLive with the disease modifiers, list order */
     int64_t race_count[4], race_first[4];             /* agents per race, list index of the first one (-1 none) */
 } ssb_ext_stats_t;
+/* the statistics of one pass over the experimental group (pass 1) or the control group (pass 2) */
+typedef struct ssb_group_stats {
+    ssb_stats_t stats;                                /* without the Lorenz sum and the environment totals */
+    ssb_ethics_stats_t ethics;
+    ssb_ext_stats_t ext;
+    int64_t to_control[SSB_GI_KINDS], to_experimental[SSB_GI_KINDS];
+    int64_t control_neighbors, experimental_neighbors;
+} ssb_group_stats_t;
+/* out[0] = everybody (only the two neighbour sums are filled), out[1] = experimental group, out[2] = control group,
+ * of the last ssb_reduce_stats; synchronises */
+int  ssb_group_stats(ssb_engine_t *e, ssb_group_stats_t out[3]);
+int  ssb_sizeof_group_stats(void);
 /* call after ssb_bind, before the first step (mode E only) */
 int  ssb_bind_ext(ssb_engine_t *e, const ssb_ext_t *ext);
 int  ssb_ext_stats(ssb_engine_t *e, ssb_ext_stats_t *host_out);   /* of the last ssb_reduce_stats; synchronises */

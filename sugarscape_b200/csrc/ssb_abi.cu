@@ -71,6 +71,7 @@ struct ssb_engine {
     ssb_ethics_stats_t *d_eth_stats;
     bool ext_bound;
     ssb_ext_stats_t *d_ext_stats;
+    ssb_group_stats_t *d_group_stats;   // [3]
 };
 
 static int fail(ssb_engine *e, int code, const char *fmt, ...) {
@@ -165,7 +166,7 @@ void ssb_destroy(ssb_engine_t *e) {
     void *ptrs[] = {e->d_mt, e->d_endow, e->d_tagbits, e->d_tile_counts, e->d_new_order, e->d_scalars,
                     e->d_born_list, e->rc.mark, e->rc.list_a, e->rc.list_b, e->rc.ready, e->rc.cnt, e->rc.trace, e->rc.bucketed, e->rc.epoch_count, e->rc.epoch_start, e->rc.epoch_fill,
                     e->d_partials, e->d_tribes, e->d_stats, e->d_ring, e->d_keys_a, e->d_keys_b, e->d_radix_hist,
-                    e->d_lorenz_blocks, e->d_plan, e->d_cand, e->sh.peer_vals, e->sh.flags, e->d_shard_vals, e->d_migrate, e->d_eth_stats, e->d_ext_stats};
+                    e->d_lorenz_blocks, e->d_plan, e->d_cand, e->sh.peer_vals, e->sh.flags, e->d_shard_vals, e->d_migrate, e->d_eth_stats, e->d_ext_stats, e->d_group_stats};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < 5; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
     delete e;
@@ -388,13 +389,38 @@ int ssb_bind_ext(ssb_engine_t *e, const ssb_ext_t *ext) {
         for (const void *p : need) if (!p) return fail(e, -1, "diseases: null array");
         if (D.max_sick < 1 || D.max_sick < D.n_diseases || D.immune_len < 1 || D.immune_len > 64) return fail(e, -1, "diseases: bad sizes");
     }
+    const ssb_misc_t &M = ext->misc;
+    if (M.universal_sugar) {
+        const void *need[] = {M.universal_spice, M.last_income_sugar, M.last_income_spice, M.racial_tags, M.race, M.depressed,
+                              M.happiness_unit, M.health_happiness, M.racial_picks, M.depression_draw};
+        for (const void *p : need) if (!p) return fail(e, -1, "misc: null array");
+        if (M.racial_len < 0 || M.racial_len > 16 || M.income_interval_sugar <= 0 || M.income_interval_spice <= 0) return fail(e, -1, "misc: bad sizes");
+    }
+    const ssb_group_t &Gr = ext->group;
+    if (Gr.with_control) {
+        if (!Gr.with_experimental || !Gr.control_neighbors || !Gr.experimental_neighbors) return fail(e, -1, "group: null array");
+        if (!M.universal_sugar) return fail(e, -1, "the experimental group \"depressed\" needs the misc family");
+    }
     CU(cudaSetDevice(e->device));
     if (!e->d_ext_stats) {
         CU(cudaMalloc(&e->d_ext_stats, sizeof(ssb_ext_stats_t)));
         CU(cudaMemset(e->d_ext_stats, 0, sizeof(ssb_ext_stats_t)));
+        CU(cudaMalloc(&e->d_group_stats, 3 * sizeof(ssb_group_stats_t)));
+        CU(cudaMemset(e->d_group_stats, 0, 3 * sizeof(ssb_group_stats_t)));
     }
     e->ctx.x = *ext;
     e->ext_bound = true;
+    return 0;
+}
+
+int ssb_sizeof_group_stats(void) { return (int)sizeof(ssb_group_stats_t); }
+
+int ssb_group_stats(ssb_engine_t *e, ssb_group_stats_t out[3]) {
+    if (!e || !out) return -1;
+    if (!e->ext_bound || !e->ctx.x.group.with_control) return fail(e, -1, "no experimental group bound");
+    CU(cudaSetDevice(e->device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(out, e->d_group_stats, 3 * sizeof(ssb_group_stats_t), cudaMemcpyDeviceToHost));
     return 0;
 }
 
@@ -591,6 +617,7 @@ int ssb_reduce_stats(ssb_engine_t *e, int32_t t, void *stream_) {
     if (e->p.rng_mode == SSB_RNG_EXACT) { k_stats_ordered<<<1, 32, 0, st>>>(c, e->d_stats); LAUNCHED(e); }
     if (e->ethics_bound) { k_ethics_stats<<<1, 32, 0, st>>>(c, e->d_eth_stats); LAUNCHED(e); }
     if (e->ext_bound) { k_ext_stats<<<1, 32, 0, st>>>(c, e->d_ext_stats); LAUNCHED(e); }
+    if (e->ext_bound && e->ctx.x.group.with_control) { k_group_stats<<<1, 32, 0, st>>>(c, e->d_group_stats); LAUNCHED(e); }
     // Lorenz numerator: sort the wealths (non-negative doubles order like their bit patterns)
     const int64_t cap = c.a.capacity;
     const int tiles = grid_for(cap, RADIX_TILE, e->num_sms * 8);

@@ -69,6 +69,10 @@ __global__ void __launch_bounds__(32, 1) k_agent_step_exact(DevCtx c, uint32_t *
 __global__ void k_ethics_stats(DevCtx c, ssb_ethics_stats_t *out) {
     if (threadIdx.x == 0 && blockIdx.x == 0) ethics_stats_body(c, out);
 }
+// the experimental-group split of the log (mode E)
+__global__ void k_group_stats(DevCtx c, ssb_group_stats_t *out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) group_stats_body(c, out);
+}
 // lending / friends reductions of the log, list order (mode E)
 __global__ void k_ext_stats(DevCtx c, ssb_ext_stats_t *out) {
     if (threadIdx.x == 0 && blockIdx.x == 0) ext_stats_body(c, out);

@@ -39,18 +39,33 @@ __device__ void agent_step_exact_body(const DevCtx &c, uint32_t *mt, const WarpS
 // Decision-model reductions of the log (sugarscape.py:1141-1160, 1218-1222): one lane, list order (the
 // difference sum is order-sensitive fp64); the dead of this step count towards the move optimality --
 // doTimestep(t) ran for every one of them.
-__device__ inline void ethics_stats_body(const DevCtx &c, ssb_ethics_stats_t *out) {
+__device__ inline void ethics_stats_body(const DevCtx &c, ssb_ethics_stats_t *out, int pass = 0) {
     ssb_ethics_stats_t r;
     r.sum_selfishness = 0; r.optimal_moves = 0; r.moves = 0; r.sum_move_rank = 0; r.sum_move_diff = 0;
     const long long n = c.a.counters[SSB_C_N_LIST], n_dead = c.a.counters[SSB_C_N_DEAD];
     for (long long i = 0; i < n; i++) {
         const int s = c.a.order[i];
+        if (!in_pass(c, s, pass)) continue;
         r.sum_selfishness += c.eth.selfishness[s];
         r.optimal_moves += c.eth.last_move_optimal[s]; r.moves += 1;
         r.sum_move_rank += c.eth.move_rank[s]; r.sum_move_diff += c.eth.move_diff[s];
     }
-    for (long long i = 0; i < n_dead; i++) { r.optimal_moves += c.eth.last_move_optimal[c.a.dead_list[i]]; r.moves += 1; }
+    for (long long i = 0; i < n_dead; i++)
+        if (in_pass(c, c.a.dead_list[i], pass)) { r.optimal_moves += c.eth.last_move_optimal[c.a.dead_list[i]]; r.moves += 1; }
     *out = r;
+}
+
+// The experimental-group split of the log: the group (pass 1) and its complement (pass 2) in full, then the
+// everybody pass (0), which only adds the neighbour sums here -- its statistics come from the regular reductions.
+// The order matters: passes 1 and 2 reset the interaction counters of their members.
+__device__ inline void group_stats_body(const DevCtx &c, ssb_group_stats_t out[3]) {
+    for (int pass = 1; pass <= 2; pass++) {
+        stats_pass_body(c, pass, &out[pass].stats);
+        if (c.eth.model != nullptr) ethics_stats_body(c, &out[pass].ethics, pass);
+        ext_stats_body(c, &out[pass].ext, pass);
+        group_counters_body(c, pass, &out[pass]);
+    }
+    group_counters_body(c, 0, &out[0]);
 }
 
 }  // namespace ssb

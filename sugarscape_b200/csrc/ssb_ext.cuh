@@ -16,6 +16,21 @@ __device__ __forceinline__ bool has_lending(const DevCtx &c) { return c.x.lendin
 __device__ __forceinline__ bool has_social(const DevCtx &c) { return c.x.social.max_friends != nullptr; }
 __device__ __forceinline__ bool has_disease(const DevCtx &c) { return c.x.diseases.immune != nullptr; }
 __device__ __forceinline__ bool has_misc(const DevCtx &c) { return c.x.misc.universal_sugar != nullptr; }
+__device__ __forceinline__ bool has_group(const DevCtx &c) { return c.x.group.with_control != nullptr; }
+// experimental group "depressed" (agent.py:1256-1284 isInGroup)
+__device__ __forceinline__ bool is_member(const DevCtx &c, int s) { return has_misc(c) && c.x.misc.depressed[s] != 0; }
+// statistics pass: 0 = everybody, 1 = the experimental group, 2 = the control group
+__device__ __forceinline__ bool in_pass(const DevCtx &c, int s, int pass) { return pass == 0 || (pass == 1) == is_member(c, s); }
+// <kind>With{Experimental,Control}Group += 1
+__device__ __forceinline__ void group_note(const DevCtx &c, int s, int kind, int partner) {
+    if (!has_group(c)) return;
+    if (is_member(c, partner)) c.x.group.with_experimental[(long long)s * SSB_GI_KINDS + kind]++;
+    else c.x.group.with_control[(long long)s * SSB_GI_KINDS + kind]++;
+}
+__device__ __forceinline__ void group_reset_slot(const DevCtx &c, int s) {
+    for (int k = 0; k < SSB_GI_KINDS; k++) { c.x.group.with_control[(long long)s * SSB_GI_KINDS + k] = 0; c.x.group.with_experimental[(long long)s * SSB_GI_KINDS + k] = 0; }
+    c.x.group.control_neighbors[s] = 0; c.x.group.experimental_neighbors[s] = 0;
+}
 // happinessUnit: 1, 0.5763 when depressed
 __device__ __forceinline__ double happiness_unit(const DevCtx &c, int s) { return has_misc(c) ? c.x.misc.happiness_unit[s] : 1.0; }
 
@@ -211,6 +226,7 @@ __device__ __noinline__ void do_disease(const DevCtx &c, int s, Rng &rng) {
         const int di = D.sick_disease[b + rand_below(rng, (uint32_t)count)];
         disease_catch(c, neighbors[k], di, s, rng);
         if (infected_with(D, neighbors[k], D.defs[di].id)) spread++;
+        group_note(c, s, SSB_GI_DISEASE, neighbors[k]);
     }
     if (spread > 0) { D.last_spread[s] = c.t; D.n_spread[s] = spread; }
 }
@@ -518,12 +534,13 @@ __device__ __noinline__ void do_lending(const DevCtx &c, int s, Rng &rng) {
         if (!(sugar_income >= 0 && spice_income >= 0)) continue;
         add_loan(c, s, b, a.last_moved[s], sugar_principal, sugar_amount, spice_principal, spice_amount, duration);
         loans++;
+        group_note(c, s, SSB_GI_LENDING, b);
     }
     if (loans > 0) { L.last_lended[s] = c.t; L.last_loans[s] = loans; }
 }
 
 // reductions of the families' log keys, list order (sugarscape.py:1130-1160, 1162, 1200-1211, 1228, 1254-1277)
-__device__ inline void ext_stats_body(const DevCtx &c, ssb_ext_stats_t *out) {
+__device__ inline void ext_stats_body(const DevCtx &c, ssb_ext_stats_t *out, int pass = 0) {
     ssb_ext_stats_t r;
     r.loan_volume = 0; r.sum_social_happiness = 0; r.sum_conflict_happiness = 0;
     r.sick_agents = 0; r.disease_incidence = 0; r.distinct_infectors = 0; r.disease_prevalence = 0; r.disease_deaths = 0;
@@ -531,8 +548,13 @@ __device__ inline void ext_stats_body(const DevCtx &c, ssb_ext_stats_t *out) {
     for (int k = 0; k < 4; k++) { r.race_count[k] = 0; r.race_first[k] = -1; }
     const long long n = c.a.counters[SSB_C_N_LIST], n_dead = c.a.counters[SSB_C_N_DEAD];
     const ssb_diseases_t &D = c.x.diseases;
+    // isDiseaseExperimentalGroup() is false for every disease unless the group names one, so the pass over the
+    // experimental group skips all incidence / prevalence bookkeeping (sugarscape.py:1200-1211, 1266-1277)
+    const bool skip_diseases = pass == 1;
+    const int mark = c.t * 4 + pass;
     for (long long i = 0; i < n; i++) {
         const int s = c.a.order[i];
+        if (!in_pass(c, s, pass)) continue;
         if (has_lending(c) && c.x.lending.last_lended[s] == c.t) r.loan_volume += c.x.lending.last_loans[s];
         if (has_social(c)) { r.sum_social_happiness += c.x.social.social_happiness[s]; r.sum_conflict_happiness += c.x.social.conflict_happiness[s]; }
         if (has_misc(c) && c.x.misc.racial_len > 0) {
@@ -548,21 +570,102 @@ __device__ inline void ext_stats_body(const DevCtx &c, ssb_ext_stats_t *out) {
         if (has_disease(c)) {
             const long long b = (long long)s * D.max_sick;
             if (D.n_sick[s] > 0) r.sick_agents++;
-            for (int k = 0; k < D.n_sick[s]; k++)
+            for (int k = 0; k < D.n_sick[s] && !skip_diseases; k++)
                 if (D.sick_caught[b + k] == c.t) {
                     r.disease_incidence++;
                     const int inf = D.sick_infector_slot[b + k];
                     // distinct infectors: within one step a slot names one acting agent
-                    if (c.t != 0 && inf >= 0 && D.stat_mark[inf] != c.t) { D.stat_mark[inf] = c.t; r.distinct_infectors++; }
+                    if (c.t != 0 && inf >= 0 && D.stat_mark[inf] != mark) { D.stat_mark[inf] = mark; r.distinct_infectors++; }
                 }
             r.sum_health_happiness += D.health_happiness[s];
             r.move_space += D.last_valid_moves[s];
         }
     }
     if (has_disease(c)) {
-        for (long long i = 0; i < n_dead; i++) r.disease_deaths += D.disease_death[c.a.dead_list[i]];    // (their disease lists are empty)
-        for (int d = 0; d < D.n_diseases; d++) r.disease_prevalence += D.defs[d].listed * D.defs[d].infected;
+        for (long long i = 0; i < n_dead; i++) if (in_pass(c, c.a.dead_list[i], pass)) r.disease_deaths += D.disease_death[c.a.dead_list[i]];    // (their disease lists are empty)
+        for (int d = 0; d < D.n_diseases && !skip_diseases; d++) r.disease_prevalence += D.defs[d].listed * D.defs[d].infected;
     }
+    *out = r;
+}
+
+// Interaction counters of a pass (sugarscape.py:1175-1198, 1230-1250): summed over the pass's live agents (then reset)
+// and this step's dead; plus the control / experimental members of the movement neighbourhoods.
+__device__ inline void group_counters_body(const DevCtx &c, int pass, ssb_group_stats_t *out) {
+    const ssb_group_t &G = c.x.group;
+    for (int k = 0; k < SSB_GI_KINDS; k++) { out->to_control[k] = 0; out->to_experimental[k] = 0; }
+    out->control_neighbors = 0; out->experimental_neighbors = 0;
+    const long long n = c.a.counters[SSB_C_N_LIST], n_dead = c.a.counters[SSB_C_N_DEAD];
+    for (long long i = 0; i < n; i++) {
+        const int s = c.a.order[i];
+        if (!in_pass(c, s, pass)) continue;
+        for (int k = 0; k < SSB_GI_KINDS; k++) {
+            const long long at = (long long)s * SSB_GI_KINDS + k;
+            out->to_control[k] += G.with_control[at];
+            out->to_experimental[k] += G.with_experimental[at];
+            if (pass != 0) { G.with_control[at] = 0; G.with_experimental[at] = 0; }
+        }
+        out->control_neighbors += G.control_neighbors[s]; out->experimental_neighbors += G.experimental_neighbors[s];
+    }
+    for (long long i = 0; i < n_dead; i++) {
+        const int s = c.a.dead_list[i];
+        if (!in_pass(c, s, pass)) continue;
+        for (int k = 0; k < SSB_GI_KINDS; k++) {
+            out->to_control[k] += G.with_control[(long long)s * SSB_GI_KINDS + k];
+            out->to_experimental[k] += G.with_experimental[(long long)s * SSB_GI_KINDS + k];
+        }
+    }
+}
+
+// The reductions of updateRuntimeStatsPerGroup (sugarscape.py:1005-1426) for the agents of one pass, list order.
+// The Lorenz sum and the environment totals stay 0: a group pass does not log them (sugarscape.py:1403-1417).
+__device__ inline void stats_pass_body(const DevCtx &c, int pass, ssb_stats_t *out) {
+    const ssb_agents_t &a = c.a;
+    ssb_stats_t r;
+    memset(&r, 0, sizeof(r));
+    const long long n = a.counters[SSB_C_N_LIST], n_dead = a.counters[SSB_C_N_DEAD];
+    const int t = c.t;
+    r.timestep = t;
+    for (int i = 0; i < 32; i++) r.tribe_first[i] = -1;
+    long long seen = 0;
+    for (long long i = 0; i < n; i++) {
+        const int s = a.order[i];
+        if (!in_pass(c, s, pass)) continue;
+        const double w = a.sugar[s] + a.spice[s];
+        r.sum_sugar_metab += a.sugar_metab[s]; r.sum_spice_metab += a.spice_metab[s];
+        r.sum_movement += a.movement[s]; r.sum_vision += a.vision[s]; r.sum_age += a.age[s];
+        r.n_acted += a.age[s] > 0;
+        r.sum_wealth += w;
+        if (seen == 0 || w > r.max_wealth) r.max_wealth = w;
+        if (seen == 0 || w < r.min_wealth) r.min_wealth = w;
+        seen++;
+        r.sum_wealth_collected += w - (a.last_sugar[s] + a.last_spice[s]);
+        r.sum_burn_rate += time_to_live_x(c, s, false);
+        r.sum_ttl_age_limited += time_to_live_x(c, s, true);
+        r.sum_neighbors += a.n_neighborhood[s];
+        r.sum_valid_moves += a.n_valid_moves[s];
+        if (a.trade_volume[s] > 0) { r.n_traders++; r.trade_volume += a.trade_volume[s]; r.sum_trade_price += a.trade_price[s]; }
+        r.sum_happiness += a.happiness[s];
+        r.sum_wealth_happiness += a.wealth_happiness[s];
+        r.sum_family_happiness += a.family_happiness[s];
+        const int tr = a.tribe[s];
+        if (tr >= 0 && tr < 32) { if (r.tribe_count[tr]++ == 0) r.tribe_first[tr] = i; }
+    }
+    r.population = seen;
+    for (long long i = 0; i < n_dead; i++) {
+        const int s = a.dead_list[i];
+        if (!in_pass(c, s, pass)) continue;
+        r.n_dead++;
+        if (a.last_moved[s] == t) r.n_dead_moved++;
+        r.sum_age_at_death += a.age[s];
+        r.dead_wealth_collected += (a.sugar[s] + a.spice[s]) - (a.last_sugar[s] + a.last_spice[s]);
+        r.dead_starvation += a.cod[s] == SSB_STARVATION;
+        r.dead_aging += a.cod[s] == SSB_AGING;
+        r.dead_combat += a.cod[s] == SSB_COMBAT;
+    }
+    // bornAgents of the pass (sugarscape.py:1359-1362): this step's newborn, alive or not
+    for (long long i = 0; i < n; i++) { const int s = a.order[i]; if (a.born[s] == t && t > 0 && in_pass(c, s, pass)) r.n_born++; }
+    for (long long i = 0; i < n_dead; i++) { const int s = a.dead_list[i]; if (a.born[s] == t && t > 0 && in_pass(c, s, pass)) r.n_born++; }
+    r.n_replaced = a.counters[SSB_C_N_REPLACED];
     *out = r;
 }
 

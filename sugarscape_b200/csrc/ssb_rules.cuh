@@ -697,6 +697,14 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rn
     const int best = b_valid ? b_cell : pos;
     if (lane == 0) {
         if (n > 0) { a.n_neighborhood[s] = hood + 1; a.n_valid_moves[s] = m; }   // + self
+        if (EXT && has_group(c) && n > 0) {      // movementNeighborhood split by group; the agent itself is part of it
+            int exp_n = is_member(c, s) ? 1 : 0, ctrl_n = 1 - exp_n;
+            for (int i = 0; i < n; i++) {
+                const int o = c.g.occ[ws.cells[i]];
+                if (o >= 0 && agent_alive(c, o)) { if (is_member(c, o)) exp_n++; else ctrl_n++; }
+            }
+            c.x.group.control_neighbors[s] = ctrl_n; c.x.group.experimental_neighbors[s] = exp_n;
+        }
         // lastValidMoves: findBestCell records len([own cell]) when the range is empty (agent.py:1398-1399, 745)
         if (diseased) c.x.diseases.last_valid_moves[s] = n > 0 ? m : 1;
         if (!b_valid) {     // stays on its own cell: its contents were not among the candidates
@@ -719,6 +727,7 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rn
                 if (heirs) { a.sugar[s] = sugar; a.spice[s] = spice; }
                 do_death<EXT>(c, prey, SSB_COMBAT);
                 if (heirs) { sugar = a.sugar[s]; spice = a.spice[s]; }
+                if (EXT) group_note(c, s, SSB_GI_COMBAT, prey);
             }
         }
         c.g.occ[pos] = -1;
@@ -848,6 +857,7 @@ __device__ __noinline__ void do_trading(const DevCtx &c, int s, Rng &rng) {
             a.trade_volume[s] += 1;
             sum_sugar_price += sugar_price;
             sum_spice_price += spice_price;
+            if (EXT) group_note(c, s, SSB_GI_TRADE, tr);
         }
     }
     a.trade_price[s] = fmax(sum_spice_price, sum_sugar_price);
@@ -1018,6 +1028,7 @@ __device__ __noinline__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
             c.eth.lookahead_discount[ch] = c.eth.lookahead_discount[from];
             c.eth.last_move_optimal[ch] = 1; c.eth.move_rank[ch] = 0; c.eth.move_diff[ch] = 0;      // lastMoveOptimal starts True
         }
+        if (EXT && has_group(c)) group_reset_slot(c, ch);
         if (diseased) disease_child(c, ch, s, m, eb);
         if (EXT && has_misc(c)) misc_child(c, ch, s, m, eb);
         if (EXT && has_social(c)) {
@@ -1063,6 +1074,7 @@ __device__ __noinline__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
         a.sugar[m] = m_sugar[k];
         a.spice[m] = m_spice[k];
         a.last_repro[s] = c.t;
+        if (EXT) group_note(c, s, SSB_GI_REPRODUCTION, m);
     }
 }
 

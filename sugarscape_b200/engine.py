@@ -77,6 +77,8 @@ def load_library():
     L.ssb_bind_ext.argtypes = [E, C.POINTER(layout.Ext)]
     L.ssb_ext_stats.argtypes = [E, C.POINTER(layout.ExtStats)]
     L.ssb_sizeof_ext.restype = C.c_int
+    L.ssb_group_stats.argtypes = [E, C.POINTER(layout.GroupStats * 3)]
+    L.ssb_sizeof_group_stats.restype = C.c_int
     L.ssb_pollution_buffer.argtypes = [E]
     L.ssb_pollution_buffer.restype = C.c_int
     L.ssb_round_trace.argtypes = [E, C.c_int32, C.c_void_p, C.c_int32]
@@ -88,7 +90,8 @@ def load_library():
     if L.ssb_abi_version() != layout.ABI_VERSION:
         raise EngineError("libssb.so ABI version does not match sugarscape_b200.layout")
     for name, struct in (("params", layout.Params), ("grid", layout.Grid), ("agents", layout.Agents),
-                         ("stats", layout.Stats), ("ethics", layout.Ethics), ("ext", layout.Ext)):
+                         ("stats", layout.Stats), ("ethics", layout.Ethics), ("ext", layout.Ext),
+                         ("group_stats", layout.GroupStats)):
         if getattr(L, "ssb_sizeof_" + name)() != C.sizeof(struct):
             raise EngineError(f"struct ssb_{name}_t: library and ctypes mirror disagree on size")
     _LIB = L
@@ -104,6 +107,7 @@ EXPORTED_SYMBOLS = (
     "ssb_fabric_destroy", "ssb_fabric_last_error", "ssb_set_shard", "ssb_migrate", "ssb_shard_barrier", "ssb_shard_broken",
     "ssb_sync", "ssb_pollution_buffer", "ssb_test_pow", "ssb_round_trace", "ssb_launch_count", "ssb_timing", "ssb_enable_timing",
     "ssb_bind_ethics", "ssb_ethics_stats", "ssb_sizeof_ethics", "ssb_bind_ext", "ssb_ext_stats", "ssb_sizeof_ext",
+    "ssb_group_stats", "ssb_sizeof_group_stats",
 )
 
 
@@ -318,6 +322,14 @@ class Engine:
                 raise EngineError("loan pool exhausted")
         out = layout.ExtStats()
         self._check(self.L.ssb_ext_stats(self.handle, C.byref(out)))
+        return out
+
+    def group_stats(self):
+        """The experimental-group split of the last reduce_stats: layout.GroupStats[3] (None without a group)."""
+        if self.ext is None or "group" not in self.ext.families:
+            return None
+        out = (layout.GroupStats * 3)()
+        self._check(self.L.ssb_group_stats(self.handle, C.byref(out)))
         return out
 
     def stats_history(self, t):

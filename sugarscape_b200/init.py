@@ -117,8 +117,10 @@ def check_supported(c):
               "agentDecisionModelSexismFactor", "agentDecisionModelTribalFactor"):
         if c[k][1] >= 0:
             problems.append(k)
-    if c["experimentalGroup"] is not None:
-        problems.append("experimentalGroup")
+    if c["experimentalGroup"] not in (None, "depressed"):
+        problems.append("experimentalGroup other than \"depressed\"")
+    if c["experimentalGroup"] is not None and c["agentReplacements"] > 0:
+        problems.append("experimentalGroup with agentReplacements")
     if c["agentTagStringLength"] > 32:
         problems.append("tag strings longer than 32")
     for k in ("environmentSugarRegrowRate", "environmentSpiceRegrowRate"):
@@ -491,12 +493,13 @@ def configure_diseases(c, state, disease_endowments):
             curr = lo
 
 
-def build_initial_state(c, capacity=None, check=True, diseases=None):
+def build_initial_state(c, capacity=None, check=True):
     """Environment + initial population + the init-time list shuffle; returns (state, population).
 
     Must be called right after verify_random_seed/verify_configuration so the main stream is
     positioned as in the reference's Sugarscape.__init__ (sugarscape.py:19-75).
-    check=False skips the support check (oracle-only tests of rule families the engine refuses)."""
+    check=False skips the support check and the ABI 2 extension state (oracle-only tests that keep the rule
+    families in the oracle binding)."""
     if check:
         check_supported(c)
     W, H = c["environmentWidth"], c["environmentHeight"]
@@ -515,7 +518,8 @@ def build_initial_state(c, capacity=None, check=True, diseases=None):
     state.sugar[:] = state.sugar_cap
     state.spice[:] = state.spice_cap
 
-    if uses_decision_models(c):
+    # (oracle-only tests pass check=False: the bare ABI 1 state, the rule families live in the oracle binding)
+    if check and uses_decision_models(c):
         state.ethics = layout.HostEthics(capacity, c)
     diseased = layout.HostExt.uses_diseases(c)
     horizon = int(min(c["timesteps"], 1 << 20)) + 8
@@ -528,7 +532,7 @@ def build_initial_state(c, capacity=None, check=True, diseases=None):
     if new_agents:
         pop.disease_endowments = randomize_disease_endowments(c, min(len(new_agents), int(c["startingDiseases"])), 0)
         random.shuffle(new_agents)
-    if layout.HostExt.needed(c):
+    if check and layout.HostExt.needed(c):
         state.ext = layout.HostExt(capacity, c, len(pop.disease_endowments) if diseased else 0, horizon)
         if diseased:
             state.ext.arrays["diseases.immune_bits"][:] = steptables.immune_tables(1, horizon, int(c["agentImmuneSystemLength"]))
@@ -537,8 +541,7 @@ def build_initial_state(c, capacity=None, check=True, diseases=None):
             state.ext.arrays["misc.racial_picks"][:] = picks
             state.ext.arrays["misc.depression_draw"][:] = draw
     state.append_agents(new_agents)
-    # (oracle-only tests pass check=False and run configureDiseases through the oracle binding instead)
-    if diseased and (check if diseases is None else diseases) and new_agents:
+    if diseased and state.ext is not None and new_agents:
         configure_diseases(c, state, pop.disease_endowments)
     state.counters[layout.C_NEXT_ID] = len(new_agents)
     state.counters[layout.C_ENDOW_INDEX] = pop.endowment_index

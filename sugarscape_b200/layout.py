@@ -309,7 +309,13 @@ MISC_LAYOUT = (
     ("happiness_unit", _F64, 1, "cap"), ("health_happiness", _F64, 0, "cap"),
     ("racial_picks", np.uint32, 0, "bits"), ("depression_draw", _F64, 1, "bits"),
 )
-EXT_FAMILIES = (("lending", LENDING_LAYOUT), ("social", SOCIAL_LAYOUT), ("diseases", DISEASE_LAYOUT), ("misc", MISC_LAYOUT))
+GI_KINDS = 5
+GROUP_LAYOUT = (
+    ("with_control", _I32, 0, "gi"), ("with_experimental", _I32, 0, "gi"),
+    ("control_neighbors", _I32, 0, "cap"), ("experimental_neighbors", _I32, 0, "cap"),
+)
+EXT_FAMILIES = (("lending", LENDING_LAYOUT), ("social", SOCIAL_LAYOUT), ("diseases", DISEASE_LAYOUT), ("misc", MISC_LAYOUT),
+                ("group", GROUP_LAYOUT))
 
 
 def _family_struct(name, table):
@@ -331,8 +337,12 @@ class Misc(C.Structure):
                    ("racial_len", C.c_int32), ("n_races", C.c_int32), ("n_tables", C.c_int32), ("_pad", C.c_int32)])
 
 
+Group = _family_struct("Group", GROUP_LAYOUT)
+
+
 class Ext(C.Structure):
-    _fields_ = [("capacity", C.c_int64), ("lending", Lending), ("social", Social), ("diseases", Diseases), ("misc", Misc)]
+    _fields_ = [("capacity", C.c_int64), ("lending", Lending), ("social", Social), ("diseases", Diseases), ("misc", Misc),
+                ("group", Group)]
 
 
 class ExtStats(C.Structure):
@@ -341,6 +351,11 @@ class ExtStats(C.Structure):
                 ("disease_prevalence", C.c_int64), ("disease_deaths", C.c_int64), ("sum_health_happiness", C.c_double),
                 ("move_space", C.c_int64), ("sum_burn_rate", C.c_double), ("sum_ttl_age_limited", C.c_double),
                 ("race_count", C.c_int64 * 4), ("race_first", C.c_int64 * 4)]
+
+
+class GroupStats(C.Structure):      # ssb_group_stats_t
+    _fields_ = [("stats", Stats), ("ethics", EthicsStats), ("ext", ExtStats), ("to_control", C.c_int64 * GI_KINDS),
+                ("to_experimental", C.c_int64 * GI_KINDS), ("control_neighbors", C.c_int64), ("experimental_neighbors", C.c_int64)]
 
 
 class HostExt:
@@ -358,13 +373,15 @@ class HostExt:
             self.families.add("diseases")
         if self.uses_misc(c):
             self.families.add("misc")
+        if c["experimentalGroup"] is not None:
+            self.families.add("group")
         self.racial_len = int(c["agentRacialTagStringLength"]) if c["environmentMaxRaces"] > 0 else 0
         self.misc_scalars = (float(c["agentDepressionPercentage"]), int(c["environmentUniversalSugarIncomeInterval"]),
                              int(c["environmentUniversalSpiceIncomeInterval"]), self.racial_len, int(c["environmentMaxRaces"]))
         self.n_diseases, self.max_sick = n_diseases, max(n_diseases, 1)
         self.immune_len = int(c["agentImmuneSystemLength"])
         self.sizes = {"cap": capacity, "pool": 8 * capacity, "dead": 4 * capacity, "friends": capacity * MAX_FRIENDS,
-                      "mods": capacity * DM_COUNT, "sick": capacity * self.max_sick, "defs": self.max_sick, "bits": horizon + 1}
+                      "gi": capacity * GI_KINDS, "mods": capacity * DM_COUNT, "sick": capacity * self.max_sick, "defs": self.max_sick, "bits": horizon + 1}
         self.arrays = {}
         for fam, table in EXT_FAMILIES:
             if fam not in self.families:
@@ -381,7 +398,7 @@ class HostExt:
     @staticmethod
     def uses_misc(c):
         return (c["agentUniversalSugar"][1] != 0 or c["agentUniversalSpice"][1] != 0 or c["agentDepressionPercentage"] > 0 or
-                (c["agentRacialTagStringLength"] > 0 and c["environmentMaxRaces"] > 0))
+                (c["agentRacialTagStringLength"] > 0 and c["environmentMaxRaces"] > 0) or c["experimentalGroup"] is not None)
 
     @staticmethod
     def needed(c):
@@ -438,6 +455,12 @@ class HostExt:
             if rt is not None:
                 A["misc.racial_tags"][slot] = sum(v << (2 * k) for k, v in enumerate(rt))
                 A["misc.race"][slot] = max(set(rt), key=rt.count)
+
+        if "group" in self.families:
+            A["group.with_control"][slot * GI_KINDS:(slot + 1) * GI_KINDS] = 0
+            A["group.with_experimental"][slot * GI_KINDS:(slot + 1) * GI_KINDS] = 0
+            A["group.control_neighbors"][slot] = 0
+            A["group.experimental_neighbors"][slot] = 0
 
     # -- diseases: the init-time part of the rule (configureDiseases, sugarscape.py:286-337) ----------------
     def define_diseases(self, disease_endowments):

@@ -101,8 +101,13 @@ class Sugarscape:
         if st is None:
             self.engine.reduce_stats(self.timestep)
             st = self.engine.stats()
-        self.stats_builder.update(st, self.timestep, int(st.n_replaced) if replaced is None else replaced,
-                                  self.engine.ethics_stats(), self.engine.ext_stats())
+        eng = self.engine
+        replaced = int(st.n_replaced) if replaced is None else replaced
+        groups = eng.group_stats()
+        if groups is not None:      # the log repeats every statistic for the experimental group and for its complement
+            self.stats_builder.update_with_groups(st, self.timestep, replaced, eng.ethics_stats(), eng.ext_stats(), groups)
+        else:
+            self.stats_builder.update(st, self.timestep, replaced, eng.ethics_stats(), eng.ext_stats())
         self.n_agents = int(st.population)
 
     # -- the run loop and the log (format: SURVEY.md Appendix F) -----------------------------------

@@ -29,12 +29,34 @@ LOG_KEYS = (
 UNVERIFIED_KEYS = ()
 
 
+INTERACTIONS = ("combat", "disease", "lending", "reproduction", "trade")      # SSB_GI_* order
+GROUP_NEIGHBOR_KEYS = ("meanControlNeighbors", "meanExperimentalNeighbors")
+# keys a group pass does not compute: the log keeps their initial 0 (sugarscape.py:1403-1417)
+GROUP_TEMPLATE_ZERO = ("timestep", "giniCoefficient", "seed", "environmentWealthCreated", "environmentWealthTotal")
+
+
+def _prefixed(prefix, key):
+    return prefix + key[0].upper() + key[1:]
+
+
 def initial_runtime_stats(c):
-    """The all-zero entry the reference logs at t = 0 (sugarscape.py:81-92, 887-905)."""
+    """The all-zero entry the reference logs at t = 0 (sugarscape.py:81-92, 887-905); with an experimental group
+    the statistics are repeated for the group and for its complement "control" (998-1003): 203 keys."""
     s = {k: 0 for k in LOG_KEYS}
     s["seed"] = c["seed"]
     s["remainingRaces"] = c["environmentMaxRaces"]
     s["remainingTribes"] = c["environmentMaxTribes"]
+    group = c["experimentalGroup"]
+    if group is not None:
+        for k in GROUP_NEIGHBOR_KEYS:
+            s[k] = 0
+        for prefix in ("control", group):
+            for k in tuple(LOG_KEYS) + GROUP_NEIGHBOR_KEYS:
+                s[_prefixed(prefix, k)] = 0
+        for kind in INTERACTIONS:
+            for side in ("Control", "Experimental"):
+                s[f"{kind}{side}GroupToControlGroup"] = 0
+                s[f"{kind}{side}GroupToExperimentalGroup"] = 0
     return s
 
 
@@ -233,6 +255,35 @@ class StatsBuilder:
         rs["giniCoefficient"] = self.gini(st, n)
         rs["timestep"] = t
         return rs
+
+    def update_with_groups(self, st, t, n_replaced, ethics, ext, gstats):
+        """The log entry with an experimental group (sugarscape.py:998-1003): the statistics of the group, of its
+        complement and of everybody.  gstats: layout.GroupStats[3] (everybody's neighbour sums, group, control).
+        A group pass starts from everybody's previous entry and its cross-step state is discarded."""
+        import copy
+        group = self.c["experimentalGroup"]
+        keys = tuple(LOG_KEYS) + GROUP_NEIGHBOR_KEYS
+        passes = {}
+        for which, prefix in ((1, group), (2, "control")):
+            g = gstats[which]
+            rs = copy.deepcopy(self).update(g.stats, t, 0, g.ethics if ethics is not None else None, g.ext)
+            n = rs["population"]
+            rs["meanControlNeighbors"] = round(g.control_neighbors / n, 2) if n else 0
+            rs["meanExperimentalNeighbors"] = round(g.experimental_neighbors / n, 2) if n else 0
+            passes[prefix] = (dict(rs), g)
+        entry = self.update(st, t, n_replaced, ethics, ext)
+        n = entry["population"]
+        entry["meanControlNeighbors"] = round(gstats[0].control_neighbors / n, 2) if n else 0
+        entry["meanExperimentalNeighbors"] = round(gstats[0].experimental_neighbors / n, 2) if n else 0
+        for prefix, (rs, g) in passes.items():
+            rs["carryingCapacity"] = entry["carryingCapacity"]          # from len(self.agents), whatever the pass
+            for k in keys:
+                entry[_prefixed(prefix, k)] = 0 if k in GROUP_TEMPLATE_ZERO else rs[k]
+            side = "Control" if prefix == "control" else "Experimental"
+            for i, kind in enumerate(INTERACTIONS):
+                entry[f"{kind}{side}GroupToControlGroup"] = int(g.to_control[i])
+                entry[f"{kind}{side}GroupToExperimentalGroup"] = int(g.to_experimental[i])
+        return entry
 
     @staticmethod
     def gini(st, n):

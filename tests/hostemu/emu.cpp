@@ -47,6 +47,17 @@ int emu_ext_stats(const ssb_agents_t *a, const ssb_ext_t *ext, int32_t t, ssb_ex
     return 0;
 }
 
+int emu_group_stats(const ssb_agents_t *a, const ssb_ethics_t *ethics, const ssb_ext_t *ext, int32_t t, ssb_group_stats_t out[3]) {
+    if (!a || !ext || !out) return -1;
+    DevCtx c;
+    memset(&c, 0, sizeof(c));
+    c.a = *a; c.x = *ext; c.t = t;
+    if (ethics) c.eth = *ethics;
+    memset(out, 0, 3 * sizeof(ssb_group_stats_t));
+    group_stats_body(c, out);
+    return 0;
+}
+
 int emu_ethics_stats(const ssb_agents_t *a, const ssb_ethics_t *ethics, ssb_ethics_stats_t *out) {
     if (!a || !ethics || !out) return -1;
     DevCtx c;

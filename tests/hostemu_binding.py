@@ -24,6 +24,7 @@ def lib():
         P, G, A = C.POINTER(layout.Params), C.POINTER(layout.Grid), C.POINTER(layout.Agents)
         L.emu_agent_step_exact.argtypes = [P, G, A, C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_int32,
                                            C.POINTER(layout.Ethics), C.POINTER(layout.Ext)]
+        L.emu_group_stats.argtypes = [A, C.POINTER(layout.Ethics), C.POINTER(layout.Ext), C.c_int32, C.POINTER(layout.GroupStats * 3)]
         L.emu_ext_stats.argtypes = [A, C.POINTER(layout.Ext), C.c_int32, C.POINTER(layout.ExtStats)]
         L.emu_ethics_stats.argtypes = [A, C.POINTER(layout.Ethics), C.POINTER(layout.EthicsStats)]
         assert L.emu_abi_version() == layout.ABI_VERSION
@@ -58,6 +59,16 @@ class HostEmu(Oracle):
         assert rc == 0, f"emu_agent_step_exact failed: {rc}"
         if self.state.ext is not None:
             self.state.ext.check_overflow()
+
+    def group_stats(self, t):
+        if self.state.ext is None or "group" not in self.state.ext.families:
+            return None
+        g, a = self.state.as_structs()
+        eth = C.byref(self.state.ethics.as_struct()) if self.state.ethics is not None else None
+        out = (layout.GroupStats * 3)()
+        rc = self.E.emu_group_stats(C.byref(a), eth, C.byref(self.state.ext.as_struct()), t, C.byref(out))
+        assert rc == 0
+        return out
 
     def ext_stats(self, t):
         if self.state.ext is None:

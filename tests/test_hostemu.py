@@ -169,3 +169,33 @@ def test_device_source_matches_reference_on_determinism_variants(variant, ethics
     history = _run_with_extensions(c, state, pop, params, endow, tags, gold, log)
     non_greedy = sum(h["agentLastMoveOptimalityPercentage"] < 100 for h in history)
     assert (non_greedy > 150) == ethics
+
+
+@pytest.mark.parametrize("name", ["determinism", "all_features"])
+def test_device_source_matches_reference_on_all_features_examples(name):
+    """examples/determinism.json (the example BASELINE.json's north star names) and all_features.json AS SHIPPED on the
+    device source: every rule family, the ethics decision models and the experimental group "depressed" -- every digest
+    of every step and ALL 203 log keys (59 base keys, the neighbourhood split, the complete group / control copies
+    with their interaction counters)."""
+    c, state, pop, params, endow, tags = pu.build(name)
+    meta, _ = pu.load_golden(name)
+    gold, log = meta["steps"], meta["log"]
+    assert state.ext.families == {"lending", "social", "diseases", "misc", "group"} and state.ethics is not None
+    emu = HostEmu(params, state, endow, tags)
+    emu.set_mt_from_python()
+    d, _ = pu.state_digests(state, *emu.mt_state())
+    assert d == gold[0]["digests"], "t=0 state differs"
+    sb = stats.StatsBuilder(c, init.equator(c))
+    assert len(sb.runtime_stats) == 203
+    rs = sb.update_with_groups(emu.stats(0), 0, 0, emu.ethics_stats(), emu.ext_stats(0), emu.group_stats(0))
+    for t in range(0, len(gold)):
+        if t > 0:
+            emu.env_step(t)
+            emu.agent_step(t, rs["meanWealth"])
+            emu.compact(t)
+            d, snap = pu.state_digests(state, *emu.mt_state())
+            assert d == gold[t]["digests"], f"state differs at t={t}"
+            rs = sb.update_with_groups(emu.stats(t), t, 0, emu.ethics_stats(), emu.ext_stats(t), emu.group_stats(t))
+        assert len(log[t]) == 203
+        for k in log[t]:
+            assert k in rs and _close(rs[k], log[t][k]), f"log key {k} differs at t={t}: {rs.get(k)} vs {log[t][k]}"

@@ -22,7 +22,7 @@ SUPPORTED = [
     "trade_pollution", "trade_replacement", "trade_reproduction", "trade_tagging",
     "trade_tagging_reproduction",
 ]
-UNSUPPORTED = ["all_features", "determinism"]
+ALL_FEATURES = ["all_features", "determinism", "disease_basic", "dune", "lending_basic"]      # beyond the ABI 1 state
 
 
 def _close(a, b):
@@ -393,10 +393,14 @@ def test_oracle_environment_file_matches_reference_trajectory():
             assert _close(rs[k], log[t][k]), f"log key {k} differs at t={t}: {rs[k]} vs {log[t][k]}"
 
 
-@pytest.mark.parametrize("name", UNSUPPORTED)
-def test_unsupported_rule_families_fail_loudly(name):
+@pytest.mark.parametrize("overrides", [{"agentVisionMode": "radial"}, {"neighborhoodMode": "moore"},
+                                       {"environmentWraparound": False}, {"agentDecisionModels": ["temperance"]},
+                                       {"agentDecisionModels": ["benthamDynamic"]}, {"experimentalGroup": "female"},
+                                       {"agentLeader": True}, {"agentMaxFriends": [20, 20]}])
+def test_unsupported_options_fail_loudly(overrides):
+    """All 29 shipped examples are supported; the options outside the CUDA implementation are refused, not half-run."""
     with pytest.raises(init.UnsupportedConfiguration):
-        pu.build(name)
+        pu.build("determinism", overrides=overrides)
 
 
 @pytest.mark.parametrize("name,mode", [("reproduction_basic", "exact"), ("trade_tagging_reproduction", "exact"),

@@ -106,6 +106,71 @@ def test_disease_cases_match_reference_trajectory(case):
     eng.close()
 
 
+@pytest.mark.parametrize("variant,ethics", [("determinism_plain", False), ("determinism_ethics", True)])
+def test_determinism_variants_match_reference_trajectory(variant, ethics):
+    """examples/determinism.json without / with the ethics models, experimental-group split off (variant fixtures of the
+    unmodified reference): every rule family at once."""
+    base, overrides, gold, log = pu.load_variant(variant)
+    c, state, pop, params, endow, tags, eng = _engine(base, layout.RNG_EXACT, overrides)
+    sb = stats.StatsBuilder(c, init.equator(c))
+    eng.reduce_stats(0)
+    rs = sb.update(eng.stats(), 0, 0, eng.ethics_stats(), eng.ext_stats())
+    for t in range(1, len(gold)):
+        eng.env_step(t)
+        eng.agent_step(t, rs["meanWealth"])
+        eng.compact(t)
+        eng.reduce_stats(t)
+        rs = sb.update(eng.stats(), t, 0, eng.ethics_stats(), eng.ext_stats())
+        d, snap = pu.state_digests(eng.download(), *eng.mt_state())
+        assert d == gold[t]["digests"], f"{variant}: state differs from the reference at t={t}"
+        for k in stats.LOG_KEYS:
+            assert _close(rs[k], log[t][k]), f"{variant}: log key {k} at t={t}: {rs[k]} vs {log[t][k]}"
+    eng.close()
+
+
+@pytest.mark.parametrize("name", ["determinism", "all_features"])
+def test_all_features_examples_match_reference_trajectory_and_full_log(name):
+    """examples/determinism.json (the example BASELINE.json names) and all_features.json as shipped: every digest of the
+    200-step protocol and ALL 203 log keys, experimental group "depressed" included."""
+    c, state, pop, params, endow, tags, eng = _engine(name)
+    meta, _ = pu.load_golden(name)
+    gold, log = meta["steps"], meta["log"]
+    sb = stats.StatsBuilder(c, init.equator(c))
+    eng.reduce_stats(0)
+    rs = sb.update_with_groups(eng.stats(), 0, 0, eng.ethics_stats(), eng.ext_stats(), eng.group_stats())
+    for t in range(0, len(gold)):
+        if t > 0:
+            eng.env_step(t)
+            eng.agent_step(t, rs["meanWealth"])
+            eng.compact(t)
+            eng.reduce_stats(t)
+            rs = sb.update_with_groups(eng.stats(), t, 0, eng.ethics_stats(), eng.ext_stats(), eng.group_stats())
+            d, snap = pu.state_digests(eng.download(), *eng.mt_state())
+            assert d == gold[t]["digests"], f"{name}: state differs from the reference at t={t}"
+        assert len(log[t]) == 203
+        for k in log[t]:
+            assert k in rs and _close(rs[k], log[t][k]), f"{name}: log key {k} at t={t}: {rs.get(k)} vs {log[t][k]}"
+    eng.close()
+
+
+def test_drop_in_driver_writes_the_reference_log_for_determinism(tmp_path):
+    """`Sugarscape(conf).runSimulation()` on examples/determinism.json as shipped: the 203-key log.json."""
+    import json
+    from sugarscape_b200.simulation import Sugarscape
+    c = pu.example_configuration("determinism")
+    c["logfile"] = str(tmp_path / "log.json")
+    Sugarscape(c).runSimulation(c["timesteps"])
+    mine = json.load(open(c["logfile"]))
+    meta, _ = pu.load_golden("determinism")
+    log = meta["log"]
+    assert len(mine) == len(log) and len(mine[1]) == 203
+    for entry, ref in zip(mine[1:], log[1:]):
+        for k in ref:
+            if entry is mine[-1] and k == "environmentWealthCreated":
+                continue
+            assert _close(entry[k], ref[k]), f"log key {k} at t={entry['timestep']}: {entry[k]} vs {ref[k]}"
+
+
 def test_drop_in_driver_writes_the_reference_log_with_decision_models(tmp_path):
     """The reference-facing entry point (sugarscape_b200.simulation.Sugarscape, what `sugarscape.py --conf` runs)
     on the ethics_trade configuration: the log.json it writes equals the reference's log entry by entry."""

@@ -33,6 +33,9 @@ class HostEmuEngine(OracleEngine):
     def ext_stats(self):
         return self.orc.ext_stats(self.t_stats)
 
+    def group_stats(self):
+        return self.orc.group_stats(self.t_stats)
+
     def sync(self):
         pass
 
