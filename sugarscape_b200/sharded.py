@@ -62,6 +62,8 @@ def shard_host_state(state, world, xb=None):
     n_list, n_slots = int(state.counters[layout.C_N_LIST]), int(state.counters[layout.C_N_SLOTS])
     if int(state.counters[layout.C_N_FREE]) != 0 or n_list != n_slots:
         raise ValueError("shard_host_state expects a freshly built state (no free slots)")
+    if state.ethics is not None or state.ext is not None:
+        raise ValueError("decision models, lending, friends, diseases ... exist in the exact RNG mode only: not shardable")
     xb = balanced_slab_bounds(state, world) if xb is None else list(xb)
     sb = slot_bounds(state.capacity, world)
     old = state.a_order[:n_list].astype(np.int64)
