@@ -72,6 +72,9 @@ struct ssb_engine {
     bool ext_bound;
     ssb_ext_stats_t *d_ext_stats;
     ssb_group_stats_t *d_group_stats;   // [3]
+    ssb_ethics_t *d_eth;                // device copies of the bound extension structs (DevCtx points at them)
+    ssb_ext_t *d_ext;
+    bool group_bound;
 };
 
 static int fail(ssb_engine *e, int code, const char *fmt, ...) {
@@ -166,7 +169,7 @@ void ssb_destroy(ssb_engine_t *e) {
     void *ptrs[] = {e->d_mt, e->d_endow, e->d_tagbits, e->d_tile_counts, e->d_new_order, e->d_scalars,
                     e->d_born_list, e->rc.mark, e->rc.list_a, e->rc.list_b, e->rc.ready, e->rc.cnt, e->rc.trace, e->rc.bucketed, e->rc.epoch_count, e->rc.epoch_start, e->rc.epoch_fill,
                     e->d_partials, e->d_tribes, e->d_stats, e->d_ring, e->d_keys_a, e->d_keys_b, e->d_radix_hist,
-                    e->d_lorenz_blocks, e->d_plan, e->d_cand, e->sh.peer_vals, e->sh.flags, e->d_shard_vals, e->d_migrate, e->d_eth_stats, e->d_ext_stats, e->d_group_stats};
+                    e->d_lorenz_blocks, e->d_plan, e->d_cand, e->sh.peer_vals, e->sh.flags, e->d_shard_vals, e->d_migrate, e->d_eth_stats, e->d_ext_stats, e->d_group_stats, e->d_eth, e->d_ext};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < 5; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
     delete e;
@@ -354,7 +357,9 @@ int ssb_bind_ethics(ssb_engine_t *e, const ssb_ethics_t *eth) {
         CU(cudaMalloc(&e->d_eth_stats, sizeof(ssb_ethics_stats_t)));
         CU(cudaMemset(e->d_eth_stats, 0, sizeof(ssb_ethics_stats_t)));
     }
-    e->ctx.eth = *eth;
+    if (!e->d_eth) CU(cudaMalloc(&e->d_eth, sizeof(ssb_ethics_t)));
+    CU(cudaMemcpy(e->d_eth, eth, sizeof(ssb_ethics_t), cudaMemcpyHostToDevice));
+    e->ctx.eth = e->d_eth;
     e->ethics_bound = true;
     return 0;
 }
@@ -408,7 +413,10 @@ int ssb_bind_ext(ssb_engine_t *e, const ssb_ext_t *ext) {
         CU(cudaMalloc(&e->d_group_stats, 3 * sizeof(ssb_group_stats_t)));
         CU(cudaMemset(e->d_group_stats, 0, 3 * sizeof(ssb_group_stats_t)));
     }
-    e->ctx.x = *ext;
+    if (!e->d_ext) CU(cudaMalloc(&e->d_ext, sizeof(ssb_ext_t)));
+    CU(cudaMemcpy(e->d_ext, ext, sizeof(ssb_ext_t), cudaMemcpyHostToDevice));
+    e->ctx.x = e->d_ext;
+    e->group_bound = ext->group.with_control != nullptr;
     e->ext_bound = true;
     return 0;
 }
@@ -417,7 +425,7 @@ int ssb_sizeof_group_stats(void) { return (int)sizeof(ssb_group_stats_t); }
 
 int ssb_group_stats(ssb_engine_t *e, ssb_group_stats_t out[3]) {
     if (!e || !out) return -1;
-    if (!e->ext_bound || !e->ctx.x.group.with_control) return fail(e, -1, "no experimental group bound");
+    if (!e->ext_bound || !e->group_bound) return fail(e, -1, "no experimental group bound");
     CU(cudaSetDevice(e->device));
     CU(cudaDeviceSynchronize());
     CU(cudaMemcpy(out, e->d_group_stats, 3 * sizeof(ssb_group_stats_t), cudaMemcpyDeviceToHost));
@@ -522,7 +530,9 @@ int ssb_compact(ssb_engine_t *e, int32_t t, void *stream_) {
     const int tiles = (int)((cap + COMPACT_TILE - 1) / COMPACT_TILE);
     k_compact_count<<<tiles, COMPACT_THREADS, 0, st>>>(c, e->d_tile_counts); LAUNCHED(e);
     k_scan_tiles<<<1, COMPACT_THREADS, 0, st>>>(e->d_tile_counts, c.a.counters + SSB_C_N_LIST, COMPACT_TILE, e->d_scalars + 0); LAUNCHED(e);
-    k_compact_scatter<<<tiles, COMPACT_THREADS, 0, st>>>(c, e->d_tile_counts, e->d_new_order); LAUNCHED(e);
+    if (e->ext_bound) k_compact_scatter<true><<<tiles, COMPACT_THREADS, 0, st>>>(c, e->d_tile_counts, e->d_new_order);
+    else k_compact_scatter<false><<<tiles, COMPACT_THREADS, 0, st>>>(c, e->d_tile_counts, e->d_new_order);
+    LAUNCHED(e);
     k_compact_finish<<<grid_for(cap, 256, e->num_sms * 4), 256, 0, st>>>(c, e->d_new_order, e->d_scalars + 0); LAUNCHED(e);
     k_compact_counters<<<1, 1, 0, st>>>(c, e->d_scalars + 0); LAUNCHED(e);
     if (e->p.rng_mode == SSB_RNG_SCALABLE && (e->p.flags & SSB_F_REPRO)) {
@@ -617,7 +627,7 @@ int ssb_reduce_stats(ssb_engine_t *e, int32_t t, void *stream_) {
     if (e->p.rng_mode == SSB_RNG_EXACT) { k_stats_ordered<<<1, 32, 0, st>>>(c, e->d_stats); LAUNCHED(e); }
     if (e->ethics_bound) { k_ethics_stats<<<1, 32, 0, st>>>(c, e->d_eth_stats); LAUNCHED(e); }
     if (e->ext_bound) { k_ext_stats<<<1, 32, 0, st>>>(c, e->d_ext_stats); LAUNCHED(e); }
-    if (e->ext_bound && e->ctx.x.group.with_control) { k_group_stats<<<1, 32, 0, st>>>(c, e->d_group_stats); LAUNCHED(e); }
+    if (e->ext_bound && e->group_bound) { k_group_stats<<<1, 32, 0, st>>>(c, e->d_group_stats); LAUNCHED(e); }
     // Lorenz numerator: sort the wealths (non-negative doubles order like their bit patterns)
     const int64_t cap = c.a.capacity;
     const int tiles = grid_for(cap, RADIX_TILE, e->num_sms * 8);

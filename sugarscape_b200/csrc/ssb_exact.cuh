@@ -46,12 +46,12 @@ __device__ inline void ethics_stats_body(const DevCtx &c, ssb_ethics_stats_t *ou
     for (long long i = 0; i < n; i++) {
         const int s = c.a.order[i];
         if (!in_pass(c, s, pass)) continue;
-        r.sum_selfishness += c.eth.selfishness[s];
-        r.optimal_moves += c.eth.last_move_optimal[s]; r.moves += 1;
-        r.sum_move_rank += c.eth.move_rank[s]; r.sum_move_diff += c.eth.move_diff[s];
+        r.sum_selfishness += c.eth->selfishness[s];
+        r.optimal_moves += c.eth->last_move_optimal[s]; r.moves += 1;
+        r.sum_move_rank += c.eth->move_rank[s]; r.sum_move_diff += c.eth->move_diff[s];
     }
     for (long long i = 0; i < n_dead; i++)
-        if (in_pass(c, c.a.dead_list[i], pass)) { r.optimal_moves += c.eth.last_move_optimal[c.a.dead_list[i]]; r.moves += 1; }
+        if (in_pass(c, c.a.dead_list[i], pass)) { r.optimal_moves += c.eth->last_move_optimal[c.a.dead_list[i]]; r.moves += 1; }
     *out = r;
 }
 
@@ -61,7 +61,7 @@ __device__ inline void ethics_stats_body(const DevCtx &c, ssb_ethics_stats_t *ou
 __device__ inline void group_stats_body(const DevCtx &c, ssb_group_stats_t out[3]) {
     for (int pass = 1; pass <= 2; pass++) {
         stats_pass_body(c, pass, &out[pass].stats);
-        if (c.eth.model != nullptr) ethics_stats_body(c, &out[pass].ethics, pass);
+        if (c.eth != nullptr) ethics_stats_body(c, &out[pass].ethics, pass);
         ext_stats_body(c, &out[pass].ext, pass);
         group_counters_body(c, pass, &out[pass]);
     }

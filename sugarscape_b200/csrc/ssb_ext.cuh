@@ -12,31 +12,31 @@ enum { EB_BASE_INTEREST = 12, EB_LENDING_FACTOR = 13, EB_LOAN_DURATION = 14, EB_
 
 enum { EB_PROTECTION = 16, EB_UNIVERSAL_SPICE = 17, EB_UNIVERSAL_SUGAR = 18 };
 
-__device__ __forceinline__ bool has_lending(const DevCtx &c) { return c.x.lending.lending_factor != nullptr; }
-__device__ __forceinline__ bool has_social(const DevCtx &c) { return c.x.social.max_friends != nullptr; }
-__device__ __forceinline__ bool has_disease(const DevCtx &c) { return c.x.diseases.immune != nullptr; }
-__device__ __forceinline__ bool has_misc(const DevCtx &c) { return c.x.misc.universal_sugar != nullptr; }
-__device__ __forceinline__ bool has_group(const DevCtx &c) { return c.x.group.with_control != nullptr; }
+__device__ __forceinline__ bool has_lending(const DevCtx &c) { return c.x != nullptr && c.x->lending.lending_factor != nullptr; }
+__device__ __forceinline__ bool has_social(const DevCtx &c) { return c.x != nullptr && c.x->social.max_friends != nullptr; }
+__device__ __forceinline__ bool has_disease(const DevCtx &c) { return c.x != nullptr && c.x->diseases.immune != nullptr; }
+__device__ __forceinline__ bool has_misc(const DevCtx &c) { return c.x != nullptr && c.x->misc.universal_sugar != nullptr; }
+__device__ __forceinline__ bool has_group(const DevCtx &c) { return c.x != nullptr && c.x->group.with_control != nullptr; }
 // experimental group "depressed" (agent.py:1256-1284 isInGroup)
-__device__ __forceinline__ bool is_member(const DevCtx &c, int s) { return has_misc(c) && c.x.misc.depressed[s] != 0; }
+__device__ __forceinline__ bool is_member(const DevCtx &c, int s) { return has_misc(c) && c.x->misc.depressed[s] != 0; }
 // statistics pass: 0 = everybody, 1 = the experimental group, 2 = the control group
 __device__ __forceinline__ bool in_pass(const DevCtx &c, int s, int pass) { return pass == 0 || (pass == 1) == is_member(c, s); }
 // <kind>With{Experimental,Control}Group += 1
 __device__ __forceinline__ void group_note(const DevCtx &c, int s, int kind, int partner) {
     if (!has_group(c)) return;
-    if (is_member(c, partner)) c.x.group.with_experimental[(long long)s * SSB_GI_KINDS + kind]++;
-    else c.x.group.with_control[(long long)s * SSB_GI_KINDS + kind]++;
+    if (is_member(c, partner)) c.x->group.with_experimental[(long long)s * SSB_GI_KINDS + kind]++;
+    else c.x->group.with_control[(long long)s * SSB_GI_KINDS + kind]++;
 }
 __device__ __forceinline__ void group_reset_slot(const DevCtx &c, int s) {
-    for (int k = 0; k < SSB_GI_KINDS; k++) { c.x.group.with_control[(long long)s * SSB_GI_KINDS + k] = 0; c.x.group.with_experimental[(long long)s * SSB_GI_KINDS + k] = 0; }
-    c.x.group.control_neighbors[s] = 0; c.x.group.experimental_neighbors[s] = 0;
+    for (int k = 0; k < SSB_GI_KINDS; k++) { c.x->group.with_control[(long long)s * SSB_GI_KINDS + k] = 0; c.x->group.with_experimental[(long long)s * SSB_GI_KINDS + k] = 0; }
+    c.x->group.control_neighbors[s] = 0; c.x->group.experimental_neighbors[s] = 0;
 }
 // happinessUnit: 1, 0.5763 when depressed
-__device__ __forceinline__ double happiness_unit(const DevCtx &c, int s) { return has_misc(c) ? c.x.misc.happiness_unit[s] : 1.0; }
+__device__ __forceinline__ double happiness_unit(const DevCtx &c, int s) { return has_misc(c) ? c.x->misc.happiness_unit[s] : 1.0; }
 
 // the find* accessors (agent.py:716-717, 1031-1032, 1107-1111, 1161-1162): endowment + disease modifier, floored at 0
 __device__ __forceinline__ double dis_mod(const DevCtx &c, int s, int which) {
-    return has_disease(c) ? c.x.diseases.modifier[(long long)s * SSB_DM_COUNT + which] : 0.0;
+    return has_disease(c) ? c.x->diseases.modifier[(long long)s * SSB_DM_COUNT + which] : 0.0;
 }
 __device__ __forceinline__ double pos_part(double v) { return v > 0 ? v : 0; }
 __device__ __forceinline__ double eff_sugar_metab(const DevCtx &c, int s) { return pos_part(c.a.sugar_metab[s] + dis_mod(c, s, SSB_DM_SUGAR_METAB)); }
@@ -44,7 +44,7 @@ __device__ __forceinline__ double eff_spice_metab(const DevCtx &c, int s) { retu
 __device__ __forceinline__ double eff_vision(const DevCtx &c, int s) { return pos_part(c.a.vision[s] + dis_mod(c, s, SSB_DM_VISION)); }
 __device__ __forceinline__ double eff_movement(const DevCtx &c, int s) { return pos_part(c.a.movement[s] + dis_mod(c, s, SSB_DM_MOVEMENT)); }
 __device__ __forceinline__ double eff_aggression(const DevCtx &c, int s) { return pos_part(c.a.aggression[s] + dis_mod(c, s, SSB_DM_AGGRESSION)); }
-__device__ __forceinline__ bool is_sick(const DevCtx &c, int s) { return has_disease(c) && c.x.diseases.n_sick[s] > 0; }
+__device__ __forceinline__ bool is_sick(const DevCtx &c, int s) { return has_disease(c) && c.x->diseases.n_sick[s] > 0; }
 // Agent.isFertile with the fertility modifier (agent.py:1244-1247, 1007-1008)
 __device__ __forceinline__ bool is_fertile_x(const DevCtx &c, int s) {
     return c.a.sugar[s] >= c.a.start_sugar[s] && c.a.spice[s] >= c.a.start_spice[s] &&
@@ -57,7 +57,7 @@ __device__ __forceinline__ double time_to_live_x(const DevCtx &c, int s, bool ag
     double st = sm > 0 ? c.a.sugar[s] / sm : big;
     double pt = pm > 0 ? c.a.spice[s] / pm : big;
     if (has_misc(c)) {                                   // the universal income term (agent.py:1127-1134)
-        const ssb_misc_t &M = c.x.misc;
+        const ssb_misc_t &M = c.x->misc;
         if (M.universal_sugar[s] != 0) {
             const double income = (st * M.universal_sugar[s]) / M.income_interval_sugar;
             st = sm > 0 ? (c.a.sugar[s] + income) / sm : big;
@@ -85,17 +85,17 @@ __device__ __forceinline__ int race_of(uint32_t tags, int len) {          // fin
 // Depression.trigger (condition.py:27-33), at the creation of a depressed agent (agent.py:137-141)
 __device__ inline void depress(const DevCtx &c, int s) {
     const ssb_agents_t &a = c.a;
-    c.x.misc.depressed[s] = 1;
+    c.x->misc.depressed[s] = 1;
     a.aggression[s] *= 1.145;
-    if (c.x.social.max_friends != nullptr) c.x.social.max_friends[s] = (int32_t)ceil(c.x.social.max_friends[s] * 0.6333);
-    c.x.misc.happiness_unit[s] *= 0.5763;
+    if (has_social(c)) c.x->social.max_friends[s] = (int32_t)ceil(c.x->social.max_friends[s] * 0.6333);
+    c.x->misc.happiness_unit[s] *= 0.5763;
     a.movement[s] *= (int32_t)ceil(a.movement[s] * 0.429);
     a.spice_metab[s] *= (int32_t)ceil(a.spice_metab[s] * 1.544);
     a.sugar_metab[s] *= (int32_t)ceil(a.sugar_metab[s] * 1.544);
 }
 // the child's share of the family (agent.py:845-851, 879-895); called once its endowments are in place
 __device__ inline void misc_child(const DevCtx &c, int ch, int s, int m, uint32_t eb) {
-    const ssb_misc_t &M = c.x.misc;
+    const ssb_misc_t &M = c.x->misc;
     M.universal_spice[ch] = ((eb >> EB_UNIVERSAL_SPICE) & 1u) ? M.universal_spice[m] : M.universal_spice[s];
     M.universal_sugar[ch] = ((eb >> EB_UNIVERSAL_SUGAR) & 1u) ? M.universal_sugar[m] : M.universal_sugar[s];
     M.last_income_sugar[ch] = 0; M.last_income_spice[ch] = 0;
@@ -128,7 +128,7 @@ __device__ __forceinline__ void sick_store(const ssb_diseases_t &D, long long at
     D.sick_incubation[at] = r.incubation; D.sick_infector_slot[at] = r.infector_slot; D.sick_infector_id[at] = r.infector_id;
 }
 __device__ inline void disease_reset_slot(const DevCtx &c, int s) {
-    const ssb_diseases_t &D = c.x.diseases;
+    const ssb_diseases_t &D = c.x->diseases;
     D.n_sick[s] = 0;
     for (int k = 0; k < SSB_DM_COUNT; k++) D.modifier[(long long)s * SSB_DM_COUNT + k] = 0;
     D.disease_death[s] = 0; D.last_spread[s] = -1; D.n_spread[s] = 0; D.health_happiness[s] = 0; D.last_valid_moves[s] = 0;
@@ -160,7 +160,7 @@ __device__ inline int disease_nearest(const ssb_diseases_t &D, int s, int di, in
 // catchDisease (agent.py:227-247) through doInfectionAttempt (363-371): two random.uniform(0, 1)
 template <class Rng>
 __device__ __noinline__ void disease_catch(const DevCtx &c, int s, int di, int infector, Rng &rng) {
-    const ssb_diseases_t &D = c.x.diseases;
+    const ssb_diseases_t &D = c.x->diseases;
     if (infected_with(D, s, D.defs[di].id)) return;
     SickRec rec = {di, -1, -1, c.t, D.defs[di].incubation, infector, c.a.id[infector]};
     if (disease_nearest(D, s, di, &rec.start, &rec.end) == 0) return;        // immune
@@ -178,7 +178,7 @@ __device__ __noinline__ void disease_catch(const DevCtx &c, int s, int di, int i
 // doDisease (agent.py:315-361)
 template <class Rng>
 __device__ __noinline__ void do_disease(const DevCtx &c, int s, Rng &rng) {
-    const ssb_diseases_t &D = c.x.diseases;
+    const ssb_diseases_t &D = c.x->diseases;
     const long long b = (long long)s * D.max_sick;
     rng.at(SITE_DISEASE);
     for (int i = D.n_sick[s] - 1; i >= 1; i--) {          // random.shuffle(self.diseases)
@@ -231,7 +231,7 @@ __device__ __noinline__ void do_disease(const DevCtx &c, int s, Rng &rng) {
     if (spread > 0) { D.last_spread[s] = c.t; D.n_spread[s] = spread; }
 }
 __device__ inline void disease_note_death(const DevCtx &c, int s) {        // doDeath (agent.py:302-313)
-    const ssb_diseases_t &D = c.x.diseases;
+    const ssb_diseases_t &D = c.x->diseases;
     const long long b = (long long)s * D.max_sick;
     if (D.n_sick[s] > 0) D.disease_death[s] = 1;
     for (int i = 0; i < D.n_sick[s]; i++) disease_recover(D, s, D.sick_disease[b + i]);
@@ -241,7 +241,7 @@ __device__ inline void disease_note_death(const DevCtx &c, int s) {        // do
 // startingImmuneSystem IS immuneSystem in the reference (agent.py:33,50 bind the same list): the parents pass on
 // what their immune responses have learnt.
 __device__ inline void disease_child(const DevCtx &c, int ch, int s, int m, uint32_t eb) {
-    const ssb_diseases_t &D = c.x.diseases;
+    const ssb_diseases_t &D = c.x->diseases;
     disease_reset_slot(c, ch);
     const uint64_t mine = D.immune[s], other = D.immune[m];
     const uint64_t draws = (D.immune_bits && c.t < D.n_immune_bits) ? D.immune_bits[c.t] : 0;
@@ -260,7 +260,7 @@ __device__ inline void disease_child(const DevCtx &c, int ch, int s, int m, uint
 // friends + conflict happiness (agent.py:1499-1520 updateFriends; 1099-1105, 912-918)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void social_reset_slot(const DevCtx &c, int s) {
-    const ssb_social_t &S = c.x.social;
+    const ssb_social_t &S = c.x->social;
     S.n_friends[s] = 0; S.last_combat[s] = -1; S.social_happiness[s] = 0; S.conflict_happiness[s] = 0;
 }
 
@@ -288,7 +288,7 @@ __device__ inline void friend_remove_first(const ssb_social_t &S, int s, int slo
 }
 // updateFriends (agent.py:1499-1520)
 __device__ __noinline__ void update_friends(const DevCtx &c, int s, int nb) {
-    const ssb_social_t &S = c.x.social;
+    const ssb_social_t &S = c.x->social;
     const long long b = (long long)s * SSB_MAX_FRIENDS;
     const int hd = (c.p.flags & SSB_F_TAGS) ? __popc(c.a.tags[s] ^ c.a.tags[nb]) : 0;
     const int id = c.a.id[nb];
@@ -364,7 +364,7 @@ __device__ inline void loan_clear(const ssb_lending_t &L, int32_t *head, int own
 }
 // a new agent object starts with empty lists
 __device__ inline void lending_reset_slot(const DevCtx &c, int s) {
-    const ssb_lending_t &L = c.x.lending;
+    const ssb_lending_t &L = c.x->lending;
     loan_clear(L, L.creditors_head, s); loan_clear(L, L.debtors_head, s);
     L.sugar_mean_income[s] = 1; L.spice_mean_income[s] = 1;
     L.last_lended[s] = -1; L.last_loans[s] = 0;
@@ -374,7 +374,7 @@ __device__ __forceinline__ bool loan_other_alive(const DevCtx &c, const Loan &l)
 }
 // updateMeanIncome (agent.py:1549-1553), called by collectResourcesAtCell
 __device__ __forceinline__ void lending_note_income(const DevCtx &c, int s, int cs, int cp) {
-    const ssb_lending_t &L = c.x.lending;
+    const ssb_lending_t &L = c.x->lending;
     const double alpha = 0.05;
     L.sugar_mean_income[s] = (alpha * cs) + ((1 - alpha) * L.sugar_mean_income[s]);
     L.spice_mean_income[s] = (alpha * cp) + ((1 - alpha) * L.spice_mean_income[s]);
@@ -382,7 +382,7 @@ __device__ __forceinline__ void lending_note_income(const DevCtx &c, int s, int 
 // doDeath: a creditor that dies keeps its children list in Python (the loan holds the object); remember the
 // head of its kin list, which lives on in the pool after the slot was reused
 __device__ inline void lending_note_death(const DevCtx &c, int s) {
-    const ssb_lending_t &L = c.x.lending;
+    const ssb_lending_t &L = c.x->lending;
     if (L.debtors_head[s] < 0) return;
     // (atomic: removeDeadAgents' doDeath runs in the parallel compaction kernel)
     const long long n = (long long)atomicAdd((unsigned long long *)&L.counters[SSB_LC_N_DEAD], 1ull);
@@ -392,7 +392,7 @@ __device__ inline void lending_note_death(const DevCtx &c, int s) {
 // addLoanToAgent (agent.py:199-211) incl. addLoanFromAgent (190-197)
 __device__ inline void add_loan(const DevCtx &c, int creditor, int debtor, int origin, double sugar_principal, double sugar_loan,
                                 double spice_principal, double spice_loan, int duration) {
-    const ssb_lending_t &L = c.x.lending;
+    const ssb_lending_t &L = c.x->lending;
     const ssb_agents_t &a = c.a;
     const Loan owed = {creditor, a.id[creditor], sugar_loan, spice_loan, duration, origin};
     const Loan due = {debtor, a.id[debtor], sugar_loan, spice_loan, duration, origin};
@@ -406,7 +406,7 @@ __device__ inline void add_loan(const DevCtx &c, int creditor, int debtor, int o
 // payDebtToCreditorChildren (agent.py:1362-1377): the loan is split among the dead creditor's living children
 // (the debtor itself excluded), each as a new one-step loan, in the children list's order
 __device__ __noinline__ void pay_debt_to_creditor_children(const DevCtx &c, int s, const Loan &loan) {
-    const ssb_lending_t &L = c.x.lending;
+    const ssb_lending_t &L = c.x->lending;
     const ssb_agents_t &a = c.a;
     int head = -1;
     if (a.id[loan.other_slot] == loan.other_id) head = a.children_head[loan.other_slot];
@@ -430,7 +430,7 @@ __device__ __noinline__ void pay_debt_to_creditor_children(const DevCtx &c, int 
 }
 // payDebt (agent.py:1330-1360); `loan` is an element of the creditors list of s
 __device__ __noinline__ void pay_debt(const DevCtx &c, int s, const Loan &loan) {
-    const ssb_lending_t &L = c.x.lending;
+    const ssb_lending_t &L = c.x->lending;
     const ssb_agents_t &a = c.a;
     const int cr = loan.other_slot;
     const Loan mirror = {s, a.id[s], loan.sugar, loan.spice, loan.duration, loan.origin};
@@ -463,7 +463,7 @@ __device__ __noinline__ void pay_debt(const DevCtx &c, int s, const Loan &loan) 
 }
 // updateLoans (agent.py:1532-1541): Python for-loops over lists that shrink / grow underneath
 __device__ inline void update_loans(const DevCtx &c, int s) {
-    const ssb_lending_t &L = c.x.lending;
+    const ssb_lending_t &L = c.x->lending;
     for (int p = 0;; p++) {
         const int e = loan_at(L, L.debtors_head[s], p);
         if (e < 0) break;
@@ -486,7 +486,7 @@ __device__ inline double current_debt(const ssb_lending_t &L, int head, bool spi
 // doLending (agent.py:431-483)
 template <class Rng>
 __device__ __noinline__ void do_lending(const DevCtx &c, int s, Rng &rng) {
-    const ssb_lending_t &L = c.x.lending;
+    const ssb_lending_t &L = c.x->lending;
     const ssb_agents_t &a = c.a;
     update_loans(c, s);
     // isLender (agent.py:1285-1296)
@@ -547,7 +547,7 @@ __device__ inline void ext_stats_body(const DevCtx &c, ssb_ext_stats_t *out, int
     r.sum_health_happiness = 0; r.move_space = 0; r.sum_burn_rate = 0; r.sum_ttl_age_limited = 0;
     for (int k = 0; k < 4; k++) { r.race_count[k] = 0; r.race_first[k] = -1; }
     const long long n = c.a.counters[SSB_C_N_LIST], n_dead = c.a.counters[SSB_C_N_DEAD];
-    const ssb_diseases_t &D = c.x.diseases;
+    const ssb_diseases_t &D = c.x->diseases;
     // isDiseaseExperimentalGroup() is false for every disease unless the group names one, so the pass over the
     // experimental group skips all incidence / prevalence bookkeeping (sugarscape.py:1200-1211, 1266-1277)
     const bool skip_diseases = pass == 1;
@@ -555,13 +555,13 @@ __device__ inline void ext_stats_body(const DevCtx &c, ssb_ext_stats_t *out, int
     for (long long i = 0; i < n; i++) {
         const int s = c.a.order[i];
         if (!in_pass(c, s, pass)) continue;
-        if (has_lending(c) && c.x.lending.last_lended[s] == c.t) r.loan_volume += c.x.lending.last_loans[s];
-        if (has_social(c)) { r.sum_social_happiness += c.x.social.social_happiness[s]; r.sum_conflict_happiness += c.x.social.conflict_happiness[s]; }
-        if (has_misc(c) && c.x.misc.racial_len > 0) {
-            const int race = c.x.misc.race[s];
+        if (has_lending(c) && c.x->lending.last_lended[s] == c.t) r.loan_volume += c.x->lending.last_loans[s];
+        if (has_social(c)) { r.sum_social_happiness += c.x->social.social_happiness[s]; r.sum_conflict_happiness += c.x->social.conflict_happiness[s]; }
+        if (has_misc(c) && c.x->misc.racial_len > 0) {
+            const int race = c.x->misc.race[s];
             if (race >= 0 && race < 4 && r.race_count[race]++ == 0) r.race_first[race] = i;
         }
-        if (!has_disease(c) && has_misc(c)) r.sum_health_happiness += c.x.misc.health_happiness[s];
+        if (!has_disease(c) && has_misc(c)) r.sum_health_happiness += c.x->misc.health_happiness[s];
         if (has_disease(c) || has_misc(c)) {      // findTimeToLive with the modifiers / the universal income term
             const double ttl = time_to_live_x(c, s, false);
             r.sum_burn_rate += ttl;
@@ -591,7 +591,7 @@ __device__ inline void ext_stats_body(const DevCtx &c, ssb_ext_stats_t *out, int
 // Interaction counters of a pass (sugarscape.py:1175-1198, 1230-1250): summed over the pass's live agents (then reset)
 // and this step's dead; plus the control / experimental members of the movement neighbourhoods.
 __device__ inline void group_counters_body(const DevCtx &c, int pass, ssb_group_stats_t *out) {
-    const ssb_group_t &G = c.x.group;
+    const ssb_group_t &G = c.x->group;
     for (int k = 0; k < SSB_GI_KINDS; k++) { out->to_control[k] = 0; out->to_experimental[k] = 0; }
     out->control_neighbors = 0; out->experimental_neighbors = 0;
     const long long n = c.a.counters[SSB_C_N_LIST], n_dead = c.a.counters[SSB_C_N_DEAD];

@@ -178,6 +178,8 @@ __global__ void __launch_bounds__(COMPACT_THREADS) k_scan_tiles(int32_t *tile_co
     if (threadIdx.x == 0) *total_out = carry;
 }
 
+// EXT: an ABI 2 extension is bound (doDeath then also settles the agent's loans / infections)
+template <bool EXT>
 __global__ void __launch_bounds__(COMPACT_THREADS) k_compact_scatter(DevCtx c, const int32_t *tile_offset,
                                                                      int32_t *new_order) {
     const long long n = c.a.counters[SSB_C_N_LIST];
@@ -205,9 +207,8 @@ __global__ void __launch_bounds__(COMPACT_THREADS) k_compact_scatter(DevCtx c, c
         if (alive[k]) new_order[at++] = slots[k];
         else {
             const int s = slots[k];
-            // (the <true> instantiation only adds null checks of the optional families' arrays)
-            if (c.a.cod[s] == SSB_ALIVE) do_death<true>(c, s, SSB_OTHER);   // removeDeadAgents -> doDeath()
-            else if (c.a.pos[s] >= 0) do_death<true>(c, s, c.a.cod[s]);
+            if (c.a.cod[s] == SSB_ALIVE) do_death<EXT>(c, s, SSB_OTHER);   // removeDeadAgents -> doDeath()
+            else if (c.a.pos[s] >= 0) do_death<EXT>(c, s, c.a.cod[s]);
             c.a.dead_list[dead_at++] = s;
         }
     }

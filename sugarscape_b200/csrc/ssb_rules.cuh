@@ -38,8 +38,10 @@ struct DevCtx {
     // mode S
     int32_t *born_list;              // slots of this step's newborn (unordered)
     ShardCtx sh;                     // world <= 1: the whole simulation lives on this GPU
-    ssb_ethics_t eth;                // ABI 2, mode E: decision models (eth.model == nullptr: every agent is a plain Agent)
-    ssb_ext_t x;                     // ABI 2, mode E: lending, friends ... (a family is off when its first array is null)
+    // ABI 2, mode E (null otherwise; device copies of the structs bound with ssb_bind_ethics / ssb_bind_ext -- pointers,
+    // so that the context every kernel carries does not grow with the families)
+    const ssb_ethics_t *eth;         // decision models (null: every agent is a plain Agent)
+    const ssb_ext_t *x;              // lending, friends, diseases ... (a family is off when its first array is null)
 };
 
 // ssb_ext.cuh (included below, once the basic predicates exist)
@@ -56,6 +58,9 @@ __device__ __forceinline__ int wrap1(int v, int n) { return v < 0 ? v + n : (v >
 
 // Lane groups: G consecutive lanes of a warp (G = 32, 16, 8, 4) cooperate on one agent.
 constexpr int MAXC_EXACT_RULES = 128;   // = MAXC_EXACT (ssb_exact.cuh): candidate cells of one ranking in mode E
+
+template <class Rng> struct RngTraits { static constexpr bool ordered = false; };
+template <> struct RngTraits<RngExact> { static constexpr bool ordered = true; };      // mode E: the one ordered stream
 
 template <int G> struct Group {
     static __device__ __forceinline__ int lane() { return threadIdx.x & (G - 1); }
@@ -413,10 +418,10 @@ __device__ __noinline__ double ethical_value(const DevCtx &c, int s, int my_r, c
     neighbours4(c, cell, nb4);
     double neighbor_wealth = 0;
     for (int i = 0; i < 4; i++) neighbor_wealth += c.g.sugar[nb4[i]] + (spicy ? c.g.spice[nb4[i]] : 0);
-    const double lookahead = c.eth.lookahead_factor[s];
+    const double lookahead = c.eth->lookahead_factor[s];
     // len(self.findNeighborhood(cell)): live agents on MY cross moved to `cell`, plus myself
     const double future_hood = lookahead != 0 ? (double)(1 + (my_r > 0 ? cross_live_count(c, cell, my_r) : 0)) : 1.0;
-    const double selfish = c.eth.selfishness[s];
+    const double selfish = c.eth->selfishness[s];
     double value = 0, h = 0, u = 0;
     for (int k = 0; k < n_hood; k++) {
         const int nb = hood[k];
@@ -428,10 +433,10 @@ __device__ __noinline__ double ethical_value(const DevCtx &c, int s, int my_r, c
         const double proximity = 1.0 / 1;
         const double intensity = (1 / (1 + time_to_live_x(c, nb, false)) / (1 + c.g.pollution[cell]));
         const double duration = max_site > 0 ? cell_duration / max_site : 0;
-        const double discount = c.eth.lookahead_factor[nb] != 0 ? c.eth.lookahead_discount[nb] : 0;
+        const double discount = c.eth->lookahead_factor[nb] != 0 ? c.eth->lookahead_discount[nb] : 0;
         double future_duration = metab > 0 ? (site - metab) / metab : site;
         future_duration = max_site > 0 ? future_duration / max_site : 0;
-        const double future_intensity = neighbor_wealth / (c.eth.global_max_wealth * 4);
+        const double future_intensity = neighbor_wealth / (c.eth->global_max_wealth * 4);
         const int in_range = rn > 0 ? cross_size(c, rn) : 0;                                // len(neighbor.cellsInRange)
         const double extent = in_range > 0 ? (double)n_hood / in_range : 1;
         const double future_extent = (in_range > 0 && lookahead != 0) ? future_hood / in_range : 1;
@@ -521,7 +526,7 @@ __device__ __noinline__ bool ethical_pick(const DevCtx &c, int s, int r, int n, 
         if (o >= 0 && agent_alive(c, o)) hood[nh++] = o;
     }
     hood[nh++] = s;
-    const bool positive = c.eth.selfishness[s] >= 0;
+    const bool positive = c.eth->selfishness[s] >= 0;
     int chosen = -1;
     double best_u = 0, best_h = 0;
     for (int i = 0; i < m; i++) {
@@ -671,23 +676,23 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rn
         }
         if (m == 0) m = 1;
     }
-    if (EXT && c.eth.model != nullptr) {                               // uniform
+    if (EXT && c.eth != nullptr) {                               // uniform
         // decision models: the ethical ranking may override the greedy choice (ethics.py:105-139); the
         // optimality of the move is logged for every agent (agent.py:734-745)
         if (lane == 0) {
             if (n > 0) {
                 int rank = 0, cell = b_cell;
                 double diff = 0;
-                if (b_valid && c.eth.model[s] == 1 && c.eth.decision_factor[s] > 0 &&
+                if (b_valid && c.eth->model[s] == 1 && c.eth->decision_factor[s] > 0 &&
                     ethical_pick(c, s, r, n, w, my_tribe, aggression, ws, &cell, &rank, &diff) && cell != b_cell) {
                     b_cell = cell;
                     b_cs = c.g.sugar[cell];
                     b_cp = spicy ? c.g.spice[cell] : 0;
                     b_pl = polluted ? c.g.pollution[cell] : 0.0;
                 }
-                c.eth.last_move_optimal[s] = rank == 0; c.eth.move_rank[s] = rank; c.eth.move_diff[s] = diff;
+                c.eth->last_move_optimal[s] = rank == 0; c.eth->move_rank[s] = rank; c.eth->move_diff[s] = diff;
             } else {
-                c.eth.last_move_optimal[s] = 1;      // [own cell] is its own best; rank and difference keep their values
+                c.eth->last_move_optimal[s] = 1;      // [own cell] is its own best; rank and difference keep their values
             }
         }
         b_cell = Gr::bcast(b_cell, 0);
@@ -703,10 +708,10 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rn
                 const int o = c.g.occ[ws.cells[i]];
                 if (o >= 0 && agent_alive(c, o)) { if (is_member(c, o)) exp_n++; else ctrl_n++; }
             }
-            c.x.group.control_neighbors[s] = ctrl_n; c.x.group.experimental_neighbors[s] = exp_n;
+            c.x->group.control_neighbors[s] = ctrl_n; c.x->group.experimental_neighbors[s] = exp_n;
         }
         // lastValidMoves: findBestCell records len([own cell]) when the range is empty (agent.py:1398-1399, 745)
-        if (diseased) c.x.diseases.last_valid_moves[s] = n > 0 ? m : 1;
+        if (diseased) c.x->diseases.last_valid_moves[s] = n > 0 ? m : 1;
         if (!b_valid) {     // stays on its own cell: its contents were not among the candidates
             b_cs = c.g.sugar[pos];
             b_cp = spicy ? c.g.spice[pos] : 0;
@@ -720,10 +725,10 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rn
                 const double sl = fmin(loot, a.sugar[prey]), pl = fmin(loot, a.spice[prey]);
                 sugar += sl; spice += pl;
                 a.sugar[prey] -= sl; a.spice[prey] -= pl;
-                if (EXT && has_social(c)) c.x.social.last_combat[s] = c.t;
+                if (EXT && has_social(c)) c.x->social.last_combat[s] = c.t;
                 // the prey's heirs may include the killer itself (its own parent fell): keep memory current
                 // around the inheritance (agent.py:274-294 updates self.sugar before prey.doDeath)
-                const bool heirs = c.p.inheritance_policy != 0;
+                const bool heirs = RngTraits<Rng>::ordered && c.p.inheritance_policy != 0;     // (kin lists exist in mode E only)
                 if (heirs) { a.sugar[s] = sugar; a.spice[s] = spice; }
                 do_death<EXT>(c, prey, SSB_COMBAT);
                 if (heirs) { sugar = a.sugar[s]; spice = a.spice[s]; }
@@ -738,7 +743,7 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rn
         spice += b_cp;
         if (EXT && has_lending(c)) lending_note_income(c, s, b_cs, b_cp);
         if (EXT && has_misc(c)) {        // doUniversalIncome (agent.py:708-714): spice first
-            const ssb_misc_t &M = c.x.misc;
+            const ssb_misc_t &M = c.x->misc;
             if ((c.t - M.last_income_spice[s]) >= M.income_interval_spice) { spice += M.universal_spice[s]; M.last_income_spice[s] = c.t; }
             if ((c.t - M.last_income_sugar[s]) >= M.income_interval_sugar) { sugar += M.universal_sugar[s]; M.last_income_sugar[s] = c.t; }
         }
@@ -1019,24 +1024,24 @@ __device__ __noinline__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
         const int my_id = a.id[s], mate_id = a.id[m];
         a.father[ch] = my_sex == SSB_SEX_FEMALE ? mate_id : my_id;
         a.mother[ch] = my_sex == SSB_SEX_FEMALE ? my_id : mate_id;
-        if (EXT && c.eth.model != nullptr) {
+        if (EXT && c.eth != nullptr) {
             // the paired endowments follow ONE draw (agent.py:845-851); the child's class is that parent's
             const int from = ((eb >> EB_DECISION_MODEL) & 1u) ? m : s;
-            c.eth.model[ch] = c.eth.model[from]; c.eth.selfishness[ch] = c.eth.selfishness[from];
-            c.eth.decision_factor[ch] = c.eth.decision_factor[from];
-            c.eth.lookahead_factor[ch] = c.eth.lookahead_factor[from];
-            c.eth.lookahead_discount[ch] = c.eth.lookahead_discount[from];
-            c.eth.last_move_optimal[ch] = 1; c.eth.move_rank[ch] = 0; c.eth.move_diff[ch] = 0;      // lastMoveOptimal starts True
+            c.eth->model[ch] = c.eth->model[from]; c.eth->selfishness[ch] = c.eth->selfishness[from];
+            c.eth->decision_factor[ch] = c.eth->decision_factor[from];
+            c.eth->lookahead_factor[ch] = c.eth->lookahead_factor[from];
+            c.eth->lookahead_discount[ch] = c.eth->lookahead_discount[from];
+            c.eth->last_move_optimal[ch] = 1; c.eth->move_rank[ch] = 0; c.eth->move_diff[ch] = 0;      // lastMoveOptimal starts True
         }
         if (EXT && has_group(c)) group_reset_slot(c, ch);
         if (diseased) disease_child(c, ch, s, m, eb);
         if (EXT && has_misc(c)) misc_child(c, ch, s, m, eb);
         if (EXT && has_social(c)) {
             social_reset_slot(c, ch);
-            c.x.social.max_friends[ch] = ((eb >> EB_MAX_FRIENDS) & 1u) ? c.x.social.max_friends[m] : c.x.social.max_friends[s];
+            c.x->social.max_friends[ch] = ((eb >> EB_MAX_FRIENDS) & 1u) ? c.x->social.max_friends[m] : c.x->social.max_friends[s];
         }
         if (EXT && has_lending(c)) {
-            const ssb_lending_t &L = c.x.lending;
+            const ssb_lending_t &L = c.x->lending;
             lending_reset_slot(c, ch);
             L.base_interest_rate[ch] = ((eb >> EB_BASE_INTEREST) & 1u) ? L.base_interest_rate[m] : L.base_interest_rate[s];
             L.lending_factor[ch] = ((eb >> EB_LENDING_FACTOR) & 1u) ? L.lending_factor[m] : L.lending_factor[s];
@@ -1044,8 +1049,8 @@ __device__ __noinline__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
         }
         if (EXT && has_misc(c)) {
             // the child is depressed with the configured chance, decided by the private stream (agent.py:889-895)
-            const double draw = c.t < c.x.misc.n_tables ? c.x.misc.depression_draw[c.t] : 1.0;
-            if (draw <= c.x.misc.depression_percentage) depress(c, ch);
+            const double draw = c.t < c.x->misc.n_tables ? c.x->misc.depression_draw[c.t] : 1.0;
+            if (draw <= c.x->misc.depression_percentage) depress(c, ch);
         }
         a.pos[ch] = cell;
         c.g.occ[cell] = ch;
@@ -1126,14 +1131,14 @@ __device__ void transaction_interact_phase(const DevCtx &c, int s, const AgentRe
         // findConflictHappiness (agent.py:912-918), findSocialHappiness (1099-1105), findHealthHappiness (1017-1021)
         double conflict_h = 0, social_h = 0;
         if (has_social(c)) {
-            const ssb_social_t &S = c.x.social;
+            const ssb_social_t &S = c.x->social;
             if (S.last_combat[s] == c.t) conflict_h = eff_aggression(c, s) > 1 ? unit : unit * -1;
             if (S.max_friends[s] != 0) social_h = ((S.n_friends[s] * (2.0 / S.max_friends[s])) - 1) * unit;
             S.conflict_happiness[s] = conflict_h; S.social_happiness[s] = social_h;
         }
         const double health_h = is_sick(c, s) ? unit * -1 : unit;
-        if (diseased) c.x.diseases.health_happiness[s] = health_h;
-        else if (has_misc(c)) c.x.misc.health_happiness[s] = health_h;
+        if (diseased) c.x->diseases.health_happiness[s] = health_h;
+        else if (has_misc(c)) c.x->misc.health_happiness[s] = health_h;
         a.happiness[s] = conflict_h + family_h + health_h + social_h + wealth_h;
     } else {
         a.happiness[s] = family_h + 1.0 + wealth_h;

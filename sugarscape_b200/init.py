@@ -109,8 +109,8 @@ def check_supported(c):
     bad_models = [m for m in c["agentDecisionModels"] if m not in SUPPORTED_DECISION_MODELS]
     if bad_models:
         problems.append("decision models other than rawSugarscape and the Bentham family: " + ", ".join(bad_models))
-    if c["agentDecisionModelFactor"][1] > 0 and not uses_decision_models(c):
-        problems.append("agentDecisionModelFactor")
+    # (agentDecisionModelFactor > 0 without a decision model: the plain Agent's findBestEthicalCell hands back the
+    # greedy cell, agent.py:730-733 -- nothing to refuse)
     if uses_decision_models(c) and c["agentDynamicSelfishnessFactor"][1] != 0:
         problems.append("agentDynamicSelfishnessFactor")
     for k in ("agentDecisionModelAgeismFactor", "agentDecisionModelRacismFactor",

@@ -1,0 +1,89 @@
+#!/usr/bin/env python3
+"""Fuzz the engine's mode E DEVICE SOURCE (host-compiled, tests/hostemu) against the live, UNMODIFIED reference
+(build container only): random rule / size / seed combinations over every ABI 2 family -- decision models, lending,
+friends, diseases, universal income, racial tags, depression -- and the book rules.
+
+    python tests/golden/fuzz_hostemu.py [cases] [seed]
+
+Same case generator and digests as fuzz_oracle.py; configurations the engine refuses are skipped."""
+import os
+import random
+import sys
+import traceback
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+import ref_harness as rh  # noqa: E402
+import parity_util as pu  # noqa: E402
+from fuzz_oracle import BASES, draw_overrides  # noqa: E402
+from hostemu_binding import HostEmu  # noqa: E402
+from sugarscape_b200 import init, stats  # noqa: E402
+
+
+def run_case(base, ov, steps):
+    path = os.path.join(rh.REFERENCE_DIR, "examples", base + ".json")
+    try:
+        S = rh.build_reference(path, ov)
+        S.updateRuntimeStats()
+        ref_digests = [rh.digests(rh.snapshot(S))]
+        for _ in range(steps):
+            if len(S.agents) == 0 and not S.keepAlive:
+                break
+            S.doTimestep()
+            ref_digests.append(rh.digests(rh.snapshot(S)))
+    except Exception as e:
+        return "skipped (the reference itself raised %r)" % (e,)
+    try:
+        c, state, pop, params, endow, tags = pu.build(base, overrides=ov)
+    except init.UnsupportedConfiguration as e:
+        return "skipped (refused: %s)" % e
+    if c["agentReplacements"] > 0 and ((c["agentTagging"] and c["agentTagStringLength"] > 0 and not c["environmentTribePerQuadrant"])
+                                       or (c["agentImmuneSystemLength"] > 0 and c["startingDiseases"] > 0)):
+        return "skipped (reference aliases list-valued endowments between replacement twins)"
+    emu = HostEmu(params, state, endow, tags)
+    emu.set_mt_from_python()
+    d, _ = pu.state_digests(state, *emu.mt_state())
+    if d != ref_digests[0]:
+        return "t=0 differs: " + str({k: d[k] == ref_digests[0][k] for k in d})
+    sb = stats.StatsBuilder(c, init.equator(c))
+    rs = sb.update(emu.stats(0), 0, 0, emu.ethics_stats(), emu.ext_stats(0))
+    for t in range(1, len(ref_digests)):
+        emu.env_step(t)
+        emu.agent_step(t, rs["meanWealth"])
+        emu.compact(t)
+        if c["agentReplacements"] > 0:
+            emu.push_mt_to_python()
+            pu.replace_dead_agents(c, state, pop, t)
+            emu.set_mt_from_python()
+        d, _ = pu.state_digests(state, *emu.mt_state())
+        if d != ref_digests[t]:
+            return f"t={t} differs: " + str({k: d[k] == ref_digests[t][k] for k in d})
+        rs = sb.update(emu.stats(t), t, 0, emu.ethics_stats(), emu.ext_stats(t))
+    families = sorted(state.ext.families) if state.ext is not None else []
+    return "ok %d steps, final population %d, families %s%s" % (len(ref_digests) - 1, rs["population"], families,
+                                                                " + ethics" if state.ethics is not None else "")
+
+
+def main():
+    cases = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+    rng = random.Random(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+    bad = 0
+    for i in range(cases):
+        base = rng.choice(BASES)
+        ov = draw_overrides(rng, base)
+        try:
+            res = run_case(base, ov, 60)
+        except Exception as e:
+            res = "EXCEPTION " + repr(e) + "\n" + traceback.format_exc(limit=6)
+        flag = "" if res.startswith("ok") or res.startswith("skipped") else "   <<<<<<"
+        print(f"case {i} {base}: {res}{flag}", flush=True)
+        if flag:
+            bad += 1
+            print("   overrides:", ov, flush=True)
+    print("mismatching cases:", bad)
+
+
+if __name__ == "__main__":
+    main()

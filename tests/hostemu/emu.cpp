@@ -29,8 +29,8 @@ int emu_agent_step_exact(const ssb_params_t *p, const ssb_grid_t *g, const ssb_a
     c.endow_bits = endow_bits; c.tag_bits = tag_bits; c.n_step_tables = n_tables;
     alignas(8) unsigned char scratch[warp_scratch_bytes(MAXC_EXACT)];
     if (ethics || ext) {   /* as ssb_agent_step: the extended instantiation only when an extension is bound */
-        if (ethics) c.eth = *ethics;
-        if (ext) c.x = *ext;
+        if (ethics) c.eth = ethics;
+        if (ext) c.x = ext;
         agent_step_exact_body<1, true>(c, mt, make_warp_scratch(scratch, MAXC_EXACT));
     } else {
         agent_step_exact_body<1, false>(c, mt, make_warp_scratch(scratch, MAXC_EXACT));
@@ -42,7 +42,7 @@ int emu_ext_stats(const ssb_agents_t *a, const ssb_ext_t *ext, int32_t t, ssb_ex
     if (!a || !ext || !out) return -1;
     DevCtx c;
     memset(&c, 0, sizeof(c));
-    c.a = *a; c.x = *ext; c.t = t;
+    c.a = *a; c.x = ext; c.t = t;
     ext_stats_body(c, out);
     return 0;
 }
@@ -51,8 +51,8 @@ int emu_group_stats(const ssb_agents_t *a, const ssb_ethics_t *ethics, const ssb
     if (!a || !ext || !out) return -1;
     DevCtx c;
     memset(&c, 0, sizeof(c));
-    c.a = *a; c.x = *ext; c.t = t;
-    if (ethics) c.eth = *ethics;
+    c.a = *a; c.x = ext; c.t = t;
+    if (ethics) c.eth = ethics;
     memset(out, 0, 3 * sizeof(ssb_group_stats_t));
     group_stats_body(c, out);
     return 0;
@@ -62,7 +62,7 @@ int emu_ethics_stats(const ssb_agents_t *a, const ssb_ethics_t *ethics, ssb_ethi
     if (!a || !ethics || !out) return -1;
     DevCtx c;
     memset(&c, 0, sizeof(c));
-    c.a = *a; c.eth = *ethics;
+    c.a = *a; c.eth = ethics;
     ethics_stats_body(c, out);
     return 0;
 }
