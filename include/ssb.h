@@ -239,7 +239,7 @@ typedef struct ssb_ethics_stats {
  * one in the creditor's "debtors" list; lists are chains through the loan pool in list order. */
 #define SSB_LC_POOL_USED   0  /* high-water mark of the loan pool                                         */
 #define SSB_LC_FREE_HEAD   1  /* recycled pool entries: index of the first one + 1 (0 = none)             */
-#define SSB_LC_N_DEAD      2  /* entries of the dead-creditor table                                       */
+#define SSB_LC_N_DEAD      2  /* dead creditors recorded so far (the table is a ring: entry i lives at i % dead_capacity) */
 #define SSB_LC_OVERFLOW    3  /* != 0: a pool was exhausted -> host raises                                 */
 #define SSB_LC_COUNT       8
 typedef struct ssb_lending {
@@ -252,9 +252,13 @@ typedef struct ssb_lending {
     int32_t *loan_other_slot, *loan_other_id;         /* the other party, named by (slot, id)              */
     double  *loan_sugar, *loan_spice;
     int32_t *loan_duration_v, *loan_origin, *loan_next;
-    /* a dead creditor's children list outlives its slot (payDebtToCreditorChildren, agent.py:1362-1377) */
+    /* a dead creditor's children list outlives its slot (payDebtToCreditorChildren, agent.py:1362-1377).  The
+     * table is a ring: an entry matters only while one of the creditor's loans is outstanding, i.e. for at most
+     * the longest loan duration after the death (its loans fall due at origin + duration, and only a living
+     * creditor's loans are ever renewed); overwriting a younger entry raises the overflow flag. */
     int64_t dead_capacity;
-    int32_t *dead_slot, *dead_id, *dead_children_head;
+    int64_t max_loan_duration;                        /* upper end of agentLoanDuration: how long a dead creditor can matter */
+    int32_t *dead_slot, *dead_id, *dead_children_head, *dead_time;
     int64_t *counters;                                /* SSB_LC_COUNT values                               */
 } ssb_lending_t;
 

@@ -377,7 +377,7 @@ int ssb_bind_ext(ssb_engine_t *e, const ssb_ext_t *ext) {
     if (L.lending_factor) {
         const void *need[] = {L.base_interest_rate, L.loan_duration, L.sugar_mean_income, L.spice_mean_income, L.last_lended, L.last_loans,
                               L.creditors_head, L.debtors_head, L.loan_other_slot, L.loan_other_id, L.loan_sugar, L.loan_spice,
-                              L.loan_duration_v, L.loan_origin, L.loan_next, L.dead_slot, L.dead_id, L.dead_children_head, L.counters};
+                              L.loan_duration_v, L.loan_origin, L.loan_next, L.dead_slot, L.dead_id, L.dead_children_head, L.dead_time, L.counters};
         for (const void *p : need) if (!p) return fail(e, -1, "lending: null array");
         if (L.pool_capacity <= 0 || L.dead_capacity <= 0) return fail(e, -1, "lending: empty pools");
     }

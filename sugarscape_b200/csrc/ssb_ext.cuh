@@ -386,8 +386,10 @@ __device__ inline void lending_note_death(const DevCtx &c, int s) {
     if (L.debtors_head[s] < 0) return;
     // (atomic: removeDeadAgents' doDeath runs in the parallel compaction kernel)
     const long long n = (long long)atomicAdd((unsigned long long *)&L.counters[SSB_LC_N_DEAD], 1ull);
-    if (n >= L.dead_capacity) { L.counters[SSB_LC_OVERFLOW] = 2; return; }
-    L.dead_slot[n] = s; L.dead_id[n] = c.a.id[s]; L.dead_children_head[n] = c.a.children_head[s];
+    const long long at = n % L.dead_capacity;
+    // ring: the entry overwritten must be older than any loan of that creditor can still be outstanding
+    if (n >= L.dead_capacity && c.t - L.dead_time[at] <= L.max_loan_duration + 1) L.counters[SSB_LC_OVERFLOW] = 2;
+    L.dead_slot[at] = s; L.dead_id[at] = c.a.id[s]; L.dead_children_head[at] = c.a.children_head[s]; L.dead_time[at] = c.t;
 }
 // addLoanToAgent (agent.py:199-211) incl. addLoanFromAgent (190-197)
 __device__ inline void add_loan(const DevCtx &c, int creditor, int debtor, int origin, double sugar_principal, double sugar_loan,
@@ -410,8 +412,13 @@ __device__ __noinline__ void pay_debt_to_creditor_children(const DevCtx &c, int 
     const ssb_agents_t &a = c.a;
     int head = -1;
     if (a.id[loan.other_slot] == loan.other_id) head = a.children_head[loan.other_slot];
-    else for (long long i = min((long long)L.counters[SSB_LC_N_DEAD], (long long)L.dead_capacity) - 1; i >= 0; i--)
-        if (L.dead_slot[i] == loan.other_slot && L.dead_id[i] == loan.other_id) { head = L.dead_children_head[i]; break; }
+    else {
+        const long long n = L.counters[SSB_LC_N_DEAD], lo = max(n - (long long)L.dead_capacity, 0LL);
+        for (long long i = n - 1; i >= lo; i--) {          // newest first
+            const long long at = i % L.dead_capacity;
+            if (L.dead_slot[at] == loan.other_slot && L.dead_id[at] == loan.other_id) { head = L.dead_children_head[at]; break; }
+        }
+    }
     int32_t kids[256];
     int n = 0;
     for (int e = head; e >= 0 && n < 256; e = a.kin_next[e]) {          // newest first (kin_push prepends)

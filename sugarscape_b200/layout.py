@@ -275,8 +275,9 @@ LENDING_LAYOUT = (
     ("loan_other_slot", _I32, -1, "pool"), ("loan_other_id", _I32, -1, "pool"),
     ("loan_sugar", _F64, 0, "pool"), ("loan_spice", _F64, 0, "pool"),
     ("loan_duration_v", _I32, 0, "pool"), ("loan_origin", _I32, 0, "pool"), ("loan_next", _I32, -1, "pool"),
-    ("dead_capacity", None, None, None),
+    ("dead_capacity", None, None, None), ("max_loan_duration", None, None, None),
     ("dead_slot", _I32, -1, "dead"), ("dead_id", _I32, -1, "dead"), ("dead_children_head", _I32, -1, "dead"),
+    ("dead_time", _I32, 0, "dead"),
     ("counters", _I64, 0, LC_COUNT),
 )
 SOCIAL_LAYOUT = (
@@ -375,6 +376,7 @@ class HostExt:
             self.families.add("misc")
         if c["experimentalGroup"] is not None:
             self.families.add("group")
+        self.max_loan_duration = int(max(c["agentLoanDuration"]))
         self.racial_len = int(c["agentRacialTagStringLength"]) if c["environmentMaxRaces"] > 0 else 0
         self.misc_scalars = (float(c["agentDepressionPercentage"]), int(c["environmentUniversalSugarIncomeInterval"]),
                              int(c["environmentUniversalSpiceIncomeInterval"]), self.racial_len, int(c["environmentMaxRaces"]))
@@ -522,8 +524,8 @@ class HostExt:
                 sub.max_sick, sub.immune_len, sub.n_diseases = self.max_sick, self.immune_len, self.n_diseases
                 sub.n_immune_bits = len(self.arrays["diseases.immune_bits"])
             for n, dt, _, _ in table:
-                if dt is None:
-                    setattr(sub, n, self.sizes[n.split("_")[0]])      # pool_capacity / dead_capacity
+                if dt is None:          # pool_capacity / dead_capacity / max_loan_duration
+                    setattr(sub, n, self.max_loan_duration if n == "max_loan_duration" else self.sizes[n.split("_")[0]])
                 else:
                     setattr(sub, n, pointer_of(self.arrays[fam + "." + n]))
         return x
@@ -536,7 +538,7 @@ class HostExt:
         h = HostExt.__new__(HostExt)
         h.capacity, h.families, h.sizes = self.capacity, set(self.families), dict(self.sizes)
         h.n_diseases, h.max_sick, h.immune_len = self.n_diseases, self.max_sick, self.immune_len
-        h.racial_len, h.misc_scalars = self.racial_len, self.misc_scalars
+        h.racial_len, h.misc_scalars, h.max_loan_duration = self.racial_len, self.misc_scalars, self.max_loan_duration
         h.arrays = {k: v.copy() for k, v in self.arrays.items()}
         return h
 

@@ -199,3 +199,18 @@ def test_device_source_matches_reference_on_all_features_examples(name):
         assert len(log[t]) == 203
         for k in log[t]:
             assert k in rs and _close(rs[k], log[t][k]), f"log key {k} differs at t={t}: {rs.get(k)} vs {log[t][k]}"
+
+
+def test_dead_creditor_table_wraps_around():
+    """The dead-creditor table of the lending family is a ring (include/ssb.h): with room for only 8 entries it wraps
+    more than twice during dune.json's 200 steps (22 creditors die with loans outstanding) and the trajectory still
+    equals the reference's, because an entry matters for at most the longest loan duration after the death."""
+    c, state, pop, params, endow, tags = pu.build("dune")
+    ext = state.ext
+    ext.sizes["dead"] = 8
+    for name in ("dead_slot", "dead_id", "dead_children_head", "dead_time"):
+        ext.arrays["lending." + name] = ext.arrays["lending." + name][:8].copy()
+    meta, _ = pu.load_golden("dune")
+    _run_with_extensions(c, state, pop, params, endow, tags, meta["steps"], meta["log"])
+    from sugarscape_b200 import layout
+    assert int(ext.arrays["lending.counters"][layout.LC_N_DEAD]) > 2 * 8
