@@ -325,7 +325,13 @@ typedef struct ssb_misc {
 
 /* experimental group (agent.py:1256-1284 isInGroup; sugarscape.py:998-1003, 1175-1198, 1230-1250): the log repeats
  * every statistic for the group and for its complement ("control") and counts the interactions between them.
- * Supported group: "depressed" (membership = ssb_misc_t.depressed). */
+ * Supported groups (ssb_group_t.kind): "depressed" (ssb_misc_t.depressed), "female" / "male" (ssb_agents_t.sex) --
+ * memberships that are fixed at birth.  (Groups whose membership changes during the run -- "sick", age ranges, a
+ * disease -- would need every agent's movement neighbourhood kept as a list: the reference re-evaluates the
+ * neighbours' membership at statistics time, sugarscape.py:1145-1151.) */
+#define SSB_GROUP_DEPRESSED 1
+#define SSB_GROUP_FEMALE    2
+#define SSB_GROUP_MALE      3
 #define SSB_GI_COMBAT 0
 #define SSB_GI_DISEASE 1
 #define SSB_GI_LENDING 2
@@ -335,6 +341,7 @@ typedef struct ssb_misc {
 typedef struct ssb_group {
     int32_t *with_control, *with_experimental;        /* [slot][SSB_GI_KINDS]: interactions since the last statistics pass */
     int32_t *control_neighbors, *experimental_neighbors;   /* movementNeighborhood split, as of the agent's last ranking */
+    int64_t kind;                                     /* SSB_GROUP_*                                        */
 } ssb_group_t;
 
 typedef struct ssb_ext {

@@ -404,7 +404,8 @@ int ssb_bind_ext(ssb_engine_t *e, const ssb_ext_t *ext) {
     const ssb_group_t &Gr = ext->group;
     if (Gr.with_control) {
         if (!Gr.with_experimental || !Gr.control_neighbors || !Gr.experimental_neighbors) return fail(e, -1, "group: null array");
-        if (!M.universal_sugar) return fail(e, -1, "the experimental group \"depressed\" needs the misc family");
+        if (Gr.kind < SSB_GROUP_DEPRESSED || Gr.kind > SSB_GROUP_MALE) return fail(e, -1, "group: unknown kind");
+        if (Gr.kind == SSB_GROUP_DEPRESSED && !M.universal_sugar) return fail(e, -1, "the experimental group \"depressed\" needs the misc family");
     }
     CU(cudaSetDevice(e->device));
     if (!e->d_ext_stats) {

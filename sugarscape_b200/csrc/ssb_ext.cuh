@@ -17,8 +17,16 @@ __device__ __forceinline__ bool has_social(const DevCtx &c) { return c.x != null
 __device__ __forceinline__ bool has_disease(const DevCtx &c) { return c.x != nullptr && c.x->diseases.immune != nullptr; }
 __device__ __forceinline__ bool has_misc(const DevCtx &c) { return c.x != nullptr && c.x->misc.universal_sugar != nullptr; }
 __device__ __forceinline__ bool has_group(const DevCtx &c) { return c.x != nullptr && c.x->group.with_control != nullptr; }
-// experimental group "depressed" (agent.py:1256-1284 isInGroup)
-__device__ __forceinline__ bool is_member(const DevCtx &c, int s) { return has_misc(c) && c.x->misc.depressed[s] != 0; }
+// Agent.isInGroup (agent.py:1256-1284) for the configured experimental group
+__device__ __forceinline__ bool is_member(const DevCtx &c, int s) {
+    if (!has_group(c)) return false;
+    switch (c.x->group.kind) {
+        case SSB_GROUP_DEPRESSED: return has_misc(c) && c.x->misc.depressed[s] != 0;
+        case SSB_GROUP_FEMALE: return c.a.sex[s] == SSB_SEX_FEMALE;
+        case SSB_GROUP_MALE: return c.a.sex[s] == SSB_SEX_MALE;
+    }
+    return false;
+}
 // statistics pass: 0 = everybody, 1 = the experimental group, 2 = the control group
 __device__ __forceinline__ bool in_pass(const DevCtx &c, int s, int pass) { return pass == 0 || (pass == 1) == is_member(c, s); }
 // <kind>With{Experimental,Control}Group += 1

@@ -117,8 +117,8 @@ def check_supported(c):
               "agentDecisionModelSexismFactor", "agentDecisionModelTribalFactor"):
         if c[k][1] >= 0:
             problems.append(k)
-    if c["experimentalGroup"] not in (None, "depressed"):
-        problems.append("experimentalGroup other than \"depressed\"")
+    if c["experimentalGroup"] is not None and c["experimentalGroup"] not in layout.GROUP_KINDS:
+        problems.append("experimentalGroup other than " + " / ".join(sorted(layout.GROUP_KINDS)))
     if c["experimentalGroup"] is not None and c["agentReplacements"] > 0:
         problems.append("experimentalGroup with agentReplacements")
     if c["agentTagStringLength"] > 32:

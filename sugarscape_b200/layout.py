@@ -314,7 +314,9 @@ GI_KINDS = 5
 GROUP_LAYOUT = (
     ("with_control", _I32, 0, "gi"), ("with_experimental", _I32, 0, "gi"),
     ("control_neighbors", _I32, 0, "cap"), ("experimental_neighbors", _I32, 0, "cap"),
+    ("kind", None, None, None),
 )
+GROUP_KINDS = {"depressed": 1, "female": 2, "male": 3}      # SSB_GROUP_* (memberships fixed at birth)
 EXT_FAMILIES = (("lending", LENDING_LAYOUT), ("social", SOCIAL_LAYOUT), ("diseases", DISEASE_LAYOUT), ("misc", MISC_LAYOUT),
                 ("group", GROUP_LAYOUT))
 
@@ -377,6 +379,7 @@ class HostExt:
         if c["experimentalGroup"] is not None:
             self.families.add("group")
         self.max_loan_duration = int(max(c["agentLoanDuration"]))
+        self.group_kind = GROUP_KINDS.get(c["experimentalGroup"], 0)
         self.racial_len = int(c["agentRacialTagStringLength"]) if c["environmentMaxRaces"] > 0 else 0
         self.misc_scalars = (float(c["agentDepressionPercentage"]), int(c["environmentUniversalSugarIncomeInterval"]),
                              int(c["environmentUniversalSpiceIncomeInterval"]), self.racial_len, int(c["environmentMaxRaces"]))
@@ -524,8 +527,9 @@ class HostExt:
                 sub.max_sick, sub.immune_len, sub.n_diseases = self.max_sick, self.immune_len, self.n_diseases
                 sub.n_immune_bits = len(self.arrays["diseases.immune_bits"])
             for n, dt, _, _ in table:
-                if dt is None:          # pool_capacity / dead_capacity / max_loan_duration
-                    setattr(sub, n, self.max_loan_duration if n == "max_loan_duration" else self.sizes[n.split("_")[0]])
+                if dt is None:          # pool_capacity / dead_capacity / max_loan_duration / the group's kind
+                    setattr(sub, n, self.max_loan_duration if n == "max_loan_duration" else
+                            self.group_kind if n == "kind" else self.sizes[n.split("_")[0]])
                 else:
                     setattr(sub, n, pointer_of(self.arrays[fam + "." + n]))
         return x
@@ -539,6 +543,7 @@ class HostExt:
         h.capacity, h.families, h.sizes = self.capacity, set(self.families), dict(self.sizes)
         h.n_diseases, h.max_sick, h.immune_len = self.n_diseases, self.max_sick, self.immune_len
         h.racial_len, h.misc_scalars, h.max_loan_duration = self.racial_len, self.misc_scalars, self.max_loan_duration
+        h.group_kind = self.group_kind
         h.arrays = {k: v.copy() for k, v in self.arrays.items()}
         return h
 

@@ -58,6 +58,9 @@ VARIANTS = {
         agentSelfishnessFactor=[0.2, 0.8])),
     # pollution enters the intensity term of the ethical value
     "ethics_pollution": ("trade_pollution", 120, dict(_ETHICS)),
+    # other experimental groups than the shipped "depressed" (membership by sex)
+    "determinism_group_female": ("determinism", 120, {"experimentalGroup": "female"}),
+    "determinism_group_male": ("determinism", 80, {"experimentalGroup": "male"}),
 }
 
 

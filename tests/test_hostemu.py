@@ -214,3 +214,27 @@ def test_dead_creditor_table_wraps_around():
     _run_with_extensions(c, state, pop, params, endow, tags, meta["steps"], meta["log"])
     from sugarscape_b200 import layout
     assert int(ext.arrays["lending.counters"][layout.LC_N_DEAD]) > 2 * 8
+
+
+@pytest.mark.parametrize("variant", ["determinism_group_female", "determinism_group_male"])
+def test_device_source_matches_reference_on_other_experimental_groups(variant):
+    """determinism.json with another experimental group than the shipped "depressed" (variant fixtures of the unmodified
+    reference): membership by sex -- digests and all 203 log keys.  (Groups whose membership changes during the run are refused.)"""
+    base, overrides, gold, log = pu.load_variant(variant)
+    c, state, pop, params, endow, tags = pu.build(base, overrides=overrides)
+    assert "group" in state.ext.families and state.ext.group_kind > 1
+    emu = HostEmu(params, state, endow, tags)
+    emu.set_mt_from_python()
+    sb = stats.StatsBuilder(c, init.equator(c))
+    rs = sb.update_with_groups(emu.stats(0), 0, 0, emu.ethics_stats(), emu.ext_stats(0), emu.group_stats(0))
+    for t in range(0, len(gold)):
+        if t > 0:
+            emu.env_step(t)
+            emu.agent_step(t, rs["meanWealth"])
+            emu.compact(t)
+            d, snap = pu.state_digests(state, *emu.mt_state())
+            assert d == gold[t]["digests"], f"state differs at t={t}"
+            rs = sb.update_with_groups(emu.stats(t), t, 0, emu.ethics_stats(), emu.ext_stats(t), emu.group_stats(t))
+        assert len(log[t]) == 203
+        for k in log[t]:
+            assert k in rs and _close(rs[k], log[t][k]), f"log key {k} differs at t={t}: {rs.get(k)} vs {log[t][k]}"
