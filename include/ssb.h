@@ -344,6 +344,48 @@ typedef struct ssb_group {
     int64_t kind;                                     /* SSB_GROUP_*                                        */
 } ssb_group_t;
 
+/* per-agent log (configuration["agentLogfile"]; agent.py:1567-1620 updateRuntimeStats, sugarscape.py:415-421): one
+ * record per agent that completed its transaction, in action order.  Raw values; the host rounds and formats. */
+#define SSB_AL_TIMESTEP 0
+#define SSB_AL_ID 1
+#define SSB_AL_AGE 2
+#define SSB_AL_SUGAR 3
+#define SSB_AL_SPICE 4
+#define SSB_AL_SUGAR_GAINED 5
+#define SSB_AL_SPICE_GAINED 6
+#define SSB_AL_MOVEMENT 7
+#define SSB_AL_TIME_TO_LIVE 8
+#define SSB_AL_DEPRESSION 9
+#define SSB_AL_HAPPINESS 10
+#define SSB_AL_PREY_KILLED 11
+#define SSB_AL_PREY_WEALTH 12
+#define SSB_AL_TRADE_PARTNERS 13
+#define SSB_AL_DISEASES_SPREAD 14
+#define SSB_AL_MATES 15
+#define SSB_AL_NEIGHBORS 16
+#define SSB_AL_VALID_MOVES 17
+#define SSB_AL_MOVE_RANK 18
+#define SSB_AL_LENDING_PARTNERS 19
+#define SSB_AL_POLLUTION_DIFF 20
+#define SSB_AL_TTL_DIFF 21
+#define SSB_AL_NEIGHBORS_IN_TRIBE 22
+#define SSB_AL_SAME_RACE_NEIGHBORS 23
+#define SSB_AL_EXPERIMENTAL_NEIGHBORS 24
+#define SSB_AL_CONTROL_NEIGHBORS 25
+#define SSB_AL_FIELDS 26
+typedef struct ssb_agentlog {
+    double  *time_to_live;                            /* agent.timeToLive: what the last findTimeToLive() call left  */
+    double  *last_pollution;                          /* pollution of the cell the agent left at its last move       */
+    double  *prey_wealth;                             /* lastPreyWealth                                              */
+    int32_t *last_combat;                             /* lastCombatTimestep                                          */
+    int32_t *last_mates;                              /* lastMates                                                   */
+    int32_t *valid_moves, *move_rank;                 /* lastValidMoves, lastMoveRank                                */
+    int32_t *n_neighbors, *neighbor_slot;             /* self.neighbors as of updateNeighbors: [slot][4]             */
+    double  *records;                                 /* [record_capacity][SSB_AL_FIELDS]                            */
+    int64_t record_capacity;
+    int64_t *n_records;                               /* records of the current step (the host resets it)            */
+} ssb_agentlog_t;
+
 typedef struct ssb_ext {
     int64_t capacity;
     ssb_lending_t lending;
@@ -351,6 +393,7 @@ typedef struct ssb_ext {
     ssb_diseases_t diseases;
     ssb_misc_t misc;
     ssb_group_t group;
+    ssb_agentlog_t agentlog;
 } ssb_ext_t;
 /* raw sums for the log keys of the families (sugarscape.py:1130-1160) */
 typedef struct ssb_ext_stats {

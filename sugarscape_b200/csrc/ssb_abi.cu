@@ -407,6 +407,13 @@ int ssb_bind_ext(ssb_engine_t *e, const ssb_ext_t *ext) {
         if (Gr.kind < SSB_GROUP_DEPRESSED || Gr.kind > SSB_GROUP_MALE) return fail(e, -1, "group: unknown kind");
         if (Gr.kind == SSB_GROUP_DEPRESSED && !M.universal_sugar) return fail(e, -1, "the experimental group \"depressed\" needs the misc family");
     }
+    const ssb_agentlog_t &AL = ext->agentlog;
+    if (AL.time_to_live) {
+        const void *need[] = {AL.last_pollution, AL.prey_wealth, AL.last_combat, AL.last_mates, AL.valid_moves, AL.move_rank,
+                              AL.n_neighbors, AL.neighbor_slot, AL.records, AL.n_records};
+        for (const void *p : need) if (!p) return fail(e, -1, "agentlog: null array");
+        if (AL.record_capacity <= 0) return fail(e, -1, "agentlog: empty record buffer");
+    }
     CU(cudaSetDevice(e->device));
     if (!e->d_ext_stats) {
         CU(cudaMalloc(&e->d_ext_stats, sizeof(ssb_ext_stats_t)));

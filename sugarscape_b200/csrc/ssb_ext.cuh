@@ -16,6 +16,7 @@ __device__ __forceinline__ bool has_lending(const DevCtx &c) { return c.x != nul
 __device__ __forceinline__ bool has_social(const DevCtx &c) { return c.x != nullptr && c.x->social.max_friends != nullptr; }
 __device__ __forceinline__ bool has_disease(const DevCtx &c) { return c.x != nullptr && c.x->diseases.immune != nullptr; }
 __device__ __forceinline__ bool has_misc(const DevCtx &c) { return c.x != nullptr && c.x->misc.universal_sugar != nullptr; }
+__device__ __forceinline__ bool has_agentlog(const DevCtx &c) { return c.x != nullptr && c.x->agentlog.time_to_live != nullptr; }
 __device__ __forceinline__ bool has_group(const DevCtx &c) { return c.x != nullptr && c.x->group.with_control != nullptr; }
 // Agent.isInGroup (agent.py:1256-1284) for the configured experimental group
 __device__ __forceinline__ bool is_member(const DevCtx &c, int s) {
@@ -77,6 +78,9 @@ __device__ __forceinline__ double time_to_live_x(const DevCtx &c, int s, bool ag
     }
     double ttl = st < pt ? st : pt;
     if (age_limited) { const double lim = (double)(c.a.max_age[s] - c.a.age[s]); if (lim < ttl) ttl = lim; }
+    // findTimeToLive leaves its result in agent.timeToLive (agent.py:1137-1139), whoever called it: the agent's
+    // record in the per-agent log reports the difference to the previous call
+    if (has_agentlog(c)) c.x->agentlog.time_to_live[s] = ttl;
     return ttl;
 }
 
@@ -554,6 +558,63 @@ __device__ __noinline__ void do_lending(const DevCtx &c, int s, Rng &rng) {
     if (loans > 0) { L.last_lended[s] = c.t; L.last_loans[s] = loans; }
 }
 
+// ---------------------------------------------------------------------------------------------
+// per-agent log
+// ---------------------------------------------------------------------------------------------
+__device__ inline void agentlog_reset_slot(const DevCtx &c, int s) {
+    const ssb_agentlog_t &A = c.x->agentlog;
+    A.time_to_live[s] = 0; A.last_pollution[s] = 0; A.prey_wealth[s] = 0; A.last_combat[s] = -1; A.last_mates[s] = 0;
+    A.valid_moves[s] = 0; A.move_rank[s] = 0; A.n_neighbors[s] = 0;
+}
+// updateNeighbors (agent.py:1563-1565): the occupants of the von Neumann neighbours, N S E W
+__device__ inline void agentlog_note_neighbors(const DevCtx &c, int s, int pos) {
+    const ssb_agentlog_t &A = c.x->agentlog;
+    int32_t nb4[4];
+    int n = 0;
+    neighbours4(c, pos, nb4);
+    for (int i = 0; i < 4; i++) { const int o = c.g.occ[nb4[i]]; if (o >= 0) A.neighbor_slot[(long long)s * 4 + n++] = o; }
+    A.n_neighbors[s] = n;
+}
+// Agent.updateRuntimeStats (agent.py:1567-1620), at the end of a completed transaction
+__device__ __noinline__ void agentlog_record(const DevCtx &c, int s) {
+    const ssb_agentlog_t &A = c.x->agentlog;
+    const ssb_agents_t &a = c.a;
+    const long long at = A.n_records[0];
+    if (at >= A.record_capacity) return;
+    A.n_records[0] = at + 1;
+    double *r = A.records + at * SSB_AL_FIELDS;
+    const int t = c.t;
+    int in_tribe = 0, same_race = 0, exp_n = 0, ctrl_n = 0;
+    const int my_race = has_misc(c) ? c.x->misc.race[s] : -1;
+    for (int i = 0; i < A.n_neighbors[s]; i++) {
+        const int o = A.neighbor_slot[(long long)s * 4 + i];
+        if (a.tribe[o] == a.tribe[s]) in_tribe++;
+        if ((has_misc(c) ? c.x->misc.race[o] : -1) == my_race) same_race++;
+        if (has_group(c)) { if (is_member(c, o)) exp_n++; else ctrl_n++; }
+    }
+    const double last_ttl = A.time_to_live[s];
+    const double ttl = time_to_live_x(c, s, false);          // (stores agent.timeToLive)
+    r[SSB_AL_TIMESTEP] = t; r[SSB_AL_ID] = a.id[s]; r[SSB_AL_AGE] = a.age[s];
+    r[SSB_AL_SUGAR] = a.sugar[s]; r[SSB_AL_SPICE] = a.spice[s];
+    r[SSB_AL_SUGAR_GAINED] = a.sugar[s] - a.last_sugar[s]; r[SSB_AL_SPICE_GAINED] = a.spice[s] - a.last_spice[s];
+    r[SSB_AL_MOVEMENT] = eff_movement(c, s);
+    r[SSB_AL_TIME_TO_LIVE] = ttl;
+    r[SSB_AL_DEPRESSION] = has_misc(c) ? c.x->misc.depressed[s] : 0;
+    r[SSB_AL_HAPPINESS] = a.happiness[s];
+    r[SSB_AL_PREY_KILLED] = A.last_combat[s] == t;
+    r[SSB_AL_PREY_WEALTH] = A.last_combat[s] == t ? A.prey_wealth[s] : 0;
+    r[SSB_AL_TRADE_PARTNERS] = ((c.p.flags & SSB_F_TRADE) && a.trade_factor[s] != 0) ? a.trade_volume[s] : 0;
+    r[SSB_AL_DISEASES_SPREAD] = (has_disease(c) && c.x->diseases.last_spread[s] == t) ? c.x->diseases.n_spread[s] : 0;
+    r[SSB_AL_MATES] = a.last_repro[s] == t ? A.last_mates[s] : 0;
+    r[SSB_AL_NEIGHBORS] = A.n_neighbors[s];
+    r[SSB_AL_VALID_MOVES] = A.valid_moves[s]; r[SSB_AL_MOVE_RANK] = A.move_rank[s];
+    r[SSB_AL_LENDING_PARTNERS] = (has_lending(c) && c.x->lending.last_lended[s] == t) ? c.x->lending.last_loans[s] : 0;
+    r[SSB_AL_POLLUTION_DIFF] = c.g.pollution[a.pos[s]] - A.last_pollution[s];
+    r[SSB_AL_TTL_DIFF] = ttl - last_ttl;
+    r[SSB_AL_NEIGHBORS_IN_TRIBE] = in_tribe; r[SSB_AL_SAME_RACE_NEIGHBORS] = same_race;
+    r[SSB_AL_EXPERIMENTAL_NEIGHBORS] = exp_n; r[SSB_AL_CONTROL_NEIGHBORS] = ctrl_n;
+}
+
 // reductions of the families' log keys, list order (sugarscape.py:1130-1160, 1162, 1200-1211, 1228, 1254-1277)
 __device__ inline void ext_stats_body(const DevCtx &c, ssb_ext_stats_t *out, int pass = 0) {
     ssb_ext_stats_t r;
@@ -577,10 +638,13 @@ __device__ inline void ext_stats_body(const DevCtx &c, ssb_ext_stats_t *out, int
             if (race >= 0 && race < 4 && r.race_count[race]++ == 0) r.race_first[race] = i;
         }
         if (!has_disease(c) && has_misc(c)) r.sum_health_happiness += c.x->misc.health_happiness[s];
+        // (sugarscape.py:1111-1112 leaves the age-limited value in agent.timeToLive)
+        if (has_agentlog(c) && !(has_disease(c) || has_misc(c))) { time_to_live_x(c, s, false); time_to_live_x(c, s, true); }
         if (has_disease(c) || has_misc(c)) {      // findTimeToLive with the modifiers / the universal income term
             const double ttl = time_to_live_x(c, s, false);
             r.sum_burn_rate += ttl;
             r.sum_ttl_age_limited += fmin(ttl, (double)(c.a.max_age[s] - c.a.age[s]));
+            if (has_agentlog(c)) time_to_live_x(c, s, true);
         }
         if (has_disease(c)) {
             const long long b = (long long)s * D.max_sick;

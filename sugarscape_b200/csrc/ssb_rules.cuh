@@ -518,7 +518,6 @@ __device__ __noinline__ bool ethical_pick(const DevCtx &c, int s, int r, int n, 
         }
         cand_cell[j] = cell; cand_dist[j] = dist; cand_w[j] = welfare;
     }
-    if (m == 0) return false;
     int32_t hood[MAXC_EXACT_RULES + 1];
     int nh = 0;
     for (int i = 0; i < n && i < MAXC_EXACT_RULES; i++) {
@@ -526,13 +525,22 @@ __device__ __noinline__ bool ethical_pick(const DevCtx &c, int s, int r, int n, 
         if (o >= 0 && agent_alive(c, o)) hood[nh++] = o;
     }
     hood[nh++] = s;
+    // The reference scores EVERY cell before it picks (ethics.py:113-114); the scores past the pick only matter through
+    // findTimeToLive's side effect on the agents in view (agent.timeToLive, reported by the per-agent log), so they are
+    // computed only when that log is on.  Same for the own cell when no candidate is valid.
+    const bool all_cells = has_agentlog(c);
+    if (m == 0) {
+        double h, u;
+        if (all_cells) ethical_value(c, s, r, hood, nh, a.pos[s], &h, &u);
+        return false;
+    }
     const bool positive = c.eth->selfishness[s] >= 0;
     int chosen = -1;
     double best_u = 0, best_h = 0;
     for (int i = 0; i < m; i++) {
         double h, u;
         const double v = ethical_value(c, s, r, hood, nh, cand_cell[i], &h, &u);
-        if (positive) { if (v > 0) { chosen = i; break; } }
+        if (positive) { if (v > 0 && chosen < 0) { chosen = i; if (!all_cells) break; } }
         else if (chosen < 0 || u > best_u || (u == best_u && h > best_h)) { chosen = i; best_u = u; best_h = h; }   // stable sort, reverse
     }
     const int rank = chosen >= 0 ? chosen : 0;
@@ -683,7 +691,7 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rn
             if (n > 0) {
                 int rank = 0, cell = b_cell;
                 double diff = 0;
-                if (b_valid && c.eth->model[s] == 1 && c.eth->decision_factor[s] > 0 &&
+                if ((b_valid || has_agentlog(c)) && c.eth->model[s] == 1 && c.eth->decision_factor[s] > 0 &&
                     ethical_pick(c, s, r, n, w, my_tribe, aggression, ws, &cell, &rank, &diff) && cell != b_cell) {
                     b_cell = cell;
                     b_cs = c.g.sugar[cell];
@@ -693,9 +701,18 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rn
                 c.eth->last_move_optimal[s] = rank == 0; c.eth->move_rank[s] = rank; c.eth->move_diff[s] = diff;
             } else {
                 c.eth->last_move_optimal[s] = 1;      // [own cell] is its own best; rank and difference keep their values
+                if (has_agentlog(c) && c.eth->model[s] == 1 && c.eth->decision_factor[s] > 0) {
+                    int32_t self_only[1] = {s};       // the own cell is still scored (findTimeToLive side effect, see ethical_pick)
+                    double h, u;
+                    ethical_value(c, s, r, self_only, 1, pos, &h, &u);
+                }
             }
         }
         b_cell = Gr::bcast(b_cell, 0);
+    }
+    if (EXT && has_agentlog(c) && lane == 0) {                         // lastValidMoves / lastMoveRank (agent.py:744-745)
+        c.x->agentlog.valid_moves[s] = n > 0 ? m : 1;
+        c.x->agentlog.move_rank[s] = (c.eth != nullptr && n > 0) ? c.eth->move_rank[s] : 0;
     }
     int alive = 1;
     double sugar = rec.sugar, spice = rec.spice;
@@ -726,6 +743,7 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rn
                 sugar += sl; spice += pl;
                 a.sugar[prey] -= sl; a.spice[prey] -= pl;
                 if (EXT && has_social(c)) c.x->social.last_combat[s] = c.t;
+                if (EXT && has_agentlog(c)) { c.x->agentlog.last_combat[s] = c.t; c.x->agentlog.prey_wealth[s] = sl + pl; }
                 // the prey's heirs may include the killer itself (its own parent fell): keep memory current
                 // around the inheritance (agent.py:274-294 updates self.sugar before prey.doDeath)
                 const bool heirs = RngTraits<Rng>::ordered && c.p.inheritance_policy != 0;     // (kin lists exist in mode E only)
@@ -735,8 +753,10 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rn
                 if (EXT) group_note(c, s, SSB_GI_COMBAT, prey);
             }
         }
+        if (EXT && has_agentlog(c)) c.x->agentlog.last_pollution[s] = c.g.pollution[pos];      // gotoCell (agent.py:1216)
         c.g.occ[pos] = -1;
         c.g.occ[best] = s;
+        if (EXT && has_agentlog(c)) agentlog_note_neighbors(c, s, best);
         if (EXT && has_social(c)) update_neighbors(c, s, best);   // (updateFriends reads tags and ids only: the holdings are still in registers)
         // collectResourcesAtCell (agent.py:249-259) + production pollution (cell.py:32-45)
         sugar += b_cs;
@@ -945,6 +965,7 @@ __device__ __noinline__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
     const bool age_ok = my_age >= my_fa && my_age < my_ia && (diseased ? (my_ff + my_fmod) > 0 : my_ff > 0);
     unsigned long long *cn = (unsigned long long *)a.counters;
     bool newborn_at[4] = {false, false, false, false};     // neighbour cell now holds a child of this call
+    int births = 0;                                        // = len(mates): one child per neighbour at most
     for (int k = 0; k < 4; k++) {
         if (o[k] < 0) continue;
         const int m = o[k];
@@ -1034,6 +1055,7 @@ __device__ __noinline__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
             c.eth->last_move_optimal[ch] = 1; c.eth->move_rank[ch] = 0; c.eth->move_diff[ch] = 0;      // lastMoveOptimal starts True
         }
         if (EXT && has_group(c)) group_reset_slot(c, ch);
+        if (EXT && has_agentlog(c)) agentlog_reset_slot(c, ch);
         if (diseased) disease_child(c, ch, s, m, eb);
         if (EXT && has_misc(c)) misc_child(c, ch, s, m, eb);
         if (EXT && has_social(c)) {
@@ -1079,8 +1101,10 @@ __device__ __noinline__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
         a.sugar[m] = m_sugar[k];
         a.spice[m] = m_spice[k];
         a.last_repro[s] = c.t;
+        births++;
         if (EXT) group_note(c, s, SSB_GI_REPRODUCTION, m);
     }
+    if (EXT && has_agentlog(c)) c.x->agentlog.last_mates[s] = births;
 }
 
 // INTERACT part of Agent.doTimestep (agent.py:585-598): tagging, trading, reproduction, aging,
@@ -1143,6 +1167,7 @@ __device__ void transaction_interact_phase(const DevCtx &c, int s, const AgentRe
     } else {
         a.happiness[s] = family_h + 1.0 + wealth_h;
     }
+    if (EXT && has_agentlog(c)) agentlog_record(c, s);        // updateRuntimeStats (agent.py:1567-1620)
 }
 
 }  // namespace ssb

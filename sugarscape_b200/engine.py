@@ -324,6 +324,19 @@ class Engine:
         self._check(self.L.ssb_ext_stats(self.handle, C.byref(out)))
         return out
 
+    def agent_records(self):
+        """The per-agent log records of the last agent step, in action order ([n, layout.AL_FIELDS] float64; None without
+        an agentLogfile); resets the device counter for the next step."""
+        if self.ext is None or "agentlog" not in self.ext.families:
+            return None
+        counter = self.tensors["ext:agentlog.n_records"]
+        n = int(counter.cpu().numpy().view(np.int64)[0])
+        if n >= self.capacity:
+            raise EngineError("per-agent log: record buffer exhausted")
+        raw = self.tensors["ext:agentlog.records"][:n * layout.AL_FIELDS * 8].cpu().numpy().view(np.float64)
+        counter.zero_()
+        return raw.reshape(n, layout.AL_FIELDS).copy()
+
     def group_stats(self):
         """The experimental-group split of the last reduce_stats: layout.GroupStats[3] (None without a group)."""
         if self.ext is None or "group" not in self.ext.families:

@@ -133,8 +133,6 @@ def check_supported(c):
     if c["environmentHeight"] != c["environmentWidth"] and c["environmentPollutionDiffusionDelay"] > 0:
         # reference quirk: diffusion indexes grid[i][j] with i over height
         problems.append("pollution diffusion on a non-square map")
-    if c["agentLogfile"] is not None:
-        problems.append("agentLogfile")
     if problems:
         raise UnsupportedConfiguration(
             "this engine has no CUDA implementation yet for: " + ", ".join(problems))
@@ -493,13 +491,14 @@ def configure_diseases(c, state, disease_endowments):
             curr = lo
 
 
-def build_initial_state(c, capacity=None, check=True):
+def build_initial_state(c, capacity=None, check=True, exact=True):
     """Environment + initial population + the init-time list shuffle; returns (state, population).
 
     Must be called right after verify_random_seed/verify_configuration so the main stream is
     positioned as in the reference's Sugarscape.__init__ (sugarscape.py:19-75).
     check=False skips the support check and the ABI 2 extension state (oracle-only tests that keep the rule
-    families in the oracle binding)."""
+    families in the oracle binding); exact=False (scalable RNG mode) builds the ABI 1 state only -- the caller
+    refuses configurations whose families exist in the exact mode only."""
     if check:
         check_supported(c)
     W, H = c["environmentWidth"], c["environmentHeight"]
@@ -519,7 +518,7 @@ def build_initial_state(c, capacity=None, check=True):
     state.spice[:] = state.spice_cap
 
     # (oracle-only tests pass check=False: the bare ABI 1 state, the rule families live in the oracle binding)
-    if check and uses_decision_models(c):
+    if check and exact and uses_decision_models(c):
         state.ethics = layout.HostEthics(capacity, c)
     diseased = layout.HostExt.uses_diseases(c)
     horizon = int(min(c["timesteps"], 1 << 20)) + 8
@@ -532,7 +531,7 @@ def build_initial_state(c, capacity=None, check=True):
     if new_agents:
         pop.disease_endowments = randomize_disease_endowments(c, min(len(new_agents), int(c["startingDiseases"])), 0)
         random.shuffle(new_agents)
-    if check and layout.HostExt.needed(c):
+    if check and exact and layout.HostExt.needed(c):
         state.ext = layout.HostExt(capacity, c, len(pop.disease_endowments) if diseased else 0, horizon)
         if diseased:
             state.ext.arrays["diseases.immune_bits"][:] = steptables.immune_tables(1, horizon, int(c["agentImmuneSystemLength"]))

@@ -317,8 +317,15 @@ GROUP_LAYOUT = (
     ("kind", None, None, None),
 )
 GROUP_KINDS = {"depressed": 1, "female": 2, "male": 3}      # SSB_GROUP_* (memberships fixed at birth)
+AL_FIELDS = 26          # SSB_AL_* (include/ssb.h)
+AGENTLOG_LAYOUT = (
+    ("time_to_live", _F64, 0, "cap"), ("last_pollution", _F64, 0, "cap"), ("prey_wealth", _F64, 0, "cap"),
+    ("last_combat", _I32, -1, "cap"), ("last_mates", _I32, 0, "cap"), ("valid_moves", _I32, 0, "cap"),
+    ("move_rank", _I32, 0, "cap"), ("n_neighbors", _I32, 0, "cap"), ("neighbor_slot", _I32, -1, "nbr"),
+    ("records", _F64, 0, "recs"), ("record_capacity", None, None, None), ("n_records", _I64, 0, 1),
+)
 EXT_FAMILIES = (("lending", LENDING_LAYOUT), ("social", SOCIAL_LAYOUT), ("diseases", DISEASE_LAYOUT), ("misc", MISC_LAYOUT),
-                ("group", GROUP_LAYOUT))
+                ("group", GROUP_LAYOUT), ("agentlog", AGENTLOG_LAYOUT))
 
 
 def _family_struct(name, table):
@@ -341,11 +348,12 @@ class Misc(C.Structure):
 
 
 Group = _family_struct("Group", GROUP_LAYOUT)
+AgentLog = _family_struct("AgentLog", AGENTLOG_LAYOUT)
 
 
 class Ext(C.Structure):
     _fields_ = [("capacity", C.c_int64), ("lending", Lending), ("social", Social), ("diseases", Diseases), ("misc", Misc),
-                ("group", Group)]
+                ("group", Group), ("agentlog", AgentLog)]
 
 
 class ExtStats(C.Structure):
@@ -370,7 +378,8 @@ class HostExt:
         self.families = set()
         if c["agentLendingFactor"][1] > 0:
             self.families.add("lending")
-        if c["agentMaxFriends"][1] > 0:
+        # friends; also the home of lastCombatTimestep: conflict happiness (agent.py:912-918) exists wherever agents fight
+        if c["agentMaxFriends"][1] > 0 or c["agentAggressionFactor"][1] > 0:
             self.families.add("social")
         if self.uses_diseases(c):
             self.families.add("diseases")
@@ -378,6 +387,8 @@ class HostExt:
             self.families.add("misc")
         if c["experimentalGroup"] is not None:
             self.families.add("group")
+        if c["agentLogfile"] is not None:
+            self.families.add("agentlog")
         self.max_loan_duration = int(max(c["agentLoanDuration"]))
         self.group_kind = GROUP_KINDS.get(c["experimentalGroup"], 0)
         self.racial_len = int(c["agentRacialTagStringLength"]) if c["environmentMaxRaces"] > 0 else 0
@@ -386,7 +397,7 @@ class HostExt:
         self.n_diseases, self.max_sick = n_diseases, max(n_diseases, 1)
         self.immune_len = int(c["agentImmuneSystemLength"])
         self.sizes = {"cap": capacity, "pool": 8 * capacity, "dead": 4 * capacity, "friends": capacity * MAX_FRIENDS,
-                      "gi": capacity * GI_KINDS, "mods": capacity * DM_COUNT, "sick": capacity * self.max_sick, "defs": self.max_sick, "bits": horizon + 1}
+                      "nbr": capacity * 4, "recs": capacity * AL_FIELDS, "record": capacity, "gi": capacity * GI_KINDS, "mods": capacity * DM_COUNT, "sick": capacity * self.max_sick, "defs": self.max_sick, "bits": horizon + 1}
         self.arrays = {}
         for fam, table in EXT_FAMILIES:
             if fam not in self.families:
@@ -406,9 +417,11 @@ class HostExt:
                 (c["agentRacialTagStringLength"] > 0 and c["environmentMaxRaces"] > 0) or c["experimentalGroup"] is not None)
 
     @staticmethod
-    def needed(c):
+    def needed(c, exact=True):
+        """exact=False: what the scalable RNG mode would have to refuse (it computes no conflict happiness; the other
+        families do not exist there)."""
         return (c["agentLendingFactor"][1] > 0 or c["agentMaxFriends"][1] > 0 or HostExt.uses_diseases(c) or
-                HostExt.uses_misc(c))
+                HostExt.uses_misc(c) or c["agentLogfile"] is not None or (exact and c["agentAggressionFactor"][1] > 0))
 
     def _free_chain(self, head):
         """Give the loan records of a list back to the pool (a new agent object starts with empty lists)."""
@@ -466,6 +479,11 @@ class HostExt:
             A["group.with_experimental"][slot * GI_KINDS:(slot + 1) * GI_KINDS] = 0
             A["group.control_neighbors"][slot] = 0
             A["group.experimental_neighbors"][slot] = 0
+
+        if "agentlog" in self.families:
+            for name, fill in (("time_to_live", 0), ("last_pollution", 0), ("prey_wealth", 0), ("last_combat", -1),
+                               ("last_mates", 0), ("valid_moves", 0), ("move_rank", 0), ("n_neighbors", 0)):
+                A["agentlog." + name][slot] = fill
 
     # -- diseases: the init-time part of the rule (configureDiseases, sugarscape.py:286-337) ----------------
     def define_diseases(self, disease_endowments):

@@ -31,9 +31,9 @@ class Sugarscape:
         self.end = False
         if not c["headlessMode"]:
             raise init.UnsupportedConfiguration("the GUI is out of scope: set headlessMode to true")
-        if self.rng_mode != layout.RNG_EXACT and (init.uses_decision_models(c) or layout.HostExt.needed(c)):
+        if self.rng_mode != layout.RNG_EXACT and (init.uses_decision_models(c) or layout.HostExt.needed(c, exact=False)):
             raise init.UnsupportedConfiguration("decision models, lending and friends need b200RngMode 'exact'")
-        state, self.population = init.build_initial_state(c)
+        state, self.population = init.build_initial_state(c, exact=self.rng_mode == layout.RNG_EXACT)
         self.params = layout.make_params(c, self.rng_mode, init.rule_flags(c), init.max_agent_range(c),
                                          init.equator(c))
         horizon = int(min(c["timesteps"], 1 << 20))
@@ -50,6 +50,8 @@ class Sugarscape:
         self.agent_steps = 0
         self.log = open(c["logfile"], "a") if c["logfile"] is not None else None
         self.logFormat = c["logfileFormat"]
+        self.agentLog = open(c["agentLogfile"], "a") if c["agentLogfile"] is not None else None
+        self.agentRuntimeStats = []
 
     # -- one timestep --------------------------------------------------------------------------
     def doTimestep(self):
@@ -69,8 +71,16 @@ class Sugarscape:
         eng.reduce_stats(t)
         st = eng.stats()
         self.updateRuntimeStats(st, replaced)
+        if self.agentLog is not None:
+            self.agentRuntimeStats += [stats.agent_log_entry(r) for r in eng.agent_records()]
         if self.timestep != self.maxTimestep and self.n_agents > 0:
             self.writeToLog()
+            # the per-agent log starts once agents have acted (sugarscape.py:417-421): startLog writes the records of
+            # step 1 and the regular write repeats them, like the reference
+            if self.timestep == 1:
+                self.startAgentLog()
+            self.writeToAgentLog()
+            self.agentRuntimeStats = []
 
     def replaceDeadAgents(self):
         """sugarscape.py:855-859.  Exact mode: placement of new agents is the init path (host,
@@ -125,7 +135,39 @@ class Sugarscape:
 
     def endSimulation(self):
         self.endLog()
+        self.endAgentLog()
         self.engine.close()
+
+    # -- the per-agent log (sugarscape.py:887-905, 423-466, 1428-1457 with log == self.agentLog) ---------------
+    def _agent_rows(self, closing=False):
+        if self.logFormat == "csv":
+            return "".join(",".join(str(v) for v in entry.values()) + "\n" for entry in self.agentRuntimeStats)
+        rows = [f"\t{json.dumps(entry)},\n" for entry in self.agentRuntimeStats]
+        if closing and rows:          # (the reference closes the array after the last record: entries equal to it, too)
+            last = self.agentRuntimeStats[-1]
+            rows = [f"\t{json.dumps(e)}\n]" if e == last else f"\t{json.dumps(e)},\n" for e in self.agentRuntimeStats]
+        return "".join(rows)
+
+    def startAgentLog(self):
+        if self.agentLog is None:
+            return
+        if self.logFormat == "csv":
+            self.agentLog.write(",".join(self.agentRuntimeStats[0]) + "\n")
+        else:
+            self.agentLog.write("[\n")
+        self.writeToAgentLog()
+
+    def writeToAgentLog(self):
+        if self.agentLog is not None:
+            self.agentLog.write(self._agent_rows())
+
+    def endAgentLog(self):
+        if self.agentLog is None:
+            return
+        self.agentLog.write(self._agent_rows(closing=True))
+        self.agentLog.flush()
+        self.agentLog.close()
+        self.agentLog = None
 
     def _csv_row(self):
         return ",".join(str(self.runtimeStats[k]) for k in sorted(self.runtimeStats)) + "\n"

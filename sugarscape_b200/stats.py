@@ -91,6 +91,27 @@ def environment_wealth_created(c, equator, t, n_cells_north, n_cells_south, capa
     return created
 
 
+def agent_log_entry(r):
+    """One entry of the per-agent log (agent.py:1609-1618) from a raw device record (layout.AL_FIELDS values)."""
+    (t, ident, age, sugar, spice, sugar_gained, spice_gained, movement, ttl, depression, happiness, prey_killed, prey_wealth,
+     trade_partners, diseases_spread, mates, neighbors, valid_moves, move_rank, lending_partners, pollution_diff, ttl_diff,
+     in_tribe, same_race, experimental, control) = [float(v) for v in r]
+    neighbors = int(neighbors)
+    return {"timestep": int(t), "ID": int(ident), "age": int(age), "wealth": _as_number(round(sugar + spice, 2)),
+            "sugar": _as_number(round(sugar, 2)), "spice": _as_number(round(spice, 2)),
+            "sugarGained": _as_number(round(sugar_gained, 2)), "spiceGained": _as_number(round(spice_gained, 2)),
+            "wealthGained": _as_number(round(spice_gained + sugar_gained, 2)), "movement": _as_number(movement),
+            "timeToLive": _as_number(round(ttl, 1)), "depression": bool(depression),
+            "compositeHappiness": _as_number(round(happiness, 1)), "preyKilled": bool(prey_killed),
+            "preyWealth": _as_number(prey_wealth), "tradePartners": int(trade_partners), "diseasesSpread": int(diseases_spread),
+            "mates": int(mates), "neighbors": neighbors, "validMoves": int(valid_moves), "moveRank": int(move_rank),
+            "lendingPartners": int(lending_partners), "pollutionDifference": _as_number(pollution_diff),
+            "timeToLiveDifference": _as_number(ttl_diff), "neighborsInTribe": int(in_tribe),
+            "neighborsNotInTribe": neighbors - int(in_tribe), "sameRaceNeighbors": int(same_race),
+            "differentRaceNeighbors": neighbors - int(same_race), "experimentalGroupNeighbors": int(experimental),
+            "controlGroupNeighbors": int(control)}
+
+
 class StatsBuilder:
     """Carries the cross-step state of the stats (carrying capacity, previous dict)."""
 

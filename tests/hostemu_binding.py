@@ -60,6 +60,16 @@ class HostEmu(Oracle):
         if self.state.ext is not None:
             self.state.ext.check_overflow()
 
+    def agent_records(self):
+        """Per-agent log records of the last agent step (like Engine.agent_records)."""
+        ext = self.state.ext
+        if ext is None or "agentlog" not in ext.families:
+            return None
+        n = int(ext.arrays["agentlog.n_records"][0])
+        raw = ext.arrays["agentlog.records"][:n * layout.AL_FIELDS].reshape(n, layout.AL_FIELDS).copy()
+        ext.arrays["agentlog.n_records"][0] = 0
+        return raw
+
     def group_stats(self, t):
         if self.state.ext is None or "group" not in self.state.ext.families:
             return None

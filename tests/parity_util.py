@@ -53,7 +53,7 @@ def example_configuration(name, overrides=None):
 
 def build(name, rng_mode=layout.RNG_EXACT, overrides=None, check=True):
     c = example_configuration(name, overrides)
-    state, pop = init.build_initial_state(c, check=check)
+    state, pop = init.build_initial_state(c, check=check, exact=rng_mode == layout.RNG_EXACT)
     flags = init.rule_flags(c)
     params = layout.make_params(c, rng_mode, flags, init.max_agent_range(c), init.equator(c))
     endow, tags = steptables.step_tables(1, min(c["timesteps"], 100000), c["agentTagStringLength"])

@@ -238,3 +238,40 @@ def test_device_source_matches_reference_on_other_experimental_groups(variant):
         assert len(log[t]) == 203
         for k in log[t]:
             assert k in rs and _close(rs[k], log[t][k]), f"log key {k} differs at t={t}: {rs.get(k)} vs {log[t][k]}"
+
+
+def _agentlog_cases():
+    import gzip
+    import json
+    import os
+    with gzip.open(os.path.join(pu.GOLDEN, "agentlog.json.gz"), "rt") as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("case", ["determinism", "combat", "trade_pollution"])
+def test_per_agent_log_matches_reference(case, tmp_path, monkeypatch):
+    """`agentLogfile` (reference agent.py:1567-1620, sugarscape.py:415-421): the drop-in driver
+    (sugarscape_b200.simulation.Sugarscape) on the host-compiled device source writes the per-agent log the unmodified
+    reference writes -- same records in the same (action) order, every field equal (1e-9), incl. the quirks: the records
+    of step 1 appear twice, agent.timeToLive is whatever the last findTimeToLive() call of anybody left."""
+    import json
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(pu.ROOT, "tools"))
+    from run_gpu_tests_on_hostemu import HostEmuEngine
+    import sugarscape_b200.simulation as simulation
+    monkeypatch.setattr(simulation, "Engine", HostEmuEngine)
+    fixture = _agentlog_cases()[case]
+    ov = dict(fixture["overrides"], agentLogfile=str(tmp_path / "agents.json"), logfile=str(tmp_path / "log.json"))
+    c = pu.example_configuration(fixture["base"], ov)
+    c["agentLogfile"], c["logfile"] = ov["agentLogfile"], ov["logfile"]
+    simulation.Sugarscape(c).runSimulation(c["timesteps"])
+    mine = json.load(open(ov["agentLogfile"]))
+    ref = fixture["agent_log"]
+    assert len(mine) == len(ref)
+    for i, (a, b) in enumerate(zip(mine, ref)):
+        assert list(a) == list(b), f"record {i}: keys differ"
+        for k in b:
+            assert _close(a[k], b[k]), f"record {i} (t={b['timestep']}, agent {b['ID']}): {k} = {a[k]} vs {b[k]}"
+    log = json.load(open(ov["logfile"]))
+    assert len(log) == len(fixture["log"])

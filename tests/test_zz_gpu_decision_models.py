@@ -171,6 +171,27 @@ def test_drop_in_driver_writes_the_reference_log_for_determinism(tmp_path):
             assert _close(entry[k], ref[k]), f"log key {k} at t={entry['timestep']}: {entry[k]} vs {ref[k]}"
 
 
+@pytest.mark.parametrize("case", ["determinism", "combat", "trade_pollution"])
+def test_drop_in_driver_writes_the_reference_per_agent_log(case, tmp_path):
+    """`agentLogfile`: the per-agent log of the drop-in driver equals the unmodified reference's, record by record
+    (tests/golden/make_golden_agentlog.py)."""
+    import gzip
+    import json
+    import os
+    from sugarscape_b200.simulation import Sugarscape
+    with gzip.open(os.path.join(pu.GOLDEN, "agentlog.json.gz"), "rt") as f:
+        fixture = json.load(f)[case]
+    ov = dict(fixture["overrides"], agentLogfile=str(tmp_path / "agents.json"), logfile=str(tmp_path / "log.json"))
+    c = pu.example_configuration(fixture["base"], ov)
+    c["agentLogfile"], c["logfile"] = ov["agentLogfile"], ov["logfile"]
+    Sugarscape(c).runSimulation(c["timesteps"])
+    mine, ref = json.load(open(ov["agentLogfile"])), fixture["agent_log"]
+    assert len(mine) == len(ref)
+    for i, (a, b) in enumerate(zip(mine, ref)):
+        for k in b:
+            assert _close(a[k], b[k]), f"record {i} (t={b['timestep']}, agent {b['ID']}): {k} = {a[k]} vs {b[k]}"
+
+
 def test_drop_in_driver_writes_the_reference_log_with_decision_models(tmp_path):
     """The reference-facing entry point (sugarscape_b200.simulation.Sugarscape, what `sugarscape.py --conf` runs)
     on the ethics_trade configuration: the log.json it writes equals the reference's log entry by entry."""

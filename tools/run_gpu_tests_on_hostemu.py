@@ -33,6 +33,9 @@ class HostEmuEngine(OracleEngine):
     def ext_stats(self):
         return self.orc.ext_stats(self.t_stats)
 
+    def agent_records(self):
+        return self.orc.agent_records()
+
     def group_stats(self):
         return self.orc.group_stats(self.t_stats)
 
