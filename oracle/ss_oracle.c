@@ -544,9 +544,10 @@ void orc_depress(const ssb_agents_t *a, int32_t s) {
     a->aggression[s] *= 1.145;
     if (g_social) g_social->max_friends[s] = (int32_t)ceil(g_social->max_friends[s] * 0.6333);
     g_misc->happiness_unit[s] *= 0.5763;
-    a->movement[s] *= (int32_t)ceil(a->movement[s] * 0.429);
-    a->spice_metab[s] *= (int32_t)ceil(a->spice_metab[s] * 1.544);
-    a->sugar_metab[s] *= (int32_t)ceil(a->sugar_metab[s] * 1.544);
+    /* v *= ceil(v * f), saturated at 2^30 (Python ints leave the i32 range within two depressed generations of
+     * agentMovement 1000; the rules only compare these values with far smaller ones) */
+    { int32_t *v[3] = {&a->movement[s], &a->spice_metab[s], &a->sugar_metab[s]}; const double f[3] = {0.429, 1.544, 1.544};
+      for (int k = 0; k < 3; k++) { const double p = (double)*v[k] * ceil(*v[k] * f[k]); *v[k] = p >= 1073741824.0 ? 1073741824 : (int32_t)p; } }
 }
 
 

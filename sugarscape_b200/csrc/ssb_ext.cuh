@@ -94,6 +94,13 @@ __device__ __forceinline__ int race_of(uint32_t tags, int len) {          // fin
     for (int r = 1; r < 4; r++) if (cnt[r] > cnt[best]) best = r;
     return best;
 }
+// v *= ceil(v * f): the reference squares the endowment, so a depressed lineage with agentMovement 1000 leaves the
+// i32 range within two generations (Python ints do not).  Saturated at 2^30: every rule compares these values with
+// ranges / holdings far below, so the trajectory is the reference's; only the logged means differ once saturated.
+__device__ __forceinline__ int32_t depress_scale(int32_t v, double f) {
+    const double p = (double)v * ceil(v * f);
+    return p >= 1073741824.0 ? 1073741824 : (int32_t)p;
+}
 // Depression.trigger (condition.py:27-33), at the creation of a depressed agent (agent.py:137-141)
 __device__ inline void depress(const DevCtx &c, int s) {
     const ssb_agents_t &a = c.a;
@@ -101,9 +108,9 @@ __device__ inline void depress(const DevCtx &c, int s) {
     a.aggression[s] *= 1.145;
     if (has_social(c)) c.x->social.max_friends[s] = (int32_t)ceil(c.x->social.max_friends[s] * 0.6333);
     c.x->misc.happiness_unit[s] *= 0.5763;
-    a.movement[s] *= (int32_t)ceil(a.movement[s] * 0.429);
-    a.spice_metab[s] *= (int32_t)ceil(a.spice_metab[s] * 1.544);
-    a.sugar_metab[s] *= (int32_t)ceil(a.sugar_metab[s] * 1.544);
+    a.movement[s] = depress_scale(a.movement[s], 0.429);
+    a.spice_metab[s] = depress_scale(a.spice_metab[s], 1.544);
+    a.sugar_metab[s] = depress_scale(a.sugar_metab[s], 1.544);
 }
 // the child's share of the family (agent.py:845-851, 879-895); called once its endowments are in place
 __device__ inline void misc_child(const DevCtx &c, int ch, int s, int m, uint32_t eb) {

@@ -379,7 +379,7 @@ class HostExt:
         if c["agentLendingFactor"][1] > 0:
             self.families.add("lending")
         # friends; also the home of lastCombatTimestep: conflict happiness (agent.py:912-918) exists wherever agents fight
-        if c["agentMaxFriends"][1] > 0 or c["agentAggressionFactor"][1] > 0:
+        if c["agentMaxFriends"][1] > 0 or self.combat_possible(c):
             self.families.add("social")
         if self.uses_diseases(c):
             self.families.add("diseases")
@@ -408,6 +408,11 @@ class HostExt:
                     self.arrays[fam + "." + n] = np.zeros(count, dtype=dt) if fill == 0 else np.full(count, fill, dtype=dt)
 
     @staticmethod
+    def combat_possible(c):
+        """Some agent may have findAggression() > 0: by endowment, or through a disease's aggression penalty."""
+        return c["agentAggressionFactor"][1] > 0 or (HostExt.uses_diseases(c) and c["diseaseAggressionPenalty"][1] > 0)
+
+    @staticmethod
     def uses_diseases(c):
         return c["startingDiseases"] > 0 and c["agentImmuneSystemLength"] > 0
 
@@ -421,7 +426,7 @@ class HostExt:
         """exact=False: what the scalable RNG mode would have to refuse (it computes no conflict happiness; the other
         families do not exist there)."""
         return (c["agentLendingFactor"][1] > 0 or c["agentMaxFriends"][1] > 0 or HostExt.uses_diseases(c) or
-                HostExt.uses_misc(c) or c["agentLogfile"] is not None or (exact and c["agentAggressionFactor"][1] > 0))
+                HostExt.uses_misc(c) or c["agentLogfile"] is not None or (exact and HostExt.combat_possible(c)))
 
     def _free_chain(self, head):
         """Give the loan records of a list back to the pool (a new agent object starts with empty lists)."""
@@ -735,9 +740,10 @@ class HostState:
         if "social" in self.ext.families:
             A["social.max_friends"][slot] = math.ceil(A["social.max_friends"][slot] * 0.6333)
         A["misc.happiness_unit"][slot] *= 0.5763
-        self.a_movement[slot] *= math.ceil(self.a_movement[slot] * 0.429)
-        self.a_spice_metab[slot] *= math.ceil(self.a_spice_metab[slot] * 1.544)
-        self.a_sugar_metab[slot] *= math.ceil(self.a_sugar_metab[slot] * 1.544)
+        # (v *= ceil(v * f), saturated at 2^30 like the device: csrc/ssb_ext.cuh:depress_scale)
+        for arr, f in ((self.a_movement, 0.429), (self.a_spice_metab, 1.544), (self.a_sugar_metab, 1.544)):
+            v = int(arr[slot])
+            arr[slot] = min(v * math.ceil(v * f), 1 << 30)
 
     def list_view(self):
         """Arrays of the live agent list in list order (for parity checks and stats)."""
