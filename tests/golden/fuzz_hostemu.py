@@ -59,7 +59,14 @@ def run_case(base, ov, steps):
     if d != ref_digests[0]:
         return "t=0 differs: " + str({k: d[k] == ref_digests[0][k] for k in d})
     sb = stats.StatsBuilder(c, init.equator(c))
-    rs = sb.update(emu.stats(0), 0, 0, emu.ethics_stats(), emu.ext_stats(0))
+    grouped = c["experimentalGroup"] is not None
+
+    def entry(t, replaced):
+        if grouped:
+            return sb.update_with_groups(emu.stats(t), t, replaced, emu.ethics_stats(), emu.ext_stats(t), emu.group_stats(t))
+        return sb.update(emu.stats(t), t, replaced, emu.ethics_stats(), emu.ext_stats(t))
+
+    rs = entry(0, 0)
     for t in range(1, len(ref_digests)):
         emu.env_step(t)
         emu.agent_step(t, rs["meanWealth"])
@@ -72,11 +79,13 @@ def run_case(base, ov, steps):
         d, _ = pu.state_digests(state, *emu.mt_state())
         if d != ref_digests[t]:
             return f"t={t} differs: " + str({k: d[k] == ref_digests[t][k] for k in d})
-        rs = sb.update(emu.stats(t), t, replaced, emu.ethics_stats(), emu.ext_stats(t))
-        for k in stats.LOG_KEYS:          # the 59 log keys of the step, too
-            if k in ("meanMovement", "meanMetabolism", "agentTotalMetabolism") and isinstance(ref_logs[t][k], (int, float)) \
+        rs = entry(t, replaced)
+        for k in (ref_logs[t] if grouped else stats.LOG_KEYS):          # the log keys of the step, too (203 with a group)
+            if k.endswith(("eanMovement", "eanMetabolism", "gentTotalMetabolism")) and isinstance(ref_logs[t][k], (int, float)) \
                     and ref_logs[t][k] > 1e6:
                 continue          # depressed lineages: the reference's endowments outgrow i32, the engine saturates
+            if k.endswith("iniCoefficient") and abs(rs[k] - ref_logs[t][k]) <= 0.0011:
+                continue          # Lorenz area summed in a different order: 1 ulp can flip round(x, 3)
             if not _close(rs[k], ref_logs[t][k]):
                 return f"t={t} log key {k} differs: {rs[k]} vs {ref_logs[t][k]}"
     families = sorted(state.ext.families) if state.ext is not None else []
@@ -91,6 +100,9 @@ def main():
     for i in range(cases):
         base = rng.choice(BASES)
         ov = draw_overrides(rng, base)
+        if rng.random() < 0.3:
+            ov["experimentalGroup"] = rng.choice(["depressed", "female", "male"])
+            ov["agentReplacements"] = 0
         try:
             res = run_case(base, ov, 60)
         except Exception as e:
