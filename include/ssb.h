@@ -216,6 +216,8 @@ typedef struct ssb_ethics {
     double  *decision_factor;       /* decisionModelFactor: the ethical ranking runs when > 0         */
     double  *lookahead_factor;      /* decisionModelLookaheadFactor                                   */
     double  *lookahead_discount;    /* decisionModelLookaheadDiscount                                 */
+    double  *dynamic_selfishness;   /* dynamicSelfishnessFactor (the "Dynamic" variants; 0 = fixed selfishness; needs
+                                       ssb_agentlog_t bound: the update compares agent.timeToLive values)   */
     /* by-products of the agent's last ranking that feed the log (agent.py:734-745) */
     int32_t *last_move_optimal;     /* lastMoveOptimal                                                */
     int32_t *move_rank;             /* index of the chosen cell in the welfare-sorted list            */
@@ -384,6 +386,7 @@ typedef struct ssb_agentlog {
     double  *records;                                 /* [record_capacity][SSB_AL_FIELDS]                            */
     int64_t record_capacity;
     int64_t *n_records;                               /* records of the current step (the host resets it)            */
+    int64_t write_records;                            /* 0: only agent.timeToLive is tracked (dynamic selfishness)   */
 } ssb_agentlog_t;
 
 typedef struct ssb_ext {

@@ -586,6 +586,17 @@ __device__ inline void agentlog_note_neighbors(const DevCtx &c, int s, int pos) 
 __device__ __noinline__ void agentlog_record(const DevCtx &c, int s) {
     const ssb_agentlog_t &A = c.x->agentlog;
     const ssb_agents_t &a = c.a;
+    const double last_ttl = A.time_to_live[s];
+    const double ttl = time_to_live_x(c, s, false);          // (stores agent.timeToLive)
+    // Bentham.updateValues -> updateSelfishnessFactor (ethics.py:246-256) runs right after updateRuntimeStats and
+    // compares exactly these two values; nothing in the record depends on the selfishness
+    if (c.eth != nullptr && c.eth->model[s] == 1 && c.eth->dynamic_selfishness[s] != 0) {
+        double sf = c.eth->selfishness[s];
+        if (ttl < last_ttl && sf < 1.0) sf += c.eth->dynamic_selfishness[s];
+        else if (ttl > last_ttl && sf > 0.0) sf -= c.eth->dynamic_selfishness[s];
+        c.eth->selfishness[s] = rint(sf * 100.0) / 100.0;    // round(x, 2)
+    }
+    if (!A.write_records) return;
     const long long at = A.n_records[0];
     if (at >= A.record_capacity) return;
     A.n_records[0] = at + 1;
@@ -599,8 +610,6 @@ __device__ __noinline__ void agentlog_record(const DevCtx &c, int s) {
         if ((has_misc(c) ? c.x->misc.race[o] : -1) == my_race) same_race++;
         if (has_group(c)) { if (is_member(c, o)) exp_n++; else ctrl_n++; }
     }
-    const double last_ttl = A.time_to_live[s];
-    const double ttl = time_to_live_x(c, s, false);          // (stores agent.timeToLive)
     r[SSB_AL_TIMESTEP] = t; r[SSB_AL_ID] = a.id[s]; r[SSB_AL_AGE] = a.age[s];
     r[SSB_AL_SUGAR] = a.sugar[s]; r[SSB_AL_SPICE] = a.spice[s];
     r[SSB_AL_SUGAR_GAINED] = a.sugar[s] - a.last_sugar[s]; r[SSB_AL_SPICE_GAINED] = a.spice[s] - a.last_spice[s];

@@ -1052,6 +1052,7 @@ __device__ __noinline__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
             c.eth->decision_factor[ch] = c.eth->decision_factor[from];
             c.eth->lookahead_factor[ch] = c.eth->lookahead_factor[from];
             c.eth->lookahead_discount[ch] = c.eth->lookahead_discount[from];
+            c.eth->dynamic_selfishness[ch] = c.eth->dynamic_selfishness[from];
             c.eth->last_move_optimal[ch] = 1; c.eth->move_rank[ch] = 0; c.eth->move_diff[ch] = 0;      // lastMoveOptimal starts True
         }
         if (EXT && has_group(c)) group_reset_slot(c, ch);

@@ -74,9 +74,9 @@ def _decimals(value):
 
 
 # decisionModel strings with a CUDA implementation: the plain Agent and ethics.Bentham with its spawn
-# variants (sugarscape.py:219-233); "Dynamic" variants, Temperance, Asimov and the Leader are refused
+# variants (sugarscape.py:219-238, dynamic selfishness included); Temperance, the "Top" orderings and the Leader are refused
 SUPPORTED_DECISION_MODELS = frozenset(("none", "rawSugarscape")) | frozenset(
-    base + suffix for base in layout.BENTHAM_MODELS for suffix in ("", "NoLookahead", "HalfLookahead"))
+    base + look + dyn for base in layout.BENTHAM_MODELS for look in ("", "NoLookahead", "HalfLookahead") for dyn in ("", "Dynamic"))
 
 
 def uses_decision_models(c):
@@ -111,8 +111,6 @@ def check_supported(c):
         problems.append("decision models other than rawSugarscape and the Bentham family: " + ", ".join(bad_models))
     # (agentDecisionModelFactor > 0 without a decision model: the plain Agent's findBestEthicalCell hands back the
     # greedy cell, agent.py:730-733 -- nothing to refuse)
-    if uses_decision_models(c) and c["agentDynamicSelfishnessFactor"][1] != 0:
-        problems.append("agentDynamicSelfishnessFactor")
     for k in ("agentDecisionModelAgeismFactor", "agentDecisionModelRacismFactor",
               "agentDecisionModelSexismFactor", "agentDecisionModelTribalFactor"):
         if c[k][1] >= 0:

@@ -181,7 +181,7 @@ class Stats(C.Structure):
 # (name, numpy dtype, fill) in the order of ssb_ethics_t after `capacity`
 ETHICS_FIELDS = (
     ("model", np.int32, 0), ("selfishness", np.float64, 0), ("decision_factor", np.float64, 0),
-    ("lookahead_factor", np.float64, 0), ("lookahead_discount", np.float64, 0),
+    ("lookahead_factor", np.float64, 0), ("lookahead_discount", np.float64, 0), ("dynamic_selfishness", np.float64, 0),
     ("last_move_optimal", np.int32, 1), ("move_rank", np.int32, 0), ("move_diff", np.float64, 0),
 )
 BENTHAM_MODELS = ("altruist", "bentham", "egoist", "negativeBentham")
@@ -216,6 +216,7 @@ class HostEthics:
         # the reference's default is the LIST [0], handed to the agents as is; only `!= 0` is ever asked of
         # it (ethics.py:160-190) and `[0] != 0` holds
         self.lookahead_factor = 1.0 if isinstance(look, list) else float(look)
+        self.default_dynamic = list(c["agentDynamicSelfishnessFactor"]) == [0.0, 0.0]
         self.arrays = {n: np.full(capacity, fill, dtype=dt) for n, dt, fill in ETHICS_FIELDS}
 
     def set_slot(self, slot, endowment):
@@ -242,6 +243,8 @@ class HostEthics:
         A["decision_factor"][slot] = endowment["decisionModelFactor"]
         A["lookahead_factor"][slot] = look
         A["lookahead_discount"][slot] = endowment["decisionModelLookaheadDiscount"]
+        # "Dynamic" without a configured factor: a small degree of dynamic selfishness (sugarscape.py:236-238)
+        A["dynamic_selfishness"][slot] = 0.01 if ("Dynamic" in name and self.default_dynamic) else endowment["dynamicSelfishnessFactor"]
         A["last_move_optimal"][slot] = 1
         A["move_rank"][slot] = 0
         A["move_diff"][slot] = 0
@@ -257,6 +260,7 @@ class HostEthics:
     def copy(self):
         h = HostEthics.__new__(HostEthics)
         h.capacity, h.global_max_wealth, h.lookahead_factor = self.capacity, self.global_max_wealth, self.lookahead_factor
+        h.default_dynamic = self.default_dynamic
         h.arrays = {k: v.copy() for k, v in self.arrays.items()}
         return h
 
@@ -323,6 +327,7 @@ AGENTLOG_LAYOUT = (
     ("last_combat", _I32, -1, "cap"), ("last_mates", _I32, 0, "cap"), ("valid_moves", _I32, 0, "cap"),
     ("move_rank", _I32, 0, "cap"), ("n_neighbors", _I32, 0, "cap"), ("neighbor_slot", _I32, -1, "nbr"),
     ("records", _F64, 0, "recs"), ("record_capacity", None, None, None), ("n_records", _I64, 0, 1),
+    ("write_records", None, None, None),
 )
 EXT_FAMILIES = (("lending", LENDING_LAYOUT), ("social", SOCIAL_LAYOUT), ("diseases", DISEASE_LAYOUT), ("misc", MISC_LAYOUT),
                 ("group", GROUP_LAYOUT), ("agentlog", AGENTLOG_LAYOUT))
@@ -387,8 +392,9 @@ class HostExt:
             self.families.add("misc")
         if c["experimentalGroup"] is not None:
             self.families.add("group")
-        if c["agentLogfile"] is not None:
-            self.families.add("agentlog")
+        if c["agentLogfile"] is not None or self.uses_dynamic_selfishness(c):
+            self.families.add("agentlog")         # (agent.timeToLive is tracked there: the dynamic selfishness update reads it)
+        self.write_records = int(c["agentLogfile"] is not None)
         self.max_loan_duration = int(max(c["agentLoanDuration"]))
         self.group_kind = GROUP_KINDS.get(c["experimentalGroup"], 0)
         self.racial_len = int(c["agentRacialTagStringLength"]) if c["environmentMaxRaces"] > 0 else 0
@@ -406,6 +412,11 @@ class HostExt:
                 if dt is not None:
                     count = self.sizes.get(length, length)
                     self.arrays[fam + "." + n] = np.zeros(count, dtype=dt) if fill == 0 else np.full(count, fill, dtype=dt)
+
+    @staticmethod
+    def uses_dynamic_selfishness(c):
+        bentham = [m for m in c["agentDecisionModels"] if decision_model_base(m) is not None]
+        return bool(bentham) and (c["agentDynamicSelfishnessFactor"][1] != 0 or any("Dynamic" in m for m in bentham))
 
     @staticmethod
     def combat_possible(c):
@@ -426,7 +437,8 @@ class HostExt:
         """exact=False: what the scalable RNG mode would have to refuse (it computes no conflict happiness; the other
         families do not exist there)."""
         return (c["agentLendingFactor"][1] > 0 or c["agentMaxFriends"][1] > 0 or HostExt.uses_diseases(c) or
-                HostExt.uses_misc(c) or c["agentLogfile"] is not None or (exact and HostExt.combat_possible(c)))
+                HostExt.uses_misc(c) or c["agentLogfile"] is not None or HostExt.uses_dynamic_selfishness(c) or
+                (exact and HostExt.combat_possible(c)))
 
     def _free_chain(self, head):
         """Give the loan records of a list back to the pool (a new agent object starts with empty lists)."""
@@ -552,7 +564,8 @@ class HostExt:
             for n, dt, _, _ in table:
                 if dt is None:          # pool_capacity / dead_capacity / max_loan_duration / the group's kind
                     setattr(sub, n, self.max_loan_duration if n == "max_loan_duration" else
-                            self.group_kind if n == "kind" else self.sizes[n.split("_")[0]])
+                            self.group_kind if n == "kind" else self.write_records if n == "write_records" else
+                            self.sizes[n.split("_")[0]])
                 else:
                     setattr(sub, n, pointer_of(self.arrays[fam + "." + n]))
         return x
@@ -566,7 +579,7 @@ class HostExt:
         h.capacity, h.families, h.sizes = self.capacity, set(self.families), dict(self.sizes)
         h.n_diseases, h.max_sick, h.immune_len = self.n_diseases, self.max_sick, self.immune_len
         h.racial_len, h.misc_scalars, h.max_loan_duration = self.racial_len, self.misc_scalars, self.max_loan_duration
-        h.group_kind = self.group_kind
+        h.group_kind, h.write_records = self.group_kind, self.write_records
         h.arrays = {k: v.copy() for k, v in self.arrays.items()}
         return h
 

@@ -100,6 +100,9 @@ def main():
     for i in range(cases):
         base = rng.choice(BASES)
         ov = draw_overrides(rng, base)
+        if "agentDecisionModels" in ov and rng.random() < 0.4:          # dynamic selfishness
+            ov["agentDecisionModels"] = [m + rng.choice(["", "Dynamic"]) if m != "none" else m for m in ov["agentDecisionModels"]]
+            ov["agentDynamicSelfishnessFactor"] = rng.choice([[0.0, 0.0], [0.02, 0.05]])
         if rng.random() < 0.3:
             ov["experimentalGroup"] = rng.choice(["depressed", "female", "male"])
             ov["agentReplacements"] = 0

@@ -58,6 +58,11 @@ VARIANTS = {
         agentSelfishnessFactor=[0.2, 0.8])),
     # pollution enters the intensity term of the ethical value
     "ethics_pollution": ("trade_pollution", 120, dict(_ETHICS)),
+    # dynamic selfishness (Bentham.updateSelfishnessFactor): the "Dynamic" names with the default 0.01, and a configured range
+    "ethics_dynamic": ("trade_tagging_reproduction", 120, dict(_ETHICS, agentDecisionModels=[
+        "none", "benthamDynamic", "egoistDynamic", "altruistNoLookaheadDynamic", "negativeBentham"])),
+    "ethics_dynamic_configured": ("combat_limited", 100, dict(_ETHICS, agentDynamicSelfishnessFactor=[0.05, 0.1],
+                                                              agentSelfishnessFactor=[0.3, 0.7], agentDecisionModels=["bentham", "none"])),
     # other experimental groups than the shipped "depressed" (membership by sex)
     "determinism_group_female": ("determinism", 120, {"experimentalGroup": "female"}),
     "determinism_group_male": ("determinism", 80, {"experimentalGroup": "male"}),

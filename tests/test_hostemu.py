@@ -46,7 +46,9 @@ def test_device_rule_source_matches_reference_trajectory(name):
     run_case(c, state, pop, params, endow, tags, meta["steps"], meta["log"])
 
 
-ETHICS_VARIANTS = ["ethics_trade", "ethics_combat", "ethics_replacement", "ethics_pollution"]
+ETHICS_VARIANTS = ["ethics_trade", "ethics_combat", "ethics_replacement", "ethics_pollution",
+                   # Bentham.updateSelfishnessFactor: the "Dynamic" names (default 0.01) and a configured range
+                   "ethics_dynamic", "ethics_dynamic_configured"]
 
 
 @pytest.mark.parametrize("variant", ETHICS_VARIANTS)

@@ -18,7 +18,8 @@ pytestmark = [pytest.mark.gpu,
               pytest.mark.xfail(strict=False, reason="first GPU run of the decision-model kernels (validated on the "
                                                      "host-compiled device source only, tests/test_hostemu.py)")]
 
-ETHICS_VARIANTS = ["ethics_trade", "ethics_combat", "ethics_replacement", "ethics_pollution"]
+ETHICS_VARIANTS = ["ethics_trade", "ethics_combat", "ethics_replacement", "ethics_pollution", "ethics_dynamic",
+                   "ethics_dynamic_configured"]
 
 
 @pytest.mark.parametrize("variant", ETHICS_VARIANTS)
