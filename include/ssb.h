@@ -211,11 +211,13 @@ typedef struct ssb_engine ssb_engine_t;
  * rawSugarscape Agent.  The host owns the arrays (capacity = ssb_agents_t.capacity slots). */
 typedef struct ssb_ethics {
     int64_t capacity;
-    int32_t *model;                 /* 0 = Agent (greedy findBestCell), 1 = ethics.Bentham             */
+    int32_t *model;                 /* 0 = Agent (greedy findBestCell), 1 = ethics.Bentham, 2 = ethics.Temperance
+                                       (simple variant: ethics.py:412-434, 464-465, 493-506; needs ssb_agentlog_t bound) */
     double  *selfishness;           /* selfishnessFactor after the spawn rules (-1 .. 1)              */
     double  *decision_factor;       /* decisionModelFactor: the ethical ranking runs when > 0         */
     double  *lookahead_factor;      /* decisionModelLookaheadFactor                                   */
     double  *lookahead_discount;    /* decisionModelLookaheadDiscount                                 */
+    double  *dynamic_decision_factor; /* dynamicDecisionModelFactor: how a Temperance agent's factor moves with its virtue rolls */
     double  *dynamic_selfishness;   /* dynamicSelfishnessFactor (the "Dynamic" variants; 0 = fixed selfishness; needs
                                        ssb_agentlog_t bound: the update compares agent.timeToLive values)   */
     /* by-products of the agent's last ranking that feed the log (agent.py:734-745) */

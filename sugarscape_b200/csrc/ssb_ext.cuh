@@ -84,6 +84,25 @@ __device__ __forceinline__ double time_to_live_x(const DevCtx &c, int s, bool ag
     return ttl;
 }
 
+// Agent.findTimeToLive(potentialCell=cell) (agent.py:1113-1140): the holdings plus what the cell and its occupant
+// would yield; the universal income term uses the current holdings; agent.timeToLive is left alone
+__device__ inline double time_to_live_potential(const DevCtx &c, int s, int cell) {
+    const double sm = eff_sugar_metab(c, s), pm = eff_spice_metab(c, s);
+    const double big = 9223372036854775807.0;
+    double sugar = c.a.sugar[s], spice = c.a.spice[s];
+    const int o = c.g.occ[cell];
+    if (o >= 0) { sugar += fmin(c.p.max_combat_loot, c.a.sugar[o]); spice += fmin(c.p.max_combat_loot, c.a.spice[o]); }
+    sugar += c.g.sugar[cell];
+    spice += (c.p.flags & SSB_F_SPICE) ? c.g.spice[cell] : 0;
+    double st = sm > 0 ? sugar / sm : big, pt = pm > 0 ? spice / pm : big;
+    if (has_misc(c)) {
+        const ssb_misc_t &M = c.x->misc;
+        if (M.universal_sugar[s] != 0) { const double income = (st * M.universal_sugar[s]) / M.income_interval_sugar; st = sm > 0 ? (c.a.sugar[s] + income) / sm : big; }
+        if (M.universal_spice[s] != 0) { const double income = (pt * M.universal_spice[s]) / M.income_interval_spice; pt = pm > 0 ? (c.a.spice[s] + income) / pm : big; }
+    }
+    return st < pt ? st : pt;
+}
+
 // ---------------------------------------------------------------------------------------------
 // universal income, racial tags, depression
 // ---------------------------------------------------------------------------------------------

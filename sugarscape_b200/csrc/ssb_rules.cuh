@@ -481,20 +481,14 @@ struct AgentRec {
     }
 };
 
-// rankCellsInRange (agent.py:1395-1443) in full -- the whole welfare-sorted list, not only its head --
-// followed by Bentham.findBestEthicalCell (ethics.py:105-139).  Lane 0, after the group's ranking pass:
-// ws holds the candidate cells, their distances, the shuffle permutation and (fighters) the retaliator
-// table.  Returns false when no candidate is valid (the agent stays put; rank 0 by definition).
-__device__ __noinline__ bool ethical_pick(const DevCtx &c, int s, int r, int n, const Welfare &w, int my_tribe,
-                                          double aggression, const WarpScratch &ws, int *out_cell, int *out_rank,
-                                          double *out_diff) {
+// rankCellsInRange in full: the valid candidates in welfare order (stable: welfare descending, range ascending,
+// shuffled position).  Returns their number; lane 0, after the group's ranking pass.
+__device__ __noinline__ int rank_candidates(const DevCtx &c, int s, int n, const Welfare &w, int my_tribe, double aggression,
+                                            const WarpScratch &ws, int32_t *cand_cell, uint8_t *cand_dist, double *cand_w) {
     const ssb_agents_t &a = c.a;
     const bool polluted = (c.p.flags & SSB_F_POLLUTION) != 0, spicy = (c.p.flags & SSB_F_SPICE) != 0;
     const bool fighter = aggression > 0;
     const double loot = c.p.max_combat_loot, my_wealth = w.sugar + w.spice;
-    int32_t cand_cell[MAXC_EXACT_RULES];
-    uint8_t cand_dist[MAXC_EXACT_RULES];
-    double cand_w[MAXC_EXACT_RULES];
     int m = 0;
     for (int k = 0; k < n && k < MAXC_EXACT_RULES; k++) {            // shuffled order
         const int i = ws.perm[k], cell = ws.cells[i];
@@ -518,6 +512,21 @@ __device__ __noinline__ bool ethical_pick(const DevCtx &c, int s, int r, int n, 
         }
         cand_cell[j] = cell; cand_dist[j] = dist; cand_w[j] = welfare;
     }
+    return m;
+}
+
+// rankCellsInRange (agent.py:1395-1443) in full -- the whole welfare-sorted list, not only its head --
+// followed by Bentham.findBestEthicalCell (ethics.py:105-139).  Lane 0, after the group's ranking pass:
+// ws holds the candidate cells, their distances, the shuffle permutation and (fighters) the retaliator
+// table.  Returns false when no candidate is valid (the agent stays put; rank 0 by definition).
+__device__ __noinline__ bool ethical_pick(const DevCtx &c, int s, int r, int n, const Welfare &w, int my_tribe,
+                                          double aggression, const WarpScratch &ws, int *out_cell, int *out_rank,
+                                          double *out_diff) {
+    const ssb_agents_t &a = c.a;
+    int32_t cand_cell[MAXC_EXACT_RULES];
+    uint8_t cand_dist[MAXC_EXACT_RULES];
+    double cand_w[MAXC_EXACT_RULES];
+    const int m = rank_candidates(c, s, n, w, my_tribe, aggression, ws, cand_cell, cand_dist, cand_w);
     int32_t hood[MAXC_EXACT_RULES + 1];
     int nh = 0;
     for (int i = 0; i < n && i < MAXC_EXACT_RULES; i++) {
@@ -546,6 +555,37 @@ __device__ __noinline__ bool ethical_pick(const DevCtx &c, int s, int r, int n, 
     const int rank = chosen >= 0 ? chosen : 0;
     *out_cell = cand_cell[rank]; *out_rank = rank; *out_diff = cand_w[0] - cand_w[rank];
     return true;
+}
+
+// Temperance.findBestEthicalCell, simple variant (ethics.py:412-434, 464-465, 493-506): every candidate is scored by
+// how much it would change the agent's time to live, |findTimeToLive(potentialCell) - agent.timeToLive|; a virtue roll
+// on the MAIN stream picks the largest or the smallest change and moves the agent's temperance factor.  Runs even
+// when the only "candidate" is the own cell (the roll is still drawn).  Lane 0.
+template <class Rng>
+__device__ __noinline__ void temperance_pick(const DevCtx &c, int s, int n, const Welfare &w, int my_tribe, double aggression,
+                                             const WarpScratch &ws, Rng &rng, int *out_cell, int *out_rank, double *out_diff) {
+    const ssb_agents_t &a = c.a;
+    int32_t cand_cell[MAXC_EXACT_RULES], order[MAXC_EXACT_RULES];
+    uint8_t cand_dist[MAXC_EXACT_RULES];
+    double cand_w[MAXC_EXACT_RULES], score[MAXC_EXACT_RULES];
+    int m = n > 0 ? rank_candidates(c, s, n, w, my_tribe, aggression, ws, cand_cell, cand_dist, cand_w) : 0;
+    if (m == 0) { cand_cell[0] = a.pos[s]; cand_dist[0] = 0; cand_w[0] = 0; m = 1; }      // rankCellsInRange: [own cell]
+    const double ttl = c.x->agentlog.time_to_live[s];
+    for (int i = 0; i < m; i++) {          // sortCellsByWealth on the scores, stable from the welfare order
+        const double sc = fabs(time_to_live_potential(c, s, cand_cell[i]) - ttl);
+        int j = i;
+        while (j > 0 && (score[j - 1] < sc || (score[j - 1] == sc && cand_dist[order[j - 1]] > cand_dist[i]))) {
+            score[j] = score[j - 1]; order[j] = order[j - 1];
+            j--;
+        }
+        score[j] = sc; order[j] = i;
+    }
+    const double roll = rand_double(rng);                          // virtueRoll = random.random()
+    const double df = c.eth->decision_factor[s], dyn = c.eth->dynamic_decision_factor[s];
+    int pick;
+    if (roll < df) { pick = order[0]; const double nf = rint((df + dyn) * 100.0) / 100.0; c.eth->decision_factor[s] = nf <= 1 ? nf : 1; }
+    else { pick = order[m - 1]; const double nf = rint((df - dyn) * 100.0) / 100.0; c.eth->decision_factor[s] = nf >= 0 ? nf : 0; }
+    *out_cell = cand_cell[pick]; *out_rank = pick; *out_diff = cand_w[0] - cand_w[pick];
 }
 
 // MOVE part of Agent.doTimestep (agent.py:568-584), executed by the G lanes of a group for ONE
@@ -691,8 +731,14 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rn
             if (n > 0) {
                 int rank = 0, cell = b_cell;
                 double diff = 0;
-                if ((b_valid || has_agentlog(c)) && c.eth->model[s] == 1 && c.eth->decision_factor[s] > 0 &&
-                    ethical_pick(c, s, r, n, w, my_tribe, aggression, ws, &cell, &rank, &diff) && cell != b_cell) {
+                bool picked = false;
+                if (c.eth->model[s] == 2 && c.eth->decision_factor[s] > 0 && has_agentlog(c)) {
+                    temperance_pick(c, s, n, w, my_tribe, aggression, ws, rng, &cell, &rank, &diff);
+                    picked = b_valid;              // (without a valid candidate the pick is the own cell: stays)
+                } else if ((b_valid || has_agentlog(c)) && c.eth->model[s] == 1 && c.eth->decision_factor[s] > 0) {
+                    picked = ethical_pick(c, s, r, n, w, my_tribe, aggression, ws, &cell, &rank, &diff);
+                }
+                if (picked && cell != b_cell) {
                     b_cell = cell;
                     b_cs = c.g.sugar[cell];
                     b_cp = spicy ? c.g.spice[cell] : 0;
@@ -705,6 +751,11 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rn
                     int32_t self_only[1] = {s};       // the own cell is still scored (findTimeToLive side effect, see ethical_pick)
                     double h, u;
                     ethical_value(c, s, r, self_only, 1, pos, &h, &u);
+                }
+                if (has_agentlog(c) && c.eth->model[s] == 2 && c.eth->decision_factor[s] > 0) {
+                    int cell, rank;                   // the virtue roll is drawn for [own cell], too
+                    double diff;
+                    temperance_pick(c, s, 0, w, my_tribe, aggression, ws, rng, &cell, &rank, &diff);
                 }
             }
         }
@@ -1053,6 +1104,7 @@ __device__ __noinline__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
             c.eth->lookahead_factor[ch] = c.eth->lookahead_factor[from];
             c.eth->lookahead_discount[ch] = c.eth->lookahead_discount[from];
             c.eth->dynamic_selfishness[ch] = c.eth->dynamic_selfishness[from];
+            c.eth->dynamic_decision_factor[ch] = c.eth->dynamic_decision_factor[from];
             c.eth->last_move_optimal[ch] = 1; c.eth->move_rank[ch] = 0; c.eth->move_diff[ch] = 0;      // lastMoveOptimal starts True
         }
         if (EXT && has_group(c)) group_reset_slot(c, ch);

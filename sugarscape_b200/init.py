@@ -76,12 +76,13 @@ def _decimals(value):
 # decisionModel strings with a CUDA implementation: the plain Agent and ethics.Bentham with its spawn
 # variants (sugarscape.py:219-238, dynamic selfishness included); Temperance, the "Top" orderings and the Leader are refused
 SUPPORTED_DECISION_MODELS = frozenset(("none", "rawSugarscape")) | frozenset(
-    base + look + dyn for base in layout.BENTHAM_MODELS for look in ("", "NoLookahead", "HalfLookahead") for dyn in ("", "Dynamic"))
+    base + look + dyn for base in layout.BENTHAM_MODELS for look in ("", "NoLookahead", "HalfLookahead") for dyn in ("", "Dynamic")
+) | frozenset(("temperance",))
 
 
 def uses_decision_models(c):
     """True if some agent may be an ethics.Bentham instance (needs the ssb_ethics_t extension, mode E)."""
-    return any(layout.decision_model_base(m) is not None for m in c["agentDecisionModels"])
+    return any(layout.decision_model_class(m) != 0 for m in c["agentDecisionModels"])
 
 
 def check_supported(c):

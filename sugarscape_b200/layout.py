@@ -181,7 +181,8 @@ class Stats(C.Structure):
 # (name, numpy dtype, fill) in the order of ssb_ethics_t after `capacity`
 ETHICS_FIELDS = (
     ("model", np.int32, 0), ("selfishness", np.float64, 0), ("decision_factor", np.float64, 0),
-    ("lookahead_factor", np.float64, 0), ("lookahead_discount", np.float64, 0), ("dynamic_selfishness", np.float64, 0),
+    ("lookahead_factor", np.float64, 0), ("lookahead_discount", np.float64, 0), ("dynamic_decision_factor", np.float64, 0),
+    ("dynamic_selfishness", np.float64, 0),
     ("last_move_optimal", np.int32, 1), ("move_rank", np.int32, 0), ("move_diff", np.float64, 0),
 )
 BENTHAM_MODELS = ("altruist", "bentham", "egoist", "negativeBentham")
@@ -195,6 +196,13 @@ class Ethics(C.Structure):
 class EthicsStats(C.Structure):
     _fields_ = [("sum_selfishness", C.c_double), ("optimal_moves", C.c_int64), ("moves", C.c_int64),
                 ("sum_move_rank", C.c_int64), ("sum_move_diff", C.c_double)]
+
+
+def decision_model_class(name):
+    """ssb_ethics_t.model of a decisionModel string: 1 = ethics.Bentham, 2 = ethics.Temperance (simple), 0 = plain Agent."""
+    if decision_model_base(name) is not None:
+        return 1
+    return 2 if "temperance" in name else 0
 
 
 def decision_model_base(name):
@@ -238,7 +246,8 @@ class HostEthics:
         elif "HalfLookahead" in name:
             look = 0.5
         A = self.arrays
-        A["model"][slot] = int(base is not None)
+        A["model"][slot] = decision_model_class(name)
+        A["dynamic_decision_factor"][slot] = endowment["dynamicDecisionModelFactor"]
         A["selfishness"][slot] = selfish
         A["decision_factor"][slot] = endowment["decisionModelFactor"]
         A["lookahead_factor"][slot] = look
@@ -415,8 +424,10 @@ class HostExt:
 
     @staticmethod
     def uses_dynamic_selfishness(c):
+        """Rules that read agent.timeToLive (tracked in the agentlog family): dynamic selfishness, Temperance."""
         bentham = [m for m in c["agentDecisionModels"] if decision_model_base(m) is not None]
-        return bool(bentham) and (c["agentDynamicSelfishnessFactor"][1] != 0 or any("Dynamic" in m for m in bentham))
+        return ((bool(bentham) and (c["agentDynamicSelfishnessFactor"][1] != 0 or any("Dynamic" in m for m in bentham))) or
+                any(decision_model_class(m) == 2 for m in c["agentDecisionModels"]))
 
     @staticmethod
     def combat_possible(c):

@@ -63,6 +63,13 @@ VARIANTS = {
         "none", "benthamDynamic", "egoistDynamic", "altruistNoLookaheadDynamic", "negativeBentham"])),
     "ethics_dynamic_configured": ("combat_limited", 100, dict(_ETHICS, agentDynamicSelfishnessFactor=[0.05, 0.1],
                                                               agentSelfishnessFactor=[0.3, 0.7], agentDecisionModels=["bentham", "none"])),
+    # ethics.Temperance, simple variant: virtue rolls on the main stream, the temperance factor moves with them
+    "ethics_temperance": ("trade_tagging_reproduction", 120, dict(_ETHICS, agentDecisionModels=["none", "temperance"],
+                                                                  agentDecisionModelFactor=[0.3, 0.9],
+                                                                  agentDynamicDecisionModelFactor=[0.05, 0.1])),
+    "ethics_temperance_mixed": ("combat_limited", 100, dict(_ETHICS, agentDecisionModels=["bentham", "temperance", "none", "egoistDynamic"],
+                                                            agentDecisionModelFactor=[0.5, 1], agentDynamicDecisionModelFactor=[0.0, 0.2],
+                                                            agentAggressionFactor=[0, 2], agentVision=[1, 3])),
     # other experimental groups than the shipped "depressed" (membership by sex)
     "determinism_group_female": ("determinism", 120, {"experimentalGroup": "female"}),
     "determinism_group_male": ("determinism", 80, {"experimentalGroup": "male"}),

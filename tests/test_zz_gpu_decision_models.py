@@ -19,7 +19,7 @@ pytestmark = [pytest.mark.gpu,
                                                      "host-compiled device source only, tests/test_hostemu.py)")]
 
 ETHICS_VARIANTS = ["ethics_trade", "ethics_combat", "ethics_replacement", "ethics_pollution", "ethics_dynamic",
-                   "ethics_dynamic_configured"]
+                   "ethics_dynamic_configured", "ethics_temperance", "ethics_temperance_mixed"]
 
 
 @pytest.mark.parametrize("variant", ETHICS_VARIANTS)
@@ -29,7 +29,7 @@ def test_decision_models_match_reference_trajectory(variant):
     assert state.ethics is not None
     sb = stats.StatsBuilder(c, init.equator(c))
     eng.reduce_stats(0)
-    rs = sb.update(eng.stats(), 0, 0, eng.ethics_stats())
+    rs = sb.update(eng.stats(), 0, 0, eng.ethics_stats(), eng.ext_stats())
     non_greedy = 0
     for t in range(1, len(gold)):
         eng.env_step(t)
@@ -37,7 +37,7 @@ def test_decision_models_match_reference_trajectory(variant):
         eng.compact(t)
         replaced = _replace(c, eng, pop, t) if c["agentReplacements"] > 0 else 0
         eng.reduce_stats(t)
-        rs = sb.update(eng.stats(), t, replaced, eng.ethics_stats())
+        rs = sb.update(eng.stats(), t, replaced, eng.ethics_stats(), eng.ext_stats())
         d, snap = pu.state_digests(eng.download(), *eng.mt_state())
         assert d == gold[t]["digests"], f"{variant}: state differs from the reference at t={t}"
         non_greedy += rs["agentLastMoveOptimalityPercentage"] < 100

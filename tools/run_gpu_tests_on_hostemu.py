@@ -21,6 +21,8 @@ from run_gpu_tests_on_oracle import OracleEngine  # noqa: E402
 
 
 class HostEmuEngine(OracleEngine):
+    _ext_stats = None
+
     def __init__(self, params, host_state, device=0, endow_bits=None, tag_bits=None):
         super().__init__(params, host_state, device, endow_bits, tag_bits)
         self.orc = HostEmu(params, host_state, endow_bits, tag_bits)
@@ -30,8 +32,12 @@ class HostEmuEngine(OracleEngine):
     def ethics_stats(self):
         return self.orc.ethics_stats() if self.ethics is not None else None
 
+    def reduce_stats(self, t):          # like ssb_reduce_stats: the extension reductions run with the regular ones
+        super().reduce_stats(t)
+        self._ext_stats = self.orc.ext_stats(t)
+
     def ext_stats(self):
-        return self.orc.ext_stats(self.t_stats)
+        return self._ext_stats
 
     def agent_records(self):
         return self.orc.agent_records()
