@@ -37,6 +37,8 @@ def build(force=False, verbose=False):
     extra = []
     if os.environ.get("SSB_GROUP_LANES"):      # tuning builds: lanes cooperating on one agent (4, 8, 16, 32)
         extra.append("-DSSB_GROUP_LANES=" + os.environ["SSB_GROUP_LANES"])
+    if os.environ.get("SSB_PARALLEL_ETHICS"):  # mode E with decision models: score the candidate cells on all lanes (round 2: to be measured)
+        extra.append("-DSSB_PARALLEL_ETHICS")
     if os.environ.get("SSB_MARK_LANES"):
         extra.append("-DSSB_MARK_LANES=" + os.environ["SSB_MARK_LANES"])
     cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]

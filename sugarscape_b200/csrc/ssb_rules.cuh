@@ -515,46 +515,79 @@ __device__ __noinline__ int rank_candidates(const DevCtx &c, int s, int n, const
     return m;
 }
 
-// rankCellsInRange (agent.py:1395-1443) in full -- the whole welfare-sorted list, not only its head --
-// followed by Bentham.findBestEthicalCell (ethics.py:105-139).  Lane 0, after the group's ranking pass:
-// ws holds the candidate cells, their distances, the shuffle permutation and (fighters) the retaliator
-// table.  Returns false when no candidate is valid (the agent stays put; rank 0 by definition).
-__device__ __noinline__ bool ethical_pick(const DevCtx &c, int s, int r, int n, const Welfare &w, int my_tribe,
-                                          double aggression, const WarpScratch &ws, int *out_cell, int *out_rank,
-                                          double *out_diff) {
-    const ssb_agents_t &a = c.a;
+// Bentham.findBestEthicalCell (ethics.py:105-139) on top of the full welfare-sorted list, in three phases so that the
+// scoring can be spread over the lanes of the group (build with -DSSB_PARALLEL_ETHICS; by default lane 0 scores
+// every candidate -- same code, same result: the candidates are independent, the only write of a score is the
+// idempotent agent.timeToLive side effect).  Scratch in shared memory, one per (single) mode E group.
+struct EthScratch {
     int32_t cand_cell[MAXC_EXACT_RULES];
     uint8_t cand_dist[MAXC_EXACT_RULES];
     double cand_w[MAXC_EXACT_RULES];
-    const int m = rank_candidates(c, s, n, w, my_tribe, aggression, ws, cand_cell, cand_dist, cand_w);
     int32_t hood[MAXC_EXACT_RULES + 1];
+    int32_t m, nh, scored;
+    double v[MAXC_EXACT_RULES], h[MAXC_EXACT_RULES], u[MAXC_EXACT_RULES];
+};
+// phase 1, lane 0: the valid candidates in welfare order and the agents in view (live agents in range + the agent)
+__device__ __noinline__ void ethical_prepare(const DevCtx &c, int s, int n, const Welfare &w, int my_tribe, double aggression,
+                                             const WarpScratch &ws, EthScratch &es) {
+    es.m = rank_candidates(c, s, n, w, my_tribe, aggression, ws, es.cand_cell, es.cand_dist, es.cand_w);
     int nh = 0;
     for (int i = 0; i < n && i < MAXC_EXACT_RULES; i++) {
         const int o = c.g.occ[ws.cells[i]];
-        if (o >= 0 && agent_alive(c, o)) hood[nh++] = o;
+        if (o >= 0 && agent_alive(c, o)) es.hood[nh++] = o;
     }
-    hood[nh++] = s;
-    // The reference scores EVERY cell before it picks (ethics.py:113-114); the scores past the pick only matter through
-    // findTimeToLive's side effect on the agents in view (agent.timeToLive, reported by the per-agent log), so they are
-    // computed only when that log is on.  Same for the own cell when no candidate is valid.
-    const bool all_cells = has_agentlog(c);
-    if (m == 0) {
+    es.hood[nh++] = s;
+    es.nh = nh;
+    es.scored = es.m;
+}
+// phase 2: candidates first, first + stride, ...  The reference scores EVERY cell before it picks (ethics.py:113-114);
+// the scores past the pick only matter through findTimeToLive's side effect on the agents in view (agent.timeToLive,
+// reported by the per-agent log), so a lane that walks the list alone stops at the pick unless that log is on.  Same
+// for the own cell when no candidate is valid.
+__device__ __noinline__ void ethical_score(const DevCtx &c, int s, int r, EthScratch &es, int first, int stride) {
+    const bool all_cells = has_agentlog(c), positive = c.eth->selfishness[s] >= 0;
+    if (es.m == 0) {
         double h, u;
-        if (all_cells) ethical_value(c, s, r, hood, nh, a.pos[s], &h, &u);
-        return false;
+        if (all_cells && first == 0) ethical_value(c, s, r, es.hood, es.nh, c.a.pos[s], &h, &u);
+        return;
     }
+    for (int i = first; i < es.m; i += stride) {
+        es.v[i] = ethical_value(c, s, r, es.hood, es.nh, es.cand_cell[i], &es.h[i], &es.u[i]);
+        if (stride == 1 && positive && es.v[i] > 0 && !all_cells) { es.scored = i + 1; break; }
+    }
+}
+// phase 3, lane 0: the pick.  Returns false when no candidate is valid (the agent stays put; rank 0 by definition).
+__device__ __noinline__ bool ethical_choose(const DevCtx &c, int s, const EthScratch &es, int *out_cell, int *out_rank,
+                                            double *out_diff) {
+    if (es.m == 0) return false;
     const bool positive = c.eth->selfishness[s] >= 0;
     int chosen = -1;
     double best_u = 0, best_h = 0;
-    for (int i = 0; i < m; i++) {
-        double h, u;
-        const double v = ethical_value(c, s, r, hood, nh, cand_cell[i], &h, &u);
-        if (positive) { if (v > 0 && chosen < 0) { chosen = i; if (!all_cells) break; } }
-        else if (chosen < 0 || u > best_u || (u == best_u && h > best_h)) { chosen = i; best_u = u; best_h = h; }   // stable sort, reverse
+    for (int i = 0; i < es.scored; i++) {
+        if (positive) { if (es.v[i] > 0) { chosen = i; break; } }
+        else if (chosen < 0 || es.u[i] > best_u || (es.u[i] == best_u && es.h[i] > best_h)) { chosen = i; best_u = es.u[i]; best_h = es.h[i]; }   // stable sort, reverse
     }
     const int rank = chosen >= 0 ? chosen : 0;
-    *out_cell = cand_cell[rank]; *out_rank = rank; *out_diff = cand_w[0] - cand_w[rank];
+    *out_cell = es.cand_cell[rank]; *out_rank = rank; *out_diff = es.cand_w[0] - es.cand_w[rank];
     return true;
+}
+// all lanes of the group (uniform call); the results are meaningful on lane 0
+template <int G>
+__device__ bool bentham_rank(const DevCtx &c, int s, int r, int n, const Welfare &w, int my_tribe, double aggression,
+                             const WarpScratch &ws, int *out_cell, int *out_rank, double *out_diff) {
+    typedef Group<G> Gr;
+    __shared__ EthScratch es;
+    const int lane = Gr::lane();
+#ifdef SSB_PARALLEL_ETHICS
+    const int first = lane, stride = G;
+#else
+    const int first = lane == 0 ? 0 : MAXC_EXACT_RULES, stride = 1;
+#endif
+    if (lane == 0) ethical_prepare(c, s, n, w, my_tribe, aggression, ws, es);
+    Gr::sync();
+    ethical_score(c, s, r, es, first, stride);
+    Gr::sync();
+    return lane == 0 ? ethical_choose(c, s, es, out_cell, out_rank, out_diff) : false;
 }
 
 // Temperance.findBestEthicalCell, simple variant (ethics.py:412-434, 464-465, 493-506): every candidate is scored by
@@ -613,7 +646,7 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rn
     const int r = diseased ? min(min((int)eff_vision(c, s), (int)eff_movement(c, s)), max(c.max_dx, c.max_dy))
                            : min(min(max(rec.vision, 0), max(rec.movement, 0)), max(c.max_dx, c.max_dy));
     const double aggression = diseased ? eff_aggression(c, s) : fmax(rec.aggression, 0.0);
-    Welfare w;
+    Welfare w = {};       // (value-initialised only to keep the front end quiet: set() assigns every field)
     w.template set<EXT>(c, s, rec.sugar, rec.spice, rec.sugar_metab, rec.spice_metab, rec.lookahead, rec.tags);
     const int my_tribe = (c.p.flags & SSB_F_TAGPREF) ? find_tribe(c, rec.tags) : rec.tribe;
     const bool polluted = (c.p.flags & SSB_F_POLLUTION) != 0;
@@ -724,19 +757,24 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rn
         }
         if (m == 0) m = 1;
     }
-    if (EXT && c.eth != nullptr) {                               // uniform
+    if constexpr (EXT) {
+    if (c.eth != nullptr) {                                      // uniform
         // decision models: the ethical ranking may override the greedy choice (ethics.py:105-139); the
         // optimality of the move is logged for every agent (agent.py:734-745)
+        const bool engaged = c.eth->decision_factor[s] > 0;
+        const bool bentham = n > 0 && engaged && c.eth->model[s] == 1 && (b_valid || has_agentlog(c));     // uniform
+        int e_cell = b_cell, e_rank = 0;
+        double e_diff = 0;
+        bool e_picked = false;
+        if (bentham) e_picked = bentham_rank<G>(c, s, r, n, w, my_tribe, aggression, ws, &e_cell, &e_rank, &e_diff);
         if (lane == 0) {
             if (n > 0) {
-                int rank = 0, cell = b_cell;
-                double diff = 0;
-                bool picked = false;
-                if (c.eth->model[s] == 2 && c.eth->decision_factor[s] > 0 && has_agentlog(c)) {
+                int rank = e_rank, cell = e_cell;
+                double diff = e_diff;
+                bool picked = e_picked;
+                if (c.eth->model[s] == 2 && engaged && has_agentlog(c)) {
                     temperance_pick(c, s, n, w, my_tribe, aggression, ws, rng, &cell, &rank, &diff);
                     picked = b_valid;              // (without a valid candidate the pick is the own cell: stays)
-                } else if ((b_valid || has_agentlog(c)) && c.eth->model[s] == 1 && c.eth->decision_factor[s] > 0) {
-                    picked = ethical_pick(c, s, r, n, w, my_tribe, aggression, ws, &cell, &rank, &diff);
                 }
                 if (picked && cell != b_cell) {
                     b_cell = cell;
@@ -747,12 +785,12 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rn
                 c.eth->last_move_optimal[s] = rank == 0; c.eth->move_rank[s] = rank; c.eth->move_diff[s] = diff;
             } else {
                 c.eth->last_move_optimal[s] = 1;      // [own cell] is its own best; rank and difference keep their values
-                if (has_agentlog(c) && c.eth->model[s] == 1 && c.eth->decision_factor[s] > 0) {
-                    int32_t self_only[1] = {s};       // the own cell is still scored (findTimeToLive side effect, see ethical_pick)
+                if (has_agentlog(c) && c.eth->model[s] == 1 && engaged) {
+                    int32_t self_only[1] = {s};       // the own cell is still scored (findTimeToLive side effect, see ethical_score)
                     double h, u;
                     ethical_value(c, s, r, self_only, 1, pos, &h, &u);
                 }
-                if (has_agentlog(c) && c.eth->model[s] == 2 && c.eth->decision_factor[s] > 0) {
+                if (has_agentlog(c) && c.eth->model[s] == 2 && engaged) {
                     int cell, rank;                   // the virtue roll is drawn for [own cell], too
                     double diff;
                     temperance_pick(c, s, 0, w, my_tribe, aggression, ws, rng, &cell, &rank, &diff);
@@ -760,6 +798,7 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rn
             }
         }
         b_cell = Gr::bcast(b_cell, 0);
+    }
     }
     if (EXT && has_agentlog(c) && lane == 0) {                         // lastValidMoves / lastMoveRank (agent.py:744-745)
         c.x->agentlog.valid_moves[s] = n > 0 ? m : 1;
