@@ -25,3 +25,20 @@ t0 = time.time(); S.runSimulation(c["timesteps"]); dt = time.time() - t0
 print("determinism.json: %d agent-steps in %.2f s = %.0f agent-steps/s (reference: about 2 k/s)" % (S.agent_steps, dt, S.agent_steps / dt))
 PY
 cat gpurun_out/r2_determinism_timing.log
+# the lane-parallel ethical ranking: rebuild with the flag, same cases, same timing
+cp sugarscape_b200/libssb.so /tmp/libssb_default.so
+SSB_PARALLEL_ETHICS=1 python -c "from sugarscape_b200 import build; build.build(force=True)" > gpurun_out/r2_parallel_build.log 2>&1; echo "parallel-ethics build exit $?"
+SSB_GPU_EXT_STEPS=0 python -m pytest tests/test_zz_gpu_decision_models.py -m gpu --runxfail -q -x -k "decision_models or determinism or all_features" > gpurun_out/r2_abi2_gpu_tests_parallel.log 2>&1; echo "ABI 2 GPU tests (parallel ethics) exit $?"
+tail -3 gpurun_out/r2_abi2_gpu_tests_parallel.log
+python - > gpurun_out/r2_determinism_timing_parallel.log 2>&1 <<'PY'
+import sys, time
+sys.path.insert(0, "tests"); sys.path.insert(0, "tests/golden")
+import parity_util as pu
+from sugarscape_b200.simulation import Sugarscape
+c = pu.example_configuration("determinism")
+S = Sugarscape(c)
+t0 = time.time(); S.runSimulation(c["timesteps"]); dt = time.time() - t0
+print("determinism.json, lane-parallel ethical ranking: %d agent-steps in %.2f s = %.0f agent-steps/s" % (S.agent_steps, dt, S.agent_steps / dt))
+PY
+cat gpurun_out/r2_determinism_timing_parallel.log
+cp /tmp/libssb_default.so sugarscape_b200/libssb.so
