@@ -255,3 +255,17 @@ def test_per_agent_log_matches_reference(case, tmp_path, monkeypatch):
             assert _close(a[k], b[k]), f"record {i} (t={b['timestep']}, agent {b['ID']}): {k} = {a[k]} vs {b[k]}"
     log = json.load(open(ov["logfile"]))
     assert len(log) == len(fixture["log"])
+
+
+def test_the_gpu_verified_examples_stay_on_the_plain_kernels():
+    """The 24 examples that were verified on a B200 in round 1 bind no ABI 2 extension, so they run the EXT = false
+    instantiations whose SASS is unchanged (profiles/r1_sass_equivalence_measured_vs_head.txt); the other five bind
+    exactly the families they configure."""
+    expected = {"lending_basic": {"lending"}, "dune": {"lending", "social"}, "disease_basic": {"diseases"},
+                "determinism": {"lending", "social", "diseases", "misc", "group"},
+                "all_features": {"lending", "social", "diseases", "misc", "group"}}
+    for name in SUPPORTED + sorted(expected):
+        c, state, pop, params, endow, tags = pu.build(name)
+        families = state.ext.families if state.ext is not None else set()
+        assert families == expected.get(name, set()), name
+        assert (state.ethics is not None) == (name in ("determinism", "all_features")), name
