@@ -212,12 +212,18 @@ typedef struct ssb_engine ssb_engine_t;
 typedef struct ssb_ethics {
     int64_t capacity;
     int32_t *model;                 /* 0 = Agent (greedy findBestCell), 1 = ethics.Bentham, 2 = ethics.Temperance
-                                       (simple variant: ethics.py:412-434, 464-465, 493-506; needs ssb_agentlog_t bound) */
+                                       (simple variant: ethics.py:412-434, 464-465, 493-506; needs ssb_agentlog_t bound),
+                                       3 = ethics.Temperance with pecs=True (ethics.py:436-491, 508-547)                 */
     double  *selfishness;           /* selfishnessFactor after the spawn rules (-1 .. 1)              */
     double  *decision_factor;       /* decisionModelFactor: the ethical ranking runs when > 0         */
     double  *lookahead_factor;      /* decisionModelLookaheadFactor                                   */
     double  *lookahead_discount;    /* decisionModelLookaheadDiscount                                 */
     double  *dynamic_decision_factor; /* dynamicDecisionModelFactor: how a Temperance agent's factor moves with its virtue rolls */
+    /* Temperance PECS state (zero for a new agent): rules = agentConsumedAdequate / Ample, communityDisapproval,
+     * agentOverconsumed, communityDisdain; counts = timeSeenOverconsuming, timesSeenIndulging, timesOverharvested */
+    int32_t *pecs_rules;            /* [slot][5]                                                      */
+    int32_t *pecs_counts;           /* [slot][3]                                                      */
+    double  *social_pressure, *last_delta_ttl, *dynamic_social_pressure, *total_metabolism;
     double  *dynamic_selfishness;   /* dynamicSelfishnessFactor (the "Dynamic" variants; 0 = fixed selfishness; needs
                                        ssb_agentlog_t bound: the update compares agent.timeToLive values)   */
     /* by-products of the agent's last ranking that feed the log (agent.py:734-745) */

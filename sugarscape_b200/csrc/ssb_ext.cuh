@@ -86,21 +86,28 @@ __device__ __forceinline__ double time_to_live_x(const DevCtx &c, int s, bool ag
 
 // Agent.findTimeToLive(potentialCell=cell) (agent.py:1113-1140): the holdings plus what the cell and its occupant
 // would yield; the universal income term uses the current holdings; agent.timeToLive is left alone
-__device__ inline double time_to_live_potential(const DevCtx &c, int s, int cell) {
+// (my_sugar / my_spice: the agent's holdings as they stand -- the move part keeps them in registers)
+__device__ inline double time_to_live_potential_of(const DevCtx &c, int s, int cell, double my_sugar, double my_spice) {
     const double sm = eff_sugar_metab(c, s), pm = eff_spice_metab(c, s);
     const double big = 9223372036854775807.0;
-    double sugar = c.a.sugar[s], spice = c.a.spice[s];
+    double sugar = my_sugar, spice = my_spice;
     const int o = c.g.occ[cell];
-    if (o >= 0) { sugar += fmin(c.p.max_combat_loot, c.a.sugar[o]); spice += fmin(c.p.max_combat_loot, c.a.spice[o]); }
+    if (o >= 0) {          // (the agent's own cell counts as occupied: by itself)
+        sugar += fmin(c.p.max_combat_loot, o == s ? my_sugar : c.a.sugar[o]);
+        spice += fmin(c.p.max_combat_loot, o == s ? my_spice : c.a.spice[o]);
+    }
     sugar += c.g.sugar[cell];
     spice += (c.p.flags & SSB_F_SPICE) ? c.g.spice[cell] : 0;
     double st = sm > 0 ? sugar / sm : big, pt = pm > 0 ? spice / pm : big;
     if (has_misc(c)) {
         const ssb_misc_t &M = c.x->misc;
-        if (M.universal_sugar[s] != 0) { const double income = (st * M.universal_sugar[s]) / M.income_interval_sugar; st = sm > 0 ? (c.a.sugar[s] + income) / sm : big; }
-        if (M.universal_spice[s] != 0) { const double income = (pt * M.universal_spice[s]) / M.income_interval_spice; pt = pm > 0 ? (c.a.spice[s] + income) / pm : big; }
+        if (M.universal_sugar[s] != 0) { const double income = (st * M.universal_sugar[s]) / M.income_interval_sugar; st = sm > 0 ? (my_sugar + income) / sm : big; }
+        if (M.universal_spice[s] != 0) { const double income = (pt * M.universal_spice[s]) / M.income_interval_spice; pt = pm > 0 ? (my_spice + income) / pm : big; }
     }
     return st < pt ? st : pt;
+}
+__device__ inline double time_to_live_potential(const DevCtx &c, int s, int cell) {
+    return time_to_live_potential_of(c, s, cell, c.a.sugar[s], c.a.spice[s]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -614,6 +621,15 @@ __device__ __noinline__ void agentlog_record(const DevCtx &c, int s) {
         if (ttl < last_ttl && sf < 1.0) sf += c.eth->dynamic_selfishness[s];
         else if (ttl > last_ttl && sf > 0.0) sf -= c.eth->dynamic_selfishness[s];
         c.eth->selfishness[s] = rint(sf * 100.0) / 100.0;    // round(x, 2)
+    }
+    // Temperance.updateValues -> updateAgentTemperanceRules (ethics.py:518-547); the neighbourhood always holds the agent
+    // itself, so its "seen by the community" branches are always taken
+    if (c.eth != nullptr && c.eth->model[s] == 3) {
+        int32_t *rules = c.eth->pecs_rules + (long long)s * 5, *counts = c.eth->pecs_counts + (long long)s * 3;
+        const double d = c.eth->last_delta_ttl[s];
+        if (d <= 1) rules[0] += 1;
+        else if (d > 1 && d <= 2) { rules[1] += 1; counts[0] += 1; rules[2] += 1; }
+        else if (d > 2) { rules[3] += 1; counts[1] += 1; rules[4] += 1; }
     }
     if (!A.write_records) return;
     const long long at = A.n_records[0];

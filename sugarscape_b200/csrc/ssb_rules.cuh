@@ -621,6 +621,56 @@ __device__ __noinline__ void temperance_pick(const DevCtx &c, int s, int n, cons
     *out_cell = cand_cell[pick]; *out_rank = pick; *out_diff = cand_w[0] - cand_w[pick];
 }
 
+// Temperance with pecs=True (ethics.py:412-491): physical + emotional + cognitive + social score per candidate, the best
+// score wins (no virtue roll).  The emotional score counts the cells it has seen (timesOverharvested moves while the
+// candidates are scored, in welfare order).  Lane 0.
+__device__ __noinline__ void pecs_pick(const DevCtx &c, int s, int n, const Welfare &w, int my_tribe, double aggression,
+                                       const WarpScratch &ws, int *out_cell, int *out_rank, double *out_diff) {
+    const ssb_agents_t &a = c.a;
+    int32_t cand_cell[MAXC_EXACT_RULES], order[MAXC_EXACT_RULES];
+    uint8_t cand_dist[MAXC_EXACT_RULES];
+    double cand_w[MAXC_EXACT_RULES], score[MAXC_EXACT_RULES];
+    int m = n > 0 ? rank_candidates(c, s, n, w, my_tribe, aggression, ws, cand_cell, cand_dist, cand_w) : 0;
+    if (m == 0) { cand_cell[0] = a.pos[s]; cand_dist[0] = 0; cand_w[0] = 0; m = 1; }      // rankCellsInRange: [own cell]
+    const double ttl = c.x->agentlog.time_to_live[s];
+    const int32_t *rules = c.eth->pecs_rules + (long long)s * 5;
+    int32_t *counts = c.eth->pecs_counts + (long long)s * 3;
+    const double pressure = c.eth->social_pressure[s];
+    for (int i = 0; i < m; i++) {
+        double sc = 0;
+        if (c.eth->total_metabolism[s] != 0) {
+            const double delta = time_to_live_potential(c, s, cand_cell[i]) - ttl;
+            const double physical = ttl > 0 ? erf(1 / ttl) : 1;
+            double e = 0;                                                   // findCellEmotionalScore
+            if (delta > 1) { e = e - counts[2]; counts[2] += 1; }
+            const double emotional = erf(e);
+            double cognitive;                                               // findCellCognitiveScore
+            if (delta < 1) cognitive = -1;
+            else {
+                double k = 0;
+                if (delta >= 1 && delta < 2 && rules[0]) k += rules[0];
+                else if (delta >= 2 && delta < 3 && rules[1]) { k += rules[1]; if (rules[2]) k -= rules[2]; }
+                else if (delta >= 3 && rules[3]) { k -= rules[3]; if (rules[4]) k -= rules[4]; }
+                cognitive = erf(k);
+            }
+            double so = 0;                                                  // findCellSocialScore
+            if (delta <= 1) so = 1;
+            else if (delta > 1 && delta <= 2) so -= counts[0];
+            else if (delta > 2) so -= counts[1];
+            so *= pressure;
+            sc = physical + emotional + cognitive + erf(so);
+        }
+        int j = i;                                                          // sortCellsByWealth on the scores
+        while (j > 0 && (score[j - 1] < sc || (score[j - 1] == sc && cand_dist[order[j - 1]] > cand_dist[i]))) {
+            score[j] = score[j - 1]; order[j] = order[j - 1];
+            j--;
+        }
+        score[j] = sc; order[j] = i;
+    }
+    const int pick = order[0];
+    *out_cell = cand_cell[pick]; *out_rank = pick; *out_diff = cand_w[0] - cand_w[pick];
+}
+
 // MOVE part of Agent.doTimestep (agent.py:568-584), executed by the G lanes of a group for ONE
 // agent: lastSugar/lastSpice, rankCellsInRange + findBestCell + moveToBestCell (1395-1443,
 // 719-746, 1321-1328), collectResourcesAtCell (249-259), doMetabolism (485-498).
@@ -775,6 +825,9 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rn
                 if (c.eth->model[s] == 2 && engaged && has_agentlog(c)) {
                     temperance_pick(c, s, n, w, my_tribe, aggression, ws, rng, &cell, &rank, &diff);
                     picked = b_valid;              // (without a valid candidate the pick is the own cell: stays)
+                } else if (c.eth->model[s] == 3 && engaged && has_agentlog(c)) {
+                    pecs_pick(c, s, n, w, my_tribe, aggression, ws, &cell, &rank, &diff);
+                    picked = b_valid;
                 }
                 if (picked && cell != b_cell) {
                     b_cell = cell;
@@ -794,6 +847,11 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rn
                     int cell, rank;                   // the virtue roll is drawn for [own cell], too
                     double diff;
                     temperance_pick(c, s, 0, w, my_tribe, aggression, ws, rng, &cell, &rank, &diff);
+                }
+                if (has_agentlog(c) && c.eth->model[s] == 3 && engaged) {
+                    int cell, rank;                   // [own cell] is scored (timesOverharvested may move)
+                    double diff;
+                    pecs_pick(c, s, 0, w, my_tribe, aggression, ws, &cell, &rank, &diff);
                 }
             }
         }
@@ -848,6 +906,14 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rn
         c.g.occ[best] = s;
         if (EXT && has_agentlog(c)) agentlog_note_neighbors(c, s, best);
         if (EXT && has_social(c)) update_neighbors(c, s, best);   // (updateFriends reads tags and ids only: the holdings are still in registers)
+        if constexpr (EXT) {
+            if (c.eth != nullptr && c.eth->model[s] == 3 && has_agentlog(c)) {
+                // Temperance.collectResourcesAtCell / doMetabolism (ethics.py:537-543, 508-516): what the new cell adds to the
+                // time to live, before collecting; the social pressure grows with every meal
+                c.eth->last_delta_ttl[s] = time_to_live_potential_of(c, s, best, sugar, spice) - c.x->agentlog.time_to_live[s];
+                c.eth->social_pressure[s] += c.eth->dynamic_social_pressure[s];
+            }
+        }
         // collectResourcesAtCell (agent.py:249-259) + production pollution (cell.py:32-45)
         sugar += b_cs;
         spice += b_cp;
@@ -1138,12 +1204,17 @@ __device__ __noinline__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
         if (EXT && c.eth != nullptr) {
             // the paired endowments follow ONE draw (agent.py:845-851); the child's class is that parent's
             const int from = ((eb >> EB_DECISION_MODEL) & 1u) ? m : s;
-            c.eth->model[ch] = c.eth->model[from]; c.eth->selfishness[ch] = c.eth->selfishness[from];
+            // (Temperance.spawnChild builds the child with the default pecs=False, ethics.py:549-550)
+            c.eth->model[ch] = c.eth->model[from] == 3 ? 2 : c.eth->model[from]; c.eth->selfishness[ch] = c.eth->selfishness[from];
             c.eth->decision_factor[ch] = c.eth->decision_factor[from];
             c.eth->lookahead_factor[ch] = c.eth->lookahead_factor[from];
             c.eth->lookahead_discount[ch] = c.eth->lookahead_discount[from];
             c.eth->dynamic_selfishness[ch] = c.eth->dynamic_selfishness[from];
             c.eth->dynamic_decision_factor[ch] = c.eth->dynamic_decision_factor[from];
+            c.eth->dynamic_social_pressure[ch] = c.eth->dynamic_social_pressure[from];
+            for (int k = 0; k < 5; k++) c.eth->pecs_rules[(long long)ch * 5 + k] = 0;
+            for (int k = 0; k < 3; k++) c.eth->pecs_counts[(long long)ch * 3 + k] = 0;
+            c.eth->social_pressure[ch] = 0; c.eth->last_delta_ttl[ch] = 0;
             c.eth->last_move_optimal[ch] = 1; c.eth->move_rank[ch] = 0; c.eth->move_diff[ch] = 0;      // lastMoveOptimal starts True
         }
         if (EXT && has_group(c)) group_reset_slot(c, ch);
@@ -1165,6 +1236,9 @@ __device__ __noinline__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
             // the child is depressed with the configured chance, decided by the private stream (agent.py:889-895)
             const double draw = c.t < c.x->misc.n_tables ? c.x->misc.depression_draw[c.t] : 1.0;
             if (draw <= c.x->misc.depression_percentage) depress(c, ch);
+        }
+        if constexpr (EXT) {       // Temperance.totalMetabolism, taken at construction (after a depression trigger)
+            if (c.eth != nullptr) c.eth->total_metabolism[ch] = (double)(max(a.sugar_metab[ch], 0) + max(a.spice_metab[ch], 0));
         }
         a.pos[ch] = cell;
         c.g.occ[cell] = ch;

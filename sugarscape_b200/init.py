@@ -77,7 +77,7 @@ def _decimals(value):
 # variants (sugarscape.py:219-238, dynamic selfishness included); Temperance, the "Top" orderings and the Leader are refused
 SUPPORTED_DECISION_MODELS = frozenset(("none", "rawSugarscape")) | frozenset(
     base + look + dyn for base in layout.BENTHAM_MODELS for look in ("", "NoLookahead", "HalfLookahead") for dyn in ("", "Dynamic")
-) | frozenset(("temperance",))
+) | frozenset(("temperance", "temperancePECS"))
 
 
 def uses_decision_models(c):

@@ -182,6 +182,8 @@ class Stats(C.Structure):
 ETHICS_FIELDS = (
     ("model", np.int32, 0), ("selfishness", np.float64, 0), ("decision_factor", np.float64, 0),
     ("lookahead_factor", np.float64, 0), ("lookahead_discount", np.float64, 0), ("dynamic_decision_factor", np.float64, 0),
+    ("pecs_rules", np.int32, 0), ("pecs_counts", np.int32, 0), ("social_pressure", np.float64, 0),
+    ("last_delta_ttl", np.float64, 0), ("dynamic_social_pressure", np.float64, 0), ("total_metabolism", np.float64, 0),
     ("dynamic_selfishness", np.float64, 0),
     ("last_move_optimal", np.int32, 1), ("move_rank", np.int32, 0), ("move_diff", np.float64, 0),
 )
@@ -202,7 +204,9 @@ def decision_model_class(name):
     """ssb_ethics_t.model of a decisionModel string: 1 = ethics.Bentham, 2 = ethics.Temperance (simple), 0 = plain Agent."""
     if decision_model_base(name) is not None:
         return 1
-    return 2 if "temperance" in name else 0
+    if "temperance" in name:
+        return 3 if "PECS" in name else 2
+    return 0
 
 
 def decision_model_base(name):
@@ -225,7 +229,8 @@ class HostEthics:
         # it (ethics.py:160-190) and `[0] != 0` holds
         self.lookahead_factor = 1.0 if isinstance(look, list) else float(look)
         self.default_dynamic = list(c["agentDynamicSelfishnessFactor"]) == [0.0, 0.0]
-        self.arrays = {n: np.full(capacity, fill, dtype=dt) for n, dt, fill in ETHICS_FIELDS}
+        widths = {"pecs_rules": 5, "pecs_counts": 3}          # values per slot
+        self.arrays = {n: np.full(capacity * widths.get(n, 1), fill, dtype=dt) for n, dt, fill in ETHICS_FIELDS}
 
     def set_slot(self, slot, endowment):
         """A freshly configured agent (sugarscape.py:219-233)."""
@@ -248,6 +253,11 @@ class HostEthics:
         A = self.arrays
         A["model"][slot] = decision_model_class(name)
         A["dynamic_decision_factor"][slot] = endowment["dynamicDecisionModelFactor"]
+        A["dynamic_social_pressure"][slot] = endowment["dynamicSocialPressureFactor"]
+        A["pecs_rules"][slot * 5:slot * 5 + 5] = 0
+        A["pecs_counts"][slot * 3:slot * 3 + 3] = 0
+        A["social_pressure"][slot] = 0
+        A["last_delta_ttl"][slot] = 0
         A["selfishness"][slot] = selfish
         A["decision_factor"][slot] = endowment["decisionModelFactor"]
         A["lookahead_factor"][slot] = look
@@ -427,7 +437,7 @@ class HostExt:
         """Rules that read agent.timeToLive (tracked in the agentlog family): dynamic selfishness, Temperance."""
         bentham = [m for m in c["agentDecisionModels"] if decision_model_base(m) is not None]
         return ((bool(bentham) and (c["agentDynamicSelfishnessFactor"][1] != 0 or any("Dynamic" in m for m in bentham))) or
-                any(decision_model_class(m) == 2 for m in c["agentDecisionModels"]))
+                any(decision_model_class(m) >= 2 for m in c["agentDecisionModels"]))
 
     @staticmethod
     def combat_possible(c):
@@ -745,6 +755,8 @@ class HostState:
                 self.ext.set_slot(slot, e)
                 if "misc" in self.ext.families and e["depressionFactor"] == 1:
                     self.depress(slot)
+            if self.ethics is not None:     # Temperance.totalMetabolism, taken at construction (after a depression trigger)
+                self.ethics.arrays["total_metabolism"][slot] = max(int(self.a_sugar_metab[slot]), 0) + max(int(self.a_spice_metab[slot]), 0)
             self.a_order[n_list] = slot
             self.occ[a["cell"]] = slot
             n_list += 1

@@ -104,7 +104,8 @@ def main():
             ov["agentDecisionModels"] = [m + rng.choice(["", "Dynamic"]) if m != "none" else m for m in ov["agentDecisionModels"]]
             ov["agentDynamicSelfishnessFactor"] = rng.choice([[0.0, 0.0], [0.02, 0.05]])
         if "agentDecisionModels" in ov and rng.random() < 0.3:          # Temperance agents among them
-            ov["agentDecisionModels"] = ov["agentDecisionModels"] + ["temperance"]
+            ov["agentDecisionModels"] = ov["agentDecisionModels"] + [rng.choice(["temperance", "temperancePECS"])]
+            ov["agentDynamicSocialPressureFactor"] = rng.choice([[0.0, 0.0], [0.02, 0.1]])
             ov["agentDecisionModelFactor"] = rng.choice([[1, 1], [0.2, 0.8]])
             ov["agentDynamicDecisionModelFactor"] = rng.choice([[0.0, 0.0], [0.05, 0.15]])
         if rng.random() < 0.3:

@@ -70,6 +70,13 @@ VARIANTS = {
     "ethics_temperance_mixed": ("combat_limited", 100, dict(_ETHICS, agentDecisionModels=["bentham", "temperance", "none", "egoistDynamic"],
                                                             agentDecisionModelFactor=[0.5, 1], agentDynamicDecisionModelFactor=[0.0, 0.2],
                                                             agentAggressionFactor=[0, 2], agentVision=[1, 3])),
+    # Temperance with the physical / emotional / cognitive / social scores (pecs=True) next to the simple variant
+    "ethics_temperance_pecs": ("trade_tagging_reproduction", 120, dict(_ETHICS, agentDecisionModels=["none", "temperancePECS", "temperance"],
+                                                                       agentDynamicSocialPressureFactor=[0.01, 0.1],
+                                                                       agentDynamicDecisionModelFactor=[0.0, 0.1])),
+    "ethics_temperance_pecs_combat": ("combat_limited", 100, dict(_ETHICS, agentDecisionModels=["temperancePECS", "bentham"],
+                                                                  agentDynamicSocialPressureFactor=[0.05, 0.05],
+                                                                  agentAggressionFactor=[0, 2], agentVision=[2, 5])),
     # other experimental groups than the shipped "depressed" (membership by sex)
     "determinism_group_female": ("determinism", 120, {"experimentalGroup": "female"}),
     "determinism_group_male": ("determinism", 80, {"experimentalGroup": "male"}),

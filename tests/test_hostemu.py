@@ -50,7 +50,9 @@ ETHICS_VARIANTS = ["ethics_trade", "ethics_combat", "ethics_replacement", "ethic
                    # Bentham.updateSelfishnessFactor: the "Dynamic" names (default 0.01) and a configured range
                    "ethics_dynamic", "ethics_dynamic_configured",
                    # ethics.Temperance (simple variant), alone and mixed with Bentham agents and live combat
-                   "ethics_temperance", "ethics_temperance_mixed"]
+                   "ethics_temperance", "ethics_temperance_mixed",
+                   # ... and with pecs=True (physical + emotional + cognitive + social scores)
+                   "ethics_temperance_pecs", "ethics_temperance_pecs_combat"]
 
 
 @pytest.mark.parametrize("variant", ETHICS_VARIANTS)

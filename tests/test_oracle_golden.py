@@ -394,7 +394,7 @@ def test_oracle_environment_file_matches_reference_trajectory():
 
 
 @pytest.mark.parametrize("overrides", [{"agentVisionMode": "radial"}, {"neighborhoodMode": "moore"},
-                                       {"environmentWraparound": False}, {"agentDecisionModels": ["temperancePECS"]}, {"agentDecisionModels": ["asimov"]},
+                                       {"environmentWraparound": False}, {"agentDecisionModels": ["asimov"]},
                                        {"agentDecisionModels": ["benthamTop"]}, {"experimentalGroup": "sick"},
                                        {"agentLeader": True}, {"agentMaxFriends": [20, 20]}])
 def test_unsupported_options_fail_loudly(overrides):

@@ -46,7 +46,8 @@ class _Budget:
 
 
 ETHICS_VARIANTS = ["ethics_trade", "ethics_combat", "ethics_replacement", "ethics_pollution", "ethics_dynamic",
-                   "ethics_dynamic_configured", "ethics_temperance", "ethics_temperance_mixed"]
+                   "ethics_dynamic_configured", "ethics_temperance", "ethics_temperance_mixed",
+                   "ethics_temperance_pecs", "ethics_temperance_pecs_combat"]
 
 
 @pytest.mark.parametrize("variant", ETHICS_VARIANTS)
