@@ -350,7 +350,7 @@ int ssb_bind_ethics(ssb_engine_t *e, const ssb_ethics_t *eth) {
     if (e->p.rng_mode != SSB_RNG_EXACT) return fail(e, -1, "decision models need the exact RNG mode (the ethical ranking reads agents anywhere in view)");
     if (e->sharded) return fail(e, -1, "decision models are not available on a sharded engine");
     if (eth->capacity != e->ctx.a.capacity) return fail(e, -1, "ethics capacity differs from the agent capacity");
-    if (!eth->model || !eth->selfishness || !eth->decision_factor || !eth->lookahead_factor || !eth->lookahead_discount || !eth->dynamic_selfishness || !eth->dynamic_decision_factor || !eth->pecs_rules || !eth->pecs_counts ||
+    if (!eth->model || !eth->top_ordering || !eth->selfishness || !eth->decision_factor || !eth->lookahead_factor || !eth->lookahead_discount || !eth->dynamic_selfishness || !eth->dynamic_decision_factor || !eth->pecs_rules || !eth->pecs_counts ||
         !eth->social_pressure || !eth->last_delta_ttl || !eth->dynamic_social_pressure || !eth->total_metabolism ||
         !eth->last_move_optimal || !eth->move_rank || !eth->move_diff) return fail(e, -1, "ethics: null array");
     CU(cudaSetDevice(e->device));

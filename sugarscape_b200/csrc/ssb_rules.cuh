@@ -545,7 +545,7 @@ __device__ __noinline__ void ethical_prepare(const DevCtx &c, int s, int n, cons
 // reported by the per-agent log), so a lane that walks the list alone stops at the pick unless that log is on.  Same
 // for the own cell when no candidate is valid.
 __device__ __noinline__ void ethical_score(const DevCtx &c, int s, int r, EthScratch &es, int first, int stride) {
-    const bool all_cells = has_agentlog(c), positive = c.eth->selfishness[s] >= 0;
+    const bool all_cells = has_agentlog(c) || c.eth->top_ordering[s] != 0, positive = c.eth->selfishness[s] >= 0;
     if (es.m == 0) {
         double h, u;
         if (all_cells && first == 0) ethical_value(c, s, r, es.hood, es.nh, c.a.pos[s], &h, &u);
@@ -567,7 +567,14 @@ __device__ __noinline__ bool ethical_choose(const DevCtx &c, int s, const EthScr
         if (positive) { if (es.v[i] > 0) { chosen = i; break; } }
         else if (chosen < 0 || es.u[i] > best_u || (es.u[i] == best_u && es.h[i] > best_h)) { chosen = i; best_u = es.u[i]; best_h = es.h[i]; }   // stable sort, reverse
     }
-    const int rank = chosen >= 0 ? chosen : 0;
+    int rank = chosen >= 0 ? chosen : 0;
+    if (c.eth->top_ordering[s] != 0 && positive) {
+        // "Top" variants (ethics.py:124-129): the cells re-sorted by ethical value (stable: value descending, range
+        // ascending, welfare order); the first one wins whatever its sign
+        rank = 0;
+        for (int i = 1; i < es.m; i++)
+            if (es.v[i] > es.v[rank] || (es.v[i] == es.v[rank] && es.cand_dist[i] < es.cand_dist[rank])) rank = i;
+    }
     *out_cell = es.cand_cell[rank]; *out_rank = rank; *out_diff = es.cand_w[0] - es.cand_w[rank];
     return true;
 }
@@ -1206,6 +1213,7 @@ __device__ __noinline__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
             const int from = ((eb >> EB_DECISION_MODEL) & 1u) ? m : s;
             // (Temperance.spawnChild builds the child with the default pecs=False, ethics.py:549-550)
             c.eth->model[ch] = c.eth->model[from] == 3 ? 2 : c.eth->model[from]; c.eth->selfishness[ch] = c.eth->selfishness[from];
+            c.eth->top_ordering[ch] = c.eth->top_ordering[from];
             c.eth->decision_factor[ch] = c.eth->decision_factor[from];
             c.eth->lookahead_factor[ch] = c.eth->lookahead_factor[from];
             c.eth->lookahead_discount[ch] = c.eth->lookahead_discount[from];

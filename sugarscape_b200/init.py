@@ -76,7 +76,8 @@ def _decimals(value):
 # decisionModel strings with a CUDA implementation: the plain Agent and ethics.Bentham with its spawn
 # variants (sugarscape.py:219-238, dynamic selfishness included); Temperance, the "Top" orderings and the Leader are refused
 SUPPORTED_DECISION_MODELS = frozenset(("none", "rawSugarscape")) | frozenset(
-    base + look + dyn for base in layout.BENTHAM_MODELS for look in ("", "NoLookahead", "HalfLookahead") for dyn in ("", "Dynamic")
+    base + look + dyn + top for base in layout.BENTHAM_MODELS for look in ("", "NoLookahead", "HalfLookahead")
+    for dyn in ("", "Dynamic") for top in ("", "Top") if not (top and base == "negativeBentham")      # (that one raises in the reference)
 ) | frozenset(("temperance", "temperancePECS"))
 
 

@@ -180,7 +180,7 @@ class Stats(C.Structure):
 # ---- ABI 2: decision models (ssb_ethics_t; reference ethics.py, spawn rules sugarscape.py:219-233) ----
 # (name, numpy dtype, fill) in the order of ssb_ethics_t after `capacity`
 ETHICS_FIELDS = (
-    ("model", np.int32, 0), ("selfishness", np.float64, 0), ("decision_factor", np.float64, 0),
+    ("model", np.int32, 0), ("top_ordering", np.int32, 0), ("selfishness", np.float64, 0), ("decision_factor", np.float64, 0),
     ("lookahead_factor", np.float64, 0), ("lookahead_discount", np.float64, 0), ("dynamic_decision_factor", np.float64, 0),
     ("pecs_rules", np.int32, 0), ("pecs_counts", np.int32, 0), ("social_pressure", np.float64, 0),
     ("last_delta_ttl", np.float64, 0), ("dynamic_social_pressure", np.float64, 0), ("total_metabolism", np.float64, 0),
@@ -252,6 +252,7 @@ class HostEthics:
             look = 0.5
         A = self.arrays
         A["model"][slot] = decision_model_class(name)
+        A["top_ordering"][slot] = int(base is not None and "Top" in name)
         A["dynamic_decision_factor"][slot] = endowment["dynamicDecisionModelFactor"]
         A["dynamic_social_pressure"][slot] = endowment["dynamicSocialPressureFactor"]
         A["pecs_rules"][slot * 5:slot * 5 + 5] = 0

@@ -101,7 +101,8 @@ def main():
         base = rng.choice(BASES)
         ov = draw_overrides(rng, base)
         if "agentDecisionModels" in ov and rng.random() < 0.4:          # dynamic selfishness
-            ov["agentDecisionModels"] = [m + rng.choice(["", "Dynamic"]) if m != "none" else m for m in ov["agentDecisionModels"]]
+            ov["agentDecisionModels"] = [m + rng.choice(["", "Dynamic"]) + (rng.choice(["", "Top"]) if "negative" not in m else "")
+                                         if m != "none" else m for m in ov["agentDecisionModels"]]
             ov["agentDynamicSelfishnessFactor"] = rng.choice([[0.0, 0.0], [0.02, 0.05]])
         if "agentDecisionModels" in ov and rng.random() < 0.3:          # Temperance agents among them
             ov["agentDecisionModels"] = ov["agentDecisionModels"] + [rng.choice(["temperance", "temperancePECS"])]

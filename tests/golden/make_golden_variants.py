@@ -77,6 +77,8 @@ VARIANTS = {
     "ethics_temperance_pecs_combat": ("combat_limited", 100, dict(_ETHICS, agentDecisionModels=["temperancePECS", "bentham"],
                                                                   agentDynamicSocialPressureFactor=[0.05, 0.05],
                                                                   agentAggressionFactor=[0, 2], agentVision=[2, 5])),
+    # the "Top" orderings: the cell with the best ethical value wins
+    "ethics_top": ("trade_tagging_reproduction", 100, dict(_ETHICS, agentDecisionModels=["benthamTop", "egoistTop", "altruistNoLookaheadTop", "none", "bentham"])),
     # other experimental groups than the shipped "depressed" (membership by sex)
     "determinism_group_female": ("determinism", 120, {"experimentalGroup": "female"}),
     "determinism_group_male": ("determinism", 80, {"experimentalGroup": "male"}),

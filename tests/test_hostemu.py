@@ -52,7 +52,9 @@ ETHICS_VARIANTS = ["ethics_trade", "ethics_combat", "ethics_replacement", "ethic
                    # ethics.Temperance (simple variant), alone and mixed with Bentham agents and live combat
                    "ethics_temperance", "ethics_temperance_mixed",
                    # ... and with pecs=True (physical + emotional + cognitive + social scores)
-                   "ethics_temperance_pecs", "ethics_temperance_pecs_combat"]
+                   "ethics_temperance_pecs", "ethics_temperance_pecs_combat",
+                   # the "Top" orderings of the Bentham family
+                   "ethics_top"]
 
 
 @pytest.mark.parametrize("variant", ETHICS_VARIANTS)

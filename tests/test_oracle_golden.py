@@ -395,7 +395,7 @@ def test_oracle_environment_file_matches_reference_trajectory():
 
 @pytest.mark.parametrize("overrides", [{"agentVisionMode": "radial"}, {"neighborhoodMode": "moore"},
                                        {"environmentWraparound": False}, {"agentDecisionModels": ["asimov"]},
-                                       {"agentDecisionModels": ["benthamTop"]}, {"experimentalGroup": "sick"},
+                                       {"agentDecisionModels": ["negativeBenthamTop"]}, {"experimentalGroup": "sick"},
                                        {"agentLeader": True}, {"agentMaxFriends": [20, 20]}])
 def test_unsupported_options_fail_loudly(overrides):
     """All 29 shipped examples are supported; the options outside the CUDA implementation are refused, not half-run."""

@@ -47,7 +47,7 @@ class _Budget:
 
 ETHICS_VARIANTS = ["ethics_trade", "ethics_combat", "ethics_replacement", "ethics_pollution", "ethics_dynamic",
                    "ethics_dynamic_configured", "ethics_temperance", "ethics_temperance_mixed",
-                   "ethics_temperance_pecs", "ethics_temperance_pecs_combat"]
+                   "ethics_temperance_pecs", "ethics_temperance_pecs_combat", "ethics_top"]
 
 
 @pytest.mark.parametrize("variant", ETHICS_VARIANTS)
