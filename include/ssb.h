@@ -503,7 +503,18 @@ int  ssb_get_mt_state(ssb_engine_t *e, uint32_t state[624], int32_t *index);
  * tag_bits[t] bit k = k-th draw for tag positions where the parents differ. */
 int  ssb_set_step_tables(ssb_engine_t *e, const uint32_t *endow_bits, const uint32_t *tag_bits, int32_t n);
 
-/* mode S tuning: number of priority epochs of the sliding-prefix commit (power of two, default 128) */
+/* Mode S scheduler.  Both reproduce "agents act one at a time in ascending priority" (the reference's
+ * random.shuffle + agent loop, sugarscape.py:400-407) bit for bit:
+ *   SSB_SCHED_DATAFLOW (default on one GPU): the conflict DAG of the step is built once from the agents'
+ *     start positions (csrc/ssb_flow_core.cuh) and executed as a dataflow without barriers;
+ *   SSB_SCHED_ROUNDS: deterministic reservation rounds over a sliding priority prefix (round 1 kernel;
+ *     sharded engines use it).  Environment override at bind time: SSB_SCHEDULER=rounds|dataflow. */
+#define SSB_SCHED_ROUNDS   0
+#define SSB_SCHED_DATAFLOW 1
+int  ssb_set_scheduler(ssb_engine_t *e, int32_t scheduler);
+int  ssb_get_scheduler(const ssb_engine_t *e);
+
+/* mode S tuning (SSB_SCHED_ROUNDS): number of priority epochs of the sliding-prefix commit (power of two, default 128) */
 int  ssb_set_epochs(ssb_engine_t *e, int32_t epochs);
 /* mode S tuning: reservation marks on a grid coarsened by 2^shift cells per side (default 1 when the map allows it) */
 int  ssb_set_mark_shift(ssb_engine_t *e, int32_t shift);

@@ -1632,8 +1632,10 @@ void orc_env_step(const ssb_params_t *p, const ssb_grid_t *g, int32_t t) {
                 g->spice[i] = q < g->spice_cap[i] ? q : g->spice_cap[i];
             }
         }
+    /* the reference's countdown (environment.py:192-197) is decremented on every step inside the timeframe, the first
+     * step being t = 1: it diffuses on the k-th such step when k is a multiple of the delay */
     if (p->diffusion_delay > 0 && p->diffusion_start <= t && t <= p->diffusion_end &&
-        ((t - p->diffusion_start + 1) % p->diffusion_delay) == 0) {
+        ((t - (p->diffusion_start > 1 ? p->diffusion_start : 1) + 1) % p->diffusion_delay) == 0) {
         for (int x = 0; x < W; x++)
             for (int y = 0; y < H; y++) {
                 double m = 0;

@@ -8,6 +8,7 @@
 
 #include "../../include/ssb.h"
 #include "ssb_agent_step.cuh"
+#include "ssb_dataflow.cuh"
 #include "ssb_kernels.cuh"
 #include <stdlib.h>
 #include "ssb_sort.cuh"
@@ -39,6 +40,10 @@ struct ssb_engine {
     // mode S rounds
     RoundCtx rc;
     int coop_blocks;
+    // mode S dataflow (ssb_dataflow.cuh)
+    FlowCtx flow;
+    int flow_blocks, flow_build_blocks;
+    int scheduler;           // SSB_SCHED_*
     // stats
     StatsPartial *d_partials;
     int n_partials;
@@ -169,7 +174,8 @@ void ssb_destroy(ssb_engine_t *e) {
     void *ptrs[] = {e->d_mt, e->d_endow, e->d_tagbits, e->d_tile_counts, e->d_new_order, e->d_scalars,
                     e->d_born_list, e->rc.mark, e->rc.list_a, e->rc.list_b, e->rc.ready, e->rc.cnt, e->rc.trace, e->rc.bucketed, e->rc.epoch_count, e->rc.epoch_start, e->rc.epoch_fill,
                     e->d_partials, e->d_tribes, e->d_stats, e->d_ring, e->d_keys_a, e->d_keys_b, e->d_radix_hist,
-                    e->d_lorenz_blocks, e->d_plan, e->d_cand, e->sh.peer_vals, e->sh.flags, e->d_shard_vals, e->d_migrate, e->d_eth_stats, e->d_ext_stats, e->d_group_stats, e->d_eth, e->d_ext};
+                    e->d_lorenz_blocks, e->d_plan, e->d_cand, e->sh.peer_vals, e->sh.flags, e->d_shard_vals, e->d_migrate, e->d_eth_stats, e->d_ext_stats, e->d_group_stats, e->d_eth, e->d_ext,
+                    e->flow.desc, e->flow.entries, e->flow.dep, e->flow.span, e->flow.pool, e->flow.cursor, e->flow.queue, e->flow.tail, e->flow.tile_pop};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < 5; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
     delete e;
@@ -243,10 +249,60 @@ int ssb_bind(ssb_engine_t *e, const ssb_grid_t *grid, const ssb_agents_t *agents
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_agent_step_scalable, AGENT_THREADS, AGENT_SMEM_BYTES));
         if (per_sm < 1) return fail(e, -3, "cooperative kernel does not fit on an SM");
         e->coop_blocks = per_sm * e->num_sms;
+        // the dataflow scheduler (default on one GPU): descriptor word per cell, DAG arrays per list entry
+        FlowCtx &f = e->flow;
+        f.rb = maxd; f.kb = flow_max_dilation(e->p.flags); f.halo = flow_halo(f.rb, f.kb);
+        e->scheduler = SSB_SCHED_DATAFLOW;
+        if (const char *env = getenv("SSB_SCHEDULER")) e->scheduler = strcmp(env, "rounds") == 0 ? SSB_SCHED_ROUNDS : SSB_SCHED_DATAFLOW;
+        if (f.halo > FLOW_MAX_HALO || cap >= (1LL << FLOW_INDEX_BITS)) e->scheduler = SSB_SCHED_ROUNDS;
+        if (e->scheduler == SSB_SCHED_DATAFLOW) {
+            f.tiles_x = (e->p.width + FLOW_TX - 1) / FLOW_TX; f.tiles_y = (e->p.height + FLOW_TY - 1) / FLOW_TY;
+            CU(cudaFuncSetAttribute(k_flow_execute, cudaFuncAttributeMaxDynamicSharedMemorySize, AGENT_SMEM_BYTES));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_flow_execute, AGENT_THREADS, AGENT_SMEM_BYTES));
+            if (per_sm < 1) return fail(e, -3, "the dataflow kernel does not fit on an SM");
+            e->flow_blocks = per_sm * e->num_sms;
+            const int build_smem = flow_build_smem_bytes(f.halo);
+            CU(cudaFuncSetAttribute(k_flow_build, cudaFuncAttributeMaxDynamicSharedMemorySize, build_smem));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_flow_build, FLOW_BUILD_THREADS, build_smem));
+            if (per_sm < 1) return fail(e, -3, "the DAG build kernel does not fit on an SM (%d bytes of shared memory)", build_smem);
+            e->flow_build_blocks = per_sm * e->num_sms;
+            f.n_queues = e->flow_blocks * AGENT_GROUPS;
+            f.queue_cap = (int32_t)((cap + f.n_queues - 1) / f.n_queues) + 1;
+            long long pool = cap * 24;
+            if (const char *env = getenv("SSB_FLOW_POOL_FACTOR")) pool = cap * (long long)atoi(env);
+            if (pool > 0x7fffffffLL) pool = 0x7fffffffLL;
+            f.pool_capacity = pool;
+            CU(cudaMalloc(&f.desc, sizeof(unsigned long long) * (size_t)cells));
+            CU(cudaMemset(f.desc, 0, sizeof(unsigned long long) * (size_t)cells));
+            CU(cudaMalloc(&f.entries, sizeof(int4) * cap));
+            CU(cudaMalloc(&f.dep, sizeof(int32_t) * cap));
+            CU(cudaMalloc(&f.span, sizeof(int2) * cap));
+            CU(cudaMalloc(&f.pool, sizeof(int32_t) * (size_t)pool));
+            CU(cudaMalloc(&f.cursor, sizeof(unsigned long long) * 2));
+            CU(cudaMemset(f.cursor, 0, sizeof(unsigned long long) * 2));
+            CU(cudaMalloc(&f.queue, sizeof(int32_t) * (size_t)f.n_queues * f.queue_cap));
+            CU(cudaMemset(f.queue, 0, sizeof(int32_t) * (size_t)f.n_queues * f.queue_cap));
+            CU(cudaMalloc(&f.tail, sizeof(int32_t) * f.n_queues));
+            CU(cudaMemset(f.tail, 0, sizeof(int32_t) * f.n_queues));
+            CU(cudaMalloc(&f.tile_pop, sizeof(int32_t) * f.tiles_x * f.tiles_y));
+            CU(cudaMemset(f.tile_pop, 0, sizeof(int32_t) * f.tiles_x * f.tiles_y));
+        }
     }
     e->bound = true;
     return 0;
 }
+
+// Mode S scheduler: SSB_SCHED_DATAFLOW (static conflict DAG, ssb_dataflow.cuh) or SSB_SCHED_ROUNDS (deterministic
+// reservation rounds, ssb_agent_step.cuh).  Both reproduce the sequential priority order bit for bit.
+int ssb_set_scheduler(ssb_engine_t *e, int32_t scheduler) {
+    if (!e || !e->bound || e->p.rng_mode != SSB_RNG_SCALABLE) return fail(e, -1, "the scheduler choice needs a bound scalable engine");
+    if (scheduler != SSB_SCHED_ROUNDS && scheduler != SSB_SCHED_DATAFLOW) return fail(e, -1, "unknown scheduler %d", scheduler);
+    if (scheduler == SSB_SCHED_DATAFLOW && !e->flow.desc) return fail(e, -1, "the dataflow scheduler was not set up at bind time (range or capacity beyond its limits, or SSB_SCHEDULER=rounds)");
+    e->scheduler = scheduler;
+    return 0;
+}
+
+int ssb_get_scheduler(const ssb_engine_t *e) { return e ? e->scheduler : -1; }
 
 int ssb_set_mark_shift(ssb_engine_t *e, int32_t shift) {
     if (!e || !e->bound || e->p.rng_mode != SSB_RNG_SCALABLE) return fail(e, -1, "mark shift needs a bound scalable engine");
@@ -493,8 +549,10 @@ int ssb_env_step(ssb_engine_t *e, int32_t t, void *stream_) {
         if (vec) k_growback_v4<<<blocks, 256, 0, st>>>(g); else k_growback_scalar<<<blocks, 256, 0, st>>>(g);
         LAUNCHED(e);
     }
+    /* the reference's countdown (environment.py:192-197) is decremented on every step inside the timeframe, the first
+     * step being t = 1: it diffuses on the k-th such step when k is a multiple of the delay */
     if (p.diffusion_delay > 0 && p.diffusion_start <= t && t <= p.diffusion_end &&
-        ((t - p.diffusion_start + 1) % p.diffusion_delay) == 0) {
+        ((t - (p.diffusion_start > 1 ? p.diffusion_start : 1) + 1) % p.diffusion_delay) == 0) {
         if ((p.height % 2) == 0)
             k_diffuse_v2<<<grid_for(my_cells / 2, 256, e->num_sms * 8), 256, 0, st>>>(e->ctx.g.pollution, e->ctx.g.pollution_flux, p.width, p.height, g.cell_lo, g.cell_hi);
         else
@@ -518,6 +576,14 @@ int ssb_agent_step(ssb_engine_t *e, int32_t t, double prev_mean_wealth, void *st
     if (e->p.rng_mode == SSB_RNG_EXACT) {
         if (e->ethics_bound || e->ext_bound) k_agent_step_exact<true><<<1, 32, 0, st>>>(c, e->d_mt);
         else k_agent_step_exact<false><<<1, 32, 0, st>>>(c, e->d_mt);
+        LAUNCHED(e);
+    } else if (e->scheduler == SSB_SCHED_DATAFLOW && !e->sharded) {
+        FlowCtx f = e->flow;
+        f.key = step_key(e->p.seed, t);
+        k_flow_prepare<<<e->num_sms * 8, 256, 0, st>>>(c, f); LAUNCHED(e);
+        k_flow_build<<<e->flow_build_blocks, FLOW_BUILD_THREADS, flow_build_smem_bytes(f.halo), st>>>(c, f); LAUNCHED(e);
+        void *args[] = {&c, &f};
+        CU(cudaLaunchCooperativeKernel((void *)k_flow_execute, dim3(e->flow_blocks), dim3(AGENT_THREADS), args, AGENT_SMEM_BYTES, st));
         LAUNCHED(e);
     } else {
         RoundCtx rc = e->rc;

@@ -44,6 +44,7 @@
 #include <cooperative_groups.h>
 
 #include "ssb_exact.cuh"
+#include "ssb_flow_core.cuh"      // footprint_dilation (shared with the dataflow scheduler)
 
 namespace ssb {
 namespace cg = cooperative_groups;
@@ -120,29 +121,6 @@ __device__ __forceinline__ unsigned long long global_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
-}
-
-// Dilation of the footprint required by the rule set, for agent s (agent.py:585-588), evaluated
-// BEFORE the agent moves.  Reproduction (k = 2) is only possible if the agent can be fertile when
-// it gets there: fertile age, and holdings that can still reach the starting endowment -- other
-// agents can only LOWER them (mate costs), the agent's own move adds at most one cell's capacity
-// (plus combat loot) and subtracts its metabolism.  Computed once per step: a value that was
-// valid at the start of the step stays a superset later.
-__device__ __forceinline__ int footprint_dilation(const DevCtx &c, int s) {
-    int k = 0;
-    if (c.p.flags & (SSB_F_TAGGING | SSB_F_TRADE)) k = 1;
-    if ((c.p.flags & SSB_F_REPRO) && c.a.fert_factor[s] > 0 &&
-        c.a.age[s] >= c.a.fert_age[s] && c.a.age[s] < c.a.infert_age[s]) {
-        bool can = true;
-        if (!(c.p.flags & SSB_F_TRADE)) {
-            const double loot = c.a.aggression[s] > 0 ? c.p.max_combat_loot : 0.0;
-            const double gain_s = (double)c.p.max_sugar_capacity + loot - (double)max(c.a.sugar_metab[s], 0);
-            const double gain_p = (double)c.p.max_spice_capacity + loot - (double)max(c.a.spice_metab[s], 0);
-            can = c.a.sugar[s] + gain_s >= c.a.start_sugar[s] && c.a.spice[s] + gain_p >= c.a.start_spice[s];
-        }
-        if (can) k = 2;
-    }
-    return k;
 }
 
 // the same from the register copy of the record, after the move part (holdings are final)

@@ -71,6 +71,7 @@ template <int G> struct Group {
     template <class T> static __device__ __forceinline__ T bcast(T v, int src) { return __shfl_sync(mask(), v, src, G); }
     template <class T> static __device__ __forceinline__ T xor_(T v, int o) { return __shfl_xor_sync(mask(), v, o, G); }
     static __device__ __forceinline__ bool any(bool p) { return __any_sync(mask(), p) != 0; }
+    static __device__ __forceinline__ bool all(bool p) { return __any_sync(mask(), !p) == 0; }
 };
 
 // Per-group scratch of the move ranking, in SHARED memory.

@@ -79,6 +79,15 @@ VARIANTS = {
                                                                   agentAggressionFactor=[0, 2], agentVision=[2, 5])),
     # the "Top" orderings: the cell with the best ethical value wins
     "ethics_top": ("trade_tagging_reproduction", 100, dict(_ETHICS, agentDecisionModels=["benthamTop", "egoistTop", "altruistNoLookaheadTop", "none", "bentham"])),
+    # diffusion timeframe that starts before the first step, delay > 1: the reference's countdown is first decremented
+    # at t = 1, so it diffuses at t = 2, 4, ... (the engine fired one step early); and a window
+    # that opens later with delay 3
+    "pollution_diffusion_delay2": ("pollution_formation", 60, {"environmentPollutionDiffusionTimeframe": [0, 500],
+                                                               "environmentPollutionDiffusionDelay": 2,
+                                                               "environmentPollutionTimeframe": [1, 500]}),
+    "pollution_diffusion_delay3": ("pollution_formation", 60, {"environmentPollutionDiffusionTimeframe": [-1, -1],
+                                                               "environmentPollutionDiffusionDelay": 3,
+                                                               "environmentPollutionTimeframe": [0, 500]}),
     # other experimental groups than the shipped "depressed" (membership by sex)
     "determinism_group_female": ("determinism", 120, {"experimentalGroup": "female"}),
     "determinism_group_male": ("determinism", 80, {"experimentalGroup": "male"}),

@@ -5,6 +5,9 @@
 #include "cuda_shim.h"
 
 #include "../../sugarscape_b200/csrc/ssb_exact.cuh"
+#include "../../sugarscape_b200/csrc/ssb_flow_core.cuh"
+
+#include <vector>
 
 using namespace ssb;
 
@@ -66,5 +69,111 @@ int emu_ethics_stats(const ssb_agents_t *a, const ssb_ethics_t *ethics, ssb_ethi
     ethics_stats_body(c, out);
     return 0;
 }
+
+
+/* Mode S agent step through the engine's static conflict DAG (csrc/ssb_flow_core.cuh: the SAME conflict predicate
+ * and the SAME staged-tile scan the CUDA build kernel runs), executed in an ADVERSARIAL topological order:
+ * order_mode 0 = FIFO (about level order), 1 = LIFO (depth first, as far from the priority order as the DAG
+ * allows), 2 = pseudo-random pick among the ready agents.  The result must equal the oracle's sequential
+ * priority order bit for bit -- that is the claim the dataflow scheduler rests on.
+ * out_stats (may be null): {agents, edges, longest path, tiles visited}. */
+int emu_agent_step_flow(const ssb_params_t *p, const ssb_grid_t *g, const ssb_agents_t *a, int32_t t, double prev_mean_wealth,
+                        const uint32_t *endow_bits, const uint32_t *tag_bits, int32_t n_tables, int32_t *born_list,
+                        int32_t order_mode, int64_t *out_stats) {
+    if (!p || !g || !a || p->rng_mode != SSB_RNG_SCALABLE) return -1;
+    DevCtx c;
+    memset(&c, 0, sizeof(c));
+    c.p = *p; c.g = *g; c.a = *a;
+    const int rmax = p->max_agent_range;
+    c.max_dx = rmax < p->width / 2 ? rmax : p->width / 2;
+    c.max_dy = rmax < p->height / 2 ? rmax : p->height / 2;
+    const int RB = c.max_dx > c.max_dy ? c.max_dx : c.max_dy, KB = flow_max_dilation(p->flags), R = flow_halo(RB, KB);
+    if (4 * RB > 32 || R > FLOW_MAX_HALO) return -2;
+    c.t = t; c.prev_mean_wealth = prev_mean_wealth;
+    c.endow_bits = endow_bits; c.tag_bits = tag_bits; c.n_step_tables = n_tables;
+    c.born_list = born_list;
+    const uint64_t key = step_key(p->seed, t);
+    const int W = p->width, H = p->height;
+    const int n_list = (int)a->counters[SSB_C_N_LIST];
+    a->counters[SSB_C_N_BORN] = 0;
+    /* prepare (k_flow_prepare) */
+    struct Entry { int slot, pos; uint32_t prio; int rk; };
+    std::vector<Entry> entries(n_list);
+    std::vector<unsigned long long> desc((size_t)W * H, 0ull);
+    std::vector<int> dep(n_list, 0), ready;
+    std::vector<std::vector<int>> succ(n_list);
+    for (int i = 0; i < n_list; i++) {
+        const int s = a->order[i];
+        const uint32_t pr = priority_of(key, (uint32_t)a->id[s], p->id_bits);
+        const int r = min(min(max(a->vision[s], 0), max(a->movement[s], 0)), max(c.max_dx, c.max_dy));
+        const int k = footprint_dilation(c, s);
+        entries[i] = {s, a->pos[s], pr, r | (k << 8)};
+        if (a->pos[s] >= 0) desc[a->pos[s]] = flow_pack((uint32_t)i, pr, r, k); else ready.push_back(i);
+    }
+    /* build (k_flow_build): tile by tile, staged with the torus wrap, masks, one scan per agent */
+    const int sw = FLOW_TX + 2 * R, sh = FLOW_TY + 2 * R;
+    std::vector<unsigned long long> cell((size_t)sw * sh), mask((size_t)sw * 2);
+    long long edges = 0, tiles = 0;
+    for (int tx = 0; tx * FLOW_TX < W; tx++) for (int ty = 0; ty * FLOW_TY < H; ty++) {
+        const int x0 = tx * FLOW_TX - R, y0 = ty * FLOW_TY - R;
+        for (int col = 0; col < sw; col++) for (int row = 0; row < sh; row++)
+            cell[(size_t)col * sh + row] = desc[(size_t)wrapi(x0 + col, W) * H + wrapi(y0 + row, H)];
+        for (int col = 0; col < sw; col++) {
+            mask[col * 2] = mask[col * 2 + 1] = 0;
+            for (int row = 0; row < sh; row++) if (cell[(size_t)col * sh + row]) mask[col * 2 + (row >> 6)] |= 1ull << (row & 63);
+        }
+        FlowTile tile;
+        tile.cell = cell.data(); tile.mask = mask.data(); tile.sw = sw; tile.sh = sh; tile.halo = R;
+        tiles++;
+        for (int ix = 0; ix < FLOW_TX && tx * FLOW_TX + ix < W; ix++) for (int iy = 0; iy < FLOW_TY && ty * FLOW_TY + iy < H; iy++) {
+            const int sc = (R + ix) * sh + R + iy;
+            const unsigned long long da = cell[sc];
+            if (!da) continue;
+            const int ia = (int)flow_index(da);
+            const uint32_t pa = flow_prio(da);
+            flow_scan_agent(tile, R + ix, R + iy, da, RB, KB, [&](int, unsigned long long db) {
+                if (flow_prio(db) < pa) dep[ia]++;
+                else if (flow_prio(db) > pa) { succ[ia].push_back((int)flow_index(db)); edges++; }
+            });
+            if (dep[ia] == 0) ready.push_back(ia);
+        }
+    }
+    /* execute (k_flow_execute) in the requested topological order */
+    alignas(8) unsigned char scratch[warp_scratch_bytes(32)];
+    const WarpScratch ws = make_warp_scratch(scratch, 32);
+    std::vector<int> level(n_list, 0);
+    long long done = 0, depth = 0;
+    uint64_t lcg = 0x9E3779B97F4A7C15ull ^ (uint64_t)t;
+    size_t fifo_head = 0;
+    while (order_mode == 0 ? fifo_head < ready.size() : !ready.empty()) {
+        int i;
+        if (order_mode == 0) i = ready[fifo_head++];
+        else if (order_mode == 1) { i = ready.back(); ready.pop_back(); }
+        else {
+            lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
+            const size_t k = (size_t)((lcg >> 33) % ready.size());
+            i = ready[k]; ready[k] = ready.back(); ready.pop_back();
+        }
+        const int s = entries[i].slot;
+        AgentRec rec;
+        rec.load(c, s);
+        RngStream rng{key, (uint32_t)rec.id, 0u, 0u, nullptr};
+        if (transaction_move_phase<1, 4>(c, s, rec, rng, ws, 32)) transaction_interact_phase<RngStream, false>(c, s, rec, rng);
+        done++;
+        if (level[i] + 1 > depth) depth = level[i] + 1;
+        for (int b : succ[i]) {
+            if (level[i] + 1 > level[b]) level[b] = level[i] + 1;
+            if (--dep[b] == 0) ready.push_back(b);
+        }
+    }
+    if (out_stats) { out_stats[0] = n_list; out_stats[1] = edges; out_stats[2] = depth; out_stats[3] = tiles; }
+    return done == n_list ? 0 : -3;     /* -3: the graph was not acyclic / a counter never reached zero */
+}
+
+
+int emu_flow_conflict(int32_t dx, int32_t dy, int32_t ra, int32_t rb, int32_t ka, int32_t kb) {
+    return flow_conflict(dx < 0 ? -dx : dx, dy < 0 ? -dy : dy, ra, rb, ka + kb) ? 1 : 0;
+}
+int emu_flow_column_reach(int32_t adx, int32_t ra, int32_t ka, int32_t RB, int32_t KB) { return flow_column_reach(adx, ra, ka, RB, KB); }
 
 }

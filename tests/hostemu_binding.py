@@ -97,3 +97,34 @@ class HostEmu(Oracle):
         rc = self.E.emu_ethics_stats(C.byref(a), C.byref(self.state.ethics.as_struct()), C.byref(out))
         assert rc == 0
         return out
+
+
+class HostEmuFlow(Oracle):
+    """Mode S agent step through the engine's static conflict DAG (csrc/ssb_flow_core.cuh, host-compiled) in an
+    adversarial topological order (1 = depth first, 2 = pseudo-random among the ready agents, 0 = FIFO);
+    environment step, compaction, replacement and reductions stay the oracle's."""
+
+    def __init__(self, params, state, endow_bits=None, tag_bits=None, order_mode=1):
+        super().__init__(params, state, endow_bits, tag_bits)
+        assert params.rng_mode == layout.RNG_SCALABLE
+        self.E = lib()
+        P, G, A = C.POINTER(layout.Params), C.POINTER(layout.Grid), C.POINTER(layout.Agents)
+        self.E.emu_agent_step_flow.argtypes = [P, G, A, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_int32,
+                                               C.c_void_p, C.c_int32, C.c_void_p]
+        self.order_mode = order_mode
+        self.born = np.zeros(state.capacity, dtype=np.int32)
+        self.dag = np.zeros(4, dtype=np.int64)       # agents, edges, longest path, tiles of the last step
+
+    def agent_step(self, t, prev_mean_wealth=0.0):
+        g, a = self.state.as_structs()
+        eb = self.endow_bits.ctypes.data if self.endow_bits is not None else None
+        tb = self.tag_bits.ctypes.data if self.tag_bits is not None else None
+        n = len(self.endow_bits) if self.endow_bits is not None else 0
+        rc = self.E.emu_agent_step_flow(C.byref(self.params), C.byref(g), C.byref(a), t, prev_mean_wealth, eb, tb, n,
+                                        self.born.ctypes.data, self.order_mode, self.dag.ctypes.data)
+        assert rc == 0, f"emu_agent_step_flow failed: {rc}"
+        # the engine appends the newborn at compaction; the oracle's compaction expects them on the list
+        cn = self.state.counters
+        n_born, n_list = int(cn[layout.C_N_BORN]), int(cn[layout.C_N_LIST])
+        self.state.a_order[n_list:n_list + n_born] = self.born[:n_born]
+        cn[layout.C_N_LIST] = n_list + n_born

@@ -27,14 +27,32 @@ POW_EXAMPLES = ["spice_growback", "foresight_basic", "trade_basic", "trade_repla
                 "trade_pollution", "trade_reproduction", "trade_tagging_reproduction"]
 
 
-def _engine(name, rng_mode=layout.RNG_EXACT, overrides=None):
+# Mode S schedulers (include/ssb.h SSB_SCHED_*): the dataflow over the static conflict DAG (default on one GPU) and
+# the reservation rounds; for the rounds also the tuning bench.py's S2 run uses on one GPU (4 x 4 marks, 256 epochs).
+SCHEDULERS = ["dataflow", "rounds", "rounds-ms2-e256"]
+
+
+def _set_scheduler(eng, scheduler):
+    if scheduler is None:
+        return
+    eng.set_scheduler(scheduler.split("-")[0])
+    if scheduler == "rounds-ms2-e256":
+        if eng.width % 4 or eng.height % 4 or min(eng.width, eng.height) < 64:
+            pytest.skip("4 x 4 marks need a map side that is a multiple of 4 (and >= 64)")
+        eng.set_mark_shift(2)
+        eng.set_epochs(256)
+
+
+def _engine(name, rng_mode=layout.RNG_EXACT, overrides=None, scheduler=None):
     from sugarscape_b200.engine import Engine
     c, state, pop, params, endow, tags = pu.build(name, rng_mode, overrides)
     eng = Engine(params, state, 0, endow, tags)
     if rng_mode == layout.RNG_EXACT:
         eng.set_mt_from_python()
-    elif c["agentReplacements"] > 0:
-        eng.bind_endowments(pop.endowments)
+    else:
+        if c["agentReplacements"] > 0:
+            eng.bind_endowments(pop.endowments)
+        _set_scheduler(eng, scheduler)
     return c, state, pop, params, endow, tags, eng
 
 
@@ -149,14 +167,17 @@ SCALABLE_CASES = [("constant_growback", {}), ("pollution_formation", {}), ("repr
                                       "agentReplacements": 4000, "agentMaxAge": [5, 30]})]
 
 
+@pytest.mark.parametrize("scheduler", SCHEDULERS)
 @pytest.mark.parametrize("name,overrides", SCALABLE_CASES)
-def test_scalable_mode_parallel_rounds_equal_sequential_oracle(name, overrides):
-    """Mode S: the parallel reservation rounds must reproduce the sequential priority order
-    exactly -- compared step by step with the CPU oracle run in the same mode."""
+def test_scalable_mode_parallel_rounds_equal_sequential_oracle(name, overrides, scheduler):
+    """Mode S: the parallel schedulers (dataflow over the conflict DAG; reservation rounds, also with the
+    tuning of the benchmarked S2 run) must reproduce the sequential priority order exactly -- compared step
+    by step with the CPU oracle run in the same mode."""
     from oracle_binding import Oracle
     ov = dict(overrides)
     ov.setdefault("agentMovement", [6, 6])
-    c, state, pop, params, endow, tags, eng = _engine(name, layout.RNG_SCALABLE, ov)
+    c, state, pop, params, endow, tags, eng = _engine(name, layout.RNG_SCALABLE, ov, scheduler)
+    assert eng.scheduler() == scheduler.split("-")[0]
     ostate = state.copy()
     orc = Oracle(params, ostate, endow, tags)
     if c["agentReplacements"] > 0:
@@ -191,12 +212,13 @@ def test_scalable_mode_parallel_rounds_equal_sequential_oracle(name, overrides):
 SCALABLE_GOLDEN = pu.load_scalable_golden()
 
 
+@pytest.mark.parametrize("scheduler", ["dataflow", "rounds"])
 @pytest.mark.parametrize("name", sorted(SCALABLE_GOLDEN))
-def test_scalable_mode_matches_patched_reference(name):
+def test_scalable_mode_matches_patched_reference(name, scheduler):
     """The CUDA engine in mode S against the UNMODIFIED reference run with its randomness
     redirected to the mode S definitions (tests/golden/make_golden_scalable.py)."""
     case = SCALABLE_GOLDEN[name]
-    c, state, pop, params, endow, tags, eng = _engine(name, layout.RNG_SCALABLE, case["overrides"])
+    c, state, pop, params, endow, tags, eng = _engine(name, layout.RNG_SCALABLE, case["overrides"], scheduler)
     for rec in case["steps"]:
         eng.step(rec["t"], 0.0)
         d, snap = pu.state_digests_by_id(eng.download())
@@ -235,9 +257,10 @@ def test_env_step_properties_at_full_size():
 
 @pytest.mark.parametrize("workload", ["S1", "S2"])
 def test_state_invariants_at_full_size(workload):
-    """BASELINE's synthetic shapes, where neither the oracle nor the reference can follow: S1 = 4096 x 4096,
-    1.6 M agents, reproduction rules; S2 rules (combat_limited + replacement) on the same map size.  After
-    every step the state must be self-consistent (tests/invariants.py: occupancy points back, no shared
+    """BASELINE's synthetic shapes (the reference cannot instantiate them; the oracle comparison at this size
+    is test_full_size_steps_equal_the_oracle below): S1 = 4096 x 4096, 1.6 M agents, reproduction rules; S2
+    rules (combat_limited + replacement) on the same map size.  After every step the state must be
+    self-consistent (tests/invariants.py: occupancy points back, no shared
     cells, unique IDs, levels within capacity, the stats reduction agrees with the list) and the
     population must follow deaths, births and replacements."""
     import invariants
@@ -272,6 +295,54 @@ def test_state_invariants_at_full_size(workload):
             assert invariants.check_state(eng.download(), st) == population
         changed += int(st.n_dead) + int(st.n_born) + int(st.n_replaced)
     assert changed > 0          # the rules were exercised (deaths, births or replacements happened)
+    eng.close()
+
+
+@pytest.mark.parametrize("workload,scheduler,steps", [("S1", "dataflow", 5), ("S2", "dataflow", 4), ("S2", "rounds-ms2-e256", 3)])
+def test_full_size_steps_equal_the_oracle(workload, scheduler, steps):
+    """BASELINE configs[3] at full size (S1: 4096 x 4096, 1.6 M agents, reproduction rules) and the S2 rule set
+    (combat_limited + replacement, short lives so that replacement bites) on the same map: a few whole steps of
+    the CUDA engine against the sequential CPU oracle from the same initial state -- ID-sorted digests of every
+    agent field, the grid and the integer statistics."""
+    from oracle_binding import Oracle
+    from sugarscape_b200 import synthetic, steptables
+    from sugarscape_b200.engine import Engine
+    if workload == "S1":
+        n_agents = 1600000
+        c = synthetic.configuration(synthetic.S1_OPTIONS, {"timesteps": 1 << 20})
+    else:
+        n_agents = 1562500
+        c = synthetic.configuration(synthetic.S2_OPTIONS, {"environmentWidth": 4096, "environmentHeight": 4096,
+                                                           "startingAgents": n_agents, "agentReplacements": n_agents,
+                                                           "agentMaxAge": [2, 12], "timesteps": 1 << 20})
+    state, params = synthetic.build_state(c)
+    if workload == "S1":                    # fertile from the first step on: births inside the compared window
+        state.a_age[:n_agents] = 20
+    endow, tags = steptables.step_tables(1, 32, c["agentTagStringLength"])
+    eng = Engine(params, state, 0, endow, tags)
+    _set_scheduler(eng, scheduler)
+    ostate = state.copy()
+    orc = Oracle(params, ostate, endow, tags)
+    if c["agentReplacements"] > 0:
+        table = synthetic.endowment_table(state, n_agents)
+        eng.bind_endowments(table)
+        orc.bind_endowments(table)
+    changed = 0
+    for t in range(1, steps + 1):
+        eng.step(t, 0.0)
+        orc.env_step(t); orc.agent_step(t, 0.0); orc.compact(t)
+        if c["agentReplacements"] > 0:
+            orc.replace(t)
+        st_gpu, st_cpu = eng.stats(), orc.stats(t)
+        for field in ("population", "n_dead", "n_born", "n_replaced", "sum_age", "sum_vision", "sum_neighbors", "sum_valid_moves", "env_wealth_total"):
+            assert int(getattr(st_gpu, field)) == int(getattr(st_cpu, field)), f"stats.{field} at t={t}"
+        changed += int(st_gpu.n_dead) + int(st_gpu.n_born) + int(st_gpu.n_replaced)
+    assert int(eng.counters()[layout.C_OVERFLOW]) == 0
+    d_gpu, s_gpu = pu.state_digests_by_id(eng.download())
+    d_cpu, s_cpu = pu.state_digests_by_id(ostate)
+    for k in ("agents_int", "agents_f64", "agents_tags", "grid_int", "pollution"):
+        assert d_gpu[k] == d_cpu[k], f"{workload}: {k} differs from the oracle after {steps} steps"
+    assert changed > 0
     eng.close()
 
 

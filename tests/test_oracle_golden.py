@@ -508,3 +508,30 @@ def test_scalable_mode_oracle_matches_patched_reference(name):
         assert len(snap["a_id"]) == rec["population"], f"population differs at t={t}"
         for k in ("agents_int", "agents_f64", "agents_tags", "grid_int", "pollution"):
             assert d[k] == rec["digests"][k], f"{k} differs from the patched reference at t={t}"
+
+
+PLAIN_VARIANTS = ["pollution_diffusion_delay2", "pollution_diffusion_delay3"]
+
+
+@pytest.mark.parametrize("variant", PLAIN_VARIANTS)
+def test_oracle_plain_variants_match_reference_trajectory(variant):
+    """Shipped examples with option overrides that only touch rule families of ABI 1 (fixtures from the unmodified
+    reference, tests/golden/make_golden_variants.py).  pollution_diffusion_delay*: a diffusion timeframe that is
+    open from the first step with a delay > 1 -- the countdown of environment.py:192-197 fires on t = 2, 4, ..."""
+    base, overrides, gold, log = pu.load_variant(variant)
+    c, state, pop, params, endow, tags = pu.build(base, overrides=overrides)
+    orc = Oracle(params, state, endow, tags)
+    orc.set_mt_from_python()
+    d, _ = pu.state_digests(state, *orc.mt_state())
+    assert d == gold[0]["digests"], "t=0 state differs"
+    sb = stats.StatsBuilder(c, init.equator(c))
+    rs = sb.update(orc.stats(0), 0)
+    for t in range(1, len(gold)):
+        orc.env_step(t)
+        orc.agent_step(t, rs["meanWealth"])
+        orc.compact(t)
+        d, snap = pu.state_digests(state, *orc.mt_state())
+        assert d == gold[t]["digests"], f"state differs at t={t}"
+        rs = sb.update(orc.stats(t), t, 0)
+        for k in stats.LOG_KEYS:
+            assert _close(rs[k], log[t][k]), f"log key {k} differs at t={t}: {rs[k]} vs {log[t][k]}"
