@@ -508,11 +508,15 @@ int  ssb_set_step_tables(ssb_engine_t *e, const uint32_t *endow_bits, const uint
  *   SSB_SCHED_DATAFLOW (default on one GPU): the conflict DAG of the step is built once from the agents'
  *     start positions (csrc/ssb_flow_core.cuh) and executed as a dataflow without barriers;
  *   SSB_SCHED_ROUNDS: deterministic reservation rounds over a sliding priority prefix (round 1 kernel;
- *     sharded engines use it).  Environment override at bind time: SSB_SCHEDULER=rounds|dataflow. */
+ *     sharded engines use it).  Environment override at bind time: SSB_SCHEDULER=rounds|dataflow|generic. */
 #define SSB_SCHED_ROUNDS   0
 #define SSB_SCHED_DATAFLOW 1
+#define SSB_SCHED_DATAFLOW_GENERIC 2   /* the dataflow with the generic lane-group transaction even where the lean one applies */
 int  ssb_set_scheduler(ssb_engine_t *e, int32_t scheduler);
 int  ssb_get_scheduler(const ssb_engine_t *e);
+/* 1 if the agent step runs the lean transaction (csrc/ssb_lean.cuh: one thread per agent on packed 32-byte
+ * records; rule sets without tagging / trading / reproduction / tag preferences under SSB_SCHED_DATAFLOW) */
+int  ssb_uses_lean_transaction(const ssb_engine_t *e);
 
 /* mode S tuning (SSB_SCHED_ROUNDS): number of priority epochs of the sliding-prefix commit (power of two, default 128) */
 int  ssb_set_epochs(ssb_engine_t *e, int32_t epochs);

@@ -44,6 +44,10 @@ struct ssb_engine {
     FlowCtx flow;
     int flow_blocks, flow_build_blocks;
     int scheduler;           // SSB_SCHED_*
+    // lean transaction on packed records (ssb_lean.cuh): same DAG, one thread per agent, one queue per warp
+    bool lean_ok;
+    LeanCtx lean;
+    int lean_blocks, lean_queues, lean_queue_cap;
     // stats
     StatsPartial *d_partials;
     int n_partials;
@@ -175,7 +179,8 @@ void ssb_destroy(ssb_engine_t *e) {
                     e->d_born_list, e->rc.mark, e->rc.list_a, e->rc.list_b, e->rc.ready, e->rc.cnt, e->rc.trace, e->rc.bucketed, e->rc.epoch_count, e->rc.epoch_start, e->rc.epoch_fill,
                     e->d_partials, e->d_tribes, e->d_stats, e->d_ring, e->d_keys_a, e->d_keys_b, e->d_radix_hist,
                     e->d_lorenz_blocks, e->d_plan, e->d_cand, e->sh.peer_vals, e->sh.flags, e->d_shard_vals, e->d_migrate, e->d_eth_stats, e->d_ext_stats, e->d_group_stats, e->d_eth, e->d_ext,
-                    e->flow.desc, e->flow.entries, e->flow.dep, e->flow.span, e->flow.pool, e->flow.cursor, e->flow.queue, e->flow.tail, e->flow.tile_pop};
+                    e->flow.desc, e->flow.entries, e->flow.dep, e->flow.span, e->flow.pool, e->flow.cursor, e->flow.queue, e->flow.tail, e->flow.tile_pop,
+                    e->lean.a, e->lean.b, e->lean.c, e->lean.expect, e->lean.live};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < 5; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
     delete e;
@@ -253,9 +258,10 @@ int ssb_bind(ssb_engine_t *e, const ssb_grid_t *grid, const ssb_agents_t *agents
         FlowCtx &f = e->flow;
         f.rb = maxd; f.kb = flow_max_dilation(e->p.flags); f.halo = flow_halo(f.rb, f.kb);
         e->scheduler = SSB_SCHED_DATAFLOW;
-        if (const char *env = getenv("SSB_SCHEDULER")) e->scheduler = strcmp(env, "rounds") == 0 ? SSB_SCHED_ROUNDS : SSB_SCHED_DATAFLOW;
+        if (const char *env = getenv("SSB_SCHEDULER"))
+            e->scheduler = strcmp(env, "rounds") == 0 ? SSB_SCHED_ROUNDS : (strcmp(env, "generic") == 0 ? SSB_SCHED_DATAFLOW_GENERIC : SSB_SCHED_DATAFLOW);
         if (f.halo > FLOW_MAX_HALO || cap >= (1LL << FLOW_INDEX_BITS)) e->scheduler = SSB_SCHED_ROUNDS;
-        if (e->scheduler == SSB_SCHED_DATAFLOW) {
+        if (e->scheduler != SSB_SCHED_ROUNDS) {
             f.tiles_x = (e->p.width + FLOW_TX - 1) / FLOW_TX; f.tiles_y = (e->p.height + FLOW_TY - 1) / FLOW_TY;
             CU(cudaFuncSetAttribute(k_flow_execute, cudaFuncAttributeMaxDynamicSharedMemorySize, AGENT_SMEM_BYTES));
             CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_flow_execute, AGENT_THREADS, AGENT_SMEM_BYTES));
@@ -268,6 +274,30 @@ int ssb_bind(ssb_engine_t *e, const ssb_grid_t *grid, const ssb_agents_t *agents
             e->flow_build_blocks = per_sm * e->num_sms;
             f.n_queues = e->flow_blocks * AGENT_GROUPS;
             f.queue_cap = (int32_t)((cap + f.n_queues - 1) / f.n_queues) + 1;
+            size_t queue_words = (size_t)f.n_queues * f.queue_cap;
+            int tail_words = f.n_queues;
+            e->lean_ok = lean_supported(e->p) && 4 * maxd <= 32;
+            if (e->lean_ok) {
+                LeanCtx &L = e->lean;
+                L.maxc = 4 * maxd;
+                const int lean_smem = lean_smem_bytes(L.maxc, LEAN_THREADS);
+                CU(cudaFuncSetAttribute(k_lean_execute, cudaFuncAttributeMaxDynamicSharedMemorySize, lean_smem));
+                CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lean_execute, LEAN_THREADS, lean_smem));
+                if (per_sm < 1) return fail(e, -3, "the lean agent kernel does not fit on an SM (%d bytes of shared memory)", lean_smem);
+                e->lean_blocks = per_sm * e->num_sms;
+                e->lean_queues = e->lean_blocks * (LEAN_THREADS / 32);
+                e->lean_queue_cap = (int32_t)((cap + e->lean_queues - 1) / e->lean_queues) + 1;
+                if ((size_t)e->lean_queues * e->lean_queue_cap > queue_words) queue_words = (size_t)e->lean_queues * e->lean_queue_cap;
+                if (e->lean_queues > tail_words) tail_words = e->lean_queues;
+                CU(cudaMalloc(&L.a, sizeof(LeanA) * cap));
+                CU(cudaMemset(L.a, 0, sizeof(LeanA) * cap));
+                CU(cudaMalloc(&L.b, sizeof(LeanB) * cap));
+                CU(cudaMalloc(&L.c, sizeof(LeanC) * cap));
+                CU(cudaMalloc(&L.expect, sizeof(int32_t) * e->lean_queues));
+                CU(cudaMemset(L.expect, 0, sizeof(int32_t) * e->lean_queues));
+                CU(cudaMalloc(&L.live, sizeof(unsigned long long)));
+                CU(cudaMemset(L.live, 0, sizeof(unsigned long long)));
+            }
             long long pool = cap * 24;
             if (const char *env = getenv("SSB_FLOW_POOL_FACTOR")) pool = cap * (long long)atoi(env);
             if (pool > 0x7fffffffLL) pool = 0x7fffffffLL;
@@ -280,10 +310,10 @@ int ssb_bind(ssb_engine_t *e, const ssb_grid_t *grid, const ssb_agents_t *agents
             CU(cudaMalloc(&f.pool, sizeof(int32_t) * (size_t)pool));
             CU(cudaMalloc(&f.cursor, sizeof(unsigned long long) * 2));
             CU(cudaMemset(f.cursor, 0, sizeof(unsigned long long) * 2));
-            CU(cudaMalloc(&f.queue, sizeof(int32_t) * (size_t)f.n_queues * f.queue_cap));
-            CU(cudaMemset(f.queue, 0, sizeof(int32_t) * (size_t)f.n_queues * f.queue_cap));
-            CU(cudaMalloc(&f.tail, sizeof(int32_t) * f.n_queues));
-            CU(cudaMemset(f.tail, 0, sizeof(int32_t) * f.n_queues));
+            CU(cudaMalloc(&f.queue, sizeof(int32_t) * queue_words));
+            CU(cudaMemset(f.queue, 0, sizeof(int32_t) * queue_words));
+            CU(cudaMalloc(&f.tail, sizeof(int32_t) * tail_words));
+            CU(cudaMemset(f.tail, 0, sizeof(int32_t) * tail_words));
             CU(cudaMalloc(&f.tile_pop, sizeof(int32_t) * f.tiles_x * f.tiles_y));
             CU(cudaMemset(f.tile_pop, 0, sizeof(int32_t) * f.tiles_x * f.tiles_y));
         }
@@ -296,13 +326,16 @@ int ssb_bind(ssb_engine_t *e, const ssb_grid_t *grid, const ssb_agents_t *agents
 // reservation rounds, ssb_agent_step.cuh).  Both reproduce the sequential priority order bit for bit.
 int ssb_set_scheduler(ssb_engine_t *e, int32_t scheduler) {
     if (!e || !e->bound || e->p.rng_mode != SSB_RNG_SCALABLE) return fail(e, -1, "the scheduler choice needs a bound scalable engine");
-    if (scheduler != SSB_SCHED_ROUNDS && scheduler != SSB_SCHED_DATAFLOW) return fail(e, -1, "unknown scheduler %d", scheduler);
-    if (scheduler == SSB_SCHED_DATAFLOW && !e->flow.desc) return fail(e, -1, "the dataflow scheduler was not set up at bind time (range or capacity beyond its limits, or SSB_SCHEDULER=rounds)");
+    if (scheduler != SSB_SCHED_ROUNDS && scheduler != SSB_SCHED_DATAFLOW && scheduler != SSB_SCHED_DATAFLOW_GENERIC) return fail(e, -1, "unknown scheduler %d", scheduler);
+    if (scheduler != SSB_SCHED_ROUNDS && !e->flow.desc) return fail(e, -1, "the dataflow scheduler was not set up at bind time (range or capacity beyond its limits, or SSB_SCHEDULER=rounds)");
     e->scheduler = scheduler;
     return 0;
 }
 
 int ssb_get_scheduler(const ssb_engine_t *e) { return e ? e->scheduler : -1; }
+
+// 1 if the agent step of this engine runs the lean transaction on packed records (ssb_lean.cuh)
+int ssb_uses_lean_transaction(const ssb_engine_t *e) { return e && e->scheduler == SSB_SCHED_DATAFLOW && e->lean_ok && !e->sharded ? 1 : 0; }
 
 int ssb_set_mark_shift(ssb_engine_t *e, int32_t shift) {
     if (!e || !e->bound || e->p.rng_mode != SSB_RNG_SCALABLE) return fail(e, -1, "mark shift needs a bound scalable engine");
@@ -577,7 +610,18 @@ int ssb_agent_step(ssb_engine_t *e, int32_t t, double prev_mean_wealth, void *st
         if (e->ethics_bound || e->ext_bound) k_agent_step_exact<true><<<1, 32, 0, st>>>(c, e->d_mt);
         else k_agent_step_exact<false><<<1, 32, 0, st>>>(c, e->d_mt);
         LAUNCHED(e);
-    } else if (e->scheduler == SSB_SCHED_DATAFLOW && !e->sharded) {
+    } else if (e->scheduler == SSB_SCHED_DATAFLOW && e->lean_ok && !e->sharded) {
+        FlowCtx f = e->flow;
+        f.key = step_key(e->p.seed, t);
+        f.n_queues = e->lean_queues; f.queue_cap = e->lean_queue_cap;
+        LeanCtx L = e->lean;
+        k_lean_pack<<<e->lean_blocks, 256, 0, st>>>(c, f, L); LAUNCHED(e);       // threads = 32 * queues: one queue per thread
+        k_flow_build<<<e->flow_build_blocks, FLOW_BUILD_THREADS, flow_build_smem_bytes(f.halo), st>>>(c, f); LAUNCHED(e);
+        void *args[] = {&c, &f, &L};
+        CU(cudaLaunchCooperativeKernel((void *)k_lean_execute, dim3(e->lean_blocks), dim3(LEAN_THREADS), args, lean_smem_bytes(L.maxc, LEAN_THREADS), st));
+        LAUNCHED(e);
+        k_lean_unpack<<<e->num_sms * 8, 256, 0, st>>>(c, L); LAUNCHED(e);
+    } else if (e->scheduler != SSB_SCHED_ROUNDS && !e->sharded) {
         FlowCtx f = e->flow;
         f.key = step_key(e->p.seed, t);
         k_flow_prepare<<<e->num_sms * 8, 256, 0, st>>>(c, f); LAUNCHED(e);

@@ -47,6 +47,7 @@ def load_library():
     L.ssb_set_epochs.argtypes = [E, C.c_int32]
     L.ssb_set_scheduler.argtypes = [E, C.c_int32]
     L.ssb_get_scheduler.argtypes = [E]
+    L.ssb_uses_lean_transaction.argtypes = [E]
     L.ssb_set_mark_shift.argtypes = [E, C.c_int32]
     L.ssb_set_l2_persist.argtypes = [E, C.c_void_p, C.c_int32]
     L.ssb_env_step.argtypes = [E, C.c_int32, C.c_void_p]
@@ -102,7 +103,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = (
     "ssb_abi_version", "ssb_create", "ssb_bind", "ssb_destroy", "ssb_last_error",
-    "ssb_set_mt_state", "ssb_get_mt_state", "ssb_set_step_tables", "ssb_set_scheduler", "ssb_get_scheduler", "ssb_set_epochs", "ssb_set_mark_shift", "ssb_set_l2_persist",
+    "ssb_set_mt_state", "ssb_get_mt_state", "ssb_set_step_tables", "ssb_set_scheduler", "ssb_get_scheduler", "ssb_uses_lean_transaction", "ssb_set_epochs", "ssb_set_mark_shift", "ssb_set_l2_persist",
     "ssb_sizeof_params", "ssb_sizeof_grid", "ssb_sizeof_agents", "ssb_sizeof_stats",
     "ssb_env_step", "ssb_agent_step", "ssb_compact", "ssb_bind_endowments", "ssb_replace", "ssb_reduce_stats", "ssb_step", "ssb_stats", "ssb_stats_history",
     "ssb_fabric_create", "ssb_fabric_alloc", "ssb_fabric_map", "ssb_fabric_copy", "ssb_fabric_granularity",
@@ -368,11 +369,15 @@ class Engine:
         self._check(self.L.ssb_set_l2_persist(self.handle, self.stream, 1 if on else 0))
 
     def set_scheduler(self, name):
-        """Mode S scheduler: "dataflow" (static conflict DAG, default on one GPU) or "rounds" (reservation rounds)."""
-        self._check(self.L.ssb_set_scheduler(self.handle, {"rounds": 0, "dataflow": 1}[name]))
+        """Mode S scheduler: "dataflow" (static conflict DAG, default on one GPU; lean transaction where the rule set allows),
+        "generic" (the dataflow with the generic transaction) or "rounds" (reservation rounds)."""
+        self._check(self.L.ssb_set_scheduler(self.handle, {"rounds": 0, "dataflow": 1, "generic": 2}[name]))
 
     def scheduler(self):
-        return {0: "rounds", 1: "dataflow"}.get(int(self.L.ssb_get_scheduler(self.handle)), "n/a")
+        return {0: "rounds", 1: "dataflow", 2: "generic"}.get(int(self.L.ssb_get_scheduler(self.handle)), "n/a")
+
+    def uses_lean_transaction(self):
+        return bool(self.L.ssb_uses_lean_transaction(self.handle))
 
     def set_epochs(self, epochs):
         self._check(self.L.ssb_set_epochs(self.handle, epochs))
