@@ -115,6 +115,7 @@ typedef struct ssb_grid {
 #define SSB_C_ENDOW_INDEX 9 /* sugarscape.agentEndowmentIndex                                  */
 #define SSB_C_N_REPLACED 10 /* agents created by the last replacement                           */
 #define SSB_C_N_MIGRATED 11 /* sharded: agents this rank handed to other ranks in the last step */
+#define SSB_C_KIN_FREE 12  /* kin pool: first entry of the free chain + 1 (0: empty); entries of removed owners are recycled */
 #define SSB_C_COUNT    16
 
 typedef struct ssb_agents {
@@ -505,17 +506,22 @@ int  ssb_set_step_tables(ssb_engine_t *e, const uint32_t *endow_bits, const uint
 
 /* Mode S scheduler.  Both reproduce "agents act one at a time in ascending priority" (the reference's
  * random.shuffle + agent loop, sugarscape.py:400-407) bit for bit:
- *   SSB_SCHED_DATAFLOW (default on one GPU): the conflict DAG of the step is built once from the agents'
- *     start positions (csrc/ssb_flow_core.cuh) and executed as a dataflow without barriers;
- *   SSB_SCHED_ROUNDS: deterministic reservation rounds over a sliding priority prefix (round 1 kernel;
- *     sharded engines use it).  Environment override at bind time: SSB_SCHEDULER=rounds|dataflow|generic. */
+ *   SSB_SCHED_SWEEP (default on one GPU): the conflict DAG of the step is built once from the agents' start
+ *     positions (csrc/ssb_flow_core.cuh) as per-agent predecessor masks; a persistent grid walks the agents in
+ *     priority-bucket order and runs each one as soon as its predecessors' done bits are set
+ *     (csrc/ssb_sweep_core.cuh).  Rule sets without tagging / trading / reproduction run the lean transaction (one
+ *     thread per agent on packed 32-byte records); SSB_SCHED_SWEEP_GENERIC forces the generic one;
+ *   SSB_SCHED_DATAFLOW: the same DAG executed through ready queues and dependency counters (csrc/ssb_dataflow.cuh);
+ *   SSB_SCHED_ROUNDS: deterministic reservation rounds over a sliding priority prefix (round 1 kernel; sharded
+ *     engines use it).  Environment override at bind time: SSB_SCHEDULER=rounds|dataflow|sweep|sweep-generic. */
 #define SSB_SCHED_ROUNDS   0
 #define SSB_SCHED_DATAFLOW 1
-#define SSB_SCHED_DATAFLOW_GENERIC 2   /* the dataflow with the generic lane-group transaction even where the lean one applies */
+#define SSB_SCHED_SWEEP    3
+#define SSB_SCHED_SWEEP_GENERIC 4
 int  ssb_set_scheduler(ssb_engine_t *e, int32_t scheduler);
 int  ssb_get_scheduler(const ssb_engine_t *e);
-/* 1 if the agent step runs the lean transaction (csrc/ssb_lean.cuh: one thread per agent on packed 32-byte
- * records; rule sets without tagging / trading / reproduction / tag preferences under SSB_SCHED_DATAFLOW) */
+/* 1 if the agent step runs the lean transaction (csrc/ssb_sweep_core.cuh: one thread per agent on packed 32-byte
+ * records; rule sets without tagging / trading / reproduction / tag preferences under SSB_SCHED_SWEEP) */
 int  ssb_uses_lean_transaction(const ssb_engine_t *e);
 
 /* mode S tuning (SSB_SCHED_ROUNDS): number of priority epochs of the sliding-prefix commit (power of two, default 128) */

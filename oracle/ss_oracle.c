@@ -315,8 +315,14 @@ static double find_welfare(const ctx_t *c, int s, double sugar_reward, double sp
 /* kin lists: socialNetwork["children"] / ["mates"] of the initiating parent (agent.py:521-527) */
 static void kin_push(ctx_t *c, int32_t *head, int owner, int other) {
     int64_t *cn = c->a.counters;
-    if (cn[SSB_C_N_KIN] >= c->a.kin_capacity) { cn[SSB_C_OVERFLOW] = 3; return; }
-    int e = (int)cn[SSB_C_N_KIN]++;
+    int e;
+    if (cn[SSB_C_KIN_FREE] != 0) {               /* recycled entry of a removed owner */
+        e = (int)cn[SSB_C_KIN_FREE] - 1;
+        cn[SSB_C_KIN_FREE] = c->a.kin_next[e] + 1;
+    } else {
+        if (cn[SSB_C_N_KIN] >= c->a.kin_capacity) { cn[SSB_C_OVERFLOW] = 3; return; }
+        e = (int)cn[SSB_C_N_KIN]++;
+    }
     c->a.kin_slot[e] = other; c->a.kin_id[e] = c->a.id[other]; c->a.kin_next[e] = head[owner];
     head[owner] = e;
 }
@@ -1694,6 +1700,10 @@ static int cmp_i64(const void *x, const void *y) {
 
 /* removeDeadAgents, sugarscape.py:843-853: order-preserving; dead slots are recycled.
  * Mode S additionally numbers this step's newborn in cell order ("mode S"). */
+/* tests/hostemu: lending lives in the host-compiled device source there, and so do the dead creditors' children lists */
+static int g_keep_children_lists = 0;
+void orc_keep_children_lists(int on) { g_keep_children_lists = on; }
+
 void orc_compact(const ssb_params_t *p, const ssb_grid_t *g, const ssb_agents_t *a, int32_t t) {
     ctx_t c;
     make_ctx(&c, p, g, a, NULL, t);
@@ -1709,6 +1719,20 @@ void orc_compact(const ssb_params_t *p, const ssb_grid_t *g, const ssb_agents_t 
     for (int64_t i = 0; i < nd; i++) a->free_slots[cn[SSB_C_N_FREE]++] = a->dead_list[i];
     cn[SSB_C_N_LIST] = w;
     cn[SSB_C_N_DEAD] = nd;
+    if (p->rng_mode == SSB_RNG_EXACT && a->children_head && a->kin_next) {
+        /* the kin lists of a removed agent die with it: their pool entries go to the free chain */
+        int64_t free_head = cn[SSB_C_KIN_FREE] - 1;
+        for (int64_t i = 0; i < nd; i++) {
+            int s = a->dead_list[i];
+            for (int list = (g_lend || g_keep_children_lists) ? 1 : 0; list < 2; list++) {      /* a dead creditor's children inherit its loans: those lists stay */
+                int32_t *head = list == 0 ? a->children_head : a->mates_head;
+                int e = head[s];
+                while (e >= 0) { int nx = a->kin_next[e]; a->kin_next[e] = (int32_t)free_head; free_head = e; e = nx; }
+                head[s] = -1;
+            }
+        }
+        cn[SSB_C_KIN_FREE] = free_head + 1;
+    }
     if (p->rng_mode == SSB_RNG_SCALABLE) {
         /* newborn survivors: re-ordered and numbered by cell index */
         int64_t first = w;

@@ -7,8 +7,11 @@
 #include <string.h>
 
 #include "../../include/ssb.h"
+#include <vector>
+
 #include "ssb_agent_step.cuh"
 #include "ssb_dataflow.cuh"
+#include "ssb_sweep.cuh"
 #include "ssb_kernels.cuh"
 #include <stdlib.h>
 #include "ssb_sort.cuh"
@@ -40,14 +43,17 @@ struct ssb_engine {
     // mode S rounds
     RoundCtx rc;
     int coop_blocks;
-    // mode S dataflow (ssb_dataflow.cuh)
+    // mode S dataflow (ssb_dataflow.cuh): set up on demand (ssb_set_scheduler / SSB_SCHEDULER=dataflow)
     FlowCtx flow;
     int flow_blocks, flow_build_blocks;
     int scheduler;           // SSB_SCHED_*
-    // lean transaction on packed records (ssb_lean.cuh): same DAG, one thread per agent, one queue per warp
-    bool lean_ok;
+    // mode S ordered sweep (ssb_sweep.cuh, default on one GPU); lean transaction on packed records where the rule set allows
+    bool sweep_ok, lean_ok, sweep_fenced;
+    SweepCtx sweep;
     LeanCtx lean;
-    int lean_blocks, lean_queues, lean_queue_cap;
+    int sweep_prepare_blocks, sweep_build_blocks, sweep_lean_blocks, sweep_generic_blocks;
+    size_t sweep_done_bytes;
+    int sweep_bits_generic, sweep_bits_lean;
     // stats
     StatsPartial *d_partials;
     int n_partials;
@@ -180,10 +186,128 @@ void ssb_destroy(ssb_engine_t *e) {
                     e->d_partials, e->d_tribes, e->d_stats, e->d_ring, e->d_keys_a, e->d_keys_b, e->d_radix_hist,
                     e->d_lorenz_blocks, e->d_plan, e->d_cand, e->sh.peer_vals, e->sh.flags, e->d_shard_vals, e->d_migrate, e->d_eth_stats, e->d_ext_stats, e->d_group_stats, e->d_eth, e->d_ext,
                     e->flow.desc, e->flow.entries, e->flow.dep, e->flow.span, e->flow.pool, e->flow.cursor, e->flow.queue, e->flow.tail, e->flow.tile_pop,
-                    e->lean.a, e->lean.b, e->lean.c, e->lean.expect, e->lean.live};
+                    e->sweep.desc, e->sweep.entries, e->sweep.preds, e->sweep.done, e->sweep.bucket_count, e->sweep.bucket_start, e->sweep.bucket_fill,
+                    e->sweep.tile_pop, e->sweep.ctl, (void *)e->sweep.tables, e->lean.a, e->lean.b};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < 5; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
     delete e;
+}
+
+// The queue dataflow (ssb_dataflow.cuh): descriptor word per cell, DAG arrays per list entry.  Set up on first use.
+static int setup_flow(ssb_engine *e) {
+    FlowCtx &f = e->flow;
+    if (f.desc) return 0;
+    const int64_t cap = e->ctx.a.capacity, cells = e->ctx.g.n_cells;
+    const int maxd = e->ctx.max_dx > e->ctx.max_dy ? e->ctx.max_dx : e->ctx.max_dy;
+    f.rb = maxd; f.kb = flow_max_dilation(e->p.flags); f.halo = flow_halo(f.rb, f.kb);
+    if (f.halo > FLOW_MAX_HALO || cap >= (1LL << FLOW_INDEX_BITS)) return fail(e, -1, "the dataflow scheduler does not cover this engine (range or capacity beyond its limits)");
+    int per_sm = 0;
+    f.tiles_x = (e->p.width + FLOW_TX - 1) / FLOW_TX; f.tiles_y = (e->p.height + FLOW_TY - 1) / FLOW_TY;
+    CU(cudaFuncSetAttribute(k_flow_execute, cudaFuncAttributeMaxDynamicSharedMemorySize, AGENT_SMEM_BYTES));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_flow_execute, AGENT_THREADS, AGENT_SMEM_BYTES));
+    if (per_sm < 1) return fail(e, -3, "the dataflow kernel does not fit on an SM");
+    e->flow_blocks = per_sm * e->num_sms;
+    const int build_smem = flow_build_smem_bytes(f.halo);
+    CU(cudaFuncSetAttribute(k_flow_build, cudaFuncAttributeMaxDynamicSharedMemorySize, build_smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_flow_build, FLOW_BUILD_THREADS, build_smem));
+    if (per_sm < 1) return fail(e, -3, "the DAG build kernel does not fit on an SM (%d bytes of shared memory)", build_smem);
+    e->flow_build_blocks = per_sm * e->num_sms;
+    f.n_queues = e->flow_blocks * AGENT_GROUPS;
+    f.queue_cap = (int32_t)((cap + f.n_queues - 1) / f.n_queues) + 1;
+    const size_t queue_words = (size_t)f.n_queues * f.queue_cap;
+    long long pool = cap * 24;
+    if (const char *env = getenv("SSB_FLOW_POOL_FACTOR")) pool = cap * (long long)atoi(env);
+    if (pool > 0x7fffffffLL) pool = 0x7fffffffLL;
+    f.pool_capacity = pool;
+    CU(cudaMalloc(&f.desc, sizeof(unsigned long long) * (size_t)cells));
+    CU(cudaMemset(f.desc, 0, sizeof(unsigned long long) * (size_t)cells));
+    CU(cudaMalloc(&f.entries, sizeof(int4) * cap));
+    CU(cudaMalloc(&f.dep, sizeof(int32_t) * cap));
+    CU(cudaMalloc(&f.span, sizeof(int2) * cap));
+    CU(cudaMalloc(&f.pool, sizeof(int32_t) * (size_t)pool));
+    CU(cudaMalloc(&f.cursor, sizeof(unsigned long long) * 2));
+    CU(cudaMemset(f.cursor, 0, sizeof(unsigned long long) * 2));
+    CU(cudaMalloc(&f.queue, sizeof(int32_t) * queue_words));
+    CU(cudaMemset(f.queue, 0, sizeof(int32_t) * queue_words));
+    CU(cudaMalloc(&f.tail, sizeof(int32_t) * f.n_queues));
+    CU(cudaMemset(f.tail, 0, sizeof(int32_t) * f.n_queues));
+    CU(cudaMalloc(&f.tile_pop, sizeof(int32_t) * f.tiles_x * f.tiles_y));
+    CU(cudaMemset(f.tile_pop, 0, sizeof(int32_t) * f.tiles_x * f.tiles_y));
+    return 0;
+}
+
+// The ordered sweep (ssb_sweep.cuh).  e->sweep_ok stays false when the engine is outside its limits (the rounds
+// scheduler then stays the default); a negative return is a real error.
+static int setup_sweep(ssb_engine *e, int maxd) {
+    SweepCtx &w = e->sweep;
+    const int64_t cap = e->ctx.a.capacity, cells = e->ctx.g.n_cells;
+    w.rb = maxd; w.kb = flow_max_dilation(e->p.flags); w.halo = flow_halo(w.rb, w.kb);
+    e->sweep_ok = false;
+    if (w.halo > SWEEP_MAX_HALO || w.halo >= e->p.width || w.halo >= e->p.height || maxd > SWEEP_MAX_RANGE || cells >= (1LL << 32) - 64) return 0;
+    int per_sm = 0;
+    w.tiles_x = (e->p.width + FLOW_TX - 1) / FLOW_TX; w.tiles_y = (e->p.height + FLOW_TY - 1) / FLOW_TY;
+    e->lean_ok = lean_supported(e->p) && 4 * maxd <= 32;
+    const int prepare_smem = sweep_prepare_smem_bytes(SWEEP_MAX_KEYS);
+    CU(cudaFuncSetAttribute(k_sweep_prepare<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, prepare_smem));
+    CU(cudaFuncSetAttribute(k_sweep_prepare<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, prepare_smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_prepare<false>, SWEEP_PREPARE_THREADS, prepare_smem));
+    int per_sm_lean = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_lean, k_sweep_prepare<true>, SWEEP_PREPARE_THREADS, prepare_smem));
+    if (per_sm_lean < per_sm) per_sm = per_sm_lean;
+    if (per_sm < 1) return fail(e, -3, "the sweep's prepare kernel does not fit on an SM");
+    e->sweep_prepare_blocks = (per_sm > 4 ? 4 : per_sm) * e->num_sms;
+    const int build_smem = sweep_build_smem_bytes(w.rb, w.kb, w.halo);
+    CU(cudaFuncSetAttribute(k_sweep_build, cudaFuncAttributeMaxDynamicSharedMemorySize, build_smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_build, SWEEP_BUILD_THREADS, build_smem));
+    if (per_sm < 1) return fail(e, -3, "the sweep's build kernel does not fit on an SM (%d bytes of shared memory)", build_smem);
+    e->sweep_build_blocks = per_sm * e->num_sms;
+    CU(cudaFuncSetAttribute(k_sweep_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, AGENT_SMEM_BYTES));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_generic, AGENT_THREADS, AGENT_SMEM_BYTES));
+    if (per_sm < 1) return fail(e, -3, "the sweep kernel does not fit on an SM");
+    e->sweep_generic_blocks = per_sm * e->num_sms;
+    long long concurrent = (long long)e->sweep_generic_blocks * AGENT_GROUPS;
+    if (e->lean_ok) {
+        LeanCtx &L = e->lean;
+        L.maxc = 4 * maxd;
+        const int lean_smem = lean_smem_bytes(L.maxc, LEAN_THREADS);
+        CU(cudaFuncSetAttribute(k_sweep_lean<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lean_smem));
+        CU(cudaFuncSetAttribute(k_sweep_lean<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lean_smem));
+        e->sweep_fenced = getenv("SSB_SWEEP_FENCED") && atoi(getenv("SSB_SWEEP_FENCED")) != 0;
+        if (e->sweep_fenced) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_lean<true>, LEAN_THREADS, lean_smem));
+        else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_lean<false>, LEAN_THREADS, lean_smem));
+        if (per_sm < 1) return fail(e, -3, "the lean sweep kernel does not fit on an SM (%d bytes of shared memory)", lean_smem);
+        e->sweep_lean_blocks = per_sm * e->num_sms;
+        CU(cudaMalloc(&L.a, sizeof(LeanA) * cap));
+        CU(cudaMemset(L.a, 0, sizeof(LeanA) * cap));
+        CU(cudaMalloc(&L.b, sizeof(LeanB) * cap));
+    }
+    // priority buckets: sized for a full agent array and the grid that will walk them
+    e->sweep_bits_generic = sweep_bucket_bits(cap, concurrent, e->p.id_bits, SWEEP_MAX_KEY_BITS);
+    e->sweep_bits_lean = e->lean_ok ? sweep_bucket_bits(cap, (long long)e->sweep_lean_blocks * LEAN_THREADS, e->p.id_bits, SWEEP_MAX_KEY_BITS - SWEEP_LEAN_SUB_BITS) : 0;
+    CU(cudaMalloc(&w.desc, sizeof(unsigned long long) * (size_t)cells));
+    CU(cudaMemset(w.desc, 0, sizeof(unsigned long long) * (size_t)cells));
+    CU(cudaMalloc(&w.entries, sizeof(int4) * cap));
+    CU(cudaMalloc(&w.preds, sizeof(uint32_t) * SWEEP_COLS * (size_t)cap));
+    e->sweep_done_bytes = sizeof(uint32_t) * ((size_t)cells / 32 + 2);
+    CU(cudaMalloc(&w.done, e->sweep_done_bytes));
+    CU(cudaMalloc(&w.bucket_count, sizeof(int32_t) * (SWEEP_MAX_KEYS + 1)));
+    CU(cudaMalloc(&w.bucket_start, sizeof(int32_t) * (SWEEP_MAX_KEYS + 1)));
+    CU(cudaMalloc(&w.bucket_fill, sizeof(int32_t) * (SWEEP_MAX_KEYS + 1)));
+    CU(cudaMalloc(&w.tile_pop, sizeof(int32_t) * w.tiles_x * w.tiles_y));
+    CU(cudaMemset(w.tile_pop, 0, sizeof(int32_t) * w.tiles_x * w.tiles_y));
+    CU(cudaMalloc(&w.ctl, sizeof(unsigned long long) * 4));
+    CU(cudaMemset(w.ctl, 0, sizeof(unsigned long long) * 4));
+    {
+        const int bytes = sweep_tables_bytes(w.rb, w.kb, w.halo);
+        std::vector<int8_t> host_tables(bytes, 0);
+        sweep_fill_tables(w.rb, w.kb, w.halo, host_tables.data(), host_tables.data() + sweep_any_size(w.rb, w.kb, w.halo));
+        int8_t *d_tables = nullptr;
+        CU(cudaMalloc(&d_tables, bytes));
+        CU(cudaMemcpy(d_tables, host_tables.data(), bytes, cudaMemcpyHostToDevice));
+        w.tables = d_tables;
+    }
+    e->sweep_ok = true;
+    return 0;
 }
 
 int ssb_bind(ssb_engine_t *e, const ssb_grid_t *grid, const ssb_agents_t *agents) {
@@ -254,88 +378,46 @@ int ssb_bind(ssb_engine_t *e, const ssb_grid_t *grid, const ssb_agents_t *agents
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_agent_step_scalable, AGENT_THREADS, AGENT_SMEM_BYTES));
         if (per_sm < 1) return fail(e, -3, "cooperative kernel does not fit on an SM");
         e->coop_blocks = per_sm * e->num_sms;
-        // the dataflow scheduler (default on one GPU): descriptor word per cell, DAG arrays per list entry
-        FlowCtx &f = e->flow;
-        f.rb = maxd; f.kb = flow_max_dilation(e->p.flags); f.halo = flow_halo(f.rb, f.kb);
-        e->scheduler = SSB_SCHED_DATAFLOW;
-        if (const char *env = getenv("SSB_SCHEDULER"))
-            e->scheduler = strcmp(env, "rounds") == 0 ? SSB_SCHED_ROUNDS : (strcmp(env, "generic") == 0 ? SSB_SCHED_DATAFLOW_GENERIC : SSB_SCHED_DATAFLOW);
-        if (f.halo > FLOW_MAX_HALO || cap >= (1LL << FLOW_INDEX_BITS)) e->scheduler = SSB_SCHED_ROUNDS;
-        if (e->scheduler != SSB_SCHED_ROUNDS) {
-            f.tiles_x = (e->p.width + FLOW_TX - 1) / FLOW_TX; f.tiles_y = (e->p.height + FLOW_TY - 1) / FLOW_TY;
-            CU(cudaFuncSetAttribute(k_flow_execute, cudaFuncAttributeMaxDynamicSharedMemorySize, AGENT_SMEM_BYTES));
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_flow_execute, AGENT_THREADS, AGENT_SMEM_BYTES));
-            if (per_sm < 1) return fail(e, -3, "the dataflow kernel does not fit on an SM");
-            e->flow_blocks = per_sm * e->num_sms;
-            const int build_smem = flow_build_smem_bytes(f.halo);
-            CU(cudaFuncSetAttribute(k_flow_build, cudaFuncAttributeMaxDynamicSharedMemorySize, build_smem));
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_flow_build, FLOW_BUILD_THREADS, build_smem));
-            if (per_sm < 1) return fail(e, -3, "the DAG build kernel does not fit on an SM (%d bytes of shared memory)", build_smem);
-            e->flow_build_blocks = per_sm * e->num_sms;
-            f.n_queues = e->flow_blocks * AGENT_GROUPS;
-            f.queue_cap = (int32_t)((cap + f.n_queues - 1) / f.n_queues) + 1;
-            size_t queue_words = (size_t)f.n_queues * f.queue_cap;
-            int tail_words = f.n_queues;
-            e->lean_ok = lean_supported(e->p) && 4 * maxd <= 32;
-            if (e->lean_ok) {
-                LeanCtx &L = e->lean;
-                L.maxc = 4 * maxd;
-                const int lean_smem = lean_smem_bytes(L.maxc, LEAN_THREADS);
-                CU(cudaFuncSetAttribute(k_lean_execute, cudaFuncAttributeMaxDynamicSharedMemorySize, lean_smem));
-                CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lean_execute, LEAN_THREADS, lean_smem));
-                if (per_sm < 1) return fail(e, -3, "the lean agent kernel does not fit on an SM (%d bytes of shared memory)", lean_smem);
-                e->lean_blocks = per_sm * e->num_sms;
-                e->lean_queues = e->lean_blocks * (LEAN_THREADS / 32);
-                e->lean_queue_cap = (int32_t)((cap + e->lean_queues - 1) / e->lean_queues) + 1;
-                if ((size_t)e->lean_queues * e->lean_queue_cap > queue_words) queue_words = (size_t)e->lean_queues * e->lean_queue_cap;
-                if (e->lean_queues > tail_words) tail_words = e->lean_queues;
-                CU(cudaMalloc(&L.a, sizeof(LeanA) * cap));
-                CU(cudaMemset(L.a, 0, sizeof(LeanA) * cap));
-                CU(cudaMalloc(&L.b, sizeof(LeanB) * cap));
-                CU(cudaMalloc(&L.c, sizeof(LeanC) * cap));
-                CU(cudaMalloc(&L.expect, sizeof(int32_t) * e->lean_queues));
-                CU(cudaMemset(L.expect, 0, sizeof(int32_t) * e->lean_queues));
-                CU(cudaMalloc(&L.live, sizeof(unsigned long long)));
-                CU(cudaMemset(L.live, 0, sizeof(unsigned long long)));
-            }
-            long long pool = cap * 24;
-            if (const char *env = getenv("SSB_FLOW_POOL_FACTOR")) pool = cap * (long long)atoi(env);
-            if (pool > 0x7fffffffLL) pool = 0x7fffffffLL;
-            f.pool_capacity = pool;
-            CU(cudaMalloc(&f.desc, sizeof(unsigned long long) * (size_t)cells));
-            CU(cudaMemset(f.desc, 0, sizeof(unsigned long long) * (size_t)cells));
-            CU(cudaMalloc(&f.entries, sizeof(int4) * cap));
-            CU(cudaMalloc(&f.dep, sizeof(int32_t) * cap));
-            CU(cudaMalloc(&f.span, sizeof(int2) * cap));
-            CU(cudaMalloc(&f.pool, sizeof(int32_t) * (size_t)pool));
-            CU(cudaMalloc(&f.cursor, sizeof(unsigned long long) * 2));
-            CU(cudaMemset(f.cursor, 0, sizeof(unsigned long long) * 2));
-            CU(cudaMalloc(&f.queue, sizeof(int32_t) * queue_words));
-            CU(cudaMemset(f.queue, 0, sizeof(int32_t) * queue_words));
-            CU(cudaMalloc(&f.tail, sizeof(int32_t) * tail_words));
-            CU(cudaMemset(f.tail, 0, sizeof(int32_t) * tail_words));
-            CU(cudaMalloc(&f.tile_pop, sizeof(int32_t) * f.tiles_x * f.tiles_y));
-            CU(cudaMemset(f.tile_pop, 0, sizeof(int32_t) * f.tiles_x * f.tiles_y));
+        // schedulers beyond the rounds: the ordered sweep (default on one GPU) and the queue dataflow (on demand)
+        e->scheduler = SSB_SCHED_ROUNDS;
+        int rc_sweep = setup_sweep(e, maxd);
+        if (rc_sweep < 0) return rc_sweep;
+        if (e->sweep_ok) e->scheduler = SSB_SCHED_SWEEP;
+        if (const char *env = getenv("SSB_SCHEDULER")) {
+            int want = e->scheduler;
+            if (strcmp(env, "rounds") == 0) want = SSB_SCHED_ROUNDS;
+            else if (strcmp(env, "dataflow") == 0) want = SSB_SCHED_DATAFLOW;
+            else if (strcmp(env, "sweep") == 0) want = SSB_SCHED_SWEEP;
+            else if (strcmp(env, "sweep-generic") == 0) want = SSB_SCHED_SWEEP_GENERIC;
+            else return fail(e, -1, "SSB_SCHEDULER=%s: expected rounds, dataflow, sweep or sweep-generic", env);
+            e->bound = true;
+            const int rc_set = ssb_set_scheduler(e, want);
+            if (rc_set != 0) { e->bound = false; return rc_set; }
         }
     }
     e->bound = true;
     return 0;
 }
 
-// Mode S scheduler: SSB_SCHED_DATAFLOW (static conflict DAG, ssb_dataflow.cuh) or SSB_SCHED_ROUNDS (deterministic
-// reservation rounds, ssb_agent_step.cuh).  Both reproduce the sequential priority order bit for bit.
+// Mode S scheduler: SSB_SCHED_SWEEP (ordered sweep over the static conflict DAG, ssb_sweep.cuh), SSB_SCHED_DATAFLOW
+// (the same DAG through ready queues, ssb_dataflow.cuh) or SSB_SCHED_ROUNDS (deterministic reservation rounds,
+// ssb_agent_step.cuh).  All reproduce the sequential priority order bit for bit.
 int ssb_set_scheduler(ssb_engine_t *e, int32_t scheduler) {
     if (!e || !e->bound || e->p.rng_mode != SSB_RNG_SCALABLE) return fail(e, -1, "the scheduler choice needs a bound scalable engine");
-    if (scheduler != SSB_SCHED_ROUNDS && scheduler != SSB_SCHED_DATAFLOW && scheduler != SSB_SCHED_DATAFLOW_GENERIC) return fail(e, -1, "unknown scheduler %d", scheduler);
-    if (scheduler != SSB_SCHED_ROUNDS && !e->flow.desc) return fail(e, -1, "the dataflow scheduler was not set up at bind time (range or capacity beyond its limits, or SSB_SCHEDULER=rounds)");
+    if (scheduler == SSB_SCHED_SWEEP || scheduler == SSB_SCHED_SWEEP_GENERIC) {
+        if (!e->sweep_ok) return fail(e, -1, "the sweep scheduler does not cover this engine (conflict reach %d beyond %d cells or beyond the map, or too many agents)", e->sweep.halo, SWEEP_MAX_HALO);
+    } else if (scheduler == SSB_SCHED_DATAFLOW) {
+        const int rc = setup_flow(e);
+        if (rc != 0) return rc;
+    } else if (scheduler != SSB_SCHED_ROUNDS) return fail(e, -1, "unknown scheduler %d", scheduler);
     e->scheduler = scheduler;
     return 0;
 }
 
 int ssb_get_scheduler(const ssb_engine_t *e) { return e ? e->scheduler : -1; }
 
-// 1 if the agent step of this engine runs the lean transaction on packed records (ssb_lean.cuh)
-int ssb_uses_lean_transaction(const ssb_engine_t *e) { return e && e->scheduler == SSB_SCHED_DATAFLOW && e->lean_ok && !e->sharded ? 1 : 0; }
+// 1 if the agent step of this engine runs the lean transaction on packed records (ssb_sweep_core.cuh)
+int ssb_uses_lean_transaction(const ssb_engine_t *e) { return e && e->scheduler == SSB_SCHED_SWEEP && e->lean_ok && !e->sharded ? 1 : 0; }
 
 int ssb_set_mark_shift(ssb_engine_t *e, int32_t shift) {
     if (!e || !e->bound || e->p.rng_mode != SSB_RNG_SCALABLE) return fail(e, -1, "mark shift needs a bound scalable engine");
@@ -610,18 +692,31 @@ int ssb_agent_step(ssb_engine_t *e, int32_t t, double prev_mean_wealth, void *st
         if (e->ethics_bound || e->ext_bound) k_agent_step_exact<true><<<1, 32, 0, st>>>(c, e->d_mt);
         else k_agent_step_exact<false><<<1, 32, 0, st>>>(c, e->d_mt);
         LAUNCHED(e);
-    } else if (e->scheduler == SSB_SCHED_DATAFLOW && e->lean_ok && !e->sharded) {
-        FlowCtx f = e->flow;
-        f.key = step_key(e->p.seed, t);
-        f.n_queues = e->lean_queues; f.queue_cap = e->lean_queue_cap;
+    } else if ((e->scheduler == SSB_SCHED_SWEEP || e->scheduler == SSB_SCHED_SWEEP_GENERIC) && !e->sharded) {
+        SweepCtx w = e->sweep;
+        w.key = step_key(e->p.seed, t);
         LeanCtx L = e->lean;
-        k_lean_pack<<<e->lean_blocks, 256, 0, st>>>(c, f, L); LAUNCHED(e);       // threads = 32 * queues: one queue per thread
-        k_flow_build<<<e->flow_build_blocks, FLOW_BUILD_THREADS, flow_build_smem_bytes(f.halo), st>>>(c, f); LAUNCHED(e);
-        void *args[] = {&c, &f, &L};
-        CU(cudaLaunchCooperativeKernel((void *)k_lean_execute, dim3(e->lean_blocks), dim3(LEAN_THREADS), args, lean_smem_bytes(L.maxc, LEAN_THREADS), st));
+        const bool lean = e->scheduler == SSB_SCHED_SWEEP && e->lean_ok;
+        w.concurrent = lean ? e->sweep_lean_blocks * LEAN_THREADS : e->sweep_generic_blocks * AGENT_GROUPS;
+        w.bucket_bits = lean ? e->sweep_bits_lean : e->sweep_bits_generic;
+        w.n_keys = (1 << w.bucket_bits) << (lean ? SWEEP_LEAN_SUB_BITS : 0);
+        CU(cudaMemsetAsync(w.done, 0, e->sweep_done_bytes, st));
+        void *pargs[] = {&c, &w, &L};
+        CU(cudaLaunchCooperativeKernel(lean ? (void *)k_sweep_prepare<true> : (void *)k_sweep_prepare<false>, dim3(e->sweep_prepare_blocks),
+                                       dim3(SWEEP_PREPARE_THREADS), pargs, sweep_prepare_smem_bytes(w.n_keys), st));
         LAUNCHED(e);
-        k_lean_unpack<<<e->num_sms * 8, 256, 0, st>>>(c, L); LAUNCHED(e);
-    } else if (e->scheduler != SSB_SCHED_ROUNDS && !e->sharded) {
+        k_sweep_build<<<e->sweep_build_blocks, SWEEP_BUILD_THREADS, sweep_build_smem_bytes(w.rb, w.kb, w.halo), st>>>(c, w); LAUNCHED(e);
+        k_sweep_clear<<<e->num_sms * 8, 256, 0, st>>>(c, w); LAUNCHED(e);
+        if (lean) {
+            CU(cudaLaunchCooperativeKernel(e->sweep_fenced ? (void *)k_sweep_lean<true> : (void *)k_sweep_lean<false>, dim3(e->sweep_lean_blocks), dim3(LEAN_THREADS), pargs, lean_smem_bytes(L.maxc, LEAN_THREADS), st));
+            LAUNCHED(e);
+            k_lean_unpack<<<e->num_sms * 8, 256, 0, st>>>(c, L); LAUNCHED(e);
+        } else {
+            void *args[] = {&c, &w};
+            CU(cudaLaunchCooperativeKernel((void *)k_sweep_generic, dim3(e->sweep_generic_blocks), dim3(AGENT_THREADS), args, AGENT_SMEM_BYTES, st));
+            LAUNCHED(e);
+        }
+    } else if (e->scheduler == SSB_SCHED_DATAFLOW && !e->sharded) {
         FlowCtx f = e->flow;
         f.key = step_key(e->p.seed, t);
         k_flow_prepare<<<e->num_sms * 8, 256, 0, st>>>(c, f); LAUNCHED(e);
@@ -654,6 +749,7 @@ int ssb_compact(ssb_engine_t *e, int32_t t, void *stream_) {
     LAUNCHED(e);
     k_compact_finish<<<grid_for(cap, 256, e->num_sms * 4), 256, 0, st>>>(c, e->d_new_order, e->d_scalars + 0); LAUNCHED(e);
     k_compact_counters<<<1, 1, 0, st>>>(c, e->d_scalars + 0); LAUNCHED(e);
+    if (e->p.rng_mode == SSB_RNG_EXACT) { k_kin_reclaim<<<1, 1, 0, st>>>(c); LAUNCHED(e); }
     if (e->p.rng_mode == SSB_RNG_SCALABLE && (e->p.flags & SSB_F_REPRO)) {
         const long long my_cells = e->sharded ? e->sh.cell_hi - e->sh.cell_lo : c.g.n_cells;     // d_scalars[2]
         const int ctiles = (int)((my_cells + COMPACT_TILE - 1) / COMPACT_TILE);
@@ -889,12 +985,26 @@ int ssb_step(ssb_engine_t *e, int32_t t, double prev_mean_wealth, void *stream) 
     return step_tail(e, t, stream);
 }
 
+// counters[SSB_C_OVERFLOW] != 0: a capacity was exceeded or a scheduler gave up -- the state is no longer the
+// reference's.  Every stats read (one per step in the drop-in driver) checks it, so no run continues silently.
+static int check_overflow(ssb_engine_t *e) {
+    long long code = 0;
+    CU(cudaMemcpy(&code, e->ctx.a.counters + SSB_C_OVERFLOW, sizeof(code), cudaMemcpyDeviceToHost));
+    if (code == 0) return e->sharded && ssb_shard_broken(e) ? fail(e, -4, "a peer of the sharded run was lost (ssb_shard_broken)") : 0;
+    static const char *what[] = {"", "agent capacity exceeded: births were dropped", "the commit rounds did not terminate",
+                                 "kin pool exhausted: children / mates were not recorded", "", "", "", "a peer of the sharded run was lost",
+                                 "migration outbox overflow", "successor pool of the dataflow scheduler exhausted",
+                                 "a scheduler made no progress for seconds", "live slots differ from the agent list",
+                                 "a priority bucket of the sweep is longer than its grid"};
+    return fail(e, -4, "engine overflow code %lld: %s", code, code > 0 && code < 13 ? what[code] : "?");
+}
+
 int ssb_stats(ssb_engine_t *e, ssb_stats_t *host_out) {
     CHECK_BOUND(e);
     if (!host_out) return -1;
     CU(cudaDeviceSynchronize());
     CU(cudaMemcpy(host_out, e->d_stats, sizeof(ssb_stats_t), cudaMemcpyDeviceToHost));
-    return 0;
+    return check_overflow(e);
 }
 
 int ssb_stats_history(ssb_engine_t *e, int32_t t, ssb_stats_t *host_out) {
@@ -903,7 +1013,7 @@ int ssb_stats_history(ssb_engine_t *e, int32_t t, ssb_stats_t *host_out) {
     CU(cudaDeviceSynchronize());
     CU(cudaMemcpy(host_out, e->d_ring + (((t % SSB_STATS_RING) + SSB_STATS_RING) % SSB_STATS_RING), sizeof(ssb_stats_t), cudaMemcpyDeviceToHost));
     if (host_out->timestep != t) return fail(e, -1, "step %d is no longer (or not yet) in the stats ring", t);
-    return 0;
+    return check_overflow(e);
 }
 
 // 1 if the pollution field currently lives in the buffer that was bound as grid->pollution_flux

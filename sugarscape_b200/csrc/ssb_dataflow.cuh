@@ -19,7 +19,6 @@
 // so a step needs no memset.
 #pragma once
 #include "ssb_agent_step.cuh"
-#include "ssb_lean.cuh"
 
 namespace ssb {
 
@@ -27,7 +26,6 @@ constexpr int FLOW_BUILD_THREADS = 256;
 constexpr int FLOW_BUF = 40;              // successors buffered per thread (staged cell ids); longer lists are re-scanned
 constexpr int FLOW_OVERFLOW_POOL = 9;     // counters[SSB_C_OVERFLOW] code: successor pool exhausted
 constexpr int FLOW_OVERFLOW_STALL = 10;   // ... a ready queue stayed empty for FLOW_STALL_NS: fail loudly instead of hanging the GPU
-constexpr int FLOW_OVERFLOW_LIVE = 11;    // ... the live slots differ from the agent list (lean path: every live slot must be a list entry)
 constexpr unsigned long long FLOW_STALL_NS = 4000000000ull;
 
 struct FlowCtx {
@@ -245,102 +243,5 @@ __global__ void __launch_bounds__(AGENT_THREADS, 2) k_flow_execute(DevCtx c, Flo
     if (lane == 0 && q < f.n_queues) f.tail[q] = 0;
 }
 
-
-// ---------------------------------------------------------------------------------------------
-// The lean path (ssb_lean.cuh): one thread per agent on packed records, one ready queue per WARP.
-//   k_lean_pack     slot order (coalesced): records A / B, DAG descriptor, tile flag, entries expected per queue
-//   k_flow_build    (above; the DAG arrays are indexed by slot here)
-//   k_lean_execute  entry p of a warp's queue belongs to lane p mod 32; every lane runs whole transactions
-//   k_lean_unpack   slot order: mutable fields back to the ABI's arrays
-// ---------------------------------------------------------------------------------------------
-constexpr int LEAN_THREADS = 256;
-
-__host__ __device__ constexpr int lean_smem_bytes(int maxc, int threads) { return threads * ((2 * maxc + 1) * 4 + 2 * maxc); }
-
-// grid: blockDim * gridDim must be a multiple of f.n_queues (every thread then only meets slots of ONE queue)
-__global__ void __launch_bounds__(256) k_lean_pack(DevCtx c, FlowCtx f, LeanCtx L) {
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
-    const int n_slots = (int)c.a.counters[SSB_C_N_SLOTS];
-    if (tid == 0) { c.a.counters[SSB_C_N_BORN] = 0; c.a.counters[SSB_C_ROUNDS] = 1; f.cursor[0] = 0; f.cursor[1] = 0; }
-    const int H = c.p.height;
-    int mine = 0;
-    for (int s = tid; s < n_slots; s += nthreads) {
-        if (!lean_pack_slot(c, L, s)) continue;
-        const int pos = c.a.pos[s];
-        const uint32_t pr = priority_of(f.key, (uint32_t)c.a.id[s], c.p.id_bits);
-        const int r = min(min(max(c.a.vision[s], 0), max(c.a.movement[s], 0)), max(c.max_dx, c.max_dy));
-        f.desc[pos] = flow_pack((uint32_t)s, pr, r, 0);
-        const int x = pos / H, y = pos - x * H;
-        f.tile_pop[(x / FLOW_TX) * f.tiles_y + y / FLOW_TY] = 1;
-        mine++;
-    }
-    if (mine) atomicAdd(&L.expect[tid % f.n_queues], mine);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
-    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(L.live, (unsigned long long)mine);
-}
-
-__global__ void __launch_bounds__(256) k_lean_unpack(DevCtx c, LeanCtx L) {
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
-    const int n_slots = (int)c.a.counters[SSB_C_N_SLOTS];
-    for (int s = tid; s < n_slots; s += nthreads) lean_unpack_slot(c, L, s);
-}
-
-__global__ void __launch_bounds__(LEAN_THREADS) k_lean_execute(DevCtx c, FlowCtx f, LeanCtx L) {
-    extern __shared__ __align__(16) unsigned char lean_smem[];
-    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31;
-    int32_t *occ_st = reinterpret_cast<int32_t *>(lean_smem);
-    int32_t *sug_st = occ_st + L.maxc * T;
-    uint8_t *perm = reinterpret_cast<uint8_t *>(sug_st + (L.maxc + 1) * T);
-    const LeanStage st = {occ_st + tid, sug_st + tid, perm + tid, perm + L.maxc * T + tid, T};
-    const int wq = (blockIdx.x * T + tid) >> 5;                  // this warp's queue
-    const int n_q = L.expect[wq];
-    int32_t *my_queue = f.queue + (size_t)wq * f.queue_cap;
-    const volatile unsigned long long *abort_flag = f.cursor + 1;
-    if (blockIdx.x == 0 && tid == 0 && (long long)L.live[0] != c.a.counters[SSB_C_N_LIST])
-        atomicExch((unsigned long long *)&c.a.counters[SSB_C_OVERFLOW], (unsigned long long)FLOW_OVERFLOW_LIVE);
-    int mine = lane;                                             // entries lane, lane + 32, ... are this lane's
-    unsigned long long idle_since = 0;
-    for (;;) {
-        int idx = 0;
-        if (mine < n_q) idx = flow_ld_acquire(my_queue + mine);
-        const bool have = idx != 0;
-        if (have) {
-            const int s = idx - 1;
-            my_queue[mine] = 0;
-            mine += 32;
-            const LeanB B = L.b[s];
-            lean_transaction(c, L, s, B, f.key, st);
-            f.desc[B.start] = 0ull;
-            flow_fence();                                        // my writes happen before my releases
-            const int2 sp = f.span[s];
-            for (int j0 = 0; j0 < sp.y; j0 += 4) {
-                int b[4], old[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) b[u] = j0 + u < sp.y ? f.pool[sp.x + j0 + u] : -1;
-#pragma unroll
-                for (int u = 0; u < 4; u++) old[u] = b[u] >= 0 ? atomicSub(&f.dep[b[u]], 1) : 0;
-#pragma unroll
-                for (int u = 0; u < 4; u++)
-                    if (old[u] == 1) { flow_fence(); flow_push(f, b[u]); }
-            }
-        }
-        __syncwarp();
-        if (!__any_sync(0xffffffffu, mine < n_q)) break;
-        if (*abort_flag) break;
-        if (__any_sync(0xffffffffu, have)) idle_since = 0;
-        else {
-            __nanosleep(100);
-            const unsigned long long now = global_ns();
-            if (idle_since == 0) idle_since = now;
-            else if (now - idle_since > FLOW_STALL_NS) {
-                if (lane == 0) { atomicExch((unsigned long long *)&c.a.counters[SSB_C_OVERFLOW], (unsigned long long)FLOW_OVERFLOW_STALL); atomicExch(f.cursor + 1, 1ull); }
-                break;
-            }
-        }
-    }
-    if (lane == 0) { f.tail[wq] = 0; L.expect[wq] = 0; }
-    if (blockIdx.x == 0 && tid == 0) L.live[0] = 0;
-}
 
 }  // namespace ssb

@@ -233,6 +233,8 @@ __global__ void k_compact_counters(DevCtx c, const int64_t *n_alive_ptr) {
     c.a.counters[SSB_C_N_LIST] = n_alive;
 }
 
+__global__ void k_kin_reclaim(DevCtx c) { kin_reclaim(c); }
+
 // Mode S: this step's surviving newborn are numbered and appended in CELL order (the oracle does
 // the same; DESIGN.md "mode S").  Same count / scan / scatter pattern, over the cells.
 __device__ __forceinline__ bool cell_has_unnumbered_newborn(const DevCtx &c, long long cell) {

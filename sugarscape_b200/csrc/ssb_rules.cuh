@@ -190,10 +190,37 @@ __device__ __forceinline__ double find_welfare(const DevCtx &c, int s, double su
 // (agent.py:521-527) as singly linked lists in the kin pool.
 __device__ __forceinline__ void kin_push(const DevCtx &c, int32_t *head, int owner, int other) {
     unsigned long long *cn = (unsigned long long *)c.a.counters;
-    const long long e = (long long)atomicAdd(&cn[SSB_C_N_KIN], 1ull);
-    if (e >= c.a.kin_capacity) { atomicExch(&cn[SSB_C_OVERFLOW], 3ull); return; }
+    long long e;
+    if (cn[SSB_C_KIN_FREE] != 0ull) {            // recycled entry of a removed owner (mode E: one ordered warp, no race)
+        e = (long long)cn[SSB_C_KIN_FREE] - 1;
+        cn[SSB_C_KIN_FREE] = (unsigned long long)(c.a.kin_next[e] + 1);
+    } else {
+        e = (long long)atomicAdd(&cn[SSB_C_N_KIN], 1ull);
+        if (e >= c.a.kin_capacity) { atomicExch(&cn[SSB_C_OVERFLOW], 3ull); return; }
+    }
     c.a.kin_slot[e] = other; c.a.kin_id[e] = c.a.id[other]; c.a.kin_next[e] = head[owner];
     head[owner] = (int32_t)e;
+}
+
+// removeDeadAgents: the kin lists of a removed agent die with it -- their pool entries go to the free chain
+// (one thread, after the compaction; the lists of an agent are only ever read through its own record -- except
+// with lending, where a dead creditor's children inherit its loans (agent.py:1362-1377): children lists stay then)
+__device__ inline void kin_reclaim(const DevCtx &c) {
+    const ssb_agents_t &a = c.a;
+    if (!a.children_head || !a.kin_next) return;
+    const bool keep_children = has_lending(c);
+    long long free_head = a.counters[SSB_C_KIN_FREE] - 1;
+    const long long n_dead = a.counters[SSB_C_N_DEAD];
+    for (long long i = 0; i < n_dead; i++) {
+        const int s = a.dead_list[i];
+        for (int list = keep_children ? 1 : 0; list < 2; list++) {
+            int32_t *head = list == 0 ? a.children_head : a.mates_head;
+            int e = head[s];
+            while (e >= 0) { const int nx = a.kin_next[e]; a.kin_next[e] = (int32_t)free_head; free_head = e; e = nx; }
+            head[s] = -1;
+        }
+    }
+    a.counters[SSB_C_KIN_FREE] = free_head + 1;
 }
 
 // the relative of pool entry e, or -1 if it is no longer alive (dead, removed, slot recycled)

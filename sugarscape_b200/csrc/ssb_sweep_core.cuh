@@ -1,0 +1,494 @@
+// ssb_sweep_core.cuh -- the ORDERED SWEEP scheduler of the mode S agent step (host- and device-compilable part).
+//
+// Mode S defines a step as "agents act one at a time in ascending priority" (ssb_rng.cuh; the reference's
+// random.shuffle(self.agents) + agent loop, sugarscape.py:400-407).  ssb_flow_core.cuh shows that any execution
+// which orders every pair of agents with intersecting footprints by priority equals that sequential run.  The
+// sweep realises such an execution without queues, dependency counters or commit rounds:
+//
+//   prepare  the agents are bucketed by the top bits of their priority (two counting passes, no sort) into the
+//            list `entries`; every agent leaves a descriptor {priority, range, dilation | list index} on its cell;
+//   build    one CTA per 64 x 64 tile stages the descriptors of the tile and its halo in shared memory; one
+//            thread per agent finds its PREDECESSORS -- the agents with a smaller priority whose footprint
+//            intersects its own -- and stores them as one bit mask per x-column of its conflict region
+//            (bit dy + halo of column dx + halo: the agent that STARTS the step on cell (x + dx, y + dy));
+//   sweep    a persistent grid walks the bucketed list: thread j takes entries j, j + T, j + 2 T, ...  An agent
+//            runs its whole transaction once the DONE bit of every predecessor's start cell is set (one bit per
+//            cell, a few MB that live in L2), then sets its own.  No bucket is longer than T entries, so every
+//            thread meets its agents in ascending priority: the unfinished agent with the globally smallest
+//            priority is always at the head of its thread, has no unfinished predecessor, and runs -- the sweep
+//            cannot deadlock, and most agents find all predecessors done when their turn comes because the
+//            T agents in flight are a thin slice of the priority order.
+//
+// Everything in this file is plain C++ so that tests/hostemu compiles the SAME predecessor scan, the SAME done
+// test and the SAME lean transaction with g++ and replays the reference fixtures through adversarial orders.
+#pragma once
+#include "ssb_flow_core.cuh"
+
+namespace ssb {
+
+// ---- descriptor of the agent standing on a cell at the start of the step (0 = empty) ---------------------
+//   high word: list index;  low word: priority (26 bits) << 6 | (range + 1) << 2 | dilation
+constexpr int SWEEP_MAX_RANGE = 14;
+__host__ __device__ __forceinline__ uint32_t sweep_lo(uint32_t prio, int r, int k) { return (prio << 6) | ((uint32_t)(r + 1) << 2) | (uint32_t)k; }
+__host__ __device__ __forceinline__ uint32_t sweep_prio(uint32_t lo) { return lo >> 6; }
+__host__ __device__ __forceinline__ int sweep_r(uint32_t lo) { return (int)((lo >> 2) & 15u) - 1; }
+__host__ __device__ __forceinline__ int sweep_k(uint32_t lo) { return (int)(lo & 3u); }
+__host__ __device__ __forceinline__ unsigned long long sweep_desc(uint32_t index, uint32_t lo) { return ((unsigned long long)index << 32) | lo; }
+
+// Predecessor masks: SWEEP_COLS 32-bit words per agent (one 128-byte line), word dx + halo, bit dy + halo.
+constexpr int SWEEP_COLS = 32;
+constexpr int SWEEP_MAX_HALO = 15;                  // 2 * halo + 1 <= 31 rows and columns
+
+// Conflict tables (filled once per engine on the host, sweep_fill_tables; staged in shared memory by the build kernel):
+//   any [ka][ra][adx]          largest |dy| at column offset adx at which an agent of range ra / dilation ka can conflict
+//                              with ANY partner (flow_column_reach, clipped to the halo; -1: none)
+//   pair[K][ra][rb][adx]       largest |dy| at which ranges ra and rb conflict at column offset adx with K = ka + kb
+//                              (flow_conflict is monotone in |dy|; -1: never)
+__host__ __device__ __forceinline__ int sweep_any_size(int RB, int KB, int halo) { return (KB + 1) * (RB + 1) * (halo + 1); }
+__host__ __device__ __forceinline__ int sweep_pair_size(int RB, int KB, int halo) { return (2 * KB + 1) * (RB + 1) * (RB + 1) * (halo + 1); }
+__host__ __device__ __forceinline__ int sweep_tables_bytes(int RB, int KB, int halo) { return (sweep_any_size(RB, KB, halo) + sweep_pair_size(RB, KB, halo) + 15) & ~15; }
+inline void sweep_fill_tables(int RB, int KB, int halo, int8_t *any, int8_t *pair) {
+    for (int ka = 0; ka <= KB; ka++) for (int ra = 0; ra <= RB; ra++) for (int adx = 0; adx <= halo; adx++) {
+        int h = flow_column_reach(adx, ra, ka, RB, KB);
+        if (h > halo) h = halo;
+        any[(ka * (RB + 1) + ra) * (halo + 1) + adx] = (int8_t)h;
+    }
+    for (int K = 0; K <= 2 * KB; K++) for (int ra = 0; ra <= RB; ra++) for (int rb = 0; rb <= RB; rb++) for (int adx = 0; adx <= halo; adx++) {
+        int h = -1;
+        for (int ady = halo; ady >= 0; ady--) if (flow_conflict(adx, ady, ra, rb, K)) { h = ady; break; }
+        pair[((K * (RB + 1) + ra) * (RB + 1) + rb) * (halo + 1) + adx] = (int8_t)h;
+    }
+}
+
+struct SweepTile {
+    const uint32_t *cell;                // [sw * sh] low descriptor words, column (x) major like the grid
+    const unsigned long long *mask;      // [sw * 2] occupancy bits of every staged column (sh <= 128)
+    const int8_t *any, *pair;            // conflict tables
+    int sw, sh, halo;
+};
+
+// The predecessors of the agent with low descriptor word `la` on staged cell (lx, ly), column by column:
+// emit(column index dx + halo, mask).  RB / KB: the largest range / dilation of any agent in this step.
+template <class F>
+__host__ __device__ __forceinline__ void sweep_pred_masks(const SweepTile &tile, int lx, int ly, uint32_t la, int RB, int KB, F emit) {
+    const int ra = sweep_r(la), ka = sweep_k(la), halo = tile.halo, hs = halo + 1;
+    const uint32_t pa = sweep_prio(la);
+    const int8_t *any = tile.any + (ka * (RB + 1) + ra) * hs;
+    const int8_t *pair = tile.pair + ((ka * (RB + 1) + ra) * (RB + 1)) * hs;       // + (kb (RB + 1) (RB + 1) + rb) hs + adx
+    const int k_stride = (RB + 1) * (RB + 1) * hs;
+    for (int dx = -halo; dx <= halo; dx++) {
+        const int adx = dx < 0 ? -dx : dx;
+        const int h = any[adx];
+        uint32_t m = 0;
+        if (h >= 0) {
+            const int col = lx + dx, y0 = ly - h;
+            unsigned long long bits = flow_mask_window(tile.mask + col * 2, y0, 2 * h + 1);
+            if (dx == 0) bits &= ~(1ull << h);
+            const uint32_t *column = tile.cell + col * tile.sh + y0;
+            while (bits) {
+                const int j = flow_ctz64(bits);
+                bits &= bits - 1;
+                const uint32_t lb = column[j];
+                if (sweep_prio(lb) >= pa) continue;
+                const int dy = j - h, ady = dy < 0 ? -dy : dy;
+                if (ady <= pair[sweep_k(lb) * k_stride + sweep_r(lb) * hs + adx]) m |= 1u << (dy + halo);
+            }
+        }
+        emit(dx + halo, m);
+    }
+}
+
+// Have all predecessors of the agent that starts on (x, y) finished?  The done bitmap has one bit per cell (bit
+// index = cell index x * H + y); ld(w) reads word w past every cache that could hold a stale copy.
+struct SweepWindow { int x, y0, W, H, span; bool straight; };
+__host__ __device__ __forceinline__ SweepWindow sweep_window(int x, int y, int W, int H, int halo) {
+    SweepWindow win;
+    win.x = x - halo; win.y0 = y - halo; win.W = W; win.H = H; win.span = 2 * halo + 1;
+    win.straight = win.y0 >= 0 && win.y0 + win.span <= H;
+    return win;
+}
+// column `col` (= dx + halo) with predecessor mask m, for an agent whose window crosses the torus seam in y: bit by bit
+template <class LoadDone>
+__host__ __device__ inline bool sweep_column_done_seam(const SweepWindow &win, uint32_t m, int cx, LoadDone ld) {
+    bool ok = true;
+#pragma unroll 1
+    for (int j = 0; j < win.span; j++) {
+        if (!((m >> j) & 1u)) continue;
+        int cy = win.y0 + j;
+        if (cy < 0) cy += win.H; else if (cy >= win.H) cy -= win.H;
+        const uint32_t bit = (uint32_t)cx * (uint32_t)win.H + (uint32_t)cy;
+        if (!((ld(bit >> 5) >> (bit & 31u)) & 1u)) ok = false;
+    }
+    return ok;
+}
+template <class LoadDone>
+__host__ __device__ __forceinline__ bool sweep_column_done(const SweepWindow &win, uint32_t m, int col, LoadDone ld) {
+    int cx = win.x + col;
+    if (cx < 0) cx += win.W; else if (cx >= win.W) cx -= win.W;
+    if (!win.straight) return sweep_column_done_seam(win, m, cx, ld);
+    const uint32_t bit = (uint32_t)cx * (uint32_t)win.H + (uint32_t)win.y0;
+    const uint32_t wd = bit >> 5;
+    const int s = (int)(bit & 31u);
+    uint32_t window = ld(wd) >> s;
+    if (s + win.span > 32) window |= ld(wd + 1) << (32 - s);
+    return (window & m) == m;
+}
+// masks = the agent's SWEEP_COLS words
+template <class LoadDone>
+__host__ __device__ __forceinline__ bool sweep_preds_done(const uint32_t *masks, LoadDone ld, int x, int y, int W, int H, int halo) {
+    const SweepWindow win = sweep_window(x, y, W, H, halo);
+    bool ok = true;
+    for (int col = 0; col < win.span; col++)
+        if (masks[col] && !sweep_column_done(win, masks[col], col, ld)) ok = false;
+    return ok;
+}
+
+// number of priority buckets for n agents walked by T concurrent transactions: every bucket must stay well below T
+// entries (a thread meets entries T apart, which must lie in different buckets)
+__host__ __device__ __forceinline__ int sweep_bucket_bits(long long n, long long T, int id_bits, int max_bits) {
+    int bits = 0;
+    while (bits < max_bits && bits < id_bits && (n >> bits) * 4 > T) bits++;
+    return bits;
+}
+
+// =============================================================================================================
+// The lean transaction: Agent.doTimestep for rule sets whose transaction stays inside the cross (no tagging /
+// trading / reproduction: footprint dilation 0 -- S2's combat_limited rules, the growback / pollution / combat /
+// replacement examples), on two sector-sized records, ONE THREAD PER AGENT:
+//
+//   LeanA [slot]        read + written   holdings, position, tribe, cause of death, by-products for the log
+//                                        (what neighbours read through cell.agent)
+//   LeanB [list index]  read only        slot, id, range, metabolisms, aggression, lookahead  (coalesced in sweep order)
+//
+// k_sweep_prepare fills both from the ABI's arrays in slot order, k_lean_unpack writes the mutable fields back
+// (and evaluates happiness, agent.py:1522-1530) -- the ABI arrays stay the canonical state between steps.
+// =============================================================================================================
+enum { LEAN_COD_MASK = 7, LEAN_ACTED = 8, LEAN_RANGED = 16, LEAN_AGED = 32, LEAN_PACKED = 64 };
+enum : uint32_t { LEANB_ID_MASK = (1u << 26) - 1u, LEANB_RANGE_SHIFT = 26, LEANB_DIES = 1u << 30, LEANB_SKIP = 1u << 31 };
+
+struct __align__(32) LeanA {
+    double sugar, spice;
+    int32_t pos;
+    int8_t tribe;
+    uint8_t hood, valid, state;      // len(movementNeighborhood), len(validMoves), cause of death | LEAN_* flags
+    int32_t pad[2];
+};
+struct __align__(32) LeanB {
+    int32_t slot;
+    uint32_t idf;                    // id | range << 26 | LEANB_DIES (reaches its maximum age in this step) | LEANB_SKIP
+    int32_t sugar_metab, spice_metab;
+    double aggression, lookahead;
+};
+static_assert(sizeof(LeanA) == 32 && sizeof(LeanB) == 32, "one 32-byte sector per record");
+
+struct LeanCtx {
+    LeanA *a;                  // [capacity] by slot
+    LeanB *b;                  // [capacity] by list index
+    int32_t maxc;              // 4 * largest range: candidate cells staged per agent
+};
+
+__device__ __forceinline__ LeanA lean_load_a(const LeanA *p) {
+#if defined(__CUDA_ARCH__)
+    union { LeanA a; uint4 q[2]; } u;
+    u.q[0] = __ldcg(reinterpret_cast<const uint4 *>(p));
+    u.q[1] = __ldcg(reinterpret_cast<const uint4 *>(p) + 1);
+    return u.a;
+#else
+    return *p;
+#endif
+}
+
+// The rule sets the lean transaction covers (anything else runs the generic transaction): scalable RNG mode,
+// footprint dilation 0, no tag preferences, at most 25 tribes, and a map on which every distance of the cross has
+// four distinct cells (environment.py:111-122 merges them when 2 d equals the map side).
+__host__ __device__ inline bool lean_supported(const ssb_params_t &p) {
+    if (p.rng_mode != SSB_RNG_SCALABLE) return false;
+    if (p.flags & (SSB_F_TAGGING | SSB_F_TRADE | SSB_F_REPRO | SSB_F_TAGPREF)) return false;
+    if (p.max_tribes > 25) return false;
+    const int side = p.width < p.height ? p.width : p.height;
+    return p.max_agent_range >= 0 && p.max_agent_range <= 7 && 2 * p.max_agent_range + 1 < side;
+}
+
+// Per-thread staging arrays (shared memory on the device, element i of this thread at [i * stride]).
+struct LeanStage {
+    int32_t *occ, *sugar;      // [maxc + 1]: the candidates in enumeration order, then the own cell
+    uint8_t *perm, *rank;      // [maxc]
+    int stride;
+};
+
+// Everything a transaction reads that another transaction of the same step may have written (records A, cell
+// contents) is loaded PAST the L1 cache (ld.global.cg = LDG.STRONG.GPU): a predecessor on another SM wrote it to L2
+// before it set its done bit, and a stale L1 line is the only thing that could hide that.  This replaces the acquire
+// fence on the consumer side, whose CCTL.IVALL (invalidate the whole L1, once per transaction and thread) dominated
+// the first version of the sweep kernel.
+template <class T> __device__ __forceinline__ T lean_ld(const T *p) {
+#if defined(__CUDA_ARCH__)
+    return __ldcg(p);
+#else
+    return *p;
+#endif
+}
+__device__ __forceinline__ void lean_prefetch(const void *p) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
+// Candidate i of Agent.findCellsInRange in the insertion order of Environment.findCardinalCellRanges
+// (environment.py:111-122): distance d = i / 4 + 1; within a distance the order is
+// W N E S in the interior, N E S W if the west cell wraps (x < d), W E S N if the north cell wraps (y < d),
+// E S N W if both.  (2 d < map side: the four cells are distinct, lean_supported.)
+__device__ __forceinline__ int lean_candidate(int i, int x, int y, int W, int H) {
+    const int d = (i >> 2) + 1, j = i & 3;
+    const unsigned order = (x < d) ? ((y < d) ? 0x1Eu : 0x39u) : ((y < d) ? 0x78u : 0xE4u);
+    const int dir = (order >> (2 * j)) & 3;                       // 0 W, 1 N, 2 E, 3 S
+    int cx = x, cy = y;
+    if (dir == 0) { cx = x - d; if (cx < 0) cx += W; }
+    else if (dir == 1) { cy = y - d; if (cy < 0) cy += H; }
+    else if (dir == 2) { cx = x + d; if (cx >= W) cx -= W; }
+    else { cy = y + d; if (cy >= H) cy -= H; }
+    return cx * H + cy;
+}
+
+// the four candidates at distance d (candidates 4 (d - 1) .. 4 (d - 1) + 3) in that order
+__device__ __forceinline__ void lean_ring(int d, int x, int y, int W, int H, int out[4]) {
+    int xw = x - d, xe = x + d, yn = y - d, ys = y + d;
+    if (xw < 0) xw += W;
+    if (xe >= W) xe -= W;
+    if (yn < 0) yn += H;
+    if (ys >= H) ys -= H;
+    const int cw = xw * H + y, ce = xe * H + y, cn = x * H + yn, cs = x * H + ys;
+    if (x < d) {
+        if (y < d) { out[0] = ce; out[1] = cs; out[2] = cn; out[3] = cw; }
+        else { out[0] = cn; out[1] = ce; out[2] = cs; out[3] = cw; }
+    } else {
+        if (y < d) { out[0] = cw; out[1] = ce; out[2] = cs; out[3] = cn; }
+        else { out[0] = cw; out[1] = cn; out[2] = ce; out[3] = cs; }
+    }
+}
+
+// the range of Agent.findCellsInRange for slot s: min(vision, movement), clipped to the per-axis memoised range
+__device__ __forceinline__ int lean_range(const DevCtx &c, int s) {
+    return min(min(max(c.a.vision[s], 0), max(c.a.movement[s], 0)), max(c.max_dx, c.max_dy));
+}
+
+// k_sweep_prepare for one slot: record A.  live = the slot holds an agent of the list (every agent that is alive
+// and on the map is on the list after a compaction).
+__device__ __forceinline__ bool lean_pack_a(const DevCtx &c, const LeanCtx &L, int s) {
+    const ssb_agents_t &a = c.a;
+    const int pos = a.pos[s], cod = a.cod[s];
+    const bool live = cod == SSB_ALIVE && pos >= 0;
+    LeanA A;
+    A.sugar = a.sugar[s]; A.spice = a.spice[s];
+    A.pos = pos; A.tribe = (int8_t)a.tribe[s];
+    A.hood = 0; A.valid = 0;
+    A.state = live ? (uint8_t)LEAN_PACKED : (uint8_t)0;
+    A.pad[0] = 0; A.pad[1] = 0;
+    L.a[s] = A;
+    return live;
+}
+// ... and record B at its list index
+__device__ __forceinline__ void lean_pack_b(const DevCtx &c, const LeanCtx &L, int s, int index, int r) {
+    const ssb_agents_t &a = c.a;
+    LeanB B;
+    B.slot = s;
+    const int age = a.age[s], max_age = a.max_age[s];
+    B.idf = ((uint32_t)a.id[s] & LEANB_ID_MASK) | ((uint32_t)r << LEANB_RANGE_SHIFT) |
+            ((max_age != -1 && age + 1 >= max_age) ? (uint32_t)LEANB_DIES : 0u) | (a.last_moved[s] == c.t ? (uint32_t)LEANB_SKIP : 0u);
+    B.sugar_metab = a.sugar_metab[s]; B.spice_metab = a.spice_metab[s];
+    B.aggression = a.aggression[s]; B.lookahead = a.lookahead[s];
+    L.b[index] = B;
+}
+
+// k_lean_unpack for one slot: the mutable fields go back to the ABI's arrays; happiness of the agents that are
+// still alive after aging (updateHappiness, agent.py:1522-1530: family 0 in mode S, health 1, wealth erf).
+__device__ __forceinline__ void lean_unpack_slot(const DevCtx &c, const LeanCtx &L, int s) {
+    const LeanA A = L.a[s];
+    if (!(A.state & LEAN_PACKED)) return;
+    const ssb_agents_t &a = c.a;
+    const int cod = A.state & LEAN_COD_MASK;
+    const double sugar0 = a.sugar[s], spice0 = a.spice[s];     // holdings at the start of the step
+    a.sugar[s] = A.sugar; a.spice[s] = A.spice; a.pos[s] = cod == SSB_ALIVE ? A.pos : -1; a.cod[s] = cod;
+    if (!(A.state & LEAN_ACTED)) return;
+    // nobody touches the holdings of a living agent before its own transaction in these rule sets (combat kills):
+    // lastSugar / lastSpice (agent.py:578-579) are the holdings the step started with
+    a.last_moved[s] = c.t;
+    a.last_sugar[s] = sugar0; a.last_spice[s] = spice0;
+    if (A.state & LEAN_RANGED) { a.n_neighborhood[s] = A.hood; a.n_valid_moves[s] = A.valid; }
+    if (!(A.state & LEAN_AGED)) return;
+    a.age[s] = a.age[s] + 1;
+    if (cod != SSB_ALIVE) return;
+    const double wealth_h = erf((A.sugar + A.spice) - c.prev_mean_wealth);
+    const double family_h = erf(0.0);
+    a.wealth_happiness[s] = wealth_h;
+    a.family_happiness[s] = family_h;
+    a.happiness[s] = family_h + 1.0 + wealth_h;
+}
+
+// Agent.doTimestep (agent.py:568-598) for a rule set with footprint dilation 0: findBestCell with the shuffled
+// tie-break (1395-1443, 1479-1490), doCombat (274-294), gotoCell, collectResourcesAtCell (249-259), doMetabolism
+// (485-498) with the pollution terms (cell.py:27-45), starvation, doAging (266-272).  Mirrors
+// transaction_move_phase / transaction_interact_phase of ssb_rules.cuh statement by statement.
+__device__ inline void lean_transaction(const DevCtx &c, const LeanCtx &L, const LeanB &B, uint64_t key, const LeanStage &st) {
+    const int s = B.slot;
+    LeanA A = lean_load_a(L.a + s);
+    if (!((A.state & LEAN_COD_MASK) == SSB_ALIVE && A.sugar >= 0 && A.spice >= 0) || (B.idf & LEANB_SKIP)) return;
+    const int W = c.p.width, H = c.p.height, pos = A.pos, x = pos / H, y = pos - x * H;
+    const int r = (int)((B.idf >> LEANB_RANGE_SHIFT) & 15u), n = 4 * r, S = st.stride;
+    const uint32_t id = B.idf & LEANB_ID_MASK;
+    const bool polluted = (c.p.flags & SSB_F_POLLUTION) != 0, spicy = (c.p.flags & SSB_F_SPICE) != 0;
+    const double aggression = fmax(B.aggression, 0.0);
+    const bool fighter = aggression > 0;
+    // the cross (and the own cell, in case the agent stays): two distances = sixteen independent loads in flight
+    for (int d = 1; d <= r; d += 2) {
+        int cell[8];
+        int32_t v_occ[8], v_sugar[8];
+        lean_ring(d, x, y, W, H, cell);
+        const bool two = d + 1 <= r;
+        if (two) lean_ring(d + 1, x, y, W, H, cell + 4);
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+            if (u < 4 || two) { v_occ[u] = lean_ld(c.g.occ + cell[u]); v_sugar[u] = lean_ld(c.g.sugar + cell[u]); }
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+            if (u < 4 || two) { st.occ[(4 * (d - 1) + u) * S] = v_occ[u]; st.sugar[(4 * (d - 1) + u) * S] = v_sugar[u]; }
+    }
+    st.sugar[n * S] = lean_ld(c.g.sugar + pos);
+    // findWelfare's per-agent part (agent.py:1170-1201, no tag preferences)
+    Welfare w;
+    const double sm = (double)max(B.sugar_metab, 0), pm = (double)max(B.spice_metab, 0);
+    {
+        w.sugar = A.sugar; w.spice = A.spice;
+        w.s_look = sm * B.lookahead; w.p_look = pm * B.lookahead;
+        const double total = sm + pm;
+        w.e_s = 0; w.e_p = 0;
+        if (pm == 0) { if (sm != 0) w.e_s = 1.0; }          // x / x == 1 and 0 / x == 0 exactly: no division (its zero-numerator
+        else if (sm == 0) w.e_p = 1.0;                      // case takes the slow path of the software fp64 division)
+        else { w.e_s = sm / total; w.e_p = pm / total; }
+    }
+    const double my_wealth = A.sugar + A.spice, loot = c.p.max_combat_loot;
+    int b_cell = pos, b_dist = 1 << 30, b_rank = 1 << 30, b_cs = 0, b_cp = 0, b_occ = -1, hood = 0, m = 0;
+    double b_welfare = -1.0, b_pl = 0.0;
+    bool b_valid = false;
+    if (n > 0) {
+        // random.shuffle(cellsInRange), agent.py:1400-1401: rank[i] = shuffled position of candidate i
+        RngStream rng{key, id, 0u, 0u, nullptr};
+        rng.at(SITE_MOVE);
+        for (int i = 0; i < n; i++) st.perm[i * S] = (uint8_t)i;
+        for (int i = n - 1; i >= 1; i--) {
+            const uint32_t j = rand_below(rng, (uint32_t)i + 1u);
+            const uint8_t t = st.perm[i * S]; st.perm[i * S] = st.perm[j * S]; st.perm[j * S] = t;
+        }
+        for (int k = 0; k < n; k++) st.rank[st.perm[k * S] * S] = (uint8_t)k;
+        // findRetaliatorsInVision (agent.py:1088-1098): the richest visible agent of every tribe
+        double retaliator[27];
+        if (fighter) {
+            for (int i = 0; i < n; i++) { const int o = st.occ[i * S]; if (o >= 0) lean_prefetch(L.a + o); }
+            for (int i = 0; i < 27; i++) retaliator[i] = 0.0;
+            for (int i = 0; i < n; i++) {
+                const int o = st.occ[i * S];
+                if (o < 0) continue;
+                const LeanA O = lean_load_a(L.a + o);
+                const double ow = fmax(O.sugar + O.spice, 0.0);
+                const int slot = min((int)O.tribe + 1, 26);
+                if (ow > retaliator[slot]) retaliator[slot] = ow;
+            }
+        }
+        for (int d = 1; d <= r; d++) {
+            int ring[4];
+            lean_ring(d, x, y, W, H, ring);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int i = 4 * (d - 1) + j, cell = ring[j];
+                const int o = st.occ[i * S], cs = st.sugar[i * S];
+                const bool occupied = o >= 0;
+                int otribe = -1;
+                double ps = 0, pp = 0;
+                if (occupied) {
+                    // findNeighborhood (agent.py:1052-1065): an agent found through a cell's occupant pointer is alive
+                    // (every death of this rule family clears the pointer in the same transaction)
+                    hood++;
+                    if (!fighter) continue;
+                    const LeanA O = lean_load_a(L.a + o);
+                    otribe = O.tribe;
+                    // isNeighborValidPrey (agent.py:1309-1314)
+                    if (!(A.tribe != otribe && my_wealth >= O.sugar + O.spice)) continue;
+                    ps = O.sugar; pp = O.spice;
+                }
+                const int cp = spicy ? lean_ld(c.g.spice + cell) : 0;
+                const double pl = polluted ? lean_ld(c.g.pollution + cell) : 0.0;
+                double sugar_reward = (double)cs, spice_reward = (double)cp;
+                if (fighter) { sugar_reward += aggression * fmin(loot, ps); spice_reward += aggression * fmin(loot, pp); }   // (+ 0.0 otherwise)
+                if (polluted) { sugar_reward /= 1 + pl; spice_reward /= 1 + pl; }                                            // (/ 1.0 otherwise)
+                const double welfare = w.eval(sugar_reward, spice_reward);
+                if (occupied && retaliator[min(otribe + 1, 26)] > my_wealth + welfare) continue;
+                const int rk = st.rank[i * S];
+                if (!b_valid || welfare > b_welfare || (welfare == b_welfare && (d < b_dist || (d == b_dist && rk < b_rank)))) {
+                    b_cell = cell; b_welfare = welfare; b_dist = d; b_rank = rk; b_valid = true;
+                    b_cs = cs; b_cp = cp; b_pl = pl; b_occ = o;
+                }
+                m++;
+            }
+        }
+        if (m == 0) m = 1;
+    }
+    uint8_t state = (uint8_t)(LEAN_PACKED | LEAN_ACTED | (n > 0 ? LEAN_RANGED : 0));
+    double sugar = A.sugar, spice = A.spice;
+    const int best = b_valid ? b_cell : pos;
+    if (!b_valid) {          // stays on its own cell: its contents were not among the candidates
+        b_cs = st.sugar[n * S];
+        b_cp = spicy ? lean_ld(c.g.spice + pos) : 0;
+        b_pl = polluted ? lean_ld(c.g.pollution + pos) : 0.0;
+    }
+    // doCombat (agent.py:274-294) then gotoCell (agent.py:1213-1219)
+    if (fighter && b_valid && b_occ >= 0 && b_occ != s) {
+        LeanA P = lean_load_a(L.a + b_occ);
+        const double sl = fmin(loot, P.sugar), pl = fmin(loot, P.spice);
+        sugar += sl; spice += pl;
+        P.sugar -= sl; P.spice -= pl;
+        P.state = (uint8_t)((P.state & ~LEAN_COD_MASK) | SSB_COMBAT);       // doDeath("combat"): the killer takes the cell below
+        L.a[b_occ] = P;
+    }
+    c.g.occ[pos] = -1;
+    c.g.occ[best] = s;
+    // collectResourcesAtCell (agent.py:249-259) + production pollution (cell.py:32-45)
+    sugar += b_cs;
+    spice += b_cp;
+    const bool polluting = c.p.pollution_start <= c.t && c.t <= c.p.pollution_end;
+    double cell_poll = b_pl;
+    if (polluting) {
+        cell_poll += c.p.sugar_prod_pollution * b_cs;
+        cell_poll += c.p.spice_prod_pollution * b_cp;
+    }
+    c.g.sugar[best] = 0;
+    if (spicy) c.g.spice[best] = 0;
+    // doMetabolism (agent.py:485-498) + consumption pollution (cell.py:27-40)
+    sugar -= sm;
+    spice -= pm;
+    if (polluting) {
+        cell_poll += c.p.sugar_cons_pollution * sm;
+        cell_poll += c.p.spice_cons_pollution * pm;
+        c.g.pollution[best] = cell_poll;
+    }
+    A.sugar = sugar; A.spice = spice; A.pos = best;
+    A.hood = (uint8_t)(hood + 1); A.valid = (uint8_t)m;
+    if (sugar < 0 || spice < 0 || (sugar <= 0 && sm > 0) || (spice <= 0 && pm > 0)) {
+        state |= SSB_STARVATION;                                              // doDeath("starvation") (agent.py:296-313)
+        c.g.occ[best] = -1;
+    } else {
+        // doAging (agent.py:266-272); isAlive() holds here: both holdings are positive or their metabolism is 0
+        if (sugar >= 0 && spice >= 0) {
+            state |= LEAN_AGED;
+            if (B.idf & LEANB_DIES) {
+                state |= SSB_AGING;
+                c.g.occ[best] = -1;
+            }
+        }
+    }
+    A.state = state;
+    L.a[s] = A;
+}
+
+}  // namespace ssb

@@ -369,12 +369,13 @@ class Engine:
         self._check(self.L.ssb_set_l2_persist(self.handle, self.stream, 1 if on else 0))
 
     def set_scheduler(self, name):
-        """Mode S scheduler: "dataflow" (static conflict DAG, default on one GPU; lean transaction where the rule set allows),
-        "generic" (the dataflow with the generic transaction) or "rounds" (reservation rounds)."""
-        self._check(self.L.ssb_set_scheduler(self.handle, {"rounds": 0, "dataflow": 1, "generic": 2}[name]))
+        """Mode S scheduler: "sweep" (ordered sweep over the static conflict DAG, default on one GPU; lean transaction where
+        the rule set allows), "sweep-generic" (the sweep with the generic transaction), "dataflow" (the DAG through ready
+        queues) or "rounds" (reservation rounds)."""
+        self._check(self.L.ssb_set_scheduler(self.handle, {"rounds": 0, "dataflow": 1, "sweep": 3, "sweep-generic": 4}[name]))
 
     def scheduler(self):
-        return {0: "rounds", 1: "dataflow", 2: "generic"}.get(int(self.L.ssb_get_scheduler(self.handle)), "n/a")
+        return {0: "rounds", 1: "dataflow", 3: "sweep", 4: "sweep-generic"}.get(int(self.L.ssb_get_scheduler(self.handle)), "n/a")
 
     def uses_lean_transaction(self):
         return bool(self.L.ssb_uses_lean_transaction(self.handle))

@@ -18,7 +18,7 @@ F_SPICE, F_POLLUTION, F_REPRO, F_TAGS, F_TAGGING, F_COMBAT, F_TRADE, F_TAGPREF =
     1 << 0, 1 << 1, 1 << 2, 1 << 3, 1 << 4, 1 << 5, 1 << 6, 1 << 7)
 
 (C_N_LIST, C_N_SLOTS, C_NEXT_ID, C_N_FREE, C_N_BORN, C_N_DEAD, C_ROUNDS, C_OVERFLOW, C_N_KIN,
- C_ENDOW_INDEX, C_N_REPLACED, C_N_MIGRATED) = range(12)
+ C_ENDOW_INDEX, C_N_REPLACED, C_N_MIGRATED, C_KIN_FREE) = range(13)
 INHERITANCE_CODE = {"none": 0, "children": 1, "sons": 2, "daughters": 3}
 C_COUNT = 16
 

@@ -21,6 +21,7 @@
 #define __forceinline__ inline
 #define __noinline__
 #define __launch_bounds__(...)
+#define __align__(n) alignas(n)
 
 struct ssb_emu_dim3 { unsigned x, y, z; };
 static const ssb_emu_dim3 threadIdx = {0, 0, 0};

@@ -6,7 +6,9 @@
 
 #include "../../sugarscape_b200/csrc/ssb_exact.cuh"
 #include "../../sugarscape_b200/csrc/ssb_flow_core.cuh"
+#include "../../sugarscape_b200/csrc/ssb_sweep_core.cuh"
 
+#include <algorithm>
 #include <vector>
 
 using namespace ssb;
@@ -168,6 +170,140 @@ int emu_agent_step_flow(const ssb_params_t *p, const ssb_grid_t *g, const ssb_ag
     }
     if (out_stats) { out_stats[0] = n_list; out_stats[1] = edges; out_stats[2] = depth; out_stats[3] = tiles; }
     return done == n_list ? 0 : -3;     /* -3: the graph was not acyclic / a counter never reached zero */
+}
+
+
+/* Mode S agent step through the ORDERED SWEEP (csrc/ssb_sweep_core.cuh: the SAME predecessor scan, done test and --
+ * with lean != 0 -- the SAME lean transaction on packed records that the CUDA kernels run).  The list indices are
+ * handed out in an arbitrary order and the agents run in passes over the pending entries, in an ADVERSARIAL order:
+ * order_mode 0 = ascending list index, 1 = DESCENDING priority (as far from the sequential order as the predecessor
+ * masks allow), 2 = pseudo-random.  An entry runs only when sweep_preds_done says so, exactly like a sweep thread.
+ * out_stats (may be null): {agents, predecessor bits, passes, tiles visited}. */
+int emu_agent_step_sweep(const ssb_params_t *p, const ssb_grid_t *g, const ssb_agents_t *a, int32_t t, double prev_mean_wealth,
+                         const uint32_t *endow_bits, const uint32_t *tag_bits, int32_t n_tables, int32_t *born_list,
+                         int32_t order_mode, int32_t lean, int64_t *out_stats) {
+    if (!p || !g || !a || p->rng_mode != SSB_RNG_SCALABLE) return -1;
+    DevCtx c;
+    memset(&c, 0, sizeof(c));
+    c.p = *p; c.g = *g; c.a = *a;
+    const int rmax = p->max_agent_range;
+    c.max_dx = rmax < p->width / 2 ? rmax : p->width / 2;
+    c.max_dy = rmax < p->height / 2 ? rmax : p->height / 2;
+    const int RB = c.max_dx > c.max_dy ? c.max_dx : c.max_dy, KB = flow_max_dilation(p->flags), R = flow_halo(RB, KB);
+    const int W = p->width, H = p->height;
+    if (4 * RB > 32 || R > SWEEP_MAX_HALO || R >= W || R >= H) return -2;
+    if (lean && !(lean_supported(*p) && 4 * RB <= 32)) return -4;
+    c.t = t; c.prev_mean_wealth = prev_mean_wealth;
+    c.endow_bits = endow_bits; c.tag_bits = tag_bits; c.n_step_tables = n_tables;
+    c.born_list = born_list;
+    const uint64_t key = step_key(p->seed, t);
+    const int n_list = (int)a->counters[SSB_C_N_LIST], n_slots = (int)a->counters[SSB_C_N_SLOTS];
+    a->counters[SSB_C_N_BORN] = 0;
+    /* prepare (k_sweep_prepare): list indices in a scrambled order */
+    std::vector<LeanA> recA(lean ? (size_t)a->capacity : 0);
+    std::vector<LeanB> recB(lean ? (size_t)a->capacity : 0);
+    LeanCtx L;
+    L.a = recA.data(); L.b = recB.data(); L.maxc = 4 * RB;
+    struct Entry { int slot, pos; uint32_t prio; };
+    std::vector<Entry> entries;
+    std::vector<unsigned long long> desc((size_t)W * H, 0ull);
+    std::vector<int> live;
+    if (lean) { for (int s = 0; s < n_slots; s++) if (lean_pack_a(c, L, s)) live.push_back(s); }
+    else { for (int i = 0; i < n_list; i++) if (a->pos[a->order[i]] >= 0) live.push_back(a->order[i]); }
+    if (lean && (int)live.size() != n_list) return -5;
+    const int n = (int)live.size();
+    {   /* scramble: index = position in a pseudo-random permutation */
+        uint64_t lcg = 0x2545F4914F6CDD1Dull ^ (uint64_t)t;
+        for (int i = n - 1; i > 0; i--) {
+            lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
+            const int j = (int)((lcg >> 33) % (uint64_t)(i + 1));
+            const int tmp = live[i]; live[i] = live[j]; live[j] = tmp;
+        }
+    }
+    entries.resize(n);
+    for (int index = 0; index < n; index++) {
+        const int s = live[index], pos = a->pos[s];
+        const uint32_t pr = priority_of(key, (uint32_t)a->id[s], p->id_bits);
+        const int r = lean_range(c, s), k = lean ? 0 : footprint_dilation(c, s);
+        desc[pos] = sweep_desc((uint32_t)index, sweep_lo(pr, r, k));
+        entries[index] = {s, pos, pr};
+        if (lean) lean_pack_b(c, L, s, index, r);
+    }
+    /* build (k_sweep_build): tile by tile, staged with the torus wrap, masks, one scan per agent */
+    const int sw = FLOW_TX + 2 * R, sh = FLOW_TY + 2 * R;
+    std::vector<uint32_t> cell((size_t)sw * sh), preds((size_t)n * SWEEP_COLS, 0u);
+    std::vector<unsigned long long> mask((size_t)sw * 2);
+    std::vector<int8_t> tables((size_t)sweep_tables_bytes(RB, KB, R), 0);
+    sweep_fill_tables(RB, KB, R, tables.data(), tables.data() + sweep_any_size(RB, KB, R));
+    long long bits = 0, tiles = 0;
+    for (int tx = 0; tx * FLOW_TX < W; tx++) for (int ty = 0; ty * FLOW_TY < H; ty++) {
+        const int x0 = tx * FLOW_TX - R, y0 = ty * FLOW_TY - R;
+        for (int col = 0; col < sw; col++) for (int row = 0; row < sh; row++)
+            cell[(size_t)col * sh + row] = (uint32_t)desc[(size_t)wrapi(x0 + col, W) * H + wrapi(y0 + row, H)];
+        for (int col = 0; col < sw; col++) {
+            mask[col * 2] = mask[col * 2 + 1] = 0;
+            for (int row = 0; row < sh; row++) if (cell[(size_t)col * sh + row]) mask[col * 2 + (row >> 6)] |= 1ull << (row & 63);
+        }
+        SweepTile tile;
+        tile.cell = cell.data(); tile.mask = mask.data(); tile.sw = sw; tile.sh = sh; tile.halo = R;
+        tile.any = tables.data(); tile.pair = tables.data() + sweep_any_size(RB, KB, R);
+        tiles++;
+        for (int ix = 0; ix < FLOW_TX && tx * FLOW_TX + ix < W; ix++) for (int iy = 0; iy < FLOW_TY && ty * FLOW_TY + iy < H; iy++) {
+            const uint32_t la = cell[(size_t)(R + ix) * sh + R + iy];
+            if (!la) continue;
+            const uint32_t gcell = (uint32_t)((tx * FLOW_TX + ix) * H + ty * FLOW_TY + iy);
+            const uint32_t index = (uint32_t)(desc[gcell] >> 32);
+            uint32_t *out = preds.data() + (size_t)index * SWEEP_COLS;
+            sweep_pred_masks(tile, R + ix, R + iy, la, RB, KB, [&](int col, uint32_t m) { out[col] = m; bits += __builtin_popcount(m); });
+            out[31] = gcell;
+        }
+    }
+    /* sweep (k_sweep_lean / k_sweep_generic): passes over the pending entries */
+    std::vector<uint32_t> done((size_t)W * H / 32 + 2, 0u);
+    auto ld = [&](uint32_t wd) { return done[wd]; };
+    std::vector<int> pending(n);
+    for (int i = 0; i < n; i++) pending[i] = i;
+    if (order_mode == 1) std::sort(pending.begin(), pending.end(), [&](int x, int y) { return entries[x].prio > entries[y].prio; });
+    alignas(8) unsigned char scratch[warp_scratch_bytes(32)];
+    const WarpScratch ws = make_warp_scratch(scratch, 32);
+    int32_t st_occ[33], st_sugar[34];
+    uint8_t st_perm[33], st_rank[33];
+    const LeanStage st = {st_occ, st_sugar, st_perm, st_rank, 1};
+    long long passes = 0, ran_total = 0;
+    uint64_t lcg = 0x9E3779B97F4A7C15ull ^ (uint64_t)t;
+    while (!pending.empty()) {
+        passes++;
+        if (order_mode == 2)
+            for (int i = (int)pending.size() - 1; i > 0; i--) {
+                lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
+                const int j = (int)((lcg >> 33) % (uint64_t)(i + 1));
+                const int tmp = pending[i]; pending[i] = pending[j]; pending[j] = tmp;
+            }
+        std::vector<int> left;
+        int ran = 0;
+        for (int i : pending) {
+            const uint32_t *pm = preds.data() + (size_t)i * SWEEP_COLS;
+            const int x = (int)(pm[31] / (uint32_t)H), y = (int)(pm[31] % (uint32_t)H);
+            if ((int)pm[31] != entries[i].pos) return -6;
+            if (!sweep_preds_done(pm, ld, x, y, W, H, R)) { left.push_back(i); continue; }
+            if (lean) lean_transaction(c, L, L.b[i], key, st);
+            else {
+                const int s = entries[i].slot;
+                AgentRec rec;
+                rec.load(c, s);
+                RngStream rng{key, (uint32_t)rec.id, 0u, 0u, nullptr};
+                if (transaction_move_phase<1, 4>(c, s, rec, rng, ws, 32)) transaction_interact_phase<RngStream, false>(c, s, rec, rng);
+            }
+            done[pm[31] >> 5] |= 1u << (pm[31] & 31u);
+            ran++;
+        }
+        if (ran == 0) return -3;     /* nobody could run: the predecessor relation is not acyclic */
+        ran_total += ran;
+        pending.swap(left);
+    }
+    if (lean) for (int s = 0; s < n_slots; s++) lean_unpack_slot(c, L, s);
+    if (out_stats) { out_stats[0] = n; out_stats[1] = bits; out_stats[2] = passes; out_stats[3] = tiles; }
+    return ran_total == n ? 0 : -3;
 }
 
 

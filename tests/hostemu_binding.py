@@ -128,3 +128,29 @@ class HostEmuFlow(Oracle):
         n_born, n_list = int(cn[layout.C_N_BORN]), int(cn[layout.C_N_LIST])
         self.state.a_order[n_list:n_list + n_born] = self.born[:n_born]
         cn[layout.C_N_LIST] = n_list + n_born
+
+
+class HostEmuSweep(HostEmuFlow):
+    """Mode S agent step through the ordered sweep (csrc/ssb_sweep_core.cuh, host-compiled): predecessor masks, done
+    bitmap and -- with lean=True -- the lean transaction on packed records, run in passes over the pending entries in an
+    adversarial order (1 = descending priority, 2 = pseudo-random, 0 = ascending list index)."""
+
+    def __init__(self, params, state, endow_bits=None, tag_bits=None, order_mode=1, lean=False):
+        super().__init__(params, state, endow_bits, tag_bits, order_mode)
+        P, G, A = C.POINTER(layout.Params), C.POINTER(layout.Grid), C.POINTER(layout.Agents)
+        self.E.emu_agent_step_sweep.argtypes = [P, G, A, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_int32,
+                                                C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+        self.lean = lean
+
+    def agent_step(self, t, prev_mean_wealth=0.0):
+        g, a = self.state.as_structs()
+        eb = self.endow_bits.ctypes.data if self.endow_bits is not None else None
+        tb = self.tag_bits.ctypes.data if self.tag_bits is not None else None
+        n = len(self.endow_bits) if self.endow_bits is not None else 0
+        rc = self.E.emu_agent_step_sweep(C.byref(self.params), C.byref(g), C.byref(a), t, prev_mean_wealth, eb, tb, n,
+                                         self.born.ctypes.data, self.order_mode, 1 if self.lean else 0, self.dag.ctypes.data)
+        assert rc == 0, f"emu_agent_step_sweep failed: {rc}"
+        cn = self.state.counters
+        n_born, n_list = int(cn[layout.C_N_BORN]), int(cn[layout.C_N_LIST])
+        self.state.a_order[n_list:n_list + n_born] = self.born[:n_born]
+        cn[layout.C_N_LIST] = n_list + n_born

@@ -81,6 +81,8 @@ class Oracle:
 
     def compact(self, t):
         g, a = self.state.as_structs()
+        ext = getattr(self.state, "ext", None)
+        self.L.orc_keep_children_lists(1 if ext is not None and "lending" in ext.families else 0)
         self.L.orc_compact(C.byref(self.params), C.byref(g), C.byref(a), t)
 
     def bind_endowments(self, endowments):

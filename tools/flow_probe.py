@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """A/B probe of the two mode S schedulers on a synthetic workload (one GPU).
 
-    python tools/flow_probe.py --workload S2 --size 8192 --steps 6 [--schedulers dataflow,rounds]
+    python tools/flow_probe.py --workload S2 --size 8192 --steps 6 [--schedulers sweep,sweep-generic,dataflow,rounds]
 
 Runs the same initial state through each scheduler, prints the per-phase CUDA-event times of every step and
 compares the ID-sorted state digests after the last step (they must be equal: both reproduce the sequential
@@ -24,7 +24,7 @@ def main():
     ap.add_argument("--workload", default="S2")
     ap.add_argument("--size", type=int, default=4096)
     ap.add_argument("--steps", type=int, default=6)
-    ap.add_argument("--schedulers", default="dataflow,rounds")
+    ap.add_argument("--schedulers", default="sweep,rounds")
     ap.add_argument("--no-digest", action="store_true")
     args = ap.parse_args()
     import parity_util as pu
@@ -46,7 +46,7 @@ def main():
         eng = Engine(params, state, 0, endow, tags)
         if table is not None:
             eng.bind_endowments(table)
-        eng.set_scheduler(sched.split("-")[0])
+        eng.set_scheduler("rounds" if sched.startswith("rounds") else sched)
         if sched.endswith("ms2-e256"):
             eng.set_mark_shift(2)
             eng.set_epochs(256)
