@@ -523,6 +523,9 @@ int  ssb_get_scheduler(const ssb_engine_t *e);
 /* 1 if the agent step runs the lean transaction (csrc/ssb_sweep_core.cuh: one thread per agent on packed 32-byte
  * records; rule sets without tagging / trading / reproduction / tag preferences under SSB_SCHED_SWEEP) */
 int  ssb_uses_lean_transaction(const ssb_engine_t *e);
+/* diagnostics of the sweep kernel since bind (SSB_SWEEP_DIAG=1 at bind time; -1 otherwise):
+ * {warp iterations, entries held at a readiness check, entries run} */
+int  ssb_sweep_diag(ssb_engine_t *e, unsigned long long out[3]);
 
 /* mode S tuning (SSB_SCHED_ROUNDS): number of priority epochs of the sliding-prefix commit (power of two, default 128) */
 int  ssb_set_epochs(ssb_engine_t *e, int32_t epochs);

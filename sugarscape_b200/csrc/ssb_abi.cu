@@ -48,11 +48,13 @@ struct ssb_engine {
     int flow_blocks, flow_build_blocks;
     int scheduler;           // SSB_SCHED_*
     // mode S ordered sweep (ssb_sweep.cuh, default on one GPU); lean transaction on packed records where the rule set allows
-    bool sweep_ok, lean_ok, sweep_fenced;
+    bool sweep_ok, lean_ok;
+    int lean_mode;           // LEAN_M_*: which instantiation of the lean kernel runs
     SweepCtx sweep;
     LeanCtx lean;
     int sweep_prepare_blocks, sweep_build_blocks, sweep_lean_blocks, sweep_generic_blocks;
     size_t sweep_done_bytes;
+    int sweep_stamp;
     int sweep_bits_generic, sweep_bits_lean;
     // stats
     StatsPartial *d_partials;
@@ -187,7 +189,7 @@ void ssb_destroy(ssb_engine_t *e) {
                     e->d_lorenz_blocks, e->d_plan, e->d_cand, e->sh.peer_vals, e->sh.flags, e->d_shard_vals, e->d_migrate, e->d_eth_stats, e->d_ext_stats, e->d_group_stats, e->d_eth, e->d_ext,
                     e->flow.desc, e->flow.entries, e->flow.dep, e->flow.span, e->flow.pool, e->flow.cursor, e->flow.queue, e->flow.tail, e->flow.tile_pop,
                     e->sweep.desc, e->sweep.entries, e->sweep.preds, e->sweep.done, e->sweep.bucket_count, e->sweep.bucket_start, e->sweep.bucket_fill,
-                    e->sweep.tile_pop, e->sweep.ctl, (void *)e->sweep.tables, e->lean.a, e->lean.b};
+                    e->sweep.tile_pop, e->sweep.tile_need, e->sweep.ctl, (void *)e->sweep.tables, e->lean.a, e->lean.b, e->lean.pcell};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < 5; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
     delete e;
@@ -255,7 +257,7 @@ static int setup_sweep(ssb_engine *e, int maxd) {
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_lean, k_sweep_prepare<true>, SWEEP_PREPARE_THREADS, prepare_smem));
     if (per_sm_lean < per_sm) per_sm = per_sm_lean;
     if (per_sm < 1) return fail(e, -3, "the sweep's prepare kernel does not fit on an SM");
-    e->sweep_prepare_blocks = (per_sm > 4 ? 4 : per_sm) * e->num_sms;
+    e->sweep_prepare_blocks = (per_sm > 8 ? 8 : per_sm) * e->num_sms;
     const int build_smem = sweep_build_smem_bytes(w.rb, w.kb, w.halo);
     CU(cudaFuncSetAttribute(k_sweep_build, cudaFuncAttributeMaxDynamicSharedMemorySize, build_smem));
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_build, SWEEP_BUILD_THREADS, build_smem));
@@ -270,16 +272,18 @@ static int setup_sweep(ssb_engine *e, int maxd) {
         LeanCtx &L = e->lean;
         L.maxc = 4 * maxd;
         const int lean_smem = lean_smem_bytes(L.maxc, LEAN_THREADS);
-        CU(cudaFuncSetAttribute(k_sweep_lean<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lean_smem));
-        CU(cudaFuncSetAttribute(k_sweep_lean<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lean_smem));
-        e->sweep_fenced = getenv("SSB_SWEEP_FENCED") && atoi(getenv("SSB_SWEEP_FENCED")) != 0;
-        if (e->sweep_fenced) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_lean<true>, LEAN_THREADS, lean_smem));
-        else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_lean<false>, LEAN_THREADS, lean_smem));
+        CU(cudaFuncSetAttribute(k_sweep_lean<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lean_smem));
+        CU(cudaFuncSetAttribute(k_sweep_lean<LEAN_M_ALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, lean_smem));
+        e->lean_mode = lean_mode(e->p);
+        if (e->lean_mode == 0) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_lean<0>, LEAN_THREADS, lean_smem));
+        else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_lean<LEAN_M_ALL>, LEAN_THREADS, lean_smem));
         if (per_sm < 1) return fail(e, -3, "the lean sweep kernel does not fit on an SM (%d bytes of shared memory)", lean_smem);
         e->sweep_lean_blocks = per_sm * e->num_sms;
         CU(cudaMalloc(&L.a, sizeof(LeanA) * cap));
         CU(cudaMemset(L.a, 0, sizeof(LeanA) * cap));
         CU(cudaMalloc(&L.b, sizeof(LeanB) * cap));
+        L.ty4 = (e->p.height + 3) / 4;
+        CU(cudaMalloc(&L.pcell, sizeof(int2) * (size_t)lean_tiled_cells(e->p.width, e->p.height)));
     }
     // priority buckets: sized for a full agent array and the grid that will walk them
     e->sweep_bits_generic = sweep_bucket_bits(cap, concurrent, e->p.id_bits, SWEEP_MAX_KEY_BITS);
@@ -288,15 +292,19 @@ static int setup_sweep(ssb_engine *e, int maxd) {
     CU(cudaMemset(w.desc, 0, sizeof(unsigned long long) * (size_t)cells));
     CU(cudaMalloc(&w.entries, sizeof(int4) * cap));
     CU(cudaMalloc(&w.preds, sizeof(uint32_t) * SWEEP_COLS * (size_t)cap));
-    e->sweep_done_bytes = sizeof(uint32_t) * ((size_t)cells / 32 + 2);
+    e->sweep_done_bytes = sizeof(unsigned long long) * sweep_done_words(e->p.width, e->p.height);
     CU(cudaMalloc(&w.done, e->sweep_done_bytes));
     CU(cudaMalloc(&w.bucket_count, sizeof(int32_t) * (SWEEP_MAX_KEYS + 1)));
     CU(cudaMalloc(&w.bucket_start, sizeof(int32_t) * (SWEEP_MAX_KEYS + 1)));
     CU(cudaMalloc(&w.bucket_fill, sizeof(int32_t) * (SWEEP_MAX_KEYS + 1)));
     CU(cudaMalloc(&w.tile_pop, sizeof(int32_t) * w.tiles_x * w.tiles_y));
     CU(cudaMemset(w.tile_pop, 0, sizeof(int32_t) * w.tiles_x * w.tiles_y));
-    CU(cudaMalloc(&w.ctl, sizeof(unsigned long long) * 4));
-    CU(cudaMemset(w.ctl, 0, sizeof(unsigned long long) * 4));
+    CU(cudaMalloc(&w.tile_need, sizeof(int32_t) * w.tiles_x * w.tiles_y));
+    CU(cudaMemset(w.tile_need, 0, sizeof(int32_t) * w.tiles_x * w.tiles_y));
+    e->sweep_stamp = 0;
+    CU(cudaMalloc(&w.ctl, sizeof(unsigned long long) * SWEEP_CTL_WORDS));
+    CU(cudaMemset(w.ctl, 0, sizeof(unsigned long long) * SWEEP_CTL_WORDS));
+    w.diag = getenv("SSB_SWEEP_DIAG") && atoi(getenv("SSB_SWEEP_DIAG")) ? w.ctl + 4 : nullptr;
     {
         const int bytes = sweep_tables_bytes(w.rb, w.kb, w.halo);
         std::vector<int8_t> host_tables(bytes, 0);
@@ -415,6 +423,14 @@ int ssb_set_scheduler(ssb_engine_t *e, int32_t scheduler) {
 }
 
 int ssb_get_scheduler(const ssb_engine_t *e) { return e ? e->scheduler : -1; }
+
+// diagnostics of the sweep kernel since bind (SSB_SWEEP_DIAG=1): {warp iterations, entries held at a check, entries run}
+int ssb_sweep_diag(ssb_engine_t *e, unsigned long long out[3]) {
+    if (!e || !e->bound || !e->sweep.diag) return -1;
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(out, e->sweep.diag, sizeof(unsigned long long) * 3, cudaMemcpyDeviceToHost));
+    return 0;
+}
 
 // 1 if the agent step of this engine runs the lean transaction on packed records (ssb_sweep_core.cuh)
 int ssb_uses_lean_transaction(const ssb_engine_t *e) { return e && e->scheduler == SSB_SCHED_SWEEP && e->lean_ok && !e->sharded ? 1 : 0; }
@@ -695,6 +711,7 @@ int ssb_agent_step(ssb_engine_t *e, int32_t t, double prev_mean_wealth, void *st
     } else if ((e->scheduler == SSB_SCHED_SWEEP || e->scheduler == SSB_SCHED_SWEEP_GENERIC) && !e->sharded) {
         SweepCtx w = e->sweep;
         w.key = step_key(e->p.seed, t);
+        w.stamp = ++e->sweep_stamp;
         LeanCtx L = e->lean;
         const bool lean = e->scheduler == SSB_SCHED_SWEEP && e->lean_ok;
         w.concurrent = lean ? e->sweep_lean_blocks * LEAN_THREADS : e->sweep_generic_blocks * AGENT_GROUPS;
@@ -708,8 +725,10 @@ int ssb_agent_step(ssb_engine_t *e, int32_t t, double prev_mean_wealth, void *st
         k_sweep_build<<<e->sweep_build_blocks, SWEEP_BUILD_THREADS, sweep_build_smem_bytes(w.rb, w.kb, w.halo), st>>>(c, w); LAUNCHED(e);
         k_sweep_clear<<<e->num_sms * 8, 256, 0, st>>>(c, w); LAUNCHED(e);
         if (lean) {
-            CU(cudaLaunchCooperativeKernel(e->sweep_fenced ? (void *)k_sweep_lean<true> : (void *)k_sweep_lean<false>, dim3(e->sweep_lean_blocks), dim3(LEAN_THREADS), pargs, lean_smem_bytes(L.maxc, LEAN_THREADS), st));
+            k_lean_cells<true><<<e->num_sms * 8, 256, 0, st>>>(c, w, L); LAUNCHED(e);
+            CU(cudaLaunchCooperativeKernel(e->lean_mode == 0 ? (void *)k_sweep_lean<0> : (void *)k_sweep_lean<LEAN_M_ALL>, dim3(e->sweep_lean_blocks), dim3(LEAN_THREADS), pargs, lean_smem_bytes(L.maxc, LEAN_THREADS), st));
             LAUNCHED(e);
+            k_lean_cells<false><<<e->num_sms * 8, 256, 0, st>>>(c, w, L); LAUNCHED(e);
             k_lean_unpack<<<e->num_sms * 8, 256, 0, st>>>(c, L); LAUNCHED(e);
         } else {
             void *args[] = {&c, &w};
@@ -995,8 +1014,9 @@ static int check_overflow(ssb_engine_t *e) {
                                  "kin pool exhausted: children / mates were not recorded", "", "", "", "a peer of the sharded run was lost",
                                  "migration outbox overflow", "successor pool of the dataflow scheduler exhausted",
                                  "a scheduler made no progress for seconds", "live slots differ from the agent list",
-                                 "a priority bucket of the sweep is longer than its grid"};
-    return fail(e, -4, "engine overflow code %lld: %s", code, code > 0 && code < 13 ? what[code] : "?");
+                                 "a priority bucket of the sweep is longer than its grid",
+                                 "an agent contradicts the rule flags the lean kernel was chosen by"};
+    return fail(e, -4, "engine overflow code %lld: %s", code, code > 0 && code < 14 ? what[code] : "?");
 }
 
 int ssb_stats(ssb_engine_t *e, ssb_stats_t *host_out) {

@@ -98,12 +98,33 @@ __host__ __device__ __forceinline__ void sweep_pred_masks(const SweepTile &tile,
     }
 }
 
-// Have all predecessors of the agent that starts on (x, y) finished?  The done bitmap has one bit per cell (bit
-// index = cell index x * H + y); ld(w) reads word w past every cache that could hold a stale copy.
-struct SweepWindow { int x, y0, W, H, span; bool straight; };
+// The DONE bitmap: one bit per cell -- "the agent that started the step on this cell has finished" -- in 64-bit words
+// along y, kept in TWO copies whose words are offset by 32 rows: copy A word k of column x covers rows [64 k, 64 k + 64),
+// copy B word k covers rows [64 k + 32, 64 k + 96).  Any window of up to 33 rows lies inside ONE word of one of the
+// copies, so testing the predecessors of a column is one load, one shift and one compare.
+//   words per column wpc = H / 64 + 2;  copy A at done[x * wpc + k], copy B at done[(W + x) * wpc + k]
+__host__ __device__ __forceinline__ int sweep_done_wpc(int H) { return H / 64 + 2; }
+__host__ __device__ __forceinline__ size_t sweep_done_words(int W, int H) { return (size_t)2 * W * sweep_done_wpc(H); }
+// word index and shift of the window that starts at row y0 >= 0 of column cx (span <= 33 rows, y0 + span <= H)
+__host__ __device__ __forceinline__ size_t sweep_done_window(int cx, int y0, int W, int wpc, int *shift) {
+    const bool copy_b = (y0 & 63) > 31;
+    const int yy = copy_b ? y0 - 32 : y0;
+    *shift = yy & 63;
+    return (size_t)(copy_b ? W + cx : cx) * wpc + (yy >> 6);
+}
+// set(word index, bit) is called once or twice
+template <class SetBit>
+__host__ __device__ __forceinline__ void sweep_done_set(int x, int y, int W, int wpc, SetBit set) {
+    set((size_t)x * wpc + (y >> 6), y & 63);
+    if (y >= 32) set((size_t)(W + x) * wpc + ((y - 32) >> 6), (y - 32) & 63);
+}
+
+// Have all predecessors of the agent that starts on (x, y) finished?  masks = its SWEEP_COLS words; ld(w) reads word w of
+// the bitmap past every cache that could hold a stale copy.
+struct SweepWindow { int x, y0, W, H, span, wpc; bool straight; };
 __host__ __device__ __forceinline__ SweepWindow sweep_window(int x, int y, int W, int H, int halo) {
     SweepWindow win;
-    win.x = x - halo; win.y0 = y - halo; win.W = W; win.H = H; win.span = 2 * halo + 1;
+    win.x = x - halo; win.y0 = y - halo; win.W = W; win.H = H; win.span = 2 * halo + 1; win.wpc = sweep_done_wpc(H);
     win.straight = win.y0 >= 0 && win.y0 + win.span <= H;
     return win;
 }
@@ -116,8 +137,7 @@ __host__ __device__ inline bool sweep_column_done_seam(const SweepWindow &win, u
         if (!((m >> j) & 1u)) continue;
         int cy = win.y0 + j;
         if (cy < 0) cy += win.H; else if (cy >= win.H) cy -= win.H;
-        const uint32_t bit = (uint32_t)cx * (uint32_t)win.H + (uint32_t)cy;
-        if (!((ld(bit >> 5) >> (bit & 31u)) & 1u)) ok = false;
+        if (!((ld((size_t)cx * win.wpc + (cy >> 6)) >> (cy & 63)) & 1ull)) ok = false;
     }
     return ok;
 }
@@ -126,14 +146,10 @@ __host__ __device__ __forceinline__ bool sweep_column_done(const SweepWindow &wi
     int cx = win.x + col;
     if (cx < 0) cx += win.W; else if (cx >= win.W) cx -= win.W;
     if (!win.straight) return sweep_column_done_seam(win, m, cx, ld);
-    const uint32_t bit = (uint32_t)cx * (uint32_t)win.H + (uint32_t)win.y0;
-    const uint32_t wd = bit >> 5;
-    const int s = (int)(bit & 31u);
-    uint32_t window = ld(wd) >> s;
-    if (s + win.span > 32) window |= ld(wd + 1) << (32 - s);
-    return (window & m) == m;
+    int shift;
+    const size_t wd = sweep_done_window(cx, win.y0, win.W, win.wpc, &shift);
+    return ((uint32_t)(ld(wd) >> shift) & m) == m;
 }
-// masks = the agent's SWEEP_COLS words
 template <class LoadDone>
 __host__ __device__ __forceinline__ bool sweep_preds_done(const uint32_t *masks, LoadDone ld, int x, int y, int W, int H, int halo) {
     const SweepWindow win = sweep_window(x, y, W, H, halo);
@@ -184,8 +200,18 @@ static_assert(sizeof(LeanA) == 32 && sizeof(LeanB) == 32, "one 32-byte sector pe
 struct LeanCtx {
     LeanA *a;                  // [capacity] by slot
     LeanB *b;                  // [capacity] by list index
+    int2 *pcell;               // [lean_tiled_cells] {occupant slot, sugar} of every cell in 4 x 4 tiles (lean_tiled)
+    int32_t ty4;               // tiles per column of tiles: (H + 3) / 4
     int32_t maxc;              // 4 * largest range: candidate cells staged per agent
 };
+
+// The cells as the transactions see them: {cell.agent, cell.sugar} in one 8-byte word, 4 x 4 cells per 128-byte line
+// and 2 x 2 cells per 32-byte sector, so that a cross of radius r touches about 2 r + 1 sectors instead of one sector
+// per candidate and array.  Packed from / unpacked to the ABI's x-major arrays around the sweep (populated tiles only).
+__host__ __device__ __forceinline__ uint32_t lean_tiled(int x, int y, int ty4) {
+    return ((((uint32_t)(x >> 2) * (uint32_t)ty4 + (uint32_t)(y >> 2)) << 4) | (uint32_t)(((x & 2) << 2) | ((y & 2) << 1) | ((x & 1) << 1) | (y & 1)));
+}
+__host__ __device__ __forceinline__ long long lean_tiled_cells(int W, int H) { return (long long)((W + 3) / 4) * ((H + 3) / 4) * 16; }
 
 __device__ __forceinline__ LeanA lean_load_a(const LeanA *p) {
 #if defined(__CUDA_ARCH__)
@@ -204,15 +230,22 @@ __device__ __forceinline__ LeanA lean_load_a(const LeanA *p) {
 __host__ __device__ inline bool lean_supported(const ssb_params_t &p) {
     if (p.rng_mode != SSB_RNG_SCALABLE) return false;
     if (p.flags & (SSB_F_TAGGING | SSB_F_TRADE | SSB_F_REPRO | SSB_F_TAGPREF)) return false;
-    if (p.max_tribes > 25) return false;
+    if (p.max_tribes > 25 || p.max_sugar_capacity > 32767) return false;
     const int side = p.width < p.height ? p.width : p.height;
     return p.max_agent_range >= 0 && p.max_agent_range <= 7 && 2 * p.max_agent_range + 1 < side;
 }
 
+// MODE: which rule families the instantiation can handle (LEAN_M_*); the plain instantiation (0) of rule sets without
+// combat, spice and pollution (S2) carries no fp64 pow, no occupant records and no per-tribe table.
+enum { LEAN_M_FIGHT = 1, LEAN_M_SPICE = 2, LEAN_M_POLLUTION = 4, LEAN_M_ALL = 7 };
+__host__ __device__ inline int lean_mode(const ssb_params_t &p) {
+    return (p.flags & (SSB_F_COMBAT | SSB_F_SPICE | SSB_F_POLLUTION)) ? LEAN_M_ALL : 0;
+}
+
 // Per-thread staging arrays (shared memory on the device, element i of this thread at [i * stride]).
 struct LeanStage {
-    int32_t *occ, *sugar;      // [maxc + 1]: the candidates in enumeration order, then the own cell
-    uint8_t *perm, *rank;      // [maxc]
+    int32_t *occ;              // [maxc]: occupants of the candidates in enumeration order
+    int16_t *sugar;            // [maxc + 1]: their sugar, then the own cell's (lean_supported: capacities fit 15 bits)
     int stride;
 };
 
@@ -252,14 +285,17 @@ __device__ __forceinline__ int lean_candidate(int i, int x, int y, int W, int H)
     return cx * H + cy;
 }
 
-// the four candidates at distance d (candidates 4 (d - 1) .. 4 (d - 1) + 3) in that order
-__device__ __forceinline__ void lean_ring(int d, int x, int y, int W, int H, int out[4]) {
+// the four candidates at distance d (candidates 4 (d - 1) .. 4 (d - 1) + 3) in that order, as x-major cell indices
+// (TILED = false) or as indices of the tiled cell array (TILED = true; hy = ty4 instead of H)
+template <bool TILED>
+__device__ __forceinline__ void lean_ring(int d, int x, int y, int W, int H, int hy, int out[4]) {
     int xw = x - d, xe = x + d, yn = y - d, ys = y + d;
     if (xw < 0) xw += W;
     if (xe >= W) xe -= W;
     if (yn < 0) yn += H;
     if (ys >= H) ys -= H;
-    const int cw = xw * H + y, ce = xe * H + y, cn = x * H + yn, cs = x * H + ys;
+    const int cw = TILED ? (int)lean_tiled(xw, y, hy) : xw * H + y, ce = TILED ? (int)lean_tiled(xe, y, hy) : xe * H + y;
+    const int cn = TILED ? (int)lean_tiled(x, yn, hy) : x * H + yn, cs = TILED ? (int)lean_tiled(x, ys, hy) : x * H + ys;
     if (x < d) {
         if (y < d) { out[0] = ce; out[1] = cs; out[2] = cn; out[3] = cw; }
         else { out[0] = cn; out[1] = ce; out[2] = cs; out[3] = cw; }
@@ -300,6 +336,9 @@ __device__ __forceinline__ void lean_pack_b(const DevCtx &c, const LeanCtx &L, i
     B.sugar_metab = a.sugar_metab[s]; B.spice_metab = a.spice_metab[s];
     B.aggression = a.aggression[s]; B.lookahead = a.lookahead[s];
     L.b[index] = B;
+    // the plain instantiation relies on the rule flags: an agent that contradicts them stops the run (overflow code 13)
+    if (lean_mode(c.p) == 0 && (B.aggression > 0 || B.spice_metab > 0 || a.spice[s] != 0))
+        atomicExch((unsigned long long *)&c.a.counters[SSB_C_OVERFLOW], 13ull);
 }
 
 // k_lean_unpack for one slot: the mutable fields go back to the ABI's arrays; happiness of the agents that are
@@ -331,31 +370,41 @@ __device__ __forceinline__ void lean_unpack_slot(const DevCtx &c, const LeanCtx 
 // tie-break (1395-1443, 1479-1490), doCombat (274-294), gotoCell, collectResourcesAtCell (249-259), doMetabolism
 // (485-498) with the pollution terms (cell.py:27-45), starvation, doAging (266-272).  Mirrors
 // transaction_move_phase / transaction_interact_phase of ssb_rules.cuh statement by statement.
-__device__ inline void lean_transaction(const DevCtx &c, const LeanCtx &L, const LeanB &B, uint64_t key, const LeanStage &st) {
+// warpm: the lanes of the warp that enter together (they must be converged at the call).  The lanes are independent
+// agents, but they run the same loops with the same trip counts (the sweep groups agents by range), so the function
+// re-converges them after every data-dependent stretch -- otherwise a warp drifts apart into a handful of sub-warps
+// that each pay the full instruction stream.
+template <int MODE>
+__device__ inline void lean_transaction(const DevCtx &c, const LeanCtx &L, const LeanB &B, uint64_t key, const LeanStage &st, unsigned warpm) {
     const int s = B.slot;
     LeanA A = lean_load_a(L.a + s);
-    if (!((A.state & LEAN_COD_MASK) == SSB_ALIVE && A.sugar >= 0 && A.spice >= 0) || (B.idf & LEANB_SKIP)) return;
+    const bool acting = (A.state & LEAN_COD_MASK) == SSB_ALIVE && A.sugar >= 0 && A.spice >= 0 && !(B.idf & LEANB_SKIP);
+    const unsigned actm = __ballot_sync(warpm, acting);
+    if (!acting) return;
     const int W = c.p.width, H = c.p.height, pos = A.pos, x = pos / H, y = pos - x * H;
     const int r = (int)((B.idf >> LEANB_RANGE_SHIFT) & 15u), n = 4 * r, S = st.stride;
     const uint32_t id = B.idf & LEANB_ID_MASK;
-    const bool polluted = (c.p.flags & SSB_F_POLLUTION) != 0, spicy = (c.p.flags & SSB_F_SPICE) != 0;
-    const double aggression = fmax(B.aggression, 0.0);
-    const bool fighter = aggression > 0;
-    // the cross (and the own cell, in case the agent stays): two distances = sixteen independent loads in flight
+    const bool polluted = (MODE & LEAN_M_POLLUTION) && (c.p.flags & SSB_F_POLLUTION) != 0, spicy = (MODE & LEAN_M_SPICE) && (c.p.flags & SSB_F_SPICE) != 0;
+    const double aggression = (MODE & LEAN_M_FIGHT) ? fmax(B.aggression, 0.0) : 0.0;
+    const bool fighter = (MODE & LEAN_M_FIGHT) && aggression > 0;
+    // the cross (and the own cell, in case the agent stays): two distances = eight independent 8-byte loads in flight
+    const int2 *pcell = L.pcell;
+    const uint32_t tpos = lean_tiled(x, y, L.ty4);
     for (int d = 1; d <= r; d += 2) {
         int cell[8];
-        int32_t v_occ[8], v_sugar[8];
-        lean_ring(d, x, y, W, H, cell);
+        int2 v[8];
+        lean_ring<true>(d, x, y, W, H, L.ty4, cell);
         const bool two = d + 1 <= r;
-        if (two) lean_ring(d + 1, x, y, W, H, cell + 4);
+        if (two) lean_ring<true>(d + 1, x, y, W, H, L.ty4, cell + 4);
 #pragma unroll
         for (int u = 0; u < 8; u++)
-            if (u < 4 || two) { v_occ[u] = lean_ld(c.g.occ + cell[u]); v_sugar[u] = lean_ld(c.g.sugar + cell[u]); }
+            if (u < 4 || two) v[u] = lean_ld(pcell + cell[u]);
 #pragma unroll
         for (int u = 0; u < 8; u++)
-            if (u < 4 || two) { st.occ[(4 * (d - 1) + u) * S] = v_occ[u]; st.sugar[(4 * (d - 1) + u) * S] = v_sugar[u]; }
+            if (u < 4 || two) { st.occ[(4 * (d - 1) + u) * S] = v[u].x; st.sugar[(4 * (d - 1) + u) * S] = (int16_t)v[u].y; }
     }
-    st.sugar[n * S] = lean_ld(c.g.sugar + pos);
+    st.sugar[n * S] = (int16_t)lean_ld(pcell + tpos).y;
+    __syncwarp(actm);
     // findWelfare's per-agent part (agent.py:1170-1201, no tag preferences)
     Welfare w;
     const double sm = (double)max(B.sugar_metab, 0), pm = (double)max(B.spice_metab, 0);
@@ -369,21 +418,13 @@ __device__ inline void lean_transaction(const DevCtx &c, const LeanCtx &L, const
         else { w.e_s = sm / total; w.e_p = pm / total; }
     }
     const double my_wealth = A.sugar + A.spice, loot = c.p.max_combat_loot;
-    int b_cell = pos, b_dist = 1 << 30, b_rank = 1 << 30, b_cs = 0, b_cp = 0, b_occ = -1, hood = 0, m = 0;
+    int b_cell = pos, b_dist = 0, b_cs = 0, b_cp = 0, b_occ = -1, hood = 0, m = 0;
+    unsigned b_ties = 0;                       // candidates j of ring b_dist that share the best (welfare, distance)
     double b_welfare = -1.0, b_pl = 0.0;
     bool b_valid = false;
-    if (n > 0) {
-        // random.shuffle(cellsInRange), agent.py:1400-1401: rank[i] = shuffled position of candidate i
-        RngStream rng{key, id, 0u, 0u, nullptr};
-        rng.at(SITE_MOVE);
-        for (int i = 0; i < n; i++) st.perm[i * S] = (uint8_t)i;
-        for (int i = n - 1; i >= 1; i--) {
-            const uint32_t j = rand_below(rng, (uint32_t)i + 1u);
-            const uint8_t t = st.perm[i * S]; st.perm[i * S] = st.perm[j * S]; st.perm[j * S] = t;
-        }
-        for (int k = 0; k < n; k++) st.rank[st.perm[k * S] * S] = (uint8_t)k;
+    {   // (no `if (n > 0)` around this block: every lane must reach the __syncwarp()s; with n == 0 the loops do nothing)
         // findRetaliatorsInVision (agent.py:1088-1098): the richest visible agent of every tribe
-        double retaliator[27];
+        double retaliator[(MODE & LEAN_M_FIGHT) ? 27 : 1];
         if (fighter) {
             for (int i = 0; i < n; i++) { const int o = st.occ[i * S]; if (o >= 0) lean_prefetch(L.a + o); }
             for (int i = 0; i < 27; i++) retaliator[i] = 0.0;
@@ -396,9 +437,12 @@ __device__ inline void lean_transaction(const DevCtx &c, const LeanCtx &L, const
                 if (ow > retaliator[slot]) retaliator[slot] = ow;
             }
         }
+        // rankCellsInRange (agent.py:1395-1443): best welfare, then the smallest distance, then the position in the
+        // shuffled candidate list.  Candidates that tie in (welfare, distance) lie on ONE ring of four cells, so the
+        // shuffle is only consulted for those (below) -- and not at all when the best candidate is unique.
         for (int d = 1; d <= r; d++) {
             int ring[4];
-            lean_ring(d, x, y, W, H, ring);
+            lean_ring<false>(d, x, y, W, H, H, ring);
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const int i = 4 * (d - 1) + j, cell = ring[j];
@@ -422,18 +466,53 @@ __device__ inline void lean_transaction(const DevCtx &c, const LeanCtx &L, const
                 double sugar_reward = (double)cs, spice_reward = (double)cp;
                 if (fighter) { sugar_reward += aggression * fmin(loot, ps); spice_reward += aggression * fmin(loot, pp); }   // (+ 0.0 otherwise)
                 if (polluted) { sugar_reward /= 1 + pl; spice_reward /= 1 + pl; }                                            // (/ 1.0 otherwise)
-                const double welfare = w.eval(sugar_reward, spice_reward);
-                if (occupied && retaliator[min(otribe + 1, 26)] > my_wealth + welfare) continue;
-                const int rk = st.rank[i * S];
-                if (!b_valid || welfare > b_welfare || (welfare == b_welfare && (d < b_dist || (d == b_dist && rk < b_rank)))) {
-                    b_cell = cell; b_welfare = welfare; b_dist = d; b_rank = rk; b_valid = true;
-                    b_cs = cs; b_cp = cp; b_pl = pl; b_occ = o;
+                double welfare;
+                if (MODE & LEAN_M_SPICE) welfare = w.eval(sugar_reward, spice_reward);
+                else {      // no spice anywhere: the exponents are (1, 0) -- or (0, 0) without a sugar metabolism -- and x ** 1 == x, x ** 0 == 1
+                    double ts = (w.sugar + sugar_reward) - w.s_look;
+                    if (ts < 0) ts = 0;
+                    welfare = w.e_s != 0 ? ts : 1.0;
                 }
+                if ((MODE & LEAN_M_FIGHT) && occupied && retaliator[min(otribe + 1, 26)] > my_wealth + welfare) continue;
                 m++;
+                if (!b_valid || welfare > b_welfare) { b_welfare = welfare; b_dist = d; b_ties = 1u << j; b_valid = true; }    // (rings come in ascending distance)
+                else if (welfare == b_welfare && d == b_dist) b_ties |= 1u << j;
             }
         }
-        if (m == 0) m = 1;
+        if (n > 0 && m == 0) m = 1;
     }
+    __syncwarp(actm);
+    if (b_valid) {
+        int jw = __ffs(b_ties) - 1;
+        if (b_ties & (b_ties - 1u)) {
+            // random.shuffle(cellsInRange), agent.py:1400-1401, replayed for the positions of this ring's four candidates only:
+            // x[i], x[j] = x[j], x[i] for i = n - 1 .. 1 moves whoever stands on position i to j and vice versa
+            RngStream rng{key, id, 0u, 0u, nullptr};
+            rng.at(SITE_MOVE);
+            const int base = 4 * (b_dist - 1);
+            int p0 = base, p1 = base + 1, p2 = base + 2, p3 = base + 3;
+            for (int i = n - 1; i >= 1; i--) {
+                const int j = (int)rand_below(rng, (uint32_t)i + 1u);
+                p0 = p0 == i ? j : (p0 == j ? i : p0);
+                p1 = p1 == i ? j : (p1 == j ? i : p1);
+                p2 = p2 == i ? j : (p2 == j ? i : p2);
+                p3 = p3 == i ? j : (p3 == j ? i : p3);
+            }
+            int best_pos = 1 << 30;
+            if ((b_ties & 1u) && p0 < best_pos) { best_pos = p0; jw = 0; }
+            if ((b_ties & 2u) && p1 < best_pos) { best_pos = p1; jw = 1; }
+            if ((b_ties & 4u) && p2 < best_pos) { best_pos = p2; jw = 2; }
+            if ((b_ties & 8u) && p3 < best_pos) { best_pos = p3; jw = 3; }
+        }
+        int ring[4];
+        lean_ring<false>(b_dist, x, y, W, H, H, ring);
+        const int i = 4 * (b_dist - 1) + jw;
+        b_cell = ring[jw];
+        b_cs = st.sugar[i * S]; b_occ = st.occ[i * S];
+        b_cp = spicy ? lean_ld(c.g.spice + b_cell) : 0;
+        b_pl = polluted ? lean_ld(c.g.pollution + b_cell) : 0.0;
+    }
+    __syncwarp(actm);
     uint8_t state = (uint8_t)(LEAN_PACKED | LEAN_ACTED | (n > 0 ? LEAN_RANGED : 0));
     double sugar = A.sugar, spice = A.spice;
     const int best = b_valid ? b_cell : pos;
@@ -451,8 +530,10 @@ __device__ inline void lean_transaction(const DevCtx &c, const LeanCtx &L, const
         P.state = (uint8_t)((P.state & ~LEAN_COD_MASK) | SSB_COMBAT);       // doDeath("combat"): the killer takes the cell below
         L.a[b_occ] = P;
     }
-    c.g.occ[pos] = -1;
-    c.g.occ[best] = s;
+    const int bx = best / H;
+    int2 *pbest = L.pcell + lean_tiled(bx, best - bx * H, L.ty4);
+    L.pcell[tpos].x = -1;
+    *pbest = make_int2(s, 0);                                    // the agent stands there; the cell's sugar is collected below
     // collectResourcesAtCell (agent.py:249-259) + production pollution (cell.py:32-45)
     sugar += b_cs;
     spice += b_cp;
@@ -462,7 +543,6 @@ __device__ inline void lean_transaction(const DevCtx &c, const LeanCtx &L, const
         cell_poll += c.p.sugar_prod_pollution * b_cs;
         cell_poll += c.p.spice_prod_pollution * b_cp;
     }
-    c.g.sugar[best] = 0;
     if (spicy) c.g.spice[best] = 0;
     // doMetabolism (agent.py:485-498) + consumption pollution (cell.py:27-40)
     sugar -= sm;
@@ -476,14 +556,14 @@ __device__ inline void lean_transaction(const DevCtx &c, const LeanCtx &L, const
     A.hood = (uint8_t)(hood + 1); A.valid = (uint8_t)m;
     if (sugar < 0 || spice < 0 || (sugar <= 0 && sm > 0) || (spice <= 0 && pm > 0)) {
         state |= SSB_STARVATION;                                              // doDeath("starvation") (agent.py:296-313)
-        c.g.occ[best] = -1;
+        pbest->x = -1;
     } else {
         // doAging (agent.py:266-272); isAlive() holds here: both holdings are positive or their metabolism is 0
         if (sugar >= 0 && spice >= 0) {
             state |= LEAN_AGED;
             if (B.idf & LEANB_DIES) {
                 state |= SSB_AGING;
-                c.g.occ[best] = -1;
+                pbest->x = -1;
             }
         }
     }

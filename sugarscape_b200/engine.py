@@ -48,6 +48,7 @@ def load_library():
     L.ssb_set_scheduler.argtypes = [E, C.c_int32]
     L.ssb_get_scheduler.argtypes = [E]
     L.ssb_uses_lean_transaction.argtypes = [E]
+    L.ssb_sweep_diag.argtypes = [E, C.c_void_p]
     L.ssb_set_mark_shift.argtypes = [E, C.c_int32]
     L.ssb_set_l2_persist.argtypes = [E, C.c_void_p, C.c_int32]
     L.ssb_env_step.argtypes = [E, C.c_int32, C.c_void_p]
@@ -103,7 +104,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = (
     "ssb_abi_version", "ssb_create", "ssb_bind", "ssb_destroy", "ssb_last_error",
-    "ssb_set_mt_state", "ssb_get_mt_state", "ssb_set_step_tables", "ssb_set_scheduler", "ssb_get_scheduler", "ssb_uses_lean_transaction", "ssb_set_epochs", "ssb_set_mark_shift", "ssb_set_l2_persist",
+    "ssb_set_mt_state", "ssb_get_mt_state", "ssb_set_step_tables", "ssb_set_scheduler", "ssb_get_scheduler", "ssb_uses_lean_transaction", "ssb_sweep_diag", "ssb_set_epochs", "ssb_set_mark_shift", "ssb_set_l2_persist",
     "ssb_sizeof_params", "ssb_sizeof_grid", "ssb_sizeof_agents", "ssb_sizeof_stats",
     "ssb_env_step", "ssb_agent_step", "ssb_compact", "ssb_bind_endowments", "ssb_replace", "ssb_reduce_stats", "ssb_step", "ssb_stats", "ssb_stats_history",
     "ssb_fabric_create", "ssb_fabric_alloc", "ssb_fabric_map", "ssb_fabric_copy", "ssb_fabric_granularity",
@@ -376,6 +377,13 @@ class Engine:
 
     def scheduler(self):
         return {0: "rounds", 1: "dataflow", 3: "sweep", 4: "sweep-generic"}.get(int(self.L.ssb_get_scheduler(self.handle)), "n/a")
+
+    def sweep_diag(self):
+        """{warp iterations, entries held at a readiness check, entries run} of the sweep kernel (SSB_SWEEP_DIAG=1), else None."""
+        out = np.zeros(3, dtype=np.uint64)
+        if self.L.ssb_sweep_diag(self.handle, out.ctypes.data) != 0:
+            return None
+        return [int(v) for v in out]
 
     def uses_lean_transaction(self):
         return bool(self.L.ssb_uses_lean_transaction(self.handle))

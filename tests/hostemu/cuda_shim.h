@@ -24,17 +24,21 @@
 #define __align__(n) alignas(n)
 
 struct ssb_emu_dim3 { unsigned x, y, z; };
+struct int2 { int x, y; };
+static inline int2 make_int2(int x, int y) { int2 v = {x, y}; return v; }
 static const ssb_emu_dim3 threadIdx = {0, 0, 0};
 
 template <class T> static inline T __shfl_sync(unsigned, T v, int, int = 32) { return v; }
 template <class T> static inline T __shfl_xor_sync(unsigned, T v, int, int = 32) { return v; }
 static inline void __syncwarp(unsigned = 0xffffffffu) {}
 static inline int __any_sync(unsigned, int p) { return p; }
+static inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }
 static inline int __all_sync(unsigned, int p) { return p; }
 static inline void __threadfence_block() {}
 static inline void __threadfence() {}
 
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 static inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
 static inline long long __double_as_longlong(double d) { long long u; memcpy(&u, &d, 8); return u; }

@@ -202,8 +202,12 @@ int emu_agent_step_sweep(const ssb_params_t *p, const ssb_grid_t *g, const ssb_a
     /* prepare (k_sweep_prepare): list indices in a scrambled order */
     std::vector<LeanA> recA(lean ? (size_t)a->capacity : 0);
     std::vector<LeanB> recB(lean ? (size_t)a->capacity : 0);
+    std::vector<int2> pcell(lean ? (size_t)lean_tiled_cells(W, H) : 0);
     LeanCtx L;
     L.a = recA.data(); L.b = recB.data(); L.maxc = 4 * RB;
+    L.pcell = pcell.data(); L.ty4 = (H + 3) / 4;
+    if (lean)   /* k_lean_cells<true>: {cell.agent, cell.sugar} into the tiled cell array */
+        for (int x = 0; x < W; x++) for (int y = 0; y < H; y++) pcell[lean_tiled(x, y, L.ty4)] = make_int2(g->occ[(size_t)x * H + y], g->sugar[(size_t)x * H + y]);
     struct Entry { int slot, pos; uint32_t prio; };
     std::vector<Entry> entries;
     std::vector<unsigned long long> desc((size_t)W * H, 0ull);
@@ -259,16 +263,17 @@ int emu_agent_step_sweep(const ssb_params_t *p, const ssb_grid_t *g, const ssb_a
         }
     }
     /* sweep (k_sweep_lean / k_sweep_generic): passes over the pending entries */
-    std::vector<uint32_t> done((size_t)W * H / 32 + 2, 0u);
-    auto ld = [&](uint32_t wd) { return done[wd]; };
+    std::vector<unsigned long long> done(sweep_done_words(W, H), 0ull);
+    auto ld = [&](size_t wd) { return done[wd]; };
+    const int wpc = sweep_done_wpc(H);
     std::vector<int> pending(n);
     for (int i = 0; i < n; i++) pending[i] = i;
     if (order_mode == 1) std::sort(pending.begin(), pending.end(), [&](int x, int y) { return entries[x].prio > entries[y].prio; });
     alignas(8) unsigned char scratch[warp_scratch_bytes(32)];
     const WarpScratch ws = make_warp_scratch(scratch, 32);
-    int32_t st_occ[33], st_sugar[34];
-    uint8_t st_perm[33], st_rank[33];
-    const LeanStage st = {st_occ, st_sugar, st_perm, st_rank, 1};
+    int32_t st_occ[33];
+    int16_t st_sugar[34];
+    const LeanStage st = {st_occ, st_sugar, 1};
     long long passes = 0, ran_total = 0;
     uint64_t lcg = 0x9E3779B97F4A7C15ull ^ (uint64_t)t;
     while (!pending.empty()) {
@@ -286,7 +291,7 @@ int emu_agent_step_sweep(const ssb_params_t *p, const ssb_grid_t *g, const ssb_a
             const int x = (int)(pm[31] / (uint32_t)H), y = (int)(pm[31] % (uint32_t)H);
             if ((int)pm[31] != entries[i].pos) return -6;
             if (!sweep_preds_done(pm, ld, x, y, W, H, R)) { left.push_back(i); continue; }
-            if (lean) lean_transaction(c, L, L.b[i], key, st);
+            if (lean) { if (lean_mode(*p) == 0) lean_transaction<0>(c, L, L.b[i], key, st, 1u); else lean_transaction<LEAN_M_ALL>(c, L, L.b[i], key, st, 1u); }
             else {
                 const int s = entries[i].slot;
                 AgentRec rec;
@@ -294,14 +299,20 @@ int emu_agent_step_sweep(const ssb_params_t *p, const ssb_grid_t *g, const ssb_a
                 RngStream rng{key, (uint32_t)rec.id, 0u, 0u, nullptr};
                 if (transaction_move_phase<1, 4>(c, s, rec, rng, ws, 32)) transaction_interact_phase<RngStream, false>(c, s, rec, rng);
             }
-            done[pm[31] >> 5] |= 1u << (pm[31] & 31u);
+            sweep_done_set(x, y, W, wpc, [&](size_t wd, int bit) { done[wd] |= 1ull << bit; });
             ran++;
         }
         if (ran == 0) return -3;     /* nobody could run: the predecessor relation is not acyclic */
         ran_total += ran;
         pending.swap(left);
     }
-    if (lean) for (int s = 0; s < n_slots; s++) lean_unpack_slot(c, L, s);
+    if (lean) {
+        for (int x = 0; x < W; x++) for (int y = 0; y < H; y++) {      /* k_lean_cells<false> */
+            const int2 v = pcell[lean_tiled(x, y, L.ty4)];
+            g->occ[(size_t)x * H + y] = v.x; g->sugar[(size_t)x * H + y] = v.y;
+        }
+        for (int s = 0; s < n_slots; s++) lean_unpack_slot(c, L, s);
+    }
     if (out_stats) { out_stats[0] = n; out_stats[1] = bits; out_stats[2] = passes; out_stats[3] = tiles; }
     return ran_total == n ? 0 : -3;
 }

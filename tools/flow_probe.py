@@ -58,8 +58,11 @@ def main():
             st = eng.stats()
             rows.append({"t": t, "population": int(st.population), "rounds": int(st.rounds), **{k: round(v, 3) for k, v in tim.items()}})
         code = int(eng.counters()[layout.C_OVERFLOW])
+        diag = eng.sweep_diag() if hasattr(eng, "sweep_diag") else None
         line = {"scheduler": sched, "workload": args.workload, "size": args.size, "agents": n, "overflow": code, "steps": rows,
                 "mean_agent_ms": float(np.mean([r["agent_ms"] for r in rows[1:]] or [rows[0]["agent_ms"]]))}
+        if diag:
+            line["sweep_diag"] = {"warp_iterations": diag[0], "held": diag[1], "ran": diag[2]}
         if not args.no_digest:
             d, snap = pu.state_digests_by_id(eng.download())
             digests[sched] = d
