@@ -8,9 +8,8 @@ A "step" is one full Sugarscape timestep (environment stencil, agent loop, remov
 replacement, stats reductions) in scalable RNG mode.  Default workload S2:
 16384 x 16384 map, 25 M agents, combat_limited rules -- the same simulation at every N (strong
 scaling): one GPU holds it whole, N > 1 shards it by x-slabs over NVLink-stitched memory
-(sugarscape_b200/sharded.py), results bit-identical to the single-GPU run.  --workload S1 is the
-4096 x 4096 / 1.6 M agents / reproduction_basic shape (one GPU, or N replicas: sharded births are
-experimental).
+(sugarscape_b200/sharded.py), results bit-identical to the single-GPU run ("state_digest" is the
+same at every N).  --workload S1 is the 4096 x 4096 / 1.6 M agents / reproduction_basic shape.
 
 Timed regions
   value   K steps enqueued back to back, state resident in HBM, CUDA events on the launching
@@ -18,15 +17,18 @@ Timed regions
   e2e     the same K steps through the public host API (Sugarscape-style doTimestep: stats read
           back to the host every step and turned into the log dict) INCLUDING the upload of the
           whole initial state from host memory and the download of the final agent state.
-  roofline  average duration of the dominant kernel (the agent-step kernel) from CUDA events
-          recorded inside libssb around each phase, over separately run steps.
-  cpu_baseline  the CPU oracle (C port of the reference's algorithm, oracle/ss_oracle.c) on a
-          bounded sample of the same workload, one host core.  The reference itself is pure
-          Python (about 6-8 k agent-steps/s/core measured in the build container)
-          and is not present on the GPU box.
-  --impl reference  the same port on ALL host cores: one simulation is strictly serial in the
-          reference, its only parallelism is one process per seed (data/run.py:155-180), so the arm
-          runs os.cpu_count() independent replicas of a bounded sample (same rules and density).
+  roofline  the dominant kernel (one GPU: the sweep kernel k_sweep_lean; sharded: the rounds kernel): its
+          algorithmic bytes / its average launch duration from CUDA events recorded inside libssb around that
+          launch, over separately run steps; the other kernels of the agent step are listed beside it.
+  cpu_baseline  the CPU oracle (C port of the reference's algorithm, oracle/ss_oracle.c) on one timestep of the
+          SAME initial state, one host core; its result is compared with the GPU's first step from that state
+          ("parity_at_scale").  The reference itself is pure Python; when it is present (build container) its own
+          doTimestep loop is timed on the shipped examples ("python_reference"), on the GPU box it is absent.
+  e_configs / s1  (N = 1) the shipped examples of BASELINE configs[0..2] + determinism through the drop-in driver
+          (exact RNG mode, Sugarscape.runSimulation), and the S1 shape (configs[3]).
+  --impl reference  the same port on the same S2 state: ONE simulation is strictly serial in the reference (its only
+          parallelism is one process per seed, data/run.py:155-180), so the arm runs one timestep on one core;
+          an all-core figure over independent small replicas is added as context and labelled as such.
 """
 import argparse
 import ctypes as C
@@ -66,6 +68,8 @@ def parse_args():
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=0, help="timesteps of the CPU port (default: 1 for S2, 3 for S1)")
+    ap.add_argument("--skip-extra", action="store_true", help="no e_configs / s1 / python_reference blocks")
+    ap.add_argument("--scheduler", default="", help="mode S scheduler of the single-GPU engine (default: the engine's choice)")
     return ap.parse_args()
 
 
@@ -213,6 +217,122 @@ def run_cpu_port_all_cores(args, c, steps):
     return total / slowest, slowest, total, cores, f"{cores} replicas of {side}x{side} / {n} agents, {steps} timesteps each"
 
 
+def measured_traffic(kernel, args):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture of this workload (profiles/), or None."""
+    path = os.path.join(ROOT, "profiles", "r2_kernel_traffic.json")
+    try:
+        with open(path) as f:
+            table = json.load(f)
+        rec = table[f"{args.workload}:{args.size}:{kernel}"]
+        return rec["dram_bytes_per_launch"], rec["source"]
+    except Exception:
+        return None, "no ncu capture of this kernel at this shape under profiles/r2_kernel_traffic.json"
+
+
+def run_s1_block(args, local_rank):
+    """BASELINE configs[3]: synthetic 4096 x 4096 map, 1.6 M agents, reproduction_basic rules, one GPU, device-resident."""
+    import torch
+    from sugarscape_b200 import synthetic, steptables, layout
+    from sugarscape_b200.engine import Engine
+    c = synthetic.configuration(synthetic.S1_OPTIONS, {"timesteps": 1 << 20})
+    state, params = synthetic.build_state(c)
+    warm, steps = 5, 20
+    endow, tags = steptables.step_tables(1, warm + steps + 16, c["agentTagStringLength"])
+    eng = Engine(params, state, local_rank, endow, tags)
+    t = 0
+    for _ in range(warm):
+        t += 1
+        eng.step(t, 0.0)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    first = t + 1
+    for _ in range(steps):
+        t += 1
+        eng.step(t, 0.0)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    acting = sum(int(eng.stats_history(s - 1).population) for s in range(first, t + 1))
+    eng.enable_timing(True)
+    t += 1
+    eng.step(t, 0.0)
+    tim = eng.timing()
+    code = int(eng.counters()[layout.C_OVERFLOW])
+    out = {"workload": "S1 synthetic 4096x4096, 1600000 agents, reproduction_basic rules", "value": acting / (ms / 1000.0), "unit": UNIT,
+           "steps": steps, "warmup": warm, "ms_per_step": ms / steps, "scheduler": eng.scheduler(), "phase_ms": tim, "overflow": code,
+           "roofline_frac_agent_step": int(eng.stats_history(t - 1).population) * BYTES_PER_AGENT_STEP["S1"] / (tim["agent_ms"] / 1000.0) / 1e9 / measured_peak_gbs()[0]}
+    eng.close()
+    return out
+
+
+E_CONFIGS = ["constant_growback", "pollution_formation", "seasonal_migration", "trade_basic", "determinism"]
+PYTHON_REFERENCE_PER_CORE = {"constant_growback": "4.9-5.4 k", "pollution_formation": "5.8-7.2 k", "seasonal_migration": "5.2-6.0 k",
+                             "trade_basic": "5.9-6.2 k", "determinism": "2.0-3.1 k"}     # BASELINE.md section 2 (survey container, one core)
+
+
+def example_config(name, timesteps):
+    import parity_util as pu
+    return pu.example_configuration(name, {"timesteps": timesteps})
+
+
+def run_e_configs(args):
+    """The shipped examples through the drop-in driver (exact RNG mode: the reference's own trajectory), wall clock of
+    Sugarscape.runSimulation including the per-step stats readback and log formatting (no log file)."""
+    from sugarscape_b200.simulation import Sugarscape
+    out = {}
+    for name in E_CONFIGS:
+        try:
+            c = example_config(name, 200)
+            c["logfile"] = None
+            S = Sugarscape(c)
+            t0 = time.perf_counter()
+            S.runSimulation(c["timesteps"])
+            dt = time.perf_counter() - t0
+            out[name] = {"agent_steps": int(S.agent_steps), "timesteps": int(S.timestep), "seconds": dt, "value": S.agent_steps / dt, "unit": UNIT,
+                         "python_reference_one_core": PYTHON_REFERENCE_PER_CORE[name] + " agent-steps/s (BASELINE.md, survey container)"}
+        except Exception as err:          # an example the engine refuses must not take the bench line down
+            out[name] = {"error": f"{type(err).__name__}: {err}"}
+    return out
+
+
+def run_python_reference(args):
+    """The reference's own doTimestep loop (sugarscape.py:871-880) on the shipped examples, when the reference is present
+    (build container, or baseline/_ref); the GPU box does not have it."""
+    for root in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        if os.path.exists(os.path.join(root, "sugarscape.py")):
+            break
+    else:
+        return "absent"
+    code = r"""
+import json, os, sys, time
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+os.environ["SUGARSCAPE_REFERENCE"] = REF
+import ref_harness as rh
+out = {}
+for name in NAMES:
+    S = rh.build_reference(os.path.join(REF, "examples", name + ".json"), {"timesteps": 60})
+    S.updateRuntimeStats()
+    n = 0
+    t0 = time.perf_counter()
+    for t in range(60):
+        if len(S.agents) == 0: break
+        n += len(S.agents)
+        S.doTimestep()
+    dt = time.perf_counter() - t0
+    out[name] = {"agent_steps": n, "seconds": dt, "value": n / dt}
+print(json.dumps(out))
+"""
+    code = code.replace("ROOT", repr(ROOT)).replace("REF", repr(root)).replace("NAMES", repr(E_CONFIGS))
+    try:
+        res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=240)
+        rec = json.loads(res.stdout.strip().splitlines()[-1])
+        return {"kind": "reference", "cores": 1, "unit": UNIT, "where": root, "examples": rec,
+                "note": "unmodified reference classes, 60 timesteps each, one process on one core (the reference is single-threaded)"}
+    except Exception as err:
+        return f"present at {root} but failed: {type(err).__name__}: {err}"
+
+
 class Job:
     """Host state of the workload (built once per process) and engines over it."""
 
@@ -241,6 +361,8 @@ class Job:
             h2d += sum(v.numel() * v.element_size() for v in eng.tensors.values() if not isinstance(v, sharded.StitchedArray))
         else:
             eng = Engine(self.params, self.state, self.local_rank, self.endow, self.tags)
+            if a.scheduler:
+                eng.set_scheduler(a.scheduler)
             if a.mark_shift >= 0:
                 eng.set_mark_shift(a.mark_shift)
             h2d = sum(v.numel() * v.element_size() for v in eng.tensors.values())
@@ -288,21 +410,26 @@ def device_resident_leg(job, eng, args, barrier, dev):
     acting = [int(eng.stats_history(s - 1).population) if s > 1 else start_pop for s in range(first, t + 1)]
     rounds = [int(eng.stats_history(s).rounds) for s in range(first, t + 1)]
     job.check(eng)
+    # the state after the warm-up + timed steps: the same at every N (one simulation, whatever the sharding / scheduler)
+    from sugarscape_b200 import digest
+    checksum = digest.sharded_partial_checksum(eng) if job.sharded else digest.engine_checksum(eng)
     # per-phase kernel times (separate steps, CUDA events inside libssb)
     eng.enable_timing(True)
-    phase = {"env_ms": [], "agent_ms": [], "compact_ms": [], "stats_ms": []}
+    phase = {}
     phase_acting = []
     for _ in range(min(args.steps, 10)):
         phase_acting.append(int(eng.stats_history(t).population))
         t += 1
         eng.step(t, 0.0)
-        tim = eng.timing()
-        for k in phase:
-            phase[k].append(tim[k])
+        for k, v in eng.timing().items():
+            phase.setdefault(k, []).append(v)
     eng.enable_timing(False)
+    scheduler = eng.scheduler() if hasattr(eng, "scheduler") else "rounds"
+    lean = bool(eng.uses_lean_transaction()) if hasattr(eng, "uses_lean_transaction") else False
     barrier()
     return {"ms": ms, "launches": launches, "acting": acting, "rounds": rounds, "clocks": sampler.summary(),
-            "phase": {k: float(np.mean(v)) for k, v in phase.items()}, "phase_acting": float(np.mean(phase_acting))}
+            "phase": {k: float(np.mean(v)) for k, v in phase.items()}, "phase_acting": float(np.mean(phase_acting)),
+            "checksum": checksum, "after_steps": t - min(args.steps, 10), "scheduler": scheduler, "lean": lean}
 
 
 def e2e_leg(job, args, barrier, dev):
@@ -353,19 +480,39 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
+        # ONE simulation of the arm's own workload on the CPU: the reference's step is strictly serial, so this is one core.
+        # A "step" of this arm is one full timestep of the same S2 / S1 state (about a minute for S2): the run is bounded
+        # to one step, whatever --steps says.
         c, n_agents = workload(args)
-        steps = max(3, min(args.steps, 8))
-        value, dt, agent_steps, cores, sample = run_cpu_port_all_cores(args, c, steps)
+        from sugarscape_b200 import digest, synthetic
+        steps = args.cpu_steps
+        state, params = synthetic.build_state(c)
+        table = synthetic.endowment_table(state, n_agents) if c["agentReplacements"] > 0 else None
+        value, dt, agent_steps = run_cpu_port(args, c, steps, state, table)
+        chk = digest.as_text(digest.host_state_checksum(state))
+        del state
+        context = None
+        try:
+            v2, dt2, n2, cores, sample = run_cpu_port_all_cores(args, c, 3)
+            context = {"value": v2, "unit": UNIT, "cores": cores, "sample": sample,
+                       "note": "NOT this workload: independent small replicas with other seeds (the reference's only parallelism, "
+                               "data/run.py:155-180) -- what the box's cores deliver on the port when the problem is many small runs"}
+        except Exception as err:
+            context = {"error": f"{type(err).__name__}: {err}"}
         line = {
             "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": 0, "ms_per_step": 1000.0 * dt / steps, "higher_is_better": True,
             "scaling": "strong" if args.workload == "S2" else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": describe(args, n_agents), "rng_mode": "scalable"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": sample + "; oracle/ss_oracle.c (C port of the reference's algorithm), one process per "
-                                       "core like the reference's own data/run.py pool -- one simulation is strictly serial "
-                                       "(the reference itself is pure Python and absent from this box: 6-8 k agent-steps/s/core "
-                                       "measured in the build container, BASELINE.md)"},
+            "config": {"workload": describe(args, n_agents), "rng_mode": "scalable",
+                       "ran": f"{steps} full timestep(s) of exactly this state on ONE host core ({agent_steps} agent-steps in {dt:.1f} s); "
+                              "--steps / --warmup beyond that are not run (a step takes about a minute)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": f"{steps} timestep(s) of the same initial state as the GPU arm; oracle/ss_oracle.c (C port of the "
+                                       "reference's algorithm, pinned on the reference's fixtures).  One simulation is strictly serial in the "
+                                       "reference, so one core is all it can use; the reference itself is pure Python (6-8 k agent-steps/s/core, "
+                                       "BASELINE.md), absent from this box, and cannot instantiate this map (3.4 KB per cell)",
+                             "state_after": chk},
+            "all_core_replicas_context": context,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
         print(json.dumps(line))
@@ -401,19 +548,28 @@ def main():
     avg = res["phase"]
     peak, peak_kind = measured_peak_gbs()
     agent_bytes = res["phase_acting"] * BYTES_PER_AGENT_STEP[args.workload]
-    achieved = agent_bytes / (avg["agent_ms"] / 1000.0) / 1e9
     env_bytes = (n_cells // world if sharded_run else n_cells) * BYTES_PER_CELL_GROWBACK
-    roofline = {"bound": "hbm", "kernel": "k_agent_step_scalable", "achieved": achieved, "peak": peak,
+    sweep = "agent_sweep_ms" in avg
+    if sweep:       # one GPU, sweep scheduler: the agent step is five kernels, the sweep kernel dominates
+        kernel = "k_sweep_lean" if res["lean"] else "k_sweep_generic"
+        kernel_ms = avg["agent_sweep_ms"]
+    else:
+        kernel = "k_agent_step_scalable" if res["scheduler"] == "rounds" else "k_flow_execute"
+        kernel_ms = avg["agent_ms"]
+    achieved = agent_bytes / (kernel_ms / 1000.0) / 1e9
+    traffic, traffic_note = measured_traffic(kernel, args)
+    roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak,
                 "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback 6.65 TB/s",
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "traffic_note": "not captured for this launch; ncu --set full of the same kernel on the 4096^2 map with S2 rules: "
-                                "8.9 GB DRAM traffic per launch = 5.7 KB per agent-step, 29x the algorithmic bytes "
-                                "(profiles/r1_agent_step_s2rules_4096_ncu_full.csv)",
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
                 "per": "rank 0's GPU",
-                "algorithmic_bytes_per_launch": agent_bytes, "avg_launch_ms": avg["agent_ms"],
+                "algorithmic_bytes_per_launch": agent_bytes, "avg_launch_ms": kernel_ms,
+                "agent_step": {"what": "all kernels of the agent step (" + ("prepare, build + clear, cell pack, sweep, unpack" if sweep else kernel) + ")",
+                               "avg_ms": avg["agent_ms"], "achieved": agent_bytes / (avg["agent_ms"] / 1000.0) / 1e9,
+                               "frac": agent_bytes / (avg["agent_ms"] / 1000.0) / 1e9 / peak},
                 "env_step": {"kernel": "k_growback_v4", "achieved": env_bytes / (avg["env_ms"] / 1000.0) / 1e9,
                              "frac": env_bytes / (avg["env_ms"] / 1000.0) / 1e9 / peak, "avg_launch_ms": avg["env_ms"],
-                             "note": "12 B/cell assumed; the store is skipped for vectors already at capacity, so > 1 is possible"
+                             "note": "12 B/cell by convention (level read + write, capacity read); the store is skipped for vectors already "
+                                     "at capacity, so the bytes moved are 8-12 B/cell and the fraction on bytes moved is 2/3 of this at worst"
                                      + ("; includes the box-wide barrier that follows the stencil" if sharded_run else "")},
                 "phase_ms": avg}
 
@@ -426,14 +582,48 @@ def main():
                "includes": "upload of the initial state, per-step stats readback + log formatting, download of the final agents"
                            + (" (bytes per rank)" if world > 1 else "")}
 
-    # ---- CPU baseline (rank 0, N = 1 only; runs last: it consumes the host state) ----------------------
-    cpu = None
+    # ---- the state after the timed steps: one checksum for the whole box ---------------------------------------
+    from sugarscape_b200 import digest
+    if world > 1 and sharded_run:
+        parts = [None] * world
+        dist.all_gather_object(parts, res["checksum"])
+        checksum = digest.combine(parts)
+    else:
+        checksum = res["checksum"]
+    state_digest = {"after_steps": res["after_steps"], "value": digest.as_text(checksum),
+                    "note": "population : sum over agents of mix(id, position, age, holdings, tribe) : sum over cells -- order-independent, "
+                            "the same at every N and under every scheduler (sugarscape_b200/digest.py)"}
+
+    # ---- extras (rank 0, N = 1): S1 shape, shipped examples through the drop-in driver, the Python reference if present ------
+    extras = {}
+    if rank == 0 and world == 1 and not args.skip_extra and args.workload == "S2":
+        for key, fn in (("s1", lambda: run_s1_block(args, local_rank)), ("e_configs", lambda: run_e_configs(args)),
+                        ("python_reference", lambda: run_python_reference(args))):
+            try:
+                extras[key] = fn()
+            except Exception as err:
+                extras[key] = {"error": f"{type(err).__name__}: {err}"}
+        torch.cuda.empty_cache()
+
+    # ---- CPU baseline + parity at scale (rank 0, N = 1 only; runs last: it consumes the host state) --------------
+    cpu, parity = None, None
     if rank == 0 and world == 1 and not args.skip_cpu:
+        eng1, _ = job.engine()                      # the GPU's first step(s) from the same initial state
+        for t in range(1, args.cpu_steps + 1):
+            eng1.step(t, 0.0)
+        job.check(eng1)
+        gpu_chk = digest.engine_checksum(eng1)
+        eng1.close()
+        del eng1
+        torch.cuda.empty_cache()
         v, dt, n_as = run_cpu_port(args, c, args.cpu_steps, job.state, job.table)
+        cpu_chk = digest.host_state_checksum(job.state)
+        parity = "ok" if gpu_chk == cpu_chk else "FAIL"
         cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"{args.cpu_steps} timesteps of the same {args.workload} initial state ({n_as} agent-steps, {dt:.1f} s), "
                          "oracle/ss_oracle.c single thread; the Python reference itself runs 6-8 k agent-steps/s/core "
-                         "(build container, BASELINE.md) and cannot instantiate this map"}
+                         "(build container, BASELINE.md) and cannot instantiate this map",
+               "state_after": digest.as_text(cpu_chk), "gpu_state_after": digest.as_text(gpu_chk)}
 
     if rank == 0:
         if sharded_run:
@@ -449,8 +639,12 @@ def main():
                        "rng_mode": "scalable", "l2": "inputs larger than L2 (state > 500 MB per GPU)",
                        "parallelism": parallelism,
                        "mean_commit_rounds": float(np.mean(res["rounds"])), "mean_acting_agents_rank0": float(np.mean(res["acting"]))},
-            "clocks": res["clocks"], "gpu_launches": launches, "roofline": roofline,
+            "clocks": res["clocks"], "gpu_launches": launches, "roofline": roofline, "state_digest": state_digest,
         }
+        line["config"]["scheduler"] = res["scheduler"] + (" (lean transaction)" if res["lean"] else "")
+        if parity is not None:
+            line["parity_at_scale"] = parity
+        line.update(extras)
         if e2e is not None:
             line["e2e"] = e2e
         if cpu is not None:
@@ -458,6 +652,9 @@ def main():
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    if rank == 0 and parity == "FAIL":
+        sys.stderr.write("parity_at_scale FAILED: the CUDA engine and the CPU oracle disagree on the state after the first step(s)\n")
+        return 1
     return 0
 
 

@@ -523,6 +523,9 @@ int  ssb_get_scheduler(const ssb_engine_t *e);
 /* 1 if the agent step runs the lean transaction (csrc/ssb_sweep_core.cuh: one thread per agent on packed 32-byte
  * records; rule sets without tagging / trading / reproduction / tag preferences under SSB_SCHED_SWEEP) */
 int  ssb_uses_lean_transaction(const ssb_engine_t *e);
+/* sub-phases of the last timed agent step under the sweep scheduler, milliseconds:
+ * {prepare, build + clear, cell pack, sweep kernel, cell + record unpack}; -1 if none was timed */
+int  ssb_agent_phases(ssb_engine_t *e, float out[5]);
 /* diagnostics of the sweep kernel since bind (SSB_SWEEP_DIAG=1 at bind time; -1 otherwise):
  * {warp iterations, entries held at a readiness check, entries run} */
 int  ssb_sweep_diag(ssb_engine_t *e, unsigned long long out[3]);

@@ -68,6 +68,8 @@ struct ssb_engine {
     // timing
     bool timing;
     cudaEvent_t ev[5];
+    cudaEvent_t sub_ev[6];   // sweep scheduler: before prepare / build / cell pack / sweep kernel / unpack, after unpack
+    bool sub_recorded;
     bool ev_recorded;
     bool pollution_swapped;  // the pollution field currently lives in the buffer bound as pollution_flux
     // replacement (mode S)
@@ -176,6 +178,7 @@ int ssb_create(const ssb_params_t *params, int device, ssb_engine_t **out) {
     CU(cudaMalloc(&e->d_ring, sizeof(ssb_stats_t) * SSB_STATS_RING));
     CU(cudaMemset(e->d_ring, 0, sizeof(ssb_stats_t) * SSB_STATS_RING));
     for (int i = 0; i < 5; i++) CU(cudaEventCreate(&e->ev[i]));
+    for (int i = 0; i < 6; i++) CU(cudaEventCreate(&e->sub_ev[i]));
     return 0;
 }
 
@@ -192,6 +195,7 @@ void ssb_destroy(ssb_engine_t *e) {
                     e->sweep.tile_pop, e->sweep.tile_need, e->sweep.ctl, (void *)e->sweep.tables, e->lean.a, e->lean.b, e->lean.pcell};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < 5; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+    for (int i = 0; i < 6; i++) if (e->sub_ev[i]) cudaEventDestroy(e->sub_ev[i]);
     delete e;
 }
 
@@ -422,7 +426,7 @@ int ssb_set_scheduler(ssb_engine_t *e, int32_t scheduler) {
     return 0;
 }
 
-int ssb_get_scheduler(const ssb_engine_t *e) { return e ? e->scheduler : -1; }
+int ssb_get_scheduler(const ssb_engine_t *e) { return e ? (e->sharded ? SSB_SCHED_ROUNDS : e->scheduler) : -1; }     // (sharded engines run the rounds)
 
 // diagnostics of the sweep kernel since bind (SSB_SWEEP_DIAG=1): {warp iterations, entries held at a check, entries run}
 int ssb_sweep_diag(ssb_engine_t *e, unsigned long long out[3]) {
@@ -717,24 +721,35 @@ int ssb_agent_step(ssb_engine_t *e, int32_t t, double prev_mean_wealth, void *st
         w.concurrent = lean ? e->sweep_lean_blocks * LEAN_THREADS : e->sweep_generic_blocks * AGENT_GROUPS;
         w.bucket_bits = lean ? e->sweep_bits_lean : e->sweep_bits_generic;
         w.n_keys = (1 << w.bucket_bits) << (lean ? SWEEP_LEAN_SUB_BITS : 0);
+#define SUB_EVENT(k) do { if (e->timing) CU(cudaEventRecord(e->sub_ev[k], st)); } while (0)
+        SUB_EVENT(0);
         CU(cudaMemsetAsync(w.done, 0, e->sweep_done_bytes, st));
         void *pargs[] = {&c, &w, &L};
         CU(cudaLaunchCooperativeKernel(lean ? (void *)k_sweep_prepare<true> : (void *)k_sweep_prepare<false>, dim3(e->sweep_prepare_blocks),
                                        dim3(SWEEP_PREPARE_THREADS), pargs, sweep_prepare_smem_bytes(w.n_keys), st));
         LAUNCHED(e);
+        SUB_EVENT(1);
         k_sweep_build<<<e->sweep_build_blocks, SWEEP_BUILD_THREADS, sweep_build_smem_bytes(w.rb, w.kb, w.halo), st>>>(c, w); LAUNCHED(e);
         k_sweep_clear<<<e->num_sms * 8, 256, 0, st>>>(c, w); LAUNCHED(e);
+        SUB_EVENT(2);
         if (lean) {
             k_lean_cells<true><<<e->num_sms * 8, 256, 0, st>>>(c, w, L); LAUNCHED(e);
+            SUB_EVENT(3);
             CU(cudaLaunchCooperativeKernel(e->lean_mode == 0 ? (void *)k_sweep_lean<0> : (void *)k_sweep_lean<LEAN_M_ALL>, dim3(e->sweep_lean_blocks), dim3(LEAN_THREADS), pargs, lean_smem_bytes(L.maxc, LEAN_THREADS), st));
             LAUNCHED(e);
+            SUB_EVENT(4);
             k_lean_cells<false><<<e->num_sms * 8, 256, 0, st>>>(c, w, L); LAUNCHED(e);
             k_lean_unpack<<<e->num_sms * 8, 256, 0, st>>>(c, L); LAUNCHED(e);
         } else {
+            SUB_EVENT(3);
             void *args[] = {&c, &w};
             CU(cudaLaunchCooperativeKernel((void *)k_sweep_generic, dim3(e->sweep_generic_blocks), dim3(AGENT_THREADS), args, AGENT_SMEM_BYTES, st));
             LAUNCHED(e);
+            SUB_EVENT(4);
         }
+        SUB_EVENT(5);
+        e->sub_recorded = e->timing;
+#undef SUB_EVENT
     } else if (e->scheduler == SSB_SCHED_DATAFLOW && !e->sharded) {
         FlowCtx f = e->flow;
         f.key = step_key(e->p.seed, t);
@@ -1052,6 +1067,7 @@ int ssb_enable_timing(ssb_engine_t *e, int32_t on) {
     if (!e) return -1;
     e->timing = on != 0;
     e->ev_recorded = false;
+    e->sub_recorded = false;
     return 0;
 }
 
@@ -1062,6 +1078,16 @@ int ssb_timing(ssb_engine_t *e, float *env_ms, float *agent_ms, float *compact_m
     float *out[4] = {env_ms, agent_ms, compact_ms, stats_ms};
     for (int i = 0; i < 4; i++)
         if (out[i]) CU(cudaEventElapsedTime(out[i], e->ev[i], e->ev[i + 1]));
+    return 0;
+}
+
+// Sub-phases of the last agent step under the sweep scheduler (timing enabled): milliseconds of
+// {prepare (bucketing + records), build (predecessor masks) + clear, cell pack, the sweep kernel, cell + record unpack}
+int ssb_agent_phases(ssb_engine_t *e, float out[5]) {
+    CHECK_BOUND(e);
+    if (!e->timing || !e->sub_recorded) return fail(e, -1, "no sweep-scheduled agent step was timed");
+    CU(cudaEventSynchronize(e->sub_ev[5]));
+    for (int i = 0; i < 5; i++) CU(cudaEventElapsedTime(out + i, e->sub_ev[i], e->sub_ev[i + 1]));
     return 0;
 }
 

@@ -49,6 +49,7 @@ def load_library():
     L.ssb_get_scheduler.argtypes = [E]
     L.ssb_uses_lean_transaction.argtypes = [E]
     L.ssb_sweep_diag.argtypes = [E, C.c_void_p]
+    L.ssb_agent_phases.argtypes = [E, C.c_void_p]
     L.ssb_set_mark_shift.argtypes = [E, C.c_int32]
     L.ssb_set_l2_persist.argtypes = [E, C.c_void_p, C.c_int32]
     L.ssb_env_step.argtypes = [E, C.c_int32, C.c_void_p]
@@ -104,7 +105,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = (
     "ssb_abi_version", "ssb_create", "ssb_bind", "ssb_destroy", "ssb_last_error",
-    "ssb_set_mt_state", "ssb_get_mt_state", "ssb_set_step_tables", "ssb_set_scheduler", "ssb_get_scheduler", "ssb_uses_lean_transaction", "ssb_sweep_diag", "ssb_set_epochs", "ssb_set_mark_shift", "ssb_set_l2_persist",
+    "ssb_set_mt_state", "ssb_get_mt_state", "ssb_set_step_tables", "ssb_set_scheduler", "ssb_get_scheduler", "ssb_uses_lean_transaction", "ssb_sweep_diag", "ssb_agent_phases", "ssb_set_epochs", "ssb_set_mark_shift", "ssb_set_l2_persist",
     "ssb_sizeof_params", "ssb_sizeof_grid", "ssb_sizeof_agents", "ssb_sizeof_stats",
     "ssb_env_step", "ssb_agent_step", "ssb_compact", "ssb_bind_endowments", "ssb_replace", "ssb_reduce_stats", "ssb_step", "ssb_stats", "ssb_stats_history",
     "ssb_fabric_create", "ssb_fabric_alloc", "ssb_fabric_map", "ssb_fabric_copy", "ssb_fabric_granularity",
@@ -400,5 +401,10 @@ class Engine:
     def timing(self):
         vals = [C.c_float(0) for _ in range(4)]
         self._check(self.L.ssb_timing(self.handle, *[C.byref(v) for v in vals]))
-        return {"env_ms": vals[0].value, "agent_ms": vals[1].value, "compact_ms": vals[2].value,
-                "stats_ms": vals[3].value}
+        out = {"env_ms": vals[0].value, "agent_ms": vals[1].value, "compact_ms": vals[2].value,
+               "stats_ms": vals[3].value}
+        sub = np.zeros(5, dtype=np.float32)
+        if self.L.ssb_agent_phases(self.handle, sub.ctypes.data) == 0:      # sweep scheduler: the kernels of the agent step
+            out.update({"agent_prepare_ms": float(sub[0]), "agent_build_ms": float(sub[1]), "agent_pack_ms": float(sub[2]),
+                        "agent_sweep_ms": float(sub[3]), "agent_unpack_ms": float(sub[4])})
+        return out
