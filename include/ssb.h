@@ -527,8 +527,8 @@ int  ssb_uses_lean_transaction(const ssb_engine_t *e);
  * {prepare, build + clear, cell pack, sweep kernel, cell + record unpack}; -1 if none was timed */
 int  ssb_agent_phases(ssb_engine_t *e, float out[5]);
 /* diagnostics of the sweep kernel since bind (SSB_SWEEP_DIAG=1 at bind time; -1 otherwise):
- * {warp iterations, entries held at a readiness check, entries run} */
-int  ssb_sweep_diag(ssb_engine_t *e, unsigned long long out[3]);
+ * {warp iterations, entries held at a readiness check, entries run, entries held back by the watermark} */
+int  ssb_sweep_diag(ssb_engine_t *e, unsigned long long out[4]);
 
 /* mode S tuning (SSB_SCHED_ROUNDS): number of priority epochs of the sliding-prefix commit (power of two, default 128) */
 int  ssb_set_epochs(ssb_engine_t *e, int32_t epochs);

@@ -130,6 +130,21 @@ static void rng_shuffle_i32(orc_rng_t *r, int32_t *x, int n) {
     }
 }
 
+/* Mode S, move ranking only: the KEYED shuffle -- the permutation that sorts the list by one substream word per element
+ * (ties by position); mode E keeps random.shuffle.  (tests/golden/make_golden_scalable.py, Substreams.shuffle) */
+static void rng_move_shuffle_i32(orc_rng_t *r, int32_t *x, int n) {
+    if (r->mode == SSB_RNG_EXACT) { rng_shuffle_i32(r, x, n); return; }
+    uint32_t key[256];
+    int32_t out[256];
+    for (int i = 0; i < n; i++) key[i] = rng_next32(r);
+    for (int i = 0; i < n; i++) {
+        int rank = 0;
+        for (int j = 0; j < n; j++) if (key[j] < key[i] || (key[j] == key[i] && j < i)) rank++;
+        out[rank] = x[i];
+    }
+    for (int i = 0; i < n; i++) x[i] = out[i];
+}
+
 /* ------------------------------------------------------------------------------------------
  * context
  * ---------------------------------------------------------------------------------------- */
@@ -1202,7 +1217,7 @@ static int move_to_best_cell(ctx_t *c, int s) {
         int32_t perm[MAX_CAND];
         for (int i = 0; i < n; i++) perm[i] = i;
         rng_at(c->rng, SITE_MOVE);
-        rng_shuffle_i32(c->rng, perm, n);
+        rng_move_shuffle_i32(c->rng, perm, n);
         /* findRetaliatorsInVision (agent.py:1088-1098): richest visible member per tribe */
         double retaliator[34]; int have[34];
         for (int i = 0; i < 34; i++) { retaliator[i] = 0; have[i] = 0; }

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "csrc", "ssb_abi.cu")
-OUT = os.path.join(HERE, "libssb.so")
+OUT = os.environ.get("SSB_LIBSSB") or os.path.join(HERE, "libssb.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     # fp64 parity with the reference's CPython arithmetic: no FMA contraction, IEEE div/sqrt
@@ -39,6 +39,10 @@ def build(force=False, verbose=False):
         extra.append("-DSSB_GROUP_LANES=" + os.environ["SSB_GROUP_LANES"])
     if os.environ.get("SSB_PARALLEL_ETHICS"):  # mode E with decision models: score the candidate cells on all lanes (round 2: to be measured)
         extra.append("-DSSB_PARALLEL_ETHICS")
+    if os.environ.get("SSB_SLAB_BITS"):        # tuning builds: slabs of the sweep's priority order = 1 << bits
+        extra.append("-DSSB_SLAB_BITS=" + os.environ["SSB_SLAB_BITS"])
+    if os.environ.get("SSB_LEAN_PREFETCH"):
+        extra.append("-DSSB_LEAN_PREFETCH=" + os.environ["SSB_LEAN_PREFETCH"])
     if os.environ.get("SSB_MARK_LANES"):
         extra.append("-DSSB_MARK_LANES=" + os.environ["SSB_MARK_LANES"])
     cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]

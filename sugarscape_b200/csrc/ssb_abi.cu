@@ -191,7 +191,7 @@ void ssb_destroy(ssb_engine_t *e) {
                     e->d_partials, e->d_tribes, e->d_stats, e->d_ring, e->d_keys_a, e->d_keys_b, e->d_radix_hist,
                     e->d_lorenz_blocks, e->d_plan, e->d_cand, e->sh.peer_vals, e->sh.flags, e->d_shard_vals, e->d_migrate, e->d_eth_stats, e->d_ext_stats, e->d_group_stats, e->d_eth, e->d_ext,
                     e->flow.desc, e->flow.entries, e->flow.dep, e->flow.span, e->flow.pool, e->flow.cursor, e->flow.queue, e->flow.tail, e->flow.tile_pop,
-                    e->sweep.desc, e->sweep.entries, e->sweep.preds, e->sweep.done, e->sweep.bucket_count, e->sweep.bucket_start, e->sweep.bucket_fill,
+                    e->sweep.desc, e->sweep.entries, e->sweep.preds, e->sweep.gate, e->sweep.bucket_fin, e->sweep.done, e->sweep.bucket_count, e->sweep.bucket_start, e->sweep.bucket_fill,
                     e->sweep.tile_pop, e->sweep.tile_need, e->sweep.ctl, (void *)e->sweep.tables, e->lean.a, e->lean.b, e->lean.pcell};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < 5; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
@@ -262,11 +262,6 @@ static int setup_sweep(ssb_engine *e, int maxd) {
     if (per_sm_lean < per_sm) per_sm = per_sm_lean;
     if (per_sm < 1) return fail(e, -3, "the sweep's prepare kernel does not fit on an SM");
     e->sweep_prepare_blocks = (per_sm > 8 ? 8 : per_sm) * e->num_sms;
-    const int build_smem = sweep_build_smem_bytes(w.rb, w.kb, w.halo);
-    CU(cudaFuncSetAttribute(k_sweep_build, cudaFuncAttributeMaxDynamicSharedMemorySize, build_smem));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_build, SWEEP_BUILD_THREADS, build_smem));
-    if (per_sm < 1) return fail(e, -3, "the sweep's build kernel does not fit on an SM (%d bytes of shared memory)", build_smem);
-    e->sweep_build_blocks = per_sm * e->num_sms;
     CU(cudaFuncSetAttribute(k_sweep_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, AGENT_SMEM_BYTES));
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_generic, AGENT_THREADS, AGENT_SMEM_BYTES));
     if (per_sm < 1) return fail(e, -3, "the sweep kernel does not fit on an SM");
@@ -292,10 +287,20 @@ static int setup_sweep(ssb_engine *e, int maxd) {
     // priority buckets: sized for a full agent array and the grid that will walk them
     e->sweep_bits_generic = sweep_bucket_bits(cap, concurrent, e->p.id_bits, SWEEP_MAX_KEY_BITS);
     e->sweep_bits_lean = e->lean_ok ? sweep_bucket_bits(cap, (long long)e->sweep_lean_blocks * LEAN_THREADS, e->p.id_bits, SWEEP_MAX_KEY_BITS - SWEEP_LEAN_SUB_BITS) : 0;
+    {   // the build kernel stages one occupancy bit-plane per slab
+        const int bits = e->sweep_bits_lean > e->sweep_bits_generic ? e->sweep_bits_lean : e->sweep_bits_generic;
+        const int build_smem = sweep_build_smem_bytes(w.rb, w.kb, w.halo, sweep_n_slabs(bits));
+        CU(cudaFuncSetAttribute(k_sweep_build, cudaFuncAttributeMaxDynamicSharedMemorySize, build_smem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_build, SWEEP_BUILD_THREADS, build_smem));
+        if (per_sm < 1) return fail(e, -3, "the sweep's build kernel does not fit on an SM (%d bytes of shared memory)", build_smem);
+        e->sweep_build_blocks = per_sm * e->num_sms;
+    }
     CU(cudaMalloc(&w.desc, sizeof(unsigned long long) * (size_t)cells));
     CU(cudaMemset(w.desc, 0, sizeof(unsigned long long) * (size_t)cells));
     CU(cudaMalloc(&w.entries, sizeof(int4) * cap));
     CU(cudaMalloc(&w.preds, sizeof(uint32_t) * SWEEP_COLS * (size_t)cap));
+    CU(cudaMalloc(&w.gate, sizeof(unsigned long long) * (size_t)cap));
+    CU(cudaMalloc(&w.bucket_fin, sizeof(int32_t) * (SWEEP_MAX_KEYS + 1)));
     e->sweep_done_bytes = sizeof(unsigned long long) * sweep_done_words(e->p.width, e->p.height);
     CU(cudaMalloc(&w.done, e->sweep_done_bytes));
     CU(cudaMalloc(&w.bucket_count, sizeof(int32_t) * (SWEEP_MAX_KEYS + 1)));
@@ -429,10 +434,10 @@ int ssb_set_scheduler(ssb_engine_t *e, int32_t scheduler) {
 int ssb_get_scheduler(const ssb_engine_t *e) { return e ? (e->sharded ? SSB_SCHED_ROUNDS : e->scheduler) : -1; }     // (sharded engines run the rounds)
 
 // diagnostics of the sweep kernel since bind (SSB_SWEEP_DIAG=1): {warp iterations, entries held at a check, entries run}
-int ssb_sweep_diag(ssb_engine_t *e, unsigned long long out[3]) {
+int ssb_sweep_diag(ssb_engine_t *e, unsigned long long out[4]) {
     if (!e || !e->bound || !e->sweep.diag) return -1;
     CU(cudaDeviceSynchronize());
-    CU(cudaMemcpy(out, e->sweep.diag, sizeof(unsigned long long) * 3, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out, e->sweep.diag, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost));
     return 0;
 }
 
@@ -720,16 +725,18 @@ int ssb_agent_step(ssb_engine_t *e, int32_t t, double prev_mean_wealth, void *st
         const bool lean = e->scheduler == SSB_SCHED_SWEEP && e->lean_ok;
         w.concurrent = lean ? e->sweep_lean_blocks * LEAN_THREADS : e->sweep_generic_blocks * AGENT_GROUPS;
         w.bucket_bits = lean ? e->sweep_bits_lean : e->sweep_bits_generic;
-        w.n_keys = (1 << w.bucket_bits) << (lean ? SWEEP_LEAN_SUB_BITS : 0);
+        w.sub_bits = lean ? SWEEP_LEAN_SUB_BITS : 0;
+        w.n_keys = (1 << w.bucket_bits) << w.sub_bits;
 #define SUB_EVENT(k) do { if (e->timing) CU(cudaEventRecord(e->sub_ev[k], st)); } while (0)
         SUB_EVENT(0);
         CU(cudaMemsetAsync(w.done, 0, e->sweep_done_bytes, st));
+        CU(cudaMemsetAsync(w.gate, 0, sizeof(unsigned long long) * (size_t)c.a.capacity, st));
         void *pargs[] = {&c, &w, &L};
         CU(cudaLaunchCooperativeKernel(lean ? (void *)k_sweep_prepare<true> : (void *)k_sweep_prepare<false>, dim3(e->sweep_prepare_blocks),
                                        dim3(SWEEP_PREPARE_THREADS), pargs, sweep_prepare_smem_bytes(w.n_keys), st));
         LAUNCHED(e);
         SUB_EVENT(1);
-        k_sweep_build<<<e->sweep_build_blocks, SWEEP_BUILD_THREADS, sweep_build_smem_bytes(w.rb, w.kb, w.halo), st>>>(c, w); LAUNCHED(e);
+        k_sweep_build<<<e->sweep_build_blocks, SWEEP_BUILD_THREADS, sweep_build_smem_bytes(w.rb, w.kb, w.halo, sweep_n_slabs(w.bucket_bits)), st>>>(c, w); LAUNCHED(e);
         k_sweep_clear<<<e->num_sms * 8, 256, 0, st>>>(c, w); LAUNCHED(e);
         SUB_EVENT(2);
         if (lean) {

@@ -185,7 +185,10 @@ __device__ __forceinline__ void for_each_mark_cell(const DevCtx &c, const RoundC
 
 template <int G>
 __device__ __forceinline__ void group_mark_region(const DevCtx &c, const RoundCtx &rc, int pos, int r, int k, uint32_t v) {
-    for_each_mark_cell<G>(c, rc, pos, r, k, [&](size_t m) { atomicMin(rc.mark + m, v); });
+    // sharded: the mark field is NVLink-stitched memory that several GPUs update concurrently -- device-scope atomics of
+    // different GPUs are not morally strong against each other, so the reservation needs system scope there
+    if (c.sh.world > 1) for_each_mark_cell<G>(c, rc, pos, r, k, [&](size_t m) { atomicMin_system(rc.mark + m, v); });
+    else for_each_mark_cell<G>(c, rc, pos, r, k, [&](size_t m) { atomicMin(rc.mark + m, v); });
 }
 
 // true (on every lane of the group) iff every mark cell of the region holds v

@@ -142,16 +142,29 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int *total) {
     return base + inc - v;
 }
 
+// the COMPACT_ITEMS consecutive list entries of this thread (-1 beyond the end of the list): one 16-byte load
+static_assert(COMPACT_ITEMS == 4, "compact_load_entries reads one int4 per thread");
+__device__ __forceinline__ void compact_load_entries(const DevCtx &c, long long tile0, long long n, int slots[COMPACT_ITEMS]) {
+    const long long i0 = tile0 + (long long)threadIdx.x * COMPACT_ITEMS;
+    if (i0 + COMPACT_ITEMS <= n) {
+        const int4 v = *reinterpret_cast<const int4 *>(c.a.order + i0);
+        slots[0] = v.x; slots[1] = v.y; slots[2] = v.z; slots[3] = v.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < COMPACT_ITEMS; k++) slots[k] = i0 + k < n ? c.a.order[i0 + k] : -1;
+    }
+}
+
 __global__ void __launch_bounds__(COMPACT_THREADS) k_compact_count(DevCtx c, int32_t *tile_alive) {
     const long long n = c.a.counters[SSB_C_N_LIST];
     const long long tile0 = (long long)blockIdx.x * COMPACT_TILE;
     if (tile0 >= n) { if (threadIdx.x == 0) tile_alive[blockIdx.x] = 0; return; }
+    int slots[COMPACT_ITEMS];
+    compact_load_entries(c, tile0, n, slots);
     int cnt = 0;
 #pragma unroll
-    for (int k = 0; k < COMPACT_ITEMS; k++) {
-        const long long i = tile0 + (long long)threadIdx.x * COMPACT_ITEMS + k;
-        if (i < n && list_entry_survives(c, c.a.order[i])) cnt++;
-    }
+    for (int k = 0; k < COMPACT_ITEMS; k++)
+        if (slots[k] >= 0 && list_entry_survives(c, slots[k])) cnt++;
     int total;
     block_exclusive_scan(cnt, &total);
     if (threadIdx.x == 0) tile_alive[blockIdx.x] = total;
@@ -185,13 +198,13 @@ __global__ void __launch_bounds__(COMPACT_THREADS) k_compact_scatter(DevCtx c, c
     const long long n = c.a.counters[SSB_C_N_LIST];
     const long long tile0 = (long long)blockIdx.x * COMPACT_TILE;
     if (tile0 >= n) return;
+    __shared__ int32_t staged[COMPACT_TILE];     // the survivors of this tile in list order: written out coalesced
     int slots[COMPACT_ITEMS];
     bool alive[COMPACT_ITEMS];
+    compact_load_entries(c, tile0, n, slots);
     int cnt = 0;
 #pragma unroll
     for (int k = 0; k < COMPACT_ITEMS; k++) {
-        const long long i = tile0 + (long long)threadIdx.x * COMPACT_ITEMS + k;
-        slots[k] = i < n ? c.a.order[i] : -1;
         alive[k] = slots[k] >= 0 && list_entry_survives(c, slots[k]);
         cnt += alive[k];
     }
@@ -200,11 +213,10 @@ __global__ void __launch_bounds__(COMPACT_THREADS) k_compact_scatter(DevCtx c, c
     // survivors keep list order; the dead of this tile go to dead_list[(tile0 - offset) ...]
     const int alive_base = tile_offset[blockIdx.x];
     int dead_at = (int)(tile0 - alive_base) + (threadIdx.x * COMPACT_ITEMS - at);
-    at += alive_base;
 #pragma unroll
     for (int k = 0; k < COMPACT_ITEMS; k++) {
         if (slots[k] < 0) continue;
-        if (alive[k]) new_order[at++] = slots[k];
+        if (alive[k]) staged[at++] = slots[k];
         else {
             const int s = slots[k];
             if (c.a.cod[s] == SSB_ALIVE) do_death<EXT>(c, s, SSB_OTHER);   // removeDeadAgents -> doDeath()
@@ -212,6 +224,8 @@ __global__ void __launch_bounds__(COMPACT_THREADS) k_compact_scatter(DevCtx c, c
             c.a.dead_list[dead_at++] = s;
         }
     }
+    __syncthreads();
+    for (int j = threadIdx.x; j < total; j += COMPACT_THREADS) new_order[alive_base + j] = staged[j];
 }
 
 // finish: publish the new list, recycle dead slots

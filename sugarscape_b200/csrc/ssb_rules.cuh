@@ -750,17 +750,31 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rn
         // words with all lanes first.
         rng.at(SITE_MOVE);
         rng.template prefetch<G>(ws.words, lane);
-        for (int i = lane; i < n; i += G) ws.perm[i] = (uint8_t)i;
-        Gr::sync();
-        if (lane == 0) {
-            for (int i = n - 1; i >= 1; i--) {
-                const uint32_t j = rand_below(rng, (uint32_t)i + 1u);
-                const uint8_t t = ws.perm[i]; ws.perm[i] = ws.perm[j]; ws.perm[j] = t;
+        if (RngTraits<Rng>::ordered) {
+            for (int i = lane; i < n; i += G) ws.perm[i] = (uint8_t)i;
+            Gr::sync();
+            if (lane == 0) {
+                for (int i = n - 1; i >= 1; i--) {
+                    const uint32_t j = rand_below(rng, (uint32_t)i + 1u);
+                    const uint8_t t = ws.perm[i]; ws.perm[i] = ws.perm[j]; ws.perm[j] = t;
+                }
+                rng.end_prefetch();
             }
-            rng.end_prefetch();
+            Gr::sync();
+            for (int k = lane; k < n; k += G) ws.rank[ws.perm[k]] = (uint8_t)k;
+        } else {
+            // mode S: the KEYED shuffle (tests/golden/make_golden_scalable.py) -- element i goes to the position its
+            // word i has among the n words (ties by i); the words are the ones just prefetched (n <= 64)
+            Gr::sync();
+            for (int i = lane; i < n; i += G) {
+                const uint32_t ki = ws.words[i];
+                int rk = 0;
+                for (int j = 0; j < n; j++) { const uint32_t kj = ws.words[j]; rk += (kj < ki || (kj == ki && j < i)) ? 1 : 0; }
+                ws.rank[i] = (uint8_t)rk;
+                ws.perm[rk] = (uint8_t)i;
+            }
+            if (lane == 0) rng.end_prefetch();
         }
-        Gr::sync();
-        for (int k = lane; k < n; k += G) ws.rank[ws.perm[k]] = (uint8_t)k;
         const double loot = c.p.max_combat_loot;
         const double my_wealth = w.sugar + w.spice;
         // findRetaliatorsInVision (agent.py:1088-1098): every occupant must be seen before any

@@ -1,21 +1,24 @@
 // ssb_sweep.cuh -- the kernels of the ordered sweep (ssb_sweep_core.cuh has the algorithm and its proof sketch).
 //
 // Per step, on one stream:
-//   cudaMemsetAsync   done bitmap (one bit per cell)
+//   cudaMemsetAsync   done bitmap (one bit per cell), gates (one 64-bit word per list entry)
 //   k_sweep_prepare   cooperative, three phases separated by grid barriers: histogram of the priority buckets,
 //                     exclusive scan, scatter.  LEAN: walks the SLOTS (coalesced reads of the ABI's arrays), writes
 //                     record A by slot and record B at the agent's list index; otherwise walks the agent list and
 //                     writes `entries`.  Either way every agent leaves its descriptor on its cell and flags its tile.
 //   k_sweep_build     one CTA per populated 64 x 64 tile (dynamic tile cursor): descriptors of tile + halo staged
-//                     in shared memory as 4-byte words, occupancy masks by ballot, one thread per agent computes
-//                     the predecessor masks and stores them as one 128-byte line (word 31 = the start cell).
+//                     in shared memory as 4-byte words, one occupancy bit-plane per slab (shared-memory atomics), one
+//                     thread per agent scans the bit-planes of its two near slabs and stores its gate (only agents
+//                     WITH near predecessors store anything).
 //   k_sweep_clear     zeroes the descriptors of the populated tiles and their flags (the arrays are clean again).
-//   k_sweep_lean /    persistent cooperative grid (co-residency is what the progress argument needs): thread /
-//   k_sweep_generic   lane group j takes entries j, j + T, ...; an entry runs once its predecessors' done bits
-//                     are set.  Lanes never wait inside the transaction: a lane whose agent is not ready simply
-//                     retries in the next iteration of its warp, so lanes of one warp can depend on each other.
-//                     Memory ordering: writes -> fence.acq_rel.gpu -> red.or (done bit);  consumer: ld.relaxed.gpu
-//                     (done words) -> fence.acq_rel.gpu -> reads.
+//   k_sweep_lean /    persistent cooperative grid (co-residency is what the progress argument needs): a lane draws a
+//   k_sweep_generic   ticket for the next list entry whenever it is free; the entry runs once the watermark has
+//                     passed the slabs before its near slabs and the done bits of its near predecessors are set.
+//                     Lanes never wait inside the transaction: a lane whose agent is not ready simply retries in the
+//                     next iteration of its warp, so lanes of one warp can depend on each other.
+//                     Memory ordering: writes -> red.release.gpu (done bit) -> warp barrier -> atom.release.gpu (bucket
+//                     count; the thread that completes a bucket advances the watermark behind a fence.sc);
+//                     consumer: ld.relaxed.gpu (watermark, done words) -> reads past L1 (lean) / acquire fence (generic).
 //   k_lean_unpack     LEAN: mutable fields of record A back to the ABI's arrays, slot order.
 #pragma once
 #include "ssb_agent_step.cuh"
@@ -28,7 +31,7 @@ constexpr int SWEEP_MAX_KEYS = 1 << SWEEP_MAX_KEY_BITS;
 constexpr int SWEEP_LEAN_SUB_BITS = 3;                 // lean path: entries of one priority bucket are grouped by range, so that the
                                                        // 32 agents a warp works on have the same number of candidate cells
 constexpr int SWEEP_PREPARE_THREADS = 256;
-constexpr int SWEEP_BUILD_THREADS = 256;
+constexpr int SWEEP_BUILD_THREADS = 512;
 constexpr int SWEEP_OVERFLOW_STALL = 10;    // counters[SSB_C_OVERFLOW] code: no agent of a warp became ready for SWEEP_STALL_NS
 constexpr int SWEEP_OVERFLOW_LIVE = 11;     // ... the live slots differ from the agent list (lean path: every live slot must be a list entry)
 constexpr int SWEEP_OVERFLOW_BUCKET = 12;   // ... a priority bucket is longer than the number of concurrent transactions
@@ -40,16 +43,20 @@ constexpr int SWEEP_CTL_WORDS = 16 + SWEEP_STRIPES * 16;            // ctl[16 + 
 struct SweepCtx {
     unsigned long long *desc;        // [n_cells] descriptor of the agent that starts the step on the cell (0: none)
     int4 *entries;                   // [capacity] generic path, by list index: {slot, cell, priority, r | k << 8}
-    uint32_t *preds;                 // [capacity * SWEEP_COLS] predecessor masks by list index; word 31 = start cell
-    unsigned long long *done;        // [sweep_done_words] two offset copies of the done bitmap (ssb_sweep_core.cuh)
+    unsigned long long *gate;        // [capacity] near predecessors by list index (ssb_sweep_core.cuh); 0: none
+    uint32_t *preds;                 // [capacity * SWEEP_COLS] mask lines of the entries whose gate is SWEEP_GATE_LINE
+    unsigned long long *done;        // [sweep_done_words] the done bitmap (ssb_sweep_core.cuh)
     int32_t *bucket_count, *bucket_start, *bucket_fill;      // [SWEEP_MAX_KEYS + 1]
+    int32_t *bucket_fin;             // [SWEEP_MAX_KEYS + 1] finished agents per priority bucket
     int32_t *tile_pop;               // [tiles_x * tiles_y] != 0: agents stand on the tile
     int32_t *tile_need;              // [tiles_x * tiles_y] == stamp: the tile or a neighbour is populated (lean path: its cells are packed)
     int32_t stamp;                   // changes with every agent step
-    unsigned long long *ctl;         // [0] tile cursor of the build, [1] abort flag, [2] live agents seen by prepare, [4..6] diagnostics, [16 + 16 k] tickets
+    unsigned long long *ctl;         // [0] tile cursor of the build, [1] abort flag, [2] live agents seen by prepare, [3] overflowing gates, [4..7] diagnostics,
+                                     // [8] the watermark (own 64-byte half line), [16 + 16 k] tickets
     const int8_t *tables;            // conflict tables `any` then `pair` (sweep_fill_tables)
-    unsigned long long *diag;        // optional (SSB_SWEEP_DIAG=1): [0] warp iterations, [1] entries checked, [2] entries run
+    unsigned long long *diag;        // optional (SSB_SWEEP_DIAG=1): [0] warp iterations, [1] entries checked, [2] entries run, [3] entries behind the watermark
     int32_t bucket_bits;             // priority buckets = 1 << bucket_bits
+    int32_t sub_bits;                // bucket keys per priority bucket = 1 << sub_bits (lean path: by range)
     int32_t n_keys;                  // bucket keys (= buckets << sub bits); bucket_start[n_keys] = live agents
     int32_t rb, kb, halo;            // largest range / dilation of the step, halo = flow_halo(rb, kb)
     int32_t tiles_x, tiles_y;
@@ -70,16 +77,13 @@ __device__ __forceinline__ unsigned long long sweep_ld_relaxed_if(const unsigned
     return v;
 }
 __device__ __forceinline__ void sweep_fence() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
-// release: MEMBAR.ALL.GPU (my writes are in L2) + the reductions that set my done bit in both copies, WITHOUT the L1
-// invalidation of a full fence; RELEASE = false: after an explicit fence
+// release: MEMBAR.ALL.GPU (my writes are in L2) + the reduction that sets my done bit, WITHOUT the L1 invalidation of a
+// full fence; RELEASE = false: after an explicit fence
 template <bool RELEASE>
-__device__ __forceinline__ void sweep_set_done(const SweepCtx &w, int x, int y, int W, int wpc) {
-    bool first = RELEASE;
-    sweep_done_set(x, y, W, wpc, [&](size_t wd, int bit) {
-        if (first) asm volatile("red.release.gpu.global.or.b64 [%0], %1;" ::"l"(w.done + wd), "l"(1ull << bit) : "memory");
-        else asm volatile("red.relaxed.gpu.global.or.b64 [%0], %1;" ::"l"(w.done + wd), "l"(1ull << bit) : "memory");
-        first = false;
-    });
+__device__ __forceinline__ void sweep_set_done(const SweepCtx &w, int x, int y, int wpc) {
+    unsigned long long *p = w.done + sweep_done_word(x, y, wpc);
+    if (RELEASE) asm volatile("red.release.gpu.global.or.b64 [%0], %1;" ::"l"(p), "l"(1ull << (y & 63)) : "memory");
+    else asm volatile("red.relaxed.gpu.global.or.b64 [%0], %1;" ::"l"(p), "l"(1ull << (y & 63)) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -103,8 +107,9 @@ __global__ void __launch_bounds__(SWEEP_PREPARE_THREADS) k_sweep_prepare(DevCtx 
     for (int e = tid; e < NK; e += blockDim.x) sh_count[e] = 0;
     if (blockIdx.x == 0) {
         for (int e = tid; e <= NK; e += blockDim.x) { w.bucket_count[e] = 0; w.bucket_fill[e] = 0; }
+        for (int e = tid; e <= E; e += blockDim.x) w.bucket_fin[e] = 0;
         for (int k = tid; k < SWEEP_STRIPES; k += blockDim.x) w.ctl[16 + 16 * k] = 0;
-        if (tid == 0) { w.ctl[0] = 0; w.ctl[1] = 0; w.ctl[2] = 0; c.a.counters[SSB_C_N_BORN] = 0; c.a.counters[SSB_C_ROUNDS] = 1; }
+        if (tid == 0) { w.ctl[0] = 0; w.ctl[1] = 0; w.ctl[2] = 0; w.ctl[3] = 0; w.ctl[8] = 0; c.a.counters[SSB_C_N_BORN] = 0; c.a.counters[SSB_C_ROUNDS] = 1; }
     }
     grid.sync();
     // phase A: histogram of the bucket keys (the per-block work assignment is repeated exactly in phase B)
@@ -143,6 +148,13 @@ __global__ void __launch_bounds__(SWEEP_PREPARE_THREADS) k_sweep_prepare(DevCtx 
             longest = max(longest, v);
         }
         if (longest > w.concurrent) atomicExch((unsigned long long *)&c.a.counters[SSB_C_OVERFLOW], (unsigned long long)SWEEP_OVERFLOW_BUCKET);
+        // the watermark starts behind the leading EMPTY buckets (nobody would ever complete them)
+        __syncthreads();
+        if (tid == 0) {
+            int wb = 0;
+            while (wb < E && w.bucket_start[(wb + 1) << SUB] == w.bucket_start[wb << SUB]) wb++;
+            w.ctl[8] = (unsigned long long)wb;
+        }
         if (LEAN && tid == 0 && (long long)w.ctl[2] != c.a.counters[SSB_C_N_LIST])
             atomicExch((unsigned long long *)&c.a.counters[SSB_C_OVERFLOW], (unsigned long long)SWEEP_OVERFLOW_LIVE);
     }
@@ -174,60 +186,54 @@ __global__ void __launch_bounds__(SWEEP_PREPARE_THREADS) k_sweep_prepare(DevCtx 
 // ---------------------------------------------------------------------------------------------
 // build
 // ---------------------------------------------------------------------------------------------
-__host__ __device__ inline int sweep_build_smem_bytes(int rb, int kb, int halo) {
-    return (FLOW_TX + 2 * halo) * (FLOW_TY + 2 * halo) * 4 + (FLOW_TX + 2 * halo) * 16 + FLOW_TX * FLOW_TY * 2 + sweep_tables_bytes(rb, kb, halo) + 16;
+__host__ __device__ inline int sweep_build_smem_bytes(int rb, int kb, int halo, int n_slabs) {
+    return (FLOW_TX + 2 * halo) * (FLOW_TY + 2 * halo) * 4 + n_slabs * (FLOW_TX + 2 * halo) * 16 + FLOW_TX * FLOW_TY * 2 + sweep_tables_bytes(rb, kb, halo) + 16;
 }
 
 __global__ void __launch_bounds__(SWEEP_BUILD_THREADS) k_sweep_build(DevCtx c, SweepCtx w) {
     extern __shared__ __align__(16) unsigned char sweep_smem[];
     __shared__ int sh_tile, sh_n_agents, sh_class[16];
     const int R = w.halo, sw = FLOW_TX + 2 * R, sh = FLOW_TY + 2 * R;
-    unsigned long long *mask = reinterpret_cast<unsigned long long *>(sweep_smem);
-    uint32_t *cell = reinterpret_cast<uint32_t *>(mask + sw * 2);
+    const int n_slabs = sweep_n_slabs(w.bucket_bits);
+    const int slab_prio_shift = c.p.id_bits - w.bucket_bits + sweep_slab_shift(w.bucket_bits);
+    unsigned long long *smask = reinterpret_cast<unsigned long long *>(sweep_smem);
+    uint32_t *cell = reinterpret_cast<uint32_t *>(smask + (size_t)n_slabs * sw * 2);
     uint16_t *agents = reinterpret_cast<uint16_t *>(cell + sw * sh);
     int8_t *tables = reinterpret_cast<int8_t *>(agents + FLOW_TX * FLOW_TY);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const int W = c.p.width, H = c.p.height;
     const int n_tiles = w.tiles_x * w.tiles_y;
     for (int i = tid; i < sweep_tables_bytes(w.rb, w.kb, R); i += SWEEP_BUILD_THREADS) tables[i] = w.tables[i];
     SweepTile tile;
-    tile.cell = cell; tile.mask = mask; tile.sw = sw; tile.sh = sh; tile.halo = R;
+    tile.cell = cell; tile.smask = smask; tile.sw = sw; tile.sh = sh; tile.halo = R; tile.slab_prio_shift = slab_prio_shift;
     tile.any = tables; tile.pair = tables + sweep_any_size(w.rb, w.kb, R);
     for (;;) {
         __syncthreads();                                        // the previous tile's shared state is dead
         if (tid == 0) { sh_tile = (int)atomicAdd(&w.ctl[0], 1ull); sh_n_agents = 0; }
+        if (tid < 16) sh_class[tid] = 0;
         __syncthreads();
         const int t = sh_tile;
         if (t >= n_tiles) break;
         if (w.tile_pop[t] == 0) continue;
         const int tx = t / w.tiles_y, ty = t - tx * w.tiles_y;
         const int x0 = tx * FLOW_TX - R, y0 = ty * FLOW_TY - R;
-        // stage the low descriptor words: a column of the staged tile is a contiguous run of the x-major grid (up to the torus seam)
+        for (int i = tid; i < n_slabs * sw * 2; i += SWEEP_BUILD_THREADS) smask[i] = 0ull;
+        __syncthreads();
+        // stage the low descriptor words (a column of the staged tile is a contiguous run of the x-major grid, up to the
+        // torus seam) and set every agent's bit in the plane of its slab
         const bool inside = x0 >= 0 && y0 >= 0 && x0 + sw <= W && y0 + sh <= H;
-        if (inside) {
-            const unsigned long long *src = w.desc + (size_t)x0 * H + y0;
+        const unsigned long long *src = w.desc + (size_t)(inside ? x0 : 0) * H + (inside ? y0 : 0);
 #pragma unroll 4
-            for (int job = tid; job < sw * sh; job += SWEEP_BUILD_THREADS) {
-                const int col = job / sh, row = job - col * sh;
-                cell[job] = (uint32_t)__ldg(src + (size_t)col * H + row);
-            }
-        } else {
-            for (int job = tid; job < sw * sh; job += SWEEP_BUILD_THREADS) {
-                const int col = job / sh, row = job - col * sh;
-                cell[job] = (uint32_t)__ldg(w.desc + (size_t)wrapi(x0 + col, W) * H + wrapi(y0 + row, H));
-            }
+        for (int job = tid; job < sw * sh; job += SWEEP_BUILD_THREADS) {
+            const int col = job / sh, row = job - col * sh;
+            const uint32_t lo = inside ? (uint32_t)__ldg(src + (size_t)col * H + row)
+                                       : (uint32_t)__ldg(w.desc + (size_t)wrapi(x0 + col, W) * H + wrapi(y0 + row, H));
+            cell[job] = lo;
+            if (lo != 0u) atomicOr(smask + ((size_t)(sweep_prio(lo) >> slab_prio_shift) * sw + col) * 2 + (row >> 6), 1ull << (row & 63));
         }
         __syncthreads();
-        // occupancy masks: one ballot per 32 rows
-        for (int job = warp; job < sw * 4; job += SWEEP_BUILD_THREADS / 32) {
-            const int col = job >> 2, part = job & 3, row = part * 32 + lane;
-            const unsigned bits = __ballot_sync(0xffffffffu, row < sh && cell[col * sh + row] != 0u);
-            if (lane == 0) reinterpret_cast<unsigned *>(mask + col * 2)[part] = bits;
-        }
         // the tile's own agents (interior cells that lie on the map), grouped by range: the 32 agents a warp scans have
         // conflict regions of the same size
-        if (tid < 16) sh_class[tid] = 0;
-        __syncthreads();
         for (int idx = tid; idx < FLOW_TX * FLOW_TY; idx += SWEEP_BUILD_THREADS) {
             const int ix = idx / FLOW_TY, iy = idx - ix * FLOW_TY;
             if (tx * FLOW_TX + ix >= W || ty * FLOW_TY + iy >= H) continue;
@@ -252,19 +258,22 @@ __global__ void __launch_bounds__(SWEEP_BUILD_THREADS) k_sweep_build(DevCtx c, S
         const int n_agents = sh_n_agents;
         for (int a = tid; a < n_agents; a += SWEEP_BUILD_THREADS) {
             const int sc = agents[a], lx = sc / sh, ly = sc - lx * sh;
+            unsigned long long gate = 0ull;
+            int n_near = 0;
+            sweep_near_preds(tile, lx, ly, cell[sc], w.rb, w.kb, [&](int dx, int dy) {
+                if (n_near < SWEEP_GATE_PREDS) gate |= sweep_gate_code(dx, dy, R) << (10 * n_near);
+                n_near++;
+            });
+            if (n_near == 0) continue;                           // (the gates were zeroed before the launch)
             const uint32_t gcell = (uint32_t)((tx * FLOW_TX + lx - R) * H + (ty * FLOW_TY + ly - R));
             const uint32_t index = (uint32_t)(__ldg(w.desc + gcell) >> 32);
-            uint4 *out = reinterpret_cast<uint4 *>(w.preds + (size_t)index * SWEEP_COLS);
-            uint4 acc = make_uint4(0u, 0u, 0u, 0u);
-            sweep_pred_masks(tile, lx, ly, cell[sc], w.rb, w.kb, [&](int col, uint32_t m) {
-                const int u = col & 3;
-                if (u == 0) acc.x = m; else if (u == 1) acc.y = m; else if (u == 2) acc.z = m; else acc.w = m;
-                if (u == 3) { out[col >> 2] = acc; acc = make_uint4(0u, 0u, 0u, 0u); }
-            });
-            // columns 2 R + 1 .. 30 stay empty; word 31 carries the start cell
-            const int first = (2 * R + 1) >> 2;
-            if (first == 7) { acc.w = gcell; out[7] = acc; }
-            else { out[first] = acc; out[7] = make_uint4(0u, 0u, 0u, gcell); }
+            if (n_near <= SWEEP_GATE_PREDS) { w.gate[index] = gate; continue; }
+            // more near predecessors than a gate holds (rare): a line of column masks
+            uint32_t *line = w.preds + (size_t)index * SWEEP_COLS;
+            for (int k = 0; k < SWEEP_COLS; k++) line[k] = 0u;
+            sweep_near_preds(tile, lx, ly, cell[sc], w.rb, w.kb, [&](int dx, int dy) { line[dx + R] |= 1u << (dy + R); });
+            w.gate[index] = SWEEP_GATE_LINE;
+            atomicAdd(&w.ctl[3], 1ull);
         }
     }
 }
@@ -318,46 +327,74 @@ __global__ void __launch_bounds__(256) k_lean_cells(DevCtx c, SweepCtx w, LeanCt
 // ---------------------------------------------------------------------------------------------
 // sweep
 // ---------------------------------------------------------------------------------------------
-// All predecessors of list entry i done?  Straight-line code: the eight 16-byte loads of the agent's mask line are in
-// flight together, then the done words of its columns in batches of eight (one 64-bit word per column, see the
-// bitmap layout in ssb_sweep_core.cuh).  Also returns the start cell of the entry.
-__device__ __noinline__ bool sweep_entry_ready_seam(const SweepCtx &w, const uint32_t *pm, int x, int y, int W, int H) {
+// May list entry i run?  The caller has compared the watermark; this is the individual part: the done bits of the near
+// predecessors in the entry's gate.  Straight-line code: the (at most six) done words are loaded under predicates and
+// are in flight together.  pos: the entry's start cell.
+__device__ __noinline__ bool sweep_line_ready(const SweepCtx &w, int i, int x, int y, int W, int H) {
+    const uint32_t *line = w.preds + (size_t)i * SWEEP_COLS;
     uint32_t masks[SWEEP_COLS];
-    for (int k = 0; k < SWEEP_COLS; k++) masks[k] = __ldg(pm + k);
-    return sweep_preds_done(masks, [&](size_t wd) { return sweep_ld_relaxed(w.done + wd); }, x, y, W, H, w.halo);
+    for (int k = 0; k < SWEEP_COLS; k++) masks[k] = __ldg(line + k);
+    return sweep_line_done(masks, [&](size_t wd) { return sweep_ld_relaxed(w.done + wd); }, x, y, W, H, w.halo);
 }
-__device__ __forceinline__ bool sweep_entry_ready(const SweepCtx &w, int i, int W, int H, int *sx, int *sy) {
-    const uint32_t *pm = w.preds + (size_t)i * SWEEP_COLS;
-    uint4 v[8];
+__device__ __forceinline__ bool sweep_gate_ready(const SweepCtx &w, unsigned long long gate, int i, int pos, int W, int H) {
+    if (gate == 0ull) return true;
+    const int x = pos / H, y = pos - x * H;
+    if (gate == SWEEP_GATE_LINE) return sweep_line_ready(w, i, x, y, W, H);
+    const int wpc = sweep_done_wpc(H), R = w.halo;
+    unsigned long long dw[SWEEP_GATE_PREDS];
+    int bit[SWEEP_GATE_PREDS];
 #pragma unroll
-    for (int g = 0; g < 8; g++) v[g] = __ldg(reinterpret_cast<const uint4 *>(pm) + g);
-    const uint32_t cell = v[7].w;                                      // (word 31 is the start cell, not a mask)
-    const int x = (int)(cell / (uint32_t)H), y = (int)(cell - (uint32_t)x * (uint32_t)H);
-    *sx = x; *sy = y;
-    const SweepWindow win = sweep_window(x, y, W, H, w.halo);
-    if (!win.straight) return sweep_entry_ready_seam(w, pm, x, y, W, H);
-    int shift;
-    const unsigned long long *col0 = w.done + sweep_done_window(0, win.y0, W, win.wpc, &shift);
+    for (int k = 0; k < SWEEP_GATE_PREDS; k++) {
+        const int code = (int)(gate >> (10 * k)) & 1023;
+        int cx, cy;
+        sweep_offset_cell(x, y, (code & 31) - 1 - R, (code >> 5) - R, W, H, &cx, &cy);       // (an empty slot decodes to a cell that is not loaded)
+        dw[k] = sweep_ld_relaxed_if(w.done + sweep_done_word(cx, cy, wpc), (uint32_t)(code & 31));
+        bit[k] = cy & 63;
+    }
     bool ok = true;
 #pragma unroll
-    for (int c0 = 0; c0 < 32; c0 += 8) {
-        if (c0 >= win.span) break;
-        unsigned long long dw[8];
-        uint32_t m[8];
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-            const int col = c0 + u;
-            const uint4 q = v[col >> 2];
-            m[u] = (col & 3) == 0 ? q.x : ((col & 3) == 1 ? q.y : ((col & 3) == 2 ? q.z : q.w));
-            if (col >= win.span || col == 31) m[u] = 0u;
-            int cx = win.x + col;
-            if (cx < 0) cx += W; else if (cx >= W) cx -= W;
-            dw[u] = sweep_ld_relaxed_if(col0 + (size_t)cx * win.wpc, m[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < 8; u++) ok &= ((uint32_t)(dw[u] >> shift) & m[u]) == m[u];
-    }
+    for (int k = 0; k < SWEEP_GATE_PREDS; k++) ok &= (bool)((dw[k] >> bit[k]) & 1ull);
     return ok;
+}
+
+// The watermark (ctl[8]): the number of leading priority buckets whose agents have all finished.  The lanes of a warp
+// that finished an agent in this iteration count themselves in their buckets (one fire-and-forget reduction per
+// distinct bucket, released); ONE warp of the grid (sweep_watermark_warp) does nothing but walk the watermark over the
+// complete buckets.  Everybody else keeps a copy of the watermark in a register and re-reads it only when one of its
+// agents fails the comparison (the watermark only grows: a stale copy is merely conservative).
+// all lanes of the warp; ran: this lane finished an agent of `bucket` in this iteration (its done bit is set: its writes
+// are released)
+__device__ __forceinline__ void sweep_count_finished(const SweepCtx &w, bool ran, int bucket) {
+    const unsigned ranm = __ballot_sync(0xffffffffu, ran);
+    if (!ran) return;
+    __syncwarp(ranm);
+    const unsigned peers = __match_any_sync(ranm, bucket);
+    if ((int)(threadIdx.x & 31) != __ffs(peers) - 1) return;
+    asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(w.bucket_fin + bucket), "r"(__popc(peers)) : "memory");
+}
+__device__ __noinline__ void sweep_watermark_warp(const DevCtx &c, const SweepCtx &w) {
+    if ((threadIdx.x & 31) != 0) return;
+    const int E = 1 << w.bucket_bits, SUB = w.sub_bits;
+    int b = (int)sweep_ld_relaxed(w.ctl + 8);
+    unsigned long long last = global_ns();
+    while (b < E) {
+        const int size = w.bucket_start[(b + 1) << SUB] - w.bucket_start[b << SUB];
+        int fin;
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(fin) : "l"(w.bucket_fin + b) : "memory");
+        if (fin == size) {
+            b++;
+            asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(w.ctl + 8), "l"((unsigned long long)b) : "memory");
+            last = global_ns();
+            continue;
+        }
+        __nanosleep(100);
+        if (*(const volatile unsigned long long *)(w.ctl + 1) != 0ull) return;
+        if (global_ns() - last > SWEEP_STALL_NS) {
+            atomicExch((unsigned long long *)&c.a.counters[SSB_C_OVERFLOW], (unsigned long long)SWEEP_OVERFLOW_STALL);
+            atomicExch(w.ctl + 1, 1ull);
+            return;
+        }
+    }
 }
 
 // Entries are handed out in list order by ticket counters, one entry per lane (group) whenever it has finished its
@@ -405,8 +442,12 @@ __host__ __device__ constexpr int lean_smem_bytes(int maxc, int threads) { retur
 // The lean transaction reads everything mutable past L1 (lean_ld), so the consumer needs no acquire fence (whose
 // CCTL.IVALL would invalidate the whole L1 once per agent); the producer's release rides on the reduction that sets
 // the done bit.  MODE: see lean_transaction.
+#ifndef SSB_LEAN_PREFETCH
+#define SSB_LEAN_PREFETCH 0      /* measured on S2: requesting the cross ahead of the gate check costs 7 ms (L2 request rate) */
+#endif
 template <int MODE>
 __global__ void __launch_bounds__(LEAN_THREADS, MODE == 0 ? 5 : 3) k_sweep_lean(DevCtx c, SweepCtx w, LeanCtx L) {
+    constexpr bool PREFETCH = SSB_LEAN_PREFETCH != 0;
     extern __shared__ __align__(16) unsigned char lean_smem[];
     const int T = blockDim.x, tid = threadIdx.x;
     int32_t *occ_st = reinterpret_cast<int32_t *>(lean_smem);
@@ -414,27 +455,43 @@ __global__ void __launch_bounds__(LEAN_THREADS, MODE == 0 ? 5 : 3) k_sweep_lean(
     const LeanStage st = {occ_st + tid, sug_st + tid, T};
     const int n = w.bucket_start[w.n_keys];
     const int W = c.p.width, H = c.p.height, wpc = sweep_done_wpc(H);
+    const int prio_shift = c.p.id_bits - w.bucket_bits, slab_shift = sweep_slab_shift(w.bucket_bits);
+    if (blockIdx.x == 0 && tid < 32) { sweep_watermark_warp(c, w); return; }
     int i = -1;
     bool exhausted = false;
     unsigned long long idle_since = 0;
+    int watermark = 0;
     for (;;) {
+        const int held = i;
         sweep_claim(w, n, true, i, exhausted);
         if (!__any_sync(0xffffffffu, i >= 0)) break;
-        bool ran = false;
-        int x = 0, y = 0;
+        bool ran = false, ready = false;
+        int bucket = 0, need = 0;
         LeanB B;
-        if (i >= 0) B = L.b[i];                                  // (read-only: in flight together with the mask line)
-        const bool ready = i >= 0 && sweep_entry_ready(w, i, W, H, &x, &y);
+        unsigned long long gate = 0ull;
+        if (i >= 0) {
+            B = L.b[i];                                          // (read-only: in flight together with the gate)
+            gate = __ldg(w.gate + i);
+            if (PREFETCH && i != held) lean_prefetch_agent(L, B.slot, B.pos, (int)((B.idf >> LEANB_RANGE_SHIFT) & 15u), W, H);
+            bucket = (int)(priority_of(w.key, B.idf & LEANB_ID_MASK, c.p.id_bits) >> prio_shift);
+            need = sweep_watermark_needed(bucket, slab_shift);
+        }
+        if (__any_sync(0xffffffffu, i >= 0 && watermark < need)) watermark = (int)sweep_ld_relaxed(w.ctl + 8);
+        const bool passed = i >= 0 && watermark >= need;
+        if (passed) ready = sweep_gate_ready(w, gate, i, B.pos, W, H);
         const unsigned readym = __ballot_sync(0xffffffffu, ready);      // (also re-converges the warp after the check)
         if (ready) {
             lean_transaction<MODE>(c, L, B, w.key, st, readym);
-            sweep_set_done<true>(w, x, y, W, wpc);               // release: my writes happen before my done bit
+            const int x = B.pos / H;
+            sweep_set_done<true>(w, x, B.pos - x * H, wpc);      // release: my writes happen before my done bit
             i = -1;
             ran = true;
         }
+        sweep_count_finished(w, ran, bucket);
         if (w.diag) {
             const unsigned held = __ballot_sync(0xffffffffu, i >= 0 || ran), did = __ballot_sync(0xffffffffu, ran);
-            if ((tid & 31) == 0) { atomicAdd(w.diag, 1ull); atomicAdd(w.diag + 1, (unsigned long long)__popc(held)); atomicAdd(w.diag + 2, (unsigned long long)__popc(did)); }
+            const unsigned late = __ballot_sync(0xffffffffu, i >= 0 && !passed);
+            if ((tid & 31) == 0) { atomicAdd(w.diag, 1ull); atomicAdd(w.diag + 1, (unsigned long long)__popc(held)); atomicAdd(w.diag + 2, (unsigned long long)__popc(did)); atomicAdd(w.diag + 3, (unsigned long long)__popc(late)); }
         }
         if (__any_sync(0xffffffffu, ran)) idle_since = 0;
         else if (sweep_idle(c, w, idle_since)) break;
@@ -447,31 +504,44 @@ __global__ void __launch_bounds__(AGENT_THREADS, 2) k_sweep_generic(DevCtx c, Sw
     const WarpScratch ws = make_warp_scratch(scratch_mem + (threadIdx.x / GL) * warp_scratch_bytes(MAXC_SCALABLE), MAXC_SCALABLE);
     const int n = w.bucket_start[w.n_keys];
     const int W = c.p.width, H = c.p.height, lane = Group<GL>::lane(), wpc = sweep_done_wpc(H);
+    const int prio_shift = c.p.id_bits - w.bucket_bits, slab_shift = sweep_slab_shift(w.bucket_bits);
+    if (blockIdx.x == 0 && threadIdx.x < 32) { sweep_watermark_warp(c, w); return; }
     int i = -1;
     bool exhausted = false;
     unsigned long long idle_since = 0;
+    int watermark = 0;
     for (;;) {
         sweep_claim(w, n, lane == 0, i, exhausted);             // lane 0 of every group claims, the group follows
         i = Group<GL>::bcast(i, 0);
         if (!__any_sync(0xffffffffu, i >= 0)) break;
         bool ran = false;
-        int x = 0, y = 0;
-        if (i >= 0 && sweep_entry_ready(w, i, W, H, &x, &y)) {    // (every lane of the group reads the same words)
-            sweep_fence();
-            const int4 en = w.entries[i];
-            const int s = en.x;
-            AgentRec rec;
-            rec.load(c, s);
-            RngStream rng{w.key, (uint32_t)rec.id, 0u, 0u, nullptr};
-            if (transaction_move_phase<GL, 4>(c, s, rec, rng, ws, MAXC_SCALABLE)) {
-                if (lane == 0) transaction_interact_phase<RngStream, false>(c, s, rec, rng);
-            }
-            Group<GL>::sync();
-            sweep_fence();
-            if (lane == 0) sweep_set_done<false>(w, x, y, W, wpc);
-            i = -1;
-            ran = true;
+        int bucket = 0, need = 0;
+        int4 en = make_int4(0, 0, 0, 0);
+        if (i >= 0) {                                            // (every lane of the group reads the same words)
+            en = w.entries[i];
+            bucket = (int)((uint32_t)en.z >> prio_shift);
+            need = sweep_watermark_needed(bucket, slab_shift);
         }
+        if (__any_sync(0xffffffffu, i >= 0 && watermark < need)) watermark = (int)sweep_ld_relaxed(w.ctl + 8);
+        if (i >= 0) {
+            if (watermark >= need && sweep_gate_ready(w, __ldg(w.gate + i), i, en.y, W, H)) {
+                sweep_fence();
+                const int s = en.x;
+                AgentRec rec;
+                rec.load(c, s);
+                RngStream rng{w.key, (uint32_t)rec.id, 0u, 0u, nullptr};
+                if (transaction_move_phase<GL, 4>(c, s, rec, rng, ws, MAXC_SCALABLE)) {
+                    if (lane == 0) transaction_interact_phase<RngStream, false>(c, s, rec, rng);
+                }
+                Group<GL>::sync();
+                sweep_fence();
+                const int x = en.y / H;
+                if (lane == 0) sweep_set_done<false>(w, x, en.y - x * H, wpc);
+                i = -1;
+                ran = true;
+            }
+        }
+        sweep_count_finished(w, ran && lane == 0, bucket);
         if (__any_sync(0xffffffffu, ran)) idle_since = 0;
         else if (sweep_idle(c, w, idle_since)) break;
     }

@@ -7,19 +7,23 @@
 //
 //   prepare  the agents are bucketed by the top bits of their priority (two counting passes, no sort) into the
 //            list `entries`; every agent leaves a descriptor {priority, range, dilation | list index} on its cell;
-//   build    one CTA per 64 x 64 tile stages the descriptors of the tile and its halo in shared memory; one
-//            thread per agent finds its PREDECESSORS -- the agents with a smaller priority whose footprint
-//            intersects its own -- and stores them as one bit mask per x-column of its conflict region
-//            (bit dy + halo of column dx + halo: the agent that STARTS the step on cell (x + dx, y + dy));
-//   sweep    a persistent grid walks the bucketed list: thread j takes entries j, j + T, j + 2 T, ...  An agent
-//            runs its whole transaction once the DONE bit of every predecessor's start cell is set (one bit per
-//            cell, a few MB that live in L2), then sets its own.  No bucket is longer than T entries, so every
-//            thread meets its agents in ascending priority: the unfinished agent with the globally smallest
-//            priority is always at the head of its thread, has no unfinished predecessor, and runs -- the sweep
-//            cannot deadlock, and most agents find all predecessors done when their turn comes because the
-//            T agents in flight are a thin slice of the priority order.
+//            16 consecutive groups of buckets are the SLABS of the priority order;
+//   sweep    a persistent grid walks the bucketed list by tickets.  An agent runs its whole transaction once all
+//            its PREDECESSORS -- the agents with a smaller priority whose footprint intersects its own -- have
+//            finished, then sets the DONE bit of its start cell and counts itself in its bucket.  The agents in
+//            flight are a thin slice of the priority order (a few buckets), so almost every predecessor of an
+//            agent finished long ago.  The WATERMARK -- the number of leading buckets whose agents have ALL
+//            finished -- certifies that wholesale: an agent of slab g waits until the watermark has passed every
+//            bucket of the slabs < g - 1, and checks individually only its NEAR predecessors, those of the slabs
+//            g - 1 and g (about one per agent).  Both waits are for agents of smaller priority only, so the
+//            unfinished agent with the globally smallest priority can always run: the sweep cannot deadlock.
+//   build    one CTA per 64 x 64 tile stages the descriptors of the tile and its halo in shared memory, with one
+//            occupancy bit-plane per slab; one thread per agent scans the two bit-planes of its near slabs over
+//            its conflict region and stores the near predecessors it finds as the agent's GATE: up to six
+//            (dx, dy) offsets in one 64-bit word.  (More than six: the gate says so and the predecessors go to a
+//            128-byte line of column bit masks, as bit dy + halo of word dx + halo.)
 //
-// Everything in this file is plain C++ so that tests/hostemu compiles the SAME predecessor scan, the SAME done
+// Everything in this file is plain C++ so that tests/hostemu compiles the SAME predecessor scan, the SAME gate
 // test and the SAME lean transaction with g++ and replays the reference fixtures through adversarial orders.
 #pragma once
 #include "ssb_flow_core.cuh"
@@ -35,9 +39,29 @@ __host__ __device__ __forceinline__ int sweep_r(uint32_t lo) { return (int)((lo 
 __host__ __device__ __forceinline__ int sweep_k(uint32_t lo) { return (int)(lo & 3u); }
 __host__ __device__ __forceinline__ unsigned long long sweep_desc(uint32_t index, uint32_t lo) { return ((unsigned long long)index << 32) | lo; }
 
-// Predecessor masks: SWEEP_COLS 32-bit words per agent (one 128-byte line), word dx + halo, bit dy + halo.
-constexpr int SWEEP_COLS = 32;
+constexpr int SWEEP_COLS = 32;                      // words of a predecessor mask line (one 128-byte line)
 constexpr int SWEEP_MAX_HALO = 15;                  // 2 * halo + 1 <= 31 rows and columns
+
+// ---- slabs: groups of consecutive priority buckets --------------------------------------------------------
+#ifndef SSB_SLAB_BITS
+#define SSB_SLAB_BITS 4
+#endif
+constexpr int SWEEP_SLAB_BITS = SSB_SLAB_BITS;
+constexpr int SWEEP_MAX_SLABS = 1 << SWEEP_SLAB_BITS;
+// buckets per slab = 1 << sweep_slab_shift; slabs = 1 << min(bucket_bits, SWEEP_SLAB_BITS)
+__host__ __device__ __forceinline__ int sweep_slab_shift(int bucket_bits) { return bucket_bits > SWEEP_SLAB_BITS ? bucket_bits - SWEEP_SLAB_BITS : 0; }
+__host__ __device__ __forceinline__ int sweep_n_slabs(int bucket_bits) { return 1 << (bucket_bits < SWEEP_SLAB_BITS ? bucket_bits : SWEEP_SLAB_BITS); }
+// the watermark an agent of bucket b waits for: the first bucket of the slab before its own
+__host__ __device__ __forceinline__ int sweep_watermark_needed(int bucket, int slab_shift) {
+    const int slab = bucket >> slab_shift;
+    return slab > 0 ? (slab - 1) << slab_shift : 0;
+}
+
+// ---- gates -------------------------------------------------------------------------------------------------
+// up to SWEEP_GATE_PREDS near predecessors, 10 bits each: (dx + halo + 1) | (dy + halo) << 5; 0 ends the list
+constexpr int SWEEP_GATE_PREDS = 6;
+constexpr unsigned long long SWEEP_GATE_LINE = ~0ull;      // too many: see the agent's mask line
+__host__ __device__ __forceinline__ unsigned long long sweep_gate_code(int dx, int dy, int halo) { return (unsigned long long)((dx + halo + 1) | ((dy + halo) << 5)); }
 
 // Conflict tables (filled once per engine on the host, sweep_fill_tables; staged in shared memory by the build kernel):
 //   any [ka][ra][adx]          largest |dy| at column offset adx at which an agent of range ra / dilation ka can conflict
@@ -62,100 +86,88 @@ inline void sweep_fill_tables(int RB, int KB, int halo, int8_t *any, int8_t *pai
 
 struct SweepTile {
     const uint32_t *cell;                // [sw * sh] low descriptor words, column (x) major like the grid
-    const unsigned long long *mask;      // [sw * 2] occupancy bits of every staged column (sh <= 128)
+    const unsigned long long *smask;     // [slabs][sw * 2] per slab: occupancy bits of every staged column (sh <= 128)
     const int8_t *any, *pair;            // conflict tables
     int sw, sh, halo;
+    int slab_prio_shift;                 // slab = priority >> slab_prio_shift
 };
 
-// The predecessors of the agent with low descriptor word `la` on staged cell (lx, ly), column by column:
-// emit(column index dx + halo, mask).  RB / KB: the largest range / dilation of any agent in this step.
+// The NEAR predecessors of the agent with low descriptor word `la` on staged cell (lx, ly): the agents of its own slab
+// and of the slab before it that have a smaller priority and an intersecting footprint.  emit(dx, dy) for each.
+// RB / KB: the largest range / dilation of any agent in this step.
 template <class F>
-__host__ __device__ __forceinline__ void sweep_pred_masks(const SweepTile &tile, int lx, int ly, uint32_t la, int RB, int KB, F emit) {
+__host__ __device__ __forceinline__ void sweep_near_preds(const SweepTile &tile, int lx, int ly, uint32_t la, int RB, int KB, F emit) {
     const int ra = sweep_r(la), ka = sweep_k(la), halo = tile.halo, hs = halo + 1;
     const uint32_t pa = sweep_prio(la);
+    const int g = (int)(pa >> tile.slab_prio_shift);
+    const unsigned long long *m1 = tile.smask + (size_t)g * tile.sw * 2, *m0 = g > 0 ? m1 - tile.sw * 2 : m1;
     const int8_t *any = tile.any + (ka * (RB + 1) + ra) * hs;
     const int8_t *pair = tile.pair + ((ka * (RB + 1) + ra) * (RB + 1)) * hs;       // + (kb (RB + 1) (RB + 1) + rb) hs + adx
     const int k_stride = (RB + 1) * (RB + 1) * hs;
     for (int dx = -halo; dx <= halo; dx++) {
         const int adx = dx < 0 ? -dx : dx;
         const int h = any[adx];
-        uint32_t m = 0;
-        if (h >= 0) {
-            const int col = lx + dx, y0 = ly - h;
-            unsigned long long bits = flow_mask_window(tile.mask + col * 2, y0, 2 * h + 1);
-            if (dx == 0) bits &= ~(1ull << h);
-            const uint32_t *column = tile.cell + col * tile.sh + y0;
-            while (bits) {
-                const int j = flow_ctz64(bits);
-                bits &= bits - 1;
-                const uint32_t lb = column[j];
-                if (sweep_prio(lb) >= pa) continue;
-                const int dy = j - h, ady = dy < 0 ? -dy : dy;
-                if (ady <= pair[sweep_k(lb) * k_stride + sweep_r(lb) * hs + adx]) m |= 1u << (dy + halo);
-            }
+        if (h < 0) continue;
+        const int col = lx + dx, y0 = ly - h;
+        const unsigned long long both[2] = {m1[col * 2] | m0[col * 2], m1[col * 2 + 1] | m0[col * 2 + 1]};
+        unsigned long long bits = flow_mask_window(both, y0, 2 * h + 1);
+        if (dx == 0) bits &= ~(1ull << h);
+        const uint32_t *column = tile.cell + col * tile.sh + y0;
+        while (bits) {
+            const int j = flow_ctz64(bits);
+            bits &= bits - 1;
+            const uint32_t lb = column[j];
+            if (sweep_prio(lb) >= pa) continue;
+            const int dy = j - h, ady = dy < 0 ? -dy : dy;
+            if (ady <= pair[sweep_k(lb) * k_stride + sweep_r(lb) * hs + adx]) emit(dx, dy);
         }
-        emit(dx + halo, m);
     }
 }
 
 // The DONE bitmap: one bit per cell -- "the agent that started the step on this cell has finished" -- in 64-bit words
-// along y, kept in TWO copies whose words are offset by 32 rows: copy A word k of column x covers rows [64 k, 64 k + 64),
-// copy B word k covers rows [64 k + 32, 64 k + 96).  Any window of up to 33 rows lies inside ONE word of one of the
-// copies, so testing the predecessors of a column is one load, one shift and one compare.
-//   words per column wpc = H / 64 + 2;  copy A at done[x * wpc + k], copy B at done[(W + x) * wpc + k]
-__host__ __device__ __forceinline__ int sweep_done_wpc(int H) { return H / 64 + 2; }
-__host__ __device__ __forceinline__ size_t sweep_done_words(int W, int H) { return (size_t)2 * W * sweep_done_wpc(H); }
-// word index and shift of the window that starts at row y0 >= 0 of column cx (span <= 33 rows, y0 + span <= H)
-__host__ __device__ __forceinline__ size_t sweep_done_window(int cx, int y0, int W, int wpc, int *shift) {
-    const bool copy_b = (y0 & 63) > 31;
-    const int yy = copy_b ? y0 - 32 : y0;
-    *shift = yy & 63;
-    return (size_t)(copy_b ? W + cx : cx) * wpc + (yy >> 6);
-}
-// set(word index, bit) is called once or twice
-template <class SetBit>
-__host__ __device__ __forceinline__ void sweep_done_set(int x, int y, int W, int wpc, SetBit set) {
-    set((size_t)x * wpc + (y >> 6), y & 63);
-    if (y >= 32) set((size_t)(W + x) * wpc + ((y - 32) >> 6), (y - 32) & 63);
+// along y:  done[x * wpc + (y >> 6)], bit y & 63.
+__host__ __device__ __forceinline__ int sweep_done_wpc(int H) { return (H + 63) >> 6; }
+__host__ __device__ __forceinline__ size_t sweep_done_words(int W, int H) { return (size_t)W * sweep_done_wpc(H); }
+__host__ __device__ __forceinline__ size_t sweep_done_word(int x, int y, int wpc) { return (size_t)x * wpc + (y >> 6); }
+
+// the cell at offset (dx, dy) from (x, y) on the torus (|dx|, |dy| < W, H)
+__host__ __device__ __forceinline__ void sweep_offset_cell(int x, int y, int dx, int dy, int W, int H, int *cx, int *cy) {
+    int u = x + dx, v = y + dy;
+    if (u < 0) u += W; else if (u >= W) u -= W;
+    if (v < 0) v += H; else if (v >= H) v -= H;
+    *cx = u; *cy = v;
 }
 
-// Have all predecessors of the agent that starts on (x, y) finished?  masks = its SWEEP_COLS words; ld(w) reads word w of
-// the bitmap past every cache that could hold a stale copy.
-struct SweepWindow { int x, y0, W, H, span, wpc; bool straight; };
-__host__ __device__ __forceinline__ SweepWindow sweep_window(int x, int y, int W, int H, int halo) {
-    SweepWindow win;
-    win.x = x - halo; win.y0 = y - halo; win.W = W; win.H = H; win.span = 2 * halo + 1; win.wpc = sweep_done_wpc(H);
-    win.straight = win.y0 >= 0 && win.y0 + win.span <= H;
-    return win;
-}
-// column `col` (= dx + halo) with predecessor mask m, for an agent whose window crosses the torus seam in y: bit by bit
+// Have the near predecessors listed in `gate` finished?  (x, y): the agent's start cell; ld(w) reads word w of the done
+// bitmap past every cache that could hold a stale copy.
 template <class LoadDone>
-__host__ __device__ inline bool sweep_column_done_seam(const SweepWindow &win, uint32_t m, int cx, LoadDone ld) {
+__host__ __device__ __forceinline__ bool sweep_gate_done(unsigned long long gate, LoadDone ld, int x, int y, int W, int H, int halo) {
+    const int wpc = sweep_done_wpc(H);
     bool ok = true;
-#pragma unroll 1
-    for (int j = 0; j < win.span; j++) {
-        if (!((m >> j) & 1u)) continue;
-        int cy = win.y0 + j;
-        if (cy < 0) cy += win.H; else if (cy >= win.H) cy -= win.H;
-        if (!((ld((size_t)cx * win.wpc + (cy >> 6)) >> (cy & 63)) & 1ull)) ok = false;
+    for (int k = 0; k < SWEEP_GATE_PREDS; k++) {
+        const int code = (int)(gate >> (10 * k)) & 1023;
+        if ((code & 31) == 0) break;
+        int cx, cy;
+        sweep_offset_cell(x, y, (code & 31) - 1 - halo, (code >> 5) - halo, W, H, &cx, &cy);
+        if (!((ld(sweep_done_word(cx, cy, wpc)) >> (cy & 63)) & 1ull)) ok = false;
     }
     return ok;
 }
+// ... and those of a mask line (the rare agent with more near predecessors than a gate holds)
 template <class LoadDone>
-__host__ __device__ __forceinline__ bool sweep_column_done(const SweepWindow &win, uint32_t m, int col, LoadDone ld) {
-    int cx = win.x + col;
-    if (cx < 0) cx += win.W; else if (cx >= win.W) cx -= win.W;
-    if (!win.straight) return sweep_column_done_seam(win, m, cx, ld);
-    int shift;
-    const size_t wd = sweep_done_window(cx, win.y0, win.W, win.wpc, &shift);
-    return ((uint32_t)(ld(wd) >> shift) & m) == m;
-}
-template <class LoadDone>
-__host__ __device__ __forceinline__ bool sweep_preds_done(const uint32_t *masks, LoadDone ld, int x, int y, int W, int H, int halo) {
-    const SweepWindow win = sweep_window(x, y, W, H, halo);
+__host__ __device__ inline bool sweep_line_done(const uint32_t *masks, LoadDone ld, int x, int y, int W, int H, int halo) {
+    const int wpc = sweep_done_wpc(H);
     bool ok = true;
-    for (int col = 0; col < win.span; col++)
-        if (masks[col] && !sweep_column_done(win, masks[col], col, ld)) ok = false;
+    for (int col = 0; col <= 2 * halo; col++) {
+        uint32_t m = masks[col];
+        while (m) {
+            const int j = flow_ctz64((unsigned long long)m);
+            m &= m - 1;
+            int cx, cy;
+            sweep_offset_cell(x, y, col - halo, j - halo, W, H, &cx, &cy);
+            if (!((ld(sweep_done_word(cx, cy, wpc)) >> (cy & 63)) & 1ull)) ok = false;
+        }
+    }
     return ok;
 }
 
@@ -192,7 +204,8 @@ struct __align__(32) LeanA {
 struct __align__(32) LeanB {
     int32_t slot;
     uint32_t idf;                    // id | range << 26 | LEANB_DIES (reaches its maximum age in this step) | LEANB_SKIP
-    int32_t sugar_metab, spice_metab;
+    uint32_t metab;                  // sugar metabolism | spice metabolism << 16 (both clipped at 0)
+    int32_t pos;                     // the cell the agent starts the step on
     double aggression, lookahead;
 };
 static_assert(sizeof(LeanA) == 32 && sizeof(LeanB) == 32, "one 32-byte sector per record");
@@ -305,6 +318,21 @@ __device__ __forceinline__ void lean_ring(int d, int x, int y, int W, int H, int
     }
 }
 
+// Ahead of the readiness check: the lines a freshly claimed agent will read -- its record A, its own cell and its cross
+// -- are requested from DRAM into L2 (the coherence point: nothing can go stale there), so that the gate check, the
+// record and the cross overlap instead of queueing up as dependent round trips.
+__device__ __forceinline__ void lean_prefetch_agent(const LeanCtx &L, int slot, int pos, int r, int W, int H) {
+    lean_prefetch(L.a + slot);
+    const int x = pos / H, y = pos - x * H;
+    lean_prefetch(L.pcell + lean_tiled(x, y, L.ty4));
+    for (int d = 1; d <= r; d++) {
+        int cell[4];
+        lean_ring<true>(d, x, y, W, H, L.ty4, cell);
+#pragma unroll
+        for (int u = 0; u < 4; u++) lean_prefetch(L.pcell + cell[u]);
+    }
+}
+
 // the range of Agent.findCellsInRange for slot s: min(vision, movement), clipped to the per-axis memoised range
 __device__ __forceinline__ int lean_range(const DevCtx &c, int s) {
     return min(min(max(c.a.vision[s], 0), max(c.a.movement[s], 0)), max(c.max_dx, c.max_dy));
@@ -333,11 +361,14 @@ __device__ __forceinline__ void lean_pack_b(const DevCtx &c, const LeanCtx &L, i
     const int age = a.age[s], max_age = a.max_age[s];
     B.idf = ((uint32_t)a.id[s] & LEANB_ID_MASK) | ((uint32_t)r << LEANB_RANGE_SHIFT) |
             ((max_age != -1 && age + 1 >= max_age) ? (uint32_t)LEANB_DIES : 0u) | (a.last_moved[s] == c.t ? (uint32_t)LEANB_SKIP : 0u);
-    B.sugar_metab = a.sugar_metab[s]; B.spice_metab = a.spice_metab[s];
+    const int sugar_metab = max(a.sugar_metab[s], 0), spice_metab = max(a.spice_metab[s], 0);
+    B.metab = (uint32_t)min(sugar_metab, 65535) | ((uint32_t)min(spice_metab, 65535) << 16);
+    B.pos = a.pos[s];
     B.aggression = a.aggression[s]; B.lookahead = a.lookahead[s];
     L.b[index] = B;
-    // the plain instantiation relies on the rule flags: an agent that contradicts them stops the run (overflow code 13)
-    if (lean_mode(c.p) == 0 && (B.aggression > 0 || B.spice_metab > 0 || a.spice[s] != 0))
+    // the plain instantiation relies on the rule flags, the record on 16-bit metabolisms: an agent that contradicts them
+    // stops the run (overflow code 13)
+    if ((lean_mode(c.p) == 0 && (B.aggression > 0 || spice_metab > 0 || a.spice[s] != 0)) || sugar_metab > 65535 || spice_metab > 65535)
         atomicExch((unsigned long long *)&c.a.counters[SSB_C_OVERFLOW], 13ull);
 }
 
@@ -407,7 +438,7 @@ __device__ inline void lean_transaction(const DevCtx &c, const LeanCtx &L, const
     __syncwarp(actm);
     // findWelfare's per-agent part (agent.py:1170-1201, no tag preferences)
     Welfare w;
-    const double sm = (double)max(B.sugar_metab, 0), pm = (double)max(B.spice_metab, 0);
+    const double sm = (double)(B.metab & 65535u), pm = (double)(B.metab >> 16);
     {
         w.sugar = A.sugar; w.spice = A.spice;
         w.s_look = sm * B.lookahead; w.p_look = pm * B.lookahead;
@@ -485,24 +516,20 @@ __device__ inline void lean_transaction(const DevCtx &c, const LeanCtx &L, const
     if (b_valid) {
         int jw = __ffs(b_ties) - 1;
         if (b_ties & (b_ties - 1u)) {
-            // random.shuffle(cellsInRange), agent.py:1400-1401, replayed for the positions of this ring's four candidates only:
-            // x[i], x[j] = x[j], x[i] for i = n - 1 .. 1 moves whoever stands on position i to j and vice versa
+            // random.shuffle(cellsInRange), agent.py:1400-1401, in mode S the keyed shuffle: candidate i stands where its
+            // substream word i stands among all words (ties by i) -- of the tied candidates of this ring the one with the
+            // smallest word comes first
             RngStream rng{key, id, 0u, 0u, nullptr};
             rng.at(SITE_MOVE);
             const int base = 4 * (b_dist - 1);
-            int p0 = base, p1 = base + 1, p2 = base + 2, p3 = base + 3;
-            for (int i = n - 1; i >= 1; i--) {
-                const int j = (int)rand_below(rng, (uint32_t)i + 1u);
-                p0 = p0 == i ? j : (p0 == j ? i : p0);
-                p1 = p1 == i ? j : (p1 == j ? i : p1);
-                p2 = p2 == i ? j : (p2 == j ? i : p2);
-                p3 = p3 == i ? j : (p3 == j ? i : p3);
+            uint32_t best_key = 0;
+            bool have = false;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (!((b_ties >> j) & 1u)) continue;
+                const uint32_t kj = rng.word((uint32_t)(base + j));
+                if (!have || kj < best_key) { best_key = kj; jw = j; have = true; }
             }
-            int best_pos = 1 << 30;
-            if ((b_ties & 1u) && p0 < best_pos) { best_pos = p0; jw = 0; }
-            if ((b_ties & 2u) && p1 < best_pos) { best_pos = p1; jw = 1; }
-            if ((b_ties & 4u) && p2 < best_pos) { best_pos = p2; jw = 2; }
-            if ((b_ties & 8u) && p3 < best_pos) { best_pos = p3; jw = 3; }
         }
         int ring[4];
         lean_ring<false>(b_dist, x, y, W, H, H, ring);

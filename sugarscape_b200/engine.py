@@ -381,7 +381,7 @@ class Engine:
 
     def sweep_diag(self):
         """{warp iterations, entries held at a readiness check, entries run} of the sweep kernel (SSB_SWEEP_DIAG=1), else None."""
-        out = np.zeros(3, dtype=np.uint64)
+        out = np.zeros(4, dtype=np.uint64)
         if self.L.ssb_sweep_diag(self.handle, out.ctypes.data) != 0:
             return None
         return [int(v) for v in out]

@@ -33,6 +33,9 @@ class Sugarscape:
             raise init.UnsupportedConfiguration("the GUI is out of scope: set headlessMode to true")
         if self.rng_mode != layout.RNG_EXACT and (init.uses_decision_models(c) or layout.HostExt.needed(c, exact=False)):
             raise init.UnsupportedConfiguration("decision models, lending and friends need b200RngMode 'exact'")
+        if self.rng_mode != layout.RNG_EXACT and c["agentInheritancePolicy"] != "none":
+            # (the scalable transaction has no inheritance step: running on would silently change the wealth dynamics)
+            raise init.UnsupportedConfiguration("agentInheritancePolicy needs b200RngMode 'exact'")
         state, self.population = init.build_initial_state(c, exact=self.rng_mode == layout.RNG_EXACT)
         self.params = layout.make_params(c, self.rng_mode, init.rule_flags(c), init.max_agent_range(c),
                                          init.equator(c))

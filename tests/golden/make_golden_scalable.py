@@ -6,7 +6,10 @@ randomness: (1) the per-step agent order is the ascending order of a keyed bijec
 id instead of `random.shuffle(self.agents)` (reference sugarscape.py:400), (2) every draw inside
 an agent's transaction comes from that agent's counter-based substream of the current call site
 (agent.py:1401 move ranking, 560-564 tagging, 616 trading, 505-513 reproduction) instead of the
-global MT19937 stream, (3) a step's newborn are numbered in cell order at the end of the step, (4) replacement
+global MT19937 stream; the shuffle of the move ranking is the KEYED shuffle -- the permutation that
+sorts the candidate list by one substream word per element (ties by position), which any one
+element's place can be read from without replaying a Fisher-Yates pass -- the other shuffles
+stay Fisher-Yates over the substream, (3) a step's newborn are numbered in cell order at the end of the step, (4) replacement
 (sugarscape.py:171-267,855-859): the empty cells of a quadrant are ordered by a hash of the cell,
 the quadrants by a hash of their index, and a new agent's tribe tags come from the substream of
 its own id.
@@ -101,6 +104,11 @@ class Substreams:
         if site is None or self.agent_id is None:
             if len(x) > 1:
                 raise RuntimeError("unexpected main-stream shuffle in " + sys._getframe(2).f_code.co_name)
+            return
+        if site == SITES["rankCellsInRange"]:      # the keyed shuffle: sort by one word per element, ties by position
+            keys = [self.word(site) for _ in x]
+            order = sorted(range(len(x)), key=lambda i: (keys[i], i))
+            x[:] = [x[i] for i in order]
             return
         for i in reversed(range(1, len(x))):
             j = self.below(site, i + 1)

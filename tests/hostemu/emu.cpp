@@ -178,7 +178,8 @@ int emu_agent_step_flow(const ssb_params_t *p, const ssb_grid_t *g, const ssb_ag
  * handed out in an arbitrary order and the agents run in passes over the pending entries, in an ADVERSARIAL order:
  * order_mode 0 = ascending list index, 1 = DESCENDING priority (as far from the sequential order as the predecessor
  * masks allow), 2 = pseudo-random.  An entry runs only when sweep_preds_done says so, exactly like a sweep thread.
- * out_stats (may be null): {agents, predecessor bits, passes, tiles visited}. */
+ * order_mode | 0x100: one priority bucket (every predecessor is a near one) instead of 128 buckets in 32 slabs.
+ * out_stats (may be null): {agents, near predecessors, passes, tiles visited, mask lines}. */
 int emu_agent_step_sweep(const ssb_params_t *p, const ssb_grid_t *g, const ssb_agents_t *a, int32_t t, double prev_mean_wealth,
                          const uint32_t *endow_bits, const uint32_t *tag_bits, int32_t n_tables, int32_t *born_list,
                          int32_t order_mode, int32_t lean, int64_t *out_stats) {
@@ -216,7 +217,7 @@ int emu_agent_step_sweep(const ssb_params_t *p, const ssb_grid_t *g, const ssb_a
     else { for (int i = 0; i < n_list; i++) if (a->pos[a->order[i]] >= 0) live.push_back(a->order[i]); }
     if (lean && (int)live.size() != n_list) return -5;
     const int n = (int)live.size();
-    {   /* scramble: index = position in a pseudo-random permutation */
+    {   /* scramble: index = position in a pseudo-random permutation ... */
         uint64_t lcg = 0x2545F4914F6CDD1Dull ^ (uint64_t)t;
         for (int i = n - 1; i > 0; i--) {
             lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
@@ -224,6 +225,14 @@ int emu_agent_step_sweep(const ssb_params_t *p, const ssb_grid_t *g, const ssb_a
             const int tmp = live[i]; live[i] = live[j]; live[j] = tmp;
         }
     }
+    /* ... grouped by priority bucket like k_sweep_prepare (128 buckets = 32 slabs of 4, or one bucket: order_mode & 0x100) */
+    const int bucket_bits = (order_mode & 0x100) ? 0 : (p->id_bits < 7 ? p->id_bits : 7);
+    order_mode &= 0xff;
+    const int E = 1 << bucket_bits, prio_shift = p->id_bits - bucket_bits, slab_shift = sweep_slab_shift(bucket_bits);
+    const int n_slabs = sweep_n_slabs(bucket_bits), slab_prio_shift = prio_shift + slab_shift;
+    auto bucket_of = [&](int s) { return (int)(priority_of(key, (uint32_t)a->id[s], p->id_bits) >> prio_shift); };
+    std::stable_sort(live.begin(), live.end(), [&](int x, int y) { return bucket_of(x) < bucket_of(y); });
+    std::vector<int> bucket_size(E, 0), bucket_fin(E, 0);
     entries.resize(n);
     for (int index = 0; index < n; index++) {
         const int s = live[index], pos = a->pos[s];
@@ -231,25 +240,27 @@ int emu_agent_step_sweep(const ssb_params_t *p, const ssb_grid_t *g, const ssb_a
         const int r = lean_range(c, s), k = lean ? 0 : footprint_dilation(c, s);
         desc[pos] = sweep_desc((uint32_t)index, sweep_lo(pr, r, k));
         entries[index] = {s, pos, pr};
+        bucket_size[pr >> prio_shift]++;
         if (lean) lean_pack_b(c, L, s, index, r);
     }
-    /* build (k_sweep_build): tile by tile, staged with the torus wrap, masks, one scan per agent */
+    /* build (k_sweep_build): tile by tile, staged with the torus wrap, one bit-plane per slab, one scan per agent */
     const int sw = FLOW_TX + 2 * R, sh = FLOW_TY + 2 * R;
     std::vector<uint32_t> cell((size_t)sw * sh), preds((size_t)n * SWEEP_COLS, 0u);
-    std::vector<unsigned long long> mask((size_t)sw * 2);
+    std::vector<unsigned long long> gates((size_t)n, 0ull);
+    std::vector<unsigned long long> smask((size_t)n_slabs * sw * 2);
     std::vector<int8_t> tables((size_t)sweep_tables_bytes(RB, KB, R), 0);
     sweep_fill_tables(RB, KB, R, tables.data(), tables.data() + sweep_any_size(RB, KB, R));
-    long long bits = 0, tiles = 0;
+    long long bits = 0, tiles = 0, lines = 0;
     for (int tx = 0; tx * FLOW_TX < W; tx++) for (int ty = 0; ty * FLOW_TY < H; ty++) {
         const int x0 = tx * FLOW_TX - R, y0 = ty * FLOW_TY - R;
-        for (int col = 0; col < sw; col++) for (int row = 0; row < sh; row++)
-            cell[(size_t)col * sh + row] = (uint32_t)desc[(size_t)wrapi(x0 + col, W) * H + wrapi(y0 + row, H)];
-        for (int col = 0; col < sw; col++) {
-            mask[col * 2] = mask[col * 2 + 1] = 0;
-            for (int row = 0; row < sh; row++) if (cell[(size_t)col * sh + row]) mask[col * 2 + (row >> 6)] |= 1ull << (row & 63);
+        std::fill(smask.begin(), smask.end(), 0ull);
+        for (int col = 0; col < sw; col++) for (int row = 0; row < sh; row++) {
+            const uint32_t lo = (uint32_t)desc[(size_t)wrapi(x0 + col, W) * H + wrapi(y0 + row, H)];
+            cell[(size_t)col * sh + row] = lo;
+            if (lo) smask[((size_t)(sweep_prio(lo) >> slab_prio_shift) * sw + col) * 2 + (row >> 6)] |= 1ull << (row & 63);
         }
         SweepTile tile;
-        tile.cell = cell.data(); tile.mask = mask.data(); tile.sw = sw; tile.sh = sh; tile.halo = R;
+        tile.cell = cell.data(); tile.smask = smask.data(); tile.sw = sw; tile.sh = sh; tile.halo = R; tile.slab_prio_shift = slab_prio_shift;
         tile.any = tables.data(); tile.pair = tables.data() + sweep_any_size(RB, KB, R);
         tiles++;
         for (int ix = 0; ix < FLOW_TX && tx * FLOW_TX + ix < W; ix++) for (int iy = 0; iy < FLOW_TY && ty * FLOW_TY + iy < H; iy++) {
@@ -257,15 +268,27 @@ int emu_agent_step_sweep(const ssb_params_t *p, const ssb_grid_t *g, const ssb_a
             if (!la) continue;
             const uint32_t gcell = (uint32_t)((tx * FLOW_TX + ix) * H + ty * FLOW_TY + iy);
             const uint32_t index = (uint32_t)(desc[gcell] >> 32);
-            uint32_t *out = preds.data() + (size_t)index * SWEEP_COLS;
-            sweep_pred_masks(tile, R + ix, R + iy, la, RB, KB, [&](int col, uint32_t m) { out[col] = m; bits += __builtin_popcount(m); });
-            out[31] = gcell;
+            unsigned long long gate = 0ull;
+            int n_near = 0;
+            sweep_near_preds(tile, R + ix, R + iy, la, RB, KB, [&](int dx, int dy) {
+                if (n_near < SWEEP_GATE_PREDS) gate |= sweep_gate_code(dx, dy, R) << (10 * n_near);
+                n_near++;
+            });
+            bits += n_near;
+            if (n_near <= SWEEP_GATE_PREDS) { gates[index] = gate; continue; }
+            uint32_t *line = preds.data() + (size_t)index * SWEEP_COLS;
+            sweep_near_preds(tile, R + ix, R + iy, la, RB, KB, [&](int dx, int dy) { line[dx + R] |= 1u << (dy + R); });
+            gates[index] = SWEEP_GATE_LINE;
+            lines++;
         }
     }
-    /* sweep (k_sweep_lean / k_sweep_generic): passes over the pending entries */
+    /* sweep (k_sweep_lean / k_sweep_generic): passes over the pending entries; an entry runs only when the watermark has
+     * passed the slabs before its near slabs and its gate is open, exactly like a sweep thread */
     std::vector<unsigned long long> done(sweep_done_words(W, H), 0ull);
     auto ld = [&](size_t wd) { return done[wd]; };
     const int wpc = sweep_done_wpc(H);
+    int watermark = 0;
+    while (watermark < E && bucket_size[watermark] == 0) watermark++;
     std::vector<int> pending(n);
     for (int i = 0; i < n; i++) pending[i] = i;
     if (order_mode == 1) std::sort(pending.begin(), pending.end(), [&](int x, int y) { return entries[x].prio > entries[y].prio; });
@@ -287,10 +310,13 @@ int emu_agent_step_sweep(const ssb_params_t *p, const ssb_grid_t *g, const ssb_a
         std::vector<int> left;
         int ran = 0;
         for (int i : pending) {
-            const uint32_t *pm = preds.data() + (size_t)i * SWEEP_COLS;
-            const int x = (int)(pm[31] / (uint32_t)H), y = (int)(pm[31] % (uint32_t)H);
-            if ((int)pm[31] != entries[i].pos) return -6;
-            if (!sweep_preds_done(pm, ld, x, y, W, H, R)) { left.push_back(i); continue; }
+            const int pos = entries[i].pos, x = pos / H, y = pos % H;
+            const int bucket = (int)(entries[i].prio >> prio_shift);
+            if (lean && L.b[i].pos != pos) return -6;
+            bool ready = watermark >= sweep_watermark_needed(bucket, slab_shift);
+            if (ready) ready = gates[i] == SWEEP_GATE_LINE ? sweep_line_done(preds.data() + (size_t)i * SWEEP_COLS, ld, x, y, W, H, R)
+                                                            : sweep_gate_done(gates[i], ld, x, y, W, H, R);
+            if (!ready) { left.push_back(i); continue; }
             if (lean) { if (lean_mode(*p) == 0) lean_transaction<0>(c, L, L.b[i], key, st, 1u); else lean_transaction<LEAN_M_ALL>(c, L, L.b[i], key, st, 1u); }
             else {
                 const int s = entries[i].slot;
@@ -299,10 +325,12 @@ int emu_agent_step_sweep(const ssb_params_t *p, const ssb_grid_t *g, const ssb_a
                 RngStream rng{key, (uint32_t)rec.id, 0u, 0u, nullptr};
                 if (transaction_move_phase<1, 4>(c, s, rec, rng, ws, 32)) transaction_interact_phase<RngStream, false>(c, s, rec, rng);
             }
-            sweep_done_set(x, y, W, wpc, [&](size_t wd, int bit) { done[wd] |= 1ull << bit; });
+            done[sweep_done_word(x, y, wpc)] |= 1ull << (y & 63);
+            bucket_fin[bucket]++;
+            while (watermark < E && bucket_fin[watermark] == bucket_size[watermark]) watermark++;
             ran++;
         }
-        if (ran == 0) return -3;     /* nobody could run: the predecessor relation is not acyclic */
+        if (ran == 0) return -3;     /* nobody could run: the gates deadlock */
         ran_total += ran;
         pending.swap(left);
     }
@@ -313,7 +341,7 @@ int emu_agent_step_sweep(const ssb_params_t *p, const ssb_grid_t *g, const ssb_a
         }
         for (int s = 0; s < n_slots; s++) lean_unpack_slot(c, L, s);
     }
-    if (out_stats) { out_stats[0] = n; out_stats[1] = bits; out_stats[2] = passes; out_stats[3] = tiles; }
+    if (out_stats) { out_stats[0] = n; out_stats[1] = bits; out_stats[2] = passes; out_stats[3] = tiles; out_stats[4] = lines; }
     return ran_total == n ? 0 : -3;
 }
 

@@ -131,9 +131,10 @@ class HostEmuFlow(Oracle):
 
 
 class HostEmuSweep(HostEmuFlow):
-    """Mode S agent step through the ordered sweep (csrc/ssb_sweep_core.cuh, host-compiled): predecessor masks, done
-    bitmap and -- with lean=True -- the lean transaction on packed records, run in passes over the pending entries in an
-    adversarial order (1 = descending priority, 2 = pseudo-random, 0 = ascending list index)."""
+    """Mode S agent step through the ordered sweep (csrc/ssb_sweep_core.cuh, host-compiled): slabs, gates (near
+    predecessors), watermark, done bitmap and -- with lean=True -- the lean transaction on packed records, run in passes
+    over the pending entries in an adversarial order (1 = descending priority, 2 = pseudo-random, 0 = ascending list
+    index; | 0x100: one priority bucket, so that every predecessor is a near one and the mask lines are exercised)."""
 
     def __init__(self, params, state, endow_bits=None, tag_bits=None, order_mode=1, lean=False):
         super().__init__(params, state, endow_bits, tag_bits, order_mode)
@@ -141,6 +142,7 @@ class HostEmuSweep(HostEmuFlow):
         self.E.emu_agent_step_sweep.argtypes = [P, G, A, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_int32,
                                                 C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
         self.lean = lean
+        self.dag = np.zeros(5, dtype=np.int64)       # agents, near predecessors, passes, tiles, mask lines of the last step
 
     def agent_step(self, t, prev_mean_wealth=0.0):
         g, a = self.state.as_structs()

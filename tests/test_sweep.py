@@ -1,10 +1,11 @@
 """The ordered sweep of the mode S agent step (sugarscape_b200/csrc/ssb_sweep_core.cuh) under the CPU suite.
 
-The sweep scheduler of the CUDA engine runs an agent as soon as the done bits of its PREDECESSORS -- the agents with a
-smaller priority whose footprint intersects its own, found tile by tile and stored as column bit masks -- are set.
-tests/hostemu compiles the engine's own predecessor scan, done test and lean transaction (packed records, one thread
-per agent) with g++ and runs the agents in passes over the pending entries in descending priority / pseudo-random
-order -- as far from the sequential order as the masks allow.  The results must equal (a) the fixtures generated from
+The sweep scheduler of the CUDA engine runs an agent once its PREDECESSORS -- the agents with a smaller priority whose
+footprint intersects its own -- have finished: the watermark over the priority buckets vouches for the distant ones,
+the agent's gate lists the near ones (found tile by tile in per-slab occupancy bit-planes).  tests/hostemu compiles the
+engine's own predecessor scan, gate test and lean transaction (packed records, one thread per agent) with g++ and runs
+the agents in passes over the pending entries in descending priority / pseudo-random order -- as far from the
+sequential order as the gates allow.  The results must equal (a) the fixtures generated from
 the unmodified reference with its randomness redirected (tests/golden/make_golden_scalable.py) and (b) the sequential
 oracle, bit for bit."""
 import pytest
@@ -39,7 +40,7 @@ def _replay_golden(name, lean, order_mode):
     assert bits > 0 and passes > 1
 
 
-@pytest.mark.parametrize("order_mode", [1, 2])
+@pytest.mark.parametrize("order_mode", [1, 2, 0x101])
 @pytest.mark.parametrize("name", LEAN_RULES)
 def test_lean_transaction_under_the_sweep_matches_patched_reference(name, order_mode):
     _replay_golden(name, True, order_mode)
@@ -67,24 +68,28 @@ BIG_CASES = [
 ]
 
 
+@pytest.mark.parametrize("order_mode", [1, 0x102])
 @pytest.mark.parametrize("name,overrides,steps,lean", BIG_CASES)
-def test_sweep_equals_sequential_oracle_across_tiles(name, overrides, steps, lean):
+def test_sweep_equals_sequential_oracle_across_tiles(name, overrides, steps, lean, order_mode):
     c, state, pop, params, endow, tags = pu.build(name, layout.RNG_SCALABLE, overrides)
     ostate = state.copy()
-    emu = HostEmuSweep(params, state, endow, tags, order_mode=1, lean=lean)
+    emu = HostEmuSweep(params, state, endow, tags, order_mode=order_mode, lean=lean)
     orc = Oracle(params, ostate, endow, tags)
     if c["agentReplacements"] > 0:
         emu.bind_endowments(pop.endowments)
         orc.bind_endowments(pop.endowments)
-    deepest = 0
+    deepest = lines = 0
     for t in range(1, steps + 1):
         for sim in (emu, orc):
             sim.env_step(t); sim.agent_step(t, 0.0); sim.compact(t)
             if c["agentReplacements"] > 0:
                 sim.replace(t)
         deepest = max(deepest, int(emu.dag[2]))
+        lines += int(emu.dag[4])
         d_emu, s_emu = pu.state_digests_by_id(state)
         d_orc, s_orc = pu.state_digests_by_id(ostate)
         for k in ("agents_int", "agents_f64", "agents_tags", "grid_int", "pollution"):
             assert d_emu[k] == d_orc[k], f"{name}: {k} differs from the sequential oracle at t={t}"
     assert deepest > 3, "the case never produced a dependency chain"
+    if order_mode & 0x100:
+        assert lines > 0, "no agent had more near predecessors than a gate holds: the mask lines were not exercised"

@@ -62,7 +62,7 @@ def main():
         line = {"scheduler": sched, "workload": args.workload, "size": args.size, "agents": n, "overflow": code, "steps": rows,
                 "mean_agent_ms": float(np.mean([r["agent_ms"] for r in rows[1:]] or [rows[0]["agent_ms"]]))}
         if diag:
-            line["sweep_diag"] = {"warp_iterations": diag[0], "held": diag[1], "ran": diag[2]}
+            line["sweep_diag"] = {"warp_iterations": diag[0], "held": diag[1], "ran": diag[2], "behind_watermark": diag[3]}
         if not args.no_digest:
             d, snap = pu.state_digests_by_id(eng.download())
             digests[sched] = d
