@@ -439,6 +439,8 @@ def e2e_leg(job, args, barrier, dev):
     barrier()
     w0 = time.perf_counter()
     eng, h2d = job.engine()                                          # H2D of the whole initial state
+    eng.sync()
+    w_setup = time.perf_counter() - w0
     sb = stats_mod.StatsBuilder(job.c, init.equator(job.c))
     get_stats = eng.global_stats if job.sharded else eng.stats
     eng.reduce_stats(0)
@@ -449,6 +451,7 @@ def e2e_leg(job, args, barrier, dev):
         eng.step(s, rs["meanWealth"])
         rs = sb.update(get_stats(), s)                              # D2H of the step's reductions
         json.dumps(rs)                                              # the log line the CLI writes
+    w_steps = time.perf_counter() - w0 - w_setup
     n = int(eng.counters()[layout.C_N_LIST])
     order = eng.tensors["a_order"][:n].cpu().numpy()                # D2H of this rank's final agents
     d2h = order.nbytes + args.steps * C.sizeof(layout.Stats)
@@ -465,6 +468,7 @@ def e2e_leg(job, args, barrier, dev):
     eng.close()
     if job.sharded:                       # every rank counted the box-wide population
         agent_steps = agent_steps / job.world
+    e2e_leg.split = {"setup_and_upload_s": w_setup, "steps_with_stats_readback_s": w_steps, "final_download_s": wall - w_setup - w_steps}
     return wall, agent_steps, h2d, d2h
 
 
@@ -578,7 +582,7 @@ def main():
         wall, e2e_steps, h2d, d2h = e2e_leg(job, args, barrier, dev)
         wall, e2e_steps = aggregate_over_ranks(wall, e2e_steps, dev)
         e2e = {"value": e2e_steps / wall, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps,
-               "d2h_bytes_per_step": d2h / args.steps, "wall_s": wall,
+               "d2h_bytes_per_step": d2h / args.steps, "wall_s": wall, "split_rank0": e2e_leg.split,
                "includes": "upload of the initial state, per-step stats readback + log formatting, download of the final agents"
                            + (" (bytes per rank)" if world > 1 else "")}
 

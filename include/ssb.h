@@ -479,6 +479,13 @@ typedef struct ssb_shard_t {
  * first step; grid and agent arrays bound must be stitched.  Per-rank state: order[], free_slots[],
  * dead_list[], counters[] (N_LIST / N_SLOTS / N_FREE are per rank; NEXT_ID / ENDOW_INDEX global). */
 int  ssb_set_shard(ssb_engine_t *e, const ssb_shard_t *shard);
+/* The sweep scheduler on a sharded engine (after ssb_set_shard; collective: all ranks or none).  Possible for the rule sets
+ * of the plain lean transaction (no combat / spice / pollution / tagging / trade / births) when every slab consists of
+ * whole 64-column tiles; ssb_shard_sweep_possible tells.  desc: u64 per cell, done: u64 x width x ceil(height / 64),
+ * pcell: 8 bytes per cell of the 4 x 4-tiled cell array (width and height rounded up to 4) -- stitched like the grid
+ * (rank r backs the columns of its slab) and zero-filled.  Without it a sharded engine runs the reservation rounds. */
+int  ssb_shard_sweep_possible(const ssb_engine_t *e);
+int  ssb_set_shard_sweep(ssb_engine_t *e, void *desc, void *done, void *pcell);
 /* last phase of a sharded step (ssb_step calls it): records of agents that walked onto another
  * rank's slab move to that rank (slot of its range, its list); collective, no-op unless sharded */
 int  ssb_migrate(ssb_engine_t *e, int32_t t, void *stream);

@@ -41,6 +41,8 @@ def build(force=False, verbose=False):
         extra.append("-DSSB_PARALLEL_ETHICS")
     if os.environ.get("SSB_SLAB_BITS"):        # tuning builds: slabs of the sweep's priority order = 1 << bits
         extra.append("-DSSB_SLAB_BITS=" + os.environ["SSB_SLAB_BITS"])
+    if os.environ.get("SSB_LEAN_BLOCKS"):      # tuning builds: resident blocks per SM the plain lean sweep kernel is compiled for
+        extra.append("-DSSB_LEAN_BLOCKS=" + os.environ["SSB_LEAN_BLOCKS"])
     if os.environ.get("SSB_LEAN_PREFETCH"):
         extra.append("-DSSB_LEAN_PREFETCH=" + os.environ["SSB_LEAN_PREFETCH"])
     if os.environ.get("SSB_MARK_LANES"):

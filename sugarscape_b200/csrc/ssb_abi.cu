@@ -56,6 +56,9 @@ struct ssb_engine {
     size_t sweep_done_bytes;
     int sweep_stamp;
     int sweep_bits_generic, sweep_bits_lean;
+    int sweep_slab_bits_generic, sweep_slab_bits_lean;
+    bool shard_sweep;            // sharded AND the sweep's arrays are stitched (ssb_set_shard_sweep): the ranks sweep their slabs
+    void *own_desc, *own_done, *own_pcell;     // the engine's own allocations while the stitched ones are in use
     // stats
     StatsPartial *d_partials;
     int n_partials;
@@ -65,6 +68,7 @@ struct ssb_engine {
     uint64_t *d_keys_a, *d_keys_b;
     uint32_t *d_radix_hist, *d_radix_rows;
     double *d_lorenz_blocks;
+    unsigned long long *d_lorenz_hist;   // [1 + LORENZ_BINS]: flag + histogram of the integral wealths
     // timing
     bool timing;
     cudaEvent_t ev[5];
@@ -186,10 +190,11 @@ void ssb_destroy(ssb_engine_t *e) {
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->sharded) e->rc.mark = e->local_marks;       // the stitched marks belong to the fabric
+    if (e->shard_sweep) { e->sweep.desc = (unsigned long long *)e->own_desc; e->sweep.done = (unsigned long long *)e->own_done; e->lean.pcell = (int2 *)e->own_pcell; }
     void *ptrs[] = {e->d_mt, e->d_endow, e->d_tagbits, e->d_tile_counts, e->d_new_order, e->d_scalars,
                     e->d_born_list, e->rc.mark, e->rc.list_a, e->rc.list_b, e->rc.ready, e->rc.cnt, e->rc.trace, e->rc.bucketed, e->rc.epoch_count, e->rc.epoch_start, e->rc.epoch_fill,
                     e->d_partials, e->d_tribes, e->d_stats, e->d_ring, e->d_keys_a, e->d_keys_b, e->d_radix_hist,
-                    e->d_lorenz_blocks, e->d_plan, e->d_cand, e->sh.peer_vals, e->sh.flags, e->d_shard_vals, e->d_migrate, e->d_eth_stats, e->d_ext_stats, e->d_group_stats, e->d_eth, e->d_ext,
+                    e->d_lorenz_blocks, e->d_lorenz_hist, e->d_plan, e->d_cand, e->sh.peer_vals, e->sh.flags, e->d_shard_vals, e->d_migrate, e->d_eth_stats, e->d_ext_stats, e->d_group_stats, e->d_eth, e->d_ext,
                     e->flow.desc, e->flow.entries, e->flow.dep, e->flow.span, e->flow.pool, e->flow.cursor, e->flow.queue, e->flow.tail, e->flow.tile_pop,
                     e->sweep.desc, e->sweep.entries, e->sweep.preds, e->sweep.gate, e->sweep.bucket_fin, e->sweep.done, e->sweep.bucket_count, e->sweep.bucket_start, e->sweep.bucket_fill,
                     e->sweep.tile_pop, e->sweep.tile_need, e->sweep.ctl, (void *)e->sweep.tables, e->lean.a, e->lean.b, e->lean.pcell};
@@ -244,6 +249,18 @@ static int setup_flow(ssb_engine *e) {
 
 // The ordered sweep (ssb_sweep.cuh).  e->sweep_ok stays false when the engine is outside its limits (the rounds
 // scheduler then stays the default); a negative return is a real error.
+// the build kernel stages one occupancy bit-plane per slab: its grid (resident CTAs) depends on their number
+static int size_build_grid(ssb_engine *e, int n_slabs) {
+    SweepCtx &w = e->sweep;
+    int per_sm = 0;
+    const int build_smem = sweep_build_smem_bytes(w.rb, w.kb, w.halo, n_slabs);
+    CU(cudaFuncSetAttribute(k_sweep_build, cudaFuncAttributeMaxDynamicSharedMemorySize, sweep_build_smem_bytes(w.rb, w.kb, w.halo, SWEEP_MAX_SLABS)));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_build, SWEEP_BUILD_THREADS, build_smem));
+    if (per_sm < 1) return fail(e, -3, "the sweep's build kernel does not fit on an SM (%d bytes of shared memory)", build_smem);
+    e->sweep_build_blocks = per_sm * e->num_sms;
+    return 0;
+}
+
 static int setup_sweep(ssb_engine *e, int maxd) {
     SweepCtx &w = e->sweep;
     const int64_t cap = e->ctx.a.capacity, cells = e->ctx.g.n_cells;
@@ -270,7 +287,8 @@ static int setup_sweep(ssb_engine *e, int maxd) {
     if (e->lean_ok) {
         LeanCtx &L = e->lean;
         L.maxc = 4 * maxd;
-        const int lean_smem = lean_smem_bytes(L.maxc, LEAN_THREADS);
+        e->lean_mode = lean_mode(e->p);
+        const int lean_smem = lean_smem_bytes(L.maxc, LEAN_THREADS, e->lean_mode == 0);
         CU(cudaFuncSetAttribute(k_sweep_lean<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lean_smem));
         CU(cudaFuncSetAttribute(k_sweep_lean<LEAN_M_ALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, lean_smem));
         e->lean_mode = lean_mode(e->p);
@@ -287,13 +305,13 @@ static int setup_sweep(ssb_engine *e, int maxd) {
     // priority buckets: sized for a full agent array and the grid that will walk them
     e->sweep_bits_generic = sweep_bucket_bits(cap, concurrent, e->p.id_bits, SWEEP_MAX_KEY_BITS);
     e->sweep_bits_lean = e->lean_ok ? sweep_bucket_bits(cap, (long long)e->sweep_lean_blocks * LEAN_THREADS, e->p.id_bits, SWEEP_MAX_KEY_BITS - SWEEP_LEAN_SUB_BITS) : 0;
-    {   // the build kernel stages one occupancy bit-plane per slab
-        const int bits = e->sweep_bits_lean > e->sweep_bits_generic ? e->sweep_bits_lean : e->sweep_bits_generic;
-        const int build_smem = sweep_build_smem_bytes(w.rb, w.kb, w.halo, sweep_n_slabs(bits));
-        CU(cudaFuncSetAttribute(k_sweep_build, cudaFuncAttributeMaxDynamicSharedMemorySize, build_smem));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_build, SWEEP_BUILD_THREADS, build_smem));
-        if (per_sm < 1) return fail(e, -3, "the sweep's build kernel does not fit on an SM (%d bytes of shared memory)", build_smem);
-        e->sweep_build_blocks = per_sm * e->num_sms;
+    e->sweep_slab_bits_generic = sweep_slab_bits(cap, concurrent);
+    e->sweep_slab_bits_lean = e->lean_ok ? sweep_slab_bits(cap, (long long)e->sweep_lean_blocks * LEAN_THREADS) : 0;
+    {
+        const int slabs_generic = sweep_n_slabs(e->sweep_bits_generic, e->sweep_slab_bits_generic);
+        const int slabs_lean = e->lean_ok ? sweep_n_slabs(e->sweep_bits_lean, e->sweep_slab_bits_lean) : 1;
+        int rc = size_build_grid(e, slabs_lean > slabs_generic ? slabs_lean : slabs_generic);
+        if (rc < 0) return rc;
     }
     CU(cudaMalloc(&w.desc, sizeof(unsigned long long) * (size_t)cells));
     CU(cudaMemset(w.desc, 0, sizeof(unsigned long long) * (size_t)cells));
@@ -361,6 +379,7 @@ int ssb_bind(ssb_engine_t *e, const ssb_grid_t *grid, const ssb_agents_t *agents
     CU(cudaMalloc(&e->d_radix_hist, sizeof(uint32_t) * (256 * radix_tiles + 256)));      // + the 256 row totals
     e->d_radix_rows = e->d_radix_hist + 256 * radix_tiles;
     CU(cudaMalloc(&e->d_lorenz_blocks, sizeof(double) * e->num_sms * 4));
+    CU(cudaMalloc(&e->d_lorenz_hist, sizeof(unsigned long long) * (1 + LORENZ_BINS)));
     if (e->p.rng_mode == SSB_RNG_SCALABLE) {
         RoundCtx &rc = e->rc;
         // marks on 2 x 2 cell blocks when the map allows it: a quarter of the mark array and about
@@ -431,7 +450,7 @@ int ssb_set_scheduler(ssb_engine_t *e, int32_t scheduler) {
     return 0;
 }
 
-int ssb_get_scheduler(const ssb_engine_t *e) { return e ? (e->sharded ? SSB_SCHED_ROUNDS : e->scheduler) : -1; }     // (sharded engines run the rounds)
+int ssb_get_scheduler(const ssb_engine_t *e) { return e ? (e->sharded ? (e->shard_sweep ? SSB_SCHED_SWEEP : SSB_SCHED_ROUNDS) : e->scheduler) : -1; }
 
 // diagnostics of the sweep kernel since bind (SSB_SWEEP_DIAG=1): {warp iterations, entries held at a check, entries run}
 int ssb_sweep_diag(ssb_engine_t *e, unsigned long long out[4]) {
@@ -442,7 +461,7 @@ int ssb_sweep_diag(ssb_engine_t *e, unsigned long long out[4]) {
 }
 
 // 1 if the agent step of this engine runs the lean transaction on packed records (ssb_sweep_core.cuh)
-int ssb_uses_lean_transaction(const ssb_engine_t *e) { return e && e->scheduler == SSB_SCHED_SWEEP && e->lean_ok && !e->sharded ? 1 : 0; }
+int ssb_uses_lean_transaction(const ssb_engine_t *e) { return e && ((e->scheduler == SSB_SCHED_SWEEP && e->lean_ok && !e->sharded) || e->shard_sweep) ? 1 : 0; }
 
 int ssb_set_mark_shift(ssb_engine_t *e, int32_t shift) {
     if (!e || !e->bound || e->p.rng_mode != SSB_RNG_SCALABLE) return fail(e, -1, "mark shift needs a bound scalable engine");
@@ -717,36 +736,56 @@ int ssb_agent_step(ssb_engine_t *e, int32_t t, double prev_mean_wealth, void *st
         if (e->ethics_bound || e->ext_bound) k_agent_step_exact<true><<<1, 32, 0, st>>>(c, e->d_mt);
         else k_agent_step_exact<false><<<1, 32, 0, st>>>(c, e->d_mt);
         LAUNCHED(e);
-    } else if ((e->scheduler == SSB_SCHED_SWEEP || e->scheduler == SSB_SCHED_SWEEP_GENERIC) && !e->sharded) {
+    } else if ((e->scheduler == SSB_SCHED_SWEEP || e->scheduler == SSB_SCHED_SWEEP_GENERIC) && (!e->sharded || e->shard_sweep)) {
         SweepCtx w = e->sweep;
         w.key = step_key(e->p.seed, t);
         w.stamp = ++e->sweep_stamp;
         LeanCtx L = e->lean;
-        const bool lean = e->scheduler == SSB_SCHED_SWEEP && e->lean_ok;
+        const bool lean = (e->scheduler == SSB_SCHED_SWEEP && e->lean_ok) || e->shard_sweep;
+        const bool box = e->shard_sweep;             // x-slabs over the GPUs of a box: box-wide barriers between the phases
+        long long *overflow = (long long *)c.a.counters + SSB_C_OVERFLOW;
         w.concurrent = lean ? e->sweep_lean_blocks * LEAN_THREADS : e->sweep_generic_blocks * AGENT_GROUPS;
         w.bucket_bits = lean ? e->sweep_bits_lean : e->sweep_bits_generic;
+        w.slab_bits = lean ? e->sweep_slab_bits_lean : e->sweep_slab_bits_generic;
         w.sub_bits = lean ? SWEEP_LEAN_SUB_BITS : 0;
         w.n_keys = (1 << w.bucket_bits) << w.sub_bits;
+        const int n_slabs = sweep_n_slabs(w.bucket_bits, w.slab_bits);
 #define SUB_EVENT(k) do { if (e->timing) CU(cudaEventRecord(e->sub_ev[k], st)); } while (0)
         SUB_EVENT(0);
-        CU(cudaMemsetAsync(w.done, 0, e->sweep_done_bytes, st));
-        CU(cudaMemsetAsync(w.gate, 0, sizeof(unsigned long long) * (size_t)c.a.capacity, st));
+        if (box) {      // this rank's columns of the done bitmap, the gates of its own list
+            const int wpc = sweep_done_wpc(e->p.height);
+            const long long x_lo = e->sh.cell_lo / e->p.height, x_hi = e->sh.cell_hi / e->p.height;
+            CU(cudaMemsetAsync(w.done + (size_t)x_lo * wpc, 0, sizeof(unsigned long long) * (size_t)(x_hi - x_lo) * wpc, st));
+            CU(cudaMemsetAsync(w.gate, 0, sizeof(unsigned long long) * (size_t)(e->local_slots < c.a.capacity ? e->local_slots : c.a.capacity), st));
+        } else {
+            CU(cudaMemsetAsync(w.done, 0, e->sweep_done_bytes, st));
+            CU(cudaMemsetAsync(w.gate, 0, sizeof(unsigned long long) * (size_t)c.a.capacity, st));
+        }
         void *pargs[] = {&c, &w, &L};
         CU(cudaLaunchCooperativeKernel(lean ? (void *)k_sweep_prepare<true> : (void *)k_sweep_prepare<false>, dim3(e->sweep_prepare_blocks),
                                        dim3(SWEEP_PREPARE_THREADS), pargs, sweep_prepare_smem_bytes(w.n_keys), st));
         LAUNCHED(e);
+        // (the build stages the descriptors of the halo: the neighbours' agents must have left theirs)
+        if (box) { k_shard_barrier<<<1, 32, 0, st>>>(e->sh, nullptr, overflow); LAUNCHED(e); }
         SUB_EVENT(1);
-        k_sweep_build<<<e->sweep_build_blocks, SWEEP_BUILD_THREADS, sweep_build_smem_bytes(w.rb, w.kb, w.halo, sweep_n_slabs(w.bucket_bits)), st>>>(c, w); LAUNCHED(e);
-        k_sweep_clear<<<e->num_sms * 8, 256, 0, st>>>(c, w); LAUNCHED(e);
+        k_sweep_build<<<e->sweep_build_blocks, SWEEP_BUILD_THREADS, sweep_build_smem_bytes(w.rb, w.kb, w.halo, n_slabs), st>>>(c, w); LAUNCHED(e);
+        if (!box) { k_sweep_clear<<<e->num_sms * 8, 256, 0, st>>>(c, w); LAUNCHED(e); }
         SUB_EVENT(2);
         if (lean) {
             k_lean_cells<true><<<e->num_sms * 8, 256, 0, st>>>(c, w, L); LAUNCHED(e);
+            if (box) {      // every build has read its halo, every slab is packed: descriptors can go, transactions may cross the boundary
+                k_shard_barrier<<<1, 32, 0, st>>>(e->sh, nullptr, overflow); LAUNCHED(e);
+                k_sweep_clear<<<e->num_sms * 8, 256, 0, st>>>(c, w); LAUNCHED(e);
+            }
             SUB_EVENT(3);
-            CU(cudaLaunchCooperativeKernel(e->lean_mode == 0 ? (void *)k_sweep_lean<0> : (void *)k_sweep_lean<LEAN_M_ALL>, dim3(e->sweep_lean_blocks), dim3(LEAN_THREADS), pargs, lean_smem_bytes(L.maxc, LEAN_THREADS), st));
+            void *kernel = box ? (void *)k_sweep_lean<0, true> : (e->lean_mode == 0 ? (void *)k_sweep_lean<0> : (void *)k_sweep_lean<LEAN_M_ALL>);
+            CU(cudaLaunchCooperativeKernel(kernel, dim3(e->sweep_lean_blocks), dim3(LEAN_THREADS), pargs, lean_smem_bytes(L.maxc, LEAN_THREADS, e->lean_mode == 0), st));
             LAUNCHED(e);
+            // (a neighbour's agents may have moved onto this slab: its cells are final once every rank has finished)
+            if (box) { k_shard_barrier<<<1, 32, 0, st>>>(e->sh, nullptr, overflow); LAUNCHED(e); }
             SUB_EVENT(4);
             k_lean_cells<false><<<e->num_sms * 8, 256, 0, st>>>(c, w, L); LAUNCHED(e);
-            k_lean_unpack<<<e->num_sms * 8, 256, 0, st>>>(c, L); LAUNCHED(e);
+            k_lean_unpack<<<e->num_sms * 8, 256, 0, st>>>(c, L, w.slot0); LAUNCHED(e);
         } else {
             SUB_EVENT(3);
             void *args[] = {&c, &w};
@@ -896,16 +935,21 @@ int ssb_reduce_stats(ssb_engine_t *e, int32_t t, void *stream_) {
         n_ptr = (const int64_t *)e->d_shard_vals;
         varying = e->d_shard_vals + 1;
     }
+    // integral wealths below LORENZ_BINS: exact histogram instead of the sort (d_lorenz_hist[0] tells the sort kernels)
+    k_lorenz_reset<<<8, 256, 0, st>>>(e->d_lorenz_hist); LAUNCHED(e);
+    k_lorenz_hist<<<e->num_sms * 4, LORENZ_THREADS, 0, st>>>((const double *)e->d_keys_a, n_ptr, e->d_lorenz_hist); LAUNCHED(e);
+    k_lorenz_from_hist<<<1, LORENZ_THREADS, 0, st>>>(e->d_lorenz_hist, n_ptr, e->d_stats); LAUNCHED(e);
+    const unsigned long long *needed = e->d_lorenz_hist;
     uint64_t *src = e->d_keys_a, *dst = e->d_keys_b;
     for (int shift = 0; shift < 64; shift += 8) {
-        k_radix_hist<<<tiles, RADIX_THREADS, 0, st>>>(src, n_ptr, shift, e->d_radix_hist, varying); LAUNCHED(e);
-        k_radix_scan<<<256, RADIX_THREADS, 0, st>>>(e->d_radix_hist, n_ptr, shift, varying, e->d_radix_rows); LAUNCHED(e);
-        k_radix_scatter<<<tiles, RADIX_THREADS, 0, st>>>(src, dst, n_ptr, shift, e->d_radix_hist, varying, e->d_radix_rows); LAUNCHED(e);
+        k_radix_hist<<<tiles, RADIX_THREADS, 0, st>>>(src, n_ptr, shift, e->d_radix_hist, varying, needed); LAUNCHED(e);
+        k_radix_scan<<<256, RADIX_THREADS, 0, st>>>(e->d_radix_hist, n_ptr, shift, varying, e->d_radix_rows, needed); LAUNCHED(e);
+        k_radix_scatter<<<tiles, RADIX_THREADS, 0, st>>>(src, dst, n_ptr, shift, e->d_radix_hist, varying, e->d_radix_rows, needed); LAUNCHED(e);
         uint64_t *tmp = src; src = dst; dst = tmp;
     }
     const int lb = e->num_sms * 4;
-    k_lorenz<<<lb, 256, 0, st>>>((const double *)src, n_ptr, e->d_lorenz_blocks); LAUNCHED(e);
-    k_lorenz_final<<<1, 1, 0, st>>>(e->d_lorenz_blocks, lb, e->d_stats, e->d_ring + (((t % SSB_STATS_RING) + SSB_STATS_RING) % SSB_STATS_RING)); LAUNCHED(e);
+    k_lorenz<<<lb, 256, 0, st>>>((const double *)src, n_ptr, e->d_lorenz_blocks, needed); LAUNCHED(e);
+    k_lorenz_final<<<1, 1, 0, st>>>(e->d_lorenz_blocks, lb, e->d_stats, e->d_ring + (((t % SSB_STATS_RING) + SSB_STATS_RING) % SSB_STATS_RING), needed); LAUNCHED(e);
     if (e->timing) { CU(cudaEventRecord(e->ev[4], st)); e->ev_recorded = true; }
     return 0;
 }
@@ -973,6 +1017,45 @@ int ssb_set_shard(ssb_engine_t *e, const ssb_shard_t *sd) {
     e->local_marks = e->rc.mark;
     e->rc.mark = (uint32_t *)sd->marks;
     e->sharded = true;
+    return 0;
+}
+
+// 1 if a sharded engine with these parameters can run the sweep scheduler over its slabs (ssb_set_shard_sweep): the rule
+// set of the plain lean transaction (nobody reads a neighbour's record), slabs made of whole 64-column tiles
+static bool shard_sweep_possible(const ssb_engine *e) {
+    if (!e->sharded || !e->sweep_ok || !e->lean_ok || e->lean_mode != 0) return false;
+    const long long H = e->p.height;
+    for (int r = 0; r < e->sh.world; r++) if ((e->sh.cell_end[r] / H) % FLOW_TX) return false;
+    return true;
+}
+int ssb_shard_sweep_possible(const ssb_engine_t *e) { return e && shard_sweep_possible(e) ? 1 : 0; }
+
+// The sweep scheduler on a sharded engine: every rank sweeps the agents of its own list; descriptors, done bitmap and the
+// packed cells are stitched arrays (rank r backs the columns of its slab), zero-filled; the ranks' watermarks live in
+// their control pages.  Collective: every rank calls it (or none).
+int ssb_set_shard_sweep(ssb_engine_t *e, void *desc, void *done, void *pcell) {
+    CHECK_BOUND(e);
+    if (!shard_sweep_possible(e)) return fail(e, -1, "the sweep scheduler cannot run on this sharded engine (rule set beyond the plain lean transaction, or slabs that are not made of whole 64-column tiles)");
+    if (!desc || !done || !pcell) return fail(e, -1, "stitched descriptor / done / cell arrays required");
+    if (e->shard_sweep) return fail(e, -1, "already set");
+    SweepCtx &w = e->sweep;
+    e->own_desc = w.desc; e->own_done = w.done; e->own_pcell = e->lean.pcell;
+    w.desc = (unsigned long long *)desc; w.done = (unsigned long long *)done; e->lean.pcell = (int2 *)pcell;
+    w.slot0 = (int32_t)e->sh.slot_lo;
+    w.tile_x_lo = (int32_t)(e->sh.cell_lo / e->p.height / FLOW_TX);
+    w.tile_x_hi = (int32_t)((e->sh.cell_hi / e->p.height + FLOW_TX - 1) / FLOW_TX);
+    w.pack_all = 1;
+    w.world = e->sh.world; w.rank = e->sh.rank;
+    w.wm_pages = e->sh.ctrl + 256;                    // (the pages' message slots end at word 192)
+    w.wm_stride = e->sh.ctrl_stride;
+    // a rank walks its own list: buckets and slabs sized for a rank's share of the slots (the same on every rank)
+    const long long T = (long long)e->sweep_lean_blocks * LEAN_THREADS;
+    e->sweep_bits_lean = sweep_bucket_bits(e->local_slots, T, e->p.id_bits, SWEEP_MAX_KEY_BITS - SWEEP_LEAN_SUB_BITS);
+    e->sweep_slab_bits_lean = sweep_slab_bits(e->local_slots, T);
+    int rc = size_build_grid(e, sweep_n_slabs(e->sweep_bits_lean, e->sweep_slab_bits_lean));
+    if (rc < 0) return rc;
+    e->shard_sweep = true;
+    e->scheduler = SSB_SCHED_SWEEP;
     return 0;
 }
 

@@ -192,8 +192,10 @@ __global__ void __launch_bounds__(COMPACT_THREADS) k_scan_tiles(int32_t *tile_co
 }
 
 // EXT: an ABI 2 extension is bound (doDeath then also settles the agent's loans / infections)
+// (__grid_constant__: do_death takes the context by reference and is not inlined -- without it every thread would first copy
+// the 850-byte parameter struct to its local memory: 8 GB of DRAM writes per S2 step, measured)
 template <bool EXT>
-__global__ void __launch_bounds__(COMPACT_THREADS) k_compact_scatter(DevCtx c, const int32_t *tile_offset,
+__global__ void __launch_bounds__(COMPACT_THREADS) k_compact_scatter(const __grid_constant__ DevCtx c, const int32_t *tile_offset,
                                                                      int32_t *new_order) {
     const long long n = c.a.counters[SSB_C_N_LIST];
     const long long tile0 = (long long)blockIdx.x * COMPACT_TILE;
@@ -531,9 +533,64 @@ __global__ void k_stats_ordered(DevCtx c, ssb_stats_t *out) {
     out->dead_wealth_collected = dead_collected;
 }
 
+// Lorenz numerator WITHOUT a sort, for populations whose wealths are all small non-negative integers (S2: integral
+// holdings and metabolisms): a histogram over the values [0, LORENZ_BINS) gives every value its rank range
+// [start, start + count), and  sum_j w_(j) * (n - 1/2 - j)  is then a sum over the bins in exact integer arithmetic
+// (128 bits), rounded once at the end.  lz[0] != 0: some wealth is not such an integer -- the radix sort below takes over
+// (every kernel of that path returns at once otherwise).  lz[1 ..]: the histogram.
+constexpr int LORENZ_BINS = 8192;
+constexpr int LORENZ_THREADS = 256;
+__global__ void __launch_bounds__(LORENZ_THREADS) k_lorenz_hist(const double *keys, const int64_t *n_ptr, unsigned long long *lz) {
+    __shared__ uint32_t h[LORENZ_BINS];
+    for (int i = threadIdx.x; i < LORENZ_BINS; i += LORENZ_THREADS) h[i] = 0u;
+    __syncthreads();
+    const long long n = *n_ptr, stride = (long long)gridDim.x * blockDim.x;
+    bool bad = false;
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        const double w = keys[j];
+        const int v = (w >= 0.0 && w < (double)LORENZ_BINS) ? (int)w : -1;
+        if (v < 0 || (double)v != w) { bad = true; continue; }
+        atomicAdd(&h[v], 1u);
+    }
+    if (bad) lz[0] = 1ull;
+    __syncthreads();
+    for (int i = threadIdx.x; i < LORENZ_BINS; i += LORENZ_THREADS) if (h[i]) atomicAdd(lz + 1 + i, (unsigned long long)h[i]);
+}
+__global__ void k_lorenz_reset(unsigned long long *lz) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= LORENZ_BINS; i += gridDim.x * blockDim.x) lz[i] = 0ull;
+}
+// one block: 2 * numerator = sum_v v * count_v * (2 n - 1 - 2 start_v - (count_v - 1))
+__global__ void __launch_bounds__(LORENZ_THREADS) k_lorenz_from_hist(const unsigned long long *lz, const int64_t *n_ptr, ssb_stats_t *out) {
+    if (lz[0] != 0ull) return;
+    constexpr int PER = LORENZ_BINS / LORENZ_THREADS;
+    __shared__ unsigned long long scan[LORENZ_THREADS], lo_sum[LORENZ_THREADS], hi_sum[LORENZ_THREADS];
+    const int tid = threadIdx.x;
+    unsigned long long mine = 0;
+    for (int k = 0; k < PER; k++) mine += lz[1 + tid * PER + k];
+    scan[tid] = mine;
+    __syncthreads();
+    if (tid == 0) { unsigned long long run = 0; for (int i = 0; i < LORENZ_THREADS; i++) { const unsigned long long v = scan[i]; scan[i] = run; run += v; } }
+    __syncthreads();
+    const unsigned long long n = (unsigned long long)*n_ptr;
+    unsigned long long start = scan[tid];
+    unsigned __int128 acc = 0;
+    for (int k = 0; k < PER; k++) {
+        const unsigned long long v = (unsigned long long)(tid * PER + k), cnt = lz[1 + tid * PER + k];
+        if (cnt) acc += (unsigned __int128)(v * cnt) * (unsigned __int128)(2ull * n - 1ull - 2ull * start - (cnt - 1ull));
+        start += cnt;
+    }
+    lo_sum[tid] = (unsigned long long)acc; hi_sum[tid] = (unsigned long long)(acc >> 64);
+    __syncthreads();
+    if (tid != 0) return;
+    unsigned __int128 total = 0;
+    for (int i = 0; i < LORENZ_THREADS; i++) total += ((unsigned __int128)hi_sum[i] << 64) | lo_sum[i];
+    out->lorenz_weighted_sum = ((double)(unsigned long long)(total >> 64) * 18446744073709551616.0 + (double)(unsigned long long)total) * 0.5;
+}
+
 // Lorenz numerator from the ascending wealth keys (updateGiniCoefficient, sugarscape.py:913-934):
 // sum_{i<n-1} cum_i + cum_{n-1}/2 = sum_j w_j * (n - 1 - j) + w_j / 2 ... folded per block.
-__global__ void __launch_bounds__(256) k_lorenz(const double *sorted, const int64_t *n_ptr, double *block_sums) {
+__global__ void __launch_bounds__(256) k_lorenz(const double *sorted, const int64_t *n_ptr, double *block_sums, const unsigned long long *needed) {
+    if (needed && *needed == 0ull) return;       // (the histogram path has the result)
     const long long n = *n_ptr;
     const long long stride = (long long)gridDim.x * blockDim.x;
     double acc = 0;
@@ -549,10 +606,12 @@ __global__ void __launch_bounds__(256) k_lorenz(const double *sorted, const int6
     if (threadIdx.x == 0) block_sums[blockIdx.x] = sm[0];
 }
 
-__global__ void k_lorenz_final(const double *block_sums, int n_blocks, ssb_stats_t *out, ssb_stats_t *ring_slot) {
-    double acc = 0;
-    for (int i = 0; i < n_blocks; i++) acc += block_sums[i];
-    out->lorenz_weighted_sum = acc;
+__global__ void k_lorenz_final(const double *block_sums, int n_blocks, ssb_stats_t *out, ssb_stats_t *ring_slot, const unsigned long long *needed) {
+    if (!needed || *needed != 0ull) {
+        double acc = 0;
+        for (int i = 0; i < n_blocks; i++) acc += block_sums[i];
+        out->lorenz_weighted_sum = acc;
+    }
     *ring_slot = *out;      // the step's stats are complete: publish them in the history ring
 }
 

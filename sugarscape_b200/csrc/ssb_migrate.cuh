@@ -147,7 +147,11 @@ __global__ void __launch_bounds__(256) k_migrate_recycle(DevCtx c, MigratePlan *
     for (int d = 0; d < c.sh.world; d++) {
         if (d == c.sh.rank) continue;
         const long long n = (long long)mp->out_count[d];
-        for (long long k = tid; k < n; k += stride) c.a.free_slots[n_free + base + k] = (int32_t)mine[(long long)d * box_cap + k];
+        for (long long k = tid; k < n; k += stride) {
+            const int32_t s = (int32_t)mine[(long long)d * box_cap + k];
+            c.a.free_slots[n_free + base + k] = s;
+            c.a.pos[s] = -1;             // the record lives on at its new rank: this slot holds no agent (the sweep's prepare walks the slots)
+        }
         base += n;
     }
 }

@@ -22,8 +22,10 @@ __device__ __forceinline__ bool digit_is_constant(const unsigned long long *vary
     return (((varying[0] ^ varying[1]) >> shift) & 255ull) == 0ull;
 }
 
+// needed (may be null): the sort only runs if *needed != 0 (ssb_kernels.cuh: the Lorenz histogram covers integral wealths)
 __global__ void __launch_bounds__(RADIX_THREADS) k_radix_hist(const uint64_t *keys, const int64_t *n_ptr, int shift,
-                                                              uint32_t *hist, const unsigned long long *varying) {
+                                                              uint32_t *hist, const unsigned long long *varying, const unsigned long long *needed = nullptr) {
+    if (needed && *needed == 0ull) return;
     if (digit_is_constant(varying, shift)) return;
     const long long n = *n_ptr;
     const int n_tiles = (int)((n + RADIX_TILE - 1) / RADIX_TILE);
@@ -46,7 +48,8 @@ __global__ void __launch_bounds__(RADIX_THREADS) k_radix_hist(const uint64_t *ke
 // scanned in place (exclusive) and its total goes to row_total[digit]; the scatter kernel adds the
 // exclusive prefix of the row totals.  Launch with 256 blocks.
 __global__ void __launch_bounds__(RADIX_THREADS) k_radix_scan(uint32_t *hist, const int64_t *n_ptr, int shift,
-                                                              const unsigned long long *varying, uint32_t *row_total) {
+                                                              const unsigned long long *varying, uint32_t *row_total, const unsigned long long *needed = nullptr) {
+    if (needed && *needed == 0ull) return;
     if (digit_is_constant(varying, shift)) return;
     const long long n = *n_ptr;
     const int n_tiles = (int)((n + RADIX_TILE - 1) / RADIX_TILE);
@@ -74,7 +77,8 @@ __global__ void __launch_bounds__(RADIX_THREADS) k_radix_scan(uint32_t *hist, co
 
 __global__ void __launch_bounds__(RADIX_THREADS) k_radix_scatter(const uint64_t *keys, uint64_t *out, const int64_t *n_ptr,
                                                                  int shift, const uint32_t *hist,
-                                                                 const unsigned long long *varying, const uint32_t *row_total) {
+                                                                 const unsigned long long *varying, const uint32_t *row_total, const unsigned long long *needed = nullptr) {
+    if (needed && *needed == 0ull) return;
     const long long n = *n_ptr;
     const int n_tiles = (int)((n + RADIX_TILE - 1) / RADIX_TILE);
     if (digit_is_constant(varying, shift)) {       // nothing to reorder: keep the ping-pong going

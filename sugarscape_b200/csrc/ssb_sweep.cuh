@@ -57,6 +57,16 @@ struct SweepCtx {
     unsigned long long *diag;        // optional (SSB_SWEEP_DIAG=1): [0] warp iterations, [1] entries checked, [2] entries run, [3] entries behind the watermark
     int32_t bucket_bits;             // priority buckets = 1 << bucket_bits
     int32_t sub_bits;                // bucket keys per priority bucket = 1 << sub_bits (lean path: by range)
+    int32_t slab_bits;               // slabs = 1 << min(bucket_bits, slab_bits) (sweep_slab_bits)
+    // x-slab sharding (ssb_shard.cuh; world 1: slot0 = 0, all tiles, no peers): this rank walks ITS slots and tiles; the
+    // descriptors, the done bitmap and the packed cells are stitched arrays, the ranks publish their watermarks in their
+    // control pages and every rank waits on the smallest
+    int32_t slot0;                   // first slot of this rank
+    int32_t tile_x_lo, tile_x_hi;    // tile columns of this rank's slab
+    int32_t pack_all;                // pack / unpack every tile of the slab (agents of a peer may walk in)
+    int32_t world, rank;
+    unsigned long long *wm_pages;    // stitched control pages: rank r's watermark at wm_pages[r * wm_stride]
+    long long wm_stride;
     int32_t n_keys;                  // bucket keys (= buckets << sub bits); bucket_start[n_keys] = live agents
     int32_t rb, kb, halo;            // largest range / dilation of the step, halo = flow_halo(rb, kb)
     int32_t tiles_x, tiles_y;
@@ -76,13 +86,21 @@ __device__ __forceinline__ unsigned long long sweep_ld_relaxed_if(const unsigned
                  : "=l"(v) : "l"(p), "r"(on) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned long long sweep_ld_relaxed_sys_if(const unsigned long long *p, uint32_t on) {
+    unsigned long long v;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tmov.u64 %0, 0xffffffffffffffff;\n\t@p ld.relaxed.sys.global.u64 %0, [%1];\n\t}"
+                 : "=l"(v) : "l"(p), "r"(on) : "memory");
+    return v;
+}
 __device__ __forceinline__ void sweep_fence() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 // release: MEMBAR.ALL.GPU (my writes are in L2) + the reduction that sets my done bit, WITHOUT the L1 invalidation of a
 // full fence; RELEASE = false: after an explicit fence
-template <bool RELEASE>
+// SYS: sharded -- a peer GPU reads the bit over NVLink, and the transaction may have written into the peer's memory
+template <bool RELEASE, bool SYS = false>
 __device__ __forceinline__ void sweep_set_done(const SweepCtx &w, int x, int y, int wpc) {
     unsigned long long *p = w.done + sweep_done_word(x, y, wpc);
-    if (RELEASE) asm volatile("red.release.gpu.global.or.b64 [%0], %1;" ::"l"(p), "l"(1ull << (y & 63)) : "memory");
+    if (SYS) asm volatile("red.release.sys.global.or.b64 [%0], %1;" ::"l"(p), "l"(1ull << (y & 63)) : "memory");
+    else if (RELEASE) asm volatile("red.release.gpu.global.or.b64 [%0], %1;" ::"l"(p), "l"(1ull << (y & 63)) : "memory");
     else asm volatile("red.relaxed.gpu.global.or.b64 [%0], %1;" ::"l"(p), "l"(1ull << (y & 63)) : "memory");
 }
 
@@ -100,7 +118,7 @@ __global__ void __launch_bounds__(SWEEP_PREPARE_THREADS) k_sweep_prepare(DevCtx 
     const int E = 1 << w.bucket_bits, NK = E << SUB, shift = c.p.id_bits - w.bucket_bits;
     int32_t *sh_count = reinterpret_cast<int32_t *>(prepare_smem);
     const int tid = threadIdx.x, H = c.p.height;
-    const long long n = LEAN ? c.a.counters[SSB_C_N_SLOTS] : c.a.counters[SSB_C_N_LIST];
+    const long long n = LEAN ? c.a.counters[SSB_C_N_SLOTS] - w.slot0 : c.a.counters[SSB_C_N_LIST];      // (LEAN: this rank's slots)
     long long chunk = (n + gridDim.x - 1) / gridDim.x;
     chunk = (chunk + SWEEP_PREPARE_THREADS - 1) / SWEEP_PREPARE_THREADS * SWEEP_PREPARE_THREADS;
     const long long lo = min((long long)blockIdx.x * chunk, n), hi = min(lo + chunk, n);
@@ -115,7 +133,7 @@ __global__ void __launch_bounds__(SWEEP_PREPARE_THREADS) k_sweep_prepare(DevCtx 
     // phase A: histogram of the bucket keys (the per-block work assignment is repeated exactly in phase B)
     int mine = 0;
     for (long long i = lo + tid; i < hi; i += blockDim.x) {
-        const int s = LEAN ? (int)i : c.a.order[i];
+        const int s = LEAN ? w.slot0 + (int)i : c.a.order[i];
         const bool live = c.a.pos[s] >= 0 && (!LEAN || c.a.cod[s] == SSB_ALIVE);
         if (!live) continue;
         const uint32_t pr = priority_of(w.key, (uint32_t)c.a.id[s], c.p.id_bits);
@@ -153,7 +171,9 @@ __global__ void __launch_bounds__(SWEEP_PREPARE_THREADS) k_sweep_prepare(DevCtx 
         if (tid == 0) {
             int wb = 0;
             while (wb < E && w.bucket_start[(wb + 1) << SUB] == w.bucket_start[wb << SUB]) wb++;
-            w.ctl[8] = (unsigned long long)wb;
+            w.ctl[8] = w.world > 1 ? 0ull : (unsigned long long)wb;
+            w.ctl[9] = (unsigned long long)wb;                       // this rank's own watermark
+            if (w.world > 1) st_release_sys(w.wm_pages + (long long)w.rank * w.wm_stride, (unsigned long long)wb);
         }
         if (LEAN && tid == 0 && (long long)w.ctl[2] != c.a.counters[SSB_C_N_LIST])
             atomicExch((unsigned long long *)&c.a.counters[SSB_C_OVERFLOW], (unsigned long long)SWEEP_OVERFLOW_LIVE);
@@ -164,7 +184,7 @@ __global__ void __launch_bounds__(SWEEP_PREPARE_THREADS) k_sweep_prepare(DevCtx 
         sh_count[e] = sh_count[e] ? w.bucket_start[e] + atomicAdd(&w.bucket_fill[e], sh_count[e]) : 0;
     __syncthreads();
     for (long long i = lo + tid; i < hi; i += blockDim.x) {
-        const int s = LEAN ? (int)i : c.a.order[i];
+        const int s = LEAN ? w.slot0 + (int)i : c.a.order[i];
         bool live;
         if (LEAN) live = lean_pack_a(c, L, s);
         else live = c.a.pos[s] >= 0;
@@ -194,8 +214,8 @@ __global__ void __launch_bounds__(SWEEP_BUILD_THREADS) k_sweep_build(DevCtx c, S
     extern __shared__ __align__(16) unsigned char sweep_smem[];
     __shared__ int sh_tile, sh_n_agents, sh_class[16];
     const int R = w.halo, sw = FLOW_TX + 2 * R, sh = FLOW_TY + 2 * R;
-    const int n_slabs = sweep_n_slabs(w.bucket_bits);
-    const int slab_prio_shift = c.p.id_bits - w.bucket_bits + sweep_slab_shift(w.bucket_bits);
+    const int n_slabs = sweep_n_slabs(w.bucket_bits, w.slab_bits);
+    const int slab_prio_shift = c.p.id_bits - w.bucket_bits + sweep_slab_shift(w.bucket_bits, w.slab_bits);
     unsigned long long *smask = reinterpret_cast<unsigned long long *>(sweep_smem);
     uint32_t *cell = reinterpret_cast<uint32_t *>(smask + (size_t)n_slabs * sw * 2);
     uint16_t *agents = reinterpret_cast<uint16_t *>(cell + sw * sh);
@@ -303,8 +323,8 @@ template <bool PACK>
 __global__ void __launch_bounds__(256) k_lean_cells(DevCtx c, SweepCtx w, LeanCtx L) {
     const int W = c.p.width, H = c.p.height, n_tiles = w.tiles_x * w.tiles_y;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        if (w.tile_need[t] != w.stamp) continue;
         const int tx = t / w.tiles_y, ty = t - tx * w.tiles_y;
+        if (w.pack_all ? (tx < w.tile_x_lo || tx >= w.tile_x_hi) : (w.tile_need[t] != w.stamp)) continue;
         static_assert(FLOW_TX == 64 && FLOW_TY == 64, "sector enumeration below");
         for (int sct = threadIdx.x; sct < (FLOW_TX / 2) * (FLOW_TY / 2); sct += blockDim.x) {
             // consecutive sectors of the tiled array: 4 x 4 tile (xq, yq), then the 2 x 2 sector (sx, sy) inside it
@@ -330,16 +350,18 @@ __global__ void __launch_bounds__(256) k_lean_cells(DevCtx c, SweepCtx w, LeanCt
 // May list entry i run?  The caller has compared the watermark; this is the individual part: the done bits of the near
 // predecessors in the entry's gate.  Straight-line code: the (at most six) done words are loaded under predicates and
 // are in flight together.  pos: the entry's start cell.
+template <bool SYS>
 __device__ __noinline__ bool sweep_line_ready(const SweepCtx &w, int i, int x, int y, int W, int H) {
     const uint32_t *line = w.preds + (size_t)i * SWEEP_COLS;
     uint32_t masks[SWEEP_COLS];
     for (int k = 0; k < SWEEP_COLS; k++) masks[k] = __ldg(line + k);
-    return sweep_line_done(masks, [&](size_t wd) { return sweep_ld_relaxed(w.done + wd); }, x, y, W, H, w.halo);
+    return sweep_line_done(masks, [&](size_t wd) { return SYS ? ld_relaxed_sys(w.done + wd) : sweep_ld_relaxed(w.done + wd); }, x, y, W, H, w.halo);
 }
+template <bool SYS = false>
 __device__ __forceinline__ bool sweep_gate_ready(const SweepCtx &w, unsigned long long gate, int i, int pos, int W, int H) {
     if (gate == 0ull) return true;
     const int x = pos / H, y = pos - x * H;
-    if (gate == SWEEP_GATE_LINE) return sweep_line_ready(w, i, x, y, W, H);
+    if (gate == SWEEP_GATE_LINE) return sweep_line_ready<SYS>(w, i, x, y, W, H);
     const int wpc = sweep_done_wpc(H), R = w.halo;
     unsigned long long dw[SWEEP_GATE_PREDS];
     int bit[SWEEP_GATE_PREDS];
@@ -348,7 +370,8 @@ __device__ __forceinline__ bool sweep_gate_ready(const SweepCtx &w, unsigned lon
         const int code = (int)(gate >> (10 * k)) & 1023;
         int cx, cy;
         sweep_offset_cell(x, y, (code & 31) - 1 - R, (code >> 5) - R, W, H, &cx, &cy);       // (an empty slot decodes to a cell that is not loaded)
-        dw[k] = sweep_ld_relaxed_if(w.done + sweep_done_word(cx, cy, wpc), (uint32_t)(code & 31));
+        const unsigned long long *p = w.done + sweep_done_word(cx, cy, wpc);
+        dw[k] = SYS ? sweep_ld_relaxed_sys_if(p, (uint32_t)(code & 31)) : sweep_ld_relaxed_if(p, (uint32_t)(code & 31));
         bit[k] = cy & 63;
     }
     bool ok = true;
@@ -364,26 +387,43 @@ __device__ __forceinline__ bool sweep_gate_ready(const SweepCtx &w, unsigned lon
 // agents fails the comparison (the watermark only grows: a stale copy is merely conservative).
 // all lanes of the warp; ran: this lane finished an agent of `bucket` in this iteration (its done bit is set: its writes
 // are released)
+template <bool SYS = false>
 __device__ __forceinline__ void sweep_count_finished(const SweepCtx &w, bool ran, int bucket) {
     const unsigned ranm = __ballot_sync(0xffffffffu, ran);
     if (!ran) return;
     __syncwarp(ranm);
     const unsigned peers = __match_any_sync(ranm, bucket);
     if ((int)(threadIdx.x & 31) != __ffs(peers) - 1) return;
-    asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(w.bucket_fin + bucket), "r"(__popc(peers)) : "memory");
+    if (SYS) asm volatile("red.release.sys.global.add.s32 [%0], %1;" ::"l"(w.bucket_fin + bucket), "r"(__popc(peers)) : "memory");
+    else asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(w.bucket_fin + bucket), "r"(__popc(peers)) : "memory");
 }
+// Sharded (w.world > 1): the walk yields THIS rank's watermark (ctl[9], published in its control page); ctl[8] -- what the
+// agents compare with -- is the smallest watermark of the box, read from the peers' pages over NVLink.
 __device__ __noinline__ void sweep_watermark_warp(const DevCtx &c, const SweepCtx &w) {
     if ((threadIdx.x & 31) != 0) return;
     const int E = 1 << w.bucket_bits, SUB = w.sub_bits;
-    int b = (int)sweep_ld_relaxed(w.ctl + 8);
+    const bool sharded = w.world > 1;
+    int mine = (int)sweep_ld_relaxed(w.ctl + 9), box = (int)sweep_ld_relaxed(w.ctl + 8);
     unsigned long long last = global_ns();
-    while (b < E) {
-        const int size = w.bucket_start[(b + 1) << SUB] - w.bucket_start[b << SUB];
-        int fin;
-        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(fin) : "l"(w.bucket_fin + b) : "memory");
-        if (fin == size) {
-            b++;
-            asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(w.ctl + 8), "l"((unsigned long long)b) : "memory");
+    while (box < E) {
+        bool moved = false;
+        while (mine < E) {
+            const int size = w.bucket_start[(mine + 1) << SUB] - w.bucket_start[mine << SUB];
+            int fin;
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(fin) : "l"(w.bucket_fin + mine) : "memory");
+            if (fin != size) break;
+            mine++;
+            moved = true;
+        }
+        int all = mine;
+        if (sharded) {
+            if (moved) st_release_sys(w.wm_pages + (long long)w.rank * w.wm_stride, (unsigned long long)mine);
+            for (int r = 0; r < w.world; r++)
+                if (r != w.rank) { const int v = (int)ld_acquire_sys(w.wm_pages + (long long)r * w.wm_stride); if (v < all) all = v; }
+        }
+        if (all > box) {
+            box = all;
+            asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(w.ctl + 8), "l"((unsigned long long)box) : "memory");
             last = global_ns();
             continue;
         }
@@ -437,25 +477,31 @@ __device__ __forceinline__ bool sweep_idle(const DevCtx &c, const SweepCtx &w, u
     return *(const volatile unsigned long long *)(w.ctl + 1) != 0ull;
 }
 
-__host__ __device__ constexpr int lean_smem_bytes(int maxc, int threads) { return threads * (maxc * 4 + (maxc + 1) * 2); }
+// per thread: [maxc + 1] 16-bit sugar words, then (not in the plain instantiation) [maxc] 32-bit occupants
+__host__ __device__ constexpr int lean_smem_bytes(int maxc, int threads, bool slim) { return threads * (((maxc + 2) & ~1) * 2 + (slim ? 0 : maxc * 4)); }
 
 // The lean transaction reads everything mutable past L1 (lean_ld), so the consumer needs no acquire fence (whose
 // CCTL.IVALL would invalidate the whole L1 once per agent); the producer's release rides on the reduction that sets
 // the done bit.  MODE: see lean_transaction.
+#ifndef SSB_LEAN_BLOCKS
+#define SSB_LEAN_BLOCKS 5
+#endif
 #ifndef SSB_LEAN_PREFETCH
 #define SSB_LEAN_PREFETCH 0      /* measured on S2: requesting the cross ahead of the gate check costs 7 ms (L2 request rate) */
 #endif
-template <int MODE>
-__global__ void __launch_bounds__(LEAN_THREADS, MODE == 0 ? 5 : 3) k_sweep_lean(DevCtx c, SweepCtx w, LeanCtx L) {
+// SYS: the sharded sweep (x-slabs over the GPUs of a box): done bits, bucket counts and watermarks at system scope
+template <int MODE, bool SYS = false>
+__global__ void __launch_bounds__(LEAN_THREADS, MODE == 0 ? SSB_LEAN_BLOCKS : 3) k_sweep_lean(DevCtx c, SweepCtx w, LeanCtx L) {
+    static_assert(!SYS || !(MODE & LEAN_M_FIGHT), "the sharded sweep keeps the records A private: no instantiation that reads a neighbour's record");
     constexpr bool PREFETCH = SSB_LEAN_PREFETCH != 0;
     extern __shared__ __align__(16) unsigned char lean_smem[];
     const int T = blockDim.x, tid = threadIdx.x;
-    int32_t *occ_st = reinterpret_cast<int32_t *>(lean_smem);
-    int16_t *sug_st = reinterpret_cast<int16_t *>(occ_st + L.maxc * T);
+    int16_t *sug_st = reinterpret_cast<int16_t *>(lean_smem);
+    int32_t *occ_st = reinterpret_cast<int32_t *>(sug_st + ((L.maxc + 2) & ~1) * T);
     const LeanStage st = {occ_st + tid, sug_st + tid, T};
     const int n = w.bucket_start[w.n_keys];
     const int W = c.p.width, H = c.p.height, wpc = sweep_done_wpc(H);
-    const int prio_shift = c.p.id_bits - w.bucket_bits, slab_shift = sweep_slab_shift(w.bucket_bits);
+    const int prio_shift = c.p.id_bits - w.bucket_bits, slab_shift = sweep_slab_shift(w.bucket_bits, w.slab_bits);
     if (blockIdx.x == 0 && tid < 32) { sweep_watermark_warp(c, w); return; }
     int i = -1;
     bool exhausted = false;
@@ -478,16 +524,20 @@ __global__ void __launch_bounds__(LEAN_THREADS, MODE == 0 ? 5 : 3) k_sweep_lean(
         }
         if (__any_sync(0xffffffffu, i >= 0 && watermark < need)) watermark = (int)sweep_ld_relaxed(w.ctl + 8);
         const bool passed = i >= 0 && watermark >= need;
-        if (passed) ready = sweep_gate_ready(w, gate, i, B.pos, W, H);
+        LeanA A0;
+        if (passed) {
+            if (!(MODE & LEAN_M_FIGHT)) A0 = lean_load_a(L.a + B.slot);     // (nobody else writes it: in flight with the done words)
+            ready = sweep_gate_ready<SYS>(w, gate, i, B.pos, W, H);
+        }
         const unsigned readym = __ballot_sync(0xffffffffu, ready);      // (also re-converges the warp after the check)
         if (ready) {
-            lean_transaction<MODE>(c, L, B, w.key, st, readym);
+            lean_transaction<MODE>(c, L, B, w.key, st, readym, (MODE & LEAN_M_FIGHT) ? nullptr : &A0);
             const int x = B.pos / H;
-            sweep_set_done<true>(w, x, B.pos - x * H, wpc);      // release: my writes happen before my done bit
+            sweep_set_done<true, SYS>(w, x, B.pos - x * H, wpc); // release: my writes happen before my done bit
             i = -1;
             ran = true;
         }
-        sweep_count_finished(w, ran, bucket);
+        sweep_count_finished<SYS>(w, ran, bucket);
         if (w.diag) {
             const unsigned held = __ballot_sync(0xffffffffu, i >= 0 || ran), did = __ballot_sync(0xffffffffu, ran);
             const unsigned late = __ballot_sync(0xffffffffu, i >= 0 && !passed);
@@ -504,7 +554,7 @@ __global__ void __launch_bounds__(AGENT_THREADS, 2) k_sweep_generic(DevCtx c, Sw
     const WarpScratch ws = make_warp_scratch(scratch_mem + (threadIdx.x / GL) * warp_scratch_bytes(MAXC_SCALABLE), MAXC_SCALABLE);
     const int n = w.bucket_start[w.n_keys];
     const int W = c.p.width, H = c.p.height, lane = Group<GL>::lane(), wpc = sweep_done_wpc(H);
-    const int prio_shift = c.p.id_bits - w.bucket_bits, slab_shift = sweep_slab_shift(w.bucket_bits);
+    const int prio_shift = c.p.id_bits - w.bucket_bits, slab_shift = sweep_slab_shift(w.bucket_bits, w.slab_bits);
     if (blockIdx.x == 0 && threadIdx.x < 32) { sweep_watermark_warp(c, w); return; }
     int i = -1;
     bool exhausted = false;
@@ -547,10 +597,10 @@ __global__ void __launch_bounds__(AGENT_THREADS, 2) k_sweep_generic(DevCtx c, Sw
     }
 }
 
-__global__ void __launch_bounds__(256) k_lean_unpack(DevCtx c, LeanCtx L) {
+__global__ void __launch_bounds__(256) k_lean_unpack(DevCtx c, LeanCtx L, int slot0) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
     const int n_slots = (int)c.a.counters[SSB_C_N_SLOTS];
-    for (int s = tid; s < n_slots; s += nthreads) lean_unpack_slot(c, L, s);
+    for (int s = slot0 + tid; s < n_slots; s += nthreads) lean_unpack_slot(c, L, s);
 }
 
 }  // namespace ssb

@@ -7,7 +7,7 @@
 //
 //   prepare  the agents are bucketed by the top bits of their priority (two counting passes, no sort) into the
 //            list `entries`; every agent leaves a descriptor {priority, range, dilation | list index} on its cell;
-//            16 consecutive groups of buckets are the SLABS of the priority order;
+//            consecutive groups of buckets (at most 32) are the SLABS of the priority order;
 //   sweep    a persistent grid walks the bucketed list by tickets.  An agent runs its whole transaction once all
 //            its PREDECESSORS -- the agents with a smaller priority whose footprint intersects its own -- have
 //            finished, then sets the DONE bit of its start cell and counts itself in its bucket.  The agents in
@@ -43,14 +43,20 @@ constexpr int SWEEP_COLS = 32;                      // words of a predecessor ma
 constexpr int SWEEP_MAX_HALO = 15;                  // 2 * halo + 1 <= 31 rows and columns
 
 // ---- slabs: groups of consecutive priority buckets --------------------------------------------------------
-#ifndef SSB_SLAB_BITS
-#define SSB_SLAB_BITS 4
-#endif
-constexpr int SWEEP_SLAB_BITS = SSB_SLAB_BITS;
-constexpr int SWEEP_MAX_SLABS = 1 << SWEEP_SLAB_BITS;
-// buckets per slab = 1 << sweep_slab_shift; slabs = 1 << min(bucket_bits, SWEEP_SLAB_BITS)
-__host__ __device__ __forceinline__ int sweep_slab_shift(int bucket_bits) { return bucket_bits > SWEEP_SLAB_BITS ? bucket_bits - SWEEP_SLAB_BITS : 0; }
-__host__ __device__ __forceinline__ int sweep_n_slabs(int bucket_bits) { return 1 << (bucket_bits < SWEEP_SLAB_BITS ? bucket_bits : SWEEP_SLAB_BITS); }
+// The number of slabs is chosen per engine (sweep_slab_bits): a slab must be several times longer than the slice of the
+// priority order that is in flight, or the watermark holds agents back; shorter slabs mean fewer near predecessors.
+constexpr int SWEEP_MAX_SLAB_BITS = 5;
+constexpr int SWEEP_MAX_SLABS = 1 << SWEEP_MAX_SLAB_BITS;
+// slabs for `n` list entries walked by T concurrent transactions: a slab holds at least 8 T entries (measured on S2: with
+// 4 T a fifth of all readiness checks fail on the watermark, with 8 T one in a hundred); one slab: every predecessor is near
+__host__ __device__ __forceinline__ int sweep_slab_bits(long long n, long long T) {
+    int bits = 0;
+    while (bits < SWEEP_MAX_SLAB_BITS && (n >> (bits + 1)) >= 8 * T) bits++;
+    return bits;
+}
+// buckets per slab = 1 << sweep_slab_shift; slabs = 1 << min(bucket_bits, slab_bits)
+__host__ __device__ __forceinline__ int sweep_slab_shift(int bucket_bits, int slab_bits) { return bucket_bits > slab_bits ? bucket_bits - slab_bits : 0; }
+__host__ __device__ __forceinline__ int sweep_n_slabs(int bucket_bits, int slab_bits) { return 1 << (bucket_bits < slab_bits ? bucket_bits : slab_bits); }
 // the watermark an agent of bucket b waits for: the first bucket of the slab before its own
 __host__ __device__ __forceinline__ int sweep_watermark_needed(int bucket, int slab_shift) {
     const int slab = bucket >> slab_shift;
@@ -405,10 +411,16 @@ __device__ __forceinline__ void lean_unpack_slot(const DevCtx &c, const LeanCtx 
 // agents, but they run the same loops with the same trip counts (the sweep groups agents by range), so the function
 // re-converges them after every data-dependent stretch -- otherwise a warp drifts apart into a handful of sub-warps
 // that each pay the full instruction stream.
+// preloaded: the agent's record A, loaded by the caller ahead of the readiness check -- only for instantiations in which
+// nobody but the agent itself writes its record (MODE without LEAN_M_FIGHT); otherwise null.
+// The plain instantiation (MODE 0) only needs to know WHETHER a candidate is occupied: it stages one 16-bit word per
+// candidate (sugar | occupied << 15) and never touches st.occ.
 template <int MODE>
-__device__ inline void lean_transaction(const DevCtx &c, const LeanCtx &L, const LeanB &B, uint64_t key, const LeanStage &st, unsigned warpm) {
+__device__ inline void lean_transaction(const DevCtx &c, const LeanCtx &L, const LeanB &B, uint64_t key, const LeanStage &st, unsigned warpm,
+                                        const LeanA *preloaded = nullptr) {
+    constexpr bool SLIM = MODE == 0;
     const int s = B.slot;
-    LeanA A = lean_load_a(L.a + s);
+    LeanA A = (preloaded && !(MODE & LEAN_M_FIGHT)) ? *preloaded : lean_load_a(L.a + s);
     const bool acting = (A.state & LEAN_COD_MASK) == SSB_ALIVE && A.sugar >= 0 && A.spice >= 0 && !(B.idf & LEANB_SKIP);
     const unsigned actm = __ballot_sync(warpm, acting);
     if (!acting) return;
@@ -421,6 +433,7 @@ __device__ inline void lean_transaction(const DevCtx &c, const LeanCtx &L, const
     // the cross (and the own cell, in case the agent stays): two distances = eight independent 8-byte loads in flight
     const int2 *pcell = L.pcell;
     const uint32_t tpos = lean_tiled(x, y, L.ty4);
+    const int2 own = lean_ld(pcell + tpos);                     // (in flight together with the first rings)
     for (int d = 1; d <= r; d += 2) {
         int cell[8];
         int2 v[8];
@@ -432,9 +445,12 @@ __device__ inline void lean_transaction(const DevCtx &c, const LeanCtx &L, const
             if (u < 4 || two) v[u] = lean_ld(pcell + cell[u]);
 #pragma unroll
         for (int u = 0; u < 8; u++)
-            if (u < 4 || two) { st.occ[(4 * (d - 1) + u) * S] = v[u].x; st.sugar[(4 * (d - 1) + u) * S] = (int16_t)v[u].y; }
+            if (u < 4 || two) {
+                if (SLIM) st.sugar[(4 * (d - 1) + u) * S] = (int16_t)(v[u].y | (v[u].x >= 0 ? 0x8000 : 0));
+                else { st.occ[(4 * (d - 1) + u) * S] = v[u].x; st.sugar[(4 * (d - 1) + u) * S] = (int16_t)v[u].y; }
+            }
     }
-    st.sugar[n * S] = (int16_t)lean_ld(pcell + tpos).y;
+    st.sugar[n * S] = (int16_t)own.y;
     __syncwarp(actm);
     // findWelfare's per-agent part (agent.py:1170-1201, no tag preferences)
     Welfare w;
@@ -477,8 +493,9 @@ __device__ inline void lean_transaction(const DevCtx &c, const LeanCtx &L, const
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const int i = 4 * (d - 1) + j, cell = ring[j];
-                const int o = st.occ[i * S], cs = st.sugar[i * S];
-                const bool occupied = o >= 0;
+                const int staged = st.sugar[i * S];
+                const int o = SLIM ? -1 : st.occ[i * S], cs = SLIM ? (staged & 0x7fff) : staged;
+                const bool occupied = SLIM ? staged < 0 : o >= 0;
                 int otribe = -1;
                 double ps = 0, pp = 0;
                 if (occupied) {
@@ -535,7 +552,7 @@ __device__ inline void lean_transaction(const DevCtx &c, const LeanCtx &L, const
         lean_ring<false>(b_dist, x, y, W, H, H, ring);
         const int i = 4 * (b_dist - 1) + jw;
         b_cell = ring[jw];
-        b_cs = st.sugar[i * S]; b_occ = st.occ[i * S];
+        b_cs = st.sugar[i * S] & 0x7fff; b_occ = SLIM ? -1 : st.occ[i * S];        // (a chosen cell is empty in the plain instantiation)
         b_cp = spicy ? lean_ld(c.g.spice + b_cell) : 0;
         b_pl = polluted ? lean_ld(c.g.pollution + b_cell) : 0.0;
     }

@@ -19,6 +19,66 @@ class EngineError(RuntimeError):
     pass
 
 
+class _Uploader:
+    """Host -> device copies of large pageable arrays at PCIe speed: worker threads copy chunks into a small ring of pinned
+    staging buffers (numpy releases the GIL), each chunk is DMAed asynchronously on a side stream while the next ones
+    are being staged.  (A plain tensor.to(device) of pageable memory runs at a fraction of the link rate, and the
+    whole initial state of a large map -- 20 GB for the S2 shape -- goes through here.)"""
+    THRESHOLD = 32 << 20
+    CHUNK = 32 << 20
+    RING = 8
+    WORKERS = 4
+    _instances = {}
+
+    @classmethod
+    def get(cls, torch, device):
+        key = (device.type, device.index)
+        if key not in cls._instances:
+            cls._instances[key] = cls(torch, device)
+        return cls._instances[key]
+
+    def __init__(self, torch, device):
+        from concurrent.futures import ThreadPoolExecutor
+        self.torch, self.device = torch, device
+        self.pinned = [torch.empty(self.CHUNK, dtype=torch.uint8, pin_memory=True) for _ in range(self.RING)]
+        self.views = [b.numpy() for b in self.pinned]
+        self.events = [None] * self.RING
+        self.stream = torch.cuda.Stream(device)
+        self.pool = ThreadPoolExecutor(self.WORKERS)
+
+    def upload(self, arr):
+        t = self.torch
+        src = arr.reshape(-1).view(np.uint8)
+        out = t.empty(arr.shape, dtype=t.from_numpy(arr[:0]).dtype, device=self.device)
+        dst = out.view(t.uint8).reshape(-1)
+        staged = []
+
+        def issue():
+            fut, k, off, n = staged.pop(0)
+            fut.result()
+            with t.cuda.stream(self.stream):
+                dst[off:off + n].copy_(self.pinned[k][:n], non_blocking=True)
+                ev = t.cuda.Event()
+                ev.record(self.stream)
+            self.events[k] = ev
+
+        for idx, off in enumerate(range(0, src.nbytes, self.CHUNK)):
+            k = idx % self.RING
+            while any(item[1] == k for item in staged):      # the ring wrapped around: the buffer is still queued
+                issue()
+            if self.events[k] is not None:
+                self.events[k].synchronize()
+                self.events[k] = None
+            n = min(self.CHUNK, src.nbytes - off)
+            staged.append((self.pool.submit(np.copyto, self.views[k][:n], src[off:off + n]), k, off, n))
+            while len(staged) > self.WORKERS:
+                issue()
+        while staged:
+            issue()
+        self.stream.synchronize()
+        return out
+
+
 def load_library():
     """Load libssb.so (built in-tree by sugarscape_b200/build.py); fail loudly if absent."""
     global _LIB
@@ -50,6 +110,8 @@ def load_library():
     L.ssb_uses_lean_transaction.argtypes = [E]
     L.ssb_sweep_diag.argtypes = [E, C.c_void_p]
     L.ssb_agent_phases.argtypes = [E, C.c_void_p]
+    L.ssb_shard_sweep_possible.argtypes = [E]
+    L.ssb_set_shard_sweep.argtypes = [E, C.c_void_p, C.c_void_p, C.c_void_p]
     L.ssb_set_mark_shift.argtypes = [E, C.c_int32]
     L.ssb_set_l2_persist.argtypes = [E, C.c_void_p, C.c_int32]
     L.ssb_env_step.argtypes = [E, C.c_int32, C.c_void_p]
@@ -105,7 +167,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = (
     "ssb_abi_version", "ssb_create", "ssb_bind", "ssb_destroy", "ssb_last_error",
-    "ssb_set_mt_state", "ssb_get_mt_state", "ssb_set_step_tables", "ssb_set_scheduler", "ssb_get_scheduler", "ssb_uses_lean_transaction", "ssb_sweep_diag", "ssb_agent_phases", "ssb_set_epochs", "ssb_set_mark_shift", "ssb_set_l2_persist",
+    "ssb_set_mt_state", "ssb_get_mt_state", "ssb_set_step_tables", "ssb_set_scheduler", "ssb_get_scheduler", "ssb_uses_lean_transaction", "ssb_sweep_diag", "ssb_agent_phases", "ssb_shard_sweep_possible", "ssb_set_shard_sweep", "ssb_set_epochs", "ssb_set_mark_shift", "ssb_set_l2_persist",
     "ssb_sizeof_params", "ssb_sizeof_grid", "ssb_sizeof_agents", "ssb_sizeof_stats",
     "ssb_env_step", "ssb_agent_step", "ssb_compact", "ssb_bind_endowments", "ssb_replace", "ssb_reduce_stats", "ssb_step", "ssb_stats", "ssb_stats_history",
     "ssb_fabric_create", "ssb_fabric_alloc", "ssb_fabric_map", "ssb_fabric_copy", "ssb_fabric_granularity",
@@ -167,9 +229,12 @@ class Engine:
 
     def _to_device(self, arr):
         t = self.torch
+        arr = np.ascontiguousarray(arr)
         if arr.dtype == np.uint32:
-            return t.from_numpy(arr.view(np.int32).copy()).to(self.device)
-        return t.from_numpy(np.ascontiguousarray(arr)).to(self.device)
+            arr = arr.view(np.int32)
+        if arr.nbytes >= _Uploader.THRESHOLD and self.device.type == "cuda":
+            return _Uploader.get(t, self.device).upload(arr)
+        return t.from_numpy(arr).to(self.device)
 
     def _upload_all(self, hs):
         for name, _ in layout.GRID_FIELDS:

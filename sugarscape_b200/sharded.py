@@ -40,6 +40,10 @@ def balanced_slab_bounds(state, world):
     if n == 0 or world == 1:
         return slab_bounds(W, world)
     align = GRANULE // (H * 4) if GRANULE % (H * 4) == 0 and GRANULE // (H * 4) * 4 * world <= W else 1
+    if SWEEP_TILE * 2 * world <= W:        # whole 64-column tiles per slab: the ranks can run the sweep scheduler
+        align = align * SWEEP_TILE // np.gcd(align, SWEEP_TILE)
+        if align * 2 * world > W:
+            align = SWEEP_TILE
     x = state.a_pos[state.a_order[:n]] // H
     cum = np.cumsum(np.bincount(x, minlength=W))
     bounds = [0]
@@ -48,6 +52,21 @@ def balanced_slab_bounds(state, world):
         b = int(round(b / align)) * align
         bounds.append(min(max(b, bounds[-1] + align), W - (world - r) * align))
     return bounds + [W]
+
+
+SWEEP_TILE = 64          # the sweep scheduler works on 64 x 64 tiles (csrc/ssb_flow_core.cuh): slabs of whole tiles can run it
+
+
+def sweep_slabs_possible(params, xb):
+    """Mirror of the engine's ssb_shard_sweep_possible as far as it can be told before the bind: the rule set of the plain
+    lean transaction (csrc/ssb_sweep_core.cuh, lean_supported + lean_mode == 0) and slab boundaries on tile boundaries."""
+    heavy = (layout.F_TAGGING | layout.F_TRADE | layout.F_REPRO | layout.F_TAGPREF | layout.F_COMBAT | layout.F_SPICE | layout.F_POLLUTION)
+    if params.flags & heavy or params.max_tribes > 25 or params.max_sugar_capacity > 32767:
+        return False
+    side = min(params.width, params.height)
+    if not (0 <= params.max_agent_range <= 7 and 2 * params.max_agent_range + 1 < side):
+        return False
+    return all(b % SWEEP_TILE == 0 for b in xb[:-1])
 
 
 def slot_bounds(capacity, world):
@@ -276,6 +295,15 @@ class ShardedEngine(Engine):
         plan += [("_ctrl", (GRANULE // 8) * world, np.uint64, uniform((GRANULE // 8) * world)), ("_marks", wc * hc, np.uint32, mark_end)]
         gather_words = -(-5 * local_slots * 8 // GRANULE) * GRANULE // 8
         plan += [("_gather", gather_words * world, np.uint64, uniform(gather_words * world))]
+        # the sweep scheduler's arrays (ssb_set_shard_sweep): descriptors, done bitmap, packed cells -- stitched like the grid,
+        # if the slabs consist of whole 64-column tiles (the engine decides after the bind whether it can use them)
+        self.sweep_arrays = sweep_slabs_possible(self.params, xb)
+        if self.sweep_arrays:
+            wpc = (self.height + 63) // 64
+            ty4 = (self.height + 3) // 4
+            plan += [("_sw_desc", n_cells, np.uint64, [xb[r + 1] * self.height for r in range(world)]),
+                     ("_sw_done", self.width * wpc, np.uint64, [xb[r + 1] * wpc for r in range(world)]),
+                     ("_sw_pcell", ((self.width + 3) // 4) * ty4 * 16, np.uint64, [min((xb[r + 1] + 3) // 4, (self.width + 3) // 4) * ty4 * 16 for r in range(world)])]
         bounds = {key: chunk_boundaries(ends, np.dtype(dt).itemsize, world) for key, n, dt, ends in plan}
         self._fcheck(L.ssb_fabric_create(rank, world, self.device.index, C.byref(self.fabric)))
         if GRANULE % int(L.ssb_fabric_granularity(self.fabric)):
@@ -342,6 +370,11 @@ class ShardedEngine(Engine):
         sd.gather, sd.gather_stride = self.stitched["_gather"].data_ptr(), self.bounds["_gather"][1]
         self._check(self.L.ssb_set_shard(self.handle, C.byref(sd)))
         self._barrier()
+        # every rank reaches the same verdict (same parameters, same slabs): all of them switch to the sweep, or none
+        if self.sweep_arrays and os.environ.get("SSB_SCHEDULER", "") != "rounds" and self.L.ssb_shard_sweep_possible(self.handle):
+            self._check(self.L.ssb_set_shard_sweep(self.handle, self.stitched["_sw_desc"].data_ptr(), self.stitched["_sw_done"].data_ptr(),
+                                                   self.stitched["_sw_pcell"].data_ptr()))
+            self._barrier()
 
     def close(self):
         if getattr(self, "handle", None):

@@ -228,8 +228,8 @@ int emu_agent_step_sweep(const ssb_params_t *p, const ssb_grid_t *g, const ssb_a
     /* ... grouped by priority bucket like k_sweep_prepare (128 buckets = 32 slabs of 4, or one bucket: order_mode & 0x100) */
     const int bucket_bits = (order_mode & 0x100) ? 0 : (p->id_bits < 7 ? p->id_bits : 7);
     order_mode &= 0xff;
-    const int E = 1 << bucket_bits, prio_shift = p->id_bits - bucket_bits, slab_shift = sweep_slab_shift(bucket_bits);
-    const int n_slabs = sweep_n_slabs(bucket_bits), slab_prio_shift = prio_shift + slab_shift;
+    const int E = 1 << bucket_bits, prio_shift = p->id_bits - bucket_bits, slab_shift = sweep_slab_shift(bucket_bits, SWEEP_MAX_SLAB_BITS);
+    const int n_slabs = sweep_n_slabs(bucket_bits, SWEEP_MAX_SLAB_BITS), slab_prio_shift = prio_shift + slab_shift;
     auto bucket_of = [&](int s) { return (int)(priority_of(key, (uint32_t)a->id[s], p->id_bits) >> prio_shift); };
     std::stable_sort(live.begin(), live.end(), [&](int x, int y) { return bucket_of(x) < bucket_of(y); });
     std::vector<int> bucket_size(E, 0), bucket_fin(E, 0);

@@ -82,7 +82,7 @@ def main():
         if not (params.flags & layout.F_REPRO):     # (a child's record is allocated by the acting parent's rank)
             assert np.all((slots >= eng.slot_lo) & (slots < eng.slot_hi)), "a record outside this rank's slot range"
         migrated += int(eng.counters()[layout.C_N_MIGRATED])
-    print(f"SHARDED_PARITY_OK rank {rank}/{world} case {args.case} steps {args.steps} "
+    print(f"SHARDED_PARITY_OK rank {rank}/{world} case {args.case} steps {args.steps} scheduler {eng.scheduler()} "
           f"population {want_pop} migrated away {migrated}", flush=True)
     eng.close()
     dist.destroy_process_group()

@@ -117,6 +117,11 @@ SHARDED_CASES = [
     ("combat_limited", {}, 60),
     ("combat_limited", {"environmentWidth": 300, "environmentHeight": 300, "startingAgents": 4000, "agentReplacements": 4000,
                         "agentMaxAge": [5, 30], "agentAggressionFactor": [0, 1]}, 40),
+    # maps wide enough for slabs of whole 64-column tiles and rule sets of the plain lean transaction: the ranks run the SWEEP
+    # scheduler over their slabs (done bits, cells and watermarks across NVLink) -- the S2 configuration of bench.py
+    ("combat_limited", {"environmentWidth": 320, "environmentHeight": 200, "startingAgents": 9000, "agentReplacements": 9000,
+                        "agentMaxAge": [5, 30]}, 40),
+    ("constant_growback", {"environmentWidth": 512, "environmentHeight": 150, "startingAgents": 12000, "agentVision": [1, 6]}, 30),
 ]
 
 
@@ -134,21 +139,28 @@ SHARDED_BIRTH_CASES = [
 def test_two_gpu_slabs_with_births_experimental(name, overrides, steps):
     if not os.environ.get("SSB_EXPERIMENTAL_SHARDED_BIRTHS"):
         pytest.skip("sharded births are experimental (set SSB_EXPERIMENTAL_SHARDED_BIRTHS=1)")
-    test_two_gpu_slabs_equal_the_single_gpu_run(name, overrides, steps)
+    test_slabs_equal_the_single_gpu_run(name, overrides, steps, 2)
 
 
+# The world sizes a box offers are compared with the single-GPU run: 2 GPUs on a 2-GPU lease, 2 and 4 on a larger box (the
+# 50-wide examples give slabs of 12 columns at world 4 -- about an agent's reach, so a transaction can touch three
+# slabs).  A 1-GPU lease skips them (the CPU suite covers the host side of the sharding, above).
 @pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 4])
 @pytest.mark.parametrize("name,overrides,steps", SHARDED_CASES)
-def test_two_gpu_slabs_equal_the_single_gpu_run(name, overrides, steps):
+def test_slabs_equal_the_single_gpu_run(name, overrides, steps, world):
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs")
-    world = 2
-    res = subprocess.run(["timeout", "240", sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    res = subprocess.run(["timeout", "300", sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
                           "--master-addr", "127.0.0.1", "--master-port", str(29900 + os.getpid() % 90),
                           os.path.join(ROOT, "tests", "sharded_worker.py"), "--case", name, "--overrides", json.dumps(overrides),
-                          "--steps", str(steps)], capture_output=True, text=True, timeout=300)
+                          "--steps", str(steps)], capture_output=True, text=True, timeout=360)
     log = res.stdout + res.stderr
     errors = [ln for ln in log.splitlines() if "Error" in ln or "rror:" in ln or "SystemExit" in ln or "differs" in ln]
     assert res.returncode == 0, "\n".join(errors[:12]) or log[-3000:]
     assert res.stdout.count("SHARDED_PARITY_OK") == world, res.stdout[-2000:]
+    # the last two cases run the sweep scheduler when the map gives every rank slabs of whole 64-column tiles
+    sweepable = SHARDED_CASES.index((name, overrides, steps)) >= len(SHARDED_CASES) - 2 and 128 * world <= overrides["environmentWidth"]
+    want = "sweep" if sweepable else "rounds"
+    assert res.stdout.count(f"scheduler {want} ") == world, f"expected the {want} scheduler on every rank:\n" + res.stdout[-1500:]

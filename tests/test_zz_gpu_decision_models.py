@@ -4,10 +4,9 @@ friends through the C ABI (ssb_bind_ethics / ssb_bind_ext, the extended instanti
 replacement, pollution).  Integer state, tags, grid and the MT19937 stream bit-exact on every step, fp64 holdings
 through their digest, all 59 log keys.
 
-Status of this file: the same device source passes these fixtures compiled for the host
-(tests/test_hostemu.py); round 1 ran out of GPU minutes before the first run on a B200, so the cases are
-marked xfail(strict=False) -- XPASS in the GPU log is the confirmation, and the marker goes away with it.
-The file sorts last so that nothing runs after it in the same process."""
+Every case replays its WHOLE fixture (200 timesteps) and fails if it did not: the first B200 run of these kernels
+(round 1, as xfail(strict=False) cases) passed, so the marker is gone.  The file sorts last so that nothing runs after
+it in the same process."""
 import os
 import time
 
@@ -17,18 +16,15 @@ import parity_util as pu
 from sugarscape_b200 import init, layout, stats
 from test_gpu_parity import _close, _engine, _replace
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first GPU run of the decision-model kernels (validated on the "
-                                                     "host-compiled device source only, tests/test_hostemu.py)")]
+pytestmark = [pytest.mark.gpu]
 
-# The one-warp extended kernel walks Python-list semantics on a single lane: seconds per 100 steps with every family
-# on.  The GPU cases replay the first STEPS steps of each fixture (SSB_GPU_EXT_STEPS=0: all of them); the CPU suite
-# replays the same fixtures in full on the host-compiled device source (tests/test_hostemu.py).
-STEPS = int(os.environ.get("SSB_GPU_EXT_STEPS", "80"))
-# ... and stop early once a case has used its wall-clock budget (at least 10 steps are always compared): the whole file
-# stays within minutes whatever the single-lane kernel costs on the box (SSB_GPU_EXT_SECONDS=0: no budget)
-SECONDS = float(os.environ.get("SSB_GPU_EXT_SECONDS", "20"))
-DRIVER_STEPS = 30           # the drop-in driver runs cannot be interrupted: a fixed, short run
+# The one-warp extended kernel walks Python-list semantics on a single lane; a 200-step replay with a state download and
+# digests after every step takes some tens of seconds.  SSB_GPU_EXT_STEPS > 0 caps the replay for quick local runs (the
+# default 0 replays everything); SSB_GPU_EXT_SECONDS is a safety net per case -- a case that hits it FAILS (it did not
+# cover its fixture), it does not pass on a prefix.
+STEPS = int(os.environ.get("SSB_GPU_EXT_STEPS", "0"))
+SECONDS = float(os.environ.get("SSB_GPU_EXT_SECONDS", "240"))
+DRIVER_STEPS = 30           # (with SSB_GPU_EXT_STEPS > 0 only) the drop-in driver runs cannot be interrupted: a fixed, short run
 
 
 def _cap(gold):
@@ -42,7 +38,9 @@ class _Budget:
 
     def spent(self, t):
         self.ran = t
-        return SECONDS > 0 and t >= 10 and time.time() - self.t0 > SECONDS
+        if SECONDS > 0 and t >= 10 and time.time() - self.t0 > SECONDS:
+            pytest.fail(f"only {t} timesteps compared in {SECONDS:.0f} s: the case did not cover its fixture")
+        return False
 
 
 ETHICS_VARIANTS = ["ethics_trade", "ethics_combat", "ethics_replacement", "ethics_pollution", "ethics_dynamic",
