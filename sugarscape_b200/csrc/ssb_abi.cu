@@ -52,7 +52,7 @@ struct ssb_engine {
     int lean_mode;           // LEAN_M_*: which instantiation of the lean kernel runs
     SweepCtx sweep;
     LeanCtx lean;
-    int sweep_prepare_blocks, sweep_build_blocks, sweep_lean_blocks, sweep_generic_blocks;
+    int sweep_prepare_blocks, sweep_build_blocks_lean, sweep_build_blocks_generic, sweep_lean_blocks, sweep_generic_blocks;
     size_t sweep_done_bytes;
     int sweep_stamp;
     int sweep_bits_generic, sweep_bits_lean;
@@ -250,14 +250,14 @@ static int setup_flow(ssb_engine *e) {
 // The ordered sweep (ssb_sweep.cuh).  e->sweep_ok stays false when the engine is outside its limits (the rounds
 // scheduler then stays the default); a negative return is a real error.
 // the build kernel stages one occupancy bit-plane per slab: its grid (resident CTAs) depends on their number
-static int size_build_grid(ssb_engine *e, int n_slabs) {
+static int size_build_grid(ssb_engine *e, int n_slabs, int *blocks) {
     SweepCtx &w = e->sweep;
     int per_sm = 0;
     const int build_smem = sweep_build_smem_bytes(w.rb, w.kb, w.halo, n_slabs);
     CU(cudaFuncSetAttribute(k_sweep_build, cudaFuncAttributeMaxDynamicSharedMemorySize, sweep_build_smem_bytes(w.rb, w.kb, w.halo, SWEEP_MAX_SLABS)));
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_build, SWEEP_BUILD_THREADS, build_smem));
     if (per_sm < 1) return fail(e, -3, "the sweep's build kernel does not fit on an SM (%d bytes of shared memory)", build_smem);
-    e->sweep_build_blocks = per_sm * e->num_sms;
+    *blocks = per_sm * e->num_sms;
     return 0;
 }
 
@@ -308,9 +308,8 @@ static int setup_sweep(ssb_engine *e, int maxd) {
     e->sweep_slab_bits_generic = sweep_slab_bits(cap, concurrent);
     e->sweep_slab_bits_lean = e->lean_ok ? sweep_slab_bits(cap, (long long)e->sweep_lean_blocks * LEAN_THREADS) : 0;
     {
-        const int slabs_generic = sweep_n_slabs(e->sweep_bits_generic, e->sweep_slab_bits_generic);
-        const int slabs_lean = e->lean_ok ? sweep_n_slabs(e->sweep_bits_lean, e->sweep_slab_bits_lean) : 1;
-        int rc = size_build_grid(e, slabs_lean > slabs_generic ? slabs_lean : slabs_generic);
+        int rc = size_build_grid(e, sweep_n_slabs(e->sweep_bits_generic, e->sweep_slab_bits_generic), &e->sweep_build_blocks_generic);
+        if (rc == 0) rc = size_build_grid(e, e->lean_ok ? sweep_n_slabs(e->sweep_bits_lean, e->sweep_slab_bits_lean) : 1, &e->sweep_build_blocks_lean);
         if (rc < 0) return rc;
     }
     CU(cudaMalloc(&w.desc, sizeof(unsigned long long) * (size_t)cells));
@@ -750,6 +749,7 @@ int ssb_agent_step(ssb_engine_t *e, int32_t t, double prev_mean_wealth, void *st
         w.sub_bits = lean ? SWEEP_LEAN_SUB_BITS : 0;
         w.n_keys = (1 << w.bucket_bits) << w.sub_bits;
         const int n_slabs = sweep_n_slabs(w.bucket_bits, w.slab_bits);
+        w.lines_only = n_slabs <= 4;
 #define SUB_EVENT(k) do { if (e->timing) CU(cudaEventRecord(e->sub_ev[k], st)); } while (0)
         SUB_EVENT(0);
         if (box) {      // this rank's columns of the done bitmap, the gates of its own list
@@ -768,7 +768,7 @@ int ssb_agent_step(ssb_engine_t *e, int32_t t, double prev_mean_wealth, void *st
         // (the build stages the descriptors of the halo: the neighbours' agents must have left theirs)
         if (box) { k_shard_barrier<<<1, 32, 0, st>>>(e->sh, nullptr, overflow); LAUNCHED(e); }
         SUB_EVENT(1);
-        k_sweep_build<<<e->sweep_build_blocks, SWEEP_BUILD_THREADS, sweep_build_smem_bytes(w.rb, w.kb, w.halo, n_slabs), st>>>(c, w); LAUNCHED(e);
+        k_sweep_build<<<lean ? e->sweep_build_blocks_lean : e->sweep_build_blocks_generic, SWEEP_BUILD_THREADS, sweep_build_smem_bytes(w.rb, w.kb, w.halo, n_slabs), st>>>(c, w); LAUNCHED(e);
         if (!box) { k_sweep_clear<<<e->num_sms * 8, 256, 0, st>>>(c, w); LAUNCHED(e); }
         SUB_EVENT(2);
         if (lean) {
@@ -1052,7 +1052,7 @@ int ssb_set_shard_sweep(ssb_engine_t *e, void *desc, void *done, void *pcell) {
     const long long T = (long long)e->sweep_lean_blocks * LEAN_THREADS;
     e->sweep_bits_lean = sweep_bucket_bits(e->local_slots, T, e->p.id_bits, SWEEP_MAX_KEY_BITS - SWEEP_LEAN_SUB_BITS);
     e->sweep_slab_bits_lean = sweep_slab_bits(e->local_slots, T);
-    int rc = size_build_grid(e, sweep_n_slabs(e->sweep_bits_lean, e->sweep_slab_bits_lean));
+    int rc = size_build_grid(e, sweep_n_slabs(e->sweep_bits_lean, e->sweep_slab_bits_lean), &e->sweep_build_blocks_lean);
     if (rc < 0) return rc;
     e->shard_sweep = true;
     e->scheduler = SSB_SCHED_SWEEP;

@@ -58,6 +58,7 @@ struct SweepCtx {
     int32_t bucket_bits;             // priority buckets = 1 << bucket_bits
     int32_t sub_bits;                // bucket keys per priority bucket = 1 << sub_bits (lean path: by range)
     int32_t slab_bits;               // slabs = 1 << min(bucket_bits, slab_bits) (sweep_slab_bits)
+    int32_t lines_only;              // few slabs (most predecessors are near ones): every agent with predecessors gets a mask line
     // x-slab sharding (ssb_shard.cuh; world 1: slot0 = 0, all tiles, no peers): this rank walks ITS slots and tiles; the
     // descriptors, the done bitmap and the packed cells are stitched arrays, the ranks publish their watermarks in their
     // control pages and every rank waits on the smallest
@@ -90,6 +91,14 @@ __device__ __forceinline__ unsigned long long sweep_ld_relaxed_sys_if(const unsi
     unsigned long long v;
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tmov.u64 %0, 0xffffffffffffffff;\n\t@p ld.relaxed.sys.global.u64 %0, [%1];\n\t}"
                  : "=l"(v) : "l"(p), "r"(on) : "memory");
+    return v;
+}
+// 32-bit halves of the done words (little endian: bit b of word k is bit b & 31 of half 2 k + (b >> 5)), under a predicate
+template <bool SYS>
+__device__ __forceinline__ uint32_t sweep_ld32_relaxed_if(const uint32_t *p, uint32_t on) {
+    uint32_t v;
+    if (SYS) asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tmov.u32 %0, 0xffffffff;\n\t@p ld.relaxed.sys.global.u32 %0, [%1];\n\t}" : "=r"(v) : "l"(p), "r"(on) : "memory");
+    else asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tmov.u32 %0, 0xffffffff;\n\t@p ld.relaxed.gpu.global.u32 %0, [%1];\n\t}" : "=r"(v) : "l"(p), "r"(on) : "memory");
     return v;
 }
 __device__ __forceinline__ void sweep_fence() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
@@ -210,7 +219,7 @@ __host__ __device__ inline int sweep_build_smem_bytes(int rb, int kb, int halo, 
     return (FLOW_TX + 2 * halo) * (FLOW_TY + 2 * halo) * 4 + n_slabs * (FLOW_TX + 2 * halo) * 16 + FLOW_TX * FLOW_TY * 2 + sweep_tables_bytes(rb, kb, halo) + 16;
 }
 
-__global__ void __launch_bounds__(SWEEP_BUILD_THREADS) k_sweep_build(DevCtx c, SweepCtx w) {
+__global__ void __launch_bounds__(SWEEP_BUILD_THREADS, 3) k_sweep_build(DevCtx c, SweepCtx w) {
     extern __shared__ __align__(16) unsigned char sweep_smem[];
     __shared__ int sh_tile, sh_n_agents, sh_class[16];
     const int R = w.halo, sw = FLOW_TX + 2 * R, sh = FLOW_TY + 2 * R;
@@ -276,6 +285,25 @@ __global__ void __launch_bounds__(SWEEP_BUILD_THREADS) k_sweep_build(DevCtx c, S
         }
         __syncthreads();
         const int n_agents = sh_n_agents;
+        if (w.lines_only) {      // one pass: the column masks stream into the agent's line, 16 bytes at a time
+            for (int a = tid; a < n_agents; a += SWEEP_BUILD_THREADS) {
+                const int sc = agents[a], lx = sc / sh, ly = sc - lx * sh;
+                const uint32_t gcell = (uint32_t)((tx * FLOW_TX + lx - R) * H + (ty * FLOW_TY + ly - R));
+                const uint32_t index = (uint32_t)(__ldg(w.desc + gcell) >> 32);
+                uint4 *out = reinterpret_cast<uint4 *>(w.preds + (size_t)index * SWEEP_COLS);
+                uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+                uint32_t any_pred = 0u;
+                sweep_near_masks(tile, lx, ly, cell[sc], w.rb, w.kb, [&](int col, uint32_t m) {
+                    const int u = col & 3;
+                    any_pred |= m;
+                    if (u == 0) acc.x = m; else if (u == 1) acc.y = m; else if (u == 2) acc.z = m; else acc.w = m;
+                    if (u == 3) { out[col >> 2] = acc; acc = make_uint4(0u, 0u, 0u, 0u); }
+                });
+                out[(2 * R + 1) >> 2] = acc;                    // the last, partial group (2 R + 1 columns; the words behind them are not read)
+                if (any_pred) w.gate[index] = SWEEP_GATE_LINE;
+            }
+            continue;
+        }
         for (int a = tid; a < n_agents; a += SWEEP_BUILD_THREADS) {
             const int sc = agents[a], lx = sc / sh, ly = sc - lx * sh;
             unsigned long long gate = 0ull;
@@ -350,12 +378,49 @@ __global__ void __launch_bounds__(256) k_lean_cells(DevCtx c, SweepCtx w, LeanCt
 // May list entry i run?  The caller has compared the watermark; this is the individual part: the done bits of the near
 // predecessors in the entry's gate.  Straight-line code: the (at most six) done words are loaded under predicates and
 // are in flight together.  pos: the entry's start cell.
+// ... of a mask line: straight-line code like the gate -- the eight 16-byte loads of the line are in flight together, then
+// the done words of its columns in batches of eight (the 2 halo + 1 rows of a column lie in one or two 64-bit words)
 template <bool SYS>
-__device__ __noinline__ bool sweep_line_ready(const SweepCtx &w, int i, int x, int y, int W, int H) {
+__device__ __noinline__ bool sweep_line_ready_seam(const SweepCtx &w, int i, int x, int y, int W, int H) {
     const uint32_t *line = w.preds + (size_t)i * SWEEP_COLS;
     uint32_t masks[SWEEP_COLS];
-    for (int k = 0; k < SWEEP_COLS; k++) masks[k] = __ldg(line + k);
+    for (int k = 0; k <= 2 * w.halo; k++) masks[k] = __ldg(line + k);
     return sweep_line_done(masks, [&](size_t wd) { return SYS ? ld_relaxed_sys(w.done + wd) : sweep_ld_relaxed(w.done + wd); }, x, y, W, H, w.halo);
+}
+template <bool SYS>
+__device__ __forceinline__ bool sweep_line_ready(const SweepCtx &w, int i, int x, int y, int W, int H) {
+    const int R = w.halo, span = 2 * R + 1, y0 = y - R;
+    if (y0 < 0 || y0 + span > H) return sweep_line_ready_seam<SYS>(w, i, x, y, W, H);      // the window crosses the torus seam in y
+    const uint4 *pm = reinterpret_cast<const uint4 *>(w.preds + (size_t)i * SWEEP_COLS);
+    uint4 v[8];
+#pragma unroll
+    for (int g = 0; g < 8; g++) v[g] = __ldg(pm + g);
+    const int hpc = 2 * sweep_done_wpc(H), shift = y0 & 31;        // 32-bit halves per column; the window lies in one or two of them
+    const bool two = shift + span > 32;
+    const uint32_t *col0 = reinterpret_cast<const uint32_t *>(w.done) + (y0 >> 5);
+    bool ok = true;
+#pragma unroll
+    for (int g = 0; g < 8; g++) {
+        if (4 * g >= span) break;
+        const uint32_t m[4] = {v[g].x, v[g].y, v[g].z, v[g].w};
+        uint32_t lo[4], hi[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int col = 4 * g + u;
+            const uint32_t on = col < span ? m[u] : 0u;
+            int cx = x - R + col;
+            if (cx < 0) cx += W; else if (cx >= W) cx -= W;
+            const uint32_t *p = col0 + (size_t)cx * hpc;
+            lo[u] = sweep_ld32_relaxed_if<SYS>(p, on);
+            hi[u] = sweep_ld32_relaxed_if<SYS>(p + 1, two ? on : 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint32_t on = 4 * g + u < span ? m[u] : 0u;
+            ok &= (__funnelshift_r(lo[u], hi[u], shift) & on) == on;
+        }
+    }
+    return ok;
 }
 template <bool SYS = false>
 __device__ __forceinline__ bool sweep_gate_ready(const SweepCtx &w, unsigned long long gate, int i, int pos, int W, int H) {

@@ -99,10 +99,11 @@ struct SweepTile {
 };
 
 // The NEAR predecessors of the agent with low descriptor word `la` on staged cell (lx, ly): the agents of its own slab
-// and of the slab before it that have a smaller priority and an intersecting footprint.  emit(dx, dy) for each.
-// RB / KB: the largest range / dilation of any agent in this step.
+// and of the slab before it that have a smaller priority and an intersecting footprint, column by column:
+// emit_col(column index dx + halo, mask with bit dy + halo per predecessor) for every column of the conflict region
+// (also the empty ones).  RB / KB: the largest range / dilation of any agent in this step.
 template <class F>
-__host__ __device__ __forceinline__ void sweep_near_preds(const SweepTile &tile, int lx, int ly, uint32_t la, int RB, int KB, F emit) {
+__host__ __device__ __forceinline__ void sweep_near_masks(const SweepTile &tile, int lx, int ly, uint32_t la, int RB, int KB, F emit_col) {
     const int ra = sweep_r(la), ka = sweep_k(la), halo = tile.halo, hs = halo + 1;
     const uint32_t pa = sweep_prio(la);
     const int g = (int)(pa >> tile.slab_prio_shift);
@@ -113,21 +114,36 @@ __host__ __device__ __forceinline__ void sweep_near_preds(const SweepTile &tile,
     for (int dx = -halo; dx <= halo; dx++) {
         const int adx = dx < 0 ? -dx : dx;
         const int h = any[adx];
-        if (h < 0) continue;
-        const int col = lx + dx, y0 = ly - h;
-        const unsigned long long both[2] = {m1[col * 2] | m0[col * 2], m1[col * 2 + 1] | m0[col * 2 + 1]};
-        unsigned long long bits = flow_mask_window(both, y0, 2 * h + 1);
-        if (dx == 0) bits &= ~(1ull << h);
-        const uint32_t *column = tile.cell + col * tile.sh + y0;
-        while (bits) {
-            const int j = flow_ctz64(bits);
-            bits &= bits - 1;
-            const uint32_t lb = column[j];
-            if (sweep_prio(lb) >= pa) continue;
-            const int dy = j - h, ady = dy < 0 ? -dy : dy;
-            if (ady <= pair[sweep_k(lb) * k_stride + sweep_r(lb) * hs + adx]) emit(dx, dy);
+        uint32_t m = 0;
+        if (h >= 0) {
+            const int col = lx + dx, y0 = ly - h;
+            const unsigned long long both[2] = {m1[col * 2] | m0[col * 2], m1[col * 2 + 1] | m0[col * 2 + 1]};
+            unsigned long long bits = flow_mask_window(both, y0, 2 * h + 1);
+            if (dx == 0) bits &= ~(1ull << h);
+            const uint32_t *column = tile.cell + col * tile.sh + y0;
+            while (bits) {
+                const int j = flow_ctz64(bits);
+                bits &= bits - 1;
+                const uint32_t lb = column[j];
+                if (sweep_prio(lb) >= pa) continue;
+                const int dy = j - h, ady = dy < 0 ? -dy : dy;
+                if (ady <= pair[sweep_k(lb) * k_stride + sweep_r(lb) * hs + adx]) m |= 1u << (dy + halo);
+            }
         }
+        emit_col(dx + halo, m);
     }
+}
+// ... one by one: emit(dx, dy)
+template <class F>
+__host__ __device__ __forceinline__ void sweep_near_preds(const SweepTile &tile, int lx, int ly, uint32_t la, int RB, int KB, F emit) {
+    const int halo = tile.halo;
+    sweep_near_masks(tile, lx, ly, la, RB, KB, [&](int col, uint32_t m) {
+        while (m) {
+            const int j = flow_ctz64((unsigned long long)m);
+            m &= m - 1;
+            emit(col - halo, j - halo);
+        }
+    });
 }
 
 // The DONE bitmap: one bit per cell -- "the agent that started the step on this cell has finished" -- in 64-bit words

@@ -160,7 +160,9 @@ def test_slabs_equal_the_single_gpu_run(name, overrides, steps, world):
     errors = [ln for ln in log.splitlines() if "Error" in ln or "rror:" in ln or "SystemExit" in ln or "differs" in ln]
     assert res.returncode == 0, "\n".join(errors[:12]) or log[-3000:]
     assert res.stdout.count("SHARDED_PARITY_OK") == world, res.stdout[-2000:]
-    # the last two cases run the sweep scheduler when the map gives every rank slabs of whole 64-column tiles
-    sweepable = SHARDED_CASES.index((name, overrides, steps)) >= len(SHARDED_CASES) - 2 and 128 * world <= overrides["environmentWidth"]
-    want = "sweep" if sweepable else "rounds"
-    assert res.stdout.count(f"scheduler {want} ") == world, f"expected the {want} scheduler on every rank:\n" + res.stdout[-1500:]
+    # every rank runs the same scheduler; the last two cases must run the sweep when the map gives every rank slabs of whole
+    # 64-column tiles whatever the population balance
+    counts = {k: res.stdout.count(f"scheduler {k} ") for k in ("sweep", "rounds")}
+    assert sorted(counts.values()) == [0, world], f"the ranks disagree on the scheduler: {counts}"
+    if SHARDED_CASES.index((name, overrides, steps)) >= len(SHARDED_CASES) - 2 and 128 * world <= overrides["environmentWidth"]:
+        assert counts["sweep"] == world, "expected the sweep scheduler:\n" + res.stdout[-1500:]

@@ -1,5 +1,16 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests/test_sharded.py -m gpu -x -q -k "320 or 512 or overrides7 or overrides8" > gpurun_out/r2_d2_sharded.log 2>&1; echo "pytest rc=$?"
-tail -25 gpurun_out/r2_d2_sharded.log
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 --skip-cpu > gpurun_out/r2_d2_bench_n2.json 2> gpurun_out/r2_d2_bench_n2.err; echo "bench2 rc=$?"
-tail -c 3000 gpurun_out/r2_d2_bench_n2.json; tail -5 gpurun_out/r2_d2_bench_n2.err
+for n in 8 4 2; do
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n bench.py --gpus $n --steps 5 --warmup 3 --skip-cpu > gpurun_out/r2_d5_bench_n$n.json 2> gpurun_out/r2_d5_bench_n$n.err; echo "bench$n rc=$?"
+python - <<PY
+import json
+l=json.loads(open("gpurun_out/r2_d5_bench_n$n.json").read().strip().splitlines()[-1])
+print($n, l["value"], l["ms_per_step"], l["state_digest"]["value"], {k: round(v,2) for k,v in l["roofline"]["phase_ms"].items()}, l["e2e"]["value"], l["e2e"]["split_rank0"])
+PY
+tail -2 gpurun_out/r2_d5_bench_n$n.err
+done
+timeout 600 python bench.py --gpus 1 --steps 5 --warmup 3 --skip-cpu --skip-extra > gpurun_out/r2_d5_bench_n1.json 2> gpurun_out/r2_d5_bench_n1.err; echo "bench1 rc=$?"
+python - <<PY
+import json
+l=json.loads(open("gpurun_out/r2_d5_bench_n1.json").read().strip().splitlines()[-1])
+print(1, l["value"], l["ms_per_step"], l["state_digest"]["value"], {k: round(v,2) for k,v in l["roofline"]["phase_ms"].items()}, l["e2e"]["value"])
+PY
