@@ -8,8 +8,8 @@ A "step" is one full Sugarscape timestep (environment stencil, agent loop, remov
 replacement, stats reductions) in scalable RNG mode.  Default workload S2:
 16384 x 16384 map, 25 M agents, combat_limited rules -- the same simulation at every N (strong
 scaling): one GPU holds it whole, N > 1 shards it by x-slabs over NVLink-stitched memory
-(sugarscape_b200/sharded.py), results bit-identical to the single-GPU run ("state_digest" is the
-same at every N).  --workload S1 is the 4096 x 4096 / 1.6 M agents / reproduction_basic shape.
+(sugarscape_b200/sharded.py; the ranks run the sweep scheduler over their slabs), results bit-identical to the
+single-GPU run ("state_digest" is the same at every N).  --workload S1 is the 4096 x 4096 / 1.6 M agents / reproduction_basic shape.
 
 Timed regions
   value   K steps enqueued back to back, state resident in HBM, CUDA events on the launching
@@ -420,6 +420,8 @@ def device_resident_leg(job, eng, args, barrier, dev):
     for _ in range(min(args.steps, 10)):
         phase_acting.append(int(eng.stats_history(t).population))
         t += 1
+        if job.sharded:
+            barrier()               # (the ranks read their events at their own pace: start every timed step together)
         eng.step(t, 0.0)
         for k, v in eng.timing().items():
             phase.setdefault(k, []).append(v)
@@ -631,7 +633,8 @@ def main():
 
     if rank == 0:
         if sharded_run:
-            parallelism = f"x-slabs over {world} GPUs (one simulation; NVLink-stitched state, box-wide commit rounds)"
+            how = "every rank sweeps its slab, box-wide watermark" if res["scheduler"] == "sweep" else "box-wide commit rounds"
+            parallelism = f"x-slabs over {world} GPUs (one simulation; NVLink-stitched state, {how})"
         else:
             parallelism = "replicas" if world > 1 else "single GPU"
         line = {

@@ -202,6 +202,10 @@ typedef struct ssb_stats {
     int64_t env_capacity_total;         /* sum maxSugar + maxSpice (added once at t == 1)       */
     double  lorenz_weighted_sum;        /* sum_i (cumulative wealth after i sorted agents), trapezoid form */
     int64_t rounds;                     /* mode S commit rounds of this step                    */
+    double  gini_area;                  /* exact mode: the Lorenz curve area of updateGiniCoefficient (sugarscape.py:913-934)
+                                           accumulated in the reference's own order -- total = sum of the sorted wealths, one
+                                           division per element, / numAgents -- so that round(..., 3) can never differ;
+                                           scalable mode: -1 (the host uses lorenz_weighted_sum / sum_wealth / population)  */
 } ssb_stats_t;
 
 typedef struct ssb_engine ssb_engine_t;

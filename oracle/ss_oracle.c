@@ -1931,6 +1931,21 @@ void orc_stats(const ssb_params_t *p, const ssb_grid_t *g, const ssb_agents_t *a
     for (int64_t i = 0; i + 1 < n; i++) { cum += wealths[i]; area += cum; }
     if (n > 0) { cum += wealths[n - 1]; area += cum / 2; }
     out->lorenz_weighted_sum = area;
+    /* exact mode: updateGiniCoefficient's own arithmetic (sugarscape.py:913-934), operation by operation */
+    out->gini_area = -1.0;
+    if (p->rng_mode == SSB_RNG_EXACT && n > 0) {
+        double total = 0;
+        for (int64_t i = 0; i < n; i++) total += wealths[i];          /* sum(agentWealths), sorted order */
+        double lorenz = 0;
+        if (total != 0) {
+            double c = 0;
+            for (int64_t i = 0; i + 1 < n; i++) { c += wealths[i]; lorenz += c / total; }
+            c += wealths[n - 1];
+            lorenz += (c / 2) / total;
+            lorenz /= (double)n;
+        }
+        out->gini_area = lorenz;                                       /* total == 0: area 0 -> coefficient 1 */
+    }
     free(wealths);
     /* this step's dead (sugarscape.py:1213-1265) */
     out->n_dead = 0;

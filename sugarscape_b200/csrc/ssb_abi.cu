@@ -939,7 +939,8 @@ int ssb_reduce_stats(ssb_engine_t *e, int32_t t, void *stream_) {
     k_lorenz_reset<<<8, 256, 0, st>>>(e->d_lorenz_hist); LAUNCHED(e);
     k_lorenz_hist<<<e->num_sms * 4, LORENZ_THREADS, 0, st>>>((const double *)e->d_keys_a, n_ptr, e->d_lorenz_hist); LAUNCHED(e);
     k_lorenz_from_hist<<<1, LORENZ_THREADS, 0, st>>>(e->d_lorenz_hist, n_ptr, e->d_stats); LAUNCHED(e);
-    const unsigned long long *needed = e->d_lorenz_hist;
+    // (exact mode always sorts: the ordered Gini pass below walks the sorted wealths)
+    const unsigned long long *needed = e->p.rng_mode == SSB_RNG_EXACT ? nullptr : e->d_lorenz_hist;
     uint64_t *src = e->d_keys_a, *dst = e->d_keys_b;
     for (int shift = 0; shift < 64; shift += 8) {
         k_radix_hist<<<tiles, RADIX_THREADS, 0, st>>>(src, n_ptr, shift, e->d_radix_hist, varying, needed); LAUNCHED(e);
@@ -949,6 +950,7 @@ int ssb_reduce_stats(ssb_engine_t *e, int32_t t, void *stream_) {
     }
     const int lb = e->num_sms * 4;
     k_lorenz<<<lb, 256, 0, st>>>((const double *)src, n_ptr, e->d_lorenz_blocks, needed); LAUNCHED(e);
+    if (e->p.rng_mode == SSB_RNG_EXACT) { k_gini_ordered<<<1, 32, 0, st>>>((const double *)src, n_ptr, e->d_stats); LAUNCHED(e); }
     k_lorenz_final<<<1, 1, 0, st>>>(e->d_lorenz_blocks, lb, e->d_stats, e->d_ring + (((t % SSB_STATS_RING) + SSB_STATS_RING) % SSB_STATS_RING), needed); LAUNCHED(e);
     if (e->timing) { CU(cudaEventRecord(e->ev[4], st)); e->ev_recorded = true; }
     return 0;

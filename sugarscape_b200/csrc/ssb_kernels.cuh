@@ -474,6 +474,7 @@ __global__ void __launch_bounds__(STATS_THREADS) k_stats_final(DevCtx c, const S
     out->env_capacity_total = r.env_capacity_total;
     out->env_wealth_created = 0;   // closed form, filled in by the host
     out->rounds = c.a.counters[SSB_C_ROUNDS];
+    out->gini_area = -1.0;
 }
 
 // sharded: {population, OR, AND of the wealth keys} of this rank for the all-gather
@@ -604,6 +605,25 @@ __global__ void __launch_bounds__(256) k_lorenz(const double *sorted, const int6
         __syncthreads();
     }
     if (threadIdx.x == 0) block_sums[blockIdx.x] = sm[0];
+}
+
+// Exact mode: the Lorenz area in the reference's own order of operations (updateGiniCoefficient, sugarscape.py:913-934) over
+// the ascending wealth keys -- one thread, like everything that is ordered in that mode.
+__global__ void k_gini_ordered(const double *sorted, const int64_t *n_ptr, ssb_stats_t *out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const long long n = *n_ptr;
+    if (n <= 0) { out->gini_area = -1.0; return; }
+    double total = 0;
+    for (long long i = 0; i < n; i++) total += sorted[i];
+    double lorenz = 0;
+    if (total != 0) {
+        double cum = 0;
+        for (long long i = 0; i + 1 < n; i++) { cum += sorted[i]; lorenz += cum / total; }
+        cum += sorted[n - 1];
+        lorenz += (cum / 2) / total;
+        lorenz /= (double)n;
+    }
+    out->gini_area = lorenz;
 }
 
 __global__ void k_lorenz_final(const double *block_sums, int n_blocks, ssb_stats_t *out, ssb_stats_t *ring_slot, const unsigned long long *needed) {

@@ -173,7 +173,7 @@ class Stats(C.Structure):
         ("n_born", C.c_int64), ("n_replaced", C.c_int64), ("n_acted", C.c_int64),
         ("env_wealth_total", C.c_int64), ("env_wealth_created", C.c_int64),
         ("env_capacity_total", C.c_int64),
-        ("lorenz_weighted_sum", C.c_double), ("rounds", C.c_int64),
+        ("lorenz_weighted_sum", C.c_double), ("rounds", C.c_int64), ("gini_area", C.c_double),
     ]
 
 

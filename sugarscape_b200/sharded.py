@@ -173,7 +173,7 @@ def combine_stats(parts):
             v = vals[0]
         elif field in ("rounds",):
             v = max(vals)
-        elif field == "lorenz_weighted_sum":
+        elif field in ("lorenz_weighted_sum", "gini_area"):
             v = vals[0]
         elif field == "max_wealth":
             v = max((p.max_wealth for p in live), default=0.0)

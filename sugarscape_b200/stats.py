@@ -311,6 +311,8 @@ class StatsBuilder:
         """updateGiniCoefficient (sugarscape.py:913-934) from the sorted-wealth reduction."""
         if n == 0:
             return 0
+        if st.gini_area >= 0:          # exact mode: the area accumulated on the device in the reference's own order
+            return round((0.5 - st.gini_area) / 0.5, 3)
         total = st.sum_wealth
         if total == 0:
             return 1

@@ -84,8 +84,6 @@ def run_case(base, ov, steps):
             if k.endswith(("eanMovement", "eanMetabolism", "gentTotalMetabolism")) and isinstance(ref_logs[t][k], (int, float)) \
                     and ref_logs[t][k] > 1e6:
                 continue          # depressed lineages: the reference's endowments outgrow i32, the engine saturates
-            if k.endswith("iniCoefficient") and abs(rs[k] - ref_logs[t][k]) <= 0.0011:
-                continue          # Lorenz area summed in a different order: 1 ulp can flip round(x, 3)
             if not _close(rs[k], ref_logs[t][k]):
                 return f"t={t} log key {k} differs: {rs[k]} vs {ref_logs[t][k]}"
     families = sorted(state.ext.families) if state.ext is not None else []
