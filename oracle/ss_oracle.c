@@ -415,13 +415,24 @@ static int is_fertile(const ctx_t *c, int s) {
            (c->a.fert_factor[s] + dis_mod(s, DM_FERTILITY)) > 0;
 }
 
-/* the four von Neumann neighbours in the reference's dict order N, S, E, W (cell.py:61-75) */
-static void neighbours4(const ctx_t *c, int pos, int32_t out[4]) {
+/* the von Neumann neighbours in the reference's dict order N, S, E, W (cell.py:61-75); returns their number.
+ * environmentWraparound = false (SSB_F_NOWRAP): cell.py:47-50, 98-121 -- the neighbours across the edge are missing, and the
+ * reference's test for the south neighbour (`y + 1 < height - 1` -> None) leaves one to the last two rows only */
+static int neighbours4(const ctx_t *c, int pos, int32_t out[4]) {
     int W = c->p->width, H = c->p->height, x = pos / H, y = pos % H;
-    out[0] = x * H + wrapi(y - 1, H);
-    out[1] = x * H + wrapi(y + 1, H);
-    out[2] = wrapi(x + 1, W) * H + y;
-    out[3] = wrapi(x - 1, W) * H + y;
+    if (!(c->p->flags & SSB_F_NOWRAP)) {
+        out[0] = x * H + wrapi(y - 1, H);
+        out[1] = x * H + wrapi(y + 1, H);
+        out[2] = wrapi(x + 1, W) * H + y;
+        out[3] = wrapi(x - 1, W) * H + y;
+        return 4;
+    }
+    int n = 0;
+    if (!(y - 1 < 0)) out[n++] = x * H + (y - 1 + H) % H;
+    if (!(y + 1 < H - 1)) out[n++] = x * H + (y + 1 + H) % H;
+    if (!(x + 1 > W - 1)) out[n++] = ((x + 1 + W) % W) * H + y;
+    if (!(x - 1 < 0)) out[n++] = ((x - 1 + W) % W) * H + y;
+    return n;
 }
 
 static int alloc_slot(ctx_t *c) {
@@ -769,8 +780,8 @@ static void do_lending(ctx_t *c, int s) {
     if (rate > 1) rate = 1;
     int32_t nb[4], borrowers[4];
     int nbw = 0;
-    neighbours4(c, a->pos[s], nb);
-    for (int i = 0; i < 4; i++) {
+    const int n_nb = neighbours4(c, a->pos[s], nb);
+    for (int i = 0; i < n_nb; i++) {
         int o = c->g.occ[nb[i]];
         if (o < 0 || !agent_alive(c, o)) continue;
         /* isBorrower (1226-1229) */
@@ -935,8 +946,8 @@ static void do_disease(ctx_t *c, int s) {
     if (count == 0) return;
     int32_t nb4[4], neighbors[4];
     int nn = 0;
-    neighbours4(c, c->a.pos[s], nb4);
-    for (int i = 0; i < 4; i++) { int o = c->g.occ[nb4[i]]; if (o >= 0 && agent_alive(c, o)) neighbors[nn++] = o; }
+    const int n_nb = neighbours4(c, c->a.pos[s], nb4);
+    for (int i = 0; i < n_nb; i++) { int o = c->g.occ[nb4[i]]; if (o >= 0 && agent_alive(c, o)) neighbors[nn++] = o; }
     int spread = 0;
     rng_shuffle_i32(c->rng, neighbors, nn);
     for (int k = 0; k < nn; k++) {
@@ -1139,9 +1150,9 @@ static double ethical_value(ctx_t *c, int s, int my_r, const int32_t *hood, int 
         max_site += w < max_loot ? w : max_loot;
     }
     int32_t nb4[4];
-    neighbours4(c, cell, nb4);
+    const int n_nb = neighbours4(c, cell, nb4);
     double neighbor_wealth = 0;
-    for (int i = 0; i < 4; i++) neighbor_wealth += c->g.sugar[nb4[i]] + c->g.spice[nb4[i]];
+    for (int i = 0; i < n_nb; i++) neighbor_wealth += c->g.sugar[nb4[i]] + c->g.spice[nb4[i]];
     const double lookahead = g_eth->lookahead_factor[s];
     /* len(self.findNeighborhood(cell)): live agents in MY cross moved to `cell`, plus myself */
     double future_hood = 1;
@@ -1167,7 +1178,8 @@ static double ethical_value(ctx_t *c, int s, int my_r, const int32_t *hood, int 
         const double discount = g_eth->lookahead_factor[nb] != 0 ? g_eth->lookahead_discount[nb] : 0;
         double future_duration = metab > 0 ? (site - metab) / metab : site;
         future_duration = max_site > 0 ? future_duration / max_site : 0;
-        const double future_intensity = neighbor_wealth / (g_eth->global_max_wealth * 4);
+        int32_t nb_cells[4];
+        const double future_intensity = neighbor_wealth / (g_eth->global_max_wealth * neighbours4(c, a->pos[nb], nb_cells));   /* len(neighbor.cell.neighbors) */
         int32_t tc[MAX_CAND], td[MAX_CAND];
         const int in_range = rn > 0 ? enumerate_cross(c, a->pos[nb], rn, tc, td) : 0;          /* len(neighbor.cellsInRange) */
         const double extent = in_range > 0 ? (double)n_hood / in_range : 1;
@@ -1307,10 +1319,10 @@ static int move_to_best_cell(ctx_t *c, int s) {
 static void do_tagging(ctx_t *c, int s) {
     if (!(c->p->flags & SSB_F_TAGS) || !(c->p->flags & SSB_F_TAGGING)) return;
     int32_t nb[4];
-    neighbours4(c, c->a.pos[s], nb);
+    const int n_nb = neighbours4(c, c->a.pos[s], nb);
     rng_at(c->rng, SITE_TAGGING);
-    rng_shuffle_i32(c->rng, nb, 4);
-    for (int i = 0; i < 4; i++) {
+    rng_shuffle_i32(c->rng, nb, n_nb);
+    for (int i = 0; i < n_nb; i++) {
         int o = c->g.occ[nb[i]];
         if (o < 0) continue;
         uint32_t position = rng_below(c->rng, (uint32_t)c->p->tag_len);
@@ -1328,8 +1340,8 @@ static void do_trading(ctx_t *c, int s) {
     double sum_sugar_price = 0, sum_spice_price = 0;
     find_mrs(c, s);
     int32_t nb[4], traders[4]; int n = 0;
-    neighbours4(c, a->pos[s], nb);
-    for (int i = 0; i < 4; i++) {
+    const int n_nb = neighbours4(c, a->pos[s], nb);
+    for (int i = 0; i < n_nb; i++) {
         int o = c->g.occ[nb[i]];
         if (o >= 0 && agent_alive(c, o) && a->mrs[o] != a->mrs[s]) traders[n++] = o;
     }
@@ -1381,8 +1393,8 @@ static void do_trading(ctx_t *c, int s) {
 
 static int empty_neighbours(const ctx_t *c, int pos, int32_t *out) {
     int32_t nb[4]; int n = 0;
-    neighbours4(c, pos, nb);
-    for (int i = 0; i < 4; i++) if (c->g.occ[nb[i]] < 0) out[n++] = nb[i];
+    const int n_nb = neighbours4(c, pos, nb);
+    for (int i = 0; i < n_nb; i++) if (c->g.occ[nb[i]] < 0) out[n++] = nb[i];
     return n;
 }
 
@@ -1391,11 +1403,11 @@ static void do_reproduction(ctx_t *c, int s) {
     ssb_agents_t *a = &c->a;
     if (!agent_alive(c, s) || !is_fertile(c, s)) return;
     int32_t nb[4], own_empty[4];
-    neighbours4(c, a->pos[s], nb);
+    const int n_nb = neighbours4(c, a->pos[s], nb);
     rng_at(c->rng, SITE_REPRODUCTION);
-    rng_shuffle_i32(c->rng, nb, 4);
+    rng_shuffle_i32(c->rng, nb, n_nb);
     int n_own = empty_neighbours(c, a->pos[s], own_empty);
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < n_nb; k++) {
         int m = c->g.occ[nb[k]];
         if (m < 0 || !agent_alive(c, m)) continue;
         int compatible = ((a->sex[s] == SSB_SEX_FEMALE && a->sex[m] == SSB_SEX_MALE) ||
@@ -1539,8 +1551,8 @@ static void agent_transaction(ctx_t *c, int s) {
     int pos = move_to_best_cell(c, s);
     if (g_social) {      /* updateNeighbors -> updateSocialNetwork -> updateFriends, neighbours in N, S, E, W order */
         int32_t nb4[4];
-        neighbours4(c, pos, nb4);
-        for (int i = 0; i < 4; i++) { int o = c->g.occ[nb4[i]]; if (o >= 0) update_friends(c, s, o); }
+        const int n_nb = neighbours4(c, pos, nb4);
+        for (int i = 0; i < n_nb; i++) { int o = c->g.occ[nb4[i]]; if (o >= 0) update_friends(c, s, o); }
     }
     collect(c, s, pos);
     if (g_misc) {        /* doUniversalIncome (agent.py:708-714): spice first */
@@ -1660,6 +1672,15 @@ void orc_env_step(const ssb_params_t *p, const ssb_grid_t *g, int32_t t) {
         for (int x = 0; x < W; x++)
             for (int y = 0; y < H; y++) {
                 double m = 0;
+                if (p->flags & SSB_F_NOWRAP) {       /* cell.py:104-109 over the neighbours that exist (N, S, E, W order) */
+                    int n = 0;
+                    if (!(y - 1 < 0)) { m += g->pollution[x * H + y - 1]; n++; }
+                    if (!(y + 1 < H - 1)) { m += g->pollution[x * H + (y + 1) % H]; n++; }
+                    if (!(x + 1 > W - 1)) { m += g->pollution[(x + 1) * H + y]; n++; }
+                    if (!(x - 1 < 0)) { m += g->pollution[(x - 1) * H + y]; n++; }
+                    g->pollution_flux[x * H + y] = m / n;
+                    continue;
+                }
                 m += g->pollution[x * H + wrapi(y - 1, H)];
                 m += g->pollution[x * H + wrapi(y + 1, H)];
                 m += g->pollution[wrapi(x + 1, W) * H + y];

@@ -37,7 +37,10 @@ def build(force=False, verbose=False):
     extra = []
     if os.environ.get("SSB_GROUP_LANES"):      # tuning builds: lanes cooperating on one agent (4, 8, 16, 32)
         extra.append("-DSSB_GROUP_LANES=" + os.environ["SSB_GROUP_LANES"])
-    if os.environ.get("SSB_PARALLEL_ETHICS"):  # mode E with decision models: score the candidate cells on all lanes (round 2: to be measured)
+    # mode E with decision models: the candidate cells are scored on all lanes (SSB_PARALLEL_ETHICS=0: on lane 0, the form the
+    # host-compiled device source runs).  Round 2 on a B200: the 25 decision-model cases pass in both forms; determinism.json
+    # through the drop-in driver runs 1.2-1.7 x faster in this one (profiles/r2_examples_driver_*.json)
+    if os.environ.get("SSB_PARALLEL_ETHICS", "1") != "0":
         extra.append("-DSSB_PARALLEL_ETHICS")
     if os.environ.get("SSB_SLAB_BITS"):        # tuning builds: slabs of the sweep's priority order = 1 << bits
         extra.append("-DSSB_SLAB_BITS=" + os.environ["SSB_SLAB_BITS"])

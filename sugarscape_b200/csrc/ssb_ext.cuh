@@ -263,8 +263,8 @@ __device__ __noinline__ void do_disease(const DevCtx &c, int s, Rng &rng) {
     if (count == 0) return;
     int32_t nb4[4], neighbors[4];
     int nn = 0;
-    neighbours4(c, c.a.pos[s], nb4);
-    for (int i = 0; i < 4; i++) { const int o = c.g.occ[nb4[i]]; if (o >= 0 && agent_alive(c, o)) neighbors[nn++] = o; }
+    const int n_nb = neighbours4(c, c.a.pos[s], nb4);
+    for (int i = 0; i < n_nb; i++) { const int o = c.g.occ[nb4[i]]; if (o >= 0 && agent_alive(c, o)) neighbors[nn++] = o; }
     int spread = 0;
     shuffle(rng, neighbors, nn);
     for (int k = 0; k < nn; k++) {
@@ -350,8 +350,8 @@ __device__ __noinline__ void update_friends(const DevCtx &c, int s, int nb) {
 // updateNeighbors -> updateSocialNetwork -> updateFriends, neighbours in N, S, E, W order (agent.py:1563-1565, 1622-1632)
 __device__ inline void update_neighbors(const DevCtx &c, int s, int pos) {
     int32_t nb4[4];
-    neighbours4(c, pos, nb4);
-    for (int i = 0; i < 4; i++) { const int o = c.g.occ[nb4[i]]; if (o >= 0) update_friends(c, s, o); }
+    const int n_nb = neighbours4(c, pos, nb4);
+    for (int i = 0; i < n_nb; i++) { const int o = c.g.occ[nb4[i]]; if (o >= 0) update_friends(c, s, o); }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -549,8 +549,8 @@ __device__ __noinline__ void do_lending(const DevCtx &c, int s, Rng &rng) {
     if (rate > 1) rate = 1;
     int32_t nb[4], borrowers[4];
     int nbw = 0;
-    neighbours4(c, a.pos[s], nb);
-    for (int i = 0; i < 4; i++) {
+    const int n_nb = neighbours4(c, a.pos[s], nb);
+    for (int i = 0; i < n_nb; i++) {
         const int o = c.g.occ[nb[i]];
         if (o < 0 || !agent_alive(c, o)) continue;
         // isBorrower (agent.py:1226-1229)
@@ -604,8 +604,8 @@ __device__ inline void agentlog_note_neighbors(const DevCtx &c, int s, int pos) 
     const ssb_agentlog_t &A = c.x->agentlog;
     int32_t nb4[4];
     int n = 0;
-    neighbours4(c, pos, nb4);
-    for (int i = 0; i < 4; i++) { const int o = c.g.occ[nb4[i]]; if (o >= 0) A.neighbor_slot[(long long)s * 4 + n++] = o; }
+    const int n_nb = neighbours4(c, pos, nb4);
+    for (int i = 0; i < n_nb; i++) { const int o = c.g.occ[nb4[i]]; if (o >= 0) A.neighbor_slot[(long long)s * 4 + n++] = o; }
     A.n_neighbors[s] = n;
 }
 // Agent.updateRuntimeStats (agent.py:1567-1620), at the end of a completed transaction

@@ -87,13 +87,23 @@ __global__ void __launch_bounds__(256) k_diffuse_v2(const double *__restrict__ p
     }
 }
 
+// nowrap: environmentWraparound = false -- the mean runs over the neighbours that exist (cell.py:47-121, 104-109)
 __global__ void __launch_bounds__(256) k_diffuse(const double *__restrict__ p, double *__restrict__ flux,
-                                                 int W, int H, long long cell_lo, long long cell_hi) {
+                                                 int W, int H, long long cell_lo, long long cell_hi, int nowrap) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = cell_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cell_hi; i += stride) {
         const int x = (int)(i / H), y = (int)(i - (long long)x * H);
         const long long row = (long long)x * H;
         double m = 0.0;
+        if (nowrap) {
+            int n = 0;
+            if (y - 1 >= 0) { m += p[row + y - 1]; n++; }
+            if (!(y + 1 < H - 1)) { m += p[row + (y + 1) % H]; n++; }
+            if (!(x + 1 > W - 1)) { m += p[(long long)(x + 1) * H + y]; n++; }
+            if (x - 1 >= 0) { m += p[(long long)(x - 1) * H + y]; n++; }
+            flux[i] = m / n;
+            continue;
+        }
         m += p[row + (y == 0 ? H - 1 : y - 1)];
         m += p[row + (y == H - 1 ? 0 : y + 1)];
         m += p[(long long)(x == W - 1 ? 0 : x + 1) * H + y];

@@ -303,13 +303,25 @@ __device__ __forceinline__ bool is_fertile(const DevCtx &c, int s) {
            c.a.age[s] >= c.a.fert_age[s] && c.a.age[s] < c.a.infert_age[s] && c.a.fert_factor[s] > 0;
 }
 
-// the four von Neumann neighbours in the reference's dict order N, S, E, W (cell.py:61-75)
-__device__ __forceinline__ void neighbours4(const DevCtx &c, int pos, int32_t out[4]) {
+// The von Neumann neighbours in the reference's dict order N, S, E, W (cell.py:61-75); returns how many there are.
+// environmentWraparound = false (SSB_F_NOWRAP) drops the neighbours across the map's edge (cell.py:47-50, 98-121) --
+// with the reference's own test for the south neighbour, `y + 1 < height - 1`, which leaves a south neighbour only to the
+// last two rows (the last row's wraps to row 0).
+__device__ __forceinline__ int neighbours4(const DevCtx &c, int pos, int32_t out[4]) {
     const int W = c.p.width, H = c.p.height, x = pos / H, y = pos - x * H;
-    out[0] = x * H + (y == 0 ? H - 1 : y - 1);
-    out[1] = x * H + (y == H - 1 ? 0 : y + 1);
-    out[2] = (x == W - 1 ? 0 : x + 1) * H + y;
-    out[3] = (x == 0 ? W - 1 : x - 1) * H + y;
+    if (!(c.p.flags & SSB_F_NOWRAP)) {
+        out[0] = x * H + (y == 0 ? H - 1 : y - 1);
+        out[1] = x * H + (y == H - 1 ? 0 : y + 1);
+        out[2] = (x == W - 1 ? 0 : x + 1) * H + y;
+        out[3] = (x == 0 ? W - 1 : x - 1) * H + y;
+        return 4;
+    }
+    int n = 0;
+    if (y - 1 >= 0) out[n++] = x * H + y - 1;
+    if (!(y + 1 < H - 1)) out[n++] = x * H + (y + 1) % H;
+    if (!(x + 1 > W - 1)) out[n++] = (x + 1) * H + y;
+    if (x - 1 >= 0) out[n++] = (x - 1) * H + y;
+    return n;
 }
 
 }  // namespace ssb
@@ -443,9 +455,9 @@ __device__ __noinline__ double ethical_value(const DevCtx &c, int s, int my_r, c
         max_site += w < max_loot ? w : max_loot;
     }
     int32_t nb4[4];
-    neighbours4(c, cell, nb4);
+    const int n_nb = neighbours4(c, cell, nb4);
     double neighbor_wealth = 0;
-    for (int i = 0; i < 4; i++) neighbor_wealth += c.g.sugar[nb4[i]] + (spicy ? c.g.spice[nb4[i]] : 0);
+    for (int i = 0; i < n_nb; i++) neighbor_wealth += c.g.sugar[nb4[i]] + (spicy ? c.g.spice[nb4[i]] : 0);
     const double lookahead = c.eth->lookahead_factor[s];
     // len(self.findNeighborhood(cell)): live agents on MY cross moved to `cell`, plus myself
     const double future_hood = lookahead != 0 ? (double)(1 + (my_r > 0 ? cross_live_count(c, cell, my_r) : 0)) : 1.0;
@@ -464,7 +476,8 @@ __device__ __noinline__ double ethical_value(const DevCtx &c, int s, int my_r, c
         const double discount = c.eth->lookahead_factor[nb] != 0 ? c.eth->lookahead_discount[nb] : 0;
         double future_duration = metab > 0 ? (site - metab) / metab : site;
         future_duration = max_site > 0 ? future_duration / max_site : 0;
-        const double future_intensity = neighbor_wealth / (c.eth->global_max_wealth * 4);
+        int32_t nb_cells[4];
+        const double future_intensity = neighbor_wealth / (c.eth->global_max_wealth * neighbours4(c, a.pos[nb], nb_cells));  // len(neighbor.cell.neighbors)
         const int in_range = rn > 0 ? cross_size(c, rn) : 0;                                // len(neighbor.cellsInRange)
         const double extent = in_range > 0 ? (double)n_hood / in_range : 1;
         const double future_extent = (in_range > 0 && lookahead != 0) ? future_hood / in_range : 1;
@@ -730,6 +743,10 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rn
     const bool diseased = EXT && has_disease(c);             // uniform: the find* accessors carry disease modifiers
     const int r = diseased ? min(min((int)eff_vision(c, s), (int)eff_movement(c, s)), max(c.max_dx, c.max_dy))
                            : min(min(max(rec.vision, 0), max(rec.movement, 0)), max(c.max_dx, c.max_dy));
+    // environmentWraparound = false: the reference memoises ranges up to width - 1 instead of width // 2 (environment.py:141-144);
+    // an agent that sees beyond half the map (disease bonuses) would read them -- not reproduced: fail loudly (code 14)
+    if ((c.p.flags & SSB_F_NOWRAP) && diseased && min((int)eff_vision(c, s), (int)eff_movement(c, s)) > max(c.max_dx, c.max_dy))
+        atomicExch((unsigned long long *)&c.a.counters[SSB_C_OVERFLOW], 14ull);
     const double aggression = diseased ? eff_aggression(c, s) : fmax(rec.aggression, 0.0);
     Welfare w = {};       // (value-initialised only to keep the front end quiet: set() assigns every field)
     w.template set<EXT>(c, s, rec.sugar, rec.spice, rec.sugar_metab, rec.spice_metab, rec.lookahead, rec.tags);
@@ -1020,10 +1037,10 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rn
 template <class Rng>
 __device__ __noinline__ void do_tagging(const DevCtx &c, int s, Rng &rng) {
     int32_t nb[4];
-    neighbours4(c, c.a.pos[s], nb);
+    const int n_nb = neighbours4(c, c.a.pos[s], nb);
     rng.at(SITE_TAGGING);
-    shuffle(rng, nb, 4);
-    for (int i = 0; i < 4; i++) {
+    shuffle(rng, nb, n_nb);
+    for (int i = 0; i < n_nb; i++) {
         const int o = c.g.occ[nb[i]];
         if (o < 0) continue;
         const uint32_t bit = 1u << rand_below(rng, (uint32_t)c.p.tag_len);
@@ -1042,8 +1059,8 @@ __device__ __noinline__ void do_trading(const DevCtx &c, int s, Rng &rng) {
     find_mrs<EXT>(c, s);
     int32_t nb[4], traders[4];
     int n = 0;
-    neighbours4(c, a.pos[s], nb);
-    for (int i = 0; i < 4; i++) {
+    const int n_nb = neighbours4(c, a.pos[s], nb);
+    for (int i = 0; i < n_nb; i++) {
         const int o = c.g.occ[nb[i]];
         if (o >= 0 && agent_alive(c, o) && a.mrs[o] != a.mrs[s]) traders[n++] = o;
     }
@@ -1096,8 +1113,8 @@ __device__ __noinline__ void do_trading(const DevCtx &c, int s, Rng &rng) {
 __device__ __forceinline__ int empty_neighbours(const DevCtx &c, int pos, int32_t *out) {
     int32_t nb[4];
     int n = 0;
-    neighbours4(c, pos, nb);
-    for (int i = 0; i < 4; i++) if (c.g.occ[nb[i]] < 0) out[n++] = nb[i];
+    const int n_nb = neighbours4(c, pos, nb);
+    for (int i = 0; i < n_nb; i++) if (c.g.occ[nb[i]] < 0) out[n++] = nb[i];
     return n;
 }
 
@@ -1130,18 +1147,18 @@ __device__ __noinline__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
     if (!agent_alive(c, s) || !(diseased ? is_fertile_x(c, s) : is_fertile(c, s))) return;
     const int pos = a.pos[s];
     int32_t nb0[4], nb[4];
-    neighbours4(c, pos, nb0);
-    for (int i = 0; i < 4; i++) nb[i] = nb0[i];
+    const int n_nb = neighbours4(c, pos, nb0);               // (4 unless environmentWraparound is off)
+    for (int i = 0; i < 4; i++) nb[i] = i < n_nb ? nb0[i] : pos;
     rng.at(SITE_REPRODUCTION);
-    shuffle(rng, nb, 4);
+    shuffle(rng, nb, n_nb);
     // batch 1: occupancy of the neighbours (shuffled order) and of each neighbour's ring
-    int32_t o[4], ring[4][4], ring_occ[4][4];
+    int32_t o[4], ring[4][4], ring_occ[4][4], ring_n[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        o[k] = c.g.occ[nb[k]];
-        neighbours4(c, nb[k], ring[k]);
+        o[k] = k < n_nb ? c.g.occ[nb[k]] : -1;
+        ring_n[k] = k < n_nb ? neighbours4(c, nb[k], ring[k]) : 0;
 #pragma unroll
-        for (int j = 0; j < 4; j++) ring_occ[k][j] = c.g.occ[ring[k][j]];
+        for (int j = 0; j < 4; j++) ring_occ[k][j] = j < ring_n[k] ? c.g.occ[ring[k][j]] : 0;
     }
     // batch 2: the mates' records
     int m_cod[4], m_sex[4], m_age[4], m_fa[4], m_ia[4];
@@ -1159,8 +1176,8 @@ __device__ __noinline__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
     // own empty neighbours, N S E W order, computed ONCE (agent.py:506): stale by design
     int32_t own_empty[4];
     int n_own = 0;
-    for (int i = 0; i < 4; i++)
-        for (int k = 0; k < 4; k++)
+    for (int i = 0; i < n_nb; i++)
+        for (int k = 0; k < n_nb; k++)
             if (nb[k] == nb0[i] && o[k] < 0) { own_empty[n_own++] = nb0[i]; break; }
     // own record
     const int my_sex = a.sex[s], my_age = a.age[s], my_fa = a.fert_age[s], my_ia = a.infert_age[s];
@@ -1190,15 +1207,15 @@ __device__ __noinline__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
         int32_t pool[8];
         int np = 0;
         for (int i = 0; i < n_own; i++) pool[np++] = own_empty[i];
-        for (int j = 0; j < 4; j++) if (ring_occ[k][j] < 0) pool[np++] = ring[k][j];
+        for (int j = 0; j < ring_n[k]; j++) if (ring_occ[k][j] < 0) pool[np++] = ring[k][j];
         shuffle(rng, pool, np);    // drawn before the compatibility test (reference quirk)
         const bool fertile_now = age_ok && my_sugar >= my_ss && my_spice >= my_sp;
         if (!(fertile_now && compatible && np != 0)) continue;
         // current occupancy of a pool cell: neighbour cells and ring cells are all tracked locally
         auto occupied_now = [&](int cell) {
-            for (int q = 0; q < 4; q++) {
+            for (int q = 0; q < n_nb; q++) {
                 if (nb[q] == cell) return o[q] >= 0;
-                for (int j = 0; j < 4; j++) if (ring[q][j] == cell) return ring_occ[q][j] >= 0;
+                for (int j = 0; j < ring_n[q]; j++) if (ring[q][j] == cell) return ring_occ[q][j] >= 0;
             }
             return c.g.occ[cell] >= 0;
         };

@@ -261,6 +261,8 @@ __global__ void __launch_bounds__(SWEEP_BUILD_THREADS, 3) k_sweep_build(DevCtx c
             if (lo != 0u) atomicOr(smask + ((size_t)(sweep_prio(lo) >> slab_prio_shift) * sw + col) * 2 + (row >> 6), 1ull << (row & 63));
         }
         __syncthreads();
+        for (int word = tid; word < sw * 2; word += SWEEP_BUILD_THREADS) sweep_fold_planes(smask, n_slabs, sw, word);    // plane g: slabs g - 1 and g
+        __syncthreads();
         // the tile's own agents (interior cells that lie on the map), grouped by range: the 32 agents a warp scans have
         // conflict regions of the same size
         for (int idx = tid; idx < FLOW_TX * FLOW_TY; idx += SWEEP_BUILD_THREADS) {

@@ -92,11 +92,17 @@ inline void sweep_fill_tables(int RB, int KB, int halo, int8_t *any, int8_t *pai
 
 struct SweepTile {
     const uint32_t *cell;                // [sw * sh] low descriptor words, column (x) major like the grid
-    const unsigned long long *smask;     // [slabs][sw * 2] per slab: occupancy bits of every staged column (sh <= 128)
+    const unsigned long long *smask;     // [slabs][sw * 2] plane g: occupancy bits, per staged column (sh <= 128), of the agents of the
+                                         // slabs g - 1 and g -- the near slabs of an agent of slab g (sweep_fold_planes)
     const int8_t *any, *pair;            // conflict tables
     int sw, sh, halo;
     int slab_prio_shift;                 // slab = priority >> slab_prio_shift
 };
+
+// planes filled per slab -> planes per PAIR of slabs, for word `word` (< sw * 2) of every plane
+__host__ __device__ __forceinline__ void sweep_fold_planes(unsigned long long *smask, int n_slabs, int sw, int word) {
+    for (int g = n_slabs - 1; g >= 1; g--) smask[(size_t)g * sw * 2 + word] |= smask[(size_t)(g - 1) * sw * 2 + word];
+}
 
 // The NEAR predecessors of the agent with low descriptor word `la` on staged cell (lx, ly): the agents of its own slab
 // and of the slab before it that have a smaller priority and an intersecting footprint, column by column:
@@ -107,7 +113,7 @@ __host__ __device__ __forceinline__ void sweep_near_masks(const SweepTile &tile,
     const int ra = sweep_r(la), ka = sweep_k(la), halo = tile.halo, hs = halo + 1;
     const uint32_t pa = sweep_prio(la);
     const int g = (int)(pa >> tile.slab_prio_shift);
-    const unsigned long long *m1 = tile.smask + (size_t)g * tile.sw * 2, *m0 = g > 0 ? m1 - tile.sw * 2 : m1;
+    const unsigned long long *near = tile.smask + (size_t)g * tile.sw * 2;
     const int8_t *any = tile.any + (ka * (RB + 1) + ra) * hs;
     const int8_t *pair = tile.pair + ((ka * (RB + 1) + ra) * (RB + 1)) * hs;       // + (kb (RB + 1) (RB + 1) + rb) hs + adx
     const int k_stride = (RB + 1) * (RB + 1) * hs;
@@ -117,8 +123,7 @@ __host__ __device__ __forceinline__ void sweep_near_masks(const SweepTile &tile,
         uint32_t m = 0;
         if (h >= 0) {
             const int col = lx + dx, y0 = ly - h;
-            const unsigned long long both[2] = {m1[col * 2] | m0[col * 2], m1[col * 2 + 1] | m0[col * 2 + 1]};
-            unsigned long long bits = flow_mask_window(both, y0, 2 * h + 1);
+            unsigned long long bits = flow_mask_window(near + col * 2, y0, 2 * h + 1);
             if (dx == 0) bits &= ~(1ull << h);
             const uint32_t *column = tile.cell + col * tile.sh + y0;
             while (bits) {
@@ -133,17 +138,34 @@ __host__ __device__ __forceinline__ void sweep_near_masks(const SweepTile &tile,
         emit_col(dx + halo, m);
     }
 }
-// ... one by one: emit(dx, dy)
+// ... one by one: emit(dx, dy).  (The same scan written out once more: routing it through the column masks costs the
+// build kernel a millisecond at S2.)
 template <class F>
 __host__ __device__ __forceinline__ void sweep_near_preds(const SweepTile &tile, int lx, int ly, uint32_t la, int RB, int KB, F emit) {
-    const int halo = tile.halo;
-    sweep_near_masks(tile, lx, ly, la, RB, KB, [&](int col, uint32_t m) {
-        while (m) {
-            const int j = flow_ctz64((unsigned long long)m);
-            m &= m - 1;
-            emit(col - halo, j - halo);
+    const int ra = sweep_r(la), ka = sweep_k(la), halo = tile.halo, hs = halo + 1;
+    const uint32_t pa = sweep_prio(la);
+    const int g = (int)(pa >> tile.slab_prio_shift);
+    const unsigned long long *near = tile.smask + (size_t)g * tile.sw * 2;
+    const int8_t *any = tile.any + (ka * (RB + 1) + ra) * hs;
+    const int8_t *pair = tile.pair + ((ka * (RB + 1) + ra) * (RB + 1)) * hs;
+    const int k_stride = (RB + 1) * (RB + 1) * hs;
+    for (int dx = -halo; dx <= halo; dx++) {
+        const int adx = dx < 0 ? -dx : dx;
+        const int h = any[adx];
+        if (h < 0) continue;
+        const int col = lx + dx, y0 = ly - h;
+        unsigned long long bits = flow_mask_window(near + col * 2, y0, 2 * h + 1);
+        if (dx == 0) bits &= ~(1ull << h);
+        const uint32_t *column = tile.cell + col * tile.sh + y0;
+        while (bits) {
+            const int j = flow_ctz64(bits);
+            bits &= bits - 1;
+            const uint32_t lb = column[j];
+            if (sweep_prio(lb) >= pa) continue;
+            const int dy = j - h, ady = dy < 0 ? -dy : dy;
+            if (ady <= pair[sweep_k(lb) * k_stride + sweep_r(lb) * hs + adx]) emit(dx, dy);
         }
-    });
+    }
 }
 
 // The DONE bitmap: one bit per cell -- "the agent that started the step on this cell has finished" -- in 64-bit words

@@ -78,6 +78,36 @@ class _Uploader:
         self.stream.synchronize()
         return out
 
+    def download(self, tensor):
+        """Device -> host of a large tensor through the same ring: DMA into pinned chunks, worker threads copy them out."""
+        t = self.torch
+        t.cuda.current_stream(self.device).synchronize()
+        src = tensor.contiguous().view(t.uint8).reshape(-1)
+        out = np.empty(tensor.shape, dtype=t.empty(0, dtype=tensor.dtype).numpy().dtype)
+        dst = out.reshape(-1).view(np.uint8)
+        copies = [None] * self.RING
+        for idx, off in enumerate(range(0, dst.nbytes, self.CHUNK)):
+            k = idx % self.RING
+            if copies[k] is not None:
+                copies[k].result()
+            if self.events[k] is not None:
+                self.events[k].synchronize()
+                self.events[k] = None
+            n = min(self.CHUNK, dst.nbytes - off)
+            with t.cuda.stream(self.stream):
+                self.pinned[k][:n].copy_(src[off:off + n], non_blocking=True)
+                ev = t.cuda.Event()
+                ev.record(self.stream)
+
+            def finish(ev=ev, k=k, off=off, n=n):
+                ev.synchronize()
+                np.copyto(dst[off:off + n], self.views[k][:n])
+            copies[k] = self.pool.submit(finish)
+        for c in copies:
+            if c is not None:
+                c.result()
+        return out
+
 
 def load_library():
     """Load libssb.so (built in-tree by sugarscape_b200/build.py); fail loudly if absent."""
@@ -299,7 +329,10 @@ class Engine:
                 continue
             if swapped and key in ("pollution", "pollution_flux"):      # the buffers swap roles at diffusion steps
                 tensor = self.tensors["pollution_flux" if key == "pollution" else "pollution"]
-            arr = tensor.cpu().numpy()
+            if (hasattr(tensor, "is_cuda") and tensor.is_cuda and tensor.numel() * tensor.element_size() >= _Uploader.THRESHOLD):
+                arr = _Uploader.get(self.torch, self.device).download(tensor)
+            else:
+                arr = tensor.cpu().numpy()
             if key == "a_tags":
                 arr = arr.view(np.uint32)
             if key.startswith("eth_"):

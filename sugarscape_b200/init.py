@@ -94,7 +94,16 @@ def check_supported(c):
     if c["neighborhoodMode"] != "vonNeumann":
         problems.append("moore neighbourhood")
     if not c["environmentWraparound"]:
-        problems.append("environmentWraparound=false")
+        # cell.py:47-121: the neighbour lists lose the cells across the edge; the range tables (environment.py:111-122) do NOT
+        # change as long as no range reaches half the map (they keep wrapping by `% width`, with the plain distance)
+        # (an agent looks min(vision, movement) cells far; the memoised tables reach further without wraparound --
+        # min(range, width - 1) instead of width // 2 -- but nobody reads those entries)
+        # (disease bonuses can push an agent further: the engine flags that case at run time, overflow code 14)
+        reach = min(c["agentVision"][1], c["agentMovement"][1])
+        if reach > min(c["environmentWidth"], c["environmentHeight"]) // 2:
+            problems.append("environmentWraparound=false with agents that see beyond half the map")
+        if c.get("b200RngMode", "exact") != "exact":
+            problems.append("environmentWraparound=false in the scalable RNG mode")
     if c["agentLeader"]:
         problems.append("agentLeader")
     if c["diseaseList"]:
@@ -391,6 +400,8 @@ def rule_flags(c):
         f |= layout.F_TRADE
     if c["agentTagPreferences"]:
         f |= layout.F_TAGPREF
+    if not c["environmentWraparound"]:
+        f |= layout.F_NOWRAP
     return f
 
 

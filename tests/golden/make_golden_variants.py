@@ -77,6 +77,11 @@ VARIANTS = {
     "ethics_temperance_pecs_combat": ("combat_limited", 100, dict(_ETHICS, agentDecisionModels=["temperancePECS", "bentham"],
                                                                   agentDynamicSocialPressureFactor=[0.05, 0.05],
                                                                   agentAggressionFactor=[0, 2], agentVision=[2, 5])),
+    # ---- environmentWraparound = false (cell.py:47-121): no neighbours across the map's edge, the reference's own test for
+    # the south neighbour included; tagging + trade + births, pollution diffusion, and every family of determinism.json
+    "nowrap_trade_tagging_reproduction": ("trade_tagging_reproduction", 150, {"environmentWraparound": False}),
+    "nowrap_pollution": ("trade_pollution", 120, {"environmentWraparound": False}),
+    "nowrap_determinism": ("determinism", 120, {"environmentWraparound": False, "experimentalGroup": None}),
     # the "Top" orderings: the cell with the best ethical value wins
     "ethics_top": ("trade_tagging_reproduction", 100, dict(_ETHICS, agentDecisionModels=["benthamTop", "egoistTop", "altruistNoLookaheadTop", "none", "bentham"])),
     # diffusion timeframe that starts before the first step, delay > 1: the reference's countdown is first decremented

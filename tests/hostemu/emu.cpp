@@ -259,6 +259,7 @@ int emu_agent_step_sweep(const ssb_params_t *p, const ssb_grid_t *g, const ssb_a
             cell[(size_t)col * sh + row] = lo;
             if (lo) smask[((size_t)(sweep_prio(lo) >> slab_prio_shift) * sw + col) * 2 + (row >> 6)] |= 1ull << (row & 63);
         }
+        for (int word = 0; word < sw * 2; word++) sweep_fold_planes(smask.data(), n_slabs, sw, word);
         SweepTile tile;
         tile.cell = cell.data(); tile.smask = smask.data(); tile.sw = sw; tile.sh = sh; tile.halo = R; tile.slab_prio_shift = slab_prio_shift;
         tile.any = tables.data(); tile.pair = tables.data() + sweep_any_size(RB, KB, R);

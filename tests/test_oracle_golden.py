@@ -221,7 +221,7 @@ def _private_log_keys(orc, rs, t, ethics):
         rs.update(orc.ethics_log_keys(t, n, rs["meanNeighbors"]))
 
 
-@pytest.mark.parametrize("variant,ethics", [("determinism_plain", False), ("determinism_ethics", True)])
+@pytest.mark.parametrize("variant,ethics", [("determinism_plain", False), ("determinism_ethics", True), ("nowrap_determinism", True)])
 def test_oracle_determinism_variants_match_reference_trajectory(variant, ethics):
     """examples/determinism.json (variant fixtures from the unmodified reference,
     tests/golden/make_golden_variants.py): diseases, depression, lending, friends, racial tags,
@@ -257,7 +257,7 @@ def test_oracle_determinism_variants_match_reference_trajectory(variant, ethics)
             non_greedy += rs["agentLastMoveOptimalityPercentage"] < 100
             for k in stats.LOG_KEYS:
                 assert _close(rs[k], log[t][k]), f"log key {k} differs at t={t}: {rs[k]} vs {log[t][k]}"
-        assert (non_greedy > 150) == ethics
+        assert (non_greedy > 0.7 * (len(gold) - 1)) == ethics
     finally:
         _unbind_everything(orc)
 
@@ -394,7 +394,9 @@ def test_oracle_environment_file_matches_reference_trajectory():
 
 
 @pytest.mark.parametrize("overrides", [{"agentVisionMode": "radial"}, {"neighborhoodMode": "moore"},
-                                       {"environmentWraparound": False}, {"agentDecisionModels": ["asimov"]},
+                                       {"environmentWraparound": False, "b200RngMode": "scalable"},
+                                       {"environmentWraparound": False, "agentVision": [1, 30], "agentMovement": [30, 30]},
+                                       {"agentDecisionModels": ["asimov"]},
                                        {"agentDecisionModels": ["negativeBenthamTop"]}, {"experimentalGroup": "sick"},
                                        {"agentLeader": True}, {"agentMaxFriends": [20, 20]}])
 def test_unsupported_options_fail_loudly(overrides):
@@ -510,7 +512,9 @@ def test_scalable_mode_oracle_matches_patched_reference(name):
             assert d[k] == rec["digests"][k], f"{k} differs from the patched reference at t={t}"
 
 
-PLAIN_VARIANTS = ["pollution_diffusion_delay2", "pollution_diffusion_delay3"]
+# nowrap_*: environmentWraparound = false (cell.py:47-121) -- the neighbour lists of tagging / trade / births and the pollution
+# flux lose the cells across the map's edge (with the reference's own south-neighbour test)
+PLAIN_VARIANTS = ["pollution_diffusion_delay2", "pollution_diffusion_delay3", "nowrap_trade_tagging_reproduction", "nowrap_pollution"]
 
 
 @pytest.mark.parametrize("variant", PLAIN_VARIANTS)

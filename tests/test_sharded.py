@@ -45,6 +45,30 @@ def test_shard_host_state_moves_every_record_to_the_rank_that_owns_its_cell():
     assert d_old == d_new
 
 
+def test_slabs_of_whole_tiles_for_the_sharded_sweep():
+    """The ranks can run the sweep scheduler over their slabs when every slab consists of whole
+    64-column tiles and the rule set is the plain lean transaction's: wide maps get such slabs from the balancer, the
+    eligibility test mirrors the engine's (csrc/ssb_abi.cu, shard_sweep_possible)."""
+    wide = {"environmentWidth": 512, "environmentHeight": 150, "startingAgents": 12000, "agentMovement": [6, 6]}
+    c, state, pop, params, endow, tags = pu.build("constant_growback", layout.RNG_SCALABLE, wide)
+    for world in (2, 4):
+        new, lists = sharded.shard_host_state(state, world)
+        assert all(b % sharded.SWEEP_TILE == 0 for b in new.slab_bounds[:-1]), new.slab_bounds
+        assert sharded.sweep_slabs_possible(params, new.slab_bounds)
+        sizes = [len(x) for x in lists]
+        assert max(sizes) - min(sizes) <= 0.25 * sum(sizes) / world, sizes          # still balanced by population
+    assert not sharded.sweep_slabs_possible(params, [0, 100, 512])                  # a slab boundary inside a tile
+    # rule sets whose transaction reads a neighbour's record or dilates its footprint stay on the reservation rounds
+    for name, overrides in (("combat_unlimited", {"agentAggressionFactor": [1, 1]}), ("trade_basic", {}), ("pollution_formation", {}),
+                            ("cultural_tagging", {})):
+        c2, s2, pop2, params2, e2, t2 = pu.build(name, layout.RNG_SCALABLE, dict(wide, environmentHeight=512, **overrides))
+        assert not sharded.sweep_slabs_possible(params2, [0, 256, 512]), name
+    # narrow maps keep the page-aligned / plain balancing (no whole tiles to give)
+    c3, s3, pop3, params3, e3, t3 = pu.build("constant_growback", layout.RNG_SCALABLE, {"agentMovement": [6, 6]})
+    new3, _ = sharded.shard_host_state(s3, 2)
+    assert not sharded.sweep_slabs_possible(params3, new3.slab_bounds)
+
+
 def test_chunk_boundaries_are_page_multiples_and_follow_the_shares():
     g = sharded.GRANULE
     b = sharded.chunk_boundaries([100, 200, 300, 400], 4, 4)            # tiny array: one page per rank

@@ -142,10 +142,12 @@ def test_disease_cases_match_reference_trajectory(case):
     eng.close()
 
 
-@pytest.mark.parametrize("variant,ethics", [("determinism_plain", False), ("determinism_ethics", True)])
+@pytest.mark.parametrize("variant,ethics", [("determinism_plain", False), ("determinism_ethics", True), ("nowrap_determinism", True),
+                                            ("nowrap_trade_tagging_reproduction", False), ("nowrap_pollution", False)])
 def test_determinism_variants_match_reference_trajectory(variant, ethics):
     """examples/determinism.json without / with the ethics models, experimental-group split off (variant fixtures of the
-    unmodified reference): every rule family at once."""
+    unmodified reference): every rule family at once.  nowrap_*: environmentWraparound = false (cell.py:47-121) on
+    determinism.json, on tagging + trade + births and on pollution diffusion."""
     base, overrides, gold, log = pu.load_variant(variant)
     c, state, pop, params, endow, tags, eng = _engine(base, layout.RNG_EXACT, overrides)
     sb = stats.StatsBuilder(c, init.equator(c))
