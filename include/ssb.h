@@ -62,6 +62,7 @@ extern "C" {
 #define SSB_F_COMBAT    (1 << 5) /* some agent has aggression > 0                            */
 #define SSB_F_TRADE     (1 << 6) /* some agent has tradeFactor != 0                          */
 #define SSB_F_TAGPREF   (1 << 7) /* agentTagPreferences                                      */
+#define SSB_F_MOORE     (1 << 9) /* neighborhoodMode = "moore": cell.neighbors has eight entries (cell.py:77-89; exact mode) */
 #define SSB_F_NOWRAP    (1 << 8) /* environmentWraparound = false: no neighbours across the map's edge (cell.py:47-121; exact mode) */
 
 typedef struct ssb_params {

@@ -415,23 +415,29 @@ static int is_fertile(const ctx_t *c, int s) {
            (c->a.fert_factor[s] + dis_mod(s, DM_FERTILITY)) > 0;
 }
 
-/* the von Neumann neighbours in the reference's dict order N, S, E, W (cell.py:61-75); returns their number.
+/* cell.neighbors in the reference's dict order (cell.py:61-89): N, S, E, W, then with neighborhoodMode "moore" (SSB_F_MOORE)
+ * NE, NW, SE, SW = the east / west neighbours of the north and south cells; returns their number (out holds up to 8).
  * environmentWraparound = false (SSB_F_NOWRAP): cell.py:47-50, 98-121 -- the neighbours across the edge are missing, and the
  * reference's test for the south neighbour (`y + 1 < height - 1` -> None) leaves one to the last two rows only */
-static int neighbours4(const ctx_t *c, int pos, int32_t out[4]) {
+#define MAX_NEIGHBOURS 8
+static int neighbours4(const ctx_t *c, int pos, int32_t *out) {
     int W = c->p->width, H = c->p->height, x = pos / H, y = pos % H;
-    if (!(c->p->flags & SSB_F_NOWRAP)) {
-        out[0] = x * H + wrapi(y - 1, H);
-        out[1] = x * H + wrapi(y + 1, H);
-        out[2] = wrapi(x + 1, W) * H + y;
-        out[3] = wrapi(x - 1, W) * H + y;
-        return 4;
+    const int nowrap = (c->p->flags & SSB_F_NOWRAP) != 0;
+    int north = -1, south = -1, n = 0;
+    if (!(nowrap && y - 1 < 0)) north = x * H + (y - 1 + H) % H;
+    if (!(nowrap && y + 1 < H - 1)) south = x * H + (y + 1 + H) % H;
+    const int has_east = !(nowrap && x + 1 > W - 1), has_west = !(nowrap && x - 1 < 0);
+    const int xe = (x + 1 + W) % W, xw = (x - 1 + W) % W;
+    if (north >= 0) out[n++] = north;
+    if (south >= 0) out[n++] = south;
+    if (has_east) out[n++] = xe * H + y;
+    if (has_west) out[n++] = xw * H + y;
+    if (c->p->flags & SSB_F_MOORE) {      /* north.findEastNeighbor() ...: the east / west test is the same for the whole column */
+        if (north >= 0 && has_east) out[n++] = xe * H + north % H;
+        if (north >= 0 && has_west) out[n++] = xw * H + north % H;
+        if (south >= 0 && has_east) out[n++] = xe * H + south % H;
+        if (south >= 0 && has_west) out[n++] = xw * H + south % H;
     }
-    int n = 0;
-    if (!(y - 1 < 0)) out[n++] = x * H + (y - 1 + H) % H;
-    if (!(y + 1 < H - 1)) out[n++] = x * H + (y + 1 + H) % H;
-    if (!(x + 1 > W - 1)) out[n++] = ((x + 1 + W) % W) * H + y;
-    if (!(x - 1 < 0)) out[n++] = ((x - 1 + W) % W) * H + y;
     return n;
 }
 
@@ -778,7 +784,7 @@ static void do_lending(ctx_t *c, int s) {
     if (a->age[s] < a->fert_age[s]) return;
     double rate = g_lend->lending_factor[s] * g_lend->base_interest_rate[s];
     if (rate > 1) rate = 1;
-    int32_t nb[4], borrowers[4];
+    int32_t nb[MAX_NEIGHBOURS], borrowers[MAX_NEIGHBOURS];
     int nbw = 0;
     const int n_nb = neighbours4(c, a->pos[s], nb);
     for (int i = 0; i < n_nb; i++) {
@@ -944,7 +950,7 @@ static void do_disease(ctx_t *c, int s) {
     }
     const int count = L->n;
     if (count == 0) return;
-    int32_t nb4[4], neighbors[4];
+    int32_t nb4[MAX_NEIGHBOURS], neighbors[MAX_NEIGHBOURS];
     int nn = 0;
     const int n_nb = neighbours4(c, c->a.pos[s], nb4);
     for (int i = 0; i < n_nb; i++) { int o = c->g.occ[nb4[i]]; if (o >= 0 && agent_alive(c, o)) neighbors[nn++] = o; }
@@ -1149,7 +1155,7 @@ static double ethical_value(ctx_t *c, int s, int my_r, const int32_t *hood, int 
         site += w < max_loot ? w : max_loot;
         max_site += w < max_loot ? w : max_loot;
     }
-    int32_t nb4[4];
+    int32_t nb4[MAX_NEIGHBOURS];
     const int n_nb = neighbours4(c, cell, nb4);
     double neighbor_wealth = 0;
     for (int i = 0; i < n_nb; i++) neighbor_wealth += c->g.sugar[nb4[i]] + c->g.spice[nb4[i]];
@@ -1178,7 +1184,7 @@ static double ethical_value(ctx_t *c, int s, int my_r, const int32_t *hood, int 
         const double discount = g_eth->lookahead_factor[nb] != 0 ? g_eth->lookahead_discount[nb] : 0;
         double future_duration = metab > 0 ? (site - metab) / metab : site;
         future_duration = max_site > 0 ? future_duration / max_site : 0;
-        int32_t nb_cells[4];
+        int32_t nb_cells[MAX_NEIGHBOURS];
         const double future_intensity = neighbor_wealth / (g_eth->global_max_wealth * neighbours4(c, a->pos[nb], nb_cells));   /* len(neighbor.cell.neighbors) */
         int32_t tc[MAX_CAND], td[MAX_CAND];
         const int in_range = rn > 0 ? enumerate_cross(c, a->pos[nb], rn, tc, td) : 0;          /* len(neighbor.cellsInRange) */
@@ -1318,7 +1324,7 @@ static int move_to_best_cell(ctx_t *c, int s) {
 /* agent.py:556-566 */
 static void do_tagging(ctx_t *c, int s) {
     if (!(c->p->flags & SSB_F_TAGS) || !(c->p->flags & SSB_F_TAGGING)) return;
-    int32_t nb[4];
+    int32_t nb[MAX_NEIGHBOURS];
     const int n_nb = neighbours4(c, c->a.pos[s], nb);
     rng_at(c->rng, SITE_TAGGING);
     rng_shuffle_i32(c->rng, nb, n_nb);
@@ -1339,7 +1345,7 @@ static void do_trading(ctx_t *c, int s) {
     a->trade_volume[s] = 0;
     double sum_sugar_price = 0, sum_spice_price = 0;
     find_mrs(c, s);
-    int32_t nb[4], traders[4]; int n = 0;
+    int32_t nb[MAX_NEIGHBOURS], traders[MAX_NEIGHBOURS]; int n = 0;
     const int n_nb = neighbours4(c, a->pos[s], nb);
     for (int i = 0; i < n_nb; i++) {
         int o = c->g.occ[nb[i]];
@@ -1392,7 +1398,7 @@ static void do_trading(ctx_t *c, int s) {
 }
 
 static int empty_neighbours(const ctx_t *c, int pos, int32_t *out) {
-    int32_t nb[4]; int n = 0;
+    int32_t nb[MAX_NEIGHBOURS]; int n = 0;
     const int n_nb = neighbours4(c, pos, nb);
     for (int i = 0; i < n_nb; i++) if (c->g.occ[nb[i]] < 0) out[n++] = nb[i];
     return n;
@@ -1402,7 +1408,7 @@ static int empty_neighbours(const ctx_t *c, int pos, int32_t *out) {
 static void do_reproduction(ctx_t *c, int s) {
     ssb_agents_t *a = &c->a;
     if (!agent_alive(c, s) || !is_fertile(c, s)) return;
-    int32_t nb[4], own_empty[4];
+    int32_t nb[MAX_NEIGHBOURS], own_empty[MAX_NEIGHBOURS];
     const int n_nb = neighbours4(c, a->pos[s], nb);
     rng_at(c->rng, SITE_REPRODUCTION);
     rng_shuffle_i32(c->rng, nb, n_nb);
@@ -1412,7 +1418,7 @@ static void do_reproduction(ctx_t *c, int s) {
         if (m < 0 || !agent_alive(c, m)) continue;
         int compatible = ((a->sex[s] == SSB_SEX_FEMALE && a->sex[m] == SSB_SEX_MALE) ||
                           (a->sex[s] == SSB_SEX_MALE && a->sex[m] == SSB_SEX_FEMALE)) && is_fertile(c, m);
-        int32_t pool[8]; int np = 0;
+        int32_t pool[2 * MAX_NEIGHBOURS]; int np = 0;
         for (int i = 0; i < n_own; i++) pool[np++] = own_empty[i];
         np += empty_neighbours(c, a->pos[m], pool + np);
         rng_shuffle_i32(c->rng, pool, np);   /* drawn before the compatibility test (quirk C.7) */
@@ -1550,7 +1556,7 @@ static void agent_transaction(ctx_t *c, int s) {
     a->last_spice[s] = a->spice[s];
     int pos = move_to_best_cell(c, s);
     if (g_social) {      /* updateNeighbors -> updateSocialNetwork -> updateFriends, neighbours in N, S, E, W order */
-        int32_t nb4[4];
+        int32_t nb4[MAX_NEIGHBOURS];
         const int n_nb = neighbours4(c, pos, nb4);
         for (int i = 0; i < n_nb; i++) { int o = c->g.occ[nb4[i]]; if (o >= 0) update_friends(c, s, o); }
     }
@@ -1672,12 +1678,11 @@ void orc_env_step(const ssb_params_t *p, const ssb_grid_t *g, int32_t t) {
         for (int x = 0; x < W; x++)
             for (int y = 0; y < H; y++) {
                 double m = 0;
-                if (p->flags & SSB_F_NOWRAP) {       /* cell.py:104-109 over the neighbours that exist (N, S, E, W order) */
-                    int n = 0;
-                    if (!(y - 1 < 0)) { m += g->pollution[x * H + y - 1]; n++; }
-                    if (!(y + 1 < H - 1)) { m += g->pollution[x * H + (y + 1) % H]; n++; }
-                    if (!(x + 1 > W - 1)) { m += g->pollution[(x + 1) * H + y]; n++; }
-                    if (!(x - 1 < 0)) { m += g->pollution[(x - 1) * H + y]; n++; }
+                if (p->flags & (SSB_F_NOWRAP | SSB_F_MOORE)) {       /* cell.py:104-109 over cell.neighbors as built by cell.py:61-89 */
+                    ctx_t cc; cc.p = p;
+                    int32_t nbc[MAX_NEIGHBOURS];
+                    const int n = neighbours4(&cc, x * H + y, nbc);
+                    for (int k = 0; k < n; k++) m += g->pollution[nbc[k]];
                     g->pollution_flux[x * H + y] = m / n;
                     continue;
                 }

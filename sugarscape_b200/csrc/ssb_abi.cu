@@ -162,7 +162,8 @@ int ssb_create(const ssb_params_t *params, int device, ssb_engine_t **out) {
     if (params->rng_mode != SSB_RNG_EXACT && params->rng_mode != SSB_RNG_SCALABLE) return fail(e, -1, "bad rng_mode %d", params->rng_mode);
     if (params->id_bits < 2 || params->id_bits > 32 - TAG_BITS || (params->id_bits & 1)) return fail(e, -1, "id_bits must be even and <= %d", 32 - TAG_BITS);
     if (params->tag_len > 32 || params->max_tribes > 26) return fail(e, -1, "tag_len <= 32 and max_tribes <= 26 required");
-    if ((params->flags & SSB_F_NOWRAP) && params->rng_mode != SSB_RNG_EXACT) return fail(e, -1, "environmentWraparound = false is an exact-mode option (the scalable mode's footprints assume the torus)");
+    if ((params->flags & (SSB_F_NOWRAP | SSB_F_MOORE)) && params->rng_mode != SSB_RNG_EXACT)
+        return fail(e, -1, "environmentWraparound = false and the Moore neighbourhood are exact-mode options (the scalable mode's footprints assume the torus and von Neumann neighbours)");
     e->p = *params;
     e->device = device;
     int count = 0;
@@ -712,11 +713,11 @@ int ssb_env_step(ssb_engine_t *e, int32_t t, void *stream_) {
      * step being t = 1: it diffuses on the k-th such step when k is a multiple of the delay */
     if (p.diffusion_delay > 0 && p.diffusion_start <= t && t <= p.diffusion_end &&
         ((t - (p.diffusion_start > 1 ? p.diffusion_start : 1) + 1) % p.diffusion_delay) == 0) {
-        const int nowrap = (p.flags & SSB_F_NOWRAP) ? 1 : 0;
-        if ((p.height % 2) == 0 && !nowrap)
+        const int special = p.flags & (SSB_F_NOWRAP | SSB_F_MOORE);
+        if ((p.height % 2) == 0 && !special)
             k_diffuse_v2<<<grid_for(my_cells / 2, 256, e->num_sms * 8), 256, 0, st>>>(e->ctx.g.pollution, e->ctx.g.pollution_flux, p.width, p.height, g.cell_lo, g.cell_hi);
         else
-            k_diffuse<<<grid_for(my_cells, 256, e->num_sms * 8), 256, 0, st>>>(e->ctx.g.pollution, e->ctx.g.pollution_flux, p.width, p.height, g.cell_lo, g.cell_hi, nowrap);
+            k_diffuse<<<grid_for(my_cells, 256, e->num_sms * 8), 256, 0, st>>>(e->ctx.g.pollution, e->ctx.g.pollution_flux, p.width, p.height, g.cell_lo, g.cell_hi, special);
         LAUNCHED(e);
         // the flux buffer now holds the field: swap the roles of the two host-owned buffers
         double *tmp = e->ctx.g.pollution; e->ctx.g.pollution = e->ctx.g.pollution_flux; e->ctx.g.pollution_flux = tmp;

@@ -261,7 +261,7 @@ __device__ __noinline__ void do_disease(const DevCtx &c, int s, Rng &rng) {
     }
     const int count = D.n_sick[s];
     if (count == 0) return;
-    int32_t nb4[4], neighbors[4];
+    int32_t nb4[SSB_MAX_NEIGHBOURS], neighbors[SSB_MAX_NEIGHBOURS];
     int nn = 0;
     const int n_nb = neighbours4(c, c.a.pos[s], nb4);
     for (int i = 0; i < n_nb; i++) { const int o = c.g.occ[nb4[i]]; if (o >= 0 && agent_alive(c, o)) neighbors[nn++] = o; }
@@ -349,7 +349,7 @@ __device__ __noinline__ void update_friends(const DevCtx &c, int s, int nb) {
 }
 // updateNeighbors -> updateSocialNetwork -> updateFriends, neighbours in N, S, E, W order (agent.py:1563-1565, 1622-1632)
 __device__ inline void update_neighbors(const DevCtx &c, int s, int pos) {
-    int32_t nb4[4];
+    int32_t nb4[SSB_MAX_NEIGHBOURS];
     const int n_nb = neighbours4(c, pos, nb4);
     for (int i = 0; i < n_nb; i++) { const int o = c.g.occ[nb4[i]]; if (o >= 0) update_friends(c, s, o); }
 }
@@ -547,7 +547,7 @@ __device__ __noinline__ void do_lending(const DevCtx &c, int s, Rng &rng) {
     if (a.age[s] < a.fert_age[s]) return;
     double rate = L.lending_factor[s] * L.base_interest_rate[s];
     if (rate > 1) rate = 1;
-    int32_t nb[4], borrowers[4];
+    int32_t nb[SSB_MAX_NEIGHBOURS], borrowers[SSB_MAX_NEIGHBOURS];
     int nbw = 0;
     const int n_nb = neighbours4(c, a.pos[s], nb);
     for (int i = 0; i < n_nb; i++) {
@@ -602,7 +602,7 @@ __device__ inline void agentlog_reset_slot(const DevCtx &c, int s) {
 // updateNeighbors (agent.py:1563-1565): the occupants of the von Neumann neighbours, N S E W
 __device__ inline void agentlog_note_neighbors(const DevCtx &c, int s, int pos) {
     const ssb_agentlog_t &A = c.x->agentlog;
-    int32_t nb4[4];
+    int32_t nb4[SSB_MAX_NEIGHBOURS];      // (the record buffer holds four per agent: Moore + agentLogfile is refused by the host)
     int n = 0;
     const int n_nb = neighbours4(c, pos, nb4);
     for (int i = 0; i < n_nb; i++) { const int o = c.g.occ[nb4[i]]; if (o >= 0) A.neighbor_slot[(long long)s * 4 + n++] = o; }

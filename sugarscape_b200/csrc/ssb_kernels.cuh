@@ -87,20 +87,31 @@ __global__ void __launch_bounds__(256) k_diffuse_v2(const double *__restrict__ p
     }
 }
 
-// nowrap: environmentWraparound = false -- the mean runs over the neighbours that exist (cell.py:47-121, 104-109)
+// special: SSB_F_NOWRAP | SSB_F_MOORE bits -- the mean runs over cell.neighbors as the reference builds it (cell.py:61-89, 47-121,
+// 104-109): N, S, E, W, then NE, NW, SE, SW with the Moore neighbourhood; without wraparound only the ones that exist
 __global__ void __launch_bounds__(256) k_diffuse(const double *__restrict__ p, double *__restrict__ flux,
-                                                 int W, int H, long long cell_lo, long long cell_hi, int nowrap) {
+                                                 int W, int H, long long cell_lo, long long cell_hi, int special) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = cell_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cell_hi; i += stride) {
         const int x = (int)(i / H), y = (int)(i - (long long)x * H);
         const long long row = (long long)x * H;
         double m = 0.0;
-        if (nowrap) {
+        if (special) {
+            const bool wrap = !(special & SSB_F_NOWRAP);
+            const bool hn = wrap || y - 1 >= 0, hs = wrap || !(y + 1 < H - 1), he = wrap || !(x + 1 > W - 1), hw = wrap || x - 1 >= 0;
+            const long long yn = y == 0 ? H - 1 : y - 1, ys = y == H - 1 ? 0 : y + 1;
+            const long long re = (long long)(x == W - 1 ? 0 : x + 1) * H, rw = (long long)(x == 0 ? W - 1 : x - 1) * H;
             int n = 0;
-            if (y - 1 >= 0) { m += p[row + y - 1]; n++; }
-            if (!(y + 1 < H - 1)) { m += p[row + (y + 1) % H]; n++; }
-            if (!(x + 1 > W - 1)) { m += p[(long long)(x + 1) * H + y]; n++; }
-            if (x - 1 >= 0) { m += p[(long long)(x - 1) * H + y]; n++; }
+            if (hn) { m += p[row + yn]; n++; }
+            if (hs) { m += p[row + ys]; n++; }
+            if (he) { m += p[re + y]; n++; }
+            if (hw) { m += p[rw + y]; n++; }
+            if (special & SSB_F_MOORE) {
+                if (hn && he) { m += p[re + yn]; n++; }
+                if (hn && hw) { m += p[rw + yn]; n++; }
+                if (hs && he) { m += p[re + ys]; n++; }
+                if (hs && hw) { m += p[rw + ys]; n++; }
+            }
             flux[i] = m / n;
             continue;
         }

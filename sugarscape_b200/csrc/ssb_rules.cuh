@@ -303,24 +303,32 @@ __device__ __forceinline__ bool is_fertile(const DevCtx &c, int s) {
            c.a.age[s] >= c.a.fert_age[s] && c.a.age[s] < c.a.infert_age[s] && c.a.fert_factor[s] > 0;
 }
 
-// The von Neumann neighbours in the reference's dict order N, S, E, W (cell.py:61-75); returns how many there are.
-// environmentWraparound = false (SSB_F_NOWRAP) drops the neighbours across the map's edge (cell.py:47-50, 98-121) --
-// with the reference's own test for the south neighbour, `y + 1 < height - 1`, which leaves a south neighbour only to the
-// last two rows (the last row's wraps to row 0).
-__device__ __forceinline__ int neighbours4(const DevCtx &c, int pos, int32_t out[4]) {
+// cell.neighbors in the reference's dict order (cell.py:61-89): N, S, E, W, then -- neighborhoodMode "moore", SSB_F_MOORE --
+// NE, NW, SE, SW (the east / west neighbours of the north and south cells); returns how many there are (out holds up to
+// SSB_MAX_NEIGHBOURS).  environmentWraparound = false (SSB_F_NOWRAP) drops the neighbours across the map's edge
+// (cell.py:47-50, 98-121) -- with the reference's own test for the south neighbour, `y + 1 < height - 1`, which leaves a
+// south neighbour only to the last two rows (the last row's wraps to row 0).
+constexpr int SSB_MAX_NEIGHBOURS = 8;
+__device__ __forceinline__ int neighbours4(const DevCtx &c, int pos, int32_t *out) {
     const int W = c.p.width, H = c.p.height, x = pos / H, y = pos - x * H;
-    if (!(c.p.flags & SSB_F_NOWRAP)) {
-        out[0] = x * H + (y == 0 ? H - 1 : y - 1);
-        out[1] = x * H + (y == H - 1 ? 0 : y + 1);
-        out[2] = (x == W - 1 ? 0 : x + 1) * H + y;
-        out[3] = (x == 0 ? W - 1 : x - 1) * H + y;
+    const int yn = y == 0 ? H - 1 : y - 1, ys = y == H - 1 ? 0 : y + 1, xe = x == W - 1 ? 0 : x + 1, xw = x == 0 ? W - 1 : x - 1;
+    if (!(c.p.flags & (SSB_F_NOWRAP | SSB_F_MOORE))) {
+        out[0] = x * H + yn; out[1] = x * H + ys; out[2] = xe * H + y; out[3] = xw * H + y;
         return 4;
     }
+    const bool wrap = !(c.p.flags & SSB_F_NOWRAP);
+    const bool hn = wrap || y - 1 >= 0, hs = wrap || !(y + 1 < H - 1), he = wrap || !(x + 1 > W - 1), hw = wrap || x - 1 >= 0;
     int n = 0;
-    if (y - 1 >= 0) out[n++] = x * H + y - 1;
-    if (!(y + 1 < H - 1)) out[n++] = x * H + (y + 1) % H;
-    if (!(x + 1 > W - 1)) out[n++] = (x + 1) * H + y;
-    if (x - 1 >= 0) out[n++] = (x - 1) * H + y;
+    if (hn) out[n++] = x * H + yn;
+    if (hs) out[n++] = x * H + ys;
+    if (he) out[n++] = xe * H + y;
+    if (hw) out[n++] = xw * H + y;
+    if (c.p.flags & SSB_F_MOORE) {
+        if (hn && he) out[n++] = xe * H + yn;
+        if (hn && hw) out[n++] = xw * H + yn;
+        if (hs && he) out[n++] = xe * H + ys;
+        if (hs && hw) out[n++] = xw * H + ys;
+    }
     return n;
 }
 
@@ -454,7 +462,7 @@ __device__ __noinline__ double ethical_value(const DevCtx &c, int s, int my_r, c
         site += w < max_loot ? w : max_loot;
         max_site += w < max_loot ? w : max_loot;
     }
-    int32_t nb4[4];
+    int32_t nb4[SSB_MAX_NEIGHBOURS];
     const int n_nb = neighbours4(c, cell, nb4);
     double neighbor_wealth = 0;
     for (int i = 0; i < n_nb; i++) neighbor_wealth += c.g.sugar[nb4[i]] + (spicy ? c.g.spice[nb4[i]] : 0);
@@ -476,7 +484,7 @@ __device__ __noinline__ double ethical_value(const DevCtx &c, int s, int my_r, c
         const double discount = c.eth->lookahead_factor[nb] != 0 ? c.eth->lookahead_discount[nb] : 0;
         double future_duration = metab > 0 ? (site - metab) / metab : site;
         future_duration = max_site > 0 ? future_duration / max_site : 0;
-        int32_t nb_cells[4];
+        int32_t nb_cells[SSB_MAX_NEIGHBOURS];
         const double future_intensity = neighbor_wealth / (c.eth->global_max_wealth * neighbours4(c, a.pos[nb], nb_cells));  // len(neighbor.cell.neighbors)
         const int in_range = rn > 0 ? cross_size(c, rn) : 0;                                // len(neighbor.cellsInRange)
         const double extent = in_range > 0 ? (double)n_hood / in_range : 1;
@@ -1036,7 +1044,7 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rn
 // Agent.doTagging (agent.py:556-566)
 template <class Rng>
 __device__ __noinline__ void do_tagging(const DevCtx &c, int s, Rng &rng) {
-    int32_t nb[4];
+    int32_t nb[SSB_MAX_NEIGHBOURS];
     const int n_nb = neighbours4(c, c.a.pos[s], nb);
     rng.at(SITE_TAGGING);
     shuffle(rng, nb, n_nb);
@@ -1057,7 +1065,7 @@ __device__ __noinline__ void do_trading(const DevCtx &c, int s, Rng &rng) {
     a.trade_volume[s] = 0;
     double sum_sugar_price = 0, sum_spice_price = 0;
     find_mrs<EXT>(c, s);
-    int32_t nb[4], traders[4];
+    int32_t nb[SSB_MAX_NEIGHBOURS], traders[SSB_MAX_NEIGHBOURS];
     int n = 0;
     const int n_nb = neighbours4(c, a.pos[s], nb);
     for (int i = 0; i < n_nb; i++) {
@@ -1111,7 +1119,7 @@ __device__ __noinline__ void do_trading(const DevCtx &c, int s, Rng &rng) {
 }
 
 __device__ __forceinline__ int empty_neighbours(const DevCtx &c, int pos, int32_t *out) {
-    int32_t nb[4];
+    int32_t nb[SSB_MAX_NEIGHBOURS];
     int n = 0;
     const int n_nb = neighbours4(c, pos, nb);
     for (int i = 0; i < n_nb; i++) if (c.g.occ[nb[i]] < 0) out[n++] = nb[i];
@@ -1146,25 +1154,28 @@ __device__ __noinline__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
     const bool diseased = EXT && has_disease(c);
     if (!agent_alive(c, s) || !(diseased ? is_fertile_x(c, s) : is_fertile(c, s))) return;
     const int pos = a.pos[s];
-    int32_t nb0[4], nb[4];
-    const int n_nb = neighbours4(c, pos, nb0);               // (4 unless environmentWraparound is off)
-    for (int i = 0; i < 4; i++) nb[i] = i < n_nb ? nb0[i] : pos;
+    // NB: neighbours an agent can have -- 4, or 8 with the Moore neighbourhood, an option of the ordered mode only (the
+    // scalable mode's instantiations keep their arrays)
+    constexpr int NB = EXACT ? SSB_MAX_NEIGHBOURS : 4;
+    int32_t nb0[NB], nb[NB];
+    const int n_nb = neighbours4(c, pos, nb0);               // (4 unless environmentWraparound is off / neighborhoodMode is "moore")
+    for (int i = 0; i < NB; i++) nb[i] = i < n_nb ? nb0[i] : pos;
     rng.at(SITE_REPRODUCTION);
     shuffle(rng, nb, n_nb);
     // batch 1: occupancy of the neighbours (shuffled order) and of each neighbour's ring
-    int32_t o[4], ring[4][4], ring_occ[4][4], ring_n[4];
+    int32_t o[NB], ring[NB][NB], ring_occ[NB][NB], ring_n[NB];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < NB; k++) {
         o[k] = k < n_nb ? c.g.occ[nb[k]] : -1;
         ring_n[k] = k < n_nb ? neighbours4(c, nb[k], ring[k]) : 0;
 #pragma unroll
-        for (int j = 0; j < 4; j++) ring_occ[k][j] = j < ring_n[k] ? c.g.occ[ring[k][j]] : 0;
+        for (int j = 0; j < NB; j++) ring_occ[k][j] = j < ring_n[k] ? c.g.occ[ring[k][j]] : 0;
     }
     // batch 2: the mates' records
-    int m_cod[4], m_sex[4], m_age[4], m_fa[4], m_ia[4];
-    double m_sugar[4], m_spice[4], m_ss[4], m_sp[4], m_ff[4], m_fmod[4];      // m_fmod: the mate's fertility modifier (diseases)
+    int m_cod[NB], m_sex[NB], m_age[NB], m_fa[NB], m_ia[NB];
+    double m_sugar[NB], m_spice[NB], m_ss[NB], m_sp[NB], m_ff[NB], m_fmod[NB];      // m_fmod: the mate's fertility modifier (diseases)
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < NB; k++) {
         const bool has = o[k] >= 0;
         const int m = has ? o[k] : s;
         m_cod[k] = a.cod[m]; m_sex[k] = a.sex[m]; m_age[k] = a.age[m];
@@ -1174,7 +1185,7 @@ __device__ __noinline__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
         m_fmod[k] = diseased ? dis_mod(c, m, SSB_DM_FERTILITY) : 0.0;
     }
     // own empty neighbours, N S E W order, computed ONCE (agent.py:506): stale by design
-    int32_t own_empty[4];
+    int32_t own_empty[NB];
     int n_own = 0;
     for (int i = 0; i < n_nb; i++)
         for (int k = 0; k < n_nb; k++)
@@ -1186,9 +1197,10 @@ __device__ __noinline__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
     const double my_fmod = diseased ? dis_mod(c, s, SSB_DM_FERTILITY) : 0.0;
     const bool age_ok = my_age >= my_fa && my_age < my_ia && (diseased ? (my_ff + my_fmod) > 0 : my_ff > 0);
     unsigned long long *cn = (unsigned long long *)a.counters;
-    bool newborn_at[4] = {false, false, false, false};     // neighbour cell now holds a child of this call
+    bool newborn_at[NB];                                   // neighbour cell now holds a child of this call
+    for (int k = 0; k < NB; k++) newborn_at[k] = false;
     int births = 0;                                        // = len(mates): one child per neighbour at most
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < n_nb; k++) {
         if (o[k] < 0) continue;
         const int m = o[k];
         // neighbor.isAlive(): a newborn placed by this call is alive and never fertile at age 0
@@ -1204,7 +1216,7 @@ __device__ __noinline__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
         }
         const bool compatible = ((my_sex == SSB_SEX_FEMALE && mate_sex == SSB_SEX_MALE) ||
                                  (my_sex == SSB_SEX_MALE && mate_sex == SSB_SEX_FEMALE)) && mate_fertile;
-        int32_t pool[8];
+        int32_t pool[2 * NB];
         int np = 0;
         for (int i = 0; i < n_own; i++) pool[np++] = own_empty[i];
         for (int j = 0; j < ring_n[k]; j++) if (ring_occ[k][j] < 0) pool[np++] = ring[k][j];
@@ -1309,9 +1321,9 @@ __device__ __noinline__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
         }
         a.pos[ch] = cell;
         c.g.occ[cell] = ch;
-        for (int q = 0; q < 4; q++) {       // keep the local copies current
+        for (int q = 0; q < n_nb; q++) {    // keep the local copies current
             if (nb[q] == cell) { o[q] = ch; newborn_at[q] = true; }
-            for (int j = 0; j < 4; j++) if (ring[q][j] == cell) ring_occ[q][j] = ch;
+            for (int j = 0; j < ring_n[q]; j++) if (ring[q][j] == cell) ring_occ[q][j] = ch;
         }
         const long long nth = (long long)atomicAdd(&cn[SSB_C_N_BORN], 1ull);
         if (EXACT) {   // sugarscape.addAgent: the list grows while it is being iterated

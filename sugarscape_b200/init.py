@@ -91,8 +91,13 @@ def check_supported(c):
     problems = []
     if c["agentVisionMode"] != "cardinal" or c["agentMovementMode"] != "cardinal":
         problems.append("radial vision/movement")
-    if c["neighborhoodMode"] != "vonNeumann":
-        problems.append("moore neighbourhood")
+    if c["neighborhoodMode"] not in ("vonNeumann", "moore"):
+        problems.append("neighborhoodMode " + str(c["neighborhoodMode"]))
+    if c["neighborhoodMode"] == "moore":      # cell.py:77-89: eight neighbour cells (tagging, trade, births, lending, diseases, pollution flux)
+        if c.get("b200RngMode", "exact") != "exact":
+            problems.append("moore neighbourhood in the scalable RNG mode")
+        if c["agentLogfile"] is not None:
+            problems.append("moore neighbourhood with an agentLogfile")
     if not c["environmentWraparound"]:
         # cell.py:47-121: the neighbour lists lose the cells across the edge; the range tables (environment.py:111-122) do NOT
         # change as long as no range reaches half the map (they keep wrapping by `% width`, with the plain distance)
@@ -402,6 +407,8 @@ def rule_flags(c):
         f |= layout.F_TAGPREF
     if not c["environmentWraparound"]:
         f |= layout.F_NOWRAP
+    if c["neighborhoodMode"] == "moore":
+        f |= layout.F_MOORE
     return f
 
 

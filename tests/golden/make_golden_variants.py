@@ -82,6 +82,11 @@ VARIANTS = {
     "nowrap_trade_tagging_reproduction": ("trade_tagging_reproduction", 150, {"environmentWraparound": False}),
     "nowrap_pollution": ("trade_pollution", 120, {"environmentWraparound": False}),
     "nowrap_determinism": ("determinism", 120, {"environmentWraparound": False, "experimentalGroup": None}),
+    # ---- neighborhoodMode = "moore" (cell.py:77-89): eight neighbour cells in the order N, S, E, W, NE, NW, SE, SW -- alone
+    # and together with environmentWraparound = false
+    "moore_trade_tagging_reproduction": ("trade_tagging_reproduction", 150, {"neighborhoodMode": "moore"}),
+    "moore_pollution": ("trade_pollution", 120, {"neighborhoodMode": "moore"}),
+    "moore_nowrap_determinism": ("determinism", 120, {"neighborhoodMode": "moore", "environmentWraparound": False, "experimentalGroup": None}),
     # the "Top" orderings: the cell with the best ethical value wins
     "ethics_top": ("trade_tagging_reproduction", 100, dict(_ETHICS, agentDecisionModels=["benthamTop", "egoistTop", "altruistNoLookaheadTop", "none", "bentham"])),
     # diffusion timeframe that starts before the first step, delay > 1: the reference's countdown is first decremented

@@ -221,7 +221,7 @@ def _private_log_keys(orc, rs, t, ethics):
         rs.update(orc.ethics_log_keys(t, n, rs["meanNeighbors"]))
 
 
-@pytest.mark.parametrize("variant,ethics", [("determinism_plain", False), ("determinism_ethics", True), ("nowrap_determinism", True)])
+@pytest.mark.parametrize("variant,ethics", [("determinism_plain", False), ("determinism_ethics", True), ("nowrap_determinism", True), ("moore_nowrap_determinism", True)])
 def test_oracle_determinism_variants_match_reference_trajectory(variant, ethics):
     """examples/determinism.json (variant fixtures from the unmodified reference,
     tests/golden/make_golden_variants.py): diseases, depression, lending, friends, racial tags,
@@ -393,7 +393,7 @@ def test_oracle_environment_file_matches_reference_trajectory():
             assert _close(rs[k], log[t][k]), f"log key {k} differs at t={t}: {rs[k]} vs {log[t][k]}"
 
 
-@pytest.mark.parametrize("overrides", [{"agentVisionMode": "radial"}, {"neighborhoodMode": "moore"},
+@pytest.mark.parametrize("overrides", [{"agentVisionMode": "radial"}, {"neighborhoodMode": "moore", "b200RngMode": "scalable"},
                                        {"environmentWraparound": False, "b200RngMode": "scalable"},
                                        {"environmentWraparound": False, "agentVision": [1, 30], "agentMovement": [30, 30]},
                                        {"agentDecisionModels": ["asimov"]},
@@ -514,7 +514,8 @@ def test_scalable_mode_oracle_matches_patched_reference(name):
 
 # nowrap_*: environmentWraparound = false (cell.py:47-121) -- the neighbour lists of tagging / trade / births and the pollution
 # flux lose the cells across the map's edge (with the reference's own south-neighbour test)
-PLAIN_VARIANTS = ["pollution_diffusion_delay2", "pollution_diffusion_delay3", "nowrap_trade_tagging_reproduction", "nowrap_pollution"]
+PLAIN_VARIANTS = ["pollution_diffusion_delay2", "pollution_diffusion_delay3", "nowrap_trade_tagging_reproduction", "nowrap_pollution",
+                  "moore_trade_tagging_reproduction", "moore_pollution"]       # moore_*: neighborhoodMode "moore" (cell.py:77-89)
 
 
 @pytest.mark.parametrize("variant", PLAIN_VARIANTS)

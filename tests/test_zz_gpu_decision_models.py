@@ -143,7 +143,8 @@ def test_disease_cases_match_reference_trajectory(case):
 
 
 @pytest.mark.parametrize("variant,ethics", [("determinism_plain", False), ("determinism_ethics", True), ("nowrap_determinism", True),
-                                            ("nowrap_trade_tagging_reproduction", False), ("nowrap_pollution", False)])
+                                            ("nowrap_trade_tagging_reproduction", False), ("nowrap_pollution", False),
+                                            ("moore_nowrap_determinism", True), ("moore_trade_tagging_reproduction", False), ("moore_pollution", False)])
 def test_determinism_variants_match_reference_trajectory(variant, ethics):
     """examples/determinism.json without / with the ethics models, experimental-group split off (variant fixtures of the
     unmodified reference): every rule family at once.  nowrap_*: environmentWraparound = false (cell.py:47-121) on
