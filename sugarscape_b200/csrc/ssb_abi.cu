@@ -57,6 +57,7 @@ struct ssb_engine {
     int sweep_stamp;
     int sweep_bits_generic, sweep_bits_lean;
     int sweep_slab_bits_generic, sweep_slab_bits_lean;
+    int sweep_lean_per_sm_max;   // resident blocks per SM the lean sweep kernel could have (lean_blocks_for picks how many it gets)
     bool shard_sweep;            // sharded AND the sweep's arrays are stitched (ssb_set_shard_sweep): the ranks sweep their slabs
     void *own_desc, *own_done, *own_pcell;     // the engine's own allocations while the stitched ones are in use
     // stats
@@ -251,6 +252,20 @@ static int setup_flow(ssb_engine *e) {
 
 // The ordered sweep (ssb_sweep.cuh).  e->sweep_ok stays false when the engine is outside its limits (the rounds
 // scheduler then stays the default); a negative return is a real error.
+// Resident blocks of the lean sweep kernel for a list of up to `slots` entries.  The sweep is bound by the dependency depth of
+// the step times the latency of one transaction, not by the number of lanes: on a short list (a small map, a rank's share
+// of a sharded one) most lanes of a full grid only hold agents that wait for each other, and every resident warp slows the
+// ones that run.  Measured on S2 rules (profiles/r2_09_sweep_blocks_probe.jsonl): 1.56 M agents 3.3 ms with 5 blocks per SM,
+// 1.55 ms with 1; 6.25 M agents 5.0 ms with 5, 2.8 ms with 2; 25 M agents are fastest with all 5.  Rule: about 80 live
+// agents per lane (live agents ~ slots / 1.5).  SSB_SWEEP_BLOCKS_PER_SM overrides.
+static int lean_blocks_for(const ssb_engine *e, long long slots) {
+    int per_sm = (int)((slots * 2 / 3 + (long long)LEAN_THREADS * e->num_sms * 40) / ((long long)LEAN_THREADS * e->num_sms * 80));
+    if (getenv("SSB_SWEEP_BLOCKS_PER_SM") && atoi(getenv("SSB_SWEEP_BLOCKS_PER_SM")) > 0) per_sm = atoi(getenv("SSB_SWEEP_BLOCKS_PER_SM"));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > e->sweep_lean_per_sm_max) per_sm = e->sweep_lean_per_sm_max;
+    return per_sm * e->num_sms;
+}
+
 // the build kernel stages one occupancy bit-plane per slab: its grid (resident CTAs) depends on their number
 static int size_build_grid(ssb_engine *e, int n_slabs, int *blocks) {
     SweepCtx &w = e->sweep;
@@ -297,7 +312,8 @@ static int setup_sweep(ssb_engine *e, int maxd) {
         if (e->lean_mode == 0) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_lean<0>, LEAN_THREADS, lean_smem));
         else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_lean<LEAN_M_ALL>, LEAN_THREADS, lean_smem));
         if (per_sm < 1) return fail(e, -3, "the lean sweep kernel does not fit on an SM (%d bytes of shared memory)", lean_smem);
-        e->sweep_lean_blocks = per_sm * e->num_sms;
+        e->sweep_lean_per_sm_max = per_sm;
+        e->sweep_lean_blocks = lean_blocks_for(e, cap);
         CU(cudaMalloc(&L.a, sizeof(LeanA) * cap));
         CU(cudaMemset(L.a, 0, sizeof(LeanA) * cap));
         CU(cudaMalloc(&L.b, sizeof(LeanB) * cap));
@@ -1053,7 +1069,8 @@ int ssb_set_shard_sweep(ssb_engine_t *e, void *desc, void *done, void *pcell) {
     w.world = e->sh.world; w.rank = e->sh.rank;
     w.wm_pages = e->sh.ctrl + 256;                    // (the pages' message slots end at word 192)
     w.wm_stride = e->sh.ctrl_stride;
-    // a rank walks its own list: buckets and slabs sized for a rank's share of the slots (the same on every rank)
+    // a rank walks its own list: grid, buckets and slabs sized for a rank's share of the slots (the same on every rank)
+    e->sweep_lean_blocks = lean_blocks_for(e, e->local_slots);
     const long long T = (long long)e->sweep_lean_blocks * LEAN_THREADS;
     e->sweep_bits_lean = sweep_bucket_bits(e->local_slots, T, e->p.id_bits, SWEEP_MAX_KEY_BITS - SWEEP_LEAN_SUB_BITS);
     e->sweep_slab_bits_lean = sweep_slab_bits(e->local_slots, T);
