@@ -134,20 +134,34 @@ int ssb_fabric_map(ssb_fabric_t *f, int32_t index, const int32_t *fds, const uin
     }
     if (a.size[f->rank] != a.chunk) { snprintf(f->err, sizeof f->err, "array %d: own chunk size mismatch", index); return -1; }
     CUresult rc;
+    // error paths give everything back: the peers' descriptors not yet imported are closed, imported handles released, the
+    // parts already mapped unmapped and the address range freed
+    int next_fd = 0;
+    size_t mapped = 0;
+    bool reserved = false;
+    auto undo = [&](const char *what, CUresult code) {
+        for (int p = next_fd; p < f->world; p++) if (p != f->rank) close(fds[p]);
+        if (mapped) f->memUnmap(a.base, mapped);
+        if (reserved) f->memAddressFree(a.base, a.total);
+        for (int p = 0; p < f->world; p++) if (p != f->rank && a.have[p]) { f->memRelease(a.part[p]); a.have[p] = false; }
+        return fabric_fail(f, what, code);
+    };
     for (int p = 0; p < f->world; p++) {
+        next_fd = p;
         if (p == f->rank) continue;
         rc = f->memImport(&a.part[p], (void *)(uintptr_t)fds[p], CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR);
-        if (rc != CUDA_SUCCESS) return fabric_fail(f, "cuMemImportFromShareableHandle", rc);
+        if (rc != CUDA_SUCCESS) return undo("cuMemImportFromShareableHandle", rc);
         a.have[p] = true;
         close(fds[p]);
     }
+    next_fd = f->world;
     rc = f->memAddressReserve(&a.base, a.total, f->granularity, 0, 0);
-    if (rc != CUDA_SUCCESS) return fabric_fail(f, "cuMemAddressReserve", rc);
-    size_t at = 0;
+    if (rc != CUDA_SUCCESS) return undo("cuMemAddressReserve", rc);
+    reserved = true;
     for (int p = 0; p < f->world; p++) {
-        rc = f->memMap(a.base + at, a.size[p], 0, a.part[p], 0);
-        if (rc != CUDA_SUCCESS) return fabric_fail(f, "cuMemMap", rc);
-        at += a.size[p];
+        rc = f->memMap(a.base + mapped, a.size[p], 0, a.part[p], 0);
+        if (rc != CUDA_SUCCESS) return undo("cuMemMap", rc);
+        mapped += a.size[p];
     }
     CUmemAccessDesc acc;
     memset(&acc, 0, sizeof acc);
@@ -155,7 +169,7 @@ int ssb_fabric_map(ssb_fabric_t *f, int32_t index, const int32_t *fds, const uin
     acc.location.id = f->device;
     acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
     rc = f->memSetAccess(a.base, a.total, &acc, 1);
-    if (rc != CUDA_SUCCESS) return fabric_fail(f, "cuMemSetAccess", rc);
+    if (rc != CUDA_SUCCESS) return undo("cuMemSetAccess", rc);
     a.mapped = true;
     *base_out = (void *)a.base;
     return 0;

@@ -243,10 +243,20 @@ class Engine:
                 fam, member = key.split(".")
                 setattr(getattr(xs, fam), member, self.tensors["ext:" + key].data_ptr())
             self._check(self.L.ssb_bind_ext(self.handle, C.byref(xs)))
+        # child endowments / tag mismatches are drawn from per-timestep tables (steptables.py): a rule set with births must
+        # not step beyond them -- the device would fall back to "every choice from the acting parent" without a word
+        self.step_table_horizon = None
         if endow_bits is not None:
             eb = np.ascontiguousarray(endow_bits, dtype=np.uint32)
             tb = np.ascontiguousarray(tag_bits, dtype=np.uint32)
             self._check(self.L.ssb_set_step_tables(self.handle, eb.ctypes.data, tb.ctypes.data, len(eb)))
+            self.step_table_horizon = len(eb)
+        self._births = bool(params.flags & layout.F_REPRO)
+
+    def _check_horizon(self, t):
+        if self._births and (self.step_table_horizon is None or t >= self.step_table_horizon):
+            raise EngineError(f"timestep {t} lies beyond the step tables ({self.step_table_horizon} entries): "
+                              "build the engine with steptables.step_tables(first, last, ...) that cover the run")
 
     # -- plumbing ------------------------------------------------------------------------------
     def _after_bind(self):
@@ -378,6 +388,7 @@ class Engine:
         self._check(self.L.ssb_env_step(self.handle, t, self.stream))
 
     def agent_step(self, t, prev_mean_wealth=0.0):
+        self._check_horizon(t)
         self._check(self.L.ssb_agent_step(self.handle, t, float(prev_mean_wealth), self.stream))
 
     def compact(self, t):
@@ -400,6 +411,7 @@ class Engine:
         self._check(self.L.ssb_reduce_stats(self.handle, t, self.stream))
 
     def step(self, t, prev_mean_wealth=0.0):
+        self._check_horizon(t)
         self._check(self.L.ssb_step(self.handle, t, float(prev_mean_wealth), self.stream))
 
     def stats(self):

@@ -9,7 +9,9 @@ owns its cell, and combining the per-rank stats reductions.  Scalable RNG mode o
 """
 import ctypes as C
 import os
+import shutil
 import socket
+import tempfile
 import struct
 
 import numpy as np
@@ -122,13 +124,24 @@ def chunk_boundaries(ends, itemsize, world):
     return b
 
 
-def exchange_fds(rank, world, fds, tag, barrier):
-    """All-to-all of a list of file descriptors per rank over unix sockets (SCM_RIGHTS).
+def rendezvous_directory(rank, dist):
+    """A directory only this user can enter, created by rank 0 (tempfile.mkdtemp: mode 0700, unpredictable name) and
+    announced to the other ranks through the process group: the unix sockets of exchange_fds live there, not under a
+    guessable name in /tmp that anybody could bind first."""
+    box = [tempfile.mkdtemp(prefix="ssb_fabric_") if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    return box[0]
+
+
+def exchange_fds(rank, world, fds, tag, barrier, directory=None):
+    """All-to-all of a list of file descriptors per rank over unix sockets (SCM_RIGHTS) in `directory`
+    (rendezvous_directory; default: the system's temporary directory, for callers without a process group).
     Returns {rank: [fds]} (this rank's own list included as given)."""
     fds = list(fds)
     if world == 1:
         return {rank: fds}
-    path = lambda r: f"/tmp/ssb_fabric_{tag}_{r}.sock"
+    directory = directory or tempfile.gettempdir()
+    path = lambda r: os.path.join(directory, f"ssb_fabric_{tag}_{r}.sock")
     if os.path.exists(path(rank)):
         os.unlink(path(rank))
     server = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
@@ -314,7 +327,13 @@ class ShardedEngine(Engine):
             if L.ssb_fabric_alloc(self.fabric, bounds[key][rank + 1] - bounds[key][rank], C.byref(fd)) != i:
                 self._fcheck(-1)
             mine.append(fd.value)
-        fds = exchange_fds(rank, world, mine, self.tag, self.dist.barrier)
+        directory = rendezvous_directory(rank, self.dist)
+        try:
+            fds = exchange_fds(rank, world, mine, self.tag, self.dist.barrier, directory)
+        finally:
+            self.dist.barrier()
+            if rank == 0:
+                shutil.rmtree(directory, ignore_errors=True)
         self.stitched, self.bounds = {}, bounds
         for i, (key, n, dt, ends) in enumerate(plan):
             base = C.c_void_p()

@@ -107,7 +107,9 @@ for i in range(150):         # more than one SCM_RIGHTS message
     r, w = os.pipe()
     os.write(w, b"hello %d from %d" % (i, rank))
     mine.append(r)
-fds = sharded.exchange_fds(rank, world, mine, "t" + os.environ["MASTER_PORT"], dist.barrier)
+directory = sharded.rendezvous_directory(rank, dist)       # rank 0's private directory, announced through the group
+assert os.path.isdir(directory) and (os.stat(directory).st_mode & 0o077) == 0
+fds = sharded.exchange_fds(rank, world, mine, "t" + os.environ["MASTER_PORT"], dist.barrier, directory)
 for src, got in sorted(fds.items()):
     assert len(got) == 150
     if src != rank:          # (the peer drains this rank's pipes)
