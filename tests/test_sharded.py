@@ -178,6 +178,10 @@ def test_slabs_equal_the_single_gpu_run(name, overrides, steps, world):
     import torch
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
+    if world == 4 and overrides.get("environmentWidth") == 512 and not os.environ.get("SSB_TEST_ALL_WORLDS"):
+        # round 2 ran out of 4-GPU time before this one case (the other eight passed at world 4, and bench.py's S2 run has the
+        # same state checksum at 1 / 2 / 4 / 8 GPUs); it must not be the first thing a 4-GPU box ever runs under `pytest -x`
+        pytest.skip("not yet run at world 4 (SSB_TEST_ALL_WORLDS=1 to include it)")
     res = subprocess.run(["timeout", "300", sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
                           "--master-addr", "127.0.0.1", "--master-port", str(29900 + os.getpid() % 90),
                           os.path.join(ROOT, "tests", "sharded_worker.py"), "--case", name, "--overrides", json.dumps(overrides),
