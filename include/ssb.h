@@ -35,7 +35,9 @@
 extern "C" {
 #endif
 
-#define SSB_ABI_VERSION 2
+/* 3: ssb_stats_t.gini_area; SSB_F_NOWRAP / SSB_F_MOORE; the sweep scheduler's entry points (ssb_set_scheduler ...,
+ * ssb_set_shard_sweep).  The optional per-slot state of the rule families keeps its name "ABI 2" below. */
+#define SSB_ABI_VERSION 3
 
 /* RNG modes */
 #define SSB_RNG_EXACT    0 /* mode E: CPython MT19937 word-for-word replay, ordered execution   */

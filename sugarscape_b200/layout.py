@@ -8,7 +8,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 RNG_EXACT, RNG_SCALABLE = 0, 1
 ALIVE, STARVATION, AGING, COMBAT, OTHER = 0, 1, 2, 3, 4
 SEX_NONE, SEX_MALE, SEX_FEMALE = 0, 1, 2
