@@ -42,3 +42,15 @@ def test_reference_arm_only_rank0_prints(tmp_path):
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
                           "--size", "256", "--cpu-steps", "1"], capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0 and '"impl": "reference"' in out.stdout
+    # the contract of the reference arm's line
+    import json
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["metric"] == "agent_steps_per_second" and line["unit"] == "agent-steps/s" and line["higher_is_better"] is True
+    assert "workload" in line["config"] and "model" not in line["config"] and "ran" in line["config"]
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] == 1 and cb["value"] == line["value"] and cb["sample"] and cb["state_after"]
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["vs_baseline"] is None and line["value"] > 0
