@@ -24,10 +24,27 @@ class OracleEngine:
 
     def __init__(self, params, host_state, device=0, endow_bits=None, tag_bits=None):
         self.params, self.state = params, host_state
+        self.width, self.height, self.capacity = params.width, params.height, host_state.capacity
         self.orc = Oracle(params, host_state, endow_bits, tag_bits)
         self.t_stats = 0
         self.replacing = False
         self.tensors = {}
+
+    # the oracle IS the sequential order: every scheduler name is accepted and means the same
+    def set_scheduler(self, name):
+        self._scheduler = name
+
+    def scheduler(self):
+        return getattr(self, "_scheduler", "rounds")
+
+    def set_mark_shift(self, shift):
+        pass
+
+    def set_epochs(self, epochs):
+        pass
+
+    def uses_lean_transaction(self):
+        return False
 
     def set_mt_from_python(self):
         self.orc.set_mt_from_python()
