@@ -77,6 +77,12 @@ ENGINE_OPTIONS = {
     "b200RngMode": "exact",      # "exact" (mode E) | "scalable" (mode S)
     "b200Device": 0,
     "b200StatsEvery": 1,         # reduce + log every k-th step (1 = reference behaviour)
+    # headless stand-in for the reference's window (sugarscape_b200/frames.py): one PPM image of the map per timestep
+    "b200FrameDump": None,       # directory (None: no frames)
+    "b200FrameDumpEvery": 1,     # every k-th timestep
+    "b200FrameColor": "default",             # agents: "default" (the GUI's red) | "tribes" | "sex"
+    "b200FrameEnvironment": "sugarAndSpice", # empty cells: "sugarAndSpice" | "pollution"
+    "b200FrameScale": 1,         # pixels per cell side
 }
 
 

@@ -13,7 +13,7 @@ import random
 
 import numpy as np
 
-from . import init, layout, stats, steptables
+from . import frames, init, layout, stats, steptables
 from .engine import Engine
 
 
@@ -55,6 +55,10 @@ class Sugarscape:
         self.logFormat = c["logfileFormat"]
         self.agentLog = open(c["agentLogfile"], "a") if c["agentLogfile"] is not None else None
         self.agentRuntimeStats = []
+        # headless stand-in for the reference's window (gui.py): one image of the map per timestep (frames.py)
+        self.frames = frames.FrameDump(c)
+        if self.frames.wanted(0):
+            self.frames.write(0, self.engine.download(frames.FrameDump.FIELDS))
 
     # -- one timestep --------------------------------------------------------------------------
     def doTimestep(self):
@@ -76,6 +80,8 @@ class Sugarscape:
         self.updateRuntimeStats(st, replaced)
         if self.agentLog is not None:
             self.agentRuntimeStats += [stats.agent_log_entry(r) for r in eng.agent_records()]
+        if self.frames.wanted(t):
+            self.frames.write(t, eng.download(frames.FrameDump.FIELDS))
         if self.timestep != self.maxTimestep and self.n_agents > 0:
             self.writeToLog()
             # the per-agent log starts once agents have acted (sugarscape.py:417-421): startLog writes the records of
