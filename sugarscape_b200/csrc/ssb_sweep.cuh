@@ -75,6 +75,10 @@ struct SweepCtx {
     uint64_t key;
 };
 
+// sharded: a rank also waits for its peers' kernels to START (their hosts enqueue them on their own clocks): the limit of the
+// box-wide barriers (SHARD_TIMEOUT_NS, 20 s) applies
+__device__ __forceinline__ unsigned long long sweep_stall_limit(const SweepCtx &w) { return w.world > 1 ? SHARD_TIMEOUT_NS : SWEEP_STALL_NS; }
+
 __device__ __forceinline__ unsigned long long sweep_ld_relaxed(const unsigned long long *p) {
     unsigned long long v;
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -496,7 +500,7 @@ __device__ __noinline__ void sweep_watermark_warp(const DevCtx &c, const SweepCt
         }
         __nanosleep(100);
         if (*(const volatile unsigned long long *)(w.ctl + 1) != 0ull) return;
-        if (global_ns() - last > SWEEP_STALL_NS) {
+        if (global_ns() - last > sweep_stall_limit(w)) {
             atomicExch((unsigned long long *)&c.a.counters[SSB_C_OVERFLOW], (unsigned long long)SWEEP_OVERFLOW_STALL);
             atomicExch(w.ctl + 1, 1ull);
             return;
@@ -534,7 +538,7 @@ __device__ __forceinline__ bool sweep_idle(const DevCtx &c, const SweepCtx &w, u
     __nanosleep(64);
     const unsigned long long now = global_ns();
     if (idle_since == 0) idle_since = now;
-    else if (now - idle_since > SWEEP_STALL_NS) {
+    else if (now - idle_since > sweep_stall_limit(w)) {
         if ((threadIdx.x & 31) == 0) {
             atomicExch((unsigned long long *)&c.a.counters[SSB_C_OVERFLOW], (unsigned long long)SWEEP_OVERFLOW_STALL);
             atomicExch(w.ctl + 1, 1ull);
