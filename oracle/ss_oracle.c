@@ -1101,8 +1101,10 @@ typedef struct { int32_t cell; int32_t dist; double welfare; } cand_t;
 #define MAX_CAND 256
 
 /* agent.py:766-779 with the insertion order of environment.py:111-122 */
+static int enumerate_disc(const ctx_t *c, int pos, int r, int32_t *cells, int32_t *dists);
 static int enumerate_cross(const ctx_t *c, int pos, int r, int32_t *cells, int32_t *dists) {
     int W = c->p->width, H = c->p->height, x = pos / H, y = pos % H, n = 0;
+    if (c->p->flags & SSB_F_RADIAL) return enumerate_disc(c, pos, r, cells, dists);
     for (int d = 1; d <= r; d++) {
         int64_t key[4]; int32_t cell[4]; int m = 0;
         if (d <= c->max_dx) {
@@ -1128,10 +1130,41 @@ static int enumerate_cross(const ctx_t *c, int pos, int r, int32_t *cells, int32
 }
 
 
+/* agentVisionMode = agentMovementMode = "radial" (SSB_F_RADIAL): Environment.findRadialCellRanges (environment.py:157-173)
+ * walks every pair (i, j > i) of the x-major cell list and files each cell under ranges[floor(distance)] of the other, so
+ * ranges[g] of a cell lists its partners in ascending order of their own list index; findCellsInRange (agent.py:766-779)
+ * concatenates ranges[1 .. r].  Restated literally: one pass over the whole cell list per ring.  The travel distance
+ * sqrt(dx^2 + dy^2) is only compared by its users (agent.py:1430, 1484): dists[] carries dx^2 + dy^2. */
+static int wrap_distance(int delta, int border) {          /* findWraparoundDistance (environment.py:175-179), wraparound on */
+    delta = abs(delta);
+    if (2 * delta > border) delta = border - delta;
+    return delta;
+}
+static int enumerate_disc(const ctx_t *c, int pos, int r, int32_t *cells, int32_t *dists) {
+    const int W = c->p->width, H = c->p->height, x1 = pos / H, y1 = pos % H;
+    int n = 0;
+    for (int g = 1; g <= r; g++)
+        for (int j = 0; j < W * H; j++) {
+            const int dx = wrap_distance(x1 - j / H, W), dy = wrap_distance(y1 - j % H, H);
+            if (j == pos || dx > c->max_dx || dy > c->max_dy) continue;
+            if ((int)floor(sqrt((double)(dx * dx + dy * dy))) != g) continue;
+            if (n < MAX_CAND) { cells[n] = j; dists[n++] = dx * dx + dy * dy; }
+        }
+    return n;
+}
+/* Environment.maxCellDistance (environment.py:140-146) */
+static int max_cell_distance(const ctx_t *c) {
+    if (c->p->flags & SSB_F_RADIAL) {
+        const int hw = c->p->width / 2, hh = c->p->height / 2, lim = (int)floor(sqrt((double)(hw * hw + hh * hh)));
+        return c->p->max_agent_range < lim ? c->p->max_agent_range : lim;
+    }
+    return c->max_dx > c->max_dy ? c->max_dx : c->max_dy;
+}
+
 /* ---- Bentham: findBestEthicalCell / findEthicalValueOfCell ------------------------------------ */
 static int agent_range(const ctx_t *c, int s) {           /* findCellsInRange (agent.py:766-779) */
     int vision = (int)EFF_VISION(c, s), movement = (int)EFF_MOVEMENT(c, s);
-    int maxd = c->max_dx > c->max_dy ? c->max_dx : c->max_dy;
+    int maxd = max_cell_distance(c);
     int r = vision < movement ? vision : movement;
     return r > maxd ? maxd : r;
 }
@@ -1139,6 +1172,10 @@ static int cell_in_cross(const ctx_t *c, int centre, int r, int cell) {
     const int W = c->p->width, H = c->p->height;
     const int x = centre / H, y = centre % H, cx = cell / H, cy = cell % H;
     if (cell == centre || r <= 0) return 0;
+    if (c->p->flags & SSB_F_RADIAL) {
+        const int dx = wrap_distance(cx - x, W), dy = wrap_distance(cy - y, H);
+        return dx <= c->max_dx && dy <= c->max_dy && (int)floor(sqrt((double)(dx * dx + dy * dy))) <= r;
+    }
     if (cx == x) { int d = abs(cy - y); if (H - d < d) d = H - d; return d <= (r < c->max_dy ? r : c->max_dy); }
     if (cy == y) { int d = abs(cx - x); if (W - d < d) d = W - d; return d <= (r < c->max_dx ? r : c->max_dx); }
     return 0;
@@ -1210,7 +1247,7 @@ static int move_to_best_cell(ctx_t *c, int s) {
     const ssb_agents_t *a = &c->a;
     int pos = a->pos[s];
     int vision = (int)EFF_VISION(c, s), movement = (int)EFF_MOVEMENT(c, s);
-    int maxd = c->max_dx > c->max_dy ? c->max_dx : c->max_dy;
+    int maxd = max_cell_distance(c);
     int r = vision < movement ? vision : movement;
     if (r > maxd) r = maxd;
     int32_t cells[MAX_CAND], dists[MAX_CAND];

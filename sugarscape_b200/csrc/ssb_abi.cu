@@ -375,7 +375,12 @@ int ssb_bind(ssb_engine_t *e, const ssb_grid_t *grid, const ssb_agents_t *agents
     c.max_dx = rmax < e->p.width / 2 ? rmax : e->p.width / 2;
     c.max_dy = rmax < e->p.height / 2 ? rmax : e->p.height / 2;
     const int maxd = c.max_dx > c.max_dy ? c.max_dx : c.max_dy;
-    if (e->p.rng_mode == SSB_RNG_EXACT && 4 * maxd > MAXC_EXACT) return fail(e, -1, "agent range %d exceeds the exact-mode limit %d", maxd, MAXC_EXACT / 4);
+    if (e->p.flags & SSB_F_RADIAL) {       // discs (environment.py:146-173): exact mode, torus; the candidate arrays hold MAXC_EXACT cells
+        if (e->p.rng_mode != SSB_RNG_EXACT || (e->p.flags & SSB_F_NOWRAP)) return fail(e, -1, "radial ranges need the exact RNG mode and wraparound");
+        // (how far an agent really sees is min(vision, movement), not max_agent_range: the host checks the configured
+        // ranges, an agent pushed beyond the candidate arrays by disease bonuses stops the run -- overflow code 15)
+    }
+    if (e->p.rng_mode == SSB_RNG_EXACT && !(e->p.flags & SSB_F_RADIAL) && 4 * maxd > MAXC_EXACT) return fail(e, -1, "agent range %d exceeds the exact-mode limit %d", maxd, MAXC_EXACT / 4);
     if (e->p.rng_mode == SSB_RNG_SCALABLE && 4 * maxd > MAXC_SCALABLE) return fail(e, -1, "agent range %d exceeds the scalable-mode limit %d", maxd, MAXC_SCALABLE / 4);
     if (e->p.rng_mode == SSB_RNG_SCALABLE && (maxd + 2 >= e->p.width || maxd + 2 >= e->p.height)) return fail(e, -1, "map too small for the scalable mode footprints");
     const int64_t cap = agents->capacity, cells = grid->n_cells;
@@ -1143,8 +1148,9 @@ static int check_overflow(ssb_engine_t *e) {
                                  "a scheduler made no progress for seconds", "live slots differ from the agent list",
                                  "a priority bucket of the sweep is longer than its grid",
                                  "an agent contradicts the rule flags the lean kernel was chosen by",
-                                 "environmentWraparound = false: an agent sees beyond half the map (not reproduced)"};
-    return fail(e, -4, "engine overflow code %lld: %s", code, code > 0 && code < 15 ? what[code] : "?");
+                                 "environmentWraparound = false: an agent sees beyond half the map (not reproduced)",
+                                 "radial ranges: an agent sees more cells than the candidate arrays hold"};
+    return fail(e, -4, "engine overflow code %lld: %s", code, code > 0 && code < 16 ? what[code] : "?");
 }
 
 int ssb_stats(ssb_engine_t *e, ssb_stats_t *host_out) {

@@ -6,7 +6,7 @@
 
 namespace ssb {
 
-constexpr int MAXC_EXACT = 128;   // up to 4 * 32 candidate cells
+constexpr int MAXC_EXACT = 160;   // up to 4 * 40 candidate cells of a cross, or the 144 of a radial range of 6
 static_assert(MAXC_EXACT == MAXC_EXACT_RULES, "ssb_rules.cuh sizes its ranking arrays for MAXC_EXACT candidates");
 
 // random.shuffle(self.agents), then every agent of the list in order; the list grows while it is

@@ -57,7 +57,7 @@ __device__ __forceinline__ int wrapi(int v, int n) { v %= n; return v < 0 ? v + 
 __device__ __forceinline__ int wrap1(int v, int n) { return v < 0 ? v + n : (v >= n ? v - n : v); }
 
 // Lane groups: G consecutive lanes of a warp (G = 32, 16, 8, 4) cooperate on one agent.
-constexpr int MAXC_EXACT_RULES = 128;   // = MAXC_EXACT (ssb_exact.cuh): candidate cells of one ranking in mode E
+constexpr int MAXC_EXACT_RULES = 160;   // = MAXC_EXACT (ssb_exact.cuh): candidate cells of one ranking in mode E
 
 template <class Rng> struct RngTraits { static constexpr bool ordered = false; };
 template <> struct RngTraits<RngExact> { static constexpr bool ordered = true; };      // mode E: the one ordered stream
@@ -354,6 +354,67 @@ __device__ __forceinline__ void collect(const DevCtx &c, int s, int pos) {
     if (c.p.flags & SSB_F_SPICE) c.g.spice[pos] = 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// agentVisionMode = agentMovementMode = "radial" (SSB_F_RADIAL; environment.py:146-173, exact mode, with wraparound): the
+// cells in range of an agent are the disc floor(sqrt(dx^2 + dy^2)) <= r of the cells with dx <= max_dx and dy <= max_dy
+// (wraparound distances).  Environment.findRadialCellRanges walks the pairs (i, j > i) of the x-major cell list, so within
+// one ring g = floor(distance) a cell's partners enter its dict in ascending order of THEIR x * height + y; findCellsInRange
+// concatenates the rings 1 .. r.  The travel distance sqrt(dx^2 + dy^2) is only ever compared (agent.py:1430, 1484), so
+// the engine keeps dx^2 + dy^2 in its place (same order; < 256 for the ranges the candidate arrays hold).
+// ---------------------------------------------------------------------------------------------
+constexpr int SSB_MAX_RADIAL = 15;      // (r + 1)^2 <= 256: squared distances fit the 8-bit distance field
+__device__ __forceinline__ bool radial(const DevCtx &c) { return (c.p.flags & SSB_F_RADIAL) != 0; }
+__device__ __forceinline__ int isqrt_small(int v) { int g = 0; while ((g + 1) * (g + 1) <= v) g++; return g; }
+// Environment.maxCellDistance (environment.py:140-146): the cap of findCellsInRange (agent.py:770)
+__device__ __forceinline__ int max_cell_distance(const DevCtx &c) {
+    if (!radial(c)) return max(c.max_dx, c.max_dy);
+    const int hw = c.p.width / 2, hh = c.p.height / 2;
+    return min(c.p.max_agent_range, isqrt_small(hw * hw + hh * hh));
+}
+// the coordinates within wraparound distance md of `centre` on an axis of n cells, ascending: at most 2 * md + 1 (n when
+// 2 * md = n: the two ends coincide); out_v / out_d = coordinate and distance
+__device__ __forceinline__ int axis_span(int centre, int md, int n, int *out_v, int *out_d) {
+    const int lo = centre - md, hi = 2 * md >= n ? lo + n - 1 : centre + md;
+    int k = 0;
+    for (int p = max(lo, n); p <= hi; p++) { out_v[k] = p - n; out_d[k++] = abs(p - centre); }                 // wrapped past the end
+    for (int p = max(lo, 0); p <= min(hi, n - 1); p++) { out_v[k] = p; out_d[k++] = abs(p - centre); }
+    for (int p = lo; p <= min(hi, -1); p++) { out_v[k] = p + n; out_d[k++] = abs(p - centre); }                // wrapped before 0
+    return k;
+}
+// f(cell, squared distance, ring) over the disc of range r around (x, y), cells in ascending x * height + y
+template <class F>
+__device__ __forceinline__ void for_disc(const DevCtx &c, int x, int y, int r, F f) {
+    int xs[2 * SSB_MAX_RADIAL + 1], dxs[2 * SSB_MAX_RADIAL + 1], ys[2 * SSB_MAX_RADIAL + 1], dys[2 * SSB_MAX_RADIAL + 1];
+    const int H = c.p.height;
+    r = min(r, SSB_MAX_RADIAL);                                         // (enumerate_disc flags longer ranges)
+    const int nx = axis_span(x, min(c.max_dx, r), c.p.width, xs, dxs), ny = axis_span(y, min(c.max_dy, r), H, ys, dys);     // dx, dy <= r inside the disc
+    for (int i = 0; i < nx; i++)
+        for (int j = 0; j < ny; j++) {
+            const int d2 = dxs[i] * dxs[i] + dys[j] * dys[j];
+            if (d2 == 0 || d2 >= (r + 1) * (r + 1)) continue;
+            f(xs[i] * H + ys[j], d2, isqrt_small(d2));
+        }
+}
+__device__ int enumerate_disc(const DevCtx &c, int x, int y, int r, const WarpScratch &ws, int maxc) {
+    int start[SSB_MAX_RADIAL + 2] = {};
+    const bool too_far = r > SSB_MAX_RADIAL;
+    if (!too_far) {
+        for_disc(c, x, y, r, [&](int, int, int g) { start[g + 1]++; });
+        for (int g = 1; g <= r + 1; g++) start[g] += start[g - 1];      // start[g]: first slot of ring g
+    }
+    if (too_far || start[r + 1] > maxc) {                                 // the host refuses such ranges; disease bonuses can still get here
+        atomicExch((unsigned long long *)&c.a.counters[SSB_C_OVERFLOW], 15ull);
+        return 0;
+    }
+    for_disc(c, x, y, r, [&](int cell, int d2, int g) { const int i = start[g]++; ws.cells[i] = cell; ws.dist[i] = (uint8_t)d2; });
+    return start[r];
+}
+__device__ int disc_size(const DevCtx &c, int r) {                       // len(cellsInRange): the same wherever the agent stands
+    int n = 0;
+    for_disc(c, 0, 0, r, [&](int, int, int) { n++; });
+    return n;
+}
+
 // Candidate cells of Agent.findCellsInRange (agent.py:766-779) in the dictionary insertion
 // order produced by Environment.findCardinalCellRanges (environment.py:111-122) -- SURVEY.md
 // Appendix A.5.  Per distance d the (up to) four cells appear in the order in which the table
@@ -387,7 +448,7 @@ __device__ int enumerate_cross(const DevCtx &c, int x, int y, int r, const WarpS
 
 __device__ __forceinline__ int agent_range(const DevCtx &c, int s) {
     const int vision = max(c.a.vision[s], 0), movement = max(c.a.movement[s], 0);
-    return min(min(vision, movement), max(c.max_dx, c.max_dy));
+    return min(min(vision, movement), max_cell_distance(c));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -408,6 +469,7 @@ __device__ __forceinline__ double time_to_live(const DevCtx &c, int s, bool age_
 
 // len(cellsInRange) of an agent with range r: the cross does not depend on where it stands
 __device__ __forceinline__ int cross_size(const DevCtx &c, int r) {
+    if (radial(c)) return disc_size(c, r);
     int n = 0;
     for (int d = 1; d <= r; d++) {
         if (d <= c.max_dx) n += (2 * d == c.p.width) ? 1 : 2;
@@ -420,6 +482,10 @@ __device__ __forceinline__ int cross_size(const DevCtx &c, int r) {
 __device__ int cross_live_count(const DevCtx &c, int centre, int r) {
     const int W = c.p.width, H = c.p.height, x = centre / H, y = centre - x * H;
     int n = 0;
+    if (radial(c)) {
+        for_disc(c, x, y, r, [&](int cell, int, int) { const int o = c.g.occ[cell]; if (o >= 0 && agent_alive(c, o)) n++; });
+        return n;
+    }
     for (int d = 1; d <= r; d++) {
         if (d <= c.max_dx) {
             const int xw = wrapi(x - d, W), xe = wrapi(x + d, W);
@@ -442,6 +508,12 @@ __device__ __forceinline__ bool cell_in_cross(const DevCtx &c, int centre, int r
     const int W = c.p.width, H = c.p.height;
     const int x = centre / H, y = centre - x * H, cx = cell / H, cy = cell - cx * H;
     if (cell == centre || r <= 0) return false;
+    if (radial(c)) {
+        int dx = abs(cx - x), dy = abs(cy - y);
+        if (W - dx < dx) dx = W - dx;
+        if (H - dy < dy) dy = H - dy;
+        return dx <= c.max_dx && dy <= c.max_dy && dx * dx + dy * dy < (r + 1) * (r + 1);
+    }
     if (cx == x) { int d = abs(cy - y); if (H - d < d) d = H - d; return d <= min(r, c.max_dy); }
     if (cy == y) { int d = abs(cx - x); if (W - d < d) d = W - d; return d <= min(r, c.max_dx); }
     return false;
@@ -474,7 +546,7 @@ __device__ __noinline__ double ethical_value(const DevCtx &c, int s, int my_r, c
     for (int k = 0; k < n_hood; k++) {
         const int nb = hood[k];
         if (!agent_alive(c, nb)) continue;
-        const int rn = min(min((int)eff_vision(c, nb), (int)eff_movement(c, nb)), max(c.max_dx, c.max_dy));   // findCellsInRange with the modifiers
+        const int rn = min(min((int)eff_vision(c, nb), (int)eff_movement(c, nb)), max_cell_distance(c));   // findCellsInRange with the modifiers
         if (!(cell == a.pos[nb] || cell_in_cross(c, a.pos[nb], rn, cell))) continue;      // canReachCell
         const double metab = (double)(a.sugar_metab[nb] + a.spice_metab[nb]);               // raw, not the find* accessors
         const double cell_duration = metab > 0 ? site / metab : 0;
@@ -749,8 +821,9 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rn
     const int pos = rec.pos;
     const int H = c.p.height, x = pos / H, y = pos - x * H;
     const bool diseased = EXT && has_disease(c);             // uniform: the find* accessors carry disease modifiers
-    const int r = diseased ? min(min((int)eff_vision(c, s), (int)eff_movement(c, s)), max(c.max_dx, c.max_dy))
-                           : min(min(max(rec.vision, 0), max(rec.movement, 0)), max(c.max_dx, c.max_dy));
+    const int rcap = max_cell_distance(c);
+    const int r = diseased ? min(min((int)eff_vision(c, s), (int)eff_movement(c, s)), rcap)
+                           : min(min(max(rec.vision, 0), max(rec.movement, 0)), rcap);
     // environmentWraparound = false: the reference memoises ranges up to width - 1 instead of width // 2 (environment.py:141-144);
     // an agent that sees beyond half the map (disease bonuses) would read them -- not reproduced: fail loudly (code 14)
     if ((c.p.flags & SSB_F_NOWRAP) && diseased && min((int)eff_vision(c, s), (int)eff_movement(c, s)) > max(c.max_dx, c.max_dy))
@@ -763,7 +836,7 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rn
     const bool spicy = (c.p.flags & SSB_F_SPICE) != 0;
     const bool fighter = aggression > 0;
     int n = 0;
-    if (lane == 0 && r > 0) n = enumerate_cross(c, x, y, r, ws, maxc);
+    if (lane == 0 && r > 0) n = radial(c) ? enumerate_disc(c, x, y, r, ws, maxc) : enumerate_cross(c, x, y, r, ws, maxc);
     n = Gr::bcast(n, 0);
     int b_cell = pos, b_dist = 1 << 30, b_rank = 1 << 30, b_cs = 0, b_cp = 0;
     double b_welfare = -1.0, b_pl = 0.0;

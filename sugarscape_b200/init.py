@@ -89,8 +89,17 @@ def uses_decision_models(c):
 def check_supported(c):
     """Fail loudly on rule families without a CUDA implementation yet (DESIGN.md 'scope')."""
     problems = []
-    if c["agentVisionMode"] != "cardinal" or c["agentMovementMode"] != "cardinal":
-        problems.append("radial vision/movement")
+    if is_radial(c):
+        # environment.py:146-173: discs of floor(distance) <= range instead of crosses (exact mode, torus; the engine's
+        # candidate arrays hold RADIAL_MAX_CELLS cells -- a range of 6 on a map at least 13 cells wide)
+        if c.get("b200RngMode", "exact") != "exact":
+            problems.append("radial ranges in the scalable RNG mode")
+        if not c["environmentWraparound"]:
+            problems.append("radial ranges with environmentWraparound=false")
+        if c["agentLogfile"] is not None:
+            problems.append("radial ranges with an agentLogfile")
+        if radial_cells_in_range(c) > RADIAL_MAX_CELLS:
+            problems.append("radial ranges of more than %d cells" % RADIAL_MAX_CELLS)
     if c["neighborhoodMode"] not in ("vonNeumann", "moore"):
         problems.append("neighborhoodMode " + str(c["neighborhoodMode"]))
     if c["neighborhoodMode"] == "moore":      # cell.py:77-89: eight neighbour cells (tagging, trade, births, lending, diseases, pollution flux)
@@ -176,6 +185,29 @@ def max_agent_range(c):
     max_vision = c["startingDiseases"] * max(c["diseaseVisionPenalty"][1], 0) + c["agentVision"][1]
     max_movement = c["startingDiseases"] * max(c["diseaseMovementPenalty"][1], 0) + c["agentMovement"][1]
     return int(min(max(max_vision, max_movement), 2 ** 30))
+
+
+RADIAL_MAX_CELLS = 160      # MAXC_EXACT of csrc/ssb_exact.cuh
+
+
+def is_radial(c):
+    """environment.py:146, 152: radial ranges only when BOTH modes say so; anything else is the cardinal cross."""
+    return c["agentVisionMode"] == "radial" and c["agentMovementMode"] == "radial"
+
+
+def radial_cells_in_range(c):
+    """len(cellsInRange) of the furthest-seeing agent the configured ranges allow (environment.py:132-173,
+    agent.py:766-779; disease bonuses can push an agent further: the engine flags that at run time, overflow code 15)."""
+    W, H, memo = c["environmentWidth"], c["environmentHeight"], max_agent_range(c)
+    mdx, mdy = min(memo, W // 2), min(memo, H // 2)
+    cap = min(c["agentVision"][1], c["agentMovement"][1], memo, math.isqrt((W // 2) ** 2 + (H // 2) ** 2))
+    n = 0
+    for ox in range(-mdx, mdx + 1):
+        for oy in range(-mdy, mdy + 1):
+            if (ox == -mdx and 2 * mdx == W) or (oy == -mdy and 2 * mdy == H):
+                continue
+            n += 0 < ox * ox + oy * oy < (cap + 1) ** 2
+    return n
 
 
 def equator(c):
@@ -409,6 +441,8 @@ def rule_flags(c):
         f |= layout.F_NOWRAP
     if c["neighborhoodMode"] == "moore":
         f |= layout.F_MOORE
+    if is_radial(c):
+        f |= layout.F_RADIAL
     return f
 
 

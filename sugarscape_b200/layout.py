@@ -14,8 +14,8 @@ ALIVE, STARVATION, AGING, COMBAT, OTHER = 0, 1, 2, 3, 4
 SEX_NONE, SEX_MALE, SEX_FEMALE = 0, 1, 2
 SEX_CODE = {None: SEX_NONE, "male": SEX_MALE, "female": SEX_FEMALE}
 
-F_SPICE, F_POLLUTION, F_REPRO, F_TAGS, F_TAGGING, F_COMBAT, F_TRADE, F_TAGPREF, F_NOWRAP, F_MOORE = (
-    1 << 0, 1 << 1, 1 << 2, 1 << 3, 1 << 4, 1 << 5, 1 << 6, 1 << 7, 1 << 8, 1 << 9)
+F_SPICE, F_POLLUTION, F_REPRO, F_TAGS, F_TAGGING, F_COMBAT, F_TRADE, F_TAGPREF, F_NOWRAP, F_MOORE, F_RADIAL = (
+    1 << 0, 1 << 1, 1 << 2, 1 << 3, 1 << 4, 1 << 5, 1 << 6, 1 << 7, 1 << 8, 1 << 9, 1 << 10)
 
 (C_N_LIST, C_N_SLOTS, C_NEXT_ID, C_N_FREE, C_N_BORN, C_N_DEAD, C_ROUNDS, C_OVERFLOW, C_N_KIN,
  C_ENDOW_INDEX, C_N_REPLACED, C_N_MIGRATED, C_KIN_FREE) = range(13)

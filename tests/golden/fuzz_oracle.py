@@ -78,6 +78,16 @@ def draw_overrides(rng, base):
     if rng.random() < 0.3:
         ov["environmentSeasonInterval"] = rng.choice([0, 5, 20])
         ov["environmentSeasonalGrowbackDelay"] = rng.choice([0, 2])
+    # radial vision / movement (environment.py:146-173); SSB_FUZZ_RADIAL=1 puts every case there, half of them on maps
+    # smaller than the ranges (per-axis caps, odd and even axes)
+    forced = os.environ.get("SSB_FUZZ_RADIAL") == "1"
+    if forced or rng.random() < 0.15:
+        ov["agentVisionMode"] = ov["agentMovementMode"] = "radial"
+        if forced and rng.random() < 0.5:
+            ov["environmentWidth"], ov["environmentHeight"] = rng.choice([7, 8, 9, 10, 12, 13]), rng.choice([7, 8, 9, 11, 12, 20])
+            ov["startingAgents"] = rng.randrange(5, ov["environmentWidth"] * ov["environmentHeight"] // 3)
+            if "agentReplacements" in ov:
+                ov["agentReplacements"] = min(ov["agentReplacements"], ov["startingAgents"])
     return ov
 
 

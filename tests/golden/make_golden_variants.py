@@ -87,6 +87,18 @@ VARIANTS = {
     "moore_trade_tagging_reproduction": ("trade_tagging_reproduction", 150, {"neighborhoodMode": "moore"}),
     "moore_pollution": ("trade_pollution", 120, {"neighborhoodMode": "moore"}),
     "moore_nowrap_determinism": ("determinism", 120, {"neighborhoodMode": "moore", "environmentWraparound": False, "experimentalGroup": None}),
+    # ---- agentVisionMode = agentMovementMode = "radial" (environment.py:146-173): discs of floor(distance) <= range, the
+    # rings in the insertion order of findRadialCellRanges -- tagging + trade + births, live combat with retaliators, and
+    # every family of determinism.json incl. the Bentham models (disease bonuses to vision / movement switched off: they
+    # would push agents beyond the engine's candidate arrays)
+    "radial_trade_tagging_reproduction": ("trade_tagging_reproduction", 120, {"agentVisionMode": "radial", "agentMovementMode": "radial"}),
+    "radial_combat": ("combat_limited", 120, {"agentVisionMode": "radial", "agentMovementMode": "radial"}),
+    "radial_determinism": ("determinism", 100, {"agentVisionMode": "radial", "agentMovementMode": "radial", "experimentalGroup": None,
+                                                "diseaseVisionPenalty": [-1, 0], "diseaseMovementPenalty": [-1, 0]}),
+    # a map smaller than the ranges: the per-axis caps (width // 2) and the coinciding ends of an even axis
+    "radial_small_map": ("trade_tagging_reproduction", 100, {"agentVisionMode": "radial", "agentMovementMode": "radial",
+                                                             "environmentWidth": 10, "environmentHeight": 8, "startingAgents": 30,
+                                                             "agentVision": [1, 6]}),
     # the "Top" orderings: the cell with the best ethical value wins
     "ethics_top": ("trade_tagging_reproduction", 100, dict(_ETHICS, agentDecisionModels=["benthamTop", "egoistTop", "altruistNoLookaheadTop", "none", "bentham"])),
     # diffusion timeframe that starts before the first step, delay > 1: the reference's countdown is first decremented

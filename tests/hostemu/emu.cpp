@@ -28,7 +28,7 @@ int emu_agent_step_exact(const ssb_params_t *p, const ssb_grid_t *g, const ssb_a
     const int rmax = p->max_agent_range;          /* as ssb_bind */
     c.max_dx = rmax < p->width / 2 ? rmax : p->width / 2;
     c.max_dy = rmax < p->height / 2 ? rmax : p->height / 2;
-    if (4 * (c.max_dx > c.max_dy ? c.max_dx : c.max_dy) > MAXC_EXACT) return -2;
+    if (!(p->flags & SSB_F_RADIAL) && 4 * (c.max_dx > c.max_dy ? c.max_dx : c.max_dy) > MAXC_EXACT) return -2;
     c.t = t;
     c.prev_mean_wealth = prev_mean_wealth;
     c.endow_bits = endow_bits; c.tag_bits = tag_bits; c.n_step_tables = n_tables;

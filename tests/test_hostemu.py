@@ -141,17 +141,21 @@ def test_device_disease_source_matches_reference_on_variants(variant, min_sick_s
     assert sum(h["sickAgents"] > 0 for h in history) >= min_sick_steps
 
 
-@pytest.mark.parametrize("variant", ["nowrap_trade_tagging_reproduction", "nowrap_pollution", "moore_trade_tagging_reproduction", "moore_pollution"])
+@pytest.mark.parametrize("variant", ["nowrap_trade_tagging_reproduction", "nowrap_pollution", "moore_trade_tagging_reproduction", "moore_pollution",
+                                     "radial_trade_tagging_reproduction", "radial_combat", "radial_small_map"])
 def test_device_source_without_wraparound_matches_reference(variant):
     """environmentWraparound = false (cell.py:47-121; variant fixtures from the unmodified reference): tagging, trade and
-    births over neighbour lists that stop at the map's edge, pollution flux over the neighbours that exist."""
+    births over neighbour lists that stop at the map's edge, pollution flux over the neighbours that exist.  moore_*: eight
+    neighbours (cell.py:77-89).  radial_*: discs instead of crosses (environment.py:146-173), with live combat and on a
+    map smaller than the ranges."""
     base, overrides, gold, log = pu.load_variant(variant)
     c, state, pop, params, endow, tags = pu.build(base, overrides=overrides)
-    assert params.flags & (layout.F_NOWRAP | layout.F_MOORE)
+    assert params.flags & (layout.F_NOWRAP | layout.F_MOORE | layout.F_RADIAL)
     _run_with_extensions(c, state, pop, params, endow, tags, gold, log)
 
 
-@pytest.mark.parametrize("variant,ethics", [("determinism_plain", False), ("determinism_ethics", True), ("nowrap_determinism", True), ("moore_nowrap_determinism", True)])
+@pytest.mark.parametrize("variant,ethics", [("determinism_plain", False), ("determinism_ethics", True), ("nowrap_determinism", True), ("moore_nowrap_determinism", True),
+                                            ("radial_determinism", True)])
 def test_device_source_matches_reference_on_determinism_variants(variant, ethics):
     """examples/determinism.json (variant fixtures from the unmodified reference): diseases, depression, lending,
     friends, racial tags, universal income, live combat, trade, tags, inheritance, pollution and seasons at once --

@@ -221,7 +221,8 @@ def _private_log_keys(orc, rs, t, ethics):
         rs.update(orc.ethics_log_keys(t, n, rs["meanNeighbors"]))
 
 
-@pytest.mark.parametrize("variant,ethics", [("determinism_plain", False), ("determinism_ethics", True), ("nowrap_determinism", True), ("moore_nowrap_determinism", True)])
+@pytest.mark.parametrize("variant,ethics", [("determinism_plain", False), ("determinism_ethics", True), ("nowrap_determinism", True), ("moore_nowrap_determinism", True),
+                                            ("radial_determinism", True)])
 def test_oracle_determinism_variants_match_reference_trajectory(variant, ethics):
     """examples/determinism.json (variant fixtures from the unmodified reference,
     tests/golden/make_golden_variants.py): diseases, depression, lending, friends, racial tags,
@@ -393,7 +394,10 @@ def test_oracle_environment_file_matches_reference_trajectory():
             assert _close(rs[k], log[t][k]), f"log key {k} differs at t={t}: {rs[k]} vs {log[t][k]}"
 
 
-@pytest.mark.parametrize("overrides", [{"agentVisionMode": "radial"}, {"neighborhoodMode": "moore", "b200RngMode": "scalable"},
+@pytest.mark.parametrize("overrides", [{"agentVisionMode": "radial", "agentMovementMode": "radial", "b200RngMode": "scalable"},
+                                       {"agentVisionMode": "radial", "agentMovementMode": "radial", "environmentWraparound": False},
+                                       {"agentVisionMode": "radial", "agentMovementMode": "radial", "agentVision": [1, 8], "agentMovement": [8, 8]},
+                                       {"neighborhoodMode": "moore", "b200RngMode": "scalable"},
                                        {"environmentWraparound": False, "b200RngMode": "scalable"},
                                        {"environmentWraparound": False, "agentVision": [1, 30], "agentMovement": [30, 30]},
                                        {"agentDecisionModels": ["asimov"]},
@@ -515,7 +519,9 @@ def test_scalable_mode_oracle_matches_patched_reference(name):
 # nowrap_*: environmentWraparound = false (cell.py:47-121) -- the neighbour lists of tagging / trade / births and the pollution
 # flux lose the cells across the map's edge (with the reference's own south-neighbour test)
 PLAIN_VARIANTS = ["pollution_diffusion_delay2", "pollution_diffusion_delay3", "nowrap_trade_tagging_reproduction", "nowrap_pollution",
-                  "moore_trade_tagging_reproduction", "moore_pollution"]       # moore_*: neighborhoodMode "moore" (cell.py:77-89)
+                  "moore_trade_tagging_reproduction", "moore_pollution",       # moore_*: neighborhoodMode "moore" (cell.py:77-89)
+                  # radial_*: agentVisionMode = agentMovementMode = "radial" (environment.py:146-173) -- discs instead of crosses
+                  "radial_trade_tagging_reproduction", "radial_combat", "radial_small_map"]
 
 
 @pytest.mark.parametrize("variant", PLAIN_VARIANTS)
@@ -535,8 +541,13 @@ def test_oracle_plain_variants_match_reference_trajectory(variant):
         orc.env_step(t)
         orc.agent_step(t, rs["meanWealth"])
         orc.compact(t)
+        replaced = 0
+        if c["agentReplacements"] > 0:
+            orc.push_mt_to_python()
+            replaced = pu.replace_dead_agents(c, state, pop, t)
+            orc.set_mt_from_python()
         d, snap = pu.state_digests(state, *orc.mt_state())
         assert d == gold[t]["digests"], f"state differs at t={t}"
-        rs = sb.update(orc.stats(t), t, 0)
+        rs = sb.update(orc.stats(t), t, replaced)
         for k in stats.LOG_KEYS:
             assert _close(rs[k], log[t][k]), f"log key {k} differs at t={t}: {rs[k]} vs {log[t][k]}"

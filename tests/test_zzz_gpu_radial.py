@@ -1,0 +1,44 @@
+"""SURVEY row (f)3 on the GPU: agentVisionMode = agentMovementMode = "radial" (reference environment.py:146-173, agent.py:766-779)
+through the C ABI against fixtures of the unmodified reference (tests/golden/make_golden_variants.py, radial_*): the candidate
+cells of a move are the disc floor(distance) <= range in the insertion order of Environment.findRadialCellRanges, for plain
+agents (tagging + trade + births, live combat with retaliators and host-side replacement, a map smaller than the ranges) and
+for every family of determinism.json incl. the Bentham decision models.  Integer state, tags, grid and the MT19937 stream
+bit-exact on every step, fp64 holdings through their digest, all 59 log keys.
+
+Status: the radial seam (`enumerate_disc` & co. in csrc/ssb_rules.cuh) was written after round 2's GPU minutes were spent.  The
+same four fixtures pass on the CPU oracle (tests/test_oracle_golden.py) and on the device rule source compiled for the host
+(tests/test_hostemu.py); these cases have NOT run on a B200 yet.  The file sorts after every other test file so that its
+first GPU run cannot hide anything else."""
+import pytest
+
+import parity_util as pu
+from sugarscape_b200 import init, layout, stats
+from test_gpu_parity import _close, _engine, _replace
+from test_zz_gpu_decision_models import _Budget, _cap
+
+pytestmark = [pytest.mark.gpu]
+
+
+@pytest.mark.parametrize("variant", ["radial_small_map", "radial_trade_tagging_reproduction", "radial_combat", "radial_determinism"])
+def test_radial_ranges_match_reference_trajectory(variant):
+    base, overrides, gold, log = pu.load_variant(variant)
+    c, state, pop, params, endow, tags, eng = _engine(base, layout.RNG_EXACT, overrides)
+    assert params.flags & layout.F_RADIAL
+    sb = stats.StatsBuilder(c, init.equator(c))
+    eng.reduce_stats(0)
+    rs = sb.update(eng.stats(), 0, 0, eng.ethics_stats(), eng.ext_stats())
+    gold, budget = _cap(gold), _Budget()
+    for t in range(1, len(gold)):
+        if budget.spent(t - 1):
+            break
+        eng.env_step(t)
+        eng.agent_step(t, rs["meanWealth"])
+        eng.compact(t)
+        replaced = _replace(c, eng, pop, t) if c["agentReplacements"] > 0 else 0
+        eng.reduce_stats(t)
+        rs = sb.update(eng.stats(), t, replaced, eng.ethics_stats(), eng.ext_stats())
+        d, snap = pu.state_digests(eng.download(), *eng.mt_state())
+        assert d == gold[t]["digests"], f"{variant}: state differs from the reference at t={t}"
+        for k in stats.LOG_KEYS:
+            assert _close(rs[k], log[t][k]), f"{variant}: log key {k} at t={t}: {rs[k]} vs {log[t][k]}"
+    eng.close()
