@@ -223,7 +223,8 @@ typedef struct ssb_ethics {
     int64_t capacity;
     int32_t *model;                 /* 0 = Agent (greedy findBestCell), 1 = ethics.Bentham, 2 = ethics.Temperance
                                        (simple variant: ethics.py:412-434, 464-465, 493-506; needs ssb_agentlog_t bound),
-                                       3 = ethics.Temperance with pecs=True (ethics.py:436-491, 508-547)                 */
+                                       3 = ethics.Temperance with pecs=True (ethics.py:436-491, 508-547),
+                                       4 = ethics.Asimov (ethics.py:8-98; among plain agents only)                       */
     int32_t *top_ordering;          /* 1: a "Top" Bentham variant -- the cell with the best ethical value wins (ethics.py:124-129) */
     double  *selfishness;           /* selfishnessFactor after the spawn rules (-1 .. 1)              */
     double  *decision_factor;       /* decisionModelFactor: the ethical ranking runs when > 0         */

@@ -799,6 +799,84 @@ __device__ __noinline__ void pecs_pick(const DevCtx &c, int s, int n, const Welf
     *out_cell = cand_cell[pick]; *out_rank = pick; *out_diff = cand_w[0] - cand_w[pick];
 }
 
+// ethics.Asimov (ethics.py:8-98) among plain agents (the host refuses configurations that mix it with the Bentham family or
+// Temperance: the second law would ask such a neighbour's own findEthicalValueOfCell, which reads the neighbourhood list the
+// neighbour stored at ITS last move).  Lane 0.
+//   findEthicalValueOfCell: (third-law score + number of agents in view that cannot reach the cell) * (site wealth + loot), or
+//     -sys.maxsize as soon as the first law is broken -- the cell's occupant is a human, or a human who can reach the cell
+//     would starve on it (in a sugar-only run `0 + 0 - 0 <= 0` holds for every human: the reference's own arithmetic);
+//   findBestEthicalCell: the cells re-sorted by that value; walking them, the LAST cell some human in view orders the robot to
+//     (second law: a plain agent's own welfare for the cell when another robot stands on it) wins; before any order, the
+//     first cell with a positive value is taken at once; nothing found -> the robot stays where it is.
+// *out_rank = -1: stays although candidates exist (lastMoveOptimal False, no rank / difference entry in the log).
+constexpr int SSB_MODEL_ASIMOV = 4;
+__device__ __forceinline__ bool asimov_can_reach(const DevCtx &c, int nb, int cell) {      // canReachCell (agent.py:213-216)
+    const int rn = min(min((int)eff_vision(c, nb), (int)eff_movement(c, nb)), max_cell_distance(c));
+    return cell == c.a.pos[nb] || cell_in_cross(c, c.a.pos[nb], rn, cell);
+}
+__device__ __noinline__ void asimov_pick(const DevCtx &c, int s, int n, const Welfare &w, int my_tribe, double aggression,
+                                         const WarpScratch &ws, int *out_cell, int *out_rank, double *out_diff) {
+    const ssb_agents_t &a = c.a;
+    const bool polluted = (c.p.flags & SSB_F_POLLUTION) != 0, spicy = (c.p.flags & SSB_F_SPICE) != 0;
+    int32_t cand_cell[MAXC_EXACT_RULES], order[MAXC_EXACT_RULES], hood[MAXC_EXACT_RULES + 1];
+    uint8_t cand_dist[MAXC_EXACT_RULES];
+    double cand_w[MAXC_EXACT_RULES], score[MAXC_EXACT_RULES];
+    int m = n > 0 ? rank_candidates(c, s, n, w, my_tribe, aggression, ws, cand_cell, cand_dist, cand_w) : 0;
+    const bool own_only = m == 0;
+    if (own_only) { cand_cell[0] = a.pos[s]; cand_dist[0] = 0; cand_w[0] = 0; m = 1; }      // rankCellsInRange: [own cell]
+    int nh = 0;                                                    // self.neighborhood: live agents in range, then the agent
+    for (int i = 0; i < n && i < MAXC_EXACT_RULES; i++) {
+        const int o = c.g.occ[ws.cells[i]];
+        if (o >= 0 && agent_alive(c, o)) hood[nh++] = o;
+    }
+    hood[nh++] = s;
+    const double loot = c.p.max_combat_loot, never = -9223372036854775807.0;      // -1 * sys.maxsize
+    const double my_sm = eff_sugar_metab(c, s), my_pm = eff_spice_metab(c, s);
+    for (int i = 0; i < m; i++) {                                  // findEthicalValueOfCell (ethics.py:41-56), then sortCellsByWealth
+        const int cell = cand_cell[i], occupant = c.g.occ[cell];
+        const double cs = (double)c.g.sugar[cell], cp = spicy ? (double)c.g.spice[cell] : 0.0;
+        double value = cs + cp;
+        if (occupant >= 0) value += fmin(a.sugar[occupant] + a.spice[occupant], loot * 2);
+        const bool spice_up = cp + a.spice[s] - my_pm > 0, sugar_up = cs + a.sugar[s] - my_sm > 0;      // scoreLawThree
+        double modifier = (spice_up && sugar_up) ? 1 : ((!spice_up && !sugar_up) ? -1 : 0);
+        bool broken = false;
+        for (int k = 0; k < nh && !broken; k++) {                  // scoreLawOne (ethics.py:58-69)
+            const int nb = hood[k];
+            const bool human = c.eth->model[nb] != SSB_MODEL_ASIMOV;
+            const bool starves = cp + a.spice[nb] - eff_spice_metab(c, nb) <= 0 || cs + a.sugar[nb] - eff_sugar_metab(c, nb) <= 0;
+            if (occupant >= 0 && nb == occupant && human) broken = true;
+            else if (!asimov_can_reach(c, nb, cell)) modifier += 1;
+            else if (human && starves) broken = true;
+        }
+        const double sc = broken ? never : modifier * value;
+        int j = i;
+        while (j > 0 && (score[j - 1] < sc || (score[j - 1] == sc && cand_dist[order[j - 1]] > cand_dist[i]))) {
+            score[j] = score[j - 1]; order[j] = order[j - 1];
+            j--;
+        }
+        score[j] = sc; order[j] = i;
+    }
+    int best = -1;
+    for (int oi = 0; oi < m; oi++) {                               // findBestEthicalCell (ethics.py:19-33)
+        const int i = order[oi], cell = cand_cell[i], robot = c.g.occ[cell];
+        if (robot >= 0 && c.eth->model[robot] == SSB_MODEL_ASIMOV)          // scoreLawTwo: only a robot on the cell earns an order
+            for (int k = 0; k < nh; k++) {
+                const int nb = hood[k];
+                if (c.eth->model[nb] == SSB_MODEL_ASIMOV || !asimov_can_reach(c, nb, cell)) continue;
+                const double agg = eff_aggression(c, nb);
+                const double rs = agg * fmin(loot, a.sugar[robot]), rp = agg * fmin(loot, a.spice[robot]);
+                const double pl = polluted ? c.g.pollution[cell] : 0.0;
+                Welfare wn = {};
+                wn.template load<true>(c, nb);                     // neighbor.findValueOfCell (agent.py:1153-1159)
+                const double order_value = wn.eval(((double)c.g.sugar[cell] + rs) / (1 + pl), ((double)(spicy ? c.g.spice[cell] : 0) + rp) / (1 + pl));
+                if (order_value > 0) best = i;
+            }
+        if (best < 0 && score[oi] > 0) { best = i; break; }
+    }
+    if (best < 0 || own_only) { *out_cell = a.pos[s]; *out_rank = own_only ? 0 : -1; *out_diff = 0; return; }
+    *out_cell = cand_cell[best]; *out_rank = best; *out_diff = cand_w[0] - cand_w[best];
+}
+
 // MOVE part of Agent.doTimestep (agent.py:568-584), executed by the G lanes of a group for ONE
 // agent: lastSugar/lastSpice, rankCellsInRange + findBestCell + moveToBestCell (1395-1443,
 // 719-746, 1321-1328), collectResourcesAtCell (249-259), doMetabolism (485-498).
@@ -975,6 +1053,9 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rn
                 } else if (c.eth->model[s] == 3 && engaged && has_agentlog(c)) {
                     pecs_pick(c, s, n, w, my_tribe, aggression, ws, &cell, &rank, &diff);
                     picked = b_valid;
+                } else if (c.eth->model[s] == SSB_MODEL_ASIMOV && engaged) {
+                    asimov_pick(c, s, n, w, my_tribe, aggression, ws, &cell, &rank, &diff);
+                    picked = b_valid;              // (no valid candidate: [own cell] is ranked, the robot stays)
                 }
                 if (picked && cell != b_cell) {
                     b_cell = cell;
@@ -982,7 +1063,9 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rn
                     b_cp = spicy ? c.g.spice[cell] : 0;
                     b_pl = polluted ? c.g.pollution[cell] : 0.0;
                 }
-                c.eth->last_move_optimal[s] = rank == 0; c.eth->move_rank[s] = rank; c.eth->move_diff[s] = diff;
+                // (rank < 0: an Asimov agent that stays although it has candidates -- not the greedy cell, and agent.cell is not among
+                // validMoves when the log looks for it, sugarscape.py:1154-1160)
+                c.eth->last_move_optimal[s] = rank == 0; c.eth->move_rank[s] = rank < 0 ? 0 : rank; c.eth->move_diff[s] = diff;
             } else {
                 c.eth->last_move_optimal[s] = 1;      // [own cell] is its own best; rank and difference keep their values
                 if (has_agentlog(c) && c.eth->model[s] == 1 && engaged) {

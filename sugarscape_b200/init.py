@@ -78,7 +78,7 @@ def _decimals(value):
 SUPPORTED_DECISION_MODELS = frozenset(("none", "rawSugarscape")) | frozenset(
     base + look + dyn + top for base in layout.BENTHAM_MODELS for look in ("", "NoLookahead", "HalfLookahead")
     for dyn in ("", "Dynamic") for top in ("", "Top") if not (top and base == "negativeBentham")      # (that one raises in the reference)
-) | frozenset(("temperance", "temperancePECS"))
+) | frozenset(("temperance", "temperancePECS", "asimov"))
 
 
 def uses_decision_models(c):
@@ -131,6 +131,13 @@ def check_supported(c):
         problems.append("inheritance policy " + str(c["agentInheritancePolicy"]))
     if c["agentMaxFriends"][1] > layout.MAX_FRIENDS:
         problems.append("more than %d friends" % layout.MAX_FRIENDS)
+    if "asimov" in c["agentDecisionModels"]:
+        # ethics.Asimov (ethics.py:8-98) among plain agents only: its second law asks a neighbour with a decision model of its
+        # own for THAT neighbour's findEthicalValueOfCell, which reads the neighbourhood list stored at the neighbour's last move
+        if any(m not in ("asimov", "none", "rawSugarscape") for m in c["agentDecisionModels"]):
+            problems.append("asimov mixed with other decision models")
+        if c["agentLogfile"] is not None:
+            problems.append("asimov with an agentLogfile")
     bad_models = [m for m in c["agentDecisionModels"] if m not in SUPPORTED_DECISION_MODELS]
     if bad_models:
         problems.append("decision models other than rawSugarscape and the Bentham family: " + ", ".join(bad_models))

@@ -201,7 +201,10 @@ class EthicsStats(C.Structure):
 
 
 def decision_model_class(name):
-    """ssb_ethics_t.model of a decisionModel string: 1 = ethics.Bentham, 2 = ethics.Temperance (simple), 0 = plain Agent."""
+    """ssb_ethics_t.model of a decisionModel string: 1 = ethics.Bentham, 2 = ethics.Temperance (simple), 3 = with PECS,
+    4 = ethics.Asimov (sugarscape.py:245-246 replaces whatever class the earlier tests chose), 0 = plain Agent."""
+    if "asimov" in name:
+        return 4
     if decision_model_base(name) is not None:
         return 1
     if "temperance" in name:
@@ -438,7 +441,7 @@ class HostExt:
         """Rules that read agent.timeToLive (tracked in the agentlog family): dynamic selfishness, Temperance."""
         bentham = [m for m in c["agentDecisionModels"] if decision_model_base(m) is not None]
         return ((bool(bentham) and (c["agentDynamicSelfishnessFactor"][1] != 0 or any("Dynamic" in m for m in bentham))) or
-                any(decision_model_class(m) >= 2 for m in c["agentDecisionModels"]))
+                any(decision_model_class(m) in (2, 3) for m in c["agentDecisionModels"]))
 
     @staticmethod
     def combat_possible(c):

@@ -20,7 +20,7 @@ import ref_harness as rh  # noqa: E402
 import parity_util as pu  # noqa: E402
 from fuzz_oracle import BASES, draw_overrides  # noqa: E402
 from hostemu_binding import HostEmu  # noqa: E402
-from sugarscape_b200 import init, stats  # noqa: E402
+from sugarscape_b200 import init, layout, stats  # noqa: E402
 
 
 def _close(a, b):
@@ -71,6 +71,8 @@ def run_case(base, ov, steps):
         emu.env_step(t)
         emu.agent_step(t, rs["meanWealth"])
         emu.compact(t)
+        if state.counters[layout.C_OVERFLOW] != 0:       # the engine stops such a run (ssb_stats fails with the code); nothing to compare
+            return "skipped (the engine stops this run at t=%d: overflow code %d)" % (t, state.counters[layout.C_OVERFLOW])
         replaced = 0
         if c["agentReplacements"] > 0:
             emu.push_mt_to_python()

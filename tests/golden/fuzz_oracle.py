@@ -78,6 +78,10 @@ def draw_overrides(rng, base):
     if rng.random() < 0.3:
         ov["environmentSeasonInterval"] = rng.choice([0, 5, 20])
         ov["environmentSeasonalGrowbackDelay"] = rng.choice([0, 2])
+    # ethics.Asimov among plain agents (device source only: fuzz_hostemu.py; the oracle has no Asimov, fuzz_oracle.py skips it)
+    if os.environ.get("SSB_FUZZ_ASIMOV") == "1" or rng.random() < 0.1:
+        ov["agentDecisionModels"] = rng.choice([["asimov"], ["asimov", "none"], ["none", "none", "asimov"], ["asimov", "rawSugarscape", "asimov"]])
+        ov["agentDecisionModelFactor"] = rng.choice([[1, 1], [0, 1], [0.5, 1]])
     # radial vision / movement (environment.py:146-173); SSB_FUZZ_RADIAL=1 puts every case there, half of them on maps
     # smaller than the ranges (per-axis caps, odd and even axes)
     forced = os.environ.get("SSB_FUZZ_RADIAL") == "1"
@@ -107,6 +111,8 @@ def run_case(base, ov, steps):
     c, state, pop, params, endow, tags = pu.build(base, overrides=ov, check=False)
     if c["experimentalGroup"] is not None or c["agentLeader"]:
         return "skipped"
+    if any("asimov" in m or "temperance" in m for m in c["agentDecisionModels"]):
+        return "skipped (the oracle restates the Bentham family only; Asimov and Temperance are pinned on the device source, fuzz_hostemu.py)"
     if c["agentReplacements"] > 0 and ((c["agentTagging"] and c["agentTagStringLength"] > 0 and not c["environmentTribePerQuadrant"])
                                        or (c["agentImmuneSystemLength"] > 0 and c["startingDiseases"] > 0)):
         # Known deviation: the reference shares the tag / immune-system LIST objects between the

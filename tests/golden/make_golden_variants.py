@@ -99,7 +99,13 @@ VARIANTS = {
     "radial_small_map": ("trade_tagging_reproduction", 100, {"agentVisionMode": "radial", "agentMovementMode": "radial",
                                                              "environmentWidth": 10, "environmentHeight": 8, "startingAgents": 30,
                                                              "agentVision": [1, 6]}),
-    # the "Top" orderings: the cell with the best ethical value wins
+    # ---- ethics.Asimov (ethics.py:8-98) among plain agents: the three laws over the agents in view.  With spice (trade +
+    # tagging + births: children take the class of the parent whose decision model the endowment draw picked), sugar-only
+    # with live combat and replacement (humans order robots onto other robots), and on top of diseases / lending / friends
+    "asimov_trade": ("trade_tagging_reproduction", 120, dict(_ETHICS, agentDecisionModels=["asimov", "none"])),
+    "asimov_combat": ("combat_limited", 120, dict(_ETHICS, agentDecisionModels=["none", "asimov", "asimov"], agentAggressionFactor=[0, 2])),
+    "asimov_determinism": ("determinism", 100, dict(_ETHICS, agentDecisionModels=["asimov", "rawSugarscape"], experimentalGroup=None,
+                                                    agentDecisionModelFactor=[0, 1])),
     "ethics_top": ("trade_tagging_reproduction", 100, dict(_ETHICS, agentDecisionModels=["benthamTop", "egoistTop", "altruistNoLookaheadTop", "none", "bentham"])),
     # diffusion timeframe that starts before the first step, delay > 1: the reference's countdown is first decremented
     # at t = 1, so it diffuses at t = 2, 4, ... (the engine fired one step early); and a window

@@ -54,7 +54,10 @@ ETHICS_VARIANTS = ["ethics_trade", "ethics_combat", "ethics_replacement", "ethic
                    # ... and with pecs=True (physical + emotional + cognitive + social scores)
                    "ethics_temperance_pecs", "ethics_temperance_pecs_combat",
                    # the "Top" orderings of the Bentham family
-                   "ethics_top"]
+                   "ethics_top",
+                   # ethics.Asimov among plain agents (ethics.py:8-98): with spice and births, sugar-only with live combat and
+                   # replacement, and on top of every other family of determinism.json
+                   "asimov_trade", "asimov_combat", "asimov_determinism"]
 
 
 @pytest.mark.parametrize("variant", ETHICS_VARIANTS)

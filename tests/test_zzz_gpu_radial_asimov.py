@@ -1,13 +1,19 @@
-"""SURVEY row (f)3 on the GPU: agentVisionMode = agentMovementMode = "radial" (reference environment.py:146-173, agent.py:766-779)
+"""SURVEY row (f)3 on the GPU, the two pieces written after round 2's GPU minutes were spent.
+
+(1) agentVisionMode = agentMovementMode = "radial" (reference environment.py:146-173, agent.py:766-779)
 through the C ABI against fixtures of the unmodified reference (tests/golden/make_golden_variants.py, radial_*): the candidate
 cells of a move are the disc floor(distance) <= range in the insertion order of Environment.findRadialCellRanges, for plain
 agents (tagging + trade + births, live combat with retaliators and host-side replacement, a map smaller than the ranges) and
 for every family of determinism.json incl. the Bentham decision models.  Integer state, tags, grid and the MT19937 stream
 bit-exact on every step, fp64 holdings through their digest, all 59 log keys.
 
-Status: the radial seam (`enumerate_disc` & co. in csrc/ssb_rules.cuh) was written after round 2's GPU minutes were spent.  The
-same four fixtures pass on the CPU oracle (tests/test_oracle_golden.py) and on the device rule source compiled for the host
-(tests/test_hostemu.py); these cases have NOT run on a B200 yet.  The file sorts after every other test file so that its
+(2) ethics.Asimov among plain agents (reference ethics.py:8-98; `asimov_pick` in csrc/ssb_rules.cuh) against three fixtures of the
+unmodified reference (asimov_*): with spice and births, sugar-only with live combat and replacement, and on top of every other
+family of determinism.json.
+
+Status: the four radial fixtures pass on the CPU oracle (tests/test_oracle_golden.py) and on the device rule source compiled for
+the host (tests/test_hostemu.py), the three Asimov fixtures on the latter (the oracle restates the Bentham family only); these
+cases have NOT run on a B200 yet.  The file sorts after every other test file so that its
 first GPU run cannot hide anything else."""
 import pytest
 
@@ -19,11 +25,12 @@ from test_zz_gpu_decision_models import _Budget, _cap
 pytestmark = [pytest.mark.gpu]
 
 
-@pytest.mark.parametrize("variant", ["radial_small_map", "radial_trade_tagging_reproduction", "radial_combat", "radial_determinism"])
-def test_radial_ranges_match_reference_trajectory(variant):
+@pytest.mark.parametrize("variant", ["radial_small_map", "radial_trade_tagging_reproduction", "radial_combat", "radial_determinism",
+                                     "asimov_trade", "asimov_combat", "asimov_determinism"])
+def test_radial_ranges_and_asimov_match_reference_trajectory(variant):
     base, overrides, gold, log = pu.load_variant(variant)
     c, state, pop, params, endow, tags, eng = _engine(base, layout.RNG_EXACT, overrides)
-    assert params.flags & layout.F_RADIAL
+    assert (params.flags & layout.F_RADIAL) if variant.startswith("radial") else (state.ethics.arrays["model"] == 4).any()
     sb = stats.StatsBuilder(c, init.equator(c))
     eng.reduce_stats(0)
     rs = sb.update(eng.stats(), 0, 0, eng.ethics_stats(), eng.ext_stats())
