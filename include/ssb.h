@@ -225,7 +225,8 @@ typedef struct ssb_ethics {
                                        (simple variant: ethics.py:412-434, 464-465, 493-506; needs ssb_agentlog_t bound),
                                        3 = ethics.Temperance with pecs=True (ethics.py:436-491, 508-547),
                                        4 = ethics.Asimov (ethics.py:8-98; among plain agents only)                       */
-    int32_t *top_ordering;          /* 1: a "Top" Bentham variant -- the cell with the best ethical value wins (ethics.py:124-129) */
+    int32_t *top_ordering;          /* bit 0: a "Top" Bentham variant -- the cell with the best ethical value wins (ethics.py:124-129);
+                                       bit 1: the agent's decisionModel string is the experimental group (SSB_GROUP_MODEL) */
     double  *selfishness;           /* selfishnessFactor after the spawn rules (-1 .. 1)              */
     double  *decision_factor;       /* decisionModelFactor: the ethical ranking runs when > 0         */
     double  *lookahead_factor;      /* decisionModelLookaheadFactor                                   */
@@ -347,13 +348,17 @@ typedef struct ssb_misc {
 
 /* experimental group (agent.py:1256-1284 isInGroup; sugarscape.py:998-1003, 1175-1198, 1230-1250): the log repeats
  * every statistic for the group and for its complement ("control") and counts the interactions between them.
- * Supported groups (ssb_group_t.kind): "depressed" (ssb_misc_t.depressed), "female" / "male" (ssb_agents_t.sex) --
+ * Supported groups (ssb_group_t.kind): "depressed" (ssb_misc_t.depressed), "female" / "male" (ssb_agents_t.sex), "race<N>"
+ * (ssb_misc_t.race == N, N in bits 8.. of kind), a decision model's name (agent.decisionModel == group: bit 1 of
+ * ssb_ethics_t.top_ordering, set by the host and handed on to the children with the parent's class) --
  * memberships that are fixed at birth.  (Groups whose membership changes during the run -- "sick", age ranges, a
  * disease -- would need every agent's movement neighbourhood kept as a list: the reference re-evaluates the
  * neighbours' membership at statistics time, sugarscape.py:1145-1151.) */
 #define SSB_GROUP_DEPRESSED 1
 #define SSB_GROUP_FEMALE    2
 #define SSB_GROUP_MALE      3
+#define SSB_GROUP_RACE      4   /* kind = SSB_GROUP_RACE | (race id << 8)                                       */
+#define SSB_GROUP_MODEL     5   /* needs ssb_ethics_t                                                           */
 #define SSB_GI_COMBAT 0
 #define SSB_GI_DISEASE 1
 #define SSB_GI_LENDING 2

@@ -642,8 +642,10 @@ int ssb_bind_ext(ssb_engine_t *e, const ssb_ext_t *ext) {
     const ssb_group_t &Gr = ext->group;
     if (Gr.with_control) {
         if (!Gr.with_experimental || !Gr.control_neighbors || !Gr.experimental_neighbors) return fail(e, -1, "group: null array");
-        if (Gr.kind < SSB_GROUP_DEPRESSED || Gr.kind > SSB_GROUP_MALE) return fail(e, -1, "group: unknown kind");
-        if (Gr.kind == SSB_GROUP_DEPRESSED && !M.universal_sugar) return fail(e, -1, "the experimental group \"depressed\" needs the misc family");
+        const long long gk = Gr.kind & 0xff;
+        if (gk < SSB_GROUP_DEPRESSED || gk > SSB_GROUP_MODEL || (gk != SSB_GROUP_RACE && Gr.kind != gk)) return fail(e, -1, "group: unknown kind");
+        if ((gk == SSB_GROUP_DEPRESSED || gk == SSB_GROUP_RACE) && !M.universal_sugar) return fail(e, -1, "the experimental groups \"depressed\" and \"race<N>\" need the misc family");
+        if (gk == SSB_GROUP_MODEL && !e->ctx.eth) return fail(e, -1, "a decision model as experimental group needs ssb_bind_ethics first");
     }
     const ssb_agentlog_t &AL = ext->agentlog;
     if (AL.time_to_live) {

@@ -21,10 +21,13 @@ __device__ __forceinline__ bool has_group(const DevCtx &c) { return c.x != nullp
 // Agent.isInGroup (agent.py:1256-1284) for the configured experimental group
 __device__ __forceinline__ bool is_member(const DevCtx &c, int s) {
     if (!has_group(c)) return false;
-    switch (c.x->group.kind) {
+    const long long kind = c.x->group.kind;
+    switch ((int)(kind & 0xff)) {
         case SSB_GROUP_DEPRESSED: return has_misc(c) && c.x->misc.depressed[s] != 0;
         case SSB_GROUP_FEMALE: return c.a.sex[s] == SSB_SEX_FEMALE;
         case SSB_GROUP_MALE: return c.a.sex[s] == SSB_SEX_MALE;
+        case SSB_GROUP_RACE: return has_misc(c) && c.x->misc.race[s] == (int)(kind >> 8);      // self.race == raceID (agent.py:1273-1275)
+        case SSB_GROUP_MODEL: return c.eth != nullptr && (c.eth->top_ordering[s] & 2) != 0;    // group == self.decisionModel (agent.py:1262)
     }
     return false;
 }

@@ -666,7 +666,7 @@ __device__ __noinline__ void ethical_prepare(const DevCtx &c, int s, int n, cons
 // reported by the per-agent log), so a lane that walks the list alone stops at the pick unless that log is on.  Same
 // for the own cell when no candidate is valid.
 __device__ __noinline__ void ethical_score(const DevCtx &c, int s, int r, EthScratch &es, int first, int stride) {
-    const bool all_cells = has_agentlog(c) || c.eth->top_ordering[s] != 0, positive = c.eth->selfishness[s] >= 0;
+    const bool all_cells = has_agentlog(c) || (c.eth->top_ordering[s] & 1) != 0, positive = c.eth->selfishness[s] >= 0;
     if (es.m == 0) {
         double h, u;
         if (all_cells && first == 0) ethical_value(c, s, r, es.hood, es.nh, c.a.pos[s], &h, &u);
@@ -689,7 +689,7 @@ __device__ __noinline__ bool ethical_choose(const DevCtx &c, int s, const EthScr
         else if (chosen < 0 || es.u[i] > best_u || (es.u[i] == best_u && es.h[i] > best_h)) { chosen = i; best_u = es.u[i]; best_h = es.h[i]; }   // stable sort, reverse
     }
     int rank = chosen >= 0 ? chosen : 0;
-    if (c.eth->top_ordering[s] != 0 && positive) {
+    if ((c.eth->top_ordering[s] & 1) != 0 && positive) {
         // "Top" variants (ethics.py:124-129): the cells re-sorted by ethical value (stable: value descending, range
         // ascending, welfare order); the first one wins whatever its sign
         rank = 0;

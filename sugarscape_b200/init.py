@@ -147,8 +147,10 @@ def check_supported(c):
               "agentDecisionModelSexismFactor", "agentDecisionModelTribalFactor"):
         if c[k][1] >= 0:
             problems.append(k)
-    if c["experimentalGroup"] is not None and c["experimentalGroup"] not in layout.GROUP_KINDS:
-        problems.append("experimentalGroup other than " + " / ".join(sorted(layout.GROUP_KINDS)))
+    if c["experimentalGroup"] is not None and layout.group_kind(c) == 0:
+        problems.append("experimentalGroup other than " + " / ".join(sorted(layout.GROUP_KINDS)) + " / race<N> / a decision model's name")
+    if layout.group_kind(c) == layout.GROUP_MODEL and not uses_decision_models(c):
+        problems.append("a decision model as experimentalGroup without decision models")
     if c["experimentalGroup"] is not None and c["agentReplacements"] > 0:
         problems.append("experimentalGroup with agentReplacements")
     if c["agentTagStringLength"] > 32:

@@ -232,6 +232,7 @@ class HostEthics:
         # it (ethics.py:160-190) and `[0] != 0` holds
         self.lookahead_factor = 1.0 if isinstance(look, list) else float(look)
         self.default_dynamic = list(c["agentDynamicSelfishnessFactor"]) == [0.0, 0.0]
+        self.group_model = c["experimentalGroup"] if group_kind(c) == GROUP_MODEL else None
         widths = {"pecs_rules": 5, "pecs_counts": 3}          # values per slot
         self.arrays = {n: np.full(capacity * widths.get(n, 1), fill, dtype=dt) for n, dt, fill in ETHICS_FIELDS}
 
@@ -255,7 +256,8 @@ class HostEthics:
             look = 0.5
         A = self.arrays
         A["model"][slot] = decision_model_class(name)
-        A["top_ordering"][slot] = int(base is not None and "Top" in name)
+        # bit 1: the agent's decisionModel is the experimental group (agent.py:1262; SSB_GROUP_MODEL)
+        A["top_ordering"][slot] = int(base is not None and "Top" in name) | (2 if name == self.group_model else 0)
         A["dynamic_decision_factor"][slot] = endowment["dynamicDecisionModelFactor"]
         A["dynamic_social_pressure"][slot] = endowment["dynamicSocialPressureFactor"]
         A["pecs_rules"][slot * 5:slot * 5 + 5] = 0
@@ -283,7 +285,7 @@ class HostEthics:
     def copy(self):
         h = HostEthics.__new__(HostEthics)
         h.capacity, h.global_max_wealth, h.lookahead_factor = self.capacity, self.global_max_wealth, self.lookahead_factor
-        h.default_dynamic = self.default_dynamic
+        h.default_dynamic, h.group_model = self.default_dynamic, self.group_model
         h.arrays = {k: v.copy() for k, v in self.arrays.items()}
         return h
 
@@ -344,6 +346,28 @@ GROUP_LAYOUT = (
     ("kind", None, None, None),
 )
 GROUP_KINDS = {"depressed": 1, "female": 2, "male": 3}      # SSB_GROUP_* (memberships fixed at birth)
+GROUP_RACE, GROUP_MODEL = 4, 5
+
+
+def group_kind(c):
+    """ssb_group_t.kind of configuration["experimentalGroup"] (0: none / not supported).  Agent.isInGroup (agent.py:1256-1284)
+    tests, in this order: "ageRange" in the name, name == the agent's decisionModel, "depressed", "disease" in the name,
+    "female", "male", "race" in the name (race<N>), ..."""
+    import re
+    g = c["experimentalGroup"]
+    if g is None or "ageRange" in g:
+        return 0
+    models = ["none" if m == "rawSugarscape" else m for m in c["agentDecisionModels"]]      # sugarscape.py:720-721
+    if g in models and not (g in GROUP_KINDS or "disease" in g or "race" in g):
+        return GROUP_MODEL if g != "none" else 0      # ("none": no ssb_ethics_t to carry the bit when every agent is plain)
+    if g in GROUP_KINDS:
+        return GROUP_KINDS[g]
+    if "disease" in g:
+        return 0
+    m = re.search(r"race(?P<ID>\d+)", g) if "race" in g else None
+    if m is not None and c["environmentMaxRaces"] > 0 and c["agentRacialTagStringLength"] > 0:
+        return GROUP_RACE | (int(m.group("ID")) << 8)
+    return 0
 AL_FIELDS = 26          # SSB_AL_* (include/ssb.h)
 AGENTLOG_LAYOUT = (
     ("time_to_live", _F64, 0, "cap"), ("last_pollution", _F64, 0, "cap"), ("prey_wealth", _F64, 0, "cap"),
@@ -419,7 +443,7 @@ class HostExt:
             self.families.add("agentlog")         # (agent.timeToLive is tracked there: the dynamic selfishness update reads it)
         self.write_records = int(c["agentLogfile"] is not None)
         self.max_loan_duration = int(max(c["agentLoanDuration"]))
-        self.group_kind = GROUP_KINDS.get(c["experimentalGroup"], 0)
+        self.group_kind = group_kind(c)
         self.racial_len = int(c["agentRacialTagStringLength"]) if c["environmentMaxRaces"] > 0 else 0
         self.misc_scalars = (float(c["agentDepressionPercentage"]), int(c["environmentUniversalSugarIncomeInterval"]),
                              int(c["environmentUniversalSpiceIncomeInterval"]), self.racial_len, int(c["environmentMaxRaces"]))

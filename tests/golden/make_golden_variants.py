@@ -119,6 +119,10 @@ VARIANTS = {
     # other experimental groups than the shipped "depressed" (membership by sex)
     "determinism_group_female": ("determinism", 120, {"experimentalGroup": "female"}),
     "determinism_group_male": ("determinism", 80, {"experimentalGroup": "male"}),
+    # ... by race (race<N>: the most common racial tag, fixed at birth) and by decision model (the agent's decisionModel string
+    # is the group's name; children carry the string of the parent whose class they take)
+    "determinism_group_race1": ("determinism", 100, {"experimentalGroup": "race1"}),
+    "determinism_group_bentham": ("determinism", 100, {"experimentalGroup": "bentham"}),
 }
 
 

@@ -217,10 +217,11 @@ def test_dead_creditor_table_wraps_around():
     assert int(ext.arrays["lending.counters"][layout.LC_N_DEAD]) > 2 * 8
 
 
-@pytest.mark.parametrize("variant", ["determinism_group_female", "determinism_group_male"])
+@pytest.mark.parametrize("variant", ["determinism_group_female", "determinism_group_male", "determinism_group_race1", "determinism_group_bentham"])
 def test_device_source_matches_reference_on_other_experimental_groups(variant):
     """determinism.json with another experimental group than the shipped "depressed" (variant fixtures of the unmodified
-    reference): membership by sex -- digests and all 203 log keys.  (Groups whose membership changes during the run are refused.)"""
+    reference): membership by sex, by race (race<N>) and by decision model (the group is a decisionModel string) -- digests
+    and all 203 log keys.  (Groups whose membership changes during the run are refused.)"""
     base, overrides, gold, log = pu.load_variant(variant)
     c, state, pop, params, endow, tags = pu.build(base, overrides=overrides)
     assert "group" in state.ext.families and state.ext.group_kind > 1

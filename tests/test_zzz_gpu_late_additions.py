@@ -11,9 +11,13 @@ bit-exact on every step, fp64 holdings through their digest, all 59 log keys.
 unmodified reference (asimov_*): with spice and births, sugar-only with live combat and replacement, and on top of every other
 family of determinism.json.
 
+(3) experimental groups other than the shipped "depressed": membership by sex, by race (race<N>) and by decision model (the
+group is a decisionModel string) on determinism.json -- digests and all 203 log keys against four fixtures of the unmodified
+reference (determinism_group_*).
+
 Status: the four radial fixtures pass on the CPU oracle (tests/test_oracle_golden.py) and on the device rule source compiled for
-the host (tests/test_hostemu.py), the three Asimov fixtures on the latter (the oracle restates the Bentham family only); these
-cases have NOT run on a B200 yet.  The file sorts after every other test file so that its
+the host (tests/test_hostemu.py), the three Asimov fixtures on the latter (the oracle restates the Bentham family only); the
+four group fixtures on the latter as well (the oracle's group is "depressed"); these cases have NOT run on a B200 yet.  The file sorts after every other test file so that its
 first GPU run cannot hide anything else."""
 import pytest
 
@@ -48,4 +52,30 @@ def test_radial_ranges_and_asimov_match_reference_trajectory(variant):
         assert d == gold[t]["digests"], f"{variant}: state differs from the reference at t={t}"
         for k in stats.LOG_KEYS:
             assert _close(rs[k], log[t][k]), f"{variant}: log key {k} at t={t}: {rs[k]} vs {log[t][k]}"
+    eng.close()
+
+
+@pytest.mark.parametrize("variant", ["determinism_group_female", "determinism_group_male", "determinism_group_race1", "determinism_group_bentham"])
+def test_other_experimental_groups_match_reference_trajectory_and_full_log(variant):
+    base, overrides, gold, log = pu.load_variant(variant)
+    c, state, pop, params, endow, tags, eng = _engine(base, layout.RNG_EXACT, overrides)
+    assert "group" in state.ext.families and state.ext.group_kind > 1
+    sb = stats.StatsBuilder(c, init.equator(c))
+    eng.reduce_stats(0)
+    rs = sb.update_with_groups(eng.stats(), 0, 0, eng.ethics_stats(), eng.ext_stats(), eng.group_stats())
+    gold, budget = _cap(gold), _Budget()
+    for t in range(0, len(gold)):
+        if budget.spent(t - 1):
+            break
+        if t > 0:
+            eng.env_step(t)
+            eng.agent_step(t, rs["meanWealth"])
+            eng.compact(t)
+            eng.reduce_stats(t)
+            rs = sb.update_with_groups(eng.stats(), t, 0, eng.ethics_stats(), eng.ext_stats(), eng.group_stats())
+            d, snap = pu.state_digests(eng.download(), *eng.mt_state())
+            assert d == gold[t]["digests"], f"{variant}: state differs from the reference at t={t}"
+        assert len(log[t]) == 203
+        for k in log[t]:
+            assert k in rs and _close(rs[k], log[t][k]), f"{variant}: log key {k} at t={t}: {rs.get(k)} vs {log[t][k]}"
     eng.close()
