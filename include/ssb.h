@@ -36,7 +36,9 @@ extern "C" {
 #endif
 
 /* 3: ssb_stats_t.gini_area; SSB_F_NOWRAP / SSB_F_MOORE; the sweep scheduler's entry points (ssb_set_scheduler ...,
- * ssb_set_shard_sweep).  The optional per-slot state of the rule families keeps its name "ABI 2" below. */
+ * ssb_set_shard_sweep).  The optional per-slot state of the rule families keeps its name "ABI 2" below.
+ * Added since without a layout change (same version): SSB_F_RADIAL, ssb_ethics_t.model 4 (ethics.Asimov), bit 1 of
+ * ssb_ethics_t.top_ordering, SSB_GROUP_RACE / SSB_GROUP_MODEL, overflow code 15. */
 #define SSB_ABI_VERSION 3
 
 /* RNG modes */

@@ -78,6 +78,18 @@ def draw_overrides(rng, base):
     if rng.random() < 0.3:
         ov["environmentSeasonInterval"] = rng.choice([0, 5, 20])
         ov["environmentSeasonalGrowbackDelay"] = rng.choice([0, 2])
+    # neighborhoodMode "moore" (cell.py:77-89) and environmentWraparound = false (cell.py:47-121); SSB_FUZZ_NEIGHBOURS=1: always one of them
+    forced_nb = os.environ.get("SSB_FUZZ_NEIGHBOURS") == "1"
+    pick = rng.random()
+    if forced_nb:
+        pick = pick * 0.3
+    if pick < 0.1:
+        ov["neighborhoodMode"] = "moore"
+    elif pick < 0.2:
+        ov["environmentWraparound"] = False
+    elif pick < 0.3:
+        ov["neighborhoodMode"] = "moore"
+        ov["environmentWraparound"] = False
     # ethics.Asimov among plain agents (device source only: fuzz_hostemu.py; the oracle has no Asimov, fuzz_oracle.py skips it)
     if os.environ.get("SSB_FUZZ_ASIMOV") == "1" or rng.random() < 0.1:
         ov["agentDecisionModels"] = rng.choice([["asimov"], ["asimov", "none"], ["none", "none", "asimov"], ["asimov", "rawSugarscape", "asimov"]])
