@@ -68,7 +68,7 @@ extern "C" {
 #define SSB_F_TAGPREF   (1 << 7) /* agentTagPreferences                                      */
 #define SSB_F_MOORE     (1 << 9) /* neighborhoodMode = "moore": cell.neighbors has eight entries (cell.py:77-89; exact mode) */
 #define SSB_F_NOWRAP    (1 << 8) /* environmentWraparound = false: no neighbours across the map's edge (cell.py:47-121; exact mode) */
-#define SSB_F_RADIAL    (1 << 10) /* agentVisionMode = agentMovementMode = "radial": discs instead of crosses (environment.py:146-173; exact mode, with wraparound) */
+#define SSB_F_RADIAL    (1 << 10) /* agentVisionMode = agentMovementMode = "radial": discs instead of crosses (environment.py:146-173; exact mode) */
 
 typedef struct ssb_params {
     int32_t abi_version;

@@ -1135,18 +1135,23 @@ static int enumerate_cross(const ctx_t *c, int pos, int r, int32_t *cells, int32
  * ranges[g] of a cell lists its partners in ascending order of their own list index; findCellsInRange (agent.py:766-779)
  * concatenates ranges[1 .. r].  Restated literally: one pass over the whole cell list per ring.  The travel distance
  * sqrt(dx^2 + dy^2) is only compared by its users (agent.py:1430, 1484): dists[] carries dx^2 + dy^2. */
-static int wrap_distance(int delta, int border) {          /* findWraparoundDistance (environment.py:175-179), wraparound on */
+static int wrap_distance(const ctx_t *c, int delta, int border) {          /* findWraparoundDistance (environment.py:175-179) */
     delta = abs(delta);
-    if (2 * delta > border) delta = border - delta;
+    if (!(c->p->flags & SSB_F_NOWRAP) && 2 * delta > border) delta = border - delta;
     return delta;
+}
+/* maxDeltaX / maxDeltaY of findCellRanges (environment.py:138-144): width - 1 instead of width // 2 without wraparound */
+static int radial_cap(const ctx_t *c, int border) {
+    const int far = (c->p->flags & SSB_F_NOWRAP) ? border - 1 : border / 2;
+    return c->p->max_agent_range < far ? c->p->max_agent_range : far;
 }
 static int enumerate_disc(const ctx_t *c, int pos, int r, int32_t *cells, int32_t *dists) {
     const int W = c->p->width, H = c->p->height, x1 = pos / H, y1 = pos % H;
     int n = 0;
     for (int g = 1; g <= r; g++)
         for (int j = 0; j < W * H; j++) {
-            const int dx = wrap_distance(x1 - j / H, W), dy = wrap_distance(y1 - j % H, H);
-            if (j == pos || dx > c->max_dx || dy > c->max_dy) continue;
+            const int dx = wrap_distance(c, x1 - j / H, W), dy = wrap_distance(c, y1 - j % H, H);
+            if (j == pos || dx > radial_cap(c, W) || dy > radial_cap(c, H)) continue;
             if ((int)floor(sqrt((double)(dx * dx + dy * dy))) != g) continue;
             if (n < MAX_CAND) { cells[n] = j; dists[n++] = dx * dx + dy * dy; }
         }
@@ -1155,7 +1160,9 @@ static int enumerate_disc(const ctx_t *c, int pos, int r, int32_t *cells, int32_
 /* Environment.maxCellDistance (environment.py:140-146) */
 static int max_cell_distance(const ctx_t *c) {
     if (c->p->flags & SSB_F_RADIAL) {
-        const int hw = c->p->width / 2, hh = c->p->height / 2, lim = (int)floor(sqrt((double)(hw * hw + hh * hh)));
+        const int nowrap = (c->p->flags & SSB_F_NOWRAP) != 0;
+        const int hw = nowrap ? c->p->width - 1 : c->p->width / 2, hh = nowrap ? c->p->height - 1 : c->p->height / 2;
+        const int lim = (int)floor(sqrt((double)(hw * hw + hh * hh)));
         return c->p->max_agent_range < lim ? c->p->max_agent_range : lim;
     }
     return c->max_dx > c->max_dy ? c->max_dx : c->max_dy;
@@ -1173,8 +1180,8 @@ static int cell_in_cross(const ctx_t *c, int centre, int r, int cell) {
     const int x = centre / H, y = centre % H, cx = cell / H, cy = cell % H;
     if (cell == centre || r <= 0) return 0;
     if (c->p->flags & SSB_F_RADIAL) {
-        const int dx = wrap_distance(cx - x, W), dy = wrap_distance(cy - y, H);
-        return dx <= c->max_dx && dy <= c->max_dy && (int)floor(sqrt((double)(dx * dx + dy * dy))) <= r;
+        const int dx = wrap_distance(c, cx - x, W), dy = wrap_distance(c, cy - y, H);
+        return dx <= radial_cap(c, W) && dy <= radial_cap(c, H) && (int)floor(sqrt((double)(dx * dx + dy * dy))) <= r;
     }
     if (cx == x) { int d = abs(cy - y); if (H - d < d) d = H - d; return d <= (r < c->max_dy ? r : c->max_dy); }
     if (cy == y) { int d = abs(cx - x); if (W - d < d) d = W - d; return d <= (r < c->max_dx ? r : c->max_dx); }

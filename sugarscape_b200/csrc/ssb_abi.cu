@@ -376,7 +376,7 @@ int ssb_bind(ssb_engine_t *e, const ssb_grid_t *grid, const ssb_agents_t *agents
     c.max_dy = rmax < e->p.height / 2 ? rmax : e->p.height / 2;
     const int maxd = c.max_dx > c.max_dy ? c.max_dx : c.max_dy;
     if (e->p.flags & SSB_F_RADIAL) {       // discs (environment.py:146-173): exact mode, torus; the candidate arrays hold MAXC_EXACT cells
-        if (e->p.rng_mode != SSB_RNG_EXACT || (e->p.flags & SSB_F_NOWRAP)) return fail(e, -1, "radial ranges need the exact RNG mode and wraparound");
+        if (e->p.rng_mode != SSB_RNG_EXACT) return fail(e, -1, "radial ranges need the exact RNG mode");
         // (how far an agent really sees is min(vision, movement), not max_agent_range: the host checks the configured
         // ranges, an agent pushed beyond the candidate arrays by disease bonuses stops the run -- overflow code 15)
     }

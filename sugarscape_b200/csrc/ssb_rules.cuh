@@ -355,12 +355,14 @@ __device__ __forceinline__ void collect(const DevCtx &c, int s, int pos) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// agentVisionMode = agentMovementMode = "radial" (SSB_F_RADIAL; environment.py:146-173, exact mode, with wraparound): the
+// agentVisionMode = agentMovementMode = "radial" (SSB_F_RADIAL; environment.py:146-173, exact mode): the
 // cells in range of an agent are the disc floor(sqrt(dx^2 + dy^2)) <= r of the cells with dx <= max_dx and dy <= max_dy
 // (wraparound distances).  Environment.findRadialCellRanges walks the pairs (i, j > i) of the x-major cell list, so within
 // one ring g = floor(distance) a cell's partners enter its dict in ascending order of THEIR x * height + y; findCellsInRange
 // concatenates the rings 1 .. r.  The travel distance sqrt(dx^2 + dy^2) is only ever compared (agent.py:1430, 1484), so
 // the engine keeps dx^2 + dy^2 in its place (same order; < 256 for the ranges the candidate arrays hold).
+// environmentWraparound = false (SSB_F_NOWRAP): plain distances (findWraparoundDistance, environment.py:175-179), per-axis
+// caps of width - 1 / height - 1 (environment.py:141-144) -- the disc is clipped at the map's edge.
 // ---------------------------------------------------------------------------------------------
 constexpr int SSB_MAX_RADIAL = 15;      // (r + 1)^2 <= 256: squared distances fit the 8-bit distance field
 __device__ __forceinline__ bool radial(const DevCtx &c) { return (c.p.flags & SSB_F_RADIAL) != 0; }
@@ -368,14 +370,19 @@ __device__ __forceinline__ int isqrt_small(int v) { int g = 0; while ((g + 1) * 
 // Environment.maxCellDistance (environment.py:140-146): the cap of findCellsInRange (agent.py:770)
 __device__ __forceinline__ int max_cell_distance(const DevCtx &c) {
     if (!radial(c)) return max(c.max_dx, c.max_dy);
-    const int hw = c.p.width / 2, hh = c.p.height / 2;
+    const bool nowrap = (c.p.flags & SSB_F_NOWRAP) != 0;
+    const int hw = nowrap ? c.p.width - 1 : c.p.width / 2, hh = nowrap ? c.p.height - 1 : c.p.height / 2;
     return min(c.p.max_agent_range, isqrt_small(hw * hw + hh * hh));
 }
 // the coordinates within wraparound distance md of `centre` on an axis of n cells, ascending: at most 2 * md + 1 (n when
 // 2 * md = n: the two ends coincide); out_v / out_d = coordinate and distance
-__device__ __forceinline__ int axis_span(int centre, int md, int n, int *out_v, int *out_d) {
-    const int lo = centre - md, hi = 2 * md >= n ? lo + n - 1 : centre + md;
+__device__ __forceinline__ int axis_span(int centre, int md, int n, bool nowrap, int *out_v, int *out_d) {
+    const int lo = centre - md, hi = (!nowrap && 2 * md >= n) ? lo + n - 1 : centre + md;
     int k = 0;
+    if (nowrap) {                                                       // clipped at the edge, nothing wraps
+        for (int p = max(lo, 0); p <= min(hi, n - 1); p++) { out_v[k] = p; out_d[k++] = abs(p - centre); }
+        return k;
+    }
     for (int p = max(lo, n); p <= hi; p++) { out_v[k] = p - n; out_d[k++] = abs(p - centre); }                 // wrapped past the end
     for (int p = max(lo, 0); p <= min(hi, n - 1); p++) { out_v[k] = p; out_d[k++] = abs(p - centre); }
     for (int p = lo; p <= min(hi, -1); p++) { out_v[k] = p + n; out_d[k++] = abs(p - centre); }                // wrapped before 0
@@ -387,7 +394,9 @@ __device__ __forceinline__ void for_disc(const DevCtx &c, int x, int y, int r, F
     int xs[2 * SSB_MAX_RADIAL + 1], dxs[2 * SSB_MAX_RADIAL + 1], ys[2 * SSB_MAX_RADIAL + 1], dys[2 * SSB_MAX_RADIAL + 1];
     const int H = c.p.height;
     r = min(r, SSB_MAX_RADIAL);                                         // (enumerate_disc flags longer ranges)
-    const int nx = axis_span(x, min(c.max_dx, r), c.p.width, xs, dxs), ny = axis_span(y, min(c.max_dy, r), H, ys, dys);     // dx, dy <= r inside the disc
+    const bool nowrap = (c.p.flags & SSB_F_NOWRAP) != 0;            // (then the per-axis caps are min(range, width - 1): never below r)
+    const int nx = axis_span(x, nowrap ? r : min(c.max_dx, r), c.p.width, nowrap, xs, dxs);       // dx, dy <= r inside the disc
+    const int ny = axis_span(y, nowrap ? r : min(c.max_dy, r), H, nowrap, ys, dys);
     for (int i = 0; i < nx; i++)
         for (int j = 0; j < ny; j++) {
             const int d2 = dxs[i] * dxs[i] + dys[j] * dys[j];
@@ -409,9 +418,10 @@ __device__ int enumerate_disc(const DevCtx &c, int x, int y, int r, const WarpSc
     for_disc(c, x, y, r, [&](int cell, int d2, int g) { const int i = start[g]++; ws.cells[i] = cell; ws.dist[i] = (uint8_t)d2; });
     return start[r];
 }
-__device__ int disc_size(const DevCtx &c, int r) {                       // len(cellsInRange): the same wherever the agent stands
+__device__ int disc_size(const DevCtx &c, int centre, int r) {           // len(cellsInRange) (on the torus the same wherever the agent stands)
     int n = 0;
-    for_disc(c, 0, 0, r, [&](int, int, int) { n++; });
+    const int x = centre / c.p.height;
+    for_disc(c, x, centre - x * c.p.height, r, [&](int, int, int) { n++; });
     return n;
 }
 
@@ -468,8 +478,8 @@ __device__ __forceinline__ double time_to_live(const DevCtx &c, int s, bool age_
 }
 
 // len(cellsInRange) of an agent with range r: the cross does not depend on where it stands
-__device__ __forceinline__ int cross_size(const DevCtx &c, int r) {
-    if (radial(c)) return disc_size(c, r);
+__device__ __forceinline__ int cross_size(const DevCtx &c, int centre, int r) {
+    if (radial(c)) return disc_size(c, centre, r);
     int n = 0;
     for (int d = 1; d <= r; d++) {
         if (d <= c.max_dx) n += (2 * d == c.p.width) ? 1 : 2;
@@ -510,6 +520,7 @@ __device__ __forceinline__ bool cell_in_cross(const DevCtx &c, int centre, int r
     if (cell == centre || r <= 0) return false;
     if (radial(c)) {
         int dx = abs(cx - x), dy = abs(cy - y);
+        if (c.p.flags & SSB_F_NOWRAP) return dx * dx + dy * dy < (r + 1) * (r + 1);      // (caps of width - 1 / height - 1 never bind)
         if (W - dx < dx) dx = W - dx;
         if (H - dy < dy) dy = H - dy;
         return dx <= c.max_dx && dy <= c.max_dy && dx * dx + dy * dy < (r + 1) * (r + 1);
@@ -558,7 +569,7 @@ __device__ __noinline__ double ethical_value(const DevCtx &c, int s, int my_r, c
         future_duration = max_site > 0 ? future_duration / max_site : 0;
         int32_t nb_cells[SSB_MAX_NEIGHBOURS];
         const double future_intensity = neighbor_wealth / (c.eth->global_max_wealth * neighbours4(c, a.pos[nb], nb_cells));  // len(neighbor.cell.neighbors)
-        const int in_range = rn > 0 ? cross_size(c, rn) : 0;                                // len(neighbor.cellsInRange)
+        const int in_range = rn > 0 ? cross_size(c, a.pos[nb], rn) : 0;                                // len(neighbor.cellsInRange)
         const double extent = in_range > 0 ? (double)n_hood / in_range : 1;
         const double future_extent = (in_range > 0 && lookahead != 0) ? future_hood / in_range : 1;
         const double current_reward = extent * (intensity + duration);
@@ -904,7 +915,7 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rn
                            : min(min(max(rec.vision, 0), max(rec.movement, 0)), rcap);
     // environmentWraparound = false: the reference memoises ranges up to width - 1 instead of width // 2 (environment.py:141-144);
     // an agent that sees beyond half the map (disease bonuses) would read them -- not reproduced: fail loudly (code 14)
-    if ((c.p.flags & SSB_F_NOWRAP) && diseased && min((int)eff_vision(c, s), (int)eff_movement(c, s)) > max(c.max_dx, c.max_dy))
+    if ((c.p.flags & SSB_F_NOWRAP) && !radial(c) && diseased && min((int)eff_vision(c, s), (int)eff_movement(c, s)) > max(c.max_dx, c.max_dy))
         atomicExch((unsigned long long *)&c.a.counters[SSB_C_OVERFLOW], 14ull);
     const double aggression = diseased ? eff_aggression(c, s) : fmax(rec.aggression, 0.0);
     Welfare w = {};       // (value-initialised only to keep the front end quiet: set() assigns every field)

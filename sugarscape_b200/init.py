@@ -94,8 +94,6 @@ def check_supported(c):
         # candidate arrays hold RADIAL_MAX_CELLS cells -- a range of 6 on a map at least 13 cells wide)
         if c.get("b200RngMode", "exact") != "exact":
             problems.append("radial ranges in the scalable RNG mode")
-        if not c["environmentWraparound"]:
-            problems.append("radial ranges with environmentWraparound=false")
         if c["agentLogfile"] is not None:
             problems.append("radial ranges with an agentLogfile")
         if radial_cells_in_range(c) > RADIAL_MAX_CELLS:
@@ -107,7 +105,10 @@ def check_supported(c):
             problems.append("moore neighbourhood in the scalable RNG mode")
         if c["agentLogfile"] is not None:
             problems.append("moore neighbourhood with an agentLogfile")
-    if not c["environmentWraparound"]:
+    if not c["environmentWraparound"] and is_radial(c):
+        if c.get("b200RngMode", "exact") != "exact":
+            problems.append("environmentWraparound=false in the scalable RNG mode")
+    elif not c["environmentWraparound"]:
         # cell.py:47-121: the neighbour lists lose the cells across the edge; the range tables (environment.py:111-122) do NOT
         # change as long as no range reaches half the map (they keep wrapping by `% width`, with the plain distance)
         # (an agent looks min(vision, movement) cells far; the memoised tables reach further without wraparound --
@@ -208,8 +209,12 @@ def radial_cells_in_range(c):
     """len(cellsInRange) of the furthest-seeing agent the configured ranges allow (environment.py:132-173,
     agent.py:766-779; disease bonuses can push an agent further: the engine flags that at run time, overflow code 15)."""
     W, H, memo = c["environmentWidth"], c["environmentHeight"], max_agent_range(c)
-    mdx, mdy = min(memo, W // 2), min(memo, H // 2)
-    cap = min(c["agentVision"][1], c["agentMovement"][1], memo, math.isqrt((W // 2) ** 2 + (H // 2) ** 2))
+    wrap = c["environmentWraparound"]
+    far_x, far_y = (W // 2, H // 2) if wrap else (W - 1, H - 1)
+    mdx, mdy = min(memo, far_x), min(memo, far_y)
+    cap = min(c["agentVision"][1], c["agentMovement"][1], memo, math.isqrt(far_x ** 2 + far_y ** 2))
+    if not wrap:        # the disc is clipped at the map's edge: the agent in the middle sees most (the per-axis caps never bind)
+        return sum(0 < (x - W // 2) ** 2 + (y - H // 2) ** 2 < (cap + 1) ** 2 for x in range(W) for y in range(H))
     n = 0
     for ox in range(-mdx, mdx + 1):
         for oy in range(-mdy, mdy + 1):

@@ -95,6 +95,14 @@ VARIANTS = {
     "radial_combat": ("combat_limited", 120, {"agentVisionMode": "radial", "agentMovementMode": "radial"}),
     "radial_determinism": ("determinism", 100, {"agentVisionMode": "radial", "agentMovementMode": "radial", "experimentalGroup": None,
                                                 "diseaseVisionPenalty": [-1, 0], "diseaseMovementPenalty": [-1, 0]}),
+    # radial ranges without wraparound: plain distances, discs clipped at the map's edge (environment.py:141-144, 175-179) -- on
+    # every family of determinism.json (with the Moore neighbourhood on top) and on a map smaller than the ranges
+    "radial_nowrap_determinism": ("determinism", 100, {"agentVisionMode": "radial", "agentMovementMode": "radial", "experimentalGroup": None,
+                                                       "environmentWraparound": False, "neighborhoodMode": "moore",
+                                                       "diseaseVisionPenalty": [-1, 0], "diseaseMovementPenalty": [-1, 0]}),
+    "radial_nowrap_small_map": ("trade_tagging_reproduction", 100, {"agentVisionMode": "radial", "agentMovementMode": "radial",
+                                                                    "environmentWraparound": False, "environmentWidth": 9, "environmentHeight": 12,
+                                                                    "startingAgents": 30, "agentVision": [1, 6]}),
     # a map smaller than the ranges: the per-axis caps (width // 2) and the coinciding ends of an even axis
     "radial_small_map": ("trade_tagging_reproduction", 100, {"agentVisionMode": "radial", "agentMovementMode": "radial",
                                                              "environmentWidth": 10, "environmentHeight": 8, "startingAgents": 30,

@@ -145,7 +145,7 @@ def test_device_disease_source_matches_reference_on_variants(variant, min_sick_s
 
 
 @pytest.mark.parametrize("variant", ["nowrap_trade_tagging_reproduction", "nowrap_pollution", "moore_trade_tagging_reproduction", "moore_pollution",
-                                     "radial_trade_tagging_reproduction", "radial_combat", "radial_small_map"])
+                                     "radial_trade_tagging_reproduction", "radial_combat", "radial_small_map", "radial_nowrap_small_map"])
 def test_device_source_without_wraparound_matches_reference(variant):
     """environmentWraparound = false (cell.py:47-121; variant fixtures from the unmodified reference): tagging, trade and
     births over neighbour lists that stop at the map's edge, pollution flux over the neighbours that exist.  moore_*: eight
@@ -158,7 +158,7 @@ def test_device_source_without_wraparound_matches_reference(variant):
 
 
 @pytest.mark.parametrize("variant,ethics", [("determinism_plain", False), ("determinism_ethics", True), ("nowrap_determinism", True), ("moore_nowrap_determinism", True),
-                                            ("radial_determinism", True)])
+                                            ("radial_determinism", True), ("radial_nowrap_determinism", True)])
 def test_device_source_matches_reference_on_determinism_variants(variant, ethics):
     """examples/determinism.json (variant fixtures from the unmodified reference): diseases, depression, lending,
     friends, racial tags, universal income, live combat, trade, tags, inheritance, pollution and seasons at once --

@@ -222,7 +222,7 @@ def _private_log_keys(orc, rs, t, ethics):
 
 
 @pytest.mark.parametrize("variant,ethics", [("determinism_plain", False), ("determinism_ethics", True), ("nowrap_determinism", True), ("moore_nowrap_determinism", True),
-                                            ("radial_determinism", True)])
+                                            ("radial_determinism", True), ("radial_nowrap_determinism", True)])
 def test_oracle_determinism_variants_match_reference_trajectory(variant, ethics):
     """examples/determinism.json (variant fixtures from the unmodified reference,
     tests/golden/make_golden_variants.py): diseases, depression, lending, friends, racial tags,
@@ -395,7 +395,7 @@ def test_oracle_environment_file_matches_reference_trajectory():
 
 
 @pytest.mark.parametrize("overrides", [{"agentVisionMode": "radial", "agentMovementMode": "radial", "b200RngMode": "scalable"},
-                                       {"agentVisionMode": "radial", "agentMovementMode": "radial", "environmentWraparound": False},
+                                       {"agentVisionMode": "radial", "agentMovementMode": "radial", "environmentWraparound": False, "b200RngMode": "scalable"},
                                        {"agentVisionMode": "radial", "agentMovementMode": "radial", "agentVision": [1, 8], "agentMovement": [8, 8]},
                                        {"neighborhoodMode": "moore", "b200RngMode": "scalable"},
                                        {"environmentWraparound": False, "b200RngMode": "scalable"},
@@ -521,7 +521,7 @@ def test_scalable_mode_oracle_matches_patched_reference(name):
 PLAIN_VARIANTS = ["pollution_diffusion_delay2", "pollution_diffusion_delay3", "nowrap_trade_tagging_reproduction", "nowrap_pollution",
                   "moore_trade_tagging_reproduction", "moore_pollution",       # moore_*: neighborhoodMode "moore" (cell.py:77-89)
                   # radial_*: agentVisionMode = agentMovementMode = "radial" (environment.py:146-173) -- discs instead of crosses
-                  "radial_trade_tagging_reproduction", "radial_combat", "radial_small_map"]
+                  "radial_trade_tagging_reproduction", "radial_combat", "radial_small_map", "radial_nowrap_small_map"]
 
 
 @pytest.mark.parametrize("variant", PLAIN_VARIANTS)

@@ -30,6 +30,7 @@ pytestmark = [pytest.mark.gpu]
 
 
 @pytest.mark.parametrize("variant", ["radial_small_map", "radial_trade_tagging_reproduction", "radial_combat", "radial_determinism",
+                                     "radial_nowrap_small_map", "radial_nowrap_determinism",
                                      "asimov_trade", "asimov_combat", "asimov_determinism"])
 def test_radial_ranges_and_asimov_match_reference_trajectory(variant):
     base, overrides, gold, log = pu.load_variant(variant)
