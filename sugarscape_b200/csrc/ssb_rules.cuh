@@ -1043,6 +1043,7 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rn
         }
         if (m == 0) m = 1;
     }
+    bool stays_unranked = false;      // lane 0: an Asimov agent that stays although it has candidates (lastMoveRank = len(potentialCells))
     if constexpr (EXT) {
     if (c.eth != nullptr) {                                      // uniform
         // decision models: the ethical ranking may override the greedy choice (ethics.py:105-139); the
@@ -1077,6 +1078,7 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rn
                 // (rank < 0: an Asimov agent that stays although it has candidates -- not the greedy cell, and agent.cell is not among
                 // validMoves when the log looks for it, sugarscape.py:1154-1160)
                 c.eth->last_move_optimal[s] = rank == 0; c.eth->move_rank[s] = rank < 0 ? 0 : rank; c.eth->move_diff[s] = diff;
+                stays_unranked = rank < 0;
             } else {
                 c.eth->last_move_optimal[s] = 1;      // [own cell] is its own best; rank and difference keep their values
                 if (has_agentlog(c) && c.eth->model[s] == 1 && engaged) {
@@ -1101,7 +1103,7 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rn
     }
     if (EXT && has_agentlog(c) && lane == 0) {                         // lastValidMoves / lastMoveRank (agent.py:744-745)
         c.x->agentlog.valid_moves[s] = n > 0 ? m : 1;
-        c.x->agentlog.move_rank[s] = (c.eth != nullptr && n > 0) ? c.eth->move_rank[s] : 0;
+        c.x->agentlog.move_rank[s] = stays_unranked ? m : ((c.eth != nullptr && n > 0) ? c.eth->move_rank[s] : 0);
     }
     int alive = 1;
     double sugar = rec.sugar, spice = rec.spice;

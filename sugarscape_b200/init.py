@@ -94,8 +94,6 @@ def check_supported(c):
         # candidate arrays hold RADIAL_MAX_CELLS cells -- a range of 6 on a map at least 13 cells wide)
         if c.get("b200RngMode", "exact") != "exact":
             problems.append("radial ranges in the scalable RNG mode")
-        if c["agentLogfile"] is not None:
-            problems.append("radial ranges with an agentLogfile")
         if radial_cells_in_range(c) > RADIAL_MAX_CELLS:
             problems.append("radial ranges of more than %d cells" % RADIAL_MAX_CELLS)
     if c["neighborhoodMode"] not in ("vonNeumann", "moore"):
@@ -137,8 +135,6 @@ def check_supported(c):
         # own for THAT neighbour's findEthicalValueOfCell, which reads the neighbourhood list stored at the neighbour's last move
         if any(m not in ("asimov", "none", "rawSugarscape") for m in c["agentDecisionModels"]):
             problems.append("asimov mixed with other decision models")
-        if c["agentLogfile"] is not None:
-            problems.append("asimov with an agentLogfile")
     bad_models = [m for m in c["agentDecisionModels"] if m not in SUPPORTED_DECISION_MODELS]
     if bad_models:
         problems.append("decision models other than rawSugarscape and the Bentham family: " + ", ".join(bad_models))

@@ -25,6 +25,10 @@ CASES = {
     "trade_pollution": ("trade_pollution", dict(SMALL, timesteps=30, agentFertilityFactor=[1, 1], agentFemaleFertilityAge=[12, 15],
                                                 agentMaleFertilityAge=[12, 15], agentFemaleInfertilityAge=[40, 50],
                                                 agentMaleInfertilityAge=[50, 60], agentMaxAge=[60, 100])),
+    # radial ranges + ethics.Asimov among plain agents (a robot that stays although it has candidates logs moveRank = validMoves)
+    "radial_asimov": ("determinism", dict(SMALL, timesteps=30, agentVisionMode="radial", agentMovementMode="radial",
+                                          agentDecisionModels=["asimov", "none"], agentDecisionModelFactor=[0, 1], experimentalGroup=None,
+                                          diseaseVisionPenalty=[-1, 0], diseaseMovementPenalty=[-1, 0])),
 }
 
 

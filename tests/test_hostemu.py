@@ -250,7 +250,7 @@ def _agentlog_cases():
         return json.load(f)
 
 
-@pytest.mark.parametrize("case", ["determinism", "combat", "trade_pollution"])
+@pytest.mark.parametrize("case", ["determinism", "combat", "trade_pollution", "radial_asimov"])
 def test_per_agent_log_matches_reference(case, tmp_path, monkeypatch):
     """`agentLogfile` (reference agent.py:1567-1620, sugarscape.py:415-421): the drop-in driver
     (sugarscape_b200.simulation.Sugarscape) on the host-compiled device source writes the per-agent log the unmodified

@@ -1,7 +1,7 @@
 """SURVEY row (f)3 on the GPU, the two pieces written after round 2's GPU minutes were spent.
 
 (1) agentVisionMode = agentMovementMode = "radial" (reference environment.py:146-173, agent.py:766-779)
-through the C ABI against fixtures of the unmodified reference (tests/golden/make_golden_variants.py, radial_*): the candidate
+through the C ABI against six fixtures of the unmodified reference (tests/golden/make_golden_variants.py, radial_*; two of them without wraparound): the candidate
 cells of a move are the disc floor(distance) <= range in the insertion order of Environment.findRadialCellRanges, for plain
 agents (tagging + trade + births, live combat with retaliators and host-side replacement, a map smaller than the ranges) and
 for every family of determinism.json incl. the Bentham decision models.  Integer state, tags, grid and the MT19937 stream
@@ -15,7 +15,7 @@ family of determinism.json.
 group is a decisionModel string) on determinism.json -- digests and all 203 log keys against four fixtures of the unmodified
 reference (determinism_group_*).
 
-Status: the four radial fixtures pass on the CPU oracle (tests/test_oracle_golden.py) and on the device rule source compiled for
+Status: the six radial fixtures pass on the CPU oracle (tests/test_oracle_golden.py) and on the device rule source compiled for
 the host (tests/test_hostemu.py), the three Asimov fixtures on the latter (the oracle restates the Bentham family only); the
 four group fixtures on the latter as well (the oracle's group is "depressed"); these cases have NOT run on a B200 yet.  The file sorts after every other test file so that its
 first GPU run cannot hide anything else."""
@@ -25,6 +25,7 @@ import parity_util as pu
 from sugarscape_b200 import init, layout, stats
 from test_gpu_parity import _close, _engine, _replace
 from test_zz_gpu_decision_models import _Budget, _cap
+from test_zz_gpu_decision_models import test_drop_in_driver_writes_the_reference_per_agent_log as _per_agent_log_case
 
 pytestmark = [pytest.mark.gpu]
 
@@ -80,3 +81,9 @@ def test_other_experimental_groups_match_reference_trajectory_and_full_log(varia
         for k in log[t]:
             assert k in rs and _close(rs[k], log[t][k]), f"{variant}: log key {k} at t={t}: {rs.get(k)} vs {log[t][k]}"
     eng.close()
+
+
+def test_drop_in_driver_writes_the_per_agent_log_with_radial_ranges_and_asimov(tmp_path):
+    """`agentLogfile` through `Sugarscape(conf).runSimulation()` on determinism.json with radial ranges and Asimov robots among
+    plain agents (tests/golden/make_golden_agentlog.py, case radial_asimov): record by record."""
+    _per_agent_log_case("radial_asimov", tmp_path)
