@@ -39,7 +39,8 @@ extern "C" {
  * ssb_set_shard_sweep).  The optional per-slot state of the rule families keeps its name "ABI 2" below.
  * Added since without a layout change (same version): SSB_F_RADIAL, ssb_ethics_t.model 4 (ethics.Asimov), bit 1 of
  * ssb_ethics_t.top_ordering, SSB_GROUP_RACE / SSB_GROUP_MODEL, overflow code 15. */
-#define SSB_ABI_VERSION 3
+/* 4: ssb_group_t.hood_list / hood_n (experimental groups whose membership changes during the run). */
+#define SSB_ABI_VERSION 4
 
 /* RNG modes */
 #define SSB_RNG_EXACT    0 /* mode E: CPython MT19937 word-for-word replay, ordered execution   */
@@ -353,14 +354,19 @@ typedef struct ssb_misc {
  * Supported groups (ssb_group_t.kind): "depressed" (ssb_misc_t.depressed), "female" / "male" (ssb_agents_t.sex), "race<N>"
  * (ssb_misc_t.race == N, N in bits 8.. of kind), a decision model's name (agent.decisionModel == group: bit 1 of
  * ssb_ethics_t.top_ordering, set by the host and handed on to the children with the parent's class) --
- * memberships that are fixed at birth.  (Groups whose membership changes during the run -- "sick", age ranges, a
- * disease -- would need every agent's movement neighbourhood kept as a list: the reference re-evaluates the
- * neighbours' membership at statistics time, sugarscape.py:1145-1151.) */
+ * memberships that are fixed at birth -- and "sick" (ssb_diseases_t.n_sick > 0), whose membership changes during the run:
+ * the reference re-evaluates the
+ * membership of every agent of agent.movementNeighborhood at statistics time (sugarscape.py:1145-1151), so each agent's
+ * movement neighbourhood is kept as a list of slots (hood_list, written at its ranking) and split again at the end of the
+ * agent step, before the dead leave their slots.  ("disease<N>" has statistics rules of its own, sugarscape.py:1203-1272,
+ * and is not built; "raceInGroup" and, at the first death, "ageRange<N>" raise in the reference's isInGroup.) */
 #define SSB_GROUP_DEPRESSED 1
 #define SSB_GROUP_FEMALE    2
 #define SSB_GROUP_MALE      3
 #define SSB_GROUP_RACE      4   /* kind = SSB_GROUP_RACE | (race id << 8)                                       */
 #define SSB_GROUP_MODEL     5   /* needs ssb_ethics_t                                                           */
+#define SSB_GROUP_SICK      6   /* from here on: membership changes during the run (hood_list is written)       */
+#define SSB_GROUP_HOOD_MAX  161 /* entries per slot of hood_list: the candidate cells of mode E + the agent itself */
 #define SSB_GI_COMBAT 0
 #define SSB_GI_DISEASE 1
 #define SSB_GI_LENDING 2
@@ -371,6 +377,8 @@ typedef struct ssb_group {
     int32_t *with_control, *with_experimental;        /* [slot][SSB_GI_KINDS]: interactions since the last statistics pass */
     int32_t *control_neighbors, *experimental_neighbors;   /* movementNeighborhood split, as of the agent's last ranking */
     int64_t kind;                                     /* SSB_GROUP_*                                        */
+    int32_t *hood_list;                               /* [slot][SSB_GROUP_HOOD_MAX] slots of agent.movementNeighborhood (kinds >= SSB_GROUP_SICK) */
+    int32_t *hood_n;                                  /* its length                                         */
 } ssb_group_t;
 
 /* per-agent log (configuration["agentLogfile"]; agent.py:1567-1620 updateRuntimeStats, sugarscape.py:415-421): one

@@ -643,7 +643,9 @@ int ssb_bind_ext(ssb_engine_t *e, const ssb_ext_t *ext) {
     if (Gr.with_control) {
         if (!Gr.with_experimental || !Gr.control_neighbors || !Gr.experimental_neighbors) return fail(e, -1, "group: null array");
         const long long gk = Gr.kind & 0xff;
-        if (gk < SSB_GROUP_DEPRESSED || gk > SSB_GROUP_MODEL || (gk != SSB_GROUP_RACE && Gr.kind != gk)) return fail(e, -1, "group: unknown kind");
+        if (gk < SSB_GROUP_DEPRESSED || gk > SSB_GROUP_SICK || (gk != SSB_GROUP_RACE && Gr.kind != gk)) return fail(e, -1, "group: unknown kind");
+        if (gk >= SSB_GROUP_SICK && (!Gr.hood_list || !Gr.hood_n)) return fail(e, -1, "group: a membership that changes during the run needs hood_list / hood_n");
+        static_assert(SSB_GROUP_HOOD_MAX >= MAXC_EXACT + 1, "hood_list holds the candidate cells of mode E + the agent");
         if ((gk == SSB_GROUP_DEPRESSED || gk == SSB_GROUP_RACE) && !M.universal_sugar) return fail(e, -1, "the experimental groups \"depressed\" and \"race<N>\" need the misc family");
         if (gk == SSB_GROUP_MODEL && !e->ctx.eth) return fail(e, -1, "a decision model as experimental group needs ssb_bind_ethics first");
     }
@@ -1151,8 +1153,9 @@ static int check_overflow(ssb_engine_t *e) {
                                  "a priority bucket of the sweep is longer than its grid",
                                  "an agent contradicts the rule flags the lean kernel was chosen by",
                                  "environmentWraparound = false: an agent sees beyond half the map (not reproduced)",
-                                 "radial ranges: an agent sees more cells than the candidate arrays hold"};
-    return fail(e, -4, "engine overflow code %lld: %s", code, code > 0 && code < 16 ? what[code] : "?");
+                                 "radial ranges: an agent sees more cells than the candidate arrays hold",
+                                 "experimental group with changing membership: an agent with an empty range keeps an older neighbourhood list (not reproduced)"};
+    return fail(e, -4, "engine overflow code %lld: %s", code, code > 0 && code < 17 ? what[code] : "?");
 }
 
 int ssb_stats(ssb_engine_t *e, ssb_stats_t *host_out) {

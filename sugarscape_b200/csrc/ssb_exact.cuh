@@ -34,6 +34,9 @@ __device__ void agent_step_exact_body(const DevCtx &c, uint32_t *mt, const WarpS
         __threadfence_block();
         Gr::sync();
     }
+    if constexpr (EXT) {
+        if (group_dynamic(c)) group_resplit_neighbors<G>(c);
+    }
 }
 
 // Decision-model reductions of the log (sugarscape.py:1141-1160, 1218-1222): one lane, list order (the

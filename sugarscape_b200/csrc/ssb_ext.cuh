@@ -28,9 +28,12 @@ __device__ __forceinline__ bool is_member(const DevCtx &c, int s) {
         case SSB_GROUP_MALE: return c.a.sex[s] == SSB_SEX_MALE;
         case SSB_GROUP_RACE: return has_misc(c) && c.x->misc.race[s] == (int)(kind >> 8);      // self.race == raceID (agent.py:1273-1275)
         case SSB_GROUP_MODEL: return c.eth != nullptr && (c.eth->top_ordering[s] & 2) != 0;    // group == self.decisionModel (agent.py:1262)
+        case SSB_GROUP_SICK: return has_disease(c) && c.x->diseases.n_sick[s] > 0;             // isSick (a dead agent's list is empty, agent.py:309-313)
     }
     return false;
 }
+// membership can change during the run: agent.movementNeighborhood is kept as a list and split at the end of the step
+__device__ __forceinline__ bool group_dynamic(const DevCtx &c) { return has_group(c) && (c.x->group.kind & 0xff) >= SSB_GROUP_SICK; }
 // statistics pass: 0 = everybody, 1 = the experimental group, 2 = the control group
 __device__ __forceinline__ bool in_pass(const DevCtx &c, int s, int pass) { return pass == 0 || (pass == 1) == is_member(c, s); }
 // <kind>With{Experimental,Control}Group += 1
@@ -42,6 +45,21 @@ __device__ __forceinline__ void group_note(const DevCtx &c, int s, int kind, int
 __device__ __forceinline__ void group_reset_slot(const DevCtx &c, int s) {
     for (int k = 0; k < SSB_GI_KINDS; k++) { c.x->group.with_control[(long long)s * SSB_GI_KINDS + k] = 0; c.x->group.with_experimental[(long long)s * SSB_GI_KINDS + k] = 0; }
     c.x->group.control_neighbors[s] = 0; c.x->group.experimental_neighbors[s] = 0;
+    if (group_dynamic(c)) c.x->group.hood_n[s] = 0;
+}
+// sugarscape.py:1145-1151 for the groups whose membership moves: every agent's stored movement neighbourhood split by the
+// membership its members have at the END of the agent step (the dead are still in their slots and, like the reference's
+// dead agent objects, no longer sick).  All lanes of the group; called once after the last agent of the step.
+template <int G>
+__device__ inline void group_resplit_neighbors(const DevCtx &c) {
+    const ssb_group_t &Gp = c.x->group;
+    const long long n_list = c.a.counters[SSB_C_N_LIST];
+    for (long long i = threadIdx.x & (G - 1); i < n_list; i += G) {
+        const int s = c.a.order[i];
+        int exp_n = 0, ctrl_n = 0;
+        for (int k = 0; k < Gp.hood_n[s]; k++) { if (is_member(c, Gp.hood_list[(long long)s * SSB_GROUP_HOOD_MAX + k])) exp_n++; else ctrl_n++; }
+        Gp.control_neighbors[s] = ctrl_n; Gp.experimental_neighbors[s] = exp_n;
+    }
 }
 // happinessUnit: 1, 0.5763 when depressed
 __device__ __forceinline__ double happiness_unit(const DevCtx &c, int s) { return has_misc(c) ? c.x->misc.happiness_unit[s] : 1.0; }

@@ -1117,6 +1117,21 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rn
                 if (o >= 0 && agent_alive(c, o)) { if (is_member(c, o)) exp_n++; else ctrl_n++; }
             }
             c.x->group.control_neighbors[s] = ctrl_n; c.x->group.experimental_neighbors[s] = exp_n;
+            if (group_dynamic(c)) {               // the list itself: split again at the end of the step (group_resplit_neighbors)
+                int32_t *list = c.x->group.hood_list + (long long)s * SSB_GROUP_HOOD_MAX;
+                int k = 0;
+                for (int i = 0; i < n && k < SSB_GROUP_HOOD_MAX - 1; i++) {
+                    const int o = c.g.occ[ws.cells[i]];
+                    if (o >= 0 && agent_alive(c, o)) list[k++] = o;
+                }
+                list[k++] = s;
+                c.x->group.hood_n[s] = k;
+            }
+        }
+        if (EXT && n == 0 && group_dynamic(c) && c.x->group.hood_n[s] > 0) {
+            // an empty range leaves movementNeighborhood as it was (agent.py:1398-1399 returns before updateMovementStats): a list
+            // from an earlier step, whose dead have left their slots -- not reproduced: fail loudly (code 16)
+            atomicExch((unsigned long long *)&c.a.counters[SSB_C_OVERFLOW], 16ull);
         }
         // lastValidMoves: findBestCell records len([own cell]) when the range is empty (agent.py:1398-1399, 745)
         if (diseased) c.x->diseases.last_valid_moves[s] = n > 0 ? m : 1;

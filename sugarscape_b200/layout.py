@@ -8,7 +8,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 RNG_EXACT, RNG_SCALABLE = 0, 1
 ALIVE, STARVATION, AGING, COMBAT, OTHER = 0, 1, 2, 3, 4
 SEX_NONE, SEX_MALE, SEX_FEMALE = 0, 1, 2
@@ -344,9 +344,11 @@ GROUP_LAYOUT = (
     ("with_control", _I32, 0, "gi"), ("with_experimental", _I32, 0, "gi"),
     ("control_neighbors", _I32, 0, "cap"), ("experimental_neighbors", _I32, 0, "cap"),
     ("kind", None, None, None),
+    ("hood_list", _I32, -1, "hood"), ("hood_n", _I32, 0, "cap"),
 )
+GROUP_HOOD_MAX = 161        # SSB_GROUP_HOOD_MAX
 GROUP_KINDS = {"depressed": 1, "female": 2, "male": 3}      # SSB_GROUP_* (memberships fixed at birth)
-GROUP_RACE, GROUP_MODEL = 4, 5
+GROUP_RACE, GROUP_MODEL, GROUP_SICK = 4, 5, 6      # (from GROUP_SICK on: membership changes during the run)
 
 
 def group_kind(c):
@@ -355,7 +357,9 @@ def group_kind(c):
     "female", "male", "race" in the name (race<N>), ..."""
     import re
     g = c["experimentalGroup"]
-    if g is None or "ageRange" in g:
+    if g is None:
+        return 0
+    if "ageRange" in g:        # (isInGroup reads self.cell.environment: the reference raises on the first dead agent it asks)
         return 0
     models = ["none" if m == "rawSugarscape" else m for m in c["agentDecisionModels"]]      # sugarscape.py:720-721
     if g in models and not (g in GROUP_KINDS or "disease" in g or "race" in g):
@@ -364,6 +368,8 @@ def group_kind(c):
         return GROUP_KINDS[g]
     if "disease" in g:
         return 0
+    if g == "sick":
+        return GROUP_SICK
     m = re.search(r"race(?P<ID>\d+)", g) if "race" in g else None
     if m is not None and c["environmentMaxRaces"] > 0 and c["agentRacialTagStringLength"] > 0:
         return GROUP_RACE | (int(m.group("ID")) << 8)
@@ -450,7 +456,7 @@ class HostExt:
         self.n_diseases, self.max_sick = n_diseases, max(n_diseases, 1)
         self.immune_len = int(c["agentImmuneSystemLength"])
         self.sizes = {"cap": capacity, "pool": 8 * capacity, "dead": 4 * capacity, "friends": capacity * MAX_FRIENDS,
-                      "nbr": capacity * 4, "recs": capacity * AL_FIELDS, "record": capacity, "gi": capacity * GI_KINDS, "mods": capacity * DM_COUNT, "sick": capacity * self.max_sick, "defs": self.max_sick, "bits": horizon + 1}
+                      "hood": capacity * GROUP_HOOD_MAX if (self.group_kind & 0xff) >= GROUP_SICK else 1, "nbr": capacity * 4, "recs": capacity * AL_FIELDS, "record": capacity, "gi": capacity * GI_KINDS, "mods": capacity * DM_COUNT, "sick": capacity * self.max_sick, "defs": self.max_sick, "bits": horizon + 1}
         self.arrays = {}
         for fam, table in EXT_FAMILIES:
             if fam not in self.families:
@@ -545,6 +551,7 @@ class HostExt:
             A["group.with_experimental"][slot * GI_KINDS:(slot + 1) * GI_KINDS] = 0
             A["group.control_neighbors"][slot] = 0
             A["group.experimental_neighbors"][slot] = 0
+            A["group.hood_n"][slot] = 0
 
         if "agentlog" in self.families:
             for name, fill in (("time_to_live", 0), ("last_pollution", 0), ("prey_wealth", 0), ("last_combat", -1),

@@ -109,8 +109,9 @@ def main():
             ov["agentDynamicSocialPressureFactor"] = rng.choice([[0.0, 0.0], [0.02, 0.1]])
             ov["agentDecisionModelFactor"] = rng.choice([[1, 1], [0.2, 0.8]])
             ov["agentDynamicDecisionModelFactor"] = rng.choice([[0.0, 0.0], [0.05, 0.15]])
-        if rng.random() < 0.3:
-            ov["experimentalGroup"] = rng.choice(["depressed", "female", "male"])
+        if rng.random() < 0.3 or os.environ.get("SSB_FUZZ_GROUPS") == "1":      # SSB_FUZZ_GROUPS=1: every case with a group
+            ov["experimentalGroup"] = rng.choice(["depressed", "female", "male", "sick", "sick", "race0", "race1", "race2"] +
+                                                 [m for m in ov.get("agentDecisionModels", []) if m != "none"])
             ov["agentReplacements"] = 0
         try:
             res = run_case(base, ov, 60)

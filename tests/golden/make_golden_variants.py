@@ -20,14 +20,15 @@ _ETHICS = {"agentDecisionModels": ["none", "bentham", "altruist", "egoist", "neg
            "agentDecisionModelFactor": [1, 1], "agentDecisionModelLookaheadDiscount": [0.5, 0.5],
            "agentDecisionModelLookaheadFactor": 0.5, "agentSelfishnessFactor": [-1, -1]}
 
+_MILD = {"diseaseSugarMetabolismPenalty": [0, 1], "diseaseSpiceMetabolismPenalty": [0, 0],
+         "diseaseVisionPenalty": [-1, 1], "diseaseFertilityPenalty": [-1, 0], "diseaseIncubationPeriod": [0, 3],
+         "diseaseTransmissionChance": [0.3, 1.0], "agentDiseaseProtectionChance": [0.0, 0.5],
+         "startingDiseases": 12, "startingDiseasesPerAgent": [0, 2], "diseaseTagStringLength": [3, 8],
+         "agentImmuneSystemLength": 20}
+
 VARIANTS = {
     # diseases that incubate, spread with a chance, can be resisted and are recovered from
-    "disease_mild": ("disease_basic", 150, {
-        "diseaseSugarMetabolismPenalty": [0, 1], "diseaseSpiceMetabolismPenalty": [0, 0],
-        "diseaseVisionPenalty": [-1, 1], "diseaseFertilityPenalty": [-1, 0], "diseaseIncubationPeriod": [0, 3],
-        "diseaseTransmissionChance": [0.3, 1.0], "agentDiseaseProtectionChance": [0.0, 0.5],
-        "startingDiseases": 12, "startingDiseasesPerAgent": [0, 2], "diseaseTagStringLength": [3, 8],
-        "agentImmuneSystemLength": 20}),
+    "disease_mild": ("disease_basic", 150, dict(_MILD)),
     # long tag strings against a short immune system: slow recovery, the diseases stay around
     "disease_endemic": ("disease_basic", 120, {
         "diseaseSugarMetabolismPenalty": [0, 1], "diseaseSpiceMetabolismPenalty": [0, 0], "diseaseVisionPenalty": [-1, 0],
@@ -131,6 +132,10 @@ VARIANTS = {
     # is the group's name; children carry the string of the parent whose class they take)
     "determinism_group_race1": ("determinism", 100, {"experimentalGroup": "race1"}),
     "determinism_group_bentham": ("determinism", 100, {"experimentalGroup": "bentham"}),
+    # ... and a group whose membership CHANGES during the run: the sick (age ranges raise in the reference at the first death:
+    # isInGroup reads self.cell.environment of a dead agent)
+    "determinism_group_sick": ("determinism", 100, {"experimentalGroup": "sick"}),
+    "disease_mild_group_sick": ("disease_basic", 150, dict(_MILD, experimentalGroup="sick")),
 }
 
 

@@ -217,7 +217,8 @@ def test_dead_creditor_table_wraps_around():
     assert int(ext.arrays["lending.counters"][layout.LC_N_DEAD]) > 2 * 8
 
 
-@pytest.mark.parametrize("variant", ["determinism_group_female", "determinism_group_male", "determinism_group_race1", "determinism_group_bentham"])
+@pytest.mark.parametrize("variant", ["determinism_group_female", "determinism_group_male", "determinism_group_race1", "determinism_group_bentham",
+                                     "determinism_group_sick", "disease_mild_group_sick"])
 def test_device_source_matches_reference_on_other_experimental_groups(variant):
     """determinism.json with another experimental group than the shipped "depressed" (variant fixtures of the unmodified
     reference): membership by sex, by race (race<N>) and by decision model (the group is a decisionModel string) -- digests

@@ -11,9 +11,9 @@ bit-exact on every step, fp64 holdings through their digest, all 59 log keys.
 unmodified reference (asimov_*): with spice and births, sugar-only with live combat and replacement, and on top of every other
 family of determinism.json.
 
-(3) experimental groups other than the shipped "depressed": membership by sex, by race (race<N>) and by decision model (the
-group is a decisionModel string) on determinism.json -- digests and all 203 log keys against four fixtures of the unmodified
-reference (determinism_group_*).
+(3) experimental groups other than the shipped "depressed": membership by sex, by race (race<N>), by decision model (the
+group is a decisionModel string) and -- changing during the run -- the sick, on determinism.json and on a disease example --
+digests and all 203 log keys against six fixtures of the unmodified reference (*_group_*).
 
 Status: the six radial fixtures pass on the CPU oracle (tests/test_oracle_golden.py) and on the device rule source compiled for
 the host (tests/test_hostemu.py), the three Asimov fixtures on the latter (the oracle restates the Bentham family only); the
@@ -57,7 +57,8 @@ def test_radial_ranges_and_asimov_match_reference_trajectory(variant):
     eng.close()
 
 
-@pytest.mark.parametrize("variant", ["determinism_group_female", "determinism_group_male", "determinism_group_race1", "determinism_group_bentham"])
+@pytest.mark.parametrize("variant", ["determinism_group_female", "determinism_group_male", "determinism_group_race1", "determinism_group_bentham",
+                                     "determinism_group_sick", "disease_mild_group_sick"])
 def test_other_experimental_groups_match_reference_trajectory_and_full_log(variant):
     base, overrides, gold, log = pu.load_variant(variant)
     c, state, pop, params, endow, tags, eng = _engine(base, layout.RNG_EXACT, overrides)
