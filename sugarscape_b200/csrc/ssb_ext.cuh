@@ -53,7 +53,7 @@ __device__ __forceinline__ void group_reset_slot(const DevCtx &c, int s) {
 template <int G>
 __device__ inline void group_resplit_neighbors(const DevCtx &c) {
     const ssb_group_t &Gp = c.x->group;
-    const long long n_list = c.a.counters[SSB_C_N_LIST];
+    const long long n_list = (long long)((volatile unsigned long long *)c.a.counters)[SSB_C_N_LIST];      // (lane 0 appended the newborn)
     for (long long i = threadIdx.x & (G - 1); i < n_list; i += G) {
         const int s = c.a.order[i];
         int exp_n = 0, ctrl_n = 0;

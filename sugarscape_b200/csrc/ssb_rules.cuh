@@ -910,7 +910,8 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rn
     const int pos = rec.pos;
     const int H = c.p.height, x = pos / H, y = pos - x * H;
     const bool diseased = EXT && has_disease(c);             // uniform: the find* accessors carry disease modifiers
-    const int rcap = max_cell_distance(c);
+    // (radial ranges exist in mode E only: the mode S instantiations keep the cross, at compile time)
+    const int rcap = RngTraits<Rng>::ordered ? max_cell_distance(c) : max(c.max_dx, c.max_dy);
     const int r = diseased ? min(min((int)eff_vision(c, s), (int)eff_movement(c, s)), rcap)
                            : min(min(max(rec.vision, 0), max(rec.movement, 0)), rcap);
     // environmentWraparound = false: the reference memoises ranges up to width - 1 instead of width // 2 (environment.py:141-144);
@@ -925,7 +926,10 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rn
     const bool spicy = (c.p.flags & SSB_F_SPICE) != 0;
     const bool fighter = aggression > 0;
     int n = 0;
-    if (lane == 0 && r > 0) n = radial(c) ? enumerate_disc(c, x, y, r, ws, maxc) : enumerate_cross(c, x, y, r, ws, maxc);
+    if (lane == 0 && r > 0) {
+        if constexpr (RngTraits<Rng>::ordered) n = radial(c) ? enumerate_disc(c, x, y, r, ws, maxc) : enumerate_cross(c, x, y, r, ws, maxc);
+        else n = enumerate_cross(c, x, y, r, ws, maxc);
+    }
     n = Gr::bcast(n, 0);
     int b_cell = pos, b_dist = 1 << 30, b_rank = 1 << 30, b_cs = 0, b_cp = 0;
     double b_welfare = -1.0, b_pl = 0.0;
