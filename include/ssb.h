@@ -359,7 +359,7 @@ typedef struct ssb_misc {
  * membership of every agent of agent.movementNeighborhood at statistics time (sugarscape.py:1145-1151), so each agent's
  * movement neighbourhood is kept as a list of slots (hood_list, written at its ranking) and split again at the end of the
  * agent step, before the dead leave their slots.  ("disease<N>" has statistics rules of its own, sugarscape.py:1203-1272,
- * and is not built; "raceInGroup" and, at the first death, "ageRange<N>" raise in the reference's isInGroup.) */
+ * never has a member in the reference (a string compared with integer ids) and is not built; "raceInGroup" and, at the first death, "ageRange<N>" raise in the reference's isInGroup.) */
 #define SSB_GROUP_DEPRESSED 1
 #define SSB_GROUP_FEMALE    2
 #define SSB_GROUP_MALE      3
