@@ -810,9 +810,10 @@ __device__ __noinline__ void pecs_pick(const DevCtx &c, int s, int n, const Welf
     *out_cell = cand_cell[pick]; *out_rank = pick; *out_diff = cand_w[0] - cand_w[pick];
 }
 
-// ethics.Asimov (ethics.py:8-98) among plain agents (the host refuses configurations that mix it with the Bentham family or
-// Temperance: the second law would ask such a neighbour's own findEthicalValueOfCell, which reads the neighbourhood list the
-// neighbour stored at ITS last move).  Lane 0.
+// ethics.Asimov (ethics.py:8-98) among plain agents and simple Temperance agents (the host refuses configurations that mix it
+// with the Bentham family: the second law would ask such a neighbour's own findEthicalValueOfCell, which reads the
+// neighbourhood list the neighbour stored at ITS last move; and with Temperance's PECS variant, whose value moves its own
+// counters).  Lane 0.
 //   findEthicalValueOfCell: (third-law score + number of agents in view that cannot reach the cell) * (site wealth + loot), or
 //     -sys.maxsize as soon as the first law is broken -- the cell's occupant is a human, or a human who can reach the cell
 //     would starve on it (in a sugar-only run `0 + 0 - 0 <= 0` holds for every human: the reference's own arithmetic);
@@ -868,12 +869,23 @@ __device__ __noinline__ void asimov_pick(const DevCtx &c, int s, int n, const We
         score[j] = sc; order[j] = i;
     }
     int best = -1;
+    bool temperance_around = false;
+    if (has_agentlog(c)) for (int k = 0; k < nh; k++) temperance_around |= c.eth->model[hood[k]] == 2;
     for (int oi = 0; oi < m; oi++) {                               // findBestEthicalCell (ethics.py:19-33)
         const int i = order[oi], cell = cand_cell[i], robot = c.g.occ[cell];
-        if (robot >= 0 && c.eth->model[robot] == SSB_MODEL_ASIMOV)          // scoreLawTwo: only a robot on the cell earns an order
+        const bool robot_there = robot >= 0 && c.eth->model[robot] == SSB_MODEL_ASIMOV;
+        if (robot_there || temperance_around)                      // scoreLawTwo (ethics.py:71-86)
             for (int k = 0; k < nh; k++) {
-                const int nb = hood[k];
-                if (c.eth->model[nb] == SSB_MODEL_ASIMOV || !asimov_can_reach(c, nb, cell)) continue;
+                const int nb = hood[k], nb_model = c.eth->model[nb];
+                if (nb_model == SSB_MODEL_ASIMOV || !asimov_can_reach(c, nb, cell)) continue;
+                if (nb_model == 2) {
+                    // a simple Temperance agent with a live decision factor answers with its own findEthicalValueOfCell:
+                    // |time to live on the cell - agent.timeToLive| (ethics.py:464-465, 479-480); with factor 0 it says nothing
+                    if (c.eth->decision_factor[nb] > 0 &&
+                        fabs(time_to_live_potential(c, nb, cell) - c.x->agentlog.time_to_live[nb]) > 0) best = i;
+                    continue;
+                }
+                if (!robot_there) continue;                        // a plain agent only orders the robot onto another robot
                 const double agg = eff_aggression(c, nb);
                 const double rs = agg * fmin(loot, a.sugar[robot]), rp = agg * fmin(loot, a.spice[robot]);
                 const double pl = polluted ? c.g.pollution[cell] : 0.0;

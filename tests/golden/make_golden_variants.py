@@ -113,6 +113,9 @@ VARIANTS = {
     # with live combat and replacement (humans order robots onto other robots), and on top of diseases / lending / friends
     "asimov_trade": ("trade_tagging_reproduction", 120, dict(_ETHICS, agentDecisionModels=["asimov", "none"])),
     "asimov_combat": ("combat_limited", 120, dict(_ETHICS, agentDecisionModels=["none", "asimov", "asimov"], agentAggressionFactor=[0, 2])),
+    # robots next to simple Temperance agents: those answer the second law with their own |delta time to live|
+    "asimov_temperance": ("combat_limited", 100, dict(_ETHICS, agentDecisionModels=["asimov", "temperance", "none"], agentAggressionFactor=[0, 2],
+                                                      agentDecisionModelFactor=[0.3, 1], agentDynamicDecisionModelFactor=[0.0, 0.1])),
     "asimov_determinism": ("determinism", 100, dict(_ETHICS, agentDecisionModels=["asimov", "rawSugarscape"], experimentalGroup=None,
                                                     agentDecisionModelFactor=[0, 1])),
     "ethics_top": ("trade_tagging_reproduction", 100, dict(_ETHICS, agentDecisionModels=["benthamTop", "egoistTop", "altruistNoLookaheadTop", "none", "bentham"])),
