@@ -760,6 +760,35 @@ __device__ __noinline__ void temperance_pick(const DevCtx &c, int s, int n, cons
     *out_cell = cand_cell[pick]; *out_rank = pick; *out_diff = cand_w[0] - cand_w[pick];
 }
 
+// Temperance.findEthicalValueOfCell with pecs=True (ethics.py:436-491): physical + emotional + cognitive + social score of one
+// cell.  The emotional score counts the cells it has seen: timesOverharvested moves with every call.
+__device__ __forceinline__ double pecs_value(const DevCtx &c, int s, int cell) {
+    if (c.eth->total_metabolism[s] == 0) return 0;
+    const double ttl = c.x->agentlog.time_to_live[s];
+    const int32_t *rules = c.eth->pecs_rules + (long long)s * 5;
+    int32_t *counts = c.eth->pecs_counts + (long long)s * 3;
+    const double delta = time_to_live_potential(c, s, cell) - ttl;
+    const double physical = ttl > 0 ? erf(1 / ttl) : 1;
+    double e = 0;                                                   // findCellEmotionalScore
+    if (delta > 1) { e = e - counts[2]; counts[2] += 1; }
+    const double emotional = erf(e);
+    double cognitive;                                               // findCellCognitiveScore
+    if (delta < 1) cognitive = -1;
+    else {
+        double k = 0;
+        if (delta >= 1 && delta < 2 && rules[0]) k += rules[0];
+        else if (delta >= 2 && delta < 3 && rules[1]) { k += rules[1]; if (rules[2]) k -= rules[2]; }
+        else if (delta >= 3 && rules[3]) { k -= rules[3]; if (rules[4]) k -= rules[4]; }
+        cognitive = erf(k);
+    }
+    double so = 0;                                                  // findCellSocialScore
+    if (delta <= 1) so = 1;
+    else if (delta > 1 && delta <= 2) so -= counts[0];
+    else if (delta > 2) so -= counts[1];
+    so *= c.eth->social_pressure[s];
+    return physical + emotional + cognitive + erf(so);
+}
+
 // Temperance with pecs=True (ethics.py:412-491): physical + emotional + cognitive + social score per candidate, the best
 // score wins (no virtue roll).  The emotional score counts the cells it has seen (timesOverharvested moves while the
 // candidates are scored, in welfare order).  Lane 0.
@@ -771,34 +800,8 @@ __device__ __noinline__ void pecs_pick(const DevCtx &c, int s, int n, const Welf
     double cand_w[MAXC_EXACT_RULES], score[MAXC_EXACT_RULES];
     int m = n > 0 ? rank_candidates(c, s, n, w, my_tribe, aggression, ws, cand_cell, cand_dist, cand_w) : 0;
     if (m == 0) { cand_cell[0] = a.pos[s]; cand_dist[0] = 0; cand_w[0] = 0; m = 1; }      // rankCellsInRange: [own cell]
-    const double ttl = c.x->agentlog.time_to_live[s];
-    const int32_t *rules = c.eth->pecs_rules + (long long)s * 5;
-    int32_t *counts = c.eth->pecs_counts + (long long)s * 3;
-    const double pressure = c.eth->social_pressure[s];
     for (int i = 0; i < m; i++) {
-        double sc = 0;
-        if (c.eth->total_metabolism[s] != 0) {
-            const double delta = time_to_live_potential(c, s, cand_cell[i]) - ttl;
-            const double physical = ttl > 0 ? erf(1 / ttl) : 1;
-            double e = 0;                                                   // findCellEmotionalScore
-            if (delta > 1) { e = e - counts[2]; counts[2] += 1; }
-            const double emotional = erf(e);
-            double cognitive;                                               // findCellCognitiveScore
-            if (delta < 1) cognitive = -1;
-            else {
-                double k = 0;
-                if (delta >= 1 && delta < 2 && rules[0]) k += rules[0];
-                else if (delta >= 2 && delta < 3 && rules[1]) { k += rules[1]; if (rules[2]) k -= rules[2]; }
-                else if (delta >= 3 && rules[3]) { k -= rules[3]; if (rules[4]) k -= rules[4]; }
-                cognitive = erf(k);
-            }
-            double so = 0;                                                  // findCellSocialScore
-            if (delta <= 1) so = 1;
-            else if (delta > 1 && delta <= 2) so -= counts[0];
-            else if (delta > 2) so -= counts[1];
-            so *= pressure;
-            sc = physical + emotional + cognitive + erf(so);
-        }
+        const double sc = pecs_value(c, s, cand_cell[i]);
         int j = i;                                                          // sortCellsByWealth on the scores
         while (j > 0 && (score[j - 1] < sc || (score[j - 1] == sc && cand_dist[order[j - 1]] > cand_dist[i]))) {
             score[j] = score[j - 1]; order[j] = order[j - 1];
@@ -810,10 +813,9 @@ __device__ __noinline__ void pecs_pick(const DevCtx &c, int s, int n, const Welf
     *out_cell = cand_cell[pick]; *out_rank = pick; *out_diff = cand_w[0] - cand_w[pick];
 }
 
-// ethics.Asimov (ethics.py:8-98) among plain agents and simple Temperance agents (the host refuses configurations that mix it
+// ethics.Asimov (ethics.py:8-98) among plain agents and Temperance agents (the host refuses configurations that mix it
 // with the Bentham family: the second law would ask such a neighbour's own findEthicalValueOfCell, which reads the
-// neighbourhood list the neighbour stored at ITS last move; and with Temperance's PECS variant, whose value moves its own
-// counters).  Lane 0.
+// neighbourhood list the neighbour stored at ITS last move).  Lane 0.
 //   findEthicalValueOfCell: (third-law score + number of agents in view that cannot reach the cell) * (site wealth + loot), or
 //     -sys.maxsize as soon as the first law is broken -- the cell's occupant is a human, or a human who can reach the cell
 //     would starve on it (in a sugar-only run `0 + 0 - 0 <= 0` holds for every human: the reference's own arithmetic);
@@ -870,7 +872,7 @@ __device__ __noinline__ void asimov_pick(const DevCtx &c, int s, int n, const We
     }
     int best = -1;
     bool temperance_around = false;
-    if (has_agentlog(c)) for (int k = 0; k < nh; k++) temperance_around |= c.eth->model[hood[k]] == 2;
+    if (has_agentlog(c)) for (int k = 0; k < nh; k++) temperance_around |= c.eth->model[hood[k]] == 2 || c.eth->model[hood[k]] == 3;
     for (int oi = 0; oi < m; oi++) {                               // findBestEthicalCell (ethics.py:19-33)
         const int i = order[oi], cell = cand_cell[i], robot = c.g.occ[cell];
         const bool robot_there = robot >= 0 && c.eth->model[robot] == SSB_MODEL_ASIMOV;
@@ -878,11 +880,15 @@ __device__ __noinline__ void asimov_pick(const DevCtx &c, int s, int n, const We
             for (int k = 0; k < nh; k++) {
                 const int nb = hood[k], nb_model = c.eth->model[nb];
                 if (nb_model == SSB_MODEL_ASIMOV || !asimov_can_reach(c, nb, cell)) continue;
-                if (nb_model == 2) {
-                    // a simple Temperance agent with a live decision factor answers with its own findEthicalValueOfCell:
-                    // |time to live on the cell - agent.timeToLive| (ethics.py:464-465, 479-480); with factor 0 it says nothing
-                    if (c.eth->decision_factor[nb] > 0 &&
-                        fabs(time_to_live_potential(c, nb, cell) - c.x->agentlog.time_to_live[nb]) > 0) best = i;
+                if (nb_model == 2 || nb_model == 3) {
+                    // a Temperance agent with a live decision factor answers with its own findEthicalValueOfCell: |time to live on
+                    // the cell - agent.timeToLive| (ethics.py:464-465, 479-480), with pecs=True its four scores (its
+                    // timesOverharvested counter moves, as in the reference); with factor 0 it says nothing
+                    if (c.eth->decision_factor[nb] > 0) {
+                        const double v = nb_model == 3 ? pecs_value(c, nb, cell)
+                                                       : fabs(time_to_live_potential(c, nb, cell) - c.x->agentlog.time_to_live[nb]);
+                        if (v > 0) best = i;
+                    }
                     continue;
                 }
                 if (!robot_there) continue;                        // a plain agent only orders the robot onto another robot

@@ -116,6 +116,9 @@ VARIANTS = {
     # robots next to simple Temperance agents: those answer the second law with their own |delta time to live|
     "asimov_temperance": ("combat_limited", 100, dict(_ETHICS, agentDecisionModels=["asimov", "temperance", "none"], agentAggressionFactor=[0, 2],
                                                       agentDecisionModelFactor=[0.3, 1], agentDynamicDecisionModelFactor=[0.0, 0.1])),
+    "asimov_temperance_pecs": ("trade_tagging_reproduction", 100, dict(_ETHICS, agentDecisionModels=["asimov", "temperancePECS", "none", "temperance"],
+                                                                       agentDecisionModelFactor=[0.3, 1], agentDynamicSocialPressureFactor=[0.01, 0.1],
+                                                                       agentDynamicDecisionModelFactor=[0.0, 0.1])),
     "asimov_determinism": ("determinism", 100, dict(_ETHICS, agentDecisionModels=["asimov", "rawSugarscape"], experimentalGroup=None,
                                                     agentDecisionModelFactor=[0, 1])),
     "ethics_top": ("trade_tagging_reproduction", 100, dict(_ETHICS, agentDecisionModels=["benthamTop", "egoistTop", "altruistNoLookaheadTop", "none", "bentham"])),
