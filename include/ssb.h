@@ -41,6 +41,7 @@ extern "C" {
  * ssb_ethics_t.top_ordering, SSB_GROUP_RACE / SSB_GROUP_MODEL, overflow code 15. */
 /* 4: ssb_group_t.hood_list / hood_n (experimental groups whose membership changes during the run). */
 #define SSB_ABI_VERSION 4
+#define SSB_GROUP_HOOD_MAX  161 /* entries per slot of a stored neighbourhood list: the candidate cells of mode E + the agent itself */
 
 /* RNG modes */
 #define SSB_RNG_EXACT    0 /* mode E: CPython MT19937 word-for-word replay, ordered execution   */
@@ -247,6 +248,14 @@ typedef struct ssb_ethics {
     int32_t *move_rank;             /* index of the chosen cell in the welfare-sorted list            */
     double  *move_diff;             /* welfare of the top cell minus welfare of the chosen one        */
     double  global_max_wealth;      /* environment.globalMaxSugar + globalMaxSpice                    */
+    /* ABI 4, Asimov robots next to the Bentham family: a robot's second law asks a Bentham neighbour for ITS value of a cell
+     * (ethics.py:74-75), and that value walks agent.neighborhood as the neighbour last stored it -- at its own ranking, at
+     * birth, or when the agents were (re)configured (agent.py:1052-1065, 526; sugarscape.py:265-267).  Kept per slot as
+     * (slot, id) pairs in list order when hood_stride > 0; hood_n = -1: to be rebuilt at the start of the next agent step
+     * (the host sets it for every slot when it places agents). */
+    int32_t *hood_list, *hood_id;   /* [slot][hood_stride]                                            */
+    int32_t *hood_n;
+    int64_t hood_stride;            /* 0: not kept; else SSB_GROUP_HOOD_MAX                           */
 } ssb_ethics_t;
 /* raw sums of sugarscape.py:1141-1160, 1218-1222 over the agent list (+ this step's dead for the moves) */
 typedef struct ssb_ethics_stats {
@@ -366,7 +375,6 @@ typedef struct ssb_misc {
 #define SSB_GROUP_RACE      4   /* kind = SSB_GROUP_RACE | (race id << 8)                                       */
 #define SSB_GROUP_MODEL     5   /* needs ssb_ethics_t                                                           */
 #define SSB_GROUP_SICK      6   /* from here on: membership changes during the run (hood_list is written)       */
-#define SSB_GROUP_HOOD_MAX  161 /* entries per slot of hood_list: the candidate cells of mode E + the agent itself */
 #define SSB_GI_COMBAT 0
 #define SSB_GI_DISEASE 1
 #define SSB_GI_LENDING 2

@@ -590,6 +590,7 @@ int ssb_bind_ethics(ssb_engine_t *e, const ssb_ethics_t *eth) {
     if (!eth->model || !eth->top_ordering || !eth->selfishness || !eth->decision_factor || !eth->lookahead_factor || !eth->lookahead_discount || !eth->dynamic_selfishness || !eth->dynamic_decision_factor || !eth->pecs_rules || !eth->pecs_counts ||
         !eth->social_pressure || !eth->last_delta_ttl || !eth->dynamic_social_pressure || !eth->total_metabolism ||
         !eth->last_move_optimal || !eth->move_rank || !eth->move_diff) return fail(e, -1, "ethics: null array");
+    if (eth->hood_stride != 0 && (eth->hood_stride != SSB_GROUP_HOOD_MAX || !eth->hood_list || !eth->hood_id || !eth->hood_n)) return fail(e, -1, "ethics: bad neighbourhood lists");
     CU(cudaSetDevice(e->device));
     if (!e->d_eth_stats) {
         CU(cudaMalloc(&e->d_eth_stats, sizeof(ssb_ethics_stats_t)));

@@ -23,6 +23,15 @@ __device__ void agent_step_exact_body(const DevCtx &c, uint32_t *mt, const WarpS
         shuffle(rng, c.a.order, (int)cn[SSB_C_N_LIST]);        // random.shuffle(self.agents), sugarscape.py:400
     }
     Gr::sync();
+    if constexpr (EXT) {
+        // robots next to the Bentham family: the agents were (re)configured since the last step -- every agent's stored
+        // neighbourhood is rebuilt where it stands (sugarscape.py:265-267; the host marked the lists with -1)
+        if (keeps_hoods(c) && lane == 0) {
+            const long long n0 = (long long)cn[SSB_C_N_LIST];
+            for (long long i = 0; i < n0; i++) if (c.eth->hood_n[c.a.order[i]] == -1) hood_store_here(c, c.a.order[i]);
+        }
+        Gr::sync();
+    }
     for (long long i = 0;; i++) {
         const long long n_list = Gr::bcast((long long)cn[SSB_C_N_LIST], 0);
         if (i >= n_list) break;

@@ -556,7 +556,7 @@ __device__ __noinline__ double ethical_value(const DevCtx &c, int s, int my_r, c
     double value = 0, h = 0, u = 0;
     for (int k = 0; k < n_hood; k++) {
         const int nb = hood[k];
-        if (!agent_alive(c, nb)) continue;
+        if (nb < 0 || !agent_alive(c, nb)) continue;      // (nb < 0: a stored list's member whose slot has a new tenant -- dead)
         const int rn = min(min((int)eff_vision(c, nb), (int)eff_movement(c, nb)), max_cell_distance(c));   // findCellsInRange with the modifiers
         if (!(cell == a.pos[nb] || cell_in_cross(c, a.pos[nb], rn, cell))) continue;      // canReachCell
         const double metab = (double)(a.sugar_metab[nb] + a.spice_metab[nb]);               // raw, not the find* accessors
@@ -824,6 +824,31 @@ __device__ __noinline__ void pecs_pick(const DevCtx &c, int s, int n, const Welf
 //     first cell with a positive value is taken at once; nothing found -> the robot stays where it is.
 // *out_rank = -1: stays although candidates exist (lastMoveOptimal False, no rank / difference entry in the log).
 constexpr int SSB_MODEL_ASIMOV = 4;
+// agent.neighborhood as stored lists (ssb_ethics_t.hood_*): only when robots live next to the Bentham family
+__device__ __forceinline__ bool keeps_hoods(const DevCtx &c) { return c.eth != nullptr && c.eth->hood_stride > 0; }
+// findNeighborhood (agent.py:1052-1065): the live agents on `cells` (the agent's cells in range, in their order), then the agent
+__device__ inline void hood_store(const DevCtx &c, int s, const int32_t *cells, int n) {
+    int32_t *ls = c.eth->hood_list + (long long)s * c.eth->hood_stride, *li = c.eth->hood_id + (long long)s * c.eth->hood_stride;
+    int k = 0;
+    for (int i = 0; i < n && k < (int)c.eth->hood_stride - 1; i++) {
+        const int o = c.g.occ[cells[i]];
+        if (o >= 0 && agent_alive(c, o)) { ls[k] = o; li[k++] = c.a.id[o]; }
+    }
+    ls[k] = s; li[k++] = c.a.id[s];
+    c.eth->hood_n[s] = k;
+}
+// ... for an agent that is not ranking: a newborn (agent.py:525-526), everybody after a (re)placement (sugarscape.py:265-267)
+__device__ __noinline__ void hood_store_here(const DevCtx &c, int s) {
+    int32_t cells[MAXC_EXACT_RULES];
+    uint8_t dist[MAXC_EXACT_RULES];
+    WarpScratch ws = {};
+    ws.cells = cells; ws.dist = dist;
+    const int r = min(min((int)eff_vision(c, s), (int)eff_movement(c, s)), max_cell_distance(c));
+    const int H = c.p.height, x = c.a.pos[s] / H, y = c.a.pos[s] - x * H;
+    int n = 0;
+    if (r > 0) n = radial(c) ? enumerate_disc(c, x, y, r, ws, MAXC_EXACT_RULES) : enumerate_cross(c, x, y, r, ws, MAXC_EXACT_RULES);
+    hood_store(c, s, cells, n);
+}
 __device__ __forceinline__ bool asimov_can_reach(const DevCtx &c, int nb, int cell) {      // canReachCell (agent.py:213-216)
     const int rn = min(min((int)eff_vision(c, nb), (int)eff_movement(c, nb)), max_cell_distance(c));
     return cell == c.a.pos[nb] || cell_in_cross(c, c.a.pos[nb], rn, cell);
@@ -871,8 +896,11 @@ __device__ __noinline__ void asimov_pick(const DevCtx &c, int s, int n, const We
         score[j] = sc; order[j] = i;
     }
     int best = -1;
-    bool temperance_around = false;
-    if (has_agentlog(c)) for (int k = 0; k < nh; k++) temperance_around |= c.eth->model[hood[k]] == 2 || c.eth->model[hood[k]] == 3;
+    bool temperance_around = false;       // (or Bentham: somebody whose own value of a cell is an order)
+    for (int k = 0; k < nh; k++) {
+        const int mk = c.eth->model[hood[k]];
+        temperance_around |= (has_agentlog(c) && (mk == 2 || mk == 3)) || (mk == 1 && keeps_hoods(c));
+    }
     for (int oi = 0; oi < m; oi++) {                               // findBestEthicalCell (ethics.py:19-33)
         const int i = order[oi], cell = cand_cell[i], robot = c.g.occ[cell];
         const bool robot_there = robot >= 0 && c.eth->model[robot] == SSB_MODEL_ASIMOV;
@@ -880,6 +908,20 @@ __device__ __noinline__ void asimov_pick(const DevCtx &c, int s, int n, const We
             for (int k = 0; k < nh; k++) {
                 const int nb = hood[k], nb_model = c.eth->model[nb];
                 if (nb_model == SSB_MODEL_ASIMOV || !asimov_can_reach(c, nb, cell)) continue;
+                if (nb_model == 1) {
+                    // a Bentham neighbour with a live decision factor answers with ITS findEthicalValueOfCell (ethics.py:141-244)
+                    // over the neighbourhood it last stored; members that died since are skipped but still counted
+                    if (c.eth->decision_factor[nb] > 0 && keeps_hoods(c)) {
+                        int32_t theirs[SSB_GROUP_HOOD_MAX];
+                        const int32_t *ls = c.eth->hood_list + (long long)nb * c.eth->hood_stride, *li = c.eth->hood_id + (long long)nb * c.eth->hood_stride;
+                        const int n_theirs = max(c.eth->hood_n[nb], 0);
+                        for (int q = 0; q < n_theirs; q++) theirs[q] = c.a.id[ls[q]] == li[q] ? ls[q] : -1;
+                        const int r_nb = min(min((int)eff_vision(c, nb), (int)eff_movement(c, nb)), max_cell_distance(c));
+                        double h, u;
+                        if (ethical_value(c, nb, r_nb, theirs, n_theirs, cell, &h, &u) > 0) best = i;
+                    }
+                    continue;
+                }
                 if (nb_model == 2 || nb_model == 3) {
                     // a Temperance agent with a live decision factor answers with its own findEthicalValueOfCell: |time to live on
                     // the cell - agent.timeToLive| (ethics.py:464-465, 479-480), with pecs=True its four scores (its
@@ -1131,6 +1173,7 @@ __device__ bool transaction_move_phase(const DevCtx &c, int s, AgentRec &rec, Rn
     double sugar = rec.sugar, spice = rec.spice;
     const int best = b_valid ? b_cell : pos;
     if (lane == 0) {
+        if constexpr (EXT) { if (keeps_hoods(c)) hood_store(c, s, ws.cells, n); }      // self.neighborhood, as of this ranking
         if (n > 0) { a.n_neighborhood[s] = hood + 1; a.n_valid_moves[s] = m; }   // + self
         if (EXT && has_group(c) && n > 0) {      // movementNeighborhood split by group; the agent itself is part of it
             int exp_n = is_member(c, s) ? 1 : 0, ctrl_n = 1 - exp_n;
@@ -1539,6 +1582,7 @@ __device__ __noinline__ void do_reproduction(const DevCtx &c, int s, Rng &rng) {
             if (nth < a.capacity) c.born_list[nth] = ch; else atomicExch(&cn[SSB_C_OVERFLOW], 1ull);
         }
         collect<EXT>(c, ch, cell);      // the child collects at birth (agent.py:175)
+        if constexpr (EXT) { if (keeps_hoods(c)) hood_store_here(c, ch); }      // child.findCellsInRange(); child.findNeighborhood() (agent.py:525-526)
         if (EXACT) {               // kin bookkeeping of the initiating parent (agent.py:521-527)
             bool known = false;
             for (int e = a.mates_head[s]; e >= 0; e = a.kin_next[e])

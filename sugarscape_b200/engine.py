@@ -233,7 +233,7 @@ class Engine:
         self.ethics = host_state.ethics          # HostEthics (its arrays live in self.tensors as eth_*) or None
         if self.ethics is not None:
             es = self.ethics.as_struct(lambda arr: None)
-            for name, _, _ in layout.ETHICS_FIELDS:
+            for name, _, _ in layout.ETHICS_FIELDS + layout.ETHICS_HOOD_FIELDS:
                 setattr(es, name, self.tensors["eth_" + name].data_ptr())
             self._check(self.L.ssb_bind_ethics(self.handle, C.byref(es)))
         self.ext = host_state.ext                # HostExt (arrays in self.tensors as "ext:<family>.<member>") or None
@@ -285,7 +285,7 @@ class Engine:
         for name in layout.KIN_FIELDS:
             self.tensors[name] = self._to_device(getattr(hs, name))
         if hs.ethics is not None:
-            for name, _, _ in layout.ETHICS_FIELDS:
+            for name, _, _ in layout.ETHICS_FIELDS + layout.ETHICS_HOOD_FIELDS:
                 self.tensors["eth_" + name] = self._to_device(hs.ethics.arrays[name])
         if hs.ext is not None:      # as raw bytes: the families hold uint64 and struct arrays torch has no dtype for
             self._ext_dtype = {key: arr.dtype for key, arr in hs.ext.arrays.items()}

@@ -133,8 +133,9 @@ def check_supported(c):
     if "asimov" in c["agentDecisionModels"]:
         # ethics.Asimov (ethics.py:8-98) among plain agents only: its second law asks a neighbour with a decision model of its
         # own for THAT neighbour's findEthicalValueOfCell, which reads the neighbourhood list stored at the neighbour's last move
-        if any(m not in ("asimov", "none", "rawSugarscape", "temperance", "temperancePECS") for m in c["agentDecisionModels"]):
-            problems.append("asimov mixed with other decision models")
+        # (negativeBentham's value is a dict: the reference raises when a robot compares it with 0, ethics.py:27)
+        if any("negativeBentham" in m for m in c["agentDecisionModels"]):
+            problems.append("asimov next to negativeBentham")
     bad_models = [m for m in c["agentDecisionModels"] if m not in SUPPORTED_DECISION_MODELS]
     if bad_models:
         problems.append("decision models other than rawSugarscape and the Bentham family: " + ", ".join(bad_models))

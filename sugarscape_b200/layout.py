@@ -187,12 +187,15 @@ ETHICS_FIELDS = (
     ("dynamic_selfishness", np.float64, 0),
     ("last_move_optimal", np.int32, 1), ("move_rank", np.int32, 0), ("move_diff", np.float64, 0),
 )
+# after global_max_wealth: the stored neighbourhood lists (robots next to the Bentham family), [slot][hood_stride]
+ETHICS_HOOD_FIELDS = (("hood_list", np.int32, -1), ("hood_id", np.int32, -1), ("hood_n", np.int32, -1))
 BENTHAM_MODELS = ("altruist", "bentham", "egoist", "negativeBentham")
 
 
 class Ethics(C.Structure):
     _fields_ = ([("capacity", C.c_int64)] + [(n, C.c_void_p) for n, _, _ in ETHICS_FIELDS]
-                + [("global_max_wealth", C.c_double)])
+                + [("global_max_wealth", C.c_double)] + [(n, C.c_void_p) for n, _, _ in ETHICS_HOOD_FIELDS]
+                + [("hood_stride", C.c_int64)])
 
 
 class EthicsStats(C.Structure):
@@ -233,8 +236,11 @@ class HostEthics:
         self.lookahead_factor = 1.0 if isinstance(look, list) else float(look)
         self.default_dynamic = list(c["agentDynamicSelfishnessFactor"]) == [0.0, 0.0]
         self.group_model = c["experimentalGroup"] if group_kind(c) == GROUP_MODEL else None
-        widths = {"pecs_rules": 5, "pecs_counts": 3}          # values per slot
-        self.arrays = {n: np.full(capacity * widths.get(n, 1), fill, dtype=dt) for n, dt, fill in ETHICS_FIELDS}
+        # robots next to the Bentham family: every agent's neighbourhood as a stored list (ssb_ethics_t.hood_*)
+        models = c["agentDecisionModels"]
+        self.hood_stride = 161 if ("asimov" in models and any(decision_model_class(m) == 1 for m in models)) else 0      # SSB_GROUP_HOOD_MAX
+        widths = {"pecs_rules": 5, "pecs_counts": 3, "hood_list": max(self.hood_stride, 1), "hood_id": max(self.hood_stride, 1)}   # values per slot
+        self.arrays = {n: np.full(capacity * widths.get(n, 1), fill, dtype=dt) for n, dt, fill in ETHICS_FIELDS + ETHICS_HOOD_FIELDS}
 
     def set_slot(self, slot, endowment):
         """A freshly configured agent (sugarscape.py:219-233)."""
@@ -277,15 +283,16 @@ class HostEthics:
     def as_struct(self, pointer_of=lambda arr: arr.ctypes.data):
         e = Ethics()
         e.capacity = self.capacity
-        for n, _, _ in ETHICS_FIELDS:
+        for n, _, _ in ETHICS_FIELDS + ETHICS_HOOD_FIELDS:
             setattr(e, n, pointer_of(self.arrays[n]))
         e.global_max_wealth = self.global_max_wealth
+        e.hood_stride = self.hood_stride
         return e
 
     def copy(self):
         h = HostEthics.__new__(HostEthics)
         h.capacity, h.global_max_wealth, h.lookahead_factor = self.capacity, self.global_max_wealth, self.lookahead_factor
-        h.default_dynamic, h.group_model = self.default_dynamic, self.group_model
+        h.default_dynamic, h.group_model, h.hood_stride = self.default_dynamic, self.group_model, self.hood_stride
         h.arrays = {k: v.copy() for k, v in self.arrays.items()}
         return h
 
@@ -795,6 +802,8 @@ class HostState:
             self.a_order[n_list] = slot
             self.occ[a["cell"]] = slot
             n_list += 1
+        if self.ethics is not None and self.ethics.hood_stride and len(new_agents):
+            self.ethics.arrays["hood_n"][:] = -1       # configureAgents ends with findNeighborhood() for EVERY agent (sugarscape.py:265-267)
         if protect_last:
             self.a_free_slots[n_free:n_free + protect_last] = protected
             n_free += protect_last

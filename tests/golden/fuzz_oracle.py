@@ -92,7 +92,8 @@ def draw_overrides(rng, base):
         ov["environmentWraparound"] = False
     # ethics.Asimov among plain agents (device source only: fuzz_hostemu.py; the oracle has no Asimov, fuzz_oracle.py skips it)
     if os.environ.get("SSB_FUZZ_ASIMOV") == "1" or rng.random() < 0.1:
-        ov["agentDecisionModels"] = rng.choice([["asimov"], ["asimov", "none"], ["none", "none", "asimov"], ["asimov", "rawSugarscape", "asimov"]])
+        ov["agentDecisionModels"] = rng.choice([["asimov"], ["asimov", "none"], ["none", "none", "asimov"], ["asimov", "rawSugarscape", "asimov"],
+                                                ["asimov", "bentham"], ["asimov", "egoist", "none", "altruist"], ["bentham", "asimov", "none"]])
         ov["agentDecisionModelFactor"] = rng.choice([[1, 1], [0, 1], [0.5, 1]])
     # radial vision / movement (environment.py:146-173); SSB_FUZZ_RADIAL=1 puts every case there, half of them on maps
     # smaller than the ranges (per-axis caps, odd and even axes)

@@ -119,6 +119,11 @@ VARIANTS = {
     "asimov_temperance_pecs": ("trade_tagging_reproduction", 100, dict(_ETHICS, agentDecisionModels=["asimov", "temperancePECS", "none", "temperance"],
                                                                        agentDecisionModelFactor=[0.3, 1], agentDynamicSocialPressureFactor=[0.01, 0.1],
                                                                        agentDynamicDecisionModelFactor=[0.0, 0.1])),
+    # robots next to the Bentham family: a Bentham neighbour answers the second law with ITS value of the cell, over the
+    # neighbourhood it stored at its own last ranking / at birth / at the last (re)placement
+    "asimov_bentham": ("trade_tagging_reproduction", 120, dict(_ETHICS, agentDecisionModels=["asimov", "bentham", "none", "egoist", "altruistHalfLookahead"])),
+    "asimov_bentham_combat": ("combat_limited", 100, dict(_ETHICS, agentDecisionModels=["asimov", "bentham", "altruist", "none"], agentAggressionFactor=[0, 2],
+                                                          agentDecisionModelFactor=[0, 1])),
     "asimov_determinism": ("determinism", 100, dict(_ETHICS, agentDecisionModels=["asimov", "rawSugarscape"], experimentalGroup=None,
                                                     agentDecisionModelFactor=[0, 1])),
     "ethics_top": ("trade_tagging_reproduction", 100, dict(_ETHICS, agentDecisionModels=["benthamTop", "egoistTop", "altruistNoLookaheadTop", "none", "bentham"])),

@@ -57,7 +57,7 @@ ETHICS_VARIANTS = ["ethics_trade", "ethics_combat", "ethics_replacement", "ethic
                    "ethics_top",
                    # ethics.Asimov among plain agents (ethics.py:8-98): with spice and births, sugar-only with live combat and
                    # replacement, and on top of every other family of determinism.json
-                   "asimov_trade", "asimov_combat", "asimov_determinism", "asimov_temperance", "asimov_temperance_pecs"]
+                   "asimov_trade", "asimov_combat", "asimov_determinism", "asimov_temperance", "asimov_temperance_pecs", "asimov_bentham", "asimov_bentham_combat"]
 
 
 @pytest.mark.parametrize("variant", ETHICS_VARIANTS)

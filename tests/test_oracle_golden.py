@@ -400,7 +400,7 @@ def test_oracle_environment_file_matches_reference_trajectory():
                                        {"neighborhoodMode": "moore", "b200RngMode": "scalable"},
                                        {"environmentWraparound": False, "b200RngMode": "scalable"},
                                        {"environmentWraparound": False, "agentVision": [1, 30], "agentMovement": [30, 30]},
-                                       {"agentDecisionModels": ["asimov", "bentham"]}, {"agentDecisionModels": ["asimovTop"]},
+                                       {"agentDecisionModels": ["asimov", "negativeBentham"]}, {"agentDecisionModels": ["asimovTop"]},
                                        {"agentDecisionModels": ["negativeBenthamTop"]}, {"experimentalGroup": "raceInGroup"}, {"experimentalGroup": "disease3"}, {"experimentalGroup": "ageRange0", "environmentAgeistAbsoluteRanges": [[0, 30]]},
                                        {"agentLeader": True}, {"agentMaxFriends": [20, 20]}])
 def test_unsupported_options_fail_loudly(overrides):

@@ -7,16 +7,17 @@ agents (tagging + trade + births, live combat with retaliators and host-side rep
 for every family of determinism.json incl. the Bentham decision models.  Integer state, tags, grid and the MT19937 stream
 bit-exact on every step, fp64 holdings through their digest, all 59 log keys.
 
-(2) ethics.Asimov among plain agents and Temperance agents (both variants) (reference ethics.py:8-98; `asimov_pick` in csrc/ssb_rules.cuh)
-against five fixtures of the unmodified reference (asimov_*): with spice and births, sugar-only with live combat and replacement,
-on top of every other family of determinism.json, and next to Temperance agents that answer the second law.
+(2) ethics.Asimov among plain agents, Temperance agents (both variants) and the Bentham family (reference ethics.py:8-98; `asimov_pick` in csrc/ssb_rules.cuh)
+against seven fixtures of the unmodified reference (asimov_*): with spice and births, sugar-only with live combat and replacement,
+on top of every other family of determinism.json, and next to Temperance and Bentham agents that answer the second law (the
+latter over the neighbourhood lists they stored at their own last ranking, at birth or at the last replacement).
 
 (3) experimental groups other than the shipped "depressed": membership by sex, by race (race<N>), by decision model (the
 group is a decisionModel string) and -- changing during the run -- the sick, on determinism.json and on a disease example --
 digests and all 203 log keys against six fixtures of the unmodified reference (*_group_*).
 
 Status: the six radial fixtures pass on the CPU oracle (tests/test_oracle_golden.py) and on the device rule source compiled for
-the host (tests/test_hostemu.py), the five Asimov fixtures on the latter (the oracle restates the Bentham family only); the
+the host (tests/test_hostemu.py), the seven Asimov fixtures on the latter (the oracle restates the Bentham family only); the
 four group fixtures on the latter as well (the oracle's group is "depressed"); these cases have NOT run on a B200 yet.  The file sorts after every other test file so that its
 first GPU run cannot hide anything else."""
 import pytest
@@ -32,7 +33,8 @@ pytestmark = [pytest.mark.gpu]
 
 @pytest.mark.parametrize("variant", ["radial_small_map", "radial_trade_tagging_reproduction", "radial_combat", "radial_determinism",
                                      "radial_nowrap_small_map", "radial_nowrap_determinism",
-                                     "asimov_trade", "asimov_combat", "asimov_determinism", "asimov_temperance", "asimov_temperance_pecs"])
+                                     "asimov_trade", "asimov_combat", "asimov_determinism", "asimov_temperance", "asimov_temperance_pecs",
+                                     "asimov_bentham", "asimov_bentham_combat"])
 def test_radial_ranges_and_asimov_match_reference_trajectory(variant):
     base, overrides, gold, log = pu.load_variant(variant)
     c, state, pop, params, endow, tags, eng = _engine(base, layout.RNG_EXACT, overrides)
