@@ -149,8 +149,6 @@ def check_supported(c):
         problems.append("experimentalGroup other than " + " / ".join(sorted(layout.GROUP_KINDS)) + " / race<N> / a decision model's name")
     if layout.group_kind(c) == layout.GROUP_MODEL and not uses_decision_models(c):
         problems.append("a decision model as experimentalGroup without decision models")
-    if c["experimentalGroup"] is not None and c["agentReplacements"] > 0:
-        problems.append("experimentalGroup with agentReplacements")
     if c["agentTagStringLength"] > 32:
         problems.append("tag strings longer than 32")
     for k in ("environmentSugarRegrowRate", "environmentSpiceRegrowRate"):

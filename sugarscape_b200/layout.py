@@ -811,6 +811,26 @@ class HostState:
         self.counters[C_N_SLOTS] = n_slots
         self.counters[C_N_FREE] = n_free
 
+    def newest_members(self, k):
+        """How many of the k agents at the end of the list (this step's replacements) are in the experimental group
+        (Agent.isInGroup, agent.py:1256-1284, for the kinds ssb_group_t.kind holds): `<group>AgentsReplaced` of the log."""
+        if self.ext is None or "group" not in self.ext.families or k <= 0:
+            return 0
+        n_list, kind = int(self.counters[C_N_LIST]), self.ext.group_kind
+        slots, A = self.a_order[n_list - k:n_list], self.ext.arrays
+        which = kind & 0xff
+        if which == GROUP_KINDS["depressed"]:
+            return int((A["misc.depressed"][slots] != 0).sum())
+        if which in (GROUP_KINDS["female"], GROUP_KINDS["male"]):
+            return int((self.a_sex[slots] == (SEX_FEMALE if which == GROUP_KINDS["female"] else SEX_MALE)).sum())
+        if which == GROUP_RACE:
+            return int((A["misc.race"][slots] == (kind >> 8)).sum())
+        if which == GROUP_MODEL:
+            return int(((self.ethics.arrays["top_ordering"][slots] & 2) != 0).sum())
+        if which == GROUP_SICK:
+            return int((A["diseases.n_sick"][slots] > 0).sum()) if "diseases" in self.ext.families else 0
+        raise ValueError("unknown experimental group kind %d" % kind)
+
     def depress(self, slot):
         """Depression.trigger (condition.py:27-33) at the creation of a depressed agent (agent.py:137-141)."""
         import math

@@ -114,6 +114,7 @@ class Sugarscape:
         hs.counters[layout.C_NEXT_ID] += len(new_agents)
         eng.upload(hs, [k for k in eng.tensors if k not in ("pollution_flux",)])
         eng.set_mt_from_python()
+        self.replaced_members = hs.newest_members(len(new_agents))       # (for the experimental-group split of the log)
         return len(new_agents)
 
     def updateRuntimeStats(self, st=None, replaced=0):
@@ -124,7 +125,8 @@ class Sugarscape:
         replaced = int(st.n_replaced) if replaced is None else replaced
         groups = eng.group_stats()
         if groups is not None:      # the log repeats every statistic for the experimental group and for its complement
-            self.stats_builder.update_with_groups(st, self.timestep, replaced, eng.ethics_stats(), eng.ext_stats(), groups)
+            self.stats_builder.update_with_groups(st, self.timestep, replaced, eng.ethics_stats(), eng.ext_stats(), groups,
+                                                  getattr(self, "replaced_members", 0) if replaced else 0)
         else:
             self.stats_builder.update(st, self.timestep, replaced, eng.ethics_stats(), eng.ext_stats())
         self.n_agents = int(st.population)

@@ -277,7 +277,7 @@ class StatsBuilder:
         rs["timestep"] = t
         return rs
 
-    def update_with_groups(self, st, t, n_replaced, ethics, ext, gstats):
+    def update_with_groups(self, st, t, n_replaced, ethics, ext, gstats, n_replaced_members=0):
         """The log entry with an experimental group (sugarscape.py:998-1003): the statistics of the group, of its
         complement and of everybody.  gstats: layout.GroupStats[3] (everybody's neighbour sums, group, control).
         A group pass starts from everybody's previous entry and its cross-step state is discarded."""
@@ -287,7 +287,10 @@ class StatsBuilder:
         passes = {}
         for which, prefix in ((1, group), (2, "control")):
             g = gstats[which]
-            rs = copy.deepcopy(self).update(g.stats, t, 0, g.ethics if ethics is not None else None, g.ext)
+            # agentsReplaced of a pass: this step's replacements that are in the group / in its complement (sugarscape.py:1353-1356)
+            n_rep = n_replaced_members if which == 1 else n_replaced - n_replaced_members
+            rs = copy.deepcopy(self).update(g.stats, t, n_rep, g.ethics if ethics is not None else None, g.ext)
+            rs["agentsBorn"] -= n_rep        # (the pass counts its members born at t: the replacements were placed at t, too)
             n = rs["population"]
             rs["meanControlNeighbors"] = round(g.control_neighbors / n, 2) if n else 0
             rs["meanExperimentalNeighbors"] = round(g.experimental_neighbors / n, 2) if n else 0

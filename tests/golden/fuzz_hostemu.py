@@ -63,7 +63,8 @@ def run_case(base, ov, steps):
 
     def entry(t, replaced):
         if grouped:
-            return sb.update_with_groups(emu.stats(t), t, replaced, emu.ethics_stats(), emu.ext_stats(t), emu.group_stats(t))
+            return sb.update_with_groups(emu.stats(t), t, replaced, emu.ethics_stats(), emu.ext_stats(t), emu.group_stats(t),
+                                         state.newest_members(replaced))
         return sb.update(emu.stats(t), t, replaced, emu.ethics_stats(), emu.ext_stats(t))
 
     rs = entry(0, 0)
@@ -112,7 +113,8 @@ def main():
         if rng.random() < 0.3 or os.environ.get("SSB_FUZZ_GROUPS") == "1":      # SSB_FUZZ_GROUPS=1: every case with a group
             ov["experimentalGroup"] = rng.choice(["depressed", "female", "male", "sick", "sick", "race0", "race1", "race2"] +
                                                  [m for m in ov.get("agentDecisionModels", []) if m != "none"])
-            ov["agentReplacements"] = 0
+            if rng.random() < 0.5:
+                ov["agentReplacements"] = 0
         try:
             res = run_case(base, ov, 60)
         except Exception as e:

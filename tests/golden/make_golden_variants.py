@@ -147,6 +147,9 @@ VARIANTS = {
     # isInGroup reads self.cell.environment of a dead agent)
     "determinism_group_sick": ("determinism", 100, {"experimentalGroup": "sick"}),
     "disease_mild_group_sick": ("disease_basic", 150, dict(_MILD, experimentalGroup="sick")),
+    # an experimental group together with agentReplacements: <group>AgentsReplaced / controlAgentsReplaced split the step's
+    # replacements by their membership
+    "combat_group_male_replacement": ("combat_limited", 100, {"experimentalGroup": "male", "agentAggressionFactor": [0, 2]}),
 }
 
 

@@ -218,7 +218,7 @@ def test_dead_creditor_table_wraps_around():
 
 
 @pytest.mark.parametrize("variant", ["determinism_group_female", "determinism_group_male", "determinism_group_race1", "determinism_group_bentham",
-                                     "determinism_group_sick", "disease_mild_group_sick"])
+                                     "determinism_group_sick", "disease_mild_group_sick", "combat_group_male_replacement"])
 def test_device_source_matches_reference_on_other_experimental_groups(variant):
     """determinism.json with another experimental group than the shipped "depressed" (variant fixtures of the unmodified
     reference): membership by sex, by race (race<N>) and by decision model (the group is a decisionModel string) -- digests
@@ -235,9 +235,15 @@ def test_device_source_matches_reference_on_other_experimental_groups(variant):
             emu.env_step(t)
             emu.agent_step(t, rs["meanWealth"])
             emu.compact(t)
+            replaced = 0
+            if c["agentReplacements"] > 0:
+                emu.push_mt_to_python()
+                replaced = pu.replace_dead_agents(c, state, pop, t)
+                emu.set_mt_from_python()
             d, snap = pu.state_digests(state, *emu.mt_state())
             assert d == gold[t]["digests"], f"state differs at t={t}"
-            rs = sb.update_with_groups(emu.stats(t), t, 0, emu.ethics_stats(), emu.ext_stats(t), emu.group_stats(t))
+            rs = sb.update_with_groups(emu.stats(t), t, replaced, emu.ethics_stats(), emu.ext_stats(t), emu.group_stats(t),
+                                       state.newest_members(replaced))
         assert len(log[t]) == 203
         for k in log[t]:
             assert k in rs and _close(rs[k], log[t][k]), f"log key {k} differs at t={t}: {rs.get(k)} vs {log[t][k]}"

@@ -60,7 +60,7 @@ def test_radial_ranges_and_asimov_match_reference_trajectory(variant):
 
 
 @pytest.mark.parametrize("variant", ["determinism_group_female", "determinism_group_male", "determinism_group_race1", "determinism_group_bentham",
-                                     "determinism_group_sick", "disease_mild_group_sick"])
+                                     "determinism_group_sick", "disease_mild_group_sick", "combat_group_male_replacement"])
 def test_other_experimental_groups_match_reference_trajectory_and_full_log(variant):
     base, overrides, gold, log = pu.load_variant(variant)
     c, state, pop, params, endow, tags, eng = _engine(base, layout.RNG_EXACT, overrides)
@@ -76,8 +76,16 @@ def test_other_experimental_groups_match_reference_trajectory_and_full_log(varia
             eng.env_step(t)
             eng.agent_step(t, rs["meanWealth"])
             eng.compact(t)
+            replaced = members = 0
+            if c["agentReplacements"] > 0 and int(eng.counters()[layout.C_N_LIST]) < c["agentReplacements"]:
+                hs = eng.download()              # (test_gpu_parity._replace, keeping the host state for the membership count)
+                eng.push_mt_to_python()
+                replaced = pu.replace_dead_agents(c, hs, pop, t)
+                eng.upload(hs, [key for key in eng.tensors if key != "pollution_flux"])
+                eng.set_mt_from_python()
+                members = hs.newest_members(replaced)
             eng.reduce_stats(t)
-            rs = sb.update_with_groups(eng.stats(), t, 0, eng.ethics_stats(), eng.ext_stats(), eng.group_stats())
+            rs = sb.update_with_groups(eng.stats(), t, replaced, eng.ethics_stats(), eng.ext_stats(), eng.group_stats(), members)
             d, snap = pu.state_digests(eng.download(), *eng.mt_state())
             assert d == gold[t]["digests"], f"{variant}: state differs from the reference at t={t}"
         assert len(log[t]) == 203
