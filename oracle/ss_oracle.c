@@ -1757,6 +1757,20 @@ void orc_agent_step(const ssb_params_t *p, const ssb_grid_t *g, const ssb_agents
     if (p->rng_mode == SSB_RNG_EXACT) {
         rng->mode = SSB_RNG_EXACT;
         rng_shuffle_i32(rng, a->order, (int)cn[SSB_C_N_LIST]);
+        /* addRemainingDiseases (sugarscape.py:139-151, called right after the shuffle): a disease whose start has come goes to
+         * the first agent of the list that is not immune to it -- no infection attempt, no infector -- and joins
+         * sugarscape.diseases; one that finds nobody waits for the next step.  start_timestep > 0 marks the waiting ones. */
+        if (g_dis)
+            for (int d = 0; d < g_dis->n_diseases; d++) {
+                if (g_dis->diseases[d].start_timestep <= 0 || g_dis->diseases[d].start_timestep > t) continue;
+                for (int64_t i = 0; i < cn[SSB_C_N_LIST]; i++) {
+                    if (orc_disease_nearest(a->order[i], d, NULL, NULL) == 0) continue;
+                    orc_disease_catch(a->order[i], d, -1, -1, t, 1, NULL);
+                    g_dis->diseases[d].listed++;
+                    g_dis->diseases[d].start_timestep = 0;
+                    break;
+                }
+            }
         /* the list may grow while iterating (children are appended and skipped) */
         for (int64_t i = 0; i < cn[SSB_C_N_LIST]; i++) agent_transaction(&c, a->order[i]);
     } else {

@@ -21,6 +21,7 @@ __device__ void agent_step_exact_body(const DevCtx &c, uint32_t *mt, const WarpS
     if (lane == 0) {
         cn[SSB_C_N_BORN] = 0;
         shuffle(rng, c.a.order, (int)cn[SSB_C_N_LIST]);        // random.shuffle(self.agents), sugarscape.py:400
+        if constexpr (EXT) { if (has_disease(c)) disease_add_remaining(c); }       // self.addRemainingDiseases(), sugarscape.py:401
     }
     Gr::sync();
     if constexpr (EXT) {

@@ -241,6 +241,31 @@ __device__ __noinline__ void disease_catch(const DevCtx &c, int s, int di, int i
         if (rec.incubation == 0) disease_trigger(D, s, di);
     }
 }
+// addRemainingDiseases (sugarscape.py:139-151; called right after the list shuffle of a step): a disease whose start has come
+// goes to the first agent of the list that is not immune to it -- catchDisease(initial=True): no infection attempt, no
+// infector, caught = this step -- and joins sugarscape.diseases; one that finds nobody waits for the next step.
+// ssb_disease_def_t.start_timestep > 0 marks the waiting ones.  One lane.
+__device__ __noinline__ void disease_add_remaining(const DevCtx &c) {
+    const ssb_diseases_t &D = c.x->diseases;
+    const long long n_list = c.a.counters[SSB_C_N_LIST];
+    for (int di = 0; di < D.n_diseases; di++) {
+        if (D.defs[di].start_timestep <= 0 || D.defs[di].start_timestep > c.t) continue;
+        for (long long i = 0; i < n_list; i++) {
+            const int s = c.a.order[i];
+            SickRec rec = {di, -1, -1, c.t, D.defs[di].incubation, -1, -1};
+            if (disease_nearest(D, s, di, &rec.start, &rec.end) == 0) continue;        // immune: the next agent
+            if (!infected_with(D, s, D.defs[di].id) && D.n_sick[s] < D.max_sick) {
+                sick_store(D, (long long)s * D.max_sick + D.n_sick[s], rec);
+                D.n_sick[s] += 1;
+                D.defs[di].infected++;
+                if (rec.incubation == 0) disease_trigger(D, s, di);
+            }
+            D.defs[di].listed++;
+            D.defs[di].start_timestep = 0;
+            break;
+        }
+    }
+}
 // doDisease (agent.py:315-361)
 template <class Rng>
 __device__ __noinline__ void do_disease(const DevCtx &c, int s, Rng &rng) {
@@ -692,6 +717,7 @@ __device__ inline void ext_stats_body(const DevCtx &c, ssb_ext_stats_t *out, int
     ssb_ext_stats_t r;
     r.loan_volume = 0; r.sum_social_happiness = 0; r.sum_conflict_happiness = 0;
     r.sick_agents = 0; r.disease_incidence = 0; r.distinct_infectors = 0; r.disease_prevalence = 0; r.disease_deaths = 0;
+    bool none_infector = false;
     r.sum_health_happiness = 0; r.move_space = 0; r.sum_burn_rate = 0; r.sum_ttl_age_limited = 0;
     for (int k = 0; k < 4; k++) { r.race_count[k] = 0; r.race_first[k] = -1; }
     const long long n = c.a.counters[SSB_C_N_LIST], n_dead = c.a.counters[SSB_C_N_DEAD];
@@ -727,6 +753,8 @@ __device__ inline void ext_stats_body(const DevCtx &c, ssb_ext_stats_t *out, int
                     const int inf = D.sick_infector_slot[b + k];
                     // distinct infectors: within one step a slot names one acting agent
                     if (c.t != 0 && inf >= 0 && D.stat_mark[inf] != mark) { D.stat_mark[inf] = mark; r.distinct_infectors++; }
+                    // (a disease that started this step came from nobody: `None` is one more member of the reference's set)
+                    if (c.t != 0 && inf < 0 && !none_infector) { none_infector = true; r.distinct_infectors++; }
                 }
             r.sum_health_happiness += D.health_happiness[s];
             r.move_space += D.last_valid_moves[s];

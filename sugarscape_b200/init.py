@@ -122,8 +122,8 @@ def check_supported(c):
     if c["diseaseList"]:
         problems.append("diseaseList")
     if c["startingDiseases"] > 0 and (c["agentImmuneSystemLength"] > 64 or c["diseaseTagStringLength"][1] > 32 or
-                                      c["diseaseTimeframe"] != [0, 0] or c["startingDiseases"] > 64):
-        problems.append("immune systems longer than 64 / disease tags longer than 32 / later-starting diseases / more than 64 diseases")
+                                      c["startingDiseases"] > 64):
+        problems.append("immune systems longer than 64 / disease tags longer than 32 / more than 64 diseases")
     if c["environmentMaxRaces"] > 0 and (c["agentRacialTagStringLength"] > 16 or c["environmentMaxRaces"] > 4):
         problems.append("racial tag strings longer than 16 / more than 4 races")
     if c["agentInheritancePolicy"] not in ("none", "children", "sons", "daughters"):
@@ -530,7 +530,7 @@ def configure_diseases(c, state, disease_endowments):
     ext.define_diseases(disease_endowments)
     n = int(state.counters[layout.C_N_LIST])
     agents = [int(s) for s in state.a_order[:n]]
-    initial = list(range(len(disease_endowments)))
+    initial = [i for i, e in enumerate(disease_endowments) if int(e["startTimestep"]) == 0]      # (the others wait: remainingDiseases)
     lo, hi = c["startingDiseasesPerAgent"]
     unlimited = [lo, hi] == [0, 0]
     curr = lo

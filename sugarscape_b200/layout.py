@@ -569,10 +569,10 @@ class HostExt:
     def define_diseases(self, disease_endowments):
         defs = self.arrays["diseases.defs"]
         for i, e in enumerate(disease_endowments):
-            if e["startTimestep"] != 0 or len(e["tags"]) > 32:
-                raise NotImplementedError("later-starting diseases / disease tags longer than 32")
-            d = defs[i]
-            d["id"], d["incubation"], d["start_timestep"], d["tag_len"] = i, int(e["incubationPeriod"]), 0, len(e["tags"])
+            if len(e["tags"]) > 32:
+                raise NotImplementedError("disease tags longer than 32")
+            d = defs[i]       # (start_timestep > 0: the disease waits in remainingDiseases, sugarscape.py:311-314)
+            d["id"], d["incubation"], d["start_timestep"], d["tag_len"] = i, int(e["incubationPeriod"]), int(e["startTimestep"]), len(e["tags"])
             d["tags"] = sum(b << k for k, b in enumerate(e["tags"]))
             d["transmission"] = float(e["transmissionChance"])
             d["penalty"] = [float(e[name]) for name in DISEASE_PENALTIES]

@@ -57,6 +57,10 @@ def draw_overrides(rng, base):
                    "diseaseFertilityPenalty": rng.choice([[0, 0], [-1, 0]]), "diseaseAggressionPenalty": rng.choice([[0, 0], [-1, 1]]),
                    "diseaseIncubationPeriod": rng.choice([[0, 0], [0, 3]]), "diseaseTransmissionChance": rng.choice([[1.0, 1.0], [0.2, 0.9]]),
                    "agentDiseaseProtectionChance": rng.choice([[0.0, 0.0], [0.0, 0.6]])})
+        if rng.random() < 0.4 or os.environ.get("SSB_FUZZ_LATE_DISEASES") == "1":      # diseases that start during the run
+            ov["diseaseTimeframe"] = rng.choice([[0, 20], [5, 30], [1, 1], [0, 100]])
+            if ov["startingDiseases"] == 0:
+                ov["startingDiseases"] = 10
     if rng.random() < 0.4:
         ov["agentDepressionPercentage"] = rng.choice([0, 0.05, 0.3])
     if rng.random() < 0.3:

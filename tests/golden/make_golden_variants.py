@@ -30,6 +30,10 @@ VARIANTS = {
     # diseases that incubate, spread with a chance, can be resisted and are recovered from
     "disease_mild": ("disease_basic", 150, dict(_MILD)),
     # long tag strings against a short immune system: slow recovery, the diseases stay around
+    # diseases that start during the run (diseaseTimeframe): addRemainingDiseases hands each one to the first agent of the
+    # shuffled list that is not immune, from its start timestep on
+    "disease_late_start": ("disease_basic", 150, dict(_MILD, diseaseTimeframe=[0, 40], startingDiseases=20)),
+    "determinism_late_diseases": ("determinism", 100, {"diseaseTimeframe": [0, 30], "experimentalGroup": None}),
     "disease_endemic": ("disease_basic", 120, {
         "diseaseSugarMetabolismPenalty": [0, 1], "diseaseSpiceMetabolismPenalty": [0, 0], "diseaseVisionPenalty": [-1, 0],
         "diseaseIncubationPeriod": [0, 2], "diseaseTransmissionChance": [0.6, 1.0], "agentDiseaseProtectionChance": [0.0, 0.3],

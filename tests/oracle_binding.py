@@ -159,8 +159,8 @@ class Oracle:
                  "spiceMetabolismPenalty", "sugarMetabolismPenalty", "visionPenalty")
         for i, e in enumerate(disease_endowments):
             d = self.disease_table[i]
-            assert e["startTimestep"] == 0 and len(e["tags"]) <= 32, "later-starting diseases are not restated"
-            d.id, d.incubation, d.start_timestep, d.tag_len = i, int(e["incubationPeriod"]), 0, len(e["tags"])
+            assert len(e["tags"]) <= 32
+            d.id, d.incubation, d.start_timestep, d.tag_len = i, int(e["incubationPeriod"]), int(e["startTimestep"]), len(e["tags"])
             d.tags = sum(b << k for k, b in enumerate(e["tags"]))
             d.transmission = float(e["transmissionChance"])
             for k, name in enumerate(order):
@@ -196,7 +196,7 @@ class Oracle:
                                                                "disease_death", "last_spread", "n_spread", "health_happiness",
                                                                "last_valid_moves", "immune_bits")], cap)
         # configureDiseases, after the agent shuffle (sugarscape.py:317-337)
-        initial = list(range(n_d))
+        initial = [i for i in range(n_d) if int(disease_endowments[i]["startTimestep"]) == 0]      # (the others wait: remainingDiseases)
         lo, hi = c["startingDiseasesPerAgent"]
         unlimited = [lo, hi] == [0, 0]
         curr = lo

@@ -134,7 +134,7 @@ def test_device_disease_source_matches_reference_on_disease_basic():
     assert sum(h["sickAgents"] > 0 for h in history) >= 4
 
 
-@pytest.mark.parametrize("variant,min_sick_steps", [("disease_mild", 15), ("disease_endemic", 80)])
+@pytest.mark.parametrize("variant,min_sick_steps", [("disease_mild", 15), ("disease_endemic", 80), ("disease_late_start", 25)])
 def test_device_disease_source_matches_reference_on_variants(variant, min_sick_steps):
     """Milder diseases (variant fixtures from the unmodified reference): incubation, transmission / protection draws,
     recovery through the immune response, births with inherited immune systems, vision pushed to 0."""
@@ -158,7 +158,7 @@ def test_device_source_without_wraparound_matches_reference(variant):
 
 
 @pytest.mark.parametrize("variant,ethics", [("determinism_plain", False), ("determinism_ethics", True), ("nowrap_determinism", True), ("moore_nowrap_determinism", True),
-                                            ("radial_determinism", True), ("radial_nowrap_determinism", True)])
+                                            ("radial_determinism", True), ("radial_nowrap_determinism", True), ("determinism_late_diseases", True)])
 def test_device_source_matches_reference_on_determinism_variants(variant, ethics):
     """examples/determinism.json (variant fixtures from the unmodified reference): diseases, depression, lending,
     friends, racial tags, universal income, live combat, trade, tags, inheritance, pollution and seasons at once --

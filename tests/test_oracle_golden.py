@@ -175,7 +175,7 @@ def test_oracle_disease_basic_matches_reference_trajectory():
     assert _disease_case("disease_basic", None, meta["steps"], meta["log"]) >= 4
 
 
-@pytest.mark.parametrize("variant,min_sick_steps", [("disease_mild", 15), ("disease_endemic", 80)])
+@pytest.mark.parametrize("variant,min_sick_steps", [("disease_mild", 15), ("disease_endemic", 80), ("disease_late_start", 25)])
 def test_oracle_disease_variants_match_reference_trajectory(variant, min_sick_steps):
     """disease_basic with milder diseases (tests/golden/make_golden_variants.py, run on the unmodified
     reference): incubation, transmission / protection draws, recovery through the immune response,
@@ -222,7 +222,7 @@ def _private_log_keys(orc, rs, t, ethics):
 
 
 @pytest.mark.parametrize("variant,ethics", [("determinism_plain", False), ("determinism_ethics", True), ("nowrap_determinism", True), ("moore_nowrap_determinism", True),
-                                            ("radial_determinism", True), ("radial_nowrap_determinism", True)])
+                                            ("radial_determinism", True), ("radial_nowrap_determinism", True), ("determinism_late_diseases", True)])
 def test_oracle_determinism_variants_match_reference_trajectory(variant, ethics):
     """examples/determinism.json (variant fixtures from the unmodified reference,
     tests/golden/make_golden_variants.py): diseases, depression, lending, friends, racial tags,

@@ -16,6 +16,9 @@ latter over the neighbourhood lists they stored at their own last ranking, at bi
 group is a decisionModel string) and -- changing during the run -- the sick, on determinism.json and on a disease example --
 digests and all 203 log keys against six fixtures of the unmodified reference (*_group_*).
 
+(4) diseases that start during the run (diseaseTimeframe; Sugarscape.addRemainingDiseases, sugarscape.py:139-151): two fixtures
+(*late*), oracle and device source.
+
 Status: the six radial fixtures pass on the CPU oracle (tests/test_oracle_golden.py) and on the device rule source compiled for
 the host (tests/test_hostemu.py), the seven Asimov fixtures on the latter (the oracle restates the Bentham family only); the
 four group fixtures on the latter as well (the oracle's group is "depressed"); these cases have NOT run on a B200 yet.  The file sorts after every other test file so that its
@@ -34,11 +37,13 @@ pytestmark = [pytest.mark.gpu]
 @pytest.mark.parametrize("variant", ["radial_small_map", "radial_trade_tagging_reproduction", "radial_combat", "radial_determinism",
                                      "radial_nowrap_small_map", "radial_nowrap_determinism",
                                      "asimov_trade", "asimov_combat", "asimov_determinism", "asimov_temperance", "asimov_temperance_pecs",
-                                     "asimov_bentham", "asimov_bentham_combat"])
+                                     "asimov_bentham", "asimov_bentham_combat",
+                                     "disease_late_start", "determinism_late_diseases"])
 def test_radial_ranges_and_asimov_match_reference_trajectory(variant):
     base, overrides, gold, log = pu.load_variant(variant)
     c, state, pop, params, endow, tags, eng = _engine(base, layout.RNG_EXACT, overrides)
-    assert (params.flags & layout.F_RADIAL) if variant.startswith("radial") else (state.ethics.arrays["model"] == 4).any()
+    assert ((params.flags & layout.F_RADIAL) if variant.startswith("radial") else (state.ethics.arrays["model"] == 4).any() if variant.startswith("asimov")
+            else c["diseaseTimeframe"] != [0, 0])
     sb = stats.StatsBuilder(c, init.equator(c))
     eng.reduce_stats(0)
     rs = sb.update(eng.stats(), 0, 0, eng.ethics_stats(), eng.ext_stats())
