@@ -1098,7 +1098,7 @@ static void collect(ctx_t *c, int s, int pos) {
 /* candidate record of rankCellsInRange */
 typedef struct { int32_t cell; int32_t dist; double welfare; } cand_t;
 
-#define MAX_CAND 256
+#define MAX_CAND 4096      /* (a radial range can hold a whole small map: no silent truncation in the checker) */
 
 /* agent.py:766-779 with the insertion order of environment.py:111-122 */
 static int enumerate_disc(const ctx_t *c, int pos, int r, int32_t *cells, int32_t *dists);
