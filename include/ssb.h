@@ -252,7 +252,8 @@ typedef struct ssb_ethics {
      * (ethics.py:74-75), and that value walks agent.neighborhood as the neighbour last stored it -- at its own ranking, at
      * birth, or when the agents were (re)configured (agent.py:1052-1065, 526; sugarscape.py:265-267).  Kept per slot as
      * (slot, id) pairs in list order when hood_stride > 0; hood_n = -1: to be rebuilt at the start of the next agent step
-     * (the host sets it for every slot when it places agents). */
+     * (the host sets it for every slot when it places agents; -2 for the initial population, whose lists the reference
+     * makes before the first infections: ranges without the disease modifiers). */
     int32_t *hood_list, *hood_id;   /* [slot][hood_stride]                                            */
     int32_t *hood_n;
     int64_t hood_stride;            /* 0: not kept; else SSB_GROUP_HOOD_MAX                           */

@@ -29,7 +29,10 @@ __device__ void agent_step_exact_body(const DevCtx &c, uint32_t *mt, const WarpS
         // neighbourhood is rebuilt where it stands (sugarscape.py:265-267; the host marked the lists with -1)
         if (keeps_hoods(c) && lane == 0) {
             const long long n0 = (long long)cn[SSB_C_N_LIST];
-            for (long long i = 0; i < n0; i++) if (c.eth->hood_n[c.a.order[i]] == -1) hood_store_here(c, c.a.order[i]);
+            for (long long i = 0; i < n0; i++) {       // -1: after a replacement; -2: the initial population (before its diseases)
+                const int mark = c.eth->hood_n[c.a.order[i]];
+                if (mark == -1 || mark == -2) hood_store_here(c, c.a.order[i], mark == -2);
+            }
         }
         Gr::sync();
     }

@@ -838,12 +838,15 @@ __device__ inline void hood_store(const DevCtx &c, int s, const int32_t *cells, 
     c.eth->hood_n[s] = k;
 }
 // ... for an agent that is not ranking: a newborn (agent.py:525-526), everybody after a (re)placement (sugarscape.py:265-267)
-__device__ __noinline__ void hood_store_here(const DevCtx &c, int s) {
+// (bare: the lists of the initial population are made by configureAgents BEFORE configureDiseases hands out the first
+// infections, sugarscape.py:73-75 -- with the endowed vision and movement, whatever the diseases do to them afterwards)
+__device__ __noinline__ void hood_store_here(const DevCtx &c, int s, bool bare = false) {
     int32_t cells[MAXC_EXACT_RULES];
     uint8_t dist[MAXC_EXACT_RULES];
     WarpScratch ws = {};
     ws.cells = cells; ws.dist = dist;
-    const int r = min(min((int)eff_vision(c, s), (int)eff_movement(c, s)), max_cell_distance(c));
+    const int r = bare ? min(min(max(c.a.vision[s], 0), max(c.a.movement[s], 0)), max_cell_distance(c))
+                       : min(min((int)eff_vision(c, s), (int)eff_movement(c, s)), max_cell_distance(c));
     const int H = c.p.height, x = c.a.pos[s] / H, y = c.a.pos[s] - x * H;
     int n = 0;
     if (r > 0) n = radial(c) ? enumerate_disc(c, x, y, r, ws, MAXC_EXACT_RULES) : enumerate_cross(c, x, y, r, ws, MAXC_EXACT_RULES);

@@ -754,6 +754,7 @@ class HostState:
         yet (the slots of this step's dead, which the stats reduction still has to read)."""
         n_list = int(self.counters[C_N_LIST])
         n_slots = int(self.counters[C_N_SLOTS])
+        first_placement = n_slots == 0
         n_free = int(self.counters[C_N_FREE])
         protected = self.a_free_slots[n_free - protect_last:n_free].copy() if protect_last else None
         n_free -= protect_last
@@ -803,7 +804,9 @@ class HostState:
             self.occ[a["cell"]] = slot
             n_list += 1
         if self.ethics is not None and self.ethics.hood_stride and len(new_agents):
-            self.ethics.arrays["hood_n"][:] = -1       # configureAgents ends with findNeighborhood() for EVERY agent (sugarscape.py:265-267)
+            # configureAgents ends with findNeighborhood() for EVERY agent (sugarscape.py:265-267); the first time this happens
+            # before the diseases are handed out (-2: ranges without their modifiers), at a replacement with them (-1)
+            self.ethics.arrays["hood_n"][:] = -2 if first_placement else -1
         if protect_last:
             self.a_free_slots[n_free:n_free + protect_last] = protected
             n_free += protect_last

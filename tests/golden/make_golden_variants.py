@@ -128,6 +128,18 @@ VARIANTS = {
     "asimov_bentham": ("trade_tagging_reproduction", 120, dict(_ETHICS, agentDecisionModels=["asimov", "bentham", "none", "egoist", "altruistHalfLookahead"])),
     "asimov_bentham_combat": ("combat_limited", 100, dict(_ETHICS, agentDecisionModels=["asimov", "bentham", "altruist", "none"], agentAggressionFactor=[0, 2],
                                                           agentDecisionModelFactor=[0, 1])),
+    # ... with diseases that change vision: the initial population's stored neighbourhoods date from before the first infections
+    "asimov_bentham_determinism": ("determinism", 100, dict(_ETHICS, agentDecisionModels=["asimov", "bentham", "egoist", "none"], experimentalGroup=None,
+                                                            agentDecisionModelFactor=[0.5, 1], diseaseIncubationPeriod=[0, 0])),
+    # (found by fuzzing: radial ranges without wraparound + diseases that change vision + robots next to Bentham agents)
+    "asimov_bentham_radial_diseases": ("dune", 40, {
+        "seed": 246036, "environmentWidth": 36, "environmentHeight": 36, "startingAgents": 165, "experimentalGroup": None,
+        "agentLendingFactor": [0, 0], "agentMaxFriends": [5, 10], "startingDiseases": 30, "startingDiseasesPerAgent": [1, 4],
+        "agentImmuneSystemLength": 40, "diseaseTagStringLength": [2, 6], "diseaseSugarMetabolismPenalty": [0, 1], "diseaseVisionPenalty": [-1, 1],
+        "diseaseIncubationPeriod": [0, 0], "diseaseTransmissionChance": [0.2, 0.9], "diseaseTimeframe": [0, 100], "agentUniversalSpice": [1, 1],
+        "environmentUniversalSugarIncomeInterval": 3, "environmentUniversalSpiceIncomeInterval": 2, "agentDecisionModels": ["asimov", "bentham"],
+        "agentDecisionModelFactor": [0.5, 1], "agentDecisionModelLookaheadFactor": 1, "environmentWraparound": False,
+        "agentVisionMode": "radial", "agentMovementMode": "radial"}),
     "asimov_determinism": ("determinism", 100, dict(_ETHICS, agentDecisionModels=["asimov", "rawSugarscape"], experimentalGroup=None,
                                                     agentDecisionModelFactor=[0, 1])),
     "ethics_top": ("trade_tagging_reproduction", 100, dict(_ETHICS, agentDecisionModels=["benthamTop", "egoistTop", "altruistNoLookaheadTop", "none", "bentham"])),

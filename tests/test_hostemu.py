@@ -57,7 +57,9 @@ ETHICS_VARIANTS = ["ethics_trade", "ethics_combat", "ethics_replacement", "ethic
                    "ethics_top",
                    # ethics.Asimov among plain agents (ethics.py:8-98): with spice and births, sugar-only with live combat and
                    # replacement, and on top of every other family of determinism.json
-                   "asimov_trade", "asimov_combat", "asimov_determinism", "asimov_temperance", "asimov_temperance_pecs", "asimov_bentham", "asimov_bentham_combat"]
+                   "asimov_trade", "asimov_combat", "asimov_determinism", "asimov_temperance", "asimov_temperance_pecs", "asimov_bentham", "asimov_bentham_combat", "asimov_bentham_determinism",
+                   # found by fuzzing: the initial population's stored neighbourhoods date from before the first infections
+                   "asimov_bentham_radial_diseases"]
 
 
 @pytest.mark.parametrize("variant", ETHICS_VARIANTS)

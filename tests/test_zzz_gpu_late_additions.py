@@ -8,7 +8,7 @@ for every family of determinism.json incl. the Bentham decision models.  Integer
 bit-exact on every step, fp64 holdings through their digest, all 59 log keys.
 
 (2) ethics.Asimov among plain agents, Temperance agents (both variants) and the Bentham family (reference ethics.py:8-98; `asimov_pick` in csrc/ssb_rules.cuh)
-against seven fixtures of the unmodified reference (asimov_*): with spice and births, sugar-only with live combat and replacement,
+against nine fixtures of the unmodified reference (asimov_*): with spice and births, sugar-only with live combat and replacement,
 on top of every other family of determinism.json, and next to Temperance and Bentham agents that answer the second law (the
 latter over the neighbourhood lists they stored at their own last ranking, at birth or at the last replacement).
 
@@ -20,7 +20,7 @@ digests and all 203 log keys against six fixtures of the unmodified reference (*
 (*late*), oracle and device source.
 
 Status: the six radial fixtures pass on the CPU oracle (tests/test_oracle_golden.py) and on the device rule source compiled for
-the host (tests/test_hostemu.py), the seven Asimov fixtures on the latter (the oracle restates the Bentham family only); the
+the host (tests/test_hostemu.py), the nine Asimov fixtures on the latter (the oracle restates the Bentham family only); the
 four group fixtures on the latter as well (the oracle's group is "depressed"); these cases have NOT run on a B200 yet.  The file sorts after every other test file so that its
 first GPU run cannot hide anything else."""
 import pytest
@@ -37,7 +37,7 @@ pytestmark = [pytest.mark.gpu]
 @pytest.mark.parametrize("variant", ["radial_small_map", "radial_trade_tagging_reproduction", "radial_combat", "radial_determinism",
                                      "radial_nowrap_small_map", "radial_nowrap_determinism",
                                      "asimov_trade", "asimov_combat", "asimov_determinism", "asimov_temperance", "asimov_temperance_pecs",
-                                     "asimov_bentham", "asimov_bentham_combat",
+                                     "asimov_bentham", "asimov_bentham_combat", "asimov_bentham_determinism", "asimov_bentham_radial_diseases",
                                      "disease_late_start", "determinism_late_diseases"])
 def test_radial_ranges_and_asimov_match_reference_trajectory(variant):
     base, overrides, gold, log = pu.load_variant(variant)
