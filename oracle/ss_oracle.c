@@ -1098,7 +1098,12 @@ static void collect(ctx_t *c, int s, int pos) {
 /* candidate record of rankCellsInRange */
 typedef struct { int32_t cell; int32_t dist; double welfare; } cand_t;
 
-#define MAX_CAND 4096      /* (a radial range can hold a whole small map: no silent truncation in the checker) */
+/* candidate arrays: a cross holds at most 4 * 64 cells; a radial range can hold a whole small map -- no silent truncation in
+ * the checker (the engine stops such a run, overflow code 15).  Sized per call (C11 variable-length arrays), so that the
+ * cross keeps the small frames the CPU baseline of bench.py is timed with. */
+#define MAX_CAND_CROSS 256
+#define MAX_CAND_RADIAL 4096
+#define MAX_CAND(c) (((c)->p->flags & SSB_F_RADIAL) ? MAX_CAND_RADIAL : MAX_CAND_CROSS)
 
 /* agent.py:766-779 with the insertion order of environment.py:111-122 */
 static int enumerate_disc(const ctx_t *c, int pos, int r, int32_t *cells, int32_t *dists);
@@ -1124,7 +1129,7 @@ static int enumerate_cross(const ctx_t *c, int pos, int r, int32_t *cells, int32
                 int64_t tk = key[j]; key[j] = key[j - 1]; key[j - 1] = tk;
                 int32_t tc = cell[j]; cell[j] = cell[j - 1]; cell[j - 1] = tc;
             }
-        for (int i = 0; i < m && n < MAX_CAND; i++) { cells[n] = cell[i]; dists[n++] = d; }
+        for (int i = 0; i < m && n < MAX_CAND(c); i++) { cells[n] = cell[i]; dists[n++] = d; }
     }
     return n;
 }
@@ -1153,7 +1158,7 @@ static int enumerate_disc(const ctx_t *c, int pos, int r, int32_t *cells, int32_
             const int dx = wrap_distance(c, x1 - j / H, W), dy = wrap_distance(c, y1 - j % H, H);
             if (j == pos || dx > radial_cap(c, W) || dy > radial_cap(c, H)) continue;
             if ((int)floor(sqrt((double)(dx * dx + dy * dy))) != g) continue;
-            if (n < MAX_CAND) { cells[n] = j; dists[n++] = dx * dx + dy * dy; }
+            if (n < MAX_CAND(c)) { cells[n] = j; dists[n++] = dx * dx + dy * dy; }
         }
     return n;
 }
@@ -1207,7 +1212,7 @@ static double ethical_value(ctx_t *c, int s, int my_r, const int32_t *hood, int 
     /* len(self.findNeighborhood(cell)): live agents in MY cross moved to `cell`, plus myself */
     double future_hood = 1;
     if (lookahead != 0) {
-        int32_t fc[MAX_CAND], fd[MAX_CAND];
+        int32_t fc[MAX_CAND(c)], fd[MAX_CAND(c)];
         const int fn = my_r > 0 ? enumerate_cross(c, cell, my_r, fc, fd) : 0;
         int cnt = 1;
         for (int i = 0; i < fn; i++) { int o = c->g.occ[fc[i]]; if (o >= 0 && agent_alive(c, o)) cnt++; }
@@ -1230,7 +1235,7 @@ static double ethical_value(ctx_t *c, int s, int my_r, const int32_t *hood, int 
         future_duration = max_site > 0 ? future_duration / max_site : 0;
         int32_t nb_cells[MAX_NEIGHBOURS];
         const double future_intensity = neighbor_wealth / (g_eth->global_max_wealth * neighbours4(c, a->pos[nb], nb_cells));   /* len(neighbor.cell.neighbors) */
-        int32_t tc[MAX_CAND], td[MAX_CAND];
+        int32_t tc[MAX_CAND(c)], td[MAX_CAND(c)];
         const int in_range = rn > 0 ? enumerate_cross(c, a->pos[nb], rn, tc, td) : 0;          /* len(neighbor.cellsInRange) */
         const double extent = in_range > 0 ? (double)n_hood / in_range : 1;
         const double future_extent = (in_range > 0 && lookahead != 0) ? future_hood / in_range : 1;
@@ -1257,7 +1262,7 @@ static int move_to_best_cell(ctx_t *c, int s) {
     int maxd = max_cell_distance(c);
     int r = vision < movement ? vision : movement;
     if (r > maxd) r = maxd;
-    int32_t cells[MAX_CAND], dists[MAX_CAND];
+    int32_t cells[MAX_CAND(c)], dists[MAX_CAND(c)];
     int n = r > 0 ? enumerate_cross(c, pos, r, cells, dists) : 0;
     double aggression = EFF_AGGRESSION(c, s);
     int best = pos;
@@ -1276,7 +1281,7 @@ static int move_to_best_cell(ctx_t *c, int s) {
         }
         if (g_group) { g_group->control_neighbors[s] = hood_ctrl; g_group->experimental_neighbors[s] = hood_exp; }
         /* random.shuffle(list(cellsInRange.items())) -- shuffle an index permutation */
-        int32_t perm[MAX_CAND];
+        int32_t perm[MAX_CAND(c)];
         for (int i = 0; i < n; i++) perm[i] = i;
         rng_at(c->rng, SITE_MOVE);
         rng_move_shuffle_i32(c->rng, perm, n);
@@ -1291,7 +1296,7 @@ static int move_to_best_cell(ctx_t *c, int s) {
                 double w = a->sugar[o] + a->spice[o];
                 if (!have[tr] || retaliator[tr] < w) { retaliator[tr] = w; have[tr] = 1; }
             }
-        cand_t cand[MAX_CAND]; int m = 0;
+        cand_t cand[MAX_CAND(c)]; int m = 0;
         double loot = c->p->max_combat_loot;
         double my_wealth = a->sugar[s] + a->spice[s];
         for (int k = 0; k < n; k++) {
@@ -1322,7 +1327,7 @@ static int move_to_best_cell(ctx_t *c, int s) {
         int rank = 0;
         if (g_eth && g_eth->model[s] == 1 && g_eth->decision_factor[s] > 0) {
             /* findBestEthicalCell (ethics.py:105-139): re-score the welfare-sorted cells */
-            int32_t hoodv[MAX_CAND + 1]; int nh = 0;
+            int32_t hoodv[MAX_CAND(c) + 1]; int nh = 0;
             for (int i = 0; i < n; i++) { int o = c->g.occ[cells[i]]; if (o >= 0 && agent_alive(c, o)) hoodv[nh++] = o; }
             hoodv[nh++] = s;
             int chosen = -1;
